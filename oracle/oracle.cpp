@@ -1,0 +1,1472 @@
+// oracle/oracle.cpp — TEST INFRASTRUCTURE ONLY (see oracle.h).
+//
+// CPU restatement of the reference's search core: tokenizer, inverted index,
+// posting-list set algebra, BM25 and score sort, and the regular path of the
+// search pipeline. Every function cites the reference file:line it follows
+// (paths relative to /root/reference/). It is the checker for the CUDA path
+// and the "port" CPU baseline; it is never linked into or called by libmgx.so.
+//
+// Deliberate differences from the reference, none of which can change a result:
+//   * posting lists are plain sorted std::vector<uint32_t> (the reference keeps
+//     the same set as fixed-width deltas or a Roaring bitmap,
+//     posting_list.cpp:20-21,242-324 -- an encoding, not a semantic);
+//   * no locks / RCU snapshots (single writer, readers after build);
+//   * logging dropped.
+
+#include "oracle.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <queue>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <tuple>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// Tokenizer (src/utils/string_utils.cpp)
+// ---------------------------------------------------------------------------
+
+// TryParseUtf8Char, string_utils.cpp:92-164.
+int TryParseUtf8Char(const unsigned char* data, size_t available, uint32_t* out_cp) {
+  if (available == 0) {
+    return -1;
+  }
+  const unsigned char b0 = data[0];
+  if ((b0 & 0x80) == 0) {
+    *out_cp = b0;
+    return 1;
+  }
+  if ((b0 & 0xE0) == 0xC0) {
+    if (b0 < 0xC2 || available < 2) {  // :105-110 overlong / truncated
+      return -1;
+    }
+    if ((data[1] & 0xC0) != 0x80) {
+      return -1;
+    }
+    *out_cp = (static_cast<uint32_t>(b0 & 0x1F) << 6) | (data[1] & 0x3F);
+    return 2;
+  }
+  if ((b0 & 0xF0) == 0xE0) {
+    if (available < 3) {
+      return -1;
+    }
+    if ((data[1] & 0xC0) != 0x80 || (data[2] & 0xC0) != 0x80) {
+      return -1;
+    }
+    const uint32_t cp =
+        (static_cast<uint32_t>(b0 & 0x0F) << 12) | (static_cast<uint32_t>(data[1] & 0x3F) << 6) | (data[2] & 0x3F);
+    if (cp < 0x800 || (cp >= 0xD800 && cp <= 0xDFFF)) {  // :131 overlong or surrogate
+      return -1;
+    }
+    *out_cp = cp;
+    return 3;
+  }
+  if ((b0 & 0xF8) == 0xF0) {
+    if (b0 > 0xF4 || available < 4) {  // :139-144
+      return -1;
+    }
+    if ((data[1] & 0xC0) != 0x80 || (data[2] & 0xC0) != 0x80 || (data[3] & 0xC0) != 0x80) {
+      return -1;
+    }
+    const uint32_t cp = (static_cast<uint32_t>(b0 & 0x07) << 18) | (static_cast<uint32_t>(data[1] & 0x3F) << 12) |
+                        (static_cast<uint32_t>(data[2] & 0x3F) << 6) | (data[3] & 0x3F);
+    if (cp < 0x10000 || cp > 0x10FFFF) {  // :156
+      return -1;
+    }
+    *out_cp = cp;
+    return 4;
+  }
+  return -1;  // :162 invalid start byte
+}
+
+// Utf8ToCodepoints, string_utils.cpp:200-219: invalid byte => skip one byte.
+std::vector<uint32_t> Utf8ToCodepoints(std::string_view text) {
+  std::vector<uint32_t> cps;
+  cps.reserve(text.size() / 2 + 1);
+  const auto* data = reinterpret_cast<const unsigned char*>(text.data());
+  size_t i = 0;
+  while (i < text.size()) {
+    uint32_t cp = 0;
+    const int len = TryParseUtf8Char(data + i, text.size() - i, &cp);
+    if (len > 0) {
+      cps.push_back(cp);
+      i += static_cast<size_t>(len);
+    } else {
+      ++i;
+    }
+  }
+  return cps;
+}
+
+// CodepointsToUtf8, string_utils.cpp:243-272 (surrogates / >0x10FFFF skipped).
+void AppendUtf8(std::string& out, const uint32_t* begin, const uint32_t* end) {
+  for (const uint32_t* it = begin; it != end; ++it) {
+    const uint32_t cp = *it;
+    if ((cp >= 0xD800 && cp <= 0xDFFF) || cp > 0x10FFFF) {
+      continue;
+    }
+    if (cp <= 0x7F) {
+      out += static_cast<char>(cp);
+    } else if (cp <= 0x7FF) {
+      out += static_cast<char>(0xC0 | (cp >> 6));
+      out += static_cast<char>(0x80 | (cp & 0x3F));
+    } else if (cp <= 0xFFFF) {
+      out += static_cast<char>(0xE0 | (cp >> 12));
+      out += static_cast<char>(0x80 | ((cp >> 6) & 0x3F));
+      out += static_cast<char>(0x80 | (cp & 0x3F));
+    } else {
+      out += static_cast<char>(0xF0 | (cp >> 18));
+      out += static_cast<char>(0x80 | ((cp >> 12) & 0x3F));
+      out += static_cast<char>(0x80 | ((cp >> 6) & 0x3F));
+      out += static_cast<char>(0x80 | (cp & 0x3F));
+    }
+  }
+}
+
+std::string CodepointsToUtf8(const uint32_t* begin, const uint32_t* end) {
+  std::string out;
+  out.reserve(static_cast<size_t>(end - begin) * 3);
+  AppendUtf8(out, begin, end);
+  return out;
+}
+
+// CountCodePoints, string_utils.cpp:655-669.
+size_t CountCodePoints(std::string_view text) {
+  size_t count = 0;
+  const auto* data = reinterpret_cast<const unsigned char*>(text.data());
+  for (size_t i = 0; i < text.size();) {
+    uint32_t cp = 0;
+    const int len = TryParseUtf8Char(data + i, text.size() - i, &cp);
+    if (len < 0) {
+      ++i;
+      continue;
+    }
+    i += static_cast<size_t>(len);
+    ++count;
+  }
+  return count;
+}
+
+// IsCJKIdeograph, string_utils.cpp:441-448 (ranges :176-187).
+bool IsCJKIdeograph(uint32_t cp) {
+  return (cp >= 0x4E00 && cp <= 0x9FFF) || (cp >= 0x3400 && cp <= 0x4DBF) || (cp >= 0x20000 && cp <= 0x2A6DF) ||
+         (cp >= 0x2A700 && cp <= 0x2B73F) || (cp >= 0x2B740 && cp <= 0x2B81F) || (cp >= 0xF900 && cp <= 0xFAFF);
+}
+
+// GenerateNgrams, string_utils.cpp:382-423.
+std::vector<std::string> GenerateNgrams(std::string_view text, int n) {
+  std::vector<std::string> ngrams;
+  const std::vector<uint32_t> cps = Utf8ToCodepoints(text);
+  const size_t cp_count = cps.size();
+  if (cp_count == 0 || n <= 0) {
+    return ngrams;
+  }
+  if (n == 1) {
+    ngrams.reserve(cp_count);
+    for (size_t i = 0; i < cp_count; ++i) {
+      ngrams.push_back(CodepointsToUtf8(cps.data() + i, cps.data() + i + 1));
+    }
+    return ngrams;
+  }
+  if (cp_count < static_cast<size_t>(n)) {
+    return ngrams;
+  }
+  ngrams.reserve(cp_count - static_cast<size_t>(n) + 1);
+  for (size_t i = 0; i <= cp_count - static_cast<size_t>(n); ++i) {
+    ngrams.push_back(CodepointsToUtf8(cps.data() + i, cps.data() + i + n));
+  }
+  return ngrams;
+}
+
+// GenerateHybridNgrams, string_utils.cpp:452-509.
+std::vector<std::string> GenerateHybridNgrams(std::string_view text, int ascii_n, int kanji_n, bool cross_boundary) {
+  std::vector<std::string> ngrams;
+  if (ascii_n <= 0 || kanji_n <= 0) {  // :456
+    return ngrams;
+  }
+  const std::vector<uint32_t> cps = Utf8ToCodepoints(text);
+  const size_t cp_count = cps.size();
+  if (cp_count == 0) {
+    return ngrams;
+  }
+  ngrams.reserve(cp_count);
+  for (size_t i = 0; i < cp_count; ++i) {
+    const bool start_is_cjk = IsCJKIdeograph(cps[i]);  // :484 size chosen by the START code point
+    const int size = start_is_cjk ? kanji_n : ascii_n;
+    if (i + static_cast<size_t>(size) > cp_count) {  // :487
+      continue;
+    }
+    if (!cross_boundary) {  // :491-503 legacy: reject windows mixing CJK / non-CJK
+      bool crossed = false;
+      for (int j = 1; j < size; ++j) {
+        if (IsCJKIdeograph(cps[i + static_cast<size_t>(j)]) != start_is_cjk) {
+          crossed = true;
+          break;
+        }
+      }
+      if (crossed) {
+        continue;
+      }
+    }
+    ngrams.push_back(CodepointsToUtf8(cps.data() + i, cps.data() + i + size));
+  }
+  return ngrams;
+}
+
+// GenerateQueryNgrams, string_utils.cpp:639-653.
+std::vector<std::string> GenerateQueryNgrams(std::string_view normalized, int ngram_size, int kanji_ngram_size,
+                                             bool cross_boundary) {
+  if (kanji_ngram_size > 0) {
+    const int effective = (ngram_size > 0) ? ngram_size : 2;
+    return GenerateHybridNgrams(normalized, effective, kanji_ngram_size, cross_boundary);
+  }
+  if (ngram_size == 0) {
+    return GenerateHybridNgrams(normalized, 2, 1, true);  // header defaults, string_utils.h
+  }
+  return GenerateNgrams(normalized, ngram_size);
+}
+
+// DeduplicateSorted, string_utils.h:192-196.
+template <typename T>
+void DeduplicateSorted(std::vector<T>& vec) {
+  std::sort(vec.begin(), vec.end());
+  vec.erase(std::unique(vec.begin(), vec.end()), vec.end());
+}
+
+// ---------------------------------------------------------------------------
+// Index (src/index/index.cpp) over sorted-vector posting lists
+// ---------------------------------------------------------------------------
+
+using DocId = uint32_t;
+using Posting = std::vector<DocId>;
+
+struct SvHash {
+  using is_transparent = void;
+  size_t operator()(std::string_view s) const { return std::hash<std::string_view>{}(s); }
+  size_t operator()(const std::string& s) const { return std::hash<std::string_view>{}(s); }
+};
+struct SvEq {
+  using is_transparent = void;
+  bool operator()(std::string_view a, std::string_view b) const { return a == b; }
+};
+
+}  // namespace
+
+struct orc_index {
+  int ngram_size = 2;
+  int kanji_ngram_size = 2;  // effective, index.cpp:32
+  bool cross_boundary = true;
+  std::unordered_map<std::string, Posting, SvHash, SvEq> postings;
+
+  // DocumentStore stand-in: normalised text per doc id (document_store.cpp:144-147).
+  // Two backings: owned strings for incremental adds, or a borrowed arena with
+  // ascending doc ids for bulk builds.
+  std::unordered_map<DocId, std::string> texts;
+  std::unordered_set<DocId> known_docs;  // every doc id ever added (DocumentStore::GetAllDocIds)
+  const uint8_t* arena = nullptr;
+  const uint64_t* arena_offsets = nullptr;
+  const uint32_t* arena_doc_ids = nullptr;
+  uint64_t arena_docs = 0;
+  bool arena_sequential = false;  // doc_ids[i] == doc_ids[0] + i
+
+  // BM25Stats, server_types.h:157-220.
+  uint64_t total_doc_length = 0;
+  uint64_t doc_count = 0;
+
+  const Posting* Find(std::string_view term) const {
+    auto it = postings.find(term);
+    return it == postings.end() ? nullptr : &it->second;
+  }
+
+  // text pointer or nullptr (VisitNormalizedTextsFor, document_store_retrieval.cpp:289-322)
+  bool GetText(DocId doc, std::string_view* out) const {
+    if (arena != nullptr) {
+      uint64_t pos;
+      if (arena_sequential) {
+        if (doc < arena_doc_ids[0] || doc - arena_doc_ids[0] >= arena_docs) {
+          return false;
+        }
+        pos = doc - arena_doc_ids[0];
+      } else {
+        const uint32_t* it = std::lower_bound(arena_doc_ids, arena_doc_ids + arena_docs, doc);
+        if (it == arena_doc_ids + arena_docs || *it != doc) {
+          return false;
+        }
+        pos = static_cast<uint64_t>(it - arena_doc_ids);
+      }
+      const uint64_t b = arena_offsets[pos];
+      const uint64_t e = arena_offsets[pos + 1];
+      if (e == b) {
+        return false;  // empty text is never stored
+      }
+      *out = std::string_view(reinterpret_cast<const char*>(arena) + b, e - b);
+      return true;
+    }
+    auto it = texts.find(doc);
+    if (it == texts.end()) {
+      return false;
+    }
+    *out = it->second;
+    return true;
+  }
+};
+
+namespace {
+
+std::vector<std::string> IndexNgrams(const orc_index& idx, std::string_view text) {
+  // index.cpp:41-42,88: always the hybrid generator with the effective kanji size.
+  auto ngrams = GenerateHybridNgrams(text, idx.ngram_size, idx.kanji_ngram_size, idx.cross_boundary);
+  DeduplicateSorted(ngrams);
+  return ngrams;
+}
+
+// PostingList::Add, posting_list.cpp:242-289 (set insert keeping order).
+void PostingAdd(Posting& list, DocId doc) {
+  if (list.empty() || list.back() < doc) {
+    list.push_back(doc);
+    return;
+  }
+  auto pos = std::lower_bound(list.begin(), list.end(), doc);
+  if (pos == list.end() || *pos != doc) {
+    list.insert(pos, doc);
+  }
+}
+
+// PostingList::AddBatch, posting_list.cpp:291-324 (set_union with sorted batch).
+void PostingAddBatch(Posting& list, const std::vector<DocId>& sorted_docs) {
+  if (list.empty()) {
+    list = sorted_docs;
+    list.erase(std::unique(list.begin(), list.end()), list.end());
+    return;
+  }
+  if (!sorted_docs.empty() && list.back() < sorted_docs.front()) {
+    size_t old = list.size();
+    list.insert(list.end(), sorted_docs.begin(), sorted_docs.end());
+    list.erase(std::unique(list.begin() + static_cast<std::ptrdiff_t>(old) - 1, list.end()), list.end());
+    return;
+  }
+  Posting merged;
+  merged.reserve(list.size() + sorted_docs.size());
+  std::set_union(list.begin(), list.end(), sorted_docs.begin(), sorted_docs.end(), std::back_inserter(merged));
+  list.swap(merged);
+}
+
+void StoreTextAndStats(orc_index& idx, DocId doc, std::string_view text) {
+  idx.known_docs.insert(doc);
+  if (!text.empty()) {
+    idx.texts[doc] = std::string(text);
+    // binlog_event_processor.cpp:98-100 / server_orchestrator.cpp:758-772
+    idx.total_doc_length += CountCodePoints(text);
+    idx.doc_count += 1;
+  }
+}
+
+// TakePostingSnapshots, index.cpp:728-747.
+std::vector<const Posting*> Snapshots(const orc_index& idx, const std::vector<std::string_view>& terms) {
+  std::vector<const Posting*> out;
+  out.reserve(terms.size());
+  for (auto term : terms) {
+    out.push_back(idx.Find(term));
+  }
+  return out;
+}
+
+// Index::SearchAnd, index.cpp:199-368. The planner branches (:221-332) pick a
+// cheaper evaluation order but compute the same set; the standard path is
+// restated, then limit/reverse is applied as :356-366 (and GetTopN :476-545).
+std::vector<DocId> SearchAnd(const orc_index& idx, const std::vector<std::string_view>& terms, size_t limit,
+                             bool reverse) {
+  if (terms.empty()) {
+    return {};
+  }
+  auto snaps = Snapshots(idx, terms);
+  for (const auto* s : snaps) {
+    if (s == nullptr) {
+      return {};
+    }
+  }
+  std::vector<DocId> result = *snaps[0];  // GetAll() materialises a copy (:338)
+  for (size_t i = 1; i < snaps.size(); ++i) {
+    const std::vector<DocId> term_docs = *snaps[i];  // GetAll() (:342)
+    std::vector<DocId> inter;
+    std::set_intersection(result.begin(), result.end(), term_docs.begin(), term_docs.end(),
+                          std::back_inserter(inter));
+    result = std::move(inter);
+    if (result.empty()) {
+      break;
+    }
+  }
+  if (limit > 0 && result.size() > limit) {
+    if (reverse) {
+      result.erase(result.begin(), result.begin() + static_cast<std::ptrdiff_t>(result.size() - limit));
+      std::reverse(result.begin(), result.end());
+    } else {
+      result.resize(limit);
+    }
+  } else if (reverse) {
+    std::reverse(result.begin(), result.end());
+  }
+  return result;
+}
+
+// PostingList::RetainPresent, posting_list.cpp:432-474: keep sorted candidates present in the list.
+std::vector<DocId> RetainPresent(const Posting& list, const std::vector<DocId>& sorted_candidates) {
+  std::vector<DocId> out;
+  size_t j = 0;
+  for (DocId c : sorted_candidates) {
+    while (j < list.size() && list[j] < c) {
+      ++j;
+    }
+    if (j < list.size() && list[j] == c) {
+      out.push_back(c);  // duplicates in the candidate list are each retained
+    }
+  }
+  return out;
+}
+
+// Index::FilterByNgrams, index.cpp:370-416.
+std::vector<DocId> FilterByNgrams(const orc_index& idx, const std::vector<DocId>& candidates,
+                                  const std::vector<std::string_view>& terms) {
+  if (candidates.empty()) {
+    return {};
+  }
+  auto snaps = Snapshots(idx, terms);
+  if (snaps.empty()) {
+    return candidates;
+  }
+  for (const auto* s : snaps) {
+    if (s == nullptr) {
+      return {};
+    }
+  }
+  const bool ascending = std::is_sorted(candidates.begin(), candidates.end());
+  std::vector<DocId> sorted_candidates;
+  if (!ascending) {
+    sorted_candidates = candidates;
+    std::sort(sorted_candidates.begin(), sorted_candidates.end());
+  }
+  std::vector<DocId> retained = RetainPresent(*snaps[0], ascending ? candidates : sorted_candidates);
+  for (size_t i = 1; i < snaps.size() && !retained.empty(); ++i) {
+    retained = RetainPresent(*snaps[i], retained);
+  }
+  if (ascending || retained.empty()) {
+    return retained;
+  }
+  const std::unordered_set<DocId> kept(retained.begin(), retained.end());
+  std::vector<DocId> ordered;
+  for (DocId d : candidates) {
+    if (kept.find(d) != kept.end()) {
+      ordered.push_back(d);
+    }
+  }
+  return ordered;
+}
+
+// Index::SearchOr, index.cpp:418-448.
+std::vector<DocId> SearchOr(const orc_index& idx, const std::vector<std::string_view>& terms) {
+  if (terms.empty()) {
+    return {};
+  }
+  std::vector<DocId> result;
+  std::vector<DocId> temp;
+  for (const auto* s : Snapshots(idx, terms)) {
+    if (s != nullptr) {
+      temp.clear();
+      std::set_union(result.begin(), result.end(), s->begin(), s->end(), std::back_inserter(temp));
+      result.swap(temp);
+    }
+  }
+  return result;
+}
+
+// Index::SearchNot, index.cpp:450-486.
+std::vector<DocId> SearchNot(const orc_index& idx, const std::vector<DocId>& all_docs,
+                             const std::vector<std::string_view>& terms) {
+  if (terms.empty()) {
+    return all_docs;
+  }
+  const std::vector<DocId> excluded = SearchOr(idx, terms);
+  std::vector<DocId> result;
+  std::set_difference(all_docs.begin(), all_docs.end(), excluded.begin(), excluded.end(), std::back_inserter(result));
+  return result;
+}
+
+// Index::SearchByThreshold, index.cpp:488-578.
+std::vector<DocId> SearchByThreshold(const orc_index& idx, const std::vector<std::string_view>& terms,
+                                     size_t threshold) {
+  if (terms.empty() || threshold == 0) {
+    return {};
+  }
+  std::vector<std::string_view> unique_terms = terms;
+  DeduplicateSorted(unique_terms);
+  if (threshold > unique_terms.size()) {
+    return {};
+  }
+  if (threshold == unique_terms.size()) {
+    return SearchAnd(idx, unique_terms, 0, false);
+  }
+  std::vector<const Posting*> valid;
+  for (const auto* s : Snapshots(idx, unique_terms)) {
+    if (s != nullptr) {
+      valid.push_back(s);
+    }
+  }
+  if (valid.size() < threshold) {
+    return {};
+  }
+  using HeapEntry = std::tuple<DocId, size_t, size_t>;
+  std::priority_queue<HeapEntry, std::vector<HeapEntry>, std::greater<HeapEntry>> heap;
+  for (size_t i = 0; i < valid.size(); ++i) {
+    if (!valid[i]->empty()) {
+      heap.emplace((*valid[i])[0], i, 0);
+    }
+  }
+  std::vector<DocId> result;
+  DocId current = 0;
+  size_t count = 0;
+  bool has_current = false;
+  while (!heap.empty()) {
+    auto [doc, li, pos] = heap.top();
+    heap.pop();
+    if (!has_current || doc != current) {
+      if (has_current && count >= threshold) {
+        result.push_back(current);
+      }
+      current = doc;
+      count = 1;
+      has_current = true;
+    } else {
+      ++count;
+    }
+    if (pos + 1 < valid[li]->size()) {
+      heap.emplace((*valid[li])[pos + 1], li, pos + 1);
+    }
+  }
+  if (has_current && count >= threshold) {
+    result.push_back(current);
+  }
+  return result;
+}
+
+// ---------------------------------------------------------------------------
+// BM25 (src/index/bm25_scorer.cpp) and score sort (src/query/result_sorter.cpp)
+// ---------------------------------------------------------------------------
+
+// BM25Scorer::ComputeIDF, bm25_scorer.cpp:14-25.
+double ComputeIDF(uint64_t total_docs, uint64_t doc_freq) {
+  if (total_docs == 0) {
+    return 0.0;
+  }
+  if (doc_freq > total_docs) {
+    doc_freq = total_docs;
+  }
+  const auto n = static_cast<double>(total_docs);
+  const auto df = static_cast<double>(doc_freq);
+  return std::log((n - df + 0.5) / (df + 0.5) + 1.0);
+}
+
+// BM25Scorer::CountTermOccurrences, bm25_scorer.cpp:27-45 (bytes, non-overlapping).
+uint32_t CountTermOccurrences(std::string_view text, std::string_view term) {
+  if (text.empty() || term.empty() || term.size() > text.size()) {
+    return 0;
+  }
+  uint32_t count = 0;
+  size_t pos = 0;
+  while (pos <= text.size() - term.size()) {
+    const auto found = text.find(term, pos);
+    if (found == std::string_view::npos) {
+      break;
+    }
+    ++count;
+    pos = found + term.size();
+  }
+  return count;
+}
+
+// BM25Scorer::ScoreDocuments, bm25_scorer.cpp:47-99. The arithmetic is written
+// operation by operation so that -ffp-contract=off reproduces the reference's
+// unfused evaluation order.
+double ScoreOne(std::string_view text, const std::vector<std::string_view>& terms, const std::vector<double>& idfs,
+                double avg_doc_length, double k1, double b) {
+  double score = 0.0;
+  const auto doc_length = static_cast<double>(CountCodePoints(text));
+  for (size_t i = 0; i < terms.size(); ++i) {
+    const auto tf = static_cast<double>(CountTermOccurrences(text, terms[i]));
+    if (tf > 0.0) {
+      const double length_norm = 1.0 - b + b * doc_length / std::max(avg_doc_length, 1.0);
+      const double numerator = tf * (k1 + 1.0);
+      const double denominator = tf + k1 * length_norm;
+      score += idfs[i] * numerator / denominator;
+    }
+  }
+  return score;
+}
+
+void ScoreDocuments(const orc_index& idx, const DocId* candidates, size_t n, const std::vector<std::string_view>& terms,
+                    const uint64_t* dfs, uint64_t total_docs, double avg_doc_length, double k1, double b,
+                    double* out) {
+  std::vector<double> idfs;
+  idfs.reserve(terms.size());
+  for (size_t i = 0; i < terms.size(); ++i) {
+    idfs.push_back(ComputeIDF(total_docs, dfs[i]));
+  }
+  for (size_t c = 0; c < n; ++c) {
+    std::string_view text;
+    double score = 0.0;
+    if (idx.GetText(candidates[c], &text) && !text.empty()) {
+      score = ScoreOne(text, terms, idfs, avg_doc_length, k1, b);
+    }
+    out[c] = score;
+  }
+}
+
+// ResultSorter::SortByScore, result_sorter.cpp:661-716 (kPartialSortThreshold = 0.5).
+std::vector<DocId> SortByScore(const DocId* results, const double* scores, size_t n, bool descending, uint32_t limit,
+                               uint32_t offset) {
+  if (n == 0) {
+    return {};
+  }
+  struct Entry {
+    size_t index;
+    DocId doc;
+    double score;
+  };
+  std::vector<Entry> entries;
+  entries.reserve(n);
+  for (size_t i = 0; i < n; ++i) {
+    entries.push_back({i, results[i], scores[i]});
+  }
+  auto cmp = [descending](const Entry& l, const Entry& r) {
+    if (l.score == r.score) {
+      return descending ? (l.doc > r.doc) : (l.doc < r.doc);  // :681-686 tie => same direction on doc_id
+    }
+    return descending ? (l.score > r.score) : (l.score < r.score);
+  };
+  const uint64_t needed64 = static_cast<uint64_t>(offset) + static_cast<uint64_t>(limit);
+  const size_t needed = (limit == 0 || needed64 > entries.size()) ? entries.size() : static_cast<size_t>(needed64);
+  const bool partial =
+      needed < entries.size() && static_cast<double>(needed) < static_cast<double>(entries.size()) * 0.5;
+  if (partial) {
+    std::partial_sort(entries.begin(), entries.begin() + static_cast<std::ptrdiff_t>(needed), entries.end(), cmp);
+  } else {
+    std::sort(entries.begin(), entries.end(), cmp);
+  }
+  const size_t start = std::min(static_cast<size_t>(offset), entries.size());
+  const size_t end = (limit == 0) ? entries.size() : std::min(start + static_cast<size_t>(limit), entries.size());
+  std::vector<DocId> out;
+  out.reserve(end - start);
+  for (size_t i = start; i < end; ++i) {
+    out.push_back(results[entries[i].index]);
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------
+// Search pipeline, regular path (src/server/search_pipeline.cpp)
+// ---------------------------------------------------------------------------
+
+struct TermInfo {  // SearchTermInfo, search_pipeline.h
+  std::vector<std::string> ngrams;
+  size_t estimated_size = 0;
+  uint64_t df = 0;
+  std::string normalized;
+  size_t source_index = 0;  // position in the caller's term table (for out_df)
+};
+
+std::vector<std::string_view> Views(const std::vector<std::string>& v) {
+  return std::vector<std::string_view>(v.begin(), v.end());
+}
+
+// query::SearchNormalizedSubstring, query/substring_search.h:24-42: every stored
+// text in ascending doc-id order.
+std::vector<DocId> SearchNormalizedSubstring(const orc_index& idx, std::string_view term) {
+  std::vector<DocId> matches;
+  if (term.empty()) {
+    return matches;
+  }
+  if (idx.arena != nullptr) {
+    for (uint64_t i = 0; i < idx.arena_docs; ++i) {
+      const uint64_t b = idx.arena_offsets[i];
+      const uint64_t e = idx.arena_offsets[i + 1];
+      if (e > b && std::string_view(reinterpret_cast<const char*>(idx.arena) + b, e - b).find(term) !=
+                       std::string_view::npos) {
+        matches.push_back(idx.arena_doc_ids[i]);
+      }
+    }
+    if (!idx.arena_sequential) {
+      std::sort(matches.begin(), matches.end());
+    }
+    return matches;
+  }
+  for (const auto& [doc, text] : idx.texts) {
+    if (text.find(term) != std::string::npos) {
+      matches.push_back(doc);
+    }
+  }
+  std::sort(matches.begin(), matches.end());
+  return matches;
+}
+
+// SearchTermDocuments, search_pipeline.cpp:438-446.
+std::vector<DocId> SearchTermDocuments(const orc_index& idx, const TermInfo& ti) {
+  if (ti.ngrams.empty()) {
+    return SearchNormalizedSubstring(idx, ti.normalized);
+  }
+  return SearchAnd(idx, Views(ti.ngrams), 0, false);
+}
+
+// GenerateTermInfos + PopulateTermDocumentFrequency, search_pipeline.cpp:569-603, 542-565.
+// Index::NormalizeText is the identity here: the path's contract is that text
+// and terms arrive normalised (index.h:83-84; ICU stays on the host).
+TermInfo MakeTermInfo(const orc_index& idx, std::string_view term, const orc_query_params_t& p, bool compute_df) {
+  TermInfo ti;
+  ti.normalized = std::string(term);
+  ti.ngrams = GenerateQueryNgrams(ti.normalized, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0);
+  DeduplicateSorted(ti.ngrams);
+  size_t min_size = std::numeric_limits<size_t>::max();
+  for (const auto& g : ti.ngrams) {
+    const Posting* list = idx.Find(g);
+    const uint64_t size = list != nullptr ? list->size() : 0;  // EstimatePostingSize, index.cpp:756-759
+    if (size > 0) {
+      min_size = std::min(min_size, static_cast<size_t>(size));
+    } else {
+      min_size = 0;
+      break;
+    }
+  }
+  ti.estimated_size = min_size;
+  ti.df = 0;
+  if (compute_df && !ti.ngrams.empty() && ti.estimated_size != 0 &&
+      ti.estimated_size != std::numeric_limits<size_t>::max()) {
+    const auto candidates = SearchAnd(idx, Views(ti.ngrams), 0, false);
+    uint64_t matching = 0;
+    for (DocId d : candidates) {
+      std::string_view text;
+      if (idx.GetText(d, &text) && text.find(ti.normalized) != std::string_view::npos) {
+        ++matching;
+      }
+    }
+    ti.df = matching;
+  }
+  return ti;
+}
+
+struct QueryOutput {
+  std::vector<DocId> results;  // ascending result set
+  std::vector<TermInfo> term_infos;
+};
+
+// ExecuteFullPipeline regular path (:2002-2033) + Execute (:795-869) + ApplyNotFilter (:871-932).
+QueryOutput RunQuery(const orc_index& idx, const orc_query_params_t& p, const std::vector<std::string_view>& terms,
+                     size_t first_term_index, const std::vector<std::string_view>& not_terms) {
+  QueryOutput out;
+  for (size_t i = 0; i < terms.size(); ++i) {
+    out.term_infos.push_back(MakeTermInfo(idx, terms[i], p, p.compute_score != 0));
+    out.term_infos.back().source_index = first_term_index + i;
+  }
+  // :2012-2014 std::sort by estimated_size. libstdc++ runs a plain insertion
+  // sort for <= 16 elements, i.e. equal keys keep their query order; a stable
+  // sort reproduces that (queries are limited to 64 terms, query_ast.h:184-185;
+  // beyond 16 the reference's own order for equal sizes is unspecified).
+  std::stable_sort(out.term_infos.begin(), out.term_infos.end(),
+                   [](const TermInfo& l, const TermInfo& r) { return l.estimated_size < r.estimated_size; });
+
+  // Execute :804-810 early exit
+  for (const auto& ti : out.term_infos) {
+    if ((ti.estimated_size == 0 || ti.estimated_size == std::numeric_limits<size_t>::max()) &&
+        (!ti.ngrams.empty() || ti.normalized.empty())) {
+      return out;  // empty_term_detected => results cleared
+    }
+  }
+  std::vector<DocId> results;
+  if (!out.term_infos.empty()) {
+    results = SearchTermDocuments(idx, out.term_infos[0]);
+    for (size_t i = 1; i < out.term_infos.size() && !results.empty(); ++i) {
+      const auto& ti = out.term_infos[i];
+      if (ti.ngrams.empty() || results.size() > p.filter_threshold) {
+        const auto and_results = SearchTermDocuments(idx, ti);
+        std::vector<DocId> inter;
+        std::set_intersection(results.begin(), results.end(), and_results.begin(), and_results.end(),
+                              std::back_inserter(inter));
+        results = std::move(inter);
+      } else {
+        results = FilterByNgrams(idx, results, Views(ti.ngrams));  // :826-828
+      }
+    }
+  }
+  // ApplyNotFilter :871-932
+  if (!results.empty() && !not_terms.empty()) {
+    std::vector<DocId> excluded;
+    std::vector<DocId> temp;
+    for (auto nt : not_terms) {
+      const TermInfo ti = MakeTermInfo(idx, nt, p, false);
+      const std::vector<DocId> term_docs = SearchTermDocuments(idx, ti);
+      temp.clear();
+      std::set_union(excluded.begin(), excluded.end(), term_docs.begin(), term_docs.end(), std::back_inserter(temp));
+      excluded.swap(temp);
+    }
+    if (!excluded.empty()) {
+      std::vector<DocId> filtered;
+      std::set_difference(results.begin(), results.end(), excluded.begin(), excluded.end(),
+                          std::back_inserter(filtered));
+      results = std::move(filtered);
+    }
+  }
+  out.results = std::move(results);
+  return out;
+}
+
+std::vector<std::string_view> TermList(const uint8_t* bytes, const uint64_t* offsets, uint64_t begin, uint64_t end) {
+  std::vector<std::string_view> out;
+  out.reserve(end - begin);
+  for (uint64_t i = begin; i < end; ++i) {
+    out.emplace_back(reinterpret_cast<const char*>(bytes) + offsets[i], offsets[i + 1] - offsets[i]);
+  }
+  return out;
+}
+
+uint64_t CopyOut(const std::vector<DocId>& v, uint32_t* out, uint64_t cap) {
+  if (out != nullptr) {
+    std::memcpy(out, v.data(), std::min<uint64_t>(v.size(), cap) * sizeof(uint32_t));
+  }
+  return v.size();
+}
+
+// Packed key used only by the bulk builder: (cp+1) in 21-bit fields, first
+// code point in the most significant field, so that integer order == bytewise
+// order of the UTF-8 n-gram strings.
+inline uint64_t PackKey(const uint32_t* cps, int n, int width) {
+  uint64_t key = 0;
+  for (int j = 0; j < width; ++j) {
+    key = (key << 21) | (j < n ? static_cast<uint64_t>(cps[j]) + 1 : 0);
+  }
+  return key;
+}
+
+std::string UnpackKey(uint64_t key, int width) {
+  uint32_t cps[3];
+  int n = 0;
+  for (int j = width - 1; j >= 0; --j) {
+    const uint64_t f = (key >> (21 * j)) & 0x1FFFFF;
+    if (f != 0) {
+      cps[n++] = static_cast<uint32_t>(f - 1);
+    }
+  }
+  // CodepointsToUtf8 would drop surrogates; keys only ever hold decoded (valid) code points.
+  return CodepointsToUtf8(cps, cps + n);
+}
+
+struct Pair {
+  uint64_t key;
+  uint32_t doc;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+
+extern "C" {
+
+uint64_t orc_utf8_to_codepoints(const uint8_t* text, uint64_t len, uint32_t* out, uint64_t cap) {
+  const auto cps = Utf8ToCodepoints(std::string_view(reinterpret_cast<const char*>(text), len));
+  if (out != nullptr) {
+    std::memcpy(out, cps.data(), std::min<uint64_t>(cps.size(), cap) * sizeof(uint32_t));
+  }
+  return cps.size();
+}
+
+uint64_t orc_codepoints_to_utf8(const uint32_t* cps, uint64_t n, uint8_t* out) {
+  const std::string s = CodepointsToUtf8(cps, cps + n);
+  std::memcpy(out, s.data(), s.size());
+  return s.size();
+}
+
+uint64_t orc_count_code_points(const uint8_t* text, uint64_t len) {
+  return CountCodePoints(std::string_view(reinterpret_cast<const char*>(text), len));
+}
+
+int orc_is_cjk_ideograph(uint32_t cp) { return IsCJKIdeograph(cp) ? 1 : 0; }
+
+int64_t orc_ngrams(int mode, const uint8_t* text, uint64_t len, int a, int k, int cross, uint8_t* out_bytes,
+                   uint64_t cap_bytes, uint64_t* out_offsets, uint64_t cap_ngrams) {
+  const std::string_view sv(reinterpret_cast<const char*>(text), len);
+  std::vector<std::string> ngrams;
+  if (mode == 0) {
+    ngrams = GenerateNgrams(sv, a);
+  } else if (mode == 1) {
+    ngrams = GenerateHybridNgrams(sv, a, k, cross != 0);
+  } else {
+    ngrams = GenerateQueryNgrams(sv, a, k, cross != 0);
+  }
+  uint64_t total = 0;
+  for (const auto& g : ngrams) {
+    total += g.size();
+  }
+  if (ngrams.size() > cap_ngrams || total > cap_bytes) {
+    return -static_cast<int64_t>(std::max<uint64_t>(ngrams.size(), total) + 1);
+  }
+  uint64_t pos = 0;
+  for (size_t i = 0; i < ngrams.size(); ++i) {
+    out_offsets[i] = pos;
+    std::memcpy(out_bytes + pos, ngrams[i].data(), ngrams[i].size());
+    pos += ngrams[i].size();
+  }
+  out_offsets[ngrams.size()] = pos;
+  return static_cast<int64_t>(ngrams.size());
+}
+
+orc_index_t* orc_index_create(int ngram_size, int kanji_ngram_size, int cross_boundary) {
+  auto* idx = new orc_index();
+  idx->ngram_size = ngram_size;
+  idx->kanji_ngram_size = kanji_ngram_size > 0 ? kanji_ngram_size : ngram_size;  // index.cpp:32
+  idx->cross_boundary = cross_boundary != 0;
+  return idx;
+}
+
+void orc_index_destroy(orc_index_t* idx) { delete idx; }
+
+int orc_index_add_document(orc_index_t* idx, uint32_t doc_id, const uint8_t* text, uint64_t len) {
+  const std::string_view sv(reinterpret_cast<const char*>(text), len);
+  StoreTextAndStats(*idx, doc_id, sv);
+  const auto ngrams = IndexNgrams(*idx, sv);
+  if (ngrams.empty()) {
+    return 0;  // index.cpp:49-57
+  }
+  for (const auto& g : ngrams) {
+    PostingAdd(idx->postings[g], doc_id);
+  }
+  return 1;
+}
+
+void orc_index_add_batch(orc_index_t* idx, const uint32_t* doc_ids, const uint8_t* text, const uint64_t* offsets,
+                         uint64_t n_docs, uint64_t batch) {
+  if (batch == 0) {
+    batch = 1000;  // initial_loader.cpp:41
+  }
+  for (uint64_t begin = 0; begin < n_docs; begin += batch) {
+    const uint64_t end = std::min(n_docs, begin + batch);
+    std::unordered_map<std::string, std::vector<DocId>> term_to_docs;  // index.cpp:83
+    for (uint64_t d = begin; d < end; ++d) {
+      const std::string_view sv(reinterpret_cast<const char*>(text) + offsets[d], offsets[d + 1] - offsets[d]);
+      StoreTextAndStats(*idx, doc_ids[d], sv);
+      const auto ngrams = IndexNgrams(*idx, sv);
+      for (const auto& g : ngrams) {  // empty => skipped (:93-101)
+        term_to_docs[g].push_back(doc_ids[d]);
+      }
+    }
+    for (auto& [term, docs] : term_to_docs) {
+      std::sort(docs.begin(), docs.end());  // :110-112
+      PostingAddBatch(idx->postings[term], docs);
+    }
+  }
+}
+
+int orc_index_build_bulk(orc_index_t* idx, const uint32_t* doc_ids, const uint8_t* text, const uint64_t* offsets,
+                         uint64_t n_docs, int n_threads) {
+  const int width = std::max(idx->ngram_size, idx->kanji_ngram_size);
+  if (width > 3 || idx->ngram_size <= 0) {
+    return -1;
+  }
+  if (n_threads <= 0) {
+    n_threads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+  }
+  n_threads = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(n_threads), std::max<uint64_t>(1, n_docs)));
+  idx->arena = text;
+  idx->arena_offsets = offsets;
+  idx->arena_doc_ids = doc_ids;
+  idx->arena_docs = n_docs;
+  idx->arena_sequential = true;
+  for (uint64_t i = 1; i < n_docs; ++i) {
+    if (doc_ids[i] != doc_ids[0] + i) {
+      idx->arena_sequential = false;
+      break;
+    }
+  }
+  if (!idx->arena_sequential && !std::is_sorted(doc_ids, doc_ids + n_docs)) {
+    return -2;
+  }
+
+  // Phase 1: tokenise per thread (doc ranges), per-doc sort+unique like index.cpp:88-91.
+  std::vector<std::vector<Pair>> parts(static_cast<size_t>(n_threads));
+  std::vector<uint64_t> len_sum(static_cast<size_t>(n_threads), 0);
+  std::vector<uint64_t> cnt_sum(static_cast<size_t>(n_threads), 0);
+  auto tokenize = [&](int t) {
+    const uint64_t begin = n_docs * static_cast<uint64_t>(t) / static_cast<uint64_t>(n_threads);
+    const uint64_t end = n_docs * static_cast<uint64_t>(t + 1) / static_cast<uint64_t>(n_threads);
+    auto& out = parts[static_cast<size_t>(t)];
+    std::vector<uint64_t> keys;
+    for (uint64_t d = begin; d < end; ++d) {
+      const std::string_view sv(reinterpret_cast<const char*>(text) + offsets[d], offsets[d + 1] - offsets[d]);
+      if (sv.empty()) {
+        continue;
+      }
+      const auto cps = Utf8ToCodepoints(sv);
+      len_sum[static_cast<size_t>(t)] += cps.size();
+      cnt_sum[static_cast<size_t>(t)] += 1;
+      keys.clear();
+      for (size_t i = 0; i < cps.size(); ++i) {
+        const bool cjk = IsCJKIdeograph(cps[i]);
+        const int size = cjk ? idx->kanji_ngram_size : idx->ngram_size;
+        if (i + static_cast<size_t>(size) > cps.size()) {
+          continue;
+        }
+        if (!idx->cross_boundary) {
+          bool crossed = false;
+          for (int j = 1; j < size; ++j) {
+            if (IsCJKIdeograph(cps[i + static_cast<size_t>(j)]) != cjk) {
+              crossed = true;
+              break;
+            }
+          }
+          if (crossed) {
+            continue;
+          }
+        }
+        keys.push_back(PackKey(cps.data() + i, size, width));
+      }
+      std::sort(keys.begin(), keys.end());
+      keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+      for (uint64_t k : keys) {
+        out.push_back({k, doc_ids[d]});
+      }
+    }
+  };
+  {
+    std::vector<std::thread> threads;
+    for (int t = 0; t < n_threads; ++t) {
+      threads.emplace_back(tokenize, t);
+    }
+    for (auto& th : threads) {
+      th.join();
+    }
+  }
+  for (int t = 0; t < n_threads; ++t) {
+    idx->total_doc_length += len_sum[static_cast<size_t>(t)];
+    idx->doc_count += cnt_sum[static_cast<size_t>(t)];
+  }
+
+  // Phase 2: bucket by the top key bits so each bucket can be sorted independently.
+  uint64_t total = 0;
+  for (const auto& p : parts) {
+    total += p.size();
+  }
+  constexpr int kBucketBits = 12;
+  const int shift = std::max(0, 21 * width - kBucketBits);
+  const size_t n_buckets = static_cast<size_t>(1) << kBucketBits;
+  std::vector<uint64_t> bucket_count(n_buckets + 1, 0);
+  for (const auto& p : parts) {
+    for (const auto& pr : p) {
+      bucket_count[(pr.key >> shift) + 1]++;
+    }
+  }
+  for (size_t i = 0; i < n_buckets; ++i) {
+    bucket_count[i + 1] += bucket_count[i];
+  }
+  std::vector<Pair> all(total);
+  {
+    std::vector<uint64_t> cursor(bucket_count.begin(), bucket_count.end() - 1);
+    for (auto& p : parts) {  // parts are in ascending doc order, so buckets stay doc-ordered
+      for (const auto& pr : p) {
+        all[cursor[pr.key >> shift]++] = pr;
+      }
+      std::vector<Pair>().swap(p);
+    }
+  }
+  std::atomic<size_t> next_bucket{0};
+  auto sort_buckets = [&]() {
+    for (;;) {
+      const size_t bkt = next_bucket.fetch_add(1);
+      if (bkt >= n_buckets) {
+        break;
+      }
+      std::stable_sort(all.begin() + static_cast<std::ptrdiff_t>(bucket_count[bkt]),
+                       all.begin() + static_cast<std::ptrdiff_t>(bucket_count[bkt + 1]),
+                       [](const Pair& l, const Pair& r) { return l.key < r.key; });
+    }
+  };
+  {
+    std::vector<std::thread> threads;
+    for (int t = 0; t < n_threads; ++t) {
+      threads.emplace_back(sort_buckets);
+    }
+    for (auto& th : threads) {
+      th.join();
+    }
+  }
+
+  // Phase 3: one posting list per distinct key (docs already ascending and unique per key).
+  size_t i = 0;
+  idx->postings.reserve(static_cast<size_t>(total / 8 + 16));
+  while (i < all.size()) {
+    size_t j = i;
+    while (j < all.size() && all[j].key == all[i].key) {
+      ++j;
+    }
+    Posting list;
+    list.reserve(j - i);
+    for (size_t k = i; k < j; ++k) {
+      list.push_back(all[k].doc);
+    }
+    idx->postings.emplace(UnpackKey(all[i].key, width), std::move(list));
+    i = j;
+  }
+  return 0;
+}
+
+void orc_index_remove_document(orc_index_t* idx, uint32_t doc_id, const uint8_t* text, uint64_t len) {
+  const std::string_view sv(reinterpret_cast<const char*>(text), len);
+  for (const auto& g : IndexNgrams(*idx, sv)) {  // index.cpp:175-189
+    auto it = idx->postings.find(g);
+    if (it == idx->postings.end()) {
+      continue;
+    }
+    auto pos = std::lower_bound(it->second.begin(), it->second.end(), doc_id);
+    if (pos != it->second.end() && *pos == doc_id) {
+      it->second.erase(pos);
+    }
+    if (it->second.empty()) {
+      idx->postings.erase(it);  // RemoveFromPostingList erases empty lists, index.cpp:693-717
+    }
+  }
+  auto t = idx->texts.find(doc_id);
+  if (t != idx->texts.end()) {
+    // BM25Stats::RemoveDocument saturating subtract, server_types.h:204-218
+    const uint64_t dl = CountCodePoints(t->second);
+    idx->total_doc_length = idx->total_doc_length > dl ? idx->total_doc_length - dl : 0;
+    idx->doc_count = idx->doc_count > 1 ? idx->doc_count - 1 : 0;
+    idx->texts.erase(t);
+  }
+  idx->known_docs.erase(doc_id);
+}
+
+void orc_index_update_document(orc_index_t* idx, uint32_t doc_id, const uint8_t* old_text, uint64_t old_len,
+                               const uint8_t* new_text, uint64_t new_len) {
+  const std::string_view old_sv(reinterpret_cast<const char*>(old_text), old_len);
+  const std::string_view new_sv(reinterpret_cast<const char*>(new_text), new_len);
+  const auto old_ngrams = IndexNgrams(*idx, old_sv);  // index.cpp:123-130
+  const auto new_ngrams = IndexNgrams(*idx, new_sv);
+  std::vector<std::string> to_remove;
+  std::vector<std::string> to_add;
+  std::set_difference(old_ngrams.begin(), old_ngrams.end(), new_ngrams.begin(), new_ngrams.end(),
+                      std::back_inserter(to_remove));
+  std::set_difference(new_ngrams.begin(), new_ngrams.end(), old_ngrams.begin(), old_ngrams.end(),
+                      std::back_inserter(to_add));
+  for (const auto& g : to_remove) {
+    auto it = idx->postings.find(g);
+    if (it == idx->postings.end()) {
+      continue;
+    }
+    auto pos = std::lower_bound(it->second.begin(), it->second.end(), doc_id);
+    if (pos != it->second.end() && *pos == doc_id) {
+      it->second.erase(pos);
+    }
+    if (it->second.empty()) {
+      idx->postings.erase(it);
+    }
+  }
+  for (const auto& g : to_add) {
+    PostingAdd(idx->postings[g], doc_id);
+  }
+  // text + stats follow binlog_event_processor.cpp:236-243 (remove old length, add new)
+  auto t = idx->texts.find(doc_id);
+  if (t != idx->texts.end()) {
+    const uint64_t dl = CountCodePoints(t->second);
+    idx->total_doc_length = idx->total_doc_length > dl ? idx->total_doc_length - dl : 0;
+    idx->doc_count = idx->doc_count > 1 ? idx->doc_count - 1 : 0;
+    idx->texts.erase(t);
+  }
+  StoreTextAndStats(*idx, doc_id, new_sv);
+}
+
+uint64_t orc_index_term_count(const orc_index_t* idx) { return idx->postings.size(); }
+
+uint64_t orc_index_posting_size(const orc_index_t* idx, const uint8_t* term, uint64_t len) {
+  const Posting* list = idx->Find(std::string_view(reinterpret_cast<const char*>(term), len));
+  return list != nullptr ? list->size() : 0;
+}
+
+uint64_t orc_index_total_postings(const orc_index_t* idx) {
+  uint64_t total = 0;
+  for (const auto& [term, list] : idx->postings) {
+    total += list.size();
+  }
+  return total;
+}
+
+uint64_t orc_index_get_postings(const orc_index_t* idx, const uint8_t* term, uint64_t len, uint32_t* out,
+                                uint64_t cap) {
+  const Posting* list = idx->Find(std::string_view(reinterpret_cast<const char*>(term), len));
+  if (list == nullptr) {
+    return 0;
+  }
+  return CopyOut(*list, out, cap);
+}
+
+uint64_t orc_index_export(const orc_index_t* idx, uint8_t* term_bytes_out, uint64_t* term_offsets_out,
+                          uint64_t* posting_offsets_out, uint32_t* postings_out, uint64_t* total_term_bytes) {
+  std::vector<const std::pair<const std::string, Posting>*> order;
+  order.reserve(idx->postings.size());
+  uint64_t bytes = 0;
+  for (const auto& kv : idx->postings) {
+    order.push_back(&kv);
+    bytes += kv.first.size();
+  }
+  if (total_term_bytes != nullptr) {
+    *total_term_bytes = bytes;
+  }
+  if (term_bytes_out == nullptr) {
+    return order.size();
+  }
+  std::sort(order.begin(), order.end(), [](const auto* l, const auto* r) { return l->first < r->first; });
+  uint64_t tb = 0;
+  uint64_t pb = 0;
+  for (size_t i = 0; i < order.size(); ++i) {
+    term_offsets_out[i] = tb;
+    posting_offsets_out[i] = pb;
+    std::memcpy(term_bytes_out + tb, order[i]->first.data(), order[i]->first.size());
+    tb += order[i]->first.size();
+    std::memcpy(postings_out + pb, order[i]->second.data(), order[i]->second.size() * sizeof(uint32_t));
+    pb += order[i]->second.size();
+  }
+  term_offsets_out[order.size()] = tb;
+  posting_offsets_out[order.size()] = pb;
+  return order.size();
+}
+
+void orc_index_bm25_stats(const orc_index_t* idx, uint64_t* total_doc_length, uint64_t* doc_count) {
+  *total_doc_length = idx->total_doc_length;
+  *doc_count = idx->doc_count;
+}
+
+uint64_t orc_search_and(const orc_index_t* idx, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                        uint64_t n_terms, uint64_t limit, int reverse, uint32_t* out, uint64_t cap) {
+  return CopyOut(SearchAnd(*idx, TermList(term_bytes, term_offsets, 0, n_terms), limit, reverse != 0), out, cap);
+}
+
+uint64_t orc_search_or(const orc_index_t* idx, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                       uint64_t n_terms, uint32_t* out, uint64_t cap) {
+  return CopyOut(SearchOr(*idx, TermList(term_bytes, term_offsets, 0, n_terms)), out, cap);
+}
+
+uint64_t orc_search_not(const orc_index_t* idx, const uint32_t* all_docs, uint64_t n_all, const uint8_t* term_bytes,
+                        const uint64_t* term_offsets, uint64_t n_terms, uint32_t* out, uint64_t cap) {
+  const std::vector<DocId> all(all_docs, all_docs + n_all);
+  return CopyOut(SearchNot(*idx, all, TermList(term_bytes, term_offsets, 0, n_terms)), out, cap);
+}
+
+uint64_t orc_filter_by_ngrams(const orc_index_t* idx, const uint32_t* candidates, uint64_t n_candidates,
+                              const uint8_t* term_bytes, const uint64_t* term_offsets, uint64_t n_terms,
+                              uint32_t* out, uint64_t cap) {
+  const std::vector<DocId> cands(candidates, candidates + n_candidates);
+  return CopyOut(FilterByNgrams(*idx, cands, TermList(term_bytes, term_offsets, 0, n_terms)), out, cap);
+}
+
+uint64_t orc_search_by_threshold(const orc_index_t* idx, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                                 uint64_t n_terms, uint64_t threshold, uint32_t* out, uint64_t cap) {
+  return CopyOut(SearchByThreshold(*idx, TermList(term_bytes, term_offsets, 0, n_terms), threshold), out, cap);
+}
+
+double orc_compute_idf(uint64_t total_docs, uint64_t doc_freq) { return ComputeIDF(total_docs, doc_freq); }
+
+uint32_t orc_count_term_occurrences(const uint8_t* text, uint64_t text_len, const uint8_t* term, uint64_t term_len) {
+  return CountTermOccurrences(std::string_view(reinterpret_cast<const char*>(text), text_len),
+                              std::string_view(reinterpret_cast<const char*>(term), term_len));
+}
+
+void orc_score_documents(const orc_index_t* idx, const uint32_t* candidates, uint64_t n_candidates,
+                         const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* term_doc_freqs,
+                         uint64_t n_terms, uint64_t total_docs, double avg_doc_length, double k1, double b,
+                         double* out_scores) {
+  ScoreDocuments(*idx, candidates, n_candidates, TermList(term_bytes, term_offsets, 0, n_terms), term_doc_freqs,
+                 total_docs, avg_doc_length, k1, b, out_scores);
+}
+
+uint64_t orc_sort_by_score(const uint32_t* results, const double* scores, uint64_t n, int descending, uint32_t limit,
+                           uint32_t offset, uint32_t* out) {
+  const auto sorted = SortByScore(results, scores, n, descending != 0, limit, offset);
+  std::memcpy(out, sorted.data(), sorted.size() * sizeof(uint32_t));
+  return sorted.size();
+}
+
+int orc_query_batch(const orc_index_t* idx, const orc_query_params_t* params, uint64_t n_queries,
+                    const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                    const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                    uint64_t stride, uint32_t* out_ids, double* out_scores, uint32_t* out_count,
+                    uint64_t* out_total, uint64_t* out_df, uint32_t* out_sets, uint64_t sets_cap,
+                    uint64_t* out_sets_offsets, int n_threads) {
+  const orc_query_params_t p = *params;
+  uint64_t total_docs = p.total_docs_override != 0 ? p.total_docs_override : idx->doc_count;
+  uint64_t total_len = p.total_docs_override != 0 ? p.total_len_override : idx->total_doc_length;
+  const double avgdl =
+      total_docs > 0 ? static_cast<double>(total_len) / static_cast<double>(total_docs) : 0.0;  // server_types.h:182-187
+  if (n_threads <= 0) {
+    n_threads = 1;
+  }
+  std::vector<std::vector<DocId>> sets;
+  if (out_sets_offsets != nullptr) {
+    sets.resize(n_queries);
+  }
+  std::atomic<uint64_t> next{0};
+  auto worker = [&]() {
+    for (;;) {
+      const uint64_t q = next.fetch_add(1);
+      if (q >= n_queries) {
+        break;
+      }
+      const auto terms = TermList(term_bytes, term_offsets, q_term_begin[q], q_term_begin[q + 1]);
+      std::vector<std::string_view> not_terms;
+      if (q_not_begin != nullptr) {
+        not_terms = TermList(not_bytes, not_offsets, q_not_begin[q], q_not_begin[q + 1]);
+      }
+      QueryOutput qo = RunQuery(*idx, p, terms, q_term_begin[q], not_terms);
+      out_total[q] = qo.results.size();
+      if (out_df != nullptr) {
+        for (const auto& ti : qo.term_infos) {
+          out_df[ti.source_index] = ti.df;
+        }
+      }
+      uint32_t* ids = out_ids + q * stride;
+      uint64_t written = 0;
+      if (p.compute_score != 0) {
+        // handlers/search_handler.cpp:436-470: terms and dfs in term_infos (size-sorted) order
+        std::vector<std::string_view> norm_terms;
+        std::vector<uint64_t> dfs;
+        for (const auto& ti : qo.term_infos) {
+          norm_terms.emplace_back(ti.normalized);
+          dfs.push_back(ti.df);
+        }
+        std::vector<double> scores(qo.results.size());
+        ScoreDocuments(*idx, qo.results.data(), qo.results.size(), norm_terms, dfs.data(), total_docs, avgdl, p.k1,
+                       p.b, scores.data());
+        const auto sorted =
+            SortByScore(qo.results.data(), scores.data(), qo.results.size(), p.descending != 0, p.limit, p.offset);
+        written = std::min<uint64_t>(sorted.size(), stride);
+        for (uint64_t i = 0; i < written; ++i) {
+          ids[i] = sorted[i];
+          if (out_scores != nullptr) {
+            // results are ascending => locate the score by binary search
+            const auto pos = std::lower_bound(qo.results.begin(), qo.results.end(), sorted[i]) - qo.results.begin();
+            out_scores[q * stride + i] = scores[static_cast<size_t>(pos)];
+          }
+        }
+      } else {
+        const size_t start = std::min<size_t>(p.offset, qo.results.size());
+        const size_t end = p.limit == 0 ? qo.results.size() : std::min<size_t>(start + p.limit, qo.results.size());
+        written = std::min<uint64_t>(end - start, stride);
+        std::memcpy(ids, qo.results.data() + start, written * sizeof(uint32_t));
+      }
+      out_count[q] = static_cast<uint32_t>(written);
+      if (out_sets_offsets != nullptr) {
+        sets[q] = std::move(qo.results);
+      }
+    }
+  };
+  std::vector<std::thread> threads;
+  for (int t = 1; t < n_threads; ++t) {
+    threads.emplace_back(worker);
+  }
+  worker();
+  for (auto& th : threads) {
+    th.join();
+  }
+  if (out_sets_offsets != nullptr) {
+    uint64_t pos = 0;
+    for (uint64_t q = 0; q < n_queries; ++q) {
+      out_sets_offsets[q] = pos;
+      if (pos + sets[q].size() <= sets_cap && out_sets != nullptr) {
+        std::memcpy(out_sets + pos, sets[q].data(), sets[q].size() * sizeof(uint32_t));
+      }
+      pos += sets[q].size();
+    }
+    out_sets_offsets[n_queries] = pos;
+  }
+  return 0;
+}
+
+uint64_t orc_eval_boolean(const orc_index_t* idx, const int32_t* ops, const int32_t* args, uint64_t n_ops,
+                          const uint8_t* term_bytes, const uint64_t* term_offsets, uint32_t* out, uint64_t cap) {
+  // QueryNode::Evaluate, query_ast.cpp:67-161, over a postfix encoding.
+  orc_query_params_t p{};
+  p.ngram_size = idx->ngram_size;
+  p.kanji_ngram_size = idx->kanji_ngram_size;  // Evaluate reads Index::GetKanjiNgramSize() (effective value)
+  p.cross_boundary = idx->cross_boundary ? 1 : 0;
+  std::vector<DocId> all_docs;  // DocumentStore::GetAllDocIds (document_store_retrieval.cpp:242-258), lazily
+  bool have_all = false;
+  auto get_all = [&]() -> const std::vector<DocId>& {
+    if (!have_all) {
+      if (idx->arena != nullptr) {
+        all_docs.assign(idx->arena_doc_ids, idx->arena_doc_ids + idx->arena_docs);
+      } else {
+        all_docs.assign(idx->known_docs.begin(), idx->known_docs.end());
+      }
+      std::sort(all_docs.begin(), all_docs.end());
+      have_all = true;
+    }
+    return all_docs;
+  };
+  std::vector<std::vector<DocId>> stack;
+  for (uint64_t i = 0; i < n_ops; ++i) {
+    const int op = ops[i];
+    if (op == 0) {
+      const auto t = static_cast<uint64_t>(args[i]);
+      const std::string_view term(reinterpret_cast<const char*>(term_bytes) + term_offsets[t],
+                                  term_offsets[t + 1] - term_offsets[t]);
+      const TermInfo ti = MakeTermInfo(*idx, term, p, false);
+      stack.push_back(SearchTermDocuments(*idx, ti));  // :76-93
+    } else if (op == 1 || op == 2) {
+      const auto n = static_cast<size_t>(args[i]);
+      if (n > stack.size()) {
+        return 0;
+      }
+      std::vector<DocId> result;
+      const size_t base = stack.size() - n;
+      if (op == 1) {  // AND :96-123 (early break cannot change the value)
+        for (size_t c = 0; c < n; ++c) {
+          if (c == 0) {
+            result = stack[base];
+          } else {
+            std::vector<DocId> inter;
+            std::set_intersection(result.begin(), result.end(), stack[base + c].begin(), stack[base + c].end(),
+                                  std::back_inserter(inter));
+            result = std::move(inter);
+          }
+        }
+      } else {  // OR :125-136 concat + sort + unique
+        for (size_t c = 0; c < n; ++c) {
+          result.insert(result.end(), stack[base + c].begin(), stack[base + c].end());
+        }
+        std::sort(result.begin(), result.end());
+        result.erase(std::unique(result.begin(), result.end()), result.end());
+      }
+      stack.resize(base);
+      stack.push_back(std::move(result));
+    } else if (op == 3) {  // NOT :138-157
+      if (stack.empty()) {
+        return 0;
+      }
+      const auto& all = get_all();
+      std::vector<DocId> result;
+      std::set_difference(all.begin(), all.end(), stack.back().begin(), stack.back().end(),
+                          std::back_inserter(result));
+      stack.back() = std::move(result);
+    }
+  }
+  if (stack.empty()) {
+    return 0;
+  }
+  return CopyOut(stack.back(), out, cap);
+}
+
+}  // extern "C"
