@@ -1,0 +1,254 @@
+/* include/mgx.h — C ABI of the B200-native MygramDB search core (libmgx.so).
+ *
+ * This is the drop-in boundary. The reference has no FFI layer for this path:
+ * the path sits behind in-process C++ classes (mygramdb_index, mygramdb_query;
+ * src/index/CMakeLists.txt:1-22). Each entry point below names the reference
+ * interface it replaces (paths relative to the reference tree). The C++17
+ * adapter in mygram-db_b200/adapter/mygram_adapter.h re-creates the reference's
+ * class signatures on top of this ABI; INTEGRATION.md shows the binding.
+ *
+ * Conventions (modelled on the reference's own C client, src/client/mygramclient_c.h):
+ * opaque handles, `int` status (0 = ok, negative = error), caller-owned output
+ * buffers, mgx_last_error() for a thread-local message. No torch / C++ types.
+ * Unless a name ends in `_device`, every pointer is a HOST pointer; the library
+ * does its own H2D/D2H copies (pinned host memory makes them asynchronous).
+ *
+ * Document ids are the reference's DocId = uint32_t (src/types/doc_id.h:31).
+ * Text is normalised UTF-8 (ICU normalisation stays on the host, index.h:83-84).
+ * Strings are passed flattened: `bytes` + `offsets[n+1]` (uint64), string i is
+ * bytes[offsets[i] .. offsets[i+1]).
+ */
+#ifndef MGX_H_
+#define MGX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGX_OK 0
+#define MGX_ERR_INVALID_ARGUMENT (-1) /* reference: ErrorCode::kInvalidArgument (utils/error.h) */
+#define MGX_ERR_CUDA (-2)             /* reference: ErrorCode::kInternalError                  */
+#define MGX_ERR_UNSUPPORTED (-3)      /* a configuration this build refuses rather than guesses */
+#define MGX_ERR_CAPACITY (-4)         /* a caller buffer was too small; nothing partial is valid */
+#define MGX_ERR_NO_DEVICE (-5)        /* no CUDA device: the library has no CPU fallback        */
+
+/* Thread-local description of the last failure on this thread ("" if none). */
+const char* mgx_last_error(void);
+/* Library / build identification, e.g. "mgx 0.1 sm_100a". */
+const char* mgx_version(void);
+/* Number of kernels this library has launched in this process so far. */
+uint64_t mgx_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------ index */
+
+typedef struct mgx_index mgx_index_t;
+
+/* Mirrors Index::Index(ngram_size, kanji_ngram_size, roaring_threshold,
+ * cross_boundary_ngrams, ...) — src/index/index.h:58-60, index.cpp:29-37.
+ * kanji_ngram_size <= 0 means "use ngram_size" (index.cpp:32). */
+typedef struct {
+  int32_t ngram_size;            /* 1..3 in this build (reference allows 1..10)            */
+  int32_t kanji_ngram_size;      /* 0..3                                                    */
+  int32_t cross_boundary_ngrams; /* config.h:211-213 default true                           */
+  int32_t device;                /* CUDA device ordinal                                     */
+  double dense_threshold;        /* posting density at which a list ALSO gets a doc bitmap; */
+                                 /* <= 0 selects 1/32 (the size break-even: 4*|P| = N/8)    */
+  uint64_t max_dense_bytes;      /* cap for all dense bitmaps together; 0 = 8 GiB           */
+  uint64_t scratch_bytes;        /* per-batch query scratch; 0 = 4 GiB                      */
+} mgx_index_config_t;
+
+int mgx_index_create(const mgx_index_config_t* config, mgx_index_t** out);
+void mgx_index_destroy(mgx_index_t* index);
+
+/* Bulk build of one shard: replaces the loop of DocumentStore::AddDocumentBatch +
+ * Index::AddDocumentBatch over 1000-document batches (loader/initial_loader.cpp:450-512,
+ * index.cpp:76-119) and the BM25Stats rebuild (app/server_orchestrator.cpp:758-772).
+ * doc_ids must be strictly ascending. Replaces any previous content.
+ * The text arena, the code-point lengths and the doc ids stay resident on the
+ * device as the mirror of DocumentStore's normalised text (document_store.h:380-426). */
+int mgx_index_build(mgx_index_t* index, const uint32_t* doc_ids, const uint8_t* text, const uint64_t* text_offsets,
+                    uint64_t n_docs);
+/* Same, but all three arrays are already DEVICE pointers on index's device
+ * (kernel-only timing: no H2D inside). */
+int mgx_index_build_device(mgx_index_t* index, const uint32_t* d_doc_ids, const uint8_t* d_text,
+                           const uint64_t* d_text_offsets, uint64_t n_docs);
+
+typedef struct {
+  uint64_t n_docs;
+  uint64_t n_terms;          /* Index::TermCount, index.h:193                       */
+  uint64_t n_postings;       /* IndexStatistics::total_postings, index.cpp:604-633  */
+  uint64_t n_dense_terms;    /* lists that also have a bitmap                        */
+  uint64_t text_bytes;
+  uint64_t total_doc_length; /* BM25Stats::total_doc_length, server_types.h:158     */
+  uint64_t doc_count;        /* BM25Stats::doc_count (docs with non-empty text)     */
+  uint64_t device_bytes;     /* resident device memory of this index                */
+  uint64_t n_pair_slots;     /* (n-gram, doc) slots sorted by the last build        */
+  int32_t all_valid_utf8;    /* 1 if no document contained an invalid byte          */
+  int32_t key_width;         /* code points per packed key = max(ngram, kanji)      */
+  double last_build_ms;      /* device time of the last build (CUDA events)         */
+} mgx_index_stats_t;
+
+int mgx_index_get_stats(const mgx_index_t* index, mgx_index_stats_t* out);
+
+/* Index::PostingSize / Count (index.cpp:580-588): `term` is one n-gram. */
+int mgx_index_posting_size(const mgx_index_t* index, const uint8_t* term, uint64_t term_len, uint64_t* out);
+/* PostingList::GetAll (posting_list.cpp:421-430): ascending doc ids of one n-gram. */
+int mgx_index_get_postings(const mgx_index_t* index, const uint8_t* term, uint64_t term_len, uint32_t* out,
+                           uint64_t cap, uint64_t* out_count);
+/* Whole index as CSR in ascending term (UTF-8 byte) order. keys are packed
+ * n-grams (mgx_key_to_utf8 decodes them). Sizes come from mgx_index_get_stats:
+ * keys[n_terms], offsets[n_terms+1], postings[n_postings] (global doc ids). */
+int mgx_index_export(const mgx_index_t* index, uint64_t* keys, uint64_t* offsets, uint32_t* postings);
+/* Per-document code-point lengths (CountCodePoints, string_utils.cpp:655-669). out[n_docs]. */
+int mgx_index_doc_lengths(const mgx_index_t* index, uint32_t* out);
+
+/* Packed key -> UTF-8 n-gram. `out` needs 4*width bytes. Returns the byte length. */
+int mgx_key_to_utf8(uint64_t key, int32_t width, uint8_t* out);
+
+/* --------------------------------------------------------------- tokenizer */
+
+/* GenerateHybridNgrams (utils/string_utils.cpp:452-509) for a batch of documents
+ * on the GPU, in generation order (before the per-document sort+unique of
+ * index.cpp:88-91). Output: packed key + index of the document in the batch.
+ * out_keys/out_doc need room for one entry per code point; *out_count receives
+ * the number of n-grams. */
+int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, const uint64_t* text_offsets,
+                       uint64_t n_docs, uint64_t* out_keys, uint32_t* out_doc, uint64_t cap, uint64_t* out_count);
+
+/* ------------------------------------------------- Index set-algebra calls */
+
+/* Index::SearchAnd(terms, limit, reverse) — index.cpp:199-368. `terms` are
+ * n-gram strings. Unknown term or empty list => empty. *out_count = result
+ * size after limit; MGX_ERR_CAPACITY if it exceeds cap. */
+int mgx_search_and(const mgx_index_t* index, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                   uint64_t n_terms, uint64_t limit, int32_t reverse, uint32_t* out, uint64_t cap,
+                   uint64_t* out_count);
+/* Index::SearchOr — index.cpp:418-448 (unknown terms ignored). */
+int mgx_search_or(const mgx_index_t* index, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                  uint64_t n_terms, uint32_t* out, uint64_t cap, uint64_t* out_count);
+/* Index::SearchNot(all_docs, terms) — index.cpp:450-486. all_docs ascending. */
+int mgx_search_not(const mgx_index_t* index, const uint32_t* all_docs, uint64_t n_all, const uint8_t* term_bytes,
+                   const uint64_t* term_offsets, uint64_t n_terms, uint32_t* out, uint64_t cap, uint64_t* out_count);
+/* Index::FilterByNgrams(candidates, terms) — index.cpp:370-416: keeps caller
+ * order and duplicates; no terms => candidates; unknown term => empty. */
+int mgx_filter_by_ngrams(const mgx_index_t* index, const uint32_t* candidates, uint64_t n_candidates,
+                         const uint8_t* term_bytes, const uint64_t* term_offsets, uint64_t n_terms, uint32_t* out,
+                         uint64_t cap, uint64_t* out_count);
+
+/* ------------------------------------------------------- batched pipeline */
+
+/* One batch of SEARCH queries through the regular path of
+ * search_pipeline::ExecuteFullPipeline (server/search_pipeline.cpp:1757-2059):
+ * GenerateTermInfos (:569-603) with verified document frequencies (:542-565),
+ * terms ordered by estimated size (:2012-2014), Execute (:795-869: early exit,
+ * AND, ApplyNotFilter :871-932), then — for SORT _score —
+ * BM25Scorer::ScoreDocuments (index/bm25_scorer.cpp:47-99) and
+ * ResultSorter::SortByScore (query/result_sorter.cpp:661-716) exactly as
+ * SearchHandler::HandleSearch chains them (handlers/search_handler.cpp:405-470). */
+typedef struct {
+  int32_t ngram_size;        /* RAW table config values handed to GenerateQueryNgrams   */
+  int32_t kanji_ngram_size;  /* (search_pipeline.cpp:578); 0 is meaningful there         */
+  int32_t cross_boundary;
+  int32_t compute_score;     /* 1: SORT _score; 0: ascending doc ids                      */
+  int32_t descending;        /* SortOrder::DESC (default) / ASC for _score                */
+  uint32_t limit;            /* query_parser.h:217 default 100; limit+offset <= 1024     */
+  uint32_t offset;
+  int32_t verify_text;       /* 0 = "off" (config.h:329): n-gram AND incl. false positives; */
+                             /* 1 = "all": PostFilterByText (search_pipeline.cpp:1239-1246) */
+  double k1;                 /* BM25Params, bm25_scorer.h:23-26 (1.2)                     */
+  double b;                  /* (0.75)                                                    */
+  /* Corpus statistics for scoring. 0/0 => this index's own BM25Stats. A sharded
+   * deployment passes the GLOBAL totals so every shard scores identically. */
+  uint64_t total_docs;
+  uint64_t total_doc_length;
+} mgx_query_params_t;
+
+/* Queries are ranges into flat term tables:
+ *   search terms of query q: terms [q_term_begin[q], q_term_begin[q+1])
+ *   NOT terms of query q:    not-terms [q_not_begin[q], q_not_begin[q+1])  (q_not_begin may be NULL)
+ * Outputs (host): for query q, out_count[q] ids at out_ids[q*stride..] (+ scores
+ * at out_scores[q*stride..] when compute_score), out_total[q] = size of the full
+ * result set (SearchHandler's total_results), out_df[t] = verified document
+ * frequency of search term t (may be NULL). stride >= min(limit, ...) entries. */
+int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                    const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                    const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                    uint64_t stride, uint32_t* out_ids, double* out_scores, uint32_t* out_count, uint64_t* out_total,
+                    uint64_t* out_df);
+
+/* Staged form of the same call, for doc-range sharded deployments (one process
+ * per GPU): the two exchange points of SURVEY.md §8(e) sit between the stages.
+ *   prepare : host compile + H2D + dictionary lookup + planning
+ *   df      : per-shard verified document frequencies -> d_df (DEVICE, n_terms uint64)
+ *             [caller all-reduces d_df (SUM) across shards]
+ *   search  : AND + NOT + BM25 + top-k with the GLOBAL df -> DEVICE outputs
+ *             [caller all-gathers the per-shard top-k records]
+ *   merge   : mgx_merge_topk_device over the gathered runs
+ * All stages are enqueued on `stream` (a cudaStream_t passed as void*; NULL =
+ * the legacy default stream) and do not synchronise the host except where a
+ * size has to be read back (documented in DESIGN.md). */
+typedef struct mgx_batch mgx_batch_t;
+
+int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                      const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                      const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                      void* stream, mgx_batch_t** out);
+/* Number of search-term slots (= length of d_df / out_df). */
+uint64_t mgx_batch_term_slots(const mgx_batch_t* batch);
+int mgx_batch_df_device(mgx_batch_t* batch, uint64_t* d_df);
+int mgx_batch_search_device(mgx_batch_t* batch, const uint64_t* d_df, uint64_t stride, uint32_t* d_ids,
+                            double* d_scores, uint32_t* d_count, uint64_t* d_total);
+void mgx_batch_destroy(mgx_batch_t* batch);
+
+/* Merge of per-shard top-k runs (already in final order within each shard):
+ * inputs are [n_shards][n_queries][stride] DEVICE arrays as produced by an
+ * all-gather of mgx_batch_search_device outputs. Order = SortByScore's
+ * comparator (result_sorter.cpp:681-686). For compute_score == 0 the runs are
+ * ascending id lists of disjoint ascending ranges and are concatenated. */
+int mgx_merge_topk_device(int32_t device, void* stream, const mgx_query_params_t* params, uint32_t n_shards,
+                          uint64_t n_queries, uint64_t stride, const uint32_t* d_ids_all, const double* d_scores_all,
+                          const uint32_t* d_count_all, const uint64_t* d_total_all, uint32_t* d_ids_out,
+                          double* d_scores_out, uint32_t* d_count_out, uint64_t* d_total_out);
+
+/* Timing / accounting of the last mgx_query_batch or staged run on this index
+ * (device times from CUDA events on the launch stream; bytes as defined in
+ * SURVEY.md §8(d) and DESIGN.md). */
+typedef struct {
+  double ms_total;            /* prepare .. outputs ready, device time                 */
+  double ms_df;               /* df stage kernels                                       */
+  double ms_search;           /* intersect + score kernels                              */
+  double ms_topk;             /* top-k kernels                                          */
+  uint64_t launches;          /* kernels launched for the batch                         */
+  uint64_t algo_bytes_intersect; /* B_intersect: sum min(4|P|, N/8) + 4|R|              */
+  uint64_t algo_bytes_score;     /* B_score                                             */
+  uint64_t algo_bytes_df;        /* B_df                                                */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+  uint64_t driver_entries;    /* posting entries actually walked by the intersect kernel */
+  uint64_t result_docs;       /* sum |R|                                                 */
+  uint64_t df_candidates;     /* docs whose text was scanned for df                      */
+  uint64_t unique_terms;
+} mgx_batch_stats_t;
+
+int mgx_index_last_batch_stats(const mgx_index_t* index, mgx_batch_stats_t* out);
+
+/* ---------------------------------------------------------------- scoring */
+
+/* BM25Scorer::ScoreDocuments (index/bm25_scorer.cpp:47-99) for explicit
+ * candidates, terms and document frequencies: one score per candidate in
+ * candidate order, 0.0 for a candidate without stored text. */
+int mgx_score_documents(mgx_index_t* index, const uint32_t* candidates, uint64_t n_candidates,
+                        const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* term_doc_freqs,
+                        uint64_t n_terms, uint64_t total_docs, double avg_doc_length, double k1, double b,
+                        double* out_scores);
+/* ResultSorter::SortByScore (query/result_sorter.cpp:661-716). limit+offset <= 1024, limit > 0. */
+int mgx_sort_by_score(mgx_index_t* index, const uint32_t* results, const double* scores, uint64_t n,
+                      int32_t descending, uint32_t limit, uint32_t offset, uint32_t* out, uint64_t* out_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGX_H_ */

@@ -1,0 +1,399 @@
+"""mygram-db_b200 — host-side Python mirror of the reference's index/query interface
+over the C ABI of libmgx.so (include/mgx.h).
+
+The directory name carries a hyphen (it is the name the project was given), so
+import it through :func:`load` in ``mgx_loader.py`` at the repository root, or::
+
+    import importlib.util, sys
+    spec = importlib.util.spec_from_file_location("mygram_db_b200", ".../mygram-db_b200/__init__.py")
+
+What lives here is plumbing only: ctypes signatures, numpy buffer marshalling and
+three small classes whose method names and argument meaning follow the reference
+(``Index`` — src/index/index.h:49-413, ``BM25Scorer`` — src/index/bm25_scorer.h:43-83,
+``ResultSorter.sort_by_score`` — src/query/result_sorter.h:75). All work happens in
+the CUDA kernels behind the C ABI; if libmgx.so is missing or no GPU is visible the
+calls raise — there is no CPU fallback and nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmgx.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include", "mgx.h")
+
+MGX_OK = 0
+ERRORS = {-1: "MGX_ERR_INVALID_ARGUMENT", -2: "MGX_ERR_CUDA", -3: "MGX_ERR_UNSUPPORTED", -4: "MGX_ERR_CAPACITY",
+          -5: "MGX_ERR_NO_DEVICE"}
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+f64p = C.POINTER(C.c_double)
+
+
+class MgxError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"{ERRORS.get(code, code)}: {message}")
+        self.code = code
+
+
+class IndexConfig(C.Structure):
+    _fields_ = [("ngram_size", C.c_int32), ("kanji_ngram_size", C.c_int32), ("cross_boundary_ngrams", C.c_int32),
+                ("device", C.c_int32), ("dense_threshold", C.c_double), ("max_dense_bytes", C.c_uint64),
+                ("scratch_bytes", C.c_uint64)]
+
+
+class IndexStats(C.Structure):
+    _fields_ = [("n_docs", C.c_uint64), ("n_terms", C.c_uint64), ("n_postings", C.c_uint64),
+                ("n_dense_terms", C.c_uint64), ("text_bytes", C.c_uint64), ("total_doc_length", C.c_uint64),
+                ("doc_count", C.c_uint64), ("device_bytes", C.c_uint64), ("n_pair_slots", C.c_uint64),
+                ("all_valid_utf8", C.c_int32), ("key_width", C.c_int32), ("last_build_ms", C.c_double)]
+
+
+class QueryParams(C.Structure):
+    _fields_ = [("ngram_size", C.c_int32), ("kanji_ngram_size", C.c_int32), ("cross_boundary", C.c_int32),
+                ("compute_score", C.c_int32), ("descending", C.c_int32), ("limit", C.c_uint32), ("offset", C.c_uint32),
+                ("verify_text", C.c_int32), ("k1", C.c_double), ("b", C.c_double), ("total_docs", C.c_uint64),
+                ("total_doc_length", C.c_uint64)]
+
+
+class BatchStats(C.Structure):
+    _fields_ = [("ms_total", C.c_double), ("ms_df", C.c_double), ("ms_search", C.c_double), ("ms_topk", C.c_double),
+                ("launches", C.c_uint64), ("algo_bytes_intersect", C.c_uint64), ("algo_bytes_score", C.c_uint64),
+                ("algo_bytes_df", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("driver_entries", C.c_uint64), ("result_docs", C.c_uint64), ("df_candidates", C.c_uint64),
+                ("unique_terms", C.c_uint64)]
+
+
+_lib = None
+
+
+def build(force=False):
+    """Compile libmgx.so in-tree with nvcc for sm_100a (see Makefile)."""
+    if force:
+        subprocess.check_call(["make", "-C", HERE, "clean"])
+    subprocess.check_call(["make", "-C", HERE, "-j4"])
+
+
+def lib():
+    """The loaded C ABI. Raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MgxError(-2, f"{LIB_PATH} is missing: run `make -C {HERE}` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.mgx_last_error.restype = C.c_char_p
+    L.mgx_version.restype = C.c_char_p
+    L.mgx_kernel_launch_count.restype = C.c_uint64
+    L.mgx_index_create.argtypes = [C.POINTER(IndexConfig), C.POINTER(C.c_void_p)]
+    L.mgx_index_destroy.argtypes = [C.c_void_p]
+    L.mgx_index_build.argtypes = [C.c_void_p, u32p, u8p, u64p, C.c_uint64]
+    L.mgx_index_build_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.mgx_index_get_stats.argtypes = [C.c_void_p, C.POINTER(IndexStats)]
+    L.mgx_index_posting_size.argtypes = [C.c_void_p, u8p, C.c_uint64, u64p]
+    L.mgx_index_get_postings.argtypes = [C.c_void_p, u8p, C.c_uint64, u32p, C.c_uint64, u64p]
+    L.mgx_index_export.argtypes = [C.c_void_p, u64p, u64p, u32p]
+    L.mgx_index_doc_lengths.argtypes = [C.c_void_p, u32p]
+    L.mgx_key_to_utf8.argtypes = [C.c_uint64, C.c_int32, u8p]
+    L.mgx_tokenize_batch.argtypes = [C.POINTER(IndexConfig), u8p, u64p, C.c_uint64, u64p, u32p, C.c_uint64, u64p]
+    L.mgx_search_and.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint64, C.c_int32, u32p, C.c_uint64, u64p]
+    L.mgx_search_or.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u32p, C.c_uint64, u64p]
+    L.mgx_search_not.argtypes = [C.c_void_p, u32p, C.c_uint64, u8p, u64p, C.c_uint64, u32p, C.c_uint64, u64p]
+    L.mgx_filter_by_ngrams.argtypes = [C.c_void_p, u32p, C.c_uint64, u8p, u64p, C.c_uint64, u32p, C.c_uint64, u64p]
+    L.mgx_query_batch.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
+                                  C.c_uint64, u32p, f64p, u32p, u64p, u64p]
+    L.mgx_batch_prepare.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
+                                    C.c_void_p, C.POINTER(C.c_void_p)]
+    L.mgx_batch_term_slots.restype = C.c_uint64
+    L.mgx_batch_term_slots.argtypes = [C.c_void_p]
+    L.mgx_batch_df_device.argtypes = [C.c_void_p, C.c_void_p]
+    L.mgx_batch_search_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+    L.mgx_batch_destroy.argtypes = [C.c_void_p]
+    L.mgx_merge_topk_device.argtypes = [C.c_int32, C.c_void_p, C.POINTER(QueryParams), C.c_uint32, C.c_uint64,
+                                        C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mgx_index_last_batch_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
+    L.mgx_score_documents.argtypes = [C.c_void_p, u32p, C.c_uint64, u8p, u64p, u64p, C.c_uint64, C.c_uint64,
+                                      C.c_double, C.c_double, C.c_double, f64p]
+    L.mgx_sort_by_score.argtypes = [C.c_void_p, u32p, f64p, C.c_uint64, C.c_int32, C.c_uint32, C.c_uint32, u32p, u64p]
+    _lib = L
+    return L
+
+
+def exported_symbols_in_header():
+    """Names of every function include/mgx.h declares (for the symbol-presence test)."""
+    import re
+    text = open(INCLUDE).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mgx_[a-z0-9_]+)\s*\(", text)))
+
+
+def _check(rc):
+    if rc != MGX_OK:
+        raise MgxError(rc, lib().mgx_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(arr, typ):
+    return None if arr is None else arr.ctypes.data_as(typ)
+
+
+def _bytes(s):
+    return s.encode("utf-8") if isinstance(s, str) else bytes(s)
+
+
+def pack_strings(strings):
+    """list[bytes|str] -> (uint8 arena (>=1 byte), uint64 offsets[n+1])"""
+    bs = [_bytes(s) for s in strings]
+    offsets = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        offsets[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    joined = b"".join(bs)
+    arena = np.frombuffer(joined, dtype=np.uint8).copy() if joined else np.zeros(1, np.uint8)
+    return arena, offsets
+
+
+def key_to_utf8(key, width):
+    out = np.zeros(16, dtype=np.uint8)
+    n = lib().mgx_key_to_utf8(int(key), width, _ptr(out, u8p))
+    return out[:n].tobytes()
+
+
+def tokenize_batch(texts, ngram_size=2, kanji_ngram_size=0, cross_boundary=True, device=0):
+    """GenerateHybridNgrams for every text on the GPU -> list (per doc) of n-gram byte strings,
+    in generation order (string_utils.cpp:452-509)."""
+    arena, offsets = pack_strings(texts)
+    cfg = IndexConfig(ngram_size, kanji_ngram_size, int(cross_boundary), device, 0.0, 0, 0)
+    cap = max(1, int(offsets[-1]))
+    keys = np.zeros(cap, dtype=np.uint64)
+    docs = np.zeros(cap, dtype=np.uint32)
+    n = C.c_uint64(0)
+    _check(lib().mgx_tokenize_batch(C.byref(cfg), _ptr(arena, u8p), _ptr(offsets, u64p), len(texts), _ptr(keys, u64p),
+                                    _ptr(docs, u32p), cap, C.byref(n)))
+    eff_kanji = kanji_ngram_size if kanji_ngram_size > 0 else ngram_size
+    width = max(ngram_size, eff_kanji)
+    out = [[] for _ in texts]
+    for k, d in zip(keys[:n.value], docs[:n.value]):
+        out[int(d)].append(key_to_utf8(k, width))
+    return out
+
+
+@dataclass
+class BatchResult:
+    ids: np.ndarray     # [Q, stride] uint32
+    scores: np.ndarray  # [Q, stride] float64
+    count: np.ndarray   # [Q] uint32
+    total: np.ndarray   # [Q] uint64
+    df: np.ndarray      # [n_term_slots] uint64
+
+
+def flatten_queries(queries):
+    flat, begin = [], [0]
+    for q in queries:
+        flat += [_bytes(t) for t in q]
+        begin.append(len(flat))
+    arena, offsets = pack_strings(flat)
+    return arena, offsets, np.asarray(begin, dtype=np.uint64), len(flat)
+
+
+class Index:
+    """Mirror of mygramdb::index::Index (src/index/index.h:49-413) backed by a device-resident shard."""
+
+    def __init__(self, ngram_size=2, kanji_ngram_size=0, cross_boundary_ngrams=True, device=0, dense_threshold=0.0,
+                 max_dense_bytes=0, scratch_bytes=0):
+        self.ngram_size = ngram_size
+        self.kanji_ngram_size = kanji_ngram_size
+        self.cross_boundary_ngrams = cross_boundary_ngrams
+        self.device = device
+        cfg = IndexConfig(ngram_size, kanji_ngram_size, int(cross_boundary_ngrams), device, dense_threshold,
+                          max_dense_bytes, scratch_bytes)
+        self._h = C.c_void_p()
+        _check(lib().mgx_index_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mgx_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- build -------------------------------------------------------------------------------------
+    def add_document_batch(self, doc_ids, texts):
+        """Index::AddDocumentBatch (index.cpp:76-119) for a whole shard: replaces the index content."""
+        arena, offsets = pack_strings(texts)
+        self.build(np.asarray(doc_ids, dtype=np.uint32), arena, offsets)
+
+    def build(self, doc_ids, arena, offsets):
+        doc_ids = np.ascontiguousarray(doc_ids, dtype=np.uint32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if arena.size == 0:
+            arena = np.zeros(1, np.uint8)
+        _check(lib().mgx_index_build(self._h, _ptr(doc_ids, u32p), _ptr(arena, u8p), _ptr(offsets, u64p),
+                                     doc_ids.size))
+
+    def build_device(self, d_doc_ids_ptr, d_text_ptr, d_offsets_ptr, n_docs):
+        _check(lib().mgx_index_build_device(self._h, d_doc_ids_ptr, d_text_ptr, d_offsets_ptr, n_docs))
+
+    def stats(self):
+        s = IndexStats()
+        _check(lib().mgx_index_get_stats(self._h, C.byref(s)))
+        return s
+
+    def term_count(self):
+        return int(self.stats().n_terms)
+
+    def posting_size(self, term):
+        b = _bytes(term)
+        buf = np.frombuffer(b, dtype=np.uint8).copy() if b else np.zeros(1, np.uint8)
+        out = C.c_uint64(0)
+        _check(lib().mgx_index_posting_size(self._h, _ptr(buf, u8p), len(b), C.byref(out)))
+        return out.value
+
+    count = posting_size
+
+    def export(self):
+        """-> (terms list[bytes] ascending, posting offsets uint64[T+1], postings uint32[P] global ids)"""
+        s = self.stats()
+        keys = np.zeros(max(1, s.n_terms), dtype=np.uint64)
+        offs = np.zeros(s.n_terms + 1, dtype=np.uint64)
+        posts = np.zeros(max(1, s.n_postings), dtype=np.uint32)
+        _check(lib().mgx_index_export(self._h, _ptr(keys, u64p), _ptr(offs, u64p), _ptr(posts, u32p)))
+        terms = [key_to_utf8(k, s.key_width) for k in keys[:s.n_terms]]
+        return terms, offs, posts[:s.n_postings]
+
+    def doc_lengths(self):
+        s = self.stats()
+        out = np.zeros(max(1, s.n_docs), dtype=np.uint32)
+        _check(lib().mgx_index_doc_lengths(self._h, _ptr(out, u32p)))
+        return out[:s.n_docs]
+
+    # -- set algebra -------------------------------------------------------------------------------
+    def _set_call(self, fn, terms, pre=(), cap=4096):
+        arena, offsets = pack_strings(terms)
+        while True:
+            out = np.zeros(cap, dtype=np.uint32)
+            n = C.c_uint64(0)
+            rc = fn(*pre, _ptr(arena, u8p), _ptr(offsets, u64p), len(terms), out, cap, n)
+            if rc == -4:
+                cap = max(int(n.value), cap * 2)
+                continue
+            _check(rc)
+            return out[:n.value].copy()
+
+    def search_and(self, terms, limit=0, reverse=False):
+        """Index::SearchAnd (index.cpp:199-368); terms are n-gram strings."""
+        L = lib()
+        return self._set_call(lambda a, o, nt, out, cap, n: L.mgx_search_and(self._h, a, o, nt, limit, int(reverse),
+                                                                              _ptr(out, u32p), cap, C.byref(n)), terms)
+
+    def search_or(self, terms):
+        L = lib()
+        return self._set_call(lambda a, o, nt, out, cap, n: L.mgx_search_or(self._h, a, o, nt, _ptr(out, u32p), cap,
+                                                                             C.byref(n)), terms)
+
+    def search_not(self, all_docs, terms):
+        L = lib()
+        ad = np.ascontiguousarray(all_docs, dtype=np.uint32)
+        adp = ad if ad.size else np.zeros(1, np.uint32)
+        return self._set_call(lambda a, o, nt, out, cap, n: L.mgx_search_not(self._h, _ptr(adp, u32p), ad.size, a, o,
+                                                                              nt, _ptr(out, u32p), cap, C.byref(n)),
+                              terms, cap=max(4096, ad.size))
+
+    def filter_by_ngrams(self, candidates, terms):
+        L = lib()
+        c = np.ascontiguousarray(candidates, dtype=np.uint32)
+        cp = c if c.size else np.zeros(1, np.uint32)
+        return self._set_call(lambda a, o, nt, out, cap, n: L.mgx_filter_by_ngrams(self._h, _ptr(cp, u32p), c.size, a,
+                                                                                    o, nt, _ptr(out, u32p), cap,
+                                                                                    C.byref(n)),
+                              terms, cap=max(4096, c.size))
+
+    def postings(self, term):
+        return self.search_and([term])
+
+    # -- batched pipeline --------------------------------------------------------------------------
+    def params(self, score=True, descending=True, limit=100, offset=0, verify_text=0, k1=1.2, b=0.75, total_docs=0,
+               total_doc_length=0, raw_ngram=None, raw_kanji=None):
+        return QueryParams(self.ngram_size if raw_ngram is None else raw_ngram,
+                           self.kanji_ngram_size if raw_kanji is None else raw_kanji,
+                           int(self.cross_boundary_ngrams), int(score), int(descending), limit, offset, verify_text,
+                           k1, b, total_docs, total_doc_length)
+
+    def query_batch(self, queries, not_terms=None, stride=None, **kw):
+        """Batch of SEARCH queries (regular path of ExecuteFullPipeline + ScoreDocuments + SortByScore)."""
+        p = self.params(**kw)
+        arena, offsets, qbeg, n_slots = flatten_queries(queries)
+        if not_terms is not None:
+            narena, noffsets, nbeg, _ = flatten_queries(not_terms)
+        else:
+            narena = noffsets = nbeg = None
+        return self.query_batch_flat(p, len(queries), arena, offsets, qbeg, narena, noffsets, nbeg, n_slots, stride)
+
+    def query_batch_flat(self, p, n_queries, arena, offsets, qbeg, narena=None, noffsets=None, nbeg=None,
+                         n_slots=None, stride=None, out=None):
+        stride = stride or max(1, p.limit)
+        if n_slots is None:
+            n_slots = int(qbeg[-1])
+        if out is None:
+            out = BatchResult(np.zeros((n_queries, stride), dtype=np.uint32),
+                              np.zeros((n_queries, stride), dtype=np.float64), np.zeros(n_queries, dtype=np.uint32),
+                              np.zeros(n_queries, dtype=np.uint64), np.zeros(max(1, n_slots), dtype=np.uint64))
+        _check(lib().mgx_query_batch(self._h, C.byref(p), n_queries, _ptr(arena, u8p), _ptr(offsets, u64p),
+                                     _ptr(qbeg, u64p), _ptr(narena, u8p), _ptr(noffsets, u64p), _ptr(nbeg, u64p),
+                                     stride, _ptr(out.ids, u32p), _ptr(out.scores, f64p), _ptr(out.count, u32p),
+                                     _ptr(out.total, u64p), _ptr(out.df, u64p)))
+        out.df = out.df[:n_slots]
+        return out
+
+    def last_batch_stats(self):
+        s = BatchStats()
+        _check(lib().mgx_index_last_batch_stats(self._h, C.byref(s)))
+        return s
+
+
+class BM25Scorer:
+    """Mirror of mygramdb::index::BM25Scorer (src/index/bm25_scorer.h:43-83)."""
+
+    @staticmethod
+    def score_documents(index: Index, candidates, search_terms, term_doc_freqs, total_docs, avg_doc_length, k1=1.2,
+                        b=0.75):
+        if len(search_terms) != len(term_doc_freqs):
+            # bm25_scorer.cpp:51-55 -> ErrorCode::kInvalidArgument
+            raise MgxError(-1, "BM25 search_terms and term_doc_freqs must have identical lengths")
+        c = np.ascontiguousarray(candidates, dtype=np.uint32)
+        arena, offsets = pack_strings(search_terms)
+        dfs = np.ascontiguousarray(term_doc_freqs, dtype=np.uint64)
+        dfp = dfs if dfs.size else np.zeros(1, np.uint64)
+        out = np.zeros(max(1, c.size), dtype=np.float64)
+        cp = c if c.size else np.zeros(1, np.uint32)
+        _check(lib().mgx_score_documents(index._h, _ptr(cp, u32p), c.size, _ptr(arena, u8p), _ptr(offsets, u64p),
+                                         _ptr(dfp, u64p), len(search_terms), total_docs, avg_doc_length, k1, b,
+                                         _ptr(out, f64p)))
+        return out[:c.size]
+
+
+class ResultSorter:
+    """ResultSorter::SortByScore (src/query/result_sorter.cpp:661-716)."""
+
+    @staticmethod
+    def sort_by_score(index: Index, results, scores, descending=True, limit=100, offset=0):
+        r = np.ascontiguousarray(results, dtype=np.uint32)
+        s = np.ascontiguousarray(scores, dtype=np.float64)
+        out = np.zeros(max(1, limit), dtype=np.uint32)
+        n = C.c_uint64(0)
+        rp = r if r.size else np.zeros(1, np.uint32)
+        sp = s if s.size else np.zeros(1, np.float64)
+        _check(lib().mgx_sort_by_score(index._h, _ptr(rp, u32p), _ptr(sp, f64p), r.size, int(descending), limit, offset,
+                                       _ptr(out, u32p), C.byref(n)))
+        return out[:n.value].copy()

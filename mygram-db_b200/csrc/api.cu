@@ -1,0 +1,1094 @@
+// api.cu — the C ABI of libmgx.so (include/mgx.h) and the host-side query compiler.
+//
+// Host work is limited to what the reference also does per request on the CPU
+// before touching the index: decoding the (short) query terms and cutting them
+// into n-grams (GenerateQueryNgrams, utils/string_utils.cpp:639-653). Everything
+// that touches postings, document text or scores runs in the kernels of
+// build.cu / query.cu. There is no CPU fallback: without a CUDA device every
+// entry point fails with MGX_ERR_NO_DEVICE.
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+
+#include "query.cuh"
+
+namespace mgx {
+
+namespace {
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+}  // namespace
+
+void set_last_error(const std::string& message) { g_last_error = message; }
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------ host tokenizer for query terms
+std::vector<uint32_t> host_utf8_to_codepoints(const uint8_t* text, uint64_t len) {
+  std::vector<uint32_t> cps;
+  cps.reserve(len / 2 + 1);
+  uint64_t i = 0;
+  while (i < len) {
+    uint32_t cp = 0;
+    const uint64_t avail = len - i;
+    const int n = parse_utf8(text[i], avail > 1 ? text[i + 1] : 0, avail > 2 ? text[i + 2] : 0,
+                             avail > 3 ? text[i + 3] : 0, avail, &cp);
+    if (n > 0) {
+      cps.push_back(cp);
+      i += static_cast<uint64_t>(n);
+    } else {
+      ++i;  // string_utils.cpp:212-215: skip one byte and retry
+    }
+  }
+  return cps;
+}
+
+namespace {
+
+// GenerateHybridNgrams (string_utils.cpp:452-509) as packed keys; windows wider
+// than the index's key width cannot exist in the dictionary => kInvalidKey.
+void hybrid_keys(const std::vector<uint32_t>& cps, int ascii_n, int kanji_n, bool cross, int width,
+                 std::vector<uint64_t>* keys) {
+  if (ascii_n <= 0 || kanji_n <= 0) {
+    return;
+  }
+  for (size_t i = 0; i < cps.size(); ++i) {
+    const bool cjk = is_cjk_ideograph(cps[i]);
+    const int size = cjk ? kanji_n : ascii_n;
+    if (i + static_cast<size_t>(size) > cps.size()) {
+      continue;
+    }
+    if (!cross) {
+      bool crossed = false;
+      for (int j = 1; j < size; ++j) {
+        if (is_cjk_ideograph(cps[i + static_cast<size_t>(j)]) != cjk) {
+          crossed = true;
+          break;
+        }
+      }
+      if (crossed) {
+        continue;
+      }
+    }
+    keys->push_back(size <= width ? pack_key(cps.data() + i, size, width) : kInvalidKey);
+  }
+}
+
+// the pipeline's private, slightly wider CJK classifier (search_pipeline.cpp:73-78)
+bool pipeline_is_cjk(uint32_t cp) {
+  return is_cjk_ideograph(cp) || (cp >= 0x2B820u && cp <= 0x2CEAFu);
+}
+
+// HasUncoveredHybridFragment, search_pipeline.cpp:80-136
+bool has_uncovered_hybrid_fragment(const uint8_t* term, uint64_t len, int ngram_size, int kanji_ngram_size,
+                                   bool cross) {
+  if (len == 0 || kanji_ngram_size <= 0) {
+    return false;
+  }
+  const int ascii_n = ngram_size > 0 ? ngram_size : 2;
+  const auto cps = host_utf8_to_codepoints(term, len);
+  if (cps.size() < 2) {
+    return false;
+  }
+  bool has_cjk = false;
+  bool has_non = false;
+  for (uint32_t cp : cps) {
+    (pipeline_is_cjk(cp) ? has_cjk : has_non) = true;
+  }
+  if (!has_cjk || !has_non) {
+    return false;
+  }
+  std::vector<bool> covered(cps.size(), false);
+  for (size_t i = 0; i < cps.size(); ++i) {
+    const bool start_cjk = pipeline_is_cjk(cps[i]);
+    const int size = start_cjk ? kanji_ngram_size : ascii_n;
+    if (size <= 0 || i + static_cast<size_t>(size) > cps.size()) {
+      continue;
+    }
+    if (!cross) {
+      bool crossed = false;
+      for (int j = 1; j < size; ++j) {
+        if (pipeline_is_cjk(cps[i + static_cast<size_t>(j)]) != start_cjk) {
+          crossed = true;
+          break;
+        }
+      }
+      if (crossed) {
+        continue;
+      }
+    }
+    for (int j = 0; j < size; ++j) {
+      covered[i + static_cast<size_t>(j)] = true;
+    }
+  }
+  return std::any_of(covered.begin(), covered.end(), [](bool c) { return !c; });
+}
+
+}  // namespace
+
+bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanji_ngram_size, bool cross_boundary,
+                     int key_width, std::vector<uint64_t>* keys) {
+  keys->clear();
+  const auto cps = host_utf8_to_codepoints(term, len);
+  if (kanji_ngram_size > 0) {
+    hybrid_keys(cps, ngram_size > 0 ? ngram_size : 2, kanji_ngram_size, cross_boundary, key_width, keys);
+  } else if (ngram_size == 0) {
+    hybrid_keys(cps, 2, 1, true, key_width, keys);  // GenerateHybridNgrams defaults, string_utils.h
+  } else if (ngram_size > 0 && !cps.empty()) {
+    // GenerateNgrams, string_utils.cpp:382-423
+    const size_t n = static_cast<size_t>(ngram_size);
+    if (cps.size() >= n) {
+      for (size_t i = 0; i + n <= cps.size(); ++i) {
+        keys->push_back(ngram_size <= key_width ? pack_key(cps.data() + i, ngram_size, key_width) : kInvalidKey);
+      }
+    }
+  }
+  std::sort(keys->begin(), keys->end());  // DeduplicateSorted, string_utils.h:192-196
+  keys->erase(std::unique(keys->begin(), keys->end()), keys->end());
+  return true;
+}
+
+bool host_ngram_to_key(const uint8_t* term, uint64_t len, int key_width, uint64_t* key) {
+  // a dictionary key is the UTF-8 re-encoding of 1..width decoded code points;
+  // a byte string with invalid sequences can therefore never equal one
+  uint32_t cps[kMaxKeyWidth];
+  int n = 0;
+  uint64_t i = 0;
+  while (i < len) {
+    uint32_t cp = 0;
+    const uint64_t avail = len - i;
+    const int l = parse_utf8(term[i], avail > 1 ? term[i + 1] : 0, avail > 2 ? term[i + 2] : 0,
+                             avail > 3 ? term[i + 3] : 0, avail, &cp);
+    if (l <= 0 || n >= key_width) {
+      return false;
+    }
+    cps[n++] = cp;
+    i += static_cast<uint64_t>(l);
+  }
+  if (n == 0) {
+    return false;
+  }
+  *key = pack_key(cps, n, key_width);
+  return true;
+}
+
+namespace {
+
+int require_device() {
+  int count = 0;
+  const cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count <= 0) {
+    (void)cudaGetLastError();
+    set_last_error("no CUDA device is visible; libmgx has no CPU fallback");
+    return MGX_ERR_NO_DEVICE;
+  }
+  return MGX_OK;
+}
+
+template <typename F>
+int guarded(F&& fn) {
+  try {
+    return fn();
+  } catch (const CudaFailure& f) {
+    return f.code;
+  } catch (const std::bad_alloc&) {
+    set_last_error("host allocation failed");
+    return MGX_ERR_CUDA;
+  } catch (const std::exception& e) {
+    set_last_error(std::string("unexpected: ") + e.what());
+    return MGX_ERR_CUDA;
+  }
+}
+
+int invalid(const char* what) {
+  set_last_error(what);
+  return MGX_ERR_INVALID_ARGUMENT;
+}
+
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) {
+      cudaSetDevice(dev);
+    }
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+// Compile the caller's flat query description into unique terms + queries.
+int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queries, const uint8_t* term_bytes,
+                  const uint64_t* term_offsets, const uint64_t* q_term_begin, const uint8_t* not_bytes,
+                  const uint64_t* not_offsets, const uint64_t* q_not_begin, std::vector<HostTerm>* terms,
+                  std::vector<HostQuery>* queries, std::vector<uint32_t>* slot_tid) {
+  std::unordered_map<std::string, uint32_t> ids;
+  auto intern = [&](const uint8_t* bytes, uint64_t b, uint64_t e, uint32_t* out) -> int {
+    if (e - b > kMaxTermBytes) {
+      set_last_error("query term longer than 256 bytes is not supported");
+      return MGX_ERR_UNSUPPORTED;
+    }
+    std::string s(reinterpret_cast<const char*>(bytes) + b, e - b);
+    auto it = ids.find(s);
+    if (it != ids.end()) {
+      *out = it->second;
+      return MGX_OK;
+    }
+    HostTerm t;
+    t.bytes = s;
+    host_query_keys(bytes + b, e - b, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0, ix.width, &t.keys);
+    if (t.keys.size() == 1 && t.keys[0] != kInvalidKey) {
+      uint8_t enc[4 * kMaxKeyWidth];
+      const int n = mgx_key_to_utf8(t.keys[0], ix.width, enc);
+      t.exact_single = static_cast<uint64_t>(n) == e - b && std::memcmp(enc, bytes + b, e - b) == 0;
+    }
+    const uint32_t id = static_cast<uint32_t>(terms->size());
+    terms->push_back(std::move(t));
+    ids.emplace(std::move(s), id);
+    *out = id;
+    return MGX_OK;
+  };
+  const uint64_t n_slots = n_queries > 0 ? q_term_begin[n_queries] : 0;
+  slot_tid->assign(n_slots, 0);
+  queries->resize(n_queries);
+  for (uint64_t q = 0; q < n_queries; ++q) {
+    HostQuery& hq = (*queries)[q];
+    bool all_ascii = true;
+    bool hybrid_exact = false;
+    if (q_term_begin[q + 1] < q_term_begin[q]) {
+      return invalid("q_term_begin must be non-decreasing");
+    }
+    for (uint64_t s = q_term_begin[q]; s < q_term_begin[q + 1]; ++s) {
+      uint32_t tid = 0;
+      const int rc = intern(term_bytes, term_offsets[s], term_offsets[s + 1], &tid);
+      if (rc != MGX_OK) {
+        return rc;
+      }
+      (*slot_tid)[s] = tid;
+      hq.terms.push_back(tid);
+      for (uint64_t i = term_offsets[s]; i < term_offsets[s + 1]; ++i) {
+        all_ascii &= term_bytes[i] < 0x80;
+      }
+      hybrid_exact |= has_uncovered_hybrid_fragment(term_bytes + term_offsets[s], term_offsets[s + 1] - term_offsets[s],
+                                                    p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0);
+    }
+    if (hq.terms.size() > 64) {
+      set_last_error("more than 64 search terms in one query (reference limit, query_ast.h:184-185)");
+      return MGX_ERR_UNSUPPORTED;
+    }
+    if (q_not_begin != nullptr) {
+      for (uint64_t s = q_not_begin[q]; s < q_not_begin[q + 1]; ++s) {
+        uint32_t tid = 0;
+        const int rc = intern(not_bytes, not_offsets[s], not_offsets[s + 1], &tid);
+        if (rc != MGX_OK) {
+          return rc;
+        }
+        hq.not_terms.push_back(tid);
+      }
+    }
+    // ShouldApplyVerifyText (search_pipeline.cpp:48-66) and the hybrid-fragment rule (:858-866)
+    const bool verify = p.verify_text == 1 || (p.verify_text == 2 && all_ascii) || hybrid_exact;
+    hq.flags = verify ? kQVerify : 0u;
+  }
+  return MGX_OK;
+}
+
+int check_params(const mgx_query_params_t& p) {
+  if (p.compute_score != 0) {
+    if (p.limit == 0 || static_cast<uint64_t>(p.limit) + p.offset > kMaxTopK) {
+      set_last_error("SORT _score needs 0 < limit and limit + offset <= 1024 in this build");
+      return MGX_ERR_UNSUPPORTED;
+    }
+  }
+  return MGX_OK;
+}
+
+void new_batch_events(Batch& b) {
+  for (auto& e : b.ev) {
+    MGX_CUDA(cudaEventCreate(&e));
+  }
+}
+
+void finish_stats(Batch& b, uint64_t d2h_bytes) {
+  Index& ix = *b.ix;
+  float ms = 0.f;
+  mgx_batch_stats_t& s = ix.last_stats;
+  cudaEventElapsedTime(&ms, b.ev[0], b.ev[4]);
+  s.ms_total = ms;
+  cudaEventElapsedTime(&ms, b.ev[1], b.ev[2]);
+  s.ms_df = ms;
+  cudaEventElapsedTime(&ms, b.ev[2], b.ev[3]);
+  s.ms_search = ms;
+  s.ms_topk = 0.0;
+  s.launches = g_launches.load() - b.launches_at_start;
+  s.h2d_bytes = b.h2d_bytes;
+  s.d2h_bytes = d2h_bytes;
+  s.unique_terms = b.n_terms;
+}
+
+}  // namespace
+}  // namespace mgx
+
+using namespace mgx;
+
+struct mgx_index {
+  Index ix;
+  std::mutex mu;  // serialises build vs. query on one handle (the reference's table generation lock)
+};
+
+struct mgx_batch {
+  Batch b;
+};
+
+extern "C" {
+
+const char* mgx_last_error(void) { return g_last_error.c_str(); }
+const char* mgx_version(void) { return "mgx 0.1 (sm_100a, CUDA kernels only, no CPU fallback)"; }
+uint64_t mgx_kernel_launch_count(void) { return g_launches.load(); }
+
+int mgx_index_create(const mgx_index_config_t* config, mgx_index_t** out) {
+  if (config == nullptr || out == nullptr) {
+    return invalid("config/out is null");
+  }
+  *out = nullptr;
+  if (int rc = require_device(); rc != MGX_OK) {
+    return rc;
+  }
+  const int kanji = config->kanji_ngram_size > 0 ? config->kanji_ngram_size : config->ngram_size;  // index.cpp:32
+  if (config->ngram_size < 1 || config->ngram_size > kMaxKeyWidth || kanji < 1 || kanji > kMaxKeyWidth) {
+    set_last_error("n-gram sizes must be 1..3 in this build (packed 64-bit keys)");
+    return MGX_ERR_UNSUPPORTED;
+  }
+  return guarded([&]() {
+    int count = 0;
+    MGX_CUDA(cudaGetDeviceCount(&count));
+    if (config->device < 0 || config->device >= count) {
+      return invalid("device ordinal out of range");
+    }
+    auto h = std::make_unique<mgx_index>();
+    h->ix.cfg = *config;
+    h->ix.ngram = config->ngram_size;
+    h->ix.kanji = kanji;
+    h->ix.cross = config->cross_boundary_ngrams != 0;
+    h->ix.width = std::max(h->ix.ngram, h->ix.kanji);
+    h->ix.device = config->device;
+    DeviceGuard guard(config->device);
+    MGX_CUDA(cudaStreamCreateWithFlags(&h->ix.stream, cudaStreamNonBlocking));
+    *out = h.release();
+    return MGX_OK;
+  });
+}
+
+void mgx_index_destroy(mgx_index_t* index) {
+  if (index == nullptr) {
+    return;
+  }
+  {
+    DeviceGuard guard(index->ix.device);
+    if (index->ix.stream != nullptr) {
+      cudaStreamSynchronize(index->ix.stream);
+      cudaStreamDestroy(index->ix.stream);
+    }
+    delete index;
+  }
+}
+
+static int build_common(mgx_index_t* index, const uint32_t* doc_ids, const uint8_t* text, const uint64_t* text_offsets,
+                        uint64_t n_docs, bool device_inputs) {
+  if (index == nullptr || (n_docs > 0 && (doc_ids == nullptr || text_offsets == nullptr))) {
+    return invalid("null argument");
+  }
+  if (n_docs >= (1ULL << 32) - 1) {
+    return invalid("too many documents in one shard");
+  }
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(index->mu);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    uint64_t text_bytes = 0;
+    uint64_t first_off = 0;
+    static const uint64_t kZeroOff[1] = {0};
+    const uint64_t* offs = n_docs > 0 ? text_offsets : kZeroOff;
+    if (device_inputs && n_docs > 0) {
+      MGX_CUDA(cudaMemcpy(&first_off, text_offsets, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+      MGX_CUDA(cudaMemcpy(&text_bytes, text_offsets + n_docs, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    } else if (n_docs > 0) {
+      first_off = text_offsets[0];
+      text_bytes = text_offsets[n_docs];
+      for (uint64_t i = 1; i < n_docs; ++i) {
+        if (doc_ids[i] <= doc_ids[i - 1]) {
+          return invalid("doc_ids must be strictly ascending");
+        }
+      }
+    }
+    if (first_off != 0) {
+      return invalid("text_offsets[0] must be 0");
+    }
+    static const uint8_t kNoText[1] = {0};
+    build_index_device(ix, doc_ids, text != nullptr ? text : kNoText, offs, n_docs, text_bytes, ix.stream);
+    return MGX_OK;
+  });
+}
+
+int mgx_index_build(mgx_index_t* index, const uint32_t* doc_ids, const uint8_t* text, const uint64_t* text_offsets,
+                    uint64_t n_docs) {
+  return build_common(index, doc_ids, text, text_offsets, n_docs, false);
+}
+
+int mgx_index_build_device(mgx_index_t* index, const uint32_t* d_doc_ids, const uint8_t* d_text,
+                           const uint64_t* d_text_offsets, uint64_t n_docs) {
+  return build_common(index, d_doc_ids, d_text, d_text_offsets, n_docs, true);
+}
+
+int mgx_index_get_stats(const mgx_index_t* index, mgx_index_stats_t* out) {
+  if (index == nullptr || out == nullptr) {
+    return invalid("null argument");
+  }
+  const Index& ix = index->ix;
+  out->n_docs = ix.n_docs;
+  out->n_terms = ix.n_terms;
+  out->n_postings = ix.n_postings;
+  out->n_dense_terms = ix.n_dense;
+  out->text_bytes = ix.text_bytes;
+  out->total_doc_length = ix.total_doc_length;
+  out->doc_count = ix.doc_count;
+  out->device_bytes = ix.device_bytes();
+  out->n_pair_slots = ix.n_pair_slots;
+  out->all_valid_utf8 = ix.all_valid_utf8 ? 1 : 0;
+  out->key_width = ix.width;
+  out->last_build_ms = ix.last_build_ms;
+  return MGX_OK;
+}
+
+int mgx_key_to_utf8(uint64_t key, int32_t width, uint8_t* out) {
+  if (out == nullptr || width < 1 || width > kMaxKeyWidth) {
+    return invalid("bad width/out");
+  }
+  int n = 0;
+  for (int j = width - 1; j >= 0; --j) {
+    const uint64_t f = (key >> (21 * j)) & 0x1FFFFFULL;
+    if (f == 0) {
+      continue;
+    }
+    const uint32_t cp = static_cast<uint32_t>(f - 1);
+    if (cp <= 0x7F) {
+      out[n++] = static_cast<uint8_t>(cp);
+    } else if (cp <= 0x7FF) {
+      out[n++] = static_cast<uint8_t>(0xC0 | (cp >> 6));
+      out[n++] = static_cast<uint8_t>(0x80 | (cp & 0x3F));
+    } else if (cp <= 0xFFFF) {
+      out[n++] = static_cast<uint8_t>(0xE0 | (cp >> 12));
+      out[n++] = static_cast<uint8_t>(0x80 | ((cp >> 6) & 0x3F));
+      out[n++] = static_cast<uint8_t>(0x80 | (cp & 0x3F));
+    } else {
+      out[n++] = static_cast<uint8_t>(0xF0 | (cp >> 18));
+      out[n++] = static_cast<uint8_t>(0x80 | ((cp >> 12) & 0x3F));
+      out[n++] = static_cast<uint8_t>(0x80 | ((cp >> 6) & 0x3F));
+      out[n++] = static_cast<uint8_t>(0x80 | (cp & 0x3F));
+    }
+  }
+  return n;
+}
+
+int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, const uint64_t* text_offsets,
+                       uint64_t n_docs, uint64_t* out_keys, uint32_t* out_doc, uint64_t cap, uint64_t* out_count) {
+  if (config == nullptr || out_count == nullptr || (n_docs > 0 && text_offsets == nullptr)) {
+    return invalid("null argument");
+  }
+  if (int rc = require_device(); rc != MGX_OK) {
+    return rc;
+  }
+  const int kanji = config->kanji_ngram_size > 0 ? config->kanji_ngram_size : config->ngram_size;
+  if (config->ngram_size < 1 || config->ngram_size > kMaxKeyWidth || kanji < 1 || kanji > kMaxKeyWidth) {
+    set_last_error("n-gram sizes must be 1..3 in this build");
+    return MGX_ERR_UNSUPPORTED;
+  }
+  return guarded([&]() {
+    DeviceGuard guard(config->device);
+    *out_count = 0;
+    if (n_docs == 0) {
+      return MGX_OK;
+    }
+    cudaStream_t st = nullptr;
+    MGX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const uint64_t bytes = text_offsets[n_docs];
+    DevBuf<uint8_t> d_text;
+    DevBuf<uint64_t> d_off;
+    d_text.alloc(bytes + 64);
+    d_off.alloc(n_docs + 1);
+    MGX_CUDA(cudaMemsetAsync(d_text.p, 0, bytes + 64, st));
+    if (bytes > 0) {
+      MGX_CUDA(cudaMemcpyAsync(d_text.p, text, bytes, cudaMemcpyHostToDevice, st));
+    }
+    MGX_CUDA(cudaMemcpyAsync(d_off.p, text_offsets, (n_docs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    DevBuf<uint32_t> d_len;
+    DevBuf<uint64_t> d_slot_off;
+    DevBuf<uint64_t> d_keys;
+    DevBuf<uint32_t> d_docs;
+    uint64_t n_slots = 0;
+    uint64_t counters[2];
+    tokenize_device(config->ngram_size, kanji, config->cross_boundary_ngrams != 0, std::max(config->ngram_size, kanji),
+                    d_text.p, d_off.p, n_docs, d_len, d_slot_off, d_keys, d_docs, &n_slots, counters, st);
+    std::vector<uint64_t> keys(n_slots);
+    std::vector<uint32_t> docs(n_slots);
+    if (n_slots > 0) {
+      MGX_CUDA(cudaMemcpyAsync(keys.data(), d_keys.p, n_slots * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      MGX_CUDA(cudaMemcpyAsync(docs.data(), d_docs.p, n_slots * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    MGX_CUDA(cudaStreamSynchronize(st));
+    cudaStreamDestroy(st);
+    uint64_t n = 0;
+    for (uint64_t i = 0; i < n_slots; ++i) {
+      if (keys[i] != kInvalidKey) {
+        if (n < cap && out_keys != nullptr && out_doc != nullptr) {
+          out_keys[n] = keys[i];
+          out_doc[n] = docs[i];
+        }
+        ++n;
+      }
+    }
+    *out_count = n;
+    if (n > cap) {
+      set_last_error("mgx_tokenize_batch: output capacity too small");
+      return MGX_ERR_CAPACITY;
+    }
+    return MGX_OK;
+  });
+}
+
+// ---------------------------------------------------------------- set-algebra single calls
+namespace {
+
+enum class SetOp { kAnd, kOr, kNot, kFilter };
+
+int run_set_op(mgx_index_t* index, SetOp op, const uint32_t* driver_ids, uint64_t n_driver, const uint8_t* term_bytes,
+               const uint64_t* term_offsets, uint64_t n_terms, uint64_t limit, bool reverse, uint32_t* out,
+               uint64_t cap, uint64_t* out_count) {
+  if (index == nullptr || out_count == nullptr || (n_terms > 0 && (term_bytes == nullptr || term_offsets == nullptr))) {
+    return invalid("null argument");
+  }
+  *out_count = 0;
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(index->mu);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    auto copy_ids = [&](const uint32_t* src, uint64_t n) {
+      *out_count = n;
+      if (n > cap) {
+        set_last_error("output capacity too small");
+        return MGX_ERR_CAPACITY;
+      }
+      if (n > 0) {
+        std::memcpy(out, src, n * sizeof(uint32_t));
+      }
+      return MGX_OK;
+    };
+    // trivial cases decided exactly as the reference does before touching any list
+    if (op == SetOp::kAnd && n_terms == 0) {
+      return MGX_OK;  // index.cpp:203-205
+    }
+    if (op == SetOp::kOr && n_terms == 0) {
+      return MGX_OK;  // index.cpp:420-422
+    }
+    if (op == SetOp::kNot && n_terms == 0) {
+      return copy_ids(driver_ids, n_driver);  // index.cpp:451-453
+    }
+    if (op == SetOp::kFilter && n_driver == 0) {
+      return MGX_OK;  // index.cpp:372-374
+    }
+    if (op == SetOp::kFilter && n_terms == 0) {
+      return copy_ids(driver_ids, n_driver);  // index.cpp:378-380
+    }
+    if ((op == SetOp::kNot) && n_driver == 0) {
+      return MGX_OK;
+    }
+
+    std::vector<uint64_t> keys;
+    for (uint64_t i = 0; i < n_terms; ++i) {
+      uint64_t key = kInvalidKey;
+      if (!host_ngram_to_key(term_bytes + term_offsets[i], term_offsets[i + 1] - term_offsets[i], ix.width, &key)) {
+        key = kInvalidKey;
+      }
+      keys.push_back(key);
+    }
+    std::vector<HostTerm> terms;
+    std::vector<HostQuery> queries(1);
+    if (op == SetOp::kNot) {
+      for (uint64_t key : keys) {  // one NOT group per n-gram: excluded if in ANY of the lists
+        HostTerm t;
+        t.raw = true;
+        t.keys = {key};
+        queries[0].not_terms.push_back(static_cast<uint32_t>(terms.size()));
+        terms.push_back(std::move(t));
+      }
+      queries[0].flags = kQDriverExplicit;
+    } else {
+      HostTerm t;
+      t.raw = true;
+      t.keys = keys;
+      std::sort(t.keys.begin(), t.keys.end());
+      t.keys.erase(std::unique(t.keys.begin(), t.keys.end()), t.keys.end());
+      if (op == SetOp::kOr) {
+        // unknown terms are ignored (index.cpp:437-445)
+        t.keys.erase(std::remove(t.keys.begin(), t.keys.end(), kInvalidKey), t.keys.end());
+      }
+      terms.push_back(std::move(t));
+      queries[0].terms.push_back(0);
+      queries[0].flags = op == SetOp::kOr ? kQAnyMode : (op == SetOp::kFilter ? kQDriverExplicit : 0u);
+    }
+
+    Batch b;
+    b.ix = &ix;
+    b.stream = ix.stream;
+    b.params = mgx_query_params_t{};
+    b.params.compute_score = 0;
+    b.launches_at_start = g_launches.load();
+    DevBuf<uint32_t> d_driver;
+    if (op == SetOp::kNot || op == SetOp::kFilter) {
+      if (n_driver >= (1ULL << 32)) {
+        return invalid("too many candidate ids");
+      }
+      d_driver.alloc(n_driver);
+      MGX_CUDA(cudaMemcpyAsync(d_driver.p, driver_ids, n_driver * sizeof(uint32_t), cudaMemcpyHostToDevice, b.stream));
+      b.explicit_driver.d_ids = d_driver.p;
+      b.explicit_driver.n = n_driver;
+    }
+    batch_upload(b, terms, queries, {});
+    batch_plan(b, false);
+    std::vector<uint64_t> set_off;
+    DevBuf<uint32_t> d_sets;
+    batch_search_sets(b, &set_off, &d_sets);
+    const uint64_t total = set_off[1];
+    uint64_t first = 0;
+    uint64_t n = total;
+    if (limit > 0 && total > limit) {  // index.cpp:356-366
+      n = limit;
+      first = reverse ? total - limit : 0;
+    }
+    *out_count = n;
+    if (n > cap) {
+      set_last_error("output capacity too small");
+      return MGX_ERR_CAPACITY;
+    }
+    if (n > 0) {
+      MGX_CUDA(cudaMemcpyAsync(out, d_sets.p + first, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, b.stream));
+      MGX_CUDA(cudaStreamSynchronize(b.stream));
+      if (reverse) {
+        std::reverse(out, out + n);
+      }
+    }
+    return MGX_OK;
+  });
+}
+
+}  // namespace
+
+int mgx_search_and(const mgx_index_t* index, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                   uint64_t n_terms, uint64_t limit, int32_t reverse, uint32_t* out, uint64_t cap,
+                   uint64_t* out_count) {
+  return run_set_op(const_cast<mgx_index_t*>(index), SetOp::kAnd, nullptr, 0, term_bytes, term_offsets, n_terms, limit,
+                    reverse != 0, out, cap, out_count);
+}
+
+int mgx_search_or(const mgx_index_t* index, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                  uint64_t n_terms, uint32_t* out, uint64_t cap, uint64_t* out_count) {
+  return run_set_op(const_cast<mgx_index_t*>(index), SetOp::kOr, nullptr, 0, term_bytes, term_offsets, n_terms, 0,
+                    false, out, cap, out_count);
+}
+
+int mgx_search_not(const mgx_index_t* index, const uint32_t* all_docs, uint64_t n_all, const uint8_t* term_bytes,
+                   const uint64_t* term_offsets, uint64_t n_terms, uint32_t* out, uint64_t cap, uint64_t* out_count) {
+  return run_set_op(const_cast<mgx_index_t*>(index), SetOp::kNot, all_docs, n_all, term_bytes, term_offsets, n_terms,
+                    0, false, out, cap, out_count);
+}
+
+int mgx_filter_by_ngrams(const mgx_index_t* index, const uint32_t* candidates, uint64_t n_candidates,
+                         const uint8_t* term_bytes, const uint64_t* term_offsets, uint64_t n_terms, uint32_t* out,
+                         uint64_t cap, uint64_t* out_count) {
+  return run_set_op(const_cast<mgx_index_t*>(index), SetOp::kFilter, candidates, n_candidates, term_bytes,
+                    term_offsets, n_terms, 0, false, out, cap, out_count);
+}
+
+int mgx_index_get_postings(const mgx_index_t* index, const uint8_t* term, uint64_t term_len, uint32_t* out,
+                           uint64_t cap, uint64_t* out_count) {
+  const uint64_t offs[2] = {0, term_len};
+  static const uint8_t kEmpty[1] = {0};
+  return mgx_search_and(index, term != nullptr ? term : kEmpty, offs, 1, 0, 0, out, cap, out_count);
+}
+
+int mgx_index_posting_size(const mgx_index_t* index, const uint8_t* term, uint64_t term_len, uint64_t* out) {
+  if (index == nullptr || out == nullptr) {
+    return invalid("null argument");
+  }
+  *out = 0;
+  mgx_index_t* h = const_cast<mgx_index_t*>(index);
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(h->mu);
+    Index& ix = h->ix;
+    DeviceGuard guard(ix.device);
+    uint64_t key = 0;
+    if (term == nullptr || !host_ngram_to_key(term, term_len, ix.width, &key) || ix.n_terms == 0) {
+      return MGX_OK;
+    }
+    // binary search over the device dictionary, 8 bytes per probe
+    uint64_t lo = 0;
+    uint64_t hi = ix.n_terms;
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) / 2;
+      uint64_t v = 0;
+      MGX_CUDA(cudaMemcpy(&v, ix.d_term_keys.p + mid, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+      if (v < key) {
+        lo = mid + 1;
+      } else {
+        hi = mid;
+      }
+    }
+    if (lo < ix.n_terms) {
+      uint64_t v = 0;
+      MGX_CUDA(cudaMemcpy(&v, ix.d_term_keys.p + lo, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+      if (v == key) {
+        uint64_t off[2];
+        MGX_CUDA(cudaMemcpy(off, ix.d_term_off.p + lo, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        *out = off[1] - off[0];
+      }
+    }
+    return MGX_OK;
+  });
+}
+
+int mgx_index_export(const mgx_index_t* index, uint64_t* keys, uint64_t* offsets, uint32_t* postings) {
+  if (index == nullptr || keys == nullptr || offsets == nullptr || postings == nullptr) {
+    return invalid("null argument");
+  }
+  mgx_index_t* h = const_cast<mgx_index_t*>(index);
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(h->mu);
+    Index& ix = h->ix;
+    DeviceGuard guard(ix.device);
+    if (ix.n_terms > 0) {
+      MGX_CUDA(cudaMemcpy(keys, ix.d_term_keys.p, ix.n_terms * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+    if (ix.d_term_off.p != nullptr && ix.d_term_off.n >= ix.n_terms + 1) {
+      MGX_CUDA(cudaMemcpy(offsets, ix.d_term_off.p, (ix.n_terms + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    } else {
+      offsets[0] = 0;
+    }
+    if (ix.n_postings > 0) {
+      MGX_CUDA(cudaMemcpy(postings, ix.d_postings.p, ix.n_postings * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      // local index -> global DocId (a pure relabelling done while copying out)
+      std::vector<uint32_t> ids(ix.n_docs);
+      MGX_CUDA(cudaMemcpy(ids.data(), ix.d_doc_ids.p, ix.n_docs * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      for (uint64_t i = 0; i < ix.n_postings; ++i) {
+        postings[i] = ids[postings[i]];
+      }
+    }
+    return MGX_OK;
+  });
+}
+
+int mgx_index_doc_lengths(const mgx_index_t* index, uint32_t* out) {
+  if (index == nullptr || out == nullptr) {
+    return invalid("null argument");
+  }
+  mgx_index_t* h = const_cast<mgx_index_t*>(index);
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->ix.device);
+    if (h->ix.n_docs > 0) {
+      MGX_CUDA(cudaMemcpy(out, h->ix.d_doc_len.p, h->ix.n_docs * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    return MGX_OK;
+  });
+}
+
+// ---------------------------------------------------------------- batched pipeline
+int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                      const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                      const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                      void* stream, mgx_batch_t** out) {
+  if (index == nullptr || params == nullptr || out == nullptr ||
+      (n_queries > 0 && (term_offsets == nullptr || q_term_begin == nullptr))) {
+    return invalid("null argument");
+  }
+  *out = nullptr;
+  if (n_queries >= (1ULL << 31)) {
+    return invalid("too many queries in one batch");
+  }
+  if (int rc = check_params(*params); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    auto h = std::make_unique<mgx_batch>();
+    Batch& b = h->b;
+    b.ix = &ix;
+    b.params = *params;
+    b.stream = stream != nullptr ? static_cast<cudaStream_t>(stream) : ix.stream;
+    b.launches_at_start = g_launches.load();
+    new_batch_events(b);
+    MGX_CUDA(cudaEventRecord(b.ev[0], b.stream));
+    std::vector<HostTerm> terms;
+    std::vector<HostQuery> queries;
+    std::vector<uint32_t> slot_tid;
+    static const uint8_t kEmpty[1] = {0};
+    const int rc = compile_batch(ix, *params, n_queries, term_bytes != nullptr ? term_bytes : kEmpty, term_offsets,
+                                 q_term_begin, not_bytes != nullptr ? not_bytes : kEmpty, not_offsets, q_not_begin,
+                                 &terms, &queries, &slot_tid);
+    if (rc != MGX_OK) {
+      return rc;
+    }
+    batch_upload(b, terms, queries, slot_tid);
+    batch_plan(b, params->compute_score != 0);
+    MGX_CUDA(cudaEventRecord(b.ev[1], b.stream));
+    *out = h.release();
+    return MGX_OK;
+  });
+}
+
+uint64_t mgx_batch_term_slots(const mgx_batch_t* batch) { return batch != nullptr ? batch->b.n_slots : 0; }
+
+int mgx_batch_df_device(mgx_batch_t* batch, uint64_t* d_df) {
+  if (batch == nullptr) {
+    return invalid("null batch");
+  }
+  return guarded([&]() {
+    Batch& b = batch->b;
+    DeviceGuard guard(b.ix->device);
+    if (b.params.compute_score != 0) {
+      batch_df(b);
+    }
+    if (d_df != nullptr) {
+      batch_df_to_slots(b, d_df);
+    }
+    MGX_CUDA(cudaEventRecord(b.ev[2], b.stream));
+    return MGX_OK;
+  });
+}
+
+int mgx_batch_search_device(mgx_batch_t* batch, const uint64_t* d_df, uint64_t stride, uint32_t* d_ids,
+                            double* d_scores, uint32_t* d_count, uint64_t* d_total) {
+  if (batch == nullptr || d_ids == nullptr || d_count == nullptr || d_total == nullptr) {
+    return invalid("null argument");
+  }
+  return guarded([&]() {
+    Batch& b = batch->b;
+    DeviceGuard guard(b.ix->device);
+    if (b.params.compute_score != 0 && !b.df_done) {
+      batch_df(b);
+      MGX_CUDA(cudaEventRecord(b.ev[2], b.stream));
+    }
+    // a shard returns its best (offset + limit) records un-offset; mgx_merge_topk_device applies the offset
+    const mgx_query_params_t saved = b.params;
+    if (b.params.limit != 0) {
+      b.params.limit = saved.limit + saved.offset;
+    }
+    b.params.offset = 0;
+    batch_search(b, d_df, stride, d_ids, d_scores, d_count, d_total);
+    b.params = saved;
+    MGX_CUDA(cudaEventRecord(b.ev[3], b.stream));
+    return MGX_OK;
+  });
+}
+
+void mgx_batch_destroy(mgx_batch_t* batch) {
+  if (batch == nullptr) {
+    return;
+  }
+  DeviceGuard guard(batch->b.ix->device);
+  cudaStreamSynchronize(batch->b.stream);
+  for (auto& e : batch->b.ev) {
+    if (e != nullptr) {
+      cudaEventDestroy(e);
+    }
+  }
+  delete batch;
+}
+
+int mgx_merge_topk_device(int32_t device, void* stream, const mgx_query_params_t* params, uint32_t n_shards,
+                          uint64_t n_queries, uint64_t stride, const uint32_t* d_ids_all, const double* d_scores_all,
+                          const uint32_t* d_count_all, const uint64_t* d_total_all, uint32_t* d_ids_out,
+                          double* d_scores_out, uint32_t* d_count_out, uint64_t* d_total_out) {
+  if (params == nullptr || d_ids_all == nullptr || d_count_all == nullptr || d_total_all == nullptr ||
+      d_ids_out == nullptr || d_count_out == nullptr || d_total_out == nullptr) {
+    return invalid("null argument");
+  }
+  if (int rc = require_device(); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    DeviceGuard guard(device);
+    launch_merge_topk(static_cast<cudaStream_t>(stream), *params, n_shards, n_queries, stride, d_ids_all, d_scores_all,
+                      d_count_all, d_total_all, d_ids_out, d_scores_out, d_count_out, d_total_out);
+    return MGX_OK;
+  });
+}
+
+int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                    const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                    const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                    uint64_t stride, uint32_t* out_ids, double* out_scores, uint32_t* out_count, uint64_t* out_total,
+                    uint64_t* out_df) {
+  if (index == nullptr || params == nullptr || out_ids == nullptr || out_count == nullptr || out_total == nullptr) {
+    return invalid("null argument");
+  }
+  if (params->compute_score != 0 && out_scores == nullptr) {
+    return invalid("out_scores is required for SORT _score");
+  }
+  if (n_queries == 0) {
+    return MGX_OK;
+  }
+  std::lock_guard<std::mutex> lock(index->mu);
+  mgx_batch_t* batch = nullptr;
+  int rc = mgx_batch_prepare(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
+                             q_not_begin, nullptr, &batch);
+  if (rc != MGX_OK) {
+    return rc;
+  }
+  rc = guarded([&]() {
+    Batch& b = batch->b;
+    Index& ix = *b.ix;
+    DeviceGuard guard(ix.device);
+    cudaStream_t st = b.stream;
+    DevBuf<uint32_t> d_ids;
+    DevBuf<double> d_scores;
+    DevBuf<uint32_t> d_count;
+    DevBuf<uint64_t> d_total;
+    DevBuf<uint64_t> d_df;
+    d_ids.alloc(n_queries * stride);
+    d_scores.alloc(params->compute_score != 0 ? n_queries * stride : 1);
+    d_count.alloc(n_queries);
+    d_total.alloc(n_queries);
+    d_df.alloc(b.n_slots);
+    if (params->compute_score != 0) {
+      batch_df(b);
+    }
+    batch_df_to_slots(b, d_df.p);
+    MGX_CUDA(cudaEventRecord(b.ev[2], st));
+    batch_search(b, nullptr, stride, d_ids.p, params->compute_score != 0 ? d_scores.p : nullptr, d_count.p, d_total.p);
+    MGX_CUDA(cudaEventRecord(b.ev[3], st));
+    uint64_t d2h = 0;
+    MGX_CUDA(cudaMemcpyAsync(out_ids, d_ids.p, n_queries * stride * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    d2h += n_queries * stride * sizeof(uint32_t);
+    if (params->compute_score != 0) {
+      MGX_CUDA(cudaMemcpyAsync(out_scores, d_scores.p, n_queries * stride * sizeof(double), cudaMemcpyDeviceToHost, st));
+      d2h += n_queries * stride * sizeof(double);
+    }
+    MGX_CUDA(cudaMemcpyAsync(out_count, d_count.p, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    MGX_CUDA(cudaMemcpyAsync(out_total, d_total.p, n_queries * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    d2h += n_queries * 12;
+    if (out_df != nullptr && b.n_slots > 0) {
+      MGX_CUDA(cudaMemcpyAsync(out_df, d_df.p, b.n_slots * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      d2h += b.n_slots * sizeof(uint64_t);
+    }
+    MGX_CUDA(cudaEventRecord(b.ev[4], st));
+    MGX_CUDA(cudaStreamSynchronize(st));
+    finish_stats(b, d2h);
+    return MGX_OK;
+  });
+  mgx_batch_destroy(batch);
+  return rc;
+}
+
+int mgx_index_last_batch_stats(const mgx_index_t* index, mgx_batch_stats_t* out) {
+  if (index == nullptr || out == nullptr) {
+    return invalid("null argument");
+  }
+  *out = index->ix.last_stats;
+  return MGX_OK;
+}
+
+// ---------------------------------------------------------------- scoring
+int mgx_score_documents(mgx_index_t* index, const uint32_t* candidates, uint64_t n_candidates,
+                        const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* term_doc_freqs,
+                        uint64_t n_terms, uint64_t total_docs, double avg_doc_length, double k1, double b,
+                        double* out_scores) {
+  if (index == nullptr || (n_candidates > 0 && (candidates == nullptr || out_scores == nullptr)) ||
+      (n_terms > 0 && (term_bytes == nullptr || term_offsets == nullptr || term_doc_freqs == nullptr))) {
+    return invalid("null argument");
+  }
+  if (n_candidates == 0) {
+    return MGX_OK;
+  }
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(index->mu);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    cudaStream_t st = ix.stream;
+    std::vector<uint32_t> boff(n_terms + 1, 0);
+    for (uint64_t i = 0; i < n_terms; ++i) {
+      if (term_offsets[i + 1] - term_offsets[i] > kMaxTermBytes) {
+        set_last_error("term longer than 256 bytes is not supported");
+        return MGX_ERR_UNSUPPORTED;
+      }
+      boff[i + 1] = static_cast<uint32_t>(term_offsets[i + 1] - term_offsets[0]);
+    }
+    const uint64_t nbytes = n_terms > 0 ? term_offsets[n_terms] - term_offsets[0] : 0;
+    DevBuf<uint8_t> d_bytes;
+    DevBuf<uint32_t> d_boff;
+    DevBuf<uint64_t> d_dfs;
+    DevBuf<uint32_t> d_cands;
+    DevBuf<double> d_scores;
+    d_bytes.alloc(nbytes + 16);
+    d_boff.alloc(n_terms + 1);
+    d_dfs.alloc(n_terms);
+    d_cands.alloc(n_candidates);
+    d_scores.alloc(n_candidates);
+    if (nbytes > 0) {
+      MGX_CUDA(cudaMemcpyAsync(d_bytes.p, term_bytes + term_offsets[0], nbytes, cudaMemcpyHostToDevice, st));
+    }
+    MGX_CUDA(cudaMemcpyAsync(d_boff.p, boff.data(), (n_terms + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (n_terms > 0) {
+      MGX_CUDA(cudaMemcpyAsync(d_dfs.p, term_doc_freqs, n_terms * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    }
+    MGX_CUDA(cudaMemcpyAsync(d_cands.p, candidates, n_candidates * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    launch_score_documents(ix, st, d_cands.p, n_candidates, d_bytes.p, d_boff.p, d_dfs.p,
+                           static_cast<uint32_t>(n_terms), total_docs, avg_doc_length, k1, b, d_scores.p);
+    MGX_CUDA(cudaMemcpyAsync(out_scores, d_scores.p, n_candidates * sizeof(double), cudaMemcpyDeviceToHost, st));
+    MGX_CUDA(cudaStreamSynchronize(st));
+    return MGX_OK;
+  });
+}
+
+int mgx_sort_by_score(mgx_index_t* index, const uint32_t* results, const double* scores, uint64_t n,
+                      int32_t descending, uint32_t limit, uint32_t offset, uint32_t* out, uint64_t* out_count) {
+  if (index == nullptr || out_count == nullptr || (n > 0 && (results == nullptr || scores == nullptr || out == nullptr))) {
+    return invalid("null argument");
+  }
+  *out_count = 0;
+  if (n == 0) {
+    return MGX_OK;  // result_sorter.cpp:663-665
+  }
+  if (limit == 0 || static_cast<uint64_t>(limit) + offset > kMaxTopK) {
+    set_last_error("mgx_sort_by_score needs 0 < limit and limit + offset <= 1024 in this build");
+    return MGX_ERR_UNSUPPORTED;
+  }
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(index->mu);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    cudaStream_t st = ix.stream;
+    DevBuf<uint32_t> d_docs;
+    DevBuf<double> d_scores;
+    DevBuf<uint32_t> d_out;
+    DevBuf<uint32_t> d_cnt;
+    d_docs.alloc(n);
+    d_scores.alloc(n);
+    d_out.alloc(limit);
+    d_cnt.alloc(1);
+    MGX_CUDA(cudaMemcpyAsync(d_docs.p, results, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    MGX_CUDA(cudaMemcpyAsync(d_scores.p, scores, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_sort_by_score(st, d_docs.p, d_scores.p, n, descending != 0, limit, offset, d_out.p, d_cnt.p);
+    uint32_t cnt = 0;
+    MGX_CUDA(cudaMemcpyAsync(&cnt, d_cnt.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    MGX_CUDA(cudaStreamSynchronize(st));
+    if (cnt > 0) {
+      MGX_CUDA(cudaMemcpy(out, d_out.p, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    *out_count = cnt;
+    return MGX_OK;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,326 @@
+// mgx_internal.cuh — shared declarations of libmgx.so (host + device helpers).
+//
+// Data layout of one index shard in HBM (all arrays cudaMalloc'ed, 256-B aligned):
+//   d_doc_ids   u32[N]        global DocIds, strictly ascending; postings store the
+//                             LOCAL index (rank) so bitmaps are exactly N bits
+//   d_text      u8[bytes]     normalised UTF-8 of all documents, back to back
+//   d_text_off  u64[N+1]      byte range of document i
+//   d_doc_len   u32[N]        CountCodePoints(text_i)   (string_utils.cpp:655-669)
+//   d_term_keys u64[T]        packed n-grams, ascending == UTF-8 bytewise order
+//   d_term_off  u64[T+1]      CSR offsets into d_postings
+//   d_postings  u32[P]        local doc indices, ascending inside each term
+//   d_term_bm   i32[T]        dense-bitmap slot of the term or -1
+//   d_bitmaps   u32[D][W]     W = ceil(N/32) words per dense term
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/mgx.h"
+
+namespace mgx {
+
+// ---------------------------------------------------------------- errors
+void set_last_error(const std::string& message);
+void count_launch(uint64_t n = 1);
+
+struct CudaFailure {
+  int code;
+};
+
+#define MGX_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t mgx_err__ = (expr);                                                                 \
+    if (mgx_err__ != cudaSuccess) {                                                                 \
+      ::mgx::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(mgx_err__) + " at " +    \
+                            __FILE__ + ":" + std::to_string(__LINE__));                             \
+      throw ::mgx::CudaFailure{MGX_ERR_CUDA};                                                       \
+    }                                                                                               \
+  } while (0)
+
+#define MGX_LAUNCH_CHECK()                \
+  do {                                    \
+    ::mgx::count_launch();                \
+    MGX_CUDA(cudaGetLastError());         \
+  } while (0)
+
+// Owning device buffer (cudaMalloc / cudaFree).
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) {
+    o.p = nullptr;
+    o.n = 0;
+  }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p;
+      n = o.n;
+      o.p = nullptr;
+      o.n = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p != nullptr) {
+      cudaFree(p);
+      p = nullptr;
+      n = 0;
+    }
+  }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) {
+      count = 1;
+    }
+    MGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+  }
+  // grow-only (keeps the allocation when it is already large enough)
+  void reserve(size_t count) {
+    if (p == nullptr || count > n) {
+      alloc(count);
+    }
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// Pinned host buffer (cudaMallocHost), grow-only.
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  PinBuf() = default;
+  PinBuf(const PinBuf&) = delete;
+  PinBuf& operator=(const PinBuf&) = delete;
+  ~PinBuf() {
+    if (p != nullptr) {
+      cudaFreeHost(p);
+    }
+  }
+  void reserve(size_t count) {
+    if (p != nullptr && count <= n) {
+      return;
+    }
+    if (p != nullptr) {
+      cudaFreeHost(p);
+      p = nullptr;
+    }
+    n = count == 0 ? 1 : count;
+    MGX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p), n * sizeof(T)));
+  }
+};
+
+// ---------------------------------------------------------------- packed keys
+// A key holds up to `width` (<= 3) code points as 21-bit fields storing cp+1,
+// first code point in the most significant used field, absent trailing code
+// points = 0. Integer order of keys == bytewise order of the UTF-8 n-gram
+// strings (the reference sorts std::string keys, string_utils.h:192-196), and a
+// shorter n-gram that is a prefix of a longer one sorts first, like strings do.
+constexpr int kMaxKeyWidth = 3;
+constexpr uint64_t kInvalidKey = ~0ULL;
+
+__host__ __device__ inline uint64_t pack_key(const uint32_t* cps, int n, int width) {
+  uint64_t key = 0;
+  for (int j = 0; j < width; ++j) {
+    key = (key << 21) | (j < n ? static_cast<uint64_t>(cps[j]) + 1 : 0ULL);
+  }
+  return key;
+}
+
+// IsCJKIdeograph, string_utils.cpp:441-448 (ranges :176-187).
+__host__ __device__ inline bool is_cjk_ideograph(uint32_t cp) {
+  return (cp >= 0x4E00u && cp <= 0x9FFFu) || (cp >= 0x3400u && cp <= 0x4DBFu) || (cp >= 0x20000u && cp <= 0x2A6DFu) ||
+         (cp >= 0x2A700u && cp <= 0x2B73Fu) || (cp >= 0x2B740u && cp <= 0x2B81Fu) || (cp >= 0xF900u && cp <= 0xFAFFu);
+}
+
+// TryParseUtf8Char (string_utils.cpp:92-164) on four bytes already in
+// registers: b0 is the candidate lead byte, b1..b3 the following bytes (any
+// value when beyond `available`). Returns the sequence length (1..4) or 0 when
+// no valid character starts here.
+__host__ __device__ inline int parse_utf8(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint64_t available,
+                                          uint32_t* cp) {
+  if (available == 0) {
+    return 0;
+  }
+  if (b0 < 0x80u) {
+    *cp = b0;
+    return 1;
+  }
+  if ((b0 & 0xE0u) == 0xC0u) {
+    if (b0 < 0xC2u || available < 2 || (b1 & 0xC0u) != 0x80u) {
+      return 0;
+    }
+    *cp = ((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu);
+    return 2;
+  }
+  if ((b0 & 0xF0u) == 0xE0u) {
+    if (available < 3 || (b1 & 0xC0u) != 0x80u || (b2 & 0xC0u) != 0x80u) {
+      return 0;
+    }
+    const uint32_t c = ((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu);
+    if (c < 0x800u || (c >= 0xD800u && c <= 0xDFFFu)) {
+      return 0;
+    }
+    *cp = c;
+    return 3;
+  }
+  if ((b0 & 0xF8u) == 0xF0u) {
+    if (b0 > 0xF4u || available < 4 || (b1 & 0xC0u) != 0x80u || (b2 & 0xC0u) != 0x80u || (b3 & 0xC0u) != 0x80u) {
+      return 0;
+    }
+    const uint32_t c = ((b0 & 0x07u) << 18) | ((b1 & 0x3Fu) << 12) | ((b2 & 0x3Fu) << 6) | (b3 & 0x3Fu);
+    if (c < 0x10000u || c > 0x10FFFFu) {
+      return 0;
+    }
+    *cp = c;
+    return 4;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- host tokenizer (queries)
+// Utf8ToCodepoints, string_utils.cpp:200-219.
+std::vector<uint32_t> host_utf8_to_codepoints(const uint8_t* text, uint64_t len);
+// GenerateQueryNgrams (string_utils.cpp:639-653) + DeduplicateSorted as packed
+// keys. Returns false if a window is wider than kMaxKeyWidth.
+bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanji_ngram_size, bool cross_boundary,
+                     int key_width, std::vector<uint64_t>* keys);
+// One n-gram string -> packed key (for Index::SearchAnd style calls). False if
+// it is not valid UTF-8 of 1..width code points (such a term cannot be in the index).
+bool host_ngram_to_key(const uint8_t* term, uint64_t len, int key_width, uint64_t* key);
+
+// ---------------------------------------------------------------- device-wide primitives (primitives.cu)
+// out[i] = sum_{j<i} in[j]  (u32 -> u64), out has n+1 entries (out[n] = total).
+void exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t stream);
+// Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, key_bits).
+// Buffers ping-pong; returns which pair of pointers holds the sorted data.
+struct SortResult {
+  uint64_t* keys;
+  uint32_t* vals;
+};
+SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_keys_b, uint32_t* d_vals_b, uint64_t n,
+                            int key_bits, cudaStream_t stream);
+
+// ---------------------------------------------------------------- index object
+struct Index {
+  mgx_index_config_t cfg{};
+  int ngram = 2;
+  int kanji = 2;  // effective
+  bool cross = true;
+  int width = 2;
+  int device = 0;
+
+  uint64_t n_docs = 0;
+  bool sequential_ids = true;
+  uint32_t first_id = 1;
+  DevBuf<uint32_t> d_doc_ids;
+  DevBuf<uint8_t> d_text;
+  DevBuf<uint64_t> d_text_off;
+  DevBuf<uint32_t> d_doc_len;
+  uint64_t text_bytes = 0;
+
+  uint64_t n_terms = 0;
+  uint64_t n_postings = 0;
+  DevBuf<uint64_t> d_term_keys;
+  DevBuf<uint64_t> d_term_off;
+  DevBuf<uint32_t> d_postings;
+  DevBuf<int32_t> d_term_bm;
+  DevBuf<uint32_t> d_bitmaps;
+  uint64_t n_dense = 0;
+  uint64_t bm_words = 0;
+  uint64_t dense_min_len = 0;
+
+  uint64_t total_doc_length = 0;
+  uint64_t doc_count = 0;
+  bool all_valid_utf8 = true;
+  uint64_t n_pair_slots = 0;
+  double last_build_ms = 0.0;
+
+  mgx_batch_stats_t last_stats{};
+  cudaStream_t stream = nullptr;  // owned, non-blocking; used by the non-staged calls
+
+  uint64_t device_bytes() const;
+};
+
+// Device-side view passed to kernels by value.
+struct IndexView {
+  const uint32_t* doc_ids;
+  const uint8_t* text;
+  const uint64_t* text_off;
+  const uint32_t* doc_len;
+  const uint64_t* term_keys;
+  const uint64_t* term_off;
+  const uint32_t* postings;
+  const int32_t* term_bm;
+  const uint32_t* bitmaps;
+  uint64_t n_docs;
+  uint64_t n_terms;
+  uint64_t bm_words;
+  uint32_t first_id;    // DocId of local index 0
+  int sequential_ids;   // doc_ids[i] == first_id + i (DocumentStore assigns ids sequentially, document_store.h:520)
+};
+
+// local index -> global DocId
+__device__ __forceinline__ uint32_t gid_of(const IndexView& iv, uint32_t local) {
+  return iv.sequential_ids ? iv.first_id + local : __ldg(iv.doc_ids + local);
+}
+// global DocId -> local index, or 0xFFFFFFFF if the shard does not hold it
+__device__ __forceinline__ uint32_t local_of(const IndexView& iv, uint32_t gid) {
+  if (iv.sequential_ids) {
+    const uint32_t d = gid - iv.first_id;
+    return (gid >= iv.first_id && d < iv.n_docs) ? d : 0xFFFFFFFFu;
+  }
+  uint32_t lo = 0;
+  uint32_t hi = static_cast<uint32_t>(iv.n_docs);
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(iv.doc_ids + mid) < gid) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  return (lo < iv.n_docs && __ldg(iv.doc_ids + lo) == gid) ? lo : 0xFFFFFFFFu;
+}
+
+inline IndexView make_view(const Index& ix) {
+  IndexView v;
+  v.doc_ids = ix.d_doc_ids.p;
+  v.text = ix.d_text.p;
+  v.text_off = ix.d_text_off.p;
+  v.doc_len = ix.d_doc_len.p;
+  v.term_keys = ix.d_term_keys.p;
+  v.term_off = ix.d_term_off.p;
+  v.postings = ix.d_postings.p;
+  v.term_bm = ix.d_term_bm.p;
+  v.bitmaps = ix.d_bitmaps.p;
+  v.n_docs = ix.n_docs;
+  v.n_terms = ix.n_terms;
+  v.bm_words = ix.bm_words;
+  v.first_id = ix.first_id;
+  v.sequential_ids = ix.sequential_ids ? 1 : 0;
+  return v;
+}
+
+// build.cu
+// The three inputs may be host or device pointers (cudaMemcpyDefault); the index keeps its own copies.
+void build_index_device(Index& ix, const uint32_t* doc_ids, const uint8_t* text, const uint64_t* text_off,
+                        uint64_t n_docs, uint64_t text_bytes, cudaStream_t stream);
+// Tokenise only (mgx_tokenize_batch): fills d_keys/d_docs slots (kInvalidKey for non-emitting positions).
+void tokenize_device(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
+                     uint64_t n_docs, DevBuf<uint32_t>& d_doc_len, DevBuf<uint64_t>& d_slot_off, DevBuf<uint64_t>& d_keys,
+                     DevBuf<uint32_t>& d_docs, uint64_t* n_slots, uint64_t* counters_out /* [0] non-empty docs, [1] docs with invalid bytes */,
+                     cudaStream_t stream);
+
+}  // namespace mgx

@@ -1,0 +1,282 @@
+// primitives.cu — device-wide building blocks written for this library:
+// an exclusive scan (u32 -> u64) and a stable LSD radix sort of (u64, u32) pairs.
+//
+// Both are HBM-bound streaming kernels: grids are sized from the data (many
+// waves over 148 SMs), every global access is a coalesced full-warp access on
+// the read side, and the only shared-memory traffic is per-CTA histograms.
+#include "mgx_internal.cuh"
+
+namespace mgx {
+
+namespace {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;                          // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;    // 4096 per CTA
+
+__device__ __forceinline__ uint64_t warp_inclusive_scan_u64(uint64_t v) {
+  const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= static_cast<unsigned>(d)) {
+      v += o;
+    }
+  }
+  return v;
+}
+
+// Block-wide exclusive scan of one u64 per thread; returns the exclusive prefix
+// and (to every thread) the block total. smem: one u64 per warp.
+template <int THREADS>
+__device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* total, uint64_t* smem) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint64_t inc = warp_inclusive_scan_u64(v);
+  if (lane == 31) {
+    smem[warp] = inc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t w = lane < THREADS / 32 ? smem[lane] : 0;
+    w = warp_inclusive_scan_u64(w);
+    if (lane < THREADS / 32) {
+      smem[lane] = w;
+    }
+  }
+  __syncthreads();
+  const uint64_t warp_prefix = warp == 0 ? 0 : smem[warp - 1];
+  *total = smem[THREADS / 32 - 1];
+  __syncthreads();
+  return warp_prefix + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t* __restrict__ in, uint64_t n,
+                                                                   uint64_t* __restrict__ block_sums) {
+  __shared__ uint64_t smem[kScanThreads / 32];
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanTile;
+  uint64_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t i = base + static_cast<uint64_t>(k) * kScanThreads + threadIdx.x;
+    if (i < n) {
+      sum += in[i];
+    }
+  }
+  uint64_t total;
+  (void)block_exclusive_scan_u64<kScanThreads>(sum, &total, smem);
+  if (threadIdx.x == 0) {
+    block_sums[blockIdx.x] = total;
+  }
+}
+
+// One CTA turns the block sums into exclusive block offsets (in place) and
+// writes the grand total to *total_out.
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(uint64_t* __restrict__ block_sums, uint64_t n_blocks,
+                                                               uint64_t* __restrict__ total_out) {
+  __shared__ uint64_t smem[32];
+  __shared__ uint64_t carry_s;
+  if (threadIdx.x == 0) {
+    carry_s = 0;
+  }
+  __syncthreads();
+  for (uint64_t base = 0; base < n_blocks; base += 1024) {
+    const uint64_t i = base + threadIdx.x;
+    const uint64_t v = i < n_blocks ? block_sums[i] : 0;
+    uint64_t total;
+    const uint64_t ex = block_exclusive_scan_u64<1024>(v, &total, smem);
+    const uint64_t carry = carry_s;
+    if (i < n_blocks) {
+      block_sums[i] = carry + ex;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      carry_s = carry + total;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *total_out = carry_s;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t n,
+                                                                  const uint64_t* __restrict__ block_offsets,
+                                                                  uint64_t* __restrict__ out) {
+  __shared__ uint64_t smem[kScanThreads / 32];
+  // Thread t owns kScanItems CONSECUTIVE items so the scan order is the array order.
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanTile + static_cast<uint64_t>(threadIdx.x) * kScanItems;
+  uint32_t v[kScanItems];
+  uint64_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t i = base + k;
+    v[k] = i < n ? in[i] : 0u;
+    sum += v[k];
+  }
+  uint64_t total;
+  uint64_t prefix = block_exclusive_scan_u64<kScanThreads>(sum, &total, smem) + block_offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t i = base + k;
+    if (i < n) {
+      out[i] = prefix;
+    }
+    prefix += v[k];
+  }
+}
+
+// ------------------------------------------------------------------ radix sort
+constexpr int kSortThreads = 256;
+constexpr int kSortRounds = 16;                                // items per thread
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortTile = kSortThreads * kSortRounds;          // 4096 items per CTA
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n,
+                                                                  int shift, uint32_t* __restrict__ hist,
+                                                                  uint32_t n_tiles) {
+  __shared__ uint32_t bins[kRadix];
+  bins[threadIdx.x] = 0;  // kSortThreads == kRadix
+  __syncthreads();
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kSortTile;
+#pragma unroll 4
+  for (int r = 0; r < kSortRounds; ++r) {
+    const uint64_t i = base + static_cast<uint64_t>(r) * kSortThreads + threadIdx.x;
+    if (i < n) {
+      atomicAdd(&bins[(keys[i] >> shift) & (kRadix - 1)], 1u);
+    }
+  }
+  __syncthreads();
+  hist[static_cast<uint64_t>(threadIdx.x) * n_tiles + blockIdx.x] = bins[threadIdx.x];
+}
+
+// Stable scatter. Warp w owns the contiguous items [w*512, (w+1)*512) of the
+// tile, visited in 16 rounds of 32 consecutive items, so (warp, round, lane)
+// order == input order; ranks are assigned in that order.
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint64_t* __restrict__ keys_in,
+                                                                     const uint32_t* __restrict__ vals_in,
+                                                                     uint64_t* __restrict__ keys_out,
+                                                                     uint32_t* __restrict__ vals_out, uint64_t n,
+                                                                     int shift, const uint64_t* __restrict__ hist_scan,
+                                                                     uint32_t n_tiles) {
+  __shared__ uint32_t warp_cnt[kSortWarps][kRadix];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) {
+    warp_cnt[w][threadIdx.x] = 0;
+  }
+  __syncthreads();
+
+  const uint64_t warp_base = static_cast<uint64_t>(blockIdx.x) * kSortTile + static_cast<uint64_t>(warp) * (32 * kSortRounds);
+  uint64_t key[kSortRounds];
+  uint32_t val[kSortRounds];
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const uint64_t i = warp_base + static_cast<uint64_t>(r) * 32 + lane;
+    const bool valid = i < n;
+    key[r] = valid ? keys_in[i] : 0;
+    val[r] = valid ? vals_in[i] : 0;
+  }
+  // phase 1: per-warp digit counts
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const uint64_t i = warp_base + static_cast<uint64_t>(r) * 32 + lane;
+    const bool valid = i < n;
+    const uint32_t d = valid ? static_cast<uint32_t>((key[r] >> shift) & (kRadix - 1)) : 0x1FFu;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (valid && (peers & lt_mask) == 0) {
+      warp_cnt[warp][d] += __popc(peers);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // per digit: exclusive scan over warps, seeded with this tile's global base
+  {
+    const unsigned d = threadIdx.x;
+    uint32_t running = static_cast<uint32_t>(hist_scan[static_cast<uint64_t>(d) * n_tiles + blockIdx.x]);
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = warp_cnt[w][d];
+      warp_cnt[w][d] = running;
+      running += c;
+    }
+  }
+  __syncthreads();
+  // phase 2: rank and scatter
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    const uint64_t i = warp_base + static_cast<uint64_t>(r) * 32 + lane;
+    const bool valid = i < n;
+    const uint32_t d = valid ? static_cast<uint32_t>((key[r] >> shift) & (kRadix - 1)) : 0x1FFu;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    uint32_t base = 0;
+    if (valid) {
+      base = warp_cnt[warp][d];
+    }
+    __syncwarp();
+    if (valid && (peers & lt_mask) == 0) {
+      warp_cnt[warp][d] = base + __popc(peers);
+    }
+    __syncwarp();
+    if (valid) {
+      const uint32_t pos = base + __popc(peers & lt_mask);
+      keys_out[pos] = key[r];
+      vals_out[pos] = val[r];
+    }
+  }
+}
+
+}  // namespace
+
+void exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t stream) {
+  // out[n] (the total) is written by the block-sums kernel
+  const uint64_t n_blocks = (n + kScanTile - 1) / kScanTile;
+  uint64_t* d_block_sums = nullptr;
+  MGX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_block_sums), (n_blocks + 1) * sizeof(uint64_t), stream));
+  if (n_blocks > 0) {
+    scan_reduce_kernel<<<static_cast<unsigned>(n_blocks), kScanThreads, 0, stream>>>(d_in, n, d_block_sums);
+    MGX_LAUNCH_CHECK();
+  }
+  scan_block_sums_kernel<<<1, 1024, 0, stream>>>(d_block_sums, n_blocks, d_out + n);
+  MGX_LAUNCH_CHECK();
+  if (n_blocks > 0) {
+    scan_apply_kernel<<<static_cast<unsigned>(n_blocks), kScanThreads, 0, stream>>>(d_in, n, d_block_sums, d_out);
+    MGX_LAUNCH_CHECK();
+  }
+  MGX_CUDA(cudaFreeAsync(d_block_sums, stream));
+}
+
+SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_keys_b, uint32_t* d_vals_b, uint64_t n,
+                            int key_bits, cudaStream_t stream) {
+  SortResult cur{d_keys_a, d_vals_a};
+  SortResult alt{d_keys_b, d_vals_b};
+  if (n == 0) {
+    return cur;
+  }
+  const uint32_t n_tiles = static_cast<uint32_t>((n + kSortTile - 1) / kSortTile);
+  const uint64_t hist_len = static_cast<uint64_t>(kRadix) * n_tiles;
+  uint32_t* d_hist = nullptr;
+  uint64_t* d_hist_scan = nullptr;
+  MGX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_hist), hist_len * sizeof(uint32_t), stream));
+  MGX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_hist_scan), (hist_len + 1) * sizeof(uint64_t), stream));
+  const int passes = (key_bits + kRadixBits - 1) / kRadixBits;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = p * kRadixBits;
+    radix_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(cur.keys, n, shift, d_hist, n_tiles);
+    MGX_LAUNCH_CHECK();
+    exclusive_scan_u32_u64(d_hist, d_hist_scan, hist_len, stream);
+    radix_scatter_kernel<<<n_tiles, kSortThreads, 0, stream>>>(cur.keys, cur.vals, alt.keys, alt.vals, n, shift,
+                                                               d_hist_scan, n_tiles);
+    MGX_LAUNCH_CHECK();
+    std::swap(cur, alt);
+  }
+  MGX_CUDA(cudaFreeAsync(d_hist, stream));
+  MGX_CUDA(cudaFreeAsync(d_hist_scan, stream));
+  return cur;
+}
+
+}  // namespace mgx

@@ -1,0 +1,1651 @@
+// query.cu — batched query execution on the device.
+//
+// Reference path replaced (all paths relative to the reference tree):
+//   GenerateTermInfos / PopulateTermDocumentFrequency   server/search_pipeline.cpp:569-603, 542-565
+//   Execute (AND smallest-first, early exit)             server/search_pipeline.cpp:795-869
+//   ApplyNotFilter                                       server/search_pipeline.cpp:871-932
+//   PostFilterByText (verify_text / hybrid fragments)    server/search_pipeline.cpp:1239-1266, 858-866
+//   Index::SearchAnd / FilterByNgrams / SearchOr / Not   index/index.cpp:199-486
+//   BM25Scorer::ScoreDocuments                           index/bm25_scorer.cpp:47-99
+//   ResultSorter::SortByScore                            query/result_sorter.cpp:661-716
+//
+// Execution model. A batch is compiled on the host into unique terms (bytes +
+// packed n-gram keys) and queries (term ids). On the device:
+//   lookup        keys -> dictionary slots (binary search over sorted packed keys)
+//   term_plan     per term: lists by ascending length, estimated size, df work
+//   df_tile       per 1024-entry tile of a term's shortest list: membership in the
+//                 term's other lists, then substring check of the survivors' text
+//   query_plan    per query: terms by estimated size, merged list table, driver
+//   and_tile      per 1024-entry tile of the query's shortest list ("driver"):
+//                 membership in every other list (bit probe for dense lists,
+//                 binary search for sparse ones), NOT groups, then the fused
+//                 epilogue: text scan -> tf -> BM25 (FP64) -> (doc, score) records
+//   topk          per query: count, then block-level top-k (shared-memory bitonic
+//                 for small sets, MSB radix select for large ones)
+// The driver formulation reads each query's smallest list once and probes the
+// rest, so the bytes moved are <= the SURVEY §8(d) algorithmic bytes.
+#include <algorithm>
+#include <cstring>
+
+#include "query.cuh"
+
+namespace mgx {
+
+namespace {
+
+struct BatchView {
+  // terms
+  const uint8_t* term_bytes;
+  const uint32_t* term_boff;
+  const uint32_t* term_koff;
+  uint32_t* key_list;
+  uint32_t* key_len;
+  uint64_t* t_est;
+  uint32_t* t_df_tiles;
+  const uint64_t* t_df_tile_off;
+  uint64_t* t_df;
+  uint32_t n_terms;
+  // queries
+  const uint32_t* q_toff;
+  uint32_t* q_tids;
+  const uint32_t* q_noff;
+  const uint32_t* q_ntids;
+  const uint32_t* q_loff;
+  uint32_t* q_list;
+  uint32_t* q_list_len;
+  uint32_t* q_nlists;
+  uint32_t* q_flags;
+  const uint32_t* q_host_flags;
+  uint32_t* q_driver_len;
+  uint32_t* q_ntiles;
+  const uint64_t* q_tile_off;
+  const uint64_t* q_rec_off;
+  const double* q_idf;
+  uint32_t n_queries;
+  // explicit driver (query 0)
+  const uint32_t* explicit_ids;
+  uint32_t explicit_n;
+};
+
+struct ScoreParams {
+  double k1;
+  double b;
+  double avgdl_clamped;  // max(avg_doc_length, 1.0), bm25_scorer.cpp:77
+  int compute_score;
+};
+
+// ------------------------------------------------------------------ small device helpers
+__host__ __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ p, uint32_t n, uint32_t v) {
+  uint32_t lo = 0;
+  uint32_t hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(p + mid) < v) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  return lo;
+}
+
+// largest i in [0, n) with off[i] <= v  (off ascending, off[0] <= v)
+__device__ __forceinline__ uint32_t find_segment(const uint64_t* __restrict__ off, uint32_t n, uint64_t v) {
+  uint32_t lo = 0;
+  uint32_t hi = n;  // search first index with off[idx] > v in [0, n]
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (off[mid] <= v) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  return lo - 1;
+}
+
+struct ListRef {
+  const uint32_t* p;   // sorted local doc indices
+  uint32_t len;
+  const uint32_t* bm;  // dense bitmap or nullptr
+};
+
+__device__ __forceinline__ ListRef make_list(const IndexView& iv, uint32_t dict_term, uint32_t len) {
+  ListRef r;
+  r.p = iv.postings + iv.term_off[dict_term];
+  r.len = len;
+  const int32_t slot = iv.term_bm[dict_term];
+  r.bm = slot >= 0 ? iv.bitmaps + static_cast<uint64_t>(slot) * iv.bm_words : nullptr;
+  return r;
+}
+
+__device__ __forceinline__ bool list_contains(const ListRef& l, uint32_t doc) {
+  if (l.bm != nullptr) {
+    return (__ldg(l.bm + (doc >> 5)) >> (doc & 31)) & 1u;
+  }
+  const uint32_t pos = lower_bound_u32(l.p, l.len, doc);
+  return pos < l.len && __ldg(l.p + pos) == doc;
+}
+
+// ------------------------------------------------------------------ text scanning (one warp per document)
+constexpr uint32_t kTextChunk = 1024;                         // start positions per staged chunk
+constexpr uint32_t kStageMax = kTextChunk + kMaxTermBytes;    // bytes staged at once
+constexpr uint32_t kStageBuf = kStageMax + 32;                // + alignment slack, multiple of 16
+
+__device__ __forceinline__ uint4 ld16(const uint8_t* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// Copies text[gb, gb+n) into the warp's shared buffer; returns the offset of
+// text[gb] inside it. The arena is padded by 64 bytes, so whole 16-byte vectors
+// can always be read.
+__device__ __forceinline__ uint32_t warp_stage(const uint8_t* __restrict__ text, uint64_t gb, uint32_t n, uint8_t* buf) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint64_t a = gb & ~15ULL;
+  const uint32_t shift = static_cast<uint32_t>(gb - a);
+  const uint32_t nvec = (shift + n + 15u) >> 4;
+  for (uint32_t v = lane; v < nvec; v += 32) {
+    *reinterpret_cast<uint4*>(buf + v * 16u) = ld16(text + a + static_cast<uint64_t>(v) * 16u);
+  }
+  __syncwarp();
+  return shift;
+}
+
+// Non-overlapping, left-to-right occurrence count of `term` among the start
+// positions [0, npos) of the staged bytes `s` (BM25Scorer::CountTermOccurrences,
+// bm25_scorer.cpp:27-45). `next_ok`/`count` carry the greedy state across chunks;
+// positions are relative to `pos0`. Warp-uniform result.
+__device__ __forceinline__ void warp_count_staged(const uint8_t* s, uint32_t npos, const uint8_t* __restrict__ term,
+                                                  uint32_t tl, uint64_t pos0, uint64_t* next_ok, uint32_t* count,
+                                                  bool exists_only) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint8_t t0 = __ldg(term);
+  for (uint32_t g0 = 0; g0 < npos; g0 += 32) {
+    const uint32_t p = g0 + lane;
+    bool m = false;
+    if (p < npos && s[p] == t0) {
+      m = true;
+      for (uint32_t i = 1; i < tl; ++i) {
+        if (s[p + i] != __ldg(term + i)) {
+          m = false;
+          break;
+        }
+      }
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, m);
+    while (mask != 0) {
+      const uint32_t bit = static_cast<uint32_t>(__ffs(static_cast<int>(mask))) - 1u;
+      const uint64_t pos = pos0 + g0 + bit;
+      if (pos >= *next_ok) {
+        *count += 1;
+        *next_ok = pos + tl;
+      }
+      mask &= mask - 1;
+    }
+    if (exists_only && *count != 0) {
+      return;
+    }
+  }
+}
+
+struct DocText {
+  const uint8_t* text;  // arena
+  uint64_t b;           // first byte of the document
+  uint32_t len;         // bytes
+  uint8_t* buf;         // warp staging buffer (kStageBuf bytes)
+  uint32_t shift;       // valid when whole == true
+  bool whole;           // the whole document is staged
+};
+
+__device__ __forceinline__ DocText doc_open(const IndexView& iv, uint32_t doc, uint8_t* buf) {
+  DocText d;
+  d.text = iv.text;
+  d.b = iv.text_off[doc];
+  const uint64_t e = iv.text_off[doc + 1];
+  d.len = static_cast<uint32_t>(e - d.b);
+  d.buf = buf;
+  d.whole = d.len <= kStageMax;
+  d.shift = 0;
+  if (d.whole && d.len > 0) {
+    d.shift = warp_stage(d.text, d.b, d.len, buf);
+  }
+  return d;
+}
+
+__device__ __forceinline__ uint32_t doc_count_term(DocText& d, const uint8_t* __restrict__ term, uint32_t tl,
+                                                   bool exists_only) {
+  if (tl == 0 || tl > d.len) {
+    return 0;
+  }
+  uint32_t count = 0;
+  uint64_t next_ok = 0;
+  if (d.whole) {
+    warp_count_staged(d.buf + d.shift, d.len - tl + 1, term, tl, 0, &next_ok, &count, exists_only);
+    return count;
+  }
+  for (uint64_t c0 = 0; c0 + tl <= d.len; c0 += kTextChunk) {
+    const uint32_t n = static_cast<uint32_t>(min(static_cast<uint64_t>(d.len) - c0, static_cast<uint64_t>(kTextChunk + tl - 1)));
+    __syncwarp();
+    const uint32_t shift = warp_stage(d.text, d.b + c0, n, d.buf);
+    const uint32_t npos = min(kTextChunk, n - tl + 1);
+    warp_count_staged(d.buf + shift, npos, term, tl, c0, &next_ok, &count, exists_only);
+    if (exists_only && count != 0) {
+      break;
+    }
+  }
+  __syncwarp();
+  return count;
+}
+
+// ------------------------------------------------------------------ lookup + term planning
+__global__ void lookup_kernel(const uint64_t* __restrict__ term_keys, const uint64_t* __restrict__ term_off,
+                              uint64_t n_dict, const uint64_t* __restrict__ keys, uint32_t n_keys,
+                              uint32_t* __restrict__ key_list, uint32_t* __restrict__ key_len) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_keys) {
+    return;
+  }
+  const uint64_t key = keys[i];
+  uint64_t lo = 0;
+  uint64_t hi = n_dict;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (term_keys[mid] < key) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  if (lo < n_dict && term_keys[lo] == key) {
+    key_list[i] = static_cast<uint32_t>(lo);
+    key_len[i] = static_cast<uint32_t>(term_off[lo + 1] - term_off[lo]);
+  } else {
+    key_list[i] = kNone;
+    key_len[i] = 0;
+  }
+}
+
+__global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf8, const uint8_t* __restrict__ raw_flags) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= bv.n_terms) {
+    return;
+  }
+  const uint32_t k0 = bv.term_koff[t];
+  const uint32_t k1 = bv.term_koff[t + 1];
+  uint64_t est = kEstNone;
+  if (k1 > k0) {
+    for (uint32_t i = k0 + 1; i < k1; ++i) {  // insertion sort by length (missing lists have length 0)
+      const uint32_t li = bv.key_list[i];
+      const uint32_t ln = bv.key_len[i];
+      uint32_t j = i;
+      while (j > k0 && bv.key_len[j - 1] > ln) {
+        bv.key_list[j] = bv.key_list[j - 1];
+        bv.key_len[j] = bv.key_len[j - 1];
+        --j;
+      }
+      bv.key_list[j] = li;
+      bv.key_len[j] = ln;
+    }
+    est = bv.key_len[k0];  // min posting size, 0 if any n-gram is missing (search_pipeline.cpp:583-593)
+  }
+  bv.t_est[t] = est;
+  uint64_t df = 0;
+  uint32_t tiles = 0;
+  if (compute_df && k1 > k0 && est != 0 && (raw_flags[t] & 1) == 0) {
+    if (k1 - k0 == 1 && all_valid_utf8 && (raw_flags[t] & 2) != 0) {
+      df = est;  // the term is exactly its one n-gram: every posting contains it as a substring
+    } else {
+      tiles = static_cast<uint32_t>((est + kTile - 1) / kTile);
+    }
+  }
+  bv.t_df[t] = df;
+  bv.t_df_tiles[t] = tiles;
+}
+
+// ------------------------------------------------------------------ df tiles
+__global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, BatchView bv) {
+  __shared__ uint32_t s_doc[kTile];
+  __shared__ uint32_t s_n;
+  __shared__ uint32_t s_term;
+  __shared__ uint32_t s_hits;
+  __shared__ __align__(16) uint8_t s_text[kTileThreads / 32][kStageBuf];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    s_term = find_segment(bv.t_df_tile_off, bv.n_terms, blockIdx.x);
+    s_n = 0;
+    s_hits = 0;
+  }
+  __syncthreads();
+  const uint32_t t = s_term;
+  const uint32_t k0 = bv.term_koff[t];
+  const uint32_t k1 = bv.term_koff[t + 1];
+  const uint64_t tile = blockIdx.x - bv.t_df_tile_off[t];
+  const ListRef drv = make_list(iv, bv.key_list[k0], bv.key_len[k0]);
+  const uint64_t e0 = tile * kTile;
+#pragma unroll
+  for (int k = 0; k < kTileItems; ++k) {
+    const uint64_t e = e0 + static_cast<uint64_t>(k) * kTileThreads + threadIdx.x;
+    if (e < drv.len) {
+      const uint32_t doc = __ldg(drv.p + e);
+      bool alive = true;
+      for (uint32_t j = k0 + 1; j < k1 && alive; ++j) {
+        alive = list_contains(make_list(iv, bv.key_list[j], bv.key_len[j]), doc);
+      }
+      if (alive) {
+        s_doc[atomicAdd(&s_n, 1u)] = doc;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t n = s_n;
+  const uint8_t* term = bv.term_bytes + bv.term_boff[t];
+  const uint32_t tl = bv.term_boff[t + 1] - bv.term_boff[t];
+  uint32_t hits = 0;
+  for (uint32_t s = warp; s < n; s += kTileThreads / 32) {
+    DocText d = doc_open(iv, s_doc[s], s_text[warp]);
+    hits += doc_count_term(d, term, tl, true) != 0 ? 1u : 0u;
+    __syncwarp();
+  }
+  if (lane == 0 && hits != 0) {
+    atomicAdd(&s_hits, hits);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_hits != 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(bv.t_df + t), static_cast<unsigned long long>(s_hits));
+  }
+}
+
+__global__ void df_to_slots_kernel(const uint64_t* __restrict__ t_df, const uint32_t* __restrict__ slot_tid,
+                                   uint32_t n_slots, uint64_t* __restrict__ out) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_slots) {
+    out[s] = t_df[slot_tid[s]];
+  }
+}
+
+__global__ void slots_to_df_kernel(const uint64_t* __restrict__ in, const uint32_t* __restrict__ slot_tid,
+                                   uint32_t n_slots, uint64_t* __restrict__ t_df) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_slots) {
+    t_df[slot_tid[s]] = in[s];  // all slots of one term carry the same value
+  }
+}
+
+// ------------------------------------------------------------------ query planning
+__global__ void query_plan_kernel(IndexView iv, BatchView bv) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= bv.n_queries) {
+    return;
+  }
+  uint32_t flags = bv.q_host_flags[q];
+  const bool any_mode = (flags & kQAnyMode) != 0;
+  const uint32_t t0 = bv.q_toff[q];
+  const uint32_t t1 = bv.q_toff[q + 1];
+  // terms by ascending estimated size, equal sizes keep query order
+  // (std::sort on <= 16 elements is an insertion sort, search_pipeline.cpp:2012-2014)
+  for (uint32_t i = t0 + 1; i < t1; ++i) {
+    const uint32_t tid = bv.q_tids[i];
+    const uint64_t est = bv.t_est[tid];
+    uint32_t j = i;
+    while (j > t0 && bv.t_est[bv.q_tids[j - 1]] > est) {
+      bv.q_tids[j] = bv.q_tids[j - 1];
+      --j;
+    }
+    bv.q_tids[j] = tid;
+  }
+  bool empty = false;
+  bool text_only = false;
+  const uint32_t l0 = bv.q_loff[q];
+  uint32_t n = 0;
+  for (uint32_t i = t0; i < t1; ++i) {
+    const uint32_t tid = bv.q_tids[i];
+    const uint64_t est = bv.t_est[tid];
+    const uint32_t nk = bv.term_koff[tid + 1] - bv.term_koff[tid];
+    const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+    if (!any_mode && (est == 0 || est == kEstNone) && (nk > 0 || tl == 0)) {
+      empty = true;  // Execute :804-810
+    }
+    if (nk == 0 && tl > 0) {
+      text_only = true;  // SearchNormalizedSubstring fallback, query/substring_search.h:24-42
+    }
+    for (uint32_t k = bv.term_koff[tid]; k < bv.term_koff[tid + 1]; ++k) {
+      const uint32_t li = bv.key_list[k];
+      if (li == kNone) {
+        continue;
+      }
+      bool dup = false;
+      for (uint32_t x = 0; x < n; ++x) {
+        dup |= bv.q_list[l0 + x] == li;
+      }
+      if (!dup) {
+        bv.q_list[l0 + n] = li;
+        bv.q_list_len[l0 + n] = bv.key_len[k];
+        ++n;
+      }
+    }
+  }
+  for (uint32_t i = 1; i < n; ++i) {  // lists by ascending length
+    const uint32_t li = bv.q_list[l0 + i];
+    const uint32_t ln = bv.q_list_len[l0 + i];
+    uint32_t j = i;
+    while (j > 0 && bv.q_list_len[l0 + j - 1] > ln) {
+      bv.q_list[l0 + j] = bv.q_list[l0 + j - 1];
+      bv.q_list_len[l0 + j] = bv.q_list_len[l0 + j - 1];
+      --j;
+    }
+    bv.q_list[l0 + j] = li;
+    bv.q_list_len[l0 + j] = ln;
+  }
+  uint32_t driver_len = 0;
+  if (flags & kQDriverExplicit) {
+    driver_len = bv.explicit_n;
+  } else if (t1 == t0) {
+    empty = true;  // no search terms: Execute leaves the result empty (:813)
+  } else if (any_mode) {
+    if (n == 0) {
+      empty = true;
+    } else {
+      flags |= kQDriverAll;
+      driver_len = static_cast<uint32_t>(iv.n_docs);
+    }
+  } else if (n > 0) {
+    driver_len = bv.q_list_len[l0];
+  } else if (text_only) {
+    flags |= kQDriverAll;
+    driver_len = static_cast<uint32_t>(iv.n_docs);
+  } else {
+    empty = true;
+  }
+  if (empty) {
+    flags |= kQEmpty;
+    driver_len = 0;
+  }
+  bv.q_nlists[q] = n;
+  bv.q_flags[q] = flags;
+  bv.q_driver_len[q] = driver_len;
+  bv.q_ntiles[q] = (driver_len + kTile - 1) / kTile;
+}
+
+// BM25Scorer::ComputeIDF, bm25_scorer.cpp:14-25 — one value per (query, term) in planner order.
+__global__ void idf_kernel(const uint32_t* __restrict__ q_tids, uint32_t n, const uint64_t* __restrict__ t_df,
+                           uint64_t total_docs, double* __restrict__ idf) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) {
+    return;
+  }
+  double v = 0.0;
+  if (total_docs != 0) {
+    uint64_t df = t_df[q_tids[i]];
+    if (df > total_docs) {
+      df = total_docs;
+    }
+    const double nn = static_cast<double>(total_docs);
+    const double dd = static_cast<double>(df);
+    const double num = __dadd_rn(__dsub_rn(nn, dd), 0.5);
+    const double den = __dadd_rn(dd, 0.5);
+    v = log(__dadd_rn(__ddiv_rn(num, den), 1.0));
+  }
+  idf[i] = v;
+}
+
+// ------------------------------------------------------------------ intersect + score tiles
+// Block-wide ordered compaction helper: each thread contributes `cnt` (<= kTileItems)
+// items; returns the exclusive offset and writes the block total to *total.
+__device__ __forceinline__ uint32_t block_offsets(uint32_t cnt, uint32_t* s_warp, uint32_t* total) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  uint32_t inc = cnt;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, s);
+    if (lane >= static_cast<unsigned>(s)) {
+      inc += o;
+    }
+  }
+  if (lane == 31) {
+    s_warp[warp] = inc;
+  }
+  __syncthreads();
+  uint32_t prefix = 0;
+  uint32_t tot = 0;
+#pragma unroll
+  for (int w = 0; w < kTileThreads / 32; ++w) {
+    const uint32_t c = s_warp[w];
+    if (static_cast<unsigned>(w) < warp) {
+      prefix += c;
+    }
+    tot += c;
+  }
+  __syncthreads();
+  *total = tot;
+  return prefix + inc - cnt;
+}
+
+constexpr int kMaxCachedLists = 24;
+
+__global__ void __launch_bounds__(kTileThreads)
+and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, uint64_t rec_base,
+                uint32_t* __restrict__ tile_count, uint32_t* __restrict__ rec_doc, double* __restrict__ rec_score) {
+  __shared__ uint32_t s_doc[kTile];     // local doc index of survivors (kNone = id unknown to this shard)
+  __shared__ uint32_t s_gid[kTile];     // global doc id of survivors
+  __shared__ double s_score[kTile];
+  __shared__ uint8_t s_keep[kTile];
+  __shared__ uint32_t s_warp[kTileThreads / 32];
+  __shared__ uint32_t s_q;
+  __shared__ ListRef s_lists[kMaxCachedLists];
+  __shared__ __align__(16) uint8_t s_text[kTileThreads / 32][kStageBuf];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint64_t tile_global = tile_base + blockIdx.x;
+  if (threadIdx.x == 0) {
+    s_q = find_segment(bv.q_tile_off, bv.n_queries, tile_global);
+  }
+  __syncthreads();
+  const uint32_t q = s_q;
+  const uint32_t flags = bv.q_flags[q];
+  const uint32_t l0 = bv.q_loff[q];
+  const uint32_t nl = bv.q_nlists[q];
+  const uint32_t driver_len = bv.q_driver_len[q];
+  const uint64_t tile_in_q = tile_global - bv.q_tile_off[q];
+  const bool drv_all = (flags & kQDriverAll) != 0;
+  const bool drv_explicit = (flags & kQDriverExplicit) != 0;
+  const bool any_mode = (flags & kQAnyMode) != 0;
+  const bool drv_list = !drv_all && !drv_explicit;
+  if (threadIdx.x < nl && threadIdx.x < kMaxCachedLists) {
+    s_lists[threadIdx.x] = make_list(iv, bv.q_list[l0 + threadIdx.x], bv.q_list_len[l0 + threadIdx.x]);
+  }
+  __syncthreads();
+  const uint32_t n0 = bv.q_noff[q];
+  const uint32_t n1 = bv.q_noff[q + 1];
+
+  // ---- membership: thread owns kTileItems consecutive driver entries (keeps order)
+  uint32_t my_doc[kTileItems];
+  uint32_t my_gid[kTileItems];
+  uint32_t alive_mask = 0;
+  const uint64_t e0 = tile_in_q * kTile + static_cast<uint64_t>(threadIdx.x) * kTileItems;
+#pragma unroll
+  for (int k = 0; k < kTileItems; ++k) {
+    const uint64_t e = e0 + k;
+    my_doc[k] = kNone;
+    my_gid[k] = 0;
+    if (e >= driver_len) {
+      continue;
+    }
+    uint32_t doc;
+    if (drv_list) {
+      doc = __ldg(s_lists[0].p + e);
+    } else if (drv_all) {
+      doc = static_cast<uint32_t>(e);
+    } else {
+      my_gid[k] = __ldg(bv.explicit_ids + e);
+      doc = local_of(iv, my_gid[k]);
+    }
+    bool alive;
+    if (any_mode) {
+      alive = false;
+      for (uint32_t j = 0; j < nl && !alive && doc != kNone; ++j) {
+        const ListRef l = j < kMaxCachedLists ? s_lists[j] : make_list(iv, bv.q_list[l0 + j], bv.q_list_len[l0 + j]);
+        alive = list_contains(l, doc);
+      }
+    } else {
+      alive = true;
+      for (uint32_t j = drv_list ? 1u : 0u; j < nl && alive; ++j) {
+        const ListRef l = j < kMaxCachedLists ? s_lists[j] : make_list(iv, bv.q_list[l0 + j], bv.q_list_len[l0 + j]);
+        alive = doc != kNone && list_contains(l, doc);
+      }
+    }
+    // NOT terms (ApplyNotFilter :871-932): drop the doc if it is in ALL n-gram lists of a NOT term.
+    for (uint32_t i = n0; i < n1 && alive && doc != kNone; ++i) {
+      const uint32_t tid = bv.q_ntids[i];
+      const uint32_t k0 = bv.term_koff[tid];
+      const uint32_t k1 = bv.term_koff[tid + 1];
+      if (k1 == k0 || bv.t_est[tid] == 0) {
+        continue;  // no n-grams (text stage decides) or an unknown n-gram (matches nothing)
+      }
+      bool in_all = true;
+      for (uint32_t kk = k0; kk < k1 && in_all; ++kk) {
+        in_all = list_contains(make_list(iv, bv.key_list[kk], bv.key_len[kk]), doc);
+      }
+      alive = !in_all;
+    }
+    if (alive) {
+      alive_mask |= 1u << k;
+      my_doc[k] = doc;
+    }
+  }
+  uint32_t total = 0;
+  uint32_t off = block_offsets(__popc(alive_mask), s_warp, &total);
+#pragma unroll
+  for (int k = 0; k < kTileItems; ++k) {
+    if (alive_mask & (1u << k)) {
+      s_doc[off] = my_doc[k];
+      s_gid[off] = my_gid[k];
+      ++off;
+    }
+  }
+  __syncthreads();
+
+  // ---- fused epilogue: text scan -> tf -> BM25 (bm25_scorer.cpp:67-88), text constraints
+  const uint32_t t0 = bv.q_toff[q];
+  const uint32_t t1 = bv.q_toff[q + 1];
+  bool need_text = sp.compute_score != 0 || (flags & kQVerify) != 0;
+  for (uint32_t i = t0; i < t1 && !need_text; ++i) {
+    const uint32_t tid = bv.q_tids[i];
+    need_text = bv.term_koff[tid + 1] == bv.term_koff[tid];
+  }
+  for (uint32_t i = n0; i < n1 && !need_text; ++i) {
+    const uint32_t tid = bv.q_ntids[i];
+    need_text = bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid];
+  }
+  if (need_text) {
+    for (uint32_t s = warp; s < total; s += kTileThreads / 32) {
+      const uint32_t doc = s_doc[s];
+      bool keep = true;
+      double score = 0.0;
+      if (doc != kNone) {
+        DocText d = doc_open(iv, doc, s_text[warp]);
+        if (d.len > 0) {
+          const double dl = static_cast<double>(__ldg(iv.doc_len + doc));
+          // length_norm = 1 - b + b * dl / max(avgdl, 1)
+          const double length_norm =
+              __dadd_rn(__dsub_rn(1.0, sp.b), __ddiv_rn(__dmul_rn(sp.b, dl), sp.avgdl_clamped));
+          for (uint32_t i = t0; i < t1; ++i) {
+            const uint32_t tid = bv.q_tids[i];
+            const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
+            const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+            const bool must = (flags & kQVerify) != 0 || bv.term_koff[tid + 1] == bv.term_koff[tid];
+            const uint32_t tf_u = doc_count_term(d, term, tl, sp.compute_score == 0);
+            if (must && tf_u == 0 && tl != 0) {
+              keep = false;
+            }
+            if (sp.compute_score != 0 && tf_u != 0) {
+              const double tf = static_cast<double>(tf_u);
+              const double numerator = __dmul_rn(tf, __dadd_rn(sp.k1, 1.0));
+              const double denominator = __dadd_rn(tf, __dmul_rn(sp.k1, length_norm));
+              score = __dadd_rn(score, __ddiv_rn(__dmul_rn(bv.q_idf[i], numerator), denominator));
+            }
+          }
+          for (uint32_t i = n0; i < n1 && keep; ++i) {
+            const uint32_t tid = bv.q_ntids[i];
+            const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+            if (bv.term_koff[tid + 1] == bv.term_koff[tid] && tl != 0) {
+              keep = doc_count_term(d, bv.term_bytes + bv.term_boff[tid], tl, true) == 0;
+            }
+          }
+        } else {
+          // no stored text: a substring-only search term cannot match; verify keeps the doc
+          for (uint32_t i = t0; i < t1; ++i) {
+            const uint32_t tid = bv.q_tids[i];
+            if (bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid]) {
+              keep = false;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        s_keep[s] = keep ? 1 : 0;
+        s_score[s] = score;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- ordered write of the tile's records
+  const uint64_t out_base = bv.q_rec_off[q] - rec_base + tile_in_q * kTile;
+  uint32_t keep_mask = 0;
+  const uint32_t s0 = threadIdx.x * kTileItems;
+#pragma unroll
+  for (int k = 0; k < kTileItems; ++k) {
+    const uint32_t s = s0 + k;
+    if (s < total && (!need_text || s_keep[s] != 0)) {
+      keep_mask |= 1u << k;
+    }
+  }
+  uint32_t kept_total = 0;
+  uint32_t woff = block_offsets(__popc(keep_mask), s_warp, &kept_total);
+#pragma unroll
+  for (int k = 0; k < kTileItems; ++k) {
+    if (keep_mask & (1u << k)) {
+      const uint32_t s = s0 + k;
+      rec_doc[out_base + woff] = drv_explicit ? s_gid[s] : gid_of(iv, s_doc[s]);
+      if (sp.compute_score != 0) {
+        rec_score[out_base + woff] = s_score[s];
+      }
+      ++woff;
+    }
+  }
+  if (threadIdx.x == 0) {
+    tile_count[blockIdx.x] = kept_total;
+  }
+}
+
+// ------------------------------------------------------------------ top-k
+// Sort key: (s, d) compared lexicographically, LARGER IS BETTER.
+//   DESC: s = ord(score), d = doc         (higher score first; ties: higher doc id first)
+//   ASC : s = ~ord(score), d = ~doc       (lower score first; ties: lower doc id first)
+// which is ResultSorter::SortByScore's comparator (result_sorter.cpp:681-686).
+__device__ __forceinline__ uint64_t ord_f64(double x) {
+  const uint64_t bits = static_cast<uint64_t>(__double_as_longlong(x));
+  return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double unord_f64(uint64_t o) {
+  const uint64_t bits = (o >> 63) ? (o & 0x7FFFFFFFFFFFFFFFULL) : ~o;
+  return __longlong_as_double(static_cast<long long>(bits));
+}
+
+struct SortKey {
+  uint64_t s;
+  uint32_t d;
+};
+__device__ __forceinline__ bool key_greater(const SortKey& a, const SortKey& b) {
+  return a.s > b.s || (a.s == b.s && a.d > b.d);
+}
+__device__ __forceinline__ SortKey make_sort_key(double score, uint32_t doc, bool descending) {
+  SortKey k;
+  const uint64_t o = ord_f64(score);
+  k.s = descending ? o : ~o;
+  k.d = descending ? doc : ~doc;
+  return k;
+}
+// digit `pass` (0 = most significant) of the 96-bit key, 8 bits each
+__device__ __forceinline__ uint32_t key_digit(const SortKey& k, int pass) {
+  return pass < 8 ? static_cast<uint32_t>((k.s >> (56 - 8 * pass)) & 0xFF)
+                  : static_cast<uint32_t>((k.d >> (24 - 8 * (pass - 8))) & 0xFF);
+}
+// does the key match `prefix` on its first `pass` digits
+__device__ __forceinline__ bool key_has_prefix(const SortKey& k, const SortKey& prefix, int pass) {
+  if (pass <= 0) {
+    return true;
+  }
+  if (pass < 8) {
+    const int sh = 64 - 8 * pass;
+    return (k.s >> sh) == (prefix.s >> sh);
+  }
+  if (k.s != prefix.s) {
+    return false;
+  }
+  if (pass == 8) {
+    return true;
+  }
+  const int sh = 32 - 8 * (pass - 8);
+  return (k.d >> sh) == (prefix.d >> sh);
+}
+
+constexpr uint32_t kTopkSmem = 2048;
+
+// descending bitonic sort of n_pow2 keys in shared memory (256 threads)
+__device__ void bitonic_sort_desc(SortKey* keys, uint32_t n_pow2) {
+  for (uint32_t size = 2; size <= n_pow2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n_pow2 / 2; i += blockDim.x) {
+        const uint32_t lo = 2 * i - (i & (stride - 1));
+        const uint32_t hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const SortKey a = keys[lo];
+        const SortKey b = keys[hi];
+        const bool swap = desc ? key_greater(b, a) : key_greater(a, b);
+        if (swap) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// One CTA per query. Records of tile t of the query live at rec_off + t*kTile .. +tile_count[t].
+__global__ void __launch_bounds__(256)
+topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_base,
+            const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ rec_doc,
+            const double* __restrict__ rec_score, int compute_score, int descending, uint32_t limit, uint32_t offset,
+            uint64_t stride, uint32_t* __restrict__ out_ids, double* __restrict__ out_scores,
+            uint32_t* __restrict__ out_count, uint64_t* __restrict__ out_total) {
+  __shared__ SortKey s_keys[kTopkSmem];
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_cnt;
+  __shared__ uint64_t s_scan[8];
+  __shared__ uint64_t s_carry;
+  __shared__ SortKey s_prefix;
+  __shared__ uint32_t s_need;
+  __shared__ int s_done;
+  const uint32_t q = q_first + blockIdx.x;
+  const uint64_t t0 = bv.q_tile_off[q] - tile_base;
+  const uint32_t ntiles = static_cast<uint32_t>(bv.q_tile_off[q + 1] - bv.q_tile_off[q]);
+  const uint64_t r0 = bv.q_rec_off[q] - rec_base;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  uint32_t* ids = out_ids + static_cast<uint64_t>(q) * stride;
+  double* scs = out_scores != nullptr ? out_scores + static_cast<uint64_t>(q) * stride : nullptr;
+
+  // total = sum of tile counts
+  uint64_t local = 0;
+  for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x) {
+    local += tile_count[t0 + t];
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    local += __shfl_xor_sync(0xffffffffu, local, s);
+  }
+  if (lane == 0) {
+    s_scan[warp] = local;
+  }
+  if (threadIdx.x == 0) {
+    s_cnt = 0;
+    s_carry = 0;
+  }
+  __syncthreads();
+  uint64_t total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    total += s_scan[w];
+  }
+  __syncthreads();
+  const uint64_t want_end = limit == 0 ? total : umin64(total, static_cast<uint64_t>(offset) + limit);
+  const uint64_t want_begin = umin64(offset, total);
+  const uint32_t n_out = static_cast<uint32_t>(umin64(want_end - want_begin, stride));
+  if (threadIdx.x == 0) {
+    out_total[q] = total;
+    out_count[q] = n_out;
+  }
+  if (n_out == 0) {
+    return;
+  }
+
+  if (!compute_score) {
+    // ascending ids: tiles are in driver order and each tile is compacted in order
+    for (uint32_t tb = 0; tb < ntiles; tb += blockDim.x) {
+      const uint32_t t = tb + threadIdx.x;
+      const uint32_t c = t < ntiles ? tile_count[t0 + t] : 0;
+      uint64_t inc = c;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const uint64_t o = __shfl_up_sync(0xffffffffu, inc, s);
+        if (lane >= static_cast<unsigned>(s)) {
+          inc += o;
+        }
+      }
+      if (lane == 31) {
+        s_scan[warp] = inc;
+      }
+      __syncthreads();
+      uint64_t prefix = s_carry;
+      uint64_t chunk_total = 0;
+      for (unsigned w = 0; w < 8; ++w) {
+        if (w < warp) {
+          prefix += s_scan[w];
+        }
+        chunk_total += s_scan[w];
+      }
+      const uint64_t first_rank = prefix + inc - c;
+      for (uint32_t i = 0; i < c; ++i) {
+        const uint64_t rank = first_rank + i;
+        if (rank >= want_begin && rank - want_begin < n_out) {
+          ids[rank - want_begin] = rec_doc[r0 + static_cast<uint64_t>(t) * kTile + i];
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        s_carry += chunk_total;
+      }
+      __syncthreads();
+      if (s_carry >= want_begin + n_out) {
+        break;
+      }
+    }
+    return;
+  }
+
+  const bool desc = descending != 0;
+  const uint32_t kk = static_cast<uint32_t>(want_begin) + n_out;  // how many best records are needed
+  SortKey thr;
+  thr.s = 0;
+  thr.d = 0;
+  if (total > kTopkSmem) {
+    // MSB-first radix select of the kk-th largest key
+    if (threadIdx.x == 0) {
+      s_prefix.s = 0;
+      s_prefix.d = 0;
+      s_need = kk;
+      s_done = 0;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 12; ++pass) {
+      s_hist[threadIdx.x] = 0;
+      __syncthreads();
+      const SortKey prefix = s_prefix;
+      for (uint32_t t = warp; t < ntiles; t += 8) {
+        const uint32_t c = tile_count[t0 + t];
+        const uint64_t base = r0 + static_cast<uint64_t>(t) * kTile;
+        for (uint32_t i = lane; i < c; i += 32) {
+          const SortKey k = make_sort_key(rec_score[base + i], rec_doc[base + i], desc);
+          if (key_has_prefix(k, prefix, pass)) {
+            atomicAdd(&s_hist[key_digit(k, pass)], 1u);
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t need = s_need;
+        int digit = 255;
+        for (; digit > 0; --digit) {
+          if (s_hist[digit] >= need) {
+            break;
+          }
+          need -= s_hist[digit];
+        }
+        s_need = need;
+        if (pass < 8) {
+          s_prefix.s |= static_cast<uint64_t>(digit) << (56 - 8 * pass);
+        } else {
+          s_prefix.d |= static_cast<uint32_t>(digit) << (24 - 8 * (pass - 8));
+        }
+      }
+      __syncthreads();
+    }
+    thr = s_prefix;  // exact kk-th largest key (keys are unique: doc ids are unique per query)
+  }
+  // gather every key >= thr (all keys when total <= kTopkSmem)
+  for (uint32_t t = warp; t < ntiles; t += 8) {
+    const uint32_t c = tile_count[t0 + t];
+    const uint64_t base = r0 + static_cast<uint64_t>(t) * kTile;
+    for (uint32_t i = lane; i < c; i += 32) {
+      const SortKey k = make_sort_key(rec_score[base + i], rec_doc[base + i], desc);
+      if (total <= kTopkSmem || !key_greater(thr, k)) {
+        const uint32_t pos = atomicAdd(&s_cnt, 1u);
+        if (pos < kTopkSmem) {
+          s_keys[pos] = k;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t n_keys = min(s_cnt, kTopkSmem);
+  uint32_t n_pow2 = 1;
+  while (n_pow2 < n_keys) {
+    n_pow2 <<= 1;
+  }
+  for (uint32_t i = n_keys + threadIdx.x; i < n_pow2; i += blockDim.x) {
+    s_keys[i].s = 0;  // pads sort last: real keys have s != 0 or are compared by d >= 0 after them
+    s_keys[i].d = 0;
+  }
+  // a real key can equal the pad (score -NaN never occurs; ord(x) of any finite x has s != 0
+  // unless x is the most negative NaN pattern), so pads never displace real records.
+  bitonic_sort_desc(s_keys, n_pow2);
+  for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+    const SortKey k = s_keys[want_begin + i];
+    ids[i] = desc ? k.d : ~k.d;
+    if (scs != nullptr) {
+      scs[i] = unord_f64(desc ? k.s : ~k.s);
+    }
+  }
+}
+
+// Full ascending sets: out[set_off[q] + rank] for every survivor of query q.
+__global__ void __launch_bounds__(256)
+gather_sets_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_base,
+                   const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ rec_doc,
+                   const uint64_t* __restrict__ set_off, uint32_t* __restrict__ out) {
+  __shared__ uint64_t s_scan[8];
+  __shared__ uint64_t s_carry;
+  const uint32_t q = q_first + blockIdx.x;
+  const uint64_t t0 = bv.q_tile_off[q] - tile_base;
+  const uint32_t ntiles = static_cast<uint32_t>(bv.q_tile_off[q + 1] - bv.q_tile_off[q]);
+  const uint64_t r0 = bv.q_rec_off[q] - rec_base;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    s_carry = 0;
+  }
+  __syncthreads();
+  uint32_t* dst = out + set_off[q];
+  for (uint32_t tb = 0; tb < ntiles; tb += blockDim.x) {
+    const uint32_t t = tb + threadIdx.x;
+    const uint32_t c = t < ntiles ? tile_count[t0 + t] : 0;
+    uint64_t inc = c;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const uint64_t o = __shfl_up_sync(0xffffffffu, inc, s);
+      if (lane >= static_cast<unsigned>(s)) {
+        inc += o;
+      }
+    }
+    if (lane == 31) {
+      s_scan[warp] = inc;
+    }
+    __syncthreads();
+    uint64_t prefix = s_carry;
+    uint64_t chunk_total = 0;
+    for (unsigned w = 0; w < 8; ++w) {
+      if (w < warp) {
+        prefix += s_scan[w];
+      }
+      chunk_total += s_scan[w];
+    }
+    const uint64_t first_rank = prefix + inc - c;
+    for (uint32_t i = 0; i < c; ++i) {
+      dst[first_rank + i] = rec_doc[r0 + static_cast<uint64_t>(t) * kTile + i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_carry += chunk_total;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ shard merge (rank based, no sort)
+// Every shard's run is already in final order. A record's final position is the
+// number of records (over all shards) that beat it, found by binary search in
+// each other run; records with position in [0, K) are written there.
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(uint32_t n_shards, uint64_t n_queries, uint64_t stride, int compute_score, int descending,
+                  uint32_t limit, uint32_t offset, const uint32_t* __restrict__ ids_all, const double* __restrict__ scores_all,
+                  const uint32_t* __restrict__ count_all, const uint64_t* __restrict__ total_all,
+                  uint32_t* __restrict__ ids_out, double* __restrict__ scores_out, uint32_t* __restrict__ count_out,
+                  uint64_t* __restrict__ total_out) {
+  const uint64_t q = blockIdx.x;
+  const bool desc = descending != 0;
+  uint64_t total = 0;
+  uint64_t have = 0;
+  for (uint32_t s = 0; s < n_shards; ++s) {
+    total += total_all[s * n_queries + q];
+    have += count_all[s * n_queries + q];
+  }
+  // shards return their best (offset + limit) records with offset 0; the offset is applied here
+  const uint64_t skip = umin64(have, offset);
+  const uint32_t k_out =
+      static_cast<uint32_t>(umin64(umin64(have - skip, stride), limit == 0 ? have - skip : limit));
+  if (threadIdx.x == 0) {
+    total_out[q] = total;
+    count_out[q] = k_out;
+  }
+  for (uint32_t s = 0; s < n_shards; ++s) {
+    const uint32_t c = count_all[s * n_queries + q];
+    const uint64_t base = (static_cast<uint64_t>(s) * n_queries + q) * stride;
+    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+      uint32_t rank = i;
+      if (compute_score) {
+        const SortKey me = make_sort_key(scores_all[base + i], ids_all[base + i], desc);
+        for (uint32_t o = 0; o < n_shards; ++o) {
+          if (o == s) {
+            continue;
+          }
+          const uint32_t oc = count_all[o * n_queries + q];
+          const uint64_t ob = (static_cast<uint64_t>(o) * n_queries + q) * stride;
+          uint32_t lo = 0;  // number of records in run o that beat `me`
+          uint32_t hi = oc;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const SortKey k = make_sort_key(scores_all[ob + mid], ids_all[ob + mid], desc);
+            if (key_greater(k, me)) {
+              lo = mid + 1;
+            } else {
+              hi = mid;
+            }
+          }
+          rank += lo;
+        }
+      } else {
+        // ascending ids over disjoint ascending shard ranges: concatenate in shard order
+        for (uint32_t o = 0; o < s; ++o) {
+          rank += count_all[o * n_queries + q];
+        }
+      }
+      if (rank >= skip && rank - skip < k_out) {
+        ids_out[q * stride + (rank - skip)] = ids_all[base + i];
+        if (compute_score && scores_out != nullptr) {
+          scores_out[q * stride + (rank - skip)] = scores_all[base + i];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ stand-alone scoring / sorting
+// BM25Scorer::ScoreDocuments for explicit candidates: one warp per candidate.
+__global__ void __launch_bounds__(256)
+score_docs_kernel(IndexView iv, const uint32_t* __restrict__ cands, uint64_t n_cands,
+                  const uint8_t* __restrict__ term_bytes, const uint32_t* __restrict__ term_boff,
+                  const double* __restrict__ idf, uint32_t n_terms, ScoreParams sp, double* __restrict__ out) {
+  __shared__ __align__(16) uint8_t s_text[8][kStageBuf];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint64_t c = static_cast<uint64_t>(blockIdx.x) * 8 + warp;
+  if (c >= n_cands) {
+    return;
+  }
+  const uint32_t pos = local_of(iv, cands[c]);
+  double score = 0.0;
+  if (pos != kNone) {
+    DocText d = doc_open(iv, pos, s_text[warp]);
+    if (d.len > 0) {
+      const double dl = static_cast<double>(iv.doc_len[pos]);
+      const double length_norm = __dadd_rn(__dsub_rn(1.0, sp.b), __ddiv_rn(__dmul_rn(sp.b, dl), sp.avgdl_clamped));
+      for (uint32_t i = 0; i < n_terms; ++i) {
+        const uint32_t tl = term_boff[i + 1] - term_boff[i];
+        const uint32_t tf_u = doc_count_term(d, term_bytes + term_boff[i], tl, false);
+        if (tf_u != 0) {
+          const double tf = static_cast<double>(tf_u);
+          const double numerator = __dmul_rn(tf, __dadd_rn(sp.k1, 1.0));
+          const double denominator = __dadd_rn(tf, __dmul_rn(sp.k1, length_norm));
+          score = __dadd_rn(score, __ddiv_rn(__dmul_rn(idf[i], numerator), denominator));
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    out[c] = score;
+  }
+}
+
+__global__ void idf_plain_kernel(const uint64_t* __restrict__ dfs, uint32_t n, uint64_t total_docs,
+                                 double* __restrict__ idf) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) {
+    return;
+  }
+  double v = 0.0;
+  if (total_docs != 0) {
+    uint64_t df = dfs[i];
+    if (df > total_docs) {
+      df = total_docs;
+    }
+    const double nn = static_cast<double>(total_docs);
+    const double dd = static_cast<double>(df);
+    v = log(__dadd_rn(__ddiv_rn(__dadd_rn(__dsub_rn(nn, dd), 0.5), __dadd_rn(dd, 0.5)), 1.0));
+  }
+  idf[i] = v;
+}
+
+// SortByScore over explicit arrays: single CTA, radix select + bitonic like topk_kernel.
+__global__ void __launch_bounds__(256)
+sort_by_score_kernel(const uint32_t* __restrict__ docs, const double* __restrict__ scores, uint64_t n, int descending,
+                     uint32_t limit, uint32_t offset, uint32_t* __restrict__ out, uint32_t* __restrict__ out_count) {
+  __shared__ SortKey s_keys[kTopkSmem];
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_cnt;
+  __shared__ SortKey s_prefix;
+  __shared__ uint32_t s_need;
+  const bool desc = descending != 0;
+  const uint64_t want_begin = umin64(offset, n);
+  const uint64_t want_end = umin64(n, static_cast<uint64_t>(offset) + limit);
+  const uint32_t n_out = static_cast<uint32_t>(want_end - want_begin);
+  if (threadIdx.x == 0) {
+    *out_count = n_out;
+    s_cnt = 0;
+    s_prefix.s = 0;
+    s_prefix.d = 0;
+    s_need = static_cast<uint32_t>(want_end);
+  }
+  __syncthreads();
+  if (n_out == 0) {
+    return;
+  }
+  SortKey thr;
+  thr.s = 0;
+  thr.d = 0;
+  if (n > kTopkSmem) {
+    for (int pass = 0; pass < 12; ++pass) {
+      s_hist[threadIdx.x] = 0;
+      __syncthreads();
+      const SortKey prefix = s_prefix;
+      for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const SortKey k = make_sort_key(scores[i], docs[i], desc);
+        if (key_has_prefix(k, prefix, pass)) {
+          atomicAdd(&s_hist[key_digit(k, pass)], 1u);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t need = s_need;
+        int digit = 255;
+        for (; digit > 0; --digit) {
+          if (s_hist[digit] >= need) {
+            break;
+          }
+          need -= s_hist[digit];
+        }
+        s_need = need;
+        if (pass < 8) {
+          s_prefix.s |= static_cast<uint64_t>(digit) << (56 - 8 * pass);
+        } else {
+          s_prefix.d |= static_cast<uint32_t>(digit) << (24 - 8 * (pass - 8));
+        }
+      }
+      __syncthreads();
+    }
+    thr = s_prefix;
+  }
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const SortKey k = make_sort_key(scores[i], docs[i], desc);
+    if (n <= kTopkSmem || !key_greater(thr, k)) {
+      const uint32_t pos = atomicAdd(&s_cnt, 1u);
+      if (pos < kTopkSmem) {
+        s_keys[pos] = k;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t n_keys = min(s_cnt, kTopkSmem);
+  uint32_t n_pow2 = 1;
+  while (n_pow2 < n_keys) {
+    n_pow2 <<= 1;
+  }
+  for (uint32_t i = n_keys + threadIdx.x; i < n_pow2; i += blockDim.x) {
+    s_keys[i].s = 0;
+    s_keys[i].d = 0;
+  }
+  bitonic_sort_desc(s_keys, n_pow2);
+  for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+    const SortKey k = s_keys[want_begin + i];
+    out[i] = desc ? k.d : ~k.d;
+  }
+}
+
+BatchView make_batch_view(Batch& b) {
+  BatchView v{};
+  v.term_bytes = b.d_term_bytes.p;
+  v.term_boff = b.d_term_boff.p;
+  v.term_koff = b.d_term_koff.p;
+  v.key_list = b.d_key_list.p;
+  v.key_len = b.d_key_len.p;
+  v.t_est = b.d_t_est.p;
+  v.t_df_tiles = b.d_t_df_tiles.p;
+  v.t_df_tile_off = b.d_t_df_tile_off.p;
+  v.t_df = b.d_t_df.p;
+  v.n_terms = b.n_terms;
+  v.q_toff = b.d_q_toff.p;
+  v.q_tids = b.d_q_tids.p;
+  v.q_noff = b.d_q_noff.p;
+  v.q_ntids = b.d_q_ntids.p;
+  v.q_loff = b.d_q_loff.p;
+  v.q_list = b.d_q_list.p;
+  v.q_list_len = b.d_q_list_len.p;
+  v.q_nlists = b.d_q_nlists.p;
+  v.q_flags = b.d_q_flags.p;
+  v.q_host_flags = b.d_q_host_flags.p;
+  v.q_driver_len = b.d_q_driver_len.p;
+  v.q_ntiles = b.d_q_ntiles.p;
+  v.q_tile_off = b.d_q_tile_off.p;
+  v.q_rec_off = b.d_q_rec_off.p;
+  v.q_idf = b.d_q_idf.p;
+  v.n_queries = b.n_queries;
+  v.explicit_ids = b.explicit_driver.d_ids;
+  v.explicit_n = static_cast<uint32_t>(b.explicit_driver.n);
+  return v;
+}
+
+template <typename T>
+void upload(DevBuf<T>& dst, const std::vector<T>& src, cudaStream_t stream, uint64_t* bytes) {
+  dst.alloc(src.size());
+  if (!src.empty()) {
+    MGX_CUDA(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    *bytes += src.size() * sizeof(T);
+  }
+}
+
+unsigned grid_for(uint64_t n, unsigned block) { return static_cast<unsigned>((n + block - 1) / block); }
+
+}  // namespace
+
+// ------------------------------------------------------------------ host orchestration
+void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
+                  const std::vector<uint32_t>& slot_tid) {
+  cudaStream_t st = b.stream;
+  b.n_queries = static_cast<uint32_t>(queries.size());
+  b.n_terms = static_cast<uint32_t>(terms.size());
+  b.n_slots = static_cast<uint32_t>(slot_tid.size());
+  b.h_slot_tid = slot_tid;
+
+  std::vector<uint8_t> bytes;
+  std::vector<uint32_t> boff(terms.size() + 1, 0);
+  std::vector<uint32_t> koff(terms.size() + 1, 0);
+  std::vector<uint64_t> keys;
+  std::vector<uint8_t> raw(terms.size() + 1, 0);
+  for (size_t t = 0; t < terms.size(); ++t) {
+    bytes.insert(bytes.end(), terms[t].bytes.begin(), terms[t].bytes.end());
+    boff[t + 1] = static_cast<uint32_t>(bytes.size());
+    keys.insert(keys.end(), terms[t].keys.begin(), terms[t].keys.end());
+    koff[t + 1] = static_cast<uint32_t>(keys.size());
+    raw[t] = static_cast<uint8_t>((terms[t].raw ? 1 : 0) | (terms[t].exact_single ? 2 : 0));
+  }
+  bytes.resize(bytes.size() + 16, 0);
+  b.n_keys = static_cast<uint32_t>(keys.size());
+
+  std::vector<uint32_t> toff(queries.size() + 1, 0);
+  std::vector<uint32_t> noff(queries.size() + 1, 0);
+  std::vector<uint32_t> loff(queries.size() + 1, 0);
+  std::vector<uint32_t> tids;
+  std::vector<uint32_t> ntids;
+  std::vector<uint32_t> hflags(queries.size() + 1, 0);
+  for (size_t q = 0; q < queries.size(); ++q) {
+    uint32_t cap = 0;
+    for (uint32_t tid : queries[q].terms) {
+      tids.push_back(tid);
+      cap += static_cast<uint32_t>(terms[tid].keys.size());
+    }
+    for (uint32_t tid : queries[q].not_terms) {
+      ntids.push_back(tid);
+    }
+    toff[q + 1] = static_cast<uint32_t>(tids.size());
+    noff[q + 1] = static_cast<uint32_t>(ntids.size());
+    loff[q + 1] = loff[q] + cap;
+    hflags[q] = queries[q].flags;
+  }
+
+  uint64_t h2d = 0;
+  upload(b.d_term_bytes, bytes, st, &h2d);
+  upload(b.d_term_boff, boff, st, &h2d);
+  upload(b.d_term_koff, koff, st, &h2d);
+  upload(b.d_keys, keys, st, &h2d);
+  upload(b.d_q_toff, toff, st, &h2d);
+  upload(b.d_q_tids, tids, st, &h2d);
+  upload(b.d_q_noff, noff, st, &h2d);
+  upload(b.d_q_ntids, ntids, st, &h2d);
+  upload(b.d_q_loff, loff, st, &h2d);
+  upload(b.d_q_host_flags, hflags, st, &h2d);
+  upload(b.d_slot_tid, slot_tid, st, &h2d);
+  b.d_key_list.alloc(keys.size());
+  b.d_key_len.alloc(keys.size());
+  b.d_t_est.alloc(terms.size());
+  b.d_t_df_tiles.alloc(terms.size());
+  b.d_t_df_tile_off.alloc(terms.size() + 1);
+  b.d_t_df.alloc(terms.size());
+  b.d_q_list.alloc(loff.back());
+  b.d_q_list_len.alloc(loff.back());
+  b.d_q_nlists.alloc(queries.size());
+  b.d_q_flags.alloc(queries.size());
+  b.d_q_driver_len.alloc(queries.size());
+  b.d_q_ntiles.alloc(queries.size());
+  b.d_q_tile_off.alloc(queries.size() + 1);
+  b.d_q_rec_off.alloc(queries.size() + 1);
+  b.d_q_idf.alloc(tids.size());
+  b.h2d_bytes = h2d;
+
+  // lookup + term planning need the raw flags on the device
+  DevBuf<uint8_t> d_raw;
+  upload(d_raw, raw, st, &h2d);
+  Index& ix = *b.ix;
+  if (b.n_keys > 0) {
+    lookup_kernel<<<grid_for(b.n_keys, 256), 256, 0, st>>>(ix.d_term_keys.p, ix.d_term_off.p, ix.n_terms, b.d_keys.p,
+                                                          b.n_keys, b.d_key_list.p, b.d_key_len.p);
+    MGX_LAUNCH_CHECK();
+  }
+  BatchView bv = make_batch_view(b);
+  if (b.n_terms > 0) {
+    term_plan_kernel<<<grid_for(b.n_terms, 128), 128, 0, st>>>(bv, b.params.compute_score != 0 ? 1 : 0,
+                                                               ix.all_valid_utf8 ? 1 : 0, d_raw.p);
+    MGX_LAUNCH_CHECK();
+  }
+  exclusive_scan_u32_u64(b.d_t_df_tiles.p, b.d_t_df_tile_off.p, b.n_terms, st);
+  MGX_CUDA(cudaStreamSynchronize(st));  // d_raw goes out of scope
+}
+
+void batch_plan(Batch& b, bool /*compute_df*/) {
+  cudaStream_t st = b.stream;
+  Index& ix = *b.ix;
+  BatchView bv = make_batch_view(b);
+  const IndexView iv = make_view(ix);
+  if (b.n_queries > 0) {
+    query_plan_kernel<<<grid_for(b.n_queries, 128), 128, 0, st>>>(iv, bv);
+    MGX_LAUNCH_CHECK();
+  }
+  exclusive_scan_u32_u64(b.d_q_ntiles.p, b.d_q_tile_off.p, b.n_queries, st);
+  exclusive_scan_u32_u64(b.d_q_driver_len.p, b.d_q_rec_off.p, b.n_queries, st);
+  b.h_q_tile_off.resize(b.n_queries + 1);
+  b.h_q_rec_off.resize(b.n_queries + 1);
+  MGX_CUDA(cudaMemcpyAsync(b.h_q_tile_off.data(), b.d_q_tile_off.p, (b.n_queries + 1) * sizeof(uint64_t),
+                           cudaMemcpyDeviceToHost, st));
+  MGX_CUDA(cudaMemcpyAsync(b.h_q_rec_off.data(), b.d_q_rec_off.p, (b.n_queries + 1) * sizeof(uint64_t),
+                           cudaMemcpyDeviceToHost, st));
+  MGX_CUDA(cudaStreamSynchronize(st));
+  b.planned = true;
+}
+
+void batch_df(Batch& b) {
+  cudaStream_t st = b.stream;
+  Index& ix = *b.ix;
+  uint64_t total_tiles = 0;
+  MGX_CUDA(cudaMemcpyAsync(&total_tiles, b.d_t_df_tile_off.p + b.n_terms, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  MGX_CUDA(cudaStreamSynchronize(st));
+  if (total_tiles > 0) {
+    if (total_tiles > 0x7FFFFFFFULL) {
+      set_last_error("df stage: too many tiles in one batch");
+      throw CudaFailure{MGX_ERR_UNSUPPORTED};
+    }
+    df_tile_kernel<<<static_cast<unsigned>(total_tiles), kTileThreads, 0, st>>>(make_view(ix), make_batch_view(b));
+    MGX_LAUNCH_CHECK();
+  }
+  ix.last_stats.df_candidates = total_tiles * kTile;  // upper bound on postings walked
+  b.df_done = true;
+}
+
+void batch_df_to_slots(Batch& b, uint64_t* d_df_slots) {
+  if (b.n_slots > 0) {
+    df_to_slots_kernel<<<grid_for(b.n_slots, 256), 256, 0, b.stream>>>(b.d_t_df.p, b.d_slot_tid.p, b.n_slots,
+                                                                       d_df_slots);
+    MGX_LAUNCH_CHECK();
+  }
+}
+
+namespace {
+
+struct Chunk {
+  uint32_t q0;
+  uint32_t q1;
+};
+
+// Split the batch so that each chunk's record area fits the scratch budget.
+std::vector<Chunk> make_chunks(const Batch& b, uint64_t max_records) {
+  std::vector<Chunk> chunks;
+  uint32_t q0 = 0;
+  while (q0 < b.n_queries) {
+    uint32_t q1 = q0 + 1;
+    while (q1 < b.n_queries && b.h_q_rec_off[q1 + 1] - b.h_q_rec_off[q0] <= max_records) {
+      ++q1;
+    }
+    chunks.push_back({q0, q1});
+    q0 = q1;
+  }
+  return chunks;
+}
+
+void prepare_scoring(Batch& b, const uint64_t* d_df_slots) {
+  cudaStream_t st = b.stream;
+  if (b.params.compute_score == 0) {
+    return;
+  }
+  if (d_df_slots != nullptr && b.n_slots > 0) {
+    slots_to_df_kernel<<<grid_for(b.n_slots, 256), 256, 0, st>>>(d_df_slots, b.d_slot_tid.p, b.n_slots, b.d_t_df.p);
+    MGX_LAUNCH_CHECK();
+  }
+  const uint64_t total_docs = b.params.total_docs != 0 ? b.params.total_docs : b.ix->doc_count;
+  const uint32_t n = static_cast<uint32_t>(b.d_q_tids.n);
+  if (n > 0) {
+    idf_kernel<<<grid_for(n, 256), 256, 0, st>>>(b.d_q_tids.p, n, b.d_t_df.p, total_docs, b.d_q_idf.p);
+    MGX_LAUNCH_CHECK();
+  }
+}
+
+ScoreParams score_params(const Batch& b) {
+  ScoreParams sp;
+  sp.k1 = b.params.k1;
+  sp.b = b.params.b;
+  const uint64_t total_docs = b.params.total_docs != 0 ? b.params.total_docs : b.ix->doc_count;
+  const uint64_t total_len = b.params.total_docs != 0 ? b.params.total_doc_length : b.ix->total_doc_length;
+  const double avgdl =
+      total_docs > 0 ? static_cast<double>(total_len) / static_cast<double>(total_docs) : 0.0;  // server_types.h:182-187
+  sp.avgdl_clamped = std::max(avgdl, 1.0);
+  sp.compute_score = b.params.compute_score;
+  return sp;
+}
+
+uint64_t scratch_records(const Batch& b) {
+  const uint64_t bytes = b.ix->cfg.scratch_bytes != 0 ? b.ix->cfg.scratch_bytes : (4ULL << 30);
+  return std::max<uint64_t>(bytes / 12, 1ULL << 20);
+}
+
+void run_tiles(Batch& b, const Chunk& c, const ScoreParams& sp) {
+  cudaStream_t st = b.stream;
+  const uint64_t tile_base = b.h_q_tile_off[c.q0];
+  const uint64_t n_tiles = b.h_q_tile_off[c.q1] - tile_base;
+  const uint64_t rec_base = b.h_q_rec_off[c.q0];
+  const uint64_t n_recs = b.h_q_rec_off[c.q1] - rec_base;
+  b.d_tile_count.reserve(std::max<uint64_t>(n_tiles, 1));
+  b.d_rec_doc.reserve(std::max<uint64_t>(n_recs + kTile, 1));
+  if (sp.compute_score != 0) {
+    b.d_rec_score.reserve(std::max<uint64_t>(n_recs + kTile, 1));
+  }
+  if (n_tiles > 0) {
+    if (n_tiles > 0x7FFFFFFFULL) {
+      set_last_error("search stage: too many tiles in one chunk");
+      throw CudaFailure{MGX_ERR_UNSUPPORTED};
+    }
+    and_tile_kernel<<<static_cast<unsigned>(n_tiles), kTileThreads, 0, st>>>(
+        make_view(*b.ix), make_batch_view(b), sp, tile_base, rec_base, b.d_tile_count.p, b.d_rec_doc.p,
+        b.d_rec_score.p);
+    MGX_LAUNCH_CHECK();
+  }
+}
+
+}  // namespace
+
+void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_t* d_ids, double* d_scores,
+                  uint32_t* d_count, uint64_t* d_total) {
+  cudaStream_t st = b.stream;
+  prepare_scoring(b, d_df_slots);
+  const ScoreParams sp = score_params(b);
+  const auto chunks = make_chunks(b, scratch_records(b));
+  uint64_t driver_entries = 0;
+  for (const Chunk& c : chunks) {
+    if (chunks.size() > 1) {
+      MGX_CUDA(cudaStreamSynchronize(st));  // scratch is reused by the next chunk
+    }
+    run_tiles(b, c, sp);
+    driver_entries += b.h_q_rec_off[c.q1] - b.h_q_rec_off[c.q0];
+    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.h_q_rec_off[c.q0],
+                                             b.d_tile_count.p, b.d_rec_doc.p, b.d_rec_score.p,
+                                             b.params.compute_score, b.params.descending, b.params.limit,
+                                             b.params.offset, stride, d_ids, d_scores, d_count, d_total);
+    MGX_LAUNCH_CHECK();
+  }
+  b.ix->last_stats.driver_entries = driver_entries;
+}
+
+void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32_t>* d_sets) {
+  cudaStream_t st = b.stream;
+  ScoreParams sp = score_params(b);
+  sp.compute_score = 0;
+  const auto chunks = make_chunks(b, scratch_records(b));
+  // pass 1: totals per query (topk_kernel with limit 0 / stride 0 only counts)
+  DevBuf<uint32_t> d_count;
+  DevBuf<uint64_t> d_total;
+  DevBuf<uint32_t> d_dummy;
+  d_count.alloc(b.n_queries);
+  d_total.alloc(b.n_queries + 1);
+  d_dummy.alloc(1);
+  std::vector<uint64_t> totals(b.n_queries, 0);
+  if (chunks.size() == 1) {
+    // single chunk: records stay valid between the counting and the gathering pass
+    const Chunk& c = chunks[0];
+    run_tiles(b, c, sp);
+    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.h_q_rec_off[c.q0],
+                                             b.d_tile_count.p, b.d_rec_doc.p, nullptr, 0, 0, 0, 0, 0, d_dummy.p, nullptr,
+                                             d_count.p, d_total.p);
+    MGX_LAUNCH_CHECK();
+    MGX_CUDA(cudaMemcpyAsync(totals.data(), d_total.p, b.n_queries * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MGX_CUDA(cudaStreamSynchronize(st));
+    h_set_off->assign(b.n_queries + 1, 0);
+    for (uint32_t q = 0; q < b.n_queries; ++q) {
+      (*h_set_off)[q + 1] = (*h_set_off)[q] + totals[q];
+    }
+    DevBuf<uint64_t> d_set_off;
+    d_set_off.alloc(b.n_queries + 1);
+    MGX_CUDA(cudaMemcpyAsync(d_set_off.p, h_set_off->data(), (b.n_queries + 1) * sizeof(uint64_t),
+                             cudaMemcpyHostToDevice, st));
+    d_sets->alloc(std::max<uint64_t>(1, h_set_off->back()));
+    gather_sets_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0],
+                                                    b.h_q_rec_off[c.q0], b.d_tile_count.p, b.d_rec_doc.p, d_set_off.p,
+                                                    d_sets->p);
+    MGX_LAUNCH_CHECK();
+    MGX_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
+  // several chunks: count everything first, then redo the tiles chunk by chunk and gather
+  for (const Chunk& c : chunks) {
+    MGX_CUDA(cudaStreamSynchronize(st));
+    run_tiles(b, c, sp);
+    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.h_q_rec_off[c.q0],
+                                             b.d_tile_count.p, b.d_rec_doc.p, nullptr, 0, 0, 0, 0, 0, d_dummy.p, nullptr,
+                                             d_count.p, d_total.p);
+    MGX_LAUNCH_CHECK();
+  }
+  MGX_CUDA(cudaMemcpyAsync(totals.data(), d_total.p, b.n_queries * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  MGX_CUDA(cudaStreamSynchronize(st));
+  h_set_off->assign(b.n_queries + 1, 0);
+  for (uint32_t q = 0; q < b.n_queries; ++q) {
+    (*h_set_off)[q + 1] = (*h_set_off)[q] + totals[q];
+  }
+  DevBuf<uint64_t> d_set_off;
+  d_set_off.alloc(b.n_queries + 1);
+  MGX_CUDA(cudaMemcpyAsync(d_set_off.p, h_set_off->data(), (b.n_queries + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                           st));
+  d_sets->alloc(std::max<uint64_t>(1, h_set_off->back()));
+  for (const Chunk& c : chunks) {
+    MGX_CUDA(cudaStreamSynchronize(st));
+    run_tiles(b, c, sp);
+    gather_sets_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0],
+                                                    b.h_q_rec_off[c.q0], b.d_tile_count.p, b.d_rec_doc.p, d_set_off.p,
+                                                    d_sets->p);
+    MGX_LAUNCH_CHECK();
+  }
+  MGX_CUDA(cudaStreamSynchronize(st));
+}
+
+void launch_merge_topk(cudaStream_t stream, const mgx_query_params_t& params, uint32_t n_shards, uint64_t n_queries,
+                       uint64_t stride, const uint32_t* d_ids_all, const double* d_scores_all,
+                       const uint32_t* d_count_all, const uint64_t* d_total_all, uint32_t* d_ids_out,
+                       double* d_scores_out, uint32_t* d_count_out, uint64_t* d_total_out) {
+  if (n_queries == 0) {
+    return;
+  }
+  merge_topk_kernel<<<static_cast<unsigned>(n_queries), 256, 0, stream>>>(
+      n_shards, n_queries, stride, params.compute_score, params.descending, params.limit, params.offset, d_ids_all,
+      d_scores_all,
+      d_count_all, d_total_all, d_ids_out, d_scores_out, d_count_out, d_total_out);
+  MGX_LAUNCH_CHECK();
+}
+
+void launch_score_documents(Index& ix, cudaStream_t stream, const uint32_t* d_cands, uint64_t n_cands,
+                            const uint8_t* d_term_bytes, const uint32_t* d_term_boff, const uint64_t* d_dfs,
+                            uint32_t n_terms, uint64_t total_docs, double avgdl, double k1, double b, double* d_scores) {
+  DevBuf<double> d_idf;
+  d_idf.alloc(n_terms);
+  if (n_terms > 0) {
+    idf_plain_kernel<<<grid_for(n_terms, 128), 128, 0, stream>>>(d_dfs, n_terms, total_docs, d_idf.p);
+    MGX_LAUNCH_CHECK();
+  }
+  ScoreParams sp;
+  sp.k1 = k1;
+  sp.b = b;
+  sp.avgdl_clamped = std::max(avgdl, 1.0);
+  sp.compute_score = 1;
+  if (n_cands > 0) {
+    score_docs_kernel<<<grid_for(n_cands, 8), 256, 0, stream>>>(make_view(ix), d_cands, n_cands, d_term_bytes,
+                                                                d_term_boff, d_idf.p, n_terms, sp, d_scores);
+    MGX_LAUNCH_CHECK();
+  }
+  MGX_CUDA(cudaStreamSynchronize(stream));
+}
+
+void launch_sort_by_score(cudaStream_t stream, const uint32_t* d_docs, const double* d_scores, uint64_t n,
+                          bool descending, uint32_t limit, uint32_t offset, uint32_t* d_out, uint32_t* d_out_count) {
+  sort_by_score_kernel<<<1, 256, 0, stream>>>(d_docs, d_scores, n, descending ? 1 : 0, limit, offset, d_out,
+                                              d_out_count);
+  MGX_LAUNCH_CHECK();
+}
+
+}  // namespace mgx

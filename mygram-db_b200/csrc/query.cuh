@@ -1,0 +1,130 @@
+// query.cuh — batch object shared by query.cu (kernels) and api.cu (C ABI).
+#pragma once
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "mgx_internal.cuh"
+
+namespace mgx {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint64_t kEstNone = ~0ULL;   // "term produced no n-grams" (SIZE_MAX in search_pipeline.cpp:583)
+constexpr int kTile = 1024;            // driver entries per CTA
+constexpr int kTileThreads = 256;
+constexpr int kTileItems = kTile / kTileThreads;
+constexpr uint32_t kMaxTermBytes = 256;
+constexpr uint32_t kMaxTopK = 1024;
+
+// query flag bits (q_flags)
+constexpr uint32_t kQEmpty = 1u;        // early exit / no terms: result is empty
+constexpr uint32_t kQVerify = 2u;       // every search term must also occur in the text (verify_text / hybrid fragment)
+constexpr uint32_t kQAnyMode = 4u;      // OR semantics over the lists (Index::SearchOr)
+constexpr uint32_t kQDriverAll = 8u;    // driver = every document of the shard
+constexpr uint32_t kQDriverExplicit = 16u;  // driver = caller supplied candidate ids (query 0 only)
+
+// driver kinds for single-call set APIs
+struct ExplicitDriver {
+  const uint32_t* d_ids = nullptr;  // global doc ids (device)
+  uint64_t n = 0;
+};
+
+struct Batch {
+  Index* ix = nullptr;
+  mgx_query_params_t params{};
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+
+  // ---- host-side compiled form
+  uint32_t n_queries = 0;
+  uint32_t n_terms = 0;      // unique terms (search + not)
+  uint32_t n_keys = 0;
+  uint32_t n_slots = 0;      // caller's search-term slots (for df output)
+  std::vector<uint32_t> h_slot_tid;  // slot -> unique term id
+
+  // ---- device: terms
+  DevBuf<uint8_t> d_term_bytes;
+  DevBuf<uint32_t> d_term_boff;   // [T+1]
+  DevBuf<uint32_t> d_term_koff;   // [T+1]
+  DevBuf<uint64_t> d_keys;        // [K]
+  DevBuf<uint32_t> d_key_list;    // [K] dictionary term index or kNone; sorted by length inside a term
+  DevBuf<uint32_t> d_key_len;     // [K]
+  DevBuf<uint64_t> d_t_est;       // [T]
+  DevBuf<uint32_t> d_t_df_tiles;  // [T]
+  DevBuf<uint64_t> d_t_df_tile_off;  // [T+1]
+  DevBuf<uint64_t> d_t_df;        // [T]
+  DevBuf<uint32_t> d_slot_tid;    // [S]
+
+  // ---- device: queries
+  DevBuf<uint32_t> d_q_toff;      // [Q+1] search terms
+  DevBuf<uint32_t> d_q_tids;      // [sum] unique term ids, re-ordered by estimated size by the planner
+  DevBuf<uint32_t> d_q_noff;      // [Q+1] NOT terms
+  DevBuf<uint32_t> d_q_ntids;
+  DevBuf<uint32_t> d_q_loff;      // [Q+1] capacity ranges for the merged list table
+  DevBuf<uint32_t> d_q_list;      // dictionary term index per merged list (ascending length)
+  DevBuf<uint32_t> d_q_list_len;
+  DevBuf<uint32_t> d_q_nlists;    // [Q]
+  DevBuf<uint32_t> d_q_flags;     // [Q]
+  DevBuf<uint32_t> d_q_driver_len;  // [Q]
+  DevBuf<uint32_t> d_q_ntiles;    // [Q]
+  DevBuf<uint64_t> d_q_tile_off;  // [Q+1]
+  DevBuf<uint64_t> d_q_rec_off;   // [Q+1]
+  DevBuf<double> d_q_idf;         // [sum search terms], in planner order
+  DevBuf<uint32_t> d_q_host_flags;  // [Q] flags decided on the host (verify etc.)
+
+  // ---- device: per-tile results
+  DevBuf<uint32_t> d_tile_count;  // [tiles in flight]
+  DevBuf<uint32_t> d_rec_doc;     // survivors (global doc ids), tile k of query q at rec_off[q] + k*kTile
+  DevBuf<double> d_rec_score;
+
+  // host mirrors read back after planning
+  std::vector<uint64_t> h_q_tile_off;
+  std::vector<uint64_t> h_q_rec_off;
+
+  ExplicitDriver explicit_driver;
+  uint64_t h2d_bytes = 0;
+  uint64_t launches_at_start = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool planned = false;
+  bool df_done = false;
+};
+
+// One compiled query term.
+struct HostTerm {
+  std::string bytes;
+  std::vector<uint64_t> keys;  // sorted unique packed n-grams
+  bool raw = false;            // keys given directly (Index::SearchAnd style): no text semantics
+  bool exact_single = false;   // the term IS its single n-gram, so df == posting size when all text is valid UTF-8
+};
+
+struct HostQuery {
+  std::vector<uint32_t> terms;      // unique-term ids in query order
+  std::vector<uint32_t> not_terms;
+  uint32_t flags = 0;               // kQVerify / kQAnyMode / kQDriverAll / kQDriverExplicit
+};
+
+// query.cu
+void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
+                  const std::vector<uint32_t>& slot_tid);
+void batch_plan(Batch& b, bool compute_df);
+void batch_df(Batch& b);
+// Runs the intersect/score kernels and the per-query output kernel. Outputs are DEVICE pointers.
+// set_mode: 0 = top-k by score or first ids (params.limit/offset), 1 = full ascending sets
+// written to d_sets (offsets d_set_off[Q+1] computed here), 2 = last `limit` ids descending (reverse)
+void batch_search(Batch& b, const uint64_t* d_df_global, uint64_t stride, uint32_t* d_ids, double* d_scores,
+                  uint32_t* d_count, uint64_t* d_total);
+// Full ascending result sets of every query: fills h_totals and returns a device buffer of all sets back to back.
+void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32_t>* d_sets);
+void launch_merge_topk(cudaStream_t stream, const mgx_query_params_t& params, uint32_t n_shards, uint64_t n_queries,
+                       uint64_t stride, const uint32_t* d_ids_all, const double* d_scores_all,
+                       const uint32_t* d_count_all, const uint64_t* d_total_all, uint32_t* d_ids_out,
+                       double* d_scores_out, uint32_t* d_count_out, uint64_t* d_total_out);
+void batch_df_to_slots(Batch& b, uint64_t* d_df_slots);
+void launch_score_documents(Index& ix, cudaStream_t stream, const uint32_t* d_cands, uint64_t n_cands,
+                            const uint8_t* d_term_bytes, const uint32_t* d_term_boff, const uint64_t* d_dfs,
+                            uint32_t n_terms, uint64_t total_docs, double avgdl, double k1, double b, double* d_scores);
+void launch_sort_by_score(cudaStream_t stream, const uint32_t* d_docs, const double* d_scores, uint64_t n,
+                          bool descending, uint32_t limit, uint32_t offset, uint32_t* d_out, uint32_t* d_out_count);
+
+}  // namespace mgx

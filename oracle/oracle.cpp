@@ -761,6 +761,99 @@ TermInfo MakeTermInfo(const orc_index& idx, std::string_view term, const orc_que
   return ti;
 }
 
+// Private CJK classifier of the pipeline, search_pipeline.cpp:73-78 (wider than the
+// tokenizer's: it also covers 2B820-2CEAF).
+bool PipelineIsCjk(uint32_t cp) {
+  return (cp >= 0x4E00 && cp <= 0x9FFF) || (cp >= 0x3400 && cp <= 0x4DBF) || (cp >= 0x20000 && cp <= 0x2A6DF) ||
+         (cp >= 0x2A700 && cp <= 0x2B73F) || (cp >= 0x2B740 && cp <= 0x2B81F) || (cp >= 0x2B820 && cp <= 0x2CEAF) ||
+         (cp >= 0xF900 && cp <= 0xFAFF);
+}
+
+// HasUncoveredHybridFragment, search_pipeline.cpp:80-136.
+bool HasUncoveredHybridFragment(std::string_view term, int ngram_size, int kanji_ngram_size, bool cross_boundary) {
+  if (term.empty() || kanji_ngram_size <= 0) {
+    return false;
+  }
+  const int ascii_n = ngram_size > 0 ? ngram_size : 2;
+  const auto cps = Utf8ToCodepoints(term);
+  if (cps.size() < 2) {
+    return false;
+  }
+  bool has_cjk = false;
+  bool has_non = false;
+  for (uint32_t cp : cps) {
+    (PipelineIsCjk(cp) ? has_cjk : has_non) = true;
+  }
+  if (!has_cjk || !has_non) {
+    return false;
+  }
+  std::vector<bool> covered(cps.size(), false);
+  for (size_t i = 0; i < cps.size(); ++i) {
+    const bool start_cjk = PipelineIsCjk(cps[i]);
+    const int size = start_cjk ? kanji_ngram_size : ascii_n;
+    if (size <= 0 || i + static_cast<size_t>(size) > cps.size()) {
+      continue;
+    }
+    if (!cross_boundary) {
+      bool crossed = false;
+      for (int j = 1; j < size; ++j) {
+        if (PipelineIsCjk(cps[i + static_cast<size_t>(j)]) != start_cjk) {
+          crossed = true;
+          break;
+        }
+      }
+      if (crossed) {
+        continue;
+      }
+    }
+    for (int j = 0; j < size; ++j) {
+      covered[i + static_cast<size_t>(j)] = true;
+    }
+  }
+  return std::any_of(covered.begin(), covered.end(), [](bool c) { return !c; });
+}
+
+// ShouldApplyVerifyText, search_pipeline.cpp:48-66.
+bool ShouldApplyVerifyText(int mode, const std::vector<std::string_view>& terms) {
+  if (mode == 1) {
+    return true;
+  }
+  if (mode == 2) {
+    for (auto t : terms) {
+      for (unsigned char ch : t) {
+        if (ch >= 0x80) {
+          return false;
+        }
+      }
+    }
+    return true;
+  }
+  return false;
+}
+
+// PostFilterByText / RetainCandidatesMatchingText, search_pipeline.cpp:1239-1246, 386-402:
+// a candidate without stored text is kept.
+std::vector<DocId> PostFilterByText(const orc_index& idx, const std::vector<DocId>& candidates,
+                                    const std::vector<std::string_view>& terms) {
+  std::vector<DocId> kept;
+  for (DocId d : candidates) {
+    std::string_view text;
+    bool ok = true;
+    if (idx.GetText(d, &text)) {
+      for (auto t : terms) {
+        if (text.find(t) == std::string_view::npos) {
+          ok = false;
+          break;
+        }
+      }
+    }
+    if (ok) {
+      kept.push_back(d);
+    }
+  }
+  return kept;
+}
+
 struct QueryOutput {
   std::vector<DocId> results;  // ascending result set
   std::vector<TermInfo> term_infos;
@@ -821,6 +914,20 @@ QueryOutput RunQuery(const orc_index& idx, const orc_query_params_t& p, const st
                           std::back_inserter(filtered));
       results = std::move(filtered);
     }
+  }
+  // ApplyVerifyTextFilter :1248-1266, then the hybrid-fragment exact-text filter :858-866
+  if (!results.empty() && ShouldApplyVerifyText(p.verify_text, terms)) {
+    results = PostFilterByText(idx, results, terms);
+  }
+  bool hybrid_exact = false;
+  for (auto t : terms) {
+    if (HasUncoveredHybridFragment(t, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0)) {
+      hybrid_exact = true;
+      break;
+    }
+  }
+  if (hybrid_exact) {
+    results = PostFilterByText(idx, results, terms);
   }
   out.results = std::move(results);
   return out;

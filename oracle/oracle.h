@@ -141,12 +141,15 @@ typedef struct {
   /* corpus stats override for shard-parallel runs; 0 => use the index's own */
   uint64_t total_docs_override;
   uint64_t total_len_override;
+  int32_t verify_text;         /* memory.verify_text: 0 "off" (config.h:329), 1 "all", 2 "ascii" */
+  int32_t reserved;
 } orc_query_params_t;
 
 /* One query = GenerateTermInfos (:569-603, df via PopulateTermDocumentFrequency
  * :542-565 when compute_score) -> sort by estimated_size (:2012-2014) ->
  * Execute (:795-869: early exit, AND smallest-first with FilterByNgrams below
- * filter_threshold, ApplyNotFilter :871-932) -> [ScoreDocuments -> SortByScore
+ * filter_threshold, ApplyNotFilter :871-932, ApplyVerifyTextFilter :1248-1266,
+ * hybrid-fragment PostFilterByText :858-866) -> [ScoreDocuments -> SortByScore
  * as in handlers/search_handler.cpp:405-470] else ascending ids cut to
  * [offset, offset+limit).
  *

@@ -42,6 +42,8 @@ class QueryParams(C.Structure):
         ("b", C.c_double),
         ("total_docs_override", C.c_uint64),
         ("total_len_override", C.c_uint64),
+        ("verify_text", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -365,7 +367,7 @@ class OracleIndex:
 
     def query_batch(self, queries, not_terms=None, score=True, descending=True, limit=100, offset=0,
                     filter_threshold=1000, k1=1.2, b=0.75, n_threads=1, want_sets=False, stride=None,
-                    total_docs_override=0, total_len_override=0, raw_ngram=None, raw_kanji=None):
+                    total_docs_override=0, total_len_override=0, raw_ngram=None, raw_kanji=None, verify_text=0):
         """queries: list[list[bytes|str]] search terms per query; not_terms likewise (optional)."""
         flat, qbeg = [], [0]
         for q in queries:
@@ -387,7 +389,7 @@ class OracleIndex:
         p = QueryParams(self.ngram_size if raw_ngram is None else raw_ngram,
                         self.kanji_ngram_size if raw_kanji is None else raw_kanji, int(self.cross_boundary),
                         int(score), int(descending), limit, offset, filter_threshold, k1, b, total_docs_override,
-                        total_len_override)
+                        total_len_override, verify_text, 0)
         ids = np.zeros((Q, stride), dtype=np.uint32)
         scores = np.zeros((Q, stride), dtype=np.float64)
         count = np.zeros(Q, dtype=np.uint32)

@@ -357,6 +357,7 @@ int orc_query_batch(const orc_index_t* idx, const orc_query_params_t* params, ui
   config.bm25.enable = true;
   config.bm25.k1 = p.k1;
   config.bm25.b = p.b;
+  config.memory.verify_text = p.verify_text == 1 ? "all" : (p.verify_text == 2 ? "ascii" : "off");
   const uint64_t total_docs = p.total_docs_override != 0 ? p.total_docs_override : idx->stats.doc_count.load();
   double avgdl = idx->stats.avg_doc_length();
   if (p.total_docs_override != 0) {
