@@ -179,9 +179,33 @@ int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64
                     uint64_t stride, uint32_t* out_ids, double* out_scores, uint32_t* out_count, uint64_t* out_total,
                     uint64_t* out_df);
 
+/* Timing / accounting of one batch (device times from CUDA events recorded on the launch
+ * stream around the named kernels; bytes as defined in SURVEY.md §8(d) and DESIGN.md). */
+typedef struct {
+  double ms_plan;             /* lookup + term/query planning kernels (+ the size read-back)      */
+  double ms_df_kernel;        /* df_tile_kernel launches                                          */
+  double ms_and_kernel;       /* and_tile_kernel launches (intersection + fused BM25 epilogue)    */
+  double ms_topk_kernel;      /* topk_kernel launches                                             */
+  double ms_total;            /* first event .. last event of the batch                           */
+  uint64_t launches;          /* kernels launched for the batch                                   */
+  uint64_t n_df_tiles;        /* CTAs of df_tile_kernel                                           */
+  uint64_t n_and_tiles;       /* CTAs of and_tile_kernel                                          */
+  uint64_t algo_bytes_intersect; /* B_intersect = sum_q [ sum_lists min(4|P|, ceil(N/8)) + 4|R| ]  */
+  uint64_t algo_bytes_score;     /* B_score = sum_q [ sum_{d in R}(text_bytes(d) + 4) + 12 k ]      */
+  uint64_t algo_bytes_df;        /* B_df = sum over scanned terms, sum_{d in C_t} text_bytes(d)    */
+  uint64_t algo_bytes_df_lists;  /* min(4|P|, ceil(N/8)) over the lists of the scanned terms       */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+  uint64_t driver_entries;    /* posting entries walked by and_tile_kernel                        */
+  uint64_t result_docs;       /* sum |R|                                                          */
+  uint64_t df_candidates;     /* documents whose text was scanned for df                          */
+  uint64_t unique_terms;
+} mgx_batch_stats_t;
+
 /* Staged form of the same call, for doc-range sharded deployments (one process
  * per GPU): the two exchange points of SURVEY.md §8(e) sit between the stages.
- *   prepare : host compile + H2D + dictionary lookup + planning
+ *   prepare : host compile + H2D of the compiled batch
+ *   plan    : dictionary lookup + per-term / per-query planning (device; one size read-back)
  *   df      : per-shard verified document frequencies -> d_df (DEVICE, n_terms uint64)
  *             [caller all-reduces d_df (SUM) across shards]
  *   search  : AND + NOT + BM25 + top-k with the GLOBAL df -> DEVICE outputs
@@ -196,6 +220,11 @@ int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint
                       const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
                       const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
                       void* stream, mgx_batch_t** out);
+/* Planning stage of a prepared batch (dictionary lookup, per-term and per-query plans). Called
+ * implicitly by the df / search stages if it has not run yet. */
+int mgx_batch_plan_device(mgx_batch_t* batch);
+/* Stats of a staged batch; synchronises the batch's stream. */
+int mgx_batch_get_stats(mgx_batch_t* batch, mgx_batch_stats_t* out);
 /* Number of search-term slots (= length of d_df / out_df). */
 uint64_t mgx_batch_term_slots(const mgx_batch_t* batch);
 int mgx_batch_df_device(mgx_batch_t* batch, uint64_t* d_df);
@@ -213,26 +242,7 @@ int mgx_merge_topk_device(int32_t device, void* stream, const mgx_query_params_t
                           const uint32_t* d_count_all, const uint64_t* d_total_all, uint32_t* d_ids_out,
                           double* d_scores_out, uint32_t* d_count_out, uint64_t* d_total_out);
 
-/* Timing / accounting of the last mgx_query_batch or staged run on this index
- * (device times from CUDA events on the launch stream; bytes as defined in
- * SURVEY.md §8(d) and DESIGN.md). */
-typedef struct {
-  double ms_total;            /* prepare .. outputs ready, device time                 */
-  double ms_df;               /* df stage kernels                                       */
-  double ms_search;           /* intersect + score kernels                              */
-  double ms_topk;             /* top-k kernels                                          */
-  uint64_t launches;          /* kernels launched for the batch                         */
-  uint64_t algo_bytes_intersect; /* B_intersect: sum min(4|P|, N/8) + 4|R|              */
-  uint64_t algo_bytes_score;     /* B_score                                             */
-  uint64_t algo_bytes_df;        /* B_df                                                */
-  uint64_t h2d_bytes;
-  uint64_t d2h_bytes;
-  uint64_t driver_entries;    /* posting entries actually walked by the intersect kernel */
-  uint64_t result_docs;       /* sum |R|                                                 */
-  uint64_t df_candidates;     /* docs whose text was scanned for df                      */
-  uint64_t unique_terms;
-} mgx_batch_stats_t;
-
+/* Stats of the last mgx_query_batch on this index. */
 int mgx_index_last_batch_stats(const mgx_index_t* index, mgx_batch_stats_t* out);
 
 /* ---------------------------------------------------------------- scoring */

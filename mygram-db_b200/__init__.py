@@ -64,11 +64,15 @@ class QueryParams(C.Structure):
 
 
 class BatchStats(C.Structure):
-    _fields_ = [("ms_total", C.c_double), ("ms_df", C.c_double), ("ms_search", C.c_double), ("ms_topk", C.c_double),
-                ("launches", C.c_uint64), ("algo_bytes_intersect", C.c_uint64), ("algo_bytes_score", C.c_uint64),
-                ("algo_bytes_df", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("driver_entries", C.c_uint64), ("result_docs", C.c_uint64), ("df_candidates", C.c_uint64),
-                ("unique_terms", C.c_uint64)]
+    _fields_ = [("ms_plan", C.c_double), ("ms_df_kernel", C.c_double), ("ms_and_kernel", C.c_double),
+                ("ms_topk_kernel", C.c_double), ("ms_total", C.c_double), ("launches", C.c_uint64),
+                ("n_df_tiles", C.c_uint64), ("n_and_tiles", C.c_uint64), ("algo_bytes_intersect", C.c_uint64),
+                ("algo_bytes_score", C.c_uint64), ("algo_bytes_df", C.c_uint64), ("algo_bytes_df_lists", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("driver_entries", C.c_uint64),
+                ("result_docs", C.c_uint64), ("df_candidates", C.c_uint64), ("unique_terms", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 _lib = None
@@ -111,6 +115,8 @@ def lib():
                                   C.c_uint64, u32p, f64p, u32p, u64p, u64p]
     L.mgx_batch_prepare.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
                                     C.c_void_p, C.POINTER(C.c_void_p)]
+    L.mgx_batch_plan_device.argtypes = [C.c_void_p]
+    L.mgx_batch_get_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
     L.mgx_batch_term_slots.restype = C.c_uint64
     L.mgx_batch_term_slots.argtypes = [C.c_void_p]
     L.mgx_batch_df_device.argtypes = [C.c_void_p, C.c_void_p]

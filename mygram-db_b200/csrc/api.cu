@@ -304,29 +304,6 @@ int check_params(const mgx_query_params_t& p) {
   return MGX_OK;
 }
 
-void new_batch_events(Batch& b) {
-  for (auto& e : b.ev) {
-    MGX_CUDA(cudaEventCreate(&e));
-  }
-}
-
-void finish_stats(Batch& b, uint64_t d2h_bytes) {
-  Index& ix = *b.ix;
-  float ms = 0.f;
-  mgx_batch_stats_t& s = ix.last_stats;
-  cudaEventElapsedTime(&ms, b.ev[0], b.ev[4]);
-  s.ms_total = ms;
-  cudaEventElapsedTime(&ms, b.ev[1], b.ev[2]);
-  s.ms_df = ms;
-  cudaEventElapsedTime(&ms, b.ev[2], b.ev[3]);
-  s.ms_search = ms;
-  s.ms_topk = 0.0;
-  s.launches = g_launches.load() - b.launches_at_start;
-  s.h2d_bytes = b.h2d_bytes;
-  s.d2h_bytes = d2h_bytes;
-  s.unique_terms = b.n_terms;
-}
-
 }  // namespace
 }  // namespace mgx
 
@@ -655,7 +632,7 @@ int run_set_op(mgx_index_t* index, SetOp op, const uint32_t* driver_ids, uint64_
       b.explicit_driver.n = n_driver;
     }
     batch_upload(b, terms, queries, {});
-    batch_plan(b, false);
+    batch_plan(b);
     std::vector<uint64_t> set_off;
     DevBuf<uint32_t> d_sets;
     batch_search_sets(b, &set_off, &d_sets);
@@ -827,8 +804,6 @@ int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint
     b.params = *params;
     b.stream = stream != nullptr ? static_cast<cudaStream_t>(stream) : ix.stream;
     b.launches_at_start = g_launches.load();
-    new_batch_events(b);
-    MGX_CUDA(cudaEventRecord(b.ev[0], b.stream));
     std::vector<HostTerm> terms;
     std::vector<HostQuery> queries;
     std::vector<uint32_t> slot_tid;
@@ -840,9 +815,32 @@ int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint
       return rc;
     }
     batch_upload(b, terms, queries, slot_tid);
-    batch_plan(b, params->compute_score != 0);
-    MGX_CUDA(cudaEventRecord(b.ev[1], b.stream));
     *out = h.release();
+    return MGX_OK;
+  });
+}
+
+int mgx_batch_plan_device(mgx_batch_t* batch) {
+  if (batch == nullptr) {
+    return invalid("null batch");
+  }
+  return guarded([&]() {
+    DeviceGuard guard(batch->b.ix->device);
+    if (!batch->b.planned) {
+      batch_plan(batch->b);
+    }
+    return MGX_OK;
+  });
+}
+
+int mgx_batch_get_stats(mgx_batch_t* batch, mgx_batch_stats_t* out) {
+  if (batch == nullptr || out == nullptr) {
+    return invalid("null argument");
+  }
+  return guarded([&]() {
+    DeviceGuard guard(batch->b.ix->device);
+    batch->b.collect_stats(out);
+    out->launches = g_launches.load() - batch->b.launches_at_start;
     return MGX_OK;
   });
 }
@@ -862,7 +860,6 @@ int mgx_batch_df_device(mgx_batch_t* batch, uint64_t* d_df) {
     if (d_df != nullptr) {
       batch_df_to_slots(b, d_df);
     }
-    MGX_CUDA(cudaEventRecord(b.ev[2], b.stream));
     return MGX_OK;
   });
 }
@@ -877,7 +874,6 @@ int mgx_batch_search_device(mgx_batch_t* batch, const uint64_t* d_df, uint64_t s
     DeviceGuard guard(b.ix->device);
     if (b.params.compute_score != 0 && !b.df_done) {
       batch_df(b);
-      MGX_CUDA(cudaEventRecord(b.ev[2], b.stream));
     }
     // a shard returns its best (offset + limit) records un-offset; mgx_merge_topk_device applies the offset
     const mgx_query_params_t saved = b.params;
@@ -887,7 +883,6 @@ int mgx_batch_search_device(mgx_batch_t* batch, const uint64_t* d_df, uint64_t s
     b.params.offset = 0;
     batch_search(b, d_df, stride, d_ids, d_scores, d_count, d_total);
     b.params = saved;
-    MGX_CUDA(cudaEventRecord(b.ev[3], b.stream));
     return MGX_OK;
   });
 }
@@ -898,11 +893,6 @@ void mgx_batch_destroy(mgx_batch_t* batch) {
   }
   DeviceGuard guard(batch->b.ix->device);
   cudaStreamSynchronize(batch->b.stream);
-  for (auto& e : batch->b.ev) {
-    if (e != nullptr) {
-      cudaEventDestroy(e);
-    }
-  }
   delete batch;
 }
 
@@ -965,9 +955,7 @@ int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64
       batch_df(b);
     }
     batch_df_to_slots(b, d_df.p);
-    MGX_CUDA(cudaEventRecord(b.ev[2], st));
     batch_search(b, nullptr, stride, d_ids.p, params->compute_score != 0 ? d_scores.p : nullptr, d_count.p, d_total.p);
-    MGX_CUDA(cudaEventRecord(b.ev[3], st));
     uint64_t d2h = 0;
     MGX_CUDA(cudaMemcpyAsync(out_ids, d_ids.p, n_queries * stride * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     d2h += n_queries * stride * sizeof(uint32_t);
@@ -982,9 +970,11 @@ int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64
       MGX_CUDA(cudaMemcpyAsync(out_df, d_df.p, b.n_slots * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
       d2h += b.n_slots * sizeof(uint64_t);
     }
-    MGX_CUDA(cudaEventRecord(b.ev[4], st));
+    b.mark_last();
     MGX_CUDA(cudaStreamSynchronize(st));
-    finish_stats(b, d2h);
+    b.d2h_bytes += d2h;
+    b.collect_stats(&ix.last_stats);
+    ix.last_stats.launches = g_launches.load() - b.launches_at_start;
     return MGX_OK;
   });
   mgx_batch_destroy(batch);

@@ -65,6 +65,7 @@ struct BatchView {
   // explicit driver (query 0)
   const uint32_t* explicit_ids;
   uint32_t explicit_n;
+  unsigned long long* stats;  // StatSlot counters
 };
 
 struct ScoreParams {
@@ -264,7 +265,8 @@ __global__ void lookup_kernel(const uint64_t* __restrict__ term_keys, const uint
   }
 }
 
-__global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf8, const uint8_t* __restrict__ raw_flags) {
+__global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf8, const uint8_t* __restrict__ raw_flags,
+                                 uint64_t bitmap_bytes) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= bv.n_terms) {
     return;
@@ -295,6 +297,11 @@ __global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf
       df = est;  // the term is exactly its one n-gram: every posting contains it as a substring
     } else {
       tiles = static_cast<uint32_t>((est + kTile - 1) / kTile);
+      unsigned long long bytes = 0;
+      for (uint32_t i = k0; i < k1; ++i) {
+        bytes += umin64(4ULL * bv.key_len[i], bitmap_bytes);
+      }
+      atomicAdd(bv.stats + kStatDfLists, bytes);
     }
   }
   bv.t_df[t] = df;
@@ -307,6 +314,7 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
   __shared__ uint32_t s_n;
   __shared__ uint32_t s_term;
   __shared__ uint32_t s_hits;
+  __shared__ unsigned long long s_bytes;
   __shared__ __align__(16) uint8_t s_text[kTileThreads / 32][kStageBuf];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
@@ -314,6 +322,7 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
     s_term = find_segment(bv.t_df_tile_off, bv.n_terms, blockIdx.x);
     s_n = 0;
     s_hits = 0;
+    s_bytes = 0;
   }
   __syncthreads();
   const uint32_t t = s_term;
@@ -341,17 +350,28 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
   const uint8_t* term = bv.term_bytes + bv.term_boff[t];
   const uint32_t tl = bv.term_boff[t + 1] - bv.term_boff[t];
   uint32_t hits = 0;
+  unsigned long long text_bytes = 0;
   for (uint32_t s = warp; s < n; s += kTileThreads / 32) {
     DocText d = doc_open(iv, s_doc[s], s_text[warp]);
+    text_bytes += d.len;
     hits += doc_count_term(d, term, tl, true) != 0 ? 1u : 0u;
     __syncwarp();
   }
   if (lane == 0 && hits != 0) {
     atomicAdd(&s_hits, hits);
   }
+  if (lane == 0 && text_bytes != 0) {
+    atomicAdd(&s_bytes, text_bytes);
+  }
   __syncthreads();
-  if (threadIdx.x == 0 && s_hits != 0) {
-    atomicAdd(reinterpret_cast<unsigned long long*>(bv.t_df + t), static_cast<unsigned long long>(s_hits));
+  if (threadIdx.x == 0) {
+    if (s_hits != 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(bv.t_df + t), static_cast<unsigned long long>(s_hits));
+    }
+    if (n != 0) {
+      atomicAdd(bv.stats + kStatDfBytes, s_bytes);
+      atomicAdd(bv.stats + kStatDfCandidates, static_cast<unsigned long long>(n));
+    }
   }
 }
 
@@ -460,6 +480,14 @@ __global__ void query_plan_kernel(IndexView iv, BatchView bv) {
     flags |= kQEmpty;
     driver_len = 0;
   }
+  if (!empty) {
+    const uint64_t bitmap_bytes = (iv.n_docs + 7) / 8;
+    unsigned long long bytes = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      bytes += umin64(4ULL * bv.q_list_len[l0 + i], bitmap_bytes);
+    }
+    atomicAdd(bv.stats + kStatIntersectLists, bytes);
+  }
   bv.q_nlists[q] = n;
   bv.q_flags[q] = flags;
   bv.q_driver_len[q] = driver_len;
@@ -532,6 +560,7 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   __shared__ uint8_t s_keep[kTile];
   __shared__ uint32_t s_warp[kTileThreads / 32];
   __shared__ uint32_t s_q;
+  __shared__ unsigned long long s_bytes;
   __shared__ ListRef s_lists[kMaxCachedLists];
   __shared__ __align__(16) uint8_t s_text[kTileThreads / 32][kStageBuf];
   const unsigned lane = threadIdx.x & 31u;
@@ -539,6 +568,7 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   const uint64_t tile_global = tile_base + blockIdx.x;
   if (threadIdx.x == 0) {
     s_q = find_segment(bv.q_tile_off, bv.n_queries, tile_global);
+    s_bytes = 0;
   }
   __syncthreads();
   const uint32_t q = s_q;
@@ -638,12 +668,14 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
     need_text = bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid];
   }
   if (need_text) {
+    unsigned long long text_bytes = 0;
     for (uint32_t s = warp; s < total; s += kTileThreads / 32) {
       const uint32_t doc = s_doc[s];
       bool keep = true;
       double score = 0.0;
       if (doc != kNone) {
         DocText d = doc_open(iv, doc, s_text[warp]);
+        text_bytes += d.len + 4;
         if (d.len > 0) {
           const double dl = static_cast<double>(__ldg(iv.doc_len + doc));
           // length_norm = 1 - b + b * dl / max(avgdl, 1)
@@ -688,6 +720,9 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
         s_score[s] = score;
       }
     }
+    if (lane == 0 && text_bytes != 0) {
+      atomicAdd(&s_bytes, text_bytes);
+    }
     __syncthreads();
   }
 
@@ -717,6 +752,12 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   }
   if (threadIdx.x == 0) {
     tile_count[blockIdx.x] = kept_total;
+    if (kept_total != 0) {
+      atomicAdd(bv.stats + kStatResultDocs, static_cast<unsigned long long>(kept_total));
+    }
+    if (s_bytes != 0) {
+      atomicAdd(bv.stats + kStatScoreBytes, s_bytes);
+    }
   }
 }
 
@@ -1275,6 +1316,7 @@ BatchView make_batch_view(Batch& b) {
   v.n_queries = b.n_queries;
   v.explicit_ids = b.explicit_driver.d_ids;
   v.explicit_n = static_cast<uint32_t>(b.explicit_driver.n);
+  v.stats = b.d_stats.p;
   return v;
 }
 
@@ -1290,6 +1332,88 @@ void upload(DevBuf<T>& dst, const std::vector<T>& src, cudaStream_t stream, uint
 unsigned grid_for(uint64_t n, unsigned block) { return static_cast<unsigned>((n + block - 1) / block); }
 
 }  // namespace
+
+// ------------------------------------------------------------------ batch timing / accounting
+void Batch::time_begin(int kind) {
+  Timed t{nullptr, nullptr, kind};
+  MGX_CUDA(cudaEventCreate(&t.a));
+  MGX_CUDA(cudaEventCreate(&t.b));
+  MGX_CUDA(cudaEventRecord(t.a, stream));
+  if (ev_first == nullptr) {
+    MGX_CUDA(cudaEventCreate(&ev_first));
+    MGX_CUDA(cudaEventRecord(ev_first, stream));
+  }
+  timed.push_back(t);
+}
+
+void Batch::time_end() { MGX_CUDA(cudaEventRecord(timed.back().b, stream)); }
+
+void Batch::mark_last() {
+  if (ev_last == nullptr) {
+    MGX_CUDA(cudaEventCreate(&ev_last));
+  }
+  MGX_CUDA(cudaEventRecord(ev_last, stream));
+}
+
+Batch::~Batch() {
+  for (auto& t : timed) {
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  if (ev_first != nullptr) {
+    cudaEventDestroy(ev_first);
+  }
+  if (ev_last != nullptr) {
+    cudaEventDestroy(ev_last);
+  }
+}
+
+void Batch::collect_stats(mgx_batch_stats_t* out) {
+  MGX_CUDA(cudaStreamSynchronize(stream));
+  mgx_batch_stats_t s{};
+  for (const auto& t : timed) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.a, t.b) != cudaSuccess) {
+      (void)cudaGetLastError();
+      continue;
+    }
+    if (t.kind == 0) {
+      s.ms_plan += ms;
+    } else if (t.kind == 1) {
+      s.ms_df_kernel += ms;
+    } else if (t.kind == 2) {
+      s.ms_and_kernel += ms;
+    } else {
+      s.ms_topk_kernel += ms;
+    }
+  }
+  if (ev_first != nullptr && ev_last != nullptr) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev_first, ev_last) == cudaSuccess) {
+      s.ms_total = ms;
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  unsigned long long h[kStatCount] = {0};
+  if (d_stats.p != nullptr) {
+    MGX_CUDA(cudaMemcpy(h, d_stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+  }
+  const uint64_t k = params.limit + params.offset;
+  s.n_df_tiles = n_df_tiles;
+  s.n_and_tiles = n_and_tiles;
+  s.algo_bytes_intersect = h[kStatIntersectLists] + 4ULL * h[kStatResultDocs];
+  s.algo_bytes_score = params.compute_score != 0 ? h[kStatScoreBytes] + 12ULL * k * n_queries : 0;
+  s.algo_bytes_df = h[kStatDfBytes];
+  s.algo_bytes_df_lists = h[kStatDfLists];
+  s.h2d_bytes = h2d_bytes;
+  s.d2h_bytes = d2h_bytes;
+  s.driver_entries = driver_entries;
+  s.result_docs = h[kStatResultDocs];
+  s.df_candidates = h[kStatDfCandidates];
+  s.unique_terms = n_terms;
+  *out = s;
+}
 
 // ------------------------------------------------------------------ host orchestration
 void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
@@ -1365,10 +1489,16 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vecto
   b.d_q_idf.alloc(tids.size());
   b.h2d_bytes = h2d;
 
-  // lookup + term planning need the raw flags on the device
-  DevBuf<uint8_t> d_raw;
-  upload(d_raw, raw, st, &h2d);
+  upload(b.d_term_flags, raw, st, &h2d);
+  b.d_stats.alloc(kStatCount);
+  MGX_CUDA(cudaMemsetAsync(b.d_stats.p, 0, kStatCount * sizeof(unsigned long long), st));
+  b.h2d_bytes = h2d;
+}
+
+void batch_plan(Batch& b) {
+  cudaStream_t st = b.stream;
   Index& ix = *b.ix;
+  b.time_begin(0);
   if (b.n_keys > 0) {
     lookup_kernel<<<grid_for(b.n_keys, 256), 256, 0, st>>>(ix.d_term_keys.p, ix.d_term_off.p, ix.n_terms, b.d_keys.p,
                                                           b.n_keys, b.d_key_list.p, b.d_key_len.p);
@@ -1377,17 +1507,11 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vecto
   BatchView bv = make_batch_view(b);
   if (b.n_terms > 0) {
     term_plan_kernel<<<grid_for(b.n_terms, 128), 128, 0, st>>>(bv, b.params.compute_score != 0 ? 1 : 0,
-                                                               ix.all_valid_utf8 ? 1 : 0, d_raw.p);
+                                                               ix.all_valid_utf8 ? 1 : 0, b.d_term_flags.p,
+                                                               (ix.n_docs + 7) / 8);
     MGX_LAUNCH_CHECK();
   }
   exclusive_scan_u32_u64(b.d_t_df_tiles.p, b.d_t_df_tile_off.p, b.n_terms, st);
-  MGX_CUDA(cudaStreamSynchronize(st));  // d_raw goes out of scope
-}
-
-void batch_plan(Batch& b, bool /*compute_df*/) {
-  cudaStream_t st = b.stream;
-  Index& ix = *b.ix;
-  BatchView bv = make_batch_view(b);
   const IndexView iv = make_view(ix);
   if (b.n_queries > 0) {
     query_plan_kernel<<<grid_for(b.n_queries, 128), 128, 0, st>>>(iv, bv);
@@ -1401,25 +1525,31 @@ void batch_plan(Batch& b, bool /*compute_df*/) {
                            cudaMemcpyDeviceToHost, st));
   MGX_CUDA(cudaMemcpyAsync(b.h_q_rec_off.data(), b.d_q_rec_off.p, (b.n_queries + 1) * sizeof(uint64_t),
                            cudaMemcpyDeviceToHost, st));
+  MGX_CUDA(cudaMemcpyAsync(&b.n_df_tiles, b.d_t_df_tile_off.p + b.n_terms, sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                           st));
+  b.time_end();
   MGX_CUDA(cudaStreamSynchronize(st));
+  b.d2h_bytes += 2 * (b.n_queries + 1) * sizeof(uint64_t) + sizeof(uint64_t);
   b.planned = true;
 }
 
 void batch_df(Batch& b) {
   cudaStream_t st = b.stream;
   Index& ix = *b.ix;
-  uint64_t total_tiles = 0;
-  MGX_CUDA(cudaMemcpyAsync(&total_tiles, b.d_t_df_tile_off.p + b.n_terms, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  MGX_CUDA(cudaStreamSynchronize(st));
+  if (!b.planned) {
+    batch_plan(b);
+  }
+  const uint64_t total_tiles = b.n_df_tiles;
   if (total_tiles > 0) {
     if (total_tiles > 0x7FFFFFFFULL) {
       set_last_error("df stage: too many tiles in one batch");
       throw CudaFailure{MGX_ERR_UNSUPPORTED};
     }
+    b.time_begin(1);
     df_tile_kernel<<<static_cast<unsigned>(total_tiles), kTileThreads, 0, st>>>(make_view(ix), make_batch_view(b));
     MGX_LAUNCH_CHECK();
+    b.time_end();
   }
-  ix.last_stats.df_candidates = total_tiles * kTile;  // upper bound on postings walked
   b.df_done = true;
 }
 
@@ -1504,10 +1634,13 @@ void run_tiles(Batch& b, const Chunk& c, const ScoreParams& sp) {
       set_last_error("search stage: too many tiles in one chunk");
       throw CudaFailure{MGX_ERR_UNSUPPORTED};
     }
+    b.time_begin(2);
     and_tile_kernel<<<static_cast<unsigned>(n_tiles), kTileThreads, 0, st>>>(
         make_view(*b.ix), make_batch_view(b), sp, tile_base, rec_base, b.d_tile_count.p, b.d_rec_doc.p,
         b.d_rec_score.p);
     MGX_LAUNCH_CHECK();
+    b.time_end();
+    b.n_and_tiles += n_tiles;
   }
 }
 
@@ -1516,6 +1649,9 @@ void run_tiles(Batch& b, const Chunk& c, const ScoreParams& sp) {
 void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_t* d_ids, double* d_scores,
                   uint32_t* d_count, uint64_t* d_total) {
   cudaStream_t st = b.stream;
+  if (!b.planned) {
+    batch_plan(b);
+  }
   prepare_scoring(b, d_df_slots);
   const ScoreParams sp = score_params(b);
   const auto chunks = make_chunks(b, scratch_records(b));
@@ -1526,17 +1662,23 @@ void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_
     }
     run_tiles(b, c, sp);
     driver_entries += b.h_q_rec_off[c.q1] - b.h_q_rec_off[c.q0];
+    b.time_begin(3);
     topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.h_q_rec_off[c.q0],
                                              b.d_tile_count.p, b.d_rec_doc.p, b.d_rec_score.p,
                                              b.params.compute_score, b.params.descending, b.params.limit,
                                              b.params.offset, stride, d_ids, d_scores, d_count, d_total);
     MGX_LAUNCH_CHECK();
+    b.time_end();
   }
-  b.ix->last_stats.driver_entries = driver_entries;
+  b.driver_entries += driver_entries;
+  b.mark_last();
 }
 
 void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32_t>* d_sets) {
   cudaStream_t st = b.stream;
+  if (!b.planned) {
+    batch_plan(b);
+  }
   ScoreParams sp = score_params(b);
   sp.compute_score = 0;
   const auto chunks = make_chunks(b, scratch_records(b));

@@ -82,12 +82,43 @@ struct Batch {
   std::vector<uint64_t> h_q_tile_off;
   std::vector<uint64_t> h_q_rec_off;
 
+  DevBuf<uint8_t> d_term_flags;   // [T] bit0 raw, bit1 exact_single
+  DevBuf<unsigned long long> d_stats;  // device-side accounting, see StatSlot
+
   ExplicitDriver explicit_driver;
   uint64_t h2d_bytes = 0;
+  uint64_t d2h_bytes = 0;
   uint64_t launches_at_start = 0;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t n_df_tiles = 0;
+  uint64_t n_and_tiles = 0;
+  uint64_t driver_entries = 0;
   bool planned = false;
   bool df_done = false;
+
+  // CUDA-event timing of the named kernels on the launch stream
+  struct Timed {
+    cudaEvent_t a;
+    cudaEvent_t b;
+    int kind;  // 0 plan, 1 df kernel, 2 and kernel, 3 topk kernel
+  };
+  std::vector<Timed> timed;
+  cudaEvent_t ev_first = nullptr;
+  cudaEvent_t ev_last = nullptr;
+  void time_begin(int kind);
+  void time_end();
+  void mark_last();
+  void collect_stats(mgx_batch_stats_t* out);  // synchronises the stream
+  ~Batch();
+};
+
+enum StatSlot : int {
+  kStatIntersectLists = 0,  // sum_q sum_lists min(4|P|, ceil(N/8))
+  kStatResultDocs = 1,      // sum |R|
+  kStatScoreBytes = 2,      // sum_{d in R} (text_bytes + 4)
+  kStatDfBytes = 3,         // text bytes scanned for df
+  kStatDfCandidates = 4,
+  kStatDfLists = 5,
+  kStatCount = 8
 };
 
 // One compiled query term.
@@ -107,7 +138,7 @@ struct HostQuery {
 // query.cu
 void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
                   const std::vector<uint32_t>& slot_tid);
-void batch_plan(Batch& b, bool compute_df);
+void batch_plan(Batch& b);
 void batch_df(Batch& b);
 // Runs the intersect/score kernels and the per-query output kernel. Outputs are DEVICE pointers.
 // set_mode: 0 = top-k by score or first ids (params.limit/offset), 1 = full ascending sets

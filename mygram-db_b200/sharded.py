@@ -1,0 +1,180 @@
+"""sharded.py — doc-ID-range sharding of the search core across the GPUs of one node.
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch). The reference has no
+distributed layer; this is the B200-native addition of SURVEY.md §8(e):
+
+  * shard r owns the documents of global index range [r*ceil(N/G), (r+1)*ceil(N/G)) and builds its own
+    dictionary / CSR / text arena from them -- the build needs no exchange;
+  * every rank sees the whole query batch;
+  * exchange 1 (tiny): all-reduce(SUM) of the per-term verified document frequencies and, once per index
+    generation, of the corpus statistics (doc_count, total_doc_length) -- BM25 must use GLOBAL statistics so
+    that scores are identical for every shard count;
+  * exchange 2: ONE all-gather of the fixed-size per-shard top-k records (ids u32, scores f64, counts, totals),
+    followed by the rank-based merge kernel (mgx_merge_topk_device).
+
+The protocol is written against a small backend interface so that the same code drives the CUDA library
+(`MgxShardBackend`) and, in the CPU test-suite, an oracle-backed stand-in over the gloo backend.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+
+def shard_range(n_docs_total, world_size, rank):
+    per = -(-n_docs_total // world_size)
+    lo = min(n_docs_total, rank * per)
+    hi = min(n_docs_total, lo + per)
+    return lo, hi
+
+
+class NoDist:
+    """Single-process stand-in for torch.distributed."""
+    world_size = 1
+    rank = 0
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def all_gather(self, t):
+        return t.unsqueeze(0) if hasattr(t, "unsqueeze") else t[None]
+
+    def barrier(self):
+        pass
+
+
+class TorchDist:
+    """torch.distributed wrapper (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, dist):
+        self.dist = dist
+        self.world_size = dist.get_world_size()
+        self.rank = dist.get_rank()
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t
+
+    def all_gather(self, t):
+        import torch
+        out = torch.empty((self.world_size,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1))
+        return out
+
+    def barrier(self):
+        self.dist.barrier()
+
+
+def run_sharded_batch(backend, comm, batch):
+    """One query batch over all shards. `backend` implements:
+        local_df(batch)                    -> int64 tensor [n_term_slots]   (this shard's verified df)
+        search(batch, global_df)           -> (ids [Q,S] int32-as-uint32, scores [Q,S] f64, count [Q] int32, total [Q] int64)
+        merge(ids_all, scores_all, count_all, total_all) -> (ids, scores, count, total)
+    Returns the merged (ids, scores, count, total), identical on every rank."""
+    df = backend.local_df(batch)
+    if comm.world_size > 1:
+        df = comm.all_reduce_sum(df)
+    ids, scores, count, total = backend.search(batch, df)
+    if comm.world_size == 1:
+        return backend.merge(ids[None], scores[None], count[None], total[None])
+    return backend.merge(comm.all_gather(ids), comm.all_gather(scores), comm.all_gather(count),
+                         comm.all_gather(total))
+
+
+class MgxShardBackend:
+    """CUDA backend: staged C ABI (mgx_batch_*) on the current torch stream."""
+
+    def __init__(self, mgx, index, params, stride, device):
+        import torch
+        self.torch = torch
+        self.mgx = mgx
+        self.index = index
+        self.params = params
+        self.stride = stride
+        self.device = device
+        self.L = mgx.lib()
+        self.stats = []
+        self.collect_stats = False
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def prepare(self, arena, offsets, qbeg, n_queries):
+        """Host compile + H2D of one batch; returns an opaque prepared batch."""
+        h = C.c_void_p()
+        m = self.mgx
+        m._check(self.L.mgx_batch_prepare(self.index._h, C.byref(self.params), n_queries, m._ptr(arena, m.u8p),
+                                          m._ptr(offsets, m.u64p), m._ptr(qbeg, m.u64p), None, None, None,
+                                          self._stream(), C.byref(h)))
+        return {"h": h, "n_queries": n_queries, "n_slots": int(self.L.mgx_batch_term_slots(h))}
+
+    def release(self, batch):
+        if self.collect_stats:
+            s = self.mgx.BatchStats()
+            self.mgx._check(self.L.mgx_batch_get_stats(batch["h"], C.byref(s)))
+            self.stats.append(s.as_dict())
+        self.L.mgx_batch_destroy(batch["h"])
+
+    def local_df(self, batch):
+        t = self.torch
+        df = t.zeros(max(1, batch["n_slots"]), dtype=t.int64, device=self.device)
+        self.mgx._check(self.L.mgx_batch_plan_device(batch["h"]))
+        self.mgx._check(self.L.mgx_batch_df_device(batch["h"], C.c_void_p(df.data_ptr())))
+        return df
+
+    def search(self, batch, df):
+        t = self.torch
+        Q, S = batch["n_queries"], self.stride
+        ids = t.zeros((Q, S), dtype=t.int32, device=self.device)
+        scores = t.zeros((Q, S), dtype=t.float64, device=self.device)
+        count = t.zeros(Q, dtype=t.int32, device=self.device)
+        total = t.zeros(Q, dtype=t.int64, device=self.device)
+        self.mgx._check(self.L.mgx_batch_search_device(batch["h"], C.c_void_p(df.data_ptr()), S,
+                                                       C.c_void_p(ids.data_ptr()), C.c_void_p(scores.data_ptr()),
+                                                       C.c_void_p(count.data_ptr()), C.c_void_p(total.data_ptr())))
+        return ids, scores, count, total
+
+    def merge(self, ids_all, scores_all, count_all, total_all):
+        t = self.torch
+        G, Q, S = ids_all.shape
+        ids = t.zeros((Q, S), dtype=t.int32, device=self.device)
+        scores = t.zeros((Q, S), dtype=t.float64, device=self.device)
+        count = t.zeros(Q, dtype=t.int32, device=self.device)
+        total = t.zeros(Q, dtype=t.int64, device=self.device)
+        self.mgx._check(self.L.mgx_merge_topk_device(
+            self.device.index if self.device.index is not None else 0, self._stream(), C.byref(self.params), G, Q, S,
+            C.c_void_p(ids_all.data_ptr()), C.c_void_p(scores_all.data_ptr()), C.c_void_p(count_all.data_ptr()),
+            C.c_void_p(total_all.data_ptr()), C.c_void_p(ids.data_ptr()), C.c_void_p(scores.data_ptr()),
+            C.c_void_p(count.data_ptr()), C.c_void_p(total.data_ptr())))
+        return ids, scores, count, total
+
+
+def merge_topk_reference(params_compute_score, descending, limit, offset, ids_all, scores_all, count_all, total_all,
+                         stride):
+    """Plain numpy statement of mgx_merge_topk_device (SortByScore's comparator,
+    result_sorter.cpp:681-686). Used by the gloo tests and to check the merge kernel."""
+    G, Q, _ = ids_all.shape
+    ids = np.zeros((Q, stride), dtype=np.uint32)
+    scores = np.zeros((Q, stride), dtype=np.float64)
+    count = np.zeros(Q, dtype=np.uint32)
+    total = total_all.sum(axis=0).astype(np.uint64)
+    for q in range(Q):
+        recs = []
+        for g in range(G):
+            c = int(count_all[g, q])
+            recs += [(float(scores_all[g, q, i]), int(ids_all[g, q, i]), g, i) for i in range(c)]
+        if params_compute_score:
+            recs.sort(key=lambda r: (-r[0], -r[1]) if descending else (r[0], r[1]))
+        else:
+            recs.sort(key=lambda r: (r[2], r[3]))  # concatenate shard runs in shard order
+        skip = min(len(recs), offset)
+        keep = recs[skip:]
+        if limit:
+            keep = keep[:limit]
+        keep = keep[:stride]
+        count[q] = len(keep)
+        for i, r in enumerate(keep):
+            ids[q, i] = r[1]
+            scores[q, i] = r[0]
+    return ids, scores, count, total

@@ -26,7 +26,7 @@ OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 CJK = [chr(0x4E00 + i) for i in range(24)] + ["㐀", "豈", "\U00020000", "\U0002b820"]
 OTHER = ["あ", "い", "ア", "ー", "한", "😀", "é"]
-ASCII = list("abcdefg XY01.")
+ASCII = list("abcdefg xy01.")  # inputs are pre-normalised (lower case): Index::NormalizeText stays on the host
 BAD = [b"\xff", b"\x80", b"\xe6", b"\xc0\xaf", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\xe6\x9d", b"\xf0\x9f\x98", b"\x00"]
 CONFIGS = [(2, 1, True), (2, 2, True), (3, 2, False), (1, 1, True), (3, 3, True), (2, 1, False), (1, 2, True)]
 

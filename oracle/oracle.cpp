@@ -250,6 +250,17 @@ void DeduplicateSorted(std::vector<T>& vec) {
 using DocId = uint32_t;
 using Posting = std::vector<DocId>;
 
+// Read-only view of one posting list (either a hash-map entry or a CSR slice).
+struct Span {
+  const DocId* p = nullptr;
+  size_t n = 0;
+  bool found = false;
+  const DocId* begin() const { return p; }
+  const DocId* end() const { return p + n; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+};
+
 struct SvHash {
   using is_transparent = void;
   size_t operator()(std::string_view s) const { return std::hash<std::string_view>{}(s); }
@@ -267,6 +278,13 @@ struct orc_index {
   int kanji_ngram_size = 2;  // effective, index.cpp:32
   bool cross_boundary = true;
   std::unordered_map<std::string, Posting, SvHash, SvEq> postings;
+  // Bulk-built indexes (orc_index_build_bulk) keep the same term -> sorted doc ids mapping as flat
+  // CSR arrays keyed by the packed n-gram instead of 10^7 heap-allocated map entries.
+  bool csr = false;
+  int csr_width = 0;
+  std::vector<uint64_t> csr_keys;     // ascending
+  std::vector<uint64_t> csr_offsets;  // [terms + 1]
+  std::vector<DocId> csr_postings;
 
   // DocumentStore stand-in: normalised text per doc id (document_store.cpp:144-147).
   // Two backings: owned strings for incremental adds, or a borrowed arena with
@@ -283,10 +301,7 @@ struct orc_index {
   uint64_t total_doc_length = 0;
   uint64_t doc_count = 0;
 
-  const Posting* Find(std::string_view term) const {
-    auto it = postings.find(term);
-    return it == postings.end() ? nullptr : &it->second;
-  }
+  Span Find(std::string_view term) const;
 
   // text pointer or nullptr (VisitNormalizedTextsFor, document_store_retrieval.cpp:289-322)
   bool GetText(DocId doc, std::string_view* out) const {
@@ -372,8 +387,8 @@ void StoreTextAndStats(orc_index& idx, DocId doc, std::string_view text) {
 }
 
 // TakePostingSnapshots, index.cpp:728-747.
-std::vector<const Posting*> Snapshots(const orc_index& idx, const std::vector<std::string_view>& terms) {
-  std::vector<const Posting*> out;
+std::vector<Span> Snapshots(const orc_index& idx, const std::vector<std::string_view>& terms) {
+  std::vector<Span> out;
   out.reserve(terms.size());
   for (auto term : terms) {
     out.push_back(idx.Find(term));
@@ -390,14 +405,14 @@ std::vector<DocId> SearchAnd(const orc_index& idx, const std::vector<std::string
     return {};
   }
   auto snaps = Snapshots(idx, terms);
-  for (const auto* s : snaps) {
-    if (s == nullptr) {
+  for (const auto& s : snaps) {
+    if (!s.found) {
       return {};
     }
   }
-  std::vector<DocId> result = *snaps[0];  // GetAll() materialises a copy (:338)
+  std::vector<DocId> result(snaps[0].begin(), snaps[0].end());  // GetAll() materialises a copy (:338)
   for (size_t i = 1; i < snaps.size(); ++i) {
-    const std::vector<DocId> term_docs = *snaps[i];  // GetAll() (:342)
+    const std::vector<DocId> term_docs(snaps[i].begin(), snaps[i].end());  // GetAll() (:342)
     std::vector<DocId> inter;
     std::set_intersection(result.begin(), result.end(), term_docs.begin(), term_docs.end(),
                           std::back_inserter(inter));
@@ -420,14 +435,14 @@ std::vector<DocId> SearchAnd(const orc_index& idx, const std::vector<std::string
 }
 
 // PostingList::RetainPresent, posting_list.cpp:432-474: keep sorted candidates present in the list.
-std::vector<DocId> RetainPresent(const Posting& list, const std::vector<DocId>& sorted_candidates) {
+std::vector<DocId> RetainPresent(const Span& list, const std::vector<DocId>& sorted_candidates) {
   std::vector<DocId> out;
   size_t j = 0;
   for (DocId c : sorted_candidates) {
-    while (j < list.size() && list[j] < c) {
+    while (j < list.size() && list.p[j] < c) {
       ++j;
     }
-    if (j < list.size() && list[j] == c) {
+    if (j < list.size() && list.p[j] == c) {
       out.push_back(c);  // duplicates in the candidate list are each retained
     }
   }
@@ -444,8 +459,8 @@ std::vector<DocId> FilterByNgrams(const orc_index& idx, const std::vector<DocId>
   if (snaps.empty()) {
     return candidates;
   }
-  for (const auto* s : snaps) {
-    if (s == nullptr) {
+  for (const auto& s : snaps) {
+    if (!s.found) {
       return {};
     }
   }
@@ -455,9 +470,9 @@ std::vector<DocId> FilterByNgrams(const orc_index& idx, const std::vector<DocId>
     sorted_candidates = candidates;
     std::sort(sorted_candidates.begin(), sorted_candidates.end());
   }
-  std::vector<DocId> retained = RetainPresent(*snaps[0], ascending ? candidates : sorted_candidates);
+  std::vector<DocId> retained = RetainPresent(snaps[0], ascending ? candidates : sorted_candidates);
   for (size_t i = 1; i < snaps.size() && !retained.empty(); ++i) {
-    retained = RetainPresent(*snaps[i], retained);
+    retained = RetainPresent(snaps[i], retained);
   }
   if (ascending || retained.empty()) {
     return retained;
@@ -479,10 +494,10 @@ std::vector<DocId> SearchOr(const orc_index& idx, const std::vector<std::string_
   }
   std::vector<DocId> result;
   std::vector<DocId> temp;
-  for (const auto* s : Snapshots(idx, terms)) {
-    if (s != nullptr) {
+  for (const auto& s : Snapshots(idx, terms)) {
+    if (s.found) {
       temp.clear();
-      std::set_union(result.begin(), result.end(), s->begin(), s->end(), std::back_inserter(temp));
+      std::set_union(result.begin(), result.end(), s.begin(), s.end(), std::back_inserter(temp));
       result.swap(temp);
     }
   }
@@ -515,9 +530,9 @@ std::vector<DocId> SearchByThreshold(const orc_index& idx, const std::vector<std
   if (threshold == unique_terms.size()) {
     return SearchAnd(idx, unique_terms, 0, false);
   }
-  std::vector<const Posting*> valid;
-  for (const auto* s : Snapshots(idx, unique_terms)) {
-    if (s != nullptr) {
+  std::vector<Span> valid;
+  for (const auto& s : Snapshots(idx, unique_terms)) {
+    if (s.found) {
       valid.push_back(s);
     }
   }
@@ -527,8 +542,8 @@ std::vector<DocId> SearchByThreshold(const orc_index& idx, const std::vector<std
   using HeapEntry = std::tuple<DocId, size_t, size_t>;
   std::priority_queue<HeapEntry, std::vector<HeapEntry>, std::greater<HeapEntry>> heap;
   for (size_t i = 0; i < valid.size(); ++i) {
-    if (!valid[i]->empty()) {
-      heap.emplace((*valid[i])[0], i, 0);
+    if (!valid[i].empty()) {
+      heap.emplace(valid[i].p[0], i, 0);
     }
   }
   std::vector<DocId> result;
@@ -548,8 +563,8 @@ std::vector<DocId> SearchByThreshold(const orc_index& idx, const std::vector<std
     } else {
       ++count;
     }
-    if (pos + 1 < valid[li]->size()) {
-      heap.emplace((*valid[li])[pos + 1], li, pos + 1);
+    if (pos + 1 < valid[li].size()) {
+      heap.emplace(valid[li].p[pos + 1], li, pos + 1);
     }
   }
   if (has_current && count >= threshold) {
@@ -735,8 +750,7 @@ TermInfo MakeTermInfo(const orc_index& idx, std::string_view term, const orc_que
   DeduplicateSorted(ti.ngrams);
   size_t min_size = std::numeric_limits<size_t>::max();
   for (const auto& g : ti.ngrams) {
-    const Posting* list = idx.Find(g);
-    const uint64_t size = list != nullptr ? list->size() : 0;  // EstimatePostingSize, index.cpp:756-759
+    const uint64_t size = idx.Find(g).size();  // EstimatePostingSize, index.cpp:756-759
     if (size > 0) {
       min_size = std::min(min_size, static_cast<size_t>(size));
     } else {
@@ -978,7 +992,56 @@ struct Pair {
   uint32_t doc;
 };
 
+// n-gram string -> packed key; false if it is not the UTF-8 encoding of 1..width code points
+// (then it cannot be a dictionary term).
+bool NgramToKey(std::string_view term, int width, uint64_t* key) {
+  uint32_t cps[3];
+  int n = 0;
+  const auto* data = reinterpret_cast<const unsigned char*>(term.data());
+  size_t i = 0;
+  while (i < term.size()) {
+    uint32_t cp = 0;
+    const int len = TryParseUtf8Char(data + i, term.size() - i, &cp);
+    if (len <= 0 || n >= width) {
+      return false;
+    }
+    cps[n++] = cp;
+    i += static_cast<size_t>(len);
+  }
+  if (n == 0) {
+    return false;
+  }
+  *key = PackKey(cps, n, width);
+  return true;
+}
+
 }  // namespace
+
+Span orc_index::Find(std::string_view term) const {
+  Span out;
+  if (csr) {
+    uint64_t key = 0;
+    if (!NgramToKey(term, csr_width, &key)) {
+      return out;
+    }
+    const auto it = std::lower_bound(csr_keys.begin(), csr_keys.end(), key);
+    if (it == csr_keys.end() || *it != key) {
+      return out;
+    }
+    const size_t t = static_cast<size_t>(it - csr_keys.begin());
+    out.p = csr_postings.data() + csr_offsets[t];
+    out.n = static_cast<size_t>(csr_offsets[t + 1] - csr_offsets[t]);
+    out.found = true;
+    return out;
+  }
+  auto it = postings.find(term);
+  if (it != postings.end()) {
+    out.p = it->second.data();
+    out.n = it->second.size();
+    out.found = true;
+  }
+  return out;
+}
 
 // ---------------------------------------------------------------------------
 // C ABI
@@ -1164,42 +1227,84 @@ int orc_index_build_bulk(orc_index_t* idx, const uint32_t* doc_ids, const uint8_
     idx->doc_count += cnt_sum[static_cast<size_t>(t)];
   }
 
-  // Phase 2: bucket by the top key bits so each bucket can be sorted independently.
+  // Phase 2: sample sort. Splitters are drawn from the data so that buckets are balanced even
+  // though n-gram frequencies are Zipf-skewed; every bucket is then sorted independently.
   uint64_t total = 0;
   for (const auto& p : parts) {
     total += p.size();
   }
-  constexpr int kBucketBits = 12;
-  const int shift = std::max(0, 21 * width - kBucketBits);
-  const size_t n_buckets = static_cast<size_t>(1) << kBucketBits;
-  std::vector<uint64_t> bucket_count(n_buckets + 1, 0);
-  for (const auto& p : parts) {
-    for (const auto& pr : p) {
-      bucket_count[(pr.key >> shift) + 1]++;
+  const size_t n_buckets = total < (1u << 16) ? 1 : 4096;
+  std::vector<uint64_t> splitters;  // bucket b holds keys in (splitters[b-1], splitters[b]]
+  if (n_buckets > 1) {
+    std::vector<uint64_t> sample;
+    uint64_t state = 0x9E3779B97F4A7C15ULL;
+    const size_t per_part = (n_buckets * 16) / parts.size() + 1;
+    for (const auto& p : parts) {
+      for (size_t k = 0; k < per_part && !p.empty(); ++k) {
+        state = state * 6364136223846793005ULL + 1442695040888963407ULL;
+        sample.push_back(p[(state >> 16) % p.size()].key);
+      }
+    }
+    std::sort(sample.begin(), sample.end());
+    for (size_t b = 1; b < n_buckets; ++b) {
+      splitters.push_back(sample[b * sample.size() / n_buckets]);
+    }
+    splitters.erase(std::unique(splitters.begin(), splitters.end()), splitters.end());
+  }
+  const size_t nb = splitters.size() + 1;
+  auto bucket_of = [&](uint64_t key) {
+    return static_cast<size_t>(std::lower_bound(splitters.begin(), splitters.end(), key) - splitters.begin());
+  };
+  // per-part bucket counts -> write cursors (part-major inside a bucket keeps documents ascending)
+  std::vector<std::vector<uint64_t>> counts(parts.size(), std::vector<uint64_t>(nb, 0));
+  {
+    std::vector<std::thread> threads;
+    for (size_t t = 0; t < parts.size(); ++t) {
+      threads.emplace_back([&, t]() {
+        for (const auto& pr : parts[t]) {
+          counts[t][bucket_of(pr.key)]++;
+        }
+      });
+    }
+    for (auto& th : threads) {
+      th.join();
     }
   }
-  for (size_t i = 0; i < n_buckets; ++i) {
-    bucket_count[i + 1] += bucket_count[i];
+  std::vector<uint64_t> bucket_begin(nb + 1, 0);
+  for (size_t b = 0; b < nb; ++b) {
+    uint64_t c = 0;
+    for (size_t t = 0; t < parts.size(); ++t) {
+      const uint64_t v = counts[t][b];
+      counts[t][b] = bucket_begin[b] + c;  // becomes this part's write cursor in bucket b
+      c += v;
+    }
+    bucket_begin[b + 1] = bucket_begin[b] + c;
   }
   std::vector<Pair> all(total);
   {
-    std::vector<uint64_t> cursor(bucket_count.begin(), bucket_count.end() - 1);
-    for (auto& p : parts) {  // parts are in ascending doc order, so buckets stay doc-ordered
-      for (const auto& pr : p) {
-        all[cursor[pr.key >> shift]++] = pr;
-      }
-      std::vector<Pair>().swap(p);
+    std::vector<std::thread> threads;
+    for (size_t t = 0; t < parts.size(); ++t) {
+      threads.emplace_back([&, t]() {
+        auto& cursor = counts[t];
+        for (const auto& pr : parts[t]) {
+          all[cursor[bucket_of(pr.key)]++] = pr;
+        }
+        std::vector<Pair>().swap(parts[t]);
+      });
+    }
+    for (auto& th : threads) {
+      th.join();
     }
   }
   std::atomic<size_t> next_bucket{0};
   auto sort_buckets = [&]() {
     for (;;) {
       const size_t bkt = next_bucket.fetch_add(1);
-      if (bkt >= n_buckets) {
+      if (bkt >= nb) {
         break;
       }
-      std::stable_sort(all.begin() + static_cast<std::ptrdiff_t>(bucket_count[bkt]),
-                       all.begin() + static_cast<std::ptrdiff_t>(bucket_count[bkt + 1]),
+      std::stable_sort(all.begin() + static_cast<std::ptrdiff_t>(bucket_begin[bkt]),
+                       all.begin() + static_cast<std::ptrdiff_t>(bucket_begin[bkt + 1]),
                        [](const Pair& l, const Pair& r) { return l.key < r.key; });
     }
   };
@@ -1213,22 +1318,20 @@ int orc_index_build_bulk(orc_index_t* idx, const uint32_t* doc_ids, const uint8_
     }
   }
 
-  // Phase 3: one posting list per distinct key (docs already ascending and unique per key).
-  size_t i = 0;
-  idx->postings.reserve(static_cast<size_t>(total / 8 + 16));
-  while (i < all.size()) {
-    size_t j = i;
-    while (j < all.size() && all[j].key == all[i].key) {
-      ++j;
+  // Phase 3: CSR — one posting list per distinct key (docs ascending and unique inside a key).
+  idx->csr = true;
+  idx->csr_width = width;
+  idx->csr_postings.resize(total);
+  idx->csr_keys.clear();
+  idx->csr_offsets.clear();
+  for (uint64_t i = 0; i < total; ++i) {
+    if (i == 0 || all[i].key != all[i - 1].key) {
+      idx->csr_keys.push_back(all[i].key);
+      idx->csr_offsets.push_back(i);
     }
-    Posting list;
-    list.reserve(j - i);
-    for (size_t k = i; k < j; ++k) {
-      list.push_back(all[k].doc);
-    }
-    idx->postings.emplace(UnpackKey(all[i].key, width), std::move(list));
-    i = j;
+    idx->csr_postings[i] = all[i].doc;
   }
+  idx->csr_offsets.push_back(total);
   return 0;
 }
 
@@ -1297,14 +1400,16 @@ void orc_index_update_document(orc_index_t* idx, uint32_t doc_id, const uint8_t*
   StoreTextAndStats(*idx, doc_id, new_sv);
 }
 
-uint64_t orc_index_term_count(const orc_index_t* idx) { return idx->postings.size(); }
+uint64_t orc_index_term_count(const orc_index_t* idx) { return idx->csr ? idx->csr_keys.size() : idx->postings.size(); }
 
 uint64_t orc_index_posting_size(const orc_index_t* idx, const uint8_t* term, uint64_t len) {
-  const Posting* list = idx->Find(std::string_view(reinterpret_cast<const char*>(term), len));
-  return list != nullptr ? list->size() : 0;
+  return idx->Find(std::string_view(reinterpret_cast<const char*>(term), len)).size();
 }
 
 uint64_t orc_index_total_postings(const orc_index_t* idx) {
+  if (idx->csr) {
+    return idx->csr_postings.size();
+  }
   uint64_t total = 0;
   for (const auto& [term, list] : idx->postings) {
     total += list.size();
@@ -1314,15 +1419,35 @@ uint64_t orc_index_total_postings(const orc_index_t* idx) {
 
 uint64_t orc_index_get_postings(const orc_index_t* idx, const uint8_t* term, uint64_t len, uint32_t* out,
                                 uint64_t cap) {
-  const Posting* list = idx->Find(std::string_view(reinterpret_cast<const char*>(term), len));
-  if (list == nullptr) {
-    return 0;
+  const Span list = idx->Find(std::string_view(reinterpret_cast<const char*>(term), len));
+  if (out != nullptr) {
+    std::memcpy(out, list.p, std::min<uint64_t>(list.n, cap) * sizeof(uint32_t));
   }
-  return CopyOut(*list, out, cap);
+  return list.n;
 }
 
 uint64_t orc_index_export(const orc_index_t* idx, uint8_t* term_bytes_out, uint64_t* term_offsets_out,
                           uint64_t* posting_offsets_out, uint32_t* postings_out, uint64_t* total_term_bytes) {
+  if (idx->csr) {
+    uint64_t bytes = 0;
+    for (size_t t = 0; t < idx->csr_keys.size(); ++t) {
+      const std::string term = UnpackKey(idx->csr_keys[t], idx->csr_width);
+      if (term_bytes_out != nullptr) {
+        term_offsets_out[t] = bytes;
+        std::memcpy(term_bytes_out + bytes, term.data(), term.size());
+      }
+      bytes += term.size();
+    }
+    if (total_term_bytes != nullptr) {
+      *total_term_bytes = bytes;
+    }
+    if (term_bytes_out != nullptr) {
+      term_offsets_out[idx->csr_keys.size()] = bytes;
+      std::memcpy(posting_offsets_out, idx->csr_offsets.data(), idx->csr_offsets.size() * sizeof(uint64_t));
+      std::memcpy(postings_out, idx->csr_postings.data(), idx->csr_postings.size() * sizeof(uint32_t));
+    }
+    return idx->csr_keys.size();
+  }
   std::vector<const std::pair<const std::string, Posting>*> order;
   order.reserve(idx->postings.size());
   uint64_t bytes = 0;

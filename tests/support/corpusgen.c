@@ -130,3 +130,16 @@ uint64_t corpus_gen_sizes(void* h, uint64_t first_doc, uint64_t n_docs, uint64_t
 void corpus_gen_fill(void* h, uint64_t first_doc, uint64_t n_docs, const uint64_t* offsets, uint8_t* text, int threads) {
   run((const gen_t*)h, first_doc, n_docs, (uint64_t*)offsets, text, 1, threads);
 }
+
+/* Arbitrary documents by global index (used to cut query terms out of random documents without
+ * materialising the corpus): offsets[n+1] relative to 0; call with text == NULL to size. */
+uint64_t corpus_gen_docs(void* h, const uint64_t* doc_indices, uint64_t n, uint64_t* offsets, uint8_t* text) {
+  const gen_t* g = (const gen_t*)h;
+  uint64_t pos = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    offsets[i] = pos;
+    pos += gen_doc(g, doc_indices[i], text ? text + pos : NULL);
+  }
+  offsets[n] = pos;
+  return pos;
+}
