@@ -33,6 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "support"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))  # only the CPU legs (cpu_baseline / --impl reference) import it
 
 METRIC = "batched queries/sec (AND+BM25 top-k)"
 UNIT = "queries/s"

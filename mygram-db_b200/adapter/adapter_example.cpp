@@ -1,0 +1,23 @@
+// adapter_example.cpp — compile/link check of the C++ adapter and a minimal usage sample.
+// The calls mirror tests/index/index_search_test.cpp:393-418 (BigramSearch) of the reference.
+#include <cstdio>
+
+#include "mygram_adapter.h"
+
+int main() {
+  using namespace mygramdb_b200;
+  try {
+    Index index(2);
+    index.AddDocumentBatch({{1, "abcd"}, {2, "bcde"}, {3, "cdef"}});
+    const auto hits = index.SearchAnd({"bc", "cd"});
+    std::printf("SearchAnd({bc,cd}) -> %zu docs\n", hits.size());
+    const auto scored = BM25Scorer::ScoreDocuments(hits, {"bcd"}, {2}, index, 3, 4.0);
+    const auto top = ResultSorter::SortByScore(index, hits, {scored.value[0].score, scored.value[1].score},
+                                               SortOrder::DESC, 10, 0);
+    std::printf("top doc %u\n", top.empty() ? 0 : top[0]);
+  } catch (const std::exception& e) {
+    std::printf("%s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,235 @@
+// mygram_adapter.h — C++17 adapter with the reference's class signatures over the C ABI (include/mgx.h).
+//
+// A MygramDB maintainer swaps `#include "index/index.h"` for this header (or links it behind the same names)
+// at the call sites of the hot path; everything above stays host C++. Signatures mirror, with file:line of the
+// reference declaration they replace:
+//   Index                    src/index/index.h:49-413      (ctor :58-60, AddDocumentBatch :75-100, SearchAnd :127,
+//                                                           FilterByNgrams :138, SearchOr :147, SearchNot :156,
+//                                                           PostingSize/Count :183-188, TermCount :193)
+//   BM25Scorer               src/index/bm25_scorer.h:43-83 (ScoreDocuments :79-82, BM25Params :23-26)
+//   ResultSorter::SortByScore src/query/result_sorter.h:75
+// Results are returned by value exactly as the reference does; errors follow the reference's conventions:
+// searches have no error channel (a failing device call throws std::runtime_error instead of returning wrong
+// data), ScoreDocuments reports kInvalidArgument / kInternalError through the result object.
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <string_view>
+#include <vector>
+
+#include "../../include/mgx.h"
+
+namespace mygramdb_b200 {
+
+using DocId = uint32_t;  // src/types/doc_id.h:31
+
+enum class ErrorCode { kOk = 0, kInvalidArgument, kInternalError };  // subset of utils/error.h:35-130
+enum class SortOrder : uint8_t { ASC, DESC };                        // query/query_parser.h
+
+namespace detail {
+struct Flat {
+  std::vector<uint8_t> bytes;
+  std::vector<uint64_t> offsets{0};
+  void add(std::string_view s) {
+    bytes.insert(bytes.end(), s.begin(), s.end());
+    offsets.push_back(bytes.size());
+  }
+  const uint8_t* data() const {
+    static const uint8_t kEmpty[1] = {0};
+    return bytes.empty() ? kEmpty : bytes.data();
+  }
+};
+inline void check(int rc) {
+  if (rc != MGX_OK) {
+    throw std::runtime_error(std::string("mgx: ") + mgx_last_error());
+  }
+}
+template <typename Call>
+std::vector<DocId> grow_call(Call&& call, uint64_t cap = 4096) {
+  for (;;) {
+    std::vector<DocId> out(cap);
+    uint64_t n = 0;
+    const int rc = call(out.data(), cap, &n);
+    if (rc == MGX_ERR_CAPACITY) {
+      cap = n > cap ? n : cap * 2;
+      continue;
+    }
+    check(rc);
+    out.resize(n);
+    return out;
+  }
+}
+}  // namespace detail
+
+class Index {
+ public:
+  struct DocumentItem {  // index.h:75-78
+    DocId doc_id;
+    std::string text;
+  };
+
+  explicit Index(int ngram_size = 2, int kanji_ngram_size = 0, double /*roaring_threshold*/ = 0.18,
+                 bool cross_boundary_ngrams = true, bool /*normalize_nfkc*/ = true,
+                 const std::string& /*normalize_width*/ = "keep", bool /*normalize_lower*/ = true, int device = 0)
+      : ngram_size_(ngram_size), kanji_ngram_size_(kanji_ngram_size > 0 ? kanji_ngram_size : ngram_size),
+        cross_boundary_ngrams_(cross_boundary_ngrams) {
+    mgx_index_config_t cfg{};
+    cfg.ngram_size = ngram_size;
+    cfg.kanji_ngram_size = kanji_ngram_size;
+    cfg.cross_boundary_ngrams = cross_boundary_ngrams ? 1 : 0;
+    cfg.device = device;
+    detail::check(mgx_index_create(&cfg, &handle_));
+  }
+  ~Index() { mgx_index_destroy(handle_); }
+  Index(const Index&) = delete;
+  Index& operator=(const Index&) = delete;
+
+  // Bulk (re)build of the shard from normalised texts; doc ids strictly ascending (the DocumentStore assigns
+  // them sequentially, document_store.h:520). Replaces the batches of InitialLoader::FlushBatch.
+  void AddDocumentBatch(const std::vector<DocumentItem>& documents) {
+    detail::Flat flat;
+    std::vector<DocId> ids;
+    ids.reserve(documents.size());
+    for (const auto& d : documents) {
+      ids.push_back(d.doc_id);
+      flat.add(d.text);
+    }
+    detail::check(mgx_index_build(handle_, ids.data(), flat.data(), flat.offsets.data(), documents.size()));
+  }
+
+  [[nodiscard]] std::vector<DocId> SearchAnd(const std::vector<std::string>& terms, size_t limit = 0,
+                                             bool reverse = false) const {
+    detail::Flat f = Pack(terms);
+    return detail::grow_call([&](DocId* out, uint64_t cap, uint64_t* n) {
+      return mgx_search_and(handle_, f.data(), f.offsets.data(), terms.size(), limit, reverse ? 1 : 0, out, cap, n);
+    });
+  }
+  [[nodiscard]] std::vector<DocId> FilterByNgrams(const std::vector<DocId>& candidates,
+                                                  const std::vector<std::string>& terms) const {
+    detail::Flat f = Pack(terms);
+    static const DocId kNone[1] = {0};
+    return detail::grow_call(
+        [&](DocId* out, uint64_t cap, uint64_t* n) {
+          return mgx_filter_by_ngrams(handle_, candidates.empty() ? kNone : candidates.data(), candidates.size(),
+                                      f.data(), f.offsets.data(), terms.size(), out, cap, n);
+        },
+        candidates.size() + 1);
+  }
+  [[nodiscard]] std::vector<DocId> SearchOr(const std::vector<std::string>& terms) const {
+    detail::Flat f = Pack(terms);
+    return detail::grow_call([&](DocId* out, uint64_t cap, uint64_t* n) {
+      return mgx_search_or(handle_, f.data(), f.offsets.data(), terms.size(), out, cap, n);
+    });
+  }
+  [[nodiscard]] std::vector<DocId> SearchNot(const std::vector<DocId>& all_docs,
+                                             const std::vector<std::string>& terms) const {
+    detail::Flat f = Pack(terms);
+    static const DocId kNone[1] = {0};
+    return detail::grow_call(
+        [&](DocId* out, uint64_t cap, uint64_t* n) {
+          return mgx_search_not(handle_, all_docs.empty() ? kNone : all_docs.data(), all_docs.size(), f.data(),
+                                f.offsets.data(), terms.size(), out, cap, n);
+        },
+        all_docs.size() + 1);
+  }
+  [[nodiscard]] uint64_t PostingSize(std::string_view term) const {
+    uint64_t n = 0;
+    detail::check(mgx_index_posting_size(handle_, reinterpret_cast<const uint8_t*>(term.data()), term.size(), &n));
+    return n;
+  }
+  [[nodiscard]] uint64_t Count(std::string_view term) const { return PostingSize(term); }
+  [[nodiscard]] uint64_t EstimatePostingSize(std::string_view term) const { return PostingSize(term); }
+  [[nodiscard]] size_t TermCount() const {
+    mgx_index_stats_t s{};
+    detail::check(mgx_index_get_stats(handle_, &s));
+    return s.n_terms;
+  }
+  [[nodiscard]] int GetNgramSize() const { return ngram_size_; }
+  [[nodiscard]] int GetKanjiNgramSize() const { return kanji_ngram_size_; }
+  [[nodiscard]] bool GetCrossBoundaryNgrams() const { return cross_boundary_ngrams_; }
+  // Index::NormalizeText stays on the host (ICU); the path's contract is pre-normalised text (index.h:83-84).
+  [[nodiscard]] mgx_index_t* handle() const { return handle_; }
+
+ private:
+  static detail::Flat Pack(const std::vector<std::string>& terms) {
+    detail::Flat f;
+    for (const auto& t : terms) {
+      f.add(t);
+    }
+    return f;
+  }
+  int ngram_size_;
+  int kanji_ngram_size_;
+  bool cross_boundary_ngrams_;
+  mgx_index_t* handle_ = nullptr;
+};
+
+struct BM25Params {  // bm25_scorer.h:23-26
+  double k1 = 1.2;
+  double b = 0.75;
+};
+struct ScoredDoc {  // bm25_scorer.h:31-34
+  DocId doc_id;
+  double score;
+};
+struct ScoreResult {  // stands in for Expected<std::vector<ScoredDoc>, Error>
+  ErrorCode code = ErrorCode::kOk;
+  std::string message;
+  std::vector<ScoredDoc> value;
+  explicit operator bool() const { return code == ErrorCode::kOk; }
+};
+
+class BM25Scorer {
+ public:
+  // The document store argument of the reference (bm25_scorer.h:79-82) is the index's device-resident text mirror.
+  static ScoreResult ScoreDocuments(const std::vector<DocId>& candidates, const std::vector<std::string>& search_terms,
+                                    const std::vector<uint64_t>& term_doc_freqs, const Index& index,
+                                    uint64_t total_docs, double avg_doc_length, const BM25Params& params = {}) {
+    ScoreResult r;
+    if (search_terms.size() != term_doc_freqs.size()) {  // bm25_scorer.cpp:51-55
+      r.code = ErrorCode::kInvalidArgument;
+      r.message = "BM25 search_terms and term_doc_freqs must have identical lengths";
+      return r;
+    }
+    detail::Flat f;
+    for (const auto& t : search_terms) {
+      f.add(t);
+    }
+    std::vector<double> scores(candidates.size());
+    const int rc = mgx_score_documents(index.handle(), candidates.data(), candidates.size(), f.data(),
+                                       f.offsets.data(), term_doc_freqs.data(), search_terms.size(), total_docs,
+                                       avg_doc_length, params.k1, params.b, scores.data());
+    if (rc != MGX_OK) {
+      r.code = ErrorCode::kInternalError;  // bm25_scorer.cpp:93-96
+      r.message = mgx_last_error();
+      return r;
+    }
+    r.value.reserve(candidates.size());
+    for (size_t i = 0; i < candidates.size(); ++i) {
+      r.value.push_back({candidates[i], scores[i]});
+    }
+    return r;
+  }
+};
+
+class ResultSorter {
+ public:
+  static std::vector<DocId> SortByScore(const Index& index, const std::vector<DocId>& results,
+                                        const std::vector<double>& scores, SortOrder order, uint32_t limit,
+                                        uint32_t offset) {
+    if (results.empty()) {
+      return {};  // result_sorter.cpp:663-665
+    }
+    const uint32_t lim = limit == 0 ? static_cast<uint32_t>(results.size()) : limit;  // 0 = everything after offset
+    std::vector<DocId> out(lim);
+    uint64_t n = 0;
+    detail::check(mgx_sort_by_score(index.handle(), results.data(), scores.data(), results.size(),
+                                    order == SortOrder::DESC ? 1 : 0, lim, offset, out.data(), &n));
+    out.resize(n);
+    return out;
+  }
+};
+
+}  // namespace mygramdb_b200

@@ -854,6 +854,9 @@ int mgx_batch_df_device(mgx_batch_t* batch, uint64_t* d_df) {
   return guarded([&]() {
     Batch& b = batch->b;
     DeviceGuard guard(b.ix->device);
+    if (!b.planned) {
+      batch_plan(b);
+    }
     if (b.params.compute_score != 0) {
       batch_df(b);
     }
@@ -951,6 +954,7 @@ int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64
     d_count.alloc(n_queries);
     d_total.alloc(n_queries);
     d_df.alloc(b.n_slots);
+    batch_plan(b);
     if (params->compute_score != 0) {
       batch_df(b);
     }

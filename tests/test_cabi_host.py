@@ -1,0 +1,112 @@
+"""CPU-side checks of the drop-in boundary: libmgx.so loads, exports every symbol include/mgx.h declares, refuses to
+run without a GPU (no CPU fallback), and the host-only helpers behave. No compute calls are made here."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+
+def test_library_exports_every_declared_symbol(mgx):
+    lib = mgx.lib()
+    names = mgx.exported_symbols_in_header()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert b"sm_100a" in lib.mgx_version()
+
+
+def test_header_cites_reference_interfaces():
+    text = open(os.path.join(os.path.dirname(__file__), "..", "include", "mgx.h")).read()
+    for cite in ("index.cpp:199-368", "index.cpp:76-119", "bm25_scorer.cpp:47-99", "result_sorter.cpp:661-716",
+                 "search_pipeline.cpp:1757-2059", "string_utils.cpp:452-509"):
+        assert cite in text, cite
+    assert "torch" not in text.lower().replace("no torch", "")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_no_cpu_fallback_without_a_device(mgx):
+    if _has_gpu():
+        pytest.skip("a GPU is visible; the refusal path needs a GPU-less host")
+    with pytest.raises(mgx.MgxError) as e:
+        mgx.Index(2, 0, True)
+    assert e.value.code == -5 and "no CPU fallback" in str(e.value)
+    cfg = mgx.IndexConfig(2, 0, 1, 0, 0.0, 0, 0)
+    n = C.c_uint64(0)
+    text = np.frombuffer(b"abc", dtype=np.uint8).copy()
+    offs = np.array([0, 3], dtype=np.uint64)
+    keys = np.zeros(8, np.uint64)
+    docs = np.zeros(8, np.uint32)
+    rc = mgx.lib().mgx_tokenize_batch(C.byref(cfg), text.ctypes.data_as(mgx.u8p), offs.ctypes.data_as(mgx.u64p), 1,
+                                      keys.ctypes.data_as(mgx.u64p), docs.ctypes.data_as(mgx.u32p), 8, C.byref(n))
+    assert rc == -5
+
+
+def test_argument_validation_is_host_side(mgx):
+    lib = mgx.lib()
+    assert lib.mgx_index_create(None, None) == -1
+    assert b"null" in lib.mgx_last_error()
+    out = np.zeros(16, np.uint8)
+    assert lib.mgx_key_to_utf8(0, 9, out.ctypes.data_as(mgx.u8p)) == -1
+    assert lib.mgx_index_get_stats(None, None) == -1
+    assert lib.mgx_batch_term_slots(None) == 0
+    lib.mgx_index_destroy(None)
+    lib.mgx_batch_destroy(None)
+
+
+def test_packed_key_order_is_utf8_byte_order(mgx, oracle):
+    """Dictionary order: integer order of packed keys == bytewise order of the UTF-8 n-grams
+    (the reference sorts std::string n-grams, string_utils.h:192-196)."""
+    rng = np.random.default_rng(5)
+    cps = [0, 1, 0x41, 0x7F, 0x80, 0x7FF, 0x800, 0x3042, 0x4E00, 0xFFFF, 0x10000, 0x20000, 0x10FFFF]
+    keys, strings = [], []
+    for _ in range(400):
+        n = int(rng.integers(1, 4))
+        seq = [int(rng.choice(cps)) for _ in range(n)]
+        key = 0
+        for j in range(3):
+            key = (key << 21) | ((seq[j] + 1) if j < n else 0)
+        keys.append(key)
+        strings.append(oracle.codepoints_to_utf8(seq))
+        assert mgx.key_to_utf8(key, 3) == strings[-1]
+    order_k = sorted(range(len(keys)), key=lambda i: keys[i])
+    order_s = sorted(range(len(keys)), key=lambda i: strings[i])
+    assert [strings[i] for i in order_k] == [strings[i] for i in order_s]
+
+
+def _build_adapter_example(tmp_path):
+    import subprocess
+    root = os.path.join(os.path.dirname(__file__), "..")
+    exe = str(tmp_path / "adapter_example")
+    libdir = os.path.abspath(os.path.join(root, "mygram-db_b200"))
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-o", exe,
+                           os.path.join(libdir, "adapter", "adapter_example.cpp"), "-L" + libdir, "-lmgx",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_adapter_compiles_and_links(mgx, tmp_path):
+    """The C++17 adapter (reference class signatures over the C ABI) builds against libmgx.so with plain g++."""
+    import subprocess
+    exe = _build_adapter_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if _has_gpu():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 1 and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_adapter_runs_on_gpu(mgx, tmp_path):
+    import subprocess
+    exe = _build_adapter_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "SearchAnd({bc,cd}) -> 2 docs" in r.stdout  # tests/index/index_search_test.cpp:393-418
