@@ -133,10 +133,10 @@ def choose_cpu_kind(args):
     if args.ref_kind != "auto":
         return args.ref_kind
     # The reference's only build path is single-threaded (initial_loader.cpp:296-385, ~minutes per million
-    # documents with the hash-map index), so above 2M documents the CPU arm uses the port, whose multi-threaded
+    # documents with the hash-map index), so above 250k documents the CPU arm uses the port, whose multi-threaded
     # bulk builder produces the identical index (tests/test_oracle_bulk.py) and whose query path restates the
     # reference's (oracle/oracle.cpp).
-    if os.path.exists(pyoracle.REF_LIB) and args.docs <= 2_000_000:
+    if os.path.exists(pyoracle.REF_LIB) and args.docs <= 250_000:
         return "reference"
     return "port"
 

@@ -802,7 +802,7 @@ int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint
     Batch& b = h->b;
     b.ix = &ix;
     b.params = *params;
-    b.stream = stream != nullptr ? static_cast<cudaStream_t>(stream) : ix.stream;
+    b.stream = static_cast<cudaStream_t>(stream);  // NULL = the legacy default stream, as documented
     b.launches_at_start = g_launches.load();
     std::vector<HostTerm> terms;
     std::vector<HostQuery> queries;
@@ -935,7 +935,7 @@ int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64
   std::lock_guard<std::mutex> lock(index->mu);
   mgx_batch_t* batch = nullptr;
   int rc = mgx_batch_prepare(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
-                             q_not_begin, nullptr, &batch);
+                             q_not_begin, index->ix.stream, &batch);
   if (rc != MGX_OK) {
     return rc;
   }

@@ -308,12 +308,193 @@ __global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf
   bv.t_df_tiles[t] = tiles;
 }
 
+// ------------------------------------------------------------------ tile membership (block-cooperative)
+// Lower bound of v in p[0, n) by a whole warp: every step probes 32 evenly spaced positions, so a 300k-entry list
+// needs 4 dependent rounds instead of 18.
+__device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t* __restrict__ p, uint32_t n, uint32_t v) {
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t lo = 0;
+  uint32_t hi = n;
+  while (hi - lo > 32) {
+    const uint32_t size = hi - lo;
+    const uint32_t idx = lo + static_cast<uint32_t>((static_cast<uint64_t>(lane + 1) * size) / 33);
+    const bool less = __ldg(p + idx) < v;
+    const unsigned mask = __ballot_sync(0xffffffffu, less);
+    const int c = __popc(mask);  // `less` is monotone in the lane index
+    const uint32_t idx_prev = __shfl_sync(0xffffffffu, idx, c > 0 ? c - 1 : 0);
+    const uint32_t idx_next = __shfl_sync(0xffffffffu, idx, c < 32 ? c : 31);
+    if (c > 0) {
+      lo = idx_prev + 1;
+    }
+    if (c < 32) {
+      hi = idx_next;
+    }
+  }
+  const uint32_t i = lo + lane;
+  const bool less = i < hi && __ldg(p + i) < v;
+  return lo + __popc(__ballot_sync(0xffffffffu, less));
+}
+
+constexpr uint32_t kStageCap = 4096;  // posting entries of one list staged per tile (16 KB)
+
+__device__ __forceinline__ bool sorted_contains(const uint32_t* p, uint32_t n, uint32_t v) {
+  uint32_t lo = 0;
+  uint32_t hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (p[mid] < v) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  return lo < n && p[lo] == v;
+}
+
+// Keeps, among the thread's kTileItems driver entries, those present in list `l`.
+// Dense list: one bit probe per entry. Sparse list: the tile's doc range [dmin, dmax] selects a sub-range of the
+// list (two warp-cooperative bound searches); if it fits, it is staged in shared memory with coalesced loads and
+// searched there, otherwise searched in place. Must be called by every thread of the CTA.
+__device__ __forceinline__ void tile_filter_list(const ListRef& l, uint32_t dmin, uint32_t dmax, bool narrow,
+                                                 uint32_t* s_stage, uint32_t* s_range,
+                                                 const uint32_t (&my_doc)[kTileItems], uint32_t* alive_mask) {
+  if (l.bm != nullptr) {
+#pragma unroll
+    for (int k = 0; k < kTileItems; ++k) {
+      if ((*alive_mask >> k) & 1u) {
+        const uint32_t d = my_doc[k];
+        if (d == kNone || ((__ldg(l.bm + (d >> 5)) >> (d & 31)) & 1u) == 0) {
+          *alive_mask &= ~(1u << k);
+        }
+      }
+    }
+    return;
+  }
+  if ((threadIdx.x >> 5) == 0) {
+    const uint32_t lo = narrow ? warp_lower_bound(l.p, l.len, dmin) : 0u;
+    const uint32_t hi = narrow ? warp_lower_bound(l.p, l.len, dmax + 1u) : l.len;
+    if ((threadIdx.x & 31u) == 0) {
+      s_range[0] = lo;
+      s_range[1] = hi;
+    }
+  }
+  __syncthreads();
+  const uint32_t lo = s_range[0];
+  const uint32_t cnt = s_range[1] - lo;
+  if (cnt == 0) {
+    *alive_mask = 0;
+  } else if (cnt <= kStageCap) {
+    for (uint32_t i = threadIdx.x; i < cnt; i += kTileThreads) {
+      s_stage[i] = __ldg(l.p + lo + i);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTileItems; ++k) {
+      if ((*alive_mask >> k) & 1u) {
+        if (my_doc[k] == kNone || !sorted_contains(s_stage, cnt, my_doc[k])) {
+          *alive_mask &= ~(1u << k);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kTileItems; ++k) {
+      if ((*alive_mask >> k) & 1u) {
+        const uint32_t d = my_doc[k];
+        const uint32_t pos = d == kNone ? cnt : lower_bound_u32(l.p + lo, cnt, d);
+        if (pos >= cnt || __ldg(l.p + lo + pos) != d) {
+          *alive_mask &= ~(1u << k);
+        }
+      }
+    }
+  }
+  __syncthreads();  // s_range / s_stage are reused by the next list
+}
+
+// ------------------------------------------------------------------ text scanning, one THREAD per document
+// Short terms (<= 16 bytes) and ordinary documents: every thread streams its own document through two 16-byte
+// registers, so a warp keeps 32 documents in flight. The first 4 bytes of the term are compared at all 16 byte
+// offsets of a chunk with funnel shifts; the rare candidates are confirmed byte by byte (L1-resident).
+constexpr uint32_t kThreadScanMaxTerm = 16;
+constexpr uint32_t kThreadScanMaxDoc = 4096;
+
+struct TermHead {
+  uint32_t w0;    // first min(4, tl) bytes, little endian
+  uint32_t mask;  // which of those bytes are significant
+};
+
+__device__ __forceinline__ TermHead load_term_head(const uint8_t* __restrict__ term, uint32_t tl) {
+  TermHead h;
+  h.w0 = 0;
+  for (uint32_t i = 0; i < 4 && i < tl; ++i) {
+    h.w0 |= static_cast<uint32_t>(__ldg(term + i)) << (8 * i);
+  }
+  h.mask = tl >= 4 ? 0xFFFFFFFFu : ((1u << (8 * tl)) - 1u);
+  return h;
+}
+
+// BM25Scorer::CountTermOccurrences (bm25_scorer.cpp:27-45): non-overlapping, left to right, on bytes.
+__device__ __forceinline__ uint32_t thread_count_term(const uint8_t* __restrict__ text, uint64_t b, uint32_t len,
+                                                      const uint8_t* __restrict__ term, uint32_t tl,
+                                                      const TermHead& head, bool exists_only) {
+  if (tl == 0 || tl > len) {
+    return 0;
+  }
+  const uint64_t last = b + len - tl;  // last admissible start
+  uint64_t next_ok = b;
+  uint32_t count = 0;
+  uint64_t a = b & ~15ULL;
+  uint4 cur = ld16(text + a);
+  for (; a <= last; a += 16) {
+    const uint4 nxt = ld16(text + a + 16);  // the arena is padded by 64 bytes
+    const uint32_t w[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
+    uint32_t cand = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t x = (j & 3) ? __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], (j & 3) * 8) : w[j >> 2];
+      if (((x ^ head.w0) & head.mask) == 0) {
+        cand |= 1u << j;
+      }
+    }
+    while (cand != 0) {
+      const uint32_t j = static_cast<uint32_t>(__ffs(static_cast<int>(cand))) - 1u;
+      cand &= cand - 1;
+      const uint64_t pos = a + j;
+      if (pos < next_ok || pos > last) {
+        continue;
+      }
+      bool ok = true;
+      for (uint32_t i = 4; i < tl; ++i) {
+        if (__ldg(text + pos + i) != __ldg(term + i)) {
+          ok = false;
+          break;
+        }
+      }
+      if (ok) {
+        ++count;
+        next_ok = pos + tl;
+        if (exists_only) {
+          return 1;
+        }
+      }
+    }
+    cur = nxt;
+  }
+  return count;
+}
+
 // ------------------------------------------------------------------ df tiles
 __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, BatchView bv) {
   __shared__ uint32_t s_doc[kTile];
+  __shared__ uint32_t s_slow[kTile];
+  __shared__ uint32_t s_stage[kStageCap];
+  __shared__ uint32_t s_range[2];
   __shared__ uint32_t s_n;
+  __shared__ uint32_t s_nslow;
   __shared__ uint32_t s_term;
   __shared__ uint32_t s_hits;
+  __shared__ uint32_t s_dmin;
+  __shared__ uint32_t s_dmax;
   __shared__ unsigned long long s_bytes;
   __shared__ __align__(16) uint8_t s_text[kTileThreads / 32][kStageBuf];
   const unsigned lane = threadIdx.x & 31u;
@@ -321,6 +502,7 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
   if (threadIdx.x == 0) {
     s_term = find_segment(bv.t_df_tile_off, bv.n_terms, blockIdx.x);
     s_n = 0;
+    s_nslow = 0;
     s_hits = 0;
     s_bytes = 0;
   }
@@ -331,37 +513,77 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
   const uint64_t tile = blockIdx.x - bv.t_df_tile_off[t];
   const ListRef drv = make_list(iv, bv.key_list[k0], bv.key_len[k0]);
   const uint64_t e0 = tile * kTile;
+  const uint32_t tile_n = static_cast<uint32_t>(umin64(kTile, drv.len - e0));
+  if (threadIdx.x == 0) {
+    s_dmin = __ldg(drv.p + e0);
+    s_dmax = __ldg(drv.p + e0 + tile_n - 1);
+  }
+  uint32_t my_doc[kTileItems];
+  uint32_t alive = 0;
 #pragma unroll
   for (int k = 0; k < kTileItems; ++k) {
-    const uint64_t e = e0 + static_cast<uint64_t>(k) * kTileThreads + threadIdx.x;
-    if (e < drv.len) {
-      const uint32_t doc = __ldg(drv.p + e);
-      bool alive = true;
-      for (uint32_t j = k0 + 1; j < k1 && alive; ++j) {
-        alive = list_contains(make_list(iv, bv.key_list[j], bv.key_len[j]), doc);
-      }
-      if (alive) {
-        s_doc[atomicAdd(&s_n, 1u)] = doc;
-      }
+    const uint32_t i = threadIdx.x * kTileItems + k;
+    my_doc[k] = kNone;
+    if (i < tile_n) {
+      my_doc[k] = __ldg(drv.p + e0 + i);
+      alive |= 1u << k;
+    }
+  }
+  __syncthreads();
+  const uint32_t dmin = s_dmin;
+  const uint32_t dmax = s_dmax;
+  for (uint32_t j = k0 + 1; j < k1; ++j) {
+    tile_filter_list(make_list(iv, bv.key_list[j], bv.key_len[j]), dmin, dmax, true, s_stage, s_range, my_doc, &alive);
+    if (__syncthreads_or(alive != 0) == 0) {
+      break;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kTileItems; ++k) {
+    if ((alive >> k) & 1u) {
+      s_doc[atomicAdd(&s_n, 1u)] = my_doc[k];
     }
   }
   __syncthreads();
   const uint32_t n = s_n;
   const uint8_t* term = bv.term_bytes + bv.term_boff[t];
   const uint32_t tl = bv.term_boff[t + 1] - bv.term_boff[t];
+  const TermHead head = load_term_head(term, tl);
   uint32_t hits = 0;
   unsigned long long text_bytes = 0;
-  for (uint32_t s = warp; s < n; s += kTileThreads / 32) {
-    DocText d = doc_open(iv, s_doc[s], s_text[warp]);
-    text_bytes += d.len;
-    hits += doc_count_term(d, term, tl, true) != 0 ? 1u : 0u;
+  // fast path: one thread per candidate document
+  for (uint32_t s = threadIdx.x; s < n; s += kTileThreads) {
+    const uint32_t doc = s_doc[s];
+    const uint64_t b = iv.text_off[doc];
+    const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
+    text_bytes += len;
+    if (tl <= kThreadScanMaxTerm && len <= kThreadScanMaxDoc) {
+      hits += thread_count_term(iv.text, b, len, term, tl, head, true);
+    } else {
+      s_slow[atomicAdd(&s_nslow, 1u)] = doc;
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    hits += __shfl_xor_sync(0xffffffffu, hits, s);
+    text_bytes += __shfl_xor_sync(0xffffffffu, text_bytes, s);
+  }
+  __syncthreads();
+  // slow path (long terms / very long documents): one warp per document through shared memory
+  const uint32_t nslow = s_nslow;
+  uint32_t slow_hits = 0;
+  for (uint32_t s = warp; s < nslow; s += kTileThreads / 32) {
+    DocText d = doc_open(iv, s_slow[s], s_text[warp]);
+    slow_hits += doc_count_term(d, term, tl, true) != 0 ? 1u : 0u;
     __syncwarp();
   }
-  if (lane == 0 && hits != 0) {
-    atomicAdd(&s_hits, hits);
-  }
-  if (lane == 0 && text_bytes != 0) {
-    atomicAdd(&s_bytes, text_bytes);
+  if (lane == 0) {
+    if (hits + slow_hits != 0) {
+      atomicAdd(&s_hits, hits + slow_hits);
+    }
+    if (text_bytes != 0) {
+      atomicAdd(&s_bytes, text_bytes);
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -551,15 +773,28 @@ __device__ __forceinline__ uint32_t block_offsets(uint32_t cnt, uint32_t* s_warp
 
 constexpr int kMaxCachedLists = 24;
 
+// BM25 contribution of one term (bm25_scorer.cpp:74-85), evaluated operation by operation (no FMA contraction).
+__device__ __forceinline__ double bm25_term(double idf, uint32_t tf_u, double length_norm, double k1) {
+  const double tf = static_cast<double>(tf_u);
+  const double numerator = __dmul_rn(tf, __dadd_rn(k1, 1.0));
+  const double denominator = __dadd_rn(tf, __dmul_rn(k1, length_norm));
+  return __ddiv_rn(__dmul_rn(idf, numerator), denominator);
+}
+
 __global__ void __launch_bounds__(kTileThreads)
 and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, uint64_t rec_base,
                 uint32_t* __restrict__ tile_count, uint32_t* __restrict__ rec_doc, double* __restrict__ rec_score) {
   __shared__ uint32_t s_doc[kTile];     // local doc index of survivors (kNone = id unknown to this shard)
-  __shared__ uint32_t s_gid[kTile];     // global doc id of survivors
+  __shared__ uint32_t s_gid[kTile];     // global doc id of survivors (explicit drivers only)
   __shared__ double s_score[kTile];
-  __shared__ uint8_t s_keep[kTile];
+  __shared__ uint8_t s_keep[kTile];     // 0 drop, 1 keep, 2 = needs the warp-cooperative slow path
+  __shared__ uint32_t s_stage[kStageCap];
+  __shared__ uint32_t s_range[2];
   __shared__ uint32_t s_warp[kTileThreads / 32];
   __shared__ uint32_t s_q;
+  __shared__ uint32_t s_dmin;
+  __shared__ uint32_t s_dmax;
+  __shared__ uint32_t s_any_slow;
   __shared__ unsigned long long s_bytes;
   __shared__ ListRef s_lists[kMaxCachedLists];
   __shared__ __align__(16) uint8_t s_text[kTileThreads / 32][kStageBuf];
@@ -569,6 +804,7 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   if (threadIdx.x == 0) {
     s_q = find_segment(bv.q_tile_off, bv.n_queries, tile_global);
     s_bytes = 0;
+    s_any_slow = 0;
   }
   __syncthreads();
   const uint32_t q = s_q;
@@ -588,66 +824,100 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   const uint32_t n0 = bv.q_noff[q];
   const uint32_t n1 = bv.q_noff[q + 1];
 
-  // ---- membership: thread owns kTileItems consecutive driver entries (keeps order)
+  // ---- driver entries: each thread owns kTileItems CONSECUTIVE entries (keeps the order)
+  const uint64_t e0 = tile_in_q * kTile;
+  const uint32_t tile_n = static_cast<uint32_t>(umin64(kTile, driver_len - e0));
   uint32_t my_doc[kTileItems];
   uint32_t my_gid[kTileItems];
-  uint32_t alive_mask = 0;
-  const uint64_t e0 = tile_in_q * kTile + static_cast<uint64_t>(threadIdx.x) * kTileItems;
+  uint32_t alive = 0;
 #pragma unroll
   for (int k = 0; k < kTileItems; ++k) {
-    const uint64_t e = e0 + k;
+    const uint32_t i = threadIdx.x * kTileItems + k;
     my_doc[k] = kNone;
     my_gid[k] = 0;
-    if (e >= driver_len) {
-      continue;
+    if (i < tile_n) {
+      const uint64_t e = e0 + i;
+      if (drv_list) {
+        my_doc[k] = __ldg(s_lists[0].p + e);
+      } else if (drv_all) {
+        my_doc[k] = static_cast<uint32_t>(e);
+      } else {
+        my_gid[k] = __ldg(bv.explicit_ids + e);
+        my_doc[k] = local_of(iv, my_gid[k]);
+      }
+      alive |= 1u << k;
     }
-    uint32_t doc;
+  }
+  if (threadIdx.x == 0) {
     if (drv_list) {
-      doc = __ldg(s_lists[0].p + e);
-    } else if (drv_all) {
-      doc = static_cast<uint32_t>(e);
+      s_dmin = __ldg(s_lists[0].p + e0);
+      s_dmax = __ldg(s_lists[0].p + e0 + tile_n - 1);
     } else {
-      my_gid[k] = __ldg(bv.explicit_ids + e);
-      doc = local_of(iv, my_gid[k]);
+      s_dmin = static_cast<uint32_t>(e0);
+      s_dmax = static_cast<uint32_t>(e0 + tile_n - 1);
     }
-    bool alive;
-    if (any_mode) {
-      alive = false;
-      for (uint32_t j = 0; j < nl && !alive && doc != kNone; ++j) {
-        const ListRef l = j < kMaxCachedLists ? s_lists[j] : make_list(iv, bv.q_list[l0 + j], bv.q_list_len[l0 + j]);
-        alive = list_contains(l, doc);
-      }
-    } else {
-      alive = true;
-      for (uint32_t j = drv_list ? 1u : 0u; j < nl && alive; ++j) {
-        const ListRef l = j < kMaxCachedLists ? s_lists[j] : make_list(iv, bv.q_list[l0 + j], bv.q_list_len[l0 + j]);
-        alive = doc != kNone && list_contains(l, doc);
+  }
+  __syncthreads();
+
+  // ---- membership
+  if (any_mode) {
+    // Index::SearchOr: keep the doc if ANY list holds it
+#pragma unroll
+    for (int k = 0; k < kTileItems; ++k) {
+      if ((alive >> k) & 1u) {
+        bool hit = false;
+        for (uint32_t j = 0; j < nl && !hit && my_doc[k] != kNone; ++j) {
+          const ListRef l = j < kMaxCachedLists ? s_lists[j] : make_list(iv, bv.q_list[l0 + j], bv.q_list_len[l0 + j]);
+          hit = list_contains(l, my_doc[k]);
+        }
+        if (!hit) {
+          alive &= ~(1u << k);
+        }
       }
     }
-    // NOT terms (ApplyNotFilter :871-932): drop the doc if it is in ALL n-gram lists of a NOT term.
-    for (uint32_t i = n0; i < n1 && alive && doc != kNone; ++i) {
-      const uint32_t tid = bv.q_ntids[i];
-      const uint32_t k0 = bv.term_koff[tid];
-      const uint32_t k1 = bv.term_koff[tid + 1];
-      if (k1 == k0 || bv.t_est[tid] == 0) {
-        continue;  // no n-grams (text stage decides) or an unknown n-gram (matches nothing)
+  } else {
+    const bool narrow = !drv_explicit;  // caller-supplied candidates may be unsorted (FilterByNgrams keeps their order)
+    const uint32_t dmin = s_dmin;
+    const uint32_t dmax = s_dmax;
+    for (uint32_t j = drv_list ? 1u : 0u; j < nl; ++j) {
+      const ListRef l = j < kMaxCachedLists ? s_lists[j] : make_list(iv, bv.q_list[l0 + j], bv.q_list_len[l0 + j]);
+      tile_filter_list(l, dmin, dmax, narrow, s_stage, s_range, my_doc, &alive);
+      if (__syncthreads_or(alive != 0) == 0) {
+        break;
       }
-      bool in_all = true;
-      for (uint32_t kk = k0; kk < k1 && in_all; ++kk) {
-        in_all = list_contains(make_list(iv, bv.key_list[kk], bv.key_len[kk]), doc);
-      }
-      alive = !in_all;
     }
-    if (alive) {
-      alive_mask |= 1u << k;
-      my_doc[k] = doc;
+  }
+  // NOT terms (ApplyNotFilter :871-932): drop the doc if it is in ALL n-gram lists of a NOT term.
+  if (n1 > n0) {
+#pragma unroll
+    for (int k = 0; k < kTileItems; ++k) {
+      if (((alive >> k) & 1u) == 0 || my_doc[k] == kNone) {
+        continue;
+      }
+      bool keep = true;
+      for (uint32_t i = n0; i < n1 && keep; ++i) {
+        const uint32_t tid = bv.q_ntids[i];
+        const uint32_t k0 = bv.term_koff[tid];
+        const uint32_t k1 = bv.term_koff[tid + 1];
+        if (k1 == k0 || bv.t_est[tid] == 0) {
+          continue;  // no n-grams (the text stage decides) or an unknown n-gram (matches nothing)
+        }
+        bool in_all = true;
+        for (uint32_t kk = k0; kk < k1 && in_all; ++kk) {
+          in_all = list_contains(make_list(iv, bv.key_list[kk], bv.key_len[kk]), my_doc[k]);
+        }
+        keep = !in_all;
+      }
+      if (!keep) {
+        alive &= ~(1u << k);
+      }
     }
   }
   uint32_t total = 0;
-  uint32_t off = block_offsets(__popc(alive_mask), s_warp, &total);
+  uint32_t off = block_offsets(__popc(alive), s_warp, &total);
 #pragma unroll
   for (int k = 0; k < kTileItems; ++k) {
-    if (alive_mask & (1u << k)) {
+    if ((alive >> k) & 1u) {
       s_doc[off] = my_doc[k];
       s_gid[off] = my_gid[k];
       ++off;
@@ -667,18 +937,38 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
     const uint32_t tid = bv.q_ntids[i];
     need_text = bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid];
   }
-  if (need_text) {
+  if (need_text && total > 0) {
+    bool all_short = true;  // every term fits the per-thread scanner
+    for (uint32_t i = t0; i < t1; ++i) {
+      const uint32_t tid = bv.q_tids[i];
+      all_short = all_short && (bv.term_boff[tid + 1] - bv.term_boff[tid]) <= kThreadScanMaxTerm;
+    }
+    for (uint32_t i = n0; i < n1; ++i) {
+      const uint32_t tid = bv.q_ntids[i];
+      all_short = all_short && (bv.term_boff[tid + 1] - bv.term_boff[tid]) <= kThreadScanMaxTerm;
+    }
     unsigned long long text_bytes = 0;
-    for (uint32_t s = warp; s < total; s += kTileThreads / 32) {
+    // fast path: one thread per surviving document
+    for (uint32_t s = threadIdx.x; s < total; s += kTileThreads) {
       const uint32_t doc = s_doc[s];
-      bool keep = true;
+      uint8_t keep = 1;
       double score = 0.0;
       if (doc != kNone) {
-        DocText d = doc_open(iv, doc, s_text[warp]);
-        text_bytes += d.len + 4;
-        if (d.len > 0) {
+        const uint64_t b = iv.text_off[doc];
+        const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
+        text_bytes += len + 4;
+        if (len == 0) {
+          // no stored text: a substring-only search term cannot match; verify keeps the doc
+          for (uint32_t i = t0; i < t1; ++i) {
+            const uint32_t tid = bv.q_tids[i];
+            if (bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid]) {
+              keep = 0;
+            }
+          }
+        } else if (!all_short || len > kThreadScanMaxDoc) {
+          keep = 2;
+        } else {
           const double dl = static_cast<double>(__ldg(iv.doc_len + doc));
-          // length_norm = 1 - b + b * dl / max(avgdl, 1)
           const double length_norm =
               __dadd_rn(__dsub_rn(1.0, sp.b), __ddiv_rn(__dmul_rn(sp.b, dl), sp.avgdl_clamped));
           for (uint32_t i = t0; i < t1; ++i) {
@@ -686,44 +976,81 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
             const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
             const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
             const bool must = (flags & kQVerify) != 0 || bv.term_koff[tid + 1] == bv.term_koff[tid];
-            const uint32_t tf_u = doc_count_term(d, term, tl, sp.compute_score == 0);
+            const uint32_t tf_u =
+                thread_count_term(iv.text, b, len, term, tl, load_term_head(term, tl), sp.compute_score == 0);
             if (must && tf_u == 0 && tl != 0) {
-              keep = false;
+              keep = 0;
             }
             if (sp.compute_score != 0 && tf_u != 0) {
-              const double tf = static_cast<double>(tf_u);
-              const double numerator = __dmul_rn(tf, __dadd_rn(sp.k1, 1.0));
-              const double denominator = __dadd_rn(tf, __dmul_rn(sp.k1, length_norm));
-              score = __dadd_rn(score, __ddiv_rn(__dmul_rn(bv.q_idf[i], numerator), denominator));
+              score = __dadd_rn(score, bm25_term(bv.q_idf[i], tf_u, length_norm, sp.k1));
             }
           }
-          for (uint32_t i = n0; i < n1 && keep; ++i) {
+          for (uint32_t i = n0; i < n1 && keep != 0; ++i) {
             const uint32_t tid = bv.q_ntids[i];
             const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
             if (bv.term_koff[tid + 1] == bv.term_koff[tid] && tl != 0) {
-              keep = doc_count_term(d, bv.term_bytes + bv.term_boff[tid], tl, true) == 0;
-            }
-          }
-        } else {
-          // no stored text: a substring-only search term cannot match; verify keeps the doc
-          for (uint32_t i = t0; i < t1; ++i) {
-            const uint32_t tid = bv.q_tids[i];
-            if (bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid]) {
-              keep = false;
+              const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
+              if (thread_count_term(iv.text, b, len, term, tl, load_term_head(term, tl), true) != 0) {
+                keep = 0;
+              }
             }
           }
         }
-        __syncwarp();
       }
-      if (lane == 0) {
-        s_keep[s] = keep ? 1 : 0;
-        s_score[s] = score;
+      s_keep[s] = keep;
+      s_score[s] = score;
+      if (keep == 2) {
+        s_any_slow = 1;
       }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      text_bytes += __shfl_xor_sync(0xffffffffu, text_bytes, s);
     }
     if (lane == 0 && text_bytes != 0) {
       atomicAdd(&s_bytes, text_bytes);
     }
     __syncthreads();
+    if (s_any_slow != 0) {
+      // slow path (terms > 16 bytes or documents > 4 KB): one warp per document through shared memory
+      for (uint32_t s = warp; s < total; s += kTileThreads / 32) {
+        if (s_keep[s] != 2) {
+          continue;
+        }
+        const uint32_t doc = s_doc[s];
+        bool keep = true;
+        double score = 0.0;
+        DocText d = doc_open(iv, doc, s_text[warp]);
+        const double dl = static_cast<double>(__ldg(iv.doc_len + doc));
+        const double length_norm = __dadd_rn(__dsub_rn(1.0, sp.b), __ddiv_rn(__dmul_rn(sp.b, dl), sp.avgdl_clamped));
+        for (uint32_t i = t0; i < t1; ++i) {
+          const uint32_t tid = bv.q_tids[i];
+          const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
+          const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+          const bool must = (flags & kQVerify) != 0 || bv.term_koff[tid + 1] == bv.term_koff[tid];
+          const uint32_t tf_u = doc_count_term(d, term, tl, sp.compute_score == 0);
+          if (must && tf_u == 0 && tl != 0) {
+            keep = false;
+          }
+          if (sp.compute_score != 0 && tf_u != 0) {
+            score = __dadd_rn(score, bm25_term(bv.q_idf[i], tf_u, length_norm, sp.k1));
+          }
+        }
+        for (uint32_t i = n0; i < n1 && keep; ++i) {
+          const uint32_t tid = bv.q_ntids[i];
+          const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+          if (bv.term_koff[tid + 1] == bv.term_koff[tid] && tl != 0) {
+            keep = doc_count_term(d, bv.term_bytes + bv.term_boff[tid], tl, true) == 0;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          s_keep[s] = keep ? 1 : 0;
+          s_score[s] = score;
+        }
+      }
+      __syncthreads();
+    }
   }
 
   // ---- ordered write of the tile's records
