@@ -66,6 +66,8 @@ struct BatchView {
   const uint32_t* explicit_ids;
   uint32_t explicit_n;
   unsigned long long* stats;  // StatSlot counters
+  const uint32_t* df_tile_term;  // [df tiles] unique-term index of each df tile
+  const uint32_t* tile_query;    // [and tiles] query index of each intersect tile
 };
 
 struct ScoreParams {
@@ -73,6 +75,7 @@ struct ScoreParams {
   double b;
   double avgdl_clamped;  // max(avg_doc_length, 1.0), bm25_scorer.cpp:77
   int compute_score;
+  int descending;
 };
 
 // ------------------------------------------------------------------ small device helpers
@@ -89,21 +92,6 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__
     }
   }
   return lo;
-}
-
-// largest i in [0, n) with off[i] <= v  (off ascending, off[0] <= v)
-__device__ __forceinline__ uint32_t find_segment(const uint64_t* __restrict__ off, uint32_t n, uint64_t v) {
-  uint32_t lo = 0;
-  uint32_t hi = n;  // search first index with off[idx] > v in [0, n]
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (off[mid] <= v) {
-      lo = mid + 1;
-    } else {
-      hi = mid;
-    }
-  }
-  return lo - 1;
 }
 
 struct ListRef {
@@ -301,7 +289,7 @@ __global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf
       for (uint32_t i = k0; i < k1; ++i) {
         bytes += umin64(4ULL * bv.key_len[i], bitmap_bytes);
       }
-      atomicAdd(bv.stats + kStatDfLists, bytes);
+      atomicAdd(bv.stats + kStatDfLists * kStatStripes + (t & (kStatStripes - 1)), bytes);
     }
   }
   bv.t_df[t] = df;
@@ -483,84 +471,157 @@ __device__ __forceinline__ uint32_t thread_count_term(const uint8_t* __restrict_
   return count;
 }
 
+// tile -> segment map: segment g owns tiles [off[g], off[g+1]); one warp per segment.
+__global__ void fill_tile_map_kernel(const uint64_t* __restrict__ off, uint32_t n_segments, uint32_t* __restrict__ out) {
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= n_segments) {
+    return;
+  }
+  const uint64_t b = off[g];
+  const uint64_t e = off[g + 1];
+  for (uint64_t i = b + (threadIdx.x & 31u); i < e; i += 32) {
+    out[i] = g;
+  }
+}
+
 // ------------------------------------------------------------------ df tiles
+// Verified document frequency of a term (PopulateTermDocumentFrequency, search_pipeline.cpp:542-565): the
+// documents of SearchAnd(term n-grams) whose text contains the term. A CTA covers one 1024-entry tile of the
+// term's shortest list, but every WARP owns its own 128 entries and runs to completion without any block barrier:
+// narrow the other lists to the warp's doc range (32-ary bound search), stage that sub-range in the warp's
+// shared-memory slice with coalesced loads, search it there, then scan the survivors' text one thread per document.
+constexpr int kWarpItems = 4;                       // driver entries per lane
+constexpr int kWarpTile = 32 * kWarpItems;          // 128 entries per warp
+constexpr uint32_t kWarpStageCap = 512;             // staged entries of one other list per warp (2 KB)
+static_assert(kWarpTile * (kTileThreads / 32) == kTile, "warps must tile the CTA tile exactly");
+
+__device__ __forceinline__ void stat_add(const BatchView& bv, int slot, unsigned long long v) {
+  atomicAdd(bv.stats + slot * kStatStripes + (blockIdx.x & (kStatStripes - 1)), v);
+}
+
 __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, BatchView bv) {
-  __shared__ uint32_t s_doc[kTile];
-  __shared__ uint32_t s_slow[kTile];
-  __shared__ uint32_t s_stage[kStageCap];
-  __shared__ uint32_t s_range[2];
-  __shared__ uint32_t s_n;
-  __shared__ uint32_t s_nslow;
-  __shared__ uint32_t s_term;
-  __shared__ uint32_t s_hits;
-  __shared__ uint32_t s_dmin;
-  __shared__ uint32_t s_dmax;
-  __shared__ unsigned long long s_bytes;
+  __shared__ uint32_t s_stage[kTileThreads / 32][kWarpStageCap];
+  __shared__ uint32_t s_surv[kTileThreads / 32][kWarpTile];
   __shared__ __align__(16) uint8_t s_text[kTileThreads / 32][kStageBuf];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    s_term = find_segment(bv.t_df_tile_off, bv.n_terms, blockIdx.x);
-    s_n = 0;
-    s_nslow = 0;
-    s_hits = 0;
-    s_bytes = 0;
-  }
-  __syncthreads();
-  const uint32_t t = s_term;
+  const uint32_t t = __ldg(bv.df_tile_term + blockIdx.x);
   const uint32_t k0 = bv.term_koff[t];
   const uint32_t k1 = bv.term_koff[t + 1];
   const uint64_t tile = blockIdx.x - bv.t_df_tile_off[t];
   const ListRef drv = make_list(iv, bv.key_list[k0], bv.key_len[k0]);
-  const uint64_t e0 = tile * kTile;
-  const uint32_t tile_n = static_cast<uint32_t>(umin64(kTile, drv.len - e0));
-  if (threadIdx.x == 0) {
-    s_dmin = __ldg(drv.p + e0);
-    s_dmax = __ldg(drv.p + e0 + tile_n - 1);
+  const uint64_t e0 = tile * kTile + static_cast<uint64_t>(warp) * kWarpTile;
+  if (e0 >= drv.len) {
+    return;  // no block-wide barrier is used below, so a warp may leave early
   }
-  uint32_t my_doc[kTileItems];
+  const uint32_t tile_n = static_cast<uint32_t>(umin64(kWarpTile, drv.len - e0));
+  const uint32_t dmin = __ldg(drv.p + e0);
+  const uint32_t dmax = __ldg(drv.p + e0 + tile_n - 1);
+  uint32_t my_doc[kWarpItems];
   uint32_t alive = 0;
 #pragma unroll
-  for (int k = 0; k < kTileItems; ++k) {
-    const uint32_t i = threadIdx.x * kTileItems + k;
+  for (int k = 0; k < kWarpItems; ++k) {
+    const uint32_t i = lane * kWarpItems + k;
     my_doc[k] = kNone;
     if (i < tile_n) {
       my_doc[k] = __ldg(drv.p + e0 + i);
       alive |= 1u << k;
     }
   }
-  __syncthreads();
-  const uint32_t dmin = s_dmin;
-  const uint32_t dmax = s_dmax;
+  uint32_t* stage = s_stage[warp];
   for (uint32_t j = k0 + 1; j < k1; ++j) {
-    tile_filter_list(make_list(iv, bv.key_list[j], bv.key_len[j]), dmin, dmax, true, s_stage, s_range, my_doc, &alive);
-    if (__syncthreads_or(alive != 0) == 0) {
-      break;
-    }
-  }
+    const ListRef l = make_list(iv, bv.key_list[j], bv.key_len[j]);
+    if (l.bm != nullptr) {
 #pragma unroll
-  for (int k = 0; k < kTileItems; ++k) {
-    if ((alive >> k) & 1u) {
-      s_doc[atomicAdd(&s_n, 1u)] = my_doc[k];
+      for (int k = 0; k < kWarpItems; ++k) {
+        if (((alive >> k) & 1u) && ((__ldg(l.bm + (my_doc[k] >> 5)) >> (my_doc[k] & 31)) & 1u) == 0) {
+          alive &= ~(1u << k);
+        }
+      }
+    } else {
+      const uint32_t lo = warp_lower_bound(l.p, l.len, dmin);
+      const uint32_t cnt = warp_lower_bound(l.p, l.len, dmax + 1u) - lo;
+      if (cnt == 0) {
+        alive = 0;
+      } else if (cnt <= kWarpStageCap) {
+        for (uint32_t i = lane; i < cnt; i += 32) {
+          stage[i] = __ldg(l.p + lo + i);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < kWarpItems; ++k) {
+          if (((alive >> k) & 1u) && !sorted_contains(stage, cnt, my_doc[k])) {
+            alive &= ~(1u << k);
+          }
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int k = 0; k < kWarpItems; ++k) {
+          if ((alive >> k) & 1u) {
+            const uint32_t pos = lower_bound_u32(l.p + lo, cnt, my_doc[k]);
+            if (pos >= cnt || __ldg(l.p + lo + pos) != my_doc[k]) {
+              alive &= ~(1u << k);
+            }
+          }
+        }
+      }
+    }
+    if (__ballot_sync(0xffffffffu, alive != 0) == 0) {
+      return;
     }
   }
-  __syncthreads();
-  const uint32_t n = s_n;
+  // survivors -> the warp's list (order irrelevant for a count)
+  const uint32_t mine = __popc(alive);
+  uint32_t inc = mine;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, s);
+    if (lane >= static_cast<unsigned>(s)) {
+      inc += o;
+    }
+  }
+  const uint32_t n = __shfl_sync(0xffffffffu, inc, 31);
+  uint32_t w = inc - mine;
+#pragma unroll
+  for (int k = 0; k < kWarpItems; ++k) {
+    if ((alive >> k) & 1u) {
+      s_surv[warp][w++] = my_doc[k];
+    }
+  }
+  __syncwarp();
   const uint8_t* term = bv.term_bytes + bv.term_boff[t];
   const uint32_t tl = bv.term_boff[t + 1] - bv.term_boff[t];
   const TermHead head = load_term_head(term, tl);
   uint32_t hits = 0;
   unsigned long long text_bytes = 0;
-  // fast path: one thread per candidate document
-  for (uint32_t s = threadIdx.x; s < n; s += kTileThreads) {
-    const uint32_t doc = s_doc[s];
-    const uint64_t b = iv.text_off[doc];
-    const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
-    text_bytes += len;
-    if (tl <= kThreadScanMaxTerm && len <= kThreadScanMaxDoc) {
-      hits += thread_count_term(iv.text, b, len, term, tl, head, true);
-    } else {
-      s_slow[atomicAdd(&s_nslow, 1u)] = doc;
+  uint32_t slow_mask_any = 0;
+  for (uint32_t s0 = 0; s0 < n; s0 += 32) {
+    const uint32_t s = s0 + lane;
+    bool slow = false;
+    if (s < n) {
+      const uint32_t doc = s_surv[warp][s];
+      const uint64_t b = iv.text_off[doc];
+      const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
+      text_bytes += len;
+      if (tl <= kThreadScanMaxTerm && len <= kThreadScanMaxDoc) {
+        hits += thread_count_term(iv.text, b, len, term, tl, head, true);
+      } else {
+        slow = true;
+      }
+    }
+    // rare: long terms / very long documents go through the warp-cooperative scanner, one document at a time
+    unsigned slow_mask = __ballot_sync(0xffffffffu, slow);
+    slow_mask_any |= slow_mask;
+    while (slow_mask != 0) {
+      const uint32_t src = static_cast<uint32_t>(__ffs(static_cast<int>(slow_mask))) - 1u;
+      slow_mask &= slow_mask - 1;
+      DocText d = doc_open(iv, s_surv[warp][s0 + src], s_text[warp]);
+      const uint32_t c = doc_count_term(d, term, tl, true);
+      __syncwarp();
+      if (lane == src) {
+        hits += c != 0 ? 1u : 0u;
+      }
     }
   }
 #pragma unroll
@@ -568,32 +629,12 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
     hits += __shfl_xor_sync(0xffffffffu, hits, s);
     text_bytes += __shfl_xor_sync(0xffffffffu, text_bytes, s);
   }
-  __syncthreads();
-  // slow path (long terms / very long documents): one warp per document through shared memory
-  const uint32_t nslow = s_nslow;
-  uint32_t slow_hits = 0;
-  for (uint32_t s = warp; s < nslow; s += kTileThreads / 32) {
-    DocText d = doc_open(iv, s_slow[s], s_text[warp]);
-    slow_hits += doc_count_term(d, term, tl, true) != 0 ? 1u : 0u;
-    __syncwarp();
-  }
   if (lane == 0) {
-    if (hits + slow_hits != 0) {
-      atomicAdd(&s_hits, hits + slow_hits);
+    if (hits != 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(bv.t_df + t), static_cast<unsigned long long>(hits));
     }
-    if (text_bytes != 0) {
-      atomicAdd(&s_bytes, text_bytes);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (s_hits != 0) {
-      atomicAdd(reinterpret_cast<unsigned long long*>(bv.t_df + t), static_cast<unsigned long long>(s_hits));
-    }
-    if (n != 0) {
-      atomicAdd(bv.stats + kStatDfBytes, s_bytes);
-      atomicAdd(bv.stats + kStatDfCandidates, static_cast<unsigned long long>(n));
-    }
+    stat_add(bv, kStatDfBytes, text_bytes);
+    stat_add(bv, kStatDfCandidates, n);
   }
 }
 
@@ -708,7 +749,7 @@ __global__ void query_plan_kernel(IndexView iv, BatchView bv) {
     for (uint32_t i = 0; i < n; ++i) {
       bytes += umin64(4ULL * bv.q_list_len[l0 + i], bitmap_bytes);
     }
-    atomicAdd(bv.stats + kStatIntersectLists, bytes);
+    atomicAdd(bv.stats + kStatIntersectLists * kStatStripes + (q & (kStatStripes - 1)), bytes);
   }
   bv.q_nlists[q] = n;
   bv.q_flags[q] = flags;
@@ -771,6 +812,82 @@ __device__ __forceinline__ uint32_t block_offsets(uint32_t cnt, uint32_t* s_warp
   return prefix + inc - cnt;
 }
 
+// ------------------------------------------------------------------ top-k
+// Sort key: (s, d) compared lexicographically, LARGER IS BETTER.
+//   DESC: s = ord(score), d = doc         (higher score first; ties: higher doc id first)
+//   ASC : s = ~ord(score), d = ~doc       (lower score first; ties: lower doc id first)
+// which is ResultSorter::SortByScore's comparator (result_sorter.cpp:681-686).
+__device__ __forceinline__ uint64_t ord_f64(double x) {
+  const uint64_t bits = static_cast<uint64_t>(__double_as_longlong(x));
+  return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double unord_f64(uint64_t o) {
+  const uint64_t bits = (o >> 63) ? (o & 0x7FFFFFFFFFFFFFFFULL) : ~o;
+  return __longlong_as_double(static_cast<long long>(bits));
+}
+
+struct SortKey {
+  uint64_t s;
+  uint32_t d;
+};
+__device__ __forceinline__ bool key_greater(const SortKey& a, const SortKey& b) {
+  return a.s > b.s || (a.s == b.s && a.d > b.d);
+}
+__device__ __forceinline__ SortKey make_sort_key(double score, uint32_t doc, bool descending) {
+  SortKey k;
+  const uint64_t o = ord_f64(score);
+  k.s = descending ? o : ~o;
+  k.d = descending ? doc : ~doc;
+  return k;
+}
+// digit `pass` (0 = most significant) of the 96-bit key, 8 bits each
+__device__ __forceinline__ uint32_t key_digit(const SortKey& k, int pass) {
+  return pass < 8 ? static_cast<uint32_t>((k.s >> (56 - 8 * pass)) & 0xFF)
+                  : static_cast<uint32_t>((k.d >> (24 - 8 * (pass - 8))) & 0xFF);
+}
+// does the key match `prefix` on its first `pass` digits
+__device__ __forceinline__ bool key_has_prefix(const SortKey& k, const SortKey& prefix, int pass) {
+  if (pass <= 0) {
+    return true;
+  }
+  if (pass < 8) {
+    const int sh = 64 - 8 * pass;
+    return (k.s >> sh) == (prefix.s >> sh);
+  }
+  if (k.s != prefix.s) {
+    return false;
+  }
+  if (pass == 8) {
+    return true;
+  }
+  const int sh = 32 - 8 * (pass - 8);
+  return (k.d >> sh) == (prefix.d >> sh);
+}
+
+constexpr uint32_t kTopkSmem = 1024;  // >= kMaxTopK: the selected keys always fit
+
+// descending bitonic sort of n_pow2 keys in shared memory (256 threads)
+__device__ void bitonic_sort_desc(SortKey* keys, uint32_t n_pow2) {
+  for (uint32_t size = 2; size <= n_pow2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n_pow2 / 2; i += blockDim.x) {
+        const uint32_t lo = 2 * i - (i & (stride - 1));
+        const uint32_t hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const SortKey a = keys[lo];
+        const SortKey b = keys[hi];
+        const bool swap = desc ? key_greater(b, a) : key_greater(a, b);
+        if (swap) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
 constexpr int kMaxCachedLists = 24;
 
 // BM25 contribution of one term (bm25_scorer.cpp:74-85), evaluated operation by operation (no FMA contraction).
@@ -783,7 +900,8 @@ __device__ __forceinline__ double bm25_term(double idf, uint32_t tf_u, double le
 
 __global__ void __launch_bounds__(kTileThreads)
 and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, uint64_t rec_base,
-                uint32_t* __restrict__ tile_count, uint32_t* __restrict__ rec_doc, double* __restrict__ rec_score) {
+                uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_total, uint32_t* __restrict__ rec_doc,
+                double* __restrict__ rec_score, uint32_t prune_k) {
   __shared__ uint32_t s_doc[kTile];     // local doc index of survivors (kNone = id unknown to this shard)
   __shared__ uint32_t s_gid[kTile];     // global doc id of survivors (explicit drivers only)
   __shared__ double s_score[kTile];
@@ -791,7 +909,6 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   __shared__ uint32_t s_stage[kStageCap];
   __shared__ uint32_t s_range[2];
   __shared__ uint32_t s_warp[kTileThreads / 32];
-  __shared__ uint32_t s_q;
   __shared__ uint32_t s_dmin;
   __shared__ uint32_t s_dmax;
   __shared__ uint32_t s_any_slow;
@@ -802,12 +919,10 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   const unsigned warp = threadIdx.x >> 5;
   const uint64_t tile_global = tile_base + blockIdx.x;
   if (threadIdx.x == 0) {
-    s_q = find_segment(bv.q_tile_off, bv.n_queries, tile_global);
     s_bytes = 0;
     s_any_slow = 0;
   }
-  __syncthreads();
-  const uint32_t q = s_q;
+  const uint32_t q = __ldg(bv.tile_query + tile_global);
   const uint32_t flags = bv.q_flags[q];
   const uint32_t l0 = bv.q_loff[q];
   const uint32_t nl = bv.q_nlists[q];
@@ -1066,119 +1181,73 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   }
   uint32_t kept_total = 0;
   uint32_t woff = block_offsets(__popc(keep_mask), s_warp, &kept_total);
+  uint32_t written = kept_total;
+  if (prune_k != 0 && kept_total > prune_k) {
+    // Block-level top-k inside the epilogue: a tile can contribute at most prune_k (= offset + limit) records to
+    // the query's answer, so only its best prune_k survive (SortByScore order). The full count still goes to
+    // tile_total. The staging buffer of the membership phase is reused as the key array.
+    SortKey* keys = reinterpret_cast<SortKey*>(s_stage);
+    static_assert(sizeof(SortKey) * kTile <= sizeof(uint32_t) * kStageCap, "key array must fit the staging buffer");
 #pragma unroll
-  for (int k = 0; k < kTileItems; ++k) {
-    if (keep_mask & (1u << k)) {
-      const uint32_t s = s0 + k;
-      rec_doc[out_base + woff] = drv_explicit ? s_gid[s] : gid_of(iv, s_doc[s]);
-      if (sp.compute_score != 0) {
-        rec_score[out_base + woff] = s_score[s];
+    for (int k = 0; k < kTileItems; ++k) {
+      if (keep_mask & (1u << k)) {
+        const uint32_t s = s0 + k;
+        keys[woff++] = make_sort_key(s_score[s], drv_explicit ? s_gid[s] : gid_of(iv, s_doc[s]), sp.descending != 0);
       }
-      ++woff;
+    }
+    for (uint32_t i = kept_total + threadIdx.x; i < kTile; i += kTileThreads) {
+      keys[i].s = 0;
+      keys[i].d = 0;
+    }
+    bitonic_sort_desc(keys, kTile);
+    written = prune_k;
+    for (uint32_t i = threadIdx.x; i < written; i += kTileThreads) {
+      rec_doc[out_base + i] = sp.descending != 0 ? keys[i].d : ~keys[i].d;
+      rec_score[out_base + i] = unord_f64(sp.descending != 0 ? keys[i].s : ~keys[i].s);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kTileItems; ++k) {
+      if (keep_mask & (1u << k)) {
+        const uint32_t s = s0 + k;
+        rec_doc[out_base + woff] = drv_explicit ? s_gid[s] : gid_of(iv, s_doc[s]);
+        if (sp.compute_score != 0) {
+          rec_score[out_base + woff] = s_score[s];
+        }
+        ++woff;
+      }
     }
   }
   if (threadIdx.x == 0) {
-    tile_count[blockIdx.x] = kept_total;
+    tile_count[blockIdx.x] = written;
+    tile_total[blockIdx.x] = kept_total;
     if (kept_total != 0) {
-      atomicAdd(bv.stats + kStatResultDocs, static_cast<unsigned long long>(kept_total));
+      atomicAdd(bv.stats + kStatResultDocs * kStatStripes + (blockIdx.x & (kStatStripes - 1)),
+                static_cast<unsigned long long>(kept_total));
     }
     if (s_bytes != 0) {
-      atomicAdd(bv.stats + kStatScoreBytes, s_bytes);
+      atomicAdd(bv.stats + kStatScoreBytes * kStatStripes + (blockIdx.x & (kStatStripes - 1)), s_bytes);
     }
   }
 }
 
-// ------------------------------------------------------------------ top-k
-// Sort key: (s, d) compared lexicographically, LARGER IS BETTER.
-//   DESC: s = ord(score), d = doc         (higher score first; ties: higher doc id first)
-//   ASC : s = ~ord(score), d = ~doc       (lower score first; ties: lower doc id first)
-// which is ResultSorter::SortByScore's comparator (result_sorter.cpp:681-686).
-__device__ __forceinline__ uint64_t ord_f64(double x) {
-  const uint64_t bits = static_cast<uint64_t>(__double_as_longlong(x));
-  return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ULL);
-}
-__device__ __forceinline__ double unord_f64(uint64_t o) {
-  const uint64_t bits = (o >> 63) ? (o & 0x7FFFFFFFFFFFFFFFULL) : ~o;
-  return __longlong_as_double(static_cast<long long>(bits));
-}
-
-struct SortKey {
-  uint64_t s;
-  uint32_t d;
-};
-__device__ __forceinline__ bool key_greater(const SortKey& a, const SortKey& b) {
-  return a.s > b.s || (a.s == b.s && a.d > b.d);
-}
-__device__ __forceinline__ SortKey make_sort_key(double score, uint32_t doc, bool descending) {
-  SortKey k;
-  const uint64_t o = ord_f64(score);
-  k.s = descending ? o : ~o;
-  k.d = descending ? doc : ~doc;
-  return k;
-}
-// digit `pass` (0 = most significant) of the 96-bit key, 8 bits each
-__device__ __forceinline__ uint32_t key_digit(const SortKey& k, int pass) {
-  return pass < 8 ? static_cast<uint32_t>((k.s >> (56 - 8 * pass)) & 0xFF)
-                  : static_cast<uint32_t>((k.d >> (24 - 8 * (pass - 8))) & 0xFF);
-}
-// does the key match `prefix` on its first `pass` digits
-__device__ __forceinline__ bool key_has_prefix(const SortKey& k, const SortKey& prefix, int pass) {
-  if (pass <= 0) {
-    return true;
-  }
-  if (pass < 8) {
-    const int sh = 64 - 8 * pass;
-    return (k.s >> sh) == (prefix.s >> sh);
-  }
-  if (k.s != prefix.s) {
-    return false;
-  }
-  if (pass == 8) {
-    return true;
-  }
-  const int sh = 32 - 8 * (pass - 8);
-  return (k.d >> sh) == (prefix.d >> sh);
-}
-
-constexpr uint32_t kTopkSmem = 2048;
-
-// descending bitonic sort of n_pow2 keys in shared memory (256 threads)
-__device__ void bitonic_sort_desc(SortKey* keys, uint32_t n_pow2) {
-  for (uint32_t size = 2; size <= n_pow2; size <<= 1) {
-    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
-      for (uint32_t i = threadIdx.x; i < n_pow2 / 2; i += blockDim.x) {
-        const uint32_t lo = 2 * i - (i & (stride - 1));
-        const uint32_t hi = lo + stride;
-        const bool desc = (lo & size) == 0;
-        const SortKey a = keys[lo];
-        const SortKey b = keys[hi];
-        const bool swap = desc ? key_greater(b, a) : key_greater(a, b);
-        if (swap) {
-          keys[lo] = b;
-          keys[hi] = a;
-        }
-      }
-    }
-  }
-  __syncthreads();
-}
-
+// ------------------------------------------------------------------ top-k kernels
 // One CTA per query. Records of tile t of the query live at rec_off + t*kTile .. +tile_count[t].
 __global__ void __launch_bounds__(256)
 topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_base,
-            const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ rec_doc,
-            const double* __restrict__ rec_score, int compute_score, int descending, uint32_t limit, uint32_t offset,
+            const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_total,
+            const uint32_t* __restrict__ rec_doc, const double* __restrict__ rec_score, int compute_score,
+            int descending, uint32_t limit, uint32_t offset,
             uint64_t stride, uint32_t* __restrict__ out_ids, double* __restrict__ out_scores,
             uint32_t* __restrict__ out_count, uint64_t* __restrict__ out_total) {
   __shared__ SortKey s_keys[kTopkSmem];
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_cnt;
   __shared__ uint64_t s_scan[8];
+  __shared__ uint64_t s_scan_rec[8];
   __shared__ uint64_t s_carry;
   __shared__ SortKey s_prefix;
   __shared__ uint32_t s_need;
-  __shared__ int s_done;
   const uint32_t q = q_first + blockIdx.x;
   const uint64_t t0 = bv.q_tile_off[q] - tile_base;
   const uint32_t ntiles = static_cast<uint32_t>(bv.q_tile_off[q + 1] - bv.q_tile_off[q]);
@@ -1188,17 +1257,21 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_bas
   uint32_t* ids = out_ids + static_cast<uint64_t>(q) * stride;
   double* scs = out_scores != nullptr ? out_scores + static_cast<uint64_t>(q) * stride : nullptr;
 
-  // total = sum of tile counts
+  // total = sum of the tiles' full survivor counts; records = what the tiles actually wrote (pruned to top-k)
   uint64_t local = 0;
+  uint64_t local_rec = 0;
   for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x) {
-    local += tile_count[t0 + t];
+    local += tile_total[t0 + t];
+    local_rec += tile_count[t0 + t];
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
     local += __shfl_xor_sync(0xffffffffu, local, s);
+    local_rec += __shfl_xor_sync(0xffffffffu, local_rec, s);
   }
   if (lane == 0) {
     s_scan[warp] = local;
+    s_scan_rec[warp] = local_rec;
   }
   if (threadIdx.x == 0) {
     s_cnt = 0;
@@ -1206,9 +1279,11 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_bas
   }
   __syncthreads();
   uint64_t total = 0;
+  uint64_t n_records = 0;
 #pragma unroll
   for (int w = 0; w < 8; ++w) {
     total += s_scan[w];
+    n_records += s_scan_rec[w];
   }
   __syncthreads();
   const uint64_t want_end = limit == 0 ? total : umin64(total, static_cast<uint64_t>(offset) + limit);
@@ -1271,13 +1346,12 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_bas
   SortKey thr;
   thr.s = 0;
   thr.d = 0;
-  if (total > kTopkSmem) {
+  if (n_records > kTopkSmem) {
     // MSB-first radix select of the kk-th largest key
     if (threadIdx.x == 0) {
       s_prefix.s = 0;
       s_prefix.d = 0;
       s_need = kk;
-      s_done = 0;
     }
     __syncthreads();
     for (int pass = 0; pass < 12; ++pass) {
@@ -1321,7 +1395,7 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_bas
     const uint64_t base = r0 + static_cast<uint64_t>(t) * kTile;
     for (uint32_t i = lane; i < c; i += 32) {
       const SortKey k = make_sort_key(rec_score[base + i], rec_doc[base + i], desc);
-      if (total <= kTopkSmem || !key_greater(thr, k)) {
+      if (n_records <= kTopkSmem || !key_greater(thr, k)) {
         const uint32_t pos = atomicAdd(&s_cnt, 1u);
         if (pos < kTopkSmem) {
           s_keys[pos] = k;
@@ -1644,6 +1718,8 @@ BatchView make_batch_view(Batch& b) {
   v.explicit_ids = b.explicit_driver.d_ids;
   v.explicit_n = static_cast<uint32_t>(b.explicit_driver.n);
   v.stats = b.d_stats.p;
+  v.df_tile_term = b.d_df_tile_term.p;
+  v.tile_query = b.d_tile_query.p;
   return v;
 }
 
@@ -1724,7 +1800,13 @@ void Batch::collect_stats(mgx_batch_stats_t* out) {
   }
   unsigned long long h[kStatCount] = {0};
   if (d_stats.p != nullptr) {
-    MGX_CUDA(cudaMemcpy(h, d_stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long> raw(static_cast<size_t>(kStatCount) * kStatStripes, 0);
+    MGX_CUDA(cudaMemcpy(raw.data(), d_stats.p, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int slot = 0; slot < kStatCount; ++slot) {
+      for (int i = 0; i < kStatStripes; ++i) {
+        h[slot] += raw[static_cast<size_t>(slot) * kStatStripes + i];
+      }
+    }
   }
   const uint64_t k = params.limit + params.offset;
   s.n_df_tiles = n_df_tiles;
@@ -1817,8 +1899,8 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vecto
   b.h2d_bytes = h2d;
 
   upload(b.d_term_flags, raw, st, &h2d);
-  b.d_stats.alloc(kStatCount);
-  MGX_CUDA(cudaMemsetAsync(b.d_stats.p, 0, kStatCount * sizeof(unsigned long long), st));
+  b.d_stats.alloc(static_cast<size_t>(kStatCount) * kStatStripes);
+  MGX_CUDA(cudaMemsetAsync(b.d_stats.p, 0, b.d_stats.bytes(), st));
   b.h2d_bytes = h2d;
 }
 
@@ -1857,6 +1939,22 @@ void batch_plan(Batch& b) {
   b.time_end();
   MGX_CUDA(cudaStreamSynchronize(st));
   b.d2h_bytes += 2 * (b.n_queries + 1) * sizeof(uint64_t) + sizeof(uint64_t);
+  // tile -> term / tile -> query maps (sizes are only known now)
+  const uint64_t n_and_tiles = b.n_queries > 0 ? b.h_q_tile_off[b.n_queries] : 0;
+  b.d_df_tile_term.alloc(b.n_df_tiles);
+  b.d_tile_query.alloc(n_and_tiles);
+  b.time_begin(0);
+  if (b.n_df_tiles > 0) {
+    fill_tile_map_kernel<<<grid_for(static_cast<uint64_t>(b.n_terms) * 32, 256), 256, 0, st>>>(
+        b.d_t_df_tile_off.p, b.n_terms, b.d_df_tile_term.p);
+    MGX_LAUNCH_CHECK();
+  }
+  if (n_and_tiles > 0) {
+    fill_tile_map_kernel<<<grid_for(static_cast<uint64_t>(b.n_queries) * 32, 256), 256, 0, st>>>(
+        b.d_q_tile_off.p, b.n_queries, b.d_tile_query.p);
+    MGX_LAUNCH_CHECK();
+  }
+  b.time_end();
   b.planned = true;
 }
 
@@ -1937,6 +2035,7 @@ ScoreParams score_params(const Batch& b) {
       total_docs > 0 ? static_cast<double>(total_len) / static_cast<double>(total_docs) : 0.0;  // server_types.h:182-187
   sp.avgdl_clamped = std::max(avgdl, 1.0);
   sp.compute_score = b.params.compute_score;
+  sp.descending = b.params.descending;
   return sp;
 }
 
@@ -1945,13 +2044,14 @@ uint64_t scratch_records(const Batch& b) {
   return std::max<uint64_t>(bytes / 12, 1ULL << 20);
 }
 
-void run_tiles(Batch& b, const Chunk& c, const ScoreParams& sp) {
+void run_tiles(Batch& b, const Chunk& c, const ScoreParams& sp, uint32_t prune_k) {
   cudaStream_t st = b.stream;
   const uint64_t tile_base = b.h_q_tile_off[c.q0];
   const uint64_t n_tiles = b.h_q_tile_off[c.q1] - tile_base;
   const uint64_t rec_base = b.h_q_rec_off[c.q0];
   const uint64_t n_recs = b.h_q_rec_off[c.q1] - rec_base;
   b.d_tile_count.reserve(std::max<uint64_t>(n_tiles, 1));
+  b.d_tile_total.reserve(std::max<uint64_t>(n_tiles, 1));
   b.d_rec_doc.reserve(std::max<uint64_t>(n_recs + kTile, 1));
   if (sp.compute_score != 0) {
     b.d_rec_score.reserve(std::max<uint64_t>(n_recs + kTile, 1));
@@ -1963,8 +2063,8 @@ void run_tiles(Batch& b, const Chunk& c, const ScoreParams& sp) {
     }
     b.time_begin(2);
     and_tile_kernel<<<static_cast<unsigned>(n_tiles), kTileThreads, 0, st>>>(
-        make_view(*b.ix), make_batch_view(b), sp, tile_base, rec_base, b.d_tile_count.p, b.d_rec_doc.p,
-        b.d_rec_score.p);
+        make_view(*b.ix), make_batch_view(b), sp, tile_base, rec_base, b.d_tile_count.p, b.d_tile_total.p,
+        b.d_rec_doc.p, b.d_rec_score.p, prune_k);
     MGX_LAUNCH_CHECK();
     b.time_end();
     b.n_and_tiles += n_tiles;
@@ -1987,11 +2087,13 @@ void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_
     if (chunks.size() > 1) {
       MGX_CUDA(cudaStreamSynchronize(st));  // scratch is reused by the next chunk
     }
-    run_tiles(b, c, sp);
+    // per-tile top-k pruning is only valid when the answer is a top-k by score
+    const uint32_t prune_k = sp.compute_score != 0 ? b.params.limit + b.params.offset : 0u;
+    run_tiles(b, c, sp, prune_k);
     driver_entries += b.h_q_rec_off[c.q1] - b.h_q_rec_off[c.q0];
     b.time_begin(3);
     topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.h_q_rec_off[c.q0],
-                                             b.d_tile_count.p, b.d_rec_doc.p, b.d_rec_score.p,
+                                             b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p, b.d_rec_score.p,
                                              b.params.compute_score, b.params.descending, b.params.limit,
                                              b.params.offset, stride, d_ids, d_scores, d_count, d_total);
     MGX_LAUNCH_CHECK();
@@ -2020,9 +2122,10 @@ void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32
   if (chunks.size() == 1) {
     // single chunk: records stay valid between the counting and the gathering pass
     const Chunk& c = chunks[0];
-    run_tiles(b, c, sp);
+    run_tiles(b, c, sp, 0);
     topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.h_q_rec_off[c.q0],
-                                             b.d_tile_count.p, b.d_rec_doc.p, nullptr, 0, 0, 0, 0, 0, d_dummy.p, nullptr,
+                                             b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p, nullptr, 0, 0, 0, 0, 0,
+                                             d_dummy.p, nullptr,
                                              d_count.p, d_total.p);
     MGX_LAUNCH_CHECK();
     MGX_CUDA(cudaMemcpyAsync(totals.data(), d_total.p, b.n_queries * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -2046,9 +2149,10 @@ void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32
   // several chunks: count everything first, then redo the tiles chunk by chunk and gather
   for (const Chunk& c : chunks) {
     MGX_CUDA(cudaStreamSynchronize(st));
-    run_tiles(b, c, sp);
+    run_tiles(b, c, sp, 0);
     topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.h_q_rec_off[c.q0],
-                                             b.d_tile_count.p, b.d_rec_doc.p, nullptr, 0, 0, 0, 0, 0, d_dummy.p, nullptr,
+                                             b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p, nullptr, 0, 0, 0, 0, 0,
+                                             d_dummy.p, nullptr,
                                              d_count.p, d_total.p);
     MGX_LAUNCH_CHECK();
   }
@@ -2065,7 +2169,7 @@ void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32
   d_sets->alloc(std::max<uint64_t>(1, h_set_off->back()));
   for (const Chunk& c : chunks) {
     MGX_CUDA(cudaStreamSynchronize(st));
-    run_tiles(b, c, sp);
+    run_tiles(b, c, sp, 0);
     gather_sets_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0],
                                                     b.h_q_rec_off[c.q0], b.d_tile_count.p, b.d_rec_doc.p, d_set_off.p,
                                                     d_sets->p);
@@ -2102,6 +2206,7 @@ void launch_score_documents(Index& ix, cudaStream_t stream, const uint32_t* d_ca
   sp.b = b;
   sp.avgdl_clamped = std::max(avgdl, 1.0);
   sp.compute_score = 1;
+  sp.descending = 1;
   if (n_cands > 0) {
     score_docs_kernel<<<grid_for(n_cands, 8), 256, 0, stream>>>(make_view(ix), d_cands, n_cands, d_term_bytes,
                                                                 d_term_boff, d_idf.p, n_terms, sp, d_scores);

@@ -74,7 +74,8 @@ struct Batch {
   DevBuf<uint32_t> d_q_host_flags;  // [Q] flags decided on the host (verify etc.)
 
   // ---- device: per-tile results
-  DevBuf<uint32_t> d_tile_count;  // [tiles in flight]
+  DevBuf<uint32_t> d_tile_count;  // [tiles in flight] records written by the tile
+  DevBuf<uint32_t> d_tile_total;  // [tiles in flight] survivors of the tile (>= records when pruned to top-k)
   DevBuf<uint32_t> d_rec_doc;     // survivors (global doc ids), tile k of query q at rec_off[q] + k*kTile
   DevBuf<double> d_rec_score;
 
@@ -83,6 +84,8 @@ struct Batch {
   std::vector<uint64_t> h_q_rec_off;
 
   DevBuf<uint8_t> d_term_flags;   // [T] bit0 raw, bit1 exact_single
+  DevBuf<uint32_t> d_df_tile_term;  // [df tiles]
+  DevBuf<uint32_t> d_tile_query;    // [and tiles]
   DevBuf<unsigned long long> d_stats;  // device-side accounting, see StatSlot
 
   ExplicitDriver explicit_driver;
@@ -120,6 +123,7 @@ enum StatSlot : int {
   kStatDfLists = 5,
   kStatCount = 8
 };
+constexpr int kStatStripes = 64;  // each counter is striped over 64 words to spread the atomics
 
 // One compiled query term.
 struct HostTerm {

@@ -305,3 +305,49 @@ def test_kernels_were_launched(mgx):
     idx.add_document_batch([1, 2], ["abc", "bcd"])
     idx.query_batch([[b"bc"]], score=True)
     assert mgx.lib().mgx_kernel_launch_count() > before + 10
+
+
+# ----------------------------------------------------------------------------------------- sharding pieces on one GPU
+def test_staged_api_and_merge_kernel_match_single_call(mgx, oracle):
+    """Two 'shards' of one corpus on ONE GPU through the staged C ABI (prepare/plan/df/search) + the merge kernel,
+    with the df all-reduce and the all-gather emulated by host adds/stacks, equal the single-index oracle answer."""
+    import ctypes as C
+    torch = pytest.importorskip("torch")
+    import mgx_loader
+    mgx_loader.load()
+    from mygram_db_b200 import sharded
+    n_total = 40000
+    c = corpus_mod.generate("cjk", n_total, 0xC2, alphabet=256, min_len=6, max_len=40)
+    oi = oracle.index(2, 0, True)
+    oi.build_bulk(c.doc_ids, c.arena, c.offsets, 8)
+    tl, dc = oi.bm25_stats()
+    qs = corpus_mod.sample_queries(c, 400, 11, n_terms=2, min_cp=2, max_cp=3)
+    arena, offs = mgx.pack_strings([t for q in qs for t in q])
+    qbeg = np.arange(0, 2 * len(qs) + 1, 2, dtype=np.uint64)
+    device = torch.device("cuda", 0)
+    for limit, offset, desc in ((100, 0, True), (10, 5, False)):
+        backends, batches = [], []
+        for r in range(2):
+            lo, hi = sharded.shard_range(n_total, 2, r)
+            gi = mgx.Index(2, 0, True)
+            gi.build(c.doc_ids[lo:hi], c.arena[int(c.offsets[lo]):int(c.offsets[hi])],
+                     c.offsets[lo:hi + 1] - c.offsets[lo])
+            p = gi.params(score=True, descending=desc, limit=limit, offset=offset, total_docs=dc, total_doc_length=tl)
+            be = sharded.MgxShardBackend(mgx, gi, p, limit + offset, device)
+            backends.append(be)
+            batches.append(be.prepare(arena, offs, qbeg, len(qs)))
+        dfs = [be.local_df(b) for be, b in zip(backends, batches)]
+        df = dfs[0] + dfs[1]  # the all-reduce
+        parts = [be.search(b, df) for be, b in zip(backends, batches)]
+        gathered = [torch.stack([parts[0][i], parts[1][i]]) for i in range(4)]  # the all-gather
+        ids, scores, count, total = backends[0].merge(*gathered)
+        torch.cuda.synchronize()
+        want = oi.query_batch(qs, score=True, descending=desc, limit=limit, offset=offset, n_threads=8)
+        g = mgx.BatchResult(ids.cpu().numpy().view(np.uint32), scores.cpu().numpy(), count.cpu().numpy().astype(np.uint32),
+                            total.cpu().numpy().astype(np.uint64), df.cpu().numpy().astype(np.uint64)[:want.df.size])
+        g.ids = g.ids[:, :limit]
+        g.scores = g.scores[:, :limit]
+        assert_batch_equal(g, want, qs)
+        assert int(want.total.max()) > limit + offset
+        for be, b in zip(backends, batches):
+            be.release(b)
