@@ -16,6 +16,8 @@
 //                       per-document unique) + compaction into CSR
 //   K5 bitmaps          doc bitmaps for lists with density >= dense_threshold
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 #include "mgx_internal.cuh"
 
@@ -489,8 +491,28 @@ __global__ void sequential_check_kernel(const uint32_t* __restrict__ ids, uint64
   }
 }
 
+namespace {
+// MGX_BUILD_TRACE=1 prints the host-side wall time of each build phase (stream synchronised) to stderr.
+struct PhaseTrace {
+  bool on;
+  cudaStream_t stream;
+  std::chrono::steady_clock::time_point t0;
+  PhaseTrace(cudaStream_t s) : on(std::getenv("MGX_BUILD_TRACE") != nullptr), stream(s), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* name) {
+    if (!on) {
+      return;
+    }
+    cudaStreamSynchronize(stream);
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[mgx build] %-28s %8.2f ms\n", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+}  // namespace
+
 void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* d_text_in,
                         const uint64_t* d_text_off_in, uint64_t n_docs, uint64_t text_bytes, cudaStream_t stream) {
+  PhaseTrace trace(stream);
   uint32_t first_id = 1;
   bool sequential_ids = true;
   cudaEvent_t ev0;
@@ -532,6 +554,7 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   ix.first_id = first_id;
   ix.sequential_ids = sequential_ids;
 
+  trace.mark("resident copies + id check");
   DevBuf<uint64_t> d_slot_off;
   DevBuf<uint64_t> d_keys_a;
   DevBuf<uint32_t> d_docs_a;
@@ -540,6 +563,7 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   tokenize_device(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, ix.d_doc_len,
                   d_slot_off, d_keys_a, d_docs_a, &n_slots, counters, stream);
   d_slot_off.release();
+  trace.mark("tokenize (count+scan+emit)");
   ix.n_pair_slots = n_slots;
   ix.total_doc_length = n_slots;  // one slot per code point
   ix.doc_count = counters[0];
@@ -553,8 +577,10 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   DevBuf<uint32_t> d_docs_b;
   d_keys_b.alloc(n_slots);
   d_docs_b.alloc(n_slots);
+  trace.mark("alloc sort buffers");
   const SortResult sorted =
       radix_sort_pairs(d_keys_a.p, d_docs_a.p, d_keys_b.p, d_docs_b.p, n_slots, 21 * ix.width, stream);
+  trace.mark("radix sort");
 
   // segmented unique + compaction
   const uint64_t n_blocks = (n_slots + kCsrTile - 1) / kCsrTile;
@@ -588,10 +614,12 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   set_u64_kernel<<<1, 1, 0, stream>>>(ix.d_term_off.p + ix.n_terms, ix.n_postings);
   MGX_LAUNCH_CHECK();
   MGX_CUDA(cudaStreamSynchronize(stream));
+  trace.mark("csr");
   d_keys_a.release();
   d_docs_a.release();
   d_keys_b.release();
   d_docs_b.release();
+  trace.mark("free sort buffers");
 
   // dense bitmaps
   ix.bm_words = (n_docs + 31) / 32;
@@ -640,6 +668,7 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
     MGX_CUDA(cudaStreamSynchronize(stream));
   }
 
+  trace.mark("dense bitmaps");
   MGX_CUDA(cudaEventRecord(ev1, stream));
   MGX_CUDA(cudaEventSynchronize(ev1));
   float ms = 0.f;

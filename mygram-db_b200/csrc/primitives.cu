@@ -152,81 +152,151 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t
   hist[static_cast<uint64_t>(threadIdx.x) * n_tiles + blockIdx.x] = bins[threadIdx.x];
 }
 
-// Stable scatter. Warp w owns the contiguous items [w*512, (w+1)*512) of the
-// tile, visited in 16 rounds of 32 consecutive items, so (warp, round, lane)
-// order == input order; ranks are assigned in that order.
+// Global digit histograms of every pass in ONE read of the keys: a pass whose digit is the same for all
+// keys is a pure copy and is skipped (e.g. the high bits of each 21-bit code-point field).
+constexpr int kMaxPasses = 8;
+__global__ void __launch_bounds__(256) radix_global_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n, int passes,
+                                                                unsigned long long* __restrict__ hist /*[passes][256]*/) {
+  __shared__ uint32_t bins[kMaxPasses][kRadix];
+  for (int p = 0; p < passes; ++p) {
+    bins[p][threadIdx.x] = 0;
+  }
+  __syncthreads();
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t k = keys[i];
+    for (int p = 0; p < passes; ++p) {
+      atomicAdd(&bins[p][(k >> (p * kRadixBits)) & (kRadix - 1)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int p = 0; p < passes; ++p) {
+    const uint32_t c = bins[p][threadIdx.x];
+    if (c != 0) {
+      atomicAdd(&hist[p * kRadix + threadIdx.x], static_cast<unsigned long long>(c));
+    }
+  }
+}
+
+// Stable scatter with a shared-memory reorder. Warp w owns the contiguous items [w*512, (w+1)*512) of the tile,
+// visited in 16 rounds of 32 consecutive items, so (warp, round, lane) order == input order; ranks are assigned in
+// that order. Items are first placed at their tile-local sorted position in shared memory; the tile is then written
+// out run by run, so consecutive threads store to consecutive global addresses.
+struct ScatterSmem {
+  uint64_t keys[kSortTile];
+  uint32_t vals[kSortTile];
+  uint32_t warp_cnt[kSortWarps][kRadix];
+  uint32_t local_start[kRadix];
+  uint32_t global_base[kRadix];
+  uint32_t scan_tmp[kSortWarps];
+};
+
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint64_t* __restrict__ keys_in,
                                                                      const uint32_t* __restrict__ vals_in,
                                                                      uint64_t* __restrict__ keys_out,
                                                                      uint32_t* __restrict__ vals_out, uint64_t n,
                                                                      int shift, const uint64_t* __restrict__ hist_scan,
                                                                      uint32_t n_tiles) {
-  __shared__ uint32_t warp_cnt[kSortWarps][kRadix];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(smem_raw);
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int w = 0; w < kSortWarps; ++w) {
-    warp_cnt[w][threadIdx.x] = 0;
+    sm.warp_cnt[w][threadIdx.x] = 0;
   }
   __syncthreads();
 
-  const uint64_t warp_base = static_cast<uint64_t>(blockIdx.x) * kSortTile + static_cast<uint64_t>(warp) * (32 * kSortRounds);
+  const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * kSortTile;
+  const uint32_t tile_n = static_cast<uint32_t>(n - tile_base < kSortTile ? n - tile_base : kSortTile);
+  const uint32_t warp_off = warp * (32 * kSortRounds);
   uint64_t key[kSortRounds];
   uint32_t val[kSortRounds];
 #pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
-    const uint64_t i = warp_base + static_cast<uint64_t>(r) * 32 + lane;
-    const bool valid = i < n;
-    key[r] = valid ? keys_in[i] : 0;
-    val[r] = valid ? vals_in[i] : 0;
+    const uint32_t i = warp_off + r * 32 + lane;
+    const bool valid = i < tile_n;
+    key[r] = valid ? keys_in[tile_base + i] : 0;
+    val[r] = valid ? vals_in[tile_base + i] : 0;
   }
   // phase 1: per-warp digit counts
 #pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
-    const uint64_t i = warp_base + static_cast<uint64_t>(r) * 32 + lane;
-    const bool valid = i < n;
+    const bool valid = warp_off + r * 32 + lane < tile_n;
     const uint32_t d = valid ? static_cast<uint32_t>((key[r] >> shift) & (kRadix - 1)) : 0x1FFu;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     if (valid && (peers & lt_mask) == 0) {
-      warp_cnt[warp][d] += __popc(peers);
+      sm.warp_cnt[warp][d] += __popc(peers);
     }
     __syncwarp();
   }
   __syncthreads();
-  // per digit: exclusive scan over warps, seeded with this tile's global base
+  // per digit (thread d): tile count, exclusive scan over digits -> tile-local start; per-warp offsets
   {
     const unsigned d = threadIdx.x;
-    uint32_t running = static_cast<uint32_t>(hist_scan[static_cast<uint64_t>(d) * n_tiles + blockIdx.x]);
+    uint32_t cnt = 0;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
-      const uint32_t c = warp_cnt[w][d];
-      warp_cnt[w][d] = running;
+      cnt += sm.warp_cnt[w][d];
+    }
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, s);
+      if (lane >= static_cast<unsigned>(s)) {
+        inc += o;
+      }
+    }
+    if (lane == 31) {
+      sm.scan_tmp[warp] = inc;
+    }
+    __syncthreads();
+    uint32_t prefix = 0;
+    for (unsigned w = 0; w < warp; ++w) {
+      prefix += sm.scan_tmp[w];
+    }
+    const uint32_t start = prefix + inc - cnt;
+    sm.local_start[d] = start;
+    sm.global_base[d] = static_cast<uint32_t>(hist_scan[static_cast<uint64_t>(d) * n_tiles + blockIdx.x]);
+    uint32_t running = start;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = sm.warp_cnt[w][d];
+      sm.warp_cnt[w][d] = running;
       running += c;
     }
   }
   __syncthreads();
-  // phase 2: rank and scatter
+  // phase 2: rank inside the tile and place into shared memory
 #pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
-    const uint64_t i = warp_base + static_cast<uint64_t>(r) * 32 + lane;
-    const bool valid = i < n;
+    const bool valid = warp_off + r * 32 + lane < tile_n;
     const uint32_t d = valid ? static_cast<uint32_t>((key[r] >> shift) & (kRadix - 1)) : 0x1FFu;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     uint32_t base = 0;
     if (valid) {
-      base = warp_cnt[warp][d];
+      base = sm.warp_cnt[warp][d];
     }
     __syncwarp();
     if (valid && (peers & lt_mask) == 0) {
-      warp_cnt[warp][d] = base + __popc(peers);
+      sm.warp_cnt[warp][d] = base + __popc(peers);
     }
     __syncwarp();
     if (valid) {
       const uint32_t pos = base + __popc(peers & lt_mask);
-      keys_out[pos] = key[r];
-      vals_out[pos] = val[r];
+      sm.keys[pos] = key[r];
+      sm.vals[pos] = val[r];
     }
+  }
+  __syncthreads();
+  // phase 3: coalesced write-out, run by run
+  for (uint32_t i = threadIdx.x; i < tile_n; i += kSortThreads) {
+    const uint64_t k = sm.keys[i];
+    const uint32_t d = static_cast<uint32_t>((k >> shift) & (kRadix - 1));
+    const uint32_t pos = sm.global_base[d] + (i - sm.local_start[d]);
+    keys_out[pos] = k;
+    vals_out[pos] = sm.vals[i];
   }
 }
 
@@ -257,25 +327,52 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
   if (n == 0) {
     return cur;
   }
+  static bool attr_set = false;
+  if (!attr_set) {
+    MGX_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(sizeof(ScatterSmem))));
+    attr_set = true;
+  }
   const uint32_t n_tiles = static_cast<uint32_t>((n + kSortTile - 1) / kSortTile);
   const uint64_t hist_len = static_cast<uint64_t>(kRadix) * n_tiles;
+  const int passes = (key_bits + kRadixBits - 1) / kRadixBits;
   uint32_t* d_hist = nullptr;
   uint64_t* d_hist_scan = nullptr;
+  unsigned long long* d_ghist = nullptr;
   MGX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_hist), hist_len * sizeof(uint32_t), stream));
   MGX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_hist_scan), (hist_len + 1) * sizeof(uint64_t), stream));
-  const int passes = (key_bits + kRadixBits - 1) / kRadixBits;
+  MGX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ghist), kMaxPasses * kRadix * sizeof(unsigned long long), stream));
+  MGX_CUDA(cudaMemsetAsync(d_ghist, 0, kMaxPasses * kRadix * sizeof(unsigned long long), stream));
+  int sm_count = 148;
+  int dev = 0;
+  MGX_CUDA(cudaGetDevice(&dev));
+  MGX_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  radix_global_hist_kernel<<<sm_count * 8, 256, 0, stream>>>(cur.keys, n, passes, d_ghist);
+  MGX_LAUNCH_CHECK();
+  std::vector<unsigned long long> ghist(static_cast<size_t>(kMaxPasses) * kRadix, 0);
+  MGX_CUDA(cudaMemcpyAsync(ghist.data(), d_ghist, ghist.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           stream));
+  MGX_CUDA(cudaStreamSynchronize(stream));
   for (int p = 0; p < passes; ++p) {
+    bool trivial = false;
+    for (int d = 0; d < kRadix; ++d) {
+      trivial = trivial || ghist[static_cast<size_t>(p) * kRadix + d] == n;
+    }
+    if (trivial) {
+      continue;  // every key has the same digit here: the pass would be a stable copy
+    }
     const int shift = p * kRadixBits;
     radix_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(cur.keys, n, shift, d_hist, n_tiles);
     MGX_LAUNCH_CHECK();
     exclusive_scan_u32_u64(d_hist, d_hist_scan, hist_len, stream);
-    radix_scatter_kernel<<<n_tiles, kSortThreads, 0, stream>>>(cur.keys, cur.vals, alt.keys, alt.vals, n, shift,
-                                                               d_hist_scan, n_tiles);
+    radix_scatter_kernel<<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(cur.keys, cur.vals, alt.keys, alt.vals,
+                                                                                  n, shift, d_hist_scan, n_tiles);
     MGX_LAUNCH_CHECK();
     std::swap(cur, alt);
   }
   MGX_CUDA(cudaFreeAsync(d_hist, stream));
   MGX_CUDA(cudaFreeAsync(d_hist_scan, stream));
+  MGX_CUDA(cudaFreeAsync(d_ghist, stream));
   return cur;
 }
 

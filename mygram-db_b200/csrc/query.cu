@@ -406,25 +406,96 @@ __device__ __forceinline__ void tile_filter_list(const ListRef& l, uint32_t dmin
 constexpr uint32_t kThreadScanMaxTerm = 16;
 constexpr uint32_t kThreadScanMaxDoc = 4096;
 
-struct TermHead {
-  uint32_t w0;    // first min(4, tl) bytes, little endian
-  uint32_t mask;  // which of those bytes are significant
+// The first 12 bytes of a term held in registers (3 little-endian words + byte masks).
+struct TermRegs {
+  uint32_t w[3];
+  uint32_t m[3];
+  uint32_t nw;  // words in use: ceil(min(tl, 12) / 4)
 };
 
-__device__ __forceinline__ TermHead load_term_head(const uint8_t* __restrict__ term, uint32_t tl) {
-  TermHead h;
-  h.w0 = 0;
-  for (uint32_t i = 0; i < 4 && i < tl; ++i) {
-    h.w0 |= static_cast<uint32_t>(__ldg(term + i)) << (8 * i);
+__device__ __forceinline__ TermRegs load_term_regs(const uint8_t* __restrict__ term, uint32_t tl) {
+  TermRegs t;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    t.w[k] = 0;
+    t.m[k] = 0;
   }
-  h.mask = tl >= 4 ? 0xFFFFFFFFu : ((1u << (8 * tl)) - 1u);
-  return h;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    if (static_cast<uint32_t>(i) < tl) {
+      t.w[i >> 2] |= static_cast<uint32_t>(__ldg(term + i)) << (8 * (i & 3));
+      t.m[i >> 2] |= 0xFFu << (8 * (i & 3));
+    }
+  }
+  t.nw = tl >= 9 ? 3u : (tl >= 5 ? 2u : 1u);
+  return t;
+}
+
+// 4 bytes of the 32-byte window w[0..7] starting at byte offset OFF (compile-time)
+template <int OFF>
+__device__ __forceinline__ uint32_t window_word(const uint32_t (&w)[8]) {
+  if constexpr ((OFF & 3) == 0) {
+    return w[OFF >> 2];
+  } else {
+    return __funnelshift_r(w[OFF >> 2], w[(OFF >> 2) + 1], (OFF & 3) * 8);
+  }
+}
+
+// Bit j of the result is set iff the first min(tl, 12) bytes of the term match at byte offset j of the window.
+template <int J>
+__device__ __forceinline__ void match_at(const uint32_t (&w)[8], const TermRegs& t, uint32_t* cand) {
+  const uint32_t x0 = window_word<J>(w);
+  if (((x0 ^ t.w[0]) & t.m[0]) == 0) {
+    bool ok = true;
+    if (t.nw > 1) {
+      ok = ((window_word<J + 4>(w) ^ t.w[1]) & t.m[1]) == 0;
+    }
+    if (ok && t.nw > 2) {
+      ok = ((window_word<J + 8>(w) ^ t.w[2]) & t.m[2]) == 0;
+    }
+    if (ok) {
+      *cand |= 1u << J;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t chunk_candidates(const uint4& cur, const uint4& nxt, const TermRegs& t) {
+  const uint32_t w[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
+  uint32_t cand = 0;
+  match_at<0>(w, t, &cand);
+  match_at<1>(w, t, &cand);
+  match_at<2>(w, t, &cand);
+  match_at<3>(w, t, &cand);
+  match_at<4>(w, t, &cand);
+  match_at<5>(w, t, &cand);
+  match_at<6>(w, t, &cand);
+  match_at<7>(w, t, &cand);
+  match_at<8>(w, t, &cand);
+  match_at<9>(w, t, &cand);
+  match_at<10>(w, t, &cand);
+  match_at<11>(w, t, &cand);
+  match_at<12>(w, t, &cand);
+  match_at<13>(w, t, &cand);
+  match_at<14>(w, t, &cand);
+  match_at<15>(w, t, &cand);
+  return cand;
+}
+
+// bytes 12.. of a longer term (13..16 bytes), confirmed from memory (rare)
+__device__ __forceinline__ bool term_tail_matches(const uint8_t* __restrict__ text, uint64_t pos,
+                                                  const uint8_t* __restrict__ term, uint32_t tl) {
+  for (uint32_t i = 12; i < tl; ++i) {
+    if (__ldg(text + pos + i) != __ldg(term + i)) {
+      return false;
+    }
+  }
+  return true;
 }
 
 // BM25Scorer::CountTermOccurrences (bm25_scorer.cpp:27-45): non-overlapping, left to right, on bytes.
 __device__ __forceinline__ uint32_t thread_count_term(const uint8_t* __restrict__ text, uint64_t b, uint32_t len,
                                                       const uint8_t* __restrict__ term, uint32_t tl,
-                                                      const TermHead& head, bool exists_only) {
+                                                      const TermRegs& t, bool exists_only) {
   if (tl == 0 || tl > len) {
     return 0;
   }
@@ -435,15 +506,7 @@ __device__ __forceinline__ uint32_t thread_count_term(const uint8_t* __restrict_
   uint4 cur = ld16(text + a);
   for (; a <= last; a += 16) {
     const uint4 nxt = ld16(text + a + 16);  // the arena is padded by 64 bytes
-    const uint32_t w[8] = {cur.x, cur.y, cur.z, cur.w, nxt.x, nxt.y, nxt.z, nxt.w};
-    uint32_t cand = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const uint32_t x = (j & 3) ? __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], (j & 3) * 8) : w[j >> 2];
-      if (((x ^ head.w0) & head.mask) == 0) {
-        cand |= 1u << j;
-      }
-    }
+    uint32_t cand = chunk_candidates(cur, nxt, t);
     while (cand != 0) {
       const uint32_t j = static_cast<uint32_t>(__ffs(static_cast<int>(cand))) - 1u;
       cand &= cand - 1;
@@ -451,24 +514,61 @@ __device__ __forceinline__ uint32_t thread_count_term(const uint8_t* __restrict_
       if (pos < next_ok || pos > last) {
         continue;
       }
-      bool ok = true;
-      for (uint32_t i = 4; i < tl; ++i) {
-        if (__ldg(text + pos + i) != __ldg(term + i)) {
-          ok = false;
-          break;
-        }
+      if (tl > 12 && !term_tail_matches(text, pos, term, tl)) {
+        continue;
       }
-      if (ok) {
-        ++count;
-        next_ok = pos + tl;
-        if (exists_only) {
-          return 1;
-        }
+      ++count;
+      next_ok = pos + tl;
+      if (exists_only) {
+        return 1;
       }
     }
     cur = nxt;
   }
   return count;
+}
+
+// Existence test with G lanes per document: lane g of the group takes the 16-byte chunks c = g, g+G, ... so one
+// document keeps G loads in flight and short survivor lists still fill the warp. All lanes of the warp must call
+// this (with their group's document, or len = 0 for idle groups); the result is uniform inside a group.
+template <int G>
+__device__ __forceinline__ bool group_contains_term(const uint8_t* __restrict__ text, uint64_t b, uint32_t len,
+                                                    const uint8_t* __restrict__ term, uint32_t tl, const TermRegs& t) {
+  const unsigned gl = threadIdx.x & (G - 1);
+  bool found = false;
+  if (tl != 0 && tl <= len) {
+    const uint64_t last = b + len - tl;
+    const uint64_t a0 = b & ~15ULL;
+    const uint32_t nchunks = static_cast<uint32_t>((last - a0) >> 4) + 1u;
+    for (uint32_t c = gl; c < nchunks && !found; c += G) {
+      const uint64_t a = a0 + static_cast<uint64_t>(c) * 16;
+      const uint4 cur = ld16(text + a);
+      const uint4 nxt = ld16(text + a + 16);
+      uint32_t cand = chunk_candidates(cur, nxt, t);
+      // admissible starts of this chunk: b <= a + j <= last
+      if (a < b) {
+        cand &= ~((1u << static_cast<uint32_t>(b - a)) - 1u);
+      }
+      if (last - a < 15) {
+        cand &= (2u << static_cast<uint32_t>(last - a)) - 1u;
+      }
+      if (tl > 12) {
+        while (cand != 0 && !found) {
+          const uint32_t j = static_cast<uint32_t>(__ffs(static_cast<int>(cand))) - 1u;
+          cand &= cand - 1;
+          found = term_tail_matches(text, a + j, term, tl);
+        }
+      } else {
+        found = cand != 0;
+      }
+    }
+  }
+  // OR over the group (xor-shuffles stay inside an aligned group of G lanes)
+#pragma unroll
+  for (int s = G / 2; s > 0; s >>= 1) {
+    found = (__shfl_xor_sync(0xffffffffu, found ? 1 : 0, s) != 0) || found;
+  }
+  return found;
 }
 
 // tile -> segment map: segment g owns tiles [off[g], off[g+1]); one warp per segment.
@@ -592,31 +692,39 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
   __syncwarp();
   const uint8_t* term = bv.term_bytes + bv.term_boff[t];
   const uint32_t tl = bv.term_boff[t + 1] - bv.term_boff[t];
-  const TermHead head = load_term_head(term, tl);
+  const TermRegs tregs = load_term_regs(term, tl);
   uint32_t hits = 0;
   unsigned long long text_bytes = 0;
-  uint32_t slow_mask_any = 0;
-  for (uint32_t s0 = 0; s0 < n; s0 += 32) {
-    const uint32_t s = s0 + lane;
+  constexpr int kGroup = 4;                 // lanes per document
+  constexpr int kDocsPerIter = 32 / kGroup; // documents per warp iteration
+  const unsigned group = lane / kGroup;
+  for (uint32_t s0 = 0; s0 < n; s0 += kDocsPerIter) {
+    const uint32_t s = s0 + group;
+    uint64_t b = 0;
+    uint32_t len = 0;
     bool slow = false;
     if (s < n) {
       const uint32_t doc = s_surv[warp][s];
-      const uint64_t b = iv.text_off[doc];
-      const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
-      text_bytes += len;
-      if (tl <= kThreadScanMaxTerm && len <= kThreadScanMaxDoc) {
-        hits += thread_count_term(iv.text, b, len, term, tl, head, true);
-      } else {
+      b = iv.text_off[doc];
+      len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
+      if ((lane & (kGroup - 1)) == 0) {
+        text_bytes += len;
+      }
+      if (tl > kThreadScanMaxTerm || len > kThreadScanMaxDoc) {
         slow = true;
+        len = 0;  // handled below
       }
     }
+    const bool found = group_contains_term<kGroup>(iv.text, b, len, term, tl, tregs);
+    if (found && (lane & (kGroup - 1)) == 0) {
+      ++hits;
+    }
     // rare: long terms / very long documents go through the warp-cooperative scanner, one document at a time
-    unsigned slow_mask = __ballot_sync(0xffffffffu, slow);
-    slow_mask_any |= slow_mask;
+    unsigned slow_mask = __ballot_sync(0xffffffffu, slow && (lane & (kGroup - 1)) == 0);
     while (slow_mask != 0) {
       const uint32_t src = static_cast<uint32_t>(__ffs(static_cast<int>(slow_mask))) - 1u;
       slow_mask &= slow_mask - 1;
-      DocText d = doc_open(iv, s_surv[warp][s0 + src], s_text[warp]);
+      DocText d = doc_open(iv, s_surv[warp][s0 + src / kGroup], s_text[warp]);
       const uint32_t c = doc_count_term(d, term, tl, true);
       __syncwarp();
       if (lane == src) {
@@ -1092,7 +1200,7 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
             const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
             const bool must = (flags & kQVerify) != 0 || bv.term_koff[tid + 1] == bv.term_koff[tid];
             const uint32_t tf_u =
-                thread_count_term(iv.text, b, len, term, tl, load_term_head(term, tl), sp.compute_score == 0);
+                thread_count_term(iv.text, b, len, term, tl, load_term_regs(term, tl), sp.compute_score == 0);
             if (must && tf_u == 0 && tl != 0) {
               keep = 0;
             }
@@ -1105,7 +1213,7 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
             const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
             if (bv.term_koff[tid + 1] == bv.term_koff[tid] && tl != 0) {
               const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
-              if (thread_count_term(iv.text, b, len, term, tl, load_term_head(term, tl), true) != 0) {
+              if (thread_count_term(iv.text, b, len, term, tl, load_term_regs(term, tl), true) != 0) {
                 keep = 0;
               }
             }
