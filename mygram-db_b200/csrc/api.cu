@@ -499,14 +499,25 @@ int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, co
       MGX_CUDA(cudaMemcpyAsync(d_text.p, text, bytes, cudaMemcpyHostToDevice, st));
     }
     MGX_CUDA(cudaMemcpyAsync(d_off.p, text_offsets, (n_docs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const int width = std::max(config->ngram_size, kanji);
     DevBuf<uint32_t> d_len;
     DevBuf<uint64_t> d_slot_off;
+    DevBuf<uint64_t> d_scratch;
     DevBuf<uint64_t> d_keys;
     DevBuf<uint32_t> d_docs;
+    d_len.alloc(n_docs);
+    d_slot_off.alloc(n_docs + 1);
+    d_scratch.alloc(8 + (n_docs + 1) / 2 + 1 + scan_scratch_elems(n_docs) + 8);
     uint64_t n_slots = 0;
-    uint64_t counters[2];
-    tokenize_device(config->ngram_size, kanji, config->cross_boundary_ngrams != 0, std::max(config->ngram_size, kanji),
-                    d_text.p, d_off.p, n_docs, d_len, d_slot_off, d_keys, d_docs, &n_slots, counters, st);
+    uint64_t counters[3];
+    tokenize_count(config->ngram_size, kanji, config->cross_boundary_ngrams != 0, width, d_text.p, d_off.p, n_docs,
+                   d_len.p, d_slot_off.p, d_scratch.p, &n_slots, counters, st);
+    d_keys.alloc(n_slots);
+    d_docs.alloc(n_slots);
+    if (n_slots > 0) {
+      tokenize_emit(config->ngram_size, kanji, config->cross_boundary_ngrams != 0, width, d_text.p, d_off.p, n_docs,
+                    d_slot_off.p, d_keys.p, d_docs.p, st);
+    }
     std::vector<uint64_t> keys(n_slots);
     std::vector<uint32_t> docs(n_slots);
     if (n_slots > 0) {

@@ -48,19 +48,28 @@ __device__ __forceinline__ uint4 ld_stream_16(const uint8_t* p) {
 // a valid multi-byte character only ever covers continuation bytes; so a code
 // point starts at byte i iff TryParseUtf8Char(i) succeeds with the bytes that
 // remain in the document.
+//
+// Both modes run the same decode + window logic (GenerateHybridNgrams,
+// string_utils.cpp:452-509). COUNT records per document the number of code points
+// (= CountCodePoints, the BM25 document length) and the number of n-grams; EMIT
+// writes exactly that many (packed key, doc) pairs at the scanned offsets, so the
+// sort never sees a placeholder.
 template <bool EMIT>
 __global__ void __launch_bounds__(kTokThreads)
 tokenize_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ text_off, uint64_t n_docs, int ngram,
-                int kanji, int cross, int width, uint32_t* __restrict__ doc_len,
+                int kanji, int cross, int width, uint32_t* __restrict__ doc_len, uint32_t* __restrict__ ngram_cnt,
                 const uint64_t* __restrict__ slot_off, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ docs_out,
-                unsigned long long* __restrict__ counters /* [0]=non-empty docs, [1]=invalid bytes seen */) {
-  __shared__ uint32_t cp_buf[EMIT ? kTokWarps : 1][EMIT ? kTokBuf : 1];
+                unsigned long long* __restrict__ counters /* [0] non-empty docs, [1] docs with invalid bytes, [2] code points */) {
+  __shared__ uint32_t cp_buf[kTokWarps][kTokBuf];
   const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned warp_in_cta = threadIdx.x >> 5;
   const uint64_t warp_global = static_cast<uint64_t>(blockIdx.x) * kTokWarps + warp_in_cta;
   const uint64_t warp_stride = static_cast<uint64_t>(gridDim.x) * kTokWarps;
   unsigned long long nonempty = 0;
   unsigned long long invalid = 0;
+  unsigned long long total_cps = 0;
+  uint32_t* buf = cp_buf[warp_in_cta];
 
   for (uint64_t d = warp_global; d < n_docs; d += warp_stride) {
     const uint64_t b = text_off[d];
@@ -68,12 +77,14 @@ tokenize_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ t
     if (e <= b) {
       if (!EMIT && lane == 0) {
         doc_len[d] = 0;
+        ngram_cnt[d] = 0;
       }
       continue;
     }
-    nonempty += (lane == 0);
-    uint64_t cps_done = 0;   // code points of this doc already finalised (EMIT: emitted)
-    uint32_t carry_n = 0;    // EMIT: undecided code points kept at the front of cp_buf
+    nonempty += 1;
+    uint64_t cps_done = 0;   // code points whose window decision is final
+    uint32_t emitted = 0;    // n-grams of this document so far
+    uint32_t carry_n = 0;    // undecided code points kept at the front of the window
     uint64_t valid_bytes = 0;
     const uint64_t slot_base = EMIT ? slot_off[d] : 0;
 
@@ -128,28 +139,29 @@ tokenize_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ t
       }
       valid_bytes += bytes_inc;
 
-      if (EMIT) {
-        uint32_t* buf = cp_buf[warp_in_cta];
-        uint32_t wpos = carry_n + inc - cnt;
+      uint32_t wpos = carry_n + inc - cnt;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (flags & (1u << j)) {
-            buf[wpos++] = cps[j];
-          }
+      for (int j = 0; j < 16; ++j) {
+        if (flags & (1u << j)) {
+          buf[wpos++] = cps[j];
         }
-        __syncwarp();
-        const uint32_t m = carry_n + tile_total;  // code points available in the window
-        const bool last_tile = base + kTokTileBytes >= e;
-        const uint32_t keep = last_tile ? 0u : min(m, static_cast<uint32_t>(width - 1));
-        const uint32_t emit_n = m - keep;
-        for (uint32_t p = lane; p < emit_n; p += 32) {
+      }
+      __syncwarp();
+      const uint32_t m = carry_n + tile_total;  // code points available in the window
+      const bool last_tile = base + kTokTileBytes >= e;
+      const uint32_t keep = last_tile ? 0u : min(m, static_cast<uint32_t>(width - 1));
+      const uint32_t emit_n = m - keep;
+      for (uint32_t p0 = 0; p0 < emit_n; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        uint64_t key = 0;
+        bool ok = false;
+        if (p < emit_n) {
           const uint32_t c0 = buf[p];
           const bool cjk = is_cjk_ideograph(c0);
           const int size = cjk ? kanji : ngram;  // string_utils.cpp:484-485: chosen by the START code point
-          uint64_t key = kInvalidKey;
           if (p + static_cast<uint32_t>(size) <= m) {  // :487 (on the last tile m is the document's end)
-            bool ok = true;
-            uint64_t k = static_cast<uint64_t>(c0) + 1;
+            ok = true;
+            key = static_cast<uint64_t>(c0) + 1;
             for (int j = 1; j < width; ++j) {
               uint64_t field = 0;
               if (j < size) {
@@ -159,37 +171,38 @@ tokenize_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ t
                 }
                 field = static_cast<uint64_t>(cj) + 1;
               }
-              k = (k << 21) | field;
-            }
-            if (ok) {
-              key = k;
+              key = (key << 21) | field;
             }
           }
-          const uint64_t slot = slot_base + cps_done + p;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, ok);
+        if (EMIT && ok) {
+          const uint64_t slot = slot_base + emitted + __popc(ballot & lt_mask);
           keys_out[slot] = key;
           docs_out[slot] = static_cast<uint32_t>(d);
         }
-        __syncwarp();
-        uint32_t carried = 0;
-        if (lane < keep) {
-          carried = buf[emit_n + lane];
-        }
-        __syncwarp();
-        if (lane < keep) {
-          buf[lane] = carried;
-        }
-        __syncwarp();
-        cps_done += emit_n;
-        carry_n = keep;
-      } else {
-        cps_done += tile_total;
+        emitted += __popc(ballot);
       }
+      __syncwarp();
+      uint32_t carried = 0;
+      if (lane < keep) {
+        carried = buf[emit_n + lane];
+      }
+      __syncwarp();
+      if (lane < keep) {
+        buf[lane] = carried;
+      }
+      __syncwarp();
+      cps_done += emit_n;
+      carry_n = keep;
     }
     if (!EMIT && lane == 0) {
       doc_len[d] = static_cast<uint32_t>(cps_done);
+      ngram_cnt[d] = emitted;
     }
+    total_cps += cps_done;
     if (valid_bytes != e - b) {
-      invalid += (lane == 0);
+      invalid += 1;
     }
   }
   if (!EMIT && lane == 0) {
@@ -198,6 +211,9 @@ tokenize_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ t
     }
     if (invalid != 0) {
       atomicAdd(&counters[1], invalid);
+    }
+    if (total_cps != 0) {
+      atomicAdd(&counters[2], total_cps);
     }
   }
 }
@@ -440,45 +456,48 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(const uint64_t* __restr
 
 }  // namespace
 
-uint64_t Index::device_bytes() const {
-  return d_doc_ids.bytes() + d_text.bytes() + d_text_off.bytes() + d_doc_len.bytes() + d_term_keys.bytes() +
-         d_term_off.bytes() + d_postings.bytes() + d_term_bm.bytes() + d_bitmaps.bytes();
-}
+uint64_t Index::device_bytes() const { return resident_a.blob.bytes() + resident_b.blob.bytes() + d_bitmaps.bytes(); }
 
-void tokenize_device(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
-                     uint64_t n_docs, DevBuf<uint32_t>& d_doc_len, DevBuf<uint64_t>& d_slot_off, DevBuf<uint64_t>& d_keys,
-                     DevBuf<uint32_t>& d_docs, uint64_t* n_slots, uint64_t* counters_out, cudaStream_t stream) {
+static unsigned tokenizer_grid(uint64_t n_docs) {
   int sm_count = 148;
   int dev = 0;
   MGX_CUDA(cudaGetDevice(&dev));
   MGX_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   // persistent-style grid: 8 CTAs of 8 warps per SM, warps stride over documents
-  const unsigned grid = static_cast<unsigned>(
+  return static_cast<unsigned>(
       std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(sm_count) * 8, (n_docs + kTokWarps - 1) / kTokWarps)));
-  d_doc_len.alloc(n_docs);
-  d_slot_off.alloc(n_docs + 1);
-  DevBuf<unsigned long long> d_counters;
-  d_counters.alloc(2);
-  MGX_CUDA(cudaMemsetAsync(d_counters.p, 0, 2 * sizeof(unsigned long long), stream));
-  tokenize_kernel<false><<<grid, kTokThreads, 0, stream>>>(d_text, d_text_off, n_docs, ngram, kanji, cross ? 1 : 0,
-                                                           width, d_doc_len.p, nullptr, nullptr, nullptr, d_counters.p);
+}
+
+void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
+                    uint64_t n_docs, uint32_t* d_doc_len, uint64_t* d_slot_off, uint64_t* d_scratch, uint64_t* n_slots,
+                    uint64_t* counters_out, cudaStream_t stream) {
+  // scratch layout: [0..7] counters, then n-gram counts (u32, n_docs), then the scan's block sums
+  unsigned long long* d_counters = reinterpret_cast<unsigned long long*>(d_scratch);
+  uint32_t* d_ngram_cnt = reinterpret_cast<uint32_t*>(d_scratch + 8);
+  uint64_t* d_scan = d_scratch + 8 + (n_docs + 1) / 2 + 1;
+  MGX_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), stream));
+  tokenize_kernel<false><<<tokenizer_grid(n_docs), kTokThreads, 0, stream>>>(
+      d_text, d_text_off, n_docs, ngram, kanji, cross ? 1 : 0, width, d_doc_len, d_ngram_cnt, nullptr, nullptr, nullptr,
+      d_counters);
   MGX_LAUNCH_CHECK();
-  exclusive_scan_u32_u64(d_doc_len.p, d_slot_off.p, n_docs, stream);
+  exclusive_scan_u32_u64(d_ngram_cnt, d_slot_off, n_docs, d_scan, stream);
   uint64_t total = 0;
-  MGX_CUDA(cudaMemcpyAsync(&total, d_slot_off.p + n_docs, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-  unsigned long long counters[2] = {0, 0};
-  MGX_CUDA(cudaMemcpyAsync(counters, d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, stream));
+  unsigned long long counters[3] = {0, 0, 0};
+  MGX_CUDA(cudaMemcpyAsync(&total, d_slot_off + n_docs, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+  MGX_CUDA(cudaMemcpyAsync(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost, stream));
   MGX_CUDA(cudaStreamSynchronize(stream));
   *n_slots = total;
   counters_out[0] = counters[0];
   counters_out[1] = counters[1];
-  d_keys.alloc(total);
-  d_docs.alloc(total);
-  if (total > 0) {
-    tokenize_kernel<true><<<grid, kTokThreads, 0, stream>>>(d_text, d_text_off, n_docs, ngram, kanji, cross ? 1 : 0,
-                                                            width, nullptr, d_slot_off.p, d_keys.p, d_docs.p, nullptr);
-    MGX_LAUNCH_CHECK();
-  }
+  counters_out[2] = counters[2];
+}
+
+void tokenize_emit(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
+                   uint64_t n_docs, const uint64_t* d_slot_off, uint64_t* d_keys, uint32_t* d_docs, cudaStream_t stream) {
+  tokenize_kernel<true><<<tokenizer_grid(n_docs), kTokThreads, 0, stream>>>(
+      d_text, d_text_off, n_docs, ngram, kanji, cross ? 1 : 0, width, nullptr, nullptr, d_slot_off, d_keys, d_docs,
+      nullptr);
+  MGX_LAUNCH_CHECK();
 }
 
 // doc ids ascending: first_id + i everywhere?  (one pass over the resident copy)
@@ -491,24 +510,19 @@ __global__ void sequential_check_kernel(const uint32_t* __restrict__ ids, uint64
   }
 }
 
-namespace {
-// MGX_BUILD_TRACE=1 prints the host-side wall time of each build phase (stream synchronised) to stderr.
-struct PhaseTrace {
-  bool on;
-  cudaStream_t stream;
-  std::chrono::steady_clock::time_point t0;
-  PhaseTrace(cudaStream_t s) : on(std::getenv("MGX_BUILD_TRACE") != nullptr), stream(s), t0(std::chrono::steady_clock::now()) {}
-  void mark(const char* name) {
-    if (!on) {
-      return;
-    }
-    cudaStreamSynchronize(stream);
-    const auto t1 = std::chrono::steady_clock::now();
-    std::fprintf(stderr, "[mgx build] %-28s %8.2f ms\n", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+PhaseTrace::PhaseTrace(cudaStream_t s) : on(std::getenv("MGX_BUILD_TRACE") != nullptr), stream(s), t0(now_ms()) {}
+void PhaseTrace::mark(const char* name) {
+  if (!on) {
+    return;
   }
-};
-}  // namespace
+  cudaStreamSynchronize(stream);
+  const double t1 = now_ms();
+  std::fprintf(stderr, "[mgx build] %-34s %8.2f ms\n", name, t1 - t0);
+  t0 = t1;
+}
 
 void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* d_text_in,
                         const uint64_t* d_text_off_in, uint64_t n_docs, uint64_t text_bytes, cudaStream_t stream) {
@@ -519,30 +533,47 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   cudaEvent_t ev1;
   MGX_CUDA(cudaEventCreate(&ev0));
   MGX_CUDA(cudaEventCreate(&ev1));
-  MGX_CUDA(cudaEventRecord(ev0, stream));
 
-  // resident copies (the device mirror of DocumentStore's normalised text); the
-  // text arena is padded so 16-byte tile loads never leave the allocation
+  // ---- resident arena A: the device mirror of DocumentStore's normalised text + ids + lengths.
+  // The text arena is padded so 16-byte tile loads never leave the allocation.
   ix.n_docs = n_docs;
   ix.text_bytes = text_bytes;
-  ix.first_id = first_id;
-  ix.sequential_ids = sequential_ids;
-  ix.d_doc_ids.alloc(n_docs);
-  ix.d_text.alloc(text_bytes + 64);
-  ix.d_text_off.alloc(n_docs + 1);
+  ix.d_doc_ids.release();
+  ix.d_text.release();
+  ix.d_text_off.release();
+  ix.d_doc_len.release();
+  ix.d_term_keys.release();
+  ix.d_term_off.release();
+  ix.d_postings.release();
+  ix.d_term_bm.release();
+  ix.d_bitmaps.release();
+  ix.resident_b.release();
+  ix.resident_a.reserve(DevArena::padded(n_docs * 4 + 4) + DevArena::padded(text_bytes + 64) +
+                        DevArena::padded((n_docs + 1) * 8) + DevArena::padded(n_docs * 4 + 4));
+  ix.d_text.borrow(ix.resident_a.take<uint8_t>(text_bytes + 64), text_bytes + 64);
+  ix.d_text_off.borrow(ix.resident_a.take<uint64_t>(n_docs + 1), n_docs + 1);
+  ix.d_doc_ids.borrow(ix.resident_a.take<uint32_t>(n_docs), n_docs);
+  ix.d_doc_len.borrow(ix.resident_a.take<uint32_t>(n_docs), n_docs);
+  MGX_CUDA(cudaEventRecord(ev0, stream));
   MGX_CUDA(cudaMemcpyAsync(ix.d_doc_ids.p, d_doc_ids_in, n_docs * sizeof(uint32_t), cudaMemcpyDefault, stream));
   MGX_CUDA(cudaMemcpyAsync(ix.d_text.p, d_text_in, text_bytes, cudaMemcpyDefault, stream));
   MGX_CUDA(cudaMemsetAsync(ix.d_text.p + text_bytes, 0, 64, stream));
   MGX_CUDA(cudaMemcpyAsync(ix.d_text_off.p, d_text_off_in, (n_docs + 1) * sizeof(uint64_t), cudaMemcpyDefault, stream));
+
+  // ---- temporary arena T0: counting stage
+  DevArena t0;
+  const size_t count_scratch = 8 + (n_docs + 1) / 2 + 1 + scan_scratch_elems(n_docs) + 8;
+  t0.reserve(DevArena::padded((n_docs + 1) * 8) + DevArena::padded(count_scratch * 8) + 512);
+  uint64_t* d_slot_off = t0.take<uint64_t>(n_docs + 1);
+  uint64_t* d_count_scratch = t0.take<uint64_t>(count_scratch);
+  unsigned int* d_bad = t0.take<unsigned int>(1);
   if (n_docs > 0) {
-    DevBuf<unsigned int> d_bad;
-    d_bad.alloc(1);
-    MGX_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(unsigned int), stream));
+    MGX_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), stream));
     sequential_check_kernel<<<static_cast<unsigned>((n_docs + 255) / 256), 256, 0, stream>>>(ix.d_doc_ids.p, n_docs,
-                                                                                             d_bad.p);
+                                                                                             d_bad);
     MGX_LAUNCH_CHECK();
     unsigned int bad = 0;
-    MGX_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, stream));
+    MGX_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, stream));
     MGX_CUDA(cudaMemcpyAsync(&first_id, ix.d_doc_ids.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     MGX_CUDA(cudaStreamSynchronize(stream));
     if (bad & 2u) {
@@ -553,92 +584,91 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   }
   ix.first_id = first_id;
   ix.sequential_ids = sequential_ids;
-
   trace.mark("resident copies + id check");
-  DevBuf<uint64_t> d_slot_off;
-  DevBuf<uint64_t> d_keys_a;
-  DevBuf<uint32_t> d_docs_a;
+
   uint64_t n_slots = 0;
-  uint64_t counters[2] = {0, 0};
-  tokenize_device(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, ix.d_doc_len,
-                  d_slot_off, d_keys_a, d_docs_a, &n_slots, counters, stream);
-  d_slot_off.release();
-  trace.mark("tokenize (count+scan+emit)");
+  uint64_t counters[3] = {0, 0, 0};
+  tokenize_count(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, ix.d_doc_len.p,
+                 d_slot_off, d_count_scratch, &n_slots, counters, stream);
+  trace.mark("tokenize: count + scan");
   ix.n_pair_slots = n_slots;
-  ix.total_doc_length = n_slots;  // one slot per code point
   ix.doc_count = counters[0];
   ix.all_valid_utf8 = counters[1] == 0;
+  ix.total_doc_length = counters[2];
   if (n_slots >= (1ULL << 32)) {
-    set_last_error("shard too large: more than 2^32 code points in one shard; split by doc-id range");
+    set_last_error("shard too large: more than 2^32 n-gram occurrences in one shard; split by doc-id range");
     throw CudaFailure{MGX_ERR_UNSUPPORTED};
   }
 
-  DevBuf<uint64_t> d_keys_b;
-  DevBuf<uint32_t> d_docs_b;
-  d_keys_b.alloc(n_slots);
-  d_docs_b.alloc(n_slots);
-  trace.mark("alloc sort buffers");
+  // ---- temporary arena T1: pairs (double-buffered), sort scratch, CSR block arrays
+  const uint64_t n_blocks = (n_slots + kCsrTile - 1) / kCsrTile;
+  DevArena t1;
+  t1.reserve(2 * (DevArena::padded(n_slots * 8 + 8) + DevArena::padded(n_slots * 4 + 4)) +
+             DevArena::padded(radix_sort_scratch_bytes(n_slots) + 512) + 2 * DevArena::padded((n_blocks + 2) * 8) + 1024);
+  uint64_t* d_keys_a = t1.take<uint64_t>(n_slots);
+  uint32_t* d_docs_a = t1.take<uint32_t>(n_slots);
+  uint64_t* d_keys_b = t1.take<uint64_t>(n_slots);
+  uint32_t* d_docs_b = t1.take<uint32_t>(n_slots);
+  uint8_t* d_sort_scratch = t1.take<uint8_t>(radix_sort_scratch_bytes(n_slots) + 256);
+  uint64_t* d_block_pairs = t1.take<uint64_t>(n_blocks + 2);
+  uint64_t* d_block_terms = t1.take<uint64_t>(n_blocks + 2);
+  uint64_t* d_totals = t1.take<uint64_t>(4);
+  trace.mark("alloc pair arena");
+  if (n_slots > 0) {
+    tokenize_emit(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, d_slot_off, d_keys_a,
+                  d_docs_a, stream);
+  }
+  trace.mark("tokenize: emit");
   const SortResult sorted =
-      radix_sort_pairs(d_keys_a.p, d_docs_a.p, d_keys_b.p, d_docs_b.p, n_slots, 21 * ix.width, stream);
+      radix_sort_pairs(d_keys_a, d_docs_a, d_keys_b, d_docs_b, n_slots, 21 * ix.width, d_sort_scratch, stream);
   trace.mark("radix sort");
 
-  // segmented unique + compaction
-  const uint64_t n_blocks = (n_slots + kCsrTile - 1) / kCsrTile;
-  DevBuf<uint64_t> d_block_pairs;
-  DevBuf<uint64_t> d_block_terms;
-  DevBuf<uint64_t> d_totals;
-  d_block_pairs.alloc(n_blocks + 1);
-  d_block_terms.alloc(n_blocks + 1);
-  d_totals.alloc(2);
+  // ---- segmented unique + compaction into CSR
   if (n_blocks > 0) {
     csr_count_kernel<<<static_cast<unsigned>(n_blocks), kCsrThreads, 0, stream>>>(sorted.keys, sorted.vals, n_slots,
-                                                                                   d_block_pairs.p, d_block_terms.p);
+                                                                                   d_block_pairs, d_block_terms);
     MGX_LAUNCH_CHECK();
   }
-  csr_scan_kernel<<<1, 1024, 0, stream>>>(d_block_pairs.p, d_block_terms.p, n_blocks, d_totals.p);
+  csr_scan_kernel<<<1, 1024, 0, stream>>>(d_block_pairs, d_block_terms, n_blocks, d_totals);
   MGX_LAUNCH_CHECK();
   uint64_t totals[2] = {0, 0};
-  MGX_CUDA(cudaMemcpyAsync(totals, d_totals.p, sizeof(totals), cudaMemcpyDeviceToHost, stream));
+  MGX_CUDA(cudaMemcpyAsync(totals, d_totals, sizeof(totals), cudaMemcpyDeviceToHost, stream));
   MGX_CUDA(cudaStreamSynchronize(stream));
   ix.n_postings = totals[0];
   ix.n_terms = totals[1];
-  ix.d_term_keys.alloc(ix.n_terms);
-  ix.d_term_off.alloc(ix.n_terms + 1);
-  ix.d_postings.alloc(ix.n_postings);
+  ix.resident_b.reserve(DevArena::padded(ix.n_terms * 8 + 8) + DevArena::padded((ix.n_terms + 1) * 8) +
+                        DevArena::padded(ix.n_postings * 4 + 4) + 2 * DevArena::padded(ix.n_terms * 4 + 4) + 512);
+  ix.d_term_keys.borrow(ix.resident_b.take<uint64_t>(ix.n_terms), ix.n_terms);
+  ix.d_term_off.borrow(ix.resident_b.take<uint64_t>(ix.n_terms + 1), ix.n_terms + 1);
+  ix.d_postings.borrow(ix.resident_b.take<uint32_t>(ix.n_postings), ix.n_postings);
+  ix.d_term_bm.borrow(ix.resident_b.take<int32_t>(ix.n_terms), ix.n_terms);
+  uint32_t* d_dense_terms = ix.resident_b.take<uint32_t>(ix.n_terms);  // only the first n_dense entries are used
+  unsigned long long* d_count = reinterpret_cast<unsigned long long*>(ix.resident_b.take<uint64_t>(2));
   if (n_blocks > 0) {
     csr_write_kernel<<<static_cast<unsigned>(n_blocks), kCsrThreads, 0, stream>>>(
-        sorted.keys, sorted.vals, n_slots, d_block_pairs.p, d_block_terms.p, ix.d_term_keys.p, ix.d_term_off.p,
+        sorted.keys, sorted.vals, n_slots, d_block_pairs, d_block_terms, ix.d_term_keys.p, ix.d_term_off.p,
         ix.d_postings.p);
     MGX_LAUNCH_CHECK();
   }
   set_u64_kernel<<<1, 1, 0, stream>>>(ix.d_term_off.p + ix.n_terms, ix.n_postings);
   MGX_LAUNCH_CHECK();
-  MGX_CUDA(cudaStreamSynchronize(stream));
   trace.mark("csr");
-  d_keys_a.release();
-  d_docs_a.release();
-  d_keys_b.release();
-  d_docs_b.release();
-  trace.mark("free sort buffers");
 
-  // dense bitmaps
+  // ---- dense bitmaps
   ix.bm_words = (n_docs + 31) / 32;
   const double thr = ix.cfg.dense_threshold > 0.0 ? ix.cfg.dense_threshold : 1.0 / 32.0;
   uint64_t min_len = std::max<uint64_t>(1, static_cast<uint64_t>(thr * static_cast<double>(n_docs)));
   // a bitmap only pays for lists long enough that probing beats searching
   min_len = std::max<uint64_t>(min_len, 1024);
   const uint64_t max_bytes = ix.cfg.max_dense_bytes != 0 ? ix.cfg.max_dense_bytes : (8ULL << 30);
-  ix.d_term_bm.alloc(ix.n_terms);
-  DevBuf<unsigned long long> d_count;
-  d_count.alloc(1);
   unsigned long long n_dense = 0;
   const unsigned term_grid = static_cast<unsigned>((ix.n_terms + 255) / 256);
   if (ix.n_terms > 0) {
     for (;;) {
-      MGX_CUDA(cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), stream));
-      dense_count_kernel<<<term_grid, 256, 0, stream>>>(ix.d_term_off.p, ix.n_terms, min_len, d_count.p);
+      MGX_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
+      dense_count_kernel<<<term_grid, 256, 0, stream>>>(ix.d_term_off.p, ix.n_terms, min_len, d_count);
       MGX_LAUNCH_CHECK();
-      MGX_CUDA(cudaMemcpyAsync(&n_dense, d_count.p, sizeof(n_dense), cudaMemcpyDeviceToHost, stream));
+      MGX_CUDA(cudaMemcpyAsync(&n_dense, d_count, sizeof(n_dense), cudaMemcpyDeviceToHost, stream));
       MGX_CUDA(cudaStreamSynchronize(stream));
       if (n_dense * ix.bm_words * 4 <= max_bytes) {
         break;
@@ -646,31 +676,28 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
       min_len *= 2;
     }
   }
+  t1.release();  // the pairs are no longer needed (one cudaFree)
   ix.n_dense = n_dense;
   ix.dense_min_len = min_len;
   ix.d_bitmaps.alloc(ix.n_dense * ix.bm_words);
   if (ix.n_terms > 0) {
-    DevBuf<uint32_t> d_dense_terms;
-    d_dense_terms.alloc(ix.n_dense);
-    MGX_CUDA(cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), stream));
+    MGX_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
     if (ix.n_dense > 0) {
       MGX_CUDA(cudaMemsetAsync(ix.d_bitmaps.p, 0, ix.d_bitmaps.bytes(), stream));
     }
-    dense_assign_kernel<<<term_grid, 256, 0, stream>>>(ix.d_term_off.p, ix.n_terms, min_len, d_count.p, ix.d_term_bm.p,
-                                                       d_dense_terms.p);
+    dense_assign_kernel<<<term_grid, 256, 0, stream>>>(ix.d_term_off.p, ix.n_terms, min_len, d_count, ix.d_term_bm.p,
+                                                       d_dense_terms);
     MGX_LAUNCH_CHECK();
     if (ix.n_dense > 0) {
       const unsigned slices = static_cast<unsigned>(std::min<uint64_t>(64, (n_docs + 65535) / 65536 + 1));
       dense_fill_kernel<<<dim3(static_cast<unsigned>(ix.n_dense), slices), 256, 0, stream>>>(
-          ix.d_term_off.p, ix.d_postings.p, d_dense_terms.p, ix.d_bitmaps.p, ix.bm_words);
+          ix.d_term_off.p, ix.d_postings.p, d_dense_terms, ix.d_bitmaps.p, ix.bm_words);
       MGX_LAUNCH_CHECK();
     }
-    MGX_CUDA(cudaStreamSynchronize(stream));
   }
-
-  trace.mark("dense bitmaps");
   MGX_CUDA(cudaEventRecord(ev1, stream));
   MGX_CUDA(cudaEventSynchronize(ev1));
+  trace.mark("dense bitmaps + free");
   float ms = 0.f;
   MGX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
   ix.last_build_ms = ms;

@@ -53,10 +53,11 @@ template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  bool owned = true;  // false: a view into a larger allocation (see DevArena)
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) {
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), owned(o.owned) {
     o.p = nullptr;
     o.n = 0;
   }
@@ -65,6 +66,7 @@ struct DevBuf {
       release();
       p = o.p;
       n = o.n;
+      owned = o.owned;
       o.p = nullptr;
       o.n = 0;
     }
@@ -72,11 +74,18 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p != nullptr) {
+    if (p != nullptr && owned) {
       cudaFree(p);
-      p = nullptr;
-      n = 0;
     }
+    p = nullptr;
+    n = 0;
+    owned = true;
+  }
+  void borrow(T* ptr, size_t count) {
+    release();
+    p = ptr;
+    n = count;
+    owned = false;
   }
   void alloc(size_t count) {
     release();
@@ -93,6 +102,33 @@ struct DevBuf {
     }
   }
   size_t bytes() const { return n * sizeof(T); }
+};
+
+// One device allocation carved into 256-byte aligned pieces. cudaMalloc / cudaFree cost ~10 ms each on this
+// platform (cudaFree synchronises the device), so a build makes a handful of them instead of dozens.
+struct DevArena {
+  DevBuf<uint8_t> blob;
+  size_t used = 0;
+  static size_t padded(size_t bytes) { return (bytes + 255) & ~static_cast<size_t>(255); }
+  void reserve(size_t bytes) {
+    blob.alloc(bytes + 256);
+    used = 0;
+  }
+  template <typename T>
+  T* take(size_t count) {
+    const size_t bytes = padded((count == 0 ? 1 : count) * sizeof(T));
+    if (used + bytes > blob.n) {
+      set_last_error("internal: device arena exhausted");
+      throw CudaFailure{MGX_ERR_CUDA};
+    }
+    T* out = reinterpret_cast<T*>(blob.p + used);
+    used += bytes;
+    return out;
+  }
+  void release() {
+    blob.release();
+    used = 0;
+  }
 };
 
 // Pinned host buffer (cudaMallocHost), grow-only.
@@ -119,6 +155,15 @@ struct PinBuf {
     n = count == 0 ? 1 : count;
     MGX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p), n * sizeof(T)));
   }
+};
+
+// MGX_BUILD_TRACE=1 prints the host-side wall time of build phases (stream synchronised) to stderr.
+struct PhaseTrace {
+  bool on;
+  cudaStream_t stream;
+  double t0;
+  explicit PhaseTrace(cudaStream_t s);
+  void mark(const char* name);
 };
 
 // ---------------------------------------------------------------- packed keys
@@ -202,15 +247,20 @@ bool host_ngram_to_key(const uint8_t* term, uint64_t len, int key_width, uint64_
 
 // ---------------------------------------------------------------- device-wide primitives (primitives.cu)
 // out[i] = sum_{j<i} in[j]  (u32 -> u64), out has n+1 entries (out[n] = total).
-void exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t stream);
+// d_scratch: scan_scratch_elems(n) uint64 of caller-provided device memory (no allocation inside).
+size_t scan_scratch_elems(uint64_t n);
+void exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_scratch,
+                            cudaStream_t stream);
 // Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, key_bits).
 // Buffers ping-pong; returns which pair of pointers holds the sorted data.
 struct SortResult {
   uint64_t* keys;
   uint32_t* vals;
 };
+// d_scratch: radix_sort_scratch_bytes(n) bytes of caller-provided device memory (no allocation inside).
+size_t radix_sort_scratch_bytes(uint64_t n);
 SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_keys_b, uint32_t* d_vals_b, uint64_t n,
-                            int key_bits, cudaStream_t stream);
+                            int key_bits, uint8_t* d_scratch, cudaStream_t stream);
 
 // ---------------------------------------------------------------- index object
 struct Index {
@@ -237,6 +287,8 @@ struct Index {
   DevBuf<uint32_t> d_postings;
   DevBuf<int32_t> d_term_bm;
   DevBuf<uint32_t> d_bitmaps;
+  DevArena resident_a;  // doc ids, text, text offsets, doc lengths
+  DevArena resident_b;  // dictionary, CSR offsets, postings, bitmap slots
   uint64_t n_dense = 0;
   uint64_t bm_words = 0;
   uint64_t dense_min_len = 0;
@@ -318,9 +370,14 @@ inline IndexView make_view(const Index& ix) {
 void build_index_device(Index& ix, const uint32_t* doc_ids, const uint8_t* text, const uint64_t* text_off,
                         uint64_t n_docs, uint64_t text_bytes, cudaStream_t stream);
 // Tokenise only (mgx_tokenize_batch): fills d_keys/d_docs slots (kInvalidKey for non-emitting positions).
-void tokenize_device(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
-                     uint64_t n_docs, DevBuf<uint32_t>& d_doc_len, DevBuf<uint64_t>& d_slot_off, DevBuf<uint64_t>& d_keys,
-                     DevBuf<uint32_t>& d_docs, uint64_t* n_slots, uint64_t* counters_out /* [0] non-empty docs, [1] docs with invalid bytes */,
-                     cudaStream_t stream);
+// Tokeniser stage 1: per-document code-point counts (d_doc_len) and n-gram counts -> d_slot_off (exclusive scan,
+// n_docs + 1 entries). counters_out: [0] non-empty docs, [1] docs with invalid bytes, [2] total code points.
+// d_scratch: (n_docs + scan_scratch_elems(n_docs) + 8) uint64 of device memory.
+void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
+                    uint64_t n_docs, uint32_t* d_doc_len, uint64_t* d_slot_off, uint64_t* d_scratch, uint64_t* n_slots,
+                    uint64_t* counters_out, cudaStream_t stream);
+// Tokeniser stage 2: (packed key, doc) pairs, exactly d_slot_off[n_docs] of them, in document order.
+void tokenize_emit(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
+                   uint64_t n_docs, const uint64_t* d_slot_off, uint64_t* d_keys, uint32_t* d_docs, cudaStream_t stream);
 
 }  // namespace mgx

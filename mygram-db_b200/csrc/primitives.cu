@@ -302,11 +302,13 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
 
 }  // namespace
 
-void exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, cudaStream_t stream) {
+size_t scan_scratch_elems(uint64_t n) { return static_cast<size_t>((n + kScanTile - 1) / kScanTile + 2); }
+
+void exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_scratch,
+                            cudaStream_t stream) {
   // out[n] (the total) is written by the block-sums kernel
   const uint64_t n_blocks = (n + kScanTile - 1) / kScanTile;
-  uint64_t* d_block_sums = nullptr;
-  MGX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_block_sums), (n_blocks + 1) * sizeof(uint64_t), stream));
+  uint64_t* d_block_sums = d_scratch;
   if (n_blocks > 0) {
     scan_reduce_kernel<<<static_cast<unsigned>(n_blocks), kScanThreads, 0, stream>>>(d_in, n, d_block_sums);
     MGX_LAUNCH_CHECK();
@@ -317,11 +319,35 @@ void exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, c
     scan_apply_kernel<<<static_cast<unsigned>(n_blocks), kScanThreads, 0, stream>>>(d_in, n, d_block_sums, d_out);
     MGX_LAUNCH_CHECK();
   }
-  MGX_CUDA(cudaFreeAsync(d_block_sums, stream));
 }
 
+namespace {
+struct SortScratch {
+  size_t hist_off, hist_scan_off, ghist_off, scan_off, total;
+};
+SortScratch sort_scratch_layout(uint64_t n) {
+  const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
+  const uint64_t hist_len = static_cast<uint64_t>(kRadix) * n_tiles;
+  SortScratch L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~static_cast<size_t>(255);
+    return at;
+  };
+  L.hist_off = take(hist_len * sizeof(uint32_t));
+  L.hist_scan_off = take((hist_len + 1) * sizeof(uint64_t));
+  L.ghist_off = take(static_cast<size_t>(kMaxPasses) * kRadix * sizeof(unsigned long long));
+  L.scan_off = take(scan_scratch_elems(hist_len) * sizeof(uint64_t));
+  L.total = off + 256;
+  return L;
+}
+}  // namespace
+
+size_t radix_sort_scratch_bytes(uint64_t n) { return sort_scratch_layout(n).total; }
+
 SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_keys_b, uint32_t* d_vals_b, uint64_t n,
-                            int key_bits, cudaStream_t stream) {
+                            int key_bits, uint8_t* d_scratch, cudaStream_t stream) {
   SortResult cur{d_keys_a, d_vals_a};
   SortResult alt{d_keys_b, d_vals_b};
   if (n == 0) {
@@ -336,13 +362,14 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
   const uint32_t n_tiles = static_cast<uint32_t>((n + kSortTile - 1) / kSortTile);
   const uint64_t hist_len = static_cast<uint64_t>(kRadix) * n_tiles;
   const int passes = (key_bits + kRadixBits - 1) / kRadixBits;
-  uint32_t* d_hist = nullptr;
-  uint64_t* d_hist_scan = nullptr;
-  unsigned long long* d_ghist = nullptr;
-  MGX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_hist), hist_len * sizeof(uint32_t), stream));
-  MGX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_hist_scan), (hist_len + 1) * sizeof(uint64_t), stream));
-  MGX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_ghist), kMaxPasses * kRadix * sizeof(unsigned long long), stream));
+  const SortScratch L = sort_scratch_layout(n);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d_scratch) + 255) & ~static_cast<uintptr_t>(255));
+  uint32_t* d_hist = reinterpret_cast<uint32_t*>(base + L.hist_off);
+  uint64_t* d_hist_scan = reinterpret_cast<uint64_t*>(base + L.hist_scan_off);
+  unsigned long long* d_ghist = reinterpret_cast<unsigned long long*>(base + L.ghist_off);
+  uint64_t* d_scan_scratch = reinterpret_cast<uint64_t*>(base + L.scan_off);
   MGX_CUDA(cudaMemsetAsync(d_ghist, 0, kMaxPasses * kRadix * sizeof(unsigned long long), stream));
+  PhaseTrace trace(stream);
   int sm_count = 148;
   int dev = 0;
   MGX_CUDA(cudaGetDevice(&dev));
@@ -353,6 +380,7 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
   MGX_CUDA(cudaMemcpyAsync(ghist.data(), d_ghist, ghist.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                            stream));
   MGX_CUDA(cudaStreamSynchronize(stream));
+  trace.mark("  sort: global hist");
   for (int p = 0; p < passes; ++p) {
     bool trivial = false;
     for (int d = 0; d < kRadix; ++d) {
@@ -364,15 +392,13 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
     const int shift = p * kRadixBits;
     radix_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(cur.keys, n, shift, d_hist, n_tiles);
     MGX_LAUNCH_CHECK();
-    exclusive_scan_u32_u64(d_hist, d_hist_scan, hist_len, stream);
+    exclusive_scan_u32_u64(d_hist, d_hist_scan, hist_len, d_scan_scratch, stream);
     radix_scatter_kernel<<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(cur.keys, cur.vals, alt.keys, alt.vals,
                                                                                   n, shift, d_hist_scan, n_tiles);
     MGX_LAUNCH_CHECK();
     std::swap(cur, alt);
+    trace.mark("  sort: pass");
   }
-  MGX_CUDA(cudaFreeAsync(d_hist, stream));
-  MGX_CUDA(cudaFreeAsync(d_hist_scan, stream));
-  MGX_CUDA(cudaFreeAsync(d_ghist, stream));
   return cur;
 }
 

@@ -2028,14 +2028,15 @@ void batch_plan(Batch& b) {
                                                                (ix.n_docs + 7) / 8);
     MGX_LAUNCH_CHECK();
   }
-  exclusive_scan_u32_u64(b.d_t_df_tiles.p, b.d_t_df_tile_off.p, b.n_terms, st);
+  b.d_scan_scratch.reserve(scan_scratch_elems(std::max<uint64_t>(b.n_terms, b.n_queries)) + 8);
+  exclusive_scan_u32_u64(b.d_t_df_tiles.p, b.d_t_df_tile_off.p, b.n_terms, b.d_scan_scratch.p, st);
   const IndexView iv = make_view(ix);
   if (b.n_queries > 0) {
     query_plan_kernel<<<grid_for(b.n_queries, 128), 128, 0, st>>>(iv, bv);
     MGX_LAUNCH_CHECK();
   }
-  exclusive_scan_u32_u64(b.d_q_ntiles.p, b.d_q_tile_off.p, b.n_queries, st);
-  exclusive_scan_u32_u64(b.d_q_driver_len.p, b.d_q_rec_off.p, b.n_queries, st);
+  exclusive_scan_u32_u64(b.d_q_ntiles.p, b.d_q_tile_off.p, b.n_queries, b.d_scan_scratch.p, st);
+  exclusive_scan_u32_u64(b.d_q_driver_len.p, b.d_q_rec_off.p, b.n_queries, b.d_scan_scratch.p, st);
   b.h_q_tile_off.resize(b.n_queries + 1);
   b.h_q_rec_off.resize(b.n_queries + 1);
   MGX_CUDA(cudaMemcpyAsync(b.h_q_tile_off.data(), b.d_q_tile_off.p, (b.n_queries + 1) * sizeof(uint64_t),

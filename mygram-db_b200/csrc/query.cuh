@@ -84,6 +84,7 @@ struct Batch {
   std::vector<uint64_t> h_q_rec_off;
 
   DevBuf<uint8_t> d_term_flags;   // [T] bit0 raw, bit1 exact_single
+  DevBuf<uint64_t> d_scan_scratch;  // block sums of the planning scans
   DevBuf<uint32_t> d_df_tile_term;  // [df tiles]
   DevBuf<uint32_t> d_tile_query;    // [and tiles]
   DevBuf<unsigned long long> d_stats;  // device-side accounting, see StatSlot
