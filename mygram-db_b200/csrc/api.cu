@@ -367,6 +367,10 @@ void mgx_index_destroy(mgx_index_t* index) {
       cudaStreamSynchronize(index->ix.stream);
       cudaStreamDestroy(index->ix.stream);
     }
+    for (void* pooled : index->ix.batch_pool) {
+      delete static_cast<mgx_batch*>(pooled);
+    }
+    index->ix.batch_pool.clear();
     delete index;
   }
 }
@@ -809,7 +813,17 @@ int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint
   return guarded([&]() {
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
-    auto h = std::make_unique<mgx_batch>();
+    std::unique_ptr<mgx_batch> h;
+    {
+      std::lock_guard<std::mutex> pool_lock(ix.pool_mu);
+      if (!ix.batch_pool.empty()) {
+        h.reset(static_cast<mgx_batch*>(ix.batch_pool.back()));
+        ix.batch_pool.pop_back();
+      }
+    }
+    if (!h) {
+      h = std::make_unique<mgx_batch>();
+    }
     Batch& b = h->b;
     b.ix = &ix;
     b.params = *params;
@@ -905,9 +919,16 @@ void mgx_batch_destroy(mgx_batch_t* batch) {
   if (batch == nullptr) {
     return;
   }
-  DeviceGuard guard(batch->b.ix->device);
+  Index& ix = *batch->b.ix;
+  DeviceGuard guard(ix.device);
   cudaStreamSynchronize(batch->b.stream);
-  delete batch;
+  batch->b.recycle();
+  std::lock_guard<std::mutex> pool_lock(ix.pool_mu);
+  if (ix.batch_pool.size() < 16) {
+    ix.batch_pool.push_back(batch);  // keep the workspace for the next batch
+  } else {
+    delete batch;
+  }
 }
 
 int mgx_merge_topk_device(int32_t device, void* stream, const mgx_query_params_t* params, uint32_t n_shards,

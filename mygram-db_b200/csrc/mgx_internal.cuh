@@ -17,6 +17,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -110,8 +111,10 @@ struct DevArena {
   DevBuf<uint8_t> blob;
   size_t used = 0;
   static size_t padded(size_t bytes) { return (bytes + 255) & ~static_cast<size_t>(255); }
-  void reserve(size_t bytes) {
-    blob.alloc(bytes + 256);
+  void reserve(size_t bytes) {  // grow-only: an arena that is big enough is reused as is
+    if (blob.p == nullptr || blob.n < bytes + 256) {
+      blob.alloc(bytes + 256);
+    }
     used = 0;
   }
   template <typename T>
@@ -301,6 +304,9 @@ struct Index {
 
   mgx_batch_stats_t last_stats{};
   cudaStream_t stream = nullptr;  // owned, non-blocking; used by the non-staged calls
+  // recycled batch workspaces (device arenas + pinned staging), so a steady stream of batches allocates nothing
+  std::vector<void*> batch_pool;
+  std::mutex pool_mu;
 
   uint64_t device_bytes() const;
 };

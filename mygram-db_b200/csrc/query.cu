@@ -1933,6 +1933,27 @@ void Batch::collect_stats(mgx_batch_stats_t* out) {
 }
 
 // ------------------------------------------------------------------ host orchestration
+void Batch::recycle() {
+  for (auto& t : timed) {
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  timed.clear();
+  if (ev_first != nullptr) {
+    cudaEventDestroy(ev_first);
+    ev_first = nullptr;
+  }
+  if (ev_last != nullptr) {
+    cudaEventDestroy(ev_last);
+    ev_last = nullptr;
+  }
+  h_slot_tid.clear();
+  explicit_driver = ExplicitDriver{};
+  h2d_bytes = d2h_bytes = 0;
+  n_df_tiles = n_and_tiles = driver_entries = 0;
+  planned = df_done = false;
+}
+
 void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
                   const std::vector<uint32_t>& slot_tid) {
   cudaStream_t st = b.stream;
@@ -1976,40 +1997,89 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vecto
     loff[q + 1] = loff[q] + cap;
     hflags[q] = queries[q].flags;
   }
+  b.n_qterms = static_cast<uint32_t>(tids.size());
 
-  uint64_t h2d = 0;
-  upload(b.d_term_bytes, bytes, st, &h2d);
-  upload(b.d_term_boff, boff, st, &h2d);
-  upload(b.d_term_koff, koff, st, &h2d);
-  upload(b.d_keys, keys, st, &h2d);
-  upload(b.d_q_toff, toff, st, &h2d);
-  upload(b.d_q_tids, tids, st, &h2d);
-  upload(b.d_q_noff, noff, st, &h2d);
-  upload(b.d_q_ntids, ntids, st, &h2d);
-  upload(b.d_q_loff, loff, st, &h2d);
-  upload(b.d_q_host_flags, hflags, st, &h2d);
-  upload(b.d_slot_tid, slot_tid, st, &h2d);
-  b.d_key_list.alloc(keys.size());
-  b.d_key_len.alloc(keys.size());
-  b.d_t_est.alloc(terms.size());
-  b.d_t_df_tiles.alloc(terms.size());
-  b.d_t_df_tile_off.alloc(terms.size() + 1);
-  b.d_t_df.alloc(terms.size());
-  b.d_q_list.alloc(loff.back());
-  b.d_q_list_len.alloc(loff.back());
-  b.d_q_nlists.alloc(queries.size());
-  b.d_q_flags.alloc(queries.size());
-  b.d_q_driver_len.alloc(queries.size());
-  b.d_q_ntiles.alloc(queries.size());
-  b.d_q_tile_off.alloc(queries.size() + 1);
-  b.d_q_rec_off.alloc(queries.size() + 1);
-  b.d_q_idf.alloc(tids.size());
-  b.h2d_bytes = h2d;
+  // ---- one pinned staging buffer, one H2D copy, views into the input arena
+  struct Piece {
+    const void* src;
+    size_t bytes;
+    size_t off;
+  };
+  std::vector<Piece> pieces;
+  size_t total = 0;
+  auto add = [&](const void* src, size_t nbytes) {
+    pieces.push_back({src, nbytes, total});
+    total += DevArena::padded(nbytes == 0 ? 1 : nbytes);
+    return pieces.size() - 1;
+  };
+  const size_t i_bytes = add(bytes.data(), bytes.size());
+  const size_t i_boff = add(boff.data(), boff.size() * 4);
+  const size_t i_koff = add(koff.data(), koff.size() * 4);
+  const size_t i_keys = add(keys.data(), keys.size() * 8);
+  const size_t i_raw = add(raw.data(), raw.size());
+  const size_t i_toff = add(toff.data(), toff.size() * 4);
+  const size_t i_tids = add(tids.data(), tids.size() * 4);
+  const size_t i_noff = add(noff.data(), noff.size() * 4);
+  const size_t i_ntids = add(ntids.data(), ntids.size() * 4);
+  const size_t i_loff = add(loff.data(), loff.size() * 4);
+  const size_t i_hflags = add(hflags.data(), hflags.size() * 4);
+  const size_t i_slot = add(slot_tid.data(), slot_tid.size() * 4);
+  b.staging.reserve(total + 256);
+  for (const Piece& pc : pieces) {
+    if (pc.bytes > 0) {
+      std::memcpy(b.staging.p + pc.off, pc.src, pc.bytes);
+    }
+  }
+  b.in_arena.reserve(total + 256);
+  uint8_t* base = b.in_arena.take<uint8_t>(total);
+  MGX_CUDA(cudaMemcpyAsync(base, b.staging.p, total, cudaMemcpyHostToDevice, st));
+  b.h2d_bytes = total;
+  auto at = [&](size_t i) { return base + pieces[i].off; };
+  b.d_term_bytes.borrow(at(i_bytes), bytes.size());
+  b.d_term_boff.borrow(reinterpret_cast<uint32_t*>(at(i_boff)), boff.size());
+  b.d_term_koff.borrow(reinterpret_cast<uint32_t*>(at(i_koff)), koff.size());
+  b.d_keys.borrow(reinterpret_cast<uint64_t*>(at(i_keys)), keys.size());
+  b.d_term_flags.borrow(at(i_raw), raw.size());
+  b.d_q_toff.borrow(reinterpret_cast<uint32_t*>(at(i_toff)), toff.size());
+  b.d_q_tids.borrow(reinterpret_cast<uint32_t*>(at(i_tids)), tids.size());
+  b.d_q_noff.borrow(reinterpret_cast<uint32_t*>(at(i_noff)), noff.size());
+  b.d_q_ntids.borrow(reinterpret_cast<uint32_t*>(at(i_ntids)), ntids.size());
+  b.d_q_loff.borrow(reinterpret_cast<uint32_t*>(at(i_loff)), loff.size());
+  b.d_q_host_flags.borrow(reinterpret_cast<uint32_t*>(at(i_hflags)), hflags.size());
+  b.d_slot_tid.borrow(reinterpret_cast<uint32_t*>(at(i_slot)), slot_tid.size());
 
-  upload(b.d_term_flags, raw, st, &h2d);
-  b.d_stats.alloc(static_cast<size_t>(kStatCount) * kStatStripes);
+  // ---- device-only planning arrays from the work arena
+  const size_t T = terms.size();
+  const size_t Q = queries.size();
+  const size_t K = keys.size();
+  const size_t Lc = loff.back();
+  const size_t scan_elems = scan_scratch_elems(std::max<uint64_t>(T, Q)) + 8;
+  size_t work = 0;
+  for (size_t nbytes : {K * 4, K * 4, T * 8, T * 4, (T + 1) * 8, T * 8, Lc * 4, Lc * 4, Q * 4, Q * 4, Q * 4, Q * 4,
+                        (Q + 1) * 8, (Q + 1) * 8, tids.size() * 8, static_cast<size_t>(kStatCount) * kStatStripes * 8,
+                        scan_elems * 8}) {
+    work += DevArena::padded(nbytes == 0 ? 1 : nbytes);
+  }
+  b.work_arena.reserve(work + 1024);
+  b.d_key_list.borrow(b.work_arena.take<uint32_t>(K), K);
+  b.d_key_len.borrow(b.work_arena.take<uint32_t>(K), K);
+  b.d_t_est.borrow(b.work_arena.take<uint64_t>(T), T);
+  b.d_t_df_tiles.borrow(b.work_arena.take<uint32_t>(T), T);
+  b.d_t_df_tile_off.borrow(b.work_arena.take<uint64_t>(T + 1), T + 1);
+  b.d_t_df.borrow(b.work_arena.take<uint64_t>(T), T);
+  b.d_q_list.borrow(b.work_arena.take<uint32_t>(Lc), Lc);
+  b.d_q_list_len.borrow(b.work_arena.take<uint32_t>(Lc), Lc);
+  b.d_q_nlists.borrow(b.work_arena.take<uint32_t>(Q), Q);
+  b.d_q_flags.borrow(b.work_arena.take<uint32_t>(Q), Q);
+  b.d_q_driver_len.borrow(b.work_arena.take<uint32_t>(Q), Q);
+  b.d_q_ntiles.borrow(b.work_arena.take<uint32_t>(Q), Q);
+  b.d_q_tile_off.borrow(b.work_arena.take<uint64_t>(Q + 1), Q + 1);
+  b.d_q_rec_off.borrow(b.work_arena.take<uint64_t>(Q + 1), Q + 1);
+  b.d_q_idf.borrow(b.work_arena.take<double>(tids.size()), tids.size());
+  const size_t n_stats = static_cast<size_t>(kStatCount) * kStatStripes;
+  b.d_stats.borrow(b.work_arena.take<unsigned long long>(n_stats), n_stats);
+  b.d_scan_scratch.borrow(b.work_arena.take<uint64_t>(scan_elems), scan_elems);
   MGX_CUDA(cudaMemsetAsync(b.d_stats.p, 0, b.d_stats.bytes(), st));
-  b.h2d_bytes = h2d;
 }
 
 void batch_plan(Batch& b) {
@@ -2028,7 +2098,6 @@ void batch_plan(Batch& b) {
                                                                (ix.n_docs + 7) / 8);
     MGX_LAUNCH_CHECK();
   }
-  b.d_scan_scratch.reserve(scan_scratch_elems(std::max<uint64_t>(b.n_terms, b.n_queries)) + 8);
   exclusive_scan_u32_u64(b.d_t_df_tiles.p, b.d_t_df_tile_off.p, b.n_terms, b.d_scan_scratch.p, st);
   const IndexView iv = make_view(ix);
   if (b.n_queries > 0) {
@@ -2050,8 +2119,8 @@ void batch_plan(Batch& b) {
   b.d2h_bytes += 2 * (b.n_queries + 1) * sizeof(uint64_t) + sizeof(uint64_t);
   // tile -> term / tile -> query maps (sizes are only known now)
   const uint64_t n_and_tiles = b.n_queries > 0 ? b.h_q_tile_off[b.n_queries] : 0;
-  b.d_df_tile_term.alloc(b.n_df_tiles);
-  b.d_tile_query.alloc(n_and_tiles);
+  b.d_df_tile_term.reserve(b.n_df_tiles);
+  b.d_tile_query.reserve(n_and_tiles);
   b.time_begin(0);
   if (b.n_df_tiles > 0) {
     fill_tile_map_kernel<<<grid_for(static_cast<uint64_t>(b.n_terms) * 32, 256), 256, 0, st>>>(
@@ -2127,7 +2196,7 @@ void prepare_scoring(Batch& b, const uint64_t* d_df_slots) {
     MGX_LAUNCH_CHECK();
   }
   const uint64_t total_docs = b.params.total_docs != 0 ? b.params.total_docs : b.ix->doc_count;
-  const uint32_t n = static_cast<uint32_t>(b.d_q_tids.n);
+  const uint32_t n = b.n_qterms;
   if (n > 0) {
     idf_kernel<<<grid_for(n, 256), 256, 0, st>>>(b.d_q_tids.p, n, b.d_t_df.p, total_docs, b.d_q_idf.p);
     MGX_LAUNCH_CHECK();

@@ -84,6 +84,12 @@ struct Batch {
   std::vector<uint64_t> h_q_rec_off;
 
   DevBuf<uint8_t> d_term_flags;   // [T] bit0 raw, bit1 exact_single
+  // Everything above is a view into one of these two grow-only arenas: `in_arena` receives the compiled batch in ONE
+  // host-to-device copy from the pinned `staging` buffer; `work_arena` holds the device-only planning arrays.
+  DevArena in_arena;
+  DevArena work_arena;
+  PinBuf<uint8_t> staging;
+  uint32_t n_qterms = 0;  // total search-term slots over all queries
   DevBuf<uint64_t> d_scan_scratch;  // block sums of the planning scans
   DevBuf<uint32_t> d_df_tile_term;  // [df tiles]
   DevBuf<uint32_t> d_tile_query;    // [and tiles]
@@ -112,6 +118,7 @@ struct Batch {
   void time_end();
   void mark_last();
   void collect_stats(mgx_batch_stats_t* out);  // synchronises the stream
+  void recycle();  // forget per-batch state, keep the allocations
   ~Batch();
 };
 
