@@ -330,22 +330,32 @@ def main():
     out_count = torch.empty(args.batch, dtype=torch.int32, pin_memory=True)
     out_total = torch.empty(args.batch, dtype=torch.int64, pin_memory=True)
 
-    def e2e_step(b):
+    e2e_parts = {"host_prepare_ms": 0.0, "enqueue_ms": 0.0, "drain_ms": 0.0}
+
+    def e2e_step(b, acc=None):
+        t_a = time.perf_counter()
         p = backend.prepare(b[1], b[2], b[3], args.batch)
+        t_b = time.perf_counter()
         ids, scores, count, total = sharded.run_sharded_batch(backend, comm, p)
         out_ids.copy_(ids, non_blocking=True)
         out_scores.copy_(scores, non_blocking=True)
         out_count.copy_(count, non_blocking=True)
         out_total.copy_(total, non_blocking=True)
+        t_c = time.perf_counter()
         torch.cuda.current_stream().synchronize()
         backend.release(p)
+        t_d = time.perf_counter()
+        if acc is not None:
+            acc["host_prepare_ms"] += 1e3 * (t_b - t_a)   # host query compile + staging + H2D enqueue
+            acc["enqueue_ms"] += 1e3 * (t_c - t_b)        # plan (one size read-back), df, search, merge, D2H enqueue
+            acc["drain_ms"] += 1e3 * (t_d - t_c)          # wait for the device + release
 
     for i in range(min(args.warmup, 2)):
         e2e_step(batches[i])
     barrier()
     t0 = time.perf_counter()
     for i in range(args.warmup, n_steps):
-        e2e_step(batches[i])
+        e2e_step(batches[i], e2e_parts)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     if world > 1:
@@ -411,10 +421,13 @@ def main():
                        "cache_note": "a different query batch every step; index (%.1f GB resident) >> 126 MB L2" %
                                      (st.device_bytes / 1e9),
                        "terms": int(st.n_terms), "postings": int(st.n_postings), "dense_terms": int(st.n_dense_terms)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "per_step_ms": {k: v / max(1, args.steps) for k, v in e2e_parts.items()}},
             "gpu_launches": gpu_launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity": parity, "kernels": kernels,
             "batch_stats_per_step": {k: (v / max(1, len(kstats))) for k, v in agg.items()} if agg else None,
+            "kernel_ms_by_step": {k: [round(s[k], 3) for s in kstats] for k in
+                                  ("ms_plan", "ms_df_kernel", "ms_and_kernel", "ms_topk_kernel", "ms_total")} if kstats else None,
             "index_build": {"docs_per_s_e2e": n_local * world / build_e2e_s, "docs_per_s_device": n_local * world / build_dev_s,
                             "device_build_ms": st.last_build_ms, "algorithmic_bytes": int(build_algo_bytes),
                             "hbm_frac_device": (build_algo_bytes / 1e9) / max(1e-9, st.last_build_ms / 1e3) / peak,

@@ -8,6 +8,8 @@
 // entry point fails with MGX_ERR_NO_DEVICE.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -833,13 +835,22 @@ int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint
     std::vector<HostQuery> queries;
     std::vector<uint32_t> slot_tid;
     static const uint8_t kEmpty[1] = {0};
+    static const bool trace = std::getenv("MGX_BATCH_TRACE") != nullptr;  // host wall time of the two host stages
+    const auto t0 = std::chrono::steady_clock::now();
     const int rc = compile_batch(ix, *params, n_queries, term_bytes != nullptr ? term_bytes : kEmpty, term_offsets,
                                  q_term_begin, not_bytes != nullptr ? not_bytes : kEmpty, not_offsets, q_not_begin,
                                  &terms, &queries, &slot_tid);
     if (rc != MGX_OK) {
       return rc;
     }
+    const auto t1 = std::chrono::steady_clock::now();
     batch_upload(b, terms, queries, slot_tid);
+    if (trace) {
+      const auto t2 = std::chrono::steady_clock::now();
+      fprintf(stderr, "[mgx batch] compile %.3f ms, stage+upload %.3f ms (%zu unique terms)\n",
+              std::chrono::duration<double, std::milli>(t1 - t0).count(),
+              std::chrono::duration<double, std::milli>(t2 - t1).count(), terms.size());
+    }
     *out = h.release();
     return MGX_OK;
   });

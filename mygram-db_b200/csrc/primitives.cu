@@ -135,7 +135,7 @@ constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n,
-                                                                  int shift, uint32_t* __restrict__ hist,
+                                                                  int shift, uint32_t mask, uint32_t* __restrict__ hist,
                                                                   uint32_t n_tiles) {
   __shared__ uint32_t bins[kRadix];
   bins[threadIdx.x] = 0;  // kSortThreads == kRadix
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t
   for (int r = 0; r < kSortRounds; ++r) {
     const uint64_t i = base + static_cast<uint64_t>(r) * kSortThreads + threadIdx.x;
     if (i < n) {
-      atomicAdd(&bins[(keys[i] >> shift) & (kRadix - 1)], 1u);
+      atomicAdd(&bins[static_cast<uint32_t>(keys[i] >> shift) & mask], 1u);
     }
   }
   __syncthreads();
@@ -154,9 +154,16 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t
 
 // Global digit histograms of every pass in ONE read of the keys: a pass whose digit is the same for all
 // keys is a pure copy and is skipped (e.g. the high bits of each 21-bit code-point field).
-constexpr int kMaxPasses = 8;
-__global__ void __launch_bounds__(256) radix_global_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n, int passes,
+constexpr int kMaxPasses = 9;
+struct PassList {
+  int n;
+  int shift[kMaxPasses];
+  uint32_t mask[kMaxPasses];
+};
+__global__ void __launch_bounds__(256) radix_global_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n,
+                                                                PassList pl,
                                                                 unsigned long long* __restrict__ hist /*[passes][256]*/) {
+  const int passes = pl.n;
   __shared__ uint32_t bins[kMaxPasses][kRadix];
   for (int p = 0; p < passes; ++p) {
     bins[p][threadIdx.x] = 0;
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(256) radix_global_hist_kernel(const uint64_t* 
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint64_t k = keys[i];
     for (int p = 0; p < passes; ++p) {
-      atomicAdd(&bins[p][(k >> (p * kRadixBits)) & (kRadix - 1)], 1u);
+      atomicAdd(&bins[p][static_cast<uint32_t>(k >> pl.shift[p]) & pl.mask[p]], 1u);
     }
   }
   __syncthreads();
@@ -195,7 +202,8 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
                                                                      const uint32_t* __restrict__ vals_in,
                                                                      uint64_t* __restrict__ keys_out,
                                                                      uint32_t* __restrict__ vals_out, uint64_t n,
-                                                                     int shift, const uint64_t* __restrict__ hist_scan,
+                                                                     int shift, uint32_t mask,
+                                                                     const uint64_t* __restrict__ hist_scan,
                                                                      uint32_t n_tiles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(smem_raw);
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
 #pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
     const bool valid = warp_off + r * 32 + lane < tile_n;
-    const uint32_t d = valid ? static_cast<uint32_t>((key[r] >> shift) & (kRadix - 1)) : 0x1FFu;
+    const uint32_t d = valid ? (static_cast<uint32_t>(key[r] >> shift) & mask) : 0x1FFu;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     if (valid && (peers & lt_mask) == 0) {
       sm.warp_cnt[warp][d] += __popc(peers);
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
 #pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
     const bool valid = warp_off + r * 32 + lane < tile_n;
-    const uint32_t d = valid ? static_cast<uint32_t>((key[r] >> shift) & (kRadix - 1)) : 0x1FFu;
+    const uint32_t d = valid ? (static_cast<uint32_t>(key[r] >> shift) & mask) : 0x1FFu;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     uint32_t base = 0;
     if (valid) {
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
   // phase 3: coalesced write-out, run by run
   for (uint32_t i = threadIdx.x; i < tile_n; i += kSortThreads) {
     const uint64_t k = sm.keys[i];
-    const uint32_t d = static_cast<uint32_t>((k >> shift) & (kRadix - 1));
+    const uint32_t d = static_cast<uint32_t>(k >> shift) & mask;
     const uint32_t pos = sm.global_base[d] + (i - sm.local_start[d]);
     keys_out[pos] = k;
     vals_out[pos] = sm.vals[i];
@@ -361,7 +369,20 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
   }
   const uint32_t n_tiles = static_cast<uint32_t>((n + kSortTile - 1) / kSortTile);
   const uint64_t hist_len = static_cast<uint64_t>(kRadix) * n_tiles;
-  const int passes = (key_bits + kRadixBits - 1) / kRadixBits;
+  // Digits are aligned to the 21-bit code-point fields of the packed key (8 + 8 + 5 bits per field), so that the
+  // constant high bits of a field (zero for every BMP code point) form a digit of their own and the pass is skipped.
+  PassList pl{};
+  for (int f = 0; f * 21 < key_bits; ++f) {
+    const int widths[3] = {8, 8, 5};
+    int off = 0;
+    for (int k = 0; k < 3; ++k) {
+      pl.shift[pl.n] = f * 21 + off;
+      pl.mask[pl.n] = (1u << widths[k]) - 1u;
+      ++pl.n;
+      off += widths[k];
+    }
+  }
+  const int passes = pl.n;
   const SortScratch L = sort_scratch_layout(n);
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d_scratch) + 255) & ~static_cast<uintptr_t>(255));
   uint32_t* d_hist = reinterpret_cast<uint32_t*>(base + L.hist_off);
@@ -374,7 +395,7 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
   int dev = 0;
   MGX_CUDA(cudaGetDevice(&dev));
   MGX_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  radix_global_hist_kernel<<<sm_count * 8, 256, 0, stream>>>(cur.keys, n, passes, d_ghist);
+  radix_global_hist_kernel<<<sm_count * 8, 256, 0, stream>>>(cur.keys, n, pl, d_ghist);
   MGX_LAUNCH_CHECK();
   std::vector<unsigned long long> ghist(static_cast<size_t>(kMaxPasses) * kRadix, 0);
   MGX_CUDA(cudaMemcpyAsync(ghist.data(), d_ghist, ghist.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -389,12 +410,13 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
     if (trivial) {
       continue;  // every key has the same digit here: the pass would be a stable copy
     }
-    const int shift = p * kRadixBits;
-    radix_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(cur.keys, n, shift, d_hist, n_tiles);
+    const int shift = pl.shift[p];
+    const uint32_t mask = pl.mask[p];
+    radix_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(cur.keys, n, shift, mask, d_hist, n_tiles);
     MGX_LAUNCH_CHECK();
     exclusive_scan_u32_u64(d_hist, d_hist_scan, hist_len, d_scan_scratch, stream);
     radix_scatter_kernel<<<n_tiles, kSortThreads, sizeof(ScatterSmem), stream>>>(cur.keys, cur.vals, alt.keys, alt.vals,
-                                                                                  n, shift, d_hist_scan, n_tiles);
+                                                                                  n, shift, mask, d_hist_scan, n_tiles);
     MGX_LAUNCH_CHECK();
     std::swap(cur, alt);
     trace.mark("  sort: pass");
