@@ -58,20 +58,53 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clocks / throttle reasons sampled DURING the timed regions, through NVML in a background thread
+    (`nvidia-smi -lms` was measured to stall the CUDA context for 50-200 ms per query on this box; an NVML
+    handle held open does not). Falls back to one-second nvidia-smi polling if pynvml is unavailable."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+               ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = threading.Event()
+        self.thread = None
         self.proc = None
         self.lines = []
 
+    def _nvml_loop(self, nv, h):
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.02)
+
     def start(self):
+        if os.environ.get("BENCH_NO_CLOCKS"):
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.gpu]) if visible and visible.split(",")[self.gpu].isdigit() else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "1000", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -79,31 +112,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                self.sm.append(float(f[1]))
+                self.mx.append(float(f[2]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(name)
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": "nvml" if self.proc is None else "nvidia-smi"}
 
 
 def flatten(queries):
@@ -323,39 +357,69 @@ def main():
         backend.release(p)
     kstats = backend.stats
 
-    # ---- e2e: host buffers in, host buffers out, every step
+    # ---- e2e: host buffers in, host buffers out, every step. The loop is software-pipelined two deep, the way a
+    # server feeds a stream of batches: while the device works on batch i the host compiles and enqueues batch
+    # i+1 (its planning stage still waits for batch i on the same stream). Every step copies its own inputs
+    # host->device and its own results device->host; a step is complete when its results are in pinned host memory.
     backend.collect_stats = False
-    out_ids = torch.empty((args.batch, TOPK), dtype=torch.int32, pin_memory=True)
-    out_scores = torch.empty((args.batch, TOPK), dtype=torch.float64, pin_memory=True)
-    out_count = torch.empty(args.batch, dtype=torch.int32, pin_memory=True)
-    out_total = torch.empty(args.batch, dtype=torch.int64, pin_memory=True)
+    outs = [dict(ids=torch.empty((args.batch, TOPK), dtype=torch.int32, pin_memory=True),
+                 scores=torch.empty((args.batch, TOPK), dtype=torch.float64, pin_memory=True),
+                 count=torch.empty(args.batch, dtype=torch.int32, pin_memory=True),
+                 total=torch.empty(args.batch, dtype=torch.int64, pin_memory=True),
+                 done=torch.cuda.Event()) for _ in range(2)]
+    out_ids, out_scores, out_count, out_total = (outs[0][k] for k in ("ids", "scores", "count", "total"))
+    e2e_parts = {"host_prepare_ms": 0.0, "enqueue_ms": 0.0, "wait_ms": 0.0}
 
-    e2e_parts = {"host_prepare_ms": 0.0, "enqueue_ms": 0.0, "drain_ms": 0.0}
-
-    def e2e_step(b, acc=None):
+    def e2e_submit(b, slot, acc=None):
         t_a = time.perf_counter()
         p = backend.prepare(b[1], b[2], b[3], args.batch)
         t_b = time.perf_counter()
-        ids, scores, count, total = sharded.run_sharded_batch(backend, comm, p)
-        out_ids.copy_(ids, non_blocking=True)
-        out_scores.copy_(scores, non_blocking=True)
-        out_count.copy_(count, non_blocking=True)
-        out_total.copy_(total, non_blocking=True)
+        if os.environ.get("BENCH_TRACE") and world == 1:
+            t1 = time.perf_counter()
+            df = backend.local_df(p)
+            t2 = time.perf_counter()
+            r = backend.search(p, df)
+            t3 = time.perf_counter()
+            ids, scores, count, total = backend.merge(r[0][None], r[1][None], r[2][None], r[3][None])
+            t4 = time.perf_counter()
+            print(f"[bench trace] local_df {1e3*(t2-t1):.2f} ms, search {1e3*(t3-t2):.2f} ms, merge {1e3*(t4-t3):.2f} ms",
+                  file=sys.stderr)
+        else:
+            ids, scores, count, total = sharded.run_sharded_batch(backend, comm, p)
+        o = outs[slot]
+        o["ids"].copy_(ids, non_blocking=True)
+        o["scores"].copy_(scores, non_blocking=True)
+        o["count"].copy_(count, non_blocking=True)
+        o["total"].copy_(total, non_blocking=True)
+        o["done"].record()
         t_c = time.perf_counter()
-        torch.cuda.current_stream().synchronize()
-        backend.release(p)
-        t_d = time.perf_counter()
         if acc is not None:
             acc["host_prepare_ms"] += 1e3 * (t_b - t_a)   # host query compile + staging + H2D enqueue
             acc["enqueue_ms"] += 1e3 * (t_c - t_b)        # plan (one size read-back), df, search, merge, D2H enqueue
-            acc["drain_ms"] += 1e3 * (t_d - t_c)          # wait for the device + release
+        return p, slot
 
-    for i in range(min(args.warmup, 2)):
-        e2e_step(batches[i])
+    def e2e_finish(pending, acc=None):
+        t_a = time.perf_counter()
+        p, slot = pending
+        outs[slot]["done"].synchronize()
+        backend.release(p)
+        if acc is not None:
+            acc["wait_ms"] += 1e3 * (time.perf_counter() - t_a)
+
+    def e2e_run(first, last, acc=None):
+        pending = None
+        for i in range(first, last):
+            cur = e2e_submit(batches[i], i & 1, acc)
+            if pending is not None:
+                e2e_finish(pending, acc)
+            pending = cur
+        if pending is not None:
+            e2e_finish(pending, acc)
+
+    e2e_run(0, min(args.warmup, 2))
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.warmup, n_steps):
-        e2e_step(batches[i], e2e_parts)
+    e2e_run(args.warmup, n_steps, e2e_parts)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     if world > 1:
@@ -422,7 +486,7 @@ def main():
                                      (st.device_bytes / 1e9),
                        "terms": int(st.n_terms), "postings": int(st.n_postings), "dense_terms": int(st.n_dense_terms)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "per_step_ms": {k: v / max(1, args.steps) for k, v in e2e_parts.items()}},
+                    "pipeline_depth": 2, "per_step_ms": {k: v / max(1, args.steps) for k, v in e2e_parts.items()}},
             "gpu_launches": gpu_launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity": parity, "kernels": kernels,
             "batch_stats_per_step": {k: (v / max(1, len(kstats))) for k, v in agg.items()} if agg else None,

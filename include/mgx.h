@@ -200,6 +200,12 @@ typedef struct {
   uint64_t result_docs;       /* sum |R|                                                          */
   uint64_t df_candidates;     /* documents whose text was scanned for df                          */
   uint64_t unique_terms;
+  double ms_df_stream_kernel; /* df_stream_kernel launch (one pass over the text arena), 0 if not chosen */
+  uint64_t df_stream_terms;   /* terms whose df came from the streaming pass                          */
+  uint64_t df_stream_bytes;   /* text bytes that pass read (= the shard's arena), its algorithmic bytes */
+  uint64_t df_stream_hits;    /* (term, document) pairs it counted                                    */
+  uint64_t df_scanned_docs;   /* df candidates whose whole text was scanned; the others were decided by one */
+                              /* comparison at the recorded first occurrence of the driver n-gram           */
 } mgx_batch_stats_t;
 
 /* Staged form of the same call, for doc-range sharded deployments (one process

@@ -69,7 +69,9 @@ class BatchStats(C.Structure):
                 ("n_df_tiles", C.c_uint64), ("n_and_tiles", C.c_uint64), ("algo_bytes_intersect", C.c_uint64),
                 ("algo_bytes_score", C.c_uint64), ("algo_bytes_df", C.c_uint64), ("algo_bytes_df_lists", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("driver_entries", C.c_uint64),
-                ("result_docs", C.c_uint64), ("df_candidates", C.c_uint64), ("unique_terms", C.c_uint64)]
+                ("result_docs", C.c_uint64), ("df_candidates", C.c_uint64), ("unique_terms", C.c_uint64),
+                ("ms_df_stream_kernel", C.c_double), ("df_stream_terms", C.c_uint64), ("df_stream_bytes", C.c_uint64),
+                ("df_stream_hits", C.c_uint64), ("df_scanned_docs", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

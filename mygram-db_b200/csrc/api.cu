@@ -52,7 +52,7 @@ namespace {
 // GenerateHybridNgrams (string_utils.cpp:452-509) as packed keys; windows wider
 // than the index's key width cannot exist in the dictionary => kInvalidKey.
 void hybrid_keys(const std::vector<uint32_t>& cps, int ascii_n, int kanji_n, bool cross, int width,
-                 std::vector<uint64_t>* keys) {
+                 std::vector<uint64_t>* keys, std::vector<uint32_t>* starts = nullptr) {
   if (ascii_n <= 0 || kanji_n <= 0) {
     return;
   }
@@ -75,6 +75,9 @@ void hybrid_keys(const std::vector<uint32_t>& cps, int ascii_n, int kanji_n, boo
       }
     }
     keys->push_back(size <= width ? pack_key(cps.data() + i, size, width) : kInvalidKey);
+    if (starts != nullptr) {
+      starts->push_back(static_cast<uint32_t>(i));  // index of the window's first code point
+    }
   }
 }
 
@@ -131,20 +134,60 @@ bool has_uncovered_hybrid_fragment(const uint8_t* term, uint64_t len, int ngram_
 }  // namespace
 
 bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanji_ngram_size, bool cross_boundary,
-                     int key_width, std::vector<uint64_t>* keys) {
+                     int key_width, std::vector<uint64_t>* keys, std::vector<uint16_t>* key_toff) {
   keys->clear();
   const auto cps = host_utf8_to_codepoints(term, len);
+  std::vector<uint32_t> starts;
   if (kanji_ngram_size > 0) {
-    hybrid_keys(cps, ngram_size > 0 ? ngram_size : 2, kanji_ngram_size, cross_boundary, key_width, keys);
+    hybrid_keys(cps, ngram_size > 0 ? ngram_size : 2, kanji_ngram_size, cross_boundary, key_width, keys, &starts);
   } else if (ngram_size == 0) {
-    hybrid_keys(cps, 2, 1, true, key_width, keys);  // GenerateHybridNgrams defaults, string_utils.h
+    hybrid_keys(cps, 2, 1, true, key_width, keys, &starts);  // GenerateHybridNgrams defaults, string_utils.h
   } else if (ngram_size > 0 && !cps.empty()) {
     // GenerateNgrams, string_utils.cpp:382-423
     const size_t n = static_cast<size_t>(ngram_size);
     if (cps.size() >= n) {
       for (size_t i = 0; i + n <= cps.size(); ++i) {
         keys->push_back(ngram_size <= key_width ? pack_key(cps.data() + i, ngram_size, key_width) : kInvalidKey);
+        starts.push_back(static_cast<uint32_t>(i));
       }
+    }
+  }
+  if (key_toff != nullptr) {
+    // Byte offset inside the term of every n-gram that occurs exactly ONCE in it (kNoTermOffset otherwise, and for
+    // every n-gram of a term that is not valid UTF-8: its windows skip bytes, so they are no contiguous byte run).
+    std::vector<uint32_t> cp_byte(cps.size() + 1, 0);
+    bool valid = true;
+    {
+      uint64_t i = 0;
+      size_t c = 0;
+      while (i < len && c < cps.size()) {
+        uint32_t cp = 0;
+        const uint64_t avail = len - i;
+        const int l = parse_utf8(term[i], avail > 1 ? term[i + 1] : 0, avail > 2 ? term[i + 2] : 0,
+                                 avail > 3 ? term[i + 3] : 0, avail, &cp);
+        if (l <= 0) {
+          valid = false;
+          break;
+        }
+        cp_byte[c++] = static_cast<uint32_t>(i);
+        i += static_cast<uint64_t>(l);
+      }
+      valid = valid && i == len;
+    }
+    std::vector<std::pair<uint64_t, uint32_t>> occ(keys->size());
+    for (size_t i = 0; i < keys->size(); ++i) {
+      occ[i] = {(*keys)[i], starts[i]};
+    }
+    std::sort(occ.begin(), occ.end());
+    key_toff->clear();
+    for (size_t i = 0; i < occ.size();) {
+      size_t j = i;
+      while (j < occ.size() && occ[j].first == occ[i].first) {
+        ++j;
+      }
+      const uint32_t off = cp_byte[occ[i].second];
+      key_toff->push_back(valid && j - i == 1 && off < kNoTermOffset ? static_cast<uint16_t>(off) : kNoTermOffset);
+      i = j;
     }
   }
   std::sort(keys->begin(), keys->end());  // DeduplicateSorted, string_utils.h:192-196
@@ -226,6 +269,17 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
                   const uint64_t* not_offsets, const uint64_t* q_not_begin, std::vector<HostTerm>* terms,
                   std::vector<HostQuery>* queries, std::vector<uint32_t>* slot_tid) {
   std::unordered_map<std::string, uint32_t> ids;
+  // The streaming df pass (df_stream_kernel) counts "documents whose text contains the term". That equals the
+  // reference's df (documents of SearchAnd(term n-grams) whose text contains the term) when every document is valid
+  // UTF-8 and the query-side windows of a term are windows the index stores for any text containing it, i.e. both
+  // sides cut with the same sizes and the index does not reject boundary windows the query side keeps.
+  const int q_ascii = p.kanji_ngram_size > 0 ? (p.ngram_size > 0 ? p.ngram_size : 2) : (p.ngram_size == 0 ? 2 : p.ngram_size);
+  const int q_kanji = p.kanji_ngram_size > 0 ? p.kanji_ngram_size : (p.ngram_size == 0 ? 1 : p.ngram_size);
+  const bool q_cross = p.kanji_ngram_size > 0 ? p.cross_boundary != 0 : true;
+  // tok_agree: every window the query side cuts from a term is a window the index stores for any text that contains
+  // the term. Needed by both text-free shortcuts of the df stage (streaming pass, first-occurrence positions).
+  const bool tok_agree = q_ascii == ix.ngram && q_kanji == ix.kanji && (ix.cross || !q_cross);
+  const bool stream_ok = p.compute_score != 0 && ix.all_valid_utf8 && tok_agree;
   auto intern = [&](const uint8_t* bytes, uint64_t b, uint64_t e, uint32_t* out) -> int {
     if (e - b > kMaxTermBytes) {
       set_last_error("query term longer than 256 bytes is not supported");
@@ -239,11 +293,27 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
     }
     HostTerm t;
     t.bytes = s;
-    host_query_keys(bytes + b, e - b, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0, ix.width, &t.keys);
+    host_query_keys(bytes + b, e - b, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0, ix.width, &t.keys,
+                    tok_agree ? &t.key_toff : nullptr);
     if (t.keys.size() == 1 && t.keys[0] != kInvalidKey) {
       uint8_t enc[4 * kMaxKeyWidth];
       const int n = mgx_key_to_utf8(t.keys[0], ix.width, enc);
       t.exact_single = static_cast<uint64_t>(n) == e - b && std::memcmp(enc, bytes + b, e - b) == 0;
+    }
+    if (stream_ok && !t.keys.empty() && (t.keys.size() > 1 || !t.exact_single) &&
+        std::find(t.keys.begin(), t.keys.end(), kInvalidKey) == t.keys.end()) {
+      // valid UTF-8 of at least kStreamMinTermBytes bytes?
+      uint64_t i = b;
+      bool valid = e - b >= kStreamMinTermBytes;
+      while (valid && i < e) {
+        uint32_t cp = 0;
+        const uint64_t avail = e - i;
+        const int l = parse_utf8(bytes[i], avail > 1 ? bytes[i + 1] : 0, avail > 2 ? bytes[i + 2] : 0,
+                                 avail > 3 ? bytes[i + 3] : 0, avail, &cp);
+        valid = l > 0;
+        i += static_cast<uint64_t>(l > 0 ? l : 1);
+      }
+      t.streamable = valid;
     }
     const uint32_t id = static_cast<uint32_t>(terms->size());
     terms->push_back(std::move(t));
@@ -522,7 +592,7 @@ int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, co
     d_docs.alloc(n_slots);
     if (n_slots > 0) {
       tokenize_emit(config->ngram_size, kanji, config->cross_boundary_ngrams != 0, width, d_text.p, d_off.p, n_docs,
-                    d_slot_off.p, d_keys.p, d_docs.p, st);
+                    d_slot_off.p, d_keys.p, d_docs.p, 0, st);
     }
     std::vector<uint64_t> keys(n_slots);
     std::vector<uint32_t> docs(n_slots);
@@ -932,7 +1002,13 @@ void mgx_batch_destroy(mgx_batch_t* batch) {
   }
   Index& ix = *batch->b.ix;
   DeviceGuard guard(ix.device);
-  cudaStreamSynchronize(batch->b.stream);
+  // wait for THIS batch only (its last kernel is followed by ev_last), not for whatever the caller has queued
+  // behind it on the same stream: a pipelined caller releases batch i while batch i+1 is already running
+  if (batch->b.ev_last != nullptr && batch->b.searched) {
+    cudaEventSynchronize(batch->b.ev_last);
+  } else {
+    cudaStreamSynchronize(batch->b.stream);
+  }
   batch->b.recycle();
   std::lock_guard<std::mutex> pool_lock(ix.pool_mu);
   if (ix.batch_pool.size() < 16) {
@@ -987,16 +1063,16 @@ int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64
     Index& ix = *b.ix;
     DeviceGuard guard(ix.device);
     cudaStream_t st = b.stream;
-    DevBuf<uint32_t> d_ids;
-    DevBuf<double> d_scores;
-    DevBuf<uint32_t> d_count;
-    DevBuf<uint64_t> d_total;
-    DevBuf<uint64_t> d_df;
-    d_ids.alloc(n_queries * stride);
-    d_scores.alloc(params->compute_score != 0 ? n_queries * stride : 1);
-    d_count.alloc(n_queries);
-    d_total.alloc(n_queries);
-    d_df.alloc(b.n_slots);
+    DevBuf<uint32_t>& d_ids = b.o_ids;
+    DevBuf<double>& d_scores = b.o_scores;
+    DevBuf<uint32_t>& d_count = b.o_count;
+    DevBuf<uint64_t>& d_total = b.o_total;
+    DevBuf<uint64_t>& d_df = b.o_df;
+    d_ids.reserve(n_queries * stride);
+    d_scores.reserve(params->compute_score != 0 ? n_queries * stride : 1);
+    d_count.reserve(n_queries);
+    d_total.reserve(n_queries);
+    d_df.reserve(b.n_slots);
     batch_plan(b);
     if (params->compute_score != 0) {
       batch_df(b);

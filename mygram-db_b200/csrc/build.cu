@@ -34,6 +34,8 @@ __device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[5], int j) {
   return (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
 }
 
+__device__ __forceinline__ uint64_t umin_u64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
 __device__ __forceinline__ uint4 ld_stream_16(const uint8_t* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -59,8 +61,10 @@ __global__ void __launch_bounds__(kTokThreads)
 tokenize_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ text_off, uint64_t n_docs, int ngram,
                 int kanji, int cross, int width, uint32_t* __restrict__ doc_len, uint32_t* __restrict__ ngram_cnt,
                 const uint64_t* __restrict__ slot_off, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ docs_out,
-                unsigned long long* __restrict__ counters /* [0] non-empty docs, [1] docs with invalid bytes, [2] code points */) {
+                unsigned long long* __restrict__ counters /* [0] non-empty docs, [1] docs with invalid bytes, [2] code points */,
+                int pos_bits) {
   __shared__ uint32_t cp_buf[kTokWarps][kTokBuf];
+  __shared__ uint32_t pos_buf[EMIT ? kTokWarps : 1][EMIT ? kTokBuf : 1];  // byte offset of each code point in its document
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned warp_in_cta = threadIdx.x >> 5;
@@ -70,6 +74,8 @@ tokenize_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ t
   unsigned long long invalid = 0;
   unsigned long long total_cps = 0;
   uint32_t* buf = cp_buf[warp_in_cta];
+  uint32_t* pbuf = pos_buf[EMIT ? warp_in_cta : 0];
+  const uint64_t pos_max = pos_bits > 0 ? ((1ULL << pos_bits) - 1) : 0;
 
   for (uint64_t d = warp_global; d < n_docs; d += warp_stride) {
     const uint64_t b = text_off[d];
@@ -143,6 +149,9 @@ tokenize_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ t
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         if (flags & (1u << j)) {
+          if (EMIT) {
+            pbuf[wpos] = static_cast<uint32_t>(umin_u64(my + j - b, 0xFFFFFFFFULL));
+          }
           buf[wpos++] = cps[j];
         }
       }
@@ -178,19 +187,26 @@ tokenize_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ t
         const unsigned ballot = __ballot_sync(0xffffffffu, ok);
         if (EMIT && ok) {
           const uint64_t slot = slot_base + emitted + __popc(ballot & lt_mask);
-          keys_out[slot] = key;
+          keys_out[slot] = pos_bits > 0 ? ((key << pos_bits) | umin_u64(pbuf[p], pos_max)) : key;
           docs_out[slot] = static_cast<uint32_t>(d);
         }
         emitted += __popc(ballot);
       }
       __syncwarp();
       uint32_t carried = 0;
+      uint32_t carried_pos = 0;
       if (lane < keep) {
         carried = buf[emit_n + lane];
+        if (EMIT) {
+          carried_pos = pbuf[emit_n + lane];
+        }
       }
       __syncwarp();
       if (lane < keep) {
         buf[lane] = carried;
+        if (EMIT) {
+          pbuf[lane] = carried_pos;
+        }
       }
       __syncwarp();
       cps_done += emit_n;
@@ -228,8 +244,9 @@ struct Heads {
   uint32_t terms;
 };
 
+// pb = position bits carried in the low end of every key (0 if none): n-gram identity is key >> pb
 __device__ __forceinline__ Heads head_flags(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ docs,
-                                            uint64_t i, uint64_t n, uint64_t* key_out) {
+                                            uint64_t i, uint64_t n, int pb, uint64_t* key_out) {
   Heads h{0, 0};
   if (i >= n) {
     return h;
@@ -239,7 +256,7 @@ __device__ __forceinline__ Heads head_flags(const uint64_t* __restrict__ keys, c
   if (k == kInvalidKey) {
     return h;
   }
-  const bool term_head = (i == 0) || keys[i - 1] != k;
+  const bool term_head = (i == 0) || (keys[i - 1] >> pb) != (k >> pb);
   const bool pair_head = term_head || docs[i - 1] != docs[i];
   h.terms = term_head;
   h.pairs = pair_head;
@@ -255,7 +272,7 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
 }
 
 __global__ void __launch_bounds__(kCsrThreads) csr_count_kernel(const uint64_t* __restrict__ keys,
-                                                                const uint32_t* __restrict__ docs, uint64_t n,
+                                                                const uint32_t* __restrict__ docs, uint64_t n, int pb,
                                                                 uint64_t* __restrict__ block_pairs,
                                                                 uint64_t* __restrict__ block_terms) {
   __shared__ uint32_t sp[kCsrThreads / 32];
@@ -267,7 +284,7 @@ __global__ void __launch_bounds__(kCsrThreads) csr_count_kernel(const uint64_t* 
   for (int k = 0; k < kCsrItems; ++k) {
     const uint64_t i = base + static_cast<uint64_t>(k) * kCsrThreads + threadIdx.x;
     uint64_t key;
-    const Heads h = head_flags(keys, docs, i, n, &key);
+    const Heads h = head_flags(keys, docs, i, n, pb, &key);
     pairs += h.pairs;
     terms += h.terms;
   }
@@ -352,12 +369,14 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(uint64_t* __restrict__ b
 }
 
 __global__ void __launch_bounds__(kCsrThreads) csr_write_kernel(const uint64_t* __restrict__ keys,
-                                                                const uint32_t* __restrict__ docs, uint64_t n,
+                                                                const uint32_t* __restrict__ docs, uint64_t n, int pb,
                                                                 const uint64_t* __restrict__ block_pairs,
                                                                 const uint64_t* __restrict__ block_terms,
                                                                 uint64_t* __restrict__ term_keys,
                                                                 uint64_t* __restrict__ term_off,
-                                                                uint32_t* __restrict__ postings) {
+                                                                uint32_t* __restrict__ postings,
+                                                                uint16_t* __restrict__ post_pos,
+                                                                uint16_t* __restrict__ post_pos2) {
   __shared__ uint32_t sp[kCsrThreads / 32];
   __shared__ uint32_t st[kCsrThreads / 32];
   // thread t owns kCsrItems consecutive items so scan order == array order
@@ -369,7 +388,7 @@ __global__ void __launch_bounds__(kCsrThreads) csr_write_kernel(const uint64_t* 
 #pragma unroll
   for (int k = 0; k < kCsrItems; ++k) {
     key[k] = 0;
-    h[k] = head_flags(keys, docs, base + k, n, &key[k]);
+    h[k] = head_flags(keys, docs, base + k, n, pb, &key[k]);
     pairs += h[k].pairs;
     terms += h[k].terms;
   }
@@ -400,9 +419,23 @@ __global__ void __launch_bounds__(kCsrThreads) csr_write_kernel(const uint64_t* 
 #pragma unroll
   for (int k = 0; k < kCsrItems; ++k) {
     if (h[k].pairs) {
-      postings[pp] = docs[base + k];
+      const uint32_t doc = docs[base + k];
+      postings[pp] = doc;
+      if (pb > 0) {
+        // The sort is stable and the tokenizer emits a document's n-grams in text order, so the head of a
+        // (n-gram, document) run is the first occurrence; a second entry of the run means "more than once".
+        const uint64_t i = base + k;
+        const uint64_t pos_mask = (1ULL << pb) - 1;
+        const uint64_t k1 = i + 1 < n ? keys[i + 1] : kInvalidKey;
+        const bool multi = i + 1 < n && (k1 >> pb) == (key[k] >> pb) && docs[i + 1] == doc;
+        const bool third = multi && i + 2 < n && (keys[i + 2] >> pb) == (key[k] >> pb) && docs[i + 2] == doc;
+        const uint64_t pos = key[k] & pos_mask;
+        const uint64_t pos2 = multi ? (k1 & pos_mask) : kPosUnknown;
+        post_pos[pp] = static_cast<uint16_t>((pos < kPosUnknown ? pos : kPosUnknown) | (multi ? kPosMulti : 0));
+        post_pos2[pp] = static_cast<uint16_t>((pos2 < kPosUnknown ? pos2 : kPosUnknown) | (third ? kPosMulti : 0));
+      }
       if (h[k].terms) {
-        term_keys[tp] = key[k];
+        term_keys[tp] = key[k] >> pb;
         term_off[tp] = pp;
         ++tp;
       }
@@ -456,6 +489,25 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(const uint64_t* __restr
 
 }  // namespace
 
+SearchScratch* Index::scratch_for(cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(pool_mu);
+  for (SearchScratch* s : scratches) {
+    if (s->stream == stream) {
+      return s;
+    }
+  }
+  SearchScratch* s = new SearchScratch();
+  s->stream = stream;
+  scratches.push_back(s);
+  return s;
+}
+
+Index::~Index() {
+  for (SearchScratch* s : scratches) {
+    delete s;
+  }
+}
+
 uint64_t Index::device_bytes() const { return resident_a.blob.bytes() + resident_b.blob.bytes() + d_bitmaps.bytes(); }
 
 static unsigned tokenizer_grid(uint64_t n_docs) {
@@ -478,7 +530,7 @@ void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* 
   MGX_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), stream));
   tokenize_kernel<false><<<tokenizer_grid(n_docs), kTokThreads, 0, stream>>>(
       d_text, d_text_off, n_docs, ngram, kanji, cross ? 1 : 0, width, d_doc_len, d_ngram_cnt, nullptr, nullptr, nullptr,
-      d_counters);
+      d_counters, 0);
   MGX_LAUNCH_CHECK();
   exclusive_scan_u32_u64(d_ngram_cnt, d_slot_off, n_docs, d_scan, stream);
   uint64_t total = 0;
@@ -493,10 +545,11 @@ void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* 
 }
 
 void tokenize_emit(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
-                   uint64_t n_docs, const uint64_t* d_slot_off, uint64_t* d_keys, uint32_t* d_docs, cudaStream_t stream) {
+                   uint64_t n_docs, const uint64_t* d_slot_off, uint64_t* d_keys, uint32_t* d_docs, int pos_bits,
+                   cudaStream_t stream) {
   tokenize_kernel<true><<<tokenizer_grid(n_docs), kTokThreads, 0, stream>>>(
       d_text, d_text_off, n_docs, ngram, kanji, cross ? 1 : 0, width, nullptr, nullptr, d_slot_off, d_keys, d_docs,
-      nullptr);
+      nullptr, pos_bits);
   MGX_LAUNCH_CHECK();
 }
 
@@ -508,6 +561,28 @@ __global__ void sequential_check_kernel(const uint32_t* __restrict__ ids, uint64
       atomicOr(bad, ids[i + 1] > ids[i] ? 1u : 2u);  // 1: gap, 2: not ascending
     }
   }
+}
+
+// tile_first_doc[t] = the document that holds byte t * kTextTileBytes of the arena: the largest d with
+// text_off[d] <= that byte (documents are stored back to back; empty documents share an offset).
+__global__ void tile_first_doc_kernel(const uint64_t* __restrict__ text_off, uint64_t n_docs, uint64_t n_tiles,
+                                      uint32_t* __restrict__ out) {
+  const uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) {
+    return;
+  }
+  const uint64_t byte = t * kTextTileBytes;
+  uint64_t lo = 0;  // invariant: text_off[lo] <= byte
+  uint64_t hi = n_docs;
+  while (hi - lo > 1) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (text_off[mid] <= byte) {
+      lo = mid;
+    } else {
+      hi = mid;
+    }
+  }
+  out[t] = static_cast<uint32_t>(lo);
 }
 
 static double now_ms() {
@@ -542,23 +617,35 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   ix.d_text.release();
   ix.d_text_off.release();
   ix.d_doc_len.release();
+  ix.d_tile_first_doc.release();
   ix.d_term_keys.release();
   ix.d_term_off.release();
   ix.d_postings.release();
+  ix.d_post_pos.release();
+  ix.d_post_pos2.release();
   ix.d_term_bm.release();
   ix.d_bitmaps.release();
   ix.resident_b.release();
+  ix.n_text_tiles = n_docs > 0 ? (text_bytes + kTextTileBytes - 1) / kTextTileBytes : 0;
   ix.resident_a.reserve(DevArena::padded(n_docs * 4 + 4) + DevArena::padded(text_bytes + 64) +
-                        DevArena::padded((n_docs + 1) * 8) + DevArena::padded(n_docs * 4 + 4));
+                        DevArena::padded((n_docs + 1) * 8) + DevArena::padded(n_docs * 4 + 4) +
+                        DevArena::padded(ix.n_text_tiles * 4 + 4));
   ix.d_text.borrow(ix.resident_a.take<uint8_t>(text_bytes + 64), text_bytes + 64);
   ix.d_text_off.borrow(ix.resident_a.take<uint64_t>(n_docs + 1), n_docs + 1);
   ix.d_doc_ids.borrow(ix.resident_a.take<uint32_t>(n_docs), n_docs);
   ix.d_doc_len.borrow(ix.resident_a.take<uint32_t>(n_docs), n_docs);
+  ix.d_tile_first_doc.borrow(ix.resident_a.take<uint32_t>(ix.n_text_tiles), ix.n_text_tiles);
   MGX_CUDA(cudaEventRecord(ev0, stream));
   MGX_CUDA(cudaMemcpyAsync(ix.d_doc_ids.p, d_doc_ids_in, n_docs * sizeof(uint32_t), cudaMemcpyDefault, stream));
   MGX_CUDA(cudaMemcpyAsync(ix.d_text.p, d_text_in, text_bytes, cudaMemcpyDefault, stream));
   MGX_CUDA(cudaMemsetAsync(ix.d_text.p + text_bytes, 0, 64, stream));
   MGX_CUDA(cudaMemcpyAsync(ix.d_text_off.p, d_text_off_in, (n_docs + 1) * sizeof(uint64_t), cudaMemcpyDefault, stream));
+
+  if (ix.n_text_tiles > 0) {
+    tile_first_doc_kernel<<<static_cast<unsigned>((ix.n_text_tiles + 255) / 256), 256, 0, stream>>>(
+        ix.d_text_off.p, n_docs, ix.n_text_tiles, ix.d_tile_first_doc.p);
+    MGX_LAUNCH_CHECK();
+  }
 
   // ---- temporary arena T0: counting stage
   DevArena t0;
@@ -600,6 +687,8 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
     throw CudaFailure{MGX_ERR_UNSUPPORTED};
   }
 
+  const int pb = pos_bits_for_width(ix.width);
+  ix.has_positions = pb > 0;
   // ---- temporary arena T1: pairs (double-buffered), sort scratch, CSR block arrays
   const uint64_t n_blocks = (n_slots + kCsrTile - 1) / kCsrTile;
   DevArena t1;
@@ -616,16 +705,16 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   trace.mark("alloc pair arena");
   if (n_slots > 0) {
     tokenize_emit(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, d_slot_off, d_keys_a,
-                  d_docs_a, stream);
+                  d_docs_a, pb, stream);
   }
   trace.mark("tokenize: emit");
   const SortResult sorted =
-      radix_sort_pairs(d_keys_a, d_docs_a, d_keys_b, d_docs_b, n_slots, 21 * ix.width, d_sort_scratch, stream);
+      radix_sort_pairs(d_keys_a, d_docs_a, d_keys_b, d_docs_b, n_slots, 21 * ix.width, pb, d_sort_scratch, stream);
   trace.mark("radix sort");
 
   // ---- segmented unique + compaction into CSR
   if (n_blocks > 0) {
-    csr_count_kernel<<<static_cast<unsigned>(n_blocks), kCsrThreads, 0, stream>>>(sorted.keys, sorted.vals, n_slots,
+    csr_count_kernel<<<static_cast<unsigned>(n_blocks), kCsrThreads, 0, stream>>>(sorted.keys, sorted.vals, n_slots, pb,
                                                                                    d_block_pairs, d_block_terms);
     MGX_LAUNCH_CHECK();
   }
@@ -637,17 +726,20 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   ix.n_postings = totals[0];
   ix.n_terms = totals[1];
   ix.resident_b.reserve(DevArena::padded(ix.n_terms * 8 + 8) + DevArena::padded((ix.n_terms + 1) * 8) +
-                        DevArena::padded(ix.n_postings * 4 + 4) + 2 * DevArena::padded(ix.n_terms * 4 + 4) + 512);
+                        DevArena::padded(ix.n_postings * 4 + 4) + 2 * DevArena::padded(ix.n_terms * 4 + 4) +
+                        2 * DevArena::padded(ix.n_postings * 2 + 4) + 512);
   ix.d_term_keys.borrow(ix.resident_b.take<uint64_t>(ix.n_terms), ix.n_terms);
   ix.d_term_off.borrow(ix.resident_b.take<uint64_t>(ix.n_terms + 1), ix.n_terms + 1);
   ix.d_postings.borrow(ix.resident_b.take<uint32_t>(ix.n_postings), ix.n_postings);
   ix.d_term_bm.borrow(ix.resident_b.take<int32_t>(ix.n_terms), ix.n_terms);
+  ix.d_post_pos.borrow(ix.resident_b.take<uint16_t>(ix.n_postings), ix.n_postings);
+  ix.d_post_pos2.borrow(ix.resident_b.take<uint16_t>(ix.n_postings), ix.n_postings);
   uint32_t* d_dense_terms = ix.resident_b.take<uint32_t>(ix.n_terms);  // only the first n_dense entries are used
   unsigned long long* d_count = reinterpret_cast<unsigned long long*>(ix.resident_b.take<uint64_t>(2));
   if (n_blocks > 0) {
     csr_write_kernel<<<static_cast<unsigned>(n_blocks), kCsrThreads, 0, stream>>>(
-        sorted.keys, sorted.vals, n_slots, d_block_pairs, d_block_terms, ix.d_term_keys.p, ix.d_term_off.p,
-        ix.d_postings.p);
+        sorted.keys, sorted.vals, n_slots, pb, d_block_pairs, d_block_terms, ix.d_term_keys.p, ix.d_term_off.p,
+        ix.d_postings.p, ix.d_post_pos.p, ix.d_post_pos2.p);
     MGX_LAUNCH_CHECK();
   }
   set_u64_kernel<<<1, 1, 0, stream>>>(ix.d_term_off.p + ix.n_terms, ix.n_postings);

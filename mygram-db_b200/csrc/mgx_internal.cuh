@@ -17,6 +17,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -96,10 +97,11 @@ struct DevBuf {
     }
     MGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
   }
-  // grow-only (keeps the allocation when it is already large enough)
+  // grow-only (keeps the allocation when it is already large enough). A buffer that has to grow takes 50 % more
+  // than asked: cudaFree synchronises the device, so per-batch workspaces must stop reallocating after a few batches.
   void reserve(size_t count) {
     if (p == nullptr || count > n) {
-      alloc(count);
+      alloc(count + count / 2 + 64);
     }
   }
   size_t bytes() const { return n * sizeof(T); }
@@ -111,9 +113,9 @@ struct DevArena {
   DevBuf<uint8_t> blob;
   size_t used = 0;
   static size_t padded(size_t bytes) { return (bytes + 255) & ~static_cast<size_t>(255); }
-  void reserve(size_t bytes) {  // grow-only: an arena that is big enough is reused as is
+  void reserve(size_t bytes, bool headroom = false) {  // grow-only: an arena that is big enough is reused as is
     if (blob.p == nullptr || blob.n < bytes + 256) {
-      blob.alloc(bytes + 256);
+      blob.alloc(bytes + 256 + (headroom ? bytes / 2 : 0));
     }
     used = 0;
   }
@@ -155,7 +157,7 @@ struct PinBuf {
       cudaFreeHost(p);
       p = nullptr;
     }
-    n = count == 0 ? 1 : count;
+    n = count + count / 2 + 64;
     MGX_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p), n * sizeof(T)));
   }
 };
@@ -176,7 +178,12 @@ struct PhaseTrace {
 // strings (the reference sorts std::string keys, string_utils.h:192-196), and a
 // shorter n-gram that is a prefix of a longer one sorts first, like strings do.
 constexpr int kMaxKeyWidth = 3;
+constexpr uint32_t kTextTileBytes = 8192;  // arena tile of the streaming df pass (256 threads x 16 B x 2 rounds)
 constexpr uint64_t kInvalidKey = ~0ULL;
+constexpr int kPosBits = 22;               // spare low bits of a packed key of width <= 2 (2 * 21 + 22 = 64)
+constexpr uint16_t kPosUnknown = 0x7FFF;   // post_pos value: first occurrence not recorded
+constexpr uint16_t kPosMulti = 0x8000;     // post_pos flag: more than one occurrence in the document
+inline int pos_bits_for_width(int width) { return 21 * width + kPosBits <= 64 ? kPosBits : 0; }
 
 __host__ __device__ inline uint64_t pack_key(const uint32_t* cps, int n, int width) {
   uint64_t key = 0;
@@ -242,8 +249,11 @@ __host__ __device__ inline int parse_utf8(uint32_t b0, uint32_t b1, uint32_t b2,
 std::vector<uint32_t> host_utf8_to_codepoints(const uint8_t* text, uint64_t len);
 // GenerateQueryNgrams (string_utils.cpp:639-653) + DeduplicateSorted as packed
 // keys. Returns false if a window is wider than kMaxKeyWidth.
+// key_toff (optional): per returned key, the byte offset inside the term of the n-gram when it occurs exactly once
+// in the term, else kNoTermOffset.
+constexpr uint16_t kNoTermOffset = 0xFFFF;
 bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanji_ngram_size, bool cross_boundary,
-                     int key_width, std::vector<uint64_t>* keys);
+                     int key_width, std::vector<uint64_t>* keys, std::vector<uint16_t>* key_toff = nullptr);
 // One n-gram string -> packed key (for Index::SearchAnd style calls). False if
 // it is not valid UTF-8 of 1..width code points (such a term cannot be in the index).
 bool host_ngram_to_key(const uint8_t* term, uint64_t len, int key_width, uint64_t* key);
@@ -262,8 +272,22 @@ struct SortResult {
 };
 // d_scratch: radix_sort_scratch_bytes(n) bytes of caller-provided device memory (no allocation inside).
 size_t radix_sort_scratch_bytes(uint64_t n);
+// Only key bits [bit_base, bit_base + key_bits) take part; lower bits ride along (stable order is kept).
 SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_keys_b, uint32_t* d_vals_b, uint64_t n,
-                            int key_bits, uint8_t* d_scratch, cudaStream_t stream);
+                            int key_bits, int bit_base, uint8_t* d_scratch, cudaStream_t stream);
+
+// Search workspace shared by all batches that run on one stream of one index (batches on a stream execute one after
+// the other, so they can share it; growing it happens during the first batches only). Grow-only.
+struct SearchScratch {
+  cudaStream_t stream = nullptr;
+  DevBuf<uint32_t> tile_count;
+  DevBuf<uint32_t> tile_total;
+  DevBuf<uint32_t> rec_doc;
+  DevBuf<double> rec_score;
+  DevBuf<uint32_t> df_tile_term;
+  DevBuf<uint32_t> tile_query;
+  uint64_t map_owner = 0;  // serial of the batch whose tile maps are in df_tile_term / tile_query
+};
 
 // ---------------------------------------------------------------- index object
 struct Index {
@@ -282,12 +306,22 @@ struct Index {
   DevBuf<uint64_t> d_text_off;
   DevBuf<uint32_t> d_doc_len;
   uint64_t text_bytes = 0;
+  // document holding the first byte of every kTextTileBytes tile of the arena (streaming df pass)
+  DevBuf<uint32_t> d_tile_first_doc;
+  uint64_t n_text_tiles = 0;
 
   uint64_t n_terms = 0;
   uint64_t n_postings = 0;
   DevBuf<uint64_t> d_term_keys;
   DevBuf<uint64_t> d_term_off;
   DevBuf<uint32_t> d_postings;
+  // First-occurrence position of every posting (only when the packed key leaves room to carry it through the sort,
+  // i.e. key width <= 2): bits 0..14 = byte offset of the n-gram's first occurrence in the document's text
+  // (0x7FFF = unknown / beyond 32 KB), bit 15 = the n-gram occurs more than once in the document.
+  DevBuf<uint16_t> d_post_pos;
+  // Second occurrence, same encoding: bits 0..14 = byte offset (0x7FFF = none / unknown), bit 15 = a third exists.
+  DevBuf<uint16_t> d_post_pos2;
+  bool has_positions = false;
   DevBuf<int32_t> d_term_bm;
   DevBuf<uint32_t> d_bitmaps;
   DevArena resident_a;  // doc ids, text, text offsets, doc lengths
@@ -307,6 +341,9 @@ struct Index {
   // recycled batch workspaces (device arenas + pinned staging), so a steady stream of batches allocates nothing
   std::vector<void*> batch_pool;
   std::mutex pool_mu;
+  std::vector<SearchScratch*> scratches;  // one per stream that has run a batch; guarded by pool_mu
+  SearchScratch* scratch_for(cudaStream_t stream);
+  ~Index();
 
   uint64_t device_bytes() const;
 };
@@ -317,9 +354,14 @@ struct IndexView {
   const uint8_t* text;
   const uint64_t* text_off;
   const uint32_t* doc_len;
+  const uint32_t* tile_first_doc;
+  uint64_t text_bytes;
+  uint64_t n_text_tiles;
   const uint64_t* term_keys;
   const uint64_t* term_off;
   const uint32_t* postings;
+  const uint16_t* post_pos;  // nullptr when the index carries no positions
+  const uint16_t* post_pos2;
   const int32_t* term_bm;
   const uint32_t* bitmaps;
   uint64_t n_docs;
@@ -358,9 +400,14 @@ inline IndexView make_view(const Index& ix) {
   v.text = ix.d_text.p;
   v.text_off = ix.d_text_off.p;
   v.doc_len = ix.d_doc_len.p;
+  v.tile_first_doc = ix.d_tile_first_doc.p;
+  v.text_bytes = ix.text_bytes;
+  v.n_text_tiles = ix.n_text_tiles;
   v.term_keys = ix.d_term_keys.p;
   v.term_off = ix.d_term_off.p;
   v.postings = ix.d_postings.p;
+  v.post_pos = ix.has_positions ? ix.d_post_pos.p : nullptr;
+  v.post_pos2 = ix.has_positions ? ix.d_post_pos2.p : nullptr;
   v.term_bm = ix.d_term_bm.p;
   v.bitmaps = ix.d_bitmaps.p;
   v.n_docs = ix.n_docs;
@@ -383,7 +430,10 @@ void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* 
                     uint64_t n_docs, uint32_t* d_doc_len, uint64_t* d_slot_off, uint64_t* d_scratch, uint64_t* n_slots,
                     uint64_t* counters_out, cudaStream_t stream);
 // Tokeniser stage 2: (packed key, doc) pairs, exactly d_slot_off[n_docs] of them, in document order.
+// pos_bits > 0: every key is shifted left by pos_bits and carries the byte offset of the n-gram in its document
+// (saturated) in the freed low bits.
 void tokenize_emit(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
-                   uint64_t n_docs, const uint64_t* d_slot_off, uint64_t* d_keys, uint32_t* d_docs, cudaStream_t stream);
+                   uint64_t n_docs, const uint64_t* d_slot_off, uint64_t* d_keys, uint32_t* d_docs, int pos_bits,
+                   cudaStream_t stream);
 
 }  // namespace mgx

@@ -355,7 +355,7 @@ SortScratch sort_scratch_layout(uint64_t n) {
 size_t radix_sort_scratch_bytes(uint64_t n) { return sort_scratch_layout(n).total; }
 
 SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_keys_b, uint32_t* d_vals_b, uint64_t n,
-                            int key_bits, uint8_t* d_scratch, cudaStream_t stream) {
+                            int key_bits, int bit_base, uint8_t* d_scratch, cudaStream_t stream) {
   SortResult cur{d_keys_a, d_vals_a};
   SortResult alt{d_keys_b, d_vals_b};
   if (n == 0) {
@@ -376,7 +376,7 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
     const int widths[3] = {8, 8, 5};
     int off = 0;
     for (int k = 0; k < 3; ++k) {
-      pl.shift[pl.n] = f * 21 + off;
+      pl.shift[pl.n] = bit_base + f * 21 + off;
       pl.mask[pl.n] = (1u << widths[k]) - 1u;
       ++pl.n;
       off += widths[k];

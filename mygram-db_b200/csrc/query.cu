@@ -25,6 +25,7 @@
 // The driver formulation reads each query's smallest list once and probes the
 // rest, so the bytes moved are <= the SURVEY §8(d) algorithmic bytes.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "query.cuh"
@@ -40,6 +41,7 @@ struct BatchView {
   const uint32_t* term_koff;
   uint32_t* key_list;
   uint32_t* key_len;
+  uint16_t* key_toff;
   uint64_t* t_est;
   uint32_t* t_df_tiles;
   const uint64_t* t_df_tile_off;
@@ -68,6 +70,14 @@ struct BatchView {
   unsigned long long* stats;  // StatSlot counters
   const uint32_t* df_tile_term;  // [df tiles] unique-term index of each df tile
   const uint32_t* tile_query;    // [and tiles] query index of each intersect tile
+  // streaming df pass
+  const uint32_t* stream_slots;        // bucket table: (first entry << 8) | count
+  const StreamEntry* stream_entries;   // entries in bucket order
+  const uint32_t* stream_bloom;        // [kStreamBloomWords]
+  uint32_t stream_len8_mask;           // stage-1 classes present (bit m: min(len, 8) == m)
+  uint32_t stream_len12_mask;          // stage-2 classes present (bit m: min(len, 12) == m)
+  uint32_t stream_slot_mask;           // n_slots - 1
+  uint32_t* df_mode;                   // [0] = 1: streaming pass chosen for this batch
 };
 
 struct ScoreParams {
@@ -266,14 +276,17 @@ __global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf
     for (uint32_t i = k0 + 1; i < k1; ++i) {  // insertion sort by length (missing lists have length 0)
       const uint32_t li = bv.key_list[i];
       const uint32_t ln = bv.key_len[i];
+      const uint16_t to = bv.key_toff[i];
       uint32_t j = i;
       while (j > k0 && bv.key_len[j - 1] > ln) {
         bv.key_list[j] = bv.key_list[j - 1];
         bv.key_len[j] = bv.key_len[j - 1];
+        bv.key_toff[j] = bv.key_toff[j - 1];
         --j;
       }
       bv.key_list[j] = li;
       bv.key_len[j] = ln;
+      bv.key_toff[j] = to;
     }
     est = bv.key_len[k0];  // min posting size, 0 if any n-gram is missing (search_pipeline.cpp:583-593)
   }
@@ -290,10 +303,42 @@ __global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf
         bytes += umin64(4ULL * bv.key_len[i], bitmap_bytes);
       }
       atomicAdd(bv.stats + kStatDfLists * kStatStripes + (t & (kStatStripes - 1)), bytes);
+      if ((raw_flags[t] & 4) != 0) {
+        atomicAdd(bv.stats + kStatStreamEntries * kStatStripes + (t & (kStatStripes - 1)),
+                  static_cast<unsigned long long>(est));
+      }
     }
   }
   bv.t_df[t] = df;
   bv.t_df_tiles[t] = tiles;
+}
+
+// Chooses, per batch, how the verified document frequencies of the stream-eligible terms are computed:
+// per-term candidate tiles (df_tile_kernel: cost ~ entries of the terms' shortest lists) or ONE pass over the
+// text arena matching all of them at once (df_stream_kernel: cost ~ text bytes). force: 0 auto, 1 tiles, 2 stream.
+constexpr unsigned long long kStreamCostRatio = 6;  // measured: ~25 ps per list entry of candidate work, ~4 ps per streamed byte
+__global__ void df_mode_kernel(BatchView bv, const uint8_t* __restrict__ raw_flags, uint64_t text_bytes, int force,
+                               int have_table) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= bv.n_terms) {
+    return;
+  }
+  unsigned long long entries = 0;
+  for (int i = 0; i < kStatStripes; ++i) {
+    entries += bv.stats[kStatStreamEntries * kStatStripes + i];
+  }
+  bool stream = have_table != 0 && entries > 0;
+  if (force == 1) {
+    stream = false;
+  } else if (force == 0) {
+    stream = stream && entries * kStreamCostRatio >= text_bytes;
+  }
+  if (stream && (raw_flags[t] & 4) != 0) {
+    bv.t_df_tiles[t] = 0;  // counted by the streaming pass instead
+  }
+  if (t == 0) {
+    bv.df_mode[0] = stream ? 1u : 0u;
+  }
 }
 
 // ------------------------------------------------------------------ tile membership (block-cooperative)
@@ -599,9 +644,23 @@ __device__ __forceinline__ void stat_add(const BatchView& bv, int slot, unsigned
   atomicAdd(bv.stats + slot * kStatStripes + (blockIdx.x & (kStatStripes - 1)), v);
 }
 
+// 12 bytes of text at an arbitrary byte address as three little-endian words (the arena is padded by 64 bytes)
+__device__ __forceinline__ void load_text_words(const uint8_t* __restrict__ text, uint64_t at, uint32_t (&x)[3]) {
+  const uint64_t base = at & ~3ULL;
+  const uint32_t sh = static_cast<uint32_t>(at - base) * 8u;
+  const uint32_t a0 = __ldg(reinterpret_cast<const uint32_t*>(text + base));
+  const uint32_t a1 = __ldg(reinterpret_cast<const uint32_t*>(text + base + 4));
+  const uint32_t a2 = __ldg(reinterpret_cast<const uint32_t*>(text + base + 8));
+  const uint32_t a3 = __ldg(reinterpret_cast<const uint32_t*>(text + base + 12));
+  x[0] = __funnelshift_r(a0, a1, sh);
+  x[1] = __funnelshift_r(a1, a2, sh);
+  x[2] = __funnelshift_r(a2, a3, sh);
+}
+
 __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, BatchView bv) {
   __shared__ uint32_t s_stage[kTileThreads / 32][kWarpStageCap];
   __shared__ uint32_t s_surv[kTileThreads / 32][kWarpTile];
+  __shared__ uint32_t s_spos[kTileThreads / 32][kWarpTile];
   __shared__ __align__(16) uint8_t s_text[kTileThreads / 32][kStageBuf];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
@@ -617,14 +676,24 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
   const uint32_t tile_n = static_cast<uint32_t>(umin64(kWarpTile, drv.len - e0));
   const uint32_t dmin = __ldg(drv.p + e0);
   const uint32_t dmax = __ldg(drv.p + e0 + tile_n - 1);
+  // first-occurrence positions of the driver n-gram in each document (see Index::d_post_pos)
+  const uint16_t* drv_pos = iv.post_pos != nullptr ? iv.post_pos + (drv.p - iv.postings) : nullptr;
+  const uint16_t* drv_pos2 = iv.post_pos2 != nullptr ? iv.post_pos2 + (drv.p - iv.postings) : nullptr;
   uint32_t my_doc[kWarpItems];
+  uint32_t my_pos[kWarpItems];  // first occurrence | second occurrence << 16
   uint32_t alive = 0;
 #pragma unroll
   for (int k = 0; k < kWarpItems; ++k) {
     const uint32_t i = lane * kWarpItems + k;
     my_doc[k] = kNone;
+    my_pos[k] = kPosUnknown;
     if (i < tile_n) {
       my_doc[k] = __ldg(drv.p + e0 + i);
+      if (drv_pos != nullptr) {
+        const uint32_t p1 = __ldg(drv_pos + e0 + i);
+        // the second position is only read when there is one
+        my_pos[k] = p1 | ((p1 & kPosMulti) != 0 ? static_cast<uint32_t>(__ldg(drv_pos2 + e0 + i)) << 16 : 0u);
+      }
       alive |= 1u << k;
     }
   }
@@ -686,7 +755,9 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
 #pragma unroll
   for (int k = 0; k < kWarpItems; ++k) {
     if ((alive >> k) & 1u) {
-      s_surv[warp][w++] = my_doc[k];
+      s_surv[warp][w] = my_doc[k];
+      s_spos[warp][w] = my_pos[k];
+      ++w;
     }
   }
   __syncwarp();
@@ -695,21 +766,73 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
   const TermRegs tregs = load_term_regs(term, tl);
   uint32_t hits = 0;
   unsigned long long text_bytes = 0;
+
+  // ---- pass 1, one lane per candidate: when the driver n-gram occurs exactly once in the document (and once in the
+  // term, at byte offset toff), the term can only sit at (position - toff): one comparison instead of a scan. The
+  // other candidates are compacted to the front of the list for the scanning pass.
+  const uint32_t toff = bv.key_toff[k0];
+  uint32_t n_scan = 0;
+  for (uint32_t s0 = 0; s0 < n; s0 += 32) {
+    const uint32_t s = s0 + lane;
+    bool scan = false;
+    uint32_t doc = 0;
+    if (s < n) {
+      doc = s_surv[warp][s];
+      const uint32_t pp = s_spos[warp][s];
+      const uint64_t b = iv.text_off[doc];
+      const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
+      text_bytes += len;
+      const uint32_t p1 = pp & 0xFFFFu;
+      const uint32_t p2 = pp >> 16;
+      const bool two = (p1 & kPosMulti) != 0;  // exactly two recorded occurrences are checked one after the other
+      if (toff == kNoTermOffset || (p1 & kPosUnknown) == kPosUnknown ||
+          (two && ((p2 & kPosMulti) != 0 || (p2 & kPosUnknown) == kPosUnknown))) {
+        scan = true;
+      } else if (tl != 0) {
+        bool found = false;
+        for (int occ = 0; occ < (two ? 2 : 1) && !found; ++occ) {
+          const uint32_t at = (occ == 0 ? p1 : p2) & kPosUnknown;
+          if (at >= toff && at - toff + tl <= len) {
+            const uint64_t start = b + (at - toff);
+            uint32_t x[3];
+            load_text_words(iv.text, start, x);
+            bool ok = ((x[0] ^ tregs.w[0]) & tregs.m[0]) == 0;
+            if (tregs.nw > 1) {
+              ok = ok && ((x[1] ^ tregs.w[1]) & tregs.m[1]) == 0;
+            }
+            if (tregs.nw > 2) {
+              ok = ok && ((x[2] ^ tregs.w[2]) & tregs.m[2]) == 0;
+            }
+            if (ok && tl > 12) {
+              ok = term_tail_matches(iv.text, start, term, tl);
+            }
+            found = ok;
+          }
+        }
+        hits += found ? 1u : 0u;
+      }
+    }
+    const unsigned scan_mask = __ballot_sync(0xffffffffu, scan);
+    if (scan) {
+      s_surv[warp][n_scan + __popc(scan_mask & ((1u << lane) - 1u))] = doc;  // n_scan + rank <= s: never ahead of the reads
+    }
+    n_scan += __popc(scan_mask);
+    __syncwarp();
+  }
+
+  // ---- pass 2: the remaining candidates are scanned, 4 lanes per document
   constexpr int kGroup = 4;                 // lanes per document
   constexpr int kDocsPerIter = 32 / kGroup; // documents per warp iteration
   const unsigned group = lane / kGroup;
-  for (uint32_t s0 = 0; s0 < n; s0 += kDocsPerIter) {
+  for (uint32_t s0 = 0; s0 < n_scan; s0 += kDocsPerIter) {
     const uint32_t s = s0 + group;
     uint64_t b = 0;
     uint32_t len = 0;
     bool slow = false;
-    if (s < n) {
+    if (s < n_scan) {
       const uint32_t doc = s_surv[warp][s];
       b = iv.text_off[doc];
       len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
-      if ((lane & (kGroup - 1)) == 0) {
-        text_bytes += len;
-      }
       if (tl > kThreadScanMaxTerm || len > kThreadScanMaxDoc) {
         slow = true;
         len = 0;  // handled below
@@ -743,6 +866,324 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
     }
     stat_add(bv, kStatDfBytes, text_bytes);
     stat_add(bv, kStatDfCandidates, n);
+    if (n_scan != 0) {
+      stat_add(bv, kStatDfScanned, n_scan);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ streaming df pass
+// df(term) = number of documents whose text contains the term. For a term that is valid UTF-8, in an index whose
+// documents are all valid UTF-8 and whose tokeniser agrees with the query side, this equals the reference's
+// definition (documents of SearchAnd(term n-grams) whose text contains the term, search_pipeline.cpp:554-564):
+// a document that contains the term contains every n-gram window of it. So ONE coalesced pass over the arena
+// serves every eligible term of the batch (see query.cuh for the two-level table). Its cost is ~4 ps per text
+// byte whatever the batch holds, so it only pays for very large batches (df_mode_kernel decides).
+constexpr int kStreamThreads = 256;
+constexpr int kStreamRounds = kTextTileBytes / (kStreamThreads * 16);
+constexpr uint32_t kStreamPosCap = 2048;    // stage-1 survivors of one tile
+constexpr uint32_t kStreamSetSlots = 2048;  // (term, document) -> first position, open addressing
+constexpr uint32_t kStreamSetFill = 1400;   // stop inserting beyond this many pairs (tile handled stand-alone)
+constexpr uint32_t kStreamDocCap = 512;     // documents of one tile whose offsets are staged
+constexpr unsigned long long kStreamSetEmpty = ~0ULL;
+static_assert(kStreamRounds * kStreamThreads * 16 == kTextTileBytes, "tile must be whole rounds");
+static_assert(kTextTileBytes <= (1u << 13), "records keep 13 bits of tile position");
+
+// any occurrence of term starting in [from, to)?  (bytes are read past `to` when an occurrence straddles it)
+__device__ __forceinline__ bool occurs_between(const uint8_t* __restrict__ text, uint64_t from, uint64_t to,
+                                               const uint8_t* __restrict__ term, uint32_t tl) {
+  const uint8_t t0 = __ldg(term);
+  for (uint64_t j = from; j < to; ++j) {
+    if (__ldg(text + j) != t0) {
+      continue;
+    }
+    uint32_t i = 1;
+    while (i < tl && __ldg(text + j + i) == __ldg(term + i)) {
+      ++i;
+    }
+    if (i == tl) {
+      return true;
+    }
+  }
+  return false;
+}
+
+__device__ __forceinline__ bool bytes_equal_from(const uint8_t* __restrict__ text, uint64_t pos,
+                                                 const uint8_t* __restrict__ term, uint32_t from, uint32_t tl) {
+  for (uint32_t i = from; i < tl; ++i) {
+    if (__ldg(text + pos + i) != __ldg(term + i)) {
+      return false;
+    }
+  }
+  return true;
+}
+
+// Stage 2 at one text position: every table entry whose key bytes equal the text there -> hit(entry, term).
+template <typename Hit>
+__device__ __forceinline__ void stream_probe_position(const uint8_t* __restrict__ text, uint64_t gpos,
+                                                      const BatchView& bv, Hit&& hit) {
+  const uint64_t base = gpos & ~3ULL;  // the arena is padded by 64 bytes
+  const uint32_t sh = static_cast<uint32_t>(gpos - base) * 8u;
+  const uint32_t a0 = __ldg(reinterpret_cast<const uint32_t*>(text + base));
+  const uint32_t a1 = __ldg(reinterpret_cast<const uint32_t*>(text + base + 4));
+  const uint32_t a2 = __ldg(reinterpret_cast<const uint32_t*>(text + base + 8));
+  const uint32_t a3 = __ldg(reinterpret_cast<const uint32_t*>(text + base + 12));
+  const uint32_t t0 = __funnelshift_r(a0, a1, sh);
+  const uint32_t t1 = __funnelshift_r(a1, a2, sh);
+  const uint32_t t2 = __funnelshift_r(a2, a3, sh);
+  uint32_t classes = bv.stream_len12_mask;
+  while (classes != 0) {
+    const uint32_t len = static_cast<uint32_t>(__ffs(static_cast<int>(classes))) - 1u;
+    classes &= classes - 1u;
+    const uint32_t w0 = t0 & low_bytes_mask(len);
+    const uint32_t w1 = len > 4 ? (t1 & low_bytes_mask(len - 4)) : 0u;
+    const uint32_t w2 = len > 8 ? (t2 & low_bytes_mask(len - 8)) : 0u;
+    const uint32_t slot = __ldg(bv.stream_slots + (stream_hash(w0, w1, w2, len) & bv.stream_slot_mask));
+    const uint32_t cnt = slot & 0xFFu;
+    const uint32_t first = slot >> 8;
+    for (uint32_t c = 0; c < cnt; ++c) {
+      const uint4 e = __ldg(reinterpret_cast<const uint4*>(bv.stream_entries + first + c));
+      if (e.x == w0 && e.y == w1 && e.z == w2 && (e.w & 0xFFu) == len) {
+        hit(first + c, e.w >> 8);
+      }
+    }
+  }
+}
+
+// Exact stand-alone handling of one key match (used when a tile's shared-memory structures overflow).
+__device__ void stream_slow_hit(const IndexView& iv, const BatchView& bv, uint64_t gpos, uint32_t tid) {
+  const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
+  const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+  uint64_t lo = 0;  // largest d with text_off[d] <= gpos
+  uint64_t hi = iv.n_docs;
+  while (hi - lo > 1) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (iv.text_off[mid] <= gpos) {
+      lo = mid;
+    } else {
+      hi = mid;
+    }
+  }
+  const uint64_t doc_b = iv.text_off[lo];
+  const uint64_t doc_e = iv.text_off[lo + 1];
+  if (gpos + tl > doc_e || (tl > kStreamKeyBytes && !bytes_equal_from(iv.text, gpos, term, kStreamKeyBytes, tl))) {
+    return;
+  }
+  if (occurs_between(iv.text, doc_b, gpos, term, tl)) {
+    return;  // not the first occurrence in this document
+  }
+  atomicAdd(reinterpret_cast<unsigned long long*>(bv.t_df + tid), 1ULL);
+}
+
+// Stage 1 over the 16 start positions of one 16-byte chunk: pass(pos_in_chunk) for every character start whose
+// first bytes hit the shared-memory filter. The window is kept aligned to the current position by funnel shifts.
+template <typename Pass>
+__device__ __forceinline__ void stream_filter_chunk(const uint8_t* __restrict__ text, uint64_t byte0, uint32_t npos,
+                                                    uint32_t len8_mask, const uint32_t* s_bloom, Pass&& pass) {
+  const uint4 a = ld16(text + byte0);
+  const uint4 b = ld16(text + byte0 + 16);  // the arena is padded by 64 bytes
+  uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y;  // bytes 0..23: position 15 needs 15..22
+  uint32_t lead = 0;  // bit i: byte i of the chunk starts a character (is not a continuation byte)
+  {
+    const uint32_t c0 = __vcmpeq4(a.x & 0xC0C0C0C0u, 0x80808080u);
+    const uint32_t c1 = __vcmpeq4(a.y & 0xC0C0C0C0u, 0x80808080u);
+    const uint32_t c2 = __vcmpeq4(a.z & 0xC0C0C0C0u, 0x80808080u);
+    const uint32_t c3 = __vcmpeq4(a.w & 0xC0C0C0C0u, 0x80808080u);
+    const uint32_t n0 = ((((c0 >> 7) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu;
+    const uint32_t n1 = ((((c1 >> 7) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu;
+    const uint32_t n2 = ((((c2 >> 7) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu;
+    const uint32_t n3 = ((((c3 >> 7) & 0x01010101u) * 0x00204081u) >> 21) & 0xFu;
+    lead = ~(n0 | (n1 << 4) | (n2 << 8) | (n3 << 12)) & ((npos >= 16 ? 0x10000u : (1u << npos)) - 1u);
+  }
+  uint32_t cur = 0;
+  while (lead != 0) {
+    const uint32_t z = static_cast<uint32_t>(__ffs(static_cast<int>(lead))) - 1u;
+    lead &= lead - 1u;
+    uint32_t d = z - cur;
+    cur = z;
+    while (d > 4) {  // only after a run of more than three continuation bytes (never in valid UTF-8)
+      w0 = w1, w1 = w2, w2 = w3, w3 = w4, w4 = w5, w5 = 0;
+      d -= 4;
+    }
+    const uint32_t sh = 8 * d;  // clamp mode: a shift of 32 moves whole words
+    w0 = __funnelshift_rc(w0, w1, sh);
+    w1 = __funnelshift_rc(w1, w2, sh);
+    w2 = __funnelshift_rc(w2, w3, sh);
+    w3 = __funnelshift_rc(w3, w4, sh);
+    w4 = __funnelshift_rc(w4, w5, sh);
+    w5 = __funnelshift_rc(w5, 0u, sh);
+    bool hit = false;
+    uint32_t classes = len8_mask;
+    do {  // warp-uniform: usually one class
+      const uint32_t len8 = static_cast<uint32_t>(__ffs(static_cast<int>(classes))) - 1u;
+      classes &= classes - 1u;
+      const uint32_t k0 = w0 & low_bytes_mask(len8);
+      const uint32_t k1 = len8 > 4 ? (w1 & low_bytes_mask(len8 - 4)) : 0u;
+      const uint32_t bit = stream_filter_bit(k0, k1, len8);
+      hit = hit || ((s_bloom[bit >> 5] >> (bit & 31)) & 1u) != 0;
+    } while (classes != 0);
+    if (hit) {
+      pass(z);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kStreamThreads) df_stream_kernel(IndexView iv, BatchView bv) {
+  __shared__ uint16_t s_pos[kStreamPosCap];                 // stage-1 survivors (position in the tile)
+  __shared__ unsigned long long s_set[kStreamSetSlots];     // entry:19 | doc in tile:10 | first pos:13
+  __shared__ int32_t s_docrel[kStreamDocCap + 1];           // start of document (first_doc + i) relative to the tile
+  __shared__ uint32_t s_bloom[kStreamBloomWords];
+  __shared__ uint32_t s_npos;
+  __shared__ uint32_t s_nset;
+  __shared__ uint32_t s_overflow;
+  unsigned long long hits = 0;
+  const uint32_t len8_mask = bv.stream_len8_mask;
+  for (uint32_t i = threadIdx.x; i < kStreamBloomWords; i += kStreamThreads) {
+    s_bloom[i] = __ldg(bv.stream_bloom + i);
+  }
+  for (uint64_t tile = blockIdx.x; tile < iv.n_text_tiles; tile += gridDim.x) {
+    const uint64_t tile_b = tile * kTextTileBytes;
+    const uint32_t tile_len = static_cast<uint32_t>(umin64(kTextTileBytes, iv.text_bytes - tile_b));
+    const uint32_t first_doc = __ldg(iv.tile_first_doc + tile);
+    // documents that start inside the tile: up to the first document of the next tile (+1 entry for the end)
+    const uint32_t last_doc =
+        tile + 1 < iv.n_text_tiles ? __ldg(iv.tile_first_doc + tile + 1) : static_cast<uint32_t>(iv.n_docs - 1);
+    const uint32_t n_tab = min(kStreamDocCap, last_doc - first_doc + 1u) + 1u;  // entries [0, n_tab) are loaded
+    for (uint32_t i = threadIdx.x; i < kStreamSetSlots; i += kStreamThreads) {
+      s_set[i] = kStreamSetEmpty;
+    }
+    for (uint32_t i = threadIdx.x; i <= kStreamDocCap; i += kStreamThreads) {
+      const uint64_t d = static_cast<uint64_t>(first_doc) + i;
+      const uint64_t off = (i < n_tab && d <= iv.n_docs) ? iv.text_off[d] : ~0ULL;
+      // relative start, saturated: far before the tile -> -2^30, not loaded / beyond the arena -> INT_MAX
+      int32_t rel;
+      if (off == ~0ULL || off >= tile_b + 0x40000000ULL) {
+        rel = 0x7FFFFFFF;
+      } else if (off + 0x40000000ULL < tile_b) {
+        rel = -0x40000000;
+      } else {
+        rel = static_cast<int32_t>(static_cast<int64_t>(off) - static_cast<int64_t>(tile_b));
+      }
+      s_docrel[i] = rel;
+    }
+    if (threadIdx.x == 0) {
+      s_npos = 0;
+      s_nset = 0;
+      s_overflow = 0;
+    }
+    __syncthreads();
+    // ---- stage 1: filter every character start of the tile
+#pragma unroll 1
+    for (int r = 0; r < kStreamRounds; ++r) {
+      const uint32_t c0 = (static_cast<uint32_t>(r) * kStreamThreads + threadIdx.x) * 16u;
+      if (c0 < tile_len) {
+        stream_filter_chunk(iv.text, tile_b + c0, min(16u, tile_len - c0), len8_mask, s_bloom, [&](uint32_t pos) {
+          const uint32_t at = atomicAdd(&s_npos, 1u);
+          if (at < kStreamPosCap) {
+            s_pos[at] = static_cast<uint16_t>(c0 + pos);
+          } else {
+            s_overflow = 1;
+          }
+        });
+      }
+    }
+    __syncthreads();
+    // the staged offsets cover the tile when the entry after the last document starting in it was loaded
+    bool standalone = s_overflow != 0 || last_doc - first_doc + 1u > kStreamDocCap;
+    const uint32_t n_pos = min(s_npos, kStreamPosCap);
+    if (!standalone) {
+      // ---- stage 2 (dense): table probe, rest of the term, document, first position per (term, document)
+      for (uint32_t i = threadIdx.x; i < n_pos; i += kStreamThreads) {
+        const uint32_t pos = s_pos[i];
+        stream_probe_position(iv.text, tile_b + pos, bv, [&](uint32_t entry, uint32_t tid) {
+          const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+          uint32_t lo = 0;  // largest j with s_docrel[j] <= pos  (s_docrel[0] <= 0 <= pos)
+          uint32_t hi = kStreamDocCap;  // s_docrel[hi] >= tile_len > pos
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_docrel[mid] <= static_cast<int32_t>(pos)) {
+              lo = mid;
+            } else {
+              hi = mid;
+            }
+          }
+          if (static_cast<int64_t>(pos) + tl > static_cast<int64_t>(s_docrel[lo + 1])) {
+            return;  // would run past the end of its document
+          }
+          if (tl > kStreamKeyBytes &&
+              !bytes_equal_from(iv.text, tile_b + pos, bv.term_bytes + bv.term_boff[tid], kStreamKeyBytes, tl)) {
+            return;
+          }
+          if (*reinterpret_cast<volatile uint32_t*>(&s_overflow) != 0) {
+            return;
+          }
+          const unsigned long long hi_key =
+              (static_cast<unsigned long long>(entry) << 23) | (static_cast<unsigned long long>(lo) << 13);
+          const unsigned long long val = hi_key | pos;
+          uint32_t slot = (entry * 0x9E3779B1u + lo * 0x85EBCA77u) & (kStreamSetSlots - 1);
+          for (;;) {
+            const unsigned long long cur = atomicCAS(&s_set[slot], kStreamSetEmpty, val);
+            if (cur == kStreamSetEmpty) {
+              if (atomicAdd(&s_nset, 1u) >= kStreamSetFill) {
+                s_overflow = 1;
+              }
+              break;
+            }
+            if ((cur >> 13) == (hi_key >> 13)) {
+              atomicMin(&s_set[slot], val);
+              break;
+            }
+            slot = (slot + 1) & (kStreamSetSlots - 1);
+          }
+        });
+      }
+      __syncthreads();
+      standalone = s_overflow != 0;
+    }
+    if (standalone) {
+      // rare: too many survivors / pairs or too many tiny documents in this tile -> exact stand-alone handling
+#pragma unroll 1
+      for (int r = 0; r < kStreamRounds; ++r) {
+        const uint32_t c0 = (static_cast<uint32_t>(r) * kStreamThreads + threadIdx.x) * 16u;
+        if (c0 < tile_len) {
+          stream_filter_chunk(iv.text, tile_b + c0, min(16u, tile_len - c0), len8_mask, s_bloom, [&](uint32_t pos) {
+            const uint64_t gpos = tile_b + c0 + pos;
+            stream_probe_position(iv.text, gpos, bv,
+                                  [&](uint32_t, uint32_t tid) { stream_slow_hit(iv, bv, gpos, tid); });
+          });
+        }
+      }
+      __syncthreads();
+      continue;
+    }
+    // ---- count: every occupied slot is the first occurrence of its term in its document within this tile
+    for (uint32_t i = threadIdx.x; i < kStreamSetSlots; i += kStreamThreads) {
+      const unsigned long long v = s_set[i];
+      if (v == kStreamSetEmpty) {
+        continue;
+      }
+      const uint32_t entry = static_cast<uint32_t>(v >> 23);
+      const uint32_t j = static_cast<uint32_t>(v >> 13) & 0x3FFu;
+      const uint32_t tid = bv.stream_entries[entry].len_term >> 8;
+      if (s_docrel[j] < 0) {
+        // the document began in an earlier tile: look for an occurrence that starts before this tile
+        const uint64_t doc_b = iv.text_off[static_cast<uint64_t>(first_doc) + j];
+        const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+        if (occurs_between(iv.text, doc_b, tile_b, bv.term_bytes + bv.term_boff[tid], tl)) {
+          continue;
+        }
+      }
+      atomicAdd(reinterpret_cast<unsigned long long*>(bv.t_df + tid), 1ULL);
+      ++hits;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    hits += __shfl_xor_sync(0xffffffffu, hits, s);
+  }
+  if ((threadIdx.x & 31u) == 0 && hits != 0) {
+    stat_add(bv, kStatStreamHits, hits);
   }
 }
 
@@ -1802,6 +2243,7 @@ BatchView make_batch_view(Batch& b) {
   v.term_koff = b.d_term_koff.p;
   v.key_list = b.d_key_list.p;
   v.key_len = b.d_key_len.p;
+  v.key_toff = b.d_key_toff.p;
   v.t_est = b.d_t_est.p;
   v.t_df_tiles = b.d_t_df_tiles.p;
   v.t_df_tile_off = b.d_t_df_tile_off.p;
@@ -1828,6 +2270,13 @@ BatchView make_batch_view(Batch& b) {
   v.stats = b.d_stats.p;
   v.df_tile_term = b.d_df_tile_term.p;
   v.tile_query = b.d_tile_query.p;
+  v.stream_slots = b.d_stream_slots.p;
+  v.stream_entries = b.d_stream_entries.p;
+  v.stream_bloom = b.d_stream_bloom.p;
+  v.stream_len8_mask = b.stream_len8_mask;
+  v.stream_len12_mask = b.stream_len12_mask;
+  v.stream_slot_mask = b.n_stream_slots > 0 ? b.n_stream_slots - 1 : 0;
+  v.df_mode = b.d_df_mode.p;
   return v;
 }
 
@@ -1894,6 +2343,8 @@ void Batch::collect_stats(mgx_batch_stats_t* out) {
       s.ms_df_kernel += ms;
     } else if (t.kind == 2) {
       s.ms_and_kernel += ms;
+    } else if (t.kind == 4) {
+      s.ms_df_stream_kernel += ms;
     } else {
       s.ms_topk_kernel += ms;
     }
@@ -1929,6 +2380,10 @@ void Batch::collect_stats(mgx_batch_stats_t* out) {
   s.result_docs = h[kStatResultDocs];
   s.df_candidates = h[kStatDfCandidates];
   s.unique_terms = n_terms;
+  s.df_stream_terms = h_df_mode != 0 ? n_stream_terms : 0;
+  s.df_stream_bytes = h_df_mode != 0 ? ix->text_bytes : 0;
+  s.df_stream_hits = h[kStatStreamHits];
+  s.df_scanned_docs = h[kStatDfScanned];
   *out = s;
 }
 
@@ -1951,12 +2406,93 @@ void Batch::recycle() {
   explicit_driver = ExplicitDriver{};
   h2d_bytes = d2h_bytes = 0;
   n_df_tiles = n_and_tiles = driver_entries = 0;
-  planned = df_done = false;
+  planned = df_done = searched = false;
+  sc = nullptr;
+  serial = 0;
+  h_df_mode = 0;
+  n_stream_slots = n_stream_terms = 0;
 }
 
-void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
+void build_stream_table(std::vector<HostTerm>& terms, HostStreamTable* out) {
+  out->slots.clear();
+  out->entries.clear();
+  out->bloom.clear();
+  out->len8_mask = out->len12_mask = 0;
+  size_t n = 0;
+  for (const HostTerm& t : terms) {
+    n += t.streamable ? 1 : 0;
+  }
+  if (n == 0) {
+    return;
+  }
+  uint32_t n_slots = 64;
+  while (n_slots < 2 * n) {
+    n_slots <<= 1;
+  }
+  struct Item {
+    uint32_t slot;
+    StreamEntry e;
+  };
+  std::vector<Item> items;
+  items.reserve(n);
+  std::vector<uint32_t> count(n_slots, 0);
+  out->bloom.assign(kStreamBloomWords, 0);
+  for (size_t t = 0; t < terms.size(); ++t) {
+    HostTerm& ht = terms[t];
+    if (!ht.streamable) {
+      continue;
+    }
+    const uint32_t tl = static_cast<uint32_t>(ht.bytes.size());
+    const uint32_t len12 = std::min(tl, kStreamKeyBytes);
+    const uint32_t len8 = std::min(tl, kStreamFilterBytes);
+    uint32_t w[3] = {0, 0, 0};
+    for (uint32_t i = 0; i < len12; ++i) {
+      w[i >> 2] |= static_cast<uint32_t>(static_cast<uint8_t>(ht.bytes[i])) << (8 * (i & 3));
+    }
+    const uint32_t slot = stream_hash(w[0], w[1], w[2], len12) & (n_slots - 1);
+    if (count[slot] >= kStreamMaxBucket || items.size() >= kStreamMaxTerms || t >= (1u << 24)) {
+      ht.streamable = false;  // stays on the candidate-tile path
+      continue;
+    }
+    ++count[slot];
+    const uint32_t f1 = len8 > 4 ? (w[1] & low_bytes_mask(len8 - 4)) : 0u;
+    const uint32_t bit = stream_filter_bit(w[0] & low_bytes_mask(len8), f1, len8);
+    out->bloom[bit >> 5] |= 1u << (bit & 31);
+    out->len8_mask |= 1u << len8;
+    out->len12_mask |= 1u << len12;
+    items.push_back({slot, {w[0], w[1], w[2], len12 | (static_cast<uint32_t>(t) << 8)}});
+  }
+  std::vector<uint32_t> first(n_slots + 1, 0);
+  for (uint32_t i = 0; i < n_slots; ++i) {
+    first[i + 1] = first[i] + count[i];
+  }
+  out->slots.resize(n_slots);
+  for (uint32_t i = 0; i < n_slots; ++i) {
+    out->slots[i] = (first[i] << 8) | count[i];
+  }
+  out->entries.resize(items.size());
+  std::vector<uint32_t> fill(first.begin(), first.end() - 1);
+  for (const Item& it : items) {
+    out->entries[fill[it.slot]++] = it.e;
+  }
+}
+
+void batch_upload(Batch& b, const std::vector<HostTerm>& terms_in, const std::vector<HostQuery>& queries,
                   const std::vector<uint32_t>& slot_tid) {
   cudaStream_t st = b.stream;
+  std::vector<HostTerm> terms_copy;
+  HostStreamTable stream_table;
+  const std::vector<HostTerm>* terms_ptr = &terms_in;
+  bool any_stream = false;
+  for (const HostTerm& t : terms_in) {
+    any_stream = any_stream || t.streamable;
+  }
+  if (any_stream) {
+    terms_copy = terms_in;  // the table builder may clear `streamable` on bucket overflow
+    build_stream_table(terms_copy, &stream_table);
+    terms_ptr = &terms_copy;
+  }
+  const std::vector<HostTerm>& terms = *terms_ptr;
   b.n_queries = static_cast<uint32_t>(queries.size());
   b.n_terms = static_cast<uint32_t>(terms.size());
   b.n_slots = static_cast<uint32_t>(slot_tid.size());
@@ -1966,13 +2502,18 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vecto
   std::vector<uint32_t> boff(terms.size() + 1, 0);
   std::vector<uint32_t> koff(terms.size() + 1, 0);
   std::vector<uint64_t> keys;
+  std::vector<uint16_t> key_toff;
   std::vector<uint8_t> raw(terms.size() + 1, 0);
   for (size_t t = 0; t < terms.size(); ++t) {
     bytes.insert(bytes.end(), terms[t].bytes.begin(), terms[t].bytes.end());
     boff[t + 1] = static_cast<uint32_t>(bytes.size());
     keys.insert(keys.end(), terms[t].keys.begin(), terms[t].keys.end());
+    for (size_t k = 0; k < terms[t].keys.size(); ++k) {
+      key_toff.push_back(k < terms[t].key_toff.size() ? terms[t].key_toff[k] : kNoTermOffset);
+    }
     koff[t + 1] = static_cast<uint32_t>(keys.size());
-    raw[t] = static_cast<uint8_t>((terms[t].raw ? 1 : 0) | (terms[t].exact_single ? 2 : 0));
+    raw[t] = static_cast<uint8_t>((terms[t].raw ? 1 : 0) | (terms[t].exact_single ? 2 : 0) |
+                                  (terms[t].streamable ? 4 : 0));
   }
   bytes.resize(bytes.size() + 16, 0);
   b.n_keys = static_cast<uint32_t>(keys.size());
@@ -2024,13 +2565,21 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vecto
   const size_t i_loff = add(loff.data(), loff.size() * 4);
   const size_t i_hflags = add(hflags.data(), hflags.size() * 4);
   const size_t i_slot = add(slot_tid.data(), slot_tid.size() * 4);
+  const size_t i_ktoff = add(key_toff.data(), key_toff.size() * 2);
+  const size_t i_sslots = add(stream_table.slots.data(), stream_table.slots.size() * 4);
+  const size_t i_sentries = add(stream_table.entries.data(), stream_table.entries.size() * sizeof(StreamEntry));
+  const size_t i_sbloom = add(stream_table.bloom.data(), stream_table.bloom.size() * 4);
+  b.n_stream_slots = static_cast<uint32_t>(stream_table.slots.size());
+  b.n_stream_terms = static_cast<uint32_t>(stream_table.entries.size());
+  b.stream_len8_mask = stream_table.len8_mask;
+  b.stream_len12_mask = stream_table.len12_mask;
   b.staging.reserve(total + 256);
   for (const Piece& pc : pieces) {
     if (pc.bytes > 0) {
       std::memcpy(b.staging.p + pc.off, pc.src, pc.bytes);
     }
   }
-  b.in_arena.reserve(total + 256);
+  b.in_arena.reserve(total + 256, true);
   uint8_t* base = b.in_arena.take<uint8_t>(total);
   MGX_CUDA(cudaMemcpyAsync(base, b.staging.p, total, cudaMemcpyHostToDevice, st));
   b.h2d_bytes = total;
@@ -2047,6 +2596,10 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vecto
   b.d_q_loff.borrow(reinterpret_cast<uint32_t*>(at(i_loff)), loff.size());
   b.d_q_host_flags.borrow(reinterpret_cast<uint32_t*>(at(i_hflags)), hflags.size());
   b.d_slot_tid.borrow(reinterpret_cast<uint32_t*>(at(i_slot)), slot_tid.size());
+  b.d_key_toff.borrow(reinterpret_cast<uint16_t*>(at(i_ktoff)), key_toff.size());
+  b.d_stream_slots.borrow(reinterpret_cast<uint32_t*>(at(i_sslots)), stream_table.slots.size());
+  b.d_stream_entries.borrow(reinterpret_cast<StreamEntry*>(at(i_sentries)), stream_table.entries.size());
+  b.d_stream_bloom.borrow(reinterpret_cast<uint32_t*>(at(i_sbloom)), stream_table.bloom.size());
 
   // ---- device-only planning arrays from the work arena
   const size_t T = terms.size();
@@ -2057,10 +2610,10 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vecto
   size_t work = 0;
   for (size_t nbytes : {K * 4, K * 4, T * 8, T * 4, (T + 1) * 8, T * 8, Lc * 4, Lc * 4, Q * 4, Q * 4, Q * 4, Q * 4,
                         (Q + 1) * 8, (Q + 1) * 8, tids.size() * 8, static_cast<size_t>(kStatCount) * kStatStripes * 8,
-                        scan_elems * 8}) {
+                        scan_elems * 8, static_cast<size_t>(64)}) {
     work += DevArena::padded(nbytes == 0 ? 1 : nbytes);
   }
-  b.work_arena.reserve(work + 1024);
+  b.work_arena.reserve(work + 1024, true);
   b.d_key_list.borrow(b.work_arena.take<uint32_t>(K), K);
   b.d_key_len.borrow(b.work_arena.take<uint32_t>(K), K);
   b.d_t_est.borrow(b.work_arena.take<uint64_t>(T), T);
@@ -2079,8 +2632,47 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vecto
   const size_t n_stats = static_cast<size_t>(kStatCount) * kStatStripes;
   b.d_stats.borrow(b.work_arena.take<unsigned long long>(n_stats), n_stats);
   b.d_scan_scratch.borrow(b.work_arena.take<uint64_t>(scan_elems), scan_elems);
+  b.d_df_mode.borrow(b.work_arena.take<uint32_t>(2), 2);
   MGX_CUDA(cudaMemsetAsync(b.d_stats.p, 0, b.d_stats.bytes(), st));
+  MGX_CUDA(cudaMemsetAsync(b.d_df_mode.p, 0, 2 * sizeof(uint32_t), st));
 }
+
+namespace {
+std::atomic<uint64_t> g_batch_serial{0};
+
+// tile -> term / tile -> query maps of a planned batch, in the shared (index, stream) workspace. Another batch
+// planned on the same stream in the meantime replaces them, so every stage re-checks the owner.
+void ensure_tile_maps(Batch& b) {
+  cudaStream_t st = b.stream;
+  if (b.sc == nullptr) {
+    b.sc = b.ix->scratch_for(st);
+  }
+  if (b.serial == 0) {
+    b.serial = ++g_batch_serial;
+  }
+  SearchScratch& sc = *b.sc;
+  const uint64_t n_and_tiles = b.n_queries > 0 ? b.h_q_tile_off[b.n_queries] : 0;
+  if (sc.map_owner != b.serial) {
+    // floors sized for batches of a few thousand queries, so that a steady stream of batches never reallocates
+    // (cudaMalloc / cudaFree cost tens to hundreds of milliseconds and synchronise the device)
+    sc.df_tile_term.reserve(std::max<uint64_t>(b.n_df_tiles, 1ULL << 19));
+    sc.tile_query.reserve(std::max<uint64_t>(n_and_tiles, 1ULL << 16));
+    if (b.n_df_tiles > 0) {
+      fill_tile_map_kernel<<<grid_for(static_cast<uint64_t>(b.n_terms) * 32, 256), 256, 0, st>>>(
+          b.d_t_df_tile_off.p, b.n_terms, sc.df_tile_term.p);
+      MGX_LAUNCH_CHECK();
+    }
+    if (n_and_tiles > 0) {
+      fill_tile_map_kernel<<<grid_for(static_cast<uint64_t>(b.n_queries) * 32, 256), 256, 0, st>>>(
+          b.d_q_tile_off.p, b.n_queries, sc.tile_query.p);
+      MGX_LAUNCH_CHECK();
+    }
+    sc.map_owner = b.serial;
+  }
+  b.d_df_tile_term.borrow(sc.df_tile_term.p, sc.df_tile_term.n);
+  b.d_tile_query.borrow(sc.tile_query.p, sc.tile_query.n);
+}
+}  // namespace
 
 void batch_plan(Batch& b) {
   cudaStream_t st = b.stream;
@@ -2097,6 +2689,15 @@ void batch_plan(Batch& b) {
                                                                ix.all_valid_utf8 ? 1 : 0, b.d_term_flags.p,
                                                                (ix.n_docs + 7) / 8);
     MGX_LAUNCH_CHECK();
+    if (b.params.compute_score != 0 && b.n_stream_terms > 0) {
+      int force = 0;  // MGX_DF_MODE=tiles|stream pins the choice (tests exercise both paths); default: cost model
+      if (const char* mode = std::getenv("MGX_DF_MODE")) {
+        force = std::strcmp(mode, "tiles") == 0 ? 1 : (std::strcmp(mode, "stream") == 0 ? 2 : 0);
+      }
+      df_mode_kernel<<<grid_for(b.n_terms, 128), 128, 0, st>>>(bv, b.d_term_flags.p, ix.text_bytes, force,
+                                                               ix.n_text_tiles > 0 ? 1 : 0);
+      MGX_LAUNCH_CHECK();
+    }
   }
   exclusive_scan_u32_u64(b.d_t_df_tiles.p, b.d_t_df_tile_off.p, b.n_terms, b.d_scan_scratch.p, st);
   const IndexView iv = make_view(ix);
@@ -2114,26 +2715,16 @@ void batch_plan(Batch& b) {
                            cudaMemcpyDeviceToHost, st));
   MGX_CUDA(cudaMemcpyAsync(&b.n_df_tiles, b.d_t_df_tile_off.p + b.n_terms, sizeof(uint64_t), cudaMemcpyDeviceToHost,
                            st));
+  uint32_t df_mode = 0;
+  MGX_CUDA(cudaMemcpyAsync(&df_mode, b.d_df_mode.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   b.time_end();
   MGX_CUDA(cudaStreamSynchronize(st));
+  b.h_df_mode = static_cast<int>(df_mode);
   b.d2h_bytes += 2 * (b.n_queries + 1) * sizeof(uint64_t) + sizeof(uint64_t);
-  // tile -> term / tile -> query maps (sizes are only known now)
-  const uint64_t n_and_tiles = b.n_queries > 0 ? b.h_q_tile_off[b.n_queries] : 0;
-  b.d_df_tile_term.reserve(b.n_df_tiles);
-  b.d_tile_query.reserve(n_and_tiles);
-  b.time_begin(0);
-  if (b.n_df_tiles > 0) {
-    fill_tile_map_kernel<<<grid_for(static_cast<uint64_t>(b.n_terms) * 32, 256), 256, 0, st>>>(
-        b.d_t_df_tile_off.p, b.n_terms, b.d_df_tile_term.p);
-    MGX_LAUNCH_CHECK();
-  }
-  if (n_and_tiles > 0) {
-    fill_tile_map_kernel<<<grid_for(static_cast<uint64_t>(b.n_queries) * 32, 256), 256, 0, st>>>(
-        b.d_q_tile_off.p, b.n_queries, b.d_tile_query.p);
-    MGX_LAUNCH_CHECK();
-  }
-  b.time_end();
   b.planned = true;
+  b.time_begin(0);
+  ensure_tile_maps(b);
+  b.time_end();
 }
 
 void batch_df(Batch& b) {
@@ -2142,7 +2733,21 @@ void batch_df(Batch& b) {
   if (!b.planned) {
     batch_plan(b);
   }
+  ensure_tile_maps(b);
   const uint64_t total_tiles = b.n_df_tiles;
+  if (b.h_df_mode != 0 && ix.n_text_tiles > 0) {
+    // one pass over the text arena for every stream-eligible term; persistent CTAs stride over the tiles
+    int sm_count = 148;
+    MGX_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ix.device));
+    int per_sm = 4;
+    MGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, df_stream_kernel, kStreamThreads, 0));
+    const unsigned grid = static_cast<unsigned>(
+        std::min<uint64_t>(ix.n_text_tiles, static_cast<uint64_t>(sm_count) * std::max(per_sm, 1)));
+    b.time_begin(4);
+    df_stream_kernel<<<grid, kStreamThreads, 0, st>>>(make_view(ix), make_batch_view(b));
+    MGX_LAUNCH_CHECK();
+    b.time_end();
+  }
   if (total_tiles > 0) {
     if (total_tiles > 0x7FFFFFFFULL) {
       set_last_error("df stage: too many tiles in one batch");
@@ -2228,12 +2833,18 @@ void run_tiles(Batch& b, const Chunk& c, const ScoreParams& sp, uint32_t prune_k
   const uint64_t n_tiles = b.h_q_tile_off[c.q1] - tile_base;
   const uint64_t rec_base = b.h_q_rec_off[c.q0];
   const uint64_t n_recs = b.h_q_rec_off[c.q1] - rec_base;
-  b.d_tile_count.reserve(std::max<uint64_t>(n_tiles, 1));
-  b.d_tile_total.reserve(std::max<uint64_t>(n_tiles, 1));
-  b.d_rec_doc.reserve(std::max<uint64_t>(n_recs + kTile, 1));
+  ensure_tile_maps(b);
+  SearchScratch& sc = *b.sc;
+  sc.tile_count.reserve(std::max<uint64_t>(n_tiles, 1ULL << 16));
+  sc.tile_total.reserve(std::max<uint64_t>(n_tiles, 1ULL << 16));
+  sc.rec_doc.reserve(std::max<uint64_t>(n_recs + kTile, 1ULL << 24));
   if (sp.compute_score != 0) {
-    b.d_rec_score.reserve(std::max<uint64_t>(n_recs + kTile, 1));
+    sc.rec_score.reserve(std::max<uint64_t>(n_recs + kTile, 1ULL << 24));
   }
+  b.d_tile_count.borrow(sc.tile_count.p, sc.tile_count.n);
+  b.d_tile_total.borrow(sc.tile_total.p, sc.tile_total.n);
+  b.d_rec_doc.borrow(sc.rec_doc.p, sc.rec_doc.n);
+  b.d_rec_score.borrow(sc.rec_score.p, sc.rec_score.n);
   if (n_tiles > 0) {
     if (n_tiles > 0x7FFFFFFFULL) {
       set_last_error("search stage: too many tiles in one chunk");
@@ -2279,6 +2890,7 @@ void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_
   }
   b.driver_entries += driver_entries;
   b.mark_last();
+  b.searched = true;
 }
 
 void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32_t>* d_sets) {

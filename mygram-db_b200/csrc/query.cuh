@@ -17,6 +17,43 @@ constexpr int kTileItems = kTile / kTileThreads;
 constexpr uint32_t kMaxTermBytes = 256;
 constexpr uint32_t kMaxTopK = 1024;
 
+// ---- streaming document-frequency pass (df_stream_kernel) ------------------------------------------------
+// For very large batches the verified document frequencies of the multi-n-gram terms are computed by ONE pass
+// over the shard's text arena that matches all of them at once, instead of visiting every candidate document
+// per term. Two levels, both built on the host per batch:
+//   stage 1  a 128 Ki-bit filter in shared memory over the first min(len, 8) bytes of every eligible term,
+//            probed at every character start of the text;
+//   stage 2  a bucket table over the first min(len, 12) bytes, probed only at the positions that passed stage 1,
+//            followed by the comparison of the remaining bytes, the attribution to a document and the
+//            per-(term, document) de-duplication.
+constexpr uint32_t kStreamKeyBytes = 12;         // bytes of a term held in a table entry
+constexpr uint32_t kStreamFilterBytes = 8;       // bytes hashed by the stage-1 filter
+constexpr uint32_t kStreamMinTermBytes = 3;
+__host__ __device__ inline uint32_t stream_hash(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t len) {
+  uint32_t h = w0 * 0x9E3779B1u ^ (w1 * 0x85EBCA77u) ^ (w2 * 0xC2B2AE3Du) ^ (len * 0x27D4EB2Fu);
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 13;
+  return h;
+}
+constexpr uint32_t kStreamBloomWords = 4096;     // 128 Ki bits
+__host__ __device__ inline uint32_t stream_filter_bit(uint32_t w0, uint32_t w1, uint32_t len8) {
+  uint32_t h = w0 * 0x85EBCA6Bu ^ (w1 * 0xC2B2AE35u) ^ (len8 * 0x165667B1u);
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  return h & (kStreamBloomWords * 32 - 1);
+}
+// bytes [0, n) of a little-endian word, n >= 4 keeps everything
+__host__ __device__ inline uint32_t low_bytes_mask(uint32_t n) { return n >= 4 ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u); }
+// One eligible term in bucket order: its first min(len, 12) bytes (zero padded), that length and its term id.
+struct StreamEntry {
+  uint32_t w0, w1, w2;
+  uint32_t len_term;  // key bytes (low 8 bits) | unique term id << 8
+};
+constexpr uint32_t kStreamMaxTerms = 1u << 19;   // entry index field of a (term, document) record
+constexpr uint32_t kStreamMaxBucket = 255;       // entries per bucket (count field of a slot)
+
 // query flag bits (q_flags)
 constexpr uint32_t kQEmpty = 1u;        // early exit / no terms: result is empty
 constexpr uint32_t kQVerify = 2u;       // every search term must also occur in the text (verify_text / hybrid fragment)
@@ -32,6 +69,8 @@ struct ExplicitDriver {
 
 struct Batch {
   Index* ix = nullptr;
+  SearchScratch* sc = nullptr;  // the (index, stream) workspace; the d_tile_* / d_rec_* members below are views into it
+  uint64_t serial = 0;          // unique per use of the batch object
   mgx_query_params_t params{};
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
@@ -50,6 +89,7 @@ struct Batch {
   DevBuf<uint64_t> d_keys;        // [K]
   DevBuf<uint32_t> d_key_list;    // [K] dictionary term index or kNone; sorted by length inside a term
   DevBuf<uint32_t> d_key_len;     // [K]
+  DevBuf<uint16_t> d_key_toff;    // [K] byte offset of the n-gram inside its term, kNoTermOffset if unusable
   DevBuf<uint64_t> d_t_est;       // [T]
   DevBuf<uint32_t> d_t_df_tiles;  // [T]
   DevBuf<uint64_t> d_t_df_tile_off;  // [T+1]
@@ -83,7 +123,16 @@ struct Batch {
   std::vector<uint64_t> h_q_tile_off;
   std::vector<uint64_t> h_q_rec_off;
 
-  DevBuf<uint8_t> d_term_flags;   // [T] bit0 raw, bit1 exact_single
+  DevBuf<uint8_t> d_term_flags;   // [T] bit0 raw, bit1 exact_single, bit2 eligible for the streaming df pass
+  DevBuf<uint32_t> d_stream_slots;      // [n_stream_slots] (first entry << 8) | entries in the bucket
+  DevBuf<StreamEntry> d_stream_entries; // [n_stream_terms] in bucket order
+  DevBuf<uint32_t> d_stream_bloom;      // [kStreamBloomWords] stage-1 filter
+  uint32_t stream_len8_mask = 0;        // bit m set: some eligible term has min(len, 8) == m   (stage-1 classes)
+  uint32_t stream_len12_mask = 0;       // bit m set: some eligible term has min(len, 12) == m  (stage-2 classes)
+  uint32_t n_stream_slots = 0;          // power of two, 0 = no eligible term
+  uint32_t n_stream_terms = 0;
+  DevBuf<uint32_t> d_df_mode;           // [2] [0] = 1 when the streaming pass was chosen (device decision)
+  int h_df_mode = 0;                    // host copy, valid after planning
   // Everything above is a view into one of these two grow-only arenas: `in_arena` receives the compiled batch in ONE
   // host-to-device copy from the pinned `staging` buffer; `work_arena` holds the device-only planning arrays.
   DevArena in_arena;
@@ -95,6 +144,13 @@ struct Batch {
   DevBuf<uint32_t> d_tile_query;    // [and tiles]
   DevBuf<unsigned long long> d_stats;  // device-side accounting, see StatSlot
 
+  // device-side result buffers of the host-buffer call (mgx_query_batch), recycled with the workspace
+  DevBuf<uint32_t> o_ids;
+  DevBuf<double> o_scores;
+  DevBuf<uint32_t> o_count;
+  DevBuf<uint64_t> o_total;
+  DevBuf<uint64_t> o_df;
+
   ExplicitDriver explicit_driver;
   uint64_t h2d_bytes = 0;
   uint64_t d2h_bytes = 0;
@@ -104,12 +160,13 @@ struct Batch {
   uint64_t driver_entries = 0;
   bool planned = false;
   bool df_done = false;
+  bool searched = false;  // batch_search has enqueued the batch's last kernels (ev_last follows them)
 
   // CUDA-event timing of the named kernels on the launch stream
   struct Timed {
     cudaEvent_t a;
     cudaEvent_t b;
-    int kind;  // 0 plan, 1 df kernel, 2 and kernel, 3 topk kernel
+    int kind;  // 0 plan, 1 df kernel, 2 and kernel, 3 topk kernel, 4 streaming df kernel
   };
   std::vector<Timed> timed;
   cudaEvent_t ev_first = nullptr;
@@ -129,7 +186,10 @@ enum StatSlot : int {
   kStatDfBytes = 3,         // text bytes scanned for df
   kStatDfCandidates = 4,
   kStatDfLists = 5,
-  kStatCount = 8
+  kStatStreamEntries = 6,   // shortest-list entries of the terms eligible for the streaming df pass
+  kStatStreamHits = 7,      // verified (term, document) pairs counted by the streaming pass
+  kStatDfScanned = 8,       // df candidates whose whole text had to be scanned (no usable first-occurrence position)
+  kStatCount = 10
 };
 constexpr int kStatStripes = 64;  // each counter is striped over 64 words to spread the atomics
 
@@ -137,8 +197,19 @@ constexpr int kStatStripes = 64;  // each counter is striped over 64 words to sp
 struct HostTerm {
   std::string bytes;
   std::vector<uint64_t> keys;  // sorted unique packed n-grams
+  std::vector<uint16_t> key_toff;  // per key: byte offset in the term if the n-gram occurs once in it (else kNoTermOffset)
   bool raw = false;            // keys given directly (Index::SearchAnd style): no text semantics
   bool exact_single = false;   // the term IS its single n-gram, so df == posting size when all text is valid UTF-8
+  bool streamable = false;     // valid UTF-8 (>= 3 bytes) that needs a text check: may use the streaming df pass
+};
+
+// Host-built bucket table of the streamable terms.
+struct HostStreamTable {
+  std::vector<uint32_t> slots;
+  std::vector<StreamEntry> entries;
+  std::vector<uint32_t> bloom;
+  uint32_t len8_mask = 0;
+  uint32_t len12_mask = 0;
 };
 
 struct HostQuery {
@@ -150,6 +221,8 @@ struct HostQuery {
 // query.cu
 void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
                   const std::vector<uint32_t>& slot_tid);
+// Bucket table over the terms with `streamable` set (clears the flag of terms that do not fit a bucket).
+void build_stream_table(std::vector<HostTerm>& terms, HostStreamTable* out);
 void batch_plan(Batch& b);
 void batch_df(Batch& b);
 // Runs the intersect/score kernels and the per-query output kernel. Outputs are DEVICE pointers.

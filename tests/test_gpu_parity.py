@@ -351,3 +351,50 @@ def test_staged_api_and_merge_kernel_match_single_call(mgx, oracle):
         assert int(want.total.max()) > limit + offset
         for be, b in zip(backends, batches):
             be.release(b)
+
+
+# ----------------------------------------------------------------------------------------- streaming df pass
+@pytest.mark.parametrize("mode", ["stream", "tiles"])
+def test_df_stream_and_tile_paths_match_oracle(mgx, oracle, mode, monkeypatch):
+    """The verified document frequencies come from df_tile_kernel (candidate tiles) or df_stream_kernel (one pass
+    over the text arena); MGX_DF_MODE pins the choice. Both must reproduce the reference's df and scores."""
+    monkeypatch.setenv("MGX_DF_MODE", mode)
+    rnd = random.Random(21)
+    # (a) mixed scripts, several n-gram configurations (the tokenisers of both sides agree or the path falls back)
+    docs = make_docs(44, 5000, 30)
+    ids = np.arange(1, len(docs) + 1, dtype=np.uint32)
+    for cfg in ((2, 0, True), (2, 1, True), (2, 1, False), (1, 1, True), (3, 2, False)):
+        gi, oi = build_pair(mgx, oracle, docs, ids, cfg)
+        qs = sample_queries_from_docs(docs, rnd, 400)
+        for kw in (dict(score=True, limit=100), dict(score=True, descending=False, limit=5, offset=1, verify_text=1)):
+            assert_batch_equal(gi.query_batch(qs, **kw), oi.query_batch(qs, **kw), qs)
+    # (b) tiny alphabet: terms repeat inside documents (first-occurrence rule), thousands of candidates per tile
+    #     (shared-memory candidate list overflows -> exact stand-alone handling)
+    for alphabet, lo, hi in ((2, 4, 60), (8, 8, 40), (64, 16, 112)):
+        c = corpus_mod.generate("cjk", 40000, 5, alphabet=alphabet, min_len=lo, max_len=hi)
+        gi = mgx.Index(2, 0, True)
+        gi.build(c.doc_ids, c.arena, c.offsets)
+        oi = oracle.index(2, 0, True)
+        oi.build_bulk(c.doc_ids, c.arena, c.offsets, 8)
+        qs = corpus_mod.sample_queries(c, 300, 3, n_terms=3, min_cp=2, max_cp=4)
+        g = gi.query_batch(qs, score=True, limit=100)
+        o = oi.query_batch(qs, score=True, limit=100, n_threads=8)
+        assert_batch_equal(g, o, qs)
+        if mode == "stream":
+            assert gi.last_batch_stats().df_stream_terms > 0
+    # (c) very short documents (more than 512 per 8 KB tile) and very long ones (spanning several tiles)
+    docs = [rnd.choice([b"abc", b"abcd", b"xabcx", b"ab", b"", b"bcd"]) for _ in range(20000)]
+    docs += [(b"abcd" * rnd.randint(1, 12000)) + b"zabc" for _ in range(6)]  # up to 48 KB: beyond the recorded positions
+    docs += ["東京都東京".encode() * rnd.randint(1, 3000) for _ in range(4)]
+    rnd.shuffle(docs)
+    ids = np.arange(1, len(docs) + 1, dtype=np.uint32)
+    gi, oi = build_pair(mgx, oracle, docs, ids, (2, 0, True))
+    qs = [[b"abc"], [b"abcd"], [b"bcd", b"abc"], [b"zabc"], [b"cdab"], ["東京都".encode()], ["京都東京".encode()],
+          ["都東".encode(), "東京都東".encode()], [b"dza"], [b"abcz"]]
+    assert_batch_equal(gi.query_batch(qs, score=True, limit=50), oi.query_batch(qs, score=True, limit=50), qs)
+    # (d) invalid UTF-8 in the corpus: the streaming pass is not eligible; results still match
+    docs = make_docs(45, 3000, 30, bad=True)
+    ids = np.arange(1, len(docs) + 1, dtype=np.uint32)
+    gi, oi = build_pair(mgx, oracle, docs, ids, (2, 0, True))
+    qs = sample_queries_from_docs(docs, rnd, 300)
+    assert_batch_equal(gi.query_batch(qs, score=True, limit=100), oi.query_batch(qs, score=True, limit=100), qs)
