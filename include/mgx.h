@@ -138,6 +138,25 @@ int mgx_filter_by_ngrams(const mgx_index_t* index, const uint32_t* candidates, u
                          const uint8_t* term_bytes, const uint64_t* term_offsets, uint64_t n_terms, uint32_t* out,
                          uint64_t cap, uint64_t* out_count);
 
+/* Index::SearchByThreshold(terms, threshold) — index.cpp:488-578: documents present in at least `threshold` of
+ * the (de-duplicated) n-gram lists, ascending. threshold == 0 or > #distinct terms => empty; == #distinct =>
+ * SearchAnd; terms without a posting list do not count. */
+int mgx_search_by_threshold(const mgx_index_t* index, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                            uint64_t n_terms, uint64_t threshold, uint32_t* out, uint64_t cap, uint64_t* out_count);
+
+/* QueryNode::Evaluate(index, doc_store, all_docs) — query/query_ast.cpp:67-161, for a boolean expression given
+ * as a postfix program over `terms` (search TERMS, not n-grams; they are tokenised with the index's own n-gram
+ * configuration exactly as Evaluate does, :80-84):
+ *   op 0 TERM  arg = index into the term table   -> SearchAnd(n-grams); no n-grams -> substring scan of the texts
+ *   op 1 AND   arg = number of children          (0 children -> empty)
+ *   op 2 OR    arg = number of children          (0 children -> empty)
+ *   op 3 NOT   one child                         -> all documents of the index minus the child
+ * Output: the ascending doc ids of the expression. all_docs is the set of documents given to mgx_index_build
+ * (DocumentStore::GetAllDocIds). */
+int mgx_eval_boolean(const mgx_index_t* index, const int32_t* ops, const int32_t* args, uint64_t n_ops,
+                     const uint8_t* term_bytes, const uint64_t* term_offsets, uint64_t n_terms, uint32_t* out,
+                     uint64_t cap, uint64_t* out_count);
+
 /* ------------------------------------------------------- batched pipeline */
 
 /* One batch of SEARCH queries through the regular path of

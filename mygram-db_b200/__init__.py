@@ -113,6 +113,9 @@ def lib():
     L.mgx_search_or.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u32p, C.c_uint64, u64p]
     L.mgx_search_not.argtypes = [C.c_void_p, u32p, C.c_uint64, u8p, u64p, C.c_uint64, u32p, C.c_uint64, u64p]
     L.mgx_filter_by_ngrams.argtypes = [C.c_void_p, u32p, C.c_uint64, u8p, u64p, C.c_uint64, u32p, C.c_uint64, u64p]
+    L.mgx_search_by_threshold.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint64, u32p, C.c_uint64, u64p]
+    L.mgx_eval_boolean.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_uint64, u8p, u64p,
+                                   C.c_uint64, u32p, C.c_uint64, u64p]
     L.mgx_query_batch.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
                                   C.c_uint64, u32p, f64p, u32p, u64p, u64p]
     L.mgx_batch_prepare.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
@@ -329,6 +332,26 @@ class Index:
 
     def postings(self, term):
         return self.search_and([term])
+
+    def search_by_threshold(self, terms, threshold):
+        """Index::SearchByThreshold (index.cpp:488-578); terms are n-gram strings."""
+        L = lib()
+        return self._set_call(lambda a, o, nt, out, cap, n: L.mgx_search_by_threshold(self._h, a, o, nt, threshold,
+                                                                                       _ptr(out, u32p), cap,
+                                                                                       C.byref(n)), terms)
+
+    def eval_boolean(self, ops, args, terms):
+        """QueryNode::Evaluate (query_ast.cpp:67-161) of a postfix program: op 0 TERM(arg = term index),
+        1 AND(arg = children), 2 OR(arg = children), 3 NOT. `terms` are search terms (not n-grams)."""
+        L = lib()
+        o = np.ascontiguousarray(ops, dtype=np.int32)
+        a = np.ascontiguousarray(args, dtype=np.int32)
+        op = o if o.size else np.zeros(1, np.int32)
+        ap = a if a.size else np.zeros(1, np.int32)
+        i32p = C.POINTER(C.c_int32)
+        return self._set_call(lambda ar, of, nt, out, cap, n: L.mgx_eval_boolean(
+            self._h, op.ctypes.data_as(i32p), ap.ctypes.data_as(i32p), o.size, ar, of, nt, _ptr(out, u32p), cap,
+            C.byref(n)), terms)
 
     # -- batched pipeline --------------------------------------------------------------------------
     def params(self, score=True, descending=True, limit=100, offset=0, verify_text=0, k1=1.2, b=0.75, total_docs=0,

@@ -626,6 +626,55 @@ namespace {
 
 enum class SetOp { kAnd, kOr, kNot, kFilter };
 
+// One query whose full ascending result set is wanted (the Index::Search* style calls): upload, plan, run the
+// tiles, gather; then the limit / reverse rules of index.cpp:356-366.
+int run_single_set_query(Index& ix, const std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
+                         const uint32_t* driver_ids, uint64_t n_driver, uint64_t limit, bool reverse, uint32_t* out,
+                         uint64_t cap, uint64_t* out_count) {
+  Batch b;
+  b.ix = &ix;
+  b.stream = ix.stream;
+  b.params = mgx_query_params_t{};
+  b.params.compute_score = 0;
+  b.launches_at_start = g_launches.load();
+  DevBuf<uint32_t> d_driver;
+  if (driver_ids != nullptr) {
+    if (n_driver >= (1ULL << 32)) {
+      return invalid("too many candidate ids");
+    }
+    d_driver.alloc(n_driver);
+    MGX_CUDA(cudaMemcpyAsync(d_driver.p, driver_ids, n_driver * sizeof(uint32_t), cudaMemcpyHostToDevice, b.stream));
+    b.explicit_driver.d_ids = d_driver.p;
+    b.explicit_driver.n = n_driver;
+  }
+  batch_upload(b, terms, queries, {});
+  batch_plan(b);
+  std::vector<uint64_t> set_off;
+  DevBuf<uint32_t> d_sets;
+  batch_search_sets(b, &set_off, &d_sets);
+  const uint64_t total = set_off[1];
+  uint64_t first = 0;
+  uint64_t n = total;
+  if (limit > 0 && total > limit) {  // index.cpp:356-366
+    n = limit;
+    first = reverse ? total - limit : 0;
+  }
+  *out_count = n;
+  if (n > cap) {
+    set_last_error("output capacity too small");
+    return MGX_ERR_CAPACITY;
+  }
+  if (n > 0) {
+    MGX_CUDA(cudaMemcpyAsync(out, d_sets.p + first, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, b.stream));
+    MGX_CUDA(cudaStreamSynchronize(b.stream));
+    if (reverse) {
+      std::reverse(out, out + n);
+    }
+  }
+  return MGX_OK;
+}
+
+
 int run_set_op(mgx_index_t* index, SetOp op, const uint32_t* driver_ids, uint64_t n_driver, const uint8_t* term_bytes,
                const uint64_t* term_offsets, uint64_t n_terms, uint64_t limit, bool reverse, uint32_t* out,
                uint64_t cap, uint64_t* out_count) {
@@ -702,47 +751,8 @@ int run_set_op(mgx_index_t* index, SetOp op, const uint32_t* driver_ids, uint64_
       queries[0].flags = op == SetOp::kOr ? kQAnyMode : (op == SetOp::kFilter ? kQDriverExplicit : 0u);
     }
 
-    Batch b;
-    b.ix = &ix;
-    b.stream = ix.stream;
-    b.params = mgx_query_params_t{};
-    b.params.compute_score = 0;
-    b.launches_at_start = g_launches.load();
-    DevBuf<uint32_t> d_driver;
-    if (op == SetOp::kNot || op == SetOp::kFilter) {
-      if (n_driver >= (1ULL << 32)) {
-        return invalid("too many candidate ids");
-      }
-      d_driver.alloc(n_driver);
-      MGX_CUDA(cudaMemcpyAsync(d_driver.p, driver_ids, n_driver * sizeof(uint32_t), cudaMemcpyHostToDevice, b.stream));
-      b.explicit_driver.d_ids = d_driver.p;
-      b.explicit_driver.n = n_driver;
-    }
-    batch_upload(b, terms, queries, {});
-    batch_plan(b);
-    std::vector<uint64_t> set_off;
-    DevBuf<uint32_t> d_sets;
-    batch_search_sets(b, &set_off, &d_sets);
-    const uint64_t total = set_off[1];
-    uint64_t first = 0;
-    uint64_t n = total;
-    if (limit > 0 && total > limit) {  // index.cpp:356-366
-      n = limit;
-      first = reverse ? total - limit : 0;
-    }
-    *out_count = n;
-    if (n > cap) {
-      set_last_error("output capacity too small");
-      return MGX_ERR_CAPACITY;
-    }
-    if (n > 0) {
-      MGX_CUDA(cudaMemcpyAsync(out, d_sets.p + first, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, b.stream));
-      MGX_CUDA(cudaStreamSynchronize(b.stream));
-      if (reverse) {
-        std::reverse(out, out + n);
-      }
-    }
-    return MGX_OK;
+    return run_single_set_query(ix, terms, queries, (op == SetOp::kNot || op == SetOp::kFilter) ? driver_ids : nullptr,
+                                n_driver, limit, reverse, out, cap, out_count);
   });
 }
 
@@ -772,6 +782,162 @@ int mgx_filter_by_ngrams(const mgx_index_t* index, const uint32_t* candidates, u
                          uint64_t cap, uint64_t* out_count) {
   return run_set_op(const_cast<mgx_index_t*>(index), SetOp::kFilter, candidates, n_candidates, term_bytes,
                     term_offsets, n_terms, 0, false, out, cap, out_count);
+}
+
+int mgx_search_by_threshold(const mgx_index_t* index_c, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                            uint64_t n_terms, uint64_t threshold, uint32_t* out, uint64_t cap, uint64_t* out_count) {
+  mgx_index_t* index = const_cast<mgx_index_t*>(index_c);
+  if (index == nullptr || out_count == nullptr || (n_terms > 0 && (term_bytes == nullptr || term_offsets == nullptr))) {
+    return invalid("null argument");
+  }
+  *out_count = 0;
+  if (n_terms == 0 || threshold == 0) {
+    return MGX_OK;  // index.cpp:489-491
+  }
+  // index.cpp:496-497: repeated terms count once
+  std::vector<std::string> uniq;
+  for (uint64_t i = 0; i < n_terms; ++i) {
+    uniq.emplace_back(reinterpret_cast<const char*>(term_bytes) + term_offsets[i], term_offsets[i + 1] - term_offsets[i]);
+  }
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  if (threshold > uniq.size()) {
+    return MGX_OK;  // :499-501
+  }
+  std::vector<uint8_t> flat;
+  std::vector<uint64_t> offs(1, 0);
+  for (const std::string& t : uniq) {
+    flat.insert(flat.end(), t.begin(), t.end());
+    offs.push_back(flat.size());
+  }
+  flat.push_back(0);
+  if (threshold == uniq.size()) {
+    return mgx_search_and(index_c, flat.data(), offs.data(), uniq.size(), 0, 0, out, cap, out_count);  // :504-506
+  }
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(index->mu);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    HostTerm t;
+    t.raw = true;
+    for (size_t i = 0; i < uniq.size(); ++i) {
+      uint64_t key = kInvalidKey;
+      if (host_ngram_to_key(flat.data() + offs[i], offs[i + 1] - offs[i], ix.width, &key)) {
+        t.keys.push_back(key);  // a term that cannot be an n-gram of this index has no posting list: it never counts
+      }
+    }
+    std::sort(t.keys.begin(), t.keys.end());
+    t.keys.erase(std::unique(t.keys.begin(), t.keys.end()), t.keys.end());
+    std::vector<HostTerm> terms;
+    terms.push_back(std::move(t));
+    std::vector<HostQuery> queries(1);
+    queries[0].terms.push_back(0);
+    queries[0].flags = kQAnyMode;
+    queries[0].threshold = static_cast<uint32_t>(threshold);
+    return run_single_set_query(ix, terms, queries, nullptr, 0, 0, false, out, cap, out_count);
+  });
+}
+
+namespace {
+// Validates a postfix program and collects the terms every result must satisfy (the operands of the root when it is
+// a TERM, or the TERM operands of a root AND, recursively through nested ANDs).
+int analyse_program(const int32_t* ops, const int32_t* args, uint64_t n_ops, uint64_t n_terms,
+                    std::vector<uint32_t>* conjuncts) {
+  struct Node {
+    int op;
+    int32_t arg;
+    std::vector<size_t> kids;
+  };
+  std::vector<Node> nodes;
+  std::vector<size_t> stack;
+  size_t depth_max = 0;
+  for (uint64_t i = 0; i < n_ops; ++i) {
+    Node nd{ops[i], args[i], {}};
+    if (ops[i] == kOpTerm) {
+      if (args[i] < 0 || static_cast<uint64_t>(args[i]) >= n_terms) {
+        return invalid("boolean program: TERM index out of range");
+      }
+    } else if (ops[i] == kOpAnd || ops[i] == kOpOr) {
+      if (args[i] < 0 || static_cast<size_t>(args[i]) > stack.size()) {
+        return invalid("boolean program: operator has more children than the stack holds");
+      }
+      nd.kids.assign(stack.end() - args[i], stack.end());
+      stack.resize(stack.size() - static_cast<size_t>(args[i]));
+    } else if (ops[i] == kOpNot) {
+      if (stack.empty()) {
+        return invalid("boolean program: NOT without an operand");
+      }
+      nd.kids.push_back(stack.back());
+      stack.pop_back();
+    } else {
+      return invalid("boolean program: unknown op");
+    }
+    nodes.push_back(std::move(nd));
+    stack.push_back(nodes.size() - 1);
+    depth_max = std::max(depth_max, stack.size());
+  }
+  if (depth_max > kMaxProgramDepth) {
+    set_last_error("boolean program deeper than 64 operands");
+    return MGX_ERR_UNSUPPORTED;
+  }
+  if (stack.empty()) {
+    return MGX_OK;
+  }
+  std::vector<size_t> todo{stack.back()};  // the value of the program is the top of the stack
+  while (!todo.empty()) {
+    const Node& nd = nodes[todo.back()];
+    todo.pop_back();
+    if (nd.op == kOpTerm) {
+      conjuncts->push_back(static_cast<uint32_t>(nd.arg));
+    } else if (nd.op == kOpAnd) {
+      todo.insert(todo.end(), nd.kids.begin(), nd.kids.end());
+    }
+  }
+  return MGX_OK;
+}
+}  // namespace
+
+int mgx_eval_boolean(const mgx_index_t* index_c, const int32_t* ops, const int32_t* args, uint64_t n_ops,
+                     const uint8_t* term_bytes, const uint64_t* term_offsets, uint64_t n_terms, uint32_t* out,
+                     uint64_t cap, uint64_t* out_count) {
+  mgx_index_t* index = const_cast<mgx_index_t*>(index_c);
+  if (index == nullptr || out_count == nullptr || (n_ops > 0 && (ops == nullptr || args == nullptr)) ||
+      (n_terms > 0 && (term_bytes == nullptr || term_offsets == nullptr))) {
+    return invalid("null argument");
+  }
+  *out_count = 0;
+  if (n_ops == 0) {
+    return MGX_OK;
+  }
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(index->mu);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    std::vector<HostQuery> queries(1);
+    HostQuery& hq = queries[0];
+    if (int rc = analyse_program(ops, args, n_ops, n_terms, &hq.conjuncts); rc != MGX_OK) {
+      return rc;
+    }
+    // TERM nodes tokenise with the index's own configuration (query_ast.cpp:80-84: GetNgramSize / the EFFECTIVE
+    // GetKanjiNgramSize / GetCrossBoundaryNgrams)
+    std::vector<HostTerm> terms(n_terms);
+    for (uint64_t t = 0; t < n_terms; ++t) {
+      const uint64_t b = term_offsets[t];
+      const uint64_t e = term_offsets[t + 1];
+      if (e - b > kMaxTermBytes) {
+        set_last_error("query term longer than 256 bytes is not supported");
+        return MGX_ERR_UNSUPPORTED;
+      }
+      terms[t].bytes.assign(reinterpret_cast<const char*>(term_bytes) + b, e - b);
+      host_query_keys(term_bytes + b, e - b, ix.ngram, ix.kanji, ix.cross, ix.width, &terms[t].keys);
+    }
+    hq.flags = kQProgram;
+    for (uint64_t i = 0; i < n_ops; ++i) {
+      hq.prog_ops.push_back(static_cast<uint8_t>(ops[i]));
+      hq.prog_args.push_back(static_cast<uint32_t>(args[i]));
+    }
+    return run_single_set_query(ix, terms, queries, nullptr, 0, 0, false, out, cap, out_count);
+  });
 }
 
 int mgx_index_get_postings(const mgx_index_t* index, const uint8_t* term, uint64_t term_len, uint32_t* out,

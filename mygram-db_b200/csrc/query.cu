@@ -58,6 +58,12 @@ struct BatchView {
   uint32_t* q_nlists;
   uint32_t* q_flags;
   const uint32_t* q_host_flags;
+  const uint32_t* q_threshold;
+  const uint32_t* q_poff;
+  const uint8_t* prog_op;
+  const uint32_t* prog_arg;
+  const uint32_t* q_coff;
+  const uint32_t* q_conj;
   uint32_t* q_driver_len;
   uint32_t* q_ntiles;
   const uint64_t* q_tile_off;
@@ -1210,6 +1216,51 @@ __global__ void query_plan_kernel(IndexView iv, BatchView bv) {
     return;
   }
   uint32_t flags = bv.q_host_flags[q];
+  if ((flags & kQProgram) != 0) {
+    // Boolean program (QueryNode::Evaluate, query_ast.cpp:67-161). Every result satisfies each conjunct term, so the
+    // shortest list of the conjunct with the smallest estimate drives; without a usable conjunct (OR / NOT at the
+    // root, text-only terms) every document of the shard is evaluated.
+    const uint32_t l0p = bv.q_loff[q];
+    uint64_t best = kEstNone;
+    uint32_t best_k = kNone;
+    bool empty = bv.q_poff[q + 1] == bv.q_poff[q];
+    for (uint32_t i = bv.q_coff[q]; i < bv.q_coff[q + 1]; ++i) {
+      const uint32_t tid = bv.q_conj[i];
+      const uint32_t k0 = bv.term_koff[tid];
+      const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+      if (bv.term_koff[tid + 1] == k0) {
+        empty = empty || tl == 0;  // an empty term matches nothing (substring_search.h:27-29)
+        continue;                  // text-only term: cannot drive
+      }
+      const uint64_t est = bv.t_est[tid];
+      if (est == 0) {
+        empty = true;  // an n-gram of a required term is not in the index
+      } else if (est < best) {
+        best = est;
+        best_k = k0;  // lists of a term are sorted by length: the first is the shortest
+      }
+    }
+    uint32_t driver_len = 0;
+    uint32_t n = 0;
+    if (!empty) {
+      if (best_k != kNone) {
+        bv.q_list[l0p] = bv.key_list[best_k];
+        bv.q_list_len[l0p] = bv.key_len[best_k];
+        n = 1;
+        driver_len = bv.key_len[best_k];
+      } else {
+        flags |= kQDriverAll;
+        driver_len = static_cast<uint32_t>(iv.n_docs);
+      }
+    } else {
+      flags |= kQEmpty;
+    }
+    bv.q_nlists[q] = n;
+    bv.q_flags[q] = flags;
+    bv.q_driver_len[q] = driver_len;
+    bv.q_ntiles[q] = (driver_len + kTile - 1) / kTile;
+    return;
+  }
   const bool any_mode = (flags & kQAnyMode) != 0;
   const uint32_t t0 = bv.q_toff[q];
   const uint32_t t1 = bv.q_toff[q + 1];
@@ -1274,7 +1325,7 @@ __global__ void query_plan_kernel(IndexView iv, BatchView bv) {
   } else if (t1 == t0) {
     empty = true;  // no search terms: Execute leaves the result empty (:813)
   } else if (any_mode) {
-    if (n == 0) {
+    if (n == 0 || n < bv.q_threshold[q]) {  // fewer existing lists than the threshold (index.cpp:520-523)
       empty = true;
     } else {
       flags |= kQDriverAll;
@@ -1439,6 +1490,80 @@ __device__ void bitonic_sort_desc(SortKey* keys, uint32_t n_pow2) {
 
 constexpr int kMaxCachedLists = 24;
 
+// TERM node of a boolean program: the documents of SearchAnd(n-grams of the term) (query_ast.cpp:76-93); a term
+// without n-grams falls back to a substring test of the stored text (query/substring_search.h:24-42).
+__device__ bool program_term_holds(const IndexView& iv, const BatchView& bv, uint32_t tid, uint32_t doc) {
+  const uint32_t k0 = bv.term_koff[tid];
+  const uint32_t k1 = bv.term_koff[tid + 1];
+  if (k1 == k0) {
+    const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+    if (tl == 0) {
+      return false;
+    }
+    const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
+    const uint64_t b = iv.text_off[doc];
+    const uint64_t e = iv.text_off[doc + 1];
+    if (e - b < tl) {
+      return false;
+    }
+    const uint8_t t0 = __ldg(term);
+    for (uint64_t j = b; j + tl <= e; ++j) {
+      if (__ldg(iv.text + j) != t0) {
+        continue;
+      }
+      uint32_t i = 1;
+      while (i < tl && __ldg(iv.text + j + i) == __ldg(term + i)) {
+        ++i;
+      }
+      if (i == tl) {
+        return true;
+      }
+    }
+    return false;
+  }
+  if (bv.t_est[tid] == 0) {
+    return false;  // one of its n-grams is not in the index
+  }
+  for (uint32_t kk = k0; kk < k1; ++kk) {
+    if (!list_contains(make_list(iv, bv.key_list[kk], bv.key_len[kk]), doc)) {
+      return false;
+    }
+  }
+  return true;
+}
+
+// Postfix evaluation with a 64-bit stack (bit 0 = top). AND / OR of zero children and NOT without a child are
+// false, as QueryNode::Evaluate returns an empty set for them (query_ast.cpp:96-140).
+__device__ bool eval_program(const IndexView& iv, const BatchView& bv, uint32_t p0, uint32_t p1, uint32_t doc) {
+  unsigned long long stack = 0;
+  uint32_t sp = 0;
+  for (uint32_t i = p0; i < p1; ++i) {
+    const uint32_t op = bv.prog_op[i];
+    const uint32_t arg = bv.prog_arg[i];
+    if (op == kOpTerm) {
+      stack = (stack << 1) | (program_term_holds(iv, bv, arg, doc) ? 1ULL : 0ULL);
+      ++sp;
+    } else if (op == kOpAnd || op == kOpOr) {
+      if (arg > sp) {
+        return false;
+      }
+      const unsigned long long mask = arg >= 64 ? ~0ULL : ((1ULL << arg) - 1ULL);
+      const unsigned long long bits = stack & mask;
+      const bool v = arg != 0 && (op == kOpAnd ? bits == mask : bits != 0);
+      stack = arg >= 64 ? 0ULL : (stack >> arg);
+      sp -= arg;
+      stack = (stack << 1) | (v ? 1ULL : 0ULL);
+      ++sp;
+    } else {
+      if (sp == 0) {
+        return false;
+      }
+      stack ^= 1ULL;
+    }
+  }
+  return sp > 0 && (stack & 1ULL) != 0;
+}
+
 // BM25 contribution of one term (bm25_scorer.cpp:74-85), evaluated operation by operation (no FMA contraction).
 __device__ __forceinline__ double bm25_term(double idf, uint32_t tf_u, double length_norm, double k1) {
   const double tf = static_cast<double>(tf_u);
@@ -1524,17 +1649,27 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   __syncthreads();
 
   // ---- membership
-  if (any_mode) {
-    // Index::SearchOr: keep the doc if ANY list holds it
+  if ((flags & kQProgram) != 0) {
+    const uint32_t p0 = bv.q_poff[q];
+    const uint32_t p1 = bv.q_poff[q + 1];
+#pragma unroll
+    for (int k = 0; k < kTileItems; ++k) {
+      if (((alive >> k) & 1u) && (my_doc[k] == kNone || !eval_program(iv, bv, p0, p1, my_doc[k]))) {
+        alive &= ~(1u << k);
+      }
+    }
+  } else if (any_mode) {
+    // Index::SearchOr / SearchByThreshold: keep the doc if at least `need` of the lists hold it
+    const uint32_t need = bv.q_threshold[q];
 #pragma unroll
     for (int k = 0; k < kTileItems; ++k) {
       if ((alive >> k) & 1u) {
-        bool hit = false;
-        for (uint32_t j = 0; j < nl && !hit && my_doc[k] != kNone; ++j) {
+        uint32_t hit = 0;
+        for (uint32_t j = 0; j < nl && hit < need && my_doc[k] != kNone; ++j) {
           const ListRef l = j < kMaxCachedLists ? s_lists[j] : make_list(iv, bv.q_list[l0 + j], bv.q_list_len[l0 + j]);
-          hit = list_contains(l, my_doc[k]);
+          hit += list_contains(l, my_doc[k]) ? 1u : 0u;
         }
-        if (!hit) {
+        if (hit < need) {
           alive &= ~(1u << k);
         }
       }
@@ -2259,6 +2394,12 @@ BatchView make_batch_view(Batch& b) {
   v.q_nlists = b.d_q_nlists.p;
   v.q_flags = b.d_q_flags.p;
   v.q_host_flags = b.d_q_host_flags.p;
+  v.q_threshold = b.d_q_threshold.p;
+  v.q_poff = b.d_q_poff.p;
+  v.prog_op = b.d_prog_op.p;
+  v.prog_arg = b.d_prog_arg.p;
+  v.q_coff = b.d_q_coff.p;
+  v.q_conj = b.d_q_conj.p;
   v.q_driver_len = b.d_q_driver_len.p;
   v.q_ntiles = b.d_q_ntiles.p;
   v.q_tile_off = b.d_q_tile_off.p;
@@ -2524,8 +2665,20 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms_in, const std::ve
   std::vector<uint32_t> tids;
   std::vector<uint32_t> ntids;
   std::vector<uint32_t> hflags(queries.size() + 1, 0);
+  std::vector<uint32_t> thresholds(queries.size() + 1, 1);
+  std::vector<uint32_t> poff(queries.size() + 1, 0);
+  std::vector<uint32_t> coff(queries.size() + 1, 0);
+  std::vector<uint8_t> prog_ops;
+  std::vector<uint32_t> prog_args;
+  std::vector<uint32_t> conj;
   for (size_t q = 0; q < queries.size(); ++q) {
-    uint32_t cap = 0;
+    prog_ops.insert(prog_ops.end(), queries[q].prog_ops.begin(), queries[q].prog_ops.end());
+    prog_args.insert(prog_args.end(), queries[q].prog_args.begin(), queries[q].prog_args.end());
+    conj.insert(conj.end(), queries[q].conjuncts.begin(), queries[q].conjuncts.end());
+    poff[q + 1] = static_cast<uint32_t>(prog_ops.size());
+    coff[q + 1] = static_cast<uint32_t>(conj.size());
+    thresholds[q] = queries[q].threshold;
+    uint32_t cap = (queries[q].flags & kQProgram) != 0 ? 1u : 0u;  // a program's only list is its driver
     for (uint32_t tid : queries[q].terms) {
       tids.push_back(tid);
       cap += static_cast<uint32_t>(terms[tid].keys.size());
@@ -2566,6 +2719,12 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms_in, const std::ve
   const size_t i_hflags = add(hflags.data(), hflags.size() * 4);
   const size_t i_slot = add(slot_tid.data(), slot_tid.size() * 4);
   const size_t i_ktoff = add(key_toff.data(), key_toff.size() * 2);
+  const size_t i_thr = add(thresholds.data(), thresholds.size() * 4);
+  const size_t i_poff = add(poff.data(), poff.size() * 4);
+  const size_t i_pops = add(prog_ops.data(), prog_ops.size());
+  const size_t i_pargs = add(prog_args.data(), prog_args.size() * 4);
+  const size_t i_coff = add(coff.data(), coff.size() * 4);
+  const size_t i_conj = add(conj.data(), conj.size() * 4);
   const size_t i_sslots = add(stream_table.slots.data(), stream_table.slots.size() * 4);
   const size_t i_sentries = add(stream_table.entries.data(), stream_table.entries.size() * sizeof(StreamEntry));
   const size_t i_sbloom = add(stream_table.bloom.data(), stream_table.bloom.size() * 4);
@@ -2597,6 +2756,12 @@ void batch_upload(Batch& b, const std::vector<HostTerm>& terms_in, const std::ve
   b.d_q_host_flags.borrow(reinterpret_cast<uint32_t*>(at(i_hflags)), hflags.size());
   b.d_slot_tid.borrow(reinterpret_cast<uint32_t*>(at(i_slot)), slot_tid.size());
   b.d_key_toff.borrow(reinterpret_cast<uint16_t*>(at(i_ktoff)), key_toff.size());
+  b.d_q_threshold.borrow(reinterpret_cast<uint32_t*>(at(i_thr)), thresholds.size());
+  b.d_q_poff.borrow(reinterpret_cast<uint32_t*>(at(i_poff)), poff.size());
+  b.d_prog_op.borrow(at(i_pops), prog_ops.size());
+  b.d_prog_arg.borrow(reinterpret_cast<uint32_t*>(at(i_pargs)), prog_args.size());
+  b.d_q_coff.borrow(reinterpret_cast<uint32_t*>(at(i_coff)), coff.size());
+  b.d_q_conj.borrow(reinterpret_cast<uint32_t*>(at(i_conj)), conj.size());
   b.d_stream_slots.borrow(reinterpret_cast<uint32_t*>(at(i_sslots)), stream_table.slots.size());
   b.d_stream_entries.borrow(reinterpret_cast<StreamEntry*>(at(i_sentries)), stream_table.entries.size());
   b.d_stream_bloom.borrow(reinterpret_cast<uint32_t*>(at(i_sbloom)), stream_table.bloom.size());

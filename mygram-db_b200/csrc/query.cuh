@@ -60,6 +60,14 @@ constexpr uint32_t kQVerify = 2u;       // every search term must also occur in 
 constexpr uint32_t kQAnyMode = 4u;      // OR semantics over the lists (Index::SearchOr)
 constexpr uint32_t kQDriverAll = 8u;    // driver = every document of the shard
 constexpr uint32_t kQDriverExplicit = 16u;  // driver = caller supplied candidate ids (query 0 only)
+constexpr uint32_t kQProgram = 32u;     // membership = a boolean postfix program over terms (QueryNode::Evaluate)
+constexpr uint32_t kMaxProgramDepth = 64;  // evaluation stack = one 64-bit word
+
+// postfix program ops (same encoding as the oracle's orc_eval_boolean)
+constexpr uint8_t kOpTerm = 0;  // arg = unique term id
+constexpr uint8_t kOpAnd = 1;   // arg = number of children
+constexpr uint8_t kOpOr = 2;    // arg = number of children
+constexpr uint8_t kOpNot = 3;   // one child
 
 // driver kinds for single-call set APIs
 struct ExplicitDriver {
@@ -112,6 +120,12 @@ struct Batch {
   DevBuf<uint64_t> d_q_rec_off;   // [Q+1]
   DevBuf<double> d_q_idf;         // [sum search terms], in planner order
   DevBuf<uint32_t> d_q_host_flags;  // [Q] flags decided on the host (verify etc.)
+  DevBuf<uint32_t> d_q_threshold;   // [Q] any-mode threshold
+  DevBuf<uint32_t> d_q_poff;        // [Q+1] program ranges
+  DevBuf<uint8_t> d_prog_op;
+  DevBuf<uint32_t> d_prog_arg;
+  DevBuf<uint32_t> d_q_coff;        // [Q+1] conjunct ranges
+  DevBuf<uint32_t> d_q_conj;
 
   // ---- device: per-tile results
   DevBuf<uint32_t> d_tile_count;  // [tiles in flight] records written by the tile
@@ -215,7 +229,11 @@ struct HostStreamTable {
 struct HostQuery {
   std::vector<uint32_t> terms;      // unique-term ids in query order
   std::vector<uint32_t> not_terms;
-  uint32_t flags = 0;               // kQVerify / kQAnyMode / kQDriverAll / kQDriverExplicit
+  uint32_t flags = 0;               // kQVerify / kQAnyMode / kQDriverAll / kQDriverExplicit / kQProgram
+  uint32_t threshold = 1;           // kQAnyMode: lists that must hold the document (Index::SearchByThreshold); 1 = OR
+  std::vector<uint8_t> prog_ops;    // kQProgram: postfix program
+  std::vector<uint32_t> prog_args;
+  std::vector<uint32_t> conjuncts;  // kQProgram: terms every result must satisfy (driver candidates)
 };
 
 // query.cu

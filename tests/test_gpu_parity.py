@@ -398,3 +398,63 @@ def test_df_stream_and_tile_paths_match_oracle(mgx, oracle, mode, monkeypatch):
     gi, oi = build_pair(mgx, oracle, docs, ids, (2, 0, True))
     qs = sample_queries_from_docs(docs, rnd, 300)
     assert_batch_equal(gi.query_batch(qs, score=True, limit=100), oi.query_batch(qs, score=True, limit=100), qs)
+
+
+# ----------------------------------------------------------------------------------------- threshold / boolean AST
+def random_program(rnd, n_terms, depth=0):
+    """Random boolean expression in the oracle's postfix encoding -> (ops, args)."""
+    r = rnd.random()
+    if depth >= 3 or r < 0.35:
+        return [0], [rnd.randrange(n_terms)]
+    if r < 0.5:
+        o, a = random_program(rnd, n_terms, depth + 1)
+        return o + [3], a + [0]
+    n = rnd.choice([0, 1, 2, 2, 3]) if depth > 0 else rnd.choice([1, 2, 2, 3])
+    ops, args = [], []
+    for _ in range(n):
+        o, a = random_program(rnd, n_terms, depth + 1)
+        ops += o
+        args += a
+    return ops + [1 if rnd.random() < 0.5 else 2], args + [n]
+
+
+@pytest.mark.parametrize("cfg", [(2, 0, True), (2, 1, True), (1, 1, True), (3, 2, False)])
+def test_search_by_threshold_and_boolean_eval(mgx, oracle, cfg):
+    """Index::SearchByThreshold (index.cpp:488-578) and QueryNode::Evaluate (query_ast.cpp:67-161)."""
+    docs = make_docs(61, 3000, 25) + [b"", b"a", b"ab"]
+    ids = np.arange(10, 10 + len(docs), dtype=np.uint32)
+    gi, oi = build_pair(mgx, oracle, docs, ids, cfg, dense_threshold=0.02)
+    rnd = random.Random(5)
+    grams = some_terms(oi, rnd, 40)
+    for _ in range(40):
+        k = rnd.randint(1, 6)
+        ts = [rnd.choice(grams) for _ in range(k)]
+        if rnd.random() < 0.3:
+            ts.append(b"\xff\xfe")          # cannot be an n-gram: has no list, never counts
+        if rnd.random() < 0.3:
+            ts.append(ts[0])                # duplicates count once
+        for thr in range(0, len(set(ts)) + 2):
+            assert np.array_equal(gi.search_by_threshold(ts, thr), oi.search_by_threshold(ts, thr)), (ts, thr)
+    assert gi.search_by_threshold([], 1).size == 0
+    # boolean programs over search terms (1..4 code points; 1-cp terms fall back to the substring scan with bigrams)
+    for _ in range(120):
+        n_terms = rnd.randint(1, 4)
+        terms = []
+        for _t in range(n_terms):
+            src = docs[rnd.randrange(len(docs))].decode("utf-8", "ignore")
+            if len(src) >= 1 and rnd.random() < 0.9:
+                ln = rnd.randint(1, 4)
+                st = rnd.randrange(0, max(1, len(src) - ln + 1))
+                terms.append(src[st:st + ln].encode())
+            else:
+                terms.append(rnd.choice([b"", b"zzzz", b"q"]))
+        ops, args = random_program(rnd, n_terms)
+        g = gi.eval_boolean(ops, args, terms)
+        o = oi.eval_boolean(ops, args, terms)
+        assert np.array_equal(g, o), (ops, args, terms, g[:10], o[:10])
+    # the reference's own cases (tests/query/query_ast_test.cpp:596-660): a AND b, a OR e, NOT a, (a OR c) AND b
+    docs2 = [b"a b", b"a c", b"b c", b"e"]
+    gi2, oi2 = build_pair(mgx, oracle, docs2, np.arange(1, 5, dtype=np.uint32), (1, 1, True))
+    for ops, args, terms in (([0, 0, 1], [0, 1, 2], [b"a", b"b"]), ([0, 0, 2], [0, 1, 2], [b"a", b"e"]),
+                             ([0, 3], [0, 0], [b"a"]), ([0, 0, 2, 0, 1], [0, 1, 2, 2, 2], [b"a", b"c", b"b"])):
+        assert np.array_equal(gi2.eval_boolean(ops, args, terms), oi2.eval_boolean(ops, args, terms))
