@@ -76,6 +76,22 @@ int mgx_index_build(mgx_index_t* index, const uint32_t* doc_ids, const uint8_t* 
 int mgx_index_build_device(mgx_index_t* index, const uint32_t* d_doc_ids, const uint8_t* d_text,
                            const uint64_t* d_text_offsets, uint64_t n_docs);
 
+/* Incremental mutations — Index::AddDocument (index.cpp:39-74), UpdateDocument (:121-173), RemoveDocument
+ * (:175-197), as the binlog applier calls them (mysql/binlog_event_processor.cpp:66-324) together with the
+ * matching DocumentStore calls: the document of `doc_id` (text + postings) is added, replaced or removed. The
+ * calls are journaled on the host and take effect before the NEXT read of the index (any search / stats / export
+ * call, or mgx_index_commit): the resident corpus is merged with the journal on the device and the shard is
+ * rebuilt (~0.1 s per 10M documents), so a burst of mutations costs one rebuild. `old_text` / `text` of update /
+ * remove must be the text the document currently has (what the reference requires to find its n-grams); the
+ * resident copy is what is actually used. *out_indexed (may be NULL) = AddDocument's return value: 0 when the text
+ * yields no n-gram (the document is stored but never matches). */
+int mgx_index_add_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* text, uint64_t text_len,
+                           int32_t* out_indexed);
+int mgx_index_update_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* old_text, uint64_t old_len,
+                              const uint8_t* new_text, uint64_t new_len);
+int mgx_index_remove_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* text, uint64_t text_len);
+int mgx_index_commit(mgx_index_t* index);
+
 typedef struct {
   uint64_t n_docs;
   uint64_t n_terms;          /* Index::TermCount, index.h:193                       */

@@ -103,6 +103,10 @@ def lib():
     L.mgx_index_build.argtypes = [C.c_void_p, u32p, u8p, u64p, C.c_uint64]
     L.mgx_index_build_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.mgx_index_get_stats.argtypes = [C.c_void_p, C.POINTER(IndexStats)]
+    L.mgx_index_add_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64, C.POINTER(C.c_int32)]
+    L.mgx_index_update_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64, u8p, C.c_uint64]
+    L.mgx_index_remove_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64]
+    L.mgx_index_commit.argtypes = [C.c_void_p]
     L.mgx_index_posting_size.argtypes = [C.c_void_p, u8p, C.c_uint64, u64p]
     L.mgx_index_get_postings.argtypes = [C.c_void_p, u8p, C.c_uint64, u32p, C.c_uint64, u64p]
     L.mgx_index_export.argtypes = [C.c_void_p, u64p, u64p, u32p]
@@ -244,6 +248,33 @@ class Index:
         """Index::AddDocumentBatch (index.cpp:76-119) for a whole shard: replaces the index content."""
         arena, offsets = pack_strings(texts)
         self.build(np.asarray(doc_ids, dtype=np.uint32), arena, offsets)
+
+    @staticmethod
+    def _text_arg(text):
+        b = _bytes(text)
+        buf = np.frombuffer(b, dtype=np.uint8).copy() if b else np.zeros(1, np.uint8)
+        return buf, len(b)
+
+    def add_document(self, doc_id, text):
+        """Index::AddDocument (index.cpp:39-74) + the DocumentStore mirror; False if the text yields no n-gram."""
+        buf, n = self._text_arg(text)
+        ok = C.c_int32(0)
+        _check(lib().mgx_index_add_document(self._h, doc_id, _ptr(buf, u8p), n, C.byref(ok)))
+        return bool(ok.value)
+
+    def update_document(self, doc_id, old_text, new_text):
+        """Index::UpdateDocument (index.cpp:121-173)."""
+        ob, on = self._text_arg(old_text)
+        nb, nn = self._text_arg(new_text)
+        _check(lib().mgx_index_update_document(self._h, doc_id, _ptr(ob, u8p), on, _ptr(nb, u8p), nn))
+
+    def remove_document(self, doc_id, text):
+        """Index::RemoveDocument (index.cpp:175-197)."""
+        buf, n = self._text_arg(text)
+        _check(lib().mgx_index_remove_document(self._h, doc_id, _ptr(buf, u8p), n))
+
+    def commit(self):
+        _check(lib().mgx_index_commit(self._h))
 
     def build(self, doc_ids, arena, offsets):
         doc_ids = np.ascontiguousarray(doc_ids, dtype=np.uint32)

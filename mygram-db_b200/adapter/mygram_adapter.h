@@ -15,6 +15,7 @@
 
 #include <cstdint>
 #include <stdexcept>
+#include <memory>
 #include <string>
 #include <string_view>
 #include <vector>
@@ -134,6 +135,29 @@ class Index {
         },
         all_docs.size() + 1);
   }
+  // index.cpp:488-578
+  [[nodiscard]] std::vector<DocId> SearchByThreshold(const std::vector<std::string>& terms, size_t threshold) const {
+    detail::Flat f = Pack(terms);
+    return detail::grow_call([&](DocId* out, uint64_t cap, uint64_t* n) {
+      return mgx_search_by_threshold(handle_, f.data(), f.offsets.data(), terms.size(), threshold, out, cap, n);
+    });
+  }
+  // Incremental mutations (index.cpp:39-74, 121-173, 175-197): journaled, visible to the next read.
+  bool AddDocument(DocId doc_id, std::string_view text) {
+    int32_t indexed = 0;
+    detail::check(mgx_index_add_document(handle_, doc_id, reinterpret_cast<const uint8_t*>(text.data()), text.size(),
+                                         &indexed));
+    return indexed != 0;
+  }
+  void UpdateDocument(DocId doc_id, std::string_view old_text, std::string_view new_text) {
+    detail::check(mgx_index_update_document(handle_, doc_id, reinterpret_cast<const uint8_t*>(old_text.data()),
+                                            old_text.size(), reinterpret_cast<const uint8_t*>(new_text.data()),
+                                            new_text.size()));
+  }
+  void RemoveDocument(DocId doc_id, std::string_view text) {
+    detail::check(mgx_index_remove_document(handle_, doc_id, reinterpret_cast<const uint8_t*>(text.data()),
+                                            text.size()));
+  }
   [[nodiscard]] uint64_t PostingSize(std::string_view term) const {
     uint64_t n = 0;
     detail::check(mgx_index_posting_size(handle_, reinterpret_cast<const uint8_t*>(term.data()), term.size(), &n));
@@ -211,6 +235,62 @@ class BM25Scorer {
       r.value.push_back({candidates[i], scores[i]});
     }
     return r;
+  }
+};
+
+// QueryNode (query/query_ast.h:59-95): the boolean AST, evaluated on the device as one postfix program.
+enum class NodeType { TERM, AND, OR, NOT };
+struct QueryNode {
+  NodeType type = NodeType::TERM;
+  std::string term;
+  std::vector<std::unique_ptr<QueryNode>> children;
+
+  // QueryNode::Evaluate(index, doc_store, all_docs) — query_ast.cpp:67-161. The document store and the all-docs
+  // list of the reference are the index's device-resident mirror.
+  [[nodiscard]] std::vector<DocId> Evaluate(const Index& index) const {
+    std::vector<int32_t> ops;
+    std::vector<int32_t> args;
+    detail::Flat terms;
+    int32_t n_terms = 0;
+    Emit(&ops, &args, &terms, &n_terms);
+    return detail::grow_call([&](DocId* out, uint64_t cap, uint64_t* n) {
+      return mgx_eval_boolean(index.handle(), ops.data(), args.data(), ops.size(), terms.data(), terms.offsets.data(),
+                              static_cast<uint64_t>(n_terms), out, cap, n);
+    });
+  }
+
+ private:
+  void Emit(std::vector<int32_t>* ops, std::vector<int32_t>* args, detail::Flat* terms, int32_t* n_terms) const {
+    switch (type) {
+      case NodeType::TERM:
+        terms->add(term);
+        ops->push_back(0);
+        args->push_back((*n_terms)++);
+        return;
+      case NodeType::AND:
+      case NodeType::OR: {
+        int32_t n = 0;
+        for (const auto& c : children) {
+          if (c != nullptr) {
+            c->Emit(ops, args, terms, n_terms);
+            ++n;
+          }
+        }
+        ops->push_back(type == NodeType::AND ? 1 : 2);
+        args->push_back(n);
+        return;
+      }
+      case NodeType::NOT:
+        if (children.empty() || children[0] == nullptr) {
+          ops->push_back(2);  // NOT without a child evaluates to the empty set (query_ast.cpp:139-141): OR of nothing
+          args->push_back(0);
+          return;
+        }
+        children[0]->Emit(ops, args, terms, n_terms);  // only the first child is used (:150)
+        ops->push_back(3);
+        args->push_back(0);
+        return;
+    }
   }
 };
 

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <unordered_map>
@@ -384,7 +385,61 @@ using namespace mgx;
 struct mgx_index {
   Index ix;
   std::mutex mu;  // serialises build vs. query on one handle (the reference's table generation lock)
+  // Journal of Index::AddDocument / UpdateDocument / RemoveDocument calls not folded in yet: doc id -> (removed, text).
+  // The last call for an id wins; the next read applies the whole journal (apply_journal_device).
+  std::map<uint32_t, std::pair<bool, std::string>> journal;
+  std::mutex journal_mu;
+  std::atomic<bool> dirty{false};
 };
+
+namespace {
+// Applies the pending mutations; called at the top of every entry point that reads the index.
+int commit_pending(mgx_index_t* index) {
+  if (index == nullptr || !index->dirty.load(std::memory_order_acquire)) {
+    return MGX_OK;
+  }
+  return guarded([&]() {
+    std::lock_guard<std::mutex> jl(index->journal_mu);
+    if (index->journal.empty()) {
+      index->dirty.store(false);
+      return MGX_OK;
+    }
+    std::lock_guard<std::mutex> lock(index->mu);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    std::vector<uint32_t> ids;
+    std::vector<uint8_t> removed;
+    std::vector<uint8_t> text;
+    std::vector<uint64_t> off(1, 0);
+    for (const auto& kv : index->journal) {  // std::map: ascending ids
+      ids.push_back(kv.first);
+      removed.push_back(kv.second.first ? 1 : 0);
+      if (!kv.second.first) {
+        text.insert(text.end(), kv.second.second.begin(), kv.second.second.end());
+      }
+      off.push_back(text.size());
+    }
+    text.push_back(0);
+    apply_journal_device(ix, ids.data(), removed.data(), text.data(), off.data(), ids.size(), ix.stream);
+    index->journal.clear();
+    index->dirty.store(false, std::memory_order_release);
+    return MGX_OK;
+  });
+}
+
+int journal_put(mgx_index_t* index, uint32_t doc_id, bool removed, const uint8_t* text, uint64_t len) {
+  if (index == nullptr || (len > 0 && text == nullptr)) {
+    return invalid("null argument");
+  }
+  if (int rc = require_device(); rc != MGX_OK) {
+    return rc;
+  }
+  std::lock_guard<std::mutex> jl(index->journal_mu);
+  index->journal[doc_id] = {removed, removed ? std::string() : std::string(reinterpret_cast<const char*>(text), len)};
+  index->dirty.store(true, std::memory_order_release);
+  return MGX_OK;
+}
+}  // namespace
 
 struct mgx_batch {
   Batch b;
@@ -455,6 +510,11 @@ static int build_common(mgx_index_t* index, const uint32_t* doc_ids, const uint8
   if (n_docs >= (1ULL << 32) - 1) {
     return invalid("too many documents in one shard");
   }
+  {
+    std::lock_guard<std::mutex> jl(index->journal_mu);  // a bulk build replaces everything, pending mutations included
+    index->journal.clear();
+    index->dirty.store(false);
+  }
   return guarded([&]() {
     std::lock_guard<std::mutex> lock(index->mu);
     Index& ix = index->ix;
@@ -494,9 +554,43 @@ int mgx_index_build_device(mgx_index_t* index, const uint32_t* d_doc_ids, const 
   return build_common(index, d_doc_ids, d_text, d_text_offsets, n_docs, true);
 }
 
+int mgx_index_add_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* text, uint64_t text_len,
+                           int32_t* out_indexed) {
+  if (out_indexed != nullptr && index != nullptr) {
+    // Index::AddDocument returns false when the text yields no n-gram (index.cpp:49-57)
+    std::vector<uint64_t> keys;
+    host_query_keys(text, text_len, index->ix.ngram, index->ix.kanji, index->ix.cross, index->ix.width, &keys);
+    *out_indexed = keys.empty() ? 0 : 1;
+  }
+  return journal_put(index, doc_id, false, text, text_len);
+}
+
+int mgx_index_update_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* old_text, uint64_t old_len,
+                              const uint8_t* new_text, uint64_t new_len) {
+  (void)old_text;  // the resident text of doc_id is what gets replaced (consistent use: it equals old_text)
+  (void)old_len;
+  return journal_put(index, doc_id, false, new_text, new_len);
+}
+
+int mgx_index_remove_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* text, uint64_t text_len) {
+  (void)text;
+  (void)text_len;
+  return journal_put(index, doc_id, true, nullptr, 0);
+}
+
+int mgx_index_commit(mgx_index_t* index) {
+  if (index == nullptr) {
+    return invalid("null argument");
+  }
+  return commit_pending(index);
+}
+
 int mgx_index_get_stats(const mgx_index_t* index, mgx_index_stats_t* out) {
   if (index == nullptr || out == nullptr) {
     return invalid("null argument");
+  }
+  if (int rc = commit_pending(const_cast<mgx_index_t*>(index)); rc != MGX_OK) {
+    return rc;
   }
   const Index& ix = index->ix;
   out->n_docs = ix.n_docs;
@@ -682,6 +776,9 @@ int run_set_op(mgx_index_t* index, SetOp op, const uint32_t* driver_ids, uint64_
     return invalid("null argument");
   }
   *out_count = 0;
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
   return guarded([&]() {
     std::lock_guard<std::mutex> lock(index->mu);
     Index& ix = index->ix;
@@ -814,6 +911,9 @@ int mgx_search_by_threshold(const mgx_index_t* index_c, const uint8_t* term_byte
   if (threshold == uniq.size()) {
     return mgx_search_and(index_c, flat.data(), offs.data(), uniq.size(), 0, 0, out, cap, out_count);  // :504-506
   }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
   return guarded([&]() {
     std::lock_guard<std::mutex> lock(index->mu);
     Index& ix = index->ix;
@@ -909,6 +1009,9 @@ int mgx_eval_boolean(const mgx_index_t* index_c, const int32_t* ops, const int32
   if (n_ops == 0) {
     return MGX_OK;
   }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
   return guarded([&]() {
     std::lock_guard<std::mutex> lock(index->mu);
     Index& ix = index->ix;
@@ -953,6 +1056,9 @@ int mgx_index_posting_size(const mgx_index_t* index, const uint8_t* term, uint64
   }
   *out = 0;
   mgx_index_t* h = const_cast<mgx_index_t*>(index);
+  if (int rc = commit_pending(h); rc != MGX_OK) {
+    return rc;
+  }
   return guarded([&]() {
     std::lock_guard<std::mutex> lock(h->mu);
     Index& ix = h->ix;
@@ -992,6 +1098,9 @@ int mgx_index_export(const mgx_index_t* index, uint64_t* keys, uint64_t* offsets
     return invalid("null argument");
   }
   mgx_index_t* h = const_cast<mgx_index_t*>(index);
+  if (int rc = commit_pending(h); rc != MGX_OK) {
+    return rc;
+  }
   return guarded([&]() {
     std::lock_guard<std::mutex> lock(h->mu);
     Index& ix = h->ix;
@@ -1022,6 +1131,9 @@ int mgx_index_doc_lengths(const mgx_index_t* index, uint32_t* out) {
     return invalid("null argument");
   }
   mgx_index_t* h = const_cast<mgx_index_t*>(index);
+  if (int rc = commit_pending(h); rc != MGX_OK) {
+    return rc;
+  }
   return guarded([&]() {
     std::lock_guard<std::mutex> lock(h->mu);
     DeviceGuard guard(h->ix.device);
@@ -1046,6 +1158,9 @@ int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint
     return invalid("too many queries in one batch");
   }
   if (int rc = check_params(*params); rc != MGX_OK) {
+    return rc;
+  }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
     return rc;
   }
   return guarded([&]() {
@@ -1217,6 +1332,9 @@ int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64
   if (n_queries == 0) {
     return MGX_OK;
   }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
   std::lock_guard<std::mutex> lock(index->mu);
   mgx_batch_t* batch = nullptr;
   int rc = mgx_batch_prepare(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
@@ -1289,6 +1407,9 @@ int mgx_score_documents(mgx_index_t* index, const uint32_t* candidates, uint64_t
   }
   if (n_candidates == 0) {
     return MGX_OK;
+  }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
   }
   return guarded([&]() {
     std::lock_guard<std::mutex> lock(index->mu);

@@ -797,4 +797,164 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   cudaEventDestroy(ev1);
 }
 
+// ------------------------------------------------------------------ incremental mutations (journal -> rebuild)
+// Index::AddDocument / UpdateDocument / RemoveDocument (index.cpp:39-197) are journaled on the host and folded in
+// here before the next read: the resident corpus (doc ids, text) is merged ON THE DEVICE with the journal's
+// documents (sorted by id; an id in the journal replaces or removes the resident document of that id), and the
+// shard is rebuilt from the merged corpus by the same tokenise / sort / CSR pipeline as a bulk build.
+namespace {
+
+__device__ __forceinline__ uint64_t lower_bound_ids(const uint32_t* __restrict__ p, uint64_t n, uint32_t v) {
+  uint64_t lo = 0;
+  uint64_t hi = n;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (p[mid] < v) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  return lo;
+}
+
+// keep[i] = 1 when resident document i is untouched by the journal
+__global__ void journal_mark_kernel(const uint32_t* __restrict__ old_ids, uint64_t n_old,
+                                    const uint32_t* __restrict__ j_ids, uint64_t n_j, uint32_t* __restrict__ keep) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_old) {
+    return;
+  }
+  const uint64_t pos = lower_bound_ids(j_ids, n_j, old_ids[i]);
+  keep[i] = (pos < n_j && j_ids[pos] == old_ids[i]) ? 0u : 1u;
+}
+
+__global__ void journal_live_kernel(const uint8_t* __restrict__ removed, uint64_t n_j, uint32_t* __restrict__ live) {
+  const uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j < n_j) {
+    live[j] = removed[j] != 0 ? 0u : 1u;
+  }
+}
+
+// position of every surviving document in the merged corpus (two sorted runs, ranks by binary search)
+__global__ void journal_place_old_kernel(const uint32_t* __restrict__ old_ids, const uint64_t* __restrict__ old_off,
+                                         uint64_t n_old, const uint32_t* __restrict__ keep,
+                                         const uint64_t* __restrict__ keep_rank, const uint32_t* __restrict__ j_ids,
+                                         uint64_t n_j, const uint64_t* __restrict__ live_rank,
+                                         uint32_t* __restrict__ new_ids, uint32_t* __restrict__ new_len,
+                                         uint32_t* __restrict__ src) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_old || keep[i] == 0) {
+    return;
+  }
+  const uint64_t dest = keep_rank[i] + live_rank[lower_bound_ids(j_ids, n_j, old_ids[i])];
+  new_ids[dest] = old_ids[i];
+  new_len[dest] = static_cast<uint32_t>(old_off[i + 1] - old_off[i]);
+  src[dest] = static_cast<uint32_t>(i);
+}
+
+__global__ void journal_place_new_kernel(const uint32_t* __restrict__ j_ids, const uint64_t* __restrict__ j_off,
+                                         uint64_t n_j, const uint32_t* __restrict__ live,
+                                         const uint64_t* __restrict__ live_rank, const uint32_t* __restrict__ old_ids,
+                                         uint64_t n_old, const uint64_t* __restrict__ keep_rank,
+                                         uint32_t* __restrict__ new_ids, uint32_t* __restrict__ new_len,
+                                         uint32_t* __restrict__ src) {
+  const uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= n_j || live[j] == 0) {
+    return;
+  }
+  // resident documents with a smaller id that survive (the resident document of the SAME id never survives)
+  const uint64_t dest = live_rank[j] + keep_rank[lower_bound_ids(old_ids, n_old, j_ids[j])];
+  new_ids[dest] = j_ids[j];
+  new_len[dest] = static_cast<uint32_t>(j_off[j + 1] - j_off[j]);
+  src[dest] = static_cast<uint32_t>(j) | 0x80000000u;
+}
+
+// one warp per merged document: bytes from the resident arena or from the journal arena
+__global__ void __launch_bounds__(256) journal_copy_kernel(const uint32_t* __restrict__ src, uint64_t n_new,
+                                                           const uint64_t* __restrict__ new_off,
+                                                           const uint8_t* __restrict__ old_text,
+                                                           const uint64_t* __restrict__ old_off,
+                                                           const uint8_t* __restrict__ j_text,
+                                                           const uint64_t* __restrict__ j_off,
+                                                           uint8_t* __restrict__ out) {
+  const uint64_t d = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (d >= n_new) {
+    return;
+  }
+  const uint32_t s = src[d];
+  const uint8_t* from = (s & 0x80000000u) != 0 ? j_text + j_off[s & 0x7FFFFFFFu] : old_text + old_off[s];
+  const uint64_t n = new_off[d + 1] - new_off[d];
+  uint8_t* to = out + new_off[d];
+  for (uint64_t i = threadIdx.x & 31u; i < n; i += 32) {
+    to[i] = from[i];
+  }
+}
+
+}  // namespace
+
+void apply_journal_device(Index& ix, const uint32_t* h_ids, const uint8_t* h_removed, const uint8_t* h_text,
+                          const uint64_t* h_off, uint64_t n_j, cudaStream_t stream) {
+  const uint64_t n_old = ix.n_docs;
+  const uint64_t j_bytes = h_off[n_j];
+  DevBuf<uint32_t> d_jids, d_keep, d_live, d_new_ids, d_new_len, d_src;
+  DevBuf<uint8_t> d_jrem, d_jtext, d_new_text;
+  DevBuf<uint64_t> d_joff, d_keep_rank, d_live_rank, d_new_off, d_scan;
+  d_jids.alloc(n_j);
+  d_jrem.alloc(n_j);
+  d_jtext.alloc(j_bytes + 64);
+  d_joff.alloc(n_j + 1);
+  d_keep.alloc(n_old + 1);
+  d_live.alloc(n_j + 1);
+  d_keep_rank.alloc(n_old + 1);
+  d_live_rank.alloc(n_j + 1);
+  d_scan.alloc(scan_scratch_elems(std::max<uint64_t>(n_old + n_j, 1)) + 8);
+  MGX_CUDA(cudaMemcpyAsync(d_jids.p, h_ids, n_j * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  MGX_CUDA(cudaMemcpyAsync(d_jrem.p, h_removed, n_j, cudaMemcpyHostToDevice, stream));
+  if (j_bytes > 0) {
+    MGX_CUDA(cudaMemcpyAsync(d_jtext.p, h_text, j_bytes, cudaMemcpyHostToDevice, stream));
+  }
+  MGX_CUDA(cudaMemcpyAsync(d_joff.p, h_off, (n_j + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+  const unsigned g_old = static_cast<unsigned>((n_old + 255) / 256);
+  const unsigned g_j = static_cast<unsigned>((n_j + 255) / 256);
+  if (n_old > 0) {
+    journal_mark_kernel<<<g_old, 256, 0, stream>>>(ix.d_doc_ids.p, n_old, d_jids.p, n_j, d_keep.p);
+    MGX_LAUNCH_CHECK();
+  }
+  journal_live_kernel<<<g_j, 256, 0, stream>>>(d_jrem.p, n_j, d_live.p);
+  MGX_LAUNCH_CHECK();
+  exclusive_scan_u32_u64(d_keep.p, d_keep_rank.p, n_old, d_scan.p, stream);
+  exclusive_scan_u32_u64(d_live.p, d_live_rank.p, n_j, d_scan.p, stream);
+  uint64_t n_keep = 0;
+  uint64_t n_live = 0;
+  MGX_CUDA(cudaMemcpyAsync(&n_keep, d_keep_rank.p + n_old, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+  MGX_CUDA(cudaMemcpyAsync(&n_live, d_live_rank.p + n_j, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+  MGX_CUDA(cudaStreamSynchronize(stream));
+  const uint64_t n_new = n_keep + n_live;
+  d_new_ids.alloc(n_new + 1);
+  d_new_len.alloc(n_new + 1);
+  d_src.alloc(n_new + 1);
+  d_new_off.alloc(n_new + 1);
+  if (n_old > 0) {
+    journal_place_old_kernel<<<g_old, 256, 0, stream>>>(ix.d_doc_ids.p, ix.d_text_off.p, n_old, d_keep.p, d_keep_rank.p,
+                                                        d_jids.p, n_j, d_live_rank.p, d_new_ids.p, d_new_len.p, d_src.p);
+    MGX_LAUNCH_CHECK();
+  }
+  journal_place_new_kernel<<<g_j, 256, 0, stream>>>(d_jids.p, d_joff.p, n_j, d_live.p, d_live_rank.p, ix.d_doc_ids.p,
+                                                    n_old, d_keep_rank.p, d_new_ids.p, d_new_len.p, d_src.p);
+  MGX_LAUNCH_CHECK();
+  exclusive_scan_u32_u64(d_new_len.p, d_new_off.p, n_new, d_scan.p, stream);
+  uint64_t new_bytes = 0;
+  MGX_CUDA(cudaMemcpyAsync(&new_bytes, d_new_off.p + n_new, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+  MGX_CUDA(cudaStreamSynchronize(stream));
+  d_new_text.alloc(new_bytes + 64);
+  if (n_new > 0) {
+    journal_copy_kernel<<<static_cast<unsigned>((n_new * 32 + 255) / 256), 256, 0, stream>>>(
+        d_src.p, n_new, d_new_off.p, ix.d_text.p, ix.d_text_off.p, d_jtext.p, d_joff.p, d_new_text.p);
+    MGX_LAUNCH_CHECK();
+  }
+  MGX_CUDA(cudaStreamSynchronize(stream));
+  build_index_device(ix, d_new_ids.p, d_new_text.p, d_new_off.p, n_new, new_bytes, stream);
+}
+
 }  // namespace mgx

@@ -422,6 +422,10 @@ inline IndexView make_view(const Index& ix) {
 // The three inputs may be host or device pointers (cudaMemcpyDefault); the index keeps its own copies.
 void build_index_device(Index& ix, const uint32_t* doc_ids, const uint8_t* text, const uint64_t* text_off,
                         uint64_t n_docs, uint64_t text_bytes, cudaStream_t stream);
+// Folds a journal of document mutations (host arrays sorted by id; removed[j] != 0 deletes, otherwise the text
+// replaces / adds the document) into the resident corpus on the device and rebuilds the shard.
+void apply_journal_device(Index& ix, const uint32_t* h_ids, const uint8_t* h_removed, const uint8_t* h_text,
+                          const uint64_t* h_off, uint64_t n_j, cudaStream_t stream);
 // Tokenise only (mgx_tokenize_batch): fills d_keys/d_docs slots (kInvalidKey for non-emitting positions).
 // Tokeniser stage 1: per-document code-point counts (d_doc_len) and n-gram counts -> d_slot_off (exclusive scan,
 // n_docs + 1 entries). counters_out: [0] non-empty docs, [1] docs with invalid bytes, [2] total code points.

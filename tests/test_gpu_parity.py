@@ -458,3 +458,54 @@ def test_search_by_threshold_and_boolean_eval(mgx, oracle, cfg):
     for ops, args, terms in (([0, 0, 1], [0, 1, 2], [b"a", b"b"]), ([0, 0, 2], [0, 1, 2], [b"a", b"e"]),
                              ([0, 3], [0, 0], [b"a"]), ([0, 0, 2, 0, 1], [0, 1, 2, 2, 2], [b"a", b"c", b"b"])):
         assert np.array_equal(gi2.eval_boolean(ops, args, terms), oi2.eval_boolean(ops, args, terms))
+
+
+# ----------------------------------------------------------------------------------------- incremental mutations
+@pytest.mark.parametrize("cfg", [(2, 0, True), (2, 1, True)])
+def test_add_update_remove_document(mgx, oracle, cfg):
+    """Index::AddDocument / UpdateDocument / RemoveDocument (index.cpp:39-197) as the binlog applier uses them:
+    journaled, folded in by a device-side merge + rebuild before the next read; results equal the oracle's
+    incrementally maintained index (postings, BM25 statistics, query answers)."""
+    ng, kj, cross = cfg
+    rnd = random.Random(77)
+    docs = {i: d for i, d in zip(range(5, 5 + 2 * 1500, 2), make_docs(88, 1500, 25))}  # odd ids 5, 7, ...
+    gi = mgx.Index(ng, kj, cross)
+    oi = oracle.index(ng, kj, cross)
+    ids0 = np.asarray(sorted(docs), dtype=np.uint32)
+    gi.add_document_batch(ids0, [docs[int(i)] for i in ids0])
+    oi.add_texts(ids0, [docs[int(i)] for i in ids0])
+    assert_same_index(gi, oi)
+    for round_ in range(3):
+        for _ in range(200):
+            r = rnd.random()
+            if r < 0.4:       # insert a new id: before the first, in a gap (even ids), after the last
+                new_id = rnd.choice([rnd.randrange(1, 5), 2 * rnd.randrange(3, 1500), 4000 + rnd.randrange(1000)])
+                if new_id in docs:
+                    continue
+                text = rand_text(rnd, 25)
+                docs[new_id] = text
+                assert gi.add_document(new_id, text) == bool(oi.add_document(new_id, text))
+            elif r < 0.7:     # update
+                doc_id = rnd.choice(sorted(docs))
+                text = rand_text(rnd, 25)
+                gi.update_document(doc_id, docs[doc_id], text)
+                oi.update_document(doc_id, docs[doc_id], text)
+                docs[doc_id] = text
+            else:             # delete
+                doc_id = rnd.choice(sorted(docs))
+                gi.remove_document(doc_id, docs[doc_id])
+                oi.remove_document(doc_id, docs[doc_id])
+                del docs[doc_id]
+        assert_same_index(gi, oi)
+        st = gi.stats()
+        assert (st.total_doc_length, st.doc_count) == oi.bm25_stats()
+        live = [d for d in docs.values()]
+        qs = sample_queries_from_docs(live, rnd, 150)
+        assert_batch_equal(gi.query_batch(qs, score=True, limit=20), oi.query_batch(qs, score=True, limit=20), qs)
+    # an index that starts empty and is filled one document at a time
+    gi2 = mgx.Index(ng, kj, cross)
+    oi2 = oracle.index(ng, kj, cross)
+    for doc_id, text in ((3, b"abc"), (1, "東京都".encode()), (2, b""), (9, b"bcd")):
+        assert gi2.add_document(doc_id, text) == bool(oi2.add_document(doc_id, text))
+    assert_same_index(gi2, oi2)
+    assert np.array_equal(gi2.search_and([b"bc"]), oi2.search_and([b"bc"]))
