@@ -357,10 +357,11 @@ def main():
         backend.release(p)
     kstats = backend.stats
 
-    # ---- e2e: host buffers in, host buffers out, every step. The loop is software-pipelined two deep, the way a
-    # server feeds a stream of batches: while the device works on batch i the host compiles and enqueues batch
-    # i+1 (its planning stage still waits for batch i on the same stream). Every step copies its own inputs
-    # host->device and its own results device->host; a step is complete when its results are in pinned host memory.
+    # ---- e2e: host buffers in, host buffers out, every step. The loop is software-pipelined the way a server feeds
+    # a stream of batches: a compile thread prepares batch i+1 (host query compile + H2D of the compiled batch)
+    # while the main thread enqueues batch i and waits for batch i-1 (the planning stage of a batch still waits for
+    # its predecessor on the same stream). Every step copies its own inputs host->device and its own results
+    # device->host; a step is complete when its results are in pinned host memory.
     backend.collect_stats = False
     outs = [dict(ids=torch.empty((args.batch, TOPK), dtype=torch.int32, pin_memory=True),
                  scores=torch.empty((args.batch, TOPK), dtype=torch.float64, pin_memory=True),
@@ -370,32 +371,22 @@ def main():
     out_ids, out_scores, out_count, out_total = (outs[0][k] for k in ("ids", "scores", "count", "total"))
     e2e_parts = {"host_prepare_ms": 0.0, "enqueue_ms": 0.0, "wait_ms": 0.0}
 
-    def e2e_submit(b, slot, acc=None):
+    def e2e_prepare(b):
         t_a = time.perf_counter()
-        p = backend.prepare(b[1], b[2], b[3], args.batch)
+        p = backend.prepare(b[1], b[2], b[3], args.batch)   # host query compile + staging + H2D enqueue
+        return p, 1e3 * (time.perf_counter() - t_a)
+
+    def e2e_enqueue(p, slot, acc=None):
         t_b = time.perf_counter()
-        if os.environ.get("BENCH_TRACE") and world == 1:
-            t1 = time.perf_counter()
-            df = backend.local_df(p)
-            t2 = time.perf_counter()
-            r = backend.search(p, df)
-            t3 = time.perf_counter()
-            ids, scores, count, total = backend.merge(r[0][None], r[1][None], r[2][None], r[3][None])
-            t4 = time.perf_counter()
-            print(f"[bench trace] local_df {1e3*(t2-t1):.2f} ms, search {1e3*(t3-t2):.2f} ms, merge {1e3*(t4-t3):.2f} ms",
-                  file=sys.stderr)
-        else:
-            ids, scores, count, total = sharded.run_sharded_batch(backend, comm, p)
+        ids, scores, count, total = sharded.run_sharded_batch(backend, comm, p)
         o = outs[slot]
         o["ids"].copy_(ids, non_blocking=True)
         o["scores"].copy_(scores, non_blocking=True)
         o["count"].copy_(count, non_blocking=True)
         o["total"].copy_(total, non_blocking=True)
         o["done"].record()
-        t_c = time.perf_counter()
         if acc is not None:
-            acc["host_prepare_ms"] += 1e3 * (t_b - t_a)   # host query compile + staging + H2D enqueue
-            acc["enqueue_ms"] += 1e3 * (t_c - t_b)        # plan (one size read-back), df, search, merge, D2H enqueue
+            acc["enqueue_ms"] += 1e3 * (time.perf_counter() - t_b)  # plan (one size read-back), df, search, merge, D2H
         return p, slot
 
     def e2e_finish(pending, acc=None):
@@ -406,15 +397,25 @@ def main():
         if acc is not None:
             acc["wait_ms"] += 1e3 * (time.perf_counter() - t_a)
 
+    from concurrent.futures import ThreadPoolExecutor
+    compiler = ThreadPoolExecutor(max_workers=1)  # ctypes releases the GIL: the compile of batch i+1 runs beside batch i
+
     def e2e_run(first, last, acc=None):
+        if first >= last:
+            return
         pending = None
+        fut = compiler.submit(e2e_prepare, batches[first])
         for i in range(first, last):
-            cur = e2e_submit(batches[i], i & 1, acc)
+            p, prep_ms = fut.result()
+            if acc is not None:
+                acc["host_prepare_ms"] += prep_ms
+            if i + 1 < last:
+                fut = compiler.submit(e2e_prepare, batches[i + 1])
+            cur = e2e_enqueue(p, i & 1, acc)
             if pending is not None:
                 e2e_finish(pending, acc)
             pending = cur
-        if pending is not None:
-            e2e_finish(pending, acc)
+        e2e_finish(pending, acc)
 
     e2e_run(0, min(args.warmup, 2))
     barrier()

@@ -58,6 +58,8 @@ typedef struct {
                                  /* <= 0 selects 1/32 (the size break-even: 4*|P| = N/8)    */
   uint64_t max_dense_bytes;      /* cap for all dense bitmaps together; 0 = 8 GiB           */
   uint64_t scratch_bytes;        /* per-batch query scratch; 0 = 4 GiB                      */
+  double roaring_threshold;      /* Index's roaring_threshold (index.h:58, default 0.18): only used to REPORT the    */
+                                 /* reference's delta / Roaring list counts (mgx_index_get_statistics); <= 0 = 0.18 */
 } mgx_index_config_t;
 
 int mgx_index_create(const mgx_index_config_t* config, mgx_index_t** out);
@@ -108,6 +110,24 @@ typedef struct {
 } mgx_index_stats_t;
 
 int mgx_index_get_stats(const mgx_index_t* index, mgx_index_stats_t* out);
+
+/* Index::GetStatistics (index.cpp:604-633) / Index::Optimize(total_docs) (index_optimization.cpp:36-120,
+ * posting_list.cpp:799-834) / Index::Clear (index.cpp:635-641). The device index keeps every list as sorted
+ * uint32 plus a bitmap for dense lists (chosen for speed, see mgx_index_config_t.dense_threshold); the reference's
+ * representation only shows in these counters, which are reproduced by rule: a list is "Roaring" when it has more
+ * than 4096 entries (posting_list.cpp:21,917-922: converted on insert) or, once Optimize(total_docs) has run, when
+ * size / total_docs >= roaring_threshold; every other list is "delta". memory_usage_bytes is the resident device
+ * memory of this index (the reference reports host bytes of its own containers). */
+typedef struct {
+  uint64_t total_terms;
+  uint64_t total_postings;
+  uint64_t delta_encoded_lists;
+  uint64_t roaring_bitmap_lists;
+  uint64_t memory_usage_bytes;
+} mgx_index_statistics_t;
+int mgx_index_get_statistics(const mgx_index_t* index, mgx_index_statistics_t* out);
+int mgx_index_optimize(mgx_index_t* index, uint64_t total_docs);
+int mgx_index_clear(mgx_index_t* index);
 
 /* Index::PostingSize / Count (index.cpp:580-588): `term` is one n-gram. */
 int mgx_index_posting_size(const mgx_index_t* index, const uint8_t* term, uint64_t term_len, uint64_t* out);

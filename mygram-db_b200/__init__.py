@@ -46,7 +46,7 @@ class MgxError(RuntimeError):
 class IndexConfig(C.Structure):
     _fields_ = [("ngram_size", C.c_int32), ("kanji_ngram_size", C.c_int32), ("cross_boundary_ngrams", C.c_int32),
                 ("device", C.c_int32), ("dense_threshold", C.c_double), ("max_dense_bytes", C.c_uint64),
-                ("scratch_bytes", C.c_uint64)]
+                ("scratch_bytes", C.c_uint64), ("roaring_threshold", C.c_double)]
 
 
 class IndexStats(C.Structure):
@@ -54,6 +54,11 @@ class IndexStats(C.Structure):
                 ("n_dense_terms", C.c_uint64), ("text_bytes", C.c_uint64), ("total_doc_length", C.c_uint64),
                 ("doc_count", C.c_uint64), ("device_bytes", C.c_uint64), ("n_pair_slots", C.c_uint64),
                 ("all_valid_utf8", C.c_int32), ("key_width", C.c_int32), ("last_build_ms", C.c_double)]
+
+
+class IndexStatistics(C.Structure):
+    _fields_ = [("total_terms", C.c_uint64), ("total_postings", C.c_uint64), ("delta_encoded_lists", C.c_uint64),
+                ("roaring_bitmap_lists", C.c_uint64), ("memory_usage_bytes", C.c_uint64)]
 
 
 class QueryParams(C.Structure):
@@ -103,6 +108,9 @@ def lib():
     L.mgx_index_build.argtypes = [C.c_void_p, u32p, u8p, u64p, C.c_uint64]
     L.mgx_index_build_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.mgx_index_get_stats.argtypes = [C.c_void_p, C.POINTER(IndexStats)]
+    L.mgx_index_get_statistics.argtypes = [C.c_void_p, C.POINTER(IndexStatistics)]
+    L.mgx_index_optimize.argtypes = [C.c_void_p, C.c_uint64]
+    L.mgx_index_clear.argtypes = [C.c_void_p]
     L.mgx_index_add_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64, C.POINTER(C.c_int32)]
     L.mgx_index_update_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64, u8p, C.c_uint64]
     L.mgx_index_remove_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64]
@@ -185,7 +193,7 @@ def tokenize_batch(texts, ngram_size=2, kanji_ngram_size=0, cross_boundary=True,
     """GenerateHybridNgrams for every text on the GPU -> list (per doc) of n-gram byte strings,
     in generation order (string_utils.cpp:452-509)."""
     arena, offsets = pack_strings(texts)
-    cfg = IndexConfig(ngram_size, kanji_ngram_size, int(cross_boundary), device, 0.0, 0, 0)
+    cfg = IndexConfig(ngram_size, kanji_ngram_size, int(cross_boundary), device, 0.0, 0, 0, 0.0)
     cap = max(1, int(offsets[-1]))
     keys = np.zeros(cap, dtype=np.uint64)
     docs = np.zeros(cap, dtype=np.uint32)
@@ -222,13 +230,13 @@ class Index:
     """Mirror of mygramdb::index::Index (src/index/index.h:49-413) backed by a device-resident shard."""
 
     def __init__(self, ngram_size=2, kanji_ngram_size=0, cross_boundary_ngrams=True, device=0, dense_threshold=0.0,
-                 max_dense_bytes=0, scratch_bytes=0):
+                 max_dense_bytes=0, scratch_bytes=0, roaring_threshold=0.18):
         self.ngram_size = ngram_size
         self.kanji_ngram_size = kanji_ngram_size
         self.cross_boundary_ngrams = cross_boundary_ngrams
         self.device = device
         cfg = IndexConfig(ngram_size, kanji_ngram_size, int(cross_boundary_ngrams), device, dense_threshold,
-                          max_dense_bytes, scratch_bytes)
+                          max_dense_bytes, scratch_bytes, roaring_threshold)
         self._h = C.c_void_p()
         _check(lib().mgx_index_create(C.byref(cfg), C.byref(self._h)))
 
@@ -272,6 +280,20 @@ class Index:
         """Index::RemoveDocument (index.cpp:175-197)."""
         buf, n = self._text_arg(text)
         _check(lib().mgx_index_remove_document(self._h, doc_id, _ptr(buf, u8p), n))
+
+    def get_statistics(self):
+        """Index::GetStatistics (index.cpp:604-633)."""
+        s = IndexStatistics()
+        _check(lib().mgx_index_get_statistics(self._h, C.byref(s)))
+        return s
+
+    def optimize(self, total_docs):
+        """Index::Optimize(total_docs) (index_optimization.cpp:36-120)."""
+        _check(lib().mgx_index_optimize(self._h, total_docs))
+
+    def clear(self):
+        """Index::Clear (index.cpp:635-641)."""
+        _check(lib().mgx_index_clear(self._h))
 
     def commit(self):
         _check(lib().mgx_index_commit(self._h))

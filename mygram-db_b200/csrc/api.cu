@@ -136,9 +136,33 @@ bool has_uncovered_hybrid_fragment(const uint8_t* term, uint64_t len, int ngram_
 
 bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanji_ngram_size, bool cross_boundary,
                      int key_width, std::vector<uint64_t>* keys, std::vector<uint16_t>* key_toff) {
+  // scratch reused across calls: a batch compiles ~10^4 terms and must not allocate per term
+  static thread_local std::vector<uint32_t> cps;
+  static thread_local std::vector<uint32_t> cp_byte;
+  static thread_local std::vector<uint32_t> starts;
+  static thread_local std::vector<std::pair<uint64_t, uint32_t>> occ;
   keys->clear();
-  const auto cps = host_utf8_to_codepoints(term, len);
-  std::vector<uint32_t> starts;
+  cps.clear();
+  cp_byte.clear();
+  starts.clear();
+  bool valid = true;  // no byte was skipped: windows are contiguous byte runs of the term
+  {
+    uint64_t i = 0;
+    while (i < len) {
+      uint32_t cp = 0;
+      const uint64_t avail = len - i;
+      const int n = parse_utf8(term[i], avail > 1 ? term[i + 1] : 0, avail > 2 ? term[i + 2] : 0,
+                               avail > 3 ? term[i + 3] : 0, avail, &cp);
+      if (n > 0) {
+        cps.push_back(cp);
+        cp_byte.push_back(static_cast<uint32_t>(i));
+        i += static_cast<uint64_t>(n);
+      } else {
+        valid = false;
+        ++i;  // string_utils.cpp:212-215: skip one byte and retry
+      }
+    }
+  }
   if (kanji_ngram_size > 0) {
     hybrid_keys(cps, ngram_size > 0 ? ngram_size : 2, kanji_ngram_size, cross_boundary, key_width, keys, &starts);
   } else if (ngram_size == 0) {
@@ -156,40 +180,24 @@ bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanj
   if (key_toff != nullptr) {
     // Byte offset inside the term of every n-gram that occurs exactly ONCE in it (kNoTermOffset otherwise, and for
     // every n-gram of a term that is not valid UTF-8: its windows skip bytes, so they are no contiguous byte run).
-    std::vector<uint32_t> cp_byte(cps.size() + 1, 0);
-    bool valid = true;
-    {
-      uint64_t i = 0;
-      size_t c = 0;
-      while (i < len && c < cps.size()) {
-        uint32_t cp = 0;
-        const uint64_t avail = len - i;
-        const int l = parse_utf8(term[i], avail > 1 ? term[i + 1] : 0, avail > 2 ? term[i + 2] : 0,
-                                 avail > 3 ? term[i + 3] : 0, avail, &cp);
-        if (l <= 0) {
-          valid = false;
-          break;
-        }
-        cp_byte[c++] = static_cast<uint32_t>(i);
-        i += static_cast<uint64_t>(l);
-      }
-      valid = valid && i == len;
-    }
-    std::vector<std::pair<uint64_t, uint32_t>> occ(keys->size());
+    occ.resize(keys->size());
     for (size_t i = 0; i < keys->size(); ++i) {
       occ[i] = {(*keys)[i], starts[i]};
     }
     std::sort(occ.begin(), occ.end());
     key_toff->clear();
+    keys->clear();
     for (size_t i = 0; i < occ.size();) {
       size_t j = i;
       while (j < occ.size() && occ[j].first == occ[i].first) {
         ++j;
       }
       const uint32_t off = cp_byte[occ[i].second];
+      keys->push_back(occ[i].first);  // sorted + unique == DeduplicateSorted, string_utils.h:192-196
       key_toff->push_back(valid && j - i == 1 && off < kNoTermOffset ? static_cast<uint16_t>(off) : kNoTermOffset);
       i = j;
     }
+    return true;
   }
   std::sort(keys->begin(), keys->end());  // DeduplicateSorted, string_utils.h:192-196
   keys->erase(std::unique(keys->begin(), keys->end()), keys->end());
@@ -269,7 +277,15 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
                   const uint64_t* term_offsets, const uint64_t* q_term_begin, const uint8_t* not_bytes,
                   const uint64_t* not_offsets, const uint64_t* q_not_begin, std::vector<HostTerm>* terms,
                   std::vector<HostQuery>* queries, std::vector<uint32_t>* slot_tid) {
-  std::unordered_map<std::string, uint32_t> ids;
+  // open-addressing table of term ids keyed by the term bytes (no string is built for a lookup)
+  const uint64_t n_search_slots = n_queries > 0 ? q_term_begin[n_queries] : 0;
+  const uint64_t n_not_slots = (n_queries > 0 && q_not_begin != nullptr) ? q_not_begin[n_queries] : 0;
+  size_t table_cap = 64;
+  while (table_cap < 2 * (n_search_slots + n_not_slots) + 16) {
+    table_cap <<= 1;
+  }
+  std::vector<uint32_t> table(table_cap, 0);  // term id + 1, 0 = empty
+  terms->reserve(n_search_slots / 2 + n_not_slots + 16);
   // The streaming df pass (df_stream_kernel) counts "documents whose text contains the term". That equals the
   // reference's df (documents of SearchAnd(term n-grams) whose text contains the term) when every document is valid
   // UTF-8 and the query-side windows of a term are windows the index stores for any text containing it, i.e. both
@@ -286,14 +302,22 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
       set_last_error("query term longer than 256 bytes is not supported");
       return MGX_ERR_UNSUPPORTED;
     }
-    std::string s(reinterpret_cast<const char*>(bytes) + b, e - b);
-    auto it = ids.find(s);
-    if (it != ids.end()) {
-      *out = it->second;
-      return MGX_OK;
+    uint64_t h = 0xcbf29ce484222325ULL;  // FNV-1a
+    for (uint64_t i = b; i < e; ++i) {
+      h = (h ^ bytes[i]) * 0x100000001b3ULL;
+    }
+    h ^= h >> 29;
+    size_t slot = static_cast<size_t>(h) & (table_cap - 1);
+    while (table[slot] != 0) {
+      const HostTerm& known = (*terms)[table[slot] - 1];
+      if (known.bytes.size() == e - b && std::memcmp(known.bytes.data(), bytes + b, e - b) == 0) {
+        *out = table[slot] - 1;
+        return MGX_OK;
+      }
+      slot = (slot + 1) & (table_cap - 1);
     }
     HostTerm t;
-    t.bytes = s;
+    t.bytes.assign(reinterpret_cast<const char*>(bytes) + b, e - b);
     host_query_keys(bytes + b, e - b, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0, ix.width, &t.keys,
                     tok_agree ? &t.key_toff : nullptr);
     if (t.keys.size() == 1 && t.keys[0] != kInvalidKey) {
@@ -318,7 +342,7 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
     }
     const uint32_t id = static_cast<uint32_t>(terms->size());
     terms->push_back(std::move(t));
-    ids.emplace(std::move(s), id);
+    table[slot] = id + 1;
     *out = id;
     return MGX_OK;
   };
@@ -608,6 +632,60 @@ int mgx_index_get_stats(const mgx_index_t* index, mgx_index_stats_t* out) {
   return MGX_OK;
 }
 
+int mgx_index_get_statistics(const mgx_index_t* index_c, mgx_index_statistics_t* out) {
+  mgx_index_t* index = const_cast<mgx_index_t*>(index_c);
+  if (index == nullptr || out == nullptr) {
+    return invalid("null argument");
+  }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(index->mu);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    const double thr = ix.cfg.roaring_threshold > 0.0 ? ix.cfg.roaring_threshold : 0.18;
+    const uint64_t roaring = count_roaring_lists(ix, thr, ix.optimized_total_docs, ix.stream);
+    out->total_terms = ix.n_terms;
+    out->total_postings = ix.n_postings;
+    out->roaring_bitmap_lists = roaring;
+    out->delta_encoded_lists = ix.n_terms - roaring;
+    out->memory_usage_bytes = ix.device_bytes();
+    return MGX_OK;
+  });
+}
+
+int mgx_index_optimize(mgx_index_t* index, uint64_t total_docs) {
+  if (index == nullptr) {
+    return invalid("null argument");
+  }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
+  // Index::Optimize re-encodes each list by density (posting_list.cpp:799-834). The device representation (sorted
+  // uint32 + bitmaps chosen at build time for probing speed) does not change; the call records total_docs so that
+  // the representation counters follow the reference's rule. total_docs == 0 is a no-op there too (:801-803).
+  if (total_docs != 0) {
+    std::lock_guard<std::mutex> lock(index->mu);
+    index->ix.optimized_total_docs = total_docs;
+  }
+  return MGX_OK;
+}
+
+int mgx_index_clear(mgx_index_t* index) {
+  if (index == nullptr) {
+    return invalid("null argument");
+  }
+  static const uint64_t kZeroOff[1] = {0};
+  static const uint32_t kNoIds[1] = {0};
+  static const uint8_t kNoText[1] = {0};
+  const int rc = mgx_index_build(index, kNoIds, kNoText, kZeroOff, 0);  // also drops pending mutations
+  if (rc == MGX_OK) {
+    index->ix.optimized_total_docs = 0;
+  }
+  return rc;
+}
+
 int mgx_key_to_utf8(uint64_t key, int32_t width, uint8_t* out) {
   if (out == nullptr || width < 1 || width > kMaxKeyWidth) {
     return invalid("bad width/out");
@@ -722,7 +800,7 @@ enum class SetOp { kAnd, kOr, kNot, kFilter };
 
 // One query whose full ascending result set is wanted (the Index::Search* style calls): upload, plan, run the
 // tiles, gather; then the limit / reverse rules of index.cpp:356-366.
-int run_single_set_query(Index& ix, const std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
+int run_single_set_query(Index& ix, std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
                          const uint32_t* driver_ids, uint64_t n_driver, uint64_t limit, bool reverse, uint32_t* out,
                          uint64_t cap, uint64_t* out_count) {
   Batch b;

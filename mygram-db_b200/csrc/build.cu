@@ -797,6 +797,43 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   cudaEventDestroy(ev1);
 }
 
+// ------------------------------------------------------------------ reference-style representation counters
+namespace {
+__global__ void count_roaring_kernel(const uint64_t* __restrict__ term_off, uint64_t n_terms, double min_density_len,
+                                     unsigned long long* __restrict__ count) {
+  const uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  bool roaring = false;
+  if (t < n_terms) {
+    const uint64_t size = term_off[t + 1] - term_off[t];
+    // > 4096 entries: Roaring since insertion (posting_list.cpp:21,917-922); otherwise only after Optimize, by density
+    roaring = size > 4096 || (min_density_len > 0.0 && static_cast<double>(size) >= min_density_len);
+  }
+  const unsigned n = __popc(__ballot_sync(0xffffffffu, roaring));
+  if ((threadIdx.x & 31u) == 0 && n != 0) {
+    atomicAdd(count, static_cast<unsigned long long>(n));
+  }
+}
+}  // namespace
+
+uint64_t count_roaring_lists(const Index& ix, double roaring_threshold, uint64_t optimized_total_docs,
+                             cudaStream_t stream) {
+  if (ix.n_terms == 0) {
+    return 0;
+  }
+  DevBuf<unsigned long long> d_count;
+  d_count.alloc(1);
+  MGX_CUDA(cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), stream));
+  // density = size / total_docs >= threshold  <=>  size >= threshold * total_docs (both sides exact in double here)
+  const double min_len = optimized_total_docs > 0 ? roaring_threshold * static_cast<double>(optimized_total_docs) : 0.0;
+  count_roaring_kernel<<<static_cast<unsigned>((ix.n_terms + 255) / 256), 256, 0, stream>>>(ix.d_term_off.p, ix.n_terms,
+                                                                                            min_len, d_count.p);
+  MGX_LAUNCH_CHECK();
+  unsigned long long h = 0;
+  MGX_CUDA(cudaMemcpyAsync(&h, d_count.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  MGX_CUDA(cudaStreamSynchronize(stream));
+  return h;
+}
+
 // ------------------------------------------------------------------ incremental mutations (journal -> rebuild)
 // Index::AddDocument / UpdateDocument / RemoveDocument (index.cpp:39-197) are journaled on the host and folded in
 // here before the next read: the resident corpus (doc ids, text) is merged ON THE DEVICE with the journal's

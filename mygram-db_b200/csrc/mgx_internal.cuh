@@ -286,6 +286,7 @@ struct SearchScratch {
   DevBuf<double> rec_score;
   DevBuf<uint32_t> df_tile_term;
   DevBuf<uint32_t> tile_query;
+  DevBuf<uint32_t> topk_groups;  // (query, first tile, end tile) triples of the top-k pre-reduction
   uint64_t map_owner = 0;  // serial of the batch whose tile maps are in df_tile_term / tile_query
 };
 
@@ -336,6 +337,7 @@ struct Index {
   uint64_t n_pair_slots = 0;
   double last_build_ms = 0.0;
 
+  uint64_t optimized_total_docs = 0;  // argument of the last Index::Optimize call, 0 = never optimised
   mgx_batch_stats_t last_stats{};
   cudaStream_t stream = nullptr;  // owned, non-blocking; used by the non-staged calls
   // recycled batch workspaces (device arenas + pinned staging), so a steady stream of batches allocates nothing
@@ -426,6 +428,9 @@ void build_index_device(Index& ix, const uint32_t* doc_ids, const uint8_t* text,
 // replaces / adds the document) into the resident corpus on the device and rebuilds the shard.
 void apply_journal_device(Index& ix, const uint32_t* h_ids, const uint8_t* h_removed, const uint8_t* h_text,
                           const uint64_t* h_off, uint64_t n_j, cudaStream_t stream);
+// Number of posting lists the reference would hold as Roaring bitmaps (see mgx_index_get_statistics).
+uint64_t count_roaring_lists(const Index& ix, double roaring_threshold, uint64_t optimized_total_docs,
+                             cudaStream_t stream);
 // Tokenise only (mgx_tokenize_batch): fills d_keys/d_docs slots (kInvalidKey for non-emitting positions).
 // Tokeniser stage 1: per-document code-point counts (d_doc_len) and n-gram counts -> d_slot_off (exclusive scan,
 // n_docs + 1 entries). counters_out: [0] non-empty docs, [1] docs with invalid bytes, [2] total code points.

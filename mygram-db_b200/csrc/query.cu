@@ -2109,6 +2109,114 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_bas
   }
 }
 
+// Pre-reduction for queries whose driver spans many tiles. One CTA takes a group of consecutive tiles of one query
+// (at most kGroupKeyCap records), keeps the group's kk best records (SortByScore order) and writes them back into
+// the first tile's record slot; the other tiles of the group are emptied. The final topk_kernel then reads
+// groups x kk records instead of tiles x kk, which removes the single-CTA tail of a batch's largest queries.
+// tile_total (the exact survivor counts) is not touched.
+constexpr uint32_t kGroupKeyCap = 3072;
+struct TopkGroup {
+  uint32_t q;
+  uint32_t t_begin;  // tile range inside the query
+  uint32_t t_end;
+};
+
+__global__ void __launch_bounds__(256)
+topk_group_kernel(BatchView bv, const TopkGroup* __restrict__ groups, uint64_t tile_base, uint64_t rec_base,
+                  uint32_t* __restrict__ tile_count, uint32_t* __restrict__ rec_doc, double* __restrict__ rec_score,
+                  int descending, uint32_t kk) {
+  __shared__ uint64_t s_ks[kGroupKeyCap];
+  __shared__ uint32_t s_kd[kGroupKeyCap];
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_n;
+  __shared__ uint32_t s_out;
+  __shared__ SortKey s_prefix;
+  __shared__ uint32_t s_need;
+  const TopkGroup g = groups[blockIdx.x];
+  const uint64_t t0 = bv.q_tile_off[g.q] - tile_base + g.t_begin;
+  const uint64_t r0 = bv.q_rec_off[g.q] - rec_base + static_cast<uint64_t>(g.t_begin) * kTile;
+  const uint32_t ntiles = g.t_end - g.t_begin;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const bool desc = descending != 0;
+  if (threadIdx.x == 0) {
+    s_n = 0;
+    s_out = 0;
+    s_prefix.s = 0;
+    s_prefix.d = 0;
+    s_need = kk;
+  }
+  __syncthreads();
+  for (uint32_t t = warp; t < ntiles; t += 8) {
+    const uint32_t c = tile_count[t0 + t];
+    const uint64_t base = r0 + static_cast<uint64_t>(t) * kTile;
+    uint32_t at = 0;
+    if (lane == 0 && c != 0) {
+      at = atomicAdd(&s_n, c);
+    }
+    at = __shfl_sync(0xffffffffu, at, 0);
+    for (uint32_t i = lane; i < c; i += 32) {
+      if (at + i < kGroupKeyCap) {
+        const SortKey k = make_sort_key(rec_score[base + i], rec_doc[base + i], desc);
+        s_ks[at + i] = k.s;
+        s_kd[at + i] = k.d;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t n = s_n;
+  if (n <= kk || n > kGroupKeyCap) {
+    return;  // nothing to prune (or, never by construction, more records than the staging holds): leave the tiles as is
+  }
+  for (int pass = 0; pass < 12; ++pass) {
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const SortKey prefix = s_prefix;
+    for (uint32_t i = threadIdx.x; i < n; i += 256) {
+      SortKey k;
+      k.s = s_ks[i];
+      k.d = s_kd[i];
+      if (key_has_prefix(k, prefix, pass)) {
+        atomicAdd(&s_hist[key_digit(k, pass)], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t need = s_need;
+      int digit = 255;
+      for (; digit > 0; --digit) {
+        if (s_hist[digit] >= need) {
+          break;
+        }
+        need -= s_hist[digit];
+      }
+      s_need = need;
+      if (pass < 8) {
+        s_prefix.s |= static_cast<uint64_t>(digit) << (56 - 8 * pass);
+      } else {
+        s_prefix.d |= static_cast<uint32_t>(digit) << (24 - 8 * (pass - 8));
+      }
+    }
+    __syncthreads();
+  }
+  const SortKey thr = s_prefix;  // the kk-th best key of the group (keys are unique)
+  // all records of the group are staged: the first tile's slot can be overwritten now
+  for (uint32_t i = threadIdx.x; i < n; i += 256) {
+    SortKey k;
+    k.s = s_ks[i];
+    k.d = s_kd[i];
+    if (!key_greater(thr, k)) {
+      const uint32_t pos = atomicAdd(&s_out, 1u);
+      rec_doc[r0 + pos] = desc ? k.d : ~k.d;
+      rec_score[r0 + pos] = unord_f64(desc ? k.s : ~k.s);
+    }
+  }
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < ntiles; t += 256) {
+    tile_count[t0 + t] = t == 0 ? s_out : 0u;
+  }
+}
+
 // Full ascending sets: out[set_off[q] + rank] for every survivor of query q.
 __global__ void __launch_bounds__(256)
 gather_sets_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_base,
@@ -2618,22 +2726,11 @@ void build_stream_table(std::vector<HostTerm>& terms, HostStreamTable* out) {
   }
 }
 
-void batch_upload(Batch& b, const std::vector<HostTerm>& terms_in, const std::vector<HostQuery>& queries,
+void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
                   const std::vector<uint32_t>& slot_tid) {
   cudaStream_t st = b.stream;
-  std::vector<HostTerm> terms_copy;
   HostStreamTable stream_table;
-  const std::vector<HostTerm>* terms_ptr = &terms_in;
-  bool any_stream = false;
-  for (const HostTerm& t : terms_in) {
-    any_stream = any_stream || t.streamable;
-  }
-  if (any_stream) {
-    terms_copy = terms_in;  // the table builder may clear `streamable` on bucket overflow
-    build_stream_table(terms_copy, &stream_table);
-    terms_ptr = &terms_copy;
-  }
-  const std::vector<HostTerm>& terms = *terms_ptr;
+  build_stream_table(terms, &stream_table);
   b.n_queries = static_cast<uint32_t>(queries.size());
   b.n_terms = static_cast<uint32_t>(terms.size());
   b.n_slots = static_cast<uint32_t>(slot_tid.size());
@@ -3046,6 +3143,30 @@ void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_
     run_tiles(b, c, sp, prune_k);
     driver_entries += b.h_q_rec_off[c.q1] - b.h_q_rec_off[c.q0];
     b.time_begin(3);
+    if (prune_k != 0 && prune_k * 2 <= kGroupKeyCap) {
+      // queries with many tiles: reduce groups of tiles to prune_k records each before the per-query top-k
+      const uint32_t group_tiles = kGroupKeyCap / prune_k;
+      std::vector<TopkGroup> groups;
+      for (uint32_t q = c.q0; q < c.q1; ++q) {
+        const uint32_t ntiles = static_cast<uint32_t>(b.h_q_tile_off[q + 1] - b.h_q_tile_off[q]);
+        if (ntiles >= 2 * group_tiles) {
+          for (uint32_t tb = 0; tb < ntiles; tb += group_tiles) {
+            groups.push_back({q, tb, std::min(ntiles, tb + group_tiles)});
+          }
+        }
+      }
+      if (!groups.empty()) {
+        SearchScratch& sc = *b.sc;
+        sc.topk_groups.reserve(std::max<uint64_t>(groups.size() * 3, 1ULL << 14));
+        MGX_CUDA(cudaMemcpyAsync(sc.topk_groups.p, groups.data(), groups.size() * sizeof(TopkGroup),
+                                 cudaMemcpyHostToDevice, st));
+        b.h2d_bytes += groups.size() * sizeof(TopkGroup);
+        topk_group_kernel<<<static_cast<unsigned>(groups.size()), 256, 0, st>>>(
+            make_batch_view(b), reinterpret_cast<const TopkGroup*>(sc.topk_groups.p), b.h_q_tile_off[c.q0],
+            b.h_q_rec_off[c.q0], b.d_tile_count.p, b.d_rec_doc.p, b.d_rec_score.p, b.params.descending, prune_k);
+        MGX_LAUNCH_CHECK();
+      }
+    }
     topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.h_q_rec_off[c.q0],
                                              b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p, b.d_rec_score.p,
                                              b.params.compute_score, b.params.descending, b.params.limit,

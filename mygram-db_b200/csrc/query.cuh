@@ -237,7 +237,8 @@ struct HostQuery {
 };
 
 // query.cu
-void batch_upload(Batch& b, const std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
+// `terms` is not const: the stream-table builder clears `streamable` of terms that do not fit a bucket.
+void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
                   const std::vector<uint32_t>& slot_tid);
 // Bucket table over the terms with `streamable` set (clears the flag of terms that do not fit a bucket).
 void build_stream_table(std::vector<HostTerm>& terms, HostStreamTable* out);

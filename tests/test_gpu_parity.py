@@ -509,3 +509,32 @@ def test_add_update_remove_document(mgx, oracle, cfg):
         assert gi2.add_document(doc_id, text) == bool(oi2.add_document(doc_id, text))
     assert_same_index(gi2, oi2)
     assert np.array_equal(gi2.search_and([b"bc"]), oi2.search_and([b"bc"]))
+
+
+# ----------------------------------------------------------------------------------------- statistics / optimize / clear
+def test_statistics_optimize_clear(mgx, oracle):
+    """Index::GetStatistics / Optimize / Clear: the reference's representation counters follow its documented rules
+    (posting_list.cpp:21, 799-834, 917-922; tests/index/posting_list_test.cpp:64-118, 677-787): a list is Roaring
+    once it holds more than 4096 entries, or after Optimize(total) when size / total >= roaring_threshold."""
+    c = corpus_mod.generate("cjk", 30000, 9, alphabet=48, min_len=6, max_len=30)
+    gi = mgx.Index(2, 0, True, roaring_threshold=0.18)
+    gi.build(c.doc_ids, c.arena, c.offsets)
+    terms, offs, posts = gi.export()
+    sizes = np.diff(offs.astype(np.int64))
+    st = gi.get_statistics()
+    assert (st.total_terms, st.total_postings) == (len(terms), posts.size)
+    assert st.roaring_bitmap_lists == int((sizes > 4096).sum())
+    assert st.delta_encoded_lists == len(terms) - st.roaring_bitmap_lists
+    assert st.memory_usage_bytes == gi.stats().device_bytes
+    gi.optimize(0)                                   # total_docs == 0 is a no-op (posting_list.cpp:801-803)
+    assert gi.get_statistics().roaring_bitmap_lists == int((sizes > 4096).sum())
+    for total in (30000, 2000):
+        gi.optimize(total)
+        want = int(((sizes > 4096) | (sizes / total >= 0.18)).sum())
+        assert gi.get_statistics().roaring_bitmap_lists == want, total
+    before = gi.search_and([terms[0]])
+    assert before.size == sizes[0]
+    gi.clear()
+    st = gi.get_statistics()
+    assert (st.total_terms, st.total_postings, st.roaring_bitmap_lists) == (0, 0, 0)
+    assert gi.search_and([terms[0]]).size == 0 and gi.term_count() == 0
