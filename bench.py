@@ -239,6 +239,8 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "port", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-threshold", type=float, default=0.0,
+                    help="posting density from which a list also gets a bitmap (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -284,7 +286,7 @@ def main():
     gen_s = time.perf_counter() - t0
 
     # ---- index build: e2e (pinned host -> queryable device index) and device-resident
-    index = mgx.Index(2, 0, True, device=local_rank)
+    index = mgx.Index(2, 0, True, device=local_rank, dense_threshold=args.dense_threshold)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     index.build(c.doc_ids, c.arena, c.offsets)

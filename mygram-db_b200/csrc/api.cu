@@ -178,8 +178,8 @@ bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanj
     }
   }
   if (key_toff != nullptr) {
-    // Byte offset inside the term of every n-gram that occurs exactly ONCE in it (kNoTermOffset otherwise, and for
-    // every n-gram of a term that is not valid UTF-8: its windows skip bytes, so they are no contiguous byte run).
+    // Per n-gram: byte offset of its first occurrence inside the term and how often it occurs there (1, 2, 3+);
+    // kNoTermOffset for every n-gram of a term that is not valid UTF-8 (its windows are no contiguous byte runs).
     occ.resize(keys->size());
     for (size_t i = 0; i < keys->size(); ++i) {
       occ[i] = {(*keys)[i], starts[i]};
@@ -194,7 +194,9 @@ bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanj
       }
       const uint32_t off = cp_byte[occ[i].second];
       keys->push_back(occ[i].first);  // sorted + unique == DeduplicateSorted, string_utils.h:192-196
-      key_toff->push_back(valid && j - i == 1 && off < kNoTermOffset ? static_cast<uint16_t>(off) : kNoTermOffset);
+      const uint32_t cnt = static_cast<uint32_t>(std::min<size_t>(j - i, 3));
+      key_toff->push_back(valid && off <= kTermOffsetMask ? static_cast<uint16_t>(off | (cnt << kTermCountShift))
+                                                          : kNoTermOffset);
       i = j;
     }
     return true;

@@ -748,7 +748,7 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
 
   // ---- dense bitmaps
   ix.bm_words = (n_docs + 31) / 32;
-  const double thr = ix.cfg.dense_threshold > 0.0 ? ix.cfg.dense_threshold : 1.0 / 32.0;
+  const double thr = ix.cfg.dense_threshold > 0.0 ? ix.cfg.dense_threshold : 1.0 / 128.0;
   uint64_t min_len = std::max<uint64_t>(1, static_cast<uint64_t>(thr * static_cast<double>(n_docs)));
   // a bitmap only pays for lists long enough that probing beats searching
   min_len = std::max<uint64_t>(min_len, 1024);

@@ -249,9 +249,12 @@ __host__ __device__ inline int parse_utf8(uint32_t b0, uint32_t b1, uint32_t b2,
 std::vector<uint32_t> host_utf8_to_codepoints(const uint8_t* text, uint64_t len);
 // GenerateQueryNgrams (string_utils.cpp:639-653) + DeduplicateSorted as packed
 // keys. Returns false if a window is wider than kMaxKeyWidth.
-// key_toff (optional): per returned key, the byte offset inside the term of the n-gram when it occurs exactly once
-// in the term, else kNoTermOffset.
+// key_toff (optional): per returned key, (byte offset of the n-gram's FIRST occurrence inside the term) |
+// (min(number of occurrences in the term, 3) << kTermCountShift); kNoTermOffset when the term is not valid UTF-8
+// (its windows skip bytes, so they are no contiguous byte runs).
 constexpr uint16_t kNoTermOffset = 0xFFFF;
+constexpr uint32_t kTermOffsetMask = 0x0FFF;
+constexpr uint32_t kTermCountShift = 12;
 bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanji_ngram_size, bool cross_boundary,
                      int key_width, std::vector<uint64_t>* keys, std::vector<uint16_t>* key_toff = nullptr);
 // One n-gram string -> packed key (for Index::SearchAnd style calls). False if

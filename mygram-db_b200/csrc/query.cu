@@ -663,11 +663,11 @@ __device__ __forceinline__ void load_text_words(const uint8_t* __restrict__ text
   x[2] = __funnelshift_r(a2, a3, sh);
 }
 
-__global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, BatchView bv) {
-  __shared__ uint32_t s_stage[kTileThreads / 32][kWarpStageCap];
+static_assert(kWarpStageCap * sizeof(uint32_t) >= kStageBuf, "the text staging buffer aliases the list staging buffer");
+__global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, BatchView bv) {
+  __shared__ __align__(16) uint32_t s_stage[kTileThreads / 32][kWarpStageCap];
   __shared__ uint32_t s_surv[kTileThreads / 32][kWarpTile];
   __shared__ uint32_t s_spos[kTileThreads / 32][kWarpTile];
-  __shared__ __align__(16) uint8_t s_text[kTileThreads / 32][kStageBuf];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   const uint32_t t = __ldg(bv.df_tile_term + blockIdx.x);
@@ -773,10 +773,16 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
   uint32_t hits = 0;
   unsigned long long text_bytes = 0;
 
-  // ---- pass 1, one lane per candidate: when the driver n-gram occurs exactly once in the document (and once in the
-  // term, at byte offset toff), the term can only sit at (position - toff): one comparison instead of a scan. The
-  // other candidates are compacted to the front of the list for the scanning pass.
-  const uint32_t toff = bv.key_toff[k0];
+  // ---- pass 1, one lane per candidate. The driver n-gram occurs m times in the term (first at byte offset o1) and
+  // c times in the document (positions recorded for c <= 2). An occurrence of the term puts m occurrences of the
+  // n-gram into the document, the first of them at (term start + o1): so m > c rules the document out, and for
+  // c <= 2 the term can only start at (p_a - o1) for a recorded position p_a -- one or two comparisons instead of a
+  // scan. Documents with three or more occurrences (or no recorded position) are compacted to the front of the
+  // list for the scanning pass.
+  const uint32_t toff_raw = bv.key_toff[k0];
+  const bool toff_ok = toff_raw != kNoTermOffset;
+  const uint32_t o1 = toff_raw & kTermOffsetMask;
+  const uint32_t m_term = toff_raw >> kTermCountShift;  // 1, 2, or 3 = "three or more"
   uint32_t n_scan = 0;
   for (uint32_t s0 = 0; s0 < n; s0 += 32) {
     const uint32_t s = s0 + lane;
@@ -790,16 +796,16 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
       text_bytes += len;
       const uint32_t p1 = pp & 0xFFFFu;
       const uint32_t p2 = pp >> 16;
-      const bool two = (p1 & kPosMulti) != 0;  // exactly two recorded occurrences are checked one after the other
-      if (toff == kNoTermOffset || (p1 & kPosUnknown) == kPosUnknown ||
-          (two && ((p2 & kPosMulti) != 0 || (p2 & kPosUnknown) == kPosUnknown))) {
+      const bool two = (p1 & kPosMulti) != 0;
+      const uint32_t c_doc = !two ? 1u : ((p2 & kPosMulti) == 0 ? 2u : 3u);
+      if (!toff_ok || c_doc == 3 || (p1 & kPosUnknown) == kPosUnknown || (two && (p2 & kPosUnknown) == kPosUnknown)) {
         scan = true;
-      } else if (tl != 0) {
+      } else if (tl != 0 && m_term <= c_doc) {
         bool found = false;
-        for (int occ = 0; occ < (two ? 2 : 1) && !found; ++occ) {
+        for (uint32_t occ = 0; occ < c_doc && !found; ++occ) {
           const uint32_t at = (occ == 0 ? p1 : p2) & kPosUnknown;
-          if (at >= toff && at - toff + tl <= len) {
-            const uint64_t start = b + (at - toff);
+          if (at >= o1 && at - o1 + tl <= len) {
+            const uint64_t start = b + (at - o1);
             uint32_t x[3];
             load_text_words(iv.text, start, x);
             bool ok = ((x[0] ^ tregs.w[0]) & tregs.m[0]) == 0;
@@ -853,7 +859,8 @@ __global__ void __launch_bounds__(kTileThreads) df_tile_kernel(IndexView iv, Bat
     while (slow_mask != 0) {
       const uint32_t src = static_cast<uint32_t>(__ffs(static_cast<int>(slow_mask))) - 1u;
       slow_mask &= slow_mask - 1;
-      DocText d = doc_open(iv, s_surv[warp][s0 + src / kGroup], s_text[warp]);
+      // the warp's list staging buffer is free after the membership phase: it stages the text now
+      DocText d = doc_open(iv, s_surv[warp][s0 + src / kGroup], reinterpret_cast<uint8_t*>(s_stage[warp]));
       const uint32_t c = doc_count_term(d, term, tl, true);
       __syncwarp();
       if (lane == src) {
