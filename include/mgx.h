@@ -235,6 +235,46 @@ int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64
                     uint64_t stride, uint32_t* out_ids, double* out_scores, uint32_t* out_count, uint64_t* out_total,
                     uint64_t* out_df);
 
+/* ----------------------------------------------- column filters + boolean programs in a batch */
+
+/* Device mirror of one DocumentStore filter column (storage/document_store.h:73-92, filter_index.h:38-123):
+ * `type` is the FilterValue variant index (1 bool, 2 int8, 3 uint8, 4 int16, 5 uint16, 6 int32, 7 uint32, 8 int64,
+ * 9 uint64, 10 TIME seconds, 11 string, 12 double); values[i] belongs to the i-th document of the last build
+ * (integer / bool / seconds value, the bits of the double, or for strings an index into the string table
+ * str_bytes / str_offsets[n_strings + 1]); nulls[i] != 0 marks NULL (may be NULL = no NULLs). `column` is a
+ * caller-chosen id < 64 (the host keeps DocumentStore::ResolveFilterColumnName). Columns are dropped by any
+ * rebuild of the shard (bulk build, committed mutations) and have to be set again. */
+int mgx_index_set_filter_column(mgx_index_t* index, uint32_t column, int32_t type, const uint64_t* values,
+                                const uint8_t* nulls, uint64_t n_docs, const uint8_t* str_bytes,
+                                const uint64_t* str_offsets, uint64_t n_strings);
+
+/* Optional per-query extensions of mgx_query_batch:
+ *  - boolean programs (QueryNode::Evaluate, query_ast.cpp:67-161): when q_prog_begin[q+1] > q_prog_begin[q] the
+ *    query's terms [q_term_begin[q], q_term_begin[q+1]) are the TERM operands of the postfix program
+ *    ops/args[q_prog_begin[q] ..) (TERM arg = index inside the query's own term range) instead of being AND-ed;
+ *    such batches need compute_score == 0;
+ *  - filter conditions (ApplyFiltersWithBitmap / ApplyFilters, search_pipeline.cpp:1098-1237): query q keeps a
+ *    document only if it passes filters [q_filter_begin[q], q_filter_begin[q+1]): column id, op (query_parser.h:
+ *    93-100: 0 EQ, 1 NE, 2 GT, 3 GTE, 4 LT, 5 LTE) and the literal as written in the query. As in the reference,
+ *    a query whose conditions are all EQ / NE follows the FilterIndex bitmap semantics (exact match with any type
+ *    interpretation of the literal), any other mix the typed per-document comparison. */
+typedef struct {
+  const int32_t* prog_ops;
+  const int32_t* prog_args;
+  const uint64_t* q_prog_begin;    /* [n_queries + 1] or NULL */
+  const uint32_t* filter_col;
+  const uint8_t* filter_op;
+  const uint8_t* filter_bytes;
+  const uint64_t* filter_offsets;  /* [n_filters + 1] */
+  const uint64_t* q_filter_begin;  /* [n_queries + 1] or NULL */
+} mgx_query_ext_t;
+
+int mgx_query_batch_ex(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                       const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                       const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                       const mgx_query_ext_t* ext, uint64_t stride, uint32_t* out_ids, double* out_scores,
+                       uint32_t* out_count, uint64_t* out_total, uint64_t* out_df);
+
 /* Timing / accounting of one batch (device times from CUDA events recorded on the launch
  * stream around the named kernels; bytes as defined in SURVEY.md §8(d) and DESIGN.md). */
 typedef struct {

@@ -61,6 +61,12 @@ class IndexStatistics(C.Structure):
                 ("roaring_bitmap_lists", C.c_uint64), ("memory_usage_bytes", C.c_uint64)]
 
 
+class QueryExt(C.Structure):
+    _fields_ = [("prog_ops", C.POINTER(C.c_int32)), ("prog_args", C.POINTER(C.c_int32)), ("q_prog_begin", u64p),
+                ("filter_col", u32p), ("filter_op", u8p), ("filter_bytes", u8p), ("filter_offsets", u64p),
+                ("q_filter_begin", u64p)]
+
+
 class QueryParams(C.Structure):
     _fields_ = [("ngram_size", C.c_int32), ("kanji_ngram_size", C.c_int32), ("cross_boundary", C.c_int32),
                 ("compute_score", C.c_int32), ("descending", C.c_int32), ("limit", C.c_uint32), ("offset", C.c_uint32),
@@ -128,6 +134,10 @@ def lib():
     L.mgx_search_by_threshold.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint64, u32p, C.c_uint64, u64p]
     L.mgx_eval_boolean.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_uint64, u8p, u64p,
                                    C.c_uint64, u32p, C.c_uint64, u64p]
+    L.mgx_index_set_filter_column.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, u64p, u8p, C.c_uint64, u8p, u64p,
+                                              C.c_uint64]
+    L.mgx_query_batch_ex.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
+                                     C.POINTER(QueryExt), C.c_uint64, u32p, f64p, u32p, u64p, u64p]
     L.mgx_query_batch.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
                                   C.c_uint64, u32p, f64p, u32p, u64p, u64p]
     L.mgx_batch_prepare.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
@@ -414,18 +424,75 @@ class Index:
                            int(self.cross_boundary_ngrams), int(score), int(descending), limit, offset, verify_text,
                            k1, b, total_docs, total_doc_length)
 
-    def query_batch(self, queries, not_terms=None, stride=None, **kw):
-        """Batch of SEARCH queries (regular path of ExecuteFullPipeline + ScoreDocuments + SortByScore)."""
+    def set_filter_column(self, column, type_code, values):
+        """Device mirror of one DocumentStore filter column. type_code = FilterValue variant index (1 bool, 2 int8,
+        ... 8 int64, 9 uint64, 10 TIME, 11 string, 12 double); values: one python value per document of the index,
+        None = NULL."""
+        n = len(values)
+        vals = np.zeros(max(1, n), dtype=np.uint64)
+        nulls = np.zeros(max(1, n), dtype=np.uint8)
+        strings = []
+        for i, v in enumerate(values):
+            if v is None:
+                nulls[i] = 1
+            elif type_code == 11:
+                vals[i] = len(strings)
+                strings.append(_bytes(v))
+            elif type_code == 12:
+                vals[i] = np.float64(v).view(np.uint64)
+            else:
+                vals[i] = np.int64(int(v)).view(np.uint64) if int(v) < 0 else np.uint64(int(v))
+        sb, so = pack_strings(strings if strings else [b""])
+        _check(lib().mgx_index_set_filter_column(self._h, column, type_code, _ptr(vals, u64p), _ptr(nulls, u8p), n,
+                                                 _ptr(sb, u8p), _ptr(so, u64p), len(strings)))
+
+    def query_batch(self, queries, not_terms=None, stride=None, programs=None, filters=None, **kw):
+        """Batch of SEARCH queries (regular path of ExecuteFullPipeline + ScoreDocuments + SortByScore).
+        programs: per query None or (ops, args) — a boolean postfix program over the query's own terms;
+        filters: per query a list of (column id, op 0..5, literal)."""
         p = self.params(**kw)
         arena, offsets, qbeg, n_slots = flatten_queries(queries)
         if not_terms is not None:
             narena, noffsets, nbeg, _ = flatten_queries(not_terms)
         else:
             narena = noffsets = nbeg = None
-        return self.query_batch_flat(p, len(queries), arena, offsets, qbeg, narena, noffsets, nbeg, n_slots, stride)
+        ext = None
+        keep = []
+        if programs is not None or filters is not None:
+            ext = QueryExt()
+            i32p = C.POINTER(C.c_int32)
+            if programs is not None:
+                ops, args, pbeg = [], [], [0]
+                for pr in programs:
+                    if pr is not None:
+                        ops += list(pr[0])
+                        args += list(pr[1])
+                    pbeg.append(len(ops))
+                o = np.asarray(ops if ops else [0], dtype=np.int32)
+                a = np.asarray(args if args else [0], dtype=np.int32)
+                pb = np.asarray(pbeg, dtype=np.uint64)
+                keep += [o, a, pb]
+                ext.prog_ops, ext.prog_args, ext.q_prog_begin = o.ctypes.data_as(i32p), a.ctypes.data_as(i32p), _ptr(pb, u64p)
+            if filters is not None:
+                cols, fops, lits, fbeg = [], [], [], [0]
+                for fl in filters:
+                    for (c, op, lit) in (fl or []):
+                        cols.append(c)
+                        fops.append(op)
+                        lits.append(_bytes(lit))
+                    fbeg.append(len(cols))
+                fc = np.asarray(cols if cols else [0], dtype=np.uint32)
+                fo = np.asarray(fops if fops else [0], dtype=np.uint8)
+                lb, lo = pack_strings(lits if lits else [b""])
+                fb = np.asarray(fbeg, dtype=np.uint64)
+                keep += [fc, fo, lb, lo, fb]
+                ext.filter_col, ext.filter_op = _ptr(fc, u32p), _ptr(fo, u8p)
+                ext.filter_bytes, ext.filter_offsets, ext.q_filter_begin = _ptr(lb, u8p), _ptr(lo, u64p), _ptr(fb, u64p)
+        return self.query_batch_flat(p, len(queries), arena, offsets, qbeg, narena, noffsets, nbeg, n_slots, stride,
+                                     ext=ext)
 
     def query_batch_flat(self, p, n_queries, arena, offsets, qbeg, narena=None, noffsets=None, nbeg=None,
-                         n_slots=None, stride=None, out=None):
+                         n_slots=None, stride=None, out=None, ext=None):
         stride = stride or max(1, p.limit)
         if n_slots is None:
             n_slots = int(qbeg[-1])
@@ -433,10 +500,11 @@ class Index:
             out = BatchResult(np.zeros((n_queries, stride), dtype=np.uint32),
                               np.zeros((n_queries, stride), dtype=np.float64), np.zeros(n_queries, dtype=np.uint32),
                               np.zeros(n_queries, dtype=np.uint64), np.zeros(max(1, n_slots), dtype=np.uint64))
-        _check(lib().mgx_query_batch(self._h, C.byref(p), n_queries, _ptr(arena, u8p), _ptr(offsets, u64p),
-                                     _ptr(qbeg, u64p), _ptr(narena, u8p), _ptr(noffsets, u64p), _ptr(nbeg, u64p),
-                                     stride, _ptr(out.ids, u32p), _ptr(out.scores, f64p), _ptr(out.count, u32p),
-                                     _ptr(out.total, u64p), _ptr(out.df, u64p)))
+        _check(lib().mgx_query_batch_ex(self._h, C.byref(p), n_queries, _ptr(arena, u8p), _ptr(offsets, u64p),
+                                        _ptr(qbeg, u64p), _ptr(narena, u8p), _ptr(noffsets, u64p), _ptr(nbeg, u64p),
+                                        C.byref(ext) if ext is not None else None, stride, _ptr(out.ids, u32p),
+                                        _ptr(out.scores, f64p), _ptr(out.count, u32p), _ptr(out.total, u64p),
+                                        _ptr(out.df, u64p)))
         out.df = out.df[:n_slots]
         return out
 

@@ -275,10 +275,67 @@ struct DeviceGuard {
 };
 
 // Compile the caller's flat query description into unique terms + queries.
+// Validates a postfix program and collects the terms every result must satisfy (the operands of the root when it is
+// a TERM, or the TERM operands of a root AND, recursively through nested ANDs).
+int analyse_program(const int32_t* ops, const int32_t* args, uint64_t n_ops, uint64_t n_terms,
+                    std::vector<uint32_t>* conjuncts) {
+  struct Node {
+    int op;
+    int32_t arg;
+    std::vector<size_t> kids;
+  };
+  std::vector<Node> nodes;
+  std::vector<size_t> stack;
+  size_t depth_max = 0;
+  for (uint64_t i = 0; i < n_ops; ++i) {
+    Node nd{ops[i], args[i], {}};
+    if (ops[i] == kOpTerm) {
+      if (args[i] < 0 || static_cast<uint64_t>(args[i]) >= n_terms) {
+        return invalid("boolean program: TERM index out of range");
+      }
+    } else if (ops[i] == kOpAnd || ops[i] == kOpOr) {
+      if (args[i] < 0 || static_cast<size_t>(args[i]) > stack.size()) {
+        return invalid("boolean program: operator has more children than the stack holds");
+      }
+      nd.kids.assign(stack.end() - args[i], stack.end());
+      stack.resize(stack.size() - static_cast<size_t>(args[i]));
+    } else if (ops[i] == kOpNot) {
+      if (stack.empty()) {
+        return invalid("boolean program: NOT without an operand");
+      }
+      nd.kids.push_back(stack.back());
+      stack.pop_back();
+    } else {
+      return invalid("boolean program: unknown op");
+    }
+    nodes.push_back(std::move(nd));
+    stack.push_back(nodes.size() - 1);
+    depth_max = std::max(depth_max, stack.size());
+  }
+  if (depth_max > kMaxProgramDepth) {
+    set_last_error("boolean program deeper than 64 operands");
+    return MGX_ERR_UNSUPPORTED;
+  }
+  if (stack.empty()) {
+    return MGX_OK;
+  }
+  std::vector<size_t> todo{stack.back()};  // the value of the program is the top of the stack
+  while (!todo.empty()) {
+    const Node& nd = nodes[todo.back()];
+    todo.pop_back();
+    if (nd.op == kOpTerm) {
+      conjuncts->push_back(static_cast<uint32_t>(nd.arg));
+    } else if (nd.op == kOpAnd) {
+      todo.insert(todo.end(), nd.kids.begin(), nd.kids.end());
+    }
+  }
+  return MGX_OK;
+}
+
 int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queries, const uint8_t* term_bytes,
                   const uint64_t* term_offsets, const uint64_t* q_term_begin, const uint8_t* not_bytes,
-                  const uint64_t* not_offsets, const uint64_t* q_not_begin, std::vector<HostTerm>* terms,
-                  std::vector<HostQuery>* queries, std::vector<uint32_t>* slot_tid) {
+                  const uint64_t* not_offsets, const uint64_t* q_not_begin, const mgx_query_ext_t* ext,
+                  std::vector<HostTerm>* terms, std::vector<HostQuery>* queries, std::vector<uint32_t>* slot_tid) {
   // open-addressing table of term ids keyed by the term bytes (no string is built for a lookup)
   const uint64_t n_search_slots = n_queries > 0 ? q_term_begin[n_queries] : 0;
   const uint64_t n_not_slots = (n_queries > 0 && q_not_begin != nullptr) ? q_not_begin[n_queries] : 0;
@@ -389,6 +446,44 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
     // ShouldApplyVerifyText (search_pipeline.cpp:48-66) and the hybrid-fragment rule (:858-866)
     const bool verify = p.verify_text == 1 || (p.verify_text == 2 && all_ascii) || hybrid_exact;
     hq.flags = verify ? kQVerify : 0u;
+    if (ext != nullptr && ext->q_prog_begin != nullptr && ext->q_prog_begin[q + 1] > ext->q_prog_begin[q]) {
+      // boolean program over the query's own terms (QueryNode::Evaluate): TERM args are local term indices
+      if (p.compute_score != 0) {
+        set_last_error("boolean programs in a batch need compute_score == 0");
+        return MGX_ERR_UNSUPPORTED;
+      }
+      const uint64_t p0 = ext->q_prog_begin[q];
+      const uint64_t pn = ext->q_prog_begin[q + 1] - p0;
+      std::vector<uint32_t> local_conj;
+      if (int rc = analyse_program(ext->prog_ops + p0, ext->prog_args + p0, pn, hq.terms.size(), &local_conj);
+          rc != MGX_OK) {
+        return rc;
+      }
+      for (uint32_t c : local_conj) {
+        hq.conjuncts.push_back(hq.terms[c]);
+      }
+      for (uint64_t i = 0; i < pn; ++i) {
+        const int32_t op = ext->prog_ops[p0 + i];
+        hq.prog_ops.push_back(static_cast<uint8_t>(op));
+        hq.prog_args.push_back(op == kOpTerm ? hq.terms[static_cast<size_t>(ext->prog_args[p0 + i])]
+                                             : static_cast<uint32_t>(ext->prog_args[p0 + i]));
+      }
+      hq.terms.clear();  // operands of the program, not AND-ed search terms
+      hq.flags = kQProgram;
+    }
+    if (ext != nullptr && ext->q_filter_begin != nullptr) {
+      for (uint64_t f = ext->q_filter_begin[q]; f < ext->q_filter_begin[q + 1]; ++f) {
+        HostFilter hf;
+        hf.col = ext->filter_col[f];
+        hf.op = ext->filter_op[f];
+        if (hf.op > 5) {
+          return invalid("filter op must be 0..5 (EQ, NE, GT, GTE, LT, LTE)");
+        }
+        hf.literal.assign(reinterpret_cast<const char*>(ext->filter_bytes) + ext->filter_offsets[f],
+                          ext->filter_offsets[f + 1] - ext->filter_offsets[f]);
+        hq.filters.push_back(std::move(hf));
+      }
+    }
   }
   return MGX_OK;
 }
@@ -632,6 +727,82 @@ int mgx_index_get_stats(const mgx_index_t* index, mgx_index_stats_t* out) {
   out->key_width = ix.width;
   out->last_build_ms = ix.last_build_ms;
   return MGX_OK;
+}
+
+int mgx_index_set_filter_column(mgx_index_t* index, uint32_t column, int32_t type, const uint64_t* values,
+                                const uint8_t* nulls, uint64_t n_docs, const uint8_t* str_bytes,
+                                const uint64_t* str_offsets, uint64_t n_strings) {
+  if (index == nullptr || (n_docs > 0 && values == nullptr)) {
+    return invalid("null argument");
+  }
+  if (column >= kMaxFilterColumns) {
+    return invalid("filter column id must be < 64");
+  }
+  FilterClass cls = kFcNone;
+  switch (type) {
+    case 1: cls = kFcBool; break;
+    case 2: case 4: case 6: case 8: case 10: cls = kFcSigned; break;   // int8..int64, TIME seconds
+    case 3: case 5: case 7: case 9: cls = kFcUnsigned; break;
+    case 11: cls = kFcString; break;
+    case 12: cls = kFcDouble; break;
+    default: return invalid("filter column type must be a FilterValue variant index 1..12");
+  }
+  if (cls == kFcString && n_docs > 0 && (str_bytes == nullptr || str_offsets == nullptr)) {
+    return invalid("string column without a string table");
+  }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(index->mu);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    if (n_docs != ix.n_docs) {
+      return invalid("a filter column needs one value per document of the index");
+    }
+    auto col = std::make_unique<FilterColumn>();
+    col->cls = cls;
+    col->n_docs = n_docs;
+    std::vector<uint64_t> ranks;
+    const uint64_t* src = values;
+    if (cls == kFcString) {
+      // dictionary-encode: the rank among the distinct strings keeps std::string's order (bytewise)
+      std::vector<std::string> strs(n_strings);
+      for (uint64_t i = 0; i < n_strings; ++i) {
+        strs[i].assign(reinterpret_cast<const char*>(str_bytes) + str_offsets[i], str_offsets[i + 1] - str_offsets[i]);
+      }
+      col->dict = strs;
+      std::sort(col->dict.begin(), col->dict.end());
+      col->dict.erase(std::unique(col->dict.begin(), col->dict.end()), col->dict.end());
+      std::vector<uint64_t> rank_of(n_strings);
+      for (uint64_t i = 0; i < n_strings; ++i) {
+        rank_of[i] = static_cast<uint64_t>(std::lower_bound(col->dict.begin(), col->dict.end(), strs[i]) - col->dict.begin());
+      }
+      ranks.resize(n_docs);
+      for (uint64_t i = 0; i < n_docs; ++i) {
+        const bool is_null = nulls != nullptr && nulls[i] != 0;
+        if (!is_null && values[i] >= n_strings) {
+          return invalid("string column: value index outside the string table");
+        }
+        ranks[i] = is_null ? 0 : rank_of[values[i]];
+      }
+      src = ranks.data();
+    }
+    col->values.alloc(n_docs);
+    col->nulls.alloc(n_docs);
+    if (n_docs > 0) {
+      MGX_CUDA(cudaMemcpyAsync(col->values.p, src, n_docs * sizeof(uint64_t), cudaMemcpyHostToDevice, ix.stream));
+      if (nulls != nullptr) {
+        MGX_CUDA(cudaMemcpyAsync(col->nulls.p, nulls, n_docs, cudaMemcpyHostToDevice, ix.stream));
+      } else {
+        MGX_CUDA(cudaMemsetAsync(col->nulls.p, 0, n_docs, ix.stream));
+      }
+      MGX_CUDA(cudaStreamSynchronize(ix.stream));
+    }
+    delete ix.columns[column];
+    ix.columns[column] = col.release();
+    return MGX_OK;
+  });
 }
 
 int mgx_index_get_statistics(const mgx_index_t* index_c, mgx_index_statistics_t* out) {
@@ -1018,65 +1189,6 @@ int mgx_search_by_threshold(const mgx_index_t* index_c, const uint8_t* term_byte
   });
 }
 
-namespace {
-// Validates a postfix program and collects the terms every result must satisfy (the operands of the root when it is
-// a TERM, or the TERM operands of a root AND, recursively through nested ANDs).
-int analyse_program(const int32_t* ops, const int32_t* args, uint64_t n_ops, uint64_t n_terms,
-                    std::vector<uint32_t>* conjuncts) {
-  struct Node {
-    int op;
-    int32_t arg;
-    std::vector<size_t> kids;
-  };
-  std::vector<Node> nodes;
-  std::vector<size_t> stack;
-  size_t depth_max = 0;
-  for (uint64_t i = 0; i < n_ops; ++i) {
-    Node nd{ops[i], args[i], {}};
-    if (ops[i] == kOpTerm) {
-      if (args[i] < 0 || static_cast<uint64_t>(args[i]) >= n_terms) {
-        return invalid("boolean program: TERM index out of range");
-      }
-    } else if (ops[i] == kOpAnd || ops[i] == kOpOr) {
-      if (args[i] < 0 || static_cast<size_t>(args[i]) > stack.size()) {
-        return invalid("boolean program: operator has more children than the stack holds");
-      }
-      nd.kids.assign(stack.end() - args[i], stack.end());
-      stack.resize(stack.size() - static_cast<size_t>(args[i]));
-    } else if (ops[i] == kOpNot) {
-      if (stack.empty()) {
-        return invalid("boolean program: NOT without an operand");
-      }
-      nd.kids.push_back(stack.back());
-      stack.pop_back();
-    } else {
-      return invalid("boolean program: unknown op");
-    }
-    nodes.push_back(std::move(nd));
-    stack.push_back(nodes.size() - 1);
-    depth_max = std::max(depth_max, stack.size());
-  }
-  if (depth_max > kMaxProgramDepth) {
-    set_last_error("boolean program deeper than 64 operands");
-    return MGX_ERR_UNSUPPORTED;
-  }
-  if (stack.empty()) {
-    return MGX_OK;
-  }
-  std::vector<size_t> todo{stack.back()};  // the value of the program is the top of the stack
-  while (!todo.empty()) {
-    const Node& nd = nodes[todo.back()];
-    todo.pop_back();
-    if (nd.op == kOpTerm) {
-      conjuncts->push_back(static_cast<uint32_t>(nd.arg));
-    } else if (nd.op == kOpAnd) {
-      todo.insert(todo.end(), nd.kids.begin(), nd.kids.end());
-    }
-  }
-  return MGX_OK;
-}
-}  // namespace
-
 int mgx_eval_boolean(const mgx_index_t* index_c, const int32_t* ops, const int32_t* args, uint64_t n_ops,
                      const uint8_t* term_bytes, const uint64_t* term_offsets, uint64_t n_terms, uint32_t* out,
                      uint64_t cap, uint64_t* out_count) {
@@ -1225,10 +1337,23 @@ int mgx_index_doc_lengths(const mgx_index_t* index, uint32_t* out) {
 }
 
 // ---------------------------------------------------------------- batched pipeline
+static int batch_prepare_ex(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                            const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                            const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                            const mgx_query_ext_t* ext, void* stream, mgx_batch_t** out);
+
 int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
                       const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
                       const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
                       void* stream, mgx_batch_t** out) {
+  return batch_prepare_ex(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
+                          q_not_begin, nullptr, stream, out);
+}
+
+static int batch_prepare_ex(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                            const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                            const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                            const mgx_query_ext_t* ext, void* stream, mgx_batch_t** out) {
   if (index == nullptr || params == nullptr || out == nullptr ||
       (n_queries > 0 && (term_offsets == nullptr || q_term_begin == nullptr))) {
     return invalid("null argument");
@@ -1270,7 +1395,7 @@ int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint
     const auto t0 = std::chrono::steady_clock::now();
     const int rc = compile_batch(ix, *params, n_queries, term_bytes != nullptr ? term_bytes : kEmpty, term_offsets,
                                  q_term_begin, not_bytes != nullptr ? not_bytes : kEmpty, not_offsets, q_not_begin,
-                                 &terms, &queries, &slot_tid);
+                                 ext, &terms, &queries, &slot_tid);
     if (rc != MGX_OK) {
       return rc;
     }
@@ -1403,6 +1528,15 @@ int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64
                     const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
                     uint64_t stride, uint32_t* out_ids, double* out_scores, uint32_t* out_count, uint64_t* out_total,
                     uint64_t* out_df) {
+  return mgx_query_batch_ex(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
+                            q_not_begin, nullptr, stride, out_ids, out_scores, out_count, out_total, out_df);
+}
+
+int mgx_query_batch_ex(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                       const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                       const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                       const mgx_query_ext_t* ext, uint64_t stride, uint32_t* out_ids, double* out_scores,
+                       uint32_t* out_count, uint64_t* out_total, uint64_t* out_df) {
   if (index == nullptr || params == nullptr || out_ids == nullptr || out_count == nullptr || out_total == nullptr) {
     return invalid("null argument");
   }
@@ -1417,8 +1551,8 @@ int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64
   }
   std::lock_guard<std::mutex> lock(index->mu);
   mgx_batch_t* batch = nullptr;
-  int rc = mgx_batch_prepare(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
-                             q_not_begin, index->ix.stream, &batch);
+  int rc = batch_prepare_ex(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
+                            q_not_begin, ext, index->ix.stream, &batch);
   if (rc != MGX_OK) {
     return rc;
   }

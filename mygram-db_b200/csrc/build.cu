@@ -506,6 +506,14 @@ Index::~Index() {
   for (SearchScratch* s : scratches) {
     delete s;
   }
+  drop_filter_columns();
+}
+
+void Index::drop_filter_columns() {
+  for (FilterColumn*& c : columns) {
+    delete c;
+    c = nullptr;
+  }
 }
 
 uint64_t Index::device_bytes() const { return resident_a.blob.bytes() + resident_b.blob.bytes() + d_bitmaps.bytes(); }
@@ -613,6 +621,7 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   // The text arena is padded so 16-byte tile loads never leave the allocation.
   ix.n_docs = n_docs;
   ix.text_bytes = text_bytes;
+  ix.drop_filter_columns();  // rows of the old corpus
   ix.d_doc_ids.release();
   ix.d_text.release();
   ix.d_text_off.release();

@@ -293,6 +293,17 @@ struct SearchScratch {
   uint64_t map_owner = 0;  // serial of the batch whose tile maps are in df_tile_term / tile_query
 };
 
+// One DocumentStore filter column mirrored on the device (see mgx_index_set_filter_column).
+constexpr uint32_t kMaxFilterColumns = 64;
+enum FilterClass : uint32_t { kFcNone = 0, kFcBool = 1, kFcSigned = 2, kFcUnsigned = 3, kFcString = 4, kFcDouble = 5 };
+struct FilterColumn {
+  FilterClass cls = kFcNone;
+  uint64_t n_docs = 0;
+  DevBuf<uint64_t> values;           // integer / bool value, double bits, or the rank of the string in `dict`
+  DevBuf<uint8_t> nulls;
+  std::vector<std::string> dict;     // sorted distinct strings (string columns)
+};
+
 // ---------------------------------------------------------------- index object
 struct Index {
   mgx_index_config_t cfg{};
@@ -340,6 +351,8 @@ struct Index {
   uint64_t n_pair_slots = 0;
   double last_build_ms = 0.0;
 
+  std::vector<FilterColumn*> columns = std::vector<FilterColumn*>(kMaxFilterColumns, nullptr);
+  void drop_filter_columns();
   uint64_t optimized_total_docs = 0;  // argument of the last Index::Optimize call, 0 = never optimised
   mgx_batch_stats_t last_stats{};
   cudaStream_t stream = nullptr;  // owned, non-blocking; used by the non-staged calls

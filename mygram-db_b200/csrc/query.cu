@@ -25,6 +25,7 @@
 // The driver formulation reads each query's smallest list once and probes the
 // rest, so the bytes moved are <= the SURVEY §8(d) algorithmic bytes.
 #include <algorithm>
+#include <charconv>
 #include <cstdlib>
 #include <cstring>
 
@@ -64,6 +65,8 @@ struct BatchView {
   const uint32_t* prog_arg;
   const uint32_t* q_coff;
   const uint32_t* q_conj;
+  const uint32_t* q_foff;
+  const FilterPred* filters;
   uint32_t* q_driver_len;
   uint32_t* q_ntiles;
   const uint64_t* q_tile_off;
@@ -1497,6 +1500,67 @@ __device__ void bitonic_sort_desc(SortKey* keys, uint32_t n_pow2) {
 
 constexpr int kMaxCachedLists = 24;
 
+// One column condition for one document: ApplyFiltersWithBitmap / ApplyFilters, search_pipeline.cpp:1098-1237.
+__device__ __forceinline__ bool filter_pass(const FilterPred& f, uint32_t doc) {
+  const uint32_t op = f.op_flags & 7u;
+  if (f.cls == kFcNone) {
+    return op == 1;  // no such column: no bitmap / no stored value -> only != holds
+  }
+  const bool is_null = f.nulls != nullptr && f.nulls[doc] != 0;
+  const uint64_t v = f.values[doc];
+  const bool valid = (f.op_flags & kFilterValid) != 0;
+  if ((f.op_flags & kFilterBitmapMode) != 0) {
+    // FilterIndex semantics: the value's serialisation equals that of a type interpretation of the literal
+    // (BuildTypeUnionBitmap :1021-1094); NULLs are not indexed, so != keeps them (:1223-1229)
+    const bool eq = !is_null && valid && (f.cls == kFcBool ? ((v != 0) == (f.c != 0)) : v == f.c);
+    return op == 0 ? eq : !eq;
+  }
+  if (is_null) {
+    return op == 1;  // :1126-1132
+  }
+  bool lt, eq, gt;
+  if (f.cls == kFcString) {  // c = rank of the literal among the column's distinct strings (lower bound)
+    const bool found = (f.op_flags & kFilterFound) != 0;
+    lt = v < f.c;
+    eq = found && v == f.c;
+    gt = found ? v > f.c : v >= f.c;
+  } else if (f.cls == kFcBool) {
+    const bool a = v != 0, c = f.c != 0;
+    lt = !a && c;
+    eq = a == c;
+    gt = a && !c;
+  } else if (!valid) {
+    return false;  // "Invalid number" :1151-1171
+  } else if (f.cls == kFcDouble) {
+    const double a = __longlong_as_double(static_cast<long long>(v));
+    const double c = __longlong_as_double(static_cast<long long>(f.c));
+    if (op <= 1) {  // CompareDoubleValues with kFilterValueEpsilon = 1e-9 (comparison_utils.h:56-61)
+      const bool close = fabs(__dsub_rn(a, c)) < 1e-9;
+      return op == 0 ? close : !close;
+    }
+    lt = a < c;
+    eq = a == c;
+    gt = a > c;
+  } else if (f.cls == kFcUnsigned) {
+    lt = v < f.c;
+    eq = v == f.c;
+    gt = v > f.c;
+  } else {
+    const long long a = static_cast<long long>(v), c = static_cast<long long>(f.c);
+    lt = a < c;
+    eq = a == c;
+    gt = a > c;
+  }
+  switch (op) {
+    case 0: return eq;
+    case 1: return !eq;
+    case 2: return gt;
+    case 3: return gt || eq;
+    case 4: return lt;
+    default: return lt || eq;
+  }
+}
+
 // TERM node of a boolean program: the documents of SearchAnd(n-grams of the term) (query_ast.cpp:76-93); a term
 // without n-grams falls back to a substring test of the stored text (query/substring_search.h:24-42).
 __device__ bool program_term_holds(const IndexView& iv, const BatchView& bv, uint32_t tid, uint32_t doc) {
@@ -1716,6 +1780,20 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
       }
       if (!keep) {
         alive &= ~(1u << k);
+      }
+    }
+  }
+  // column filters (Execute :849-852, after the NOT filter)
+  {
+    const uint32_t f0 = bv.q_foff[q];
+    const uint32_t f1 = bv.q_foff[q + 1];
+    for (uint32_t fi = f0; fi < f1 && alive != 0; ++fi) {
+      const FilterPred f = bv.filters[fi];
+#pragma unroll
+      for (int k = 0; k < kTileItems; ++k) {
+        if (((alive >> k) & 1u) && (my_doc[k] == kNone || !filter_pass(f, my_doc[k]))) {
+          alive &= ~(1u << k);
+        }
       }
     }
   }
@@ -2515,6 +2593,8 @@ BatchView make_batch_view(Batch& b) {
   v.prog_arg = b.d_prog_arg.p;
   v.q_coff = b.d_q_coff.p;
   v.q_conj = b.d_q_conj.p;
+  v.q_foff = b.d_q_foff.p;
+  v.filters = b.d_filters.p;
   v.q_driver_len = b.d_q_driver_len.p;
   v.q_ntiles = b.d_q_ntiles.p;
   v.q_tile_off = b.d_q_tile_off.p;
@@ -2669,6 +2749,75 @@ void Batch::recycle() {
   n_stream_slots = n_stream_terms = 0;
 }
 
+namespace {
+// Literal of a condition in the class of the column it addresses: ParseFilterValue (search_pipeline.cpp:954-993)
+// for the typed path, the type interpretations of BuildTypeUnionBitmap (:1021-1094) for the bitmap path.
+FilterPred resolve_filter(const Index& ix, const HostFilter& hf, bool bitmap_mode) {
+  FilterPred p{};
+  p.op_flags = (hf.op & 7u) | (bitmap_mode ? kFilterBitmapMode : 0u);
+  const FilterColumn* col = hf.col < ix.columns.size() ? ix.columns[hf.col] : nullptr;
+  if (col == nullptr || col->n_docs != ix.n_docs) {
+    p.cls = kFcNone;
+    return p;
+  }
+  p.cls = col->cls;
+  p.values = col->values.p;
+  p.nulls = col->nulls.p;
+  const std::string& v = hf.literal;
+  const char* b = v.data();
+  const char* e = v.data() + v.size();
+  bool valid = false;
+  switch (col->cls) {
+    case kFcBool:
+      if (bitmap_mode) {
+        valid = v == "1" || v == "true" || v == "0" || v == "false";
+        p.c = (v == "1" || v == "true") ? 1 : 0;
+      } else {
+        valid = true;
+        p.c = (v == "1" || v == "true") ? 1 : 0;  // parsed_value.bool_val
+      }
+      break;
+    case kFcSigned: {
+      int64_t r = 0;
+      auto [ptr, ec] = std::from_chars(b, e, r);
+      valid = ec == std::errc() && ptr == e;
+      p.c = static_cast<uint64_t>(r);
+      break;
+    }
+    case kFcUnsigned: {
+      uint64_t r = 0;
+      auto [ptr, ec] = std::from_chars(b, e, r);
+      valid = ec == std::errc() && ptr == e;
+      p.c = r;
+      break;
+    }
+    case kFcDouble: {
+      double r = 0.0;
+      auto [ptr, ec] = std::from_chars(b, e, r);
+      valid = ec == std::errc() && ptr == e;
+      std::memcpy(&p.c, &r, sizeof(r));
+      break;
+    }
+    case kFcString: {
+      const auto it = std::lower_bound(col->dict.begin(), col->dict.end(), v);
+      p.c = static_cast<uint64_t>(it - col->dict.begin());
+      const bool found = it != col->dict.end() && *it == v;
+      valid = bitmap_mode ? found : true;
+      if (found) {
+        p.op_flags |= kFilterFound;
+      }
+      break;
+    }
+    default:
+      break;
+  }
+  if (valid) {
+    p.op_flags |= kFilterValid;
+  }
+  return p;
+}
+}  // namespace
+
 void build_stream_table(std::vector<HostTerm>& terms, HostStreamTable* out) {
   out->slots.clear();
   out->entries.clear();
@@ -2775,7 +2924,17 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   std::vector<uint8_t> prog_ops;
   std::vector<uint32_t> prog_args;
   std::vector<uint32_t> conj;
+  std::vector<uint32_t> foff(queries.size() + 1, 0);
+  std::vector<FilterPred> preds;
   for (size_t q = 0; q < queries.size(); ++q) {
+    bool all_bitmap = true;  // AllFiltersHaveBitmapSupport, search_pipeline.cpp:995-1003
+    for (const HostFilter& hf : queries[q].filters) {
+      all_bitmap = all_bitmap && (hf.op == 0 || hf.op == 1);
+    }
+    for (const HostFilter& hf : queries[q].filters) {
+      preds.push_back(resolve_filter(*b.ix, hf, all_bitmap));
+    }
+    foff[q + 1] = static_cast<uint32_t>(preds.size());
     prog_ops.insert(prog_ops.end(), queries[q].prog_ops.begin(), queries[q].prog_ops.end());
     prog_args.insert(prog_args.end(), queries[q].prog_args.begin(), queries[q].prog_args.end());
     conj.insert(conj.end(), queries[q].conjuncts.begin(), queries[q].conjuncts.end());
@@ -2829,6 +2988,8 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   const size_t i_pargs = add(prog_args.data(), prog_args.size() * 4);
   const size_t i_coff = add(coff.data(), coff.size() * 4);
   const size_t i_conj = add(conj.data(), conj.size() * 4);
+  const size_t i_foff = add(foff.data(), foff.size() * 4);
+  const size_t i_preds = add(preds.data(), preds.size() * sizeof(FilterPred));
   const size_t i_sslots = add(stream_table.slots.data(), stream_table.slots.size() * 4);
   const size_t i_sentries = add(stream_table.entries.data(), stream_table.entries.size() * sizeof(StreamEntry));
   const size_t i_sbloom = add(stream_table.bloom.data(), stream_table.bloom.size() * 4);
@@ -2866,6 +3027,8 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   b.d_prog_arg.borrow(reinterpret_cast<uint32_t*>(at(i_pargs)), prog_args.size());
   b.d_q_coff.borrow(reinterpret_cast<uint32_t*>(at(i_coff)), coff.size());
   b.d_q_conj.borrow(reinterpret_cast<uint32_t*>(at(i_conj)), conj.size());
+  b.d_q_foff.borrow(reinterpret_cast<uint32_t*>(at(i_foff)), foff.size());
+  b.d_filters.borrow(reinterpret_cast<FilterPred*>(at(i_preds)), preds.size());
   b.d_stream_slots.borrow(reinterpret_cast<uint32_t*>(at(i_sslots)), stream_table.slots.size());
   b.d_stream_entries.borrow(reinterpret_cast<StreamEntry*>(at(i_sentries)), stream_table.entries.size());
   b.d_stream_bloom.borrow(reinterpret_cast<uint32_t*>(at(i_sbloom)), stream_table.bloom.size());

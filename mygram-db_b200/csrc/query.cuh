@@ -75,6 +75,24 @@ struct ExplicitDriver {
   uint64_t n = 0;
 };
 
+// One filter condition resolved against the index's columns (device form, 32 bytes).
+struct FilterPred {
+  const uint64_t* values;
+  const uint8_t* nulls;
+  uint64_t c;         // literal in the column's class (rank for strings, bits for doubles)
+  uint32_t cls;       // FilterClass; kFcNone = the index has no such column
+  uint32_t op_flags;  // op (bits 0-2) | kFilterBitmapMode | kFilterValid | kFilterFound
+};
+constexpr uint32_t kFilterBitmapMode = 8;   // EQ / NE by FilterIndex semantics (every condition of the query is EQ / NE)
+constexpr uint32_t kFilterValid = 16;       // the literal parses in the column's class
+constexpr uint32_t kFilterFound = 32;       // string literal present in the column's dictionary
+
+struct HostFilter {
+  uint32_t col = 0;
+  uint8_t op = 0;
+  std::string literal;
+};
+
 struct Batch {
   Index* ix = nullptr;
   SearchScratch* sc = nullptr;  // the (index, stream) workspace; the d_tile_* / d_rec_* members below are views into it
@@ -126,6 +144,8 @@ struct Batch {
   DevBuf<uint32_t> d_prog_arg;
   DevBuf<uint32_t> d_q_coff;        // [Q+1] conjunct ranges
   DevBuf<uint32_t> d_q_conj;
+  DevBuf<uint32_t> d_q_foff;        // [Q+1] filter ranges
+  DevBuf<FilterPred> d_filters;
 
   // ---- device: per-tile results
   DevBuf<uint32_t> d_tile_count;  // [tiles in flight] records written by the tile
@@ -234,6 +254,7 @@ struct HostQuery {
   std::vector<uint8_t> prog_ops;    // kQProgram: postfix program
   std::vector<uint32_t> prog_args;
   std::vector<uint32_t> conjuncts;  // kQProgram: terms every result must satisfy (driver candidates)
+  std::vector<HostFilter> filters;  // column conditions, AND-ed
 };
 
 // query.cu

@@ -16,6 +16,7 @@
 #include "oracle.h"
 
 #include <algorithm>
+#include <charconv>
 #include <atomic>
 #include <cmath>
 #include <cstring>
@@ -1702,3 +1703,170 @@ uint64_t orc_eval_boolean(const orc_index_t* idx, const int32_t* ops, const int3
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- column filters
+namespace {
+
+struct ParsedLiteral {  // ParseFilterValue, search_pipeline.cpp:943-993
+  std::string text;
+  bool bool_val = false;
+  double double_val = 0.0;
+  int64_t int64_val = 0;
+  uint64_t uint64_val = 0;
+  bool double_valid = false;
+  bool int64_valid = false;
+  bool uint64_valid = false;
+};
+
+ParsedLiteral ParseLiteral(std::string_view value) {
+  ParsedLiteral p;
+  p.text.assign(value);
+  p.bool_val = (value == "1" || value == "true");
+  const char* b = value.data();
+  const char* e = value.data() + value.size();
+  {
+    double r = 0.0;
+    auto [ptr, ec] = std::from_chars(b, e, r);
+    if (ec == std::errc() && ptr == e) {
+      p.double_val = r;
+      p.double_valid = true;
+    }
+  }
+  {
+    int64_t r = 0;
+    auto [ptr, ec] = std::from_chars(b, e, r);
+    if (ec == std::errc() && ptr == e) {
+      p.int64_val = r;
+      p.int64_valid = true;
+    }
+  }
+  {
+    uint64_t r = 0;
+    auto [ptr, ec] = std::from_chars(b, e, r);
+    if (ec == std::errc() && ptr == e) {
+      p.uint64_val = r;
+      p.uint64_valid = true;
+    }
+  }
+  return p;
+}
+
+template <typename T>
+bool CompareOp(const T& lhs, const T& rhs, int op) {  // utils/comparison_utils.h:28-43
+  switch (op) {
+    case 0: return lhs == rhs;
+    case 1: return lhs != rhs;
+    case 2: return lhs > rhs;
+    case 3: return lhs >= rhs;
+    case 4: return lhs < rhs;
+    case 5: return lhs <= rhs;
+  }
+  return false;
+}
+
+bool CompareDoubleOp(double lhs, double rhs, int op) {  // comparison_utils.h:56-70, epsilon constants.h:104
+  constexpr double kEps = 1e-9;
+  if (op == 0) return std::abs(lhs - rhs) < kEps;
+  if (op == 1) return std::abs(lhs - rhs) >= kEps;
+  return CompareOp(lhs, rhs, op);
+}
+
+bool IsSignedType(int t) { return t == 2 || t == 4 || t == 6 || t == 8; }
+bool IsUnsignedType(int t) { return t == 3 || t == 5 || t == 7 || t == 9; }
+
+// Does the stored value equal some type interpretation of the literal? (BuildTypeUnionBitmap :1021-1094: the
+// bitmap of a value is keyed by SerializeFilterValue, filter_index.cpp:177-255 = type tag + little-endian bytes)
+bool BitmapEqMatch(int type, uint64_t bits, std::string_view str, const ParsedLiteral& lit) {
+  if (type == 1) {
+    if (lit.text == "1" || lit.text == "true") return bits != 0;
+    if (lit.text == "0" || lit.text == "false") return bits == 0;
+    return false;
+  }
+  if (IsSignedType(type) || type == 10) {  // int8..int64 (tried when the value fits the width), TIME seconds
+    return lit.int64_valid && static_cast<int64_t>(bits) == lit.int64_val;
+  }
+  if (IsUnsignedType(type)) {
+    return lit.uint64_valid && bits == lit.uint64_val;
+  }
+  if (type == 11) {
+    return str == lit.text;
+  }
+  if (type == 12) {
+    uint64_t lb = 0;
+    std::memcpy(&lb, &lit.double_val, sizeof(lb));
+    return lit.double_valid && bits == lb;  // serialised bytes compare: bit pattern equality
+  }
+  return false;
+}
+
+// ApplyFilters' per-document visitor, :1134-1175 (value is not NULL)
+bool TypedMatch(int type, uint64_t bits, std::string_view str, const ParsedLiteral& lit, int op) {
+  if (type == 11) {
+    return CompareOp(std::string(str), lit.text, op);
+  }
+  if (type == 1) {
+    return CompareOp(bits != 0, lit.bool_val, op);
+  }
+  if (type == 12) {
+    if (!lit.double_valid) return false;
+    double v = 0.0;
+    std::memcpy(&v, &bits, sizeof(v));
+    return CompareDoubleOp(v, lit.double_val, op);
+  }
+  if (IsUnsignedType(type)) {
+    if (!lit.uint64_valid) return false;
+    return CompareOp(bits, lit.uint64_val, op);
+  }
+  if (!lit.int64_valid) return false;  // signed integers and TIME
+  return CompareOp(static_cast<int64_t>(bits), lit.int64_val, op);
+}
+
+}  // namespace
+
+extern "C" uint64_t orc_apply_filters(uint64_t n_docs, uint32_t first_doc_id, uint32_t n_cols, const int32_t* col_type,
+                                      const uint64_t* col_values, const uint8_t* col_null, const uint8_t* str_bytes,
+                                      const uint64_t* str_offsets, uint32_t n_filters, const uint32_t* filter_col,
+                                      const uint8_t* filter_op, const uint8_t* lit_bytes, const uint64_t* lit_offsets,
+                                      const uint32_t* results, uint64_t n_results, uint32_t* out) {
+  std::vector<ParsedLiteral> lits;
+  bool all_bitmap = true;  // AllFiltersHaveBitmapSupport :995-1003
+  for (uint32_t f = 0; f < n_filters; ++f) {
+    lits.push_back(ParseLiteral(std::string_view(reinterpret_cast<const char*>(lit_bytes) + lit_offsets[f],
+                                                 lit_offsets[f + 1] - lit_offsets[f])));
+    all_bitmap = all_bitmap && (filter_op[f] == 0 || filter_op[f] == 1);
+  }
+  uint64_t n_out = 0;
+  for (uint64_t i = 0; i < n_results; ++i) {
+    const uint32_t id = results[i];
+    bool keep = id >= first_doc_id && static_cast<uint64_t>(id - first_doc_id) < n_docs;
+    const uint64_t row = keep ? id - first_doc_id : 0;
+    for (uint32_t f = 0; f < n_filters && keep; ++f) {
+      const uint32_t c = filter_col[f];
+      if (c >= n_cols) {
+        // unknown column: no bitmap / no stored value => EQ matches nothing, NE everything; typed: NULL rule
+        keep = filter_op[f] == 1;
+        continue;
+      }
+      const int type = col_type[c];
+      const uint64_t bits = col_values[static_cast<uint64_t>(c) * n_docs + row];
+      const bool is_null = col_null[static_cast<uint64_t>(c) * n_docs + row] != 0;
+      std::string_view str;
+      if (type == 11 && !is_null) {
+        str = std::string_view(reinterpret_cast<const char*>(str_bytes) + str_offsets[bits],
+                               str_offsets[bits + 1] - str_offsets[bits]);
+      }
+      if (all_bitmap) {
+        const bool eq = !is_null && BitmapEqMatch(type, bits, str, lits[f]);  // only non-NULL values are indexed
+        keep = filter_op[f] == 0 ? eq : !eq;                                   // :1216-1229 and / andnot
+      } else if (is_null) {
+        keep = filter_op[f] == 1;  // :1126-1132
+      } else {
+        keep = TypedMatch(type, bits, str, lits[f], filter_op[f]);
+      }
+    }
+    if (keep) {
+      out[n_out++] = id;
+    }
+  }
+  return n_out;
+}

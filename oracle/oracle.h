@@ -178,6 +178,25 @@ int orc_query_batch(const orc_index_t* idx, const orc_query_params_t* params, ui
 uint64_t orc_eval_boolean(const orc_index_t* idx, const int32_t* ops, const int32_t* args, uint64_t n_ops,
                           const uint8_t* term_bytes, const uint64_t* term_offsets, uint32_t* out, uint64_t cap);
 
+/* ---- column filters (src/server/search_pipeline.cpp:1021-1237) ----
+ * ApplyFiltersWithBitmap (:1196-1237): when every condition is EQ / NE the FilterIndex bitmaps decide (a value
+ * matches when its serialisation equals that of some type interpretation of the literal, BuildTypeUnionBitmap
+ * :1021-1094); otherwise ApplyFilters (:1098-1194) compares every document's typed value with the pre-parsed
+ * literal (ParseFilterValue :954-993; NULL matches only NE).
+ * Stand-alone form: documents are rows 0..n_docs-1, doc id = first_doc_id + row. Column c has type
+ * col_type[c] (the FilterValue variant index, document_store.h:73-86: 1 bool, 2 int8, 3 uint8, 4 int16, 5 uint16,
+ * 6 int32, 7 uint32, 8 int64, 9 uint64, 10 TIME seconds, 11 string, 12 double); its value for a row is
+ * col_values[c * n_docs + row] (integer / bool / seconds value, the bits of the double, or for strings an index
+ * into the string table str_bytes / str_offsets) and col_null[c * n_docs + row] != 0 marks NULL.
+ * Filter f: column filter_col[f], op filter_op[f] (query_parser.h:93-100: 0 EQ, 1 NE, 2 GT, 3 GTE, 4 LT, 5 LTE),
+ * literal lit_bytes[lit_offsets[f] .. lit_offsets[f+1]). `results` are ascending doc ids. Returns the number of ids
+ * written to `out` (capacity n_results). */
+uint64_t orc_apply_filters(uint64_t n_docs, uint32_t first_doc_id, uint32_t n_cols, const int32_t* col_type,
+                           const uint64_t* col_values, const uint8_t* col_null, const uint8_t* str_bytes,
+                           const uint64_t* str_offsets, uint32_t n_filters, const uint32_t* filter_col,
+                           const uint8_t* filter_op, const uint8_t* lit_bytes, const uint64_t* lit_offsets,
+                           const uint32_t* results, uint64_t n_results, uint32_t* out);
+
 #ifdef __cplusplus
 }
 #endif

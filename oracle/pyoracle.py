@@ -68,6 +68,27 @@ def as_bytes(s):
     return s.encode("utf-8") if isinstance(s, str) else bytes(s)
 
 
+def pack_filter_columns(n_docs, columns):
+    """-> (values uint64[n_cols * n_docs], nulls uint8[...], types int32[n_cols], string table list[bytes])"""
+    vals = np.zeros(len(columns) * n_docs, dtype=np.uint64)
+    nulls = np.zeros(len(columns) * n_docs, dtype=np.uint8)
+    types = np.asarray([c[0] for c in columns], dtype=np.int32)
+    strings = []
+    for ci, (typ, values) in enumerate(columns):
+        for row, v in enumerate(values):
+            i = ci * n_docs + row
+            if v is None:
+                nulls[i] = 1
+            elif typ == 11:
+                vals[i] = len(strings)
+                strings.append(as_bytes(v))
+            elif typ == 12:
+                vals[i] = np.float64(v).view(np.uint64)
+            else:
+                vals[i] = np.int64(int(v)).view(np.uint64) if int(v) < 0 else np.uint64(int(v))
+    return vals, nulls, types, strings
+
+
 @dataclass
 class BatchResult:
     ids: np.ndarray      # [Q, stride] uint32
@@ -140,6 +161,30 @@ class OracleLib:
         L.orc_eval_boolean.argtypes = [C.c_void_p, i32p, i32p, C.c_uint64, u8p, u64p, u32p, C.c_uint64]
 
     # ---- tokenizer ----
+    def apply_filters(self, n_docs, first_doc_id, columns, filters, results):
+        """columns: list of (type_code, values, nulls); values is a list of python values per row (None = NULL;
+        str/bytes for strings, float for doubles, int/bool otherwise). filters: list of (col, op, literal).
+        -> the ids of `results` that pass (ApplyFiltersWithBitmap, search_pipeline.cpp:1196-1237)."""
+        vals, nulls, types, strings = pack_filter_columns(n_docs, columns)
+        sbytes, soffs = pack_strings(strings if strings else [b""])
+        fc = np.asarray([f[0] for f in filters], dtype=np.uint32)
+        fo = np.asarray([f[1] for f in filters], dtype=np.uint8)
+        lb, lo = pack_strings([as_bytes(f[2]) for f in filters] if filters else [b""])
+        res = np.ascontiguousarray(results, dtype=np.uint32)
+        out = np.zeros(max(1, res.size), dtype=np.uint32)
+        fn = self.lib.orc_apply_filters
+        fn.restype = C.c_uint64
+        fn.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, i32p, u64p, u8p, u8p, u64p, C.c_uint32, u32p, u8p, u8p, u64p,
+                       u32p, C.c_uint64, u32p]
+        one32 = np.zeros(1, np.uint32)
+        one8 = np.zeros(1, np.uint8)
+        n = fn(n_docs, first_doc_id, len(columns), _ptr(types if types.size else np.zeros(1, np.int32), i32p),
+               _ptr(vals if vals.size else np.zeros(1, np.uint64), u64p), _ptr(nulls if nulls.size else one8, u8p),
+               _ptr(sbytes, u8p), _ptr(soffs, u64p), len(filters), _ptr(fc if fc.size else one32, u32p),
+               _ptr(fo if fo.size else one8, u8p), _ptr(lb, u8p), _ptr(lo, u64p),
+               _ptr(res if res.size else one32, u32p), res.size, _ptr(out, u32p))
+        return out[:n].copy()
+
     def utf8_to_codepoints(self, text):
         b = as_bytes(text)
         buf = np.frombuffer(b, dtype=np.uint8).copy() if b else np.zeros(1, np.uint8)

@@ -534,3 +534,65 @@ uint64_t orc_eval_boolean(const orc_index_t* idx, const int32_t* ops, const int3
 }
 
 }  // extern "C"
+
+// Column filters through the reference's own DocumentStore / FilterIndex / ApplyFiltersWithBitmap
+// (search_pipeline.cpp:1196-1237). A fresh store is filled with one document per row carrying the typed values.
+extern "C" uint64_t orc_apply_filters(uint64_t n_docs, uint32_t first_doc_id, uint32_t n_cols, const int32_t* col_type,
+                                      const uint64_t* col_values, const uint8_t* col_null, const uint8_t* str_bytes,
+                                      const uint64_t* str_offsets, uint32_t n_filters, const uint32_t* filter_col,
+                                      const uint8_t* filter_op, const uint8_t* lit_bytes, const uint64_t* lit_offsets,
+                                      const uint32_t* results, uint64_t n_results, uint32_t* out) {
+  namespace st = ref::storage;
+  OpenDocumentStore store;
+  store.SetNextDocId(first_doc_id);
+  for (uint64_t row = 0; row < n_docs; ++row) {
+    st::FilterMap filters;
+    for (uint32_t c = 0; c < n_cols; ++c) {
+      const uint64_t bits = col_values[static_cast<uint64_t>(c) * n_docs + row];
+      const std::string name = "c" + std::to_string(c);
+      if (col_null[static_cast<uint64_t>(c) * n_docs + row] != 0) {
+        filters[name] = st::FilterValue{std::monostate{}};
+        continue;
+      }
+      switch (col_type[c]) {
+        case 1: filters[name] = st::FilterValue{bits != 0}; break;
+        case 2: filters[name] = st::FilterValue{static_cast<int8_t>(bits)}; break;
+        case 3: filters[name] = st::FilterValue{static_cast<uint8_t>(bits)}; break;
+        case 4: filters[name] = st::FilterValue{static_cast<int16_t>(bits)}; break;
+        case 5: filters[name] = st::FilterValue{static_cast<uint16_t>(bits)}; break;
+        case 6: filters[name] = st::FilterValue{static_cast<int32_t>(bits)}; break;
+        case 7: filters[name] = st::FilterValue{static_cast<uint32_t>(bits)}; break;
+        case 8: filters[name] = st::FilterValue{static_cast<int64_t>(bits)}; break;
+        case 9: filters[name] = st::FilterValue{static_cast<uint64_t>(bits)}; break;
+        case 10: filters[name] = st::FilterValue{st::TimeValue{static_cast<int64_t>(bits)}}; break;
+        case 11:
+          filters[name] = st::FilterValue{std::string(reinterpret_cast<const char*>(str_bytes) + str_offsets[bits],
+                                                      str_offsets[bits + 1] - str_offsets[bits])};
+          break;
+        case 12: {
+          double v = 0.0;
+          std::memcpy(&v, &bits, sizeof(v));
+          filters[name] = st::FilterValue{v};
+          break;
+        }
+        default: break;
+      }
+    }
+    auto added = store.AddDocument("pk" + std::to_string(row), filters, "", "");
+    if (!added) {
+      return 0;
+    }
+  }
+  std::vector<ref::query::FilterCondition> conds;
+  for (uint32_t f = 0; f < n_filters; ++f) {
+    ref::query::FilterCondition fc;
+    fc.column = "c" + std::to_string(filter_col[f]);
+    fc.op = static_cast<ref::query::FilterOp>(filter_op[f]);
+    fc.value.assign(reinterpret_cast<const char*>(lit_bytes) + lit_offsets[f], lit_offsets[f + 1] - lit_offsets[f]);
+    conds.push_back(std::move(fc));
+  }
+  const std::vector<ref::storage::DocId> in(results, results + n_results);
+  const auto kept = ref::server::search_pipeline::ApplyFiltersWithBitmap(in, conds, &store);
+  std::copy(kept.begin(), kept.end(), out);
+  return kept.size();
+}

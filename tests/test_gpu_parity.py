@@ -538,3 +538,75 @@ def test_statistics_optimize_clear(mgx, oracle):
     st = gi.get_statistics()
     assert (st.total_terms, st.total_postings, st.roaring_bitmap_lists) == (0, 0, 0)
     assert gi.search_and([terms[0]]).size == 0 and gi.term_count() == 0
+
+
+# ----------------------------------------------------------------------------------------- C4: filters + mixed boolean batch
+def test_mixed_boolean_batch_with_filters(mgx, oracle):
+    """BASELINE config 4 in small: A AND B / A OR B / A AND NOT B / (A OR B) AND C with FILTER conditions over typed
+    columns with NULLs (ApplyFiltersWithBitmap / ApplyFilters, search_pipeline.cpp:1098-1237), Zipf n-gram
+    frequencies so that dense-bitmap lists take part. Oracle: eval_boolean / query_batch sets + apply_filters."""
+    rnd = random.Random(404)
+    c = corpus_mod.generate("cjk", 30000, 0xC4, alphabet=96, min_len=6, max_len=40)
+    gi = mgx.Index(2, 0, True, dense_threshold=0.02)
+    gi.build(c.doc_ids, c.arena, c.offsets)
+    oi = oracle.index(2, 0, True)
+    oi.build_bulk(c.doc_ids, c.arena, c.offsets, 8)
+    assert gi.stats().n_dense_terms > 0
+    n = c.n_docs
+    status = [None if rnd.random() < 0.1 else rnd.choice([1, 2, 3]) for _ in range(n)]          # int64
+    category = [None if rnd.random() < 0.1 else rnd.choice([b"news", b"blog", b"wiki", b"shop", b"faq"]) for _ in range(n)]
+    score = [None if rnd.random() < 0.1 else rnd.choice([0.0, 0.5, 1.0, 2.5, 10.0]) for _ in range(n)]
+    flag = [None if rnd.random() < 0.1 else rnd.random() < 0.5 for _ in range(n)]
+    small = [None if rnd.random() < 0.1 else rnd.randint(0, 200) for _ in range(n)]             # uint8
+    columns = [(8, status), (11, category), (12, score), (1, flag), (3, small)]
+    for ci, (typ, vals) in enumerate(columns):
+        gi.set_filter_column(ci, typ, vals)
+    first = int(c.doc_ids[0])
+
+    def term():
+        t = c.text(rnd.randrange(n)).decode()
+        ln = rnd.randint(2, 3)
+        st = rnd.randrange(0, len(t) - ln + 1)
+        return t[st:st + ln].encode()
+
+    filter_pool = [[(0, 0, "1")], [(0, 1, "2")], [(1, 0, "blog")], [(1, 1, "news"), (0, 0, "3")], [(2, 3, "1")],
+                   [(2, 0, "2.5")], [(3, 0, "true")], [(3, 1, "1")], [(4, 4, "100"), (0, 0, "1")], [(1, 5, "faq")],
+                   [(0, 0, "abc")], [(7, 1, "x")], [(7, 0, "x")], [(4, 0, "300")], [(2, 1, "0.5"), (1, 2, "blog")], []]
+    queries, programs, filters, expect = [], [], [], []
+    for qi in range(200):
+        kind = qi % 4
+        A, B, Cc = term(), term(), term()
+        if kind == 0:      # A AND B
+            terms, prog = [A, B], ([0, 0, 1], [0, 1, 2])
+        elif kind == 1:    # A OR B
+            terms, prog = [A, B], ([0, 0, 2], [0, 1, 2])
+        elif kind == 2:    # A AND NOT B
+            terms, prog = [A, B], ([0, 0, 3, 1], [0, 1, 0, 2])
+        else:              # (A OR B) AND C
+            terms, prog = [A, B, Cc], ([0, 0, 2, 0, 1], [0, 1, 2, 2, 2])
+        fl = rnd.choice(filter_pool)
+        full = oi.eval_boolean(prog[0], prog[1], terms)
+        want = oracle.apply_filters(n, first, columns, fl, full) if fl else full
+        queries.append(terms)
+        programs.append(prog)
+        filters.append(fl)
+        expect.append(want)
+    g = gi.query_batch(queries, programs=programs, filters=filters, score=False, limit=50, offset=0)
+    for qi, want in enumerate(expect):
+        assert int(g.total[qi]) == want.size, (qi, queries[qi], filters[qi], int(g.total[qi]), want.size)
+        k = min(50, want.size)
+        assert np.array_equal(g.ids[qi, :k], want[:k]), (qi, filters[qi])
+    # plain AND + BM25 queries with filters: the filter applies before scoring (Execute :849-852)
+    qs = corpus_mod.sample_queries(c, 100, 8, n_terms=2, min_cp=2, max_cp=3)
+    fls = [rnd.choice(filter_pool) for _ in qs]
+    g = gi.query_batch(qs, filters=fls, score=True, limit=100)
+    o = oi.query_batch(qs, score=True, limit=c.n_docs, n_threads=8)
+    for qi in range(len(qs)):
+        k = int(o.count[qi])
+        ids = o.ids[qi, :k]
+        keep = set(oracle.apply_filters(n, first, columns, fls[qi], np.sort(ids)).tolist()) if fls[qi] else set(ids.tolist())
+        want = [(int(d), float(s)) for d, s in zip(ids, o.scores[qi, :k]) if int(d) in keep][:100]
+        assert int(g.total[qi]) == len(keep), (qi, fls[qi])
+        got = list(zip(g.ids[qi, :int(g.count[qi])].tolist(), g.scores[qi, :int(g.count[qi])].tolist()))
+        assert [d for d, _ in got] == [d for d, _ in want], (qi, fls[qi])
+        assert np.allclose([s for _, s in got], [s for _, s in want], rtol=1e-9, atol=0)
