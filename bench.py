@@ -450,8 +450,18 @@ def main():
         name = max(("and_tile_kernel", "df_tile_kernel", "topk_kernel"), key=lambda k: kernels[k]["ms"])
         kk = kernels[name]
         achieved = (kk["bytes"] / 1e9) / (kk["ms"] / 1e3) if kk["ms"] > 0 else 0.0
+        # dram__bytes_read + dram__bytes_write of that kernel per launch, from the committed `ncu --set full` capture of
+        # this command (profiles/r01_dram_traffic.json); null if the dominant kernel has no capture
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")))
+            if name in tj and args.docs == 10_000_000 and world == 1:
+                traffic, traffic_src = tj[name]["dram_bytes_per_launch"], tj[name]["source"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kk["bytes"] / max(1, kk["launches"]),
                     "avg_launch_ms": kk["ms"] / max(1, kk["launches"]),
                     "step_share": kk["ms"] / max(1e-9, sum(v["ms"] for v in kernels.values()))}
