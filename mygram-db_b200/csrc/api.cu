@@ -922,22 +922,22 @@ int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, co
     MGX_CUDA(cudaMemcpyAsync(d_off.p, text_offsets, (n_docs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     const int width = std::max(config->ngram_size, kanji);
     DevBuf<uint32_t> d_len;
-    DevBuf<uint64_t> d_slot_off;
+    DevBuf<uint64_t> d_tile_off;
     DevBuf<uint64_t> d_scratch;
     DevBuf<uint64_t> d_keys;
     DevBuf<uint32_t> d_docs;
     d_len.alloc(n_docs);
-    d_slot_off.alloc(n_docs + 1);
-    d_scratch.alloc(8 + (n_docs + 1) / 2 + 1 + scan_scratch_elems(n_docs) + 8);
+    d_tile_off.alloc(tokenize_tile_count(n_docs, bytes) + 1);
+    d_scratch.alloc(tokenize_scratch_elems(n_docs, bytes));
     uint64_t n_slots = 0;
     uint64_t counters[3];
     tokenize_count(config->ngram_size, kanji, config->cross_boundary_ngrams != 0, width, d_text.p, d_off.p, n_docs,
-                   d_len.p, d_slot_off.p, d_scratch.p, &n_slots, counters, st);
+                   bytes, d_len.p, d_tile_off.p, d_scratch.p, &n_slots, counters, st);
     d_keys.alloc(n_slots);
     d_docs.alloc(n_slots);
     if (n_slots > 0) {
       tokenize_emit(config->ngram_size, kanji, config->cross_boundary_ngrams != 0, width, d_text.p, d_off.p, n_docs,
-                    d_slot_off.p, d_keys.p, d_docs.p, 0, st);
+                    bytes, d_tile_off.p, d_scratch.p, d_keys.p, d_docs.p, 0, st);
     }
     std::vector<uint64_t> keys(n_slots);
     std::vector<uint32_t> docs(n_slots);

@@ -234,6 +234,303 @@ tokenize_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ t
   }
 }
 
+
+// ------------------------------------------------------------------ flat tokenizer
+// The arena is one byte stream (documents back to back), so tokenisation does not have to walk it document by
+// document: a CTA takes a 4 KB tile, every thread one 16-byte chunk, and the document of each byte comes from the
+// tile's document offsets staged in shared memory (documents average ~200 bytes, so a warp per document leaves
+// most lanes idle). Strict UTF-8 decoding is a LOCAL predicate per byte (see parse_utf8: every non-continuation
+// byte is reached by the reference's skip-one-byte scan, string_utils.cpp:206-216, and a character may not run
+// past the end of ITS document). Per tile:
+//   A  decode: code point + document of every character start of the chunk;
+//   B  block-wide compaction of the characters (code point, byte position, document) into shared memory, plus the
+//      first (width-1) characters after the tile that belong to the tile's last document (windows may need them);
+//   C  one thread per character: GenerateHybridNgrams' window rule (string_utils.cpp:452-509) -> emit flag;
+//      COUNT sums the flags per tile, EMIT writes (packed key << pos_bits | byte offset in the document, document)
+//      at the tile's scanned base + the flag's rank, i.e. in text order.
+// COUNT also accumulates, per document, its code points (= CountCodePoints, BM25's dl) and the bytes covered by
+// valid characters (a document is valid UTF-8 iff they equal its length). A tile whose documents do not fit the
+// staged table (more than kFlatDocCap starts in 4 KB) is processed in several rounds over ranges of documents.
+constexpr int kFlatThreads = 256;
+constexpr uint32_t kFlatTile = kFlatThreads * 16;   // 4096 bytes
+constexpr uint32_t kFlatDocCap = 1024;
+constexpr uint32_t kFlatHalo = kMaxKeyWidth - 1;    // characters after the tile a window can reach
+
+struct FlatSmem {
+  uint32_t cp[kFlatTile + kFlatHalo + 1];
+  uint16_t pos[kFlatTile + kFlatHalo + 1];   // byte position relative to the tile start (halo: >= tile length)
+  uint16_t doc[kFlatTile + kFlatHalo + 1];   // index into docrel
+  int32_t docrel[kFlatDocCap + 2];           // start of document (round_first + i) relative to the tile start
+  uint32_t doc_cps[kFlatDocCap + 1];
+  uint32_t doc_valid[kFlatDocCap + 1];
+  uint32_t warp_cnt[kFlatThreads / 32];
+  uint32_t n_halo;
+};
+
+__global__ void flat_tile_first_doc_kernel(const uint64_t* __restrict__ text_off, uint64_t n_docs, uint64_t n_tiles,
+                                           uint32_t* __restrict__ out) {
+  const uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) {
+    return;
+  }
+  const uint64_t byte = t * kFlatTile;
+  uint64_t lo = 0;  // invariant: text_off[lo] <= byte
+  uint64_t hi = n_docs;
+  while (hi - lo > 1) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (text_off[mid] <= byte) {
+      lo = mid;
+    } else {
+      hi = mid;
+    }
+  }
+  out[t] = static_cast<uint32_t>(lo);
+}
+
+__device__ __forceinline__ uint32_t flat_block_scan(uint32_t v, uint32_t* warp_cnt, uint32_t* total) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, s);
+    if (lane >= static_cast<unsigned>(s)) {
+      inc += o;
+    }
+  }
+  __syncthreads();  // warp_cnt may still be read from the previous use
+  if (lane == 31) {
+    warp_cnt[warp] = inc;
+  }
+  __syncthreads();
+  uint32_t prefix = 0;
+  uint32_t tot = 0;
+#pragma unroll
+  for (int w = 0; w < kFlatThreads / 32; ++w) {
+    const uint32_t c = warp_cnt[w];
+    if (static_cast<unsigned>(w) < warp) {
+      prefix += c;
+    }
+    tot += c;
+  }
+  *total = tot;
+  return prefix + inc - v;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kFlatThreads, 4)
+tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ text_off, uint64_t n_docs,
+                     uint64_t text_bytes, uint64_t n_tiles, const uint32_t* __restrict__ tile_first_doc, int ngram,
+                     int kanji, int cross, int width, int pos_bits, uint32_t* __restrict__ doc_len,
+                     uint32_t* __restrict__ doc_valid_bytes, uint32_t* __restrict__ tile_cnt,
+                     const uint64_t* __restrict__ tile_off, uint64_t* __restrict__ keys_out,
+                     uint32_t* __restrict__ docs_out) {
+  __shared__ FlatSmem sm;
+  const unsigned lane = threadIdx.x & 31u;
+  const uint64_t pos_max = pos_bits > 0 ? ((1ULL << pos_bits) - 1) : 0;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t tile_b = tile * kFlatTile;
+    const uint32_t tile_len = static_cast<uint32_t>(umin_u64(kFlatTile, text_bytes - tile_b));
+    const uint32_t first_doc = tile_first_doc[tile];
+    const uint32_t last_doc = tile + 1 < n_tiles ? tile_first_doc[tile + 1] : static_cast<uint32_t>(n_docs - 1);
+    uint64_t emitted_tile = 0;  // n-grams of the rounds done so far (same value in every thread)
+    // rounds over ranges of at most kFlatDocCap documents (one round unless the tile holds very many tiny documents)
+    for (uint32_t r_first = first_doc; r_first <= last_doc; r_first += kFlatDocCap) {
+      const uint32_t r_docs = min(kFlatDocCap, last_doc - r_first + 1u);  // documents of this round
+      __syncthreads();  // the previous round / tile is done with shared memory
+      for (uint32_t i = threadIdx.x; i <= r_docs; i += kFlatThreads) {
+        const uint64_t off = text_off[static_cast<uint64_t>(r_first) + i];  // i == r_docs: end of the last document
+        int64_t rel = static_cast<int64_t>(off) - static_cast<int64_t>(tile_b);
+        rel = rel < -0x40000000LL ? -0x40000000LL : (rel > 0x40000000LL ? 0x40000000LL : rel);
+        sm.docrel[i] = static_cast<int32_t>(rel);
+        if (i < r_docs) {
+          sm.doc_cps[i] = 0;
+          sm.doc_valid[i] = 0;
+        }
+      }
+      if (threadIdx.x == 0) {
+        sm.n_halo = 0;
+      }
+      __syncthreads();
+      // byte range of the tile covered by this round's documents
+      const int32_t r_begin = max(sm.docrel[0], 0);
+      const int32_t r_end = min(sm.docrel[r_docs], static_cast<int32_t>(tile_len));
+
+      // ---- A: decode the chunk
+      const int32_t c0 = static_cast<int32_t>(threadIdx.x) * 16;
+      uint32_t flags = 0;
+      uint32_t cps[16];   // code point (21 bits) | (document - dj0) << 21: a 16-byte chunk spans at most 17 documents
+      uint32_t dj0 = 0;
+      if (c0 < r_end && c0 + 16 > r_begin) {
+        const uint4 v = ld_stream_16(text + tile_b + c0);
+        const uint32_t w4 = *reinterpret_cast<const uint32_t*>(text + tile_b + c0 + 16);  // the arena is padded
+        const uint32_t w[5] = {v.x, v.y, v.z, v.w, w4};
+        // document of the first byte this thread looks at: largest j with docrel[j] <= p
+        const int32_t p0 = max(c0, r_begin);
+        uint32_t lo = 0;
+        uint32_t hi = r_docs;  // docrel[r_docs] = r_end' > p0
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (sm.docrel[mid] <= p0) {
+            lo = mid;
+          } else {
+            hi = mid;
+          }
+        }
+        uint32_t dj = lo;
+        dj0 = lo;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int32_t p = c0 + j;
+          cps[j] = 0;
+          if (p >= r_begin && p < r_end) {
+            while (p >= sm.docrel[dj + 1]) {  // next document (empty documents are stepped over)
+              ++dj;
+            }
+            uint32_t cp = 0;
+            const int len = parse_utf8(byte_of(w, j), byte_of(w, j + 1), byte_of(w, j + 2), byte_of(w, j + 3),
+                                       static_cast<uint64_t>(sm.docrel[dj + 1] - p), &cp);
+            if (len > 0) {
+              flags |= 1u << j;
+              cps[j] = cp | ((dj - dj0) << 21);
+              if (!EMIT) {
+                atomicAdd(&sm.doc_cps[dj], 1u);
+                atomicAdd(&sm.doc_valid[dj], static_cast<uint32_t>(len));
+              }
+            }
+          }
+        }
+      }
+      // ---- B: compaction in text order
+      uint32_t n_chars = 0;
+      uint32_t at = flat_block_scan(static_cast<uint32_t>(__popc(flags)), sm.warp_cnt, &n_chars);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (flags & (1u << j)) {
+          sm.cp[at] = cps[j] & 0x1FFFFFu;
+          sm.pos[at] = static_cast<uint16_t>(c0 + j);
+          sm.doc[at] = static_cast<uint16_t>(dj0 + (cps[j] >> 21));
+          ++at;
+        }
+      }
+      // halo: the first (width - 1) characters after the tile that still belong to the round's last document
+      if (threadIdx.x < 32 && width > 1 && sm.docrel[r_docs] > static_cast<int32_t>(tile_len) &&
+          r_end == static_cast<int32_t>(tile_len)) {
+        const int32_t doc_end = sm.docrel[r_docs];
+        uint32_t found = 0;
+        for (int32_t base = static_cast<int32_t>(tile_len); base < doc_end && found < static_cast<uint32_t>(width - 1);
+             base += 32) {
+          const int32_t p = base + static_cast<int32_t>(lane);
+          uint32_t cp = 0;
+          int len = 0;
+          if (p < doc_end) {
+            const uint8_t* q = text + tile_b + p;  // within the arena + padding
+            len = parse_utf8(q[0], q[1], q[2], q[3], static_cast<uint64_t>(doc_end - p), &cp);
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, len > 0);
+          const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+          if (len > 0 && found + rank < static_cast<uint32_t>(width - 1)) {
+            sm.cp[n_chars + found + rank] = cp;
+            sm.pos[n_chars + found + rank] = static_cast<uint16_t>(min(p, 0xFFFF));
+            sm.doc[n_chars + found + rank] = static_cast<uint16_t>(r_docs - 1);
+          }
+          found += __popc(m);
+        }
+        if (lane == 0) {
+          sm.n_halo = min(found, static_cast<uint32_t>(width - 1));
+        }
+      }
+      __syncthreads();
+      const uint32_t n_all = n_chars + sm.n_halo;
+
+      // ---- C: windows (GenerateHybridNgrams, string_utils.cpp:452-509), one thread per character
+      uint64_t strip_base = EMIT ? tile_off[tile] + emitted_tile : 0;  // slot of the strip's first n-gram
+      for (uint32_t k0 = 0; k0 < n_chars; k0 += kFlatThreads) {
+        const uint32_t k = k0 + threadIdx.x;
+        bool ok = false;
+        uint64_t key = 0;
+        uint32_t dk = 0;
+        if (k < n_chars) {
+          const uint32_t c = sm.cp[k];
+          dk = sm.doc[k];
+          const bool cjk = is_cjk_ideograph(c);
+          const int size = cjk ? kanji : ngram;  // :484-485: chosen by the START code point
+          // :487 the window must fit the document: its last character exists and is in the same document
+          if (k + static_cast<uint32_t>(size) <= n_all && sm.doc[k + size - 1] == dk) {
+            ok = true;
+            key = static_cast<uint64_t>(c) + 1;
+            for (int j = 1; j < width; ++j) {
+              uint64_t field = 0;
+              if (j < size) {
+                const uint32_t cj = sm.cp[k + j];
+                if (!cross && is_cjk_ideograph(cj) != cjk) {  // :491-503 legacy boundary rejection
+                  ok = false;
+                }
+                field = static_cast<uint64_t>(cj) + 1;
+              }
+              key = (key << 21) | field;
+            }
+          }
+        }
+        uint32_t n_emit = 0;
+        const uint32_t rank = flat_block_scan(ok ? 1u : 0u, sm.warp_cnt, &n_emit);
+        if (EMIT && ok) {
+          const uint64_t slot = strip_base + rank;
+          const uint64_t in_doc = static_cast<uint64_t>(static_cast<int64_t>(sm.pos[k]) - sm.docrel[dk]);
+          keys_out[slot] = pos_bits > 0 ? ((key << pos_bits) | umin_u64(in_doc, pos_max)) : key;
+          docs_out[slot] = r_first + dk;
+        }
+        strip_base += n_emit;
+        emitted_tile += n_emit;
+      }
+      // ---- per-document totals of this round (COUNT only)
+      if (!EMIT) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < r_docs; i += kFlatThreads) {
+          const uint32_t c = sm.doc_cps[i];
+          const uint32_t vb = sm.doc_valid[i];
+          if (c != 0) {
+            atomicAdd(&doc_len[static_cast<uint64_t>(r_first) + i], c);
+          }
+          if (vb != 0) {
+            atomicAdd(&doc_valid_bytes[static_cast<uint64_t>(r_first) + i], vb);
+          }
+        }
+      }
+    }
+    if (!EMIT && threadIdx.x == 0) {
+      tile_cnt[tile] = static_cast<uint32_t>(emitted_tile);
+    }
+  }
+}
+
+// After COUNT: corpus counters from the per-document totals. counters: [0] non-empty docs, [1] docs with invalid
+// bytes, [2] code points.
+__global__ void __launch_bounds__(256) flat_doc_stats_kernel(const uint64_t* __restrict__ text_off,
+                                                             const uint32_t* __restrict__ doc_len,
+                                                             const uint32_t* __restrict__ doc_valid_bytes,
+                                                             uint64_t n_docs, unsigned long long* __restrict__ counters) {
+  unsigned long long nonempty = 0, invalid = 0, cps = 0;
+  for (uint64_t d = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; d < n_docs;
+       d += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t bytes = text_off[d + 1] - text_off[d];
+    nonempty += bytes != 0 ? 1 : 0;
+    invalid += doc_valid_bytes[d] != bytes ? 1 : 0;
+    cps += doc_len[d];
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    nonempty += __shfl_xor_sync(0xffffffffu, nonempty, s);
+    invalid += __shfl_xor_sync(0xffffffffu, invalid, s);
+    cps += __shfl_xor_sync(0xffffffffu, cps, s);
+  }
+  if ((threadIdx.x & 31u) == 0) {
+    if (nonempty != 0) atomicAdd(&counters[0], nonempty);
+    if (invalid != 0) atomicAdd(&counters[1], invalid);
+    if (cps != 0) atomicAdd(&counters[2], cps);
+  }
+}
+
 // ------------------------------------------------------------------ CSR
 constexpr int kCsrThreads = 256;
 constexpr int kCsrItems = 8;
@@ -528,23 +825,77 @@ static unsigned tokenizer_grid(uint64_t n_docs) {
       std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(sm_count) * 8, (n_docs + kTokWarps - 1) / kTokWarps)));
 }
 
+namespace {
+struct TokScratch {
+  unsigned long long* counters;
+  uint32_t* tile_first_doc;
+  uint32_t* valid_bytes;
+  uint32_t* tile_cnt;
+  uint64_t* scan;
+  uint64_t n_tiles;
+};
+uint64_t flat_tiles(uint64_t n_docs, uint64_t text_bytes) {
+  return n_docs > 0 ? (text_bytes + kFlatTile - 1) / kFlatTile : 0;
+}
+TokScratch tok_scratch(uint64_t* d_scratch, uint64_t n_docs, uint64_t text_bytes) {
+  TokScratch t;
+  t.n_tiles = flat_tiles(n_docs, text_bytes);
+  uint64_t* p = d_scratch;
+  t.counters = reinterpret_cast<unsigned long long*>(p);
+  p += 8;
+  t.tile_first_doc = reinterpret_cast<uint32_t*>(p);
+  p += (t.n_tiles + 2) / 2 + 1;
+  t.valid_bytes = reinterpret_cast<uint32_t*>(p);
+  p += (n_docs + 2) / 2 + 1;
+  t.tile_cnt = reinterpret_cast<uint32_t*>(p);
+  p += (t.n_tiles + 2) / 2 + 1;
+  t.scan = p;
+  return t;
+}
+unsigned flat_grid(uint64_t n_tiles) {
+  int sm_count = 148;
+  int dev = 0;
+  MGX_CUDA(cudaGetDevice(&dev));
+  MGX_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  return static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(sm_count) * 4, n_tiles)));
+}
+}  // namespace
+
+size_t tokenize_tile_count(uint64_t n_docs, uint64_t text_bytes) { return flat_tiles(n_docs, text_bytes); }
+
+size_t tokenize_scratch_elems(uint64_t n_docs, uint64_t text_bytes) {
+  const uint64_t n_tiles = flat_tiles(n_docs, text_bytes);
+  return 8 + 2 * ((n_tiles + 2) / 2 + 1) + (n_docs + 2) / 2 + 1 + scan_scratch_elems(std::max<uint64_t>(n_tiles, 1)) + 8;
+}
+
 void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
-                    uint64_t n_docs, uint32_t* d_doc_len, uint64_t* d_slot_off, uint64_t* d_scratch, uint64_t* n_slots,
-                    uint64_t* counters_out, cudaStream_t stream) {
-  // scratch layout: [0..7] counters, then n-gram counts (u32, n_docs), then the scan's block sums
-  unsigned long long* d_counters = reinterpret_cast<unsigned long long*>(d_scratch);
-  uint32_t* d_ngram_cnt = reinterpret_cast<uint32_t*>(d_scratch + 8);
-  uint64_t* d_scan = d_scratch + 8 + (n_docs + 1) / 2 + 1;
-  MGX_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), stream));
-  tokenize_kernel<false><<<tokenizer_grid(n_docs), kTokThreads, 0, stream>>>(
-      d_text, d_text_off, n_docs, ngram, kanji, cross ? 1 : 0, width, d_doc_len, d_ngram_cnt, nullptr, nullptr, nullptr,
-      d_counters, 0);
-  MGX_LAUNCH_CHECK();
-  exclusive_scan_u32_u64(d_ngram_cnt, d_slot_off, n_docs, d_scan, stream);
+                    uint64_t n_docs, uint64_t text_bytes, uint32_t* d_doc_len, uint64_t* d_tile_off,
+                    uint64_t* d_scratch, uint64_t* n_slots, uint64_t* counters_out, cudaStream_t stream) {
+  const TokScratch ts = tok_scratch(d_scratch, n_docs, text_bytes);
+  MGX_CUDA(cudaMemsetAsync(ts.counters, 0, 8 * sizeof(unsigned long long), stream));
+  if (n_docs > 0) {
+    MGX_CUDA(cudaMemsetAsync(d_doc_len, 0, n_docs * sizeof(uint32_t), stream));
+    MGX_CUDA(cudaMemsetAsync(ts.valid_bytes, 0, n_docs * sizeof(uint32_t), stream));
+  }
+  if (ts.n_tiles > 0) {
+    flat_tile_first_doc_kernel<<<static_cast<unsigned>((ts.n_tiles + 255) / 256), 256, 0, stream>>>(
+        d_text_off, n_docs, ts.n_tiles, ts.tile_first_doc);
+    MGX_LAUNCH_CHECK();
+    tokenize_flat_kernel<false><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
+        d_text, d_text_off, n_docs, text_bytes, ts.n_tiles, ts.tile_first_doc, ngram, kanji, cross ? 1 : 0, width, 0,
+        d_doc_len, ts.valid_bytes, ts.tile_cnt, nullptr, nullptr, nullptr);
+    MGX_LAUNCH_CHECK();
+  }
+  if (n_docs > 0) {
+    flat_doc_stats_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n_docs + 255) / 256, 148 * 8)), 256, 0, stream>>>(
+        d_text_off, d_doc_len, ts.valid_bytes, n_docs, ts.counters);
+    MGX_LAUNCH_CHECK();
+  }
+  exclusive_scan_u32_u64(ts.tile_cnt, d_tile_off, ts.n_tiles, ts.scan, stream);
   uint64_t total = 0;
   unsigned long long counters[3] = {0, 0, 0};
-  MGX_CUDA(cudaMemcpyAsync(&total, d_slot_off + n_docs, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-  MGX_CUDA(cudaMemcpyAsync(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost, stream));
+  MGX_CUDA(cudaMemcpyAsync(&total, d_tile_off + ts.n_tiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+  MGX_CUDA(cudaMemcpyAsync(counters, ts.counters, sizeof(counters), cudaMemcpyDeviceToHost, stream));
   MGX_CUDA(cudaStreamSynchronize(stream));
   *n_slots = total;
   counters_out[0] = counters[0];
@@ -553,11 +904,15 @@ void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* 
 }
 
 void tokenize_emit(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
-                   uint64_t n_docs, const uint64_t* d_slot_off, uint64_t* d_keys, uint32_t* d_docs, int pos_bits,
-                   cudaStream_t stream) {
-  tokenize_kernel<true><<<tokenizer_grid(n_docs), kTokThreads, 0, stream>>>(
-      d_text, d_text_off, n_docs, ngram, kanji, cross ? 1 : 0, width, nullptr, nullptr, d_slot_off, d_keys, d_docs,
-      nullptr, pos_bits);
+                   uint64_t n_docs, uint64_t text_bytes, const uint64_t* d_tile_off, uint64_t* d_scratch,
+                   uint64_t* d_keys, uint32_t* d_docs, int pos_bits, cudaStream_t stream) {
+  const TokScratch ts = tok_scratch(d_scratch, n_docs, text_bytes);  // tile_first_doc was filled by tokenize_count
+  if (ts.n_tiles == 0) {
+    return;
+  }
+  tokenize_flat_kernel<true><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
+      d_text, d_text_off, n_docs, text_bytes, ts.n_tiles, ts.tile_first_doc, ngram, kanji, cross ? 1 : 0, width, pos_bits,
+      nullptr, nullptr, nullptr, d_tile_off, d_keys, d_docs);
   MGX_LAUNCH_CHECK();
 }
 
@@ -658,9 +1013,10 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
 
   // ---- temporary arena T0: counting stage
   DevArena t0;
-  const size_t count_scratch = 8 + (n_docs + 1) / 2 + 1 + scan_scratch_elems(n_docs) + 8;
-  t0.reserve(DevArena::padded((n_docs + 1) * 8) + DevArena::padded(count_scratch * 8) + 512);
-  uint64_t* d_slot_off = t0.take<uint64_t>(n_docs + 1);
+  const size_t count_scratch = tokenize_scratch_elems(n_docs, text_bytes);
+  const size_t n_tok_tiles = tokenize_tile_count(n_docs, text_bytes);
+  t0.reserve(DevArena::padded((n_tok_tiles + 1) * 8) + DevArena::padded(count_scratch * 8) + 512);
+  uint64_t* d_slot_off = t0.take<uint64_t>(n_tok_tiles + 1);
   uint64_t* d_count_scratch = t0.take<uint64_t>(count_scratch);
   unsigned int* d_bad = t0.take<unsigned int>(1);
   if (n_docs > 0) {
@@ -684,8 +1040,8 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
 
   uint64_t n_slots = 0;
   uint64_t counters[3] = {0, 0, 0};
-  tokenize_count(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, ix.d_doc_len.p,
-                 d_slot_off, d_count_scratch, &n_slots, counters, stream);
+  tokenize_count(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, text_bytes,
+                 ix.d_doc_len.p, d_slot_off, d_count_scratch, &n_slots, counters, stream);
   trace.mark("tokenize: count + scan");
   ix.n_pair_slots = n_slots;
   ix.doc_count = counters[0];
@@ -713,8 +1069,8 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   uint64_t* d_totals = t1.take<uint64_t>(4);
   trace.mark("alloc pair arena");
   if (n_slots > 0) {
-    tokenize_emit(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, d_slot_off, d_keys_a,
-                  d_docs_a, pb, stream);
+    tokenize_emit(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, text_bytes, d_slot_off,
+                  d_count_scratch, d_keys_a, d_docs_a, pb, stream);
   }
   trace.mark("tokenize: emit");
   const SortResult sorted =

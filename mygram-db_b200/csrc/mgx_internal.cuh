@@ -447,18 +447,19 @@ void apply_journal_device(Index& ix, const uint32_t* h_ids, const uint8_t* h_rem
 // Number of posting lists the reference would hold as Roaring bitmaps (see mgx_index_get_statistics).
 uint64_t count_roaring_lists(const Index& ix, double roaring_threshold, uint64_t optimized_total_docs,
                              cudaStream_t stream);
-// Tokenise only (mgx_tokenize_batch): fills d_keys/d_docs slots (kInvalidKey for non-emitting positions).
-// Tokeniser stage 1: per-document code-point counts (d_doc_len) and n-gram counts -> d_slot_off (exclusive scan,
-// n_docs + 1 entries). counters_out: [0] non-empty docs, [1] docs with invalid bytes, [2] total code points.
-// d_scratch: (n_docs + scan_scratch_elems(n_docs) + 8) uint64 of device memory.
+// Flat tile-based tokenizer (build.cu). Stage 1: per-document code-point counts (d_doc_len), per-tile n-gram counts
+// scanned into d_tile_off (tokenize_tile_count() + 1 entries; the last is the total). counters_out: [0] non-empty
+// docs, [1] docs with invalid bytes, [2] total code points. d_scratch: tokenize_scratch_elems() uint64 of device
+// memory, to be passed again (untouched) to stage 2.
+size_t tokenize_tile_count(uint64_t n_docs, uint64_t text_bytes);
+size_t tokenize_scratch_elems(uint64_t n_docs, uint64_t text_bytes);
 void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
-                    uint64_t n_docs, uint32_t* d_doc_len, uint64_t* d_slot_off, uint64_t* d_scratch, uint64_t* n_slots,
-                    uint64_t* counters_out, cudaStream_t stream);
-// Tokeniser stage 2: (packed key, doc) pairs, exactly d_slot_off[n_docs] of them, in document order.
-// pos_bits > 0: every key is shifted left by pos_bits and carries the byte offset of the n-gram in its document
-// (saturated) in the freed low bits.
+                    uint64_t n_docs, uint64_t text_bytes, uint32_t* d_doc_len, uint64_t* d_tile_off,
+                    uint64_t* d_scratch, uint64_t* n_slots, uint64_t* counters_out, cudaStream_t stream);
+// Stage 2: (packed key, doc) pairs, exactly d_tile_off[n_tiles] of them, in text order. pos_bits > 0: every key is
+// shifted left by pos_bits and carries the byte offset of the n-gram in its document (saturated) in the low bits.
 void tokenize_emit(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
-                   uint64_t n_docs, const uint64_t* d_slot_off, uint64_t* d_keys, uint32_t* d_docs, int pos_bits,
-                   cudaStream_t stream);
+                   uint64_t n_docs, uint64_t text_bytes, const uint64_t* d_tile_off, uint64_t* d_scratch,
+                   uint64_t* d_keys, uint32_t* d_docs, int pos_bits, cudaStream_t stream);
 
 }  // namespace mgx
