@@ -5,16 +5,16 @@
 // document, per-document sort+unique (index.cpp:88-91), term -> ascending doc
 // ids (index.cpp:104-118, posting_list.cpp:291-324).
 //
-//   K1 tokenize<COUNT>  text -> code-point count per doc (= CountCodePoints,
-//                       string_utils.cpp:655-669) ; 128-bit loads, warp per doc
-//      scan             slot offsets (one pair slot per code point)
-//   K2 tokenize<EMIT>   text -> (packed n-gram key, doc) pairs, decoded through a
-//                       per-warp shared-memory window; non-emitting positions
-//                       get kInvalidKey so no second count pass is needed
-//   K3 radix sort       stable by key => docs ascending inside a key (primitives.cu)
-//   K4 csr              segmented unique (drops duplicate (key, doc) = the
-//                       per-document unique) + compaction into CSR
-//   K5 bitmaps          doc bitmaps for lists with density >= dense_threshold
+//   K1 tokenize_flat<COUNT>  4 KB tiles of the text arena, one 16-byte chunk per thread, document boundaries from
+//                            a shared-memory table: code points per document (= CountCodePoints,
+//                            string_utils.cpp:655-669), valid bytes per document, n-grams per tile
+//      scan                  tile -> first n-gram slot
+//   K2 tokenize_flat<EMIT>   same decode; writes (packed key << 22 | byte offset in document, doc) in text order
+//   K3 radix sort            stable by key => docs ascending inside a key, occurrences in text order (primitives.cu)
+//   K4 csr                   segmented unique (drops duplicate (key, doc) = the per-document unique) + compaction
+//                            into CSR; first / second occurrence positions of every posting
+//   K5 bitmaps               doc bitmaps for lists with density >= dense_threshold
+//   K6 journal merge         resident corpus + mutation journal -> merged corpus (then K1..K5 again)
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -24,11 +24,6 @@
 namespace mgx {
 
 namespace {
-
-constexpr int kTokThreads = 256;
-constexpr int kTokWarps = kTokThreads / 32;
-constexpr int kTokTileBytes = 512;                 // bytes per warp iteration (32 lanes x 16 B)
-constexpr int kTokBuf = kTokTileBytes + 4;         // code points per warp window (+ carry)
 
 __device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[5], int j) {
   return (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
@@ -43,197 +38,6 @@ __device__ __forceinline__ uint4 ld_stream_16(const uint8_t* p) {
                : "l"(p));
   return r;
 }
-
-// One warp walks one document in 512-byte tiles. Strict UTF-8 decoding is a
-// LOCAL predicate per byte: every non-continuation byte is visited by the
-// reference's "skip one byte and retry" scan (string_utils.cpp:206-216), because
-// a valid multi-byte character only ever covers continuation bytes; so a code
-// point starts at byte i iff TryParseUtf8Char(i) succeeds with the bytes that
-// remain in the document.
-//
-// Both modes run the same decode + window logic (GenerateHybridNgrams,
-// string_utils.cpp:452-509). COUNT records per document the number of code points
-// (= CountCodePoints, the BM25 document length) and the number of n-grams; EMIT
-// writes exactly that many (packed key, doc) pairs at the scanned offsets, so the
-// sort never sees a placeholder.
-template <bool EMIT>
-__global__ void __launch_bounds__(kTokThreads)
-tokenize_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ text_off, uint64_t n_docs, int ngram,
-                int kanji, int cross, int width, uint32_t* __restrict__ doc_len, uint32_t* __restrict__ ngram_cnt,
-                const uint64_t* __restrict__ slot_off, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ docs_out,
-                unsigned long long* __restrict__ counters /* [0] non-empty docs, [1] docs with invalid bytes, [2] code points */,
-                int pos_bits) {
-  __shared__ uint32_t cp_buf[kTokWarps][kTokBuf];
-  __shared__ uint32_t pos_buf[EMIT ? kTokWarps : 1][EMIT ? kTokBuf : 1];  // byte offset of each code point in its document
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned warp_in_cta = threadIdx.x >> 5;
-  const uint64_t warp_global = static_cast<uint64_t>(blockIdx.x) * kTokWarps + warp_in_cta;
-  const uint64_t warp_stride = static_cast<uint64_t>(gridDim.x) * kTokWarps;
-  unsigned long long nonempty = 0;
-  unsigned long long invalid = 0;
-  unsigned long long total_cps = 0;
-  uint32_t* buf = cp_buf[warp_in_cta];
-  uint32_t* pbuf = pos_buf[EMIT ? warp_in_cta : 0];
-  const uint64_t pos_max = pos_bits > 0 ? ((1ULL << pos_bits) - 1) : 0;
-
-  for (uint64_t d = warp_global; d < n_docs; d += warp_stride) {
-    const uint64_t b = text_off[d];
-    const uint64_t e = text_off[d + 1];
-    if (e <= b) {
-      if (!EMIT && lane == 0) {
-        doc_len[d] = 0;
-        ngram_cnt[d] = 0;
-      }
-      continue;
-    }
-    nonempty += 1;
-    uint64_t cps_done = 0;   // code points whose window decision is final
-    uint32_t emitted = 0;    // n-grams of this document so far
-    uint32_t carry_n = 0;    // undecided code points kept at the front of the window
-    uint64_t valid_bytes = 0;
-    const uint64_t slot_base = EMIT ? slot_off[d] : 0;
-
-    for (uint64_t base = b & ~15ULL; base < e; base += kTokTileBytes) {
-      const uint64_t my = base + static_cast<uint64_t>(lane) * 16;
-      uint32_t w[5] = {0, 0, 0, 0, 0};
-      if (my < e) {
-        const uint4 v = ld_stream_16(text + my);  // arena is padded, 16-B aligned
-        w[0] = v.x;
-        w[1] = v.y;
-        w[2] = v.z;
-        w[3] = v.w;
-      }
-      uint32_t nxt = __shfl_down_sync(0xffffffffu, w[0], 1);
-      if (lane == 31) {
-        nxt = (my + 16 < e) ? *reinterpret_cast<const uint32_t*>(text + my + 16) : 0u;
-      }
-      w[4] = nxt;
-
-      uint32_t flags = 0;
-      uint32_t cps[16];
-      uint32_t len_sum = 0;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const uint64_t pos = my + j;
-        cps[j] = 0;
-        if (pos >= b && pos < e) {
-          uint32_t cp = 0;
-          const int len = parse_utf8(byte_of(w, j), byte_of(w, j + 1), byte_of(w, j + 2), byte_of(w, j + 3), e - pos, &cp);
-          if (len > 0) {
-            flags |= 1u << j;
-            cps[j] = cp;
-            len_sum += static_cast<uint32_t>(len);
-          }
-        }
-      }
-      // warp exclusive scan of per-lane code point counts
-      const uint32_t cnt = __popc(flags);
-      uint32_t inc = cnt;
-#pragma unroll
-      for (int s = 1; s < 32; s <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, s);
-        if (lane >= static_cast<unsigned>(s)) {
-          inc += o;
-        }
-      }
-      const uint32_t tile_total = __shfl_sync(0xffffffffu, inc, 31);
-      uint32_t bytes_inc = len_sum;
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1) {
-        bytes_inc += __shfl_xor_sync(0xffffffffu, bytes_inc, s);
-      }
-      valid_bytes += bytes_inc;
-
-      uint32_t wpos = carry_n + inc - cnt;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (flags & (1u << j)) {
-          if (EMIT) {
-            pbuf[wpos] = static_cast<uint32_t>(umin_u64(my + j - b, 0xFFFFFFFFULL));
-          }
-          buf[wpos++] = cps[j];
-        }
-      }
-      __syncwarp();
-      const uint32_t m = carry_n + tile_total;  // code points available in the window
-      const bool last_tile = base + kTokTileBytes >= e;
-      const uint32_t keep = last_tile ? 0u : min(m, static_cast<uint32_t>(width - 1));
-      const uint32_t emit_n = m - keep;
-      for (uint32_t p0 = 0; p0 < emit_n; p0 += 32) {
-        const uint32_t p = p0 + lane;
-        uint64_t key = 0;
-        bool ok = false;
-        if (p < emit_n) {
-          const uint32_t c0 = buf[p];
-          const bool cjk = is_cjk_ideograph(c0);
-          const int size = cjk ? kanji : ngram;  // string_utils.cpp:484-485: chosen by the START code point
-          if (p + static_cast<uint32_t>(size) <= m) {  // :487 (on the last tile m is the document's end)
-            ok = true;
-            key = static_cast<uint64_t>(c0) + 1;
-            for (int j = 1; j < width; ++j) {
-              uint64_t field = 0;
-              if (j < size) {
-                const uint32_t cj = buf[p + j];
-                if (!cross && is_cjk_ideograph(cj) != cjk) {  // :491-503 legacy boundary rejection
-                  ok = false;
-                }
-                field = static_cast<uint64_t>(cj) + 1;
-              }
-              key = (key << 21) | field;
-            }
-          }
-        }
-        const unsigned ballot = __ballot_sync(0xffffffffu, ok);
-        if (EMIT && ok) {
-          const uint64_t slot = slot_base + emitted + __popc(ballot & lt_mask);
-          keys_out[slot] = pos_bits > 0 ? ((key << pos_bits) | umin_u64(pbuf[p], pos_max)) : key;
-          docs_out[slot] = static_cast<uint32_t>(d);
-        }
-        emitted += __popc(ballot);
-      }
-      __syncwarp();
-      uint32_t carried = 0;
-      uint32_t carried_pos = 0;
-      if (lane < keep) {
-        carried = buf[emit_n + lane];
-        if (EMIT) {
-          carried_pos = pbuf[emit_n + lane];
-        }
-      }
-      __syncwarp();
-      if (lane < keep) {
-        buf[lane] = carried;
-        if (EMIT) {
-          pbuf[lane] = carried_pos;
-        }
-      }
-      __syncwarp();
-      cps_done += emit_n;
-      carry_n = keep;
-    }
-    if (!EMIT && lane == 0) {
-      doc_len[d] = static_cast<uint32_t>(cps_done);
-      ngram_cnt[d] = emitted;
-    }
-    total_cps += cps_done;
-    if (valid_bytes != e - b) {
-      invalid += 1;
-    }
-  }
-  if (!EMIT && lane == 0) {
-    if (nonempty != 0) {
-      atomicAdd(&counters[0], nonempty);
-    }
-    if (invalid != 0) {
-      atomicAdd(&counters[1], invalid);
-    }
-    if (total_cps != 0) {
-      atomicAdd(&counters[2], total_cps);
-    }
-  }
-}
-
 
 // ------------------------------------------------------------------ flat tokenizer
 // The arena is one byte stream (documents back to back), so tokenisation does not have to walk it document by
@@ -814,16 +618,6 @@ void Index::drop_filter_columns() {
 }
 
 uint64_t Index::device_bytes() const { return resident_a.blob.bytes() + resident_b.blob.bytes() + d_bitmaps.bytes(); }
-
-static unsigned tokenizer_grid(uint64_t n_docs) {
-  int sm_count = 148;
-  int dev = 0;
-  MGX_CUDA(cudaGetDevice(&dev));
-  MGX_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  // persistent-style grid: 8 CTAs of 8 warps per SM, warps stride over documents
-  return static_cast<unsigned>(
-      std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(sm_count) * 8, (n_docs + kTokWarps - 1) / kTokWarps)));
-}
 
 namespace {
 struct TokScratch {

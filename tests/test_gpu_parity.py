@@ -610,3 +610,32 @@ def test_mixed_boolean_batch_with_filters(mgx, oracle):
         got = list(zip(g.ids[qi, :int(g.count[qi])].tolist(), g.scores[qi, :int(g.count[qi])].tolist()))
         assert [d for d, _ in got] == [d for d, _ in want], (qi, fls[qi])
         assert np.allclose([s for _, s in got], [s for _, s in want], rtol=1e-9, atol=0)
+
+
+# ----------------------------------------------------------------------------------------- C5 in small: huge batches
+def test_large_batch_of_short_queries_picks_streaming_df(mgx, oracle, monkeypatch):
+    """BASELINE config 5 in small: tens of thousands of 1-2-term queries of 2-3 code points in ONE batch. With that
+    many multi-n-gram terms the candidate work exceeds one pass over the text arena, so the per-batch cost model
+    (df_mode_kernel, no MGX_DF_MODE override) must choose the streaming df pass; answers are checked against the
+    oracle on a sample, and against the candidate-tile path for every query."""
+    monkeypatch.delenv("MGX_DF_MODE", raising=False)
+    c = corpus_mod.generate("cjk", 50000, 0xC5, alphabet=300, min_len=8, max_len=40)
+    gi = mgx.Index(2, 0, True)
+    gi.build(c.doc_ids, c.arena, c.offsets)
+    oi = oracle.index(2, 0, True)
+    oi.build_bulk(c.doc_ids, c.arena, c.offsets, 8)
+    qs = corpus_mod.sample_queries(c, 32768, 55, n_terms=2, min_cp=2, max_cp=3)
+    g = gi.query_batch(qs, score=True, limit=100)
+    st = gi.last_batch_stats()
+    assert st.df_stream_terms > 0 and st.ms_df_stream_kernel > 0, "the cost model did not pick the streaming pass"
+    monkeypatch.setenv("MGX_DF_MODE", "tiles")
+    t = gi.query_batch(qs, score=True, limit=100)
+    assert gi.last_batch_stats().df_stream_terms == 0
+    assert np.array_equal(g.df, t.df) and np.array_equal(g.total, t.total) and np.array_equal(g.count, t.count)
+    valid = np.arange(g.ids.shape[1])[None, :] < g.count[:, None]   # entries beyond count are unspecified
+    assert np.array_equal(g.ids[valid], t.ids[valid]) and np.array_equal(g.scores[valid], t.scores[valid])
+    sample = list(range(0, len(qs), 64))
+    o = oi.query_batch([qs[i] for i in sample], score=True, limit=100, n_threads=8)
+    sub = type(g)(g.ids[sample], g.scores[sample], g.count[sample], g.total[sample],
+                  np.concatenate([g.df[2 * i:2 * i + 2] for i in sample]))
+    assert_batch_equal(sub, o, [qs[i] for i in sample])
