@@ -251,6 +251,8 @@ def main():
         run_reference_arm(args, rank)
         return
 
+    # host threads of the library's query compiler: the box's cores shared between the ranks
+    os.environ.setdefault("MGX_COMPILE_THREADS", str(max(1, min(4, (os.cpu_count() or 1) // (2 * world)))))
     import torch
     import torch.distributed as dist
     import corpus as corpus_mod
@@ -363,7 +365,8 @@ def main():
     # a stream of batches: a compile thread prepares batch i+1 (host query compile + H2D of the compiled batch)
     # while the main thread enqueues batch i and waits for batch i-1 (the planning stage of a batch still waits for
     # its predecessor on the same stream). Every step copies its own inputs host->device and its own results
-    # device->host; a step is complete when its results are in pinned host memory.
+    # device->host; a step is complete when its results are in pinned host memory. Batches alternate between two
+    # CUDA streams so that consecutive batches may overlap on the device.
     backend.collect_stats = False
     outs = [dict(ids=torch.empty((args.batch, TOPK), dtype=torch.int32, pin_memory=True),
                  scores=torch.empty((args.batch, TOPK), dtype=torch.float64, pin_memory=True),
@@ -373,20 +376,25 @@ def main():
     out_ids, out_scores, out_count, out_total = (outs[0][k] for k in ("ids", "scores", "count", "total"))
     e2e_parts = {"host_prepare_ms": 0.0, "enqueue_ms": 0.0, "wait_ms": 0.0}
 
-    def e2e_prepare(b):
+    # two CUDA streams, alternating per batch: the planning stage of batch i+1 (which ends in a small host
+    # read-back) overlaps the search kernels of batch i instead of leaving the device idle
+    e2e_streams = [torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)]
+
+    def e2e_prepare(b, slot):
         t_a = time.perf_counter()
-        p = backend.prepare(b[1], b[2], b[3], args.batch)   # host query compile + staging + H2D enqueue
+        p = backend.prepare(b[1], b[2], b[3], args.batch, stream=e2e_streams[slot])  # compile + staging + H2D enqueue
         return p, 1e3 * (time.perf_counter() - t_a)
 
     def e2e_enqueue(p, slot, acc=None):
         t_b = time.perf_counter()
-        ids, scores, count, total = sharded.run_sharded_batch(backend, comm, p)
-        o = outs[slot]
-        o["ids"].copy_(ids, non_blocking=True)
-        o["scores"].copy_(scores, non_blocking=True)
-        o["count"].copy_(count, non_blocking=True)
-        o["total"].copy_(total, non_blocking=True)
-        o["done"].record()
+        with torch.cuda.stream(e2e_streams[slot]):
+            ids, scores, count, total = sharded.run_sharded_batch(backend, comm, p)
+            o = outs[slot]
+            o["ids"].copy_(ids, non_blocking=True)
+            o["scores"].copy_(scores, non_blocking=True)
+            o["count"].copy_(count, non_blocking=True)
+            o["total"].copy_(total, non_blocking=True)
+            o["done"].record()
         if acc is not None:
             acc["enqueue_ms"] += 1e3 * (time.perf_counter() - t_b)  # plan (one size read-back), df, search, merge, D2H
         return p, slot
@@ -406,13 +414,13 @@ def main():
         if first >= last:
             return
         pending = None
-        fut = compiler.submit(e2e_prepare, batches[first])
+        fut = compiler.submit(e2e_prepare, batches[first], first & 1)
         for i in range(first, last):
             p, prep_ms = fut.result()
             if acc is not None:
                 acc["host_prepare_ms"] += prep_ms
             if i + 1 < last:
-                fut = compiler.submit(e2e_prepare, batches[i + 1])
+                fut = compiler.submit(e2e_prepare, batches[i + 1], (i + 1) & 1)
             cur = e2e_enqueue(p, i & 1, acc)
             if pending is not None:
                 e2e_finish(pending, acc)

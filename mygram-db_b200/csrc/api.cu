@@ -14,6 +14,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 
 #include "query.cuh"
@@ -332,13 +333,18 @@ int analyse_program(const int32_t* ops, const int32_t* args, uint64_t n_ops, uin
   return MGX_OK;
 }
 
-int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queries, const uint8_t* term_bytes,
-                  const uint64_t* term_offsets, const uint64_t* q_term_begin, const uint8_t* not_bytes,
-                  const uint64_t* not_offsets, const uint64_t* q_not_begin, const mgx_query_ext_t* ext,
-                  std::vector<HostTerm>* terms, std::vector<HostQuery>* queries, std::vector<uint32_t>* slot_tid) {
+// Compiles queries [q_first, q_last) of the caller's flat description: unique terms of THAT range into `terms` (ids
+// local to the range), the queries and the term id of every search-term slot into the caller-sized `queries` /
+// `slot_tid`. Ranges are independent, so a large batch is compiled by several threads (compile_batch below).
+int compile_range(const Index& ix, const mgx_query_params_t& p, uint64_t q_first, uint64_t q_last,
+                  const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                  const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                  const mgx_query_ext_t* ext, std::vector<HostTerm>* terms, std::vector<HostQuery>* queries,
+                  std::vector<uint32_t>* slot_tid) {
   // open-addressing table of term ids keyed by the term bytes (no string is built for a lookup)
-  const uint64_t n_search_slots = n_queries > 0 ? q_term_begin[n_queries] : 0;
-  const uint64_t n_not_slots = (n_queries > 0 && q_not_begin != nullptr) ? q_not_begin[n_queries] : 0;
+  const uint64_t n_search_slots = q_last > q_first ? q_term_begin[q_last] - q_term_begin[q_first] : 0;
+  const uint64_t n_not_slots =
+      (q_last > q_first && q_not_begin != nullptr) ? q_not_begin[q_last] - q_not_begin[q_first] : 0;
   size_t table_cap = 64;
   while (table_cap < 2 * (n_search_slots + n_not_slots) + 16) {
     table_cap <<= 1;
@@ -376,6 +382,7 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
       slot = (slot + 1) & (table_cap - 1);
     }
     HostTerm t;
+    t.hash = h;
     t.bytes.assign(reinterpret_cast<const char*>(bytes) + b, e - b);
     host_query_keys(bytes + b, e - b, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0, ix.width, &t.keys,
                     tok_agree ? &t.key_toff : nullptr);
@@ -405,10 +412,7 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
     *out = id;
     return MGX_OK;
   };
-  const uint64_t n_slots = n_queries > 0 ? q_term_begin[n_queries] : 0;
-  slot_tid->assign(n_slots, 0);
-  queries->resize(n_queries);
-  for (uint64_t q = 0; q < n_queries; ++q) {
+  for (uint64_t q = q_first; q < q_last; ++q) {
     HostQuery& hq = (*queries)[q];
     bool all_ascii = true;
     bool hybrid_exact = false;
@@ -483,6 +487,112 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
                           ext->filter_offsets[f + 1] - ext->filter_offsets[f]);
         hq.filters.push_back(std::move(hf));
       }
+    }
+  }
+  return MGX_OK;
+}
+
+unsigned compile_threads(uint64_t n_queries) {
+  if (n_queries < 2048) {
+    return 1;
+  }
+  unsigned t = std::max(1u, std::min(4u, std::thread::hardware_concurrency() / 8));
+  if (const char* env = std::getenv("MGX_COMPILE_THREADS")) {
+    t = static_cast<unsigned>(std::max(1, std::atoi(env)));
+  }
+  return std::min<unsigned>(t, 16);
+}
+
+// Compile the caller's flat query description into unique terms + queries. Large batches are cut into ranges of
+// queries compiled concurrently (tokenising the terms is the expensive part); the ranges' term tables are then
+// merged into one.
+int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queries, const uint8_t* term_bytes,
+                  const uint64_t* term_offsets, const uint64_t* q_term_begin, const uint8_t* not_bytes,
+                  const uint64_t* not_offsets, const uint64_t* q_not_begin, const mgx_query_ext_t* ext,
+                  std::vector<HostTerm>* terms, std::vector<HostQuery>* queries, std::vector<uint32_t>* slot_tid) {
+  const uint64_t n_slots = n_queries > 0 ? q_term_begin[n_queries] : 0;
+  slot_tid->assign(n_slots, 0);
+  queries->clear();
+  queries->resize(n_queries);
+  const unsigned T = compile_threads(n_queries);
+  if (T <= 1) {
+    return compile_range(ix, p, 0, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
+                         q_not_begin, ext, terms, queries, slot_tid);
+  }
+  std::vector<std::vector<HostTerm>> part_terms(T);
+  std::vector<int> rcs(T, MGX_OK);
+  std::vector<std::string> errs(T);
+  std::vector<std::thread> workers;
+  auto range_of = [&](unsigned t) { return std::make_pair(n_queries * t / T, n_queries * (t + 1) / T); };
+  for (unsigned t = 0; t < T; ++t) {
+    workers.emplace_back([&, t]() {
+      const auto [q0, q1] = range_of(t);
+      rcs[t] = compile_range(ix, p, q0, q1, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets, q_not_begin,
+                             ext, &part_terms[t], queries, slot_tid);
+      if (rcs[t] != MGX_OK) {
+        errs[t] = mgx_last_error();  // thread-local in the worker
+      }
+    });
+  }
+  for (auto& w : workers) {
+    w.join();
+  }
+  for (unsigned t = 0; t < T; ++t) {
+    if (rcs[t] != MGX_OK) {
+      set_last_error(errs[t]);
+      return rcs[t];
+    }
+  }
+  // merge: one id per distinct term over all ranges (the expensive terms are the frequent ones, which every range
+  // meets: leaving them duplicated would repeat exactly the heaviest df work)
+  size_t total_terms = 0;
+  for (const auto& pt : part_terms) {
+    total_terms += pt.size();
+  }
+  size_t cap = 64;
+  while (cap < 2 * total_terms + 16) {
+    cap <<= 1;
+  }
+  std::vector<uint32_t> table(cap, 0);  // batch term id + 1
+  terms->clear();
+  terms->reserve(total_terms);
+  std::vector<uint32_t> remap;
+  for (unsigned t = 0; t < T; ++t) {
+    remap.assign(part_terms[t].size(), 0);
+    for (size_t i = 0; i < part_terms[t].size(); ++i) {
+      HostTerm& ht = part_terms[t][i];
+      size_t slot = static_cast<size_t>(ht.hash) & (cap - 1);
+      uint32_t id = 0;
+      for (;;) {
+        if (table[slot] == 0) {
+          id = static_cast<uint32_t>(terms->size());
+          table[slot] = id + 1;
+          terms->push_back(std::move(ht));
+          break;
+        }
+        const HostTerm& known = (*terms)[table[slot] - 1];
+        if (known.hash == ht.hash && known.bytes == ht.bytes) {
+          id = table[slot] - 1;
+          break;
+        }
+        slot = (slot + 1) & (cap - 1);
+      }
+      remap[i] = id;
+    }
+    const auto [q0, q1] = range_of(t);
+    for (uint64_t q = q0; q < q1; ++q) {  // range-local term ids -> batch ids
+      HostQuery& hq = (*queries)[q];
+      for (uint32_t& id : hq.terms) id = remap[id];
+      for (uint32_t& id : hq.not_terms) id = remap[id];
+      for (uint32_t& id : hq.conjuncts) id = remap[id];
+      for (size_t i = 0; i < hq.prog_ops.size(); ++i) {
+        if (hq.prog_ops[i] == kOpTerm) {
+          hq.prog_args[i] = remap[hq.prog_args[i]];
+        }
+      }
+    }
+    for (uint64_t s2 = q_term_begin[q0]; s2 < q_term_begin[q1]; ++s2) {
+      (*slot_tid)[s2] = remap[(*slot_tid)[s2]];
     }
   }
   return MGX_OK;

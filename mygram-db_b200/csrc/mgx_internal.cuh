@@ -287,7 +287,7 @@ struct SearchScratch {
   DevBuf<uint32_t> tile_total;
   DevBuf<uint32_t> rec_doc;
   DevBuf<double> rec_score;
-  DevBuf<uint32_t> df_tile_term;
+  DevBuf<uint4> df_tile_desc;  // DfTileDesc records (two uint4 each), see query.cuh
   DevBuf<uint32_t> tile_query;
   DevBuf<uint32_t> topk_groups;  // (query, first tile, end tile) triples of the top-k pre-reduction
   uint64_t map_owner = 0;  // serial of the batch whose tile maps are in df_tile_term / tile_query

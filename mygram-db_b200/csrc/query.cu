@@ -77,7 +77,8 @@ struct BatchView {
   const uint32_t* explicit_ids;
   uint32_t explicit_n;
   unsigned long long* stats;  // StatSlot counters
-  const uint32_t* df_tile_term;  // [df tiles] unique-term index of each df tile
+  const DfTileDesc* df_tile_desc;  // [df tiles]
+  KeyRef* key_ref;                 // [K]
   const uint32_t* tile_query;    // [and tiles] query index of each intersect tile
   // streaming df pass
   const uint32_t* stream_slots;        // bucket table: (first entry << 8) | count
@@ -625,6 +626,83 @@ __device__ __forceinline__ bool group_contains_term(const uint8_t* __restrict__ 
   return found;
 }
 
+// key -> resolved list, after term_plan_kernel has ordered each term's keys by list length
+__global__ void key_ref_kernel(IndexView iv, const uint32_t* __restrict__ key_list, const uint32_t* __restrict__ key_len,
+                               uint32_t n_keys, KeyRef* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_keys) {
+    return;
+  }
+  KeyRef r{};
+  const uint32_t dict = key_list[i];
+  if (dict != kNone) {
+    r.p = iv.postings + iv.term_off[dict];
+    const int32_t slot = iv.term_bm[dict];
+    r.bm = slot >= 0 ? iv.bitmaps + static_cast<uint64_t>(slot) * iv.bm_words : nullptr;
+    r.len = key_len[i];
+  }
+  out[i] = r;
+}
+
+// df tile descriptors: term t owns tiles [off[t], off[t+1]); one warp per term.
+__global__ void fill_df_desc_kernel(const uint64_t* __restrict__ off, const uint32_t* __restrict__ term_koff,
+                                    const KeyRef* __restrict__ key_ref, uint32_t n_terms, DfTileDesc* __restrict__ out) {
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_terms) {
+    return;
+  }
+  const uint64_t b = off[t];
+  const uint64_t e = off[t + 1];
+  if (e == b) {
+    return;
+  }
+  DfTileDesc d{};
+  d.k0 = term_koff[t];
+  d.k1 = term_koff[t + 1];
+  d.term = t;
+  d.drv_p = key_ref[d.k0].p;
+  d.drv_len = key_ref[d.k0].len;
+  for (uint64_t i = b + (threadIdx.x & 31u); i < e; i += 32) {
+    d.tile = static_cast<uint32_t>(i - b);
+    out[i] = d;
+  }
+}
+
+// Two lower bounds in one list by a whole warp, the probes of both searches in flight together.
+__device__ __forceinline__ void warp_lower_bound_pair(const uint32_t* __restrict__ p, uint32_t n, uint32_t v1, uint32_t v2,
+                                                      uint32_t* out1, uint32_t* out2) {
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t lo1 = 0, hi1 = n, lo2 = 0, hi2 = n;
+  while (hi1 - lo1 > 32 || hi2 - lo2 > 32) {
+    const bool a1 = hi1 - lo1 > 32;
+    const bool a2 = hi2 - lo2 > 32;
+    const uint32_t idx1 = lo1 + static_cast<uint32_t>((static_cast<uint64_t>(lane + 1) * (hi1 - lo1)) / 33);
+    const uint32_t idx2 = lo2 + static_cast<uint32_t>((static_cast<uint64_t>(lane + 1) * (hi2 - lo2)) / 33);
+    const uint32_t x1 = a1 ? __ldg(p + idx1) : 0u;
+    const uint32_t x2 = a2 ? __ldg(p + idx2) : 0u;
+    if (a1) {
+      const int c = __popc(__ballot_sync(0xffffffffu, x1 < v1));  // monotone in the lane index
+      const uint32_t prev = __shfl_sync(0xffffffffu, idx1, c > 0 ? c - 1 : 0);
+      const uint32_t next = __shfl_sync(0xffffffffu, idx1, c < 32 ? c : 31);
+      if (c > 0) lo1 = prev + 1;
+      if (c < 32) hi1 = next;
+    }
+    if (a2) {
+      const int c = __popc(__ballot_sync(0xffffffffu, x2 < v2));
+      const uint32_t prev = __shfl_sync(0xffffffffu, idx2, c > 0 ? c - 1 : 0);
+      const uint32_t next = __shfl_sync(0xffffffffu, idx2, c < 32 ? c : 31);
+      if (c > 0) lo2 = prev + 1;
+      if (c < 32) hi2 = next;
+    }
+  }
+  const uint32_t i1 = lo1 + lane;
+  const uint32_t i2 = lo2 + lane;
+  const uint32_t y1 = i1 < hi1 ? __ldg(p + i1) : 0xFFFFFFFFu;
+  const uint32_t y2 = i2 < hi2 ? __ldg(p + i2) : 0xFFFFFFFFu;
+  *out1 = lo1 + __popc(__ballot_sync(0xffffffffu, i1 < hi1 && y1 < v1));
+  *out2 = lo2 + __popc(__ballot_sync(0xffffffffu, i2 < hi2 && y2 < v2));
+}
+
 // tile -> segment map: segment g owns tiles [off[g], off[g+1]); one warp per segment.
 __global__ void fill_tile_map_kernel(const uint64_t* __restrict__ off, uint32_t n_segments, uint32_t* __restrict__ out) {
   const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -673,11 +751,18 @@ __global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, 
   __shared__ uint32_t s_spos[kTileThreads / 32][kWarpTile];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
-  const uint32_t t = __ldg(bv.df_tile_term + blockIdx.x);
-  const uint32_t k0 = bv.term_koff[t];
-  const uint32_t k1 = bv.term_koff[t + 1];
-  const uint64_t tile = blockIdx.x - bv.t_df_tile_off[t];
-  const ListRef drv = make_list(iv, bv.key_list[k0], bv.key_len[k0]);
+  // one 32-byte descriptor instead of tile -> term -> keys -> dictionary -> offsets
+  const uint4* dp = reinterpret_cast<const uint4*>(bv.df_tile_desc + blockIdx.x);
+  const uint4 d0 = __ldg(dp);
+  const uint4 d1 = __ldg(dp + 1);
+  ListRef drv;
+  drv.p = reinterpret_cast<const uint32_t*>(static_cast<uintptr_t>(d0.x) | (static_cast<uintptr_t>(d0.y) << 32));
+  drv.len = d0.z;
+  drv.bm = nullptr;
+  const uint32_t t = d0.w;
+  const uint32_t k0 = d1.x;
+  const uint32_t k1 = d1.y;
+  const uint64_t tile = d1.z;
   const uint64_t e0 = tile * kTile + static_cast<uint64_t>(warp) * kWarpTile;
   if (e0 >= drv.len) {
     return;  // no block-wide barrier is used below, so a warp may leave early
@@ -708,7 +793,13 @@ __global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, 
   }
   uint32_t* stage = s_stage[warp];
   for (uint32_t j = k0 + 1; j < k1; ++j) {
-    const ListRef l = make_list(iv, bv.key_list[j], bv.key_len[j]);
+    const uint4* rp = reinterpret_cast<const uint4*>(bv.key_ref + j);
+    const uint4 r0 = __ldg(rp);
+    const uint4 r1 = __ldg(rp + 1);
+    ListRef l;
+    l.p = reinterpret_cast<const uint32_t*>(static_cast<uintptr_t>(r0.x) | (static_cast<uintptr_t>(r0.y) << 32));
+    l.bm = reinterpret_cast<const uint32_t*>(static_cast<uintptr_t>(r0.z) | (static_cast<uintptr_t>(r0.w) << 32));
+    l.len = r1.x;
     if (l.bm != nullptr) {
 #pragma unroll
       for (int k = 0; k < kWarpItems; ++k) {
@@ -717,8 +808,10 @@ __global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, 
         }
       }
     } else {
-      const uint32_t lo = warp_lower_bound(l.p, l.len, dmin);
-      const uint32_t cnt = warp_lower_bound(l.p, l.len, dmax + 1u) - lo;
+      uint32_t lo = 0;
+      uint32_t hi = 0;
+      warp_lower_bound_pair(l.p, l.len, dmin, dmax + 1u, &lo, &hi);
+      const uint32_t cnt = hi - lo;
       if (cnt == 0) {
         alive = 0;
       } else if (cnt <= kWarpStageCap) {
@@ -2604,7 +2697,8 @@ BatchView make_batch_view(Batch& b) {
   v.explicit_ids = b.explicit_driver.d_ids;
   v.explicit_n = static_cast<uint32_t>(b.explicit_driver.n);
   v.stats = b.d_stats.p;
-  v.df_tile_term = b.d_df_tile_term.p;
+  v.df_tile_desc = b.d_df_tile_desc.p;
+  v.key_ref = b.d_key_ref.p;
   v.tile_query = b.d_tile_query.p;
   v.stream_slots = b.d_stream_slots.p;
   v.stream_entries = b.d_stream_entries.p;
@@ -3040,12 +3134,13 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   const size_t Lc = loff.back();
   const size_t scan_elems = scan_scratch_elems(std::max<uint64_t>(T, Q)) + 8;
   size_t work = 0;
-  for (size_t nbytes : {K * 4, K * 4, T * 8, T * 4, (T + 1) * 8, T * 8, Lc * 4, Lc * 4, Q * 4, Q * 4, Q * 4, Q * 4,
+  for (size_t nbytes : {K * sizeof(KeyRef), K * 4, K * 4, T * 8, T * 4, (T + 1) * 8, T * 8, Lc * 4, Lc * 4, Q * 4, Q * 4, Q * 4, Q * 4,
                         (Q + 1) * 8, (Q + 1) * 8, tids.size() * 8, static_cast<size_t>(kStatCount) * kStatStripes * 8,
                         scan_elems * 8, static_cast<size_t>(64)}) {
     work += DevArena::padded(nbytes == 0 ? 1 : nbytes);
   }
   b.work_arena.reserve(work + 1024, true);
+  b.d_key_ref.borrow(b.work_arena.take<KeyRef>(K), K);
   b.d_key_list.borrow(b.work_arena.take<uint32_t>(K), K);
   b.d_key_len.borrow(b.work_arena.take<uint32_t>(K), K);
   b.d_t_est.borrow(b.work_arena.take<uint64_t>(T), T);
@@ -3087,11 +3182,11 @@ void ensure_tile_maps(Batch& b) {
   if (sc.map_owner != b.serial) {
     // floors sized for batches of a few thousand queries, so that a steady stream of batches never reallocates
     // (cudaMalloc / cudaFree cost tens to hundreds of milliseconds and synchronise the device)
-    sc.df_tile_term.reserve(std::max<uint64_t>(b.n_df_tiles, 1ULL << 19));
+    sc.df_tile_desc.reserve(2 * std::max<uint64_t>(b.n_df_tiles, 1ULL << 19));
     sc.tile_query.reserve(std::max<uint64_t>(n_and_tiles, 1ULL << 16));
     if (b.n_df_tiles > 0) {
-      fill_tile_map_kernel<<<grid_for(static_cast<uint64_t>(b.n_terms) * 32, 256), 256, 0, st>>>(
-          b.d_t_df_tile_off.p, b.n_terms, sc.df_tile_term.p);
+      fill_df_desc_kernel<<<grid_for(static_cast<uint64_t>(b.n_terms) * 32, 256), 256, 0, st>>>(
+          b.d_t_df_tile_off.p, b.d_term_koff.p, b.d_key_ref.p, b.n_terms, reinterpret_cast<DfTileDesc*>(sc.df_tile_desc.p));
       MGX_LAUNCH_CHECK();
     }
     if (n_and_tiles > 0) {
@@ -3101,7 +3196,7 @@ void ensure_tile_maps(Batch& b) {
     }
     sc.map_owner = b.serial;
   }
-  b.d_df_tile_term.borrow(sc.df_tile_term.p, sc.df_tile_term.n);
+  b.d_df_tile_desc.borrow(reinterpret_cast<DfTileDesc*>(sc.df_tile_desc.p), sc.df_tile_desc.n / 2);
   b.d_tile_query.borrow(sc.tile_query.p, sc.tile_query.n);
 }
 }  // namespace
@@ -3121,6 +3216,11 @@ void batch_plan(Batch& b) {
                                                                ix.all_valid_utf8 ? 1 : 0, b.d_term_flags.p,
                                                                (ix.n_docs + 7) / 8);
     MGX_LAUNCH_CHECK();
+    if (b.n_keys > 0) {
+      key_ref_kernel<<<grid_for(b.n_keys, 256), 256, 0, st>>>(make_view(ix), b.d_key_list.p, b.d_key_len.p, b.n_keys,
+                                                              b.d_key_ref.p);
+      MGX_LAUNCH_CHECK();
+    }
     if (b.params.compute_score != 0 && b.n_stream_terms > 0) {
       int force = 0;  // MGX_DF_MODE=tiles|stream pins the choice (tests exercise both paths); default: cost model
       if (const char* mode = std::getenv("MGX_DF_MODE")) {

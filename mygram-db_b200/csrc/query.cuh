@@ -93,6 +93,25 @@ struct HostFilter {
   std::string literal;
 };
 
+// Posting list of one looked-up key, resolved once per batch (instead of key -> dictionary slot -> offsets / bitmap
+// slot in every tile): 32 bytes, two 16-byte loads.
+struct KeyRef {
+  const uint32_t* p;   // sorted local doc indices (nullptr if the key is not in the dictionary)
+  const uint32_t* bm;  // dense bitmap or nullptr
+  uint32_t len;
+  uint32_t pad[3];
+};
+// One df tile (one CTA of df_tile_kernel), resolved once per batch.
+struct DfTileDesc {
+  const uint32_t* drv_p;  // the term's shortest list
+  uint32_t drv_len;
+  uint32_t term;
+  uint32_t k0;            // key range of the term
+  uint32_t k1;
+  uint32_t tile;          // tile index inside the term
+  uint32_t pad;
+};
+
 struct Batch {
   Index* ix = nullptr;
   SearchScratch* sc = nullptr;  // the (index, stream) workspace; the d_tile_* / d_rec_* members below are views into it
@@ -116,6 +135,7 @@ struct Batch {
   DevBuf<uint32_t> d_key_list;    // [K] dictionary term index or kNone; sorted by length inside a term
   DevBuf<uint32_t> d_key_len;     // [K]
   DevBuf<uint16_t> d_key_toff;    // [K] byte offset of the n-gram inside its term, kNoTermOffset if unusable
+  DevBuf<KeyRef> d_key_ref;       // [K] resolved lists, in the per-term order term_plan_kernel leaves
   DevBuf<uint64_t> d_t_est;       // [T]
   DevBuf<uint32_t> d_t_df_tiles;  // [T]
   DevBuf<uint64_t> d_t_df_tile_off;  // [T+1]
@@ -174,7 +194,7 @@ struct Batch {
   PinBuf<uint8_t> staging;
   uint32_t n_qterms = 0;  // total search-term slots over all queries
   DevBuf<uint64_t> d_scan_scratch;  // block sums of the planning scans
-  DevBuf<uint32_t> d_df_tile_term;  // [df tiles]
+  DevBuf<DfTileDesc> d_df_tile_desc;  // [df tiles]
   DevBuf<uint32_t> d_tile_query;    // [and tiles]
   DevBuf<unsigned long long> d_stats;  // device-side accounting, see StatSlot
 
@@ -235,6 +255,7 @@ struct HostTerm {
   bool raw = false;            // keys given directly (Index::SearchAnd style): no text semantics
   bool exact_single = false;   // the term IS its single n-gram, so df == posting size when all text is valid UTF-8
   bool streamable = false;     // valid UTF-8 (>= 3 bytes) that needs a text check: may use the streaming df pass
+  uint64_t hash = 0;           // hash of `bytes` (host query compiler)
 };
 
 // Host-built bucket table of the streamable terms.

@@ -100,13 +100,15 @@ class MgxShardBackend:
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
 
-    def prepare(self, arena, offsets, qbeg, n_queries):
-        """Host compile + H2D of one batch; returns an opaque prepared batch."""
+    def prepare(self, arena, offsets, qbeg, n_queries, stream=None):
+        """Host compile + H2D of one batch; returns an opaque prepared batch. `stream` (a torch.cuda.Stream; default:
+        the caller's current stream) is the stream every later stage of this batch must be enqueued on."""
         h = C.c_void_p()
         m = self.mgx
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else self._stream()
         m._check(self.L.mgx_batch_prepare(self.index._h, C.byref(self.params), n_queries, m._ptr(arena, m.u8p),
                                           m._ptr(offsets, m.u64p), m._ptr(qbeg, m.u64p), None, None, None,
-                                          self._stream(), C.byref(h)))
+                                          st, C.byref(h)))
         return {"h": h, "n_queries": n_queries, "n_slots": int(self.L.mgx_batch_term_slots(h))}
 
     def release(self, batch):
