@@ -322,6 +322,11 @@ int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint
                       const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
                       const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
                       void* stream, mgx_batch_t** out);
+/* Same with the optional per-query extensions of mgx_query_batch_ex (boolean programs, column filters). */
+int mgx_batch_prepare_ex(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                         const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                         const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                         const mgx_query_ext_t* ext, void* stream, mgx_batch_t** out);
 /* Planning stage of a prepared batch (dictionary lookup, per-term and per-query plans). Called
  * implicitly by the df / search stages if it has not run yet. */
 int mgx_batch_plan_device(mgx_batch_t* batch);

@@ -142,6 +142,8 @@ def lib():
                                   C.c_uint64, u32p, f64p, u32p, u64p, u64p]
     L.mgx_batch_prepare.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
                                     C.c_void_p, C.POINTER(C.c_void_p)]
+    L.mgx_batch_prepare_ex.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
+                                       C.POINTER(QueryExt), C.c_void_p, C.POINTER(C.c_void_p)]
     L.mgx_batch_plan_device.argtypes = [C.c_void_p]
     L.mgx_batch_get_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
     L.mgx_batch_term_slots.restype = C.c_uint64

@@ -158,6 +158,21 @@ class Index {
     detail::check(mgx_index_remove_document(handle_, doc_id, reinterpret_cast<const uint8_t*>(text.data()),
                                             text.size()));
   }
+  // Index::GetStatistics / Optimize / Clear (index.cpp:604-641, index_optimization.cpp:36-120)
+  struct IndexStatistics {
+    size_t total_terms = 0;
+    size_t total_postings = 0;
+    size_t delta_encoded_lists = 0;
+    size_t roaring_bitmap_lists = 0;
+    size_t memory_usage_bytes = 0;
+  };
+  [[nodiscard]] IndexStatistics GetStatistics() const {
+    mgx_index_statistics_t s{};
+    detail::check(mgx_index_get_statistics(handle_, &s));
+    return {s.total_terms, s.total_postings, s.delta_encoded_lists, s.roaring_bitmap_lists, s.memory_usage_bytes};
+  }
+  void Optimize(uint64_t total_docs) { detail::check(mgx_index_optimize(handle_, total_docs)); }
+  void Clear() { detail::check(mgx_index_clear(handle_)); }
   [[nodiscard]] uint64_t PostingSize(std::string_view term) const {
     uint64_t n = 0;
     detail::check(mgx_index_posting_size(handle_, reinterpret_cast<const uint8_t*>(term.data()), term.size(), &n));

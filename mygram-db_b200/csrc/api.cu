@@ -1447,23 +1447,18 @@ int mgx_index_doc_lengths(const mgx_index_t* index, uint32_t* out) {
 }
 
 // ---------------------------------------------------------------- batched pipeline
-static int batch_prepare_ex(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
-                            const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
-                            const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
-                            const mgx_query_ext_t* ext, void* stream, mgx_batch_t** out);
-
 int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
                       const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
                       const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
                       void* stream, mgx_batch_t** out) {
-  return batch_prepare_ex(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
-                          q_not_begin, nullptr, stream, out);
+  return mgx_batch_prepare_ex(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes,
+                              not_offsets, q_not_begin, nullptr, stream, out);
 }
 
-static int batch_prepare_ex(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
-                            const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
-                            const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
-                            const mgx_query_ext_t* ext, void* stream, mgx_batch_t** out) {
+int mgx_batch_prepare_ex(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                         const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                         const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                         const mgx_query_ext_t* ext, void* stream, mgx_batch_t** out) {
   if (index == nullptr || params == nullptr || out == nullptr ||
       (n_queries > 0 && (term_offsets == nullptr || q_term_begin == nullptr))) {
     return invalid("null argument");
@@ -1661,8 +1656,8 @@ int mgx_query_batch_ex(mgx_index_t* index, const mgx_query_params_t* params, uin
   }
   std::lock_guard<std::mutex> lock(index->mu);
   mgx_batch_t* batch = nullptr;
-  int rc = batch_prepare_ex(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
-                            q_not_begin, ext, index->ix.stream, &batch);
+  int rc = mgx_batch_prepare_ex(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes,
+                                not_offsets, q_not_begin, ext, index->ix.stream, &batch);
   if (rc != MGX_OK) {
     return rc;
   }
