@@ -782,8 +782,8 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   ix.d_post_pos.release();
   ix.d_post_pos2.release();
   ix.d_term_bm.release();
-  ix.d_bitmaps.release();
-  ix.resident_b.release();
+  // resident_b and the bitmaps keep their allocations (grow-only): a rebuild of a shard of similar size -- the
+  // journal commits of the mutation path -- then pays no cudaMalloc / cudaFree for them
   ix.n_text_tiles = n_docs > 0 ? (text_bytes + kTextTileBytes - 1) / kTextTileBytes : 0;
   ix.resident_a.reserve(DevArena::padded(n_docs * 4 + 4) + DevArena::padded(text_bytes + 64) +
                         DevArena::padded((n_docs + 1) * 8) + DevArena::padded(n_docs * 4 + 4) +
@@ -930,7 +930,7 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   t1.release();  // the pairs are no longer needed (one cudaFree)
   ix.n_dense = n_dense;
   ix.dense_min_len = min_len;
-  ix.d_bitmaps.alloc(ix.n_dense * ix.bm_words);
+  ix.d_bitmaps.reserve(ix.n_dense * ix.bm_words);
   if (ix.n_terms > 0) {
     MGX_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
     if (ix.n_dense > 0) {

@@ -120,7 +120,7 @@ class MgxShardBackend:
 
     def local_df(self, batch):
         t = self.torch
-        df = t.zeros(max(1, batch["n_slots"]), dtype=t.int64, device=self.device)
+        df = t.empty(max(1, batch["n_slots"]), dtype=t.int64, device=self.device)  # every slot is written
         self.mgx._check(self.L.mgx_batch_plan_device(batch["h"]))
         self.mgx._check(self.L.mgx_batch_df_device(batch["h"], C.c_void_p(df.data_ptr())))
         return df
@@ -128,10 +128,11 @@ class MgxShardBackend:
     def search(self, batch, df):
         t = self.torch
         Q, S = batch["n_queries"], self.stride
-        ids = t.zeros((Q, S), dtype=t.int32, device=self.device)
-        scores = t.zeros((Q, S), dtype=t.float64, device=self.device)
-        count = t.zeros(Q, dtype=t.int32, device=self.device)
-        total = t.zeros(Q, dtype=t.int64, device=self.device)
+        # count / total are written for every query; ids / scores are valid up to count[q] (no fill kernels)
+        ids = t.empty((Q, S), dtype=t.int32, device=self.device)
+        scores = t.empty((Q, S), dtype=t.float64, device=self.device)
+        count = t.empty(Q, dtype=t.int32, device=self.device)
+        total = t.empty(Q, dtype=t.int64, device=self.device)
         self.mgx._check(self.L.mgx_batch_search_device(batch["h"], C.c_void_p(df.data_ptr()), S,
                                                        C.c_void_p(ids.data_ptr()), C.c_void_p(scores.data_ptr()),
                                                        C.c_void_p(count.data_ptr()), C.c_void_p(total.data_ptr())))
@@ -140,10 +141,10 @@ class MgxShardBackend:
     def merge(self, ids_all, scores_all, count_all, total_all):
         t = self.torch
         G, Q, S = ids_all.shape
-        ids = t.zeros((Q, S), dtype=t.int32, device=self.device)
-        scores = t.zeros((Q, S), dtype=t.float64, device=self.device)
-        count = t.zeros(Q, dtype=t.int32, device=self.device)
-        total = t.zeros(Q, dtype=t.int64, device=self.device)
+        ids = t.empty((Q, S), dtype=t.int32, device=self.device)
+        scores = t.empty((Q, S), dtype=t.float64, device=self.device)
+        count = t.empty(Q, dtype=t.int32, device=self.device)
+        total = t.empty(Q, dtype=t.int64, device=self.device)
         self.mgx._check(self.L.mgx_merge_topk_device(
             self.device.index if self.device.index is not None else 0, self._stream(), C.byref(self.params), G, Q, S,
             C.c_void_p(ids_all.data_ptr()), C.c_void_p(scores_all.data_ptr()), C.c_void_p(count_all.data_ptr()),
