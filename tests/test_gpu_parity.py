@@ -639,3 +639,61 @@ def test_large_batch_of_short_queries_picks_streaming_df(mgx, oracle, monkeypatc
     sub = type(g)(g.ids[sample], g.scores[sample], g.count[sample], g.total[sample],
                   np.concatenate([g.df[2 * i:2 * i + 2] for i in sample]))
     assert_batch_equal(sub, o, [qs[i] for i in sample])
+
+
+# ----------------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties_10m(mgx):
+    """BASELINE config 2 at its full size (10M CJK documents, 4096 x 3-term AND + BM25 top-100) through properties
+    that need no CPU run: order, idempotence, totals, consistency of the fused BM25 epilogue with the stand-alone
+    scorer, df of single-n-gram terms == posting size, and equality of the two df paths."""
+    import os
+    c = corpus_mod.generate("cjk", 10_000_000, 0xC2)
+    gi = mgx.Index(2, 0, True)
+    gi.build(c.doc_ids, c.arena, c.offsets)
+    st = gi.stats()
+    assert st.n_docs == 10_000_000 and st.doc_count == 10_000_000 and st.all_valid_utf8 == 1
+    assert st.total_doc_length == int(gi.doc_lengths().astype(np.uint64).sum())
+    qs = corpus_mod.sample_queries_global("cjk", 0xC2, 10_000_000, 4096, 4242)
+    a = gi.query_batch(qs, score=True, limit=100)
+    b = gi.query_batch(qs, score=True, limit=100)
+    valid = np.arange(100)[None, :] < a.count[:, None]
+    assert np.array_equal(a.count, b.count) and np.array_equal(a.total, b.total) and np.array_equal(a.df, b.df)
+    assert np.array_equal(a.ids[valid], b.ids[valid]) and np.array_equal(a.scores[valid], b.scores[valid])  # idempotent
+    assert np.all(a.total >= a.count) and np.all(a.count == np.minimum(a.total, 100))
+    assert np.all(a.total >= 1)  # the three terms of a query are cut from one document
+    for q in range(0, 4096, 97):
+        k = int(a.count[q])
+        s, d = a.scores[q, :k], a.ids[q, :k].astype(np.int64)
+        # SortByScore order (result_sorter.cpp:681-686): score descending, ties by HIGHER doc id first
+        assert np.all((s[:-1] > s[1:]) | ((s[:-1] == s[1:]) & (d[:-1] > d[1:])))
+        assert len(set(d.tolist())) == k
+    # fused epilogue == BM25Scorer::ScoreDocuments on the returned documents with the returned dfs
+    slot = 0
+    checked = 0
+    for q in range(0, 4096, 511):
+        slot = 3 * q
+        k = int(a.count[q])
+        dfs = [int(x) for x in a.df[slot:slot + 3]]
+        # the pipeline scores terms in ascending estimated-size order; the sum is order-dependent only in rounding
+        sc = mgx.BM25Scorer.score_documents(gi, a.ids[q, :k], qs[q], dfs, st.doc_count,
+                                            st.total_doc_length / st.doc_count)
+        assert np.allclose(sc, a.scores[q, :k], rtol=1e-12, atol=0)
+        checked += 1
+    assert checked >= 8
+    # df of a term that IS one n-gram == its posting size; df <= min posting size always
+    for q in range(0, 4096, 173):
+        for t, df in zip(qs[q], a.df[3 * q:3 * q + 3]):
+            grams = [t.decode()[i:i + 2].encode() for i in range(len(t.decode()) - 1)]
+            sizes = [gi.posting_size(g) for g in grams]
+            assert int(df) <= min(sizes)
+            if len(grams) == 1:
+                assert int(df) == sizes[0]
+    # both df paths give the same batch answer at full size
+    os.environ["MGX_DF_MODE"] = "stream"
+    try:
+        s2 = gi.query_batch(qs, score=True, limit=100)
+        assert gi.last_batch_stats().df_stream_terms > 0
+    finally:
+        del os.environ["MGX_DF_MODE"]
+    assert np.array_equal(a.df, s2.df) and np.array_equal(a.total, s2.total)
+    assert np.array_equal(a.ids[valid], s2.ids[valid]) and np.array_equal(a.scores[valid], s2.scores[valid])
