@@ -127,6 +127,9 @@ typedef struct {
   uint64_t memory_usage_bytes;
 } mgx_index_statistics_t;
 int mgx_index_get_statistics(const mgx_index_t* index, mgx_index_statistics_t* out);
+/* Releases the build workspace the index keeps between (re)builds (about 25 bytes per n-gram occurrence of the
+ * last build: the double-buffered (key, doc) pairs and the sort scratch). The next build allocates it again. */
+int mgx_index_trim(mgx_index_t* index);
 int mgx_index_optimize(mgx_index_t* index, uint64_t total_docs);
 int mgx_index_clear(mgx_index_t* index);
 

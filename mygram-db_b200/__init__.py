@@ -116,6 +116,7 @@ def lib():
     L.mgx_index_get_stats.argtypes = [C.c_void_p, C.POINTER(IndexStats)]
     L.mgx_index_get_statistics.argtypes = [C.c_void_p, C.POINTER(IndexStatistics)]
     L.mgx_index_optimize.argtypes = [C.c_void_p, C.c_uint64]
+    L.mgx_index_trim.argtypes = [C.c_void_p]
     L.mgx_index_clear.argtypes = [C.c_void_p]
     L.mgx_index_add_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64, C.POINTER(C.c_int32)]
     L.mgx_index_update_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64, u8p, C.c_uint64]
@@ -302,6 +303,10 @@ class Index:
     def optimize(self, total_docs):
         """Index::Optimize(total_docs) (index_optimization.cpp:36-120)."""
         _check(lib().mgx_index_optimize(self._h, total_docs))
+
+    def trim(self):
+        """Release the build workspace kept between rebuilds."""
+        _check(lib().mgx_index_trim(self._h))
 
     def clear(self):
         """Index::Clear (index.cpp:635-641)."""

@@ -938,6 +938,19 @@ int mgx_index_get_statistics(const mgx_index_t* index_c, mgx_index_statistics_t*
   });
 }
 
+int mgx_index_trim(mgx_index_t* index) {
+  if (index == nullptr) {
+    return invalid("null argument");
+  }
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(index->mu);
+    DeviceGuard guard(index->ix.device);
+    index->ix.build_arena.release();
+    index->ix.build_arena0.release();
+    return MGX_OK;
+  });
+}
+
 int mgx_index_optimize(mgx_index_t* index, uint64_t total_docs) {
   if (index == nullptr) {
     return invalid("null argument");

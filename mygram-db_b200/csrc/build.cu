@@ -121,7 +121,14 @@ __device__ __forceinline__ uint32_t flat_block_scan(uint32_t v, uint32_t* warp_c
   return prefix + inc - v;
 }
 
-template <bool EMIT>
+// MODE 0 = COUNT, 1 = EMIT (after COUNT: exact slots), 2 = FUSED: one pass that both gathers the per-document
+// totals and writes the n-grams, into slots whose per-tile bases come from an UPPER bound (the tile's character-start
+// bytes, lead_count_kernel); the unused slots at the end of every tile get the placeholder key 0, which no n-gram
+// has, sorts first and is skipped by the CSR kernels.
+constexpr int kTokCount = 0;
+constexpr int kTokEmit = 1;
+constexpr int kTokFused = 2;
+template <int MODE>
 __global__ void __launch_bounds__(kFlatThreads, 4)
 tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ text_off, uint64_t n_docs,
                      uint64_t text_bytes, uint64_t n_tiles, const uint32_t* __restrict__ tile_first_doc, int ngram,
@@ -129,6 +136,8 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
                      uint32_t* __restrict__ doc_valid_bytes, uint32_t* __restrict__ tile_cnt,
                      const uint64_t* __restrict__ tile_off, uint64_t* __restrict__ keys_out,
                      uint32_t* __restrict__ docs_out) {
+  constexpr bool EMIT = MODE != kTokCount;    // writes n-grams
+  constexpr bool STATS = MODE != kTokEmit;    // gathers the per-document totals
   __shared__ FlatSmem sm;
   const unsigned lane = threadIdx.x & 31u;
   const uint64_t pos_max = pos_bits > 0 ? ((1ULL << pos_bits) - 1) : 0;
@@ -197,7 +206,7 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
             if (len > 0) {
               flags |= 1u << j;
               cps[j] = cp | ((dj - dj0) << 21);
-              if (!EMIT) {
+              if (STATS) {
                 atomicAdd(&sm.doc_cps[dj], 1u);
                 atomicAdd(&sm.doc_valid[dj], static_cast<uint32_t>(len));
               }
@@ -287,8 +296,8 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
         strip_base += n_emit;
         emitted_tile += n_emit;
       }
-      // ---- per-document totals of this round (COUNT only)
-      if (!EMIT) {
+      // ---- per-document totals of this round
+      if (STATS) {
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < r_docs; i += kFlatThreads) {
           const uint32_t c = sm.doc_cps[i];
@@ -302,8 +311,56 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
         }
       }
     }
-    if (!EMIT && threadIdx.x == 0) {
+    if (MODE == kTokCount && threadIdx.x == 0) {
       tile_cnt[tile] = static_cast<uint32_t>(emitted_tile);
+    }
+    if (MODE == kTokFused) {
+      // placeholders for the slots of the tile's upper bound that no n-gram took
+      for (uint64_t i = tile_off[tile] + emitted_tile + threadIdx.x; i < tile_off[tile + 1]; i += kFlatThreads) {
+        keys_out[i] = 0;
+        docs_out[i] = 0;
+      }
+    }
+  }
+}
+
+// Upper bound of a tile's n-grams: its character-start (non-continuation) bytes. One 16-byte chunk per thread.
+__global__ void __launch_bounds__(kFlatThreads) lead_count_kernel(const uint8_t* __restrict__ text, uint64_t text_bytes,
+                                                                  uint64_t n_tiles, uint32_t* __restrict__ tile_cnt) {
+  __shared__ uint32_t warp_cnt[kFlatThreads / 32];
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint64_t byte0 = tile * kFlatTile + static_cast<uint64_t>(threadIdx.x) * 16;
+    uint32_t c = 0;
+    if (byte0 < text_bytes) {
+      const uint4 v = ld_stream_16(text + byte0);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      const uint32_t n = static_cast<uint32_t>(umin_u64(16, text_bytes - byte0));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // bytes that are NOT 10xxxxxx; bytes beyond the arena are masked off
+        uint32_t lead = ~__vcmpeq4(w[k] & 0xC0C0C0C0u, 0x80808080u) & 0x01010101u;
+        const int valid = static_cast<int>(n) - 4 * k;
+        if (valid < 4) {
+          lead &= valid <= 0 ? 0u : ((1u << (8 * valid)) - 1u);
+        }
+        c += __popc(lead);
+      }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      c += __shfl_xor_sync(0xffffffffu, c, s);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31u) == 0) {
+      warp_cnt[threadIdx.x >> 5] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int w2 = 0; w2 < kFlatThreads / 32; ++w2) {
+        t += warp_cnt[w2];
+      }
+      tile_cnt[tile] = t;
     }
   }
 }
@@ -354,8 +411,8 @@ __device__ __forceinline__ Heads head_flags(const uint64_t* __restrict__ keys, c
   }
   const uint64_t k = keys[i];
   *key_out = k;
-  if (k == kInvalidKey) {
-    return h;
+  if (k == kInvalidKey || (k >> pb) == 0) {
+    return h;  // placeholder slots (fused tokenizer: key 0; no n-gram has it, its first field would be >= 1)
   }
   const bool term_head = (i == 0) || (keys[i - 1] >> pb) != (k >> pb);
   const bool pair_head = term_head || docs[i - 1] != docs[i];
@@ -675,7 +732,7 @@ void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* 
     flat_tile_first_doc_kernel<<<static_cast<unsigned>((ts.n_tiles + 255) / 256), 256, 0, stream>>>(
         d_text_off, n_docs, ts.n_tiles, ts.tile_first_doc);
     MGX_LAUNCH_CHECK();
-    tokenize_flat_kernel<false><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
+    tokenize_flat_kernel<kTokCount><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
         d_text, d_text_off, n_docs, text_bytes, ts.n_tiles, ts.tile_first_doc, ngram, kanji, cross ? 1 : 0, width, 0,
         d_doc_len, ts.valid_bytes, ts.tile_cnt, nullptr, nullptr, nullptr);
     MGX_LAUNCH_CHECK();
@@ -704,10 +761,58 @@ void tokenize_emit(int ngram, int kanji, bool cross, int width, const uint8_t* d
   if (ts.n_tiles == 0) {
     return;
   }
-  tokenize_flat_kernel<true><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
+  tokenize_flat_kernel<kTokEmit><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
       d_text, d_text_off, n_docs, text_bytes, ts.n_tiles, ts.tile_first_doc, ngram, kanji, cross ? 1 : 0, width, pos_bits,
       nullptr, nullptr, nullptr, d_tile_off, d_keys, d_docs);
   MGX_LAUNCH_CHECK();
+}
+
+// Fused form used by the index build. Step 1: upper bound of the n-gram slots (scanned per tile into d_tile_off).
+void tokenize_bound(const uint8_t* d_text, const uint64_t* d_text_off, uint64_t n_docs, uint64_t text_bytes,
+                    uint64_t* d_tile_off, uint64_t* d_scratch, uint64_t* n_slots_bound, cudaStream_t stream) {
+  const TokScratch ts = tok_scratch(d_scratch, n_docs, text_bytes);
+  if (ts.n_tiles > 0) {
+    flat_tile_first_doc_kernel<<<static_cast<unsigned>((ts.n_tiles + 255) / 256), 256, 0, stream>>>(
+        d_text_off, n_docs, ts.n_tiles, ts.tile_first_doc);
+    MGX_LAUNCH_CHECK();
+    lead_count_kernel<<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(d_text, text_bytes, ts.n_tiles, ts.tile_cnt);
+    MGX_LAUNCH_CHECK();
+  }
+  exclusive_scan_u32_u64(ts.tile_cnt, d_tile_off, ts.n_tiles, ts.scan, stream);
+  uint64_t total = 0;
+  MGX_CUDA(cudaMemcpyAsync(&total, d_tile_off + ts.n_tiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+  MGX_CUDA(cudaStreamSynchronize(stream));
+  *n_slots_bound = total;
+}
+
+// Step 2: per-document totals AND the (key, doc) pairs in one pass; unused slots of every tile hold key 0.
+void tokenize_fused(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
+                    uint64_t n_docs, uint64_t text_bytes, uint32_t* d_doc_len, const uint64_t* d_tile_off,
+                    uint64_t* d_scratch, uint64_t* d_keys, uint32_t* d_docs, int pos_bits, uint64_t* counters_out,
+                    cudaStream_t stream) {
+  const TokScratch ts = tok_scratch(d_scratch, n_docs, text_bytes);
+  MGX_CUDA(cudaMemsetAsync(ts.counters, 0, 8 * sizeof(unsigned long long), stream));
+  if (n_docs > 0) {
+    MGX_CUDA(cudaMemsetAsync(d_doc_len, 0, n_docs * sizeof(uint32_t), stream));
+    MGX_CUDA(cudaMemsetAsync(ts.valid_bytes, 0, n_docs * sizeof(uint32_t), stream));
+  }
+  if (ts.n_tiles > 0) {
+    tokenize_flat_kernel<kTokFused><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
+        d_text, d_text_off, n_docs, text_bytes, ts.n_tiles, ts.tile_first_doc, ngram, kanji, cross ? 1 : 0, width, pos_bits,
+        d_doc_len, ts.valid_bytes, nullptr, d_tile_off, d_keys, d_docs);
+    MGX_LAUNCH_CHECK();
+  }
+  if (n_docs > 0) {
+    flat_doc_stats_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n_docs + 255) / 256, 148 * 8)), 256, 0, stream>>>(
+        d_text_off, d_doc_len, ts.valid_bytes, n_docs, ts.counters);
+    MGX_LAUNCH_CHECK();
+  }
+  unsigned long long counters[3] = {0, 0, 0};
+  MGX_CUDA(cudaMemcpyAsync(counters, ts.counters, sizeof(counters), cudaMemcpyDeviceToHost, stream));
+  MGX_CUDA(cudaStreamSynchronize(stream));
+  counters_out[0] = counters[0];
+  counters_out[1] = counters[1];
+  counters_out[2] = counters[2];
 }
 
 // doc ids ascending: first_id + i everywhere?  (one pass over the resident copy)
@@ -805,8 +910,10 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
     MGX_LAUNCH_CHECK();
   }
 
-  // ---- temporary arena T0: counting stage
-  DevArena t0;
+  // ---- temporary arena T0: counting stage. Both build workspaces stay with the index (grow-only) until
+  // mgx_index_trim / destroy: cudaFree of a multi-GB block was measured at 0.1-0.9 s on some boxes, and an index
+  // that takes mutations rebuilds again and again
+  DevArena& t0 = ix.build_arena0;
   const size_t count_scratch = tokenize_scratch_elems(n_docs, text_bytes);
   const size_t n_tok_tiles = tokenize_tile_count(n_docs, text_bytes);
   t0.reserve(DevArena::padded((n_tok_tiles + 1) * 8) + DevArena::padded(count_scratch * 8) + 512);
@@ -834,23 +941,19 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
 
   uint64_t n_slots = 0;
   uint64_t counters[3] = {0, 0, 0};
-  tokenize_count(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, text_bytes,
-                 ix.d_doc_len.p, d_slot_off, d_count_scratch, &n_slots, counters, stream);
-  trace.mark("tokenize: count + scan");
+  tokenize_bound(ix.d_text.p, ix.d_text_off.p, n_docs, text_bytes, d_slot_off, d_count_scratch, &n_slots, stream);
+  trace.mark("tokenize: slot bound + scan");
   ix.n_pair_slots = n_slots;
-  ix.doc_count = counters[0];
-  ix.all_valid_utf8 = counters[1] == 0;
-  ix.total_doc_length = counters[2];
   if (n_slots >= (1ULL << 32)) {
     set_last_error("shard too large: more than 2^32 n-gram occurrences in one shard; split by doc-id range");
     throw CudaFailure{MGX_ERR_UNSUPPORTED};
   }
-
   const int pb = pos_bits_for_width(ix.width);
   ix.has_positions = pb > 0;
+
   // ---- temporary arena T1: pairs (double-buffered), sort scratch, CSR block arrays
   const uint64_t n_blocks = (n_slots + kCsrTile - 1) / kCsrTile;
-  DevArena t1;
+  DevArena& t1 = ix.build_arena;
   t1.reserve(2 * (DevArena::padded(n_slots * 8 + 8) + DevArena::padded(n_slots * 4 + 4)) +
              DevArena::padded(radix_sort_scratch_bytes(n_slots) + 512) + 2 * DevArena::padded((n_blocks + 2) * 8) + 1024);
   uint64_t* d_keys_a = t1.take<uint64_t>(n_slots);
@@ -862,11 +965,13 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   uint64_t* d_block_terms = t1.take<uint64_t>(n_blocks + 2);
   uint64_t* d_totals = t1.take<uint64_t>(4);
   trace.mark("alloc pair arena");
-  if (n_slots > 0) {
-    tokenize_emit(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, text_bytes, d_slot_off,
-                  d_count_scratch, d_keys_a, d_docs_a, pb, stream);
-  }
-  trace.mark("tokenize: emit");
+  // one pass: per-document totals + the (key, doc) pairs (placeholder key 0 in the unused slots of each tile)
+  tokenize_fused(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, text_bytes, ix.d_doc_len.p,
+                 d_slot_off, d_count_scratch, d_keys_a, d_docs_a, pb, counters, stream);
+  ix.doc_count = counters[0];
+  ix.all_valid_utf8 = counters[1] == 0;
+  ix.total_doc_length = counters[2];
+  trace.mark("tokenize: fused stats + emit");
   const SortResult sorted =
       radix_sort_pairs(d_keys_a, d_docs_a, d_keys_b, d_docs_b, n_slots, 21 * ix.width, pb, d_sort_scratch, stream);
   trace.mark("radix sort");
@@ -927,7 +1032,6 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
       min_len *= 2;
     }
   }
-  t1.release();  // the pairs are no longer needed (one cudaFree)
   ix.n_dense = n_dense;
   ix.dense_min_len = min_len;
   ix.d_bitmaps.reserve(ix.n_dense * ix.bm_words);

@@ -341,6 +341,8 @@ struct Index {
   DevBuf<uint32_t> d_bitmaps;
   DevArena resident_a;  // doc ids, text, text offsets, doc lengths
   DevArena resident_b;  // dictionary, CSR offsets, postings, bitmap slots
+  DevArena build_arena0;  // build workspaces (tokenizer scratch; pair arrays + sort scratch), kept between builds:
+  DevArena build_arena;   // see build_index_device; released by mgx_index_trim
   uint64_t n_dense = 0;
   uint64_t bm_words = 0;
   uint64_t dense_min_len = 0;
