@@ -251,8 +251,6 @@ def main():
         run_reference_arm(args, rank)
         return
 
-    # host threads of the library's query compiler: the box's cores shared between the ranks
-    os.environ.setdefault("MGX_COMPILE_THREADS", str(max(1, min(4, (os.cpu_count() or 1) // (2 * world)))))
     import torch
     import torch.distributed as dist
     import corpus as corpus_mod
@@ -368,12 +366,9 @@ def main():
     # device->host; a step is complete when its results are in pinned host memory. Batches alternate between two
     # CUDA streams so that consecutive batches may overlap on the device.
     backend.collect_stats = False
-    outs = [dict(ids=torch.empty((args.batch, TOPK), dtype=torch.int32, pin_memory=True),
-                 scores=torch.empty((args.batch, TOPK), dtype=torch.float64, pin_memory=True),
-                 count=torch.empty(args.batch, dtype=torch.int32, pin_memory=True),
-                 total=torch.empty(args.batch, dtype=torch.int64, pin_memory=True),
-                 done=torch.cuda.Event()) for _ in range(2)]
-    out_ids, out_scores, out_count, out_total = (outs[0][k] for k in ("ids", "scores", "count", "total"))
+    rec_bytes = sharded.record_layout(args.batch, TOPK)["bytes"]  # ids, scores, count, total of a batch in ONE buffer
+    outs = [dict(rec=torch.empty(rec_bytes, dtype=torch.uint8, pin_memory=True), done=torch.cuda.Event())
+            for _ in range(2)]
     e2e_parts = {"host_prepare_ms": 0.0, "enqueue_ms": 0.0, "wait_ms": 0.0}
 
     # two CUDA streams, alternating per batch: the planning stage of batch i+1 (which ends in a small host
@@ -388,12 +383,9 @@ def main():
     def e2e_enqueue(p, slot, acc=None):
         t_b = time.perf_counter()
         with torch.cuda.stream(e2e_streams[slot]):
-            ids, scores, count, total = sharded.run_sharded_batch(backend, comm, p)
+            sharded.run_sharded_batch(backend, comm, p)
             o = outs[slot]
-            o["ids"].copy_(ids, non_blocking=True)
-            o["scores"].copy_(scores, non_blocking=True)
-            o["count"].copy_(count, non_blocking=True)
-            o["total"].copy_(total, non_blocking=True)
+            o["rec"].copy_(backend.merged_record, non_blocking=True)  # the merged answer: one device-to-host copy
             o["done"].record()
         if acc is not None:
             acc["enqueue_ms"] += 1e3 * (time.perf_counter() - t_b)  # plan (one size read-back), df, search, merge, D2H
@@ -438,7 +430,7 @@ def main():
     clock_info = clocks.stop()
     e2e_value = args.steps * args.batch / float(e2e_s[0])
     h2d = int(batches[0][1].nbytes + batches[0][2].nbytes + batches[0][3].nbytes)
-    d2h = int(out_ids.numel() * 4 + out_scores.numel() * 8 + out_count.numel() * 4 + out_total.numel() * 8)
+    d2h = int(outs[0]["rec"].numel())
 
     # ---- roofline of the dominant kernel (times: CUDA events around the kernel launches on the launch stream)
     peak, peak_src = measured_peaks()

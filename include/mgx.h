@@ -352,6 +352,23 @@ int mgx_merge_topk_device(int32_t device, void* stream, const mgx_query_params_t
                           const uint32_t* d_count_all, const uint64_t* d_total_all, uint32_t* d_ids_out,
                           double* d_scores_out, uint32_t* d_count_out, uint64_t* d_total_out);
 
+/* Packed form of the same exchange: ONE buffer per shard, so that the per-shard top-k runs of a batch travel in
+ * a single all-gather (BASELINE north_star: "merged with a single NCCL all-gather over NVLink"). A record holds
+ * [scores f64 Q*S][total u64 Q][ids u32 Q*S][count u32 Q], padded to 16 bytes; mgx_shard_record_layout gives the
+ * byte offsets. d_records = [n_shards][layout.bytes] as gathered; d_record_out = one record (the merged answer,
+ * one device-to-host copy away from the caller). */
+typedef struct mgx_shard_record_layout {
+  uint64_t scores_offset;
+  uint64_t total_offset;
+  uint64_t ids_offset;
+  uint64_t count_offset;
+  uint64_t bytes;
+} mgx_shard_record_layout_t;
+int mgx_shard_record_layout(uint64_t n_queries, uint64_t stride, mgx_shard_record_layout_t* out);
+int mgx_batch_search_packed_device(mgx_batch_t* batch, const uint64_t* d_df, uint64_t stride, void* d_record);
+int mgx_merge_topk_packed_device(int32_t device, void* stream, const mgx_query_params_t* params, uint32_t n_shards,
+                                 uint64_t n_queries, uint64_t stride, const void* d_records, void* d_record_out);
+
 /* Stats of the last mgx_query_batch on this index. */
 int mgx_index_last_batch_stats(const mgx_index_t* index, mgx_batch_stats_t* out);
 

@@ -74,6 +74,12 @@ class QueryParams(C.Structure):
                 ("total_doc_length", C.c_uint64)]
 
 
+class ShardRecordLayout(C.Structure):
+    """mgx_shard_record_layout_t: byte offsets of the four parts of one shard's packed top-k record."""
+    _fields_ = [("scores_offset", C.c_uint64), ("total_offset", C.c_uint64), ("ids_offset", C.c_uint64),
+                ("count_offset", C.c_uint64), ("bytes", C.c_uint64)]
+
+
 class BatchStats(C.Structure):
     _fields_ = [("ms_plan", C.c_double), ("ms_df_kernel", C.c_double), ("ms_and_kernel", C.c_double),
                 ("ms_topk_kernel", C.c_double), ("ms_total", C.c_double), ("launches", C.c_uint64),
@@ -156,6 +162,10 @@ def lib():
     L.mgx_merge_topk_device.argtypes = [C.c_int32, C.c_void_p, C.POINTER(QueryParams), C.c_uint32, C.c_uint64,
                                         C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mgx_shard_record_layout.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(ShardRecordLayout)]
+    L.mgx_batch_search_packed_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.mgx_merge_topk_packed_device.argtypes = [C.c_int32, C.c_void_p, C.POINTER(QueryParams), C.c_uint32, C.c_uint64,
+                                               C.c_uint64, C.c_void_p, C.c_void_p]
     L.mgx_index_last_batch_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
     L.mgx_score_documents.argtypes = [C.c_void_p, u32p, C.c_uint64, u8p, u64p, u64p, C.c_uint64, C.c_uint64,
                                       C.c_double, C.c_double, C.c_double, f64p]

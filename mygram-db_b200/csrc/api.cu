@@ -54,7 +54,7 @@ namespace {
 // GenerateHybridNgrams (string_utils.cpp:452-509) as packed keys; windows wider
 // than the index's key width cannot exist in the dictionary => kInvalidKey.
 void hybrid_keys(const std::vector<uint32_t>& cps, int ascii_n, int kanji_n, bool cross, int width,
-                 std::vector<uint64_t>* keys, std::vector<uint32_t>* starts = nullptr) {
+                 KeyVec* keys, std::vector<uint32_t>* starts = nullptr) {
   if (ascii_n <= 0 || kanji_n <= 0) {
     return;
   }
@@ -135,8 +135,78 @@ bool has_uncovered_hybrid_fragment(const uint8_t* term, uint64_t len, int ngram_
 
 }  // namespace
 
+namespace {
+// host_query_keys for the common case -- fixed-size n-grams (GenerateNgrams, string_utils.cpp:382-423) of a term of
+// at most kFastTermBytes bytes: same result as the general path below, without its scratch vectors.
+constexpr uint64_t kFastTermBytes = 96;
+void fixed_ngram_keys_small(const uint8_t* term, uint64_t len, int ngram_size, int key_width, KeyVec* keys,
+                            TermOffsetVec* key_toff, bool* all_valid) {
+  uint32_t cps[kFastTermBytes];
+  uint16_t cp_byte[kFastTermBytes];
+  uint32_t n_cp = 0;
+  bool valid = true;
+  for (uint64_t i = 0; i < len;) {
+    uint32_t cp = 0;
+    const uint64_t avail = len - i;
+    const int n = parse_utf8(term[i], avail > 1 ? term[i + 1] : 0, avail > 2 ? term[i + 2] : 0,
+                             avail > 3 ? term[i + 3] : 0, avail, &cp);
+    if (n > 0) {
+      cps[n_cp] = cp;
+      cp_byte[n_cp++] = static_cast<uint16_t>(i);
+      i += static_cast<uint64_t>(n);
+    } else {
+      valid = false;
+      ++i;  // string_utils.cpp:212-215: skip one byte and retry
+    }
+  }
+  if (all_valid != nullptr) {
+    *all_valid = valid;
+  }
+  keys->clear();
+  if (key_toff != nullptr) {
+    key_toff->clear();
+  }
+  const uint32_t n = static_cast<uint32_t>(ngram_size);
+  if (n_cp < n) {
+    return;
+  }
+  const uint32_t n_win = n_cp - n + 1;
+  uint64_t wkey[kFastTermBytes];
+  uint16_t wstart[kFastTermBytes];
+  for (uint32_t i = 0; i < n_win; ++i) {  // insertion sort by (key, start): windows arrive in start order
+    const uint64_t k = ngram_size <= key_width ? pack_key(cps + i, ngram_size, key_width) : kInvalidKey;
+    uint32_t j = i;
+    while (j > 0 && wkey[j - 1] > k) {
+      wkey[j] = wkey[j - 1];
+      wstart[j] = wstart[j - 1];
+      --j;
+    }
+    wkey[j] = k;
+    wstart[j] = static_cast<uint16_t>(i);
+  }
+  for (uint32_t i = 0; i < n_win;) {  // sorted + unique == DeduplicateSorted, string_utils.h:192-196
+    uint32_t j = i;
+    while (j < n_win && wkey[j] == wkey[i]) {
+      ++j;
+    }
+    keys->push_back(wkey[i]);
+    if (key_toff != nullptr) {
+      const uint32_t off = cp_byte[wstart[i]];  // equal keys keep their start order: wstart[i] is the first
+      const uint32_t cnt = std::min<uint32_t>(j - i, 3);
+      key_toff->push_back(valid && off <= kTermOffsetMask ? static_cast<uint16_t>(off | (cnt << kTermCountShift))
+                                                          : kNoTermOffset);
+    }
+    i = j;
+  }
+}
+}  // namespace
+
 bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanji_ngram_size, bool cross_boundary,
-                     int key_width, std::vector<uint64_t>* keys, std::vector<uint16_t>* key_toff) {
+                     int key_width, KeyVec* keys, TermOffsetVec* key_toff, bool* all_valid) {
+  if (kanji_ngram_size <= 0 && ngram_size > 0 && len <= kFastTermBytes) {
+    fixed_ngram_keys_small(term, len, ngram_size, key_width, keys, key_toff, all_valid);
+    return true;
+  }
   // scratch reused across calls: a batch compiles ~10^4 terms and must not allocate per term
   static thread_local std::vector<uint32_t> cps;
   static thread_local std::vector<uint32_t> cp_byte;
@@ -163,6 +233,9 @@ bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanj
         ++i;  // string_utils.cpp:212-215: skip one byte and retry
       }
     }
+  }
+  if (all_valid != nullptr) {
+    *all_valid = valid;
   }
   if (kanji_ngram_size > 0) {
     hybrid_keys(cps, ngram_size > 0 ? ngram_size : 2, kanji_ngram_size, cross_boundary, key_width, keys, &starts);
@@ -350,7 +423,7 @@ int compile_range(const Index& ix, const mgx_query_params_t& p, uint64_t q_first
     table_cap <<= 1;
   }
   std::vector<uint32_t> table(table_cap, 0);  // term id + 1, 0 = empty
-  terms->reserve(n_search_slots / 2 + n_not_slots + 16);
+  terms->reserve(n_search_slots + n_not_slots + 16);
   // The streaming df pass (df_stream_kernel) counts "documents whose text contains the term". That equals the
   // reference's df (documents of SearchAnd(term n-grams) whose text contains the term) when every document is valid
   // UTF-8 and the query-side windows of a term are windows the index stores for any text containing it, i.e. both
@@ -381,33 +454,23 @@ int compile_range(const Index& ix, const mgx_query_params_t& p, uint64_t q_first
       }
       slot = (slot + 1) & (table_cap - 1);
     }
-    HostTerm t;
+    const uint32_t id = static_cast<uint32_t>(terms->size());
+    terms->emplace_back();
+    HostTerm& t = terms->back();
     t.hash = h;
     t.bytes.assign(reinterpret_cast<const char*>(bytes) + b, e - b);
+    bool valid_utf8 = false;
     host_query_keys(bytes + b, e - b, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0, ix.width, &t.keys,
-                    tok_agree ? &t.key_toff : nullptr);
+                    tok_agree ? &t.key_toff : nullptr, &valid_utf8);
     if (t.keys.size() == 1 && t.keys[0] != kInvalidKey) {
       uint8_t enc[4 * kMaxKeyWidth];
       const int n = mgx_key_to_utf8(t.keys[0], ix.width, enc);
       t.exact_single = static_cast<uint64_t>(n) == e - b && std::memcmp(enc, bytes + b, e - b) == 0;
     }
-    if (stream_ok && !t.keys.empty() && (t.keys.size() > 1 || !t.exact_single) &&
-        std::find(t.keys.begin(), t.keys.end(), kInvalidKey) == t.keys.end()) {
-      // valid UTF-8 of at least kStreamMinTermBytes bytes?
-      uint64_t i = b;
-      bool valid = e - b >= kStreamMinTermBytes;
-      while (valid && i < e) {
-        uint32_t cp = 0;
-        const uint64_t avail = e - i;
-        const int l = parse_utf8(bytes[i], avail > 1 ? bytes[i + 1] : 0, avail > 2 ? bytes[i + 2] : 0,
-                                 avail > 3 ? bytes[i + 3] : 0, avail, &cp);
-        valid = l > 0;
-        i += static_cast<uint64_t>(l > 0 ? l : 1);
-      }
-      t.streamable = valid;
-    }
-    const uint32_t id = static_cast<uint32_t>(terms->size());
-    terms->push_back(std::move(t));
+    // streaming df pass: valid UTF-8 of at least kStreamMinTermBytes bytes that needs a text check
+    t.streamable = stream_ok && valid_utf8 && e - b >= kStreamMinTermBytes && !t.keys.empty() &&
+                   (t.keys.size() > 1 || !t.exact_single) &&
+                   std::find(t.keys.begin(), t.keys.end(), kInvalidKey) == t.keys.end();
     table[slot] = id + 1;
     *out = id;
     return MGX_OK;
@@ -496,7 +559,9 @@ unsigned compile_threads(uint64_t n_queries) {
   if (n_queries < 2048) {
     return 1;
   }
-  unsigned t = std::max(1u, std::min(4u, std::thread::hardware_concurrency() / 8));
+  // one thread compiles a 4096-query batch in about a millisecond; starting workers and merging their term tables
+  // only pays for much larger batches (MGX_COMPILE_THREADS overrides)
+  unsigned t = n_queries < 16384 ? 1u : std::max(1u, std::min(4u, std::thread::hardware_concurrency() / 8));
   if (const char* env = std::getenv("MGX_COMPILE_THREADS")) {
     t = static_cast<unsigned>(std::max(1, std::atoi(env)));
   }
@@ -789,7 +854,7 @@ int mgx_index_add_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* t
                            int32_t* out_indexed) {
   if (out_indexed != nullptr && index != nullptr) {
     // Index::AddDocument returns false when the text yields no n-gram (index.cpp:49-57)
-    std::vector<uint64_t> keys;
+    KeyVec keys;
     host_query_keys(text, text_len, index->ix.ngram, index->ix.kanji, index->ix.cross, index->ix.width, &keys);
     *out_indexed = keys.empty() ? 0 : 1;
   }
@@ -1505,9 +1570,11 @@ int mgx_batch_prepare_ex(mgx_index_t* index, const mgx_query_params_t* params, u
     b.params = *params;
     b.stream = static_cast<cudaStream_t>(stream);  // NULL = the legacy default stream, as documented
     b.launches_at_start = g_launches.load();
-    std::vector<HostTerm> terms;
-    std::vector<HostQuery> queries;
-    std::vector<uint32_t> slot_tid;
+    // the compile workspace stays with the pooled batch object (capacity is kept from batch to batch)
+    std::vector<HostTerm>& terms = b.h_terms;
+    std::vector<HostQuery>& queries = b.h_queries;
+    std::vector<uint32_t>& slot_tid = b.h_slot_scratch;
+    terms.clear();
     static const uint8_t kEmpty[1] = {0};
     static const bool trace = std::getenv("MGX_BATCH_TRACE") != nullptr;  // host wall time of the two host stages
     const auto t0 = std::chrono::steady_clock::now();
@@ -1636,7 +1703,59 @@ int mgx_merge_topk_device(int32_t device, void* stream, const mgx_query_params_t
   return guarded([&]() {
     DeviceGuard guard(device);
     launch_merge_topk(static_cast<cudaStream_t>(stream), *params, n_shards, n_queries, stride, d_ids_all, d_scores_all,
-                      d_count_all, d_total_all, d_ids_out, d_scores_out, d_count_out, d_total_out);
+                      d_count_all, d_total_all, 0, d_ids_out, d_scores_out, d_count_out, d_total_out);
+    return MGX_OK;
+  });
+}
+
+int mgx_shard_record_layout(uint64_t n_queries, uint64_t stride, mgx_shard_record_layout_t* out) {
+  if (out == nullptr) {
+    return invalid("null argument");
+  }
+  // 8-byte parts first, so every part is aligned for its element type; the record is padded to 16 bytes
+  out->scores_offset = 0;
+  out->total_offset = n_queries * stride * sizeof(double);
+  out->ids_offset = out->total_offset + n_queries * sizeof(uint64_t);
+  out->count_offset = out->ids_offset + n_queries * stride * sizeof(uint32_t);
+  out->bytes = (out->count_offset + n_queries * sizeof(uint32_t) + 15) & ~static_cast<uint64_t>(15);
+  return MGX_OK;
+}
+
+int mgx_batch_search_packed_device(mgx_batch_t* batch, const uint64_t* d_df, uint64_t stride, void* d_record) {
+  if (batch == nullptr || d_record == nullptr) {
+    return invalid("null argument");
+  }
+  mgx_shard_record_layout_t lay;
+  mgx_shard_record_layout(batch->b.n_queries, stride, &lay);
+  uint8_t* base = static_cast<uint8_t*>(d_record);
+  return mgx_batch_search_device(batch, d_df, stride, reinterpret_cast<uint32_t*>(base + lay.ids_offset),
+                                 reinterpret_cast<double*>(base + lay.scores_offset),
+                                 reinterpret_cast<uint32_t*>(base + lay.count_offset),
+                                 reinterpret_cast<uint64_t*>(base + lay.total_offset));
+}
+
+int mgx_merge_topk_packed_device(int32_t device, void* stream, const mgx_query_params_t* params, uint32_t n_shards,
+                                 uint64_t n_queries, uint64_t stride, const void* d_records, void* d_record_out) {
+  if (params == nullptr || d_records == nullptr || d_record_out == nullptr) {
+    return invalid("null argument");
+  }
+  if (int rc = require_device(); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    DeviceGuard guard(device);
+    mgx_shard_record_layout_t lay;
+    mgx_shard_record_layout(n_queries, stride, &lay);
+    const uint8_t* in = static_cast<const uint8_t*>(d_records);
+    uint8_t* out = static_cast<uint8_t*>(d_record_out);
+    launch_merge_topk(static_cast<cudaStream_t>(stream), *params, n_shards, n_queries, stride,
+                      reinterpret_cast<const uint32_t*>(in + lay.ids_offset),
+                      reinterpret_cast<const double*>(in + lay.scores_offset),
+                      reinterpret_cast<const uint32_t*>(in + lay.count_offset),
+                      reinterpret_cast<const uint64_t*>(in + lay.total_offset), lay.bytes,
+                      reinterpret_cast<uint32_t*>(out + lay.ids_offset), reinterpret_cast<double*>(out + lay.scores_offset),
+                      reinterpret_cast<uint32_t*>(out + lay.count_offset),
+                      reinterpret_cast<uint64_t*>(out + lay.total_offset));
     return MGX_OK;
   });
 }

@@ -17,6 +17,11 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <initializer_list>
+#include <new>
+#include <type_traits>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -247,6 +252,124 @@ __host__ __device__ inline int parse_utf8(uint32_t b0, uint32_t b1, uint32_t b2,
 // ---------------------------------------------------------------- host tokenizer (queries)
 // Utf8ToCodepoints, string_utils.cpp:200-219.
 std::vector<uint32_t> host_utf8_to_codepoints(const uint8_t* text, uint64_t len);
+// Vector of trivially copyable elements with room for N of them inside the object: the query compiler builds ~10^4
+// terms and queries per batch, nearly all with <= 4 n-grams / terms, and a heap allocation for each of them was most
+// of its run time. Only the std::vector operations the compiler uses are provided.
+template <class T, unsigned N>
+class SmallVec {
+ public:
+  SmallVec() = default;
+  SmallVec(const SmallVec& o) { assign(o.begin(), o.end()); }
+  SmallVec(SmallVec&& o) noexcept { steal(o); }
+  SmallVec(std::initializer_list<T> il) { assign(il.begin(), il.end()); }
+  ~SmallVec() { release(); }
+  SmallVec& operator=(const SmallVec& o) {
+    if (this != &o) {
+      assign(o.begin(), o.end());
+    }
+    return *this;
+  }
+  SmallVec& operator=(SmallVec&& o) noexcept {
+    if (this != &o) {
+      release();
+      steal(o);
+    }
+    return *this;
+  }
+  SmallVec& operator=(const std::vector<T>& v) {
+    assign(v.data(), v.data() + v.size());
+    return *this;
+  }
+  SmallVec& operator=(std::initializer_list<T> il) {
+    assign(il.begin(), il.end());
+    return *this;
+  }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  T* data() { return p_; }
+  const T* data() const { return p_; }
+  T* begin() { return p_; }
+  T* end() { return p_ + n_; }
+  const T* begin() const { return p_; }
+  const T* end() const { return p_ + n_; }
+  T& operator[](size_t i) { return p_[i]; }
+  const T& operator[](size_t i) const { return p_[i]; }
+  T& back() { return p_[n_ - 1]; }
+  void clear() { n_ = 0; }
+  void reserve(size_t want) {
+    if (want > cap_) {
+      grow(want);
+    }
+  }
+  void push_back(const T& v) {
+    if (n_ == cap_) {
+      grow(static_cast<size_t>(cap_) * 2);
+    }
+    p_[n_++] = v;
+  }
+  T* erase(T* first, T* last) {  // std::vector::erase(first, last)
+    if (first != last) {
+      std::memmove(first, last, static_cast<size_t>(end() - last) * sizeof(T));
+      n_ -= static_cast<uint32_t>(last - first);
+    }
+    return first;
+  }
+
+ private:
+  static_assert(std::is_trivially_copyable<T>::value, "SmallVec holds plain data only");
+  void assign(const T* first, const T* last) {
+    const size_t n = static_cast<size_t>(last - first);
+    n_ = 0;
+    reserve(n);
+    if (n > 0) {
+      std::memcpy(p_, first, n * sizeof(T));
+    }
+    n_ = static_cast<uint32_t>(n);
+  }
+  void grow(size_t want) {
+    T* fresh = static_cast<T*>(std::malloc(want * sizeof(T)));
+    if (fresh == nullptr) {
+      throw std::bad_alloc();
+    }
+    if (n_ > 0) {
+      std::memcpy(fresh, p_, n_ * sizeof(T));
+    }
+    release();
+    p_ = fresh;
+    cap_ = static_cast<uint32_t>(want);
+  }
+  void release() {
+    if (p_ != inline_) {
+      std::free(p_);
+      p_ = inline_;
+      cap_ = N;
+    }
+  }
+  void steal(SmallVec& o) {
+    if (o.p_ != o.inline_) {
+      p_ = o.p_;
+      cap_ = o.cap_;
+      o.p_ = o.inline_;
+      o.cap_ = N;
+    } else {
+      p_ = inline_;
+      cap_ = N;
+      if (o.n_ > 0) {
+        std::memcpy(inline_, o.inline_, o.n_ * sizeof(T));
+      }
+    }
+    n_ = o.n_;
+    o.n_ = 0;
+  }
+  T* p_ = inline_;
+  uint32_t n_ = 0;
+  uint32_t cap_ = N;
+  T inline_[N];
+};
+using KeyVec = SmallVec<uint64_t, 4>;
+using TermOffsetVec = SmallVec<uint16_t, 4>;
+using TermIdVec = SmallVec<uint32_t, 4>;
+
 // GenerateQueryNgrams (string_utils.cpp:639-653) + DeduplicateSorted as packed
 // keys. Returns false if a window is wider than kMaxKeyWidth.
 // key_toff (optional): per returned key, (byte offset of the n-gram's FIRST occurrence inside the term) |
@@ -256,7 +379,8 @@ constexpr uint16_t kNoTermOffset = 0xFFFF;
 constexpr uint32_t kTermOffsetMask = 0x0FFF;
 constexpr uint32_t kTermCountShift = 12;
 bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanji_ngram_size, bool cross_boundary,
-                     int key_width, std::vector<uint64_t>* keys, std::vector<uint16_t>* key_toff = nullptr);
+                     int key_width, KeyVec* keys, TermOffsetVec* key_toff = nullptr, bool* all_valid = nullptr);
+// all_valid (optional): the term decoded without skipping a byte (it is valid UTF-8).
 // One n-gram string -> packed key (for Index::SearchAnd style calls). False if
 // it is not valid UTF-8 of 1..width code points (such a term cannot be in the index).
 bool host_ngram_to_key(const uint8_t* term, uint64_t len, int key_width, uint64_t* key);

@@ -2448,23 +2448,46 @@ gather_sets_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t 
   }
 }
 
+// The gathered per-shard runs: four arrays per shard, shard s at base + s * pitch (bytes). Dense [G][Q][S] arrays
+// and the packed one-buffer-per-shard record of mgx_shard_record_bytes() are both expressed this way.
+struct ShardRuns {
+  const uint8_t* ids_base;
+  const uint8_t* scores_base;
+  const uint8_t* count_base;
+  const uint8_t* total_base;
+  uint64_t ids_pitch;
+  uint64_t scores_pitch;
+  uint64_t count_pitch;
+  uint64_t total_pitch;
+  __device__ __forceinline__ const uint32_t* ids(uint32_t s) const {
+    return reinterpret_cast<const uint32_t*>(ids_base + s * ids_pitch);
+  }
+  __device__ __forceinline__ const double* scores(uint32_t s) const {
+    return reinterpret_cast<const double*>(scores_base + s * scores_pitch);
+  }
+  __device__ __forceinline__ const uint32_t* count(uint32_t s) const {
+    return reinterpret_cast<const uint32_t*>(count_base + s * count_pitch);
+  }
+  __device__ __forceinline__ const uint64_t* total(uint32_t s) const {
+    return reinterpret_cast<const uint64_t*>(total_base + s * total_pitch);
+  }
+};
+
 // ------------------------------------------------------------------ shard merge (rank based, no sort)
 // Every shard's run is already in final order. A record's final position is the
 // number of records (over all shards) that beat it, found by binary search in
 // each other run; records with position in [0, K) are written there.
 __global__ void __launch_bounds__(256)
 merge_topk_kernel(uint32_t n_shards, uint64_t n_queries, uint64_t stride, int compute_score, int descending,
-                  uint32_t limit, uint32_t offset, const uint32_t* __restrict__ ids_all, const double* __restrict__ scores_all,
-                  const uint32_t* __restrict__ count_all, const uint64_t* __restrict__ total_all,
-                  uint32_t* __restrict__ ids_out, double* __restrict__ scores_out, uint32_t* __restrict__ count_out,
-                  uint64_t* __restrict__ total_out) {
+                  uint32_t limit, uint32_t offset, ShardRuns runs, uint32_t* __restrict__ ids_out,
+                  double* __restrict__ scores_out, uint32_t* __restrict__ count_out, uint64_t* __restrict__ total_out) {
   const uint64_t q = blockIdx.x;
   const bool desc = descending != 0;
   uint64_t total = 0;
   uint64_t have = 0;
   for (uint32_t s = 0; s < n_shards; ++s) {
-    total += total_all[s * n_queries + q];
-    have += count_all[s * n_queries + q];
+    total += runs.total(s)[q];
+    have += runs.count(s)[q];
   }
   // shards return their best (offset + limit) records with offset 0; the offset is applied here
   const uint64_t skip = umin64(have, offset);
@@ -2475,23 +2498,25 @@ merge_topk_kernel(uint32_t n_shards, uint64_t n_queries, uint64_t stride, int co
     count_out[q] = k_out;
   }
   for (uint32_t s = 0; s < n_shards; ++s) {
-    const uint32_t c = count_all[s * n_queries + q];
-    const uint64_t base = (static_cast<uint64_t>(s) * n_queries + q) * stride;
+    const uint32_t c = runs.count(s)[q];
+    const uint32_t* my_ids = runs.ids(s) + q * stride;
+    const double* my_scores = runs.scores(s) + q * stride;
     for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
       uint32_t rank = i;
       if (compute_score) {
-        const SortKey me = make_sort_key(scores_all[base + i], ids_all[base + i], desc);
+        const SortKey me = make_sort_key(my_scores[i], my_ids[i], desc);
         for (uint32_t o = 0; o < n_shards; ++o) {
           if (o == s) {
             continue;
           }
-          const uint32_t oc = count_all[o * n_queries + q];
-          const uint64_t ob = (static_cast<uint64_t>(o) * n_queries + q) * stride;
+          const uint32_t oc = runs.count(o)[q];
+          const uint32_t* o_ids = runs.ids(o) + q * stride;
+          const double* o_scores = runs.scores(o) + q * stride;
           uint32_t lo = 0;  // number of records in run o that beat `me`
           uint32_t hi = oc;
           while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            const SortKey k = make_sort_key(scores_all[ob + mid], ids_all[ob + mid], desc);
+            const SortKey k = make_sort_key(o_scores[mid], o_ids[mid], desc);
             if (key_greater(k, me)) {
               lo = mid + 1;
             } else {
@@ -2503,13 +2528,13 @@ merge_topk_kernel(uint32_t n_shards, uint64_t n_queries, uint64_t stride, int co
       } else {
         // ascending ids over disjoint ascending shard ranges: concatenate in shard order
         for (uint32_t o = 0; o < s; ++o) {
-          rank += count_all[o * n_queries + q];
+          rank += runs.count(o)[q];
         }
       }
       if (rank >= skip && rank - skip < k_out) {
-        ids_out[q * stride + (rank - skip)] = ids_all[base + i];
+        ids_out[q * stride + (rank - skip)] = my_ids[i];
         if (compute_score && scores_out != nullptr) {
-          scores_out[q * stride + (rank - skip)] = scores_all[base + i];
+          scores_out[q * stride + (rank - skip)] = my_scores[i];
         }
       }
     }
@@ -2928,13 +2953,12 @@ void build_stream_table(std::vector<HostTerm>& terms, HostStreamTable* out) {
   while (n_slots < 2 * n) {
     n_slots <<= 1;
   }
-  struct Item {
-    uint32_t slot;
-    StreamEntry e;
-  };
-  std::vector<Item> items;
+  // scratch vectors live in the table object: a pooled batch re-uses them (no allocation, no fresh pages)
+  std::vector<HostStreamTable::Item>& items = out->items;
+  std::vector<uint32_t>& count = out->count;
+  items.clear();
   items.reserve(n);
-  std::vector<uint32_t> count(n_slots, 0);
+  count.assign(n_slots, 0);
   out->bloom.assign(kStreamBloomWords, 0);
   for (size_t t = 0; t < terms.size(); ++t) {
     HostTerm& ht = terms[t];
@@ -2961,181 +2985,216 @@ void build_stream_table(std::vector<HostTerm>& terms, HostStreamTable* out) {
     out->len12_mask |= 1u << len12;
     items.push_back({slot, {w[0], w[1], w[2], len12 | (static_cast<uint32_t>(t) << 8)}});
   }
-  std::vector<uint32_t> first(n_slots + 1, 0);
-  for (uint32_t i = 0; i < n_slots; ++i) {
-    first[i + 1] = first[i] + count[i];
-  }
   out->slots.resize(n_slots);
+  uint32_t first = 0;
   for (uint32_t i = 0; i < n_slots; ++i) {
-    out->slots[i] = (first[i] << 8) | count[i];
+    out->slots[i] = (first << 8) | count[i];
+    const uint32_t c = count[i];
+    count[i] = first;  // from here on: the bucket's fill cursor
+    first += c;
   }
   out->entries.resize(items.size());
-  std::vector<uint32_t> fill(first.begin(), first.end() - 1);
-  for (const Item& it : items) {
-    out->entries[fill[it.slot]++] = it.e;
+  for (const HostStreamTable::Item& it : items) {
+    out->entries[count[it.slot]++] = it.e;
   }
 }
 
 void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
                   const std::vector<uint32_t>& slot_tid) {
   cudaStream_t st = b.stream;
-  HostStreamTable stream_table;
+  HostStreamTable& stream_table = b.h_stream_table;
   build_stream_table(terms, &stream_table);
-  b.n_queries = static_cast<uint32_t>(queries.size());
-  b.n_terms = static_cast<uint32_t>(terms.size());
+  const size_t T = terms.size();
+  const size_t Q = queries.size();
+  b.n_queries = static_cast<uint32_t>(Q);
+  b.n_terms = static_cast<uint32_t>(T);
   b.n_slots = static_cast<uint32_t>(slot_tid.size());
   b.h_slot_tid = slot_tid;
 
-  std::vector<uint8_t> bytes;
-  std::vector<uint32_t> boff(terms.size() + 1, 0);
-  std::vector<uint32_t> koff(terms.size() + 1, 0);
-  std::vector<uint64_t> keys;
-  std::vector<uint16_t> key_toff;
-  std::vector<uint8_t> raw(terms.size() + 1, 0);
-  for (size_t t = 0; t < terms.size(); ++t) {
-    bytes.insert(bytes.end(), terms[t].bytes.begin(), terms[t].bytes.end());
-    boff[t + 1] = static_cast<uint32_t>(bytes.size());
-    keys.insert(keys.end(), terms[t].keys.begin(), terms[t].keys.end());
-    for (size_t k = 0; k < terms[t].keys.size(); ++k) {
-      key_toff.push_back(k < terms[t].key_toff.size() ? terms[t].key_toff[k] : kNoTermOffset);
-    }
-    koff[t + 1] = static_cast<uint32_t>(keys.size());
-    raw[t] = static_cast<uint8_t>((terms[t].raw ? 1 : 0) | (terms[t].exact_single ? 2 : 0) |
-                                  (terms[t].streamable ? 4 : 0));
+  // ---- sizes first, so that every array is written ONCE, straight into the pinned staging buffer
+  size_t n_bytes = 0, n_keys = 0;
+  for (const HostTerm& t : terms) {
+    n_bytes += t.bytes.size();
+    n_keys += t.keys.size();
   }
-  bytes.resize(bytes.size() + 16, 0);
-  b.n_keys = static_cast<uint32_t>(keys.size());
-
-  std::vector<uint32_t> toff(queries.size() + 1, 0);
-  std::vector<uint32_t> noff(queries.size() + 1, 0);
-  std::vector<uint32_t> loff(queries.size() + 1, 0);
-  std::vector<uint32_t> tids;
-  std::vector<uint32_t> ntids;
-  std::vector<uint32_t> hflags(queries.size() + 1, 0);
-  std::vector<uint32_t> thresholds(queries.size() + 1, 1);
-  std::vector<uint32_t> poff(queries.size() + 1, 0);
-  std::vector<uint32_t> coff(queries.size() + 1, 0);
-  std::vector<uint8_t> prog_ops;
-  std::vector<uint32_t> prog_args;
-  std::vector<uint32_t> conj;
-  std::vector<uint32_t> foff(queries.size() + 1, 0);
-  std::vector<FilterPred> preds;
-  for (size_t q = 0; q < queries.size(); ++q) {
-    bool all_bitmap = true;  // AllFiltersHaveBitmapSupport, search_pipeline.cpp:995-1003
-    for (const HostFilter& hf : queries[q].filters) {
-      all_bitmap = all_bitmap && (hf.op == 0 || hf.op == 1);
-    }
-    for (const HostFilter& hf : queries[q].filters) {
-      preds.push_back(resolve_filter(*b.ix, hf, all_bitmap));
-    }
-    foff[q + 1] = static_cast<uint32_t>(preds.size());
-    prog_ops.insert(prog_ops.end(), queries[q].prog_ops.begin(), queries[q].prog_ops.end());
-    prog_args.insert(prog_args.end(), queries[q].prog_args.begin(), queries[q].prog_args.end());
-    conj.insert(conj.end(), queries[q].conjuncts.begin(), queries[q].conjuncts.end());
-    poff[q + 1] = static_cast<uint32_t>(prog_ops.size());
-    coff[q + 1] = static_cast<uint32_t>(conj.size());
-    thresholds[q] = queries[q].threshold;
-    uint32_t cap = (queries[q].flags & kQProgram) != 0 ? 1u : 0u;  // a program's only list is its driver
-    for (uint32_t tid : queries[q].terms) {
-      tids.push_back(tid);
-      cap += static_cast<uint32_t>(terms[tid].keys.size());
-    }
-    for (uint32_t tid : queries[q].not_terms) {
-      ntids.push_back(tid);
-    }
-    toff[q + 1] = static_cast<uint32_t>(tids.size());
-    noff[q + 1] = static_cast<uint32_t>(ntids.size());
-    loff[q + 1] = loff[q] + cap;
-    hflags[q] = queries[q].flags;
+  n_bytes += 16;  // zero tail: the kernels read term bytes in words
+  size_t n_tids = 0, n_ntids = 0, n_prog = 0, n_conj = 0, n_preds = 0;
+  for (const HostQuery& q : queries) {
+    n_tids += q.terms.size();
+    n_ntids += q.not_terms.size();
+    n_prog += q.prog_ops.size();
+    n_conj += q.conjuncts.size();
+    n_preds += q.filters.size();
   }
-  b.n_qterms = static_cast<uint32_t>(tids.size());
-
-  // ---- one pinned staging buffer, one H2D copy, views into the input arena
-  struct Piece {
-    const void* src;
-    size_t bytes;
-    size_t off;
-  };
-  std::vector<Piece> pieces;
+  b.n_keys = static_cast<uint32_t>(n_keys);
+  b.n_qterms = static_cast<uint32_t>(n_tids);
   size_t total = 0;
-  auto add = [&](const void* src, size_t nbytes) {
-    pieces.push_back({src, nbytes, total});
+  auto add = [&](size_t nbytes) {
+    const size_t at = total;
     total += DevArena::padded(nbytes == 0 ? 1 : nbytes);
-    return pieces.size() - 1;
+    return at;
   };
-  const size_t i_bytes = add(bytes.data(), bytes.size());
-  const size_t i_boff = add(boff.data(), boff.size() * 4);
-  const size_t i_koff = add(koff.data(), koff.size() * 4);
-  const size_t i_keys = add(keys.data(), keys.size() * 8);
-  const size_t i_raw = add(raw.data(), raw.size());
-  const size_t i_toff = add(toff.data(), toff.size() * 4);
-  const size_t i_tids = add(tids.data(), tids.size() * 4);
-  const size_t i_noff = add(noff.data(), noff.size() * 4);
-  const size_t i_ntids = add(ntids.data(), ntids.size() * 4);
-  const size_t i_loff = add(loff.data(), loff.size() * 4);
-  const size_t i_hflags = add(hflags.data(), hflags.size() * 4);
-  const size_t i_slot = add(slot_tid.data(), slot_tid.size() * 4);
-  const size_t i_ktoff = add(key_toff.data(), key_toff.size() * 2);
-  const size_t i_thr = add(thresholds.data(), thresholds.size() * 4);
-  const size_t i_poff = add(poff.data(), poff.size() * 4);
-  const size_t i_pops = add(prog_ops.data(), prog_ops.size());
-  const size_t i_pargs = add(prog_args.data(), prog_args.size() * 4);
-  const size_t i_coff = add(coff.data(), coff.size() * 4);
-  const size_t i_conj = add(conj.data(), conj.size() * 4);
-  const size_t i_foff = add(foff.data(), foff.size() * 4);
-  const size_t i_preds = add(preds.data(), preds.size() * sizeof(FilterPred));
-  const size_t i_sslots = add(stream_table.slots.data(), stream_table.slots.size() * 4);
-  const size_t i_sentries = add(stream_table.entries.data(), stream_table.entries.size() * sizeof(StreamEntry));
-  const size_t i_sbloom = add(stream_table.bloom.data(), stream_table.bloom.size() * 4);
+  const size_t i_bytes = add(n_bytes);
+  const size_t i_boff = add((T + 1) * 4);
+  const size_t i_koff = add((T + 1) * 4);
+  const size_t i_keys = add(n_keys * 8);
+  const size_t i_raw = add(T + 1);
+  const size_t i_toff = add((Q + 1) * 4);
+  const size_t i_tids = add(n_tids * 4);
+  const size_t i_noff = add((Q + 1) * 4);
+  const size_t i_ntids = add(n_ntids * 4);
+  const size_t i_loff = add((Q + 1) * 4);
+  const size_t i_hflags = add((Q + 1) * 4);
+  const size_t i_slot = add(slot_tid.size() * 4);
+  const size_t i_ktoff = add(n_keys * 2);
+  const size_t i_thr = add((Q + 1) * 4);
+  const size_t i_poff = add((Q + 1) * 4);
+  const size_t i_pops = add(n_prog);
+  const size_t i_pargs = add(n_prog * 4);
+  const size_t i_coff = add((Q + 1) * 4);
+  const size_t i_conj = add(n_conj * 4);
+  const size_t i_foff = add((Q + 1) * 4);
+  const size_t i_preds = add(n_preds * sizeof(FilterPred));
+  const size_t i_sslots = add(stream_table.slots.size() * 4);
+  const size_t i_sentries = add(stream_table.entries.size() * sizeof(StreamEntry));
+  const size_t i_sbloom = add(stream_table.bloom.size() * 4);
   b.n_stream_slots = static_cast<uint32_t>(stream_table.slots.size());
   b.n_stream_terms = static_cast<uint32_t>(stream_table.entries.size());
   b.stream_len8_mask = stream_table.len8_mask;
   b.stream_len12_mask = stream_table.len12_mask;
   b.staging.reserve(total + 256);
-  for (const Piece& pc : pieces) {
-    if (pc.bytes > 0) {
-      std::memcpy(b.staging.p + pc.off, pc.src, pc.bytes);
+  uint8_t* const S = b.staging.p;
+
+  {  // terms
+    uint8_t* bytes = S + i_bytes;
+    uint32_t* boff = reinterpret_cast<uint32_t*>(S + i_boff);
+    uint32_t* koff = reinterpret_cast<uint32_t*>(S + i_koff);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(S + i_keys);
+    uint16_t* key_toff = reinterpret_cast<uint16_t*>(S + i_ktoff);
+    uint8_t* raw = S + i_raw;
+    uint32_t nb = 0, nk = 0;
+    boff[0] = 0;
+    koff[0] = 0;
+    for (size_t t = 0; t < T; ++t) {
+      const HostTerm& ht = terms[t];
+      std::memcpy(bytes + nb, ht.bytes.data(), ht.bytes.size());
+      nb += static_cast<uint32_t>(ht.bytes.size());
+      boff[t + 1] = nb;
+      for (size_t k = 0; k < ht.keys.size(); ++k) {
+        keys[nk + k] = ht.keys[k];
+        key_toff[nk + k] = k < ht.key_toff.size() ? ht.key_toff[k] : kNoTermOffset;
+      }
+      nk += static_cast<uint32_t>(ht.keys.size());
+      koff[t + 1] = nk;
+      raw[t] = static_cast<uint8_t>((ht.raw ? 1 : 0) | (ht.exact_single ? 2 : 0) | (ht.streamable ? 4 : 0));
     }
+    raw[T] = 0;
+    std::memset(bytes + nb, 0, 16);
+  }
+  size_t list_cap = 0;
+  {  // queries
+    uint32_t* toff = reinterpret_cast<uint32_t*>(S + i_toff);
+    uint32_t* tids = reinterpret_cast<uint32_t*>(S + i_tids);
+    uint32_t* noff = reinterpret_cast<uint32_t*>(S + i_noff);
+    uint32_t* ntids = reinterpret_cast<uint32_t*>(S + i_ntids);
+    uint32_t* loff = reinterpret_cast<uint32_t*>(S + i_loff);
+    uint32_t* hflags = reinterpret_cast<uint32_t*>(S + i_hflags);
+    uint32_t* thresholds = reinterpret_cast<uint32_t*>(S + i_thr);
+    uint32_t* poff = reinterpret_cast<uint32_t*>(S + i_poff);
+    uint8_t* prog_ops = S + i_pops;
+    uint32_t* prog_args = reinterpret_cast<uint32_t*>(S + i_pargs);
+    uint32_t* coff = reinterpret_cast<uint32_t*>(S + i_coff);
+    uint32_t* conj = reinterpret_cast<uint32_t*>(S + i_conj);
+    uint32_t* foff = reinterpret_cast<uint32_t*>(S + i_foff);
+    FilterPred* preds = reinterpret_cast<FilterPred*>(S + i_preds);
+    uint32_t nt = 0, nn = 0, np = 0, nc = 0, nf = 0, nl = 0;
+    toff[0] = noff[0] = loff[0] = poff[0] = coff[0] = foff[0] = 0;
+    for (size_t q = 0; q < Q; ++q) {
+      const HostQuery& hq = queries[q];
+      if (!hq.filters.empty()) {
+        bool all_bitmap = true;  // AllFiltersHaveBitmapSupport, search_pipeline.cpp:995-1003
+        for (const HostFilter& hf : hq.filters) {
+          all_bitmap = all_bitmap && (hf.op == 0 || hf.op == 1);
+        }
+        for (const HostFilter& hf : hq.filters) {
+          preds[nf++] = resolve_filter(*b.ix, hf, all_bitmap);
+        }
+      }
+      foff[q + 1] = nf;
+      for (size_t i = 0; i < hq.prog_ops.size(); ++i) {
+        prog_ops[np + i] = hq.prog_ops[i];
+        prog_args[np + i] = hq.prog_args[i];
+      }
+      np += static_cast<uint32_t>(hq.prog_ops.size());
+      for (uint32_t c : hq.conjuncts) {
+        conj[nc++] = c;
+      }
+      poff[q + 1] = np;
+      coff[q + 1] = nc;
+      thresholds[q] = hq.threshold;
+      uint32_t cap = (hq.flags & kQProgram) != 0 ? 1u : 0u;  // a program's only list is its driver
+      for (uint32_t tid : hq.terms) {
+        tids[nt++] = tid;
+        cap += static_cast<uint32_t>(terms[tid].keys.size());
+      }
+      for (uint32_t tid : hq.not_terms) {
+        ntids[nn++] = tid;
+      }
+      toff[q + 1] = nt;
+      noff[q + 1] = nn;
+      nl += cap;
+      loff[q + 1] = nl;
+      hflags[q] = hq.flags;
+    }
+    hflags[Q] = 0;
+    thresholds[Q] = 1;
+    list_cap = nl;
+  }
+  if (!slot_tid.empty()) {
+    std::memcpy(S + i_slot, slot_tid.data(), slot_tid.size() * 4);
+  }
+  if (!stream_table.slots.empty()) {
+    std::memcpy(S + i_sslots, stream_table.slots.data(), stream_table.slots.size() * 4);
+    std::memcpy(S + i_sentries, stream_table.entries.data(), stream_table.entries.size() * sizeof(StreamEntry));
+    std::memcpy(S + i_sbloom, stream_table.bloom.data(), stream_table.bloom.size() * 4);
   }
   b.in_arena.reserve(total + 256, true);
   uint8_t* base = b.in_arena.take<uint8_t>(total);
   MGX_CUDA(cudaMemcpyAsync(base, b.staging.p, total, cudaMemcpyHostToDevice, st));
   b.h2d_bytes = total;
-  auto at = [&](size_t i) { return base + pieces[i].off; };
-  b.d_term_bytes.borrow(at(i_bytes), bytes.size());
-  b.d_term_boff.borrow(reinterpret_cast<uint32_t*>(at(i_boff)), boff.size());
-  b.d_term_koff.borrow(reinterpret_cast<uint32_t*>(at(i_koff)), koff.size());
-  b.d_keys.borrow(reinterpret_cast<uint64_t*>(at(i_keys)), keys.size());
-  b.d_term_flags.borrow(at(i_raw), raw.size());
-  b.d_q_toff.borrow(reinterpret_cast<uint32_t*>(at(i_toff)), toff.size());
-  b.d_q_tids.borrow(reinterpret_cast<uint32_t*>(at(i_tids)), tids.size());
-  b.d_q_noff.borrow(reinterpret_cast<uint32_t*>(at(i_noff)), noff.size());
-  b.d_q_ntids.borrow(reinterpret_cast<uint32_t*>(at(i_ntids)), ntids.size());
-  b.d_q_loff.borrow(reinterpret_cast<uint32_t*>(at(i_loff)), loff.size());
-  b.d_q_host_flags.borrow(reinterpret_cast<uint32_t*>(at(i_hflags)), hflags.size());
+  auto at = [&](size_t off) { return base + off; };
+  b.d_term_bytes.borrow(at(i_bytes), n_bytes);
+  b.d_term_boff.borrow(reinterpret_cast<uint32_t*>(at(i_boff)), T + 1);
+  b.d_term_koff.borrow(reinterpret_cast<uint32_t*>(at(i_koff)), T + 1);
+  b.d_keys.borrow(reinterpret_cast<uint64_t*>(at(i_keys)), n_keys);
+  b.d_term_flags.borrow(at(i_raw), T + 1);
+  b.d_q_toff.borrow(reinterpret_cast<uint32_t*>(at(i_toff)), Q + 1);
+  b.d_q_tids.borrow(reinterpret_cast<uint32_t*>(at(i_tids)), n_tids);
+  b.d_q_noff.borrow(reinterpret_cast<uint32_t*>(at(i_noff)), Q + 1);
+  b.d_q_ntids.borrow(reinterpret_cast<uint32_t*>(at(i_ntids)), n_ntids);
+  b.d_q_loff.borrow(reinterpret_cast<uint32_t*>(at(i_loff)), Q + 1);
+  b.d_q_host_flags.borrow(reinterpret_cast<uint32_t*>(at(i_hflags)), Q + 1);
   b.d_slot_tid.borrow(reinterpret_cast<uint32_t*>(at(i_slot)), slot_tid.size());
-  b.d_key_toff.borrow(reinterpret_cast<uint16_t*>(at(i_ktoff)), key_toff.size());
-  b.d_q_threshold.borrow(reinterpret_cast<uint32_t*>(at(i_thr)), thresholds.size());
-  b.d_q_poff.borrow(reinterpret_cast<uint32_t*>(at(i_poff)), poff.size());
-  b.d_prog_op.borrow(at(i_pops), prog_ops.size());
-  b.d_prog_arg.borrow(reinterpret_cast<uint32_t*>(at(i_pargs)), prog_args.size());
-  b.d_q_coff.borrow(reinterpret_cast<uint32_t*>(at(i_coff)), coff.size());
-  b.d_q_conj.borrow(reinterpret_cast<uint32_t*>(at(i_conj)), conj.size());
-  b.d_q_foff.borrow(reinterpret_cast<uint32_t*>(at(i_foff)), foff.size());
-  b.d_filters.borrow(reinterpret_cast<FilterPred*>(at(i_preds)), preds.size());
+  b.d_key_toff.borrow(reinterpret_cast<uint16_t*>(at(i_ktoff)), n_keys);
+  b.d_q_threshold.borrow(reinterpret_cast<uint32_t*>(at(i_thr)), Q + 1);
+  b.d_q_poff.borrow(reinterpret_cast<uint32_t*>(at(i_poff)), Q + 1);
+  b.d_prog_op.borrow(at(i_pops), n_prog);
+  b.d_prog_arg.borrow(reinterpret_cast<uint32_t*>(at(i_pargs)), n_prog);
+  b.d_q_coff.borrow(reinterpret_cast<uint32_t*>(at(i_coff)), Q + 1);
+  b.d_q_conj.borrow(reinterpret_cast<uint32_t*>(at(i_conj)), n_conj);
+  b.d_q_foff.borrow(reinterpret_cast<uint32_t*>(at(i_foff)), Q + 1);
+  b.d_filters.borrow(reinterpret_cast<FilterPred*>(at(i_preds)), n_preds);
   b.d_stream_slots.borrow(reinterpret_cast<uint32_t*>(at(i_sslots)), stream_table.slots.size());
   b.d_stream_entries.borrow(reinterpret_cast<StreamEntry*>(at(i_sentries)), stream_table.entries.size());
   b.d_stream_bloom.borrow(reinterpret_cast<uint32_t*>(at(i_sbloom)), stream_table.bloom.size());
 
   // ---- device-only planning arrays from the work arena
-  const size_t T = terms.size();
-  const size_t Q = queries.size();
-  const size_t K = keys.size();
-  const size_t Lc = loff.back();
+  const size_t K = n_keys;
+  const size_t Lc = list_cap;
   const size_t scan_elems = scan_scratch_elems(std::max<uint64_t>(T, Q)) + 8;
   size_t work = 0;
   for (size_t nbytes : {K * sizeof(KeyRef), K * 4, K * 4, T * 8, T * 4, (T + 1) * 8, T * 8, Lc * 4, Lc * 4, Q * 4, Q * 4, Q * 4, Q * 4,
-                        (Q + 1) * 8, (Q + 1) * 8, tids.size() * 8, static_cast<size_t>(kStatCount) * kStatStripes * 8,
+                        (Q + 1) * 8, (Q + 1) * 8, n_tids * 8, static_cast<size_t>(kStatCount) * kStatStripes * 8,
                         scan_elems * 8, static_cast<size_t>(64)}) {
     work += DevArena::padded(nbytes == 0 ? 1 : nbytes);
   }
@@ -3155,7 +3214,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   b.d_q_ntiles.borrow(b.work_arena.take<uint32_t>(Q), Q);
   b.d_q_tile_off.borrow(b.work_arena.take<uint64_t>(Q + 1), Q + 1);
   b.d_q_rec_off.borrow(b.work_arena.take<uint64_t>(Q + 1), Q + 1);
-  b.d_q_idf.borrow(b.work_arena.take<double>(tids.size()), tids.size());
+  b.d_q_idf.borrow(b.work_arena.take<double>(n_tids), n_tids);
   const size_t n_stats = static_cast<size_t>(kStatCount) * kStatStripes;
   b.d_stats.borrow(b.work_arena.take<unsigned long long>(n_stats), n_stats);
   b.d_scan_scratch.borrow(b.work_arena.take<uint64_t>(scan_elems), scan_elems);
@@ -3526,15 +3585,24 @@ void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32
 
 void launch_merge_topk(cudaStream_t stream, const mgx_query_params_t& params, uint32_t n_shards, uint64_t n_queries,
                        uint64_t stride, const uint32_t* d_ids_all, const double* d_scores_all,
-                       const uint32_t* d_count_all, const uint64_t* d_total_all, uint32_t* d_ids_out,
-                       double* d_scores_out, uint32_t* d_count_out, uint64_t* d_total_out) {
+                       const uint32_t* d_count_all, const uint64_t* d_total_all, uint64_t shard_pitch_bytes,
+                       uint32_t* d_ids_out, double* d_scores_out, uint32_t* d_count_out, uint64_t* d_total_out) {
   if (n_queries == 0) {
     return;
   }
+  ShardRuns runs;
+  runs.ids_base = reinterpret_cast<const uint8_t*>(d_ids_all);
+  runs.scores_base = reinterpret_cast<const uint8_t*>(d_scores_all);
+  runs.count_base = reinterpret_cast<const uint8_t*>(d_count_all);
+  runs.total_base = reinterpret_cast<const uint8_t*>(d_total_all);
+  // pitch 0: four dense [n_shards][n_queries][stride] arrays; otherwise every array of shard s sits s * pitch further
+  runs.ids_pitch = shard_pitch_bytes != 0 ? shard_pitch_bytes : n_queries * stride * sizeof(uint32_t);
+  runs.scores_pitch = shard_pitch_bytes != 0 ? shard_pitch_bytes : n_queries * stride * sizeof(double);
+  runs.count_pitch = shard_pitch_bytes != 0 ? shard_pitch_bytes : n_queries * sizeof(uint32_t);
+  runs.total_pitch = shard_pitch_bytes != 0 ? shard_pitch_bytes : n_queries * sizeof(uint64_t);
   merge_topk_kernel<<<static_cast<unsigned>(n_queries), 256, 0, stream>>>(
-      n_shards, n_queries, stride, params.compute_score, params.descending, params.limit, params.offset, d_ids_all,
-      d_scores_all,
-      d_count_all, d_total_all, d_ids_out, d_scores_out, d_count_out, d_total_out);
+      n_shards, n_queries, stride, params.compute_score, params.descending, params.limit, params.offset, runs,
+      d_ids_out, d_scores_out, d_count_out, d_total_out);
   MGX_LAUNCH_CHECK();
 }
 

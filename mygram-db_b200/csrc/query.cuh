@@ -112,6 +112,44 @@ struct DfTileDesc {
   uint32_t pad;
 };
 
+// One compiled query term.
+struct HostTerm {
+  std::string bytes;
+  KeyVec keys;             // sorted unique packed n-grams
+  TermOffsetVec key_toff;  // per key: byte offset in the term if the n-gram occurs once in it (else kNoTermOffset)
+  bool raw = false;            // keys given directly (Index::SearchAnd style): no text semantics
+  bool exact_single = false;   // the term IS its single n-gram, so df == posting size when all text is valid UTF-8
+  bool streamable = false;     // valid UTF-8 (>= 3 bytes) that needs a text check: may use the streaming df pass
+  uint64_t hash = 0;           // hash of `bytes` (host query compiler)
+};
+
+// Host-built bucket table of the streamable terms.
+struct HostStreamTable {
+  std::vector<uint32_t> slots;
+  std::vector<StreamEntry> entries;
+  std::vector<uint32_t> bloom;
+  uint32_t len8_mask = 0;
+  uint32_t len12_mask = 0;
+  // builder scratch, kept with the table so that a pooled batch re-uses the memory
+  struct Item {
+    uint32_t slot;
+    StreamEntry e;
+  };
+  std::vector<Item> items;
+  std::vector<uint32_t> count;
+};
+
+struct HostQuery {
+  TermIdVec terms;                  // unique-term ids in query order
+  TermIdVec not_terms;
+  uint32_t flags = 0;               // kQVerify / kQAnyMode / kQDriverAll / kQDriverExplicit / kQProgram
+  uint32_t threshold = 1;           // kQAnyMode: lists that must hold the document (Index::SearchByThreshold); 1 = OR
+  std::vector<uint8_t> prog_ops;    // kQProgram: postfix program
+  std::vector<uint32_t> prog_args;
+  std::vector<uint32_t> conjuncts;  // kQProgram: terms every result must satisfy (driver candidates)
+  std::vector<HostFilter> filters;  // column conditions, AND-ed
+};
+
 struct Batch {
   Index* ix = nullptr;
   SearchScratch* sc = nullptr;  // the (index, stream) workspace; the d_tile_* / d_rec_* members below are views into it
@@ -126,6 +164,12 @@ struct Batch {
   uint32_t n_keys = 0;
   uint32_t n_slots = 0;      // caller's search-term slots (for df output)
   std::vector<uint32_t> h_slot_tid;  // slot -> unique term id
+  // compile workspace of the staged / batched entry points: kept with the pooled batch object, so that a steady
+  // stream of batches neither allocates nor touches fresh pages on the host
+  std::vector<HostTerm> h_terms;
+  std::vector<HostQuery> h_queries;
+  std::vector<uint32_t> h_slot_scratch;
+  HostStreamTable h_stream_table;
 
   // ---- device: terms
   DevBuf<uint8_t> d_term_bytes;
@@ -247,37 +291,6 @@ enum StatSlot : int {
 };
 constexpr int kStatStripes = 64;  // each counter is striped over 64 words to spread the atomics
 
-// One compiled query term.
-struct HostTerm {
-  std::string bytes;
-  std::vector<uint64_t> keys;  // sorted unique packed n-grams
-  std::vector<uint16_t> key_toff;  // per key: byte offset in the term if the n-gram occurs once in it (else kNoTermOffset)
-  bool raw = false;            // keys given directly (Index::SearchAnd style): no text semantics
-  bool exact_single = false;   // the term IS its single n-gram, so df == posting size when all text is valid UTF-8
-  bool streamable = false;     // valid UTF-8 (>= 3 bytes) that needs a text check: may use the streaming df pass
-  uint64_t hash = 0;           // hash of `bytes` (host query compiler)
-};
-
-// Host-built bucket table of the streamable terms.
-struct HostStreamTable {
-  std::vector<uint32_t> slots;
-  std::vector<StreamEntry> entries;
-  std::vector<uint32_t> bloom;
-  uint32_t len8_mask = 0;
-  uint32_t len12_mask = 0;
-};
-
-struct HostQuery {
-  std::vector<uint32_t> terms;      // unique-term ids in query order
-  std::vector<uint32_t> not_terms;
-  uint32_t flags = 0;               // kQVerify / kQAnyMode / kQDriverAll / kQDriverExplicit / kQProgram
-  uint32_t threshold = 1;           // kQAnyMode: lists that must hold the document (Index::SearchByThreshold); 1 = OR
-  std::vector<uint8_t> prog_ops;    // kQProgram: postfix program
-  std::vector<uint32_t> prog_args;
-  std::vector<uint32_t> conjuncts;  // kQProgram: terms every result must satisfy (driver candidates)
-  std::vector<HostFilter> filters;  // column conditions, AND-ed
-};
-
 // query.cu
 // `terms` is not const: the stream-table builder clears `streamable` of terms that do not fit a bucket.
 void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
@@ -295,8 +308,8 @@ void batch_search(Batch& b, const uint64_t* d_df_global, uint64_t stride, uint32
 void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32_t>* d_sets);
 void launch_merge_topk(cudaStream_t stream, const mgx_query_params_t& params, uint32_t n_shards, uint64_t n_queries,
                        uint64_t stride, const uint32_t* d_ids_all, const double* d_scores_all,
-                       const uint32_t* d_count_all, const uint64_t* d_total_all, uint32_t* d_ids_out,
-                       double* d_scores_out, uint32_t* d_count_out, uint64_t* d_total_out);
+                       const uint32_t* d_count_all, const uint64_t* d_total_all, uint64_t shard_pitch_bytes,
+                       uint32_t* d_ids_out, double* d_scores_out, uint32_t* d_count_out, uint64_t* d_total_out);
 void batch_df_to_slots(Batch& b, uint64_t* d_df_slots);
 void launch_score_documents(Index& ix, cudaStream_t stream, const uint32_t* d_cands, uint64_t n_cands,
                             const uint8_t* d_term_bytes, const uint32_t* d_term_boff, const uint64_t* d_dfs,

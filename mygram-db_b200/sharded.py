@@ -9,8 +9,8 @@ distributed layer; this is the B200-native addition of SURVEY.m
   * exchange 1 (tiny): all-reduce(SUM) of the per-term verified document frequencies and, once per index
     generation, of the corpus statistics (doc_count, total_doc_length) -- BM25 must use GLOBAL statistics so
     that scores are identical for every shard count;
-  * exchange 2: ONE all-gather of the fixed-size per-shard top-k records (ids u32, scores f64, counts, totals),
-    followed by the rank-based merge kernel (mgx_merge_topk_device).
+  * exchange 2: ONE all-gather of the fixed-size per-shard top-k record (ids u32, scores f64, counts, totals packed
+    in one buffer, `record_layout`), followed by the rank-based merge kernel (mgx_merge_topk_packed_device).
 
 The protocol is written against a small backend interface so that the same code drives the CUDA library
 (`MgxShardBackend`) and, in the CPU test-suite, an oracle-backed stand-in over the gloo backend.
@@ -66,20 +66,46 @@ class TorchDist:
         self.dist.barrier()
 
 
+def record_layout(n_queries, stride):
+    """Byte offsets of one shard's packed top-k record: [scores f64 Q*S][total i64 Q][ids i32 Q*S][count i32 Q],
+    padded to 16 bytes (the same layout as mgx_shard_record_layout, include/mgx.h)."""
+    o_scores = 0
+    o_total = n_queries * stride * 8
+    o_ids = o_total + n_queries * 8
+    o_count = o_ids + n_queries * stride * 4
+    return {"scores": o_scores, "total": o_total, "ids": o_ids, "count": o_count,
+            "bytes": (o_count + n_queries * 4 + 15) & ~15}
+
+
+def record_views(rec, n_queries, stride):
+    """(ids, scores, count, total) views into packed records: `rec` is a uint8 tensor [..., bytes] (one record or
+    the gathered [G, bytes]); the views keep the leading dimensions."""
+    import torch
+    lay = record_layout(n_queries, stride)
+    lead = tuple(rec.shape[:-1])
+    Q, S = n_queries, stride
+
+    def part(off, n, dtype, shape):
+        return rec[..., off:off + n].view(dtype).reshape(lead + shape)
+
+    return (part(lay["ids"], Q * S * 4, torch.int32, (Q, S)), part(lay["scores"], Q * S * 8, torch.float64, (Q, S)),
+            part(lay["count"], Q * 4, torch.int32, (Q,)), part(lay["total"], Q * 8, torch.int64, (Q,)))
+
+
 def run_sharded_batch(backend, comm, batch):
     """One query batch over all shards. `backend` implements:
-        local_df(batch)                    -> int64 tensor [n_term_slots]   (this shard's verified df)
-        search(batch, global_df)           -> (ids [Q,S] int32-as-uint32, scores [Q,S] f64, count [Q] int32, total [Q] int64)
-        merge(ids_all, scores_all, count_all, total_all) -> (ids, scores, count, total)
+        local_df(batch)            -> int64 tensor [n_term_slots]   (this shard's verified df)
+        search(batch, global_df)   -> uint8 tensor [record bytes]: this shard's packed top-k record (record_layout)
+        merge(records [G, bytes])  -> (ids [Q,S] int32-as-uint32, scores [Q,S] f64, count [Q] int32, total [Q] int64)
+    Exchanges: one all-reduce of the per-term df, ONE all-gather of the packed records.
     Returns the merged (ids, scores, count, total), identical on every rank."""
     df = backend.local_df(batch)
     if comm.world_size > 1:
         df = comm.all_reduce_sum(df)
-    ids, scores, count, total = backend.search(batch, df)
+    rec = backend.search(batch, df)
     if comm.world_size == 1:
-        return backend.merge(ids[None], scores[None], count[None], total[None])
-    return backend.merge(comm.all_gather(ids), comm.all_gather(scores), comm.all_gather(count),
-                         comm.all_gather(total))
+        return backend.merge(rec[None])
+    return backend.merge(comm.all_gather(rec))
 
 
 class MgxShardBackend:
@@ -129,28 +155,24 @@ class MgxShardBackend:
         t = self.torch
         Q, S = batch["n_queries"], self.stride
         # count / total are written for every query; ids / scores are valid up to count[q] (no fill kernels)
-        ids = t.empty((Q, S), dtype=t.int32, device=self.device)
-        scores = t.empty((Q, S), dtype=t.float64, device=self.device)
-        count = t.empty(Q, dtype=t.int32, device=self.device)
-        total = t.empty(Q, dtype=t.int64, device=self.device)
-        self.mgx._check(self.L.mgx_batch_search_device(batch["h"], C.c_void_p(df.data_ptr()), S,
-                                                       C.c_void_p(ids.data_ptr()), C.c_void_p(scores.data_ptr()),
-                                                       C.c_void_p(count.data_ptr()), C.c_void_p(total.data_ptr())))
-        return ids, scores, count, total
+        rec = t.empty(record_layout(Q, S)["bytes"], dtype=t.uint8, device=self.device)
+        self.mgx._check(self.L.mgx_batch_search_packed_device(batch["h"], C.c_void_p(df.data_ptr()), S,
+                                                              C.c_void_p(rec.data_ptr())))
+        self._shape = (Q, S)
+        return rec
 
-    def merge(self, ids_all, scores_all, count_all, total_all):
+    def merge(self, records):
+        """records: uint8 [G, record bytes] (contiguous, as gathered). Returns views into ONE merged record, so that
+        `merged_record` is a single device-to-host copy for the caller."""
         t = self.torch
-        G, Q, S = ids_all.shape
-        ids = t.empty((Q, S), dtype=t.int32, device=self.device)
-        scores = t.empty((Q, S), dtype=t.float64, device=self.device)
-        count = t.empty(Q, dtype=t.int32, device=self.device)
-        total = t.empty(Q, dtype=t.int64, device=self.device)
-        self.mgx._check(self.L.mgx_merge_topk_device(
+        Q, S = self._shape
+        G = records.shape[0]
+        out = t.empty(records.shape[1], dtype=t.uint8, device=self.device)
+        self.mgx._check(self.L.mgx_merge_topk_packed_device(
             self.device.index if self.device.index is not None else 0, self._stream(), C.byref(self.params), G, Q, S,
-            C.c_void_p(ids_all.data_ptr()), C.c_void_p(scores_all.data_ptr()), C.c_void_p(count_all.data_ptr()),
-            C.c_void_p(total_all.data_ptr()), C.c_void_p(ids.data_ptr()), C.c_void_p(scores.data_ptr()),
-            C.c_void_p(count.data_ptr()), C.c_void_p(total.data_ptr())))
-        return ids, scores, count, total
+            C.c_void_p(records.data_ptr()), C.c_void_p(out.data_ptr())))
+        self.merged_record = out
+        return record_views(out, Q, S)
 
 
 def merge_topk_reference(params_compute_score, descending, limit, offset, ids_all, scores_all, count_all, total_all,

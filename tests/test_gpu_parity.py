@@ -339,9 +339,20 @@ def test_staged_api_and_merge_kernel_match_single_call(mgx, oracle):
         dfs = [be.local_df(b) for be, b in zip(backends, batches)]
         df = dfs[0] + dfs[1]  # the all-reduce
         parts = [be.search(b, df) for be, b in zip(backends, batches)]
-        gathered = [torch.stack([parts[0][i], parts[1][i]]) for i in range(4)]  # the all-gather
-        ids, scores, count, total = backends[0].merge(*gathered)
+        gathered = torch.stack(parts)  # the ONE all-gather of the packed per-shard records
+        ids, scores, count, total = backends[0].merge(gathered)
         torch.cuda.synchronize()
+        # the unpacked form of the merge (four dense [G][Q][S] arrays) gives the same answer
+        S = limit + offset
+        d_in = [v.contiguous() for v in sharded.record_views(gathered, len(qs), S)]
+        d_out = [torch.zeros_like(v) for v in (ids, scores, count, total)]
+        mgx._check(mgx.lib().mgx_merge_topk_device(0, None, C.byref(p), 2, len(qs), S,
+                                                   *[C.c_void_p(t.data_ptr()) for t in d_in + d_out]))
+        torch.cuda.synchronize()
+        assert torch.equal(d_out[2], count) and torch.equal(d_out[3], total)
+        for q in range(len(qs)):
+            n = int(count[q])
+            assert torch.equal(d_out[0][q, :n], ids[q, :n]) and torch.equal(d_out[1][q, :n], scores[q, :n])
         want = oi.query_batch(qs, score=True, descending=desc, limit=limit, offset=offset, n_threads=8)
         g = mgx.BatchResult(ids.cpu().numpy().view(np.uint32), scores.cpu().numpy(), count.cpu().numpy().astype(np.uint32),
                             total.cpu().numpy().astype(np.uint64), df.cpu().numpy().astype(np.uint64)[:want.df.size])

@@ -70,13 +70,19 @@ class OracleShardBackend:
                 count[q] = len(top)
                 ids[q, :len(top)] = top
         t = self.torch
-        return (t.from_numpy(ids.view(np.int32)), t.from_numpy(scores), t.from_numpy(count), t.from_numpy(total))
+        from mygram_db_b200.sharded import record_layout, record_views
+        rec = t.zeros(record_layout(Q, S)["bytes"], dtype=t.uint8)
+        v_ids, v_scores, v_count, v_total = record_views(rec, Q, S)
+        v_ids.copy_(t.from_numpy(ids.view(np.int32)))
+        v_scores.copy_(t.from_numpy(scores))
+        v_count.copy_(t.from_numpy(count))
+        v_total.copy_(t.from_numpy(total))
+        self._q = Q
+        return rec
 
-    def merge(self, ids_all, scores_all, count_all, total_all):
-        sys.path.insert(0, ROOT)
-        import mgx_loader
-        mgx_loader.load()
-        from mygram_db_b200.sharded import merge_topk_reference
+    def merge(self, records):
+        from mygram_db_b200.sharded import merge_topk_reference, record_views
+        ids_all, scores_all, count_all, total_all = record_views(records, self._q, self.stride)
         return merge_topk_reference(self.score, self.descending, LIMIT, OFFSET, ids_all.numpy().view(np.uint32),
                                     scores_all.numpy(), count_all.numpy(), total_all.numpy(), LIMIT)
 
