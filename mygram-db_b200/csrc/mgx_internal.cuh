@@ -389,6 +389,14 @@ bool host_ngram_to_key(const uint8_t* term, uint64_t len, int key_width, uint64_
 // out[i] = sum_{j<i} in[j]  (u32 -> u64), out has n+1 entries (out[n] = total).
 // d_scratch: scan_scratch_elems(n) uint64 of caller-provided device memory (no allocation inside).
 size_t scan_scratch_elems(uint64_t n);
+// Up to three short, independent scans of the same kind in one launch (one CTA per array; meant for n <~ 10^5).
+struct SmallScanJobs {
+  const uint32_t* in[3];
+  uint64_t* out[3];  // n + 1 entries each
+  uint64_t n[3];
+};
+constexpr uint64_t kSmallScanMax = 1ULL << 17;
+void exclusive_scans_small(const SmallScanJobs& jobs, int n_jobs, cudaStream_t stream);
 void exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_scratch,
                             cudaStream_t stream);
 // Stable LSD radix sort of (u64 key, u32 value) pairs on key bits [0, key_bits).

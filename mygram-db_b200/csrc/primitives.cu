@@ -310,6 +310,75 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
 
 }  // namespace
 
+namespace {
+// Up to three short independent scans in ONE launch: CTA i walks array i in chunks of 4096 with a running carry.
+// The planning stage of a query batch scans three arrays of ~10^4 elements; as three-kernel device-wide scans
+// they cost nine launches of a few microseconds each.
+constexpr int kSmallScanThreads = 1024;
+__global__ void __launch_bounds__(kSmallScanThreads) small_scans_kernel(SmallScanJobs jobs) {
+  __shared__ uint64_t s_warp[kSmallScanThreads / 32];
+  __shared__ uint64_t s_carry;
+  const uint32_t* __restrict__ in = jobs.in[blockIdx.x];
+  uint64_t* __restrict__ out = jobs.out[blockIdx.x];
+  const uint64_t n = jobs.n[blockIdx.x];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    s_carry = 0;
+  }
+  __syncthreads();
+  for (uint64_t base = 0; base < n; base += 4ULL * kSmallScanThreads) {
+    const uint64_t i0 = base + 4ULL * threadIdx.x;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = i0 + k < n ? in[i0 + k] : 0u;
+    }
+    const uint64_t mine = static_cast<uint64_t>(v[0]) + v[1] + v[2] + v[3];
+    uint64_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint64_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= static_cast<unsigned>(d)) {
+        inc += o;
+      }
+    }
+    if (lane == 31) {
+      s_warp[warp] = inc;
+    }
+    __syncthreads();
+    uint64_t prefix = s_carry;
+    for (unsigned w = 0; w < warp; ++w) {
+      prefix += s_warp[w];
+    }
+    uint64_t run = prefix + inc - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < n) {
+        out[i0 + k] = run;
+      }
+      run += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == kSmallScanThreads - 1) {
+      s_carry = prefix + inc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[n] = s_carry;
+  }
+}
+}  // namespace
+
+void exclusive_scans_small(const SmallScanJobs& jobs, int n_jobs, cudaStream_t stream) {
+  if (n_jobs <= 0) {
+    return;
+  }
+  small_scans_kernel<<<static_cast<unsigned>(n_jobs), kSmallScanThreads, 0, stream>>>(jobs);
+  MGX_LAUNCH_CHECK();
+}
+
 size_t scan_scratch_elems(uint64_t n) { return static_cast<size_t>((n + kScanTile - 1) / kScanTile + 2); }
 
 void exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_scratch,

@@ -458,6 +458,8 @@ __device__ __forceinline__ void tile_filter_list(const ListRef& l, uint32_t dmin
 // Short terms (<= 16 bytes) and ordinary documents: every thread streams its own document through two 16-byte
 // registers, so a warp keeps 32 documents in flight. The first 4 bytes of the term are compared at all 16 byte
 // offsets of a chunk with funnel shifts; the rare candidates are confirmed byte by byte (L1-resident).
+constexpr int kGroupScanLanes = 8;          // lanes per document in the epilogue of a tile with few survivors
+constexpr uint32_t kGroupScanMaxDocs = 64;  // "few": at most two rounds of kTileThreads / kGroupScanLanes documents
 constexpr uint32_t kThreadScanMaxTerm = 16;
 constexpr uint32_t kThreadScanMaxDoc = 4096;
 
@@ -579,6 +581,69 @@ __device__ __forceinline__ uint32_t thread_count_term(const uint8_t* __restrict_
       }
     }
     cur = nxt;
+  }
+  return count;
+}
+
+// thread_count_term with G lanes per document: in every round the lanes of a group load G consecutive 16-byte chunks
+// (G loads in flight instead of one), then all of them replay the left-to-right, non-overlapping count over the
+// round's candidate masks, so the result is uniform inside the group. For tiles with few surviving documents, where
+// one thread per document leaves the CTA waiting on a chain of dependent loads. Every lane of an aligned group of G
+// must call this with the same arguments; shuffles use the group's own mask.
+template <int G>
+__device__ __forceinline__ uint32_t group_count_term(const uint8_t* __restrict__ text, uint64_t b, uint32_t len,
+                                                     const uint8_t* __restrict__ term, uint32_t tl, const TermRegs& t,
+                                                     bool exists_only) {
+  if (tl == 0 || tl > len) {
+    return 0;
+  }
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned gl = lane & (G - 1);
+  const unsigned gbase = lane & ~static_cast<unsigned>(G - 1);
+  const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
+  const uint64_t last = b + len - tl;  // last admissible start
+  const uint64_t a0 = b & ~15ULL;
+  const uint32_t nchunks = static_cast<uint32_t>((last - a0) >> 4) + 1u;
+  uint64_t next_ok = b;
+  uint32_t count = 0;
+  for (uint32_t c0 = 0; c0 < nchunks; c0 += G) {
+    const uint32_t c = c0 + gl;
+    uint32_t cand = 0;
+    if (c < nchunks) {
+      const uint64_t a = a0 + static_cast<uint64_t>(c) * 16;
+      const uint4 cur = ld16(text + a);
+      const uint4 nxt = ld16(text + a + 16);  // the arena is padded by 64 bytes
+      cand = chunk_candidates(cur, nxt, t);
+      if (tl > 12) {
+        uint32_t m = cand;
+        while (m != 0) {
+          const uint32_t j = static_cast<uint32_t>(__ffs(static_cast<int>(m))) - 1u;
+          m &= m - 1;
+          const uint64_t pos = a + j;
+          if (pos < b || pos > last || !term_tail_matches(text, pos, term, tl)) {
+            cand &= ~(1u << j);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      uint32_t m = __shfl_sync(gmask, cand, static_cast<int>(gbase) + g);
+      const uint64_t ag = a0 + static_cast<uint64_t>(c0 + g) * 16;
+      while (m != 0) {
+        const uint32_t j = static_cast<uint32_t>(__ffs(static_cast<int>(m))) - 1u;
+        m &= m - 1;
+        const uint64_t pos = ag + j;
+        if (pos < next_ok || pos > last) {
+          continue;
+        }
+        ++count;
+        next_ok = pos + tl;
+        if (exists_only) {
+          return 1;
+        }
+      }
+    }
   }
   return count;
 }
@@ -1925,6 +1990,68 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
       all_short = all_short && (bv.term_boff[tid + 1] - bv.term_boff[tid]) <= kThreadScanMaxTerm;
     }
     unsigned long long text_bytes = 0;
+    if (total <= kGroupScanMaxDocs) {
+      // few survivors: kGroupScanLanes lanes per document (same decisions as the thread-per-document loop below)
+      constexpr int G = kGroupScanLanes;
+      const bool leader = (threadIdx.x & (G - 1)) == 0;
+      for (uint32_t s = threadIdx.x / G; s < total; s += kTileThreads / G) {
+        const uint32_t doc = s_doc[s];
+        uint8_t keep = 1;
+        double score = 0.0;
+        if (doc != kNone) {
+          const uint64_t b = iv.text_off[doc];
+          const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
+          if (leader) {
+            text_bytes += len + 4;
+          }
+          if (len == 0) {
+            for (uint32_t i = t0; i < t1; ++i) {
+              const uint32_t tid = bv.q_tids[i];
+              if (bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid]) {
+                keep = 0;
+              }
+            }
+          } else if (!all_short || len > kThreadScanMaxDoc) {
+            keep = 2;
+          } else {
+            const double dl = static_cast<double>(__ldg(iv.doc_len + doc));
+            const double length_norm =
+                __dadd_rn(__dsub_rn(1.0, sp.b), __ddiv_rn(__dmul_rn(sp.b, dl), sp.avgdl_clamped));
+            for (uint32_t i = t0; i < t1; ++i) {
+              const uint32_t tid = bv.q_tids[i];
+              const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
+              const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+              const bool must = (flags & kQVerify) != 0 || bv.term_koff[tid + 1] == bv.term_koff[tid];
+              const uint32_t tf_u =
+                  group_count_term<G>(iv.text, b, len, term, tl, load_term_regs(term, tl), sp.compute_score == 0);
+              if (must && tf_u == 0 && tl != 0) {
+                keep = 0;
+              }
+              if (sp.compute_score != 0 && tf_u != 0) {
+                score = __dadd_rn(score, bm25_term(bv.q_idf[i], tf_u, length_norm, sp.k1));
+              }
+            }
+            for (uint32_t i = n0; i < n1 && keep != 0; ++i) {
+              const uint32_t tid = bv.q_ntids[i];
+              const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+              if (bv.term_koff[tid + 1] == bv.term_koff[tid] && tl != 0) {
+                const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
+                if (group_count_term<G>(iv.text, b, len, term, tl, load_term_regs(term, tl), true) != 0) {
+                  keep = 0;
+                }
+              }
+            }
+          }
+        }
+        if (leader) {
+          s_keep[s] = keep;
+          s_score[s] = score;
+          if (keep == 2) {
+            s_any_slow = 1;
+          }
+        }
+      }
+    } else
     // fast path: one thread per surviving document
     for (uint32_t s = threadIdx.x; s < total; s += kTileThreads) {
       const uint32_t doc = s_doc[s];
@@ -3290,14 +3417,22 @@ void batch_plan(Batch& b) {
       MGX_LAUNCH_CHECK();
     }
   }
-  exclusive_scan_u32_u64(b.d_t_df_tiles.p, b.d_t_df_tile_off.p, b.n_terms, b.d_scan_scratch.p, st);
   const IndexView iv = make_view(ix);
   if (b.n_queries > 0) {
     query_plan_kernel<<<grid_for(b.n_queries, 128), 128, 0, st>>>(iv, bv);
     MGX_LAUNCH_CHECK();
   }
-  exclusive_scan_u32_u64(b.d_q_ntiles.p, b.d_q_tile_off.p, b.n_queries, b.d_scan_scratch.p, st);
-  exclusive_scan_u32_u64(b.d_q_driver_len.p, b.d_q_rec_off.p, b.n_queries, b.d_scan_scratch.p, st);
+  if (b.n_terms <= kSmallScanMax && b.n_queries <= kSmallScanMax) {
+    // tile offsets of the df stage, tile and record offsets of the search stage: one launch
+    SmallScanJobs jobs{{b.d_t_df_tiles.p, b.d_q_ntiles.p, b.d_q_driver_len.p},
+                       {b.d_t_df_tile_off.p, b.d_q_tile_off.p, b.d_q_rec_off.p},
+                       {b.n_terms, b.n_queries, b.n_queries}};
+    exclusive_scans_small(jobs, 3, st);
+  } else {
+    exclusive_scan_u32_u64(b.d_t_df_tiles.p, b.d_t_df_tile_off.p, b.n_terms, b.d_scan_scratch.p, st);
+    exclusive_scan_u32_u64(b.d_q_ntiles.p, b.d_q_tile_off.p, b.n_queries, b.d_scan_scratch.p, st);
+    exclusive_scan_u32_u64(b.d_q_driver_len.p, b.d_q_rec_off.p, b.n_queries, b.d_scan_scratch.p, st);
+  }
   b.h_q_tile_off.resize(b.n_queries + 1);
   b.h_q_rec_off.resize(b.n_queries + 1);
   MGX_CUDA(cudaMemcpyAsync(b.h_q_tile_off.data(), b.d_q_tile_off.p, (b.n_queries + 1) * sizeof(uint64_t),
