@@ -458,6 +458,9 @@ __device__ __forceinline__ void tile_filter_list(const ListRef& l, uint32_t dmin
 // Short terms (<= 16 bytes) and ordinary documents: every thread streams its own document through two 16-byte
 // registers, so a warp keeps 32 documents in flight. The first 4 bytes of the term are compared at all 16 byte
 // offsets of a chunk with funnel shifts; the rare candidates are confirmed byte by byte (L1-resident).
+#ifndef MGX_AND_OCC
+#define MGX_AND_OCC 5  // resident CTAs per SM the register allocation of and_tile_kernel is sized for
+#endif
 constexpr int kGroupScanLanes = 8;          // lanes per document in the epilogue of a tile with few survivors
 constexpr uint32_t kGroupScanMaxDocs = 64;  // "few": at most two rounds of kTileThreads / kGroupScanLanes documents
 constexpr uint32_t kThreadScanMaxTerm = 16;
@@ -1801,7 +1804,7 @@ __device__ __forceinline__ double bm25_term(double idf, uint32_t tf_u, double le
   return __ddiv_rn(__dmul_rn(idf, numerator), denominator);
 }
 
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, MGX_AND_OCC)
 and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, uint64_t rec_base,
                 uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_total, uint32_t* __restrict__ rec_doc,
                 double* __restrict__ rec_score, uint32_t prune_k) {
@@ -1809,7 +1812,11 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   __shared__ uint32_t s_gid[kTile];     // global doc id of survivors (explicit drivers only)
   __shared__ double s_score[kTile];
   __shared__ uint8_t s_keep[kTile];     // 0 drop, 1 keep, 2 = needs the warp-cooperative slow path
-  __shared__ uint32_t s_stage[kStageCap];
+  // sub-list staging of the membership phase, text staging of the (rare) warp-per-document scan, key array of the
+  // pruning step: three phases separated by block barriers, one buffer
+  __shared__ __align__(16) uint32_t s_stage[kStageCap];
+  static_assert((kTileThreads / 32) * kStageBuf <= sizeof(uint32_t) * kStageCap, "text staging must fit s_stage");
+  uint8_t(*s_text)[kStageBuf] = reinterpret_cast<uint8_t(*)[kStageBuf]>(s_stage);
   __shared__ uint32_t s_range[2];
   __shared__ uint32_t s_warp[kTileThreads / 32];
   __shared__ uint32_t s_dmin;
@@ -1817,7 +1824,6 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   __shared__ uint32_t s_any_slow;
   __shared__ unsigned long long s_bytes;
   __shared__ ListRef s_lists[kMaxCachedLists];
-  __shared__ __align__(16) uint8_t s_text[kTileThreads / 32][kStageBuf];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   const uint64_t tile_global = tile_base + blockIdx.x;
