@@ -398,9 +398,12 @@ __device__ __forceinline__ bool sorted_contains(const uint32_t* p, uint32_t n, u
 // Dense list: one bit probe per entry. Sparse list: the tile's doc range [dmin, dmax] selects a sub-range of the
 // list (two warp-cooperative bound searches); if it fits, it is staged in shared memory with coalesced loads and
 // searched there, otherwise searched in place. Must be called by every thread of the CTA.
+// `pre` (optional): the sub-range [pre[0], pre[1]) found beforehand (and_tile_kernel searches the bounds of the first
+// lists of a query with all its warps at once, before walking the lists one after the other).
 __device__ __forceinline__ void tile_filter_list(const ListRef& l, uint32_t dmin, uint32_t dmax, bool narrow,
                                                  uint32_t* s_stage, uint32_t* s_range,
-                                                 const uint32_t (&my_doc)[kTileItems], uint32_t* alive_mask) {
+                                                 const uint32_t (&my_doc)[kTileItems], uint32_t* alive_mask,
+                                                 const uint32_t* pre = nullptr) {
   if (l.bm != nullptr) {
 #pragma unroll
     for (int k = 0; k < kTileItems; ++k) {
@@ -413,17 +416,19 @@ __device__ __forceinline__ void tile_filter_list(const ListRef& l, uint32_t dmin
     }
     return;
   }
-  if ((threadIdx.x >> 5) == 0) {
-    const uint32_t lo = narrow ? warp_lower_bound(l.p, l.len, dmin) : 0u;
-    const uint32_t hi = narrow ? warp_lower_bound(l.p, l.len, dmax + 1u) : l.len;
-    if ((threadIdx.x & 31u) == 0) {
-      s_range[0] = lo;
-      s_range[1] = hi;
+  if (pre == nullptr) {
+    const unsigned w = threadIdx.x >> 5;
+    if (w < 2) {  // the two bounds by two warps, side by side
+      const uint32_t r = narrow ? warp_lower_bound(l.p, l.len, w == 0 ? dmin : dmax + 1u) : (w == 0 ? 0u : l.len);
+      if ((threadIdx.x & 31u) == 0) {
+        s_range[w] = r;
+      }
     }
+    __syncthreads();
+    pre = s_range;
   }
-  __syncthreads();
-  const uint32_t lo = s_range[0];
-  const uint32_t cnt = s_range[1] - lo;
+  const uint32_t lo = pre[0];
+  const uint32_t cnt = pre[1] - lo;
   if (cnt == 0) {
     *alive_mask = 0;
   } else if (cnt <= kStageCap) {
@@ -1660,6 +1665,7 @@ __device__ void bitonic_sort_desc(SortKey* keys, uint32_t n_pow2) {
 }
 
 constexpr int kMaxCachedLists = 24;
+constexpr uint32_t kPreSearchLists = kTileThreads / 64;  // lists whose sub-range bounds are searched up front (2 warps each)
 
 // One column condition for one document: ApplyFiltersWithBitmap / ApplyFilters, search_pipeline.cpp:1098-1237.
 __device__ __forceinline__ bool filter_pass(const FilterPred& f, uint32_t doc) {
@@ -1824,6 +1830,7 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   __shared__ uint32_t s_any_slow;
   __shared__ unsigned long long s_bytes;
   __shared__ ListRef s_lists[kMaxCachedLists];
+  __shared__ uint32_t s_bounds[kPreSearchLists][2];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   const uint64_t tile_global = tile_base + blockIdx.x;
@@ -1913,9 +1920,23 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
     const bool narrow = !drv_explicit;  // caller-supplied candidates may be unsorted (FilterByNgrams keeps their order)
     const uint32_t dmin = s_dmin;
     const uint32_t dmax = s_dmax;
-    for (uint32_t j = drv_list ? 1u : 0u; j < nl; ++j) {
+    const uint32_t j_first = drv_list ? 1u : 0u;
+    if (narrow) {
+      // sub-range bounds of the first kPreSearchLists sparse lists, all searched at once (a warp per bound): the
+      // searches are chains of dependent loads, and one list after the other they were most of a tile's latency
+      const uint32_t j = j_first + (warp >> 1);
+      if ((warp >> 1) < kPreSearchLists && j < nl && j < kMaxCachedLists && s_lists[j].bm == nullptr) {
+        const uint32_t r = warp_lower_bound(s_lists[j].p, s_lists[j].len, (warp & 1u) != 0 ? dmax + 1u : dmin);
+        if (lane == 0) {
+          s_bounds[warp >> 1][warp & 1u] = r;
+        }
+      }
+      __syncthreads();
+    }
+    for (uint32_t j = j_first; j < nl; ++j) {
       const ListRef l = j < kMaxCachedLists ? s_lists[j] : make_list(iv, bv.q_list[l0 + j], bv.q_list_len[l0 + j]);
-      tile_filter_list(l, dmin, dmax, narrow, s_stage, s_range, my_doc, &alive);
+      const bool searched = narrow && j - j_first < kPreSearchLists && j < kMaxCachedLists;
+      tile_filter_list(l, dmin, dmax, narrow, s_stage, s_range, my_doc, &alive, searched ? s_bounds[j - j_first] : nullptr);
       if (__syncthreads_or(alive != 0) == 0) {
         break;
       }
@@ -2007,6 +2028,7 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
         if (doc != kNone) {
           const uint64_t b = iv.text_off[doc];
           const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
+          const uint32_t dl_u = __ldg(iv.doc_len + doc);  // issued with the offsets, not after the branches below
           if (leader) {
             text_bytes += len + 4;
           }
@@ -2020,7 +2042,7 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
           } else if (!all_short || len > kThreadScanMaxDoc) {
             keep = 2;
           } else {
-            const double dl = static_cast<double>(__ldg(iv.doc_len + doc));
+            const double dl = static_cast<double>(dl_u);
             const double length_norm =
                 __dadd_rn(__dsub_rn(1.0, sp.b), __ddiv_rn(__dmul_rn(sp.b, dl), sp.avgdl_clamped));
             for (uint32_t i = t0; i < t1; ++i) {
