@@ -290,7 +290,11 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     index.build(c.doc_ids, c.arena, c.offsets)
-    build_e2e_s = time.perf_counter() - t0
+    build_e2e_s = time.perf_counter() - t0  # first build of the process: includes every device allocation
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    index.build(c.doc_ids, c.arena, c.offsets)  # rebuild from the same pinned host buffers (allocations are kept)
+    build_e2e_warm_s = time.perf_counter() - t0
     st = index.stats()
     d_text = pinned["arena"][:int(c.offsets[-1])].to(device)
     d_off = offsets_t.to(device)
@@ -505,7 +509,8 @@ def main():
             "batch_stats_per_step": {k: (v / max(1, len(kstats))) for k, v in agg.items()} if agg else None,
             "kernel_ms_by_step": {k: [round(s[k], 3) for s in kstats] for k in
                                   ("ms_plan", "ms_df_kernel", "ms_and_kernel", "ms_topk_kernel", "ms_total")} if kstats else None,
-            "index_build": {"docs_per_s_e2e": n_local * world / build_e2e_s, "docs_per_s_device": n_local * world / build_dev_s,
+            "index_build": {"docs_per_s_e2e": n_local * world / build_e2e_s,
+                            "docs_per_s_e2e_rebuild": n_local * world / build_e2e_warm_s, "docs_per_s_device": n_local * world / build_dev_s,
                             "device_build_ms": st.last_build_ms, "algorithmic_bytes": int(build_algo_bytes),
                             "hbm_frac_device": (build_algo_bytes / 1e9) / max(1e-9, st.last_build_ms / 1e3) / peak,
                             "corpus_gen_s": round(gen_s, 2)},

@@ -6,6 +6,8 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err
 echo "bench rc=$?"
 timeout 900 python bench.py --impl reference > gpurun_out/bench_reference.log 2> gpurun_out/bench_reference.err
@@ -20,3 +22,8 @@ KERNEL=${KERNEL:-df_tile_kernel}
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KERNEL -s 2 -c 1 \
     -o gpurun_out/prof_${KERNEL}_10m -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
+if [ -n "${KERNEL2:-}" ]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KERNEL2 -s 2 -c 1 \
+      -o gpurun_out/prof_${KERNEL2}_10m -f $CMD > gpurun_out/ncu_full2.log 2>&1
+  echo "second capture rc=$?"
+fi
