@@ -467,6 +467,7 @@ __device__ __forceinline__ void tile_filter_list(const ListRef& l, uint32_t dmin
 #define MGX_AND_OCC 5  // resident CTAs per SM the register allocation of and_tile_kernel is sized for
 #endif
 constexpr int kGroupScanLanes = 8;          // lanes per document in the epilogue of a tile with few survivors
+constexpr uint32_t kPairScanMaxItems = 64;  // (document, term) pairs counted side by side, kGroupScanLanes lanes each
 constexpr uint32_t kGroupScanMaxDocs = 64;  // "few": at most two rounds of kTileThreads / kGroupScanLanes documents
 constexpr uint32_t kThreadScanMaxTerm = 16;
 constexpr uint32_t kThreadScanMaxDoc = 4096;
@@ -2007,17 +2008,100 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
     need_text = bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid];
   }
   if (need_text && total > 0) {
-    bool all_short = true;  // every term fits the per-thread scanner
-    for (uint32_t i = t0; i < t1; ++i) {
+    // every term fits the register scanner? (one term per thread, then a block vote: the loads of all terms are in
+    // flight together instead of one after the other in every thread)
+    bool short_here = true;
+    for (uint32_t i = t0 + threadIdx.x; i < t1; i += kTileThreads) {
       const uint32_t tid = bv.q_tids[i];
-      all_short = all_short && (bv.term_boff[tid + 1] - bv.term_boff[tid]) <= kThreadScanMaxTerm;
+      short_here = short_here && (bv.term_boff[tid + 1] - bv.term_boff[tid]) <= kThreadScanMaxTerm;
     }
-    for (uint32_t i = n0; i < n1; ++i) {
+    for (uint32_t i = n0 + threadIdx.x; i < n1; i += kTileThreads) {
       const uint32_t tid = bv.q_ntids[i];
-      all_short = all_short && (bv.term_boff[tid + 1] - bv.term_boff[tid]) <= kThreadScanMaxTerm;
+      short_here = short_here && (bv.term_boff[tid + 1] - bv.term_boff[tid]) <= kThreadScanMaxTerm;
     }
+    const bool all_short = __syncthreads_and(short_here ? 1 : 0) != 0;
     unsigned long long text_bytes = 0;
-    if (total <= kGroupScanMaxDocs) {
+    const uint32_t n_search = t1 - t0;
+    if (all_short && n1 == n0 && n_search >= 2 && total * n_search <= kPairScanMaxItems) {
+      // Very few survivors (the common tile ends with one): kGroupScanLanes lanes per (document, TERM) pair, so the
+      // terms of a document are counted side by side instead of one after the other; the BM25 contributions are
+      // added afterwards in term order, operation for operation as the per-document loops below do.
+      constexpr int G = kGroupScanLanes;
+      double* const s_contrib = reinterpret_cast<double*>(s_stage);
+      uint32_t* const s_tf = s_stage + 2 * kPairScanMaxItems;
+      static_assert(3 * kPairScanMaxItems <= kStageCap, "pair results live in the staging buffer");
+      const bool leader = (threadIdx.x & (G - 1)) == 0;
+      for (uint32_t item = threadIdx.x / G; item < total * n_search; item += kTileThreads / G) {
+        const uint32_t s = item / n_search;
+        const uint32_t i = t0 + (item - s * n_search);
+        const uint32_t doc = s_doc[s];
+        uint32_t tf_u = 0;
+        double contrib = 0.0;
+        if (doc != kNone) {
+          const uint64_t b = iv.text_off[doc];
+          const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
+          const uint32_t dl_u = __ldg(iv.doc_len + doc);
+          const uint32_t tid = bv.q_tids[i];
+          const double idf = sp.compute_score != 0 ? bv.q_idf[i] : 0.0;
+          if (len != 0 && len <= kThreadScanMaxDoc) {
+            const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
+            const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+            tf_u = group_count_term<G>(iv.text, b, len, term, tl, load_term_regs(term, tl), sp.compute_score == 0);
+            if (sp.compute_score != 0 && tf_u != 0) {
+              const double dl = static_cast<double>(dl_u);
+              const double length_norm =
+                  __dadd_rn(__dsub_rn(1.0, sp.b), __ddiv_rn(__dmul_rn(sp.b, dl), sp.avgdl_clamped));
+              contrib = bm25_term(idf, tf_u, length_norm, sp.k1);
+            }
+          }
+        }
+        if (leader) {
+          s_tf[item] = tf_u;
+          s_contrib[item] = contrib;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < total) {
+        const uint32_t s = threadIdx.x;
+        const uint32_t doc = s_doc[s];
+        uint8_t keep = 1;
+        double score = 0.0;
+        if (doc != kNone) {
+          const uint64_t b = iv.text_off[doc];
+          const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
+          text_bytes += len + 4;
+          if (len > kThreadScanMaxDoc) {
+            keep = 2;
+          } else {
+            for (uint32_t i = t0; i < t1; ++i) {
+              const uint32_t tid = bv.q_tids[i];
+              const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+              const bool no_keys = bv.term_koff[tid + 1] == bv.term_koff[tid];
+              if (len == 0) {
+                // no stored text: a substring-only search term cannot match; verify keeps the doc
+                if (no_keys && tl != 0) {
+                  keep = 0;
+                }
+                continue;
+              }
+              const bool must = (flags & kQVerify) != 0 || no_keys;
+              const uint32_t tf_u = s_tf[s * n_search + (i - t0)];
+              if (must && tf_u == 0 && tl != 0) {
+                keep = 0;
+              }
+              if (sp.compute_score != 0 && tf_u != 0) {
+                score = __dadd_rn(score, s_contrib[s * n_search + (i - t0)]);
+              }
+            }
+          }
+        }
+        s_keep[s] = keep;
+        s_score[s] = score;
+        if (keep == 2) {
+          s_any_slow = 1;
+        }
+      }
+    } else if (total <= kGroupScanMaxDocs) {
       // few survivors: kGroupScanLanes lanes per document (same decisions as the thread-per-document loop below)
       constexpr int G = kGroupScanLanes;
       const bool leader = (threadIdx.x & (G - 1)) == 0;
