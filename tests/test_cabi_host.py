@@ -110,3 +110,31 @@ def test_cpp_adapter_runs_on_gpu(mgx, tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "SearchAnd({bc,cd}) -> 2 docs" in r.stdout  # tests/index/index_search_test.cpp:393-418
+
+
+def test_shard_record_layout_matches_the_python_protocol(mgx):
+    """The packed per-shard top-k record (one all-gather, one D2H): the C layout and sharded.py's agree, parts are
+    aligned for their element types, and views into a record round-trip."""
+    torch = pytest.importorskip("torch")
+    from mygram_db_b200 import sharded
+    lib = mgx.lib()
+    for q, s in ((0, 100), (1, 1), (7, 3), (4096, 100), (65536, 10)):
+        lay = mgx.ShardRecordLayout()
+        assert lib.mgx_shard_record_layout(q, s, C.byref(lay)) == 0
+        py = sharded.record_layout(q, s)
+        assert (lay.scores_offset, lay.total_offset, lay.ids_offset, lay.count_offset, lay.bytes) == \
+               (py["scores"], py["total"], py["ids"], py["count"], py["bytes"])
+        assert lay.scores_offset % 8 == 0 and lay.total_offset % 8 == 0
+        assert lay.ids_offset % 4 == 0 and lay.count_offset % 4 == 0 and lay.bytes % 16 == 0
+        assert lay.bytes >= q * s * 12 + q * 12
+    assert lib.mgx_shard_record_layout(1, 1, None) == -1
+    rec = torch.zeros((2, sharded.record_layout(5, 3)["bytes"]), dtype=torch.uint8)
+    ids, scores, count, total = sharded.record_views(rec, 5, 3)
+    assert ids.shape == (2, 5, 3) and scores.shape == (2, 5, 3) and count.shape == (2, 5) and total.shape == (2, 5)
+    ids[1, 4, 2] = 77
+    scores[0, 0, 0] = 1.5
+    count[1, 0] = 3
+    total[0, 4] = 1 << 40
+    again = sharded.record_views(rec, 5, 3)
+    assert int(again[0][1, 4, 2]) == 77 and float(again[1][0, 0, 0]) == 1.5
+    assert int(again[2][1, 0]) == 3 and int(again[3][0, 4]) == 1 << 40
