@@ -529,6 +529,8 @@ def main():
             "gpu_launches": gpu_launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity": parity, "kernels": kernels,
             "batch_stats_per_step": {k: (v / max(1, len(kstats))) for k, v in agg.items()} if agg else None,
+            "kernel_ms_note": ("two batches in flight: the event-timed durations of the small kernels (plan, top-k) "
+                               "include queueing behind the other batch's grid-filling kernels") if in_flight > 1 else None,
             "kernel_ms_by_step": {k: [round(s[k], 3) for s in kstats] for k in
                                   ("ms_plan", "ms_df_kernel", "ms_and_kernel", "ms_topk_kernel", "ms_total")} if kstats else None,
             "index_build": {"docs_per_s_e2e": n_local * world / build_e2e_s,
