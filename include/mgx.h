@@ -191,6 +191,8 @@ int mgx_search_by_threshold(const mgx_index_t* index, const uint8_t* term_bytes,
  *   op 1 AND   arg = number of children          (0 children -> empty)
  *   op 2 OR    arg = number of children          (0 children -> empty)
  *   op 3 NOT   one child                         -> all documents of the index minus the child
+ *   op 4 ATLEAST arg = children | (t << 16)      -> documents of at least t of the children (t = 0 -> empty);
+ *              an extension with no AST counterpart: Index::SearchByThreshold (index.cpp:488-578) as a node
  * Output: the ascending doc ids of the expression. all_docs is the set of documents given to mgx_index_build
  * (DocumentStore::GetAllDocIds). */
 int mgx_eval_boolean(const mgx_index_t* index, const int32_t* ops, const int32_t* args, uint64_t n_ops,
@@ -277,6 +279,48 @@ int mgx_query_batch_ex(mgx_index_t* index, const mgx_query_params_t* params, uin
                        const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
                        const mgx_query_ext_t* ext, uint64_t stride, uint32_t* out_ids, double* out_scores,
                        uint32_t* out_count, uint64_t* out_total, uint64_t* out_df);
+
+/* ------------------------------------------------- fuzzy and synonym execution paths (single query) */
+
+/* What search_pipeline::ExecuteWithFuzzy / ExecuteWithSynonyms read besides the terms: the RAW table n-gram
+ * configuration (search_pipeline.cpp:578), memory.verify_text (0 "off", 1 "all", 2 "ascii"), the query's NOT terms
+ * (ApplyNotFilter :871-932 — on the synonym path pass every synonym of every NOT term, their union is what is
+ * excluded) and its column conditions (ApplyFiltersWithBitmap :1196-1237; columns as set by
+ * mgx_index_set_filter_column, ops as in mgx_query_ext_t). */
+typedef struct {
+  int32_t ngram_size;
+  int32_t kanji_ngram_size;
+  int32_t cross_boundary;
+  int32_t verify_text;
+  const uint8_t* not_bytes;
+  const uint64_t* not_offsets;     /* [n_not + 1] */
+  uint64_t n_not;
+  const uint32_t* filter_col;
+  const uint8_t* filter_op;
+  const uint8_t* filter_bytes;
+  const uint64_t* filter_offsets;  /* [n_filters + 1] */
+  uint64_t n_filters;
+} mgx_expanded_query_t;
+
+/* search_pipeline::ExecuteWithFuzzy (server/search_pipeline.cpp:1659-1740): per (normalised) search term the
+ * documents holding at least max(1, |ngrams| - max_distance * effective_ngram_size) of its n-grams
+ * (Index::SearchByThreshold), AND-ed over the terms; then NOT terms, column conditions and — when a term has a
+ * hybrid fragment no n-gram covers — the exact text match of every term (:1728-1737). A term too short for an
+ * n-gram, or no term at all, gives the empty result (empty_term_detected). Output: ascending doc ids.
+ * verify_text that applies to the terms needs the edit-distance verification of PostFilterByFuzzyText
+ * (:1742-1752), which is not built: MGX_ERR_UNSUPPORTED, never an unverified answer. */
+int mgx_search_fuzzy(const mgx_index_t* index, const mgx_expanded_query_t* query, const uint8_t* term_bytes,
+                     const uint64_t* term_offsets, uint64_t n_terms, uint32_t max_distance, uint32_t* out,
+                     uint64_t cap, uint64_t* out_count);
+
+/* search_pipeline::ExecuteWithSynonyms (server/search_pipeline.cpp:1580-1631) over already expanded groups
+ * (ExpandTermsWithSynonyms :1392-1406 stays on the host: group g = the normalised term and its synonyms =
+ * variants [group_begin[g], group_begin[g+1])): OR of SearchTermDocuments within a group (n-gram AND, or the
+ * substring test for a variant shorter than an n-gram), AND across groups, NOT terms, column conditions, and with
+ * verify_text the synonym-aware text check of PostFilterByTextWithSynonyms (:1633-1657). No group => empty. */
+int mgx_search_synonyms(const mgx_index_t* index, const mgx_expanded_query_t* query, const uint8_t* variant_bytes,
+                        const uint64_t* variant_offsets, const uint64_t* group_begin, uint64_t n_groups,
+                        uint32_t* out, uint64_t cap, uint64_t* out_count);
 
 /* Timing / accounting of one batch (device times from CUDA events recorded on the launch
  * stream around the named kernels; bytes as defined in SURVEY.md §8(d) and DESIGN.md). */

@@ -67,6 +67,13 @@ class QueryExt(C.Structure):
                 ("q_filter_begin", u64p)]
 
 
+class ExpandedQuery(C.Structure):
+    _fields_ = [("ngram_size", C.c_int32), ("kanji_ngram_size", C.c_int32), ("cross_boundary", C.c_int32),
+                ("verify_text", C.c_int32), ("not_bytes", u8p), ("not_offsets", u64p), ("n_not", C.c_uint64),
+                ("filter_col", u32p), ("filter_op", u8p), ("filter_bytes", u8p), ("filter_offsets", u64p),
+                ("n_filters", C.c_uint64)]
+
+
 class QueryParams(C.Structure):
     _fields_ = [("ngram_size", C.c_int32), ("kanji_ngram_size", C.c_int32), ("cross_boundary", C.c_int32),
                 ("compute_score", C.c_int32), ("descending", C.c_int32), ("limit", C.c_uint32), ("offset", C.c_uint32),
@@ -141,6 +148,10 @@ def lib():
     L.mgx_search_by_threshold.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint64, u32p, C.c_uint64, u64p]
     L.mgx_eval_boolean.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_uint64, u8p, u64p,
                                    C.c_uint64, u32p, C.c_uint64, u64p]
+    L.mgx_search_fuzzy.argtypes = [C.c_void_p, C.POINTER(ExpandedQuery), u8p, u64p, C.c_uint64, C.c_uint32, u32p,
+                                   C.c_uint64, u64p]
+    L.mgx_search_synonyms.argtypes = [C.c_void_p, C.POINTER(ExpandedQuery), u8p, u64p, u64p, C.c_uint64, u32p,
+                                      C.c_uint64, u64p]
     L.mgx_index_set_filter_column.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, u64p, u8p, C.c_uint64, u8p, u64p,
                                               C.c_uint64]
     L.mgx_query_batch_ex.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
@@ -432,6 +443,45 @@ class Index:
         return self._set_call(lambda ar, of, nt, out, cap, n: L.mgx_eval_boolean(
             self._h, op.ctypes.data_as(i32p), ap.ctypes.data_as(i32p), o.size, ar, of, nt, _ptr(out, u32p), cap,
             C.byref(n)), terms)
+
+    # -- fuzzy / synonym execution paths ---------------------------------------------------------------
+    def _expanded(self, not_terms, filters, verify_text, raw_ngram, raw_kanji):
+        eq = ExpandedQuery()
+        eq.ngram_size = self.ngram_size if raw_ngram is None else raw_ngram
+        eq.kanji_ngram_size = self.kanji_ngram_size if raw_kanji is None else raw_kanji
+        eq.cross_boundary = int(self.cross_boundary_ngrams)
+        eq.verify_text = verify_text
+        nb, no = pack_strings(list(not_terms))
+        filters = list(filters or [])
+        fc = np.asarray([f[0] for f in filters] or [0], dtype=np.uint32)
+        fo = np.asarray([f[1] for f in filters] or [0], dtype=np.uint8)
+        lb, lo = pack_strings([_bytes(f[2]) for f in filters] or [b""])
+        eq.not_bytes, eq.not_offsets, eq.n_not = _ptr(nb, u8p), _ptr(no, u64p), len(not_terms)
+        eq.filter_col, eq.filter_op = _ptr(fc, u32p), _ptr(fo, u8p)
+        eq.filter_bytes, eq.filter_offsets, eq.n_filters = _ptr(lb, u8p), _ptr(lo, u64p), len(filters)
+        return eq, (nb, no, fc, fo, lb, lo)
+
+    def search_fuzzy(self, terms, max_distance, not_terms=(), filters=None, verify_text=0, raw_ngram=None,
+                     raw_kanji=None):
+        """search_pipeline::ExecuteWithFuzzy (search_pipeline.cpp:1659-1740) over normalised terms; filters: list of
+        (column id, op 0..5, literal). Returns the ascending doc ids."""
+        L = lib()
+        eq, keep = self._expanded(not_terms, filters, verify_text, raw_ngram, raw_kanji)
+        return self._set_call(lambda a, o, nt, out, cap, n: L.mgx_search_fuzzy(
+            self._h, C.byref(eq), a, o, nt, max_distance, _ptr(out, u32p), cap, C.byref(n)), list(terms))
+
+    def search_synonyms(self, groups, not_terms=(), filters=None, verify_text=0, raw_ngram=None, raw_kanji=None):
+        """search_pipeline::ExecuteWithSynonyms (search_pipeline.cpp:1580-1657) over expanded groups: a list of
+        lists of variants (the normalised term and its synonyms). Returns the ascending doc ids."""
+        L = lib()
+        eq, keep = self._expanded(not_terms, filters, verify_text, raw_ngram, raw_kanji)
+        flat, gbeg = [], [0]
+        for g in groups:
+            flat += list(g)
+            gbeg.append(len(flat))
+        gb = np.asarray(gbeg, dtype=np.uint64)
+        return self._set_call(lambda a, o, nt, out, cap, n: L.mgx_search_synonyms(
+            self._h, C.byref(eq), a, o, _ptr(gb, u64p), len(groups), _ptr(out, u32p), cap, C.byref(n)), flat)
 
     # -- batched pipeline --------------------------------------------------------------------------
     def params(self, score=True, descending=True, limit=100, offset=0, verify_text=0, k1=1.2, b=0.75, total_docs=0,

@@ -15,6 +15,11 @@ int main() {
     const auto top = ResultSorter::SortByScore(index, hits, {scored.value[0].score, scored.value[1].score},
                                                SortOrder::DESC, 10, 0);
     std::printf("top doc %u\n", top.empty() ? 0 : top[0]);
+    search_pipeline::ExpandedQuery q;  // fuzzy / synonym paths of the pipeline (search_pipeline.cpp:1580-1740)
+    q.not_terms = {"ef"};
+    const auto fuzzy = search_pipeline::ExecuteWithFuzzy(index, q, {"bxde"}, 1);
+    const auto syn = search_pipeline::ExecuteWithSynonyms(index, q, {{"ab", "de"}, {"bc", "cd"}});
+    std::printf("fuzzy %zu docs, synonyms %zu docs\n", fuzzy.size(), syn.size());
   } catch (const std::exception& e) {
     std::printf("%s\n", e.what());
     return 1;

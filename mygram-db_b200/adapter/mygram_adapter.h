@@ -327,4 +327,82 @@ class ResultSorter {
   }
 };
 
+// search_pipeline::ExecuteWithFuzzy / ExecuteWithSynonyms (server/search_pipeline.cpp:1659-1740, 1580-1657) on the
+// device. The query's NOT terms and column conditions ride along the way ApplyNotAndFilters applies them (:470-485).
+namespace search_pipeline {
+
+struct FilterCondition {  // query::FilterCondition, query/query_parser.h:93-110 (column already resolved to its id)
+  uint32_t column = 0;
+  uint8_t op = 0;  // 0 EQ, 1 NE, 2 GT, 3 GTE, 4 LT, 5 LTE
+  std::string value;
+};
+
+struct ExpandedQuery {
+  int ngram_size = 2;        // RAW table configuration (search_pipeline.cpp:578)
+  int kanji_ngram_size = 0;
+  bool cross_boundary = true;
+  int verify_text = 0;       // memory.verify_text: 0 "off", 1 "all", 2 "ascii"
+  std::vector<std::string> not_terms;
+  std::vector<FilterCondition> filters;
+};
+
+namespace detail_sp {
+struct Packed {
+  detail::Flat nots, lits;
+  std::vector<uint32_t> cols;
+  std::vector<uint8_t> ops;
+  mgx_expanded_query_t c{};
+  explicit Packed(const ExpandedQuery& q) {
+    for (const auto& t : q.not_terms) nots.add(t);
+    for (const auto& f : q.filters) {
+      cols.push_back(f.column);
+      ops.push_back(f.op);
+      lits.add(f.value);
+    }
+    c.ngram_size = q.ngram_size;
+    c.kanji_ngram_size = q.kanji_ngram_size;
+    c.cross_boundary = q.cross_boundary ? 1 : 0;
+    c.verify_text = q.verify_text;
+    c.not_bytes = nots.data();
+    c.not_offsets = nots.offsets.data();
+    c.n_not = q.not_terms.size();
+    c.filter_col = cols.data();
+    c.filter_op = ops.data();
+    c.filter_bytes = lits.data();
+    c.filter_offsets = lits.offsets.data();
+    c.n_filters = q.filters.size();
+  }
+};
+}  // namespace detail_sp
+
+// `terms`: the query's normalised search terms (all_search_terms). Result: SearchPipelineResult::results.
+inline std::vector<DocId> ExecuteWithFuzzy(const Index& index, const ExpandedQuery& query,
+                                           const std::vector<std::string>& terms, uint32_t max_distance) {
+  detail_sp::Packed p(query);
+  detail::Flat f;
+  for (const auto& t : terms) f.add(t);
+  return detail::grow_call([&](DocId* out, uint64_t cap, uint64_t* n) {
+    return mgx_search_fuzzy(index.handle(), &p.c, f.data(), f.offsets.data(), terms.size(), max_distance, out, cap, n);
+  });
+}
+
+// `groups`: SynonymTermGroup::normalized_terms of every group (ExpandTermsWithSynonyms stays on the host); with a
+// synonym dictionary in play `query.not_terms` holds every synonym of every NOT term (ApplyNotFilter :886-899).
+inline std::vector<DocId> ExecuteWithSynonyms(const Index& index, const ExpandedQuery& query,
+                                              const std::vector<std::vector<std::string>>& groups) {
+  detail_sp::Packed p(query);
+  detail::Flat f;
+  std::vector<uint64_t> begin{0};
+  for (const auto& g : groups) {
+    for (const auto& v : g) f.add(v);
+    begin.push_back(f.offsets.size() - 1);
+  }
+  return detail::grow_call([&](DocId* out, uint64_t cap, uint64_t* n) {
+    return mgx_search_synonyms(index.handle(), &p.c, f.data(), f.offsets.data(), begin.data(), groups.size(), out, cap,
+                               n);
+  });
+}
+
+}  // namespace search_pipeline
+
 }  // namespace mygramdb_b200

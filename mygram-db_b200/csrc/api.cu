@@ -367,12 +367,13 @@ int analyse_program(const int32_t* ops, const int32_t* args, uint64_t n_ops, uin
       if (args[i] < 0 || static_cast<uint64_t>(args[i]) >= n_terms) {
         return invalid("boolean program: TERM index out of range");
       }
-    } else if (ops[i] == kOpAnd || ops[i] == kOpOr) {
-      if (args[i] < 0 || static_cast<size_t>(args[i]) > stack.size()) {
+    } else if (ops[i] == kOpAnd || ops[i] == kOpOr || ops[i] == kOpAtLeast) {
+      const int32_t n_kids = ops[i] == kOpAtLeast ? (args[i] & 0xFFFF) : args[i];
+      if (args[i] < 0 || static_cast<size_t>(n_kids) > stack.size()) {
         return invalid("boolean program: operator has more children than the stack holds");
       }
-      nd.kids.assign(stack.end() - args[i], stack.end());
-      stack.resize(stack.size() - static_cast<size_t>(args[i]));
+      nd.kids.assign(stack.end() - n_kids, stack.end());
+      stack.resize(stack.size() - static_cast<size_t>(n_kids));
     } else if (ops[i] == kOpNot) {
       if (stack.empty()) {
         return invalid("boolean program: NOT without an operand");
@@ -399,8 +400,9 @@ int analyse_program(const int32_t* ops, const int32_t* args, uint64_t n_ops, uin
     todo.pop_back();
     if (nd.op == kOpTerm) {
       conjuncts->push_back(static_cast<uint32_t>(nd.arg));
-    } else if (nd.op == kOpAnd) {
-      todo.insert(todo.end(), nd.kids.begin(), nd.kids.end());
+    } else if (nd.op == kOpAnd ||
+               (nd.op == kOpAtLeast && !nd.kids.empty() && static_cast<size_t>(nd.arg >> 16) == nd.kids.size())) {
+      todo.insert(todo.end(), nd.kids.begin(), nd.kids.end());  // "all n of n" is an AND
     }
   }
   return MGX_OK;
@@ -1420,6 +1422,286 @@ int mgx_eval_boolean(const mgx_index_t* index_c, const int32_t* ops, const int32
       hq.prog_args.push_back(static_cast<uint32_t>(args[i]));
     }
     return run_single_set_query(ix, terms, queries, nullptr, 0, 0, false, out, cap, out_count);
+  });
+}
+
+// ------------------------------------------------ fuzzy / synonym execution paths
+namespace {
+
+// A postfix program under construction over a private term table.
+struct ProgramBuilder {
+  std::vector<HostTerm> terms;
+  std::vector<int32_t> ops;
+  std::vector<int32_t> args;
+
+  void leaf(HostTerm&& t) {
+    ops.push_back(kOpTerm);
+    args.push_back(static_cast<int32_t>(terms.size()));
+    terms.push_back(std::move(t));
+  }
+  void node(uint8_t op, int32_t arg) {
+    ops.push_back(op);
+    args.push_back(arg);
+  }
+};
+
+// ShouldApplyVerifyText, search_pipeline.cpp:48-66 (0 "off", 1 "all", 2 "ascii": only when every term is ASCII)
+bool should_verify(int32_t mode, const uint8_t* bytes, const uint64_t* offsets, uint64_t n) {
+  if (mode == 1) {
+    return true;
+  }
+  if (mode != 2) {
+    return false;
+  }
+  for (uint64_t i = offsets[0]; i < offsets[n]; ++i) {
+    if (bytes[i] >= 0x80) {
+      return false;
+    }
+  }
+  return true;
+}
+
+int check_expanded(const mgx_expanded_query_t* eq) {
+  if (eq == nullptr) {
+    return invalid("null query description");
+  }
+  if (eq->n_not > 0 && (eq->not_bytes == nullptr || eq->not_offsets == nullptr)) {
+    return invalid("NOT terms without bytes / offsets");
+  }
+  if (eq->n_filters > 0 && (eq->filter_col == nullptr || eq->filter_op == nullptr || eq->filter_bytes == nullptr ||
+                            eq->filter_offsets == nullptr)) {
+    return invalid("filters without columns / ops / literals");
+  }
+  if (eq->verify_text < 0 || eq->verify_text > 2) {
+    return invalid("verify_text must be 0 (off), 1 (all) or 2 (ascii)");
+  }
+  return MGX_OK;
+}
+
+// A search term as the pipeline sees it (GenerateTermInfos, search_pipeline.cpp:569-603): its unique sorted
+// n-grams cut with the RAW table configuration; without n-grams the leaf falls back to the substring test
+// (SearchTermDocuments, :454-462).
+int term_leaf(const Index& ix, const mgx_expanded_query_t& eq, const uint8_t* bytes, uint64_t len, HostTerm* t) {
+  if (len > kMaxTermBytes) {
+    set_last_error("query term longer than 256 bytes is not supported");
+    return MGX_ERR_UNSUPPORTED;
+  }
+  t->bytes.assign(reinterpret_cast<const char*>(bytes), len);
+  host_query_keys(bytes, len, eq.ngram_size, eq.kanji_ngram_size, eq.cross_boundary != 0, ix.width, &t->keys);
+  return MGX_OK;
+}
+
+// ApplyNotAndFilters (search_pipeline.cpp:470-485): a document of ANY NOT term (ApplyNotFilter, :871-932) is
+// dropped, then the column conditions; closes the program with the AND over `children` operands.
+int finish_expanded(const Index& ix, const mgx_expanded_query_t& eq, ProgramBuilder* pb, int32_t children,
+                    HostQuery* hq) {
+  if (eq.n_not > 0) {
+    for (uint64_t i = 0; i < eq.n_not; ++i) {
+      HostTerm t;
+      if (int rc = term_leaf(ix, eq, eq.not_bytes + eq.not_offsets[i], eq.not_offsets[i + 1] - eq.not_offsets[i], &t);
+          rc != MGX_OK) {
+        return rc;
+      }
+      pb->leaf(std::move(t));
+      if (i > 0) {
+        pb->node(kOpOr, 2);  // folded pairwise: the evaluation stack stays shallow
+      }
+    }
+    pb->node(kOpNot, 0);
+    ++children;
+  }
+  pb->node(kOpAnd, children);
+  if (int rc = analyse_program(pb->ops.data(), pb->args.data(), pb->ops.size(), pb->terms.size(), &hq->conjuncts);
+      rc != MGX_OK) {
+    return rc;
+  }
+  hq->flags = kQProgram;
+  for (size_t i = 0; i < pb->ops.size(); ++i) {
+    hq->prog_ops.push_back(static_cast<uint8_t>(pb->ops[i]));
+    hq->prog_args.push_back(static_cast<uint32_t>(pb->args[i]));
+  }
+  for (uint64_t f = 0; f < eq.n_filters; ++f) {
+    HostFilter hf;
+    hf.col = eq.filter_col[f];
+    hf.op = eq.filter_op[f];
+    if (hf.op > 5) {
+      return invalid("filter op must be 0..5 (EQ, NE, GT, GTE, LT, LTE)");
+    }
+    hf.literal.assign(reinterpret_cast<const char*>(eq.filter_bytes) + eq.filter_offsets[f],
+                      eq.filter_offsets[f + 1] - eq.filter_offsets[f]);
+    hq->filters.push_back(std::move(hf));
+  }
+  return MGX_OK;
+}
+
+}  // namespace
+
+int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq, const uint8_t* term_bytes,
+                     const uint64_t* term_offsets, uint64_t n_terms, uint32_t max_distance, uint32_t* out,
+                     uint64_t cap, uint64_t* out_count) {
+  mgx_index_t* index = const_cast<mgx_index_t*>(index_c);
+  if (index == nullptr || out_count == nullptr || (n_terms > 0 && (term_bytes == nullptr || term_offsets == nullptr))) {
+    return invalid("null argument");
+  }
+  *out_count = 0;
+  if (int rc = check_expanded(eq); rc != MGX_OK) {
+    return rc;
+  }
+  if (n_terms == 0) {
+    return MGX_OK;  // search_pipeline.cpp:1667-1670
+  }
+  if (should_verify(eq->verify_text, term_bytes, term_offsets, n_terms)) {
+    // PostFilterByFuzzyText (:1742-1752) needs ContainsFuzzyMatch (utils/edit_distance.cpp) per candidate text
+    set_last_error("fuzzy search with verify_text on (edit-distance verification) is not built on the device");
+    return MGX_ERR_UNSUPPORTED;
+  }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(index->mu);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    ProgramBuilder pb;
+    int32_t children = 0;
+    bool hybrid_exact = false;
+    for (uint64_t t = 0; t < n_terms; ++t) {
+      const uint8_t* tb = term_bytes + term_offsets[t];
+      const uint64_t tl = term_offsets[t + 1] - term_offsets[t];
+      HostTerm whole;
+      if (int rc = term_leaf(ix, *eq, tb, tl, &whole); rc != MGX_OK) {
+        return rc;
+      }
+      const size_t n = whole.keys.size();
+      if (n == 0) {
+        return MGX_OK;  // too short for an n-gram: no candidates, empty_term_detected (:1674-1680)
+      }
+      if (n > kMaxProgramDepth - 2) {
+        set_last_error("fuzzy term with more than 62 distinct n-grams is not supported");
+        return MGX_ERR_UNSUPPORTED;
+      }
+      // effective n-gram size of the term (:1682-1695): the kanji size when most of its n-grams are <= 3 bytes
+      int eff = eq->ngram_size > 0 ? eq->ngram_size : 2;
+      if (eq->kanji_ngram_size > 0) {
+        size_t short_count = 0;
+        for (uint64_t key : whole.keys) {
+          uint8_t enc[4 * kMaxKeyWidth];
+          if (key == kInvalidKey) {
+            set_last_error("fuzzy term with n-grams wider than the index key");
+            return MGX_ERR_UNSUPPORTED;
+          }
+          short_count += mgx_key_to_utf8(key, ix.width, enc) <= 3 ? 1 : 0;
+        }
+        if (short_count > n / 2) {
+          eff = eq->kanji_ngram_size;
+        }
+      }
+      const size_t drop = static_cast<size_t>(max_distance) * static_cast<size_t>(eff);
+      const size_t need = n > drop ? n - drop : 1;  // :1697-1700
+      for (uint64_t key : whole.keys) {  // Index::SearchByThreshold(ngrams, need), index.cpp:488-578
+        HostTerm leaf;
+        leaf.raw = true;
+        leaf.keys.push_back(key);
+        pb.leaf(std::move(leaf));
+      }
+      pb.node(kOpAtLeast, static_cast<int32_t>(n | (need << 16)));
+      ++children;
+      hybrid_exact |= has_uncovered_hybrid_fragment(tb, tl, eq->ngram_size, eq->kanji_ngram_size,
+                                                    eq->cross_boundary != 0);
+    }
+    if (hybrid_exact) {  // RequiresExactTextForHybridFragments -> PostFilterByText (:1728-1737): every term, exactly
+      for (uint64_t t = 0; t < n_terms; ++t) {
+        HostTerm text_only;
+        text_only.bytes.assign(reinterpret_cast<const char*>(term_bytes) + term_offsets[t],
+                               term_offsets[t + 1] - term_offsets[t]);
+        pb.leaf(std::move(text_only));
+        ++children;
+      }
+    }
+    std::vector<HostQuery> queries(1);
+    if (int rc = finish_expanded(ix, *eq, &pb, children, &queries[0]); rc != MGX_OK) {
+      return rc;
+    }
+    return run_single_set_query(ix, pb.terms, queries, nullptr, 0, 0, false, out, cap, out_count);
+  });
+}
+
+int mgx_search_synonyms(const mgx_index_t* index_c, const mgx_expanded_query_t* eq, const uint8_t* variant_bytes,
+                        const uint64_t* variant_offsets, const uint64_t* group_begin, uint64_t n_groups,
+                        uint32_t* out, uint64_t cap, uint64_t* out_count) {
+  mgx_index_t* index = const_cast<mgx_index_t*>(index_c);
+  if (index == nullptr || out_count == nullptr ||
+      (n_groups > 0 && (variant_bytes == nullptr || variant_offsets == nullptr || group_begin == nullptr))) {
+    return invalid("null argument");
+  }
+  *out_count = 0;
+  if (int rc = check_expanded(eq); rc != MGX_OK) {
+    return rc;
+  }
+  if (n_groups == 0) {
+    return MGX_OK;  // no group was processed: empty_term_detected (search_pipeline.cpp:1618-1621)
+  }
+  for (uint64_t g = 0; g < n_groups; ++g) {
+    if (group_begin[g + 1] < group_begin[g]) {
+      return invalid("group_begin must be non-decreasing");
+    }
+  }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    std::lock_guard<std::mutex> lock(index->mu);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    ProgramBuilder pb;
+    int32_t children = 0;
+    const uint64_t n_variants = group_begin[n_groups];
+    // ShouldApplyVerifyTextSynonyms (:154-172): decided over the variants of all groups
+    const bool verify = n_variants > 0 && should_verify(eq->verify_text, variant_bytes, variant_offsets, n_variants);
+    for (int pass = 0; pass < (verify ? 2 : 1); ++pass) {
+      // pass 0: OR within a group of SearchTermDocuments(variant) (:1589-1608);
+      // pass 1: PostFilterByTextWithSynonyms (:1633-1657): some variant of every group occurs in the text
+      for (uint64_t g = 0; g < n_groups; ++g) {
+        bool trivially_true = false;
+        if (pass == 1) {
+          for (uint64_t v = group_begin[g]; v < group_begin[g + 1]; ++v) {
+            trivially_true |= variant_offsets[v + 1] == variant_offsets[v];  // text.find("") always succeeds
+          }
+        }
+        if (trivially_true) {
+          continue;
+        }
+        for (uint64_t v = group_begin[g]; v < group_begin[g + 1]; ++v) {
+          const uint8_t* vb = variant_bytes + variant_offsets[v];
+          const uint64_t vl = variant_offsets[v + 1] - variant_offsets[v];
+          HostTerm t;
+          if (pass == 0) {
+            if (int rc = term_leaf(ix, *eq, vb, vl, &t); rc != MGX_OK) {
+              return rc;
+            }
+          } else {
+            if (vl > kMaxTermBytes) {
+              set_last_error("query term longer than 256 bytes is not supported");
+              return MGX_ERR_UNSUPPORTED;
+            }
+            t.bytes.assign(reinterpret_cast<const char*>(vb), vl);  // text-only leaf
+          }
+          pb.leaf(std::move(t));
+          if (v > group_begin[g]) {
+            pb.node(kOpOr, 2);
+          }
+        }
+        if (group_begin[g + 1] == group_begin[g]) {
+          pb.node(kOpOr, 0);  // a group without variants matches nothing
+        }
+        ++children;
+      }
+    }
+    std::vector<HostQuery> queries(1);
+    if (int rc = finish_expanded(ix, *eq, &pb, children, &queries[0]); rc != MGX_OK) {
+      return rc;
+    }
+    return run_single_set_query(ix, pb.terms, queries, nullptr, 0, 0, false, out, cap, out_count);
   });
 }
 

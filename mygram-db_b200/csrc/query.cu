@@ -1782,15 +1782,22 @@ __device__ bool eval_program(const IndexView& iv, const BatchView& bv, uint32_t 
     if (op == kOpTerm) {
       stack = (stack << 1) | (program_term_holds(iv, bv, arg, doc) ? 1ULL : 0ULL);
       ++sp;
-    } else if (op == kOpAnd || op == kOpOr) {
-      if (arg > sp) {
+    } else if (op == kOpAnd || op == kOpOr || op == kOpAtLeast) {
+      const uint32_t n = op == kOpAtLeast ? (arg & 0xFFFFu) : arg;
+      if (n > sp) {
         return false;
       }
-      const unsigned long long mask = arg >= 64 ? ~0ULL : ((1ULL << arg) - 1ULL);
+      const unsigned long long mask = n >= 64 ? ~0ULL : ((1ULL << n) - 1ULL);
       const unsigned long long bits = stack & mask;
-      const bool v = arg != 0 && (op == kOpAnd ? bits == mask : bits != 0);
-      stack = arg >= 64 ? 0ULL : (stack >> arg);
-      sp -= arg;
+      bool v;
+      if (op == kOpAtLeast) {
+        const uint32_t need = arg >> 16;  // 0 or more than n children: nothing matches (index.cpp:489-501)
+        v = need != 0 && static_cast<uint32_t>(__popcll(bits)) >= need;
+      } else {
+        v = n != 0 && (op == kOpAnd ? bits == mask : bits != 0);
+      }
+      stack = n >= 64 ? 0ULL : (stack >> n);
+      sp -= n;
       stack = (stack << 1) | (v ? 1ULL : 0ULL);
       ++sp;
     } else {

@@ -68,6 +68,9 @@ constexpr uint8_t kOpTerm = 0;  // arg = unique term id
 constexpr uint8_t kOpAnd = 1;   // arg = number of children
 constexpr uint8_t kOpOr = 2;    // arg = number of children
 constexpr uint8_t kOpNot = 3;   // one child
+// at least t of n children (Index::SearchByThreshold as a node: the per-term candidate rule of
+// search_pipeline::ExecuteWithFuzzy, search_pipeline.cpp:1696-1702): arg = n | (t << 16)
+constexpr uint8_t kOpAtLeast = 4;
 
 // driver kinds for single-call set APIs
 struct ExplicitDriver {

@@ -948,6 +948,150 @@ QueryOutput RunQuery(const orc_index& idx, const orc_query_params_t& p, const st
   return out;
 }
 
+// ApplyNotFilter, search_pipeline.cpp:871-932, over NOT terms whose synonym expansion (if any) the caller has
+// already flattened: what is excluded is the union over all of them.
+std::vector<DocId> ApplyNotTerms(const orc_index& idx, const orc_query_params_t& p, std::vector<DocId> results,
+                                 const std::vector<std::string_view>& not_terms) {
+  if (results.empty() || not_terms.empty()) {
+    return results;
+  }
+  std::vector<DocId> excluded;
+  std::vector<DocId> temp;
+  for (auto nt : not_terms) {
+    const TermInfo ti = MakeTermInfo(idx, nt, p, false);
+    const std::vector<DocId> term_docs = SearchTermDocuments(idx, ti);
+    temp.clear();
+    std::set_union(excluded.begin(), excluded.end(), term_docs.begin(), term_docs.end(), std::back_inserter(temp));
+    excluded.swap(temp);
+  }
+  if (excluded.empty()) {
+    return results;
+  }
+  std::vector<DocId> filtered;
+  std::set_difference(results.begin(), results.end(), excluded.begin(), excluded.end(), std::back_inserter(filtered));
+  return filtered;
+}
+
+// IntersectSorted, search_pipeline.cpp:420-436.
+void IntersectSorted(std::vector<DocId>& acc, std::vector<DocId>&& fresh, bool& is_first) {
+  if (is_first) {
+    acc = std::move(fresh);
+    is_first = false;
+  } else if (!acc.empty() && !fresh.empty()) {
+    std::vector<DocId> inter;
+    std::set_intersection(acc.begin(), acc.end(), fresh.begin(), fresh.end(), std::back_inserter(inter));
+    acc = std::move(inter);
+  } else {
+    acc.clear();
+  }
+}
+
+// ExecuteWithFuzzy, search_pipeline.cpp:1659-1740, for verify_text modes that do not apply to the terms (the
+// edit-distance verification of PostFilterByFuzzyText :1742-1752 is not restated). *empty_term = the reference's
+// empty_term_detected, under which ExecuteFullPipeline clears the results (:1933-1937).
+std::vector<DocId> RunFuzzy(const orc_index& idx, const orc_query_params_t& p,
+                            const std::vector<std::string_view>& terms, uint32_t max_distance,
+                            const std::vector<std::string_view>& not_terms, bool* empty_term) {
+  *empty_term = false;
+  std::vector<DocId> results;
+  if (terms.empty()) {
+    *empty_term = true;
+    return results;
+  }
+  bool first_term = true;
+  for (auto term : terms) {
+    const TermInfo ti = MakeTermInfo(idx, term, p, false);
+    if (ti.ngrams.empty()) {
+      *empty_term = true;  // :1674-1680
+      return {};
+    }
+    int eff = p.ngram_size > 0 ? p.ngram_size : 2;  // :1682-1695
+    if (p.kanji_ngram_size > 0) {
+      size_t short_count = 0;
+      for (const auto& g : ti.ngrams) {
+        short_count += g.size() <= 3 ? 1 : 0;
+      }
+      if (short_count > ti.ngrams.size() / 2) {
+        eff = p.kanji_ngram_size;
+      }
+    }
+    const size_t n = ti.ngrams.size();
+    const size_t drop = static_cast<size_t>(max_distance) * static_cast<size_t>(eff);
+    const size_t threshold = n > drop ? n - drop : 1;  // :1697-1700
+    IntersectSorted(results, SearchByThreshold(idx, Views(ti.ngrams), threshold), first_term);
+  }
+  results = ApplyNotTerms(idx, p, std::move(results), not_terms);
+  for (auto t : terms) {  // RequiresExactTextForHybridFragments, :1728-1737
+    if (HasUncoveredHybridFragment(t, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0)) {
+      results = PostFilterByText(idx, results, terms);
+      break;
+    }
+  }
+  return results;
+}
+
+// ExecuteWithSynonyms + PostFilterByTextWithSynonyms, search_pipeline.cpp:1580-1657. A group is the list of its
+// variants (ExpandNormalizedTermWithSynonyms :1360-1388: normalized_terms == the variants' terms).
+std::vector<DocId> RunSynonyms(const orc_index& idx, const orc_query_params_t& p,
+                               const std::vector<std::vector<std::string_view>>& groups,
+                               const std::vector<std::string_view>& not_terms, bool* empty_term) {
+  *empty_term = false;
+  std::vector<DocId> results;
+  bool first_group = true;
+  for (const auto& group : groups) {
+    std::vector<DocId> group_results;
+    for (auto variant : group) {
+      const TermInfo ti = MakeTermInfo(idx, variant, p, false);
+      if (ti.normalized.empty() || (!ti.ngrams.empty() && ti.estimated_size == 0)) {
+        continue;  // :1593-1595
+      }
+      auto var_results = SearchTermDocuments(idx, ti);
+      if (group_results.empty()) {
+        group_results = std::move(var_results);
+      } else {
+        std::vector<DocId> merged;
+        std::set_union(group_results.begin(), group_results.end(), var_results.begin(), var_results.end(),
+                       std::back_inserter(merged));
+        group_results = std::move(merged);
+      }
+    }
+    IntersectSorted(results, std::move(group_results), first_group);
+  }
+  if (first_group) {
+    *empty_term = true;  // :1618-1621
+    return {};
+  }
+  results = ApplyNotTerms(idx, p, std::move(results), not_terms);
+  bool verify = p.verify_text == 1;  // ShouldApplyVerifyTextSynonyms :154-172
+  if (p.verify_text == 2) {
+    verify = true;
+    for (const auto& group : groups) {
+      verify = verify && ShouldApplyVerifyText(2, group);
+    }
+  }
+  if (verify && !results.empty()) {
+    std::vector<DocId> kept;
+    for (DocId d : results) {
+      std::string_view text;
+      bool ok = true;
+      if (idx.GetText(d, &text)) {  // a candidate without stored text is kept (:386-402)
+        for (const auto& group : groups) {
+          bool any = false;
+          for (auto v : group) {
+            any = any || text.find(v) != std::string_view::npos;
+          }
+          ok = ok && any;
+        }
+      }
+      if (ok) {
+        kept.push_back(d);
+      }
+    }
+    results = std::move(kept);
+  }
+  return results;
+}
+
 std::vector<std::string_view> TermList(const uint8_t* bytes, const uint64_t* offsets, uint64_t begin, uint64_t end) {
   std::vector<std::string_view> out;
   out.reserve(end - begin);
@@ -1705,6 +1849,41 @@ uint64_t orc_eval_boolean(const orc_index_t* idx, const int32_t* ops, const int3
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------- column filters
+extern "C" uint64_t orc_search_fuzzy(const orc_index_t* idx, const orc_query_params_t* params,
+                                     const uint8_t* term_bytes, const uint64_t* term_offsets, uint64_t n_terms,
+                                     uint32_t max_distance, const uint8_t* not_bytes, const uint64_t* not_offsets,
+                                     uint64_t n_not, uint32_t* out, uint64_t cap, int32_t* empty_term_detected) {
+  const auto terms = TermList(term_bytes, term_offsets, 0, n_terms);
+  const auto not_terms = n_not > 0 ? TermList(not_bytes, not_offsets, 0, n_not) : std::vector<std::string_view>{};
+  if (ShouldApplyVerifyText(params->verify_text, terms)) {
+    return ~0ULL;  // PostFilterByFuzzyText is not restated
+  }
+  bool empty_term = false;
+  const auto r = RunFuzzy(*idx, *params, terms, max_distance, not_terms, &empty_term);
+  if (empty_term_detected != nullptr) {
+    *empty_term_detected = empty_term ? 1 : 0;
+  }
+  return CopyOut(r, out, cap);
+}
+
+extern "C" uint64_t orc_search_synonyms(const orc_index_t* idx, const orc_query_params_t* params,
+                                        const uint8_t* variant_bytes, const uint64_t* variant_offsets,
+                                        const uint64_t* group_begin, uint64_t n_groups, const uint8_t* not_bytes,
+                                        const uint64_t* not_offsets, uint64_t n_not, uint32_t* out, uint64_t cap,
+                                        int32_t* empty_term_detected) {
+  std::vector<std::vector<std::string_view>> groups;
+  for (uint64_t g = 0; g < n_groups; ++g) {
+    groups.push_back(TermList(variant_bytes, variant_offsets, group_begin[g], group_begin[g + 1]));
+  }
+  const auto not_terms = n_not > 0 ? TermList(not_bytes, not_offsets, 0, n_not) : std::vector<std::string_view>{};
+  bool empty_term = false;
+  const auto r = RunSynonyms(*idx, *params, groups, not_terms, &empty_term);
+  if (empty_term_detected != nullptr) {
+    *empty_term_detected = empty_term ? 1 : 0;
+  }
+  return CopyOut(r, out, cap);
+}
+
 namespace {
 
 struct ParsedLiteral {  // ParseFilterValue, search_pipeline.cpp:943-993

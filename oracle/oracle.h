@@ -178,6 +178,24 @@ int orc_query_batch(const orc_index_t* idx, const orc_query_params_t* params, ui
 uint64_t orc_eval_boolean(const orc_index_t* idx, const int32_t* ops, const int32_t* args, uint64_t n_ops,
                           const uint8_t* term_bytes, const uint64_t* term_offsets, uint32_t* out, uint64_t cap);
 
+/* ---- fuzzy and synonym execution paths (src/server/search_pipeline.cpp:1580-1752) ----
+ * ExecuteWithFuzzy (:1659-1740) over normalised terms: per term Index::SearchByThreshold(ngrams,
+ * max(1, |ngrams| - max_distance * effective n-gram size)), AND-ed; NOT terms; hybrid-fragment exact text filter.
+ * Column filters are applied by the caller with orc_apply_filters (they are per-document predicates).
+ * Returns the result size (ids ascending), or ~0 when verify_text applies to the terms (the edit-distance
+ * verification is not restated). *empty_term_detected (may be NULL) as in SearchPipelineResult. */
+uint64_t orc_search_fuzzy(const orc_index_t* idx, const orc_query_params_t* params, const uint8_t* term_bytes,
+                          const uint64_t* term_offsets, uint64_t n_terms, uint32_t max_distance,
+                          const uint8_t* not_bytes, const uint64_t* not_offsets, uint64_t n_not, uint32_t* out,
+                          uint64_t cap, int32_t* empty_term_detected);
+/* ExecuteWithSynonyms (:1580-1631) + PostFilterByTextWithSynonyms (:1633-1657) over expanded groups: group g =
+ * variants [group_begin[g], group_begin[g+1]) (the term and its synonyms, ExpandTermsWithSynonyms :1392-1406).
+ * NOT terms: pass every synonym of every NOT term. */
+uint64_t orc_search_synonyms(const orc_index_t* idx, const orc_query_params_t* params, const uint8_t* variant_bytes,
+                             const uint64_t* variant_offsets, const uint64_t* group_begin, uint64_t n_groups,
+                             const uint8_t* not_bytes, const uint64_t* not_offsets, uint64_t n_not, uint32_t* out,
+                             uint64_t cap, int32_t* empty_term_detected);
+
 /* ---- column filters (src/server/search_pipeline.cpp:1021-1237) ----
  * ApplyFiltersWithBitmap (:1196-1237): when every condition is EQ / NE the FilterIndex bitmaps decide (a value
  * matches when its serialisation equals that of some type interpretation of the literal, BuildTypeUnionBitmap

@@ -159,6 +159,12 @@ class OracleLib:
                                       C.c_uint64, u32p, f64p, u32p, u64p, u64p, u32p, C.c_uint64, u64p, C.c_int]
         L.orc_eval_boolean.restype = C.c_uint64
         L.orc_eval_boolean.argtypes = [C.c_void_p, i32p, i32p, C.c_uint64, u8p, u64p, u32p, C.c_uint64]
+        L.orc_search_fuzzy.restype = C.c_uint64
+        L.orc_search_fuzzy.argtypes = [C.c_void_p, C.POINTER(QueryParams), u8p, u64p, C.c_uint64, C.c_uint32, u8p, u64p,
+                                       C.c_uint64, u32p, C.c_uint64, i32p]
+        L.orc_search_synonyms.restype = C.c_uint64
+        L.orc_search_synonyms.argtypes = [C.c_void_p, C.POINTER(QueryParams), u8p, u64p, u64p, C.c_uint64, u8p, u64p,
+                                          C.c_uint64, u32p, C.c_uint64, i32p]
 
     # ---- tokenizer ----
     def apply_filters(self, n_docs, first_doc_id, columns, filters, results):
@@ -408,6 +414,52 @@ class OracleIndex:
                                             _ptr(offs, u64p), _ptr(out, u32p), cap)
             if n <= cap:
                 return out[:n].copy()
+            cap = int(n)
+
+    def _pipeline_params(self, raw_ngram, raw_kanji, verify_text):
+        return QueryParams(self.ngram_size if raw_ngram is None else raw_ngram,
+                           self.kanji_ngram_size if raw_kanji is None else raw_kanji, int(self.cross_boundary),
+                           0, 1, 0, 0, 1000, 1.2, 0.75, 0, 0, verify_text, 0)
+
+    def search_fuzzy(self, terms, max_distance, not_terms=(), raw_ngram=None, raw_kanji=None, verify_text=0):
+        """ExecuteWithFuzzy over normalised terms -> (ascending ids, empty_term_detected); None if the edit-distance
+        verification would apply (port only)."""
+        p = self._pipeline_params(raw_ngram, raw_kanji, verify_text)
+        arena, offs = self._terms(terms)
+        narena, noffs = self._terms(not_terms)
+        empty = np.zeros(1, dtype=np.int32)
+        cap = 1024
+        while True:
+            out = np.zeros(cap, dtype=np.uint32)
+            n = self.L.lib.orc_search_fuzzy(self.h, C.byref(p), _ptr(arena, u8p), _ptr(offs, u64p), len(terms),
+                                            max_distance, _ptr(narena, u8p), _ptr(noffs, u64p), len(not_terms),
+                                            _ptr(out, u32p), cap, _ptr(empty, i32p))
+            if n == 2 ** 64 - 1:
+                return None
+            if n <= cap:
+                return out[:n].copy(), bool(empty[0])
+            cap = int(n)
+
+    def search_synonyms(self, groups, not_terms=(), raw_ngram=None, raw_kanji=None, verify_text=0):
+        """ExecuteWithSynonyms over expanded groups (list of lists of variants) -> (ascending ids,
+        empty_term_detected)."""
+        p = self._pipeline_params(raw_ngram, raw_kanji, verify_text)
+        flat, gbeg = [], [0]
+        for g in groups:
+            flat += list(g)
+            gbeg.append(len(flat))
+        arena, offs = self._terms(flat)
+        gbeg = np.asarray(gbeg, dtype=np.uint64)
+        narena, noffs = self._terms(not_terms)
+        empty = np.zeros(1, dtype=np.int32)
+        cap = 1024
+        while True:
+            out = np.zeros(cap, dtype=np.uint32)
+            n = self.L.lib.orc_search_synonyms(self.h, C.byref(p), _ptr(arena, u8p), _ptr(offs, u64p),
+                                               _ptr(gbeg, u64p), len(groups), _ptr(narena, u8p), _ptr(noffs, u64p),
+                                               len(not_terms), _ptr(out, u32p), cap, _ptr(empty, i32p))
+            if n <= cap:
+                return out[:n].copy(), bool(empty[0])
             cap = int(n)
 
     def query_batch(self, queries, not_terms=None, score=True, descending=True, limit=100, offset=0,

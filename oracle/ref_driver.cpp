@@ -533,6 +533,74 @@ uint64_t orc_eval_boolean(const orc_index_t* idx, const int32_t* ops, const int3
   return CopyOut(stack.back()->Evaluate(*idx->index, *idx->store), out, cap);
 }
 
+// The reference's own ExecuteWithFuzzy (search_pipeline.cpp:1659-1740), called the way ExecuteFullPipeline does
+// (:1908-1937): term infos from GenerateTermInfos, results cleared under empty_term_detected.
+uint64_t orc_search_fuzzy(const orc_index_t* idx, const orc_query_params_t* params, const uint8_t* term_bytes,
+                          const uint64_t* term_offsets, uint64_t n_terms, uint32_t max_distance,
+                          const uint8_t* not_bytes, const uint64_t* not_offsets, uint64_t n_not, uint32_t* out,
+                          uint64_t cap, int32_t* empty_term_detected) {
+  namespace sp = ref::server::search_pipeline;
+  const orc_query_params_t p = *params;
+  ref::config::Config config = idx->config;
+  config.memory.verify_text = p.verify_text == 1 ? "all" : (p.verify_text == 2 ? "ascii" : "off");
+  const auto terms = TermList(term_bytes, term_offsets, 0, n_terms);
+  ref::query::Query query;
+  query.type = ref::query::QueryType::SEARCH;
+  query.table = "t";
+  if (n_not > 0) {
+    query.not_terms = TermList(not_bytes, not_offsets, 0, n_not);
+  }
+  query.fuzzy_max_distance = max_distance;
+  const auto term_infos =
+      sp::GenerateTermInfos(terms, idx->index.get(), p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0);
+  auto result = sp::ExecuteWithFuzzy(query, term_infos, terms, max_distance, idx->index.get(), idx->store.get(),
+                                     &config, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0,
+                                     p.filter_threshold);
+  if (empty_term_detected != nullptr) {
+    *empty_term_detected = result.empty_term_detected ? 1 : 0;
+  }
+  if (result.empty_term_detected) {
+    result.results.clear();
+  }
+  return CopyOut(result.results, out, cap);
+}
+
+// The reference's own ExecuteWithSynonyms (search_pipeline.cpp:1580-1631) over groups built the way
+// ExpandNormalizedTermWithSynonyms does (:1360-1388; the SynonymDictionary itself only loads from a file): one
+// SearchTermInfo per variant from GenerateTermInfos, normalized_terms = the variants.
+uint64_t orc_search_synonyms(const orc_index_t* idx, const orc_query_params_t* params, const uint8_t* variant_bytes,
+                             const uint64_t* variant_offsets, const uint64_t* group_begin, uint64_t n_groups,
+                             const uint8_t* not_bytes, const uint64_t* not_offsets, uint64_t n_not, uint32_t* out,
+                             uint64_t cap, int32_t* empty_term_detected) {
+  namespace sp = ref::server::search_pipeline;
+  const orc_query_params_t p = *params;
+  ref::config::Config config = idx->config;
+  config.memory.verify_text = p.verify_text == 1 ? "all" : (p.verify_text == 2 ? "ascii" : "off");
+  std::vector<sp::SynonymTermGroup> groups;
+  for (uint64_t g = 0; g < n_groups; ++g) {
+    sp::SynonymTermGroup group;
+    group.normalized_terms = TermList(variant_bytes, variant_offsets, group_begin[g], group_begin[g + 1]);
+    group.variants = sp::GenerateTermInfos(group.normalized_terms, idx->index.get(), p.ngram_size,
+                                           p.kanji_ngram_size, p.cross_boundary != 0);
+    groups.push_back(std::move(group));
+  }
+  ref::query::Query query;
+  query.type = ref::query::QueryType::SEARCH;
+  query.table = "t";
+  if (n_not > 0) {
+    query.not_terms = TermList(not_bytes, not_offsets, 0, n_not);
+  }
+  auto result = sp::ExecuteWithSynonyms(query, groups, idx->index.get(), idx->store.get(), &config, p.ngram_size,
+                                        p.kanji_ngram_size, p.cross_boundary != 0, p.filter_threshold, nullptr);
+  if (empty_term_detected != nullptr) {
+    *empty_term_detected = result.empty_term_detected ? 1 : 0;
+  }
+  if (result.empty_term_detected) {
+    result.results.clear();
+  }
+  return CopyOut(result.results, out, cap);
+}
+
 }  // extern "C"
 
 // Column filters through the reference's own DocumentStore / FilterIndex / ApplyFiltersWithBitmap

@@ -1,0 +1,102 @@
+"""GPU parity of the fuzzy and synonym execution paths (search_pipeline::ExecuteWithFuzzy / ExecuteWithSynonyms,
+SURVEY §8f-3) through the C ABI (mgx_search_fuzzy / mgx_search_synonyms) against the CPU oracle, whose restatement
+tests/test_oracle_expanded.py pins to the reference's own functions. Bit-exact doc-id sets."""
+import random
+
+import numpy as np
+import pytest
+
+import corpus as corpus_mod
+from test_gpu_parity import build_pair, make_docs
+from test_oracle_bulk import _docs
+from test_oracle_expanded import expanded_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cfg", [(2, 0, True), (2, 1, True), (2, 1, False), (3, 2, False), (1, 1, True), (3, 0, True)])
+def test_fuzzy_and_synonyms_match_oracle(mgx, oracle, cfg):
+    rnd = random.Random(0x51 + (hash(cfg) & 0xFFF))
+    docs = _docs(rnd, 3000)
+    ids = np.arange(1, len(docs) + 1, dtype=np.uint32)
+    gi, oi = build_pair(mgx, oracle, docs, ids, cfg)
+    nonempty = 0
+    for fuzzy_terms, groups, nots, dist in expanded_cases(rnd, docs, 120):
+        want, _ = oi.search_fuzzy(fuzzy_terms, dist, nots)
+        got = gi.search_fuzzy(fuzzy_terms, dist, nots)
+        assert np.array_equal(got, want), (cfg, fuzzy_terms, dist, nots, got[:10], want[:10])
+        nonempty += want.size > 0
+        for vt in (0, 1, 2):
+            want, _ = oi.search_synonyms(groups, nots, verify_text=vt)
+            got = gi.search_synonyms(groups, nots, verify_text=vt)
+            assert np.array_equal(got, want), (cfg, groups, nots, vt, got[:10], want[:10])
+            nonempty += want.size > 0
+    assert nonempty > 40
+    assert gi.search_fuzzy([], 1).size == 0 and gi.search_synonyms([]).size == 0
+    # verify_text that applies to the terms needs the edit-distance verification: refused, never approximated
+    with pytest.raises(mgx.MgxError):
+        gi.search_fuzzy(["ab"], 1, verify_text=1)
+
+
+def test_fuzzy_and_synonyms_with_filters_dense_lists_and_invalid_utf8(mgx, oracle):
+    """Zipf corpus with dense-bitmap lists, column conditions applied after the NOT terms (ApplyNotAndFilters,
+    search_pipeline.cpp:470-485), and a corpus with invalid UTF-8."""
+    rnd = random.Random(77)
+    c = corpus_mod.generate("cjk", 20000, 0xF3, alphabet=96, min_len=6, max_len=40)
+    gi = mgx.Index(2, 0, True, dense_threshold=0.02)
+    gi.build(c.doc_ids, c.arena, c.offsets)
+    oi = oracle.index(2, 0, True)
+    oi.build_bulk(c.doc_ids, c.arena, c.offsets, 8)
+    assert gi.stats().n_dense_terms > 0
+    n = c.n_docs
+    status = [None if rnd.random() < 0.1 else rnd.choice([1, 2, 3]) for _ in range(n)]
+    category = [None if rnd.random() < 0.1 else rnd.choice([b"news", b"blog", b"wiki"]) for _ in range(n)]
+    columns = [(8, status), (11, category)]
+    for ci, (typ, vals) in enumerate(columns):
+        gi.set_filter_column(ci, typ, vals)
+    first = int(c.doc_ids[0])
+    filter_pool = [[(0, 0, "1")], [(1, 1, "news"), (0, 0, "3")], [(0, 3, "2")], [(1, 0, "blog")], []]
+
+    def piece(lo, hi):
+        t = c.text(rnd.randrange(n)).decode()
+        ln = rnd.randint(lo, min(hi, len(t)))
+        st = rnd.randrange(0, len(t) - ln + 1)
+        return t[st:st + ln]
+
+    def misspell(s):
+        i = rnd.randrange(len(s))
+        return s[:i] + chr(0x4E00 + rnd.randrange(96)) + s[i + 1:]
+
+    sizes = []
+    for _ in range(60):
+        fl = rnd.choice(filter_pool)
+        nots = [piece(2, 2)] if rnd.random() < 0.3 else []
+        terms = [misspell(piece(3, 8)) for _ in range(rnd.randint(1, 2))]
+        dist = rnd.randint(1, 2)
+        want, _ = oi.search_fuzzy(terms, dist, nots)
+        want = oracle.apply_filters(n, first, columns, fl, want) if fl else want
+        got = gi.search_fuzzy(terms, dist, nots, filters=fl)
+        assert np.array_equal(got, want), (terms, dist, nots, fl, got.size, want.size)
+        sizes.append(want.size)
+        groups = [[piece(2, 4) for _ in range(rnd.randint(1, 3))] for _ in range(rnd.randint(1, 2))]
+        want, _ = oi.search_synonyms(groups, nots)
+        want = oracle.apply_filters(n, first, columns, fl, want) if fl else want
+        got = gi.search_synonyms(groups, nots, filters=fl)
+        assert np.array_equal(got, want), (groups, nots, fl, got.size, want.size)
+        sizes.append(want.size)
+    assert max(sizes) > 100 and sum(1 for s in sizes if s > 0) > 30
+    # invalid UTF-8 in documents and terms
+    docs = make_docs(5, 2000, 30, bad=True)
+    ids = np.arange(10, 10 + len(docs), dtype=np.uint32)
+    for cfg in [(2, 1, True), (2, 0, True)]:
+        g2, o2 = build_pair(mgx, oracle, docs, ids, cfg)
+        for _ in range(80):
+            d = docs[rnd.randrange(len(docs))]
+            if len(d) < 4:
+                continue
+            st = rnd.randrange(0, len(d) - 3)
+            term = d[st:st + rnd.randint(2, 9)]
+            want, _ = o2.search_fuzzy([term], 1)
+            assert np.array_equal(g2.search_fuzzy([term], 1), want), (cfg, term)
+            want, _ = o2.search_synonyms([[term, d[:3]]], verify_text=1)
+            assert np.array_equal(g2.search_synonyms([[term, d[:3]]], verify_text=1), want), (cfg, term)
