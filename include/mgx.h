@@ -34,6 +34,8 @@ extern "C" {
 #define MGX_ERR_UNSUPPORTED (-3)      /* a configuration this build refuses rather than guesses */
 #define MGX_ERR_CAPACITY (-4)         /* a caller buffer was too small; nothing partial is valid */
 #define MGX_ERR_NO_DEVICE (-5)        /* no CUDA device: the library has no CPU fallback        */
+#define MGX_ERR_FORMAT (-6)           /* an MGIX stream was rejected; mgx_last_error() names the reference's
+                                         ErrorCode (kStorageInvalidFormat / CRCMismatch / Corrupted / ...) */
 
 /* Thread-local description of the last failure on this thread ("" if none). */
 const char* mgx_last_error(void);
@@ -157,6 +159,49 @@ int mgx_key_to_utf8(uint64_t key, int32_t width, uint8_t* out);
  * the number of n-grams. */
 int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, const uint64_t* text_offsets,
                        uint64_t n_docs, uint64_t* out_keys, uint32_t* out_doc, uint64_t cap, uint64_t* out_count);
+
+/* ------------------------------------------------- MGIX index stream (DUMP / SYNC side of the index) */
+
+/* Header and sizes of an MGIX stream: what Index::SaveToStream writes in front of the term records
+ * (index/index_serialization.cpp:111-160; kanji_ngram_size is the EFFECTIVE value the reference Index holds,
+ * index.cpp:29-37). normalize_width is NUL-terminated ("keep", "narrow", "wide"). */
+typedef struct {
+  uint32_t version;          /* decode: 1..4 as found; encode always writes 4 */
+  int32_t ngram_size;
+  int32_t kanji_ngram_size;
+  int32_t cross_boundary;
+  int32_t normalize_nfkc;
+  int32_t normalize_lower;
+  char normalize_width[32];
+  uint64_t n_terms;
+  uint64_t n_postings;
+  uint64_t term_bytes;
+} mgx_mgix_info_t;
+
+/* Index::SaveToStream (index_serialization.cpp:111-224) + PostingList::Serialize (posting_list.cpp:973-1021) of an
+ * index given as CSR: term t = term_bytes[term_offsets[t] .. term_offsets[t+1]) with the ascending doc ids
+ * postings[posting_offsets[t] .. posting_offsets[t+1]); info->n_terms terms. A list is written in the representation
+ * the reference's PostingList would hold: Roaring (portable interchange format) above 4096 entries, or when
+ * roaring_min_len > 0 (= roaring_threshold x the total_docs of the last Index::Optimize) and the list has at least
+ * that many entries; fixed-width delta otherwise. Host-only (no device needed). *out_len = stream length;
+ * MGX_ERR_CAPACITY when it exceeds cap (call with out = NULL to size the buffer). */
+int mgx_mgix_encode(const mgx_mgix_info_t* info, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                    const uint64_t* posting_offsets, const uint32_t* postings, double roaring_min_len, uint8_t* out,
+                    uint64_t cap, uint64_t* out_len);
+
+/* Index::LoadFromStream (index_serialization.cpp:279-613) + PostingList::Deserialize (posting_list.cpp:1023-1102):
+ * validates the stream exactly as the reference does (magic, version 1..4, CRC32 trailer, header, size guards,
+ * delta validity, Roaring structure incl. run containers) and returns the index as CSR in ascending term order.
+ * First call with NULL outputs fills *info (header + sizes); the second, with info's sizes as the capacities
+ * (term_offsets / posting_offsets hold n_terms + 1 entries), fills the arrays. Rejected streams: MGX_ERR_FORMAT.
+ * The configuration check of LoadFromData (:371-447) is the caller's: compare *info with the target index. */
+int mgx_mgix_decode(const uint8_t* data, uint64_t len, mgx_mgix_info_t* info, uint8_t* term_bytes,
+                    uint64_t* term_offsets, uint64_t* posting_offsets, uint32_t* postings);
+
+/* Index::SaveToStream of the device index: postings are read back once and encoded as above, with the
+ * representation rule fed by the last mgx_index_optimize call. */
+int mgx_index_save_mgix(const mgx_index_t* index, int32_t normalize_nfkc, const char* normalize_width,
+                        int32_t normalize_lower, uint8_t* out, uint64_t cap, uint64_t* out_len);
 
 /* ------------------------------------------------- Index set-algebra calls */
 

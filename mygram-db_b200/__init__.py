@@ -74,6 +74,13 @@ class ExpandedQuery(C.Structure):
                 ("n_filters", C.c_uint64)]
 
 
+class MgixInfo(C.Structure):
+    _fields_ = [("version", C.c_uint32), ("ngram_size", C.c_int32), ("kanji_ngram_size", C.c_int32),
+                ("cross_boundary", C.c_int32), ("normalize_nfkc", C.c_int32), ("normalize_lower", C.c_int32),
+                ("normalize_width", C.c_char * 32), ("n_terms", C.c_uint64), ("n_postings", C.c_uint64),
+                ("term_bytes", C.c_uint64)]
+
+
 class QueryParams(C.Structure):
     _fields_ = [("ngram_size", C.c_int32), ("kanji_ngram_size", C.c_int32), ("cross_boundary", C.c_int32),
                 ("compute_score", C.c_int32), ("descending", C.c_int32), ("limit", C.c_uint32), ("offset", C.c_uint32),
@@ -152,6 +159,9 @@ def lib():
                                    C.c_uint64, u64p]
     L.mgx_search_synonyms.argtypes = [C.c_void_p, C.POINTER(ExpandedQuery), u8p, u64p, u64p, C.c_uint64, u32p,
                                       C.c_uint64, u64p]
+    L.mgx_mgix_encode.argtypes = [C.POINTER(MgixInfo), u8p, u64p, u64p, u32p, C.c_double, u8p, C.c_uint64, u64p]
+    L.mgx_mgix_decode.argtypes = [u8p, C.c_uint64, C.POINTER(MgixInfo), u8p, u64p, u64p, u32p]
+    L.mgx_index_save_mgix.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, u8p, C.c_uint64, u64p]
     L.mgx_index_set_filter_column.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, u64p, u8p, C.c_uint64, u8p, u64p,
                                               C.c_uint64]
     L.mgx_query_batch_ex.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
@@ -215,6 +225,48 @@ def pack_strings(strings):
     joined = b"".join(bs)
     arena = np.frombuffer(joined, dtype=np.uint8).copy() if joined else np.zeros(1, np.uint8)
     return arena, offsets
+
+
+def mgix_encode(terms, posting_offsets, postings, ngram_size=2, kanji_ngram_size=2, cross_boundary=True,
+                normalize_nfkc=True, normalize_width="keep", normalize_lower=True, roaring_min_len=0.0):
+    """Index::SaveToStream of an index given as CSR (terms: list[bytes]; doc ids ascending per term) -> the MGIX v4
+    stream (bytes). Host-only codec."""
+    info = MgixInfo(4, ngram_size, kanji_ngram_size, int(cross_boundary), int(normalize_nfkc), int(normalize_lower),
+                    _bytes(normalize_width), len(terms), 0, 0)
+    tb, to = pack_strings(terms)
+    po = np.ascontiguousarray(posting_offsets, dtype=np.uint64)
+    pp = np.ascontiguousarray(postings, dtype=np.uint32)
+    if pp.size == 0:
+        pp = np.zeros(1, np.uint32)
+    n = C.c_uint64(0)
+    rc = lib().mgx_mgix_encode(C.byref(info), _ptr(tb, u8p), _ptr(to, u64p), _ptr(po, u64p), _ptr(pp, u32p),
+                               roaring_min_len, None, 0, C.byref(n))
+    if rc != -4:
+        _check(rc)
+    out = np.zeros(n.value, dtype=np.uint8)
+    _check(lib().mgx_mgix_encode(C.byref(info), _ptr(tb, u8p), _ptr(to, u64p), _ptr(po, u64p), _ptr(pp, u32p),
+                                 roaring_min_len, _ptr(out, u8p), out.size, C.byref(n)))
+    return out[:n.value].tobytes()
+
+
+def mgix_decode(data):
+    """Index::LoadFromStream of an MGIX stream -> (info dict, terms list[bytes] ascending, posting offsets,
+    postings). Raises MgxError (MGX_ERR_FORMAT) for a stream the reference would reject. Host-only codec."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8).copy() if len(data) else np.zeros(1, np.uint8)
+    info = MgixInfo()
+    _check(lib().mgx_mgix_decode(_ptr(buf, u8p), len(data), C.byref(info), None, None, None, None))
+    tb = np.zeros(max(1, info.term_bytes), dtype=np.uint8)
+    to = np.zeros(info.n_terms + 1, dtype=np.uint64)
+    po = np.zeros(info.n_terms + 1, dtype=np.uint64)
+    pp = np.zeros(max(1, info.n_postings), dtype=np.uint32)
+    _check(lib().mgx_mgix_decode(_ptr(buf, u8p), len(data), C.byref(info), _ptr(tb, u8p), _ptr(to, u64p),
+                                 _ptr(po, u64p), _ptr(pp, u32p)))
+    raw = tb.tobytes()
+    terms = [raw[int(to[i]):int(to[i + 1])] for i in range(info.n_terms)]
+    meta = {k: getattr(info, k) for k in ("version", "ngram_size", "kanji_ngram_size", "cross_boundary",
+                                          "normalize_nfkc", "normalize_lower", "n_terms", "n_postings")}
+    meta["normalize_width"] = info.normalize_width.decode()
+    return meta, terms, po, pp[:info.n_postings].copy()
 
 
 def key_to_utf8(key, width):
@@ -373,6 +425,18 @@ class Index:
         _check(lib().mgx_index_export(self._h, _ptr(keys, u64p), _ptr(offs, u64p), _ptr(posts, u32p)))
         terms = [key_to_utf8(k, s.key_width) for k in keys[:s.n_terms]]
         return terms, offs, posts[:s.n_postings]
+
+    def save_mgix(self, normalize_nfkc=True, normalize_width="keep", normalize_lower=True):
+        """Index::SaveToStream (index_serialization.cpp:111-224) of the device index -> bytes."""
+        n = C.c_uint64(0)
+        rc = lib().mgx_index_save_mgix(self._h, int(normalize_nfkc), _bytes(normalize_width), int(normalize_lower),
+                                       None, 0, C.byref(n))
+        if rc != -4:
+            _check(rc)
+        out = np.zeros(n.value, dtype=np.uint8)
+        _check(lib().mgx_index_save_mgix(self._h, int(normalize_nfkc), _bytes(normalize_width), int(normalize_lower),
+                                         _ptr(out, u8p), out.size, C.byref(n)))
+        return out[:n.value].tobytes()
 
     def doc_lengths(self):
         s = self.stats()

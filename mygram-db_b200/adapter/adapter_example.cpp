@@ -1,6 +1,7 @@
 // adapter_example.cpp — compile/link check of the C++ adapter and a minimal usage sample.
 // The calls mirror tests/index/index_search_test.cpp:393-418 (BigramSearch) of the reference.
 #include <cstdio>
+#include <sstream>
 
 #include "mygram_adapter.h"
 
@@ -20,6 +21,8 @@ int main() {
     const auto fuzzy = search_pipeline::ExecuteWithFuzzy(index, q, {"bxde"}, 1);
     const auto syn = search_pipeline::ExecuteWithSynonyms(index, q, {{"ab", "de"}, {"bc", "cd"}});
     std::printf("fuzzy %zu docs, synonyms %zu docs\n", fuzzy.size(), syn.size());
+    std::ostringstream dump;  // Index::SaveToStream: the MGIX stream DUMP SAVE writes
+    std::printf("MGIX stream %s, %zu bytes\n", index.SaveToStream(dump) ? "ok" : "failed", dump.str().size());
   } catch (const std::exception& e) {
     std::printf("%s\n", e.what());
     return 1;

@@ -5,7 +5,9 @@
 // reference declaration they replace:
 //   Index                    src/index/index.h:49-413      (ctor :58-60, AddDocumentBatch :75-100, SearchAnd :127,
 //                                                           FilterByNgrams :138, SearchOr :147, SearchNot :156,
-//                                                           PostingSize/Count :183-188, TermCount :193)
+//                                                           PostingSize/Count :183-188, TermCount :193,
+//                                                           SaveToStream :265)
+//   search_pipeline::ExecuteWithFuzzy / ExecuteWithSynonyms  src/server/search_pipeline.h:271-311
 //   BM25Scorer               src/index/bm25_scorer.h:43-83 (ScoreDocuments :79-82, BM25Params :23-26)
 //   ResultSorter::SortByScore src/query/result_sorter.h:75
 // Results are returned by value exactly as the reference does; errors follow the reference's conventions:
@@ -16,6 +18,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <memory>
+#include <ostream>
 #include <string>
 #include <string_view>
 #include <vector>
@@ -184,6 +187,26 @@ class Index {
     mgx_index_stats_t s{};
     detail::check(mgx_index_get_stats(handle_, &s));
     return s.n_terms;
+  }
+  // Index::SaveToStream (index.h:265, index_serialization.cpp:111-224): the MGIX v4 stream of the device index, what
+  // DUMP SAVE / SYNC write for the table (storage/dump_format_v2.h:13-41). Returns false where the reference
+  // returns an Error (kIndexSerializationFailed). The normalisation triple is the table's (index.h:58-60).
+  bool SaveToStream(std::ostream& output_stream, bool normalize_nfkc = true, const std::string& normalize_width = "keep",
+                    bool normalize_lower = true) const {
+    uint64_t len = 0;
+    int rc = mgx_index_save_mgix(handle_, normalize_nfkc ? 1 : 0, normalize_width.c_str(), normalize_lower ? 1 : 0,
+                                 nullptr, 0, &len);
+    if (rc != MGX_ERR_CAPACITY && rc != MGX_OK) {
+      return false;
+    }
+    std::vector<uint8_t> bytes(len);
+    rc = mgx_index_save_mgix(handle_, normalize_nfkc ? 1 : 0, normalize_width.c_str(), normalize_lower ? 1 : 0,
+                             bytes.data(), bytes.size(), &len);
+    if (rc != MGX_OK) {
+      return false;
+    }
+    output_stream.write(reinterpret_cast<const char*>(bytes.data()), static_cast<std::streamsize>(len));
+    return output_stream.good();
   }
   [[nodiscard]] int GetNgramSize() const { return ngram_size_; }
   [[nodiscard]] int GetKanjiNgramSize() const { return kanji_ngram_size_; }

@@ -1788,6 +1788,60 @@ int mgx_index_export(const mgx_index_t* index, uint64_t* keys, uint64_t* offsets
   });
 }
 
+int mgx_index_save_mgix(const mgx_index_t* index, int32_t normalize_nfkc, const char* normalize_width,
+                        int32_t normalize_lower, uint8_t* out, uint64_t cap, uint64_t* out_len) {
+  if (index == nullptr || out_len == nullptr) {
+    return invalid("null argument");
+  }
+  *out_len = 0;
+  const char* width = normalize_width != nullptr ? normalize_width : "keep";
+  mgx_mgix_info_t info{};
+  if (std::strlen(width) >= sizeof(info.normalize_width)) {
+    set_last_error("normalize_width longer than 31 bytes is not supported");
+    return MGX_ERR_UNSUPPORTED;
+  }
+  mgx_index_stats_t st{};
+  if (int rc = mgx_index_get_stats(index, &st); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    // the CSR comes back once (mgx_index_export: global doc ids, ascending term order); terms become UTF-8 strings
+    std::vector<uint64_t> keys(st.n_terms + 1);
+    std::vector<uint64_t> offsets(st.n_terms + 1);
+    std::vector<uint32_t> postings(st.n_postings + 1);
+    if (int rc = mgx_index_export(index, keys.data(), offsets.data(), postings.data()); rc != MGX_OK) {
+      return rc;
+    }
+    mgx_index_t* h = const_cast<mgx_index_t*>(index);
+    int width_cp = 0;
+    double roaring_min_len = 0.0;
+    {
+      std::lock_guard<std::mutex> lock(h->mu);
+      const Index& ix = h->ix;
+      width_cp = ix.width;
+      info.ngram_size = ix.ngram;
+      info.kanji_ngram_size = ix.kanji;  // effective: kanji > 0 ? kanji : ngram, as index.cpp:29-37 stores it
+      info.cross_boundary = ix.cross ? 1 : 0;
+      const double thr = ix.cfg.roaring_threshold > 0.0 ? ix.cfg.roaring_threshold : 0.18;
+      roaring_min_len = ix.optimized_total_docs > 0 ? thr * static_cast<double>(ix.optimized_total_docs) : 0.0;
+    }
+    info.normalize_nfkc = normalize_nfkc;
+    info.normalize_lower = normalize_lower;
+    std::strcpy(info.normalize_width, width);
+    info.n_terms = st.n_terms;
+    std::vector<uint8_t> term_bytes(st.n_terms * 4 * kMaxKeyWidth + 1);
+    std::vector<uint64_t> term_offsets(st.n_terms + 1, 0);
+    uint64_t tb = 0;
+    for (uint64_t t = 0; t < st.n_terms; ++t) {
+      term_offsets[t] = tb;
+      tb += static_cast<uint64_t>(mgx_key_to_utf8(keys[t], width_cp, term_bytes.data() + tb));
+    }
+    term_offsets[st.n_terms] = tb;
+    return mgx_mgix_encode(&info, term_bytes.data(), term_offsets.data(), offsets.data(), postings.data(),
+                           roaring_min_len, out, cap, out_len);
+  });
+}
+
 int mgx_index_doc_lengths(const mgx_index_t* index, uint32_t* out) {
   if (index == nullptr || out == nullptr) {
     return invalid("null argument");

@@ -1,0 +1,579 @@
+// mgix.cu — the MGIX index stream: the on-disk form either side of the device index.
+//
+// Host-side codec of what Index::SaveToStream / Index::LoadFromStream read and write
+// (src/index/index_serialization.cpp:111-224, 279-613) and of the posting-list bodies inside it
+// (PostingList::Serialize / Deserialize, src/index/posting_list.cpp:973-1102):
+//
+//   "MGIX" | u32 version (4) | u32 ngram_size | u32 kanji_ngram_size | u8 cross_boundary | u8 normalize_nfkc |
+//   u32 len + normalize_width | u8 normalize_lower | u64 term_count |
+//   term_count x ( u32 len + term | u64 body_len | body ) | u32 CRC32 of everything before it
+//   body = u8 strategy | u32 size | data
+//     strategy 0 (kFixedWidthDelta): size x u32 = first doc id, then the gaps (fixed width, not varint)
+//     strategy 1 (kRoaringBitmap):   size bytes of the Roaring portable interchange format
+//
+// All integers little-endian. The Roaring bytes come from CRoaring v4.6.1 in the reference (a pinned dependency that
+// is not in its tree, third_party/CMakeLists.txt:104-112); this file restates the published interchange format
+// (cookie 12346 / 12347, descriptive header, offset header, array / bitset / run containers). It is a data-format
+// codec, not a compute path: nothing here touches the device, and the search core never calls it.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <string_view>
+#include <vector>
+
+#include "../../include/mgx.h"
+#include "mgx_internal.cuh"
+
+namespace mgx {
+namespace {
+
+// ---- CRC-32 (the zlib polynomial the reference uses through utils/crc32.h), slicing-by-8
+struct Crc32Tables {
+  uint32_t t[8][256];
+  Crc32Tables() {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) {
+        c = (c & 1u) != 0 ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+      }
+      t[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i) {
+      for (int s = 1; s < 8; ++s) {
+        t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xFF];
+      }
+    }
+  }
+};
+
+uint32_t crc32(const uint8_t* p, uint64_t n) {
+  static const Crc32Tables tables;
+  const auto& t = tables.t;
+  uint32_t c = 0xFFFFFFFFu;
+  while (n >= 8) {
+    uint32_t lo;
+    uint32_t hi;
+    std::memcpy(&lo, p, 4);
+    std::memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = t[7][lo & 0xFF] ^ t[6][(lo >> 8) & 0xFF] ^ t[5][(lo >> 16) & 0xFF] ^ t[4][lo >> 24] ^ t[3][hi & 0xFF] ^
+        t[2][(hi >> 8) & 0xFF] ^ t[1][(hi >> 16) & 0xFF] ^ t[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n-- > 0) {
+    c = t[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  }
+  return c ^ 0xFFFFFFFFu;
+}
+
+constexpr uint32_t kArrayMax = 4096;            // a Roaring array container holds at most this many values
+constexpr uint32_t kBitsetBytes = 8192;         // 65536 bits
+constexpr uint32_t kCookieNoRuns = 12346;       // SERIAL_COOKIE_NO_RUNCONTAINER
+constexpr uint32_t kCookieRuns = 12347;         // SERIAL_COOKIE
+constexpr uint32_t kNoOffsetThreshold = 4;      // with runs, fewer containers carry no offset header
+constexpr uint32_t kAutoRoaringEntries = 4096;  // posting_list.cpp:21
+constexpr uint32_t kMaxTermLength = 10000;      // index_serialization.cpp:521
+constexpr uint64_t kMaxPostingBytes = 100000000ULL;  // :547
+
+// Bounded writer: counts always, stores while the bytes fit.
+struct Writer {
+  uint8_t* out;
+  uint64_t cap;
+  uint64_t pos = 0;
+  void bytes(const void* src, uint64_t n) {
+    if (out != nullptr && pos + n <= cap) {
+      std::memcpy(out + pos, src, n);
+    }
+    pos += n;
+  }
+  void u8(uint8_t v) { bytes(&v, 1); }
+  void u16(uint16_t v) {
+    const uint8_t b[2] = {static_cast<uint8_t>(v), static_cast<uint8_t>(v >> 8)};
+    bytes(b, 2);
+  }
+  void u32(uint32_t v) {
+    const uint8_t b[4] = {static_cast<uint8_t>(v), static_cast<uint8_t>(v >> 8), static_cast<uint8_t>(v >> 16),
+                          static_cast<uint8_t>(v >> 24)};
+    bytes(b, 4);
+  }
+  void u64(uint64_t v) {
+    u32(static_cast<uint32_t>(v));
+    u32(static_cast<uint32_t>(v >> 32));
+  }
+};
+
+// Size of the Roaring portable form of one ascending list (no run containers).
+uint64_t roaring_size(const uint32_t* ids, uint64_t n, uint32_t* n_containers) {
+  uint64_t bytes = 8;
+  uint32_t containers = 0;
+  for (uint64_t i = 0; i < n;) {
+    uint64_t j = i;
+    const uint32_t high = ids[i] >> 16;
+    while (j < n && (ids[j] >> 16) == high) {
+      ++j;
+    }
+    const uint64_t card = j - i;
+    bytes += 8 + (card > kArrayMax ? kBitsetBytes : card * 2);
+    ++containers;
+    i = j;
+  }
+  *n_containers = containers;
+  return bytes;
+}
+
+void write_roaring(Writer& w, const uint32_t* ids, uint64_t n, uint32_t n_containers) {
+  w.u32(kCookieNoRuns);
+  w.u32(n_containers);
+  for (uint64_t i = 0; i < n;) {  // descriptive header: key, cardinality - 1
+    uint64_t j = i;
+    const uint32_t high = ids[i] >> 16;
+    while (j < n && (ids[j] >> 16) == high) {
+      ++j;
+    }
+    w.u16(static_cast<uint16_t>(high));
+    w.u16(static_cast<uint16_t>(j - i - 1));
+    i = j;
+  }
+  uint32_t offset = 8 + n_containers * 8;
+  for (uint64_t i = 0; i < n;) {  // offset header: where each container starts, from the cookie
+    uint64_t j = i;
+    const uint32_t high = ids[i] >> 16;
+    while (j < n && (ids[j] >> 16) == high) {
+      ++j;
+    }
+    w.u32(offset);
+    offset += (j - i) > kArrayMax ? kBitsetBytes : static_cast<uint32_t>(j - i) * 2;
+    i = j;
+  }
+  std::vector<uint64_t> words;
+  for (uint64_t i = 0; i < n;) {
+    uint64_t j = i;
+    const uint32_t high = ids[i] >> 16;
+    while (j < n && (ids[j] >> 16) == high) {
+      ++j;
+    }
+    if (j - i > kArrayMax) {
+      words.assign(1024, 0);
+      for (uint64_t k = i; k < j; ++k) {
+        const uint32_t low = ids[k] & 0xFFFFu;
+        words[low >> 6] |= 1ULL << (low & 63);
+      }
+      for (uint64_t word : words) {
+        w.u64(word);
+      }
+    } else {
+      for (uint64_t k = i; k < j; ++k) {
+        w.u16(static_cast<uint16_t>(ids[k] & 0xFFFFu));
+      }
+    }
+    i = j;
+  }
+}
+
+struct Reader {
+  const uint8_t* p;
+  uint64_t n;
+  uint64_t pos = 0;
+  bool has(uint64_t k) const { return n - pos >= k; }
+  uint8_t u8() { return p[pos++]; }
+  uint16_t u16() {
+    const uint16_t v = static_cast<uint16_t>(p[pos] | (p[pos + 1] << 8));
+    pos += 2;
+    return v;
+  }
+  uint32_t u32() {
+    const uint32_t v = static_cast<uint32_t>(p[pos]) | (static_cast<uint32_t>(p[pos + 1]) << 8) |
+                       (static_cast<uint32_t>(p[pos + 2]) << 16) | (static_cast<uint32_t>(p[pos + 3]) << 24);
+    pos += 4;
+    return v;
+  }
+  uint64_t u64() {
+    const uint64_t lo = u32();
+    const uint64_t hi = u32();
+    return lo | (hi << 32);
+  }
+};
+
+int reject(const char* reference_code, const std::string& what) {
+  set_last_error(std::string("MGIX stream rejected (") + reference_code + "): " + what);
+  return MGX_ERR_FORMAT;
+}
+
+// One Roaring portable bitmap -> ascending ids appended to `out` (counted only when out == nullptr). Enforces what
+// roaring_bitmap_portable_deserialize_safe + roaring_bitmap_internal_validate do (posting_list.cpp:1082-1090).
+bool read_roaring(Reader r, uint64_t* count, uint32_t* out) {
+  if (!r.has(4)) {
+    return false;
+  }
+  const uint32_t cookie = r.u32();
+  uint32_t n = 0;
+  const uint8_t* run_flags = nullptr;
+  if ((cookie & 0xFFFFu) == kCookieRuns) {
+    n = (cookie >> 16) + 1;
+    const uint64_t flag_bytes = (n + 7) / 8;
+    if (!r.has(flag_bytes)) {
+      return false;
+    }
+    run_flags = r.p + r.pos;
+    r.pos += flag_bytes;
+  } else if (cookie == kCookieNoRuns) {
+    if (!r.has(4)) {
+      return false;
+    }
+    n = r.u32();
+    if (n > 65536) {
+      return false;
+    }
+  } else {
+    return false;
+  }
+  if (!r.has(static_cast<uint64_t>(n) * 4)) {
+    return false;
+  }
+  Reader header = r;
+  r.pos += static_cast<uint64_t>(n) * 4;
+  if (run_flags == nullptr || n >= kNoOffsetThreshold) {
+    if (!r.has(static_cast<uint64_t>(n) * 4)) {
+      return false;
+    }
+    r.pos += static_cast<uint64_t>(n) * 4;  // offsets serve random access only
+  }
+  uint64_t total = 0;
+  int64_t prev_key = -1;
+  for (uint32_t c = 0; c < n; ++c) {
+    const uint32_t key = header.u16();
+    const uint32_t card = static_cast<uint32_t>(header.u16()) + 1;
+    if (static_cast<int64_t>(key) <= prev_key) {
+      return false;  // keys strictly ascending
+    }
+    prev_key = key;
+    const uint32_t base = key << 16;
+    const bool is_run = run_flags != nullptr && ((run_flags[c / 8] >> (c % 8)) & 1) != 0;
+    if (is_run) {
+      if (!r.has(2)) {
+        return false;
+      }
+      const uint32_t n_runs = r.u16();
+      if (n_runs == 0 || !r.has(static_cast<uint64_t>(n_runs) * 4)) {
+        return false;
+      }
+      uint32_t seen = 0;
+      int64_t last_end = -2;
+      for (uint32_t i = 0; i < n_runs; ++i) {
+        const uint32_t start = r.u16();
+        const uint32_t len = r.u16();
+        if (static_cast<int64_t>(start) <= last_end + 1 || start + len > 65535) {
+          return false;  // runs ascending, disjoint and not adjacent
+        }
+        if (out != nullptr) {
+          for (uint32_t v = start; v <= start + len; ++v) {
+            out[total + seen + (v - start)] = base | v;
+          }
+        }
+        seen += len + 1;
+        last_end = start + len;
+      }
+      if (seen != card) {
+        return false;
+      }
+    } else if (card > kArrayMax) {
+      if (!r.has(kBitsetBytes)) {
+        return false;
+      }
+      uint32_t seen = 0;
+      for (uint32_t wi = 0; wi < 1024; ++wi) {
+        uint64_t word = r.u64();
+        while (word != 0) {
+          const uint32_t bit = static_cast<uint32_t>(__builtin_ctzll(word));
+          if (out != nullptr && seen < card) {
+            out[total + seen] = base | (wi << 6) | bit;
+          }
+          ++seen;
+          word &= word - 1;
+        }
+      }
+      if (seen != card) {
+        return false;
+      }
+    } else {
+      if (!r.has(static_cast<uint64_t>(card) * 2)) {
+        return false;
+      }
+      int64_t prev = -1;
+      for (uint32_t i = 0; i < card; ++i) {
+        const uint32_t v = r.u16();
+        if (static_cast<int64_t>(v) <= prev) {
+          return false;  // values strictly ascending
+        }
+        prev = v;
+        if (out != nullptr) {
+          out[total + i] = base | v;
+        }
+      }
+    }
+    total += card;
+  }
+  *count = total;
+  return true;
+}
+
+// PostingList::Deserialize (posting_list.cpp:1023-1102) of one body.
+bool read_posting(const uint8_t* body, uint64_t len, uint64_t* count, uint32_t* out) {
+  Reader r{body, len};
+  if (!r.has(1)) {
+    return false;
+  }
+  const uint8_t strategy = r.u8();
+  if (strategy > 1 || !r.has(4)) {
+    return false;
+  }
+  const uint32_t size = r.u32();
+  if (strategy == 0) {
+    if (size > (len - r.pos) / 4) {
+      return false;
+    }
+    uint64_t cumulative = 0;
+    for (uint32_t i = 0; i < size; ++i) {  // IsValidDeltaEncoding, posting_list.cpp:132-148
+      const uint32_t v = r.u32();
+      if (i > 0 && v == 0) {
+        return false;
+      }
+      cumulative += v;
+      if (cumulative > 0xFFFFFFFFULL) {
+        return false;
+      }
+      if (out != nullptr) {
+        out[i] = static_cast<uint32_t>(cumulative);
+      }
+    }
+    *count = size;
+    return true;
+  }
+  if (size > len - r.pos) {
+    return false;
+  }
+  return read_roaring(Reader{body + r.pos, size}, count, out);
+}
+
+}  // namespace
+}  // namespace mgx
+
+using namespace mgx;
+
+int mgx_mgix_encode(const mgx_mgix_info_t* info, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                    const uint64_t* posting_offsets, const uint32_t* postings, double roaring_min_len, uint8_t* out,
+                    uint64_t cap, uint64_t* out_len) {
+  if (info == nullptr || out_len == nullptr ||
+      (info->n_terms > 0 && (term_bytes == nullptr || term_offsets == nullptr || posting_offsets == nullptr))) {
+    set_last_error("null argument");
+    return MGX_ERR_INVALID_ARGUMENT;
+  }
+  *out_len = 0;
+  const size_t width_len = strnlen(info->normalize_width, sizeof(info->normalize_width));
+  Writer w{out, cap};
+  w.bytes("MGIX", 4);
+  w.u32(4);
+  w.u32(static_cast<uint32_t>(info->ngram_size));
+  w.u32(static_cast<uint32_t>(info->kanji_ngram_size));
+  w.u8(info->cross_boundary != 0 ? 1 : 0);
+  w.u8(info->normalize_nfkc != 0 ? 1 : 0);
+  w.u32(static_cast<uint32_t>(width_len));
+  w.bytes(info->normalize_width, width_len);
+  w.u8(info->normalize_lower != 0 ? 1 : 0);
+  w.u64(info->n_terms);
+  for (uint64_t t = 0; t < info->n_terms; ++t) {
+    const uint64_t tl = term_offsets[t + 1] - term_offsets[t];
+    const uint32_t* ids = postings + posting_offsets[t];
+    const uint64_t n = posting_offsets[t + 1] - posting_offsets[t];
+    for (uint64_t i = 1; i < n; ++i) {
+      if (ids[i] <= ids[i - 1]) {
+        set_last_error("posting list is not strictly ascending");
+        return MGX_ERR_INVALID_ARGUMENT;
+      }
+    }
+    w.u32(static_cast<uint32_t>(tl));
+    w.bytes(term_bytes + term_offsets[t], tl);
+    // the representation the reference's list would be in: Roaring above 4096 entries since insertion
+    // (posting_list.cpp:21,917-922), by density after Index::Optimize (:800-834)
+    const bool roaring = n > kAutoRoaringEntries || (roaring_min_len > 0.0 && static_cast<double>(n) >= roaring_min_len);
+    if (!roaring) {
+      w.u64(5 + n * 4);
+      w.u8(0);
+      w.u32(static_cast<uint32_t>(n));
+      for (uint64_t i = 0; i < n; ++i) {
+        w.u32(i == 0 ? ids[0] : ids[i] - ids[i - 1]);
+      }
+    } else {
+      uint32_t n_containers = 0;
+      const uint64_t rb = roaring_size(ids, n, &n_containers);
+      if (rb > 0xFFFFFFFFULL) {
+        set_last_error("roaring bitmap larger than 4 GiB (posting_list.cpp:1001-1008)");
+        return MGX_ERR_UNSUPPORTED;
+      }
+      w.u64(5 + rb);
+      w.u8(1);
+      w.u32(static_cast<uint32_t>(rb));
+      write_roaring(w, ids, n, n_containers);
+    }
+  }
+  const uint64_t payload = w.pos;
+  *out_len = payload + 4;
+  if (out == nullptr || *out_len > cap) {
+    set_last_error("output capacity too small");
+    return MGX_ERR_CAPACITY;
+  }
+  w.u32(crc32(out, payload));
+  return MGX_OK;
+}
+
+int mgx_mgix_decode(const uint8_t* data, uint64_t len, mgx_mgix_info_t* info, uint8_t* term_bytes,
+                    uint64_t* term_offsets, uint64_t* posting_offsets, uint32_t* postings) {
+  if (data == nullptr || info == nullptr) {
+    set_last_error("null argument");
+    return MGX_ERR_INVALID_ARGUMENT;
+  }
+  const bool fill = term_bytes != nullptr && term_offsets != nullptr && posting_offsets != nullptr &&
+                    postings != nullptr;
+  const mgx_mgix_info_t sized = *info;  // the sizes the caller allocated for (second call)
+  std::memset(info, 0, sizeof(*info));
+  // index_serialization.cpp:279-360
+  if (len < 20) {
+    return reject("kStorageInvalidFormat", "index data too short to be valid");
+  }
+  if (std::memcmp(data, "MGIX", 4) != 0) {
+    return reject("kStorageInvalidFormat", "invalid magic number");
+  }
+  Reader r{data, len};
+  r.pos = 4;
+  const uint32_t version = r.u32();
+  if (version < 1 || version > 4) {
+    return reject("kStorageVersionMismatch", "unsupported index format version " + std::to_string(version));
+  }
+  uint64_t data_size = len;
+  if (version >= 2) {
+    const uint64_t min_header = version == 4 ? 31 : (version == 3 ? 25 : 20);
+    if (len < min_header + 4) {
+      return reject("kStorageInvalidFormat", "index data missing CRC32 trailer");
+    }
+    data_size = len - 4;
+    Reader trailer{data, len};
+    trailer.pos = data_size;
+    if (trailer.u32() != crc32(data, data_size)) {
+      return reject("kStorageCRCMismatch", "CRC32 checksum mismatch in index data");
+    }
+  }
+  r.n = data_size;
+  info->version = version;
+  info->ngram_size = static_cast<int32_t>(r.u32());
+  info->kanji_ngram_size = info->ngram_size;
+  info->cross_boundary = 1;
+  if (version >= 3) {
+    info->kanji_ngram_size = static_cast<int32_t>(r.u32());
+    info->cross_boundary = r.u8() != 0 ? 1 : 0;
+    if (version == 4) {
+      info->normalize_nfkc = r.u8() != 0 ? 1 : 0;
+      const uint32_t width_len = r.u32();
+      if (width_len > data_size - r.pos - 1) {
+        return reject("kStorageInvalidFormat", "normalize_width length exceeds payload size");
+      }
+      if (width_len >= sizeof(info->normalize_width)) {
+        set_last_error("normalize_width longer than 31 bytes is not supported");
+        return MGX_ERR_UNSUPPORTED;
+      }
+      std::memcpy(info->normalize_width, data + r.pos, width_len);
+      r.pos += width_len;
+      info->normalize_lower = r.u8() != 0 ? 1 : 0;
+    }
+  }
+  if (r.pos > data_size || data_size - r.pos < 8) {
+    return reject("kStorageInvalidFormat", "index data is truncated before term count");
+  }
+  const uint64_t term_count = r.u64();
+  struct Record {
+    std::string_view term;
+    const uint8_t* body;
+    uint64_t body_len;
+    uint64_t count;
+  };
+  std::vector<Record> records;
+  records.reserve(static_cast<size_t>(std::min<uint64_t>(term_count, (data_size - r.pos) / 17 + 1)));
+  uint64_t total_term_bytes = 0;
+  uint64_t total_postings = 0;
+  for (uint64_t i = 0; i < term_count; ++i) {
+    if (!r.has(4)) {
+      return reject("kStorageCorrupted", "truncated index data at term header");
+    }
+    const uint32_t term_len = r.u32();
+    if (term_len > kMaxTermLength) {
+      return reject("kStorageCorrupted", "term length exceeds maximum allowed size");
+    }
+    if (!r.has(term_len)) {
+      return reject("kStorageCorrupted", "truncated index data at term string");
+    }
+    Record rec;
+    rec.term = std::string_view(reinterpret_cast<const char*>(data) + r.pos, term_len);
+    r.pos += term_len;
+    if (!r.has(8)) {
+      return reject("kStorageCorrupted", "truncated index data at posting list header");
+    }
+    rec.body_len = r.u64();
+    if (rec.body_len > kMaxPostingBytes) {
+      return reject("kStorageCorrupted", "posting list size exceeds maximum allowed size");
+    }
+    if (!r.has(rec.body_len)) {
+      return reject("kStorageCorrupted", "truncated index data at posting list body");
+    }
+    rec.body = data + r.pos;
+    r.pos += rec.body_len;
+    rec.count = 0;
+    if (!read_posting(rec.body, rec.body_len, &rec.count, nullptr)) {
+      return reject("kIndexDeserializationFailed", "failed to deserialize posting list of term " + std::string(rec.term));
+    }
+    total_term_bytes += term_len;
+    total_postings += rec.count;
+    records.push_back(rec);
+  }
+  // canonical order: ascending term bytes (the reference writes its hash map's order); a repeated term keeps its
+  // LAST record, as new_postings[term] = ... does (:573)
+  std::vector<uint32_t> order(records.size());
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(),
+                   [&](uint32_t a, uint32_t b) { return records[a].term < records[b].term; });
+  std::vector<uint32_t> kept;
+  kept.reserve(order.size());
+  for (size_t i = 0; i < order.size(); ++i) {
+    if (i + 1 < order.size() && records[order[i + 1]].term == records[order[i]].term) {
+      total_term_bytes -= records[order[i]].term.size();
+      total_postings -= records[order[i]].count;
+      continue;
+    }
+    kept.push_back(order[i]);
+  }
+  info->n_terms = kept.size();
+  info->n_postings = total_postings;
+  info->term_bytes = total_term_bytes;
+  if (!fill) {
+    return MGX_OK;
+  }
+  if (sized.n_terms < info->n_terms || sized.n_postings < info->n_postings || sized.term_bytes < info->term_bytes) {
+    set_last_error("output capacity too small (call once without outputs for the sizes)");
+    return MGX_ERR_CAPACITY;
+  }
+  uint64_t tb = 0;
+  uint64_t pp = 0;
+  for (size_t i = 0; i < kept.size(); ++i) {
+    const Record& rec = records[kept[i]];
+    term_offsets[i] = tb;
+    posting_offsets[i] = pp;
+    std::memcpy(term_bytes + tb, rec.term.data(), rec.term.size());
+    tb += rec.term.size();
+    uint64_t count = 0;
+    read_posting(rec.body, rec.body_len, &count, postings + pp);
+    pp += count;
+  }
+  term_offsets[kept.size()] = tb;
+  posting_offsets[kept.size()] = pp;
+  return MGX_OK;
+}

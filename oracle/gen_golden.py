@@ -126,5 +126,41 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 
+def gen_mgix():
+    """tests/golden/ref_mgix.json: Index::SaveToStream output of the reference's own sources for two small indexes
+    (one with a list above 4096 entries, i.e. a Roaring body with a bitset container), with the CSR the reference
+    itself reports (PostingList::GetAll per term)."""
+    import zlib
+    from pyoracle import PORT_LIB
+    ref, port = OracleLib(REF_LIB), OracleLib(PORT_LIB)
+    rnd = random.Random(0x316)
+    words = ["".join(rnd.choice("abcde") for _ in range(3)) for _ in range(20)]
+    big = [("zq" + rnd.choice(words)).encode() for _ in range(4500)]
+    small = [rand_text(rnd, 12, False) for _ in range(150)]
+    out = {"generator": "oracle/gen_golden.py mgix", "cases": []}
+    for cfg, docs, first in (((2, 0, True), big, 1), ((2, 1, True), small, 100)):
+        ids = np.arange(first, first + len(docs), dtype=np.uint32)
+        ri, pi = ref.index(*cfg), port.index(*cfg)
+        ri.add_texts(ids, docs)
+        pi.add_texts(ids, docs)
+        terms = [bytes(t) for t in pi.export()[0]]  # the reference has no term enumeration besides the stream itself
+        assert len(terms) == ri.term_count()
+        posts = [ri.postings(t) for t in terms]
+        offs = np.concatenate([[0], np.cumsum([p.size for p in posts])]).astype(np.uint64)
+        flat = np.concatenate(posts).astype(np.uint32)
+        out["cases"].append({"config": [cfg[0], cfg[1] if cfg[1] > 0 else cfg[0], int(cfg[2])],
+                             "stream_b64": base64.b64encode(ri.save_stream()).decode(),
+                             "terms_hex": [t.hex() for t in terms], "posting_offsets": offs.tolist(),
+                             "n_postings": int(flat.size), "postings_crc32": zlib.crc32(flat.tobytes()),
+                             "largest_list": int(max(p.size for p in posts))})
+    path = os.path.join(OUT, "ref_mgix.json")
+    json.dump(out, open(path, "w"), indent=0)
+    print("ref_mgix.json", os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "mgix":
+        gen_mgix()
+    else:
+        main()
+        gen_mgix()

@@ -416,6 +416,25 @@ class OracleIndex:
                 return out[:n].copy()
             cap = int(n)
 
+    # ---- MGIX stream (reference sources only: Index::SaveToStream / LoadFromStream) ----
+    def save_stream(self):
+        f = self.L.lib.ref_index_save_stream
+        f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, u8p, C.c_uint64]
+        n = f(self.h, None, 0)
+        assert n > 0, "SaveToStream failed"
+        out = np.zeros(n, dtype=np.uint8)
+        assert f(self.h, _ptr(out, u8p), n) == n
+        return out.tobytes()
+
+    def load_stream(self, data):
+        """Returns 0 on success, else the reference's ErrorCode."""
+        f = self.L.lib.ref_index_load_stream
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, u8p, C.c_uint64]
+        buf = np.frombuffer(bytes(data), dtype=np.uint8).copy() if len(data) else np.zeros(1, np.uint8)
+        return int(f(self.h, _ptr(buf, u8p), len(data)))
+
     def _pipeline_params(self, raw_ngram, raw_kanji, verify_text):
         return QueryParams(self.ngram_size if raw_ngram is None else raw_ngram,
                            self.kanji_ngram_size if raw_kanji is None else raw_kanji, int(self.cross_boundary),

@@ -19,6 +19,7 @@
 #include <atomic>
 #include <cstring>
 #include <memory>
+#include <sstream>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -599,6 +600,27 @@ uint64_t orc_search_synonyms(const orc_index_t* idx, const orc_query_params_t* p
     result.results.clear();
   }
   return CopyOut(result.results, out, cap);
+}
+
+// Index::SaveToStream / LoadFromStream (index_serialization.cpp:111-224, 279-613): the MGIX v4 stream of the index
+// (reference-only entry points: the MGIX codec of the product is checked against the reference itself).
+// save: returns the stream length (bytes copied if it fits `cap`), 0 on failure.
+uint64_t ref_index_save_stream(const orc_index_t* idx, uint8_t* out, uint64_t cap) {
+  std::ostringstream stream(std::ios::binary);
+  if (!idx->index->SaveToStream(stream)) {
+    return 0;
+  }
+  const std::string bytes = stream.str();
+  if (out != nullptr && bytes.size() <= cap) {
+    std::memcpy(out, bytes.data(), bytes.size());
+  }
+  return bytes.size();
+}
+// load: replaces the index content; returns 0 on success, the reference's ErrorCode otherwise.
+int ref_index_load_stream(orc_index_t* idx, const uint8_t* data, uint64_t len) {
+  std::istringstream stream(std::string(reinterpret_cast<const char*>(data), len), std::ios::binary);
+  auto loaded = idx->index->LoadFromStream(stream);
+  return loaded ? 0 : static_cast<int>(loaded.error().code());
 }
 
 }  // extern "C"

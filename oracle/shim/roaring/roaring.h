@@ -12,9 +12,10 @@
 // restates the published Roaring layout (Chambi/Lemire et al.): a sorted
 // vector of 64Ki-wide chunks keyed by the high 16 bits, each chunk either a
 // sorted uint16 array (<= 4096 values) or a 65536-bit bitset. Run containers
-// are not implemented (`run_optimize` is a no-op), and the portable
-// serialisation below is a private byte layout -- DUMP byte compatibility is
-// out of scope. Set results are identical by construction;
+// are not implemented (`run_optimize` is a no-op); the portable
+// serialisation follows the published Roaring interchange format (written
+// without run containers, read with them), so MGIX streams of this build and
+// of a CRoaring build are mutually readable. Set results are identical by construction;
 // CPU timings taken with it are labelled "reference sources + Roaring shim".
 #pragma once
 
@@ -441,75 +442,169 @@ inline bool roaring_bitmap_run_optimize(roaring_bitmap_t* /*r*/) { return false;
 // Private (non-CRoaring) byte layout: u32 n_chunks, then per chunk
 // u16 key, u32 card, u16 values[card]. Only used for size accounting and
 // same-process round trips.
+// Portable serialisation in the published Roaring interchange format (RoaringFormatSpec): this shim only ever
+// WRITES the layout without run containers
+//   u32 cookie 12346 | u32 n | n x (u16 key, u16 cardinality-1) | n x u32 byte offset | containers
+//   (cardinality <= 4096: sorted u16 values; else 1024 x u64 bitset words)
+// and READS that one plus the run-container layout CRoaring emits after run_optimize
+//   u32 (12347 | (n-1) << 16) | ceil(n/8) run-flag bytes | n x (u16 key, u16 cardinality-1) |
+//   [n >= 4: n x u32 offset] | containers (run: u16 n_runs, n_runs x (u16 start, u16 length-1)).
 inline size_t roaring_bitmap_portable_size_in_bytes(const roaring_bitmap_t* r) {
-  size_t total = sizeof(uint32_t);
+  size_t total = 8 + r->chunks.size() * 8;
   for (const auto& chunk : r->chunks) {
-    // report what CRoaring would hold in memory for this container shape
-    total += sizeof(uint16_t) + sizeof(uint32_t) +
-             (chunk.is_bitset() ? static_cast<size_t>(roaring_shim::kWords) * 8 : static_cast<size_t>(chunk.card) * 2);
+    total += chunk.is_bitset() ? static_cast<size_t>(roaring_shim::kWords) * 8 : static_cast<size_t>(chunk.card) * 2;
   }
   return total;
 }
 inline size_t roaring_bitmap_portable_serialize(const roaring_bitmap_t* r, char* buf) {
   char* out = buf;
-  const uint32_t n = static_cast<uint32_t>(r->chunks.size());
-  std::memcpy(out, &n, 4);
-  out += 4;
-  for (const auto& chunk : r->chunks) {
-    std::memcpy(out, &chunk.key, 2);
+  auto put16 = [&](uint16_t v) {
+    out[0] = static_cast<char>(v & 0xFF);
+    out[1] = static_cast<char>(v >> 8);
     out += 2;
-    std::memcpy(out, &chunk.card, 4);
-    out += 4;
+  };
+  auto put32 = [&](uint32_t v) {
+    put16(static_cast<uint16_t>(v & 0xFFFF));
+    put16(static_cast<uint16_t>(v >> 16));
+  };
+  const uint32_t n = static_cast<uint32_t>(r->chunks.size());
+  put32(12346u);
+  put32(n);
+  for (const auto& chunk : r->chunks) {
+    put16(chunk.key);
+    put16(static_cast<uint16_t>(chunk.card - 1));
+  }
+  uint32_t offset = 8 + n * 8;
+  for (const auto& chunk : r->chunks) {
+    put32(offset);
+    offset += chunk.is_bitset() ? roaring_shim::kWords * 8 : chunk.card * 2;
+  }
+  for (const auto& chunk : r->chunks) {
     if (chunk.is_bitset()) {
-      std::memcpy(out, chunk.bits.data(), static_cast<size_t>(roaring_shim::kWords) * 8);
-      out += static_cast<size_t>(roaring_shim::kWords) * 8;
+      for (uint64_t w : chunk.bits) {
+        put32(static_cast<uint32_t>(w & 0xFFFFFFFFu));
+        put32(static_cast<uint32_t>(w >> 32));
+      }
     } else {
-      std::memcpy(out, chunk.arr.data(), static_cast<size_t>(chunk.card) * 2);
-      out += static_cast<size_t>(chunk.card) * 2;
+      for (uint16_t v : chunk.arr) {
+        put16(v);
+      }
     }
   }
   return static_cast<size_t>(out - buf);
 }
 inline roaring_bitmap_t* roaring_bitmap_portable_deserialize_safe(const char* buf, size_t maxbytes) {
-  if (maxbytes < 4) {
+  const unsigned char* in = reinterpret_cast<const unsigned char*>(buf);
+  const unsigned char* end = in + maxbytes;
+  auto need = [&](size_t k) { return static_cast<size_t>(end - in) >= k; };
+  auto get16 = [&]() {
+    const uint16_t v = static_cast<uint16_t>(in[0] | (in[1] << 8));
+    in += 2;
+    return v;
+  };
+  auto get32 = [&]() {
+    const uint32_t lo = get16();
+    const uint32_t hi = get16();
+    return lo | (hi << 16);
+  };
+  if (!need(4)) {
     return nullptr;
   }
-  const char* in = buf;
-  const char* end = buf + maxbytes;
+  const uint32_t cookie = get32();
   uint32_t n = 0;
-  std::memcpy(&n, in, 4);
-  in += 4;
+  std::vector<uint8_t> run_flags;
+  bool has_runs = false;
+  if ((cookie & 0xFFFF) == 12347u) {
+    has_runs = true;
+    n = (cookie >> 16) + 1;
+    const size_t flag_bytes = (n + 7) / 8;
+    if (!need(flag_bytes)) {
+      return nullptr;
+    }
+    run_flags.assign(in, in + flag_bytes);
+    in += flag_bytes;
+  } else if (cookie == 12346u) {
+    if (!need(4)) {
+      return nullptr;
+    }
+    n = get32();
+    if (n > 65536) {
+      return nullptr;
+    }
+  } else {
+    return nullptr;
+  }
+  if (!need(static_cast<size_t>(n) * 4)) {
+    return nullptr;
+  }
   auto out = std::make_unique<roaring_bitmap_t>();
+  out->chunks.resize(n);
   for (uint32_t c = 0; c < n; ++c) {
-    if (end - in < 6) {
+    out->chunks[c].key = get16();
+    out->chunks[c].card = static_cast<uint32_t>(get16()) + 1;
+  }
+  if (!has_runs || n >= 4) {
+    if (!need(static_cast<size_t>(n) * 4)) {
       return nullptr;
     }
-    roaring_shim::Chunk chunk;
-    std::memcpy(&chunk.key, in, 2);
-    in += 2;
-    std::memcpy(&chunk.card, in, 4);
-    in += 4;
-    if (chunk.card == 0 || chunk.card > 65536) {
-      return nullptr;
-    }
-    if (chunk.card > roaring_shim::kArrayMax) {
+    in += static_cast<size_t>(n) * 4;  // the offset header only serves random access
+  }
+  for (uint32_t c = 0; c < n; ++c) {
+    roaring_shim::Chunk& chunk = out->chunks[c];
+    const bool is_run = has_runs && ((run_flags[c / 8] >> (c % 8)) & 1) != 0;
+    if (is_run) {
+      if (!need(2)) {
+        return nullptr;
+      }
+      const uint32_t n_runs = get16();
+      if (!need(static_cast<size_t>(n_runs) * 4)) {
+        return nullptr;
+      }
+      std::vector<uint16_t> values;
+      uint32_t next_free = 0;
+      for (uint32_t i = 0; i < n_runs; ++i) {
+        const uint32_t start = get16();
+        const uint32_t len = get16();
+        if (start < next_free || start + len > 65535) {
+          return nullptr;
+        }
+        for (uint32_t v = start; v <= start + len; ++v) {
+          values.push_back(static_cast<uint16_t>(v));
+        }
+        next_free = start + len + 1;
+      }
+      if (values.size() != chunk.card) {
+        return nullptr;
+      }
+      chunk.arr = std::move(values);
+      if (chunk.card > roaring_shim::kArrayMax) {
+        chunk.to_bitset();
+      }
+    } else if (chunk.card > roaring_shim::kArrayMax) {
       const size_t bytes = static_cast<size_t>(roaring_shim::kWords) * 8;
-      if (static_cast<size_t>(end - in) < bytes) {
+      if (!need(bytes)) {
         return nullptr;
       }
       chunk.bits.resize(roaring_shim::kWords);
-      std::memcpy(chunk.bits.data(), in, bytes);
-      in += bytes;
+      uint32_t pop = 0;
+      for (uint32_t w = 0; w < roaring_shim::kWords; ++w) {
+        const uint64_t lo = get32();
+        const uint64_t hi = get32();
+        chunk.bits[w] = lo | (hi << 32);
+        pop += static_cast<uint32_t>(__builtin_popcountll(chunk.bits[w]));
+      }
+      if (pop != chunk.card) {
+        return nullptr;
+      }
     } else {
-      const size_t bytes = static_cast<size_t>(chunk.card) * 2;
-      if (static_cast<size_t>(end - in) < bytes) {
+      if (!need(static_cast<size_t>(chunk.card) * 2)) {
         return nullptr;
       }
       chunk.arr.resize(chunk.card);
-      std::memcpy(chunk.arr.data(), in, bytes);
-      in += bytes;
+      for (uint32_t i = 0; i < chunk.card; ++i) {
+        chunk.arr[i] = get16();
+      }
     }
-    out->chunks.push_back(std::move(chunk));
   }
   return out.release();
 }

@@ -100,3 +100,37 @@ def test_fuzzy_and_synonyms_with_filters_dense_lists_and_invalid_utf8(mgx, oracl
             assert np.array_equal(g2.search_fuzzy([term], 1), want), (cfg, term)
             want, _ = o2.search_synonyms([[term, d[:3]]], verify_text=1)
             assert np.array_equal(g2.search_synonyms([[term, d[:3]]], verify_text=1), want), (cfg, term)
+
+
+def test_device_index_saves_an_mgix_stream(mgx, oracle):
+    """mgx_index_save_mgix (Index::SaveToStream, index_serialization.cpp:111-224): the stream of a device-built index
+    decodes to the oracle's CSR, follows the representation rule after Optimize, and — where the reference's own
+    sources are built (oracle/_ref) — loads into the reference's Index::LoadFromStream and answers like it."""
+    import os
+
+    import pyoracle
+    from test_mgix_codec import big_corpus, csr_of
+    docs, ids = big_corpus(21)
+    for cfg in [(2, 0, True), (2, 1, True)]:
+        gi, oi = build_pair(mgx, oracle, docs, ids, cfg)
+        terms, offs, posts = csr_of(oi)
+        stream = gi.save_mgix()
+        meta, t2, o2, p2 = mgx.mgix_decode(stream)
+        assert t2 == terms and np.array_equal(o2, offs) and np.array_equal(p2, posts)
+        assert (meta["ngram_size"], meta["kanji_ngram_size"]) == (cfg[0], cfg[1] if cfg[1] > 0 else cfg[0])
+        assert stream == mgx.mgix_encode(terms, offs, posts, cfg[0], meta["kanji_ngram_size"], cfg[2])
+        gi.optimize(500)  # lists of >= 0.18 * 500 entries become Roaring bodies (posting_list.cpp:800-834)
+        optimized = gi.save_mgix()
+        assert optimized == mgx.mgix_encode(terms, offs, posts, cfg[0], meta["kanji_ngram_size"], cfg[2],
+                                            roaring_min_len=0.18 * 500)
+        assert optimized != stream and np.array_equal(mgx.mgix_decode(optimized)[3], posts)
+        if os.path.exists(pyoracle.REF_LIB):
+            ri = pyoracle.OracleLib(pyoracle.REF_LIB).index(*cfg)
+            assert ri.load_stream(stream) == 0 and ri.term_count() == len(terms)
+            rnd = random.Random(3)
+            for _ in range(40):
+                pick = [terms[rnd.randrange(len(terms))] for _ in range(2)]
+                assert np.array_equal(ri.search_and(pick), gi.search_and(pick))
+    empty = mgx.Index(2, 0, True)
+    meta, terms, offs, posts = mgx.mgix_decode(empty.save_mgix())
+    assert meta["n_terms"] == 0 and posts.size == 0
