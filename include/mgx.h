@@ -350,10 +350,11 @@ typedef struct {
 /* search_pipeline::ExecuteWithFuzzy (server/search_pipeline.cpp:1659-1740): per (normalised) search term the
  * documents holding at least max(1, |ngrams| - max_distance * effective_ngram_size) of its n-grams
  * (Index::SearchByThreshold), AND-ed over the terms; then NOT terms, column conditions and — when a term has a
- * hybrid fragment no n-gram covers — the exact text match of every term (:1728-1737). A term too short for an
- * n-gram, or no term at all, gives the empty result (empty_term_detected). Output: ascending doc ids.
- * verify_text that applies to the terms needs the edit-distance verification of PostFilterByFuzzyText
- * (:1742-1752), which is not built: MGX_ERR_UNSUPPORTED, never an unverified answer. */
+ * hybrid fragment no n-gram covers — the exact text match of every term (:1728-1737). When verify_text applies to
+ * the terms, PostFilterByFuzzyText (:1742-1752) runs on the device as well: a document stays if every term occurs
+ * in its text or a whitespace-delimited word of the text is within max_distance edits of it (ContainsFuzzyMatch,
+ * utils/edit_distance.cpp; terms of at most 64 code points, else MGX_ERR_UNSUPPORTED). A term too short for an
+ * n-gram, or no term at all, gives the empty result (empty_term_detected). Output: ascending doc ids. */
 int mgx_search_fuzzy(const mgx_index_t* index, const mgx_expanded_query_t* query, const uint8_t* term_bytes,
                      const uint64_t* term_offsets, uint64_t n_terms, uint32_t max_distance, uint32_t* out,
                      uint64_t cap, uint64_t* out_count);

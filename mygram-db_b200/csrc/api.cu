@@ -367,6 +367,10 @@ int analyse_program(const int32_t* ops, const int32_t* args, uint64_t n_ops, uin
       if (args[i] < 0 || static_cast<uint64_t>(args[i]) >= n_terms) {
         return invalid("boolean program: TERM index out of range");
       }
+    } else if (ops[i] == kOpFuzzyText) {
+      if (args[i] < 0 || static_cast<uint64_t>(args[i] & 0xFFFFFF) >= n_terms) {
+        return invalid("boolean program: FUZZYTEXT term index out of range");
+      }
     } else if (ops[i] == kOpAnd || ops[i] == kOpOr || ops[i] == kOpAtLeast) {
       const int32_t n_kids = ops[i] == kOpAtLeast ? (args[i] & 0xFFFF) : args[i];
       if (args[i] < 0 || static_cast<size_t>(n_kids) > stack.size()) {
@@ -533,6 +537,9 @@ int compile_range(const Index& ix, const mgx_query_params_t& p, uint64_t q_first
       }
       for (uint64_t i = 0; i < pn; ++i) {
         const int32_t op = ext->prog_ops[p0 + i];
+        if (op == kOpFuzzyText) {
+          return invalid("boolean program: FUZZYTEXT nodes are built by mgx_search_fuzzy only");
+        }
         hq.prog_ops.push_back(static_cast<uint8_t>(op));
         hq.prog_args.push_back(op == kOpTerm ? hq.terms[static_cast<size_t>(ext->prog_args[p0 + i])]
                                              : static_cast<uint32_t>(ext->prog_args[p0 + i]));
@@ -1550,10 +1557,9 @@ int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq,
   if (n_terms == 0) {
     return MGX_OK;  // search_pipeline.cpp:1667-1670
   }
-  if (should_verify(eq->verify_text, term_bytes, term_offsets, n_terms)) {
-    // PostFilterByFuzzyText (:1742-1752) needs ContainsFuzzyMatch (utils/edit_distance.cpp) per candidate text
-    set_last_error("fuzzy search with verify_text on (edit-distance verification) is not built on the device");
-    return MGX_ERR_UNSUPPORTED;
+  const bool fuzzy_verify = should_verify(eq->verify_text, term_bytes, term_offsets, n_terms);
+  if (fuzzy_verify && max_distance > 127) {
+    return invalid("max_distance above 127");
   }
   if (int rc = commit_pending(index); rc != MGX_OK) {
     return rc;
@@ -1608,6 +1614,25 @@ int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq,
       ++children;
       hybrid_exact |= has_uncovered_hybrid_fragment(tb, tl, eq->ngram_size, eq->kanji_ngram_size,
                                                     eq->cross_boundary != 0);
+    }
+    if (fuzzy_verify) {
+      // PostFilterByFuzzyText (:1742-1752): every term occurs in the text exactly, or a word of the text is within
+      // max_distance edits of it (ContainsFuzzyMatch, utils/edit_distance.cpp)
+      for (uint64_t t = 0; t < n_terms; ++t) {
+        const uint8_t* tb = term_bytes + term_offsets[t];
+        const uint64_t tl = term_offsets[t + 1] - term_offsets[t];
+        if (host_utf8_to_codepoints(tb, tl).size() > kFuzzyMaxTermCps) {
+          set_last_error("fuzzy verification of a term longer than 64 code points is not supported");
+          return MGX_ERR_UNSUPPORTED;
+        }
+        HostTerm exact;
+        exact.bytes.assign(reinterpret_cast<const char*>(tb), tl);
+        const int32_t tid = static_cast<int32_t>(pb.terms.size());
+        pb.leaf(std::move(exact));
+        pb.node(kOpFuzzyText, tid | static_cast<int32_t>(max_distance << 24));  // same term bytes, fuzzy test
+        pb.node(kOpOr, 2);
+        ++children;
+      }
     }
     if (hybrid_exact) {  // RequiresExactTextForHybridFragments -> PostFilterByText (:1728-1737): every term, exactly
       for (uint64_t t = 0; t < n_terms; ++t) {

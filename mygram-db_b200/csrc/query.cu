@@ -1771,6 +1771,131 @@ __device__ bool program_term_holds(const IndexView& iv, const BatchView& bv, uin
   return true;
 }
 
+// Bytes of the whitespace unit that starts at text[i] (0 = none): the delimiters of ContainsFuzzyMatch after its
+// NormalizeUnicodeWhitespace pass (utils/edit_distance.cpp: " \t\r\n", U+3000 as E3 80 80 and U+00A0 as C2 A0, both
+// matched on raw bytes with the same bounds checks).
+__device__ __forceinline__ uint32_t fuzzy_ws_len(const uint8_t* text, uint64_t i, uint64_t e) {
+  const uint32_t b = __ldg(text + i);
+  if (b == ' ' || b == '\t' || b == '\r' || b == '\n') {
+    return 1;
+  }
+  if (b == 0xE3u && i + 2 < e && __ldg(text + i + 1) == 0x80u && __ldg(text + i + 2) == 0x80u) {
+    return 3;
+  }
+  if (b == 0xC2u && i + 1 < e && __ldg(text + i + 1) == 0xA0u) {
+    return 2;
+  }
+  return 0;
+}
+
+// One row of the edit-distance recurrence: dp[j] = distance between the characters consumed so far and term[0..j).
+__device__ __forceinline__ void fuzzy_row(uint16_t* dp, const uint32_t* tcp, uint32_t tl, uint32_t c, uint16_t first) {
+  uint16_t prev = dp[0];
+  dp[0] = first;
+  for (uint32_t j = 0; j < tl; ++j) {
+    const uint16_t cost = tcp[j] == c ? 0 : 1;
+    const uint16_t v = min(min(static_cast<uint16_t>(dp[j + 1] + 1), static_cast<uint16_t>(dp[j] + 1)),
+                           static_cast<uint16_t>(prev + cost));
+    prev = dp[j + 1];
+    dp[j + 1] = v;
+  }
+}
+
+// ContainsFuzzyMatch(text, term, d), utils/edit_distance.cpp: the text is cut into whitespace-delimited words; an
+// all-ASCII word matches when its Levenshtein distance to the term (in code points) is <= d; a word with non-ASCII
+// characters matches when one of its code-point windows of length |term| - d .. |term| + d does. The window test is
+// evaluated as approximate substring matching (first column held at 0): a window within distance d of the term has a
+// length within d of the term's by itself, and for |term| <= d every one-character window already matches, so the
+// two formulations accept the same words. Code points follow Utf8ToCodepoints (invalid bytes skipped one at a time).
+__device__ __noinline__ bool fuzzy_text_holds(const IndexView& iv, const BatchView& bv, uint32_t tid, uint32_t d,
+                                              uint32_t doc) {
+  const uint32_t tb0 = bv.term_boff[tid];
+  const uint32_t tbytes = bv.term_boff[tid + 1] - tb0;
+  if (tbytes == 0) {
+    return true;
+  }
+  const uint64_t b = iv.text_off[doc];
+  const uint64_t e = iv.text_off[doc + 1];
+  if (e == b) {
+    return false;
+  }
+  uint32_t tcp[kFuzzyMaxTermCps];
+  uint32_t tl = 0;
+  {
+    const uint8_t* term = bv.term_bytes + tb0;
+    uint32_t i = 0;
+    while (i < tbytes && tl < kFuzzyMaxTermCps) {
+      const uint32_t avail = tbytes - i;
+      uint32_t cp = 0;
+      const int n = parse_utf8(__ldg(term + i), avail > 1 ? __ldg(term + i + 1) : 0, avail > 2 ? __ldg(term + i + 2) : 0,
+                               avail > 3 ? __ldg(term + i + 3) : 0, avail, &cp);
+      if (n > 0) {
+        tcp[tl++] = cp;
+        i += static_cast<uint32_t>(n);
+      } else {
+        ++i;
+      }
+    }
+  }
+  uint16_t dp[kFuzzyMaxTermCps + 1];
+  const uint8_t* text = iv.text;
+  uint64_t i = b;
+  while (i < e) {
+    uint32_t w = fuzzy_ws_len(text, i, e);
+    if (w != 0) {
+      i += w;
+      continue;
+    }
+    const uint64_t ws = i;
+    bool ascii = true;
+    while (i < e && fuzzy_ws_len(text, i, e) == 0) {
+      ascii = ascii && __ldg(text + i) < 0x80u;
+      ++i;
+    }
+    const uint64_t we = i;
+    for (uint32_t j = 0; j <= tl; ++j) {
+      dp[j] = static_cast<uint16_t>(j);
+    }
+    if (ascii) {
+      const uint64_t wl = we - ws;
+      const uint64_t diff = wl > tl ? wl - tl : tl - wl;
+      if (diff > d) {
+        continue;
+      }
+      for (uint64_t p = ws; p < we; ++p) {
+        fuzzy_row(dp, tcp, tl, __ldg(text + p), static_cast<uint16_t>(p - ws + 1));
+      }
+      if (dp[tl] <= d) {
+        return true;
+      }
+    } else {
+      uint64_t p = ws;
+      while (p < we) {
+        const uint64_t avail = we - p;
+        uint32_t cp = 0;
+        const int n = parse_utf8(__ldg(text + p), avail > 1 ? __ldg(text + p + 1) : 0, avail > 2 ? __ldg(text + p + 2) : 0,
+                                 avail > 3 ? __ldg(text + p + 3) : 0, avail, &cp);
+        if (n == 0) {
+          ++p;
+          continue;
+        }
+        p += static_cast<uint64_t>(n);
+        if (tl == 0) {
+          if (d >= 1) {
+            return true;  // a one-character window against an empty term: distance 1
+          }
+          break;
+        }
+        fuzzy_row(dp, tcp, tl, cp, 0);
+        if (dp[tl] <= d) {
+          return true;
+        }
+      }
+    }
+  }
+  return false;
+}
+
 // Postfix evaluation with a 64-bit stack (bit 0 = top). AND / OR of zero children and NOT without a child are
 // false, as QueryNode::Evaluate returns an empty set for them (query_ast.cpp:96-140).
 __device__ bool eval_program(const IndexView& iv, const BatchView& bv, uint32_t p0, uint32_t p1, uint32_t doc) {
@@ -1781,6 +1906,9 @@ __device__ bool eval_program(const IndexView& iv, const BatchView& bv, uint32_t 
     const uint32_t arg = bv.prog_arg[i];
     if (op == kOpTerm) {
       stack = (stack << 1) | (program_term_holds(iv, bv, arg, doc) ? 1ULL : 0ULL);
+      ++sp;
+    } else if (op == kOpFuzzyText) {
+      stack = (stack << 1) | (fuzzy_text_holds(iv, bv, arg & 0xFFFFFFu, arg >> 24, doc) ? 1ULL : 0ULL);
       ++sp;
     } else if (op == kOpAnd || op == kOpOr || op == kOpAtLeast) {
       const uint32_t n = op == kOpAtLeast ? (arg & 0xFFFFu) : arg;

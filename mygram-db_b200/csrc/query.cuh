@@ -71,6 +71,11 @@ constexpr uint8_t kOpNot = 3;   // one child
 // at least t of n children (Index::SearchByThreshold as a node: the per-term candidate rule of
 // search_pipeline::ExecuteWithFuzzy, search_pipeline.cpp:1696-1702): arg = n | (t << 16)
 constexpr uint8_t kOpAtLeast = 4;
+// the stored text holds a whitespace-delimited word (or, in a word with non-ASCII characters, a window of it) within
+// edit distance d of the term (utils/edit_distance.cpp ContainsFuzzyMatch; PostFilterByFuzzyText,
+// search_pipeline.cpp:1742-1752): arg = unique term id | (d << 24)
+constexpr uint8_t kOpFuzzyText = 5;
+constexpr uint32_t kFuzzyMaxTermCps = 64;  // code points of a term the edit-distance rows are sized for
 
 // driver kinds for single-call set APIs
 struct ExplicitDriver {

@@ -986,9 +986,130 @@ void IntersectSorted(std::vector<DocId>& acc, std::vector<DocId>&& fresh, bool& 
   }
 }
 
-// ExecuteWithFuzzy, search_pipeline.cpp:1659-1740, for verify_text modes that do not apply to the terms (the
-// edit-distance verification of PostFilterByFuzzyText :1742-1752 is not restated). *empty_term = the reference's
-// empty_term_detected, under which ExecuteFullPipeline clears the results (:1933-1937).
+// ---- utils/edit_distance.cpp ----
+// ComputeDistanceImpl (:62-113): threshold Levenshtein over two rows folded into one, shorter sequence as the row.
+uint32_t ComputeDistance(const uint32_t* a, uint32_t a_len, const uint32_t* b, uint32_t b_len, uint32_t max_distance) {
+  if (a_len > b_len) {
+    std::swap(a, b);
+    std::swap(a_len, b_len);
+  }
+  if (b_len - a_len > max_distance) {
+    return max_distance + 1;
+  }
+  if (a_len == 0) {
+    return b_len;
+  }
+  std::vector<uint32_t> dp(a_len + 1);
+  for (uint32_t j = 0; j <= a_len; ++j) {
+    dp[j] = j;
+  }
+  for (uint32_t i = 0; i < b_len; ++i) {
+    uint32_t prev = dp[0];
+    dp[0] = i + 1;
+    uint32_t row_min = dp[0];
+    for (uint32_t j = 0; j < a_len; ++j) {
+      const uint32_t cost = a[j] == b[i] ? 0 : 1;
+      const uint32_t v = std::min({dp[j + 1] + 1, dp[j] + 1, prev + cost});
+      prev = dp[j + 1];
+      dp[j + 1] = v;
+      row_min = std::min(row_min, v);
+    }
+    if (row_min > max_distance) {
+      return max_distance + 1;
+    }
+  }
+  return dp[a_len] <= max_distance ? dp[a_len] : max_distance + 1;
+}
+
+// ContainsFuzzyCodepointWindow (:115-135).
+bool ContainsFuzzyWindow(const uint32_t* word, uint32_t word_len, const uint32_t* term, uint32_t term_len,
+                         uint32_t max_distance) {
+  const uint64_t min_len = term_len > max_distance ? term_len - max_distance : 1;
+  const uint64_t max_len = std::min<uint64_t>(word_len, static_cast<uint64_t>(term_len) + max_distance);
+  if (min_len > max_len) {
+    return false;
+  }
+  for (uint32_t start = 0; start < word_len; ++start) {
+    const uint64_t last = std::min<uint64_t>(max_len, word_len - start);
+    for (uint64_t len = min_len; len <= last; ++len) {
+      if (ComputeDistance(word + start, static_cast<uint32_t>(len), term, term_len, max_distance) <= max_distance) {
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+bool IsAsciiOnly(std::string_view s) {
+  return std::all_of(s.begin(), s.end(), [](char c) { return static_cast<unsigned char>(c) < 0x80; });
+}
+
+// ContainsFuzzyMatch (:168-255), after NormalizeUnicodeWhitespace (:25-49: U+3000 and U+00A0 become ' ').
+bool ContainsFuzzyMatch(std::string_view text, std::string_view term, uint32_t max_distance) {
+  if (term.empty()) {
+    return true;
+  }
+  if (text.empty()) {
+    return false;
+  }
+  std::string norm;
+  norm.reserve(text.size());
+  for (size_t i = 0; i < text.size();) {
+    const auto byte = static_cast<unsigned char>(text[i]);
+    if (byte == 0xE3 && i + 2 < text.size() && static_cast<unsigned char>(text[i + 1]) == 0x80 &&
+        static_cast<unsigned char>(text[i + 2]) == 0x80) {
+      norm += ' ';
+      i += 3;
+    } else if (byte == 0xC2 && i + 1 < text.size() && static_cast<unsigned char>(text[i + 1]) == 0xA0) {
+      norm += ' ';
+      i += 2;
+    } else {
+      norm += text[i];
+      ++i;
+    }
+  }
+  const std::vector<uint32_t> term_cps =
+      IsAsciiOnly(term) ? std::vector<uint32_t>(term.begin(), term.end()) : Utf8ToCodepoints(term);
+  const auto term_len = static_cast<uint32_t>(term_cps.size());
+  const std::string_view view = norm;
+  size_t pos = 0;
+  while (pos < view.size()) {
+    const size_t word_start = view.find_first_not_of(" \t\r\n", pos);
+    if (word_start == std::string_view::npos) {
+      break;
+    }
+    size_t word_end = view.find_first_of(" \t\r\n", word_start);
+    if (word_end == std::string_view::npos) {
+      word_end = view.size();
+    }
+    const std::string_view word = view.substr(word_start, word_end - word_start);
+    if (IsAsciiOnly(word)) {
+      // whole word against the term (both branches of :201-243 for an ASCII word reduce to this)
+      std::vector<uint32_t> word_cps;
+      for (char c : word) {
+        word_cps.push_back(static_cast<unsigned char>(c));
+      }
+      const auto word_len = static_cast<uint32_t>(word_cps.size());
+      const uint32_t diff = word_len > term_len ? word_len - term_len : term_len - word_len;
+      if (diff <= max_distance &&
+          ComputeDistance(word_cps.data(), word_len, term_cps.data(), term_len, max_distance) <= max_distance) {
+        return true;
+      }
+    } else {
+      const std::vector<uint32_t> word_cps = Utf8ToCodepoints(word);
+      if (ContainsFuzzyWindow(word_cps.data(), static_cast<uint32_t>(word_cps.size()), term_cps.data(), term_len,
+                              max_distance)) {
+        return true;
+      }
+    }
+    pos = word_end;
+  }
+  return false;
+}
+
+// ExecuteWithFuzzy, search_pipeline.cpp:1659-1740, with PostFilterByFuzzyText (:1742-1752) when verify_text applies
+// to the terms. *empty_term = the reference's empty_term_detected, under which ExecuteFullPipeline clears the
+// results (:1933-1937).
 std::vector<DocId> RunFuzzy(const orc_index& idx, const orc_query_params_t& p,
                             const std::vector<std::string_view>& terms, uint32_t max_distance,
                             const std::vector<std::string_view>& not_terms, bool* empty_term) {
@@ -1021,6 +1142,25 @@ std::vector<DocId> RunFuzzy(const orc_index& idx, const orc_query_params_t& p,
     IntersectSorted(results, SearchByThreshold(idx, Views(ti.ngrams), threshold), first_term);
   }
   results = ApplyNotTerms(idx, p, std::move(results), not_terms);
+  if (!results.empty() && ShouldApplyVerifyText(p.verify_text, terms)) {  // :1714-1726
+    std::vector<DocId> kept;
+    for (DocId d : results) {
+      std::string_view text;
+      bool ok = true;
+      if (idx.GetText(d, &text)) {  // a candidate without stored text is kept (:386-402)
+        for (auto t : terms) {
+          if (text.find(t) == std::string_view::npos && !ContainsFuzzyMatch(text, t, max_distance)) {
+            ok = false;
+            break;
+          }
+        }
+      }
+      if (ok) {
+        kept.push_back(d);
+      }
+    }
+    results = std::move(kept);
+  }
   for (auto t : terms) {  // RequiresExactTextForHybridFragments, :1728-1737
     if (HasUncoveredHybridFragment(t, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0)) {
       results = PostFilterByText(idx, results, terms);
@@ -1855,9 +1995,6 @@ extern "C" uint64_t orc_search_fuzzy(const orc_index_t* idx, const orc_query_par
                                      uint64_t n_not, uint32_t* out, uint64_t cap, int32_t* empty_term_detected) {
   const auto terms = TermList(term_bytes, term_offsets, 0, n_terms);
   const auto not_terms = n_not > 0 ? TermList(not_bytes, not_offsets, 0, n_not) : std::vector<std::string_view>{};
-  if (ShouldApplyVerifyText(params->verify_text, terms)) {
-    return ~0ULL;  // PostFilterByFuzzyText is not restated
-  }
   bool empty_term = false;
   const auto r = RunFuzzy(*idx, *params, terms, max_distance, not_terms, &empty_term);
   if (empty_term_detected != nullptr) {

@@ -180,10 +180,10 @@ uint64_t orc_eval_boolean(const orc_index_t* idx, const int32_t* ops, const int3
 
 /* ---- fuzzy and synonym execution paths (src/server/search_pipeline.cpp:1580-1752) ----
  * ExecuteWithFuzzy (:1659-1740) over normalised terms: per term Index::SearchByThreshold(ngrams,
- * max(1, |ngrams| - max_distance * effective n-gram size)), AND-ed; NOT terms; hybrid-fragment exact text filter.
+ * max(1, |ngrams| - max_distance * effective n-gram size)), AND-ed; NOT terms; PostFilterByFuzzyText (:1742-1752,
+ * ContainsFuzzyMatch of utils/edit_distance.cpp) when verify_text applies; hybrid-fragment exact text filter.
  * Column filters are applied by the caller with orc_apply_filters (they are per-document predicates).
- * Returns the result size (ids ascending), or ~0 when verify_text applies to the terms (the edit-distance
- * verification is not restated). *empty_term_detected (may be NULL) as in SearchPipelineResult. */
+ * Returns the result size (ids ascending). *empty_term_detected (may be NULL) as in SearchPipelineResult. */
 uint64_t orc_search_fuzzy(const orc_index_t* idx, const orc_query_params_t* params, const uint8_t* term_bytes,
                           const uint64_t* term_offsets, uint64_t n_terms, uint32_t max_distance,
                           const uint8_t* not_bytes, const uint64_t* not_offsets, uint64_t n_not, uint32_t* out,

@@ -441,8 +441,7 @@ class OracleIndex:
                            0, 1, 0, 0, 1000, 1.2, 0.75, 0, 0, verify_text, 0)
 
     def search_fuzzy(self, terms, max_distance, not_terms=(), raw_ngram=None, raw_kanji=None, verify_text=0):
-        """ExecuteWithFuzzy over normalised terms -> (ascending ids, empty_term_detected); None if the edit-distance
-        verification would apply (port only)."""
+        """ExecuteWithFuzzy over normalised terms -> (ascending ids, empty_term_detected)."""
         p = self._pipeline_params(raw_ngram, raw_kanji, verify_text)
         arena, offs = self._terms(terms)
         narena, noffs = self._terms(not_terms)
@@ -453,8 +452,6 @@ class OracleIndex:
             n = self.L.lib.orc_search_fuzzy(self.h, C.byref(p), _ptr(arena, u8p), _ptr(offs, u64p), len(terms),
                                             max_distance, _ptr(narena, u8p), _ptr(noffs, u64p), len(not_terms),
                                             _ptr(out, u32p), cap, _ptr(empty, i32p))
-            if n == 2 ** 64 - 1:
-                return None
             if n <= cap:
                 return out[:n].copy(), bool(empty[0])
             cap = int(n)

@@ -9,7 +9,7 @@ import pytest
 import corpus as corpus_mod
 from test_gpu_parity import build_pair, make_docs
 from test_oracle_bulk import _docs
-from test_oracle_expanded import expanded_cases
+from test_oracle_expanded import expanded_cases, spaced_docs
 
 pytestmark = pytest.mark.gpu
 
@@ -17,25 +17,27 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("cfg", [(2, 0, True), (2, 1, True), (2, 1, False), (3, 2, False), (1, 1, True), (3, 0, True)])
 def test_fuzzy_and_synonyms_match_oracle(mgx, oracle, cfg):
     rnd = random.Random(0x51 + (hash(cfg) & 0xFFF))
-    docs = _docs(rnd, 3000)
+    docs = spaced_docs(rnd, 3000)
     ids = np.arange(1, len(docs) + 1, dtype=np.uint32)
     gi, oi = build_pair(mgx, oracle, docs, ids, cfg)
-    nonempty = 0
+    nonempty = verified = 0
     for fuzzy_terms, groups, nots, dist in expanded_cases(rnd, docs, 120):
-        want, _ = oi.search_fuzzy(fuzzy_terms, dist, nots)
-        got = gi.search_fuzzy(fuzzy_terms, dist, nots)
-        assert np.array_equal(got, want), (cfg, fuzzy_terms, dist, nots, got[:10], want[:10])
-        nonempty += want.size > 0
+        for vt in (0, 1, 2):  # 1 / 2: PostFilterByFuzzyText (edit-distance verification) on the device
+            want, _ = oi.search_fuzzy(fuzzy_terms, dist, nots, verify_text=vt)
+            got = gi.search_fuzzy(fuzzy_terms, dist, nots, verify_text=vt)
+            assert np.array_equal(got, want), (cfg, fuzzy_terms, dist, nots, vt, got[:10], want[:10])
+            nonempty += want.size > 0
+            verified += vt == 1 and want.size > 0
         for vt in (0, 1, 2):
             want, _ = oi.search_synonyms(groups, nots, verify_text=vt)
             got = gi.search_synonyms(groups, nots, verify_text=vt)
             assert np.array_equal(got, want), (cfg, groups, nots, vt, got[:10], want[:10])
             nonempty += want.size > 0
-    assert nonempty > 40
+    assert nonempty > 40 and verified > 5
     assert gi.search_fuzzy([], 1).size == 0 and gi.search_synonyms([]).size == 0
-    # verify_text that applies to the terms needs the edit-distance verification: refused, never approximated
+    # terms beyond the edit-distance rows of the device function are refused, never approximated
     with pytest.raises(mgx.MgxError):
-        gi.search_fuzzy(["ab"], 1, verify_text=1)
+        gi.search_fuzzy(["ab" * 40], 1, verify_text=1)
 
 
 def test_fuzzy_and_synonyms_with_filters_dense_lists_and_invalid_utf8(mgx, oracle):
@@ -96,8 +98,9 @@ def test_fuzzy_and_synonyms_with_filters_dense_lists_and_invalid_utf8(mgx, oracl
                 continue
             st = rnd.randrange(0, len(d) - 3)
             term = d[st:st + rnd.randint(2, 9)]
-            want, _ = o2.search_fuzzy([term], 1)
-            assert np.array_equal(g2.search_fuzzy([term], 1), want), (cfg, term)
+            for vt in (0, 1):
+                want, _ = o2.search_fuzzy([term], 1, verify_text=vt)
+                assert np.array_equal(g2.search_fuzzy([term], 1, verify_text=vt), want), (cfg, term, vt)
             want, _ = o2.search_synonyms([[term, d[:3]]], verify_text=1)
             assert np.array_equal(g2.search_synonyms([[term, d[:3]]], verify_text=1), want), (cfg, term)
 

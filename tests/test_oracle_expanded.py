@@ -11,6 +11,20 @@ from test_oracle_bulk import _docs
 CONFIGS = [(2, 0, True), (2, 1, True), (2, 1, False), (3, 2, False), (1, 1, True), (3, 0, True)]
 
 
+def spaced_docs(rnd, n):
+    """The random corpus of test_oracle_bulk with the word separators ContainsFuzzyMatch knows (tab, newline, U+3000,
+    U+00A0) mixed in, so the edit-distance verification meets ASCII words, CJK words and mixed ones."""
+    seps = [b" ", b"\t", b"\n", "\u3000".encode(), "\u00a0".encode()]
+    docs = []
+    for d in _docs(rnd, n):
+        parts = d.split(b" ")
+        out = parts[0]
+        for part in parts[1:]:
+            out += rnd.choice(seps) + part
+        docs.append(out)
+    return docs
+
+
 def expanded_cases(rnd, docs, n):
     """Random fuzzy term lists, synonym groups and NOT lists cut from the corpus (plus misspellings and strangers)."""
     def piece(lo=1, hi=7):
@@ -44,27 +58,27 @@ def expanded_cases(rnd, docs, n):
 @pytest.mark.parametrize("cfg", CONFIGS)
 def test_fuzzy_and_synonyms_agree_with_reference_sources(oracle, reflib, cfg):
     rnd = random.Random(0xF0 + (hash(cfg) & 0xFFF))
-    docs = _docs(rnd, 1200)
+    docs = spaced_docs(rnd, 1200)
     ids = np.arange(1, len(docs) + 1, dtype=np.uint32)
     pi, ri = oracle.index(*cfg), reflib.index(*cfg)
     pi.add_texts(ids, docs)
     ri.add_texts(ids, docs)
-    nonempty = 0
+    nonempty = verified_nonempty = 0
     for fuzzy_terms, groups, nots, dist in expanded_cases(rnd, docs, 150):
-        a = pi.search_fuzzy(fuzzy_terms, dist, nots)
-        b = ri.search_fuzzy(fuzzy_terms, dist, nots)
-        assert a[1] == b[1] and np.array_equal(a[0], b[0]), (fuzzy_terms, dist, nots)
-        nonempty += len(a[0]) > 0
+        for vt in (0, 1, 2):  # 1 / 2: PostFilterByFuzzyText with ContainsFuzzyMatch (utils/edit_distance.cpp)
+            a = pi.search_fuzzy(fuzzy_terms, dist, nots, verify_text=vt)
+            b = ri.search_fuzzy(fuzzy_terms, dist, nots, verify_text=vt)
+            assert a[1] == b[1] and np.array_equal(a[0], b[0]), (fuzzy_terms, dist, nots, vt)
+            nonempty += len(a[0]) > 0
+            verified_nonempty += vt == 1 and len(a[0]) > 0
         for vt in (0, 1, 2):
             a = pi.search_synonyms(groups, nots, verify_text=vt)
             b = ri.search_synonyms(groups, nots, verify_text=vt)
             assert a[1] == b[1] and np.array_equal(a[0], b[0]), (groups, nots, vt)
             nonempty += len(a[0]) > 0
-    assert nonempty > 50
+    assert nonempty > 50 and verified_nonempty > 5
     # the documented corner cases
     a, b = pi.search_fuzzy([], 1), ri.search_fuzzy([], 1)
     assert a[1] is True and b[1] is True and len(a[0]) == 0 and len(b[0]) == 0
     a, b = pi.search_synonyms([]), ri.search_synonyms([])
     assert a[1] is True and b[1] is True and len(a[0]) == 0 and len(b[0]) == 0
-    # verify_text that applies to the terms needs the edit-distance verification: the restatement declines
-    assert pi.search_fuzzy(["ab"], 1, verify_text=1) is None
