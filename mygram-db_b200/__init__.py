@@ -428,14 +428,17 @@ class Index:
 
     def save_mgix(self, normalize_nfkc=True, normalize_width="keep", normalize_lower=True):
         """Index::SaveToStream (index_serialization.cpp:111-224) of the device index -> bytes."""
+        st = self.stats()
         n = C.c_uint64(0)
+        # one pass when the guess holds (np.zeros pages are only touched when written); exact size otherwise
+        out = np.zeros(64 + 40 * st.n_terms + 9 * st.n_postings // 2, dtype=np.uint8)
         rc = lib().mgx_index_save_mgix(self._h, int(normalize_nfkc), _bytes(normalize_width), int(normalize_lower),
-                                       None, 0, C.byref(n))
-        if rc != -4:
-            _check(rc)
-        out = np.zeros(n.value, dtype=np.uint8)
-        _check(lib().mgx_index_save_mgix(self._h, int(normalize_nfkc), _bytes(normalize_width), int(normalize_lower),
-                                         _ptr(out, u8p), out.size, C.byref(n)))
+                                       _ptr(out, u8p), out.size, C.byref(n))
+        if rc == -4:
+            out = np.zeros(n.value, dtype=np.uint8)
+            rc = lib().mgx_index_save_mgix(self._h, int(normalize_nfkc), _bytes(normalize_width),
+                                           int(normalize_lower), _ptr(out, u8p), out.size, C.byref(n))
+        _check(rc)
         return out[:n.value].tobytes()
 
     def doc_lengths(self):

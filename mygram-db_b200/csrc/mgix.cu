@@ -539,8 +539,10 @@ int mgx_mgix_decode(const uint8_t* data, uint64_t len, mgx_mgix_info_t* info, ui
   // LAST record, as new_postings[term] = ... does (:573)
   std::vector<uint32_t> order(records.size());
   std::iota(order.begin(), order.end(), 0u);
-  std::stable_sort(order.begin(), order.end(),
-                   [&](uint32_t a, uint32_t b) { return records[a].term < records[b].term; });
+  const auto by_term = [&](uint32_t a, uint32_t b) { return records[a].term < records[b].term; };
+  if (!std::is_sorted(order.begin(), order.end(), by_term)) {  // streams of mgx_mgix_encode already are
+    std::stable_sort(order.begin(), order.end(), by_term);
+  }
   std::vector<uint32_t> kept;
   kept.reserve(order.size());
   for (size_t i = 0; i < order.size(); ++i) {

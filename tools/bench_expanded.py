@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""tools/bench_expanded.py — measurement of the fuzzy / synonym execution paths and of the MGIX export on the C2 corpus
+(SURVEY §8f-3 / f-4 widened to the same parity + measurement bar as the headline path).
+
+  python tools/bench_expanded.py [--docs 10000000] [--queries 200] [--cpu-sample 24] [--out profiles/…json]
+
+Per query class (fuzzy d=1 without / with edit-distance verification, synonym groups): queries/s through the public
+single-query calls (mgx_search_fuzzy / mgx_search_synonyms: host buffers in, doc ids out, wall clock after a warm-up),
+the CPU oracle timed beside it on a bounded sample of the same queries (one thread, the reference processes one query
+per thread), and a parity check of that sample (bit-exact doc-id sets). MGIX: mgx_index_save_mgix on the whole shard,
+bytes/s, decoded back and compared with the device CSR. Prints ONE JSON line. The oracle is the checker here, as in
+bench.py's cpu_baseline leg; nothing in the product imports it."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests", "support"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+
+
+def make_queries(c, rng, n):
+    """fuzzy: 1-2 terms of 3-6 code points cut from a document, one character replaced; synonyms: two groups of two
+    2-3 code point variants, the first of each group from the same document (non-empty AND of ORs)."""
+    def piece(d, lo, hi):
+        t = c.text(d).decode()
+        ln = int(rng.integers(lo, min(hi, len(t)) + 1))
+        st = int(rng.integers(0, len(t) - ln + 1))
+        return t[st:st + ln]
+
+    fuzzy, syn = [], []
+    for _ in range(n):
+        d = int(rng.integers(0, c.n_docs))
+        terms = []
+        for _ in range(int(rng.integers(1, 3))):
+            t = piece(d, 3, 6)
+            i = int(rng.integers(0, len(t)))
+            terms.append(t[:i] + chr(0x4E00 + int(rng.integers(0, 8192))) + t[i + 1:])
+        fuzzy.append(terms)
+        syn.append([[piece(d, 2, 3), piece(int(rng.integers(0, c.n_docs)), 2, 3)] for _ in range(2)])
+    return fuzzy, syn
+
+
+def timed(fn, items, warmup=3):
+    for it in items[:warmup]:
+        fn(it)
+    t0 = time.perf_counter()
+    out = [fn(it) for it in items]
+    return out, time.perf_counter() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--docs", type=int, default=10_000_000)
+    ap.add_argument("--queries", type=int, default=200)
+    ap.add_argument("--cpu-sample", type=int, default=24)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    import corpus as corpus_mod
+    import mgx_loader
+    import pyoracle
+    m = mgx_loader.load()
+    c = corpus_mod.generate("cjk", args.docs, 0xC2)
+    gi = m.Index(2, 0, True, device=0)
+    gi.build(c.doc_ids, c.arena, c.offsets)
+    launches0 = m.lib().mgx_kernel_launch_count()
+    rng = np.random.default_rng(0xE7)
+    fuzzy, syn = make_queries(c, rng, args.queries)
+    out = {"workload": f"C2 corpus, {args.docs} documents, bigram index; single-query calls, host buffers in / doc ids out",
+           "classes": {}}
+
+    def flush():
+        line = json.dumps(out)
+        if args.out:
+            with open(args.out, "w") as f:
+                f.write(line + "\n")
+        return line
+
+    gpu_classes = [
+        ("fuzzy_d1", fuzzy, lambda q: gi.search_fuzzy(q, 1)),
+        ("fuzzy_d1_verify_all", fuzzy, lambda q: gi.search_fuzzy(q, 1, verify_text=1)),
+        ("synonyms_2x2", syn, lambda q: gi.search_synonyms(q)),
+        ("synonyms_2x2_verify_all", syn, lambda q: gi.search_synonyms(q, verify_text=1)),
+    ]
+    results = {}
+    for name, qs, gpu_fn in gpu_classes:
+        got, dt = timed(gpu_fn, qs)
+        results[name] = got
+        out["classes"][name] = {"gpu_queries_per_s": len(qs) / dt, "gpu_ms_per_query": 1e3 * dt / len(qs),
+                                "result_docs_mean": float(np.mean([g.size for g in got]))}
+        flush()
+    out["gpu_launches"] = int(m.lib().mgx_kernel_launch_count() - launches0)
+    # MGIX export of the whole shard (raw buffers: tens of millions of terms are not turned into Python objects)
+    C = m.C
+    st = gi.stats()
+    t0 = time.perf_counter()
+    stream = gi.save_mgix()
+    dt = time.perf_counter() - t0
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    info = m.MgixInfo()
+    u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    rc = m.lib().mgx_mgix_decode(buf.ctypes.data_as(u8p), buf.size, C.byref(info), None, None, None, None)
+    assert rc == 0, m.lib().mgx_last_error()
+    tb = np.zeros(max(1, info.term_bytes), dtype=np.uint8)
+    to = np.zeros(info.n_terms + 1, dtype=np.uint64)
+    po = np.zeros(info.n_terms + 1, dtype=np.uint64)
+    pp = np.zeros(max(1, info.n_postings), dtype=np.uint32)
+    t1 = time.perf_counter()
+    rc = m.lib().mgx_mgix_decode(buf.ctypes.data_as(u8p), buf.size, C.byref(info), tb.ctypes.data_as(u8p),
+                                 to.ctypes.data_as(u64p), po.ctypes.data_as(u64p), pp.ctypes.data_as(u32p))
+    decode_s = time.perf_counter() - t1
+    assert rc == 0, m.lib().mgx_last_error()
+    keys = np.zeros(max(1, st.n_terms), dtype=np.uint64)
+    goffs = np.zeros(st.n_terms + 1, dtype=np.uint64)
+    gposts = np.zeros(max(1, st.n_postings), dtype=np.uint32)
+    assert m.lib().mgx_index_export(gi._h, keys.ctypes.data_as(u64p), goffs.ctypes.data_as(u64p),
+                                    gposts.ctypes.data_as(u32p)) == 0
+    ok = (info.n_terms == st.n_terms and info.n_postings == st.n_postings and np.array_equal(po, goffs) and
+          np.array_equal(pp[:info.n_postings], gposts[:st.n_postings]))
+    out["mgix_export"] = {"stream_bytes": len(stream), "save_seconds": dt, "save_GB_per_s": len(stream) / dt / 1e9,
+                          "decode_seconds": decode_s, "terms": int(info.n_terms), "postings": int(info.n_postings),
+                          "decodes_to_device_csr": bool(ok)}
+    flush()
+    assert ok
+    del stream, buf, tb, to, po, pp, keys, goffs, gposts
+    # CPU oracle beside it, on a bounded sample of the same queries
+    oi = pyoracle.OracleLib(pyoracle.PORT_LIB).index(2, 0, True)
+    t0 = time.perf_counter()
+    oi.build_bulk(c.doc_ids, c.arena, c.offsets, os.cpu_count() or 1)
+    out["cpu_index_build_s"] = round(time.perf_counter() - t0, 2)
+    cpu_classes = {"fuzzy_d1": (fuzzy, lambda q: oi.search_fuzzy(q, 1)[0]),
+                   "fuzzy_d1_verify_all": (fuzzy, lambda q: oi.search_fuzzy(q, 1, verify_text=1)[0]),
+                   "synonyms_2x2": (syn, lambda q: oi.search_synonyms(q)[0]),
+                   "synonyms_2x2_verify_all": (syn, lambda q: oi.search_synonyms(q, verify_text=1)[0])}
+    for name, (qs, cpu_fn) in cpu_classes.items():
+        sample = qs[:args.cpu_sample]
+        want, cdt = timed(cpu_fn, sample, warmup=0)
+        same = all(np.array_equal(g, w) for g, w in zip(results[name], want))
+        out["classes"][name]["cpu_baseline"] = {
+            "value": len(sample) / cdt, "unit": "queries/s", "cores": 1, "kind": "port",
+            "sample": f"first {len(sample)} of the {len(qs)} queries, oracle port, one thread"}
+        out["classes"][name]["parity_on_sample"] = bool(same)
+        flush()
+        assert same, f"{name}: GPU result sets differ from the oracle"
+    print(flush(), flush=True)
+
+
+if __name__ == "__main__":
+    main()
