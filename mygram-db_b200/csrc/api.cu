@@ -1194,6 +1194,14 @@ int run_single_set_query(Index& ix, std::vector<HostTerm>& terms, const std::vec
   std::vector<uint64_t> set_off;
   DevBuf<uint32_t> d_sets;
   batch_search_sets(b, &set_off, &d_sets);
+  if (queries.size() > 1) {
+    // one logical query expanded into several with different drivers (finish_expanded): their result sets are
+    // disjoint by construction and their union is the answer
+    DevBuf<uint32_t> d_union;
+    merge_disjoint_runs(b.stream, d_sets.p, set_off, &d_union);
+    d_sets = std::move(d_union);
+    set_off = {0, set_off.back()};
+  }
   const uint64_t total = set_off[1];
   uint64_t first = 0;
   uint64_t n = total;
@@ -1500,8 +1508,15 @@ int term_leaf(const Index& ix, const mgx_expanded_query_t& eq, const uint8_t* by
 
 // ApplyNotAndFilters (search_pipeline.cpp:470-485): a document of ANY NOT term (ApplyNotFilter, :871-932) is
 // dropped, then the column conditions; closes the program with the AND over `children` operands.
+// `drivers`: leaves (term ids) of ONE child of the root AND such that every result lies in the posting lists of at
+// least one of them (the variants of a synonym group; any n - t + 1 leaves of an "at least t of n" node). Without a
+// conjunct term the engine would have to evaluate the program on every document of the shard; instead the query is
+// expanded into one query per driver leaf i, AND(leaf_i, NOT leaf_1, ..., NOT leaf_{i-1}, program): each is driven by
+// leaf_i's shortest list, the result sets are pairwise disjoint, and their union (merge_disjoint_runs) is the answer.
 int finish_expanded(const Index& ix, const mgx_expanded_query_t& eq, ProgramBuilder* pb, int32_t children,
-                    HostQuery* hq) {
+                    const std::vector<int32_t>& drivers, std::vector<HostQuery>* queries) {
+  queries->assign(std::max<size_t>(1, drivers.size()), HostQuery{});
+  HostQuery* hq = &(*queries)[0];
   if (eq.n_not > 0) {
     for (uint64_t i = 0; i < eq.n_not; ++i) {
       HostTerm t;
@@ -1518,14 +1533,38 @@ int finish_expanded(const Index& ix, const mgx_expanded_query_t& eq, ProgramBuil
     ++children;
   }
   pb->node(kOpAnd, children);
-  if (int rc = analyse_program(pb->ops.data(), pb->args.data(), pb->ops.size(), pb->terms.size(), &hq->conjuncts);
-      rc != MGX_OK) {
-    return rc;
+  auto install = [&](HostQuery* q, const std::vector<int32_t>& ops, const std::vector<int32_t>& args) {
+    q->conjuncts.clear();
+    if (int rc = analyse_program(ops.data(), args.data(), ops.size(), pb->terms.size(), &q->conjuncts); rc != MGX_OK) {
+      return rc;
+    }
+    q->flags = kQProgram;
+    q->prog_ops.assign(ops.begin(), ops.end());
+    q->prog_args.assign(args.begin(), args.end());
+    return MGX_OK;
+  };
+  bool expanded = !drivers.empty();
+  if (expanded) {
+    for (size_t i = 0; i < drivers.size() && expanded; ++i) {
+      std::vector<int32_t> ops{kOpTerm};
+      std::vector<int32_t> args{drivers[i]};
+      for (size_t j = 0; j < i; ++j) {
+        ops.insert(ops.end(), {kOpTerm, kOpNot, kOpAnd});
+        args.insert(args.end(), {drivers[j], 0, 2});
+      }
+      ops.insert(ops.end(), pb->ops.begin(), pb->ops.end());
+      args.insert(args.end(), pb->args.begin(), pb->args.end());
+      ops.push_back(kOpAnd);
+      args.push_back(2);
+      expanded = install(&(*queries)[i], ops, args) == MGX_OK;  // too deep for the evaluation stack: one plain query
+    }
   }
-  hq->flags = kQProgram;
-  for (size_t i = 0; i < pb->ops.size(); ++i) {
-    hq->prog_ops.push_back(static_cast<uint8_t>(pb->ops[i]));
-    hq->prog_args.push_back(static_cast<uint32_t>(pb->args[i]));
+  if (!expanded) {
+    queries->assign(1, HostQuery{});
+    hq = &(*queries)[0];
+    if (int rc = install(hq, pb->ops, pb->args); rc != MGX_OK) {
+      return rc;
+    }
   }
   for (uint64_t f = 0; f < eq.n_filters; ++f) {
     HostFilter hf;
@@ -1536,10 +1575,14 @@ int finish_expanded(const Index& ix, const mgx_expanded_query_t& eq, ProgramBuil
     }
     hf.literal.assign(reinterpret_cast<const char*>(eq.filter_bytes) + eq.filter_offsets[f],
                       eq.filter_offsets[f + 1] - eq.filter_offsets[f]);
-    hq->filters.push_back(std::move(hf));
+    for (HostQuery& q : *queries) {
+      q.filters.push_back(hf);
+    }
   }
   return MGX_OK;
 }
+
+constexpr size_t kMaxDriverLeaves = 16;  // beyond this one pass over every document is the cheaper plan
 
 }  // namespace
 
@@ -1571,6 +1614,8 @@ int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq,
     ProgramBuilder pb;
     int32_t children = 0;
     bool hybrid_exact = false;
+    bool has_conjunct = false;      // a term whose n-grams are ALL required drives by itself
+    std::vector<int32_t> drivers;   // else: the smallest sufficient leaf set over the terms
     for (uint64_t t = 0; t < n_terms; ++t) {
       const uint8_t* tb = term_bytes + term_offsets[t];
       const uint64_t tl = term_offsets[t + 1] - term_offsets[t];
@@ -1604,6 +1649,7 @@ int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq,
       }
       const size_t drop = static_cast<size_t>(max_distance) * static_cast<size_t>(eff);
       const size_t need = n > drop ? n - drop : 1;  // :1697-1700
+      const int32_t first_leaf = static_cast<int32_t>(pb.terms.size());
       for (uint64_t key : whole.keys) {  // Index::SearchByThreshold(ngrams, need), index.cpp:488-578
         HostTerm leaf;
         leaf.raw = true;
@@ -1612,6 +1658,15 @@ int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq,
       }
       pb.node(kOpAtLeast, static_cast<int32_t>(n | (need << 16)));
       ++children;
+      // a document in at least `need` of the n lists is in one of ANY n - need + 1 of them
+      const size_t sufficient = n - need + 1;
+      has_conjunct |= need == n;
+      if (need < n && sufficient <= kMaxDriverLeaves && (drivers.empty() || sufficient < drivers.size())) {
+        drivers.clear();
+        for (size_t i = 0; i < sufficient; ++i) {
+          drivers.push_back(first_leaf + static_cast<int32_t>(i));
+        }
+      }
       hybrid_exact |= has_uncovered_hybrid_fragment(tb, tl, eq->ngram_size, eq->kanji_ngram_size,
                                                     eq->cross_boundary != 0);
     }
@@ -1643,8 +1698,11 @@ int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq,
         ++children;
       }
     }
-    std::vector<HostQuery> queries(1);
-    if (int rc = finish_expanded(ix, *eq, &pb, children, &queries[0]); rc != MGX_OK) {
+    if (has_conjunct) {
+      drivers.clear();
+    }
+    std::vector<HostQuery> queries;
+    if (int rc = finish_expanded(ix, *eq, &pb, children, drivers, &queries); rc != MGX_OK) {
       return rc;
     }
     return run_single_set_query(ix, pb.terms, queries, nullptr, 0, 0, false, out, cap, out_count);
@@ -1683,6 +1741,8 @@ int mgx_search_synonyms(const mgx_index_t* index_c, const mgx_expanded_query_t* 
     const uint64_t n_variants = group_begin[n_groups];
     // ShouldApplyVerifyTextSynonyms (:154-172): decided over the variants of all groups
     const bool verify = n_variants > 0 && should_verify(eq->verify_text, variant_bytes, variant_offsets, n_variants);
+    bool has_conjunct = false;     // a group with a single variant drives by itself
+    std::vector<int32_t> drivers;  // else: the variants of the group with the fewest of them
     for (int pass = 0; pass < (verify ? 2 : 1); ++pass) {
       // pass 0: OR within a group of SearchTermDocuments(variant) (:1589-1608);
       // pass 1: PostFilterByTextWithSynonyms (:1633-1657): some variant of every group occurs in the text
@@ -1696,6 +1756,8 @@ int mgx_search_synonyms(const mgx_index_t* index_c, const mgx_expanded_query_t* 
         if (trivially_true) {
           continue;
         }
+        std::vector<int32_t> group_leaves;
+        bool can_drive = pass == 0;
         for (uint64_t v = group_begin[g]; v < group_begin[g + 1]; ++v) {
           const uint8_t* vb = variant_bytes + variant_offsets[v];
           const uint64_t vl = variant_offsets[v + 1] - variant_offsets[v];
@@ -1703,6 +1765,11 @@ int mgx_search_synonyms(const mgx_index_t* index_c, const mgx_expanded_query_t* 
           if (pass == 0) {
             if (int rc = term_leaf(ix, *eq, vb, vl, &t); rc != MGX_OK) {
               return rc;
+            }
+            if (!t.keys.empty()) {
+              group_leaves.push_back(static_cast<int32_t>(pb.terms.size()));
+            } else if (vl > 0) {
+              can_drive = false;  // a variant shorter than an n-gram is a text scan: no list to drive with
             }
           } else {
             if (vl > kMaxTermBytes) {
@@ -1720,10 +1787,19 @@ int mgx_search_synonyms(const mgx_index_t* index_c, const mgx_expanded_query_t* 
           pb.node(kOpOr, 0);  // a group without variants matches nothing
         }
         ++children;
+        if (can_drive && !group_leaves.empty()) {
+          has_conjunct |= group_begin[g + 1] - group_begin[g] == 1;
+          if (group_leaves.size() <= kMaxDriverLeaves && (drivers.empty() || group_leaves.size() < drivers.size())) {
+            drivers = group_leaves;
+          }
+        }
       }
     }
-    std::vector<HostQuery> queries(1);
-    if (int rc = finish_expanded(ix, *eq, &pb, children, &queries[0]); rc != MGX_OK) {
+    if (has_conjunct) {
+      drivers.clear();
+    }
+    std::vector<HostQuery> queries;
+    if (int rc = finish_expanded(ix, *eq, &pb, children, drivers, &queries); rc != MGX_OK) {
       return rc;
     }
     return run_single_set_query(ix, pb.terms, queries, nullptr, 0, 0, false, out, cap, out_count);

@@ -3890,6 +3890,55 @@ void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_
   b.searched = true;
 }
 
+// Union of ascending, pairwise DISJOINT runs laid back to back (the per-driver result sets of one expanded query):
+// no sort is needed, the final position of an element is its index in its own run plus the number of smaller
+// elements in every other run (a binary search each).
+__global__ void merge_disjoint_runs_kernel(const uint32_t* __restrict__ in, const uint64_t* __restrict__ run_off,
+                                           uint32_t n_runs, uint32_t* __restrict__ out) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= run_off[n_runs]) {
+    return;
+  }
+  const uint32_t v = in[i];
+  uint64_t pos = 0;
+  for (uint32_t r = 0; r < n_runs; ++r) {
+    const uint64_t r0 = run_off[r];
+    const uint64_t r1 = run_off[r + 1];
+    if (i >= r0 && i < r1) {
+      pos += i - r0;
+      continue;
+    }
+    uint64_t lo = r0;
+    uint64_t hi = r1;
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (in[mid] < v) {
+        lo = mid + 1;
+      } else {
+        hi = mid;
+      }
+    }
+    pos += lo - r0;
+  }
+  out[pos] = v;
+}
+
+void merge_disjoint_runs(cudaStream_t st, const uint32_t* d_in, const std::vector<uint64_t>& run_off,
+                         DevBuf<uint32_t>* d_out) {
+  const uint64_t total = run_off.back();
+  d_out->alloc(std::max<uint64_t>(1, total));
+  if (total == 0) {
+    return;
+  }
+  DevBuf<uint64_t> d_off;
+  d_off.alloc(run_off.size());
+  MGX_CUDA(cudaMemcpyAsync(d_off.p, run_off.data(), run_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  merge_disjoint_runs_kernel<<<blocks, 256, 0, st>>>(d_in, d_off.p, static_cast<uint32_t>(run_off.size() - 1), d_out->p);
+  MGX_LAUNCH_CHECK();
+  MGX_CUDA(cudaStreamSynchronize(st));
+}
+
 void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32_t>* d_sets) {
   cudaStream_t st = b.stream;
   if (!b.planned) {

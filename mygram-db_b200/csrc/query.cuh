@@ -314,6 +314,9 @@ void batch_search(Batch& b, const uint64_t* d_df_global, uint64_t stride, uint32
                   uint32_t* d_count, uint64_t* d_total);
 // Full ascending result sets of every query: fills h_totals and returns a device buffer of all sets back to back.
 void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32_t>* d_sets);
+// Union of the ascending, pairwise disjoint runs d_in[run_off[r] .. run_off[r+1]) into one ascending array.
+void merge_disjoint_runs(cudaStream_t st, const uint32_t* d_in, const std::vector<uint64_t>& run_off,
+                         DevBuf<uint32_t>* d_out);
 void launch_merge_topk(cudaStream_t stream, const mgx_query_params_t& params, uint32_t n_shards, uint64_t n_queries,
                        uint64_t stride, const uint32_t* d_ids_all, const double* d_scores_all,
                        const uint32_t* d_count_all, const uint64_t* d_total_all, uint64_t shard_pitch_bytes,
