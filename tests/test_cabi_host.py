@@ -49,6 +49,46 @@ def test_no_cpu_fallback_without_a_device(mgx):
     assert rc == -5
 
 
+def test_expanded_and_mgix_entry_points_validate_on_the_host(mgx):
+    """mgx_search_fuzzy / mgx_search_synonyms / mgx_index_save_mgix refuse null handles before touching a device;
+    the MGIX codec is host-only and reports sizes, capacity errors and rejected streams through its status codes."""
+    lib = mgx.lib()
+    n = C.c_uint64(7)
+    eq = mgx.ExpandedQuery()
+    assert lib.mgx_search_fuzzy(None, C.byref(eq), None, None, 0, 1, None, 0, C.byref(n)) == -1
+    assert lib.mgx_search_synonyms(None, C.byref(eq), None, None, None, 0, None, 0, C.byref(n)) == -1
+    assert lib.mgx_index_save_mgix(None, 1, b"keep", 1, None, 0, C.byref(n)) == -1
+    info = mgx.MgixInfo()
+    assert lib.mgx_mgix_encode(None, None, None, None, None, 0.0, None, 0, C.byref(n)) == -1
+    assert lib.mgx_mgix_decode(None, 0, C.byref(info), None, None, None, None) == -1
+    # sizing call, then a buffer one byte short, then the exact size
+    stream = mgx.mgix_encode([b"ab", b"bc"], [0, 2, 3], [1, 5, 9], 2, 2, True)
+    tb, to = mgx.pack_strings([b"ab", b"bc"])
+    po = np.array([0, 2, 3], dtype=np.uint64)
+    pp = np.array([1, 5, 9], dtype=np.uint32)
+    hdr = mgx.MgixInfo(4, 2, 2, 1, 1, 1, b"keep", 2, 0, 0)
+    args = (C.byref(hdr), tb.ctypes.data_as(mgx.u8p), to.ctypes.data_as(mgx.u64p), po.ctypes.data_as(mgx.u64p),
+            pp.ctypes.data_as(mgx.u32p), 0.0)
+    assert lib.mgx_mgix_encode(*args, None, 0, C.byref(n)) == -4 and n.value == len(stream)
+    short = np.zeros(len(stream) - 1, np.uint8)
+    assert lib.mgx_mgix_encode(*args, short.ctypes.data_as(mgx.u8p), short.size, C.byref(n)) == -4
+    exact = np.zeros(len(stream), np.uint8)
+    assert lib.mgx_mgix_encode(*args, exact.ctypes.data_as(mgx.u8p), exact.size, C.byref(n)) == 0
+    assert exact.tobytes() == stream
+    # decode with capacities that are too small is a capacity error, not a partial answer
+    buf = np.frombuffer(stream, dtype=np.uint8).copy()
+    small = mgx.MgixInfo()
+    small.n_terms, small.n_postings, small.term_bytes = 1, 3, 4
+    t2, o2, q2, p2 = np.zeros(8, np.uint8), np.zeros(3, np.uint64), np.zeros(3, np.uint64), np.zeros(3, np.uint32)
+    assert lib.mgx_mgix_decode(buf.ctypes.data_as(mgx.u8p), buf.size, C.byref(small), t2.ctypes.data_as(mgx.u8p),
+                               o2.ctypes.data_as(mgx.u64p), q2.ctypes.data_as(mgx.u64p),
+                               p2.ctypes.data_as(mgx.u32p)) == -4
+    assert small.n_terms == 2 and small.n_postings == 3  # the sizes needed come back
+    buf[10] ^= 1
+    assert lib.mgx_mgix_decode(buf.ctypes.data_as(mgx.u8p), buf.size, C.byref(info), None, None, None, None) == -6
+    assert b"kStorageCRCMismatch" in lib.mgx_last_error()
+
+
 def test_argument_validation_is_host_side(mgx):
     lib = mgx.lib()
     assert lib.mgx_index_create(None, None) == -1
