@@ -66,6 +66,31 @@ class TorchDist:
         self.dist.barrier()
 
 
+def gather_doc_id_sets(comm, local_ids, device=None):
+    """Un-scored result sets of one query across the shards (the Index::Search* style calls and the fuzzy / synonym
+    paths, which are per-document predicates and need no global statistics): every shard answers over its own doc-id
+    range, and because the ranges are ordered, the concatenation of the shard answers in rank order IS the ascending
+    global answer — no merge. Exchange: the sizes (one small all-gather), then the ids padded to the largest shard
+    answer (one all-gather). `local_ids`: this shard's ascending global doc ids (numpy uint32). Returns the global
+    answer (numpy uint32) on every rank."""
+    import torch
+    local = torch.from_numpy(np.ascontiguousarray(local_ids, dtype=np.uint32).view(np.int32).copy())
+    if device is not None:
+        local = local.to(device)
+    n_local = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    sizes = comm.all_gather(n_local).view(-1).cpu()
+    width = int(sizes.max()) if sizes.numel() else 0
+    if width == 0:
+        return np.zeros(0, dtype=np.uint32)
+    padded = torch.zeros(width, dtype=torch.int32, device=local.device)
+    padded[:local.numel()] = local
+    everyone = comm.all_gather(padded).cpu().numpy().view(np.uint32)
+    parts = [everyone[r, :int(sizes[r])] for r in range(everyone.shape[0])]
+    out = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint32)
+    assert out.size < 2 or bool(np.all(out[1:] > out[:-1])), "shard answers must come from ordered doc-id ranges"
+    return out
+
+
 def record_layout(n_queries, stride):
     """Byte offsets of one shard's packed top-k record: [scores f64 Q*S][total i64 Q][ids i32 Q*S][count i32 Q],
     padded to 16 bytes (the same layout as mgx_shard_record_layout, include/mgx.h)."""

@@ -142,6 +142,83 @@ def test_two_shards_equal_one_index(tmp_path, oracle, score, descending):
     assert int(want.total.max()) > LIMIT + OFFSET  # the merge really had to choose
 
 
+def _set_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "support")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    import corpus as corpus_mod
+    import mgx_loader
+    import pyoracle
+    mgx_loader.load()
+    from mygram_db_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = sharded.TorchDist(dist)
+    lo, hi = sharded.shard_range(SET_DOCS, world, rank)
+    c = corpus_mod.generate("cjk", hi - lo, 0xC2, first_doc=lo, alphabet=128, min_len=4, max_len=30)
+    idx = pyoracle.OracleLib(pyoracle.PORT_LIB).index(2, 0, True)
+    idx.build_bulk(c.doc_ids, c.arena, c.offsets, 2)
+    answers = []
+    for kind, arg in _set_queries():
+        if kind == "fuzzy":
+            local = idx.search_fuzzy(arg, 1, verify_text=1)[0]
+        elif kind == "synonyms":
+            local = idx.search_synonyms(arg)[0]
+        else:
+            local = idx.search_or(arg)
+        answers.append(sharded.gather_doc_id_sets(comm, local))
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "sets.npz"), *answers)
+    dist.destroy_process_group()
+
+
+SET_DOCS = 5000
+
+
+def _set_queries():
+    import corpus as corpus_mod
+    c = corpus_mod.generate("cjk", SET_DOCS, 0xC2, alphabet=128, min_len=4, max_len=30)
+    rng = np.random.default_rng(12)
+    out = []
+    for i in range(30):
+        t = c.text(int(rng.integers(0, SET_DOCS))).decode()
+        u = c.text(int(rng.integers(0, SET_DOCS))).decode()
+        if i % 3 == 0:
+            out.append(("fuzzy", [t[:2] + chr(0x4E00 + 200) + t[3:5]]))   # one substituted character, distance 1
+        elif i % 3 == 1:
+            out.append(("synonyms", [[t[:2], u[:3]], [t[1:3], u[2:4]]]))
+        else:
+            out.append(("or", [t[:2], u[:2], "zz"]))
+    out.append(("fuzzy", ["zzzz"]))  # empty everywhere
+    return out
+
+
+def test_two_shards_answer_set_queries_like_one_index(tmp_path, oracle):
+    """Un-scored doc-id sets (SearchOr, the fuzzy and the synonym paths) over two doc-range shards: the shard answers
+    concatenated in rank order (sharded.gather_doc_id_sets: a size all-gather + an id all-gather, no merge) equal the
+    answer of one index over the whole corpus."""
+    import torch.multiprocessing as mp
+    import corpus as corpus_mod
+    port = _free_port()
+    mp.spawn(_set_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "sets.npz")
+    c = corpus_mod.generate("cjk", SET_DOCS, 0xC2, alphabet=128, min_len=4, max_len=30)
+    idx = oracle.index(2, 0, True)
+    idx.build_bulk(c.doc_ids, c.arena, c.offsets, 2)
+    nonempty = 0
+    for i, (kind, arg) in enumerate(_set_queries()):
+        if kind == "fuzzy":
+            want = idx.search_fuzzy(arg, 1, verify_text=1)[0]
+        elif kind == "synonyms":
+            want = idx.search_synonyms(arg)[0]
+        else:
+            want = idx.search_or(arg)
+        assert np.array_equal(got[f"arr_{i}"], want), (kind, arg)
+        nonempty += want.size > 0
+    assert nonempty >= 20
+
+
 def test_shard_ranges_cover_everything():
     sys.path.insert(0, ROOT)
     import mgx_loader

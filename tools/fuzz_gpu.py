@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """tools/fuzz_gpu.py — randomized GPU-vs-oracle comparison over many small corpora, index configurations and
 query shapes (run on a B200 box: `python tools/fuzz_gpu.py [seconds] [seed]`). Not part of the test-suite; it is
-the shake-out used while developing the positional df shortcut, boolean programs, mutations and filters."""
+the shake-out used while developing the positional df shortcut, boolean programs, mutations, filters, the fuzzy /
+synonym paths and the MGIX export."""
 import os
 import random
 import sys
@@ -69,6 +70,17 @@ while time.time() < t_end:
         ops, args = T.random_program(rnd, nt)
         g, o = gi.eval_boolean(ops, args, terms), oi.eval_boolean(ops, args, terms)
         assert np.array_equal(g, o), ("boolean", seed, cfg, ops, args, terms, g[:8], o[:8])
+    # fuzzy / synonym execution paths (ExecuteWithFuzzy / ExecuteWithSynonyms) and the MGIX stream of the index
+    import test_oracle_expanded as X
+    for fuzzy_terms, groups, nots2, dist in X.expanded_cases(rnd, docs, 12):
+        vt = rnd.randrange(3)
+        g, o = gi.search_fuzzy(fuzzy_terms, dist, nots2, verify_text=vt), oi.search_fuzzy(fuzzy_terms, dist, nots2, verify_text=vt)[0]
+        assert np.array_equal(g, o), ("fuzzy", seed, cfg, fuzzy_terms, dist, nots2, vt, g[:8], o[:8])
+        g, o = gi.search_synonyms(groups, nots2, verify_text=vt), oi.search_synonyms(groups, nots2, verify_text=vt)[0]
+        assert np.array_equal(g, o), ("synonyms", seed, cfg, groups, nots2, vt, g[:8], o[:8])
+    meta, mt, mo, mp = mgx.mgix_decode(gi.save_mgix())
+    ot, oo, op_ = oi.export()
+    assert [bytes(t) for t in ot] == mt and np.array_equal(mo, oo) and np.array_equal(mp, op_), ("mgix", seed, cfg)
     # mutations: a burst of add / update / remove, then compare postings, stats and a batch
     if n >= 7 and not bad:
         os.environ.pop("MGX_DF_MODE", None)
