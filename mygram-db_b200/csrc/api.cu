@@ -1170,10 +1170,43 @@ enum class SetOp { kAnd, kOr, kNot, kFilter };
 
 // One query whose full ascending result set is wanted (the Index::Search* style calls): upload, plan, run the
 // tiles, gather; then the limit / reverse rules of index.cpp:356-366.
+// A batch object from the index's pool for the duration of one single-query call. A fresh Batch allocates its pinned
+// staging buffer and two device arenas and frees them again at the end of the call — most of the ~5 ms a single
+// Index::Search* style call cost at 10M documents (profiles/r01_h_expanded_paths_10M.md); the pooled objects keep them.
+struct PooledBatch {
+  Index& ix;
+  std::unique_ptr<mgx_batch> h;
+  int exceptions_at_entry = std::uncaught_exceptions();
+  explicit PooledBatch(Index& index) : ix(index) {
+    {
+      std::lock_guard<std::mutex> pool_lock(ix.pool_mu);
+      if (!ix.batch_pool.empty()) {
+        h.reset(static_cast<mgx_batch*>(ix.batch_pool.back()));
+        ix.batch_pool.pop_back();
+      }
+    }
+    if (!h) {
+      h = std::make_unique<mgx_batch>();
+    }
+  }
+  ~PooledBatch() {
+    if (std::uncaught_exceptions() > exceptions_at_entry) {
+      return;  // a failed call does not hand its workspace on
+    }
+    cudaStreamSynchronize(h->b.stream);
+    h->b.recycle();
+    std::lock_guard<std::mutex> pool_lock(ix.pool_mu);
+    if (ix.batch_pool.size() < 16) {
+      ix.batch_pool.push_back(h.release());
+    }
+  }
+};
+
 int run_single_set_query(Index& ix, std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
                          const uint32_t* driver_ids, uint64_t n_driver, uint64_t limit, bool reverse, uint32_t* out,
                          uint64_t cap, uint64_t* out_count) {
-  Batch b;
+  PooledBatch pooled(ix);
+  Batch& b = pooled.h->b;
   b.ix = &ix;
   b.stream = ix.stream;
   b.params = mgx_query_params_t{};

@@ -59,6 +59,7 @@ def main():
     ap.add_argument("--queries", type=int, default=200)
     ap.add_argument("--cpu-sample", type=int, default=24)
     ap.add_argument("--out", default="")
+    ap.add_argument("--gpu-only", action="store_true", help="query timings only: no MGIX export, no CPU oracle")
     args = ap.parse_args()
     import corpus as corpus_mod
     import mgx_loader
@@ -94,6 +95,9 @@ def main():
                                 "result_docs_mean": float(np.mean([g.size for g in got]))}
         flush()
     out["gpu_launches"] = int(m.lib().mgx_kernel_launch_count() - launches0)
+    if args.gpu_only:
+        print(flush(), flush=True)
+        return
     # MGIX export of the whole shard (raw buffers: tens of millions of terms are not turned into Python objects)
     C = m.C
     st = gi.stats()
