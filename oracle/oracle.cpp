@@ -1989,6 +1989,14 @@ uint64_t orc_eval_boolean(const orc_index_t* idx, const int32_t* ops, const int3
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------- column filters
+extern "C" int orc_contains_fuzzy_match(const uint8_t* text, uint64_t text_len, const uint8_t* term, uint64_t term_len,
+                                        uint32_t max_distance) {
+  return ContainsFuzzyMatch(std::string_view(reinterpret_cast<const char*>(text), text_len),
+                            std::string_view(reinterpret_cast<const char*>(term), term_len), max_distance)
+             ? 1
+             : 0;
+}
+
 extern "C" uint64_t orc_search_fuzzy(const orc_index_t* idx, const orc_query_params_t* params,
                                      const uint8_t* term_bytes, const uint64_t* term_offsets, uint64_t n_terms,
                                      uint32_t max_distance, const uint8_t* not_bytes, const uint64_t* not_offsets,

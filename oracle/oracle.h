@@ -184,6 +184,9 @@ uint64_t orc_eval_boolean(const orc_index_t* idx, const int32_t* ops, const int3
  * ContainsFuzzyMatch of utils/edit_distance.cpp) when verify_text applies; hybrid-fragment exact text filter.
  * Column filters are applied by the caller with orc_apply_filters (they are per-document predicates).
  * Returns the result size (ids ascending). *empty_term_detected (may be NULL) as in SearchPipelineResult. */
+/* ContainsFuzzyMatch (src/utils/edit_distance.cpp:168-255). */
+int orc_contains_fuzzy_match(const uint8_t* text, uint64_t text_len, const uint8_t* term, uint64_t term_len,
+                             uint32_t max_distance);
 uint64_t orc_search_fuzzy(const orc_index_t* idx, const orc_query_params_t* params, const uint8_t* term_bytes,
                           const uint64_t* term_offsets, uint64_t n_terms, uint32_t max_distance,
                           const uint8_t* not_bytes, const uint64_t* not_offsets, uint64_t n_not, uint32_t* out,

@@ -159,6 +159,8 @@ class OracleLib:
                                       C.c_uint64, u32p, f64p, u32p, u64p, u64p, u32p, C.c_uint64, u64p, C.c_int]
         L.orc_eval_boolean.restype = C.c_uint64
         L.orc_eval_boolean.argtypes = [C.c_void_p, i32p, i32p, C.c_uint64, u8p, u64p, u32p, C.c_uint64]
+        L.orc_contains_fuzzy_match.restype = C.c_int
+        L.orc_contains_fuzzy_match.argtypes = [u8p, C.c_uint64, u8p, C.c_uint64, C.c_uint32]
         L.orc_search_fuzzy.restype = C.c_uint64
         L.orc_search_fuzzy.argtypes = [C.c_void_p, C.POINTER(QueryParams), u8p, u64p, C.c_uint64, C.c_uint32, u8p, u64p,
                                        C.c_uint64, u32p, C.c_uint64, i32p]
@@ -230,6 +232,12 @@ class OracleLib:
         return [raw[int(offs[i]):int(offs[i + 1])] for i in range(n)]
 
     # ---- index ----
+    def contains_fuzzy_match(self, text, term, max_distance):
+        t = np.frombuffer(as_bytes(text) or b"\0", dtype=np.uint8).copy()
+        q = np.frombuffer(as_bytes(term) or b"\0", dtype=np.uint8).copy()
+        return bool(self.lib.orc_contains_fuzzy_match(_ptr(t, u8p), len(as_bytes(text)), _ptr(q, u8p),
+                                                      len(as_bytes(term)), max_distance))
+
     def index(self, ngram_size=2, kanji_ngram_size=0, cross_boundary=True):
         return OracleIndex(self, ngram_size, kanji_ngram_size, cross_boundary)
 

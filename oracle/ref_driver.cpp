@@ -34,6 +34,7 @@
 #include "server/search_pipeline.h"
 #include "server/server_types.h"
 #include "storage/document_store.h"
+#include "utils/edit_distance.h"
 #include "utils/string_utils.h"
 
 #include "oracle.h"
@@ -532,6 +533,15 @@ uint64_t orc_eval_boolean(const orc_index_t* idx, const int32_t* ops, const int3
     return 0;
   }
   return CopyOut(stack.back()->Evaluate(*idx->index, *idx->store), out, cap);
+}
+
+int orc_contains_fuzzy_match(const uint8_t* text, uint64_t text_len, const uint8_t* term, uint64_t term_len,
+                             uint32_t max_distance) {
+  return mygram::utils::ContainsFuzzyMatch(std::string_view(reinterpret_cast<const char*>(text), text_len),
+                                           std::string_view(reinterpret_cast<const char*>(term), term_len),
+                                           max_distance)
+             ? 1
+             : 0;
 }
 
 // The reference's own ExecuteWithFuzzy (search_pipeline.cpp:1659-1740), called the way ExecuteFullPipeline does

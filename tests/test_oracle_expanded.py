@@ -82,3 +82,41 @@ def test_fuzzy_and_synonyms_agree_with_reference_sources(oracle, reflib, cfg):
     assert a[1] is True and b[1] is True and len(a[0]) == 0 and len(b[0]) == 0
     a, b = pi.search_synonyms([]), ri.search_synonyms([])
     assert a[1] is True and b[1] is True and len(a[0]) == 0 and len(b[0]) == 0
+
+
+# ContainsFuzzyMatch known answers transcribed from the reference's own unit tests
+# (tests/utils/edit_distance_test.cpp, line of each EXPECT in the last column)
+FUZZY_KAT = [
+    ("hello world", "hello", 0, True, 86), ("hello world", "hallo", 1, True, 90), ("hello world", "xxxxx", 1, False, 94),
+    ("the quick brown fox", "quikc", 2, True, 99), ("", "hello", 1, False, 103), ("hello world", "", 1, True, 108),
+    ("a", "", 1, True, 109), ("restaurant", "restrant", 2, True, 114), ("東京都 大阪府", "東京市", 1, True, 119),
+    ("私は東京都に住む", "東京市", 1, True, 123), ("私は東西京に住む", "東京市", 1, False, 127),
+    ("concatenate", "cat", 0, False, 131), ("alpha beta gamma", "zzzzz", 2, False, 135),
+    ("a b c hello d e", "hello", 0, True, 139), ("hello\tworld", "hello", 0, True, 155),
+    ("hello\tworld", "world", 0, True, 156), ("hello\nworld", "hello", 0, True, 160),
+    ("hello\r\nworld", "world", 0, True, 161), ("one\ttwo\nthree four", "three", 0, True, 165),
+    ("one\ttwo\nthree four", "threa", 1, True, 166), ("a b c", "b", 0, True, 203), ("a b c", "x", 1, True, 204),
+]
+
+
+def test_contains_fuzzy_match_known_answers(oracle):
+    for text, term, dist, want, line in FUZZY_KAT:
+        assert oracle.contains_fuzzy_match(text, term, dist) == want, (text, term, dist, f"edit_distance_test.cpp:{line}")
+
+
+def test_contains_fuzzy_match_agrees_with_reference_sources(oracle, reflib):
+    for text, term, dist, want, line in FUZZY_KAT:
+        assert reflib.contains_fuzzy_match(text, term, dist) == want, line
+    rnd = random.Random(99)
+    alphabet = ["a", "b", "c", " ", "\t", "東", "京", "\u3000", "\u00a0", "é"]
+    raw = [b"\xe3\x80", b"\xc2", b"\xff", b"\xe6\x9d"]
+    for _ in range(20000):
+        text = "".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 14))).encode()
+        term = "".join(rnd.choice(alphabet[:3] + alphabet[5:7] + ["é"]) for _ in range(rnd.randint(0, 5))).encode()
+        if rnd.random() < 0.15:
+            cut = rnd.randrange(len(text) + 1)
+            text = text[:cut] + rnd.choice(raw) + text[cut:]
+        if rnd.random() < 0.05:
+            term += rnd.choice(raw)
+        d = rnd.randint(0, 3)
+        assert oracle.contains_fuzzy_match(text, term, d) == reflib.contains_fuzzy_match(text, term, d), (text, term, d)
