@@ -158,9 +158,59 @@ def gen_mgix():
     print("ref_mgix.json", os.path.getsize(path), "bytes")
 
 
+def gen_expanded():
+    """tests/golden/ref_expanded.json: results of the reference's own ExecuteWithFuzzy / ExecuteWithSynonyms (through
+    oracle/_ref) over the documents of ref_pipeline.json, for the configurations of its cases."""
+    ref = OracleLib(REF_LIB)
+    pipe = json.load(open(os.path.join(OUT, "ref_pipeline.json")))
+    docs = [base64.b64decode(d) for d in pipe["docs"]]
+    ids = np.array(pipe["ids"], dtype=np.uint32)
+    rnd = random.Random(0xE5)
+    texts = [d.decode("utf-8", "ignore") for d in docs]
+    texts = [t for t in texts if len(t) >= 4]
+
+    def piece(lo, hi):
+        t = rnd.choice(texts)
+        ln = rnd.randint(lo, min(hi, len(t)))
+        st = rnd.randrange(0, len(t) - ln + 1)
+        return t[st:st + ln]
+
+    def misspell(s):
+        if rnd.random() < 0.3:
+            return s
+        i = rnd.randrange(len(s))
+        return s[:i] + rnd.choice(["x", "東", ""]) + s[i + 1:]
+
+    out = {"generator": "oracle/gen_golden.py expanded", "cases": []}
+    for case in pipe["cases"]:
+        cfg = (case["ngram"], case["kanji"], case["cross"])
+        idx = ref.index(*cfg)
+        idx.add_texts(ids, docs)
+        fuzzy, syn = [], []
+        for _ in range(60):
+            terms = [misspell(piece(2, 7)) for _ in range(rnd.randint(1, 2))]
+            nots = [piece(1, 3)] if rnd.random() < 0.25 else []
+            dist, vt = rnd.randint(0, 2), rnd.randrange(3)
+            r, empty = idx.search_fuzzy(terms, dist, nots, verify_text=vt)
+            fuzzy.append({"terms": [b64(t.encode()) for t in terms], "not": [b64(t.encode()) for t in nots],
+                          "distance": dist, "verify_text": vt, "ids": r.tolist(), "empty_term": empty})
+            groups = [[piece(1, 4) for _ in range(rnd.randint(1, 3))] for _ in range(rnd.randint(1, 3))]
+            r, empty = idx.search_synonyms(groups, nots, verify_text=vt)
+            syn.append({"groups": [[b64(v.encode()) for v in g] for g in groups], "not": [b64(t.encode()) for t in nots],
+                        "verify_text": vt, "ids": r.tolist(), "empty_term": empty})
+        out["cases"].append({"ngram": cfg[0], "kanji": cfg[1], "cross": cfg[2], "fuzzy": fuzzy, "synonyms": syn})
+    path = os.path.join(OUT, "ref_expanded.json")
+    json.dump(out, open(path, "w"), indent=0)
+    print("ref_expanded.json", os.path.getsize(path), "bytes,",
+          sum(1 for c in out["cases"] for q in c["fuzzy"] + c["synonyms"] if q["ids"]), "non-empty answers")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mgix":
         gen_mgix()
+    elif len(sys.argv) > 1 and sys.argv[1] == "expanded":
+        gen_expanded()
     else:
         main()
         gen_mgix()
+        gen_expanded()

@@ -16,6 +16,9 @@ TOK = json.load(open(os.path.join(HERE, "golden", "ref_tokenizer.json")))
 PIPE = json.load(open(os.path.join(HERE, "golden", "ref_pipeline.json")))
 
 
+EXP = json.load(open(os.path.join(HERE, "golden", "ref_expanded.json")))
+
+
 def d64(s):
     return base64.b64decode(s)
 
@@ -92,7 +95,42 @@ def test_oracle_pipeline_matches_reference_fixture(oracle, ci):
     check_case(lambda a, k, c: oracle.index(a, k, c), PIPE["cases"][ci], False)
 
 
+def check_expanded_case(make_index, case, is_gpu):
+    """ref_expanded.json: answers of the reference's own ExecuteWithFuzzy / ExecuteWithSynonyms
+    (search_pipeline.cpp:1580-1752) over the documents of ref_pipeline.json."""
+    idx = make_index(case["ngram"], case["kanji"], case["cross"])
+    if is_gpu:
+        idx.add_document_batch(IDS, DOCS)
+        ids_of = lambda r: r  # noqa: E731  (the product returns the ids)
+    else:
+        idx.add_texts(IDS, DOCS)
+        ids_of = lambda r: r[0]  # noqa: E731  (the oracle returns (ids, empty_term_detected))
+    nonempty = 0
+    for q in case["fuzzy"]:
+        terms, nots = [d64(t) for t in q["terms"]], [d64(t) for t in q["not"]]
+        got = ids_of(idx.search_fuzzy(terms, q["distance"], nots, verify_text=q["verify_text"]))
+        assert got.tolist() == q["ids"], ("fuzzy", terms, q["distance"], nots, q["verify_text"])
+        nonempty += len(q["ids"]) > 0
+    for q in case["synonyms"]:
+        groups, nots = [[d64(v) for v in g] for g in q["groups"]], [d64(t) for t in q["not"]]
+        got = ids_of(idx.search_synonyms(groups, nots, verify_text=q["verify_text"]))
+        assert got.tolist() == q["ids"], ("synonyms", groups, nots, q["verify_text"])
+        nonempty += len(q["ids"]) > 0
+    assert nonempty >= 20
+
+
+@pytest.mark.parametrize("ci", range(len(EXP["cases"])))
+def test_oracle_fuzzy_and_synonyms_match_reference_fixture(oracle, ci):
+    check_expanded_case(lambda a, k, c: oracle.index(a, k, c), EXP["cases"][ci], False)
+
+
 # ------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("ci", range(len(EXP["cases"])))
+def test_gpu_fuzzy_and_synonyms_match_reference_fixture(mgx, ci):
+    check_expanded_case(lambda a, k, c: mgx.Index(a, k, c), EXP["cases"][ci], True)
+
+
 @pytest.mark.gpu
 def test_gpu_tokenizer_matches_reference_fixture(mgx):
     for cfg in TOK["hybrid"]:
