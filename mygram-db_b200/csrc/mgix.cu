@@ -16,10 +16,13 @@
 // (cookie 12346 / 12347, descriptive header, offset header, array / bitset / run containers). It is a data-format
 // codec, not a compute path: nothing here touches the device, and the search core never calls it.
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <vector>
 
 #include "../../include/mgx.h"
@@ -66,6 +69,143 @@ uint32_t crc32(const uint8_t* p, uint64_t n) {
     c = t[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
   }
   return c ^ 0xFFFFFFFFu;
+}
+
+// CRC of the concatenation of two byte strings from their CRCs (GF(2) matrix method, as zlib's crc32_combine):
+// lets the checksum of a multi-gigabyte stream be computed in independent pieces.
+uint32_t gf2_times(const uint32_t* mat, uint32_t vec) {
+  uint32_t sum = 0;
+  while (vec != 0) {
+    if ((vec & 1u) != 0) {
+      sum ^= *mat;
+    }
+    vec >>= 1;
+    ++mat;
+  }
+  return sum;
+}
+
+void gf2_square(uint32_t* square, const uint32_t* mat) {
+  for (int n = 0; n < 32; ++n) {
+    square[n] = gf2_times(mat, mat[n]);
+  }
+}
+
+uint32_t crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) {
+  if (len2 == 0) {
+    return crc1;
+  }
+  uint32_t even[32];
+  uint32_t odd[32];
+  odd[0] = 0xEDB88320u;  // the operator for one zero bit
+  uint32_t row = 1;
+  for (int n = 1; n < 32; ++n) {
+    odd[n] = row;
+    row <<= 1;
+  }
+  gf2_square(even, odd);  // two zero bits
+  gf2_square(odd, even);  // four
+  do {
+    gf2_square(even, odd);
+    if ((len2 & 1u) != 0) {
+      crc1 = gf2_times(even, crc1);
+    }
+    len2 >>= 1;
+    if (len2 == 0) {
+      break;
+    }
+    gf2_square(odd, even);
+    if ((len2 & 1u) != 0) {
+      crc1 = gf2_times(odd, crc1);
+    }
+    len2 >>= 1;
+  } while (len2 != 0);
+  return crc1 ^ crc2;
+}
+
+// Worker threads of the codec: streams of a whole shard are gigabytes (2.8 GB for 10M documents), small ones are not
+// worth a thread start. MGX_MGIX_THREADS pins the count (the tests run both paths on small inputs).
+unsigned codec_threads(uint64_t work_items) {
+  if (const char* env = std::getenv("MGX_MGIX_THREADS")) {
+    return static_cast<unsigned>(std::max(1, std::min(64, std::atoi(env))));
+  }
+  if (work_items < (1u << 20)) {
+    return 1;
+  }
+  return std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+}
+
+// fn(first, last, worker) over [0, n) cut into `threads` contiguous ranges.
+template <class Fn>
+void parallel_ranges(uint64_t n, unsigned threads, Fn&& fn) {
+  if (threads <= 1 || n < threads) {
+    fn(static_cast<uint64_t>(0), n, 0u);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned w = 0; w < threads; ++w) {
+    pool.emplace_back([&, w]() { fn(n * w / threads, n * (w + 1) / threads, w); });
+  }
+  for (auto& t : pool) {
+    t.join();
+  }
+}
+
+// Range boundaries over [0, n) with about equal weight per range; weight_before(t) = total weight of items [0, t),
+// non-decreasing (posting lists are Zipf-sized: equal item counts would leave one thread with most of the postings).
+template <class W>
+std::vector<uint64_t> balanced_bounds(uint64_t n, unsigned threads, W&& weight_before) {
+  std::vector<uint64_t> bounds(threads + 1, n);
+  bounds[0] = 0;
+  const uint64_t total = weight_before(n);
+  for (unsigned w = 1; w < threads; ++w) {
+    const uint64_t target = total / threads * w;
+    uint64_t lo = bounds[w - 1];
+    uint64_t hi = n;
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) / 2;
+      if (weight_before(mid) < target) {
+        lo = mid + 1;
+      } else {
+        hi = mid;
+      }
+    }
+    bounds[w] = lo;
+  }
+  return bounds;
+}
+
+template <class Fn>
+void parallel_bounds(const std::vector<uint64_t>& bounds, Fn&& fn) {
+  const unsigned threads = static_cast<unsigned>(bounds.size() - 1);
+  if (threads <= 1) {
+    fn(bounds.front(), bounds.back(), 0u);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned w = 0; w < threads; ++w) {
+    pool.emplace_back([&, w]() { fn(bounds[w], bounds[w + 1], w); });
+  }
+  for (auto& t : pool) {
+    t.join();
+  }
+}
+
+uint32_t crc32_parallel(const uint8_t* p, uint64_t n, unsigned threads) {
+  if (threads <= 1 || n < (1u << 22)) {
+    return crc32(p, n);
+  }
+  std::vector<uint32_t> part(threads, 0);
+  std::vector<uint64_t> len(threads, 0);
+  parallel_ranges(n, threads, [&](uint64_t a, uint64_t b, unsigned w) {
+    part[w] = crc32(p + a, b - a);
+    len[w] = b - a;
+  });
+  uint32_t c = part[0];
+  for (unsigned w = 1; w < threads; ++w) {
+    c = crc32_combine(c, part[w], len[w]);
+  }
+  return c;
 }
 
 constexpr uint32_t kArrayMax = 4096;            // a Roaring array container holds at most this many values
@@ -163,6 +303,14 @@ void write_roaring(Writer& w, const uint32_t* ids, uint64_t n, uint32_t n_contai
       for (uint64_t word : words) {
         w.u64(word);
       }
+    } else if (w.out != nullptr && w.pos + (j - i) * 2 <= w.cap) {
+      uint8_t* dst = w.out + w.pos;  // checked once for the container
+      for (uint64_t k = i; k < j; ++k) {
+        dst[0] = static_cast<uint8_t>(ids[k]);
+        dst[1] = static_cast<uint8_t>(ids[k] >> 8);
+        dst += 2;
+      }
+      w.pos += (j - i) * 2;
     } else {
       for (uint64_t k = i; k < j; ++k) {
         w.u16(static_cast<uint16_t>(ids[k] & 0xFFFFu));
@@ -383,48 +531,100 @@ int mgx_mgix_encode(const mgx_mgix_info_t* info, const uint8_t* term_bytes, cons
   w.bytes(info->normalize_width, width_len);
   w.u8(info->normalize_lower != 0 ? 1 : 0);
   w.u64(info->n_terms);
-  for (uint64_t t = 0; t < info->n_terms; ++t) {
-    const uint64_t tl = term_offsets[t + 1] - term_offsets[t];
-    const uint32_t* ids = postings + posting_offsets[t];
-    const uint64_t n = posting_offsets[t + 1] - posting_offsets[t];
-    for (uint64_t i = 1; i < n; ++i) {
-      if (ids[i] <= ids[i - 1]) {
-        set_last_error("posting list is not strictly ascending");
-        return MGX_ERR_INVALID_ARGUMENT;
-      }
-    }
-    w.u32(static_cast<uint32_t>(tl));
-    w.bytes(term_bytes + term_offsets[t], tl);
+  const uint64_t header_len = w.pos;
+  const uint64_t T = info->n_terms;
+  const uint64_t P = T > 0 ? posting_offsets[T] : 0;
+  const unsigned threads = codec_threads(P + T);
+  // pass 1 (parallel over terms): validate the lists and size every record
+  //   record = u32 term length | term | u64 body length | u8 strategy | u32 size | data
+  std::vector<uint64_t> rec_off(T + 1, 0);
+  std::atomic<int> failure{0};  // 1 = list not ascending, 2 = roaring body above 4 GiB
+  const auto is_roaring = [&](uint64_t n) {
     // the representation the reference's list would be in: Roaring above 4096 entries since insertion
     // (posting_list.cpp:21,917-922), by density after Index::Optimize (:800-834)
-    const bool roaring = n > kAutoRoaringEntries || (roaring_min_len > 0.0 && static_cast<double>(n) >= roaring_min_len);
-    if (!roaring) {
-      w.u64(5 + n * 4);
-      w.u8(0);
-      w.u32(static_cast<uint32_t>(n));
-      for (uint64_t i = 0; i < n; ++i) {
-        w.u32(i == 0 ? ids[0] : ids[i] - ids[i - 1]);
+    return n > kAutoRoaringEntries || (roaring_min_len > 0.0 && static_cast<double>(n) >= roaring_min_len);
+  };
+  const std::vector<uint64_t> bounds = balanced_bounds(
+      T, threads, [&](uint64_t t) { return (t > 0 ? posting_offsets[t] - posting_offsets[0] : 0) + 8 * t; });
+  parallel_bounds(bounds, [&](uint64_t t0, uint64_t t1, unsigned) {
+    for (uint64_t t = t0; t < t1; ++t) {
+      const uint32_t* ids = postings + posting_offsets[t];
+      const uint64_t n = posting_offsets[t + 1] - posting_offsets[t];
+      for (uint64_t i = 1; i < n; ++i) {
+        if (ids[i] <= ids[i - 1]) {
+          failure.store(1);
+          return;
+        }
       }
-    } else {
-      uint32_t n_containers = 0;
-      const uint64_t rb = roaring_size(ids, n, &n_containers);
-      if (rb > 0xFFFFFFFFULL) {
-        set_last_error("roaring bitmap larger than 4 GiB (posting_list.cpp:1001-1008)");
-        return MGX_ERR_UNSUPPORTED;
+      uint64_t body = 5 + n * 4;
+      if (is_roaring(n)) {
+        uint32_t n_containers = 0;
+        const uint64_t rb = roaring_size(ids, n, &n_containers);
+        if (rb > 0xFFFFFFFFULL) {
+          failure.store(2);
+          return;
+        }
+        body = 5 + rb;
       }
-      w.u64(5 + rb);
-      w.u8(1);
-      w.u32(static_cast<uint32_t>(rb));
-      write_roaring(w, ids, n, n_containers);
+      rec_off[t + 1] = 4 + (term_offsets[t + 1] - term_offsets[t]) + 8 + body;
     }
+  });
+  if (failure.load() == 1) {
+    set_last_error("posting list is not strictly ascending");
+    return MGX_ERR_INVALID_ARGUMENT;
   }
-  const uint64_t payload = w.pos;
+  if (failure.load() == 2) {
+    set_last_error("roaring bitmap larger than 4 GiB (posting_list.cpp:1001-1008)");
+    return MGX_ERR_UNSUPPORTED;
+  }
+  rec_off[0] = header_len;
+  for (uint64_t t = 0; t < T; ++t) {
+    rec_off[t + 1] += rec_off[t];
+  }
+  const uint64_t payload = rec_off[T];
   *out_len = payload + 4;
   if (out == nullptr || *out_len > cap) {
     set_last_error("output capacity too small");
     return MGX_ERR_CAPACITY;
   }
-  w.u32(crc32(out, payload));
+  // pass 2 (parallel): every record is written at its own offset
+  parallel_bounds(bounds, [&](uint64_t t0, uint64_t t1, unsigned) {
+    for (uint64_t t = t0; t < t1; ++t) {
+      const uint64_t tl = term_offsets[t + 1] - term_offsets[t];
+      const uint32_t* ids = postings + posting_offsets[t];
+      const uint64_t n = posting_offsets[t + 1] - posting_offsets[t];
+      Writer rw{out + rec_off[t], rec_off[t + 1] - rec_off[t]};
+      rw.u32(static_cast<uint32_t>(tl));
+      rw.bytes(term_bytes + term_offsets[t], tl);
+      if (!is_roaring(n)) {
+        rw.u64(5 + n * 4);
+        rw.u8(0);
+        rw.u32(static_cast<uint32_t>(n));
+        uint8_t* dst = rw.out + rw.pos;  // the slice was sized for exactly these n words
+        uint32_t prev = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+          const uint32_t gap = ids[i] - prev;  // the first word is the doc id itself
+          prev = ids[i];
+          dst[0] = static_cast<uint8_t>(gap);
+          dst[1] = static_cast<uint8_t>(gap >> 8);
+          dst[2] = static_cast<uint8_t>(gap >> 16);
+          dst[3] = static_cast<uint8_t>(gap >> 24);
+          dst += 4;
+        }
+        rw.pos += n * 4;
+      } else {
+        uint32_t n_containers = 0;
+        const uint64_t rb = roaring_size(ids, n, &n_containers);
+        rw.u64(5 + rb);
+        rw.u8(1);
+        rw.u32(static_cast<uint32_t>(rb));
+        write_roaring(rw, ids, n, n_containers);
+      }
+    }
+  });
+  const uint32_t crc = crc32_parallel(out, payload, threads);
+  Writer tail{out + payload, 4};
+  tail.u32(crc);
   return MGX_OK;
 }
 
@@ -460,7 +660,7 @@ int mgx_mgix_decode(const uint8_t* data, uint64_t len, mgx_mgix_info_t* info, ui
     data_size = len - 4;
     Reader trailer{data, len};
     trailer.pos = data_size;
-    if (trailer.u32() != crc32(data, data_size)) {
+    if (trailer.u32() != crc32_parallel(data, data_size, codec_threads(data_size / 4))) {
       return reject("kStorageCRCMismatch", "CRC32 checksum mismatch in index data");
     }
   }
@@ -501,39 +701,80 @@ int mgx_mgix_decode(const uint8_t* data, uint64_t len, mgx_mgix_info_t* info, ui
   records.reserve(static_cast<size_t>(std::min<uint64_t>(term_count, (data_size - r.pos) / 17 + 1)));
   uint64_t total_term_bytes = 0;
   uint64_t total_postings = 0;
+  // pass 1 (serial, headers only): record boundaries. A structural defect stops the scan; it is reported only if every
+  // posting list in front of it deserialises (the reference loads record by record, :497-575)
+  const char* structural_code = nullptr;
+  const char* structural_what = nullptr;
   for (uint64_t i = 0; i < term_count; ++i) {
     if (!r.has(4)) {
-      return reject("kStorageCorrupted", "truncated index data at term header");
+      structural_code = "kStorageCorrupted";
+      structural_what = "truncated index data at term header";
+      break;
     }
     const uint32_t term_len = r.u32();
     if (term_len > kMaxTermLength) {
-      return reject("kStorageCorrupted", "term length exceeds maximum allowed size");
+      structural_code = "kStorageCorrupted";
+      structural_what = "term length exceeds maximum allowed size";
+      break;
     }
     if (!r.has(term_len)) {
-      return reject("kStorageCorrupted", "truncated index data at term string");
+      structural_code = "kStorageCorrupted";
+      structural_what = "truncated index data at term string";
+      break;
     }
     Record rec;
     rec.term = std::string_view(reinterpret_cast<const char*>(data) + r.pos, term_len);
     r.pos += term_len;
     if (!r.has(8)) {
-      return reject("kStorageCorrupted", "truncated index data at posting list header");
+      structural_code = "kStorageCorrupted";
+      structural_what = "truncated index data at posting list header";
+      break;
     }
     rec.body_len = r.u64();
     if (rec.body_len > kMaxPostingBytes) {
-      return reject("kStorageCorrupted", "posting list size exceeds maximum allowed size");
+      structural_code = "kStorageCorrupted";
+      structural_what = "posting list size exceeds maximum allowed size";
+      break;
     }
     if (!r.has(rec.body_len)) {
-      return reject("kStorageCorrupted", "truncated index data at posting list body");
+      structural_code = "kStorageCorrupted";
+      structural_what = "truncated index data at posting list body";
+      break;
     }
     rec.body = data + r.pos;
     r.pos += rec.body_len;
     rec.count = 0;
-    if (!read_posting(rec.body, rec.body_len, &rec.count, nullptr)) {
-      return reject("kIndexDeserializationFailed", "failed to deserialize posting list of term " + std::string(rec.term));
-    }
-    total_term_bytes += term_len;
-    total_postings += rec.count;
     records.push_back(rec);
+  }
+  // pass 2 (parallel, balanced by body bytes): PostingList::Deserialize's checks and the list sizes
+  const unsigned threads = codec_threads(data_size / 4);
+  {
+    const uint8_t* base = records.empty() ? data : records.front().body;
+    const std::vector<uint64_t> bounds = balanced_bounds(records.size(), threads, [&](uint64_t t) {
+      return (t < records.size() ? static_cast<uint64_t>(records[t].body - base) : static_cast<uint64_t>(data + r.pos - base));
+    });
+    std::atomic<uint64_t> first_bad{UINT64_MAX};
+    parallel_bounds(bounds, [&](uint64_t t0, uint64_t t1, unsigned) {
+      for (uint64_t t = t0; t < t1; ++t) {
+        if (!read_posting(records[t].body, records[t].body_len, &records[t].count, nullptr)) {
+          uint64_t seen = first_bad.load();
+          while (t < seen && !first_bad.compare_exchange_weak(seen, t)) {
+          }
+          return;
+        }
+      }
+    });
+    if (first_bad.load() != UINT64_MAX) {
+      return reject("kIndexDeserializationFailed",
+                    "failed to deserialize posting list of term " + std::string(records[first_bad.load()].term));
+    }
+  }
+  if (structural_code != nullptr) {
+    return reject(structural_code, structural_what);
+  }
+  for (const Record& rec : records) {
+    total_term_bytes += rec.term.size();
+    total_postings += rec.count;
   }
   // canonical order: ascending term bytes (the reference writes its hash map's order); a repeated term keeps its
   // LAST record, as new_postings[term] = ... does (:573)
@@ -569,13 +810,21 @@ int mgx_mgix_decode(const uint8_t* data, uint64_t len, mgx_mgix_info_t* info, ui
     const Record& rec = records[kept[i]];
     term_offsets[i] = tb;
     posting_offsets[i] = pp;
-    std::memcpy(term_bytes + tb, rec.term.data(), rec.term.size());
     tb += rec.term.size();
-    uint64_t count = 0;
-    read_posting(rec.body, rec.body_len, &count, postings + pp);
-    pp += count;
+    pp += rec.count;
   }
   term_offsets[kept.size()] = tb;
   posting_offsets[kept.size()] = pp;
+  // pass 3 (parallel, balanced by postings): every list decodes into its own slice
+  const std::vector<uint64_t> fill_bounds =
+      balanced_bounds(kept.size(), threads, [&](uint64_t t) { return posting_offsets[t] + 8 * t; });
+  parallel_bounds(fill_bounds, [&](uint64_t t0, uint64_t t1, unsigned) {
+    for (uint64_t i = t0; i < t1; ++i) {
+      const Record& rec = records[kept[i]];
+      std::memcpy(term_bytes + term_offsets[i], rec.term.data(), rec.term.size());
+      uint64_t count = 0;
+      read_posting(rec.body, rec.body_len, &count, postings + posting_offsets[i]);
+    }
+  });
   return MGX_OK;
 }

@@ -202,3 +202,41 @@ def test_stream_recorded_from_the_reference(mgx):
         assert offs.tolist() == case["posting_offsets"]
         assert zlib.crc32(posts.tobytes()) == case["postings_crc32"] and posts.size == case["n_postings"]
         assert [meta["ngram_size"], meta["kanji_ngram_size"], meta["cross_boundary"]] == case["config"]
+
+
+@pytest.mark.parametrize("threads", ["1", "6"])
+def test_serial_and_threaded_codec_write_the_same_bytes(mgx, monkeypatch, threads):
+    """The codec is two-pass and multi-threaded for whole shards (ranges balanced by postings, CRC-32 computed in
+    pieces and combined); MGX_MGIX_THREADS pins the worker count. Both paths must produce the same stream, a CRC that
+    zlib agrees with, and decode back to the input; a corrupted list is reported for the FIRST bad record."""
+    rng = np.random.default_rng(5)
+    n_terms = 4000
+    sizes = np.minimum((rng.pareto(1.0, n_terms) + 1).astype(np.int64), 40000)
+    sizes[:3] = [30000, 5000, 4097]
+    offs = np.zeros(n_terms + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(sizes)
+    posts = np.concatenate([np.cumsum(rng.integers(1, 9, int(n), dtype=np.uint32), dtype=np.uint32) for n in sizes])
+    terms = [b"%05d" % i for i in range(n_terms)]
+    monkeypatch.setenv("MGX_MGIX_THREADS", "1")
+    serial = mgx.mgix_encode(terms, offs, posts, 2, 2, True)
+    monkeypatch.setenv("MGX_MGIX_THREADS", threads)
+    stream = mgx.mgix_encode(terms, offs, posts, 2, 2, True)
+    assert stream == serial
+    assert stream[-4:] == struct.pack("<I", zlib.crc32(stream[:-4]))
+    meta, t2, o2, p2 = mgx.mgix_decode(stream)
+    assert t2 == terms and np.array_equal(o2, offs) and np.array_equal(p2, posts)
+    # two corrupted delta lists (a zero gap each): the error names the first one in stream order
+    bad = bytearray(stream)
+    pos = {}
+    cursor = 27 + 8  # v4 header with "keep" (27 bytes) + term count
+    for i in range(n_terms):
+        tl = struct.unpack_from("<I", bad, cursor)[0]
+        body_len = struct.unpack_from("<Q", bad, cursor + 4 + tl)[0]
+        pos[i] = cursor + 4 + tl + 8
+        cursor = pos[i] + body_len
+    victims = [i for i in range(10, n_terms) if 3 <= sizes[i] <= 4096][:400:399]
+    for i in victims:
+        struct.pack_into("<I", bad, pos[i] + 5 + 4, 0)  # second word of the delta body = a zero gap
+    struct.pack_into("<I", bad, len(bad) - 4, zlib.crc32(bytes(bad[:-4])))
+    with pytest.raises(mgx.MgxError, match="term %05d" % victims[0]):
+        mgx.mgix_decode(bytes(bad))
