@@ -27,3 +27,13 @@ if [ -n "${KERNEL2:-}" ]; then
       -o gpurun_out/prof_${KERNEL2}_10m -f $CMD > gpurun_out/ncu_full2.log 2>&1
   echo "second capture rc=$?"
 fi
+if [ "${EXPANDED:-0}" = "1" ]; then
+  # fuzzy / synonym / MGIX measurement at 10M documents with the CPU oracle beside it
+  timeout 400 python tools/bench_expanded.py --queries 100 --cpu-sample 16 --out gpurun_out/expanded_10m.json \
+      > gpurun_out/expanded.log 2>&1
+  echo "expanded paths rc=$?"
+fi
+if [ -n "${FUZZ_SECONDS:-}" ]; then
+  timeout $((FUZZ_SECONDS + 60)) python tools/fuzz_gpu.py "$FUZZ_SECONDS" 7 > gpurun_out/fuzz.log 2>&1
+  echo "fuzz rc=$?"; tail -1 gpurun_out/fuzz.log
+fi
