@@ -28,7 +28,7 @@ def spaced_docs(rnd, n):
 def expanded_cases(rnd, docs, n):
     """Random fuzzy term lists, synonym groups and NOT lists cut from the corpus (plus misspellings and strangers)."""
     def piece(lo=1, hi=7):
-        t = docs[rnd.randrange(len(docs))].decode()
+        t = docs[rnd.randrange(len(docs))].decode("utf-8", "ignore")
         if not t:
             return "ab"
         ln = rnd.randint(lo, hi)
