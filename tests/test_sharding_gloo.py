@@ -229,3 +229,14 @@ def test_shard_ranges_cover_everything():
             r = [shard_range(n, g, k) for k in range(g)]
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(r[k][1] == r[k + 1][0] for k in range(g - 1))
+
+
+def test_gather_doc_id_sets_single_process_and_empty_answers():
+    sys.path.insert(0, ROOT)
+    import mgx_loader
+    mgx_loader.load()
+    from mygram_db_b200 import sharded
+    comm = sharded.NoDist()
+    ids = np.array([3, 9, 4_000_000_000], dtype=np.uint32)  # ids above 2^31 survive the int32 transport
+    assert np.array_equal(sharded.gather_doc_id_sets(comm, ids), ids)
+    assert sharded.gather_doc_id_sets(comm, np.zeros(0, dtype=np.uint32)).size == 0
