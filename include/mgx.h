@@ -17,6 +17,19 @@
  * Text is normalised UTF-8 (ICU normalisation stays on the host, index.h:83-84).
  * Strings are passed flattened: `bytes` + `offsets[n+1]` (uint64), string i is
  * bytes[offsets[i] .. offsets[i+1]).
+ *
+ * Threading contract (the reference calls this path from its worker pool, server/thread_pool.cpp:33, with one
+ * binlog-apply writer beside it; Index guards itself with shared_mutexes, index.h:343-359):
+ *  - every entry point may be called from any thread, concurrently, on the same handle;
+ *  - reading calls (searches, batches, stats, export) share the index; concurrent single calls run side by side on
+ *    the device, each on its own stream with its own workspace (up to 8 at a time, further callers wait);
+ *  - mgx_index_build*, mgx_index_set_filter_column, mgx_index_clear / trim / optimize and the commit of journaled
+ *    mutations take the index exclusively: they wait for the readers in flight and hold new ones back meanwhile;
+ *  - add / update / remove_document only append to a journal (never block on readers); a reading call that STARTS
+ *    after they return sees them (it commits the journal first);
+ *  - a staged batch (mgx_batch_prepare* .. mgx_batch_destroy) is a reader for its whole lifetime. A thread must not
+ *    call a committing entry point of the same index while it holds such a batch and mutations are pending: the
+ *    commit would wait for the batch. Stages of ONE batch must not be issued concurrently.
  */
 #ifndef MGX_H_
 #define MGX_H_
@@ -423,6 +436,16 @@ int mgx_batch_prepare_ex(mgx_index_t* index, const mgx_query_params_t* params, u
 /* Planning stage of a prepared batch (dictionary lookup, per-term and per-query plans). Called
  * implicitly by the df / search stages if it has not run yet. */
 int mgx_batch_plan_device(mgx_batch_t* batch);
+/* Streamed form of the staged calls: planning leaves the work sizes on the device and the df / search stages run as
+ * persistent kernels that pull their work from device-side counters, so the whole batch is enqueued without a host
+ * synchronisation. The price is a fixed-size per-stream workspace: a batch that does not fit computes nothing and
+ * reports it (mgx_batch_overflowed, after the search stage; packed records carry the flag in their status block);
+ * mgx_batch_reset returns it to its uploaded state, and the repeat runs in the synchronous form, whose workspace
+ * grows with the batch. Call before the planning stage. mgx_query_batch* and mgx_sharded_batch_* do all of this
+ * themselves. */
+int mgx_batch_set_streamed(mgx_batch_t* batch, int32_t enable);
+int mgx_batch_overflowed(mgx_batch_t* batch, int32_t* out_overflowed); /* waits for the batch's enqueued work */
+int mgx_batch_reset(mgx_batch_t* batch);
 /* Stats of a staged batch; synchronises the batch's stream. */
 int mgx_batch_get_stats(mgx_batch_t* batch, mgx_batch_stats_t* out);
 /* Number of search-term slots (= length of d_df / out_df). */
@@ -446,18 +469,56 @@ int mgx_merge_topk_device(int32_t device, void* stream, const mgx_query_params_t
  * a single all-gather (BASELINE north_star: "merged with a single NCCL all-gather over NVLink"). A record holds
  * [scores f64 Q*S][total u64 Q][ids u32 Q*S][count u32 Q], padded to 16 bytes; mgx_shard_record_layout gives the
  * byte offsets. d_records = [n_shards][layout.bytes] as gathered; d_record_out = one record (the merged answer,
- * one device-to-host copy away from the caller). */
+ * one device-to-host copy away from the caller). The record ends with a 16-byte status block (uint32[4]): word 0 is
+ * non-zero when the shard's streamed batch did not fit its workspace (see mgx_batch_set_streamed); the merged
+ * record carries the OR over the shards. stride must be >= limit + offset: a shard returns its best limit + offset
+ * records un-offset and the merge skips the offset (MGX_ERR_INVALID_ARGUMENT otherwise). */
 typedef struct mgx_shard_record_layout {
   uint64_t scores_offset;
   uint64_t total_offset;
   uint64_t ids_offset;
   uint64_t count_offset;
+  uint64_t status_offset;
   uint64_t bytes;
 } mgx_shard_record_layout_t;
 int mgx_shard_record_layout(uint64_t n_queries, uint64_t stride, mgx_shard_record_layout_t* out);
 int mgx_batch_search_packed_device(mgx_batch_t* batch, const uint64_t* d_df, uint64_t stride, void* d_record);
 int mgx_merge_topk_packed_device(int32_t device, void* stream, const mgx_query_params_t* params, uint32_t n_shards,
                                  uint64_t n_queries, uint64_t stride, const void* d_records, void* d_record_out);
+
+/* ------------------------------------------------- sharded pipeline: one process per GPU, one doc-id range each
+ *
+ * The multi-GPU protocol of SURVEY.md §8(e) behind the C ABI, for a C++ host (the reference's server is C++): the
+ * library issues the two NCCL exchanges itself, on a highest-priority stream per communicator lane, ordered with
+ * the batch's own stream by events -- so a batch is ONE uninterrupted enqueue and several batches can be in flight
+ * (one per lane) without an exchange queueing behind another batch's grid-filling kernels.
+ *   enqueue: plan -> df -> ncclAllReduce(SUM) of the per-term df -> search (GLOBAL df) -> ncclAllGather of the packed
+ *            per-shard records -> merge -> optional device-to-host copy of the merged record
+ *   finish : waits for the batch; if ANY shard's streamed batch did not fit its workspace (status block of the
+ *            merged record, identical on every rank) all ranks repeat it together in the synchronous form.
+ * Every rank must prepare the SAME batch (same queries, same order) with the GLOBAL corpus statistics in
+ * mgx_query_params_t. NCCL is bound at run time (dlopen of libnccl.so.2, MGX_NCCL_LIB overrides); without it the
+ * calls below fail with MGX_ERR_UNSUPPORTED and comm == NULL (a single shard, no exchange) still works.
+ * Bootstrap: rank 0 calls mgx_comm_unique_id once per lane and hands the ids to every rank by any means (the
+ * benchmarks hand them round with the host framework's own broadcast); every rank then calls mgx_comm_create with the same ids. */
+#define MGX_COMM_ID_BYTES 128
+#define MGX_COMM_MAX_LANES 4
+typedef struct mgx_shard_comm mgx_shard_comm_t;
+int mgx_comm_unique_id(uint8_t* out_id /* MGX_COMM_ID_BYTES */);
+int mgx_comm_create(const uint8_t* ids /* n_lanes x MGX_COMM_ID_BYTES */, int32_t n_lanes, int32_t n_ranks,
+                    int32_t rank, int32_t device, mgx_shard_comm_t** out);
+void mgx_comm_destroy(mgx_shard_comm_t* comm);
+int mgx_comm_info(const mgx_shard_comm_t* comm, int32_t* n_ranks, int32_t* rank, int32_t* n_lanes,
+                  int32_t* nccl_version);
+/* batch: freshly prepared (mgx_batch_prepare*), on the stream given there. h_record_out (may be NULL): pinned host
+ * buffer of mgx_shard_record_layout(n_queries, stride).bytes that receives the merged record. */
+int mgx_sharded_batch_enqueue(mgx_shard_comm_t* comm, int32_t lane, mgx_batch_t* batch, uint64_t stride,
+                              void* h_record_out);
+/* *d_record_out (may be NULL) = the merged record on the device, valid until the batch is destroyed;
+ * *out_repeated (may be NULL) = 1 when the batch had to be repeated. Same comm / lane / stride / h_record_out as
+ * the enqueue. */
+int mgx_sharded_batch_finish(mgx_shard_comm_t* comm, int32_t lane, mgx_batch_t* batch, uint64_t stride,
+                             void* h_record_out, const void** d_record_out, int32_t* out_repeated);
 
 /* Stats of the last mgx_query_batch on this index. */
 int mgx_index_last_batch_stats(const mgx_index_t* index, mgx_batch_stats_t* out);

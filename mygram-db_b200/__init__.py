@@ -89,9 +89,9 @@ class QueryParams(C.Structure):
 
 
 class ShardRecordLayout(C.Structure):
-    """mgx_shard_record_layout_t: byte offsets of the four parts of one shard's packed top-k record."""
+    """mgx_shard_record_layout_t: byte offsets of the parts of one shard's packed top-k record (+ status block)."""
     _fields_ = [("scores_offset", C.c_uint64), ("total_offset", C.c_uint64), ("ids_offset", C.c_uint64),
-                ("count_offset", C.c_uint64), ("bytes", C.c_uint64)]
+                ("count_offset", C.c_uint64), ("status_offset", C.c_uint64), ("bytes", C.c_uint64)]
 
 
 class BatchStats(C.Structure):
@@ -188,6 +188,17 @@ def lib():
     L.mgx_merge_topk_packed_device.argtypes = [C.c_int32, C.c_void_p, C.POINTER(QueryParams), C.c_uint32, C.c_uint64,
                                                C.c_uint64, C.c_void_p, C.c_void_p]
     L.mgx_index_last_batch_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
+    L.mgx_batch_set_streamed.argtypes = [C.c_void_p, C.c_int32]
+    L.mgx_batch_overflowed.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    L.mgx_batch_reset.argtypes = [C.c_void_p]
+    L.mgx_comm_unique_id.argtypes = [u8p]
+    L.mgx_comm_create.argtypes = [u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.mgx_comm_destroy.argtypes = [C.c_void_p]
+    L.mgx_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                C.POINTER(C.c_int32)]
+    L.mgx_sharded_batch_enqueue.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.mgx_sharded_batch_finish.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.mgx_score_documents.argtypes = [C.c_void_p, u32p, C.c_uint64, u8p, u64p, u64p, C.c_uint64, C.c_uint64,
                                       C.c_double, C.c_double, C.c_double, f64p]
     L.mgx_sort_by_score.argtypes = [C.c_void_p, u32p, f64p, C.c_uint64, C.c_int32, C.c_uint32, C.c_uint32, u32p, u64p]

@@ -9,6 +9,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -687,9 +690,54 @@ int check_params(const mgx_query_params_t& p) {
 
 using namespace mgx;
 
+// Readers / writer gate of one index handle (the reference's table generation lock, server_types.h:245: shared for a
+// whole request, exclusive for a rebuild). Not std::shared_mutex: a staged batch is prepared by one thread and
+// destroyed by another, which a std::shared_mutex does not allow. Writers have preference.
+struct RwGate {
+  std::mutex m;
+  std::condition_variable cv;
+  int readers = 0;
+  int writers_waiting = 0;
+  bool writer = false;
+  void lock_shared() {
+    std::unique_lock<std::mutex> l(m);
+    cv.wait(l, [&] { return !writer && writers_waiting == 0; });
+    ++readers;
+  }
+  void unlock_shared() {
+    std::unique_lock<std::mutex> l(m);
+    if (--readers == 0) {
+      cv.notify_all();
+    }
+  }
+  void lock() {
+    std::unique_lock<std::mutex> l(m);
+    ++writers_waiting;
+    cv.wait(l, [&] { return !writer && readers == 0; });
+    --writers_waiting;
+    writer = true;
+  }
+  void unlock() {
+    std::unique_lock<std::mutex> l(m);
+    writer = false;
+    cv.notify_all();
+  }
+};
+
+constexpr int kMaxLanes = 8;
+
 struct mgx_index {
   Index ix;
-  std::mutex mu;  // serialises build vs. query on one handle (the reference's table generation lock)
+  RwGate gate;  // build / commit / column upload exclusive; every reading call shared
+  // Execution lanes of the single-call readers: a stream with its own search workspace each, so that concurrent
+  // Index::Search* style calls from the server's worker threads (thread_pool.cpp:33) run side by side on the device
+  // instead of queueing behind one mutex. Lane 0 is ix.stream.
+  std::mutex lane_mu;
+  std::condition_variable lane_cv;
+  cudaStream_t lane_stream[kMaxLanes] = {nullptr};
+  bool lane_busy[kMaxLanes] = {false};
+  int n_lanes = 0;
+  std::mutex stats_mu;  // ix.last_stats
   // Journal of Index::AddDocument / UpdateDocument / RemoveDocument calls not folded in yet: doc id -> (removed, text).
   // The last call for an id wins; the next read applies the whole journal (apply_journal_device).
   std::map<uint32_t, std::pair<bool, std::string>> journal;
@@ -698,7 +746,69 @@ struct mgx_index {
 };
 
 namespace {
-// Applies the pending mutations; called at the top of every entry point that reads the index.
+struct WriteGuard {
+  mgx_index* h;
+  explicit WriteGuard(mgx_index* index) : h(index) { h->gate.lock(); }
+  ~WriteGuard() { h->gate.unlock(); }
+  WriteGuard(const WriteGuard&) = delete;
+  WriteGuard& operator=(const WriteGuard&) = delete;
+};
+
+// Shared access to the index plus the exclusive use of one execution lane for the duration of a reading call.
+struct Reader {
+  mgx_index* h;
+  int lane = -1;
+  explicit Reader(mgx_index* index) : h(index) {
+    h->gate.lock_shared();
+    std::unique_lock<std::mutex> l(h->lane_mu);
+    for (;;) {
+      for (int i = 0; i < h->n_lanes; ++i) {
+        if (!h->lane_busy[i]) {
+          lane = i;
+          break;
+        }
+      }
+      if (lane >= 0) {
+        break;
+      }
+      if (h->n_lanes < kMaxLanes) {
+        lane = h->n_lanes;
+        if (lane == 0) {
+          h->lane_stream[0] = h->ix.stream;
+        } else {
+          DeviceGuard guard(h->ix.device);
+          if (cudaStreamCreateWithFlags(&h->lane_stream[lane], cudaStreamNonBlocking) != cudaSuccess) {
+            (void)cudaGetLastError();
+            lane = -1;
+            if (h->n_lanes == 0) {
+              h->lane_stream[0] = h->ix.stream;
+            }
+            h->lane_cv.wait(l);  // no further stream to be had: wait for a lane like everybody else
+            continue;
+          }
+        }
+        ++h->n_lanes;
+        break;
+      }
+      h->lane_cv.wait(l);
+    }
+    h->lane_busy[lane] = true;
+  }
+  ~Reader() {
+    {
+      std::unique_lock<std::mutex> l(h->lane_mu);
+      h->lane_busy[lane] = false;
+    }
+    h->lane_cv.notify_one();
+    h->gate.unlock_shared();
+  }
+  Reader(const Reader&) = delete;
+  Reader& operator=(const Reader&) = delete;
+  cudaStream_t stream() const { return h->lane_stream[lane]; }
+};
+
+// Applies the pending mutations; called at the top of every entry point that reads the index, BEFORE the call
+// takes its shared access (never under it: the commit needs the gate exclusively).
 int commit_pending(mgx_index_t* index) {
   if (index == nullptr || !index->dirty.load(std::memory_order_acquire)) {
     return MGX_OK;
@@ -709,7 +819,7 @@ int commit_pending(mgx_index_t* index) {
       index->dirty.store(false);
       return MGX_OK;
     }
-    std::lock_guard<std::mutex> lock(index->mu);
+    WriteGuard lock(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
     std::vector<uint32_t> ids;
@@ -748,6 +858,7 @@ int journal_put(mgx_index_t* index, uint32_t doc_id, bool removed, const uint8_t
 
 struct mgx_batch {
   Batch b;
+  mgx_index* reader_of = nullptr;  // staged batches keep shared access to their index until mgx_batch_destroy
 };
 
 extern "C" {
@@ -795,6 +906,12 @@ void mgx_index_destroy(mgx_index_t* index) {
   }
   {
     DeviceGuard guard(index->ix.device);
+    for (int i = 1; i < index->n_lanes; ++i) {
+      if (index->lane_stream[i] != nullptr) {
+        cudaStreamSynchronize(index->lane_stream[i]);
+        cudaStreamDestroy(index->lane_stream[i]);
+      }
+    }
     if (index->ix.stream != nullptr) {
       cudaStreamSynchronize(index->ix.stream);
       cudaStreamDestroy(index->ix.stream);
@@ -821,7 +938,7 @@ static int build_common(mgx_index_t* index, const uint32_t* doc_ids, const uint8
     index->dirty.store(false);
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(index->mu);
+    WriteGuard lock(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
     uint64_t text_bytes = 0;
@@ -897,6 +1014,7 @@ int mgx_index_get_stats(const mgx_index_t* index, mgx_index_stats_t* out) {
   if (int rc = commit_pending(const_cast<mgx_index_t*>(index)); rc != MGX_OK) {
     return rc;
   }
+  Reader rd(const_cast<mgx_index_t*>(index));
   const Index& ix = index->ix;
   out->n_docs = ix.n_docs;
   out->n_terms = ix.n_terms;
@@ -938,7 +1056,7 @@ int mgx_index_set_filter_column(mgx_index_t* index, uint32_t column, int32_t typ
     return rc;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(index->mu);
+    WriteGuard lock(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
     if (n_docs != ix.n_docs) {
@@ -998,11 +1116,11 @@ int mgx_index_get_statistics(const mgx_index_t* index_c, mgx_index_statistics_t*
     return rc;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(index->mu);
+    Reader rd(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
     const double thr = ix.cfg.roaring_threshold > 0.0 ? ix.cfg.roaring_threshold : 0.18;
-    const uint64_t roaring = count_roaring_lists(ix, thr, ix.optimized_total_docs, ix.stream);
+    const uint64_t roaring = count_roaring_lists(ix, thr, ix.optimized_total_docs, rd.stream());
     out->total_terms = ix.n_terms;
     out->total_postings = ix.n_postings;
     out->roaring_bitmap_lists = roaring;
@@ -1017,7 +1135,7 @@ int mgx_index_trim(mgx_index_t* index) {
     return invalid("null argument");
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(index->mu);
+    WriteGuard lock(index);
     DeviceGuard guard(index->ix.device);
     index->ix.build_arena.release();
     index->ix.build_arena0.release();
@@ -1036,7 +1154,7 @@ int mgx_index_optimize(mgx_index_t* index, uint64_t total_docs) {
   // uint32 + bitmaps chosen at build time for probing speed) does not change; the call records total_docs so that
   // the representation counters follow the reference's rule. total_docs == 0 is a no-op there too (:801-803).
   if (total_docs != 0) {
-    std::lock_guard<std::mutex> lock(index->mu);
+    WriteGuard lock(index);
     index->ix.optimized_total_docs = total_docs;
   }
   return MGX_OK;
@@ -1051,6 +1169,7 @@ int mgx_index_clear(mgx_index_t* index) {
   static const uint8_t kNoText[1] = {0};
   const int rc = mgx_index_build(index, kNoIds, kNoText, kZeroOff, 0);  // also drops pending mutations
   if (rc == MGX_OK) {
+    WriteGuard lock(index);
     index->ix.optimized_total_docs = 0;
   }
   return rc;
@@ -1202,13 +1321,13 @@ struct PooledBatch {
   }
 };
 
-int run_single_set_query(Index& ix, std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
-                         const uint32_t* driver_ids, uint64_t n_driver, uint64_t limit, bool reverse, uint32_t* out,
+int run_single_set_query(Index& ix, cudaStream_t lane_stream, std::vector<HostTerm>& terms,
+                         const std::vector<HostQuery>& queries, const uint32_t* driver_ids, uint64_t n_driver, uint64_t limit, bool reverse, uint32_t* out,
                          uint64_t cap, uint64_t* out_count) {
   PooledBatch pooled(ix);
   Batch& b = pooled.h->b;
   b.ix = &ix;
-  b.stream = ix.stream;
+  b.stream = lane_stream;
   b.params = mgx_query_params_t{};
   b.params.compute_score = 0;
   b.launches_at_start = g_launches.load();
@@ -1269,7 +1388,7 @@ int run_set_op(mgx_index_t* index, SetOp op, const uint32_t* driver_ids, uint64_
     return rc;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(index->mu);
+    Reader rd(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
     auto copy_ids = [&](const uint32_t* src, uint64_t n) {
@@ -1337,7 +1456,8 @@ int run_set_op(mgx_index_t* index, SetOp op, const uint32_t* driver_ids, uint64_
       queries[0].flags = op == SetOp::kOr ? kQAnyMode : (op == SetOp::kFilter ? kQDriverExplicit : 0u);
     }
 
-    return run_single_set_query(ix, terms, queries, (op == SetOp::kNot || op == SetOp::kFilter) ? driver_ids : nullptr,
+    return run_single_set_query(ix, rd.stream(), terms, queries,
+                                (op == SetOp::kNot || op == SetOp::kFilter) ? driver_ids : nullptr,
                                 n_driver, limit, reverse, out, cap, out_count);
   });
 }
@@ -1404,7 +1524,7 @@ int mgx_search_by_threshold(const mgx_index_t* index_c, const uint8_t* term_byte
     return rc;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(index->mu);
+    Reader rd(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
     HostTerm t;
@@ -1423,7 +1543,7 @@ int mgx_search_by_threshold(const mgx_index_t* index_c, const uint8_t* term_byte
     queries[0].terms.push_back(0);
     queries[0].flags = kQAnyMode;
     queries[0].threshold = static_cast<uint32_t>(threshold);
-    return run_single_set_query(ix, terms, queries, nullptr, 0, 0, false, out, cap, out_count);
+    return run_single_set_query(ix, rd.stream(), terms, queries, nullptr, 0, 0, false, out, cap, out_count);
   });
 }
 
@@ -1443,7 +1563,7 @@ int mgx_eval_boolean(const mgx_index_t* index_c, const int32_t* ops, const int32
     return rc;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(index->mu);
+    Reader rd(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
     std::vector<HostQuery> queries(1);
@@ -1469,7 +1589,7 @@ int mgx_eval_boolean(const mgx_index_t* index_c, const int32_t* ops, const int32
       hq.prog_ops.push_back(static_cast<uint8_t>(ops[i]));
       hq.prog_args.push_back(static_cast<uint32_t>(args[i]));
     }
-    return run_single_set_query(ix, terms, queries, nullptr, 0, 0, false, out, cap, out_count);
+    return run_single_set_query(ix, rd.stream(), terms, queries, nullptr, 0, 0, false, out, cap, out_count);
   });
 }
 
@@ -1641,7 +1761,7 @@ int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq,
     return rc;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(index->mu);
+    Reader rd(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
     ProgramBuilder pb;
@@ -1738,7 +1858,7 @@ int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq,
     if (int rc = finish_expanded(ix, *eq, &pb, children, drivers, &queries); rc != MGX_OK) {
       return rc;
     }
-    return run_single_set_query(ix, pb.terms, queries, nullptr, 0, 0, false, out, cap, out_count);
+    return run_single_set_query(ix, rd.stream(), pb.terms, queries, nullptr, 0, 0, false, out, cap, out_count);
   });
 }
 
@@ -1766,7 +1886,7 @@ int mgx_search_synonyms(const mgx_index_t* index_c, const mgx_expanded_query_t* 
     return rc;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(index->mu);
+    Reader rd(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
     ProgramBuilder pb;
@@ -1835,7 +1955,7 @@ int mgx_search_synonyms(const mgx_index_t* index_c, const mgx_expanded_query_t* 
     if (int rc = finish_expanded(ix, *eq, &pb, children, drivers, &queries); rc != MGX_OK) {
       return rc;
     }
-    return run_single_set_query(ix, pb.terms, queries, nullptr, 0, 0, false, out, cap, out_count);
+    return run_single_set_query(ix, rd.stream(), pb.terms, queries, nullptr, 0, 0, false, out, cap, out_count);
   });
 }
 
@@ -1856,7 +1976,7 @@ int mgx_index_posting_size(const mgx_index_t* index, const uint8_t* term, uint64
     return rc;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(h->mu);
+    Reader rd(h);
     Index& ix = h->ix;
     DeviceGuard guard(ix.device);
     uint64_t key = 0;
@@ -1889,6 +2009,31 @@ int mgx_index_posting_size(const mgx_index_t* index, const uint8_t* term, uint64
   });
 }
 
+namespace {
+// CSR of the index with global doc ids; the caller holds shared access.
+int export_unlocked(const Index& ix, uint64_t* keys, uint64_t* offsets, uint32_t* postings) {
+  DeviceGuard guard(ix.device);
+  if (ix.n_terms > 0) {
+    MGX_CUDA(cudaMemcpy(keys, ix.d_term_keys.p, ix.n_terms * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
+  if (ix.d_term_off.p != nullptr && ix.d_term_off.n >= ix.n_terms + 1) {
+    MGX_CUDA(cudaMemcpy(offsets, ix.d_term_off.p, (ix.n_terms + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  } else {
+    offsets[0] = 0;
+  }
+  if (ix.n_postings > 0) {
+    MGX_CUDA(cudaMemcpy(postings, ix.d_postings.p, ix.n_postings * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    // local index -> global DocId (a pure relabelling done while copying out)
+    std::vector<uint32_t> ids(ix.n_docs);
+    MGX_CUDA(cudaMemcpy(ids.data(), ix.d_doc_ids.p, ix.n_docs * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < ix.n_postings; ++i) {
+      postings[i] = ids[postings[i]];
+    }
+  }
+  return MGX_OK;
+}
+}  // namespace
+
 int mgx_index_export(const mgx_index_t* index, uint64_t* keys, uint64_t* offsets, uint32_t* postings) {
   if (index == nullptr || keys == nullptr || offsets == nullptr || postings == nullptr) {
     return invalid("null argument");
@@ -1898,27 +2043,8 @@ int mgx_index_export(const mgx_index_t* index, uint64_t* keys, uint64_t* offsets
     return rc;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(h->mu);
-    Index& ix = h->ix;
-    DeviceGuard guard(ix.device);
-    if (ix.n_terms > 0) {
-      MGX_CUDA(cudaMemcpy(keys, ix.d_term_keys.p, ix.n_terms * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    }
-    if (ix.d_term_off.p != nullptr && ix.d_term_off.n >= ix.n_terms + 1) {
-      MGX_CUDA(cudaMemcpy(offsets, ix.d_term_off.p, (ix.n_terms + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    } else {
-      offsets[0] = 0;
-    }
-    if (ix.n_postings > 0) {
-      MGX_CUDA(cudaMemcpy(postings, ix.d_postings.p, ix.n_postings * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-      // local index -> global DocId (a pure relabelling done while copying out)
-      std::vector<uint32_t> ids(ix.n_docs);
-      MGX_CUDA(cudaMemcpy(ids.data(), ix.d_doc_ids.p, ix.n_docs * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-      for (uint64_t i = 0; i < ix.n_postings; ++i) {
-        postings[i] = ids[postings[i]];
-      }
-    }
-    return MGX_OK;
+    Reader rd(h);
+    return export_unlocked(h->ix, keys, offsets, postings);
   });
 }
 
@@ -1934,24 +2060,29 @@ int mgx_index_save_mgix(const mgx_index_t* index, int32_t normalize_nfkc, const 
     set_last_error("normalize_width longer than 31 bytes is not supported");
     return MGX_ERR_UNSUPPORTED;
   }
-  mgx_index_stats_t st{};
-  if (int rc = mgx_index_get_stats(index, &st); rc != MGX_OK) {
+  mgx_index_t* h = const_cast<mgx_index_t*>(index);
+  if (int rc = commit_pending(h); rc != MGX_OK) {
     return rc;
   }
   return guarded([&]() {
-    // the CSR comes back once (mgx_index_export: global doc ids, ascending term order); terms become UTF-8 strings
-    std::vector<uint64_t> keys(st.n_terms + 1);
-    std::vector<uint64_t> offsets(st.n_terms + 1);
-    std::vector<uint32_t> postings(st.n_postings + 1);
-    if (int rc = mgx_index_export(index, keys.data(), offsets.data(), postings.data()); rc != MGX_OK) {
-      return rc;
-    }
-    mgx_index_t* h = const_cast<mgx_index_t*>(index);
+    // sizes, CSR and header are read under ONE shared access, so a mutation committed by another thread cannot
+    // grow the index between the sizing and the copy. The CSR comes back once (global doc ids, ascending term order).
+    std::vector<uint64_t> keys;
+    std::vector<uint64_t> offsets;
+    std::vector<uint32_t> postings;
     int width_cp = 0;
     double roaring_min_len = 0.0;
+    uint64_t n_terms = 0;
     {
-      std::lock_guard<std::mutex> lock(h->mu);
+      Reader rd(h);
       const Index& ix = h->ix;
+      n_terms = ix.n_terms;
+      keys.resize(ix.n_terms + 1);
+      offsets.resize(ix.n_terms + 1);
+      postings.resize(ix.n_postings + 1);
+      if (int rc = export_unlocked(ix, keys.data(), offsets.data(), postings.data()); rc != MGX_OK) {
+        return rc;
+      }
       width_cp = ix.width;
       info.ngram_size = ix.ngram;
       info.kanji_ngram_size = ix.kanji;  // effective: kanji > 0 ? kanji : ngram, as index.cpp:29-37 stores it
@@ -1962,15 +2093,15 @@ int mgx_index_save_mgix(const mgx_index_t* index, int32_t normalize_nfkc, const 
     info.normalize_nfkc = normalize_nfkc;
     info.normalize_lower = normalize_lower;
     std::strcpy(info.normalize_width, width);
-    info.n_terms = st.n_terms;
-    std::vector<uint8_t> term_bytes(st.n_terms * 4 * kMaxKeyWidth + 1);
-    std::vector<uint64_t> term_offsets(st.n_terms + 1, 0);
+    info.n_terms = n_terms;
+    std::vector<uint8_t> term_bytes(n_terms * 4 * kMaxKeyWidth + 1);
+    std::vector<uint64_t> term_offsets(n_terms + 1, 0);
     uint64_t tb = 0;
-    for (uint64_t t = 0; t < st.n_terms; ++t) {
+    for (uint64_t t = 0; t < n_terms; ++t) {
       term_offsets[t] = tb;
       tb += static_cast<uint64_t>(mgx_key_to_utf8(keys[t], width_cp, term_bytes.data() + tb));
     }
-    term_offsets[st.n_terms] = tb;
+    term_offsets[n_terms] = tb;
     return mgx_mgix_encode(&info, term_bytes.data(), term_offsets.data(), offsets.data(), postings.data(),
                            roaring_min_len, out, cap, out_len);
   });
@@ -1985,7 +2116,7 @@ int mgx_index_doc_lengths(const mgx_index_t* index, uint32_t* out) {
     return rc;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(h->mu);
+    Reader rd(h);
     DeviceGuard guard(h->ix.device);
     if (h->ix.n_docs > 0) {
       MGX_CUDA(cudaMemcpy(out, h->ix.d_doc_len.p, h->ix.n_docs * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -2002,6 +2133,80 @@ int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint
   return mgx_batch_prepare_ex(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes,
                               not_offsets, q_not_begin, nullptr, stream, out);
 }
+
+namespace {
+// Host compile + upload of one batch on `stream`. The caller has committed pending mutations and holds shared access
+// to the index (its own Reader, or the one a staged batch keeps until mgx_batch_destroy).
+int prepare_unlocked(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                     const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                     const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                     const mgx_query_ext_t* ext, cudaStream_t stream, mgx_batch_t** out) {
+  Index& ix = index->ix;
+  DeviceGuard guard(ix.device);
+  std::unique_ptr<mgx_batch> h;
+  {
+    std::lock_guard<std::mutex> pool_lock(ix.pool_mu);
+    if (!ix.batch_pool.empty()) {
+      h.reset(static_cast<mgx_batch*>(ix.batch_pool.back()));
+      ix.batch_pool.pop_back();
+    }
+  }
+  if (!h) {
+    h = std::make_unique<mgx_batch>();
+  }
+  Batch& b = h->b;
+  b.ix = &ix;
+  b.params = *params;
+  b.stream = stream;  // NULL = the legacy default stream, as documented
+  b.launches_at_start = g_launches.load();
+  // the compile workspace stays with the pooled batch object (capacity is kept from batch to batch)
+  std::vector<HostTerm>& terms = b.h_terms;
+  std::vector<HostQuery>& queries = b.h_queries;
+  std::vector<uint32_t>& slot_tid = b.h_slot_scratch;
+  terms.clear();
+  static const uint8_t kEmpty[1] = {0};
+  static const bool trace = std::getenv("MGX_BATCH_TRACE") != nullptr;  // host wall time of the two host stages
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = compile_batch(ix, *params, n_queries, term_bytes != nullptr ? term_bytes : kEmpty, term_offsets,
+                               q_term_begin, not_bytes != nullptr ? not_bytes : kEmpty, not_offsets, q_not_begin, ext,
+                               &terms, &queries, &slot_tid);
+  if (rc != MGX_OK) {
+    std::lock_guard<std::mutex> pool_lock(ix.pool_mu);
+    if (ix.batch_pool.size() < 16) {
+      ix.batch_pool.push_back(h.release());  // nothing was enqueued: the workspace goes straight back
+    }
+    return rc;
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  batch_upload(b, terms, queries, slot_tid);
+  if (trace) {
+    const auto t2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mgx batch] compile %.3f ms, stage+upload %.3f ms (%zu unique terms)\n",
+            std::chrono::duration<double, std::milli>(t1 - t0).count(),
+            std::chrono::duration<double, std::milli>(t2 - t1).count(), terms.size());
+  }
+  *out = h.release();
+  return MGX_OK;
+}
+
+void release_batch(mgx_batch_t* batch) {
+  Index& ix = *batch->b.ix;
+  mgx_index* reader_of = batch->reader_of;
+  batch->reader_of = nullptr;
+  batch->b.recycle();
+  {
+    std::lock_guard<std::mutex> pool_lock(ix.pool_mu);
+    if (ix.batch_pool.size() < 16) {
+      ix.batch_pool.push_back(batch);  // keep the workspace for the next batch
+      batch = nullptr;
+    }
+  }
+  delete batch;
+  if (reader_of != nullptr) {
+    reader_of->gate.unlock_shared();
+  }
+}
+}  // namespace
 
 int mgx_batch_prepare_ex(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
                          const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
@@ -2021,50 +2226,30 @@ int mgx_batch_prepare_ex(mgx_index_t* index, const mgx_query_params_t* params, u
   if (int rc = commit_pending(index); rc != MGX_OK) {
     return rc;
   }
-  return guarded([&]() {
-    Index& ix = index->ix;
-    DeviceGuard guard(ix.device);
-    std::unique_ptr<mgx_batch> h;
-    {
-      std::lock_guard<std::mutex> pool_lock(ix.pool_mu);
-      if (!ix.batch_pool.empty()) {
-        h.reset(static_cast<mgx_batch*>(ix.batch_pool.back()));
-        ix.batch_pool.pop_back();
-      }
-    }
-    if (!h) {
-      h = std::make_unique<mgx_batch>();
-    }
-    Batch& b = h->b;
-    b.ix = &ix;
-    b.params = *params;
-    b.stream = static_cast<cudaStream_t>(stream);  // NULL = the legacy default stream, as documented
-    b.launches_at_start = g_launches.load();
-    // the compile workspace stays with the pooled batch object (capacity is kept from batch to batch)
-    std::vector<HostTerm>& terms = b.h_terms;
-    std::vector<HostQuery>& queries = b.h_queries;
-    std::vector<uint32_t>& slot_tid = b.h_slot_scratch;
-    terms.clear();
-    static const uint8_t kEmpty[1] = {0};
-    static const bool trace = std::getenv("MGX_BATCH_TRACE") != nullptr;  // host wall time of the two host stages
-    const auto t0 = std::chrono::steady_clock::now();
-    const int rc = compile_batch(ix, *params, n_queries, term_bytes != nullptr ? term_bytes : kEmpty, term_offsets,
-                                 q_term_begin, not_bytes != nullptr ? not_bytes : kEmpty, not_offsets, q_not_begin,
-                                 ext, &terms, &queries, &slot_tid);
-    if (rc != MGX_OK) {
-      return rc;
-    }
-    const auto t1 = std::chrono::steady_clock::now();
-    batch_upload(b, terms, queries, slot_tid);
-    if (trace) {
-      const auto t2 = std::chrono::steady_clock::now();
-      fprintf(stderr, "[mgx batch] compile %.3f ms, stage+upload %.3f ms (%zu unique terms)\n",
-              std::chrono::duration<double, std::milli>(t1 - t0).count(),
-              std::chrono::duration<double, std::milli>(t2 - t1).count(), terms.size());
-    }
-    *out = h.release();
-    return MGX_OK;
+  // A staged batch reads the index from here until mgx_batch_destroy: it keeps shared access for that long, so a
+  // commit of journaled mutations (or a rebuild) waits for it instead of releasing the arrays under its kernels.
+  index->gate.lock_shared();
+  const int rc = guarded([&]() {
+    return prepare_unlocked(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
+                            q_not_begin, ext, static_cast<cudaStream_t>(stream), out);
   });
+  if (rc != MGX_OK || *out == nullptr) {
+    index->gate.unlock_shared();
+    return rc;
+  }
+  (*out)->reader_of = index;
+  return MGX_OK;
+}
+
+int mgx_batch_set_streamed(mgx_batch_t* batch, int32_t enable) {
+  if (batch == nullptr) {
+    return invalid("null batch");
+  }
+  if (batch->b.planned) {
+    return invalid("mgx_batch_set_streamed must precede the planning stage");
+  }
+  batch->b.allow_streamed = enable != 0;
+  return MGX_OK;
 }
 
 int mgx_batch_plan_device(mgx_batch_t* batch) {
@@ -2114,10 +2299,37 @@ int mgx_batch_df_device(mgx_batch_t* batch, uint64_t* d_df) {
   });
 }
 
+namespace {
+// a shard returns its best (offset + limit) records un-offset; the merge applies the offset
+struct ShardParams {
+  Batch& b;
+  mgx_query_params_t saved;
+  explicit ShardParams(Batch& batch) : b(batch), saved(batch.params) {
+    if (b.params.limit != 0) {
+      b.params.limit = saved.limit + saved.offset;
+    }
+    b.params.offset = 0;
+  }
+  ~ShardParams() { b.params = saved; }
+};
+
+int check_stride(const mgx_query_params_t& p, uint64_t stride) {
+  if (p.limit != 0 && stride < static_cast<uint64_t>(p.limit) + p.offset) {
+    set_last_error("stride must hold limit + offset records per query: a shard returns its best limit + offset records "
+                   "un-offset and the merge skips the offset");
+    return MGX_ERR_INVALID_ARGUMENT;
+  }
+  return MGX_OK;
+}
+}  // namespace
+
 int mgx_batch_search_device(mgx_batch_t* batch, const uint64_t* d_df, uint64_t stride, uint32_t* d_ids,
                             double* d_scores, uint32_t* d_count, uint64_t* d_total) {
   if (batch == nullptr || d_ids == nullptr || d_count == nullptr || d_total == nullptr) {
     return invalid("null argument");
+  }
+  if (int rc = check_stride(batch->b.params, stride); rc != MGX_OK) {
+    return rc;
   }
   return guarded([&]() {
     Batch& b = batch->b;
@@ -2125,14 +2337,39 @@ int mgx_batch_search_device(mgx_batch_t* batch, const uint64_t* d_df, uint64_t s
     if (b.params.compute_score != 0 && !b.df_done) {
       batch_df(b);
     }
-    // a shard returns its best (offset + limit) records un-offset; mgx_merge_topk_device applies the offset
-    const mgx_query_params_t saved = b.params;
-    if (b.params.limit != 0) {
-      b.params.limit = saved.limit + saved.offset;
-    }
-    b.params.offset = 0;
+    ShardParams shard(b);
     batch_search(b, d_df, stride, d_ids, d_scores, d_count, d_total);
-    b.params = saved;
+    return MGX_OK;
+  });
+}
+
+int mgx_batch_overflowed(mgx_batch_t* batch, int32_t* out_overflowed) {
+  if (batch == nullptr || out_overflowed == nullptr) {
+    return invalid("null argument");
+  }
+  return guarded([&]() {
+    Batch& b = batch->b;
+    DeviceGuard guard(b.ix->device);
+    *out_overflowed = 0;
+    if (b.streamed && b.searched) {
+      if (b.ev_last != nullptr) {
+        MGX_CUDA(cudaEventSynchronize(b.ev_last));
+      } else {
+        MGX_CUDA(cudaStreamSynchronize(b.stream));
+      }
+      *out_overflowed = batch_overflowed(b) ? 1 : 0;
+    }
+    return MGX_OK;
+  });
+}
+
+int mgx_batch_reset(mgx_batch_t* batch) {
+  if (batch == nullptr) {
+    return invalid("null batch");
+  }
+  return guarded([&]() {
+    DeviceGuard guard(batch->b.ix->device);
+    batch_reset_for_repeat(batch->b);
     return MGX_OK;
   });
 }
@@ -2150,13 +2387,7 @@ void mgx_batch_destroy(mgx_batch_t* batch) {
   } else {
     cudaStreamSynchronize(batch->b.stream);
   }
-  batch->b.recycle();
-  std::lock_guard<std::mutex> pool_lock(ix.pool_mu);
-  if (ix.batch_pool.size() < 16) {
-    ix.batch_pool.push_back(batch);  // keep the workspace for the next batch
-  } else {
-    delete batch;
-  }
+  release_batch(batch);
 }
 
 int mgx_merge_topk_device(int32_t device, void* stream, const mgx_query_params_t* params, uint32_t n_shards,
@@ -2168,6 +2399,9 @@ int mgx_merge_topk_device(int32_t device, void* stream, const mgx_query_params_t
     return invalid("null argument");
   }
   if (int rc = require_device(); rc != MGX_OK) {
+    return rc;
+  }
+  if (int rc = check_stride(*params, stride); rc != MGX_OK) {
     return rc;
   }
   return guarded([&]() {
@@ -2182,12 +2416,13 @@ int mgx_shard_record_layout(uint64_t n_queries, uint64_t stride, mgx_shard_recor
   if (out == nullptr) {
     return invalid("null argument");
   }
-  // 8-byte parts first, so every part is aligned for its element type; the record is padded to 16 bytes
+  // 8-byte parts first, so every part is aligned for its element type; the record ends with a 16-byte status block
   out->scores_offset = 0;
   out->total_offset = n_queries * stride * sizeof(double);
   out->ids_offset = out->total_offset + n_queries * sizeof(uint64_t);
   out->count_offset = out->ids_offset + n_queries * stride * sizeof(uint32_t);
-  out->bytes = (out->count_offset + n_queries * sizeof(uint32_t) + 15) & ~static_cast<uint64_t>(15);
+  out->status_offset = (out->count_offset + n_queries * sizeof(uint32_t) + 15) & ~static_cast<uint64_t>(15);
+  out->bytes = out->status_offset + 16;
   return MGX_OK;
 }
 
@@ -2198,10 +2433,26 @@ int mgx_batch_search_packed_device(mgx_batch_t* batch, const uint64_t* d_df, uin
   mgx_shard_record_layout_t lay;
   mgx_shard_record_layout(batch->b.n_queries, stride, &lay);
   uint8_t* base = static_cast<uint8_t*>(d_record);
-  return mgx_batch_search_device(batch, d_df, stride, reinterpret_cast<uint32_t*>(base + lay.ids_offset),
-                                 reinterpret_cast<double*>(base + lay.scores_offset),
-                                 reinterpret_cast<uint32_t*>(base + lay.count_offset),
-                                 reinterpret_cast<uint64_t*>(base + lay.total_offset));
+  const int rc = mgx_batch_search_device(batch, d_df, stride, reinterpret_cast<uint32_t*>(base + lay.ids_offset),
+                                         reinterpret_cast<double*>(base + lay.scores_offset),
+                                         reinterpret_cast<uint32_t*>(base + lay.count_offset),
+                                         reinterpret_cast<uint64_t*>(base + lay.total_offset));
+  if (rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    Batch& b = batch->b;
+    DeviceGuard guard(b.ix->device);
+    // status block: [0] = 1 when this shard's streamed batch did not fit its workspace (nothing was computed)
+    if (b.streamed) {
+      MGX_CUDA(cudaMemcpyAsync(base + lay.status_offset, b.d_launch.p + kLaunchOverflow, sizeof(uint32_t),
+                               cudaMemcpyDeviceToDevice, b.stream));
+    } else {
+      MGX_CUDA(cudaMemsetAsync(base + lay.status_offset, 0, 16, b.stream));
+    }
+    b.mark_last();
+    return MGX_OK;
+  });
 }
 
 int mgx_merge_topk_packed_device(int32_t device, void* stream, const mgx_query_params_t* params, uint32_t n_shards,
@@ -2210,6 +2461,9 @@ int mgx_merge_topk_packed_device(int32_t device, void* stream, const mgx_query_p
     return invalid("null argument");
   }
   if (int rc = require_device(); rc != MGX_OK) {
+    return rc;
+  }
+  if (int rc = check_stride(*params, stride); rc != MGX_OK) {
     return rc;
   }
   return guarded([&]() {
@@ -2226,6 +2480,9 @@ int mgx_merge_topk_packed_device(int32_t device, void* stream, const mgx_query_p
                       reinterpret_cast<uint32_t*>(out + lay.ids_offset), reinterpret_cast<double*>(out + lay.scores_offset),
                       reinterpret_cast<uint32_t*>(out + lay.count_offset),
                       reinterpret_cast<uint64_t*>(out + lay.total_offset));
+    // status of the merged record: any shard that overflowed
+    launch_or_status(static_cast<cudaStream_t>(stream), in + lay.status_offset, lay.bytes, n_shards,
+                     out + lay.status_offset);
     return MGX_OK;
   });
 }
@@ -2244,7 +2501,8 @@ int mgx_query_batch_ex(mgx_index_t* index, const mgx_query_params_t* params, uin
                        const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
                        const mgx_query_ext_t* ext, uint64_t stride, uint32_t* out_ids, double* out_scores,
                        uint32_t* out_count, uint64_t* out_total, uint64_t* out_df) {
-  if (index == nullptr || params == nullptr || out_ids == nullptr || out_count == nullptr || out_total == nullptr) {
+  if (index == nullptr || params == nullptr || out_ids == nullptr || out_count == nullptr || out_total == nullptr ||
+      (n_queries > 0 && (term_offsets == nullptr || q_term_begin == nullptr))) {
     return invalid("null argument");
   }
   if (params->compute_score != 0 && out_scores == nullptr) {
@@ -2253,17 +2511,32 @@ int mgx_query_batch_ex(mgx_index_t* index, const mgx_query_params_t* params, uin
   if (n_queries == 0) {
     return MGX_OK;
   }
+  if (n_queries >= (1ULL << 31)) {
+    return invalid("too many queries in one batch");
+  }
+  if (int rc = check_params(*params); rc != MGX_OK) {
+    return rc;
+  }
+  // pending mutations first and OUTSIDE the shared access (the commit needs the index exclusively); a mutation
+  // journaled by another thread after this point is seen by the next call
   if (int rc = commit_pending(index); rc != MGX_OK) {
     return rc;
   }
-  std::lock_guard<std::mutex> lock(index->mu);
-  mgx_batch_t* batch = nullptr;
-  int rc = mgx_batch_prepare_ex(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes,
-                                not_offsets, q_not_begin, ext, index->ix.stream, &batch);
-  if (rc != MGX_OK) {
-    return rc;
-  }
-  rc = guarded([&]() {
+  return guarded([&]() {
+    Reader rd(index);
+    mgx_batch_t* batch = nullptr;
+    if (int rc = prepare_unlocked(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
+                                  q_not_begin, ext, rd.stream(), &batch);
+        rc != MGX_OK) {
+      return rc;
+    }
+    struct Release {
+      mgx_batch_t* b;
+      ~Release() {
+        cudaStreamSynchronize(b->b.stream);
+        release_batch(b);
+      }
+    } release{batch};
     Batch& b = batch->b;
     Index& ix = *b.ix;
     DeviceGuard guard(ix.device);
@@ -2278,41 +2551,389 @@ int mgx_query_batch_ex(mgx_index_t* index, const mgx_query_params_t* params, uin
     d_count.reserve(n_queries);
     d_total.reserve(n_queries);
     d_df.reserve(b.n_slots);
-    batch_plan(b);
-    if (params->compute_score != 0) {
-      batch_df(b);
+    b.allow_streamed = true;  // planned without a host read-back; repeated below if it does not fit the workspace
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      batch_plan(b);
+      if (params->compute_score != 0) {
+        batch_df(b);
+      }
+      batch_df_to_slots(b, d_df.p);
+      batch_search(b, nullptr, stride, d_ids.p, params->compute_score != 0 ? d_scores.p : nullptr, d_count.p, d_total.p);
+      uint64_t d2h = 0;
+      MGX_CUDA(cudaMemcpyAsync(out_ids, d_ids.p, n_queries * stride * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      d2h += n_queries * stride * sizeof(uint32_t);
+      if (params->compute_score != 0) {
+        MGX_CUDA(cudaMemcpyAsync(out_scores, d_scores.p, n_queries * stride * sizeof(double), cudaMemcpyDeviceToHost, st));
+        d2h += n_queries * stride * sizeof(double);
+      }
+      MGX_CUDA(cudaMemcpyAsync(out_count, d_count.p, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      MGX_CUDA(cudaMemcpyAsync(out_total, d_total.p, n_queries * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      d2h += n_queries * 12;
+      if (out_df != nullptr && b.n_slots > 0) {
+        MGX_CUDA(cudaMemcpyAsync(out_df, d_df.p, b.n_slots * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        d2h += b.n_slots * sizeof(uint64_t);
+      }
+      b.mark_last();
+      MGX_CUDA(cudaStreamSynchronize(st));
+      b.d2h_bytes += d2h;
+      if (!batch_overflowed(b)) {
+        break;
+      }
+      batch_reset_for_repeat(b);
     }
-    batch_df_to_slots(b, d_df.p);
-    batch_search(b, nullptr, stride, d_ids.p, params->compute_score != 0 ? d_scores.p : nullptr, d_count.p, d_total.p);
-    uint64_t d2h = 0;
-    MGX_CUDA(cudaMemcpyAsync(out_ids, d_ids.p, n_queries * stride * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    d2h += n_queries * stride * sizeof(uint32_t);
-    if (params->compute_score != 0) {
-      MGX_CUDA(cudaMemcpyAsync(out_scores, d_scores.p, n_queries * stride * sizeof(double), cudaMemcpyDeviceToHost, st));
-      d2h += n_queries * stride * sizeof(double);
+    mgx_batch_stats_t stats{};
+    b.collect_stats(&stats);
+    stats.launches = g_launches.load() - b.launches_at_start;
+    {
+      std::lock_guard<std::mutex> sl(index->stats_mu);
+      ix.last_stats = stats;
     }
-    MGX_CUDA(cudaMemcpyAsync(out_count, d_count.p, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    MGX_CUDA(cudaMemcpyAsync(out_total, d_total.p, n_queries * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    d2h += n_queries * 12;
-    if (out_df != nullptr && b.n_slots > 0) {
-      MGX_CUDA(cudaMemcpyAsync(out_df, d_df.p, b.n_slots * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-      d2h += b.n_slots * sizeof(uint64_t);
-    }
-    b.mark_last();
-    MGX_CUDA(cudaStreamSynchronize(st));
-    b.d2h_bytes += d2h;
-    b.collect_stats(&ix.last_stats);
-    ix.last_stats.launches = g_launches.load() - b.launches_at_start;
     return MGX_OK;
   });
-  mgx_batch_destroy(batch);
-  return rc;
+}
+
+// ---------------------------------------------------------------- sharded pipeline behind the C ABI
+// One process per GPU, one doc-id range each. NCCL is looked up at run time (dlopen of libnccl.so.2: the copy a
+// hosting PyTorch process has already loaded, or the system library for a plain C++ host), so libmgx.so has no link
+// dependency on it and single-GPU hosts never touch it.
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    const char* override_path = std::getenv("MGX_NCCL_LIB");
+    const char* names[] = {override_path, "libnccl.so.2", "libnccl.so"};
+    for (const char* name : names) {
+      if (name == nullptr) {
+        continue;
+      }
+      api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib != nullptr) {
+        break;
+      }
+    }
+    if (api.lib == nullptr) {
+      api.error = std::string("libnccl.so.2 not found: ") + (dlerror() != nullptr ? dlerror() : "");
+      return;
+    }
+    auto sym = [&](const char* name) {
+      void* s = dlsym(api.lib, name);
+      if (s == nullptr) {
+        api.error = std::string("NCCL symbol missing: ") + name;
+      }
+      return s;
+    };
+    api.GetVersion = reinterpret_cast<decltype(api.GetVersion)>(sym("ncclGetVersion"));
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  });
+  return &api;
+}
+
+int nccl_ready(NcclApi** out) {
+  NcclApi* api = nccl_api();
+  if (api->lib == nullptr || !api->error.empty()) {
+    set_last_error("NCCL is not available: " + api->error);
+    return MGX_ERR_UNSUPPORTED;
+  }
+  *out = api;
+  return MGX_OK;
+}
+
+#define MGX_NCCL(api, expr)                                                                       \
+  do {                                                                                            \
+    ncclResult_t mgx_nccl_rc__ = (expr);                                                          \
+    if (mgx_nccl_rc__ != ncclSuccess) {                                                           \
+      ::mgx::set_last_error(std::string(#expr) + ": " + (api)->GetErrorString(mgx_nccl_rc__));    \
+      throw ::mgx::CudaFailure{MGX_ERR_CUDA};                                                     \
+    }                                                                                             \
+  } while (0)
+}  // namespace
+
+struct mgx_shard_comm {
+  int n_ranks = 1;
+  int rank = 0;
+  int device = 0;
+  int n_lanes = 0;
+  ncclComm_t comm[MGX_COMM_MAX_LANES] = {nullptr};
+  cudaStream_t stream[MGX_COMM_MAX_LANES] = {nullptr};  // highest priority: the exchanges are latency-sized and must
+                                                        // not queue behind another batch's grid-filling kernels
+};
+
+int mgx_comm_unique_id(uint8_t* out_id) {
+  if (out_id == nullptr) {
+    return invalid("null argument");
+  }
+  NcclApi* api = nullptr;
+  if (int rc = nccl_ready(&api); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == MGX_COMM_ID_BYTES, "unique id size");
+    MGX_NCCL(api, api->GetUniqueId(&id));
+    std::memcpy(out_id, &id, sizeof(id));
+    return MGX_OK;
+  });
+}
+
+int mgx_comm_create(const uint8_t* ids, int32_t n_lanes, int32_t n_ranks, int32_t rank, int32_t device,
+                    mgx_shard_comm_t** out) {
+  if (ids == nullptr || out == nullptr) {
+    return invalid("null argument");
+  }
+  *out = nullptr;
+  if (n_lanes < 1 || n_lanes > MGX_COMM_MAX_LANES || n_ranks < 1 || rank < 0 || rank >= n_ranks) {
+    return invalid("mgx_comm_create: bad lane / rank arguments");
+  }
+  if (int rc = require_device(); rc != MGX_OK) {
+    return rc;
+  }
+  NcclApi* api = nullptr;
+  if (int rc = nccl_ready(&api); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    DeviceGuard guard(device);
+    auto c = std::make_unique<mgx_shard_comm>();
+    c->n_ranks = n_ranks;
+    c->rank = rank;
+    c->device = device;
+    int least = 0;
+    int greatest = 0;
+    MGX_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    for (int l = 0; l < n_lanes; ++l) {
+      ncclUniqueId id;
+      std::memcpy(&id, ids + static_cast<size_t>(l) * MGX_COMM_ID_BYTES, sizeof(id));
+      MGX_NCCL(api, api->CommInitRank(&c->comm[l], n_ranks, id, rank));
+      MGX_CUDA(cudaStreamCreateWithPriority(&c->stream[l], cudaStreamNonBlocking, greatest));
+      c->n_lanes = l + 1;
+    }
+    *out = c.release();
+    return MGX_OK;
+  });
+}
+
+void mgx_comm_destroy(mgx_shard_comm_t* comm) {
+  if (comm == nullptr) {
+    return;
+  }
+  NcclApi* api = nccl_api();
+  DeviceGuard guard(comm->device);
+  for (int l = 0; l < comm->n_lanes; ++l) {
+    if (comm->stream[l] != nullptr) {
+      cudaStreamSynchronize(comm->stream[l]);
+    }
+    if (comm->comm[l] != nullptr && api->CommDestroy != nullptr) {
+      api->CommDestroy(comm->comm[l]);
+    }
+    if (comm->stream[l] != nullptr) {
+      cudaStreamDestroy(comm->stream[l]);
+    }
+  }
+  delete comm;
+}
+
+int mgx_comm_info(const mgx_shard_comm_t* comm, int32_t* n_ranks, int32_t* rank, int32_t* n_lanes,
+                  int32_t* nccl_version) {
+  if (n_ranks != nullptr) {
+    *n_ranks = comm != nullptr ? comm->n_ranks : 1;
+  }
+  if (rank != nullptr) {
+    *rank = comm != nullptr ? comm->rank : 0;
+  }
+  if (n_lanes != nullptr) {
+    *n_lanes = comm != nullptr ? comm->n_lanes : 0;
+  }
+  if (nccl_version != nullptr) {
+    *nccl_version = 0;
+    NcclApi* api = nccl_api();
+    if (api->GetVersion != nullptr) {
+      int v = 0;
+      if (api->GetVersion(&v) == ncclSuccess) {
+        *nccl_version = v;
+      }
+    }
+  }
+  return MGX_OK;
+}
+
+namespace {
+cudaEvent_t batch_event(Batch& b, int i) {
+  if (b.ev_x[i] == nullptr) {
+    MGX_CUDA(cudaEventCreateWithFlags(&b.ev_x[i], cudaEventDisableTiming));
+  }
+  return b.ev_x[i];
+}
+
+// Everything of one batch, enqueued without a host synchronisation when the batch is streamed:
+//   plan -> df -> [all-reduce of the per-term df] -> search -> [all-gather of the packed records] -> merge -> D2H
+void sharded_enqueue(mgx_shard_comm_t* comm, int lane, Batch& b, uint64_t stride, void* h_record_out) {
+  const int G = comm != nullptr ? comm->n_ranks : 1;
+  const int rank = comm != nullptr ? comm->rank : 0;
+  cudaStream_t st = b.stream;
+  mgx_shard_record_layout_t lay;
+  mgx_shard_record_layout(b.n_queries, stride, &lay);
+  b.o_merged.reserve(lay.bytes);
+  if (G > 1) {
+    b.o_gather.reserve(lay.bytes * static_cast<uint64_t>(G));
+  }
+  batch_plan(b);
+  if (b.params.compute_score != 0) {
+    batch_df(b);
+  }
+  NcclApi* api = nullptr;
+  if (G > 1) {
+    if (int rc = nccl_ready(&api); rc != MGX_OK) {
+      throw CudaFailure{rc};
+    }
+    if (b.params.compute_score != 0 && b.n_terms > 0) {
+      // exchange 1: every shard scores with the GLOBAL document frequencies. The batch was compiled from the same
+      // input on every rank, so the per-term array itself is reduced, in place.
+      cudaStream_t cs = comm->stream[lane];
+      MGX_CUDA(cudaEventRecord(batch_event(b, 0), st));
+      MGX_CUDA(cudaStreamWaitEvent(cs, batch_event(b, 0), 0));
+      MGX_NCCL(api, api->AllReduce(b.d_t_df.p, b.d_t_df.p, b.n_terms, ncclUint64, ncclSum, comm->comm[lane], cs));
+      MGX_CUDA(cudaEventRecord(batch_event(b, 1), cs));
+      MGX_CUDA(cudaStreamWaitEvent(st, batch_event(b, 1), 0));
+    }
+  }
+  uint8_t* rec = G > 1 ? b.o_gather.p + lay.bytes * static_cast<uint64_t>(rank) : b.o_merged.p;
+  {
+    // a shard returns its best (offset + limit) records un-offset and the merge applies the offset; a single shard
+    // answers with the caller's own window
+    mgx_query_params_t saved = b.params;
+    if (G > 1) {
+      if (b.params.limit != 0) {
+        b.params.limit = saved.limit + saved.offset;
+      }
+      b.params.offset = 0;
+    }
+    try {
+      batch_search(b, nullptr, stride, reinterpret_cast<uint32_t*>(rec + lay.ids_offset),
+                   reinterpret_cast<double*>(rec + lay.scores_offset), reinterpret_cast<uint32_t*>(rec + lay.count_offset),
+                   reinterpret_cast<uint64_t*>(rec + lay.total_offset));
+    } catch (...) {
+      b.params = saved;
+      throw;
+    }
+    b.params = saved;
+  }
+  if (b.streamed) {
+    MGX_CUDA(cudaMemsetAsync(rec + lay.status_offset, 0, 16, st));
+    MGX_CUDA(cudaMemcpyAsync(rec + lay.status_offset, b.d_launch.p + kLaunchOverflow, sizeof(uint32_t),
+                             cudaMemcpyDeviceToDevice, st));
+  } else {
+    MGX_CUDA(cudaMemsetAsync(rec + lay.status_offset, 0, 16, st));
+  }
+  if (G > 1) {
+    // exchange 2: ONE all-gather of the fixed-size packed records, in place (every rank wrote its own slot)
+    cudaStream_t cs = comm->stream[lane];
+    MGX_CUDA(cudaEventRecord(batch_event(b, 2), st));
+    MGX_CUDA(cudaStreamWaitEvent(cs, batch_event(b, 2), 0));
+    MGX_NCCL(api, api->AllGather(rec, b.o_gather.p, lay.bytes, ncclUint8, comm->comm[lane], cs));
+    MGX_CUDA(cudaEventRecord(batch_event(b, 3), cs));
+    MGX_CUDA(cudaStreamWaitEvent(st, batch_event(b, 3), 0));
+    const uint8_t* in = b.o_gather.p;
+    uint8_t* out = b.o_merged.p;
+    launch_merge_topk(st, b.params, static_cast<uint32_t>(G), b.n_queries, stride,
+                      reinterpret_cast<const uint32_t*>(in + lay.ids_offset),
+                      reinterpret_cast<const double*>(in + lay.scores_offset),
+                      reinterpret_cast<const uint32_t*>(in + lay.count_offset),
+                      reinterpret_cast<const uint64_t*>(in + lay.total_offset), lay.bytes,
+                      reinterpret_cast<uint32_t*>(out + lay.ids_offset), reinterpret_cast<double*>(out + lay.scores_offset),
+                      reinterpret_cast<uint32_t*>(out + lay.count_offset), reinterpret_cast<uint64_t*>(out + lay.total_offset));
+    launch_or_status(st, in + lay.status_offset, lay.bytes, static_cast<uint32_t>(G), out + lay.status_offset);
+  }
+  b.h_status.reserve(4);
+  MGX_CUDA(cudaMemcpyAsync(b.h_status.p, b.o_merged.p + lay.status_offset, 16, cudaMemcpyDeviceToHost, st));
+  if (h_record_out != nullptr) {
+    MGX_CUDA(cudaMemcpyAsync(h_record_out, b.o_merged.p, lay.bytes, cudaMemcpyDeviceToHost, st));
+    b.d2h_bytes += lay.bytes;
+  }
+  b.mark_last();
+  b.searched = true;
+  b.sharded_enqueued = true;
+}
+}  // namespace
+
+int mgx_sharded_batch_enqueue(mgx_shard_comm_t* comm, int32_t lane, mgx_batch_t* batch, uint64_t stride,
+                              void* h_record_out) {
+  if (batch == nullptr) {
+    return invalid("null batch");
+  }
+  if (comm != nullptr && (lane < 0 || lane >= comm->n_lanes)) {
+    return invalid("communicator lane out of range");
+  }
+  if (batch->b.planned) {
+    return invalid("mgx_sharded_batch_enqueue needs a freshly prepared batch");
+  }
+  if (int rc = check_stride(batch->b.params, stride); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    Batch& b = batch->b;
+    DeviceGuard guard(b.ix->device);
+    b.allow_streamed = true;
+    sharded_enqueue(comm, lane, b, stride, h_record_out);
+    return MGX_OK;
+  });
+}
+
+int mgx_sharded_batch_finish(mgx_shard_comm_t* comm, int32_t lane, mgx_batch_t* batch, uint64_t stride,
+                             void* h_record_out, const void** d_record_out, int32_t* out_repeated) {
+  if (batch == nullptr) {
+    return invalid("null batch");
+  }
+  if (!batch->b.sharded_enqueued) {
+    return invalid("mgx_sharded_batch_finish without mgx_sharded_batch_enqueue");
+  }
+  return guarded([&]() {
+    Batch& b = batch->b;
+    DeviceGuard guard(b.ix->device);
+    if (out_repeated != nullptr) {
+      *out_repeated = 0;
+    }
+    MGX_CUDA(cudaEventSynchronize(b.ev_last));
+    // the status block of the MERGED record: set when any shard's streamed batch did not fit its workspace. Every
+    // rank reads the same value, so all of them repeat the batch together (in the synchronous form, which sizes its
+    // workspace from the batch) and the exchanges stay matched.
+    if (b.h_status.p != nullptr && b.h_status.p[0] != 0) {
+      batch_reset_for_repeat(b);
+      sharded_enqueue(comm, lane, b, stride, h_record_out);
+      MGX_CUDA(cudaEventSynchronize(b.ev_last));
+      if (out_repeated != nullptr) {
+        *out_repeated = 1;
+      }
+    }
+    if (d_record_out != nullptr) {
+      *d_record_out = b.o_merged.p;
+    }
+    return MGX_OK;
+  });
 }
 
 int mgx_index_last_batch_stats(const mgx_index_t* index, mgx_batch_stats_t* out) {
   if (index == nullptr || out == nullptr) {
     return invalid("null argument");
   }
+  std::lock_guard<std::mutex> sl(const_cast<mgx_index_t*>(index)->stats_mu);
   *out = index->ix.last_stats;
   return MGX_OK;
 }
@@ -2333,10 +2954,10 @@ int mgx_score_documents(mgx_index_t* index, const uint32_t* candidates, uint64_t
     return rc;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(index->mu);
+    Reader rd(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
-    cudaStream_t st = ix.stream;
+    cudaStream_t st = rd.stream();
     std::vector<uint32_t> boff(n_terms + 1, 0);
     for (uint64_t i = 0; i < n_terms; ++i) {
       if (term_offsets[i + 1] - term_offsets[i] > kMaxTermBytes) {
@@ -2386,10 +3007,10 @@ int mgx_sort_by_score(mgx_index_t* index, const uint32_t* results, const double*
     return MGX_ERR_UNSUPPORTED;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> lock(index->mu);
+    Reader rd(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
-    cudaStream_t st = ix.stream;
+    cudaStream_t st = rd.stream();
     DevBuf<uint32_t> d_docs;
     DevBuf<double> d_scores;
     DevBuf<uint32_t> d_out;

@@ -423,6 +423,7 @@ struct SearchScratch {
   DevBuf<uint32_t> tile_query;
   DevBuf<uint32_t> topk_groups;  // (query, first tile, end tile) triples of the top-k pre-reduction
   uint64_t map_owner = 0;  // serial of the batch whose tile maps are in df_tile_term / tile_query
+  int skip_streamed = 0;   // batches to run in the synchronous form after one that cannot fit any workspace
 };
 
 // One DocumentStore filter column mirrored on the device (see mgx_index_set_filter_column).

@@ -45,7 +45,7 @@ struct BatchView {
   uint16_t* key_toff;
   uint64_t* t_est;
   uint32_t* t_df_tiles;
-  const uint64_t* t_df_tile_off;
+  uint64_t* t_df_tile_off;
   uint64_t* t_df;
   uint32_t n_terms;
   // queries
@@ -69,8 +69,8 @@ struct BatchView {
   const FilterPred* filters;
   uint32_t* q_driver_len;
   uint32_t* q_ntiles;
-  const uint64_t* q_tile_off;
-  const uint64_t* q_rec_off;
+  uint64_t* q_tile_off;
+  uint64_t* q_group_off;           // [Q+1] top-k pre-reduction groups per query (streamed batches)
   const double* q_idf;
   uint32_t n_queries;
   // explicit driver (query 0)
@@ -88,6 +88,7 @@ struct BatchView {
   uint32_t stream_len12_mask;          // stage-2 classes present (bit m: min(len, 12) == m)
   uint32_t stream_slot_mask;           // n_slots - 1
   uint32_t* df_mode;                   // [0] = 1: streaming pass chosen for this batch
+  uint32_t* launch;                    // LaunchSlot block of a streamed batch, nullptr otherwise
 };
 
 struct ScoreParams {
@@ -246,13 +247,9 @@ __device__ __forceinline__ uint32_t doc_count_term(DocText& d, const uint8_t* __
 }
 
 // ------------------------------------------------------------------ lookup + term planning
-__global__ void lookup_kernel(const uint64_t* __restrict__ term_keys, const uint64_t* __restrict__ term_off,
-                              uint64_t n_dict, const uint64_t* __restrict__ keys, uint32_t n_keys,
-                              uint32_t* __restrict__ key_list, uint32_t* __restrict__ key_len) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_keys) {
-    return;
-  }
+__device__ __forceinline__ void lookup_one(const uint64_t* __restrict__ term_keys, const uint64_t* __restrict__ term_off,
+                                           uint64_t n_dict, const uint64_t* __restrict__ keys, uint32_t i,
+                                           uint32_t* __restrict__ key_list, uint32_t* __restrict__ key_len) {
   const uint64_t key = keys[i];
   uint64_t lo = 0;
   uint64_t hi = n_dict;
@@ -273,12 +270,19 @@ __global__ void lookup_kernel(const uint64_t* __restrict__ term_keys, const uint
   }
 }
 
-__global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf8, const uint8_t* __restrict__ raw_flags,
-                                 uint64_t bitmap_bytes) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= bv.n_terms) {
-    return;
+__global__ void lookup_kernel(const uint64_t* __restrict__ term_keys, const uint64_t* __restrict__ term_off,
+                              uint64_t n_dict, const uint64_t* __restrict__ keys, uint32_t n_keys,
+                              uint32_t* __restrict__ key_list, uint32_t* __restrict__ key_len) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_keys) {
+    lookup_one(term_keys, term_off, n_dict, keys, i, key_list, key_len);
   }
+}
+
+// df_unit: driver entries per df work item (kTile with tile descriptors, kDfUnit in a streamed batch)
+__device__ __forceinline__ void term_plan_one(const BatchView& bv, uint32_t t, int compute_df, int all_valid_utf8,
+                                              const uint8_t* __restrict__ raw_flags, uint64_t bitmap_bytes,
+                                              uint32_t df_unit) {
   const uint32_t k0 = bv.term_koff[t];
   const uint32_t k1 = bv.term_koff[t + 1];
   uint64_t est = kEstNone;
@@ -307,7 +311,7 @@ __global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf
     if (k1 - k0 == 1 && all_valid_utf8 && (raw_flags[t] & 2) != 0) {
       df = est;  // the term is exactly its one n-gram: every posting contains it as a substring
     } else {
-      tiles = static_cast<uint32_t>((est + kTile - 1) / kTile);
+      tiles = static_cast<uint32_t>((est + df_unit - 1) / df_unit);
       unsigned long long bytes = 0;
       for (uint32_t i = k0; i < k1; ++i) {
         bytes += umin64(4ULL * bv.key_len[i], bitmap_bytes);
@@ -323,16 +327,20 @@ __global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf
   bv.t_df_tiles[t] = tiles;
 }
 
+__global__ void term_plan_kernel(BatchView bv, int compute_df, int all_valid_utf8, const uint8_t* __restrict__ raw_flags,
+                                 uint64_t bitmap_bytes) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < bv.n_terms) {
+    term_plan_one(bv, t, compute_df, all_valid_utf8, raw_flags, bitmap_bytes, kTile);
+  }
+}
+
 // Chooses, per batch, how the verified document frequencies of the stream-eligible terms are computed:
 // per-term candidate tiles (df_tile_kernel: cost ~ entries of the terms' shortest lists) or ONE pass over the
 // text arena matching all of them at once (df_stream_kernel: cost ~ text bytes). force: 0 auto, 1 tiles, 2 stream.
 constexpr unsigned long long kStreamCostRatio = 6;  // measured: ~25 ps per list entry of candidate work, ~4 ps per streamed byte
-__global__ void df_mode_kernel(BatchView bv, const uint8_t* __restrict__ raw_flags, uint64_t text_bytes, int force,
-                               int have_table) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= bv.n_terms) {
-    return;
-  }
+__device__ __forceinline__ void df_mode_one(const BatchView& bv, uint32_t t, const uint8_t* __restrict__ raw_flags,
+                                            uint64_t text_bytes, int force, int have_table) {
   unsigned long long entries = 0;
   for (int i = 0; i < kStatStripes; ++i) {
     entries += bv.stats[kStatStreamEntries * kStatStripes + i];
@@ -348,6 +356,14 @@ __global__ void df_mode_kernel(BatchView bv, const uint8_t* __restrict__ raw_fla
   }
   if (t == 0) {
     bv.df_mode[0] = stream ? 1u : 0u;
+  }
+}
+
+__global__ void df_mode_kernel(BatchView bv, const uint8_t* __restrict__ raw_flags, uint64_t text_bytes, int force,
+                               int have_table) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < bv.n_terms) {
+    df_mode_one(bv, t, raw_flags, text_bytes, force, have_table);
   }
 }
 
@@ -701,12 +717,8 @@ __device__ __forceinline__ bool group_contains_term(const uint8_t* __restrict__ 
 }
 
 // key -> resolved list, after term_plan_kernel has ordered each term's keys by list length
-__global__ void key_ref_kernel(IndexView iv, const uint32_t* __restrict__ key_list, const uint32_t* __restrict__ key_len,
-                               uint32_t n_keys, KeyRef* __restrict__ out) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_keys) {
-    return;
-  }
+__device__ __forceinline__ void key_ref_one(const IndexView& iv, const uint32_t* __restrict__ key_list,
+                                            const uint32_t* __restrict__ key_len, uint32_t i, KeyRef* __restrict__ out) {
   KeyRef r{};
   const uint32_t dict = key_list[i];
   if (dict != kNone) {
@@ -716,6 +728,33 @@ __global__ void key_ref_kernel(IndexView iv, const uint32_t* __restrict__ key_li
     r.len = key_len[i];
   }
   out[i] = r;
+}
+
+__global__ void key_ref_kernel(IndexView iv, const uint32_t* __restrict__ key_list, const uint32_t* __restrict__ key_len,
+                               uint32_t n_keys, KeyRef* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_keys) {
+    key_ref_one(iv, key_list, key_len, i, out);
+  }
+}
+
+// Streamed planning, stage 1: everything that concerns ONE term in one thread -- dictionary lookup of its keys, lists
+// by ascending length, estimate, df work units, resolved list references (lookup + term_plan + key_ref in one launch).
+__global__ void plan_terms_kernel(IndexView iv, BatchView bv, const uint64_t* __restrict__ keys, int compute_df,
+                                  int all_valid_utf8, const uint8_t* __restrict__ raw_flags, uint64_t bitmap_bytes) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= bv.n_terms) {
+    return;
+  }
+  const uint32_t k0 = bv.term_koff[t];
+  const uint32_t k1 = bv.term_koff[t + 1];
+  for (uint32_t i = k0; i < k1; ++i) {
+    lookup_one(iv.term_keys, iv.term_off, iv.n_terms, keys, i, bv.key_list, bv.key_len);
+  }
+  term_plan_one(bv, t, compute_df, all_valid_utf8, raw_flags, bitmap_bytes, kDfUnit);
+  for (uint32_t i = k0; i < k1; ++i) {
+    key_ref_one(iv, bv.key_list, bv.key_len, i, bv.key_ref);
+  }
 }
 
 // df tile descriptors: term t owns tiles [off[t], off[t+1]); one warp per term.
@@ -804,6 +843,9 @@ static_assert(kWarpTile * (kTileThreads / 32) == kTile, "warps must tile the CTA
 __device__ __forceinline__ void stat_add(const BatchView& bv, int slot, unsigned long long v) {
   atomicAdd(bv.stats + slot * kStatStripes + (blockIdx.x & (kStatStripes - 1)), v);
 }
+__device__ __forceinline__ void stat_add_at(const BatchView& bv, int slot, uint32_t stripe, unsigned long long v) {
+  atomicAdd(bv.stats + slot * kStatStripes + (stripe & (kStatStripes - 1)), v);
+}
 
 // 12 bytes of text at an arbitrary byte address as three little-endian words (the arena is padded by 64 bytes)
 __device__ __forceinline__ void load_text_words(const uint8_t* __restrict__ text, uint64_t at, uint32_t (&x)[3]) {
@@ -819,25 +861,12 @@ __device__ __forceinline__ void load_text_words(const uint8_t* __restrict__ text
 }
 
 static_assert(kWarpStageCap * sizeof(uint32_t) >= kStageBuf, "the text staging buffer aliases the list staging buffer");
-__global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, BatchView bv) {
-  __shared__ __align__(16) uint32_t s_stage[kTileThreads / 32][kWarpStageCap];
-  __shared__ uint32_t s_surv[kTileThreads / 32][kWarpTile];
-  __shared__ uint32_t s_spos[kTileThreads / 32][kWarpTile];
+// One warp, one 128-entry piece of a term's shortest list (entries [e0, e0 + 128) of drv): the whole df work of that
+// piece. stage / surv / spos are the calling warp's own shared-memory slices; stat_stripe spreads the accounting atomics.
+__device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchView& bv, const ListRef& drv, uint32_t t,
+                                             uint32_t k0, uint32_t k1, uint64_t e0, uint32_t* stage, uint32_t* surv,
+                                             uint32_t* spos, uint32_t stat_stripe) {
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned warp = threadIdx.x >> 5;
-  // one 32-byte descriptor instead of tile -> term -> keys -> dictionary -> offsets
-  const uint4* dp = reinterpret_cast<const uint4*>(bv.df_tile_desc + blockIdx.x);
-  const uint4 d0 = __ldg(dp);
-  const uint4 d1 = __ldg(dp + 1);
-  ListRef drv;
-  drv.p = reinterpret_cast<const uint32_t*>(static_cast<uintptr_t>(d0.x) | (static_cast<uintptr_t>(d0.y) << 32));
-  drv.len = d0.z;
-  drv.bm = nullptr;
-  const uint32_t t = d0.w;
-  const uint32_t k0 = d1.x;
-  const uint32_t k1 = d1.y;
-  const uint64_t tile = d1.z;
-  const uint64_t e0 = tile * kTile + static_cast<uint64_t>(warp) * kWarpTile;
   if (e0 >= drv.len) {
     return;  // no block-wide barrier is used below, so a warp may leave early
   }
@@ -865,7 +894,6 @@ __global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, 
       alive |= 1u << k;
     }
   }
-  uint32_t* stage = s_stage[warp];
   for (uint32_t j = k0 + 1; j < k1; ++j) {
     const uint4* rp = reinterpret_cast<const uint4*>(bv.key_ref + j);
     const uint4 r0 = __ldg(rp);
@@ -931,8 +959,8 @@ __global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, 
 #pragma unroll
   for (int k = 0; k < kWarpItems; ++k) {
     if ((alive >> k) & 1u) {
-      s_surv[warp][w] = my_doc[k];
-      s_spos[warp][w] = my_pos[k];
+      surv[w] = my_doc[k];
+      spos[w] = my_pos[k];
       ++w;
     }
   }
@@ -959,8 +987,8 @@ __global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, 
     bool scan = false;
     uint32_t doc = 0;
     if (s < n) {
-      doc = s_surv[warp][s];
-      const uint32_t pp = s_spos[warp][s];
+      doc = surv[s];
+      const uint32_t pp = spos[s];
       const uint64_t b = iv.text_off[doc];
       const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
       text_bytes += len;
@@ -996,7 +1024,7 @@ __global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, 
     }
     const unsigned scan_mask = __ballot_sync(0xffffffffu, scan);
     if (scan) {
-      s_surv[warp][n_scan + __popc(scan_mask & ((1u << lane) - 1u))] = doc;  // n_scan + rank <= s: never ahead of the reads
+      surv[n_scan + __popc(scan_mask & ((1u << lane) - 1u))] = doc;  // n_scan + rank <= s: never ahead of the reads
     }
     n_scan += __popc(scan_mask);
     __syncwarp();
@@ -1012,7 +1040,7 @@ __global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, 
     uint32_t len = 0;
     bool slow = false;
     if (s < n_scan) {
-      const uint32_t doc = s_surv[warp][s];
+      const uint32_t doc = surv[s];
       b = iv.text_off[doc];
       len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
       if (tl > kThreadScanMaxTerm || len > kThreadScanMaxDoc) {
@@ -1030,7 +1058,7 @@ __global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, 
       const uint32_t src = static_cast<uint32_t>(__ffs(static_cast<int>(slow_mask))) - 1u;
       slow_mask &= slow_mask - 1;
       // the warp's list staging buffer is free after the membership phase: it stages the text now
-      DocText d = doc_open(iv, s_surv[warp][s0 + src / kGroup], reinterpret_cast<uint8_t*>(s_stage[warp]));
+      DocText d = doc_open(iv, surv[s0 + src / kGroup], reinterpret_cast<uint8_t*>(stage));
       const uint32_t c = doc_count_term(d, term, tl, true);
       __syncwarp();
       if (lane == src) {
@@ -1047,10 +1075,96 @@ __global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, 
     if (hits != 0) {
       atomicAdd(reinterpret_cast<unsigned long long*>(bv.t_df + t), static_cast<unsigned long long>(hits));
     }
-    stat_add(bv, kStatDfBytes, text_bytes);
-    stat_add(bv, kStatDfCandidates, n);
+    stat_add_at(bv, kStatDfBytes, stat_stripe, text_bytes);
+    stat_add_at(bv, kStatDfCandidates, stat_stripe, n);
     if (n_scan != 0) {
-      stat_add(bv, kStatDfScanned, n_scan);
+      stat_add_at(bv, kStatDfScanned, stat_stripe, n_scan);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTileThreads, 6) df_tile_kernel(IndexView iv, BatchView bv) {
+  __shared__ __align__(16) uint32_t s_stage[kTileThreads / 32][kWarpStageCap];
+  __shared__ uint32_t s_surv[kTileThreads / 32][kWarpTile];
+  __shared__ uint32_t s_spos[kTileThreads / 32][kWarpTile];
+  const unsigned warp = threadIdx.x >> 5;
+  // one 32-byte descriptor instead of tile -> term -> keys -> dictionary -> offsets
+  const uint4* dp = reinterpret_cast<const uint4*>(bv.df_tile_desc + blockIdx.x);
+  const uint4 d0 = __ldg(dp);
+  const uint4 d1 = __ldg(dp + 1);
+  ListRef drv;
+  drv.p = reinterpret_cast<const uint32_t*>(static_cast<uintptr_t>(d0.x) | (static_cast<uintptr_t>(d0.y) << 32));
+  drv.len = d0.z;
+  drv.bm = nullptr;
+  const uint64_t tile = d1.z;
+  df_warp_tile(iv, bv, drv, d0.w, d1.x, d1.y, tile * kTile + static_cast<uint64_t>(warp) * kWarpTile, s_stage[warp],
+               s_surv[warp], s_spos[warp], blockIdx.x);
+}
+
+// Streamed form (no host read-back of the tile count): persistent warps pull UNITS of kDfUnit entries of the terms'
+// shortest lists from a device-side counter. unit -> term by a 32-ary search over the units' prefix sums
+// (t_df_tile_off, written by the planning tail); the next unit is fetched before the current one is processed, so
+// the atomic's latency hides behind the work.
+__device__ __forceinline__ uint32_t warp_upper_bound_u64(const uint64_t* __restrict__ p, uint32_t n, uint64_t v) {
+  // number of elements <= v in the ascending array p[0, n)
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t lo = 0;
+  uint32_t hi = n;
+  while (hi - lo > 32) {
+    const uint32_t size = hi - lo;
+    const uint32_t idx = lo + static_cast<uint32_t>((static_cast<uint64_t>(lane + 1) * size) / 33);
+    const bool le = p[idx] <= v;
+    const int c = __popc(__ballot_sync(0xffffffffu, le));  // monotone in the lane index
+    const uint32_t idx_prev = __shfl_sync(0xffffffffu, idx, c > 0 ? c - 1 : 0);
+    const uint32_t idx_next = __shfl_sync(0xffffffffu, idx, c < 32 ? c : 31);
+    if (c > 0) {
+      lo = idx_prev + 1;
+    }
+    if (c < 32) {
+      hi = idx_next;
+    }
+  }
+  const uint32_t i = lo + lane;
+  const bool le = i < hi && p[i] <= v;
+  return lo + __popc(__ballot_sync(0xffffffffu, le));
+}
+
+__global__ void __launch_bounds__(kTileThreads, 6) df_units_kernel(IndexView iv, BatchView bv) {
+  __shared__ __align__(16) uint32_t s_stage[kTileThreads / 32][kWarpStageCap];
+  __shared__ uint32_t s_surv[kTileThreads / 32][kWarpTile];
+  __shared__ uint32_t s_spos[kTileThreads / 32][kWarpTile];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t n_units = bv.launch[kLaunchDfUnits];
+  uint32_t next = 0;
+  if (lane == 0) {
+    next = atomicAdd(bv.launch + kLaunchDfNext, 1u);
+  }
+  for (;;) {
+    const uint32_t unit = __shfl_sync(0xffffffffu, next, 0);
+    if (unit >= n_units) {
+      return;
+    }
+    if (lane == 0) {
+      next = atomicAdd(bv.launch + kLaunchDfNext, 1u);  // consumed in the next round
+    }
+    // largest t with off[t] <= unit (terms without units repeat the offset of their successor)
+    const uint32_t t = warp_upper_bound_u64(bv.t_df_tile_off, bv.n_terms + 1, unit) - 1u;
+    const uint32_t k0 = bv.term_koff[t];
+    const uint32_t k1 = bv.term_koff[t + 1];
+    const uint4* rp = reinterpret_cast<const uint4*>(bv.key_ref + k0);
+    const uint4 r0 = __ldg(rp);
+    const uint4 r1 = __ldg(rp + 1);
+    ListRef drv;
+    drv.p = reinterpret_cast<const uint32_t*>(static_cast<uintptr_t>(r0.x) | (static_cast<uintptr_t>(r0.y) << 32));
+    drv.len = r1.x;
+    drv.bm = nullptr;
+    const uint64_t e0 = (static_cast<uint64_t>(unit) - bv.t_df_tile_off[t]) * kDfUnit;
+#pragma unroll 1
+    for (uint32_t piece = 0; piece < kDfUnit / kWarpTile; ++piece) {
+      df_warp_tile(iv, bv, drv, t, k0, k1, e0 + static_cast<uint64_t>(piece) * kWarpTile, s_stage[warp], s_surv[warp],
+                   s_spos[warp], unit);
+      __syncwarp();
     }
   }
 }
@@ -1220,6 +1334,9 @@ __global__ void __launch_bounds__(kStreamThreads) df_stream_kernel(IndexView iv,
   __shared__ uint32_t s_nset;
   __shared__ uint32_t s_overflow;
   unsigned long long hits = 0;
+  if (bv.launch != nullptr && (bv.df_mode[0] == 0 || bv.launch[kLaunchOverflow] != 0)) {
+    return;  // streamed batch: launched before the choice was known; the candidate tiles were chosen (or nothing runs)
+  }
   const uint32_t len8_mask = bv.stream_len8_mask;
   for (uint32_t i = threadIdx.x; i < kStreamBloomWords; i += kStreamThreads) {
     s_bloom[i] = __ldg(bv.stream_bloom + i);
@@ -1387,11 +1504,7 @@ __global__ void slots_to_df_kernel(const uint64_t* __restrict__ in, const uint32
 }
 
 // ------------------------------------------------------------------ query planning
-__global__ void query_plan_kernel(IndexView iv, BatchView bv) {
-  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= bv.n_queries) {
-    return;
-  }
+__device__ __forceinline__ void query_plan_one(const IndexView& iv, const BatchView& bv, uint32_t q) {
   uint32_t flags = bv.q_host_flags[q];
   if ((flags & kQProgram) != 0) {
     // Boolean program (QueryNode::Evaluate, query_ast.cpp:67-161). Every result satisfies each conjunct term, so the
@@ -1532,6 +1645,132 @@ __global__ void query_plan_kernel(IndexView iv, BatchView bv) {
   bv.q_flags[q] = flags;
   bv.q_driver_len[q] = driver_len;
   bv.q_ntiles[q] = (driver_len + kTile - 1) / kTile;
+  if (driver_len != 0) {
+    atomicAdd(bv.stats + kStatDriverEntries * kStatStripes + (q & (kStatStripes - 1)),
+              static_cast<unsigned long long>(driver_len));
+  }
+}
+
+__global__ void query_plan_kernel(IndexView iv, BatchView bv) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < bv.n_queries) {
+    query_plan_one(iv, bv, q);
+  }
+}
+
+// Exclusive prefix sums of in(0..n) into out[0..n] (out[n] = total) by one 256-thread CTA; values written by other
+// CTAs of the same launch are read around L1.
+struct ScanSmem {
+  uint64_t warp_sums[8];
+  uint64_t carry;
+};
+template <typename In>
+__device__ __forceinline__ uint64_t block_exclusive_scan(In in, uint32_t n, uint64_t* __restrict__ out, ScanSmem& sm) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    sm.carry = 0;
+  }
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 256u * 4u) {
+    const uint32_t i0 = base + threadIdx.x * 4u;
+    uint32_t v[4];
+    uint64_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = i0 + j < n ? in(i0 + j) : 0u;
+      sum += v[j];
+    }
+    uint64_t inc = sum;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const uint64_t o = __shfl_up_sync(0xffffffffu, inc, s);
+      if (lane >= static_cast<unsigned>(s)) {
+        inc += o;
+      }
+    }
+    if (lane == 31) {
+      sm.warp_sums[warp] = inc;
+    }
+    __syncthreads();
+    uint64_t prefix = sm.carry;
+    uint64_t tile_total = 0;
+#pragma unroll
+    for (unsigned w = 0; w < 8; ++w) {
+      if (w < warp) {
+        prefix += sm.warp_sums[w];
+      }
+      tile_total += sm.warp_sums[w];
+    }
+    uint64_t run = prefix + inc - sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j < n) {
+        out[i0 + j] = run;
+        run += v[j];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      sm.carry += tile_total;
+    }
+    __syncthreads();
+  }
+  const uint64_t total = sm.carry;
+  if (threadIdx.x == 0) {
+    out[n] = total;
+  }
+  __syncthreads();
+  return total;
+}
+
+// Streamed planning, stage 2: the batch-wide df decision and the plan of every query (one thread each), and -- in the
+// CTA that finishes last -- the prefix sums that place the work items, the work sizes, and the capacity check. After
+// this kernel the batch is fully planned and nothing has visited the host.
+//   cap_tiles: intersect tiles the stream's workspace holds (tile counters and record slots)
+//   group_tiles: tiles per top-k pre-reduction group, 0 = no pre-reduction
+__global__ void __launch_bounds__(256)
+plan_queries_kernel(IndexView iv, BatchView bv, const uint8_t* __restrict__ raw_flags, int df_choice, int force,
+                    int have_table, uint32_t cap_tiles, uint32_t group_tiles) {
+  __shared__ ScanSmem s_scan;
+  __shared__ uint32_t s_last;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (df_choice != 0 && i < bv.n_terms) {
+    df_mode_one(bv, i, raw_flags, iv.text_bytes, force, have_table);
+  }
+  if (i < bv.n_queries) {
+    query_plan_one(iv, bv, i);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_last = atomicAdd(bv.launch + kLaunchTicket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last == 0) {
+    return;
+  }
+  __threadfence();
+  const uint32_t* t_units = bv.t_df_tiles;
+  const uint32_t* q_ntiles = bv.q_ntiles;
+  const uint64_t n_units =
+      block_exclusive_scan([&](uint32_t k) { return __ldcg(t_units + k); }, bv.n_terms, bv.t_df_tile_off, s_scan);
+  const uint64_t n_tiles =
+      block_exclusive_scan([&](uint32_t k) { return __ldcg(q_ntiles + k); }, bv.n_queries, bv.q_tile_off, s_scan);
+  const uint64_t n_groups = block_exclusive_scan(
+      [&](uint32_t k) {
+        const uint32_t nt = __ldcg(q_ntiles + k);
+        return group_tiles != 0 && nt >= 2 * group_tiles ? (nt + group_tiles - 1) / group_tiles : 0u;
+      },
+      bv.n_queries, bv.q_group_off, s_scan);
+  if (threadIdx.x == 0) {
+    const bool overflow = n_tiles > cap_tiles || n_units >= 0x7FFFFFFFULL || n_groups >= 0x7FFFFFFFULL;
+    bv.launch[kLaunchNeedTiles] = static_cast<uint32_t>(n_tiles > 0xFFFFFFFFULL ? 0xFFFFFFFFULL : n_tiles);
+    bv.launch[kLaunchOverflow] = overflow ? 1u : 0u;
+    bv.launch[kLaunchDfUnits] = overflow ? 0u : static_cast<uint32_t>(n_units);
+    bv.launch[kLaunchAndTiles] = overflow ? 0u : static_cast<uint32_t>(n_tiles);
+    bv.launch[kLaunchGroups] = overflow ? 0u : static_cast<uint32_t>(n_groups);
+  }
 }
 
 // BM25Scorer::ComputeIDF, bm25_scorer.cpp:14-25 — one value per (query, term) in planner order.
@@ -1946,10 +2185,13 @@ __device__ __forceinline__ double bm25_term(double idf, uint32_t tf_u, double le
   return __ddiv_rn(__dmul_rn(idf, numerator), denominator);
 }
 
-__global__ void __launch_bounds__(kTileThreads, MGX_AND_OCC)
-and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, uint64_t rec_base,
-                uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_total, uint32_t* __restrict__ rec_doc,
-                double* __restrict__ rec_score, uint32_t prune_k) {
+// One CTA, one 1024-entry tile of query q's driver (tile_in_q-th tile of the query). tile_slot = the tile's index in
+// tile_count / tile_total; its records go to rec_doc / rec_score [tile_slot * rec_slot, +written).
+__device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchView& bv, const ScoreParams& sp,
+                                              const uint32_t q, const uint64_t tile_in_q, const uint64_t tile_slot,
+                                              const uint32_t rec_slot, uint32_t* __restrict__ tile_count,
+                                              uint32_t* __restrict__ tile_total, uint32_t* __restrict__ rec_doc,
+                                              double* __restrict__ rec_score, const uint32_t prune_k) {
   __shared__ uint32_t s_doc[kTile];     // local doc index of survivors (kNone = id unknown to this shard)
   __shared__ uint32_t s_gid[kTile];     // global doc id of survivors (explicit drivers only)
   __shared__ double s_score[kTile];
@@ -1969,17 +2211,14 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   __shared__ uint32_t s_bounds[kPreSearchLists][2];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
-  const uint64_t tile_global = tile_base + blockIdx.x;
   if (threadIdx.x == 0) {
     s_bytes = 0;
     s_any_slow = 0;
   }
-  const uint32_t q = __ldg(bv.tile_query + tile_global);
   const uint32_t flags = bv.q_flags[q];
   const uint32_t l0 = bv.q_loff[q];
   const uint32_t nl = bv.q_nlists[q];
   const uint32_t driver_len = bv.q_driver_len[q];
-  const uint64_t tile_in_q = tile_global - bv.q_tile_off[q];
   const bool drv_all = (flags & kQDriverAll) != 0;
   const bool drv_explicit = (flags & kQDriverExplicit) != 0;
   const bool any_mode = (flags & kQAnyMode) != 0;
@@ -2405,7 +2644,7 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
   }
 
   // ---- ordered write of the tile's records
-  const uint64_t out_base = bv.q_rec_off[q] - rec_base + tile_in_q * kTile;
+  const uint64_t out_base = tile_slot * rec_slot;
   uint32_t keep_mask = 0;
   const uint32_t s0 = threadIdx.x * kTileItems;
 #pragma unroll
@@ -2455,22 +2694,69 @@ and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, 
     }
   }
   if (threadIdx.x == 0) {
-    tile_count[blockIdx.x] = written;
-    tile_total[blockIdx.x] = kept_total;
+    tile_count[tile_slot] = written;
+    tile_total[tile_slot] = kept_total;
     if (kept_total != 0) {
-      atomicAdd(bv.stats + kStatResultDocs * kStatStripes + (blockIdx.x & (kStatStripes - 1)),
+      atomicAdd(bv.stats + kStatResultDocs * kStatStripes + (tile_slot & (kStatStripes - 1)),
                 static_cast<unsigned long long>(kept_total));
     }
     if (s_bytes != 0) {
-      atomicAdd(bv.stats + kStatScoreBytes * kStatStripes + (blockIdx.x & (kStatStripes - 1)), s_bytes);
+      atomicAdd(bv.stats + kStatScoreBytes * kStatStripes + (tile_slot & (kStatStripes - 1)), s_bytes);
     }
   }
 }
 
+__global__ void __launch_bounds__(kTileThreads, MGX_AND_OCC)
+and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, uint32_t rec_slot,
+                uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_total, uint32_t* __restrict__ rec_doc,
+                double* __restrict__ rec_score, uint32_t prune_k) {
+  const uint64_t tile_global = tile_base + blockIdx.x;
+  const uint32_t q = __ldg(bv.tile_query + tile_global);
+  and_tile_body(iv, bv, sp, q, tile_global - bv.q_tile_off[q], blockIdx.x, rec_slot, tile_count, tile_total, rec_doc,
+                rec_score, prune_k);
+}
+
+// Streamed form: persistent CTAs pull tile indices from a device-side counter (the tile count never visits the
+// host); tile -> query by a 32-ary search over the queries' tile prefix sums.
+__global__ void __launch_bounds__(kTileThreads, MGX_AND_OCC)
+and_tiles_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint32_t rec_slot, uint32_t* __restrict__ tile_count,
+                 uint32_t* __restrict__ tile_total, uint32_t* __restrict__ rec_doc, double* __restrict__ rec_score,
+                 uint32_t prune_k) {
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_q;
+  const uint32_t n_tiles = bv.launch[kLaunchAndTiles];
+  for (;;) {
+    if (threadIdx.x < 32) {
+      uint32_t tile = 0;
+      if (threadIdx.x == 0) {
+        tile = atomicAdd(bv.launch + kLaunchAndNext, 1u);
+      }
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      uint32_t q = 0;
+      if (tile < n_tiles) {
+        q = warp_upper_bound_u64(bv.q_tile_off, bv.n_queries + 1, tile) - 1u;
+      }
+      if (threadIdx.x == 0) {
+        s_tile = tile;
+        s_q = q;
+      }
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t q = s_q;
+    if (tile >= n_tiles) {
+      return;
+    }
+    and_tile_body(iv, bv, sp, q, tile - bv.q_tile_off[q], tile, rec_slot, tile_count, tile_total, rec_doc, rec_score,
+                  prune_k);
+    __syncthreads();  // the body's shared state (and s_tile / s_q) is rewritten by the next round
+  }
+}
+
 // ------------------------------------------------------------------ top-k kernels
-// One CTA per query. Records of tile t of the query live at rec_off + t*kTile .. +tile_count[t].
+// One CTA per query. Records of tile t (index in the chunk) live at t * rec_slot .. + tile_count[t].
 __global__ void __launch_bounds__(256)
-topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_base,
+topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint32_t rec_slot,
             const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ tile_total,
             const uint32_t* __restrict__ rec_doc, const double* __restrict__ rec_score, int compute_score,
             int descending, uint32_t limit, uint32_t offset,
@@ -2486,8 +2772,11 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_bas
   __shared__ uint32_t s_need;
   const uint32_t q = q_first + blockIdx.x;
   const uint64_t t0 = bv.q_tile_off[q] - tile_base;
-  const uint32_t ntiles = static_cast<uint32_t>(bv.q_tile_off[q + 1] - bv.q_tile_off[q]);
-  const uint64_t r0 = bv.q_rec_off[q] - rec_base;
+  uint32_t ntiles = static_cast<uint32_t>(bv.q_tile_off[q + 1] - bv.q_tile_off[q]);
+  if (bv.launch != nullptr && bv.launch[kLaunchOverflow] != 0) {
+    ntiles = 0;  // the streamed batch did not fit its workspace: nothing ran, the host repeats it (see batch_search)
+  }
+  const uint64_t r0 = t0 * rec_slot;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   uint32_t* ids = out_ids + static_cast<uint64_t>(q) * stride;
@@ -2562,7 +2851,7 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_bas
       for (uint32_t i = 0; i < c; ++i) {
         const uint64_t rank = first_rank + i;
         if (rank >= want_begin && rank - want_begin < n_out) {
-          ids[rank - want_begin] = rec_doc[r0 + static_cast<uint64_t>(t) * kTile + i];
+          ids[rank - want_begin] = rec_doc[r0 + static_cast<uint64_t>(t) * rec_slot + i];
         }
       }
       __syncthreads();
@@ -2596,7 +2885,7 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_bas
       const SortKey prefix = s_prefix;
       for (uint32_t t = warp; t < ntiles; t += 8) {
         const uint32_t c = tile_count[t0 + t];
-        const uint64_t base = r0 + static_cast<uint64_t>(t) * kTile;
+        const uint64_t base = r0 + static_cast<uint64_t>(t) * rec_slot;
         for (uint32_t i = lane; i < c; i += 32) {
           const SortKey k = make_sort_key(rec_score[base + i], rec_doc[base + i], desc);
           if (key_has_prefix(k, prefix, pass)) {
@@ -2628,7 +2917,7 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_bas
   // gather every key >= thr (all keys when total <= kTopkSmem)
   for (uint32_t t = warp; t < ntiles; t += 8) {
     const uint32_t c = tile_count[t0 + t];
-    const uint64_t base = r0 + static_cast<uint64_t>(t) * kTile;
+    const uint64_t base = r0 + static_cast<uint64_t>(t) * rec_slot;
     for (uint32_t i = lane; i < c; i += 32) {
       const SortKey k = make_sort_key(rec_score[base + i], rec_doc[base + i], desc);
       if (n_records <= kTopkSmem || !key_greater(thr, k)) {
@@ -2673,10 +2962,10 @@ struct TopkGroup {
   uint32_t t_end;
 };
 
-__global__ void __launch_bounds__(256)
-topk_group_kernel(BatchView bv, const TopkGroup* __restrict__ groups, uint64_t tile_base, uint64_t rec_base,
-                  uint32_t* __restrict__ tile_count, uint32_t* __restrict__ rec_doc, double* __restrict__ rec_score,
-                  int descending, uint32_t kk) {
+__device__ __forceinline__ void topk_group_body(const BatchView& bv, const TopkGroup g, uint64_t tile_base,
+                                                uint32_t rec_slot, uint32_t* __restrict__ tile_count,
+                                                uint32_t* __restrict__ rec_doc, double* __restrict__ rec_score,
+                                                int descending, uint32_t kk) {
   __shared__ uint64_t s_ks[kGroupKeyCap];
   __shared__ uint32_t s_kd[kGroupKeyCap];
   __shared__ uint32_t s_hist[256];
@@ -2684,9 +2973,8 @@ topk_group_kernel(BatchView bv, const TopkGroup* __restrict__ groups, uint64_t t
   __shared__ uint32_t s_out;
   __shared__ SortKey s_prefix;
   __shared__ uint32_t s_need;
-  const TopkGroup g = groups[blockIdx.x];
   const uint64_t t0 = bv.q_tile_off[g.q] - tile_base + g.t_begin;
-  const uint64_t r0 = bv.q_rec_off[g.q] - rec_base + static_cast<uint64_t>(g.t_begin) * kTile;
+  const uint64_t r0 = t0 * rec_slot;
   const uint32_t ntiles = g.t_end - g.t_begin;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
@@ -2701,7 +2989,7 @@ topk_group_kernel(BatchView bv, const TopkGroup* __restrict__ groups, uint64_t t
   __syncthreads();
   for (uint32_t t = warp; t < ntiles; t += 8) {
     const uint32_t c = tile_count[t0 + t];
-    const uint64_t base = r0 + static_cast<uint64_t>(t) * kTile;
+    const uint64_t base = r0 + static_cast<uint64_t>(t) * rec_slot;
     uint32_t at = 0;
     if (lane == 0 && c != 0) {
       at = atomicAdd(&s_n, c);
@@ -2769,9 +3057,57 @@ topk_group_kernel(BatchView bv, const TopkGroup* __restrict__ groups, uint64_t t
   }
 }
 
+__global__ void __launch_bounds__(256)
+topk_group_kernel(BatchView bv, const TopkGroup* __restrict__ groups, uint64_t tile_base, uint32_t rec_slot,
+                  uint32_t* __restrict__ tile_count, uint32_t* __restrict__ rec_doc, double* __restrict__ rec_score,
+                  int descending, uint32_t kk) {
+  topk_group_body(bv, groups[blockIdx.x], tile_base, rec_slot, tile_count, rec_doc, rec_score, descending, kk);
+}
+
+// Streamed form: the groups are never listed. Query q has q_group_off[q+1] - q_group_off[q] groups of group_tiles
+// consecutive tiles (0 when it has fewer than 2 * group_tiles tiles; prefix sums by the planning tail); persistent
+// CTAs pull group indices from a device-side counter.
+__global__ void __launch_bounds__(256)
+topk_groups_kernel(BatchView bv, uint32_t group_tiles, uint32_t rec_slot, uint32_t* __restrict__ tile_count,
+                   uint32_t* __restrict__ rec_doc, double* __restrict__ rec_score, int descending, uint32_t kk) {
+  __shared__ uint32_t s_group;
+  __shared__ uint32_t s_gq;
+  const uint32_t n_groups = bv.launch[kLaunchGroups];
+  for (;;) {
+    if (threadIdx.x < 32) {
+      uint32_t gi = 0;
+      if (threadIdx.x == 0) {
+        gi = atomicAdd(bv.launch + kLaunchGroupNext, 1u);
+      }
+      gi = __shfl_sync(0xffffffffu, gi, 0);
+      uint32_t q = 0;
+      if (gi < n_groups) {
+        q = warp_upper_bound_u64(bv.q_group_off, bv.n_queries + 1, gi) - 1u;
+      }
+      if (threadIdx.x == 0) {
+        s_group = gi;
+        s_gq = q;
+      }
+    }
+    __syncthreads();
+    const uint32_t gi = s_group;
+    const uint32_t q = s_gq;
+    if (gi >= n_groups) {
+      return;
+    }
+    const uint32_t ntiles = static_cast<uint32_t>(bv.q_tile_off[q + 1] - bv.q_tile_off[q]);
+    TopkGroup g;
+    g.q = q;
+    g.t_begin = (gi - static_cast<uint32_t>(bv.q_group_off[q])) * group_tiles;
+    g.t_end = min(ntiles, g.t_begin + group_tiles);
+    topk_group_body(bv, g, 0, rec_slot, tile_count, rec_doc, rec_score, descending, kk);
+    __syncthreads();
+  }
+}
+
 // Full ascending sets: out[set_off[q] + rank] for every survivor of query q.
 __global__ void __launch_bounds__(256)
-gather_sets_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t rec_base,
+gather_sets_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint32_t rec_slot,
                    const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ rec_doc,
                    const uint64_t* __restrict__ set_off, uint32_t* __restrict__ out) {
   __shared__ uint64_t s_scan[8];
@@ -2779,7 +3115,7 @@ gather_sets_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t 
   const uint32_t q = q_first + blockIdx.x;
   const uint64_t t0 = bv.q_tile_off[q] - tile_base;
   const uint32_t ntiles = static_cast<uint32_t>(bv.q_tile_off[q + 1] - bv.q_tile_off[q]);
-  const uint64_t r0 = bv.q_rec_off[q] - rec_base;
+  const uint64_t r0 = t0 * rec_slot;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
@@ -2812,7 +3148,7 @@ gather_sets_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint64_t 
     }
     const uint64_t first_rank = prefix + inc - c;
     for (uint32_t i = 0; i < c; ++i) {
-      dst[first_rank + i] = rec_doc[r0 + static_cast<uint64_t>(t) * kTile + i];
+      dst[first_rank + i] = rec_doc[r0 + static_cast<uint64_t>(t) * rec_slot + i];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -3090,7 +3426,7 @@ BatchView make_batch_view(Batch& b) {
   v.q_driver_len = b.d_q_driver_len.p;
   v.q_ntiles = b.d_q_ntiles.p;
   v.q_tile_off = b.d_q_tile_off.p;
-  v.q_rec_off = b.d_q_rec_off.p;
+  v.q_group_off = b.d_q_group_off.p;
   v.q_idf = b.d_q_idf.p;
   v.n_queries = b.n_queries;
   v.explicit_ids = b.explicit_driver.d_ids;
@@ -3106,6 +3442,7 @@ BatchView make_batch_view(Batch& b) {
   v.stream_len12_mask = b.stream_len12_mask;
   v.stream_slot_mask = b.n_stream_slots > 0 ? b.n_stream_slots - 1 : 0;
   v.df_mode = b.d_df_mode.p;
+  v.launch = b.streamed ? b.d_launch.p : nullptr;
   return v;
 }
 
@@ -3145,6 +3482,12 @@ void Batch::mark_last() {
 }
 
 Batch::~Batch() {
+  for (cudaEvent_t& e : ev_x) {
+    if (e != nullptr) {
+      cudaEventDestroy(e);
+      e = nullptr;
+    }
+  }
   for (auto& t : timed) {
     cudaEventDestroy(t.a);
     cudaEventDestroy(t.b);
@@ -3205,7 +3548,14 @@ void Batch::collect_stats(mgx_batch_stats_t* out) {
   s.algo_bytes_df_lists = h[kStatDfLists];
   s.h2d_bytes = h2d_bytes;
   s.d2h_bytes = d2h_bytes;
-  s.driver_entries = driver_entries;
+  s.driver_entries = h[kStatDriverEntries];
+  if (streamed && status_copied && h_launch.p != nullptr) {
+    s.n_df_tiles = h_launch.p[kLaunchDfUnits];  // units of kDfUnit entries
+    s.n_and_tiles = h_launch.p[kLaunchAndTiles];
+    uint32_t mode = 0;
+    MGX_CUDA(cudaMemcpy(&mode, d_df_mode.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    h_df_mode = static_cast<int>(mode);
+  }
   s.result_docs = h[kStatResultDocs];
   s.df_candidates = h[kStatDfCandidates];
   s.unique_terms = n_terms;
@@ -3236,6 +3586,9 @@ void Batch::recycle() {
   h2d_bytes = d2h_bytes = 0;
   n_df_tiles = n_and_tiles = driver_entries = 0;
   planned = df_done = searched = false;
+  streamed = allow_streamed = status_copied = false;
+  sharded_enqueued = false;
+  rec_slot = kTile;
   sc = nullptr;
   serial = 0;
   h_df_mode = 0;
@@ -3569,7 +3922,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   size_t work = 0;
   for (size_t nbytes : {K * sizeof(KeyRef), K * 4, K * 4, T * 8, T * 4, (T + 1) * 8, T * 8, Lc * 4, Lc * 4, Q * 4, Q * 4, Q * 4, Q * 4,
                         (Q + 1) * 8, (Q + 1) * 8, n_tids * 8, static_cast<size_t>(kStatCount) * kStatStripes * 8,
-                        scan_elems * 8, static_cast<size_t>(64)}) {
+                        scan_elems * 8, static_cast<size_t>(64), static_cast<size_t>(kLaunchCount) * 4}) {
     work += DevArena::padded(nbytes == 0 ? 1 : nbytes);
   }
   b.work_arena.reserve(work + 1024, true);
@@ -3587,14 +3940,23 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   b.d_q_driver_len.borrow(b.work_arena.take<uint32_t>(Q), Q);
   b.d_q_ntiles.borrow(b.work_arena.take<uint32_t>(Q), Q);
   b.d_q_tile_off.borrow(b.work_arena.take<uint64_t>(Q + 1), Q + 1);
-  b.d_q_rec_off.borrow(b.work_arena.take<uint64_t>(Q + 1), Q + 1);
+  b.d_q_group_off.borrow(b.work_arena.take<uint64_t>(Q + 1), Q + 1);
   b.d_q_idf.borrow(b.work_arena.take<double>(n_tids), n_tids);
+  b.d_scan_scratch.borrow(b.work_arena.take<uint64_t>(scan_elems), scan_elems);
+  // accounting counters, df choice and the launch block of streamed batches lie back to back: one memset clears them
   const size_t n_stats = static_cast<size_t>(kStatCount) * kStatStripes;
   b.d_stats.borrow(b.work_arena.take<unsigned long long>(n_stats), n_stats);
-  b.d_scan_scratch.borrow(b.work_arena.take<uint64_t>(scan_elems), scan_elems);
   b.d_df_mode.borrow(b.work_arena.take<uint32_t>(2), 2);
-  MGX_CUDA(cudaMemsetAsync(b.d_stats.p, 0, b.d_stats.bytes(), st));
-  MGX_CUDA(cudaMemsetAsync(b.d_df_mode.p, 0, 2 * sizeof(uint32_t), st));
+  b.d_launch.borrow(b.work_arena.take<uint32_t>(kLaunchCount), kLaunchCount);
+  b.in_base = base;
+  b.in_total = total;
+  batch_clear_counters(b);
+}
+
+void batch_clear_counters(Batch& b) {
+  uint8_t* first = reinterpret_cast<uint8_t*>(b.d_stats.p);
+  uint8_t* last = reinterpret_cast<uint8_t*>(b.d_launch.p + kLaunchCount);
+  MGX_CUDA(cudaMemsetAsync(first, 0, static_cast<size_t>(last - first), b.stream));
 }
 
 namespace {
@@ -3634,9 +3996,166 @@ void ensure_tile_maps(Batch& b) {
 }
 }  // namespace
 
+namespace {
+int device_sm_count(int device) {
+  static int cached[64] = {0};
+  if (device >= 0 && device < 64 && cached[device] != 0) {
+    return cached[device];
+  }
+  int n = 148;
+  MGX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+  if (device >= 0 && device < 64) {
+    cached[device] = n;
+  }
+  return n;
+}
+
+// record slots a tile needs: a top-k answer keeps at most limit + offset records per tile (and_tile_body prunes)
+uint32_t rec_slot_for(const Batch& b) {
+  const uint64_t k = static_cast<uint64_t>(b.params.limit) + b.params.offset;
+  if (b.params.compute_score != 0 && b.params.limit != 0 && k < kTile) {
+    return static_cast<uint32_t>((k + 31) & ~31ULL);
+  }
+  return kTile;
+}
+uint32_t group_tiles_for(const Batch& b) {
+  const uint64_t k = static_cast<uint64_t>(b.params.limit) + b.params.offset;
+  if (b.params.compute_score != 0 && b.params.limit != 0 && k * 2 <= kGroupKeyCap) {
+    return static_cast<uint32_t>(kGroupKeyCap / k);
+  }
+  return 0;
+}
+int df_force_mode() {  // MGX_DF_MODE=tiles|stream pins the choice (tests exercise both paths); default: cost model
+  if (const char* mode = std::getenv("MGX_DF_MODE")) {
+    return std::strcmp(mode, "tiles") == 0 ? 1 : (std::strcmp(mode, "stream") == 0 ? 2 : 0);
+  }
+  return 0;
+}
+
+// Workspace of a streamed batch: sized before anything is launched, because nothing comes back to the host.
+void bind_streamed_scratch(Batch& b) {
+  if (b.sc == nullptr) {
+    b.sc = b.ix->scratch_for(b.stream);
+  }
+  SearchScratch& sc = *b.sc;
+  const uint64_t floor_tiles = 1ULL << 17;
+  sc.tile_count.reserve(floor_tiles);
+  sc.tile_total.reserve(floor_tiles);
+  sc.rec_doc.reserve(1ULL << 24);
+  if (b.params.compute_score != 0) {
+    sc.rec_score.reserve(sc.rec_doc.n);
+  }
+  b.d_tile_count.borrow(sc.tile_count.p, sc.tile_count.n);
+  b.d_tile_total.borrow(sc.tile_total.p, sc.tile_total.n);
+  b.d_rec_doc.borrow(sc.rec_doc.p, sc.rec_doc.n);
+  b.d_rec_score.borrow(sc.rec_score.p, sc.rec_score.n);
+}
+
+void batch_plan_streamed(Batch& b) {
+  cudaStream_t st = b.stream;
+  Index& ix = *b.ix;
+  b.streamed = true;
+  b.rec_slot = rec_slot_for(b);
+  bind_streamed_scratch(b);
+  uint64_t cap_tiles = std::min<uint64_t>(b.d_tile_count.n, b.d_tile_total.n);
+  cap_tiles = std::min<uint64_t>(cap_tiles, b.d_rec_doc.n / b.rec_slot);
+  if (b.params.compute_score != 0) {
+    cap_tiles = std::min<uint64_t>(cap_tiles, b.d_rec_score.n / b.rec_slot);
+  }
+  cap_tiles = std::min<uint64_t>(cap_tiles, 0x7FFFFFFFULL);
+  if (const char* e = std::getenv("MGX_STREAM_TILE_CAP")) {  // tests force the overflow path with a tiny workspace
+    cap_tiles = std::min<uint64_t>(cap_tiles, std::strtoull(e, nullptr, 10));
+  }
+  b.time_begin(0);
+  const IndexView iv = make_view(ix);
+  const BatchView bv = make_batch_view(b);
+  if (b.n_terms > 0) {
+    plan_terms_kernel<<<grid_for(b.n_terms, 128), 128, 0, st>>>(iv, bv, b.d_keys.p, b.params.compute_score != 0 ? 1 : 0,
+                                                                ix.all_valid_utf8 ? 1 : 0, b.d_term_flags.p,
+                                                                (ix.n_docs + 7) / 8);
+    MGX_LAUNCH_CHECK();
+  }
+  const int df_choice = b.params.compute_score != 0 && b.n_stream_terms > 0 ? 1 : 0;
+  const uint64_t n_plan = std::max<uint64_t>(std::max<uint64_t>(b.n_queries, df_choice != 0 ? b.n_terms : 0), 1);
+  plan_queries_kernel<<<grid_for(n_plan, 256), 256, 0, st>>>(iv, bv, b.d_term_flags.p, df_choice, df_force_mode(),
+                                                             ix.n_text_tiles > 0 ? 1 : 0,
+                                                             static_cast<uint32_t>(cap_tiles), group_tiles_for(b));
+  MGX_LAUNCH_CHECK();
+  b.time_end();
+  b.planned = true;
+}
+
+void batch_df_streamed(Batch& b) {
+  cudaStream_t st = b.stream;
+  Index& ix = *b.ix;
+  const int sms = device_sm_count(ix.device);
+  if (b.n_stream_terms > 0 && ix.n_text_tiles > 0) {
+    static int per_sm_stream = 0;
+    if (per_sm_stream == 0) {
+      MGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_stream, df_stream_kernel, kStreamThreads, 0));
+      per_sm_stream = std::max(per_sm_stream, 1);
+    }
+    const unsigned grid =
+        static_cast<unsigned>(std::min<uint64_t>(ix.n_text_tiles, static_cast<uint64_t>(sms) * per_sm_stream));
+    b.time_begin(4);
+    df_stream_kernel<<<grid, kStreamThreads, 0, st>>>(make_view(ix), make_batch_view(b));
+    MGX_LAUNCH_CHECK();
+    b.time_end();
+  }
+  if (b.n_terms > 0) {
+    static int per_sm_df = 0;
+    if (per_sm_df == 0) {
+      MGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_df, df_units_kernel, kTileThreads, 0));
+      per_sm_df = std::max(per_sm_df, 1);
+    }
+    b.time_begin(1);
+    df_units_kernel<<<static_cast<unsigned>(sms * per_sm_df), kTileThreads, 0, st>>>(make_view(ix), make_batch_view(b));
+    MGX_LAUNCH_CHECK();
+    b.time_end();
+  }
+  b.df_done = true;
+}
+}  // namespace
+
+bool batch_overflowed(Batch& b) {
+  return b.streamed && b.status_copied && b.h_launch.p != nullptr && b.h_launch.p[kLaunchOverflow] != 0;
+}
+
+// Back to the freshly uploaded state: the planning kernels permute key tables and term lists in place, so the compiled
+// batch is copied from the pinned staging buffer again. The repeat takes the synchronous form, whose workspace grows
+// with the batch, and tells the stream's workspace to stay in that form for a while when even that is chunked.
+void batch_reset_for_repeat(Batch& b) {
+  MGX_CUDA(cudaMemcpyAsync(b.in_base, b.staging.p, b.in_total, cudaMemcpyHostToDevice, b.stream));
+  b.h2d_bytes += b.in_total;
+  batch_clear_counters(b);
+  if (b.sc != nullptr) {
+    b.sc->skip_streamed = 8;
+  }
+  b.streamed = false;
+  b.allow_streamed = false;
+  b.planned = b.df_done = b.searched = b.status_copied = false;
+  b.rec_slot = kTile;
+  b.n_df_tiles = b.n_and_tiles = b.driver_entries = 0;
+}
+
 void batch_plan(Batch& b) {
   cudaStream_t st = b.stream;
   Index& ix = *b.ix;
+  if (b.allow_streamed && b.explicit_driver.d_ids == nullptr) {
+    static const bool disabled = std::getenv("MGX_NO_STREAMED") != nullptr;
+    if (b.sc == nullptr) {
+      b.sc = ix.scratch_for(st);
+    }
+    if (!disabled && b.sc->skip_streamed == 0) {
+      batch_plan_streamed(b);
+      return;
+    }
+    if (b.sc->skip_streamed > 0) {
+      --b.sc->skip_streamed;
+    }
+  }
+  b.streamed = false;
+  b.rec_slot = kTile;
   b.time_begin(0);
   if (b.n_keys > 0) {
     lookup_kernel<<<grid_for(b.n_keys, 256), 256, 0, st>>>(ix.d_term_keys.p, ix.d_term_off.p, ix.n_terms, b.d_keys.p,
@@ -3655,11 +4174,7 @@ void batch_plan(Batch& b) {
       MGX_LAUNCH_CHECK();
     }
     if (b.params.compute_score != 0 && b.n_stream_terms > 0) {
-      int force = 0;  // MGX_DF_MODE=tiles|stream pins the choice (tests exercise both paths); default: cost model
-      if (const char* mode = std::getenv("MGX_DF_MODE")) {
-        force = std::strcmp(mode, "tiles") == 0 ? 1 : (std::strcmp(mode, "stream") == 0 ? 2 : 0);
-      }
-      df_mode_kernel<<<grid_for(b.n_terms, 128), 128, 0, st>>>(bv, b.d_term_flags.p, ix.text_bytes, force,
+      df_mode_kernel<<<grid_for(b.n_terms, 128), 128, 0, st>>>(bv, b.d_term_flags.p, ix.text_bytes, df_force_mode(),
                                                                ix.n_text_tiles > 0 ? 1 : 0);
       MGX_LAUNCH_CHECK();
     }
@@ -3670,21 +4185,17 @@ void batch_plan(Batch& b) {
     MGX_LAUNCH_CHECK();
   }
   if (b.n_terms <= kSmallScanMax && b.n_queries <= kSmallScanMax) {
-    // tile offsets of the df stage, tile and record offsets of the search stage: one launch
-    SmallScanJobs jobs{{b.d_t_df_tiles.p, b.d_q_ntiles.p, b.d_q_driver_len.p},
-                       {b.d_t_df_tile_off.p, b.d_q_tile_off.p, b.d_q_rec_off.p},
-                       {b.n_terms, b.n_queries, b.n_queries}};
-    exclusive_scans_small(jobs, 3, st);
+    // tile offsets of the df stage and of the search stage: one launch
+    SmallScanJobs jobs{{b.d_t_df_tiles.p, b.d_q_ntiles.p, nullptr},
+                       {b.d_t_df_tile_off.p, b.d_q_tile_off.p, nullptr},
+                       {b.n_terms, b.n_queries, 0}};
+    exclusive_scans_small(jobs, 2, st);
   } else {
     exclusive_scan_u32_u64(b.d_t_df_tiles.p, b.d_t_df_tile_off.p, b.n_terms, b.d_scan_scratch.p, st);
     exclusive_scan_u32_u64(b.d_q_ntiles.p, b.d_q_tile_off.p, b.n_queries, b.d_scan_scratch.p, st);
-    exclusive_scan_u32_u64(b.d_q_driver_len.p, b.d_q_rec_off.p, b.n_queries, b.d_scan_scratch.p, st);
   }
   b.h_q_tile_off.resize(b.n_queries + 1);
-  b.h_q_rec_off.resize(b.n_queries + 1);
   MGX_CUDA(cudaMemcpyAsync(b.h_q_tile_off.data(), b.d_q_tile_off.p, (b.n_queries + 1) * sizeof(uint64_t),
-                           cudaMemcpyDeviceToHost, st));
-  MGX_CUDA(cudaMemcpyAsync(b.h_q_rec_off.data(), b.d_q_rec_off.p, (b.n_queries + 1) * sizeof(uint64_t),
                            cudaMemcpyDeviceToHost, st));
   MGX_CUDA(cudaMemcpyAsync(&b.n_df_tiles, b.d_t_df_tile_off.p + b.n_terms, sizeof(uint64_t), cudaMemcpyDeviceToHost,
                            st));
@@ -3693,7 +4204,7 @@ void batch_plan(Batch& b) {
   b.time_end();
   MGX_CUDA(cudaStreamSynchronize(st));
   b.h_df_mode = static_cast<int>(df_mode);
-  b.d2h_bytes += 2 * (b.n_queries + 1) * sizeof(uint64_t) + sizeof(uint64_t);
+  b.d2h_bytes += (b.n_queries + 1) * sizeof(uint64_t) + sizeof(uint64_t);
   b.planned = true;
   b.time_begin(0);
   ensure_tile_maps(b);
@@ -3705,6 +4216,10 @@ void batch_df(Batch& b) {
   Index& ix = *b.ix;
   if (!b.planned) {
     batch_plan(b);
+  }
+  if (b.streamed) {
+    batch_df_streamed(b);
+    return;
   }
   ensure_tile_maps(b);
   const uint64_t total_tiles = b.n_df_tiles;
@@ -3750,12 +4265,12 @@ struct Chunk {
 };
 
 // Split the batch so that each chunk's record area fits the scratch budget.
-std::vector<Chunk> make_chunks(const Batch& b, uint64_t max_records) {
+std::vector<Chunk> make_chunks(const Batch& b, uint64_t max_records, uint32_t rec_slot) {
   std::vector<Chunk> chunks;
   uint32_t q0 = 0;
   while (q0 < b.n_queries) {
     uint32_t q1 = q0 + 1;
-    while (q1 < b.n_queries && b.h_q_rec_off[q1 + 1] - b.h_q_rec_off[q0] <= max_records) {
+    while (q1 < b.n_queries && (b.h_q_tile_off[q1 + 1] - b.h_q_tile_off[q0]) * rec_slot <= max_records) {
       ++q1;
     }
     chunks.push_back({q0, q1});
@@ -3800,12 +4315,17 @@ uint64_t scratch_records(const Batch& b) {
   return std::max<uint64_t>(bytes / 12, 1ULL << 20);
 }
 
+// record slots per tile for a given pruning depth (0 = no pruning: a tile may keep all its kTile entries)
+uint32_t rec_slot_for_prune(uint32_t prune_k) {
+  return prune_k != 0 && prune_k < kTile ? ((prune_k + 31u) & ~31u) : static_cast<uint32_t>(kTile);
+}
+
 void run_tiles(Batch& b, const Chunk& c, const ScoreParams& sp, uint32_t prune_k) {
   cudaStream_t st = b.stream;
   const uint64_t tile_base = b.h_q_tile_off[c.q0];
   const uint64_t n_tiles = b.h_q_tile_off[c.q1] - tile_base;
-  const uint64_t rec_base = b.h_q_rec_off[c.q0];
-  const uint64_t n_recs = b.h_q_rec_off[c.q1] - rec_base;
+  b.rec_slot = rec_slot_for_prune(prune_k);
+  const uint64_t n_recs = n_tiles * b.rec_slot;
   ensure_tile_maps(b);
   SearchScratch& sc = *b.sc;
   sc.tile_count.reserve(std::max<uint64_t>(n_tiles, 1ULL << 16));
@@ -3825,7 +4345,7 @@ void run_tiles(Batch& b, const Chunk& c, const ScoreParams& sp, uint32_t prune_k
     }
     b.time_begin(2);
     and_tile_kernel<<<static_cast<unsigned>(n_tiles), kTileThreads, 0, st>>>(
-        make_view(*b.ix), make_batch_view(b), sp, tile_base, rec_base, b.d_tile_count.p, b.d_tile_total.p,
+        make_view(*b.ix), make_batch_view(b), sp, tile_base, b.rec_slot, b.d_tile_count.p, b.d_tile_total.p,
         b.d_rec_doc.p, b.d_rec_score.p, prune_k);
     MGX_LAUNCH_CHECK();
     b.time_end();
@@ -3843,16 +4363,58 @@ void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_
   }
   prepare_scoring(b, d_df_slots);
   const ScoreParams sp = score_params(b);
-  const auto chunks = make_chunks(b, scratch_records(b));
-  uint64_t driver_entries = 0;
+  // per-tile top-k pruning is only valid when the answer is a top-k by score
+  const uint32_t prune_k = sp.compute_score != 0 && b.params.limit != 0 ? b.params.limit + b.params.offset : 0u;
+  if (b.streamed) {
+    // one uninterrupted enqueue: persistent kernels size themselves from the device-side launch block
+    if (rec_slot_for_prune(prune_k) > b.rec_slot) {
+      set_last_error("internal: streamed batch searched with other limits than it was planned with");
+      throw CudaFailure{MGX_ERR_INVALID_ARGUMENT};
+    }
+    const int sms = device_sm_count(b.ix->device);
+    static int per_sm_and = 0;
+    if (per_sm_and == 0) {
+      MGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_and, and_tiles_kernel, kTileThreads, 0));
+      per_sm_and = std::max(per_sm_and, 1);
+    }
+    const BatchView bv = make_batch_view(b);
+    b.time_begin(2);
+    and_tiles_kernel<<<static_cast<unsigned>(sms * per_sm_and), kTileThreads, 0, st>>>(
+        make_view(*b.ix), bv, sp, b.rec_slot, b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p, b.d_rec_score.p, prune_k);
+    MGX_LAUNCH_CHECK();
+    b.time_end();
+    b.time_begin(3);
+    const uint32_t group_tiles = group_tiles_for(b);
+    if (group_tiles != 0 && prune_k != 0) {
+      topk_groups_kernel<<<static_cast<unsigned>(sms * 2), 256, 0, st>>>(bv, group_tiles, b.rec_slot, b.d_tile_count.p,
+                                                                        b.d_rec_doc.p, b.d_rec_score.p,
+                                                                        b.params.descending, prune_k);
+      MGX_LAUNCH_CHECK();
+    }
+    if (b.n_queries > 0) {
+      topk_kernel<<<b.n_queries, 256, 0, st>>>(bv, 0, 0, b.rec_slot, b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p,
+                                               b.d_rec_score.p, b.params.compute_score, b.params.descending,
+                                               b.params.limit, b.params.offset, stride, d_ids, d_scores, d_count, d_total);
+      MGX_LAUNCH_CHECK();
+    }
+    b.time_end();
+    // sizes, counters and the overflow flag follow the results to the host
+    b.h_launch.reserve(kLaunchCount);
+    MGX_CUDA(cudaMemcpyAsync(b.h_launch.p, b.d_launch.p, kLaunchCount * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    b.status_copied = true;
+    b.mark_last();
+    b.searched = true;
+    return;
+  }
+  const auto chunks = make_chunks(b, scratch_records(b), rec_slot_for_prune(prune_k));
   for (const Chunk& c : chunks) {
     if (chunks.size() > 1) {
       MGX_CUDA(cudaStreamSynchronize(st));  // scratch is reused by the next chunk
+      if (b.sc != nullptr) {
+        b.sc->skip_streamed = 8;  // batches of this size do not fit a streamed workspace either
+      }
     }
-    // per-tile top-k pruning is only valid when the answer is a top-k by score
-    const uint32_t prune_k = sp.compute_score != 0 ? b.params.limit + b.params.offset : 0u;
     run_tiles(b, c, sp, prune_k);
-    driver_entries += b.h_q_rec_off[c.q1] - b.h_q_rec_off[c.q0];
     b.time_begin(3);
     if (prune_k != 0 && prune_k * 2 <= kGroupKeyCap) {
       // queries with many tiles: reduce groups of tiles to prune_k records each before the per-query top-k
@@ -3874,18 +4436,17 @@ void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_
         b.h2d_bytes += groups.size() * sizeof(TopkGroup);
         topk_group_kernel<<<static_cast<unsigned>(groups.size()), 256, 0, st>>>(
             make_batch_view(b), reinterpret_cast<const TopkGroup*>(sc.topk_groups.p), b.h_q_tile_off[c.q0],
-            b.h_q_rec_off[c.q0], b.d_tile_count.p, b.d_rec_doc.p, b.d_rec_score.p, b.params.descending, prune_k);
+            b.rec_slot, b.d_tile_count.p, b.d_rec_doc.p, b.d_rec_score.p, b.params.descending, prune_k);
         MGX_LAUNCH_CHECK();
       }
     }
-    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.h_q_rec_off[c.q0],
+    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.rec_slot,
                                              b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p, b.d_rec_score.p,
                                              b.params.compute_score, b.params.descending, b.params.limit,
                                              b.params.offset, stride, d_ids, d_scores, d_count, d_total);
     MGX_LAUNCH_CHECK();
     b.time_end();
   }
-  b.driver_entries += driver_entries;
   b.mark_last();
   b.searched = true;
 }
@@ -3946,7 +4507,7 @@ void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32
   }
   ScoreParams sp = score_params(b);
   sp.compute_score = 0;
-  const auto chunks = make_chunks(b, scratch_records(b));
+  const auto chunks = make_chunks(b, scratch_records(b), kTile);
   // pass 1: totals per query (topk_kernel with limit 0 / stride 0 only counts)
   DevBuf<uint32_t> d_count;
   DevBuf<uint64_t> d_total;
@@ -3959,7 +4520,7 @@ void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32
     // single chunk: records stay valid between the counting and the gathering pass
     const Chunk& c = chunks[0];
     run_tiles(b, c, sp, 0);
-    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.h_q_rec_off[c.q0],
+    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.rec_slot,
                                              b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p, nullptr, 0, 0, 0, 0, 0,
                                              d_dummy.p, nullptr,
                                              d_count.p, d_total.p);
@@ -3976,7 +4537,7 @@ void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32
                              cudaMemcpyHostToDevice, st));
     d_sets->alloc(std::max<uint64_t>(1, h_set_off->back()));
     gather_sets_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0],
-                                                    b.h_q_rec_off[c.q0], b.d_tile_count.p, b.d_rec_doc.p, d_set_off.p,
+                                                    b.rec_slot, b.d_tile_count.p, b.d_rec_doc.p, d_set_off.p,
                                                     d_sets->p);
     MGX_LAUNCH_CHECK();
     MGX_CUDA(cudaStreamSynchronize(st));
@@ -3986,7 +4547,7 @@ void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32
   for (const Chunk& c : chunks) {
     MGX_CUDA(cudaStreamSynchronize(st));
     run_tiles(b, c, sp, 0);
-    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.h_q_rec_off[c.q0],
+    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.rec_slot,
                                              b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p, nullptr, 0, 0, 0, 0, 0,
                                              d_dummy.p, nullptr,
                                              d_count.p, d_total.p);
@@ -4007,7 +4568,7 @@ void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32
     MGX_CUDA(cudaStreamSynchronize(st));
     run_tiles(b, c, sp, 0);
     gather_sets_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0],
-                                                    b.h_q_rec_off[c.q0], b.d_tile_count.p, b.d_rec_doc.p, d_set_off.p,
+                                                    b.rec_slot, b.d_tile_count.p, b.d_rec_doc.p, d_set_off.p,
                                                     d_sets->p);
     MGX_LAUNCH_CHECK();
   }
@@ -4034,6 +4595,25 @@ void launch_merge_topk(cudaStream_t stream, const mgx_query_params_t& params, ui
   merge_topk_kernel<<<static_cast<unsigned>(n_queries), 256, 0, stream>>>(
       n_shards, n_queries, stride, params.compute_score, params.descending, params.limit, params.offset, runs,
       d_ids_out, d_scores_out, d_count_out, d_total_out);
+  MGX_LAUNCH_CHECK();
+}
+
+namespace {
+__global__ void or_status_kernel(const uint8_t* __restrict__ in, uint64_t pitch, uint32_t n_shards, uint8_t* __restrict__ out) {
+  const uint32_t w = threadIdx.x;  // four status words
+  if (w < 4) {
+    uint32_t v = 0;
+    for (uint32_t s = 0; s < n_shards; ++s) {
+      v |= reinterpret_cast<const uint32_t*>(in + static_cast<uint64_t>(s) * pitch)[w];
+    }
+    reinterpret_cast<uint32_t*>(out)[w] = v;
+  }
+}
+}  // namespace
+
+void launch_or_status(cudaStream_t stream, const uint8_t* d_status_first, uint64_t shard_pitch_bytes, uint32_t n_shards,
+                      uint8_t* d_status_out) {
+  or_status_kernel<<<1, 32, 0, stream>>>(d_status_first, shard_pitch_bytes, n_shards, d_status_out);
   MGX_LAUNCH_CHECK();
 }
 

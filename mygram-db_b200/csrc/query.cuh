@@ -17,6 +17,23 @@ constexpr int kTileItems = kTile / kTileThreads;
 constexpr uint32_t kMaxTermBytes = 256;
 constexpr uint32_t kMaxTopK = 1024;
 
+// ---- streamed batches (no host read-back between planning and the tile kernels) --------------------------------
+// The planning tail leaves the work sizes in a small device block; persistent kernels pull their work items from the
+// counters next to them. The block follows the accounting counters, so one memset clears both.
+constexpr uint32_t kDfUnit = 256;          // driver entries per df work unit of a streamed batch (kTile in the other form)
+enum LaunchSlot : int {
+  kLaunchDfUnits = 0,    // df work units of the batch
+  kLaunchAndTiles = 1,   // intersect tiles of the batch
+  kLaunchGroups = 2,     // top-k pre-reduction groups
+  kLaunchOverflow = 3,   // != 0: the batch does not fit the stream's workspace; every later kernel does nothing
+  kLaunchDfNext = 4,     // work counters of the persistent kernels
+  kLaunchAndNext = 5,
+  kLaunchGroupNext = 6,
+  kLaunchTicket = 7,     // blocks of the planning kernel that have finished
+  kLaunchNeedTiles = 8,  // what the batch would have needed (reported with an overflow)
+  kLaunchCount = 16
+};
+
 // ---- streaming document-frequency pass (df_stream_kernel) ------------------------------------------------
 // For very large batches the verified document frequencies of the multi-n-gram terms are computed by ONE pass
 // over the shard's text arena that matches all of them at once, instead of visiting every candidate document
@@ -207,7 +224,7 @@ struct Batch {
   DevBuf<uint32_t> d_q_driver_len;  // [Q]
   DevBuf<uint32_t> d_q_ntiles;    // [Q]
   DevBuf<uint64_t> d_q_tile_off;  // [Q+1]
-  DevBuf<uint64_t> d_q_rec_off;   // [Q+1]
+  DevBuf<uint64_t> d_q_group_off; // [Q+1] top-k pre-reduction groups per query (streamed batches)
   DevBuf<double> d_q_idf;         // [sum search terms], in planner order
   DevBuf<uint32_t> d_q_host_flags;  // [Q] flags decided on the host (verify etc.)
   DevBuf<uint32_t> d_q_threshold;   // [Q] any-mode threshold
@@ -225,9 +242,16 @@ struct Batch {
   DevBuf<uint32_t> d_rec_doc;     // survivors (global doc ids), tile k of query q at rec_off[q] + k*kTile
   DevBuf<double> d_rec_score;
 
-  // host mirrors read back after planning
+  // host mirror read back after planning (not for streamed batches)
   std::vector<uint64_t> h_q_tile_off;
-  std::vector<uint64_t> h_q_rec_off;
+  // streamed batches: sizes and work counters stay on the device (LaunchSlot); h_launch receives them with the results
+  DevBuf<uint32_t> d_launch;
+  PinBuf<uint32_t> h_launch;
+  bool streamed = false;       // planned without a host read-back
+  bool allow_streamed = false; // set by the entry points that can repeat an overflowed batch
+  uint32_t rec_slot = kTile;   // record slots per tile in the (index, stream) workspace
+  uint8_t* in_base = nullptr;  // device copy of the compiled batch (for a repeat after an overflow)
+  size_t in_total = 0;
 
   DevBuf<uint8_t> d_term_flags;   // [T] bit0 raw, bit1 exact_single, bit2 eligible for the streaming df pass
   DevBuf<uint32_t> d_stream_slots;      // [n_stream_slots] (first entry << 8) | entries in the bucket
@@ -250,6 +274,13 @@ struct Batch {
   DevBuf<uint32_t> d_tile_query;    // [and tiles]
   DevBuf<unsigned long long> d_stats;  // device-side accounting, see StatSlot
 
+  // sharded pipeline (mgx_sharded_batch_*): the gathered per-shard records, the merged record, and the events that
+  // order the batch's stream with the communicator's stream; all recycled with the workspace
+  DevBuf<uint8_t> o_gather;
+  DevBuf<uint8_t> o_merged;
+  cudaEvent_t ev_x[4] = {nullptr, nullptr, nullptr, nullptr};
+  PinBuf<uint32_t> h_status;  // status block of the merged record
+  bool sharded_enqueued = false;
   // device-side result buffers of the host-buffer call (mgx_query_batch), recycled with the workspace
   DevBuf<uint32_t> o_ids;
   DevBuf<double> o_scores;
@@ -266,6 +297,7 @@ struct Batch {
   uint64_t driver_entries = 0;
   bool planned = false;
   bool df_done = false;
+  bool status_copied = false;  // h_launch is being / has been filled for this batch
   bool searched = false;  // batch_search has enqueued the batch's last kernels (ev_last follows them)
 
   // CUDA-event timing of the named kernels on the launch stream
@@ -295,6 +327,7 @@ enum StatSlot : int {
   kStatStreamEntries = 6,   // shortest-list entries of the terms eligible for the streaming df pass
   kStatStreamHits = 7,      // verified (term, document) pairs counted by the streaming pass
   kStatDfScanned = 8,       // df candidates whose whole text had to be scanned (no usable first-occurrence position)
+  kStatDriverEntries = 9,   // driver entries of all queries (what the intersect tiles walk)
   kStatCount = 10
 };
 constexpr int kStatStripes = 64;  // each counter is striped over 64 words to spread the atomics
@@ -306,7 +339,12 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
 // Bucket table over the terms with `streamable` set (clears the flag of terms that do not fit a bucket).
 void build_stream_table(std::vector<HostTerm>& terms, HostStreamTable* out);
 void batch_plan(Batch& b);
+void batch_clear_counters(Batch& b);
 void batch_df(Batch& b);
+// Streamed batches only: true when the batch did not fit the stream's workspace (call after its stream work has
+// completed). The batch is then reset to its uploaded state and must be run again; it will take the synchronous form.
+bool batch_overflowed(Batch& b);
+void batch_reset_for_repeat(Batch& b);
 // Runs the intersect/score kernels and the per-query output kernel. Outputs are DEVICE pointers.
 // set_mode: 0 = top-k by score or first ids (params.limit/offset), 1 = full ascending sets
 // written to d_sets (offsets d_set_off[Q+1] computed here), 2 = last `limit` ids descending (reverse)
@@ -321,6 +359,9 @@ void launch_merge_topk(cudaStream_t stream, const mgx_query_params_t& params, ui
                        uint64_t stride, const uint32_t* d_ids_all, const double* d_scores_all,
                        const uint32_t* d_count_all, const uint64_t* d_total_all, uint64_t shard_pitch_bytes,
                        uint32_t* d_ids_out, double* d_scores_out, uint32_t* d_count_out, uint64_t* d_total_out);
+// OR of the 16-byte status blocks of n_shards packed records (first block at d_status_first, one every pitch bytes).
+void launch_or_status(cudaStream_t stream, const uint8_t* d_status_first, uint64_t shard_pitch_bytes, uint32_t n_shards,
+                      uint8_t* d_status_out);
 void batch_df_to_slots(Batch& b, uint64_t* d_df_slots);
 void launch_score_documents(Index& ix, cudaStream_t stream, const uint32_t* d_cands, uint64_t n_cands,
                             const uint8_t* d_term_bytes, const uint32_t* d_term_boff, const uint64_t* d_dfs,

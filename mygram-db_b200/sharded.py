@@ -93,13 +93,15 @@ def gather_doc_id_sets(comm, local_ids, device=None):
 
 def record_layout(n_queries, stride):
     """Byte offsets of one shard's packed top-k record: [scores f64 Q*S][total i64 Q][ids i32 Q*S][count i32 Q],
-    padded to 16 bytes (the same layout as mgx_shard_record_layout, include/mgx.h)."""
+    padded to 16 bytes, then a 16-byte status block (word 0: the shard's streamed batch overflowed its workspace) --
+    the same layout as mgx_shard_record_layout, include/mgx.h."""
     o_scores = 0
     o_total = n_queries * stride * 8
     o_ids = o_total + n_queries * 8
     o_count = o_ids + n_queries * stride * 4
-    return {"scores": o_scores, "total": o_total, "ids": o_ids, "count": o_count,
-            "bytes": (o_count + n_queries * 4 + 15) & ~15}
+    o_status = (o_count + n_queries * 4 + 15) & ~15
+    return {"scores": o_scores, "total": o_total, "ids": o_ids, "count": o_count, "status": o_status,
+            "bytes": o_status + 16}
 
 
 def record_views(rec, n_queries, stride):
@@ -228,3 +230,87 @@ def merge_topk_reference(params_compute_score, descending, limit, offset, ids_al
             ids[q, i] = r[1]
             scores[q, i] = r[0]
     return ids, scores, count, total
+
+
+class ShardComm:
+    """The library's own NCCL communicator lanes (mgx_comm_*): torch.distributed only carries the bootstrap -- rank 0
+    draws one NCCL unique id per lane and broadcasts them -- the exchanges of the data path are then issued by
+    libmgx.so itself on its own highest-priority streams (mgx_sharded_batch_*). world_size 1: no communicator."""
+
+    def __init__(self, mgx, dist, device, n_lanes=2):
+        import torch
+        self.mgx = mgx
+        self.L = mgx.lib()
+        self.h = C.c_void_p()
+        self.world_size = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.n_lanes = n_lanes
+        if self.world_size == 1:
+            return
+        ids = torch.zeros(n_lanes * 128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = np.zeros(n_lanes * 128, dtype=np.uint8)
+            for lane in range(n_lanes):
+                mgx._check(self.L.mgx_comm_unique_id(buf[lane * 128:].ctypes.data_as(mgx.u8p)))
+            ids = torch.from_numpy(buf)
+        ids = ids.to(device)
+        dist.broadcast(ids, src=0)
+        host = ids.cpu().numpy().copy()
+        dev_index = device.index if device.index is not None else 0
+        mgx._check(self.L.mgx_comm_create(host.ctypes.data_as(mgx.u8p), n_lanes, self.world_size, self.rank, dev_index,
+                                          C.byref(self.h)))
+
+    def handle(self):
+        return self.h if self.h.value else None
+
+    def nccl_version(self):
+        v = C.c_int32()
+        self.L.mgx_comm_info(self.handle(), None, None, None, C.byref(v))
+        return int(v.value)
+
+    def close(self):
+        if self.h.value:
+            self.L.mgx_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class ShardPipeline:
+    """Whole batches through mgx_sharded_batch_enqueue / _finish: plan, df, all-reduce, search, all-gather, merge and
+    the device-to-host copy of the merged record are ONE enqueue on the batch's stream (and the lane's communicator
+    stream); finish waits and, if any shard's streamed batch overflowed its workspace, repeats it collectively."""
+
+    def __init__(self, mgx, index, params, stride, comm):
+        self.mgx, self.index, self.params, self.stride, self.comm = mgx, index, params, stride, comm
+        self.L = mgx.lib()
+        self.stats = []
+        self.repeats = 0
+
+    def prepare(self, arena, offsets, qbeg, n_queries, stream):
+        h = C.c_void_p()
+        m = self.mgx
+        m._check(self.L.mgx_batch_prepare(self.index._h, C.byref(self.params), n_queries, m._ptr(arena, m.u8p),
+                                          m._ptr(offsets, m.u64p), m._ptr(qbeg, m.u64p), None, None, None,
+                                          C.c_void_p(stream.cuda_stream), C.byref(h)))
+        return {"h": h, "n_queries": n_queries}
+
+    def enqueue(self, batch, lane, host_record=None):
+        """host_record: pinned uint8 torch tensor of record_layout(...)['bytes'] (or None: result stays on the device)."""
+        ptr = C.c_void_p(host_record.data_ptr()) if host_record is not None else None
+        batch["lane"], batch["host"] = lane, ptr
+        self.mgx._check(self.L.mgx_sharded_batch_enqueue(self.comm.handle(), lane, batch["h"], self.stride, ptr))
+
+    def finish(self, batch):
+        """Returns the device address of the merged record (valid until release)."""
+        d = C.c_void_p()
+        rep = C.c_int32()
+        self.mgx._check(self.L.mgx_sharded_batch_finish(self.comm.handle(), batch["lane"], batch["h"], self.stride,
+                                                        batch["host"], C.byref(d), C.byref(rep)))
+        self.repeats += int(rep.value)
+        return d.value
+
+    def release(self, batch, collect_stats=False):
+        if collect_stats:
+            s = self.mgx.BatchStats()
+            self.mgx._check(self.L.mgx_batch_get_stats(batch["h"], C.byref(s)))
+            self.stats.append(s.as_dict())
+        self.L.mgx_batch_destroy(batch["h"])
