@@ -591,16 +591,19 @@ class Index:
         _check(lib().mgx_index_set_filter_column(self._h, column, type_code, _ptr(vals, u64p), _ptr(nulls, u8p), n,
                                                  _ptr(sb, u8p), _ptr(so, u64p), len(strings)))
 
-    def query_batch(self, queries, not_terms=None, stride=None, programs=None, filters=None, **kw):
-        """Batch of SEARCH queries (regular path of ExecuteFullPipeline + ScoreDocuments + SortByScore).
-        programs: per query None or (ops, args) — a boolean postfix program over the query's own terms;
-        filters: per query a list of (column id, op 0..5, literal)."""
-        p = self.params(**kw)
-        arena, offsets, qbeg, n_slots = flatten_queries(queries)
-        if not_terms is not None:
-            narena, noffsets, nbeg, _ = flatten_queries(not_terms)
-        else:
-            narena = noffsets = nbeg = None
+    def set_filter_column_arrays(self, column, type_code, values_u64, nulls_u8=None, strings=None):
+        """Same as set_filter_column for columns that already are arrays: values_u64[i] = the integer / bool value,
+        the bits of the double, or (type 11) an index into `strings`; nulls_u8[i] != 0 marks NULL."""
+        vals = np.ascontiguousarray(values_u64, dtype=np.uint64)
+        nulls = None if nulls_u8 is None else np.ascontiguousarray(nulls_u8, dtype=np.uint8)
+        strs = [_bytes(s) for s in (strings or [])]
+        sb, so = pack_strings(strs if strs else [b""])
+        _check(lib().mgx_index_set_filter_column(self._h, column, type_code, _ptr(vals, u64p), _ptr(nulls, u8p),
+                                                 vals.size, _ptr(sb, u8p), _ptr(so, u64p), len(strs)))
+
+    @staticmethod
+    def build_ext(programs=None, filters=None):
+        """(mgx_query_ext_t, arrays to keep alive) for per-query boolean programs / column conditions, or (None, [])."""
         ext = None
         keep = []
         if programs is not None or filters is not None:
@@ -633,6 +636,19 @@ class Index:
                 keep += [fc, fo, lb, lo, fb]
                 ext.filter_col, ext.filter_op = _ptr(fc, u32p), _ptr(fo, u8p)
                 ext.filter_bytes, ext.filter_offsets, ext.q_filter_begin = _ptr(lb, u8p), _ptr(lo, u64p), _ptr(fb, u64p)
+        return ext, keep
+
+    def query_batch(self, queries, not_terms=None, stride=None, programs=None, filters=None, **kw):
+        """Batch of SEARCH queries (regular path of ExecuteFullPipeline + ScoreDocuments + SortByScore).
+        programs: per query None or (ops, args) — a boolean postfix program over the query's own terms;
+        filters: per query a list of (column id, op 0..5, literal)."""
+        p = self.params(**kw)
+        arena, offsets, qbeg, n_slots = flatten_queries(queries)
+        if not_terms is not None:
+            narena, noffsets, nbeg, _ = flatten_queries(not_terms)
+        else:
+            narena = noffsets = nbeg = None
+        ext, keep = self.build_ext(programs, filters)
         return self.query_batch_flat(p, len(queries), arena, offsets, qbeg, narena, noffsets, nbeg, n_slots, stride,
                                      ext=ext)
 

@@ -2368,8 +2368,11 @@ int mgx_batch_reset(mgx_batch_t* batch) {
     return invalid("null batch");
   }
   return guarded([&]() {
-    DeviceGuard guard(batch->b.ix->device);
-    batch_reset_for_repeat(batch->b);
+    Batch& b = batch->b;
+    DeviceGuard guard(b.ix->device);
+    // after an overflow the repeat takes the synchronous form; otherwise this is a plain re-arm of the batch
+    batch_reset_for_repeat(b, batch_overflowed(b));
+    b.sharded_enqueued = false;
     return MGX_OK;
   });
 }
@@ -2579,7 +2582,7 @@ int mgx_query_batch_ex(mgx_index_t* index, const mgx_query_params_t* params, uin
       if (!batch_overflowed(b)) {
         break;
       }
-      batch_reset_for_repeat(b);
+      batch_reset_for_repeat(b, true);
     }
     mgx_batch_stats_t stats{};
     b.collect_stats(&stats);
@@ -2915,7 +2918,7 @@ int mgx_sharded_batch_finish(mgx_shard_comm_t* comm, int32_t lane, mgx_batch_t* 
     // rank reads the same value, so all of them repeat the batch together (in the synchronous form, which sizes its
     // workspace from the batch) and the exchanges stay matched.
     if (b.h_status.p != nullptr && b.h_status.p[0] != 0) {
-      batch_reset_for_repeat(b);
+      batch_reset_for_repeat(b, true);
       sharded_enqueue(comm, lane, b, stride, h_record_out);
       MGX_CUDA(cudaEventSynchronize(b.ev_last));
       if (out_repeated != nullptr) {

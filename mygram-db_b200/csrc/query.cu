@@ -4124,15 +4124,17 @@ bool batch_overflowed(Batch& b) {
 // Back to the freshly uploaded state: the planning kernels permute key tables and term lists in place, so the compiled
 // batch is copied from the pinned staging buffer again. The repeat takes the synchronous form, whose workspace grows
 // with the batch, and tells the stream's workspace to stay in that form for a while when even that is chunked.
-void batch_reset_for_repeat(Batch& b) {
+void batch_reset_for_repeat(Batch& b, bool after_overflow) {
   MGX_CUDA(cudaMemcpyAsync(b.in_base, b.staging.p, b.in_total, cudaMemcpyHostToDevice, b.stream));
   b.h2d_bytes += b.in_total;
   batch_clear_counters(b);
-  if (b.sc != nullptr) {
-    b.sc->skip_streamed = 8;
+  if (after_overflow) {
+    if (b.sc != nullptr) {
+      b.sc->skip_streamed = 8;
+    }
+    b.allow_streamed = false;
   }
   b.streamed = false;
-  b.allow_streamed = false;
   b.planned = b.df_done = b.searched = b.status_copied = false;
   b.rec_slot = kTile;
   b.n_df_tiles = b.n_and_tiles = b.driver_entries = 0;
@@ -4142,7 +4144,7 @@ void batch_plan(Batch& b) {
   cudaStream_t st = b.stream;
   Index& ix = *b.ix;
   if (b.allow_streamed && b.explicit_driver.d_ids == nullptr) {
-    static const bool disabled = std::getenv("MGX_NO_STREAMED") != nullptr;
+    const bool disabled = std::getenv("MGX_NO_STREAMED") != nullptr;  // read per batch: the tests flip it
     if (b.sc == nullptr) {
       b.sc = ix.scratch_for(st);
     }

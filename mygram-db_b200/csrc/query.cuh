@@ -344,7 +344,8 @@ void batch_df(Batch& b);
 // Streamed batches only: true when the batch did not fit the stream's workspace (call after its stream work has
 // completed). The batch is then reset to its uploaded state and must be run again; it will take the synchronous form.
 bool batch_overflowed(Batch& b);
-void batch_reset_for_repeat(Batch& b);
+// after_overflow: the repeat must take the synchronous form (and the stream's next batches too, for a while).
+void batch_reset_for_repeat(Batch& b, bool after_overflow);
 // Runs the intersect/score kernels and the per-query output kernel. Outputs are DEVICE pointers.
 // set_mode: 0 = top-k by score or first ids (params.limit/offset), 1 = full ascending sets
 // written to d_sets (offsets d_set_off[Q+1] computed here), 2 = last `limit` ids descending (reverse)

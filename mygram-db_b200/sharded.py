@@ -285,13 +285,20 @@ class ShardPipeline:
         self.stats = []
         self.repeats = 0
 
-    def prepare(self, arena, offsets, qbeg, n_queries, stream):
+    def prepare(self, arena, offsets, qbeg, n_queries, stream, ext=None):
+        """Host compile + H2D of one batch on `stream` (a torch.cuda.Stream); ext: mgx_query_ext_t or None."""
         h = C.c_void_p()
         m = self.mgx
-        m._check(self.L.mgx_batch_prepare(self.index._h, C.byref(self.params), n_queries, m._ptr(arena, m.u8p),
-                                          m._ptr(offsets, m.u64p), m._ptr(qbeg, m.u64p), None, None, None,
-                                          C.c_void_p(stream.cuda_stream), C.byref(h)))
+        m._check(self.L.mgx_batch_prepare_ex(self.index._h, C.byref(self.params), n_queries, m._ptr(arena, m.u8p),
+                                             m._ptr(offsets, m.u64p), m._ptr(qbeg, m.u64p), None, None, None,
+                                             C.byref(ext) if ext is not None else None,
+                                             C.c_void_p(stream.cuda_stream), C.byref(h)))
         return {"h": h, "n_queries": n_queries}
+
+    def rearm(self, batch):
+        """Back to the uploaded state (the compiled batch is copied from its pinned staging buffer again), so the
+        same batch object can be enqueued once more."""
+        self.mgx._check(self.L.mgx_batch_reset(batch["h"]))
 
     def enqueue(self, batch, lane, host_record=None):
         """host_record: pinned uint8 torch tensor of record_layout(...)['bytes'] (or None: result stays on the device)."""

@@ -89,6 +89,23 @@ def pack_filter_columns(n_docs, columns):
     return vals, nulls, types, strings
 
 
+def pack_filter_arrays(n_docs, columns):
+    """Same packing for columns that already are arrays: columns = list of (type_code, values_u64, string table or
+    None); for strings (type 11) values index the table and row i refers to strings[i] of the returned table."""
+    vals = np.zeros(len(columns) * n_docs, dtype=np.uint64)
+    nulls = np.zeros(len(columns) * n_docs, dtype=np.uint8)
+    types = np.asarray([c[0] for c in columns], dtype=np.int32)
+    strings = []
+    for ci, (typ, values, table) in enumerate(columns):
+        v = np.ascontiguousarray(values, dtype=np.uint64)
+        if typ == 11:
+            base = len(strings)
+            strings += [as_bytes(t) for t in table]
+            v = v + np.uint64(base)
+        vals[ci * n_docs:(ci + 1) * n_docs] = v
+    return vals, nulls, types, strings
+
+
 @dataclass
 class BatchResult:
     ids: np.ndarray      # [Q, stride] uint32
@@ -171,9 +188,14 @@ class OracleLib:
     # ---- tokenizer ----
     def apply_filters(self, n_docs, first_doc_id, columns, filters, results):
         """columns: list of (type_code, values, nulls); values is a list of python values per row (None = NULL;
-        str/bytes for strings, float for doubles, int/bool otherwise). filters: list of (col, op, literal).
+        str/bytes for strings, float for doubles, int/bool otherwise) -- or the tuple pack_filter_columns /
+        pack_filter_arrays returned, packed once for many calls. filters: list of (col, op, literal).
         -> the ids of `results` that pass (ApplyFiltersWithBitmap, search_pipeline.cpp:1196-1237)."""
-        vals, nulls, types, strings = pack_filter_columns(n_docs, columns)
+        if isinstance(columns, tuple) and len(columns) == 4 and isinstance(columns[0], np.ndarray):
+            vals, nulls, types, strings = columns
+            columns = list(types)
+        else:
+            vals, nulls, types, strings = pack_filter_columns(n_docs, columns)
         sbytes, soffs = pack_strings(strings if strings else [b""])
         fc = np.asarray([f[0] for f in filters], dtype=np.uint32)
         fo = np.asarray([f[1] for f in filters], dtype=np.uint8)

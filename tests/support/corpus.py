@@ -145,7 +145,8 @@ def sample_queries_global(kind, corpus_seed, n_docs_total, n_queries, seed, n_te
             if len(text) < max_cp:
                 continue
             terms = []
-            for _ in range(n_terms):
+            nt = n_terms if isinstance(n_terms, int) else int(rng.integers(n_terms[0], n_terms[1] + 1))
+            for _ in range(nt):
                 ln = int(rng.integers(min_cp, max_cp + 1))
                 st = int(rng.integers(0, len(text) - ln + 1))
                 terms.append(text[st:st + ln].encode("utf-8"))
