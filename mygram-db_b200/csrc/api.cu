@@ -2812,7 +2812,11 @@ void sharded_enqueue(mgx_shard_comm_t* comm, int lane, Batch& b, uint64_t stride
       cudaStream_t cs = comm->stream[lane];
       MGX_CUDA(cudaEventRecord(batch_event(b, 0), st));
       MGX_CUDA(cudaStreamWaitEvent(cs, batch_event(b, 0), 0));
-      MGX_NCCL(api, api->AllReduce(b.d_t_df.p, b.d_t_df.p, b.n_terms, ncclUint64, ncclSum, comm->comm[lane], cs));
+      // Behind it in the same array: every key's posting size, which gives each shard the GLOBAL estimated sizes
+      // the reference orders (and therefore sums) a query's terms by.
+      MGX_NCCL(api, api->AllReduce(b.d_t_df.p, b.d_t_df.p, static_cast<size_t>(b.n_terms) + b.n_keys, ncclUint64,
+                                   ncclSum, comm->comm[lane], cs));
+      b.global_order = true;
       MGX_CUDA(cudaEventRecord(batch_event(b, 1), cs));
       MGX_CUDA(cudaStreamWaitEvent(st, batch_event(b, 1), 0));
     }

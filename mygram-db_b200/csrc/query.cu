@@ -89,6 +89,9 @@ struct BatchView {
   uint32_t stream_slot_mask;           // n_slots - 1
   uint32_t* df_mode;                   // [0] = 1: streaming pass chosen for this batch
   uint32_t* launch;                    // LaunchSlot block of a streamed batch, nullptr otherwise
+  const uint32_t* q_tids0;             // [sum] search terms in QUERY order (q_tids is re-ordered by the planner)
+  uint64_t* key_glen;                  // [K] posting size per key in UPLOAD order; summed over the shards by the df
+                                       // exchange of the sharded pipeline (global term order, see global_order_kernel)
 };
 
 struct ScoreParams {
@@ -249,7 +252,8 @@ __device__ __forceinline__ uint32_t doc_count_term(DocText& d, const uint8_t* __
 // ------------------------------------------------------------------ lookup + term planning
 __device__ __forceinline__ void lookup_one(const uint64_t* __restrict__ term_keys, const uint64_t* __restrict__ term_off,
                                            uint64_t n_dict, const uint64_t* __restrict__ keys, uint32_t i,
-                                           uint32_t* __restrict__ key_list, uint32_t* __restrict__ key_len) {
+                                           uint32_t* __restrict__ key_list, uint32_t* __restrict__ key_len,
+                                           uint64_t* __restrict__ key_glen) {
   const uint64_t key = keys[i];
   uint64_t lo = 0;
   uint64_t hi = n_dict;
@@ -268,14 +272,18 @@ __device__ __forceinline__ void lookup_one(const uint64_t* __restrict__ term_key
     key_list[i] = kNone;
     key_len[i] = 0;
   }
+  if (key_glen != nullptr) {
+    key_glen[i] = key_len[i];  // upload order: the same position on every shard (term_plan sorts the other arrays)
+  }
 }
 
 __global__ void lookup_kernel(const uint64_t* __restrict__ term_keys, const uint64_t* __restrict__ term_off,
                               uint64_t n_dict, const uint64_t* __restrict__ keys, uint32_t n_keys,
-                              uint32_t* __restrict__ key_list, uint32_t* __restrict__ key_len) {
+                              uint32_t* __restrict__ key_list, uint32_t* __restrict__ key_len,
+                              uint64_t* __restrict__ key_glen) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_keys) {
-    lookup_one(term_keys, term_off, n_dict, keys, i, key_list, key_len);
+    lookup_one(term_keys, term_off, n_dict, keys, i, key_list, key_len, key_glen);
   }
 }
 
@@ -749,7 +757,7 @@ __global__ void plan_terms_kernel(IndexView iv, BatchView bv, const uint64_t* __
   const uint32_t k0 = bv.term_koff[t];
   const uint32_t k1 = bv.term_koff[t + 1];
   for (uint32_t i = k0; i < k1; ++i) {
-    lookup_one(iv.term_keys, iv.term_off, iv.n_terms, keys, i, bv.key_list, bv.key_len);
+    lookup_one(iv.term_keys, iv.term_off, iv.n_terms, keys, i, bv.key_list, bv.key_len, bv.key_glen);
   }
   term_plan_one(bv, t, compute_df, all_valid_utf8, raw_flags, bitmap_bytes, kDfUnit);
   for (uint32_t i = k0; i < k1; ++i) {
@@ -1793,6 +1801,56 @@ __global__ void idf_kernel(const uint32_t* __restrict__ q_tids, uint32_t n, cons
     v = log(__dadd_rn(__ddiv_rn(num, den), 1.0));
   }
   idf[i] = v;
+}
+
+// Sharded batches, after the df exchange: the reference orders a query's terms by their estimated size over the WHOLE
+// index (search_pipeline.cpp:2012-2014) and BM25Scorer adds the terms' contributions in that order, so a shard must
+// not add them in the order of its LOCAL sizes -- the FP64 sum would differ in the last bit between shard counts.
+// key_glen holds every key's posting size summed over the shards (it travels with the df all-reduce); one thread per
+// query re-derives the global estimates (min over the term's keys, 0 if a key is missing everywhere, search_pipeline.cpp:
+// 583-593), orders the query's terms by them (stable: equal sizes keep query order, as the planner does), and writes
+// the IDFs in that order.
+__global__ void global_order_kernel(BatchView bv, uint64_t total_docs, double* __restrict__ idf) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= bv.n_queries) {
+    return;
+  }
+  const uint32_t t0 = bv.q_toff[q];
+  const uint32_t t1 = bv.q_toff[q + 1];
+  auto global_est = [&](uint32_t tid) {
+    const uint32_t k0 = bv.term_koff[tid];
+    const uint32_t k1 = bv.term_koff[tid + 1];
+    uint64_t est = kEstNone;
+    for (uint32_t k = k0; k < k1; ++k) {
+      est = umin64(est, bv.key_glen[k]);
+    }
+    return est;
+  };
+  for (uint32_t i = t0; i < t1; ++i) {
+    const uint32_t tid = bv.q_tids0[i];
+    const uint64_t est = global_est(tid);
+    uint32_t j = i;
+    while (j > t0 && global_est(bv.q_tids[j - 1]) > est) {
+      bv.q_tids[j] = bv.q_tids[j - 1];
+      --j;
+    }
+    bv.q_tids[j] = tid;
+  }
+  for (uint32_t i = t0; i < t1; ++i) {
+    double v = 0.0;
+    if (total_docs != 0) {
+      uint64_t df = bv.t_df[bv.q_tids[i]];
+      if (df > total_docs) {
+        df = total_docs;
+      }
+      const double nn = static_cast<double>(total_docs);
+      const double dd = static_cast<double>(df);
+      const double num = __dadd_rn(__dsub_rn(nn, dd), 0.5);
+      const double den = __dadd_rn(dd, 0.5);
+      v = log(__dadd_rn(__ddiv_rn(num, den), 1.0));
+    }
+    idf[i] = v;
+  }
 }
 
 // ------------------------------------------------------------------ intersect + score tiles
@@ -3443,6 +3501,8 @@ BatchView make_batch_view(Batch& b) {
   v.stream_slot_mask = b.n_stream_slots > 0 ? b.n_stream_slots - 1 : 0;
   v.df_mode = b.d_df_mode.p;
   v.launch = b.streamed ? b.d_launch.p : nullptr;
+  v.q_tids0 = b.d_q_tids0.p;
+  v.key_glen = b.d_key_glen.p;
   return v;
 }
 
@@ -3588,6 +3648,7 @@ void Batch::recycle() {
   planned = df_done = searched = false;
   streamed = allow_streamed = status_copied = false;
   sharded_enqueued = false;
+  global_order = false;
   rec_slot = kTile;
   sc = nullptr;
   serial = 0;
@@ -3768,6 +3829,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   const size_t i_raw = add(T + 1);
   const size_t i_toff = add((Q + 1) * 4);
   const size_t i_tids = add(n_tids * 4);
+  const size_t i_tids0 = add(n_tids * 4);
   const size_t i_noff = add((Q + 1) * 4);
   const size_t i_ntids = add(n_ntids * 4);
   const size_t i_loff = add((Q + 1) * 4);
@@ -3822,6 +3884,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   {  // queries
     uint32_t* toff = reinterpret_cast<uint32_t*>(S + i_toff);
     uint32_t* tids = reinterpret_cast<uint32_t*>(S + i_tids);
+    uint32_t* tids0 = reinterpret_cast<uint32_t*>(S + i_tids0);
     uint32_t* noff = reinterpret_cast<uint32_t*>(S + i_noff);
     uint32_t* ntids = reinterpret_cast<uint32_t*>(S + i_ntids);
     uint32_t* loff = reinterpret_cast<uint32_t*>(S + i_loff);
@@ -3861,6 +3924,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
       thresholds[q] = hq.threshold;
       uint32_t cap = (hq.flags & kQProgram) != 0 ? 1u : 0u;  // a program's only list is its driver
       for (uint32_t tid : hq.terms) {
+        tids0[nt] = tid;
         tids[nt++] = tid;
         cap += static_cast<uint32_t>(terms[tid].keys.size());
       }
@@ -3897,6 +3961,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   b.d_term_flags.borrow(at(i_raw), T + 1);
   b.d_q_toff.borrow(reinterpret_cast<uint32_t*>(at(i_toff)), Q + 1);
   b.d_q_tids.borrow(reinterpret_cast<uint32_t*>(at(i_tids)), n_tids);
+  b.d_q_tids0.borrow(reinterpret_cast<uint32_t*>(at(i_tids0)), n_tids);
   b.d_q_noff.borrow(reinterpret_cast<uint32_t*>(at(i_noff)), Q + 1);
   b.d_q_ntids.borrow(reinterpret_cast<uint32_t*>(at(i_ntids)), n_ntids);
   b.d_q_loff.borrow(reinterpret_cast<uint32_t*>(at(i_loff)), Q + 1);
@@ -3920,7 +3985,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   const size_t Lc = list_cap;
   const size_t scan_elems = scan_scratch_elems(std::max<uint64_t>(T, Q)) + 8;
   size_t work = 0;
-  for (size_t nbytes : {K * sizeof(KeyRef), K * 4, K * 4, T * 8, T * 4, (T + 1) * 8, T * 8, Lc * 4, Lc * 4, Q * 4, Q * 4, Q * 4, Q * 4,
+  for (size_t nbytes : {K * sizeof(KeyRef), K * 4, K * 4, T * 8, T * 4, (T + 1) * 8, (T + K) * 8, Lc * 4, Lc * 4, Q * 4, Q * 4, Q * 4, Q * 4,
                         (Q + 1) * 8, (Q + 1) * 8, n_tids * 8, static_cast<size_t>(kStatCount) * kStatStripes * 8,
                         scan_elems * 8, static_cast<size_t>(64), static_cast<size_t>(kLaunchCount) * 4}) {
     work += DevArena::padded(nbytes == 0 ? 1 : nbytes);
@@ -3932,7 +3997,10 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   b.d_t_est.borrow(b.work_arena.take<uint64_t>(T), T);
   b.d_t_df_tiles.borrow(b.work_arena.take<uint32_t>(T), T);
   b.d_t_df_tile_off.borrow(b.work_arena.take<uint64_t>(T + 1), T + 1);
-  b.d_t_df.borrow(b.work_arena.take<uint64_t>(T), T);
+  // [per-term df | per-key posting sizes in upload order]: ONE array, so the sharded pipeline sums both in one exchange
+  uint64_t* xchg = b.work_arena.take<uint64_t>(T + K);
+  b.d_t_df.borrow(xchg, T);
+  b.d_key_glen.borrow(xchg + T, K);
   b.d_q_list.borrow(b.work_arena.take<uint32_t>(Lc), Lc);
   b.d_q_list_len.borrow(b.work_arena.take<uint32_t>(Lc), Lc);
   b.d_q_nlists.borrow(b.work_arena.take<uint32_t>(Q), Q);
@@ -4161,7 +4229,7 @@ void batch_plan(Batch& b) {
   b.time_begin(0);
   if (b.n_keys > 0) {
     lookup_kernel<<<grid_for(b.n_keys, 256), 256, 0, st>>>(ix.d_term_keys.p, ix.d_term_off.p, ix.n_terms, b.d_keys.p,
-                                                          b.n_keys, b.d_key_list.p, b.d_key_len.p);
+                                                          b.n_keys, b.d_key_list.p, b.d_key_len.p, b.d_key_glen.p);
     MGX_LAUNCH_CHECK();
   }
   BatchView bv = make_batch_view(b);
@@ -4284,6 +4352,15 @@ std::vector<Chunk> make_chunks(const Batch& b, uint64_t max_records, uint32_t re
 void prepare_scoring(Batch& b, const uint64_t* d_df_slots) {
   cudaStream_t st = b.stream;
   if (b.params.compute_score == 0) {
+    return;
+  }
+  if (b.global_order) {
+    // sharded pipeline: t_df and key_glen hold the sums over all shards
+    const uint64_t docs = b.params.total_docs != 0 ? b.params.total_docs : b.ix->doc_count;
+    if (b.n_queries > 0) {
+      global_order_kernel<<<grid_for(b.n_queries, 128), 128, 0, st>>>(make_batch_view(b), docs, b.d_q_idf.p);
+      MGX_LAUNCH_CHECK();
+    }
     return;
   }
   if (d_df_slots != nullptr && b.n_slots > 0) {

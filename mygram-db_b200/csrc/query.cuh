@@ -209,11 +209,14 @@ struct Batch {
   DevBuf<uint32_t> d_t_df_tiles;  // [T]
   DevBuf<uint64_t> d_t_df_tile_off;  // [T+1]
   DevBuf<uint64_t> d_t_df;        // [T]
+  DevBuf<uint64_t> d_key_glen;    // [K] posting size per key in upload order; directly behind d_t_df (one exchange)
+  bool global_order = false;      // sharded pipeline: order terms / compute IDFs from the exchanged global values
   DevBuf<uint32_t> d_slot_tid;    // [S]
 
   // ---- device: queries
   DevBuf<uint32_t> d_q_toff;      // [Q+1] search terms
   DevBuf<uint32_t> d_q_tids;      // [sum] unique term ids, re-ordered by estimated size by the planner
+  DevBuf<uint32_t> d_q_tids0;     // [sum] the same in query order, never modified
   DevBuf<uint32_t> d_q_noff;      // [Q+1] NOT terms
   DevBuf<uint32_t> d_q_ntids;
   DevBuf<uint32_t> d_q_loff;      // [Q+1] capacity ranges for the merged list table

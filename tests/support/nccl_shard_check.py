@@ -110,6 +110,27 @@ def main():
                 if not ok:
                     print(f"round {round_} batch {i}: sharded answer differs from the single-shard answer", flush=True)
                     failures += 1
+                    if failures <= 3:
+                        cu, tu, iu = count.view(np.uint32), total.view(np.uint64), ids.view(np.uint32)
+                        for q in range(args.batch):
+                            n = int(w.count[q])
+                            bad = []
+                            if int(cu[q]) != n:
+                                bad.append(f"count {int(cu[q])} vs {n}")
+                            if int(tu[q]) != int(w.total[q]):
+                                bad.append(f"total {int(tu[q])} vs {int(w.total[q])}")
+                            m = min(n, int(cu[q]))
+                            if not np.array_equal(iu[q, :m], w.ids[q, :m]):
+                                k = int(np.nonzero(iu[q, :m] != w.ids[q, :m])[0][0])
+                                bad.append(f"ids differ from rank {k}: {iu[q, k:k + 4]} vs {w.ids[q, k:k + 4]}; scores "
+                                           f"{scores[q, k:k + 4]} vs {w.scores[q, k:k + 4]}")
+                            elif scored and not np.array_equal(scores[q, :m].view(np.uint64), w.scores[q, :m].view(np.uint64)):
+                                k = int(np.nonzero(scores[q, :m] != w.scores[q, :m])[0][0])
+                                bad.append(f"scores differ at rank {k}: {scores[q, k]!r} vs {w.scores[q, k]!r} "
+                                           f"(rel {abs(scores[q, k] - w.scores[q, k]) / max(abs(w.scores[q, k]), 1e-300):.3e})")
+                            if bad:
+                                print(f"  query {q} {qs[q]}: " + "; ".join(bad), flush=True)
+                                break
     if rank == 0 and scored:
         import pyoracle
         oi = pyoracle.OracleLib(pyoracle.PORT_LIB).index(2, 0, True)
