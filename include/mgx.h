@@ -99,12 +99,22 @@ int mgx_index_build_device(mgx_index_t* index, const uint32_t* d_doc_ids, const 
  * matching DocumentStore calls: the document of `doc_id` (text + postings) is added, replaced or removed. The
  * calls are journaled on the host and take effect before the NEXT read of the index (any search / stats / export
  * call, or mgx_index_commit): the resident corpus is merged with the journal on the device and the shard is
- * rebuilt (~0.1 s per 10M documents), so a burst of mutations costs one rebuild. `old_text` / `text` of update /
+ * rebuilt (~0.1 s per 10M documents), so a burst of mutations costs one rebuild. If that commit fails (device out of
+ * memory, more than 2^32 n-gram occurrences) the reading call returns the error, the shard is EMPTY and the journal
+ * is discarded: rebuild from the DocumentStore with mgx_index_build. `old_text` / `text` of update /
  * remove must be the text the document currently has (what the reference requires to find its n-grams); the
  * resident copy is what is actually used. *out_indexed (may be NULL) = AddDocument's return value: 0 when the text
  * yields no n-gram (the document is stored but never matches). */
 int mgx_index_add_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* text, uint64_t text_len,
                            int32_t* out_indexed);
+/* Index::AddDocumentBatch (index.cpp:76-119) as InitialLoader::FlushBatch calls it for every 1000 documents
+ * (loader/initial_loader.cpp:450-512): ADDITIVE, ids in any order, the index keeps what it has. The batch is appended to
+ * the same journal as the single-document calls (three memcpys) and folded in before the next read -- a loader's ten
+ * thousand batches cost ONE merge + build at the first search. *out_indexed (may be NULL) = documents whose text yields
+ * at least one n-gram (the reference skips the others silently, :93-101; here they are stored and never match).
+ * When the whole snapshot is at hand, mgx_index_build is the direct (and faster) form of the same thing. */
+int mgx_index_add_document_batch(mgx_index_t* index, const uint32_t* doc_ids, const uint8_t* text,
+                                 const uint64_t* text_offsets, uint64_t n_docs, uint64_t* out_indexed);
 int mgx_index_update_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* old_text, uint64_t old_len,
                               const uint8_t* new_text, uint64_t new_len);
 int mgx_index_remove_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* text, uint64_t text_len);
@@ -305,8 +315,12 @@ int mgx_query_batch(mgx_index_t* index, const mgx_query_params_t* params, uint64
  * 9 uint64, 10 TIME seconds, 11 string, 12 double); values[i] belongs to the i-th document of the last build
  * (integer / bool / seconds value, the bits of the double, or for strings an index into the string table
  * str_bytes / str_offsets[n_strings + 1]); nulls[i] != 0 marks NULL (may be NULL = no NULLs). `column` is a
- * caller-chosen id < 64 (the host keeps DocumentStore::ResolveFilterColumnName). Columns are dropped by any
- * rebuild of the shard (bulk build, committed mutations) and have to be set again. */
+ * caller-chosen id < 64 (the host keeps DocumentStore::ResolveFilterColumnName). Columns follow the documents
+ * through committed mutations (add / update / remove): a surviving document keeps its values, a document the journal
+ * added or replaced is NULL in every column until the column is set again (the reference's FilterIndex is fed by the
+ * same DocumentStore calls, storage/filter_index.h:38-123). A bulk build (mgx_index_build*, mgx_index_clear) starts
+ * a new corpus and drops them. A filter that names a column the index does not hold: only != holds
+ * (no stored value, as for a document the reference has no value for). */
 int mgx_index_set_filter_column(mgx_index_t* index, uint32_t column, int32_t type, const uint64_t* values,
                                 const uint8_t* nulls, uint64_t n_docs, const uint8_t* str_bytes,
                                 const uint64_t* str_offsets, uint64_t n_strings);

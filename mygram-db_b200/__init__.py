@@ -140,6 +140,7 @@ def lib():
     L.mgx_index_clear.argtypes = [C.c_void_p]
     L.mgx_index_add_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64, C.POINTER(C.c_int32)]
     L.mgx_index_update_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64, u8p, C.c_uint64]
+    L.mgx_index_add_document_batch.argtypes = [C.c_void_p, u32p, u8p, u64p, C.c_uint64, u64p]
     L.mgx_index_remove_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64]
     L.mgx_index_commit.argtypes = [C.c_void_p]
     L.mgx_index_posting_size.argtypes = [C.c_void_p, u8p, C.c_uint64, u64p]
@@ -350,9 +351,16 @@ class Index:
 
     # -- build -------------------------------------------------------------------------------------
     def add_document_batch(self, doc_ids, texts):
-        """Index::AddDocumentBatch (index.cpp:76-119) for a whole shard: replaces the index content."""
+        """Index::AddDocumentBatch (index.cpp:76-119): ADDITIVE, ids in any order; returns the number of documents
+        whose text yields at least one n-gram. Journaled; folded in before the next read."""
         arena, offsets = pack_strings(texts)
-        self.build(np.asarray(doc_ids, dtype=np.uint32), arena, offsets)
+        ids = np.ascontiguousarray(doc_ids, dtype=np.uint32)
+        if ids.size == 0:
+            ids = np.zeros(1, dtype=np.uint32)
+        n = C.c_uint64(0)
+        _check(lib().mgx_index_add_document_batch(self._h, _ptr(ids, u32p), _ptr(arena, u8p), _ptr(offsets, u64p),
+                                                  len(texts), C.byref(n)))
+        return int(n.value)
 
     @staticmethod
     def _text_arg(text):

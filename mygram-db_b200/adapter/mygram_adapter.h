@@ -90,9 +90,23 @@ class Index {
   Index(const Index&) = delete;
   Index& operator=(const Index&) = delete;
 
-  // Bulk (re)build of the shard from normalised texts; doc ids strictly ascending (the DocumentStore assigns
-  // them sequentially, document_store.h:520). Replaces the batches of InitialLoader::FlushBatch.
+  // Index::AddDocumentBatch (index.h:75-100, index.cpp:76-119): ADDITIVE, ids in any order, exactly as
+  // InitialLoader::FlushBatch calls it for every 1000 documents (initial_loader.cpp:450-512). The batch is journaled and
+  // folded in (one device merge + build) before the next read.
   void AddDocumentBatch(const std::vector<DocumentItem>& documents) {
+    detail::Flat flat;
+    std::vector<DocId> ids;
+    ids.reserve(documents.size());
+    for (const auto& d : documents) {
+      ids.push_back(d.doc_id);
+      flat.add(d.text);
+    }
+    detail::check(mgx_index_add_document_batch(handle_, ids.data(), flat.data(), flat.offsets.data(), documents.size(),
+                                               nullptr));
+  }
+  // Not in the reference: the whole snapshot at once (ids strictly ascending), replacing any previous content -- the
+  // direct form for a loader that has collected the snapshot anyway (no journal, no merge).
+  void BuildFromSnapshot(const std::vector<DocumentItem>& documents) {
     detail::Flat flat;
     std::vector<DocId> ids;
     ids.reserve(documents.size());

@@ -14,7 +14,6 @@
 #include <nccl.h>
 #include <cstdlib>
 #include <cstring>
-#include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -675,6 +674,141 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
   return MGX_OK;
 }
 
+// Driver expansion of OR-rooted boolean programs. A program whose root is an OR has no term every result must
+// satisfy, so the tile kernel would evaluate it on EVERY document of the shard (~6 ms per query at 10M documents).
+// When every child of the root can drive (a TERM with n-grams, or an AND that holds one), the query becomes one
+// internal query per child: child_i AND NOT child_1 ... AND NOT child_{i-1} -- each driven by child_i's shortest
+// list, pairwise disjoint by construction, folded back on the device (fold_expanded_kernel). `xoff` stays empty when
+// no query of the batch qualifies.
+bool expand_or_roots(const std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
+                     std::vector<HostQuery>* expanded, std::vector<uint32_t>* xoff) {
+  constexpr size_t kMaxChildren = 16;
+  struct Plan {
+    std::vector<std::pair<size_t, size_t>> child;  // op ranges [begin, end) of the root's children
+    std::vector<std::vector<uint32_t>> conj;       // terms every result of a child satisfies
+  };
+  auto analyse = [&](const HostQuery& hq, Plan* plan) {
+    const size_t n = hq.prog_ops.size();
+    if ((hq.flags & kQProgram) == 0 || n < 3 || !hq.conjuncts.empty() || hq.prog_ops[n - 1] != kOpOr) {
+      return false;
+    }
+    // subtree of op i = ops [start[i], i]; children of an n-ary op are the subtrees that end right before it
+    std::vector<size_t> start(n, 0);
+    std::vector<size_t> stack;
+    size_t depth_max = 0;
+    for (size_t i = 0; i < n; ++i) {
+      const uint8_t op = hq.prog_ops[i];
+      size_t kids = 0;
+      if (op == kOpAnd || op == kOpOr) {
+        kids = hq.prog_args[i];
+      } else if (op == kOpAtLeast) {
+        kids = hq.prog_args[i] & 0xFFFFu;
+      } else if (op == kOpNot) {
+        kids = 1;
+      }
+      if (kids > stack.size()) {
+        return false;
+      }
+      start[i] = kids == 0 ? i : start[stack[stack.size() - kids]];
+      stack.resize(stack.size() - kids);
+      stack.push_back(i);
+      depth_max = std::max(depth_max, stack.size());
+    }
+    if (stack.size() != 1) {
+      return false;
+    }
+    const size_t k = hq.prog_args[n - 1];
+    if (k < 2 || k > kMaxChildren || depth_max + k + 1 > kMaxProgramDepth) {
+      return false;
+    }
+    size_t end = n - 1;  // children, right to left
+    std::vector<std::pair<size_t, size_t>> rev;
+    for (size_t c = 0; c < k; ++c) {
+      if (end == 0) {
+        return false;
+      }
+      const size_t root = end - 1;
+      rev.emplace_back(start[root], root + 1);
+      end = start[root];
+    }
+    plan->child.assign(rev.rbegin(), rev.rend());
+    for (const auto& [b0, e0] : plan->child) {
+      // conjunct terms of the child: itself when it is a TERM, the TERM operands of (nested) ANDs otherwise
+      std::vector<uint32_t> conj;
+      std::vector<size_t> todo{e0 - 1};
+      while (!todo.empty()) {
+        const size_t i = todo.back();
+        todo.pop_back();
+        const uint8_t op = hq.prog_ops[i];
+        if (op == kOpTerm) {
+          conj.push_back(hq.prog_args[i]);
+        } else if (op == kOpAnd) {
+          size_t e = i;
+          for (uint32_t c = 0; c < hq.prog_args[i]; ++c) {
+            todo.push_back(e - 1);
+            e = start[e - 1];
+          }
+        }
+      }
+      bool drives = false;
+      for (uint32_t tid : conj) {
+        drives = drives || !terms[tid].keys.empty();
+      }
+      if (!drives) {
+        return false;  // a child that is a text scan (or an OR / NOT itself) needs every document anyway
+      }
+      plan->conj.push_back(std::move(conj));
+    }
+    return true;
+  };
+  std::vector<Plan> plans(queries.size());
+  std::vector<uint8_t> take(queries.size(), 0);
+  bool any = false;
+  for (size_t q = 0; q < queries.size(); ++q) {
+    take[q] = analyse(queries[q], &plans[q]) ? 1 : 0;
+    any = any || take[q] != 0;
+  }
+  if (!any) {
+    return false;
+  }
+  expanded->clear();
+  xoff->assign(1, 0);
+  for (size_t q = 0; q < queries.size(); ++q) {
+    const HostQuery& hq = queries[q];
+    if (take[q] == 0) {
+      expanded->push_back(hq);
+    } else {
+      const Plan& plan = plans[q];
+      for (size_t i = 0; i < plan.child.size(); ++i) {
+        HostQuery sub;
+        sub.flags = hq.flags;
+        sub.threshold = hq.threshold;
+        sub.filters = hq.filters;
+        sub.conjuncts = plan.conj[i];
+        auto append = [&](const std::pair<size_t, size_t>& r) {
+          sub.prog_ops.insert(sub.prog_ops.end(), hq.prog_ops.begin() + static_cast<ptrdiff_t>(r.first),
+                              hq.prog_ops.begin() + static_cast<ptrdiff_t>(r.second));
+          sub.prog_args.insert(sub.prog_args.end(), hq.prog_args.begin() + static_cast<ptrdiff_t>(r.first),
+                               hq.prog_args.begin() + static_cast<ptrdiff_t>(r.second));
+        };
+        append(plan.child[i]);
+        for (size_t j = 0; j < i; ++j) {
+          append(plan.child[j]);
+          sub.prog_ops.push_back(kOpNot);
+          sub.prog_args.push_back(0);
+        }
+        if (i > 0) {
+          sub.prog_ops.push_back(kOpAnd);
+          sub.prog_args.push_back(static_cast<uint32_t>(i + 1));
+        }
+        expanded->push_back(std::move(sub));
+      }
+    }
+    xoff->push_back(static_cast<uint32_t>(expanded->size()));
+  }
+  return true;
+}
+
 int check_params(const mgx_query_params_t& p) {
   if (p.compute_score != 0) {
     if (p.limit == 0 || static_cast<uint64_t>(p.limit) + p.offset > kMaxTopK) {
@@ -738,9 +872,36 @@ struct mgx_index {
   bool lane_busy[kMaxLanes] = {false};
   int n_lanes = 0;
   std::mutex stats_mu;  // ix.last_stats
-  // Journal of Index::AddDocument / UpdateDocument / RemoveDocument calls not folded in yet: doc id -> (removed, text).
-  // The last call for an id wins; the next read applies the whole journal (apply_journal_device).
-  std::map<uint32_t, std::pair<bool, std::string>> journal;
+  // Journal of Index::AddDocument / AddDocumentBatch / UpdateDocument / RemoveDocument calls not folded in yet: an
+  // append-only log in arrival order (ids, removed flags, text ranges in one arena -- a 1000-document loader batch is
+  // three memcpys, not a thousand map nodes). The last call for an id wins; the next read applies the whole journal
+  // (apply_journal_device).
+  struct Journal {
+    std::vector<uint32_t> ids;
+    std::vector<uint8_t> removed;
+    std::vector<uint64_t> off = std::vector<uint64_t>(1, 0);
+    std::vector<uint8_t> text;
+    bool ascending = true;  // ids strictly ascending in arrival order: neither a sort nor a de-duplication is needed
+    bool empty() const { return ids.empty(); }
+    void put(uint32_t id, bool rem, const uint8_t* t, uint64_t len) {
+      if (!ids.empty() && id <= ids.back()) {
+        ascending = false;
+      }
+      ids.push_back(id);
+      removed.push_back(rem ? 1 : 0);
+      if (!rem && len > 0) {
+        text.insert(text.end(), t, t + len);
+      }
+      off.push_back(text.size());
+    }
+    void clear() {
+      ids.clear();
+      removed.clear();
+      off.assign(1, 0);
+      text.clear();
+      ascending = true;
+    }
+  } journal;
   std::mutex journal_mu;
   std::atomic<bool> dirty{false};
 };
@@ -822,22 +983,50 @@ int commit_pending(mgx_index_t* index) {
     WriteGuard lock(index);
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
+    mgx_index::Journal& j = index->journal;
+    // A failed commit leaves the shard EMPTY (build_index_device resets it rather than keep half-built arrays) and the
+    // journal is discarded either way: retrying the same journal on every later read would fail the same way. The
+    // caller learns it from this call's status and rebuilds from its DocumentStore (mgx_index_build).
+    struct Discard {
+      mgx_index* h;
+      ~Discard() {
+        h->journal.clear();
+        h->dirty.store(false, std::memory_order_release);
+      }
+    } discard{index};
+    j.text.push_back(0);
+    if (j.ascending) {
+      apply_journal_device(ix, j.ids.data(), j.removed.data(), j.text.data(), j.off.data(), j.ids.size(), ix.stream);
+      return MGX_OK;
+    }
+    // arrival order -> ascending ids, the LAST entry of an id wins (stable sort keeps arrival order among equals)
+    const size_t n = j.ids.size();
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; ++i) {
+      order[i] = static_cast<uint32_t>(i);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return j.ids[a] < j.ids[b]; });
     std::vector<uint32_t> ids;
     std::vector<uint8_t> removed;
     std::vector<uint8_t> text;
     std::vector<uint64_t> off(1, 0);
-    for (const auto& kv : index->journal) {  // std::map: ascending ids
-      ids.push_back(kv.first);
-      removed.push_back(kv.second.first ? 1 : 0);
-      if (!kv.second.first) {
-        text.insert(text.end(), kv.second.second.begin(), kv.second.second.end());
+    ids.reserve(n);
+    removed.reserve(n);
+    off.reserve(n + 1);
+    text.reserve(j.text.size());
+    for (size_t k = 0; k < n; ++k) {
+      if (k + 1 < n && j.ids[order[k + 1]] == j.ids[order[k]]) {
+        continue;  // superseded by a later call for the same id
       }
+      const uint32_t e = order[k];
+      ids.push_back(j.ids[e]);
+      removed.push_back(j.removed[e]);
+      text.insert(text.end(), j.text.begin() + static_cast<ptrdiff_t>(j.off[e]),
+                  j.text.begin() + static_cast<ptrdiff_t>(j.off[e + 1]));
       off.push_back(text.size());
     }
     text.push_back(0);
     apply_journal_device(ix, ids.data(), removed.data(), text.data(), off.data(), ids.size(), ix.stream);
-    index->journal.clear();
-    index->dirty.store(false, std::memory_order_release);
     return MGX_OK;
   });
 }
@@ -850,7 +1039,7 @@ int journal_put(mgx_index_t* index, uint32_t doc_id, bool removed, const uint8_t
     return rc;
   }
   std::lock_guard<std::mutex> jl(index->journal_mu);
-  index->journal[doc_id] = {removed, removed ? std::string() : std::string(reinterpret_cast<const char*>(text), len)};
+  index->journal.put(doc_id, removed, text, len);
   index->dirty.store(true, std::memory_order_release);
   return MGX_OK;
 }
@@ -956,6 +1145,11 @@ static int build_common(mgx_index_t* index, const uint32_t* doc_ids, const uint8
           return invalid("doc_ids must be strictly ascending");
         }
       }
+      for (uint64_t i = 0; i < n_docs; ++i) {
+        if (text_offsets[i + 1] < text_offsets[i]) {
+          return invalid("text_offsets must be non-decreasing");
+        }
+      }
     }
     if (first_off != 0) {
       return invalid("text_offsets[0] must be 0");
@@ -985,6 +1179,43 @@ int mgx_index_add_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* t
     *out_indexed = keys.empty() ? 0 : 1;
   }
   return journal_put(index, doc_id, false, text, text_len);
+}
+
+int mgx_index_add_document_batch(mgx_index_t* index, const uint32_t* doc_ids, const uint8_t* text,
+                                 const uint64_t* text_offsets, uint64_t n_docs, uint64_t* out_indexed) {
+  if (index == nullptr || (n_docs > 0 && (doc_ids == nullptr || text_offsets == nullptr))) {
+    return invalid("null argument");
+  }
+  if (int rc = require_device(); rc != MGX_OK) {
+    return rc;
+  }
+  for (uint64_t i = 0; i < n_docs; ++i) {
+    if (text_offsets[i + 1] < text_offsets[i] || (text_offsets[i + 1] > text_offsets[i] && text == nullptr)) {
+      return invalid("text_offsets must be non-decreasing (and text non-null)");
+    }
+  }
+  uint64_t indexed = 0;
+  if (out_indexed != nullptr) {
+    // Index::AddDocumentBatch silently skips a document whose text yields no n-gram (index.cpp:93-101); the count of
+    // the others is what a caller can compare with the reference's log line
+    for (uint64_t i = 0; i < n_docs; ++i) {
+      KeyVec keys;
+      host_query_keys(text + text_offsets[i], text_offsets[i + 1] - text_offsets[i], index->ix.ngram, index->ix.kanji,
+                      index->ix.cross, index->ix.width, &keys);
+      indexed += keys.empty() ? 0 : 1;
+    }
+    *out_indexed = indexed;
+  }
+  std::lock_guard<std::mutex> jl(index->journal_mu);
+  mgx_index::Journal& j = index->journal;
+  j.ids.reserve(j.ids.size() + n_docs);
+  for (uint64_t i = 0; i < n_docs; ++i) {
+    j.put(doc_ids[i], false, text + text_offsets[i], text_offsets[i + 1] - text_offsets[i]);
+  }
+  if (n_docs > 0) {
+    index->dirty.store(true, std::memory_order_release);
+  }
+  return MGX_OK;
 }
 
 int mgx_index_update_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* old_text, uint64_t old_len,
@@ -2178,7 +2409,15 @@ int prepare_unlocked(mgx_index_t* index, const mgx_query_params_t* params, uint6
     return rc;
   }
   const auto t1 = std::chrono::steady_clock::now();
-  batch_upload(b, terms, queries, slot_tid);
+  std::vector<HostQuery> expanded;
+  std::vector<uint32_t> xoff;
+  const bool no_expand = std::getenv("MGX_NO_OR_EXPANSION") != nullptr;  // read per batch: the tests flip it
+  if (ext != nullptr && ext->q_prog_begin != nullptr && params->compute_score == 0 && !no_expand &&
+      expand_or_roots(terms, queries, &expanded, &xoff)) {
+    batch_upload(b, terms, expanded, slot_tid, &xoff);
+  } else {
+    batch_upload(b, terms, queries, slot_tid);
+  }
   if (trace) {
     const auto t2 = std::chrono::steady_clock::now();
     fprintf(stderr, "[mgx batch] compile %.3f ms, stage+upload %.3f ms (%zu unique terms)\n",
@@ -2434,7 +2673,7 @@ int mgx_batch_search_packed_device(mgx_batch_t* batch, const uint64_t* d_df, uin
     return invalid("null argument");
   }
   mgx_shard_record_layout_t lay;
-  mgx_shard_record_layout(batch->b.n_queries, stride, &lay);
+  mgx_shard_record_layout(batch->b.n_out_queries, stride, &lay);
   uint8_t* base = static_cast<uint8_t*>(d_record);
   const int rc = mgx_batch_search_device(batch, d_df, stride, reinterpret_cast<uint32_t*>(base + lay.ids_offset),
                                          reinterpret_cast<double*>(base + lay.scores_offset),
@@ -2792,7 +3031,7 @@ void sharded_enqueue(mgx_shard_comm_t* comm, int lane, Batch& b, uint64_t stride
   const int rank = comm != nullptr ? comm->rank : 0;
   cudaStream_t st = b.stream;
   mgx_shard_record_layout_t lay;
-  mgx_shard_record_layout(b.n_queries, stride, &lay);
+  mgx_shard_record_layout(b.n_out_queries, stride, &lay);
   b.o_merged.reserve(lay.bytes);
   if (G > 1) {
     b.o_gather.reserve(lay.bytes * static_cast<uint64_t>(G));
@@ -2859,7 +3098,7 @@ void sharded_enqueue(mgx_shard_comm_t* comm, int lane, Batch& b, uint64_t stride
     MGX_CUDA(cudaStreamWaitEvent(st, batch_event(b, 3), 0));
     const uint8_t* in = b.o_gather.p;
     uint8_t* out = b.o_merged.p;
-    launch_merge_topk(st, b.params, static_cast<uint32_t>(G), b.n_queries, stride,
+    launch_merge_topk(st, b.params, static_cast<uint32_t>(G), b.n_out_queries, stride,
                       reinterpret_cast<const uint32_t*>(in + lay.ids_offset),
                       reinterpret_cast<const double*>(in + lay.scores_offset),
                       reinterpret_cast<const uint32_t*>(in + lay.count_offset),

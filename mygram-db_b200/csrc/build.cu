@@ -866,10 +866,52 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   PhaseTrace trace(stream);
   uint32_t first_id = 1;
   bool sequential_ids = true;
-  cudaEvent_t ev0;
-  cudaEvent_t ev1;
-  MGX_CUDA(cudaEventCreate(&ev0));
-  MGX_CUDA(cudaEventCreate(&ev1));
+  struct Events {
+    cudaEvent_t a = nullptr;
+    cudaEvent_t b = nullptr;
+    ~Events() {
+      if (a != nullptr) {
+        cudaEventDestroy(a);
+      }
+      if (b != nullptr) {
+        cudaEventDestroy(b);
+      }
+    }
+  } events;
+  MGX_CUDA(cudaEventCreate(&events.a));
+  MGX_CUDA(cudaEventCreate(&events.b));
+  cudaEvent_t ev0 = events.a;
+  cudaEvent_t ev1 = events.b;
+  // The arrays of the previous index are released below, before the first step that can fail (bad ids, too many
+  // n-gram occurrences, a CUDA error): whatever fails, the handle must not keep the OLD sizes next to released or
+  // half-written arrays. A failed build therefore leaves an EMPTY index (every query answers empty, the next build
+  // starts clean); the caller gets the error.
+  struct ResetOnFailure {
+    Index& ix;
+    bool armed = true;
+    ~ResetOnFailure() {
+      if (!armed) {
+        return;
+      }
+      ix.n_docs = ix.text_bytes = ix.n_text_tiles = 0;
+      ix.n_terms = ix.n_postings = ix.n_dense = ix.bm_words = 0;
+      ix.doc_count = ix.total_doc_length = ix.n_pair_slots = 0;
+      ix.has_positions = false;
+      ix.sequential_ids = true;
+      ix.first_id = 1;
+      ix.d_doc_ids.release();
+      ix.d_text.release();
+      ix.d_text_off.release();
+      ix.d_doc_len.release();
+      ix.d_tile_first_doc.release();
+      ix.d_term_keys.release();
+      ix.d_term_off.release();
+      ix.d_postings.release();
+      ix.d_post_pos.release();
+      ix.d_post_pos2.release();
+      ix.d_term_bm.release();
+    }
+  } reset_on_failure{ix};
 
   // ---- resident arena A: the device mirror of DocumentStore's normalised text + ids + lengths.
   // The text arena is padded so 16-byte tile loads never leave the allocation.
@@ -1056,8 +1098,7 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   float ms = 0.f;
   MGX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
   ix.last_build_ms = ms;
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
+  reset_on_failure.armed = false;
 }
 
 // ------------------------------------------------------------------ reference-style representation counters
@@ -1170,6 +1211,20 @@ __global__ void journal_place_new_kernel(const uint32_t* __restrict__ j_ids, con
   src[dest] = static_cast<uint32_t>(j) | 0x80000000u;
 }
 
+// filter columns follow the documents: a surviving document keeps its row, a document from the journal is NULL
+__global__ void journal_remap_column_kernel(const uint32_t* __restrict__ src, uint64_t n_new,
+                                            const uint64_t* __restrict__ old_values, const uint8_t* __restrict__ old_nulls,
+                                            uint64_t* __restrict__ new_values, uint8_t* __restrict__ new_nulls) {
+  const uint64_t d = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (d >= n_new) {
+    return;
+  }
+  const uint32_t s = src[d];
+  const bool from_journal = (s & 0x80000000u) != 0;
+  new_values[d] = from_journal ? 0ULL : old_values[s];
+  new_nulls[d] = from_journal ? static_cast<uint8_t>(1) : old_nulls[s];
+}
+
 // one warp per merged document: bytes from the resident arena or from the journal arena
 __global__ void __launch_bounds__(256) journal_copy_kernel(const uint32_t* __restrict__ src, uint64_t n_new,
                                                            const uint64_t* __restrict__ new_off,
@@ -1253,8 +1308,38 @@ void apply_journal_device(Index& ix, const uint32_t* h_ids, const uint8_t* h_rem
         d_src.p, n_new, d_new_off.p, ix.d_text.p, ix.d_text_off.p, d_jtext.p, d_joff.p, d_new_text.p);
     MGX_LAUNCH_CHECK();
   }
+  // the device mirror of the filter columns (mgx_index_set_filter_column) follows the documents through the rebuild
+  std::vector<FilterColumn*> carried(kMaxFilterColumns, nullptr);
+  for (uint32_t c = 0; c < kMaxFilterColumns; ++c) {
+    FilterColumn* old_col = ix.columns[c];
+    if (old_col == nullptr || old_col->n_docs != n_old) {
+      continue;
+    }
+    FilterColumn* col = new FilterColumn();
+    carried[c] = col;
+    col->cls = old_col->cls;
+    col->n_docs = n_new;
+    col->dict = old_col->dict;
+    col->values.alloc(n_new);
+    col->nulls.alloc(n_new);
+    if (n_new > 0) {
+      journal_remap_column_kernel<<<static_cast<unsigned>((n_new + 255) / 256), 256, 0, stream>>>(
+          d_src.p, n_new, old_col->values.p, old_col->nulls.p, col->values.p, col->nulls.p);
+      MGX_LAUNCH_CHECK();
+    }
+  }
   MGX_CUDA(cudaStreamSynchronize(stream));
-  build_index_device(ix, d_new_ids.p, d_new_text.p, d_new_off.p, n_new, new_bytes, stream);
+  try {
+    build_index_device(ix, d_new_ids.p, d_new_text.p, d_new_off.p, n_new, new_bytes, stream);  // drops the old columns
+  } catch (...) {
+    for (FilterColumn* c : carried) {
+      delete c;
+    }
+    throw;
+  }
+  for (uint32_t c = 0; c < kMaxFilterColumns; ++c) {
+    ix.columns[c] = carried[c];
+  }
 }
 
 }  // namespace mgx

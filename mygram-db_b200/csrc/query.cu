@@ -3788,13 +3788,19 @@ void build_stream_table(std::vector<HostTerm>& terms, HostStreamTable* out) {
 }
 
 void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
-                  const std::vector<uint32_t>& slot_tid) {
+                  const std::vector<uint32_t>& slot_tid, const std::vector<uint32_t>* xoff) {
   cudaStream_t st = b.stream;
   HostStreamTable& stream_table = b.h_stream_table;
   build_stream_table(terms, &stream_table);
   const size_t T = terms.size();
   const size_t Q = queries.size();
   b.n_queries = static_cast<uint32_t>(Q);
+  b.n_out_queries = b.n_queries;
+  b.h_xoff.clear();
+  if (xoff != nullptr && !xoff->empty()) {
+    b.h_xoff = *xoff;
+    b.n_out_queries = static_cast<uint32_t>(xoff->size() - 1);
+  }
   b.n_terms = static_cast<uint32_t>(T);
   b.n_slots = static_cast<uint32_t>(slot_tid.size());
   b.h_slot_tid = slot_tid;
@@ -3847,6 +3853,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   const size_t i_sslots = add(stream_table.slots.size() * 4);
   const size_t i_sentries = add(stream_table.entries.size() * sizeof(StreamEntry));
   const size_t i_sbloom = add(stream_table.bloom.size() * 4);
+  const size_t i_xoff = add(b.h_xoff.size() * 4);
   b.n_stream_slots = static_cast<uint32_t>(stream_table.slots.size());
   b.n_stream_terms = static_cast<uint32_t>(stream_table.entries.size());
   b.stream_len8_mask = stream_table.len8_mask;
@@ -3944,6 +3951,9 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   if (!slot_tid.empty()) {
     std::memcpy(S + i_slot, slot_tid.data(), slot_tid.size() * 4);
   }
+  if (!b.h_xoff.empty()) {
+    std::memcpy(S + i_xoff, b.h_xoff.data(), b.h_xoff.size() * 4);
+  }
   if (!stream_table.slots.empty()) {
     std::memcpy(S + i_sslots, stream_table.slots.data(), stream_table.slots.size() * 4);
     std::memcpy(S + i_sentries, stream_table.entries.data(), stream_table.entries.size() * sizeof(StreamEntry));
@@ -3979,6 +3989,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   b.d_stream_slots.borrow(reinterpret_cast<uint32_t*>(at(i_sslots)), stream_table.slots.size());
   b.d_stream_entries.borrow(reinterpret_cast<StreamEntry*>(at(i_sentries)), stream_table.entries.size());
   b.d_stream_bloom.borrow(reinterpret_cast<uint32_t*>(at(i_sbloom)), stream_table.bloom.size());
+  b.d_xoff.borrow(reinterpret_cast<uint32_t*>(at(i_xoff)), b.h_xoff.size());
 
   // ---- device-only planning arrays from the work arena
   const size_t K = n_keys;
@@ -4434,6 +4445,12 @@ void run_tiles(Batch& b, const Chunk& c, const ScoreParams& sp, uint32_t prune_k
 
 }  // namespace
 
+__global__ void fold_expanded_kernel(const uint32_t* __restrict__ xoff, uint32_t n_out, uint64_t x_stride,
+                                     const uint32_t* __restrict__ x_ids, const uint32_t* __restrict__ x_count,
+                                     const uint64_t* __restrict__ x_total, uint32_t limit, uint32_t offset,
+                                     uint64_t stride, uint32_t* __restrict__ out_ids, uint32_t* __restrict__ out_count,
+                                     uint64_t* __restrict__ out_total);
+
 void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_t* d_ids, double* d_scores,
                   uint32_t* d_count, uint64_t* d_total) {
   cudaStream_t st = b.stream;
@@ -4442,6 +4459,45 @@ void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_
   }
   prepare_scoring(b, d_df_slots);
   const ScoreParams sp = score_params(b);
+  // Expanded OR-rooted programs: the internal queries answer into the batch's own buffers with room for
+  // offset + limit ids each, and fold_expanded_kernel (at the end) writes the caller's rows.
+  const bool expanded = !b.h_xoff.empty();
+  struct Fold {
+    Batch& b;
+    bool on;
+    mgx_query_params_t user_params;
+    uint64_t stride;
+    uint32_t* d_ids;
+    uint32_t* d_count;
+    uint64_t* d_total;
+    uint64_t x_stride;
+    void run() {
+      if (!on) {
+        return;
+      }
+      fold_expanded_kernel<<<grid_for(static_cast<uint64_t>(b.n_out_queries) * 32, 256), 256, 0, b.stream>>>(
+          b.d_xoff.p, b.n_out_queries, x_stride, b.x_ids.p, b.x_count.p, b.x_total.p, user_params.limit,
+          user_params.offset, stride, d_ids, d_count, d_total);
+      MGX_LAUNCH_CHECK();
+      b.params = user_params;
+    }
+  } fold{b, expanded, b.params, stride, d_ids, d_count, d_total, 0};
+  if (expanded) {
+    if (sp.compute_score != 0) {
+      set_last_error("internal: expanded programs are unscored");
+      throw CudaFailure{MGX_ERR_INVALID_ARGUMENT};
+    }
+    fold.x_stride = (b.params.limit != 0 ? std::min<uint64_t>(b.params.limit, stride) : stride) + b.params.offset;
+    b.x_ids.reserve(static_cast<uint64_t>(b.n_queries) * fold.x_stride);
+    b.x_count.reserve(b.n_queries);
+    b.x_total.reserve(b.n_queries);
+    b.params.limit = static_cast<uint32_t>(std::min<uint64_t>(fold.x_stride, 0xFFFFFFFFULL));
+    b.params.offset = 0;
+    stride = fold.x_stride;
+    d_ids = b.x_ids.p;
+    d_count = b.x_count.p;
+    d_total = b.x_total.p;
+  }
   // per-tile top-k pruning is only valid when the answer is a top-k by score
   const uint32_t prune_k = sp.compute_score != 0 && b.params.limit != 0 ? b.params.limit + b.params.offset : 0u;
   if (b.streamed) {
@@ -4477,6 +4533,7 @@ void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_
       MGX_LAUNCH_CHECK();
     }
     b.time_end();
+    fold.run();
     // sizes, counters and the overflow flag follow the results to the host
     b.h_launch.reserve(kLaunchCount);
     MGX_CUDA(cudaMemcpyAsync(b.h_launch.p, b.d_launch.p, kLaunchCount * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -4526,8 +4583,53 @@ void batch_search(Batch& b, const uint64_t* d_df_slots, uint64_t stride, uint32_
     MGX_LAUNCH_CHECK();
     b.time_end();
   }
+  fold.run();
   b.mark_last();
   b.searched = true;
+}
+
+// Caller query q of a batch with expanded OR-rooted programs = internal queries [xoff[q], xoff[q+1]), whose answers
+// are ascending and pairwise disjoint: total = sum of totals, ids = the merged runs cut to [offset, offset + limit).
+// One warp per caller query; the merged rank of an id = its index in its own run + its rank in every other run.
+__global__ void fold_expanded_kernel(const uint32_t* __restrict__ xoff, uint32_t n_out, uint64_t x_stride,
+                                     const uint32_t* __restrict__ x_ids, const uint32_t* __restrict__ x_count,
+                                     const uint64_t* __restrict__ x_total, uint32_t limit, uint32_t offset,
+                                     uint64_t stride, uint32_t* __restrict__ out_ids, uint32_t* __restrict__ out_count,
+                                     uint64_t* __restrict__ out_total) {
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (q >= n_out) {
+    return;
+  }
+  const uint32_t s0 = xoff[q];
+  const uint32_t s1 = xoff[q + 1];
+  uint64_t total = 0;
+  for (uint32_t s = s0; s < s1; ++s) {
+    total += x_total[s];
+  }
+  const uint64_t want_end = limit == 0 ? total : umin64(total, static_cast<uint64_t>(offset) + limit);
+  const uint64_t want_begin = umin64(offset, total);
+  const uint64_t n_out_ids = umin64(want_end - want_begin, stride);
+  if (lane == 0) {
+    out_total[q] = total;
+    out_count[q] = static_cast<uint32_t>(n_out_ids);
+  }
+  for (uint32_t s = s0; s < s1; ++s) {
+    const uint32_t* run = x_ids + static_cast<uint64_t>(s) * x_stride;
+    const uint32_t c = x_count[s];
+    for (uint32_t i = lane; i < c; i += 32) {
+      const uint32_t v = run[i];
+      uint64_t rank = i;
+      for (uint32_t o = s0; o < s1; ++o) {
+        if (o != s) {
+          rank += lower_bound_u32(x_ids + static_cast<uint64_t>(o) * x_stride, x_count[o], v);
+        }
+      }
+      if (rank >= want_begin && rank - want_begin < n_out_ids) {
+        out_ids[static_cast<uint64_t>(q) * stride + (rank - want_begin)] = v;
+      }
+    }
+  }
 }
 
 // Union of ascending, pairwise DISJOINT runs laid back to back (the per-driver result sets of one expanded query):

@@ -184,7 +184,8 @@ struct Batch {
   bool owns_stream = false;
 
   // ---- host-side compiled form
-  uint32_t n_queries = 0;
+  uint32_t n_queries = 0;    // queries the kernels run (an OR-rooted program of the caller is several of them)
+  uint32_t n_out_queries = 0;  // queries of the caller = rows of the outputs
   uint32_t n_terms = 0;      // unique terms (search + not)
   uint32_t n_keys = 0;
   uint32_t n_slots = 0;      // caller's search-term slots (for df output)
@@ -291,6 +292,13 @@ struct Batch {
   DevBuf<uint64_t> o_total;
   DevBuf<uint64_t> o_df;
 
+  // Driver expansion of OR-rooted boolean programs (api.cu expand_or_roots): caller query q is run as the internal
+  // queries [h_xoff[q], h_xoff[q+1]) with pairwise disjoint answers, folded back by fold_expanded_kernel.
+  std::vector<uint32_t> h_xoff;       // [n_out_queries + 1], empty = no expansion in this batch
+  DevBuf<uint32_t> d_xoff;
+  DevBuf<uint32_t> x_ids;             // answers of the internal queries, [n_queries][x_stride]
+  DevBuf<uint32_t> x_count;
+  DevBuf<uint64_t> x_total;
   ExplicitDriver explicit_driver;
   uint64_t h2d_bytes = 0;
   uint64_t d2h_bytes = 0;
@@ -337,8 +345,9 @@ constexpr int kStatStripes = 64;  // each counter is striped over 64 words to sp
 
 // query.cu
 // `terms` is not const: the stream-table builder clears `streamable` of terms that do not fit a bucket.
+// xoff (optional): expansion table of the caller's queries, see Batch::h_xoff.
 void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<HostQuery>& queries,
-                  const std::vector<uint32_t>& slot_tid);
+                  const std::vector<uint32_t>& slot_tid, const std::vector<uint32_t>* xoff = nullptr);
 // Bucket table over the terms with `streamable` set (clears the flag of terms that do not fit a bucket).
 void build_stream_table(std::vector<HostTerm>& terms, HostStreamTable* out);
 void batch_plan(Batch& b);

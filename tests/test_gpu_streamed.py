@@ -207,3 +207,149 @@ def test_two_rank_nccl_pipeline_equals_single_shard(config):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "NCCL SHARD CHECK OK" in r.stdout
+
+
+def _rand_docs(rnd, n, alphabet="abcdefgh漢字東京都"):
+    return [("".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 30)))).encode() for _ in range(n)]
+
+
+def test_add_document_batch_is_additive_like_the_loader_loop(mgx, oracle):
+    """Index::AddDocumentBatch as InitialLoader::FlushBatch calls it (initial_loader.cpp:450-512, index.cpp:76-119):
+    1000-document batches one after the other, ids in any order; single-document mutations in between; the index
+    must equal the oracle's incrementally maintained one after every read."""
+    import random
+    from test_gpu_parity import assert_same_index
+    rnd = random.Random(5)
+    gi = mgx.Index(2, 0, True)
+    oi = oracle.index(2, 0, True)
+    ids = list(range(1, 6001))
+    docs = dict(zip(ids, _rand_docs(rnd, len(ids))))
+    order = ids[:3000] + rnd.sample(ids[3000:], 3000)  # three ascending batches, then shuffled ones
+    for b0 in range(0, len(order), 1000):
+        batch = order[b0:b0 + 1000]
+        n = gi.add_document_batch(batch, [docs[i] for i in batch])
+        oi.add_texts(np.asarray(batch, dtype=np.uint32), [docs[i] for i in batch])
+        assert n == sum(1 for i in batch if len(docs[i].decode()) >= 2)
+        if b0 == 2000:  # a read in the middle of the load commits what has arrived so far
+            assert_same_index(gi, oi)
+            assert gi.stats().n_docs == 3000
+            gi.remove_document(17, docs[17])
+            oi.remove_document(17, docs[17])
+            gi.update_document(18, docs[18], b"abcabc")
+            oi.update_document(18, docs[18], b"abcabc")
+            docs[18] = b"abcabc"
+    assert_same_index(gi, oi)
+    assert gi.stats().n_docs == 5999
+    st = gi.stats()
+    assert (st.total_doc_length, st.doc_count) == oi.bm25_stats()
+    assert np.array_equal(gi.search_and([b"ab", b"bc"]), oi.search_and([b"ab", b"bc"]))
+
+
+def test_filter_columns_follow_the_documents_through_mutations(mgx, oracle):
+    """every journal commit used to drop the filter columns silently. They now follow the documents:
+    survivors keep their values, documents the journal added or replaced are NULL until the column is set again."""
+    import random
+    rnd = random.Random(11)
+    n = 4000
+    ids = np.arange(10, 10 + 2 * n, 2, dtype=np.uint32)
+    docs = _rand_docs(rnd, n, alphabet="abcd")
+    gi = mgx.Index(2, 0, True)
+    arena, offs = mgx.pack_strings(docs)
+    gi.build(ids, arena, offs)
+    status = [(i % 3) + 1 for i in range(n)]
+    cat = [rnd.choice([b"x", b"y", b"z"]) for _ in range(n)]
+    gi.set_filter_column(0, 8, status)
+    gi.set_filter_column(1, 11, cat)
+    qs = [[b"ab"], [b"bc"], [b"cd", b"da"]]
+    fl = [[(0, 0, "1")], [(1, 0, "y")], [(0, 1, "2"), (1, 1, "x")]]
+    before = gi.query_batch(qs, filters=fl, score=False, limit=4000)
+    # mutations: remove some, update some (their column values become NULL), add new ones in gaps and at the end
+    removed = set(int(i) for i in rnd.sample(list(ids), 300))
+    for d in removed:
+        gi.remove_document(d, b"")
+    updated = set(int(i) for i in rnd.sample([int(i) for i in ids if int(i) not in removed], 300))
+    new_text = {}
+    for d in updated:
+        new_text[d] = b"abcdabcd"
+        gi.update_document(d, b"", new_text[d])
+    added = {11: b"abcd", 13: b"bcda", 20001: b"cdab"}
+    for d, t in added.items():
+        gi.add_document(d, t)
+    after = gi.query_batch(qs, filters=fl, score=False, limit=4000)
+    # expectation from first principles: model the store
+    rows = {}
+    for i, d in enumerate(ids):
+        d = int(d)
+        if d in removed:
+            continue
+        if d in updated:
+            rows[d] = (new_text[d], None, None)
+        else:
+            rows[d] = (docs[i], status[i], cat[i])
+    for d, t in added.items():
+        rows[d] = (t, None, None)
+
+    def expect(q, f):
+        out = []
+        for d in sorted(rows):
+            text, st_, ct = rows[d]
+            if not all(t in text for t in q):
+                continue
+            ok = True
+            for col, op, lit in f:
+                v = st_ if col == 0 else ct
+                lit_v = int(lit) if col == 0 else lit.encode()
+                eq = v is not None and v == lit_v
+                ok = ok and (eq if op == 0 else not eq)  # FilterIndex semantics: NULL is not indexed, != keeps it
+            if ok:
+                out.append(d)
+        return out
+
+    for qi in range(len(qs)):
+        want = expect(qs[qi], fl[qi])
+        assert int(after.total[qi]) == len(want), (qi, int(after.total[qi]), len(want))
+        assert after.ids[qi, :len(want)].tolist() == want
+    assert int(before.total[0]) > 0
+
+
+def test_or_rooted_programs_are_expanded_by_driver(mgx, oracle, shard, monkeypatch):
+    """A OR B, (A AND B) OR C, A OR B OR C with filters / offsets: the driver expansion (one internal query per child
+    of the root, folded on the device) must equal the pass over every document, and the oracle."""
+    c, gi = shard
+    n = c.n_docs
+    gi.set_filter_column_arrays(0, 8, (np.arange(n, dtype=np.uint64) % 3) + 1)
+    base = corpus_mod.sample_queries(c, 300, 21, n_terms=3, min_cp=2, max_cp=3)
+    queries, programs, filters = [], [], []
+    for i, (a, b, cc) in enumerate(base):
+        kind = i % 5
+        if kind == 0:      # A OR B
+            queries.append([a, b]); programs.append(([0, 0, 2], [0, 1, 2]))
+        elif kind == 1:    # (A AND B) OR C
+            queries.append([a, b, cc]); programs.append(([0, 0, 1, 0, 2], [0, 1, 2, 2, 2]))
+        elif kind == 2:    # A OR B OR C
+            queries.append([a, b, cc]); programs.append(([0, 0, 0, 2], [0, 1, 2, 3]))
+        elif kind == 3:    # A OR (NOT B): cannot be expanded (a child that needs every document)
+            queries.append([a, b]); programs.append(([0, 0, 3, 2], [0, 1, 0, 2]))
+        else:              # A AND B (not OR-rooted)
+            queries.append([a, b]); programs.append(([0, 0, 1], [0, 1, 2]))
+        filters.append([(0, 0, "1")] if i % 3 == 0 else [])
+    oi = oracle.index(2, 0, True)
+    oi.build_bulk(c.doc_ids, c.arena, c.offsets, 8)
+    cols = [(8, ((np.arange(n) % 3) + 1).tolist())]
+    for limit, offset in ((100, 0), (7, 5), (0, 3)):
+        monkeypatch.setenv("MGX_NO_OR_EXPANSION", "1")
+        plain = gi.query_batch(queries, programs=programs, filters=filters, score=False, limit=limit, offset=offset,
+                               stride=64 if limit == 0 else None)
+        monkeypatch.delenv("MGX_NO_OR_EXPANSION")
+        exp = gi.query_batch(queries, programs=programs, filters=filters, score=False, limit=limit, offset=offset,
+                             stride=64 if limit == 0 else None)
+        assert np.array_equal(plain.total, exp.total) and np.array_equal(plain.count, exp.count)
+        valid = np.arange(plain.ids.shape[1])[None, :] < plain.count[:, None]
+        assert np.array_equal(plain.ids[valid], exp.ids[valid])
+    for qi in range(0, len(queries), 7):
+        full = oi.eval_boolean(programs[qi][0], programs[qi][1], queries[qi])
+        want = oracle.apply_filters(n, int(c.doc_ids[0]), cols, filters[qi], full) if filters[qi] else full
+        got = gi.query_batch([queries[qi]], programs=[programs[qi]], filters=[filters[qi]], score=False, limit=100)
+        assert int(got.total[0]) == want.size
+        k = min(100, want.size)
+        assert np.array_equal(got.ids[0, :k], want[:k])
