@@ -194,7 +194,7 @@ struct ScatterSmem {
   uint32_t vals[kSortTile];
   uint32_t warp_cnt[kSortWarps][kRadix];
   uint32_t local_start[kRadix];
-  uint32_t global_base[kRadix];
+  uint64_t global_base[kRadix];  // 64-bit: a pass over more than 2^32 pairs must not wrap
   uint32_t scan_tmp[kSortWarps];
 };
 
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
     }
     const uint32_t start = prefix + inc - cnt;
     sm.local_start[d] = start;
-    sm.global_base[d] = static_cast<uint32_t>(hist_scan[static_cast<uint64_t>(d) * n_tiles + blockIdx.x]);
+    sm.global_base[d] = hist_scan[static_cast<uint64_t>(d) * n_tiles + blockIdx.x];
     uint32_t running = start;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
   for (uint32_t i = threadIdx.x; i < tile_n; i += kSortThreads) {
     const uint64_t k = sm.keys[i];
     const uint32_t d = static_cast<uint32_t>(k >> shift) & mask;
-    const uint32_t pos = sm.global_base[d] + (i - sm.local_start[d]);
+    const uint64_t pos = sm.global_base[d] + (i - sm.local_start[d]);
     keys_out[pos] = k;
     vals_out[pos] = sm.vals[i];
   }
