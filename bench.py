@@ -411,13 +411,14 @@ def main():
                     help="the timed K steps are repeated (same batches, in order) until the timed window is this long")
     ap.add_argument("--cpu-sample", type=int, default=256, help="minimum queries per step of the CPU arm")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
-    ap.add_argument("--cpu-build-docs", type=int, default=200_000, help="documents per step of the c3 CPU arm")
+    ap.add_argument("--cpu-build-docs", type=int, default=50_000, help="documents per step of the c3 CPU arm")
     ap.add_argument("--calib-docs", type=int, default=250_000,
                     help="sub-corpus on which the CPU arm also times the reference's own sources (0 = off)")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "port", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parity", default="auto", choices=["auto", "full", "off"],
-                    help="auto: CPU oracle (<= 30M docs) + single-shard GPU run (N > 1, <= 30M docs); full: always")
+    ap.add_argument("--parity", default="auto", choices=["auto", "full", "gpu", "off"],
+                    help="auto: CPU oracle (<= 30M docs) + single-shard GPU run (N > 1, <= 30M docs); full: both, always; "
+                         "gpu: only the single-shard GPU run, at any size")
     ap.add_argument("--parity-queries", type=int, default=256)
     ap.add_argument("--dense-threshold", type=float, default=0.0,
                     help="posting density from which a list also gets a bitmap (0 = library default)")
@@ -786,8 +787,8 @@ def main():
 
     # ---- parity of the measured answers + the CPU baseline beside them
     cpu_baseline, parity = None, {"n_gpus": world, "checks": []}
-    want_cpu = args.parity != "off" and (args.parity == "full" or args.docs <= 30_000_000)
-    want_single = world > 1 and args.parity != "off" and (args.parity == "full" or args.docs <= 30_000_000)
+    want_cpu = args.parity in ("auto", "full") and (args.parity == "full" or args.docs <= 30_000_000)
+    want_single = world > 1 and args.parity != "off" and (args.parity in ("full", "gpu") or args.docs <= 30_000_000)
     cores = os.cpu_count() or 1
     bt = batches[args.warmup]
     if rank == 0 and (want_cpu or want_single or (world == 1 and not args.no_cpu_baseline)):

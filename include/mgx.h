@@ -422,9 +422,6 @@ typedef struct {
   uint64_t df_stream_hits;    /* (term, document) pairs it counted                                    */
   uint64_t df_scanned_docs;   /* df candidates whose whole text was scanned; the others were decided by one */
                               /* comparison at the recorded first occurrence of the driver n-gram           */
-  uint64_t df_positional_docs; /* df candidates decided from the recorded occurrences of ALL the term's n-grams, */
-                              /* without reading the document's text; algo_bytes_df counts their text only when   */
-                              /* MGX_DF_ACCOUNT=1 (the accounting reads the lengths the check itself avoids)       */
 } mgx_batch_stats_t;
 
 /* Staged form of the same call, for doc-range sharded deployments (one process

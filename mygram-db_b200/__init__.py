@@ -102,7 +102,7 @@ class BatchStats(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("driver_entries", C.c_uint64),
                 ("result_docs", C.c_uint64), ("df_candidates", C.c_uint64), ("unique_terms", C.c_uint64),
                 ("ms_df_stream_kernel", C.c_double), ("df_stream_terms", C.c_uint64), ("df_stream_bytes", C.c_uint64),
-                ("df_stream_hits", C.c_uint64), ("df_scanned_docs", C.c_uint64), ("df_positional_docs", C.c_uint64)]
+                ("df_stream_hits", C.c_uint64), ("df_scanned_docs", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

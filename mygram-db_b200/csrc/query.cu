@@ -89,8 +89,6 @@ struct BatchView {
   uint32_t stream_slot_mask;           // n_slots - 1
   uint32_t* df_mode;                   // [0] = 1: streaming pass chosen for this batch
   uint32_t* launch;                    // LaunchSlot block of a streamed batch, nullptr otherwise
-  int pos_check;                       // df stage: positions-only phrase check allowed (MGX_DF_POSCHECK=0 turns it off)
-  int account;                         // df stage: exact B_df accounting also for documents decided without their text
   const uint32_t* q_tids0;             // [sum] search terms in QUERY order (q_tids is re-ordered by the planner)
   uint64_t* key_glen;                  // [K] posting size per key in UPLOAD order; summed over the shards by the df
                                        // exchange of the sharded pipeline (global term order, see global_order_kernel)
@@ -876,58 +874,9 @@ __device__ __forceinline__ void load_text_words(const uint8_t* __restrict__ text
 static_assert(kWarpStageCap * sizeof(uint32_t) >= kStageBuf, "the text staging buffer aliases the list staging buffer");
 // One warp, one 128-entry piece of a term's shortest list (entries [e0, e0 + 128) of drv): the whole df work of that
 // piece. stage / surv / spos are the calling warp's own shared-memory slices; stat_stripe spreads the accounting atomics.
-// index of v in the ascending array p[0, n), or n if absent
-__device__ __forceinline__ uint32_t sorted_find(const uint32_t* p, uint32_t n, uint32_t v) {
-  uint32_t lo = 0;
-  uint32_t hi = n;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (p[mid] < v) {
-      lo = mid + 1;
-    } else {
-      hi = mid;
-    }
-  }
-  return lo < n && p[lo] == v ? lo : n;
-}
-
-// Positions-only phrase check. Every posting carries the byte offsets of the first two occurrences of its n-gram in
-// the document (Index::d_post_pos / d_post_pos2). When every n-gram of the term occurs ONCE in the term, the term
-// occurs at byte offset s of a document exactly if n-gram j occurs at s + toff_j for every j (the windows overlap and
-// cover the term). The driver n-gram's recorded occurrences give at most two candidate starts (A, B); each further
-// list confirms or rejects them from ITS recorded occurrences -- the document's text (and its offset in the arena)
-// is never read. A list that cannot answer (three or more occurrences in the document, an offset beyond 32 KB, a
-// dense list that was only probed by bit) sends the document to the text comparison below instead.
-struct PosState {
-  uint32_t a_ok;   // bit k: candidate start A of item k still stands
-  uint32_t b_ok;
-  uint32_t text;   // bit k: item k must be decided from the text
-};
-
-// occurrence payload of one posting: first | second << 16 (the second is only read when there is one)
-__device__ __forceinline__ uint32_t load_pos_pair(const uint16_t* __restrict__ pos1, const uint16_t* __restrict__ pos2,
-                                                  uint64_t at) {
-  const uint32_t p1 = __ldg(pos1 + at);
-  return p1 | ((p1 & kPosMulti) != 0 ? static_cast<uint32_t>(__ldg(pos2 + at)) << 16 : 0u);
-}
-
-// does the n-gram with payload `pp` occur at byte offset `want`?  *complete = the payload lists ALL its occurrences
-__device__ __forceinline__ bool pos_has(uint32_t pp, uint32_t want, bool* complete) {
-  const uint32_t q1 = pp & 0xFFFFu;
-  const uint32_t q2 = pp >> 16;
-  const bool two = (q1 & kPosMulti) != 0;
-  const bool known1 = (q1 & kPosUnknown) != kPosUnknown;
-  const bool known2 = two && (q2 & kPosUnknown) != kPosUnknown && (q2 & kPosMulti) == 0;
-  *complete = known1 && (!two || known2);
-  return (known1 && (q1 & kPosUnknown) == want) || (known2 && (q2 & kPosUnknown) == want);
-}
-
-// One warp, one 128-entry piece of a term's shortest list (entries [e0, e0 + 128) of drv): the whole df work of that
-// piece. stage / stage_pos / surv / spos are the calling warp's own shared-memory slices; stat_stripe spreads the
-// accounting atomics.
 __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchView& bv, const ListRef& drv, uint32_t t,
-                                             uint32_t k0, uint32_t k1, uint64_t e0, uint32_t* stage, uint16_t* stage_pos,
-                                             uint32_t* surv, uint32_t* spos, uint32_t stat_stripe) {
+                                             uint32_t k0, uint32_t k1, uint64_t e0, uint32_t* stage, uint32_t* surv,
+                                             uint32_t* spos, uint32_t stat_stripe) {
   const unsigned lane = threadIdx.x & 31u;
   if (e0 >= drv.len) {
     return;  // no block-wide barrier is used below, so a warp may leave early
@@ -949,34 +898,11 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
     if (i < tile_n) {
       my_doc[k] = __ldg(drv.p + e0 + i);
       if (drv_pos != nullptr) {
-        my_pos[k] = load_pos_pair(drv_pos, drv_pos2, e0 + i);
+        const uint32_t p1 = __ldg(drv_pos + e0 + i);
+        // the second position is only read when there is one
+        my_pos[k] = p1 | ((p1 & kPosMulti) != 0 ? static_cast<uint32_t>(__ldg(drv_pos2 + e0 + i)) << 16 : 0u);
       }
       alive |= 1u << k;
-    }
-  }
-  // ---- candidate starts from the driver's own occurrences
-  const uint32_t toff_raw = bv.key_toff[k0];
-  const bool toff_ok = toff_raw != kNoTermOffset;
-  const uint32_t o1 = toff_raw & kTermOffsetMask;
-  const uint32_t m_term = toff_raw >> kTermCountShift;  // 1, 2, or 3 = "three or more"
-  bool pos_mode = drv_pos != nullptr && toff_ok && m_term == 1 && bv.pos_check != 0;
-  PosState ps{0u, 0u, 0u};
-  if (pos_mode) {
-#pragma unroll
-    for (int k = 0; k < kWarpItems; ++k) {
-      if ((alive >> k) & 1u) {
-        bool complete = false;
-        (void)pos_has(my_pos[k], 0, &complete);
-        const uint32_t p1 = my_pos[k] & kPosUnknown;
-        const uint32_t p2 = (my_pos[k] >> 16) & kPosUnknown;
-        const bool two = (my_pos[k] & kPosMulti) != 0;
-        if (!complete) {
-          ps.text |= 1u << k;
-        } else {
-          ps.a_ok |= (p1 >= o1 ? 1u : 0u) << k;
-          ps.b_ok |= (two && p2 >= o1 ? 1u : 0u) << k;
-        }
-      }
     }
   }
   for (uint32_t j = k0 + 1; j < k1; ++j) {
@@ -987,32 +913,6 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
     l.p = reinterpret_cast<const uint32_t*>(static_cast<uintptr_t>(r0.x) | (static_cast<uintptr_t>(r0.y) << 32));
     l.bm = reinterpret_cast<const uint32_t*>(static_cast<uintptr_t>(r0.z) | (static_cast<uintptr_t>(r0.w) << 32));
     l.len = r1.x;
-    // where this n-gram sits relative to a candidate start: start + toff_j = (driver position - o1) + toff_j
-    const uint32_t toff_j = bv.key_toff[j];
-    const bool j_pos = pos_mode && toff_j != kNoTermOffset && (toff_j >> kTermCountShift) == 1;
-    if (pos_mode && !j_pos) {
-      pos_mode = false;  // an n-gram that repeats inside the term: the text decides for the whole piece
-    }
-    const uint32_t oj = toff_j & kTermOffsetMask;
-    const uint16_t* l_pos = j_pos ? iv.post_pos + (l.p - iv.postings) : nullptr;
-    const uint16_t* l_pos2 = j_pos ? iv.post_pos2 + (l.p - iv.postings) : nullptr;
-    // updates the candidate starts of item k from the payload of its posting in list j
-    auto confirm = [&](int k, uint32_t pp) {
-      bool complete = false;
-      const uint32_t p1 = my_pos[k] & kPosUnknown;
-      const uint32_t p2 = (my_pos[k] >> 16) & kPosUnknown;
-      const bool a = pos_has(pp, p1 - o1 + oj, &complete);
-      const bool b = pos_has(pp, p2 - o1 + oj, &complete);
-      if (!complete) {
-        ps.text |= 1u << k;
-      }
-      if (!a) {
-        ps.a_ok &= ~(1u << k);
-      }
-      if (!b) {
-        ps.b_ok &= ~(1u << k);
-      }
-    };
     if (l.bm != nullptr) {
 #pragma unroll
       for (int k = 0; k < kWarpItems; ++k) {
@@ -1020,7 +920,6 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
           alive &= ~(1u << k);
         }
       }
-      ps.text |= alive;  // a bit probe tells nothing about where the n-gram occurs
     } else {
       uint32_t lo = 0;
       uint32_t hi = 0;
@@ -1031,24 +930,12 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
       } else if (cnt <= kWarpStageCap) {
         for (uint32_t i = lane; i < cnt; i += 32) {
           stage[i] = __ldg(l.p + lo + i);
-          if (j_pos) {
-            stage_pos[i] = __ldg(l_pos + lo + i);
-          }
         }
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < kWarpItems; ++k) {
-          if ((alive >> k) & 1u) {
-            const uint32_t at = sorted_find(stage, cnt, my_doc[k]);
-            if (at == cnt) {
-              alive &= ~(1u << k);
-            } else if (j_pos && ((ps.text >> k) & 1u) == 0) {
-              uint32_t pp = stage_pos[at];
-              if ((pp & kPosMulti) != 0) {
-                pp |= static_cast<uint32_t>(__ldg(l_pos2 + lo + at)) << 16;
-              }
-              confirm(k, pp);
-            }
+          if (((alive >> k) & 1u) && !sorted_contains(stage, cnt, my_doc[k])) {
+            alive &= ~(1u << k);
           }
         }
         __syncwarp();
@@ -1059,8 +946,6 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
             const uint32_t pos = lower_bound_u32(l.p + lo, cnt, my_doc[k]);
             if (pos >= cnt || __ldg(l.p + lo + pos) != my_doc[k]) {
               alive &= ~(1u << k);
-            } else if (j_pos && ((ps.text >> k) & 1u) == 0) {
-              confirm(k, load_pos_pair(l_pos, l_pos2, static_cast<uint64_t>(lo) + pos));
             }
           }
         }
@@ -1069,26 +954,6 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
     if (__ballot_sync(0xffffffffu, alive != 0) == 0) {
       return;
     }
-  }
-  uint32_t hits = 0;
-  uint32_t n_positional = 0;
-  unsigned long long text_bytes = 0;
-  if (pos_mode) {
-    // decided without the text: candidates whose every list answered from its recorded occurrences
-    const uint32_t decided = alive & ~ps.text;
-    hits = __popc(decided & (ps.a_ok | ps.b_ok));
-    n_positional = __popc(decided);
-    if (bv.account != 0) {
-      // B_df accounting (the text bytes of every candidate the reference scans) needs the lengths the
-      // check itself no longer reads; only on request (MGX_DF_ACCOUNT), never in a timed run
-#pragma unroll
-      for (int k = 0; k < kWarpItems; ++k) {
-        if ((decided >> k) & 1u) {
-          text_bytes += iv.text_off[my_doc[k] + 1] - iv.text_off[my_doc[k]];
-        }
-      }
-    }
-    alive &= ps.text;
   }
   // survivors -> the warp's list (order irrelevant for a count)
   const uint32_t mine = __popc(alive);
@@ -1114,6 +979,8 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
   const uint8_t* term = bv.term_bytes + bv.term_boff[t];
   const uint32_t tl = bv.term_boff[t + 1] - bv.term_boff[t];
   const TermRegs tregs = load_term_regs(term, tl);
+  uint32_t hits = 0;
+  unsigned long long text_bytes = 0;
 
   // ---- pass 1, one lane per candidate. The driver n-gram occurs m times in the term (first at byte offset o1) and
   // c times in the document (positions recorded for c <= 2). An occurrence of the term puts m occurrences of the
@@ -1121,6 +988,10 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
   // c <= 2 the term can only start at (p_a - o1) for a recorded position p_a -- one or two comparisons instead of a
   // scan. Documents with three or more occurrences (or no recorded position) are compacted to the front of the
   // list for the scanning pass.
+  const uint32_t toff_raw = bv.key_toff[k0];
+  const bool toff_ok = toff_raw != kNoTermOffset;
+  const uint32_t o1 = toff_raw & kTermOffsetMask;
+  const uint32_t m_term = toff_raw >> kTermCountShift;  // 1, 2, or 3 = "three or more"
   uint32_t n_scan = 0;
   for (uint32_t s0 = 0; s0 < n; s0 += 32) {
     const uint32_t s = s0 + lane;
@@ -1209,7 +1080,6 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
     hits += __shfl_xor_sync(0xffffffffu, hits, s);
-    n_positional += __shfl_xor_sync(0xffffffffu, n_positional, s);
     text_bytes += __shfl_xor_sync(0xffffffffu, text_bytes, s);
   }
   if (lane == 0) {
@@ -1217,10 +1087,7 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
       atomicAdd(reinterpret_cast<unsigned long long*>(bv.t_df + t), static_cast<unsigned long long>(hits));
     }
     stat_add_at(bv, kStatDfBytes, stat_stripe, text_bytes);
-    stat_add_at(bv, kStatDfCandidates, stat_stripe, n + n_positional);
-    if (n_positional != 0) {
-      stat_add_at(bv, kStatDfPositional, stat_stripe, n_positional);
-    }
+    stat_add_at(bv, kStatDfCandidates, stat_stripe, n);
     if (n_scan != 0) {
       stat_add_at(bv, kStatDfScanned, stat_stripe, n_scan);
     }
@@ -1229,7 +1096,6 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
 
 __global__ void __launch_bounds__(kTileThreads, MGX_DF_OCC) df_tile_kernel(IndexView iv, BatchView bv) {
   __shared__ __align__(16) uint32_t s_stage[kTileThreads / 32][kWarpStageCap];
-  __shared__ uint16_t s_stage_pos[kTileThreads / 32][kWarpStageCap];
   __shared__ uint32_t s_surv[kTileThreads / 32][kWarpTile];
   __shared__ uint32_t s_spos[kTileThreads / 32][kWarpTile];
   const unsigned warp = threadIdx.x >> 5;
@@ -1243,7 +1109,7 @@ __global__ void __launch_bounds__(kTileThreads, MGX_DF_OCC) df_tile_kernel(Index
   drv.bm = nullptr;
   const uint64_t tile = d1.z;
   df_warp_tile(iv, bv, drv, d0.w, d1.x, d1.y, tile * kTile + static_cast<uint64_t>(warp) * kWarpTile, s_stage[warp],
-               s_stage_pos[warp], s_surv[warp], s_spos[warp], blockIdx.x);
+               s_surv[warp], s_spos[warp], blockIdx.x);
 }
 
 // Streamed form (no host read-back of the tile count): persistent warps pull UNITS of kDfUnit entries of the terms'
@@ -1276,7 +1142,6 @@ __device__ __forceinline__ uint32_t warp_upper_bound_u64(const uint64_t* __restr
 
 __global__ void __launch_bounds__(kTileThreads, MGX_DF_OCC) df_units_kernel(IndexView iv, BatchView bv) {
   __shared__ __align__(16) uint32_t s_stage[kTileThreads / 32][kWarpStageCap];
-  __shared__ uint16_t s_stage_pos[kTileThreads / 32][kWarpStageCap];
   __shared__ uint32_t s_surv[kTileThreads / 32][kWarpTile];
   __shared__ uint32_t s_spos[kTileThreads / 32][kWarpTile];
   const unsigned lane = threadIdx.x & 31u;
@@ -1308,8 +1173,8 @@ __global__ void __launch_bounds__(kTileThreads, MGX_DF_OCC) df_units_kernel(Inde
     const uint64_t e0 = (static_cast<uint64_t>(unit) - bv.t_df_tile_off[t]) * kDfUnit;
 #pragma unroll 1
     for (uint32_t piece = 0; piece < kDfUnit / kWarpTile; ++piece) {
-      df_warp_tile(iv, bv, drv, t, k0, k1, e0 + static_cast<uint64_t>(piece) * kWarpTile, s_stage[warp],
-                   s_stage_pos[warp], s_surv[warp], s_spos[warp], unit);
+      df_warp_tile(iv, bv, drv, t, k0, k1, e0 + static_cast<uint64_t>(piece) * kWarpTile, s_stage[warp], s_surv[warp],
+                   s_spos[warp], unit);
       __syncwarp();
     }
   }
@@ -3646,8 +3511,6 @@ BatchView make_batch_view(Batch& b) {
   v.stream_slot_mask = b.n_stream_slots > 0 ? b.n_stream_slots - 1 : 0;
   v.df_mode = b.d_df_mode.p;
   v.launch = b.streamed ? b.d_launch.p : nullptr;
-  v.pos_check = b.pos_check ? 1 : 0;
-  v.account = b.account ? 1 : 0;
   v.q_tids0 = b.d_q_tids0.p;
   v.key_glen = b.d_key_glen.p;
   return v;
@@ -3770,7 +3633,6 @@ void Batch::collect_stats(mgx_batch_stats_t* out) {
   s.df_stream_bytes = h_df_mode != 0 ? ix->text_bytes : 0;
   s.df_stream_hits = h[kStatStreamHits];
   s.df_scanned_docs = h[kStatDfScanned];
-  s.df_positional_docs = h[kStatDfPositional];
   *out = s;
 }
 
@@ -4370,12 +4232,6 @@ void batch_reset_for_repeat(Batch& b, bool after_overflow) {
 void batch_plan(Batch& b) {
   cudaStream_t st = b.stream;
   Index& ix = *b.ix;
-  {
-    const char* pc = std::getenv("MGX_DF_POSCHECK");
-    b.pos_check = pc == nullptr || pc[0] != '0';
-    const char* ac = std::getenv("MGX_DF_ACCOUNT");
-    b.account = ac != nullptr && ac[0] != '0';
-  }
   if (b.allow_streamed && b.explicit_driver.d_ids == nullptr) {
     const bool disabled = std::getenv("MGX_NO_STREAMED") != nullptr;  // read per batch: the tests flip it
     if (b.sc == nullptr) {

@@ -211,8 +211,6 @@ struct Batch {
   DevBuf<uint64_t> d_t_df_tile_off;  // [T+1]
   DevBuf<uint64_t> d_t_df;        // [T]
   DevBuf<uint64_t> d_key_glen;    // [K] posting size per key in upload order; directly behind d_t_df (one exchange)
-  bool pos_check = true;          // df stage: positions-only phrase check (see df_warp_tile)
-  bool account = false;           // df stage: exact B_df accounting for candidates decided without their text
   bool global_order = false;      // sharded pipeline: order terms / compute IDFs from the exchanged global values
   DevBuf<uint32_t> d_slot_tid;    // [S]
 
@@ -341,8 +339,7 @@ enum StatSlot : int {
   kStatStreamHits = 7,      // verified (term, document) pairs counted by the streaming pass
   kStatDfScanned = 8,       // df candidates whose whole text had to be scanned (no usable first-occurrence position)
   kStatDriverEntries = 9,   // driver entries of all queries (what the intersect tiles walk)
-  kStatDfPositional = 10,   // df candidates decided from the recorded occurrences alone (no text, no text offsets)
-  kStatCount = 12
+  kStatCount = 10
 };
 constexpr int kStatStripes = 64;  // each counter is striped over 64 words to spread the atomics
 
