@@ -560,13 +560,18 @@ def main():
                                        "sample": f"Index::AddDocumentBatch over the first {n} documents of the shard in "
                                                  "1000-document batches, single-threaded as the reference's loader"}
                 # parity on the sample: the device index of the same documents equals the CPU index term by term
+                # (the port's export; the reference library has no CSR export -- the two are pinned to each other by
+                # tests/test_oracle_bulk.py)
                 gi = mgx.Index(2, 0, True, device=local_rank)
                 gi.build(c.doc_ids[:n], c.arena[:int(c.offsets[n])], c.offsets[:n + 1])
                 keys, goffs, gposts = gi.export()
-                oterms, ooffs, oposts = oi.export()
+                op = pyoracle.OracleLib(pyoracle.PORT_LIB).index(2, 0, True)
+                op.build_bulk(c.doc_ids[:n], c.arena, c.offsets[:n + 1], os.cpu_count() or 1)
+                oterms, ooffs, oposts = op.export()
                 out["parity"] = {"docs_checked": n, "terms": int(len(oterms)),
-                                 "csr_equal": bool(len(oterms) == len(keys) and np.array_equal(goffs, ooffs) and
-                                                   np.array_equal(gposts, oposts))}
+                                 "csr_equal": bool(len(oterms) == len(keys) and [bytes(x) for x in oterms] == [bytes(x) for x in keys] and
+                                                   np.array_equal(goffs, ooffs) and np.array_equal(gposts, oposts))}
+                out["parity"]["ok"] = out["parity"]["csr_equal"]
                 gi.close()
                 oi.close()
             print(json.dumps(out), flush=True)

@@ -475,6 +475,7 @@ int compile_range(const Index& ix, const mgx_query_params_t& p, uint64_t q_first
       const int n = mgx_key_to_utf8(t.keys[0], ix.width, enc);
       t.exact_single = static_cast<uint64_t>(n) == e - b && std::memcmp(enc, bytes + b, e - b) == 0;
     }
+    t.payload_tf = t.exact_single && valid_utf8 && tok_agree;
     // streaming df pass: valid UTF-8 of at least kStreamMinTermBytes bytes that needs a text check
     t.streamable = stream_ok && valid_utf8 && e - b >= kStreamMinTermBytes && !t.keys.empty() &&
                    (t.keys.size() > 1 || !t.exact_single) &&

@@ -522,6 +522,7 @@ struct IndexView {
   uint64_t bm_words;
   uint32_t first_id;    // DocId of local index 0
   int sequential_ids;   // doc_ids[i] == first_id + i (DocumentStore assigns ids sequentially, document_store.h:520)
+  int all_valid_utf8;   // no document of the shard contains an invalid byte
 };
 
 // local index -> global DocId
@@ -568,6 +569,7 @@ inline IndexView make_view(const Index& ix) {
   v.bm_words = ix.bm_words;
   v.first_id = ix.first_id;
   v.sequential_ids = ix.sequential_ids ? 1 : 0;
+  v.all_valid_utf8 = ix.all_valid_utf8 ? 1 : 0;
   return v;
 }
 

@@ -89,6 +89,7 @@ struct BatchView {
   uint32_t stream_slot_mask;           // n_slots - 1
   uint32_t* df_mode;                   // [0] = 1: streaming pass chosen for this batch
   uint32_t* launch;                    // LaunchSlot block of a streamed batch, nullptr otherwise
+  const uint8_t* term_flags;           // [T] bit0 raw, bit1 exact_single, bit2 stream-eligible, bit3 tf from the posting payload
   const uint32_t* q_tids0;             // [sum] search terms in QUERY order (q_tids is re-ordered by the planner)
   uint64_t* key_glen;                  // [K] posting size per key in UPLOAD order; summed over the shards by the df
                                        // exchange of the sharded pipeline (global term order, see global_order_kernel)
@@ -2457,7 +2458,47 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
     const bool all_short = __syncthreads_and(short_here ? 1 : 0) != 0;
     unsigned long long text_bytes = 0;
     const uint32_t n_search = t1 - t0;
-    if (all_short && n1 == n0 && n_search >= 2 && total * n_search <= kPairScanMaxItems) {
+    // A query of ONE term that is exactly its single n-gram, driven by that n-gram's list with every entry of the
+    // tile surviving (no NOT terms, no filters, no text verification): tf comes from the occurrences recorded with
+    // the posting -- one occurrence, or two that do not overlap (CountTermOccurrences counts non-overlapping matches,
+    // bm25_scorer.cpp:27-45) -- and the score needs only the document's length. No text, no text offsets: what a
+    // C5-style batch of short single-term queries over long lists spends its time on. Documents with three or more
+    // occurrences (or offsets beyond the recorded range) take the scanning path below.
+    bool pay_only = false;
+    if (sp.compute_score != 0 && drv_list && nl == 1 && n_search == 1 && n1 == n0 && (flags & kQVerify) == 0 &&
+        total == tile_n && iv.post_pos != nullptr && iv.all_valid_utf8 != 0) {
+      const uint32_t tid = bv.q_tids[t0];
+      pay_only = (bv.term_flags[tid] & 8u) != 0 && bv.term_koff[tid + 1] - bv.term_koff[tid] == 1;
+    }
+    if (pay_only) {
+      const uint32_t tid = bv.q_tids[t0];
+      const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
+      const double idf = bv.q_idf[t0];
+      const uint64_t pbase = static_cast<uint64_t>(s_lists[0].p - iv.postings) + e0;
+      for (uint32_t s = threadIdx.x; s < total; s += kTileThreads) {
+        const uint32_t doc = s_doc[s];  // survivor s is entry s of the tile: every entry survived
+        const uint32_t p1 = __ldg(iv.post_pos + pbase + s);
+        const uint32_t dl_u = __ldg(iv.doc_len + doc);
+        uint32_t tf_u = 1;
+        bool known = true;
+        if ((p1 & kPosMulti) != 0) {
+          const uint32_t p2 = __ldg(iv.post_pos2 + pbase + s);
+          known = (p1 & kPosUnknown) != kPosUnknown && (p2 & kPosUnknown) != kPosUnknown && (p2 & kPosMulti) == 0;
+          tf_u = (p2 & kPosUnknown) - (p1 & kPosUnknown) >= tl ? 2u : 1u;
+        }
+        if (!known) {
+          s_keep[s] = 2;
+          s_score[s] = 0.0;
+          s_any_slow = 1;
+        } else {
+          const double dl = static_cast<double>(dl_u);
+          const double length_norm = __dadd_rn(__dsub_rn(1.0, sp.b), __ddiv_rn(__dmul_rn(sp.b, dl), sp.avgdl_clamped));
+          s_keep[s] = 1;
+          s_score[s] = __dadd_rn(0.0, bm25_term(idf, tf_u, length_norm, sp.k1));
+          text_bytes += 4;  // B_score counts text bytes + 4 per scored document; the text was not read here
+        }
+      }
+    } else if (all_short && n1 == n0 && n_search >= 2 && total * n_search <= kPairScanMaxItems) {
       // Very few survivors (the common tile ends with one): kGroupScanLanes lanes per (document, TERM) pair, so the
       // terms of a document are counted side by side instead of one after the other; the BM25 contributions are
       // added afterwards in term order, operation for operation as the per-document loops below do.
@@ -3511,6 +3552,7 @@ BatchView make_batch_view(Batch& b) {
   v.stream_slot_mask = b.n_stream_slots > 0 ? b.n_stream_slots - 1 : 0;
   v.df_mode = b.d_df_mode.p;
   v.launch = b.streamed ? b.d_launch.p : nullptr;
+  v.term_flags = b.d_term_flags.p;
   v.q_tids0 = b.d_q_tids0.p;
   v.key_glen = b.d_key_glen.p;
   return v;
@@ -3892,7 +3934,8 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
       }
       nk += static_cast<uint32_t>(ht.keys.size());
       koff[t + 1] = nk;
-      raw[t] = static_cast<uint8_t>((ht.raw ? 1 : 0) | (ht.exact_single ? 2 : 0) | (ht.streamable ? 4 : 0));
+      raw[t] = static_cast<uint8_t>((ht.raw ? 1 : 0) | (ht.exact_single ? 2 : 0) | (ht.streamable ? 4 : 0) |
+                                    (ht.payload_tf ? 8 : 0));
     }
     raw[T] = 0;
     std::memset(bytes + nb, 0, 16);

@@ -145,6 +145,8 @@ struct HostTerm {
   bool raw = false;            // keys given directly (Index::SearchAnd style): no text semantics
   bool exact_single = false;   // the term IS its single n-gram, so df == posting size when all text is valid UTF-8
   bool streamable = false;     // valid UTF-8 (>= 3 bytes) that needs a text check: may use the streaming df pass
+  bool payload_tf = false;     // the term IS its single n-gram, valid UTF-8, and both tokenisers agree: its tf in a
+                               // document follows from the occurrences recorded with the posting
   uint64_t hash = 0;           // hash of `bytes` (host query compiler)
 };
 
