@@ -416,6 +416,8 @@ def main():
                     help="sub-corpus on which the CPU arm also times the reference's own sources (0 = off)")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "port", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-share", action="store_true",
+                    help="N > 1: every rank compiles every batch (instead of one rank per batch + the shared ring)")
     ap.add_argument("--parity", default="auto", choices=["auto", "full", "gpu", "off"],
                     help="auto: CPU oracle (<= 30M docs) + single-shard GPU run (N > 1, <= 30M docs); full: both, always; "
                          "gpu: only the single-shard GPU run, at any size")
@@ -705,21 +707,33 @@ def main():
     e2e_parts = {"host_prepare_ms": 0.0, "enqueue_ms": 0.0, "wait_ms": 0.0}
     compiler = ThreadPoolExecutor(max_workers=2)  # ctypes releases the GIL: batches i+1, i+2 compile beside batch i
 
-    def e2e_prepare(i, slot):
+    # N > 1: the ranks of the node take turns compiling (batch number seq is compiled by rank seq % N and handed to the
+    # others through the shared-memory ring of mgx_share_*), instead of every rank compiling every batch
+    share_seq = [0]
+    if world > 1 and not args.no_share:
+        name = [f"/mgx_share_{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}"]
+        dist.broadcast_object_list(name, src=0)
+        pipe.open_share(name[0], world, rank)
+        barrier()
+
+    def e2e_prepare(i, slot, seq):
         t_a = time.perf_counter()
-        p = prepare(i, slot)
+        bt = batches[i]
+        p = pipe.prepare_shared(seq, bt["arena"], bt["offs"], bt["qbeg"], args.batch, streams[slot], ext=bt["ext"])
         return p, 1e3 * (time.perf_counter() - t_a)
 
     def e2e_run(order, acc=None):
         order = list(order)
         futs, pending = {}, []
         ahead = 2
+        seq0 = share_seq[0]  # the same on every rank: all ranks run the same orders
+        share_seq[0] += len(order)
         for j in range(min(ahead, len(order))):
-            futs[j] = compiler.submit(e2e_prepare, order[j], j % in_flight)
+            futs[j] = compiler.submit(e2e_prepare, order[j], j % in_flight, seq0 + j)
         for j, i in enumerate(order):
             p, prep_ms = futs.pop(j).result()
             if j + ahead < len(order):
-                futs[j + ahead] = compiler.submit(e2e_prepare, order[j + ahead], (j + ahead) % in_flight)
+                futs[j + ahead] = compiler.submit(e2e_prepare, order[j + ahead], (j + ahead) % in_flight, seq0 + j + ahead)
             t_b = time.perf_counter()
             slot = j % in_flight
             pipe.enqueue(p, slot % comm.n_lanes if world > 1 else 0, outs[slot])
@@ -863,6 +877,9 @@ def main():
                        "nccl": comm.nccl_version() if world > 1 else None},
             "e2e": {"value": e2e_value, "unit": cfg["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pipeline_depth": in_flight, "timed_repeats": e2e_reps,
+                    "host_compile": ("every batch compiled by ONE rank of the node in turn and handed to the others "
+                                     "through a shared-memory ring (mgx_share_*)") if (world > 1 and not args.no_share)
+                    else "every rank compiles every batch",
                     "per_step_ms": {k: v / max(1, e2e_reps * args.steps) for k, v in e2e_parts.items()}},
             "gpu_launches": gpu_launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity": parity, "kernels": kernels,
@@ -875,6 +892,7 @@ def main():
                             "corpus_gen_s": round(gen_s, 2)},
         })
         print(json.dumps(out), flush=True)
+    pipe.close_share()
     comm.close()
     if world > 1:
         dist.destroy_process_group()

@@ -49,6 +49,7 @@ extern "C" {
 #define MGX_ERR_NO_DEVICE (-5)        /* no CUDA device: the library has no CPU fallback        */
 #define MGX_ERR_FORMAT (-6)           /* an MGIX stream was rejected; mgx_last_error() names the reference's
                                          ErrorCode (kStorageInvalidFormat / CRCMismatch / Corrupted / ...) */
+#define MGX_ERR_TIMEOUT (-7)          /* mgx_share_*: the other side did not arrive within timeout_ms        */
 
 /* Thread-local description of the last failure on this thread ("" if none). */
 const char* mgx_last_error(void);
@@ -533,6 +534,25 @@ int mgx_sharded_batch_enqueue(mgx_shard_comm_t* comm, int32_t lane, mgx_batch_t*
  * the enqueue. */
 int mgx_sharded_batch_finish(mgx_shard_comm_t* comm, int32_t lane, mgx_batch_t* batch, uint64_t stride,
                              void* h_record_out, const void** d_record_out, int32_t* out_repeated);
+
+/* --------------------------------------- compiled batches shared between the shard processes of one node
+ *
+ * Every shard answers every query, so without this every rank compiles every batch (the per-request host work of
+ * QueryParser / GenerateQueryNgrams, server/search_pipeline.cpp:569-603, repeated N times per node). The channel is a
+ * POSIX shared-memory ring of n_slots slots of slot_bytes payload each: ONE rank compiles batch `seq` with
+ * mgx_batch_prepare* and publishes it, every other rank imports it (a copy into its own pinned staging buffer + the
+ * same single H2D transfer a local compile ends with) -- the sequence numbers, not the call order, pair the two sides.
+ * rank 0 creates the segment (name as for shm_open, e.g. "/mgx_<port>"), the others attach. A batch with column
+ * conditions or an explicit driver set, or one larger than a slot, is refused by publish AND by every import of that
+ * seq (same status): the ranks then compile it locally. timeout_ms < 0 waits for ever, otherwise MGX_ERR_TIMEOUT. The importing index must have
+ * the compiling index's n-gram configuration; params carries the same GLOBAL corpus statistics on every rank. */
+typedef struct mgx_share mgx_share_t;
+int mgx_share_open(const char* name, int32_t n_ranks, int32_t rank, int32_t n_slots, uint64_t slot_bytes,
+                   mgx_share_t** out);
+void mgx_share_close(mgx_share_t* share);
+int mgx_share_publish(mgx_share_t* share, uint64_t seq, const mgx_batch_t* batch, int32_t timeout_ms);
+int mgx_share_import(mgx_share_t* share, uint64_t seq, mgx_index_t* index, const mgx_query_params_t* params,
+                     void* stream, int32_t timeout_ms, mgx_batch_t** out);
 
 /* Stats of the last mgx_query_batch on this index. */
 int mgx_index_last_batch_stats(const mgx_index_t* index, mgx_batch_stats_t* out);

@@ -28,8 +28,10 @@ LIB_PATH = os.environ.get("MGX_LIB_PATH") or os.path.join(HERE, "libmgx.so")  # 
 INCLUDE = os.path.join(os.path.dirname(HERE), "include", "mgx.h")
 
 MGX_OK = 0
+MGX_ERR_UNSUPPORTED = -3
+MGX_ERR_CAPACITY = -4
 ERRORS = {-1: "MGX_ERR_INVALID_ARGUMENT", -2: "MGX_ERR_CUDA", -3: "MGX_ERR_UNSUPPORTED", -4: "MGX_ERR_CAPACITY",
-          -5: "MGX_ERR_NO_DEVICE"}
+          -5: "MGX_ERR_NO_DEVICE", -6: "MGX_ERR_FORMAT", -7: "MGX_ERR_TIMEOUT"}
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -200,6 +202,12 @@ def lib():
     L.mgx_sharded_batch_enqueue.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p]
     L.mgx_sharded_batch_finish.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p,
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+    L.mgx_share_open.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.mgx_share_close.argtypes = [C.c_void_p]
+    L.mgx_share_close.restype = None
+    L.mgx_share_publish.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32]
+    L.mgx_share_import.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(QueryParams), C.c_void_p, C.c_int32,
+                                   C.POINTER(C.c_void_p)]
     L.mgx_score_documents.argtypes = [C.c_void_p, u32p, C.c_uint64, u8p, u64p, u64p, C.c_uint64, C.c_uint64,
                                       C.c_double, C.c_double, C.c_double, f64p]
     L.mgx_sort_by_score.argtypes = [C.c_void_p, u32p, f64p, C.c_uint64, C.c_int32, C.c_uint32, C.c_uint32, u32p, u64p]

@@ -11,6 +11,10 @@
 #include <chrono>
 #include <condition_variable>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <nccl.h>
 #include <cstdlib>
 #include <cstring>
@@ -2369,12 +2373,7 @@ int mgx_batch_prepare(mgx_index_t* index, const mgx_query_params_t* params, uint
 namespace {
 // Host compile + upload of one batch on `stream`. The caller has committed pending mutations and holds shared access
 // to the index (its own Reader, or the one a staged batch keeps until mgx_batch_destroy).
-int prepare_unlocked(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
-                     const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
-                     const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
-                     const mgx_query_ext_t* ext, cudaStream_t stream, mgx_batch_t** out) {
-  Index& ix = index->ix;
-  DeviceGuard guard(ix.device);
+std::unique_ptr<mgx_batch> take_pooled_batch(Index& ix) {
   std::unique_ptr<mgx_batch> h;
   {
     std::lock_guard<std::mutex> pool_lock(ix.pool_mu);
@@ -2386,6 +2385,16 @@ int prepare_unlocked(mgx_index_t* index, const mgx_query_params_t* params, uint6
   if (!h) {
     h = std::make_unique<mgx_batch>();
   }
+  return h;
+}
+
+int prepare_unlocked(mgx_index_t* index, const mgx_query_params_t* params, uint64_t n_queries,
+                     const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                     const uint8_t* not_bytes, const uint64_t* not_offsets, const uint64_t* q_not_begin,
+                     const mgx_query_ext_t* ext, cudaStream_t stream, mgx_batch_t** out) {
+  Index& ix = index->ix;
+  DeviceGuard guard(ix.device);
+  std::unique_ptr<mgx_batch> h = take_pooled_batch(ix);
   Batch& b = h->b;
   b.ix = &ix;
   b.params = *params;
@@ -2473,6 +2482,248 @@ int mgx_batch_prepare_ex(mgx_index_t* index, const mgx_query_params_t* params, u
     return prepare_unlocked(index, params, n_queries, term_bytes, term_offsets, q_term_begin, not_bytes, not_offsets,
                             q_not_begin, ext, static_cast<cudaStream_t>(stream), out);
   });
+  if (rc != MGX_OK || *out == nullptr) {
+    index->gate.unlock_shared();
+    return rc;
+  }
+  (*out)->reader_of = index;
+  return MGX_OK;
+}
+
+// ---------------------------------------------------------------- compiled batches shared between shard processes
+//
+// Every shard answers every query, so without this every rank of a node compiles every batch (hash the terms, cut the
+// n-grams, lay the batch out): at 8 GPUs that host work, not the device, bounded the end-to-end rate. The channel is a
+// POSIX shared-memory ring: the rank whose turn it is compiles the batch once and publishes the staging bytes, the
+// others copy them into their own pinned staging buffer and bind them (one H2D copy, as after a local compile).
+namespace {
+constexpr uint64_t kShareMagic = 0x317261685378676dULL;  // "mgxShar1"
+struct ShareHeader {
+  std::atomic<uint64_t> magic;
+  uint32_t n_ranks, n_slots;
+  uint64_t slot_bytes;   // payload capacity of a slot
+  uint64_t slot_stride;  // header + payload, 4 KB aligned
+  std::atomic<uint32_t> attached;
+  uint32_t pad[7];
+};
+struct ShareSlot {
+  std::atomic<uint64_t> published;     // sequence number + 1 of the batch the slot holds, 0 = never used
+  std::atomic<uint32_t> readers_left;  // importers that have not copied it yet
+  int32_t status;                      // MGX_OK, or why the publisher could not share the batch (importers compile locally)
+  uint64_t config_sig;                 // n-gram configuration of the compiling index
+  uint64_t bytes;
+  StageLayout layout;
+};
+static_assert(std::atomic<uint64_t>::is_always_lock_free, "the ring relies on lock-free 64-bit atomics in shared memory");
+
+uint64_t index_config_sig(const Index& ix) {
+  return (static_cast<uint64_t>(ix.ngram) << 32) | (static_cast<uint64_t>(ix.kanji) << 16) |
+         (static_cast<uint64_t>(ix.width) << 8) | (ix.cross ? 1u : 0u);
+}
+}  // namespace
+
+struct mgx_share {
+  std::string name;
+  int n_ranks = 0, rank = 0;
+  uint8_t* base = nullptr;
+  size_t map_bytes = 0;
+  ShareHeader* hdr = nullptr;
+  bool owner = false;
+  ShareSlot* slot(uint64_t seq) const {
+    return reinterpret_cast<ShareSlot*>(base + 4096 + (seq % hdr->n_slots) * hdr->slot_stride);
+  }
+  uint8_t* payload(uint64_t seq) const { return reinterpret_cast<uint8_t*>(slot(seq)) + 512; }
+};
+static_assert(sizeof(ShareSlot) <= 512, "slot header");
+
+namespace {
+extern "C++" template <class Pred>
+bool spin_until(Pred done, int32_t timeout_ms) {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t spins = 0; !done(); ++spins) {
+    if (spins < 2000) {
+      continue;
+    }
+    std::this_thread::sleep_for(std::chrono::microseconds(20));
+    if (timeout_ms >= 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(timeout_ms)) {
+      return false;
+    }
+  }
+  return true;
+}
+}  // namespace
+
+int mgx_share_open(const char* name, int32_t n_ranks, int32_t rank, int32_t n_slots, uint64_t slot_bytes,
+                   mgx_share_t** out) {
+  if (name == nullptr || out == nullptr || n_ranks < 1 || rank < 0 || rank >= n_ranks || n_slots < 1 || n_slots > 64 ||
+      slot_bytes == 0) {
+    return invalid("mgx_share_open: bad argument");
+  }
+  *out = nullptr;
+  return guarded([&]() {
+    auto sh = std::make_unique<mgx_share>();
+    sh->name = name;
+    sh->n_ranks = n_ranks;
+    sh->rank = rank;
+    sh->owner = rank == 0;
+    const uint64_t stride = (512 + slot_bytes + 4095) / 4096 * 4096;
+    const size_t total = 4096 + static_cast<size_t>(n_slots) * stride;
+    int fd = -1;
+    if (sh->owner) {
+      shm_unlink(name);
+      fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+      if (fd < 0 || ftruncate(fd, static_cast<off_t>(total)) != 0) {
+        if (fd >= 0) {
+          close(fd);
+          shm_unlink(name);
+        }
+        set_last_error("mgx_share_open: cannot create the shared-memory segment");
+        return MGX_ERR_UNSUPPORTED;
+      }
+    } else {
+      const auto t0 = std::chrono::steady_clock::now();
+      struct stat sb {};
+      // rank 0 sizes the segment before it writes the header, and writes the magic last
+      while ((fd = shm_open(name, O_RDWR, 0600)) < 0 || fstat(fd, &sb) != 0 || sb.st_size < 4096) {
+        if (fd >= 0) {
+          close(fd);
+          fd = -1;
+        }
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) {
+          set_last_error("mgx_share_open: rank 0 did not create the segment within 60 s");
+          return MGX_ERR_TIMEOUT;
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(2));
+      }
+      void* hm = mmap(nullptr, 4096, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      if (hm == MAP_FAILED) {
+        close(fd);
+        set_last_error("mgx_share_open: mmap failed");
+        return MGX_ERR_UNSUPPORTED;
+      }
+      const ShareHeader* hd = static_cast<const ShareHeader*>(hm);
+      const bool up = spin_until([&]() { return hd->magic.load(std::memory_order_acquire) == kShareMagic; }, 60000);
+      const bool same = up && hd->n_ranks == static_cast<uint32_t>(n_ranks) &&
+                        hd->n_slots == static_cast<uint32_t>(n_slots) && hd->slot_bytes == slot_bytes;
+      munmap(hm, 4096);
+      if (!same) {
+        close(fd);
+        set_last_error(up ? "mgx_share_open: the segment was created with other parameters"
+                          : "mgx_share_open: rank 0 did not initialise the segment within 60 s");
+        return up ? MGX_ERR_INVALID_ARGUMENT : MGX_ERR_TIMEOUT;
+      }
+    }
+    void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) {
+      set_last_error("mgx_share_open: mmap failed");
+      return MGX_ERR_UNSUPPORTED;
+    }
+    sh->base = static_cast<uint8_t*>(m);
+    sh->map_bytes = total;
+    sh->hdr = reinterpret_cast<ShareHeader*>(m);
+    if (sh->owner) {  // a fresh segment is zero-filled: every slot starts unpublished with no readers pending
+      sh->hdr->n_ranks = static_cast<uint32_t>(n_ranks);
+      sh->hdr->n_slots = static_cast<uint32_t>(n_slots);
+      sh->hdr->slot_bytes = slot_bytes;
+      sh->hdr->slot_stride = stride;
+      sh->hdr->magic.store(kShareMagic, std::memory_order_release);
+    }
+    sh->hdr->attached.fetch_add(1);
+    *out = sh.release();
+    return MGX_OK;
+  });
+}
+
+void mgx_share_close(mgx_share_t* share) {
+  if (share == nullptr) {
+    return;
+  }
+  if (share->base != nullptr) {
+    munmap(share->base, share->map_bytes);
+  }
+  if (share->owner) {
+    shm_unlink(share->name.c_str());
+  }
+  delete share;
+}
+
+int mgx_share_publish(mgx_share_t* share, uint64_t seq, const mgx_batch_t* batch, int32_t timeout_ms) {
+  if (share == nullptr || batch == nullptr) {
+    return invalid("null argument");
+  }
+  return guarded([&]() {
+    ShareSlot* sl = share->slot(seq);
+    // the slot's previous batch (seq - n_slots) must have been copied by every importer
+    if (!spin_until([&]() { return sl->readers_left.load(std::memory_order_acquire) == 0; }, timeout_ms)) {
+      set_last_error("mgx_share_publish: the other ranks did not take the slot's previous batch in time");
+      return MGX_ERR_TIMEOUT;
+    }
+    const Batch& b = batch->b;
+    const StageOffsets O = stage_offsets(b.layout);
+    int status = MGX_OK;
+    if (b.layout.n_preds != 0 || b.explicit_driver.d_ids != nullptr) {
+      status = MGX_ERR_UNSUPPORTED;  // predicates / driver sets hold device addresses of this shard
+    } else if (O.total > share->hdr->slot_bytes) {
+      status = MGX_ERR_CAPACITY;
+    }
+    sl->status = status;
+    sl->layout = b.layout;
+    sl->config_sig = index_config_sig(*b.ix);
+    sl->bytes = status == MGX_OK ? O.total : 0;
+    if (status == MGX_OK) {
+      std::memcpy(share->payload(seq), b.staging.p, O.total);
+    }
+    sl->readers_left.store(static_cast<uint32_t>(share->n_ranks - 1), std::memory_order_relaxed);
+    sl->published.store(seq + 1, std::memory_order_release);
+    if (status != MGX_OK) {
+      set_last_error(status == MGX_ERR_CAPACITY ? "mgx_share_publish: the compiled batch exceeds the slot size"
+                                                 : "mgx_share_publish: batches with column conditions or an explicit "
+                                                   "driver set cannot be shared");
+    }
+    return status;
+  });
+}
+
+int mgx_share_import(mgx_share_t* share, uint64_t seq, mgx_index_t* index, const mgx_query_params_t* params,
+                     void* stream, int32_t timeout_ms, mgx_batch_t** out) {
+  if (share == nullptr || index == nullptr || params == nullptr || out == nullptr) {
+    return invalid("null argument");
+  }
+  *out = nullptr;
+  if (int rc = check_params(*params); rc != MGX_OK) {
+    return rc;
+  }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
+  ShareSlot* sl = share->slot(seq);
+  if (!spin_until([&]() { return sl->published.load(std::memory_order_acquire) == seq + 1; }, timeout_ms)) {
+    set_last_error("mgx_share_import: the batch was not published in time");
+    return MGX_ERR_TIMEOUT;
+  }
+  index->gate.lock_shared();
+  const int rc = guarded([&]() {
+    Index& ix = index->ix;
+    if (sl->status != MGX_OK) {
+      set_last_error("mgx_share_import: the publisher could not share this batch; compile it locally");
+      return static_cast<int>(sl->status);
+    }
+    if (sl->config_sig != index_config_sig(ix)) {
+      return invalid("mgx_share_import: the batch was compiled for another n-gram configuration");
+    }
+    DeviceGuard guard(ix.device);
+    std::unique_ptr<mgx_batch> h = take_pooled_batch(ix);
+    Batch& b = h->b;
+    b.ix = &ix;
+    b.params = *params;
+    b.stream = static_cast<cudaStream_t>(stream);
+    b.launches_at_start = g_launches.load();
+    batch_import(b, sl->layout, share->payload(seq));
+    *out = h.release();
+    return MGX_OK;
+  });
+  sl->readers_left.fetch_sub(1, std::memory_order_acq_rel);  // taken (or refused): the slot is free for this rank
   if (rc != MGX_OK || *out == nullptr) {
     index->gate.unlock_shared();
     return rc;

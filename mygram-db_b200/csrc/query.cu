@@ -3874,42 +3874,34 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   }
   b.n_keys = static_cast<uint32_t>(n_keys);
   b.n_qterms = static_cast<uint32_t>(n_tids);
-  size_t total = 0;
-  auto add = [&](size_t nbytes) {
-    const size_t at = total;
-    total += DevArena::padded(nbytes == 0 ? 1 : nbytes);
-    return at;
-  };
-  const size_t i_bytes = add(n_bytes);
-  const size_t i_boff = add((T + 1) * 4);
-  const size_t i_koff = add((T + 1) * 4);
-  const size_t i_keys = add(n_keys * 8);
-  const size_t i_raw = add(T + 1);
-  const size_t i_toff = add((Q + 1) * 4);
-  const size_t i_tids = add(n_tids * 4);
-  const size_t i_tids0 = add(n_tids * 4);
-  const size_t i_noff = add((Q + 1) * 4);
-  const size_t i_ntids = add(n_ntids * 4);
-  const size_t i_loff = add((Q + 1) * 4);
-  const size_t i_hflags = add((Q + 1) * 4);
-  const size_t i_slot = add(slot_tid.size() * 4);
-  const size_t i_ktoff = add(n_keys * 2);
-  const size_t i_thr = add((Q + 1) * 4);
-  const size_t i_poff = add((Q + 1) * 4);
-  const size_t i_pops = add(n_prog);
-  const size_t i_pargs = add(n_prog * 4);
-  const size_t i_coff = add((Q + 1) * 4);
-  const size_t i_conj = add(n_conj * 4);
-  const size_t i_foff = add((Q + 1) * 4);
-  const size_t i_preds = add(n_preds * sizeof(FilterPred));
-  const size_t i_sslots = add(stream_table.slots.size() * 4);
-  const size_t i_sentries = add(stream_table.entries.size() * sizeof(StreamEntry));
-  const size_t i_sbloom = add(stream_table.bloom.size() * 4);
-  const size_t i_xoff = add(b.h_xoff.size() * 4);
-  b.n_stream_slots = static_cast<uint32_t>(stream_table.slots.size());
-  b.n_stream_terms = static_cast<uint32_t>(stream_table.entries.size());
-  b.stream_len8_mask = stream_table.len8_mask;
-  b.stream_len12_mask = stream_table.len12_mask;
+  StageLayout& L = b.layout;
+  L = StageLayout{};
+  L.n_terms = T;
+  L.n_queries = Q;
+  L.n_out_queries = b.n_out_queries;
+  L.n_slots = slot_tid.size();
+  L.n_bytes = n_bytes;
+  L.n_keys = n_keys;
+  L.n_tids = n_tids;
+  L.n_ntids = n_ntids;
+  L.n_prog = n_prog;
+  L.n_conj = n_conj;
+  L.n_preds = n_preds;
+  L.n_sslots = stream_table.slots.size();
+  L.n_sentries = stream_table.entries.size();
+  L.n_sbloom = stream_table.bloom.size();
+  L.n_xoff = b.h_xoff.size();
+  L.stream_len8_mask = stream_table.len8_mask;
+  L.stream_len12_mask = stream_table.len12_mask;
+  L.assumed_all_valid_utf8 = b.ix->all_valid_utf8 ? 1 : 0;
+  const StageOffsets O = stage_offsets(L);
+  const size_t total = O.total;
+  const size_t i_bytes = O.i_bytes, i_boff = O.i_boff, i_koff = O.i_koff, i_keys = O.i_keys, i_raw = O.i_raw;
+  const size_t i_toff = O.i_toff, i_tids = O.i_tids, i_tids0 = O.i_tids0, i_noff = O.i_noff, i_ntids = O.i_ntids;
+  const size_t i_loff = O.i_loff, i_hflags = O.i_hflags, i_slot = O.i_slot, i_ktoff = O.i_ktoff, i_thr = O.i_thr;
+  const size_t i_poff = O.i_poff, i_pops = O.i_pops, i_pargs = O.i_pargs, i_coff = O.i_coff, i_conj = O.i_conj;
+  const size_t i_foff = O.i_foff, i_preds = O.i_preds, i_sslots = O.i_sslots, i_sentries = O.i_sentries;
+  const size_t i_sbloom = O.i_sbloom, i_xoff = O.i_xoff;
   b.staging.reserve(total + 256);
   uint8_t* const S = b.staging.p;
 
@@ -4000,6 +3992,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
     hflags[Q] = 0;
     thresholds[Q] = 1;
     list_cap = nl;
+    L.list_cap = nl;
   }
   if (!slot_tid.empty()) {
     std::memcpy(S + i_slot, slot_tid.data(), slot_tid.size() * 4);
@@ -4012,6 +4005,76 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
     std::memcpy(S + i_sentries, stream_table.entries.data(), stream_table.entries.size() * sizeof(StreamEntry));
     std::memcpy(S + i_sbloom, stream_table.bloom.data(), stream_table.bloom.size() * 4);
   }
+  (void)st;
+  (void)list_cap;
+  batch_bind(b);
+}
+
+StageOffsets stage_offsets(const StageLayout& L) {
+  StageOffsets O{};
+  size_t total = 0;
+  auto add = [&](size_t nbytes) {
+    const size_t at = total;
+    total += DevArena::padded(nbytes == 0 ? 1 : nbytes);
+    return at;
+  };
+  const size_t T = L.n_terms, Q = L.n_queries;
+  O.i_bytes = add(L.n_bytes);
+  O.i_boff = add((T + 1) * 4);
+  O.i_koff = add((T + 1) * 4);
+  O.i_keys = add(L.n_keys * 8);
+  O.i_raw = add(T + 1);
+  O.i_toff = add((Q + 1) * 4);
+  O.i_tids = add(L.n_tids * 4);
+  O.i_tids0 = add(L.n_tids * 4);
+  O.i_noff = add((Q + 1) * 4);
+  O.i_ntids = add(L.n_ntids * 4);
+  O.i_loff = add((Q + 1) * 4);
+  O.i_hflags = add((Q + 1) * 4);
+  O.i_slot = add(L.n_slots * 4);
+  O.i_ktoff = add(L.n_keys * 2);
+  O.i_thr = add((Q + 1) * 4);
+  O.i_poff = add((Q + 1) * 4);
+  O.i_pops = add(L.n_prog);
+  O.i_pargs = add(L.n_prog * 4);
+  O.i_coff = add((Q + 1) * 4);
+  O.i_conj = add(L.n_conj * 4);
+  O.i_foff = add((Q + 1) * 4);
+  O.i_preds = add(L.n_preds * sizeof(FilterPred));
+  O.i_sslots = add(L.n_sslots * 4);
+  O.i_sentries = add(L.n_sentries * sizeof(StreamEntry));
+  O.i_sbloom = add(L.n_sbloom * 4);
+  O.i_xoff = add(L.n_xoff * 4);
+  O.total = total;
+  return O;
+}
+
+// The compiled batch lies in b.staging in the layout b.layout describes: copy it to the device in ONE transfer, point
+// the batch's arrays into it and carve the device-only planning arrays. Shared by the local compile (batch_upload)
+// and by a batch that was compiled elsewhere (batch_import).
+void batch_bind(Batch& b) {
+  cudaStream_t st = b.stream;
+  const StageLayout& L = b.layout;
+  const StageOffsets O = stage_offsets(L);
+  const size_t T = L.n_terms, Q = L.n_queries, n_keys = L.n_keys, n_tids = L.n_tids, n_bytes = L.n_bytes;
+  const size_t n_ntids = L.n_ntids, n_prog = L.n_prog, n_conj = L.n_conj, n_preds = L.n_preds, list_cap = L.list_cap;
+  const size_t total = O.total;
+  const size_t i_bytes = O.i_bytes, i_boff = O.i_boff, i_koff = O.i_koff, i_keys = O.i_keys, i_raw = O.i_raw;
+  const size_t i_toff = O.i_toff, i_tids = O.i_tids, i_tids0 = O.i_tids0, i_noff = O.i_noff, i_ntids = O.i_ntids;
+  const size_t i_loff = O.i_loff, i_hflags = O.i_hflags, i_slot = O.i_slot, i_ktoff = O.i_ktoff, i_thr = O.i_thr;
+  const size_t i_poff = O.i_poff, i_pops = O.i_pops, i_pargs = O.i_pargs, i_coff = O.i_coff, i_conj = O.i_conj;
+  const size_t i_foff = O.i_foff, i_preds = O.i_preds, i_sslots = O.i_sslots, i_sentries = O.i_sentries;
+  const size_t i_sbloom = O.i_sbloom, i_xoff = O.i_xoff;
+  b.n_queries = static_cast<uint32_t>(Q);
+  b.n_out_queries = static_cast<uint32_t>(L.n_out_queries);
+  b.n_terms = static_cast<uint32_t>(T);
+  b.n_slots = static_cast<uint32_t>(L.n_slots);
+  b.n_keys = static_cast<uint32_t>(n_keys);
+  b.n_qterms = static_cast<uint32_t>(n_tids);
+  b.n_stream_slots = static_cast<uint32_t>(L.n_sslots);
+  b.n_stream_terms = static_cast<uint32_t>(L.n_sentries);
+  b.stream_len8_mask = L.stream_len8_mask;
+  b.stream_len12_mask = L.stream_len12_mask;
   b.in_arena.reserve(total + 256, true);
   uint8_t* base = b.in_arena.take<uint8_t>(total);
   MGX_CUDA(cudaMemcpyAsync(base, b.staging.p, total, cudaMemcpyHostToDevice, st));
@@ -4029,7 +4092,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   b.d_q_ntids.borrow(reinterpret_cast<uint32_t*>(at(i_ntids)), n_ntids);
   b.d_q_loff.borrow(reinterpret_cast<uint32_t*>(at(i_loff)), Q + 1);
   b.d_q_host_flags.borrow(reinterpret_cast<uint32_t*>(at(i_hflags)), Q + 1);
-  b.d_slot_tid.borrow(reinterpret_cast<uint32_t*>(at(i_slot)), slot_tid.size());
+  b.d_slot_tid.borrow(reinterpret_cast<uint32_t*>(at(i_slot)), L.n_slots);
   b.d_key_toff.borrow(reinterpret_cast<uint16_t*>(at(i_ktoff)), n_keys);
   b.d_q_threshold.borrow(reinterpret_cast<uint32_t*>(at(i_thr)), Q + 1);
   b.d_q_poff.borrow(reinterpret_cast<uint32_t*>(at(i_poff)), Q + 1);
@@ -4039,10 +4102,10 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   b.d_q_conj.borrow(reinterpret_cast<uint32_t*>(at(i_conj)), n_conj);
   b.d_q_foff.borrow(reinterpret_cast<uint32_t*>(at(i_foff)), Q + 1);
   b.d_filters.borrow(reinterpret_cast<FilterPred*>(at(i_preds)), n_preds);
-  b.d_stream_slots.borrow(reinterpret_cast<uint32_t*>(at(i_sslots)), stream_table.slots.size());
-  b.d_stream_entries.borrow(reinterpret_cast<StreamEntry*>(at(i_sentries)), stream_table.entries.size());
-  b.d_stream_bloom.borrow(reinterpret_cast<uint32_t*>(at(i_sbloom)), stream_table.bloom.size());
-  b.d_xoff.borrow(reinterpret_cast<uint32_t*>(at(i_xoff)), b.h_xoff.size());
+  b.d_stream_slots.borrow(reinterpret_cast<uint32_t*>(at(i_sslots)), L.n_sslots);
+  b.d_stream_entries.borrow(reinterpret_cast<StreamEntry*>(at(i_sentries)), L.n_sentries);
+  b.d_stream_bloom.borrow(reinterpret_cast<uint32_t*>(at(i_sbloom)), L.n_sbloom);
+  b.d_xoff.borrow(reinterpret_cast<uint32_t*>(at(i_xoff)), L.n_xoff);
 
   // ---- device-only planning arrays from the work arena
   const size_t K = n_keys;
@@ -4083,6 +4146,35 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   b.in_base = base;
   b.in_total = total;
   batch_clear_counters(b);
+}
+
+void batch_import(Batch& b, const StageLayout& layout, const uint8_t* bytes) {
+  if (layout.n_preds != 0) {
+    set_last_error("a batch with column conditions cannot be shared (its predicates hold device addresses)");
+    throw CudaFailure{MGX_ERR_UNSUPPORTED};
+  }
+  const StageOffsets O = stage_offsets(layout);
+  b.layout = layout;
+  b.staging.reserve(O.total + 256);
+  std::memcpy(b.staging.p, bytes, O.total);
+  if (layout.assumed_all_valid_utf8 != 0 && !b.ix->all_valid_utf8) {
+    // the compiling shard held only valid UTF-8 and chose the streaming df pass for some terms; this shard cannot
+    // (DESIGN: exactness of the two shortcuts), so those terms go back to the candidate-tile path here
+    uint8_t* raw = b.staging.p + O.i_raw;
+    for (uint64_t t = 0; t < layout.n_terms; ++t) {
+      raw[t] &= static_cast<uint8_t>(~4u);
+    }
+  }
+  b.h_slot_tid.clear();
+  b.h_xoff.clear();
+  if (layout.n_xoff != 0) {
+    const uint32_t* x = reinterpret_cast<const uint32_t*>(b.staging.p + O.i_xoff);
+    b.h_xoff.assign(x, x + layout.n_xoff);
+  }
+  batch_bind(b);
+  if (layout.assumed_all_valid_utf8 != 0 && !b.ix->all_valid_utf8) {
+    b.n_stream_slots = b.n_stream_terms = 0;
+  }
 }
 
 void batch_clear_counters(Batch& b) {

@@ -177,8 +177,25 @@ struct HostQuery {
   std::vector<HostFilter> filters;  // column conditions, AND-ed
 };
 
+// Counts that fix the layout of a compiled batch in its staging buffer (every array padded to 256 bytes, in the
+// order stage_offsets() lays them out). Plain data: it travels with the staging bytes when a batch compiled by one
+// process is handed to others (mgx_share_*).
+struct StageLayout {
+  uint64_t n_terms = 0, n_queries = 0, n_out_queries = 0, n_slots = 0, n_bytes = 0, n_keys = 0, n_tids = 0, n_ntids = 0;
+  uint64_t n_prog = 0, n_conj = 0, n_preds = 0, n_sslots = 0, n_sentries = 0, n_sbloom = 0, n_xoff = 0, list_cap = 0;
+  uint32_t stream_len8_mask = 0, stream_len12_mask = 0;
+  uint32_t assumed_all_valid_utf8 = 0;  // the compiling shard held no invalid UTF-8 (term shortcuts were decided with that)
+  uint32_t pad = 0;
+};
+struct StageOffsets {
+  size_t i_bytes, i_boff, i_koff, i_keys, i_raw, i_toff, i_tids, i_tids0, i_noff, i_ntids, i_loff, i_hflags, i_slot, i_ktoff,
+      i_thr, i_poff, i_pops, i_pargs, i_coff, i_conj, i_foff, i_preds, i_sslots, i_sentries, i_sbloom, i_xoff, total;
+};
+StageOffsets stage_offsets(const StageLayout& L);
+
 struct Batch {
   Index* ix = nullptr;
+  StageLayout layout;
   SearchScratch* sc = nullptr;  // the (index, stream) workspace; the d_tile_* / d_rec_* members below are views into it
   uint64_t serial = 0;          // unique per use of the batch object
   mgx_query_params_t params{};
@@ -352,6 +369,11 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
                   const std::vector<uint32_t>& slot_tid, const std::vector<uint32_t>* xoff = nullptr);
 // Bucket table over the terms with `streamable` set (clears the flag of terms that do not fit a bucket).
 void build_stream_table(std::vector<HostTerm>& terms, HostStreamTable* out);
+void batch_bind(Batch& b);
+// A batch compiled by another process for an index of the same configuration: `bytes` = its staging buffer
+// (layout.total bytes). Fix-ups for this shard (term shortcuts that assumed an all-valid-UTF-8 corpus) are applied to
+// the copy. Batches with column filters cannot travel (their predicates hold device pointers of the compiling shard).
+void batch_import(Batch& b, const StageLayout& layout, const uint8_t* bytes);
 void batch_plan(Batch& b);
 void batch_clear_counters(Batch& b);
 void batch_df(Batch& b);

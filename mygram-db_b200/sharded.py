@@ -295,6 +295,39 @@ class ShardPipeline:
                                              C.c_void_p(stream.cuda_stream), C.byref(h)))
         return {"h": h, "n_queries": n_queries}
 
+    def open_share(self, name, n_ranks, rank, n_slots=8, slot_bytes=4 << 20):
+        """Attach to the node's ring of compiled batches (mgx_share_open; rank 0 creates it). Afterwards
+        prepare_shared() compiles a batch on ONE rank only."""
+        h = C.c_void_p()
+        self.mgx._check(self.L.mgx_share_open(name.encode(), n_ranks, rank, n_slots, slot_bytes, C.byref(h)))
+        self.share, self.share_ranks, self.share_rank = h, n_ranks, rank
+
+    def close_share(self):
+        if getattr(self, "share", None) is not None:
+            self.L.mgx_share_close(self.share)
+            self.share = None
+
+    def prepare_shared(self, seq, arena, offsets, qbeg, n_queries, stream, ext=None, timeout_ms=60000):
+        """Batch number `seq` of the node's common sequence: compiled by rank seq % n_ranks and published, imported by
+        the others. A batch the channel cannot carry (column conditions, larger than a slot) is compiled locally by
+        every rank -- publish and import report the same status for it."""
+        m = self.mgx
+        if getattr(self, "share", None) is None or self.share_ranks == 1:
+            return self.prepare(arena, offsets, qbeg, n_queries, stream, ext)
+        if seq % self.share_ranks == self.share_rank:
+            p = self.prepare(arena, offsets, qbeg, n_queries, stream, ext)
+            rc = self.L.mgx_share_publish(self.share, seq, p["h"], timeout_ms)
+            if rc not in (m.MGX_OK, m.MGX_ERR_UNSUPPORTED, m.MGX_ERR_CAPACITY):
+                m._check(rc)
+            return p
+        h = C.c_void_p()
+        rc = self.L.mgx_share_import(self.share, seq, self.index._h, C.byref(self.params),
+                                     C.c_void_p(stream.cuda_stream), timeout_ms, C.byref(h))
+        if rc in (m.MGX_ERR_UNSUPPORTED, m.MGX_ERR_CAPACITY):
+            return self.prepare(arena, offsets, qbeg, n_queries, stream, ext)
+        m._check(rc)
+        return {"h": h, "n_queries": n_queries}
+
     def rearm(self, batch):
         """Back to the uploaded state (the compiled batch is copied from its pinned staging buffer again), so the
         same batch object can be enqueued once more."""

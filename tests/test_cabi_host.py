@@ -178,3 +178,21 @@ def test_shard_record_layout_matches_the_python_protocol(mgx):
     again = sharded.record_views(rec, 5, 3)
     assert int(again[0][1, 4, 2]) == 77 and float(again[1][0, 0, 0]) == 1.5
     assert int(again[2][1, 0]) == 3 and int(again[3][0, 4]) == 1 << 40
+
+
+def test_share_ring_opens_and_attaches_without_a_device(mgx):
+    """mgx_share_open: rank 0 creates the shared-memory ring, another handle attaches with the same geometry; a
+    handle that disagrees about the geometry is refused. No compute call, so it runs without a GPU."""
+    import ctypes as C
+    import os
+    L = mgx.lib()
+    name = f"/mgx_cpu_share_{os.getpid()}".encode()
+    a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert L.mgx_share_open(name, 2, 0, 4, 1 << 16, C.byref(a)) == 0
+    assert L.mgx_share_open(name, 2, 1, 4, 1 << 16, C.byref(b)) == 0
+    assert L.mgx_share_open(name, 2, 1, 8, 1 << 16, C.byref(c)) != 0 and not c.value
+    assert L.mgx_share_open(name, 2, 2, 4, 1 << 16, C.byref(c)) == -1
+    assert os.path.exists("/dev/shm/" + name.decode()[1:])
+    L.mgx_share_close(b)
+    L.mgx_share_close(a)
+    assert not os.path.exists("/dev/shm/" + name.decode()[1:])

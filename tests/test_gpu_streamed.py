@@ -353,3 +353,79 @@ def test_or_rooted_programs_are_expanded_by_driver(mgx, oracle, shard, monkeypat
         assert int(got.total[0]) == want.size
         k = min(100, want.size)
         assert np.array_equal(got.ids[0, :k], want[:k])
+
+
+def test_shared_compiled_batches_equal_local_compiles(mgx, shard):
+    """mgx_share_*: a batch compiled by one shard process and imported by another must give the answers of a local
+    compile, bit for bit -- also on a shard that holds invalid UTF-8 while the compiling shard did not (the streaming
+    df pass the compiler chose is not exact there), after a re-arm, and a batch with column conditions is refused by
+    publish and import alike. Both "ranks" live in this process (two handles on one segment)."""
+    import torch
+    sharded = __import__("importlib").import_module("mygram_db_b200.sharded")
+    c, gi = shard
+    device = torch.device("cuda", 0)
+    # second shard: other documents, one of them not valid UTF-8
+    c2 = corpus_mod.generate("cjk", 30000, 0xC7, alphabet=400, min_len=8, max_len=60)
+    arena2 = c2.arena.copy()
+    arena2[int(c2.offsets[5])] = 0xFF
+    g2 = mgx.Index(2, 0, True)
+    g2.build(c2.doc_ids, arena2, c2.offsets)
+    assert g2.stats().all_valid_utf8 == 0 and gi.stats().all_valid_utf8 == 1
+    params1 = gi.params(score=True, limit=100, offset=0)
+    params2 = g2.params(score=True, limit=100, offset=0)
+    comm = sharded.ShardComm(mgx, None, device)
+    pub = sharded.ShardPipeline(mgx, gi, params1, 100, comm)
+    imp = sharded.ShardPipeline(mgx, g2, params2, 100, comm)
+    name = f"/mgx_test_share_{os.getpid()}"
+    pub.open_share(name, 2, 0, n_slots=2, slot_bytes=1 << 20)
+    imp.open_share(name, 2, 1, n_slots=2, slot_bytes=1 << 20)
+    st = torch.cuda.Stream(device=device)
+    lay = sharded.record_layout(3000, 100)
+    out = torch.empty(lay["bytes"], dtype=torch.uint8, pin_memory=True)
+
+    def answers(pipe, p):
+        pipe.enqueue(p, 0, out)
+        pipe.finish(p)
+        return [t.numpy().copy() for t in sharded.record_views(out, 3000, 100)]
+
+    for seq in range(5):  # more batches than slots: the ring wraps
+        qs = corpus_mod.sample_queries(c, 3000, 200 + seq, n_terms=2, min_cp=2, max_cp=3)  # large: streaming df pass
+        arena, offs, qbeg, _ = mgx.flatten_queries(qs)
+        p0 = pub.prepare_shared(seq * 2, arena, offs, qbeg, 3000, st)         # rank 0's turn: compile + publish
+        p1 = imp.prepare_shared(seq * 2, arena, offs, qbeg, 3000, st)         # rank 1 imports
+        want1 = g2.query_batch(qs, score=True, limit=100)
+        want0 = gi.query_batch(qs, score=True, limit=100)
+        for pipe, p, w in ((pub, p0, want0), (imp, p1, want1)):
+            for again in range(2):
+                ids, scores, count, total = answers(pipe, p)
+                assert np.array_equal(count.view(np.uint32), w.count) and np.array_equal(total.view(np.uint64), w.total)
+                valid = np.arange(100)[None, :] < w.count[:, None]
+                assert np.array_equal(ids.view(np.uint32)[valid], w.ids[valid])
+                assert np.array_equal(scores[valid].view(np.uint64), w.scores[valid].view(np.uint64))
+                pipe.rearm(p)
+            pipe.release(p)
+        # the odd sequence numbers are rank 1's turn: the invalid-UTF-8 shard compiles, the clean shard imports
+        p1 = imp.prepare_shared(seq * 2 + 1, arena, offs, qbeg, 3000, st)
+        p0 = pub.prepare_shared(seq * 2 + 1, arena, offs, qbeg, 3000, st)
+        ids, scores, count, total = answers(pub, p0)
+        assert np.array_equal(total.view(np.uint64), want0.total) and np.array_equal(count.view(np.uint32), want0.count)
+        pub.release(p0)
+        imp.release(p1)
+    # a batch with a column condition cannot travel: publish and import agree, both sides compile locally
+    n = gi.stats().n_docs
+    gi.set_filter_column_arrays(0, 8, (np.arange(n) % 3).astype(np.int64))
+    qs = corpus_mod.sample_queries(c, 8, 999)
+    arena, offs, qbeg, _ = mgx.flatten_queries(qs)
+    ext, keep = mgx.Index.build_ext(None, [[(0, 0, "1")]] * 8)
+    L = mgx.lib()
+    h = C.c_void_p()
+    mgx._check(L.mgx_batch_prepare_ex(gi._h, C.byref(params1), 8, mgx._ptr(arena, mgx.u8p), mgx._ptr(offs, mgx.u64p),
+                                      mgx._ptr(qbeg, mgx.u64p), None, None, None, C.byref(ext), None, C.byref(h)))
+    assert L.mgx_share_publish(pub.share, 10, h, 1000) == mgx.MGX_ERR_UNSUPPORTED
+    h2 = C.c_void_p()
+    assert L.mgx_share_import(imp.share, 10, g2._h, C.byref(params2), None, 1000, C.byref(h2)) == mgx.MGX_ERR_UNSUPPORTED
+    assert L.mgx_share_import(imp.share, 11, g2._h, C.byref(params2), None, 50, C.byref(h2)) == -7  # MGX_ERR_TIMEOUT: never published
+    L.mgx_batch_destroy(h)
+    imp.close_share()
+    pub.close_share()
+    g2.close()
