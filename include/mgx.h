@@ -284,7 +284,7 @@ typedef struct {
   int32_t cross_boundary;
   int32_t compute_score;     /* 1: SORT _score; 0: ascending doc ids                      */
   int32_t descending;        /* SortOrder::DESC (default) / ASC for _score                */
-  uint32_t limit;            /* query_parser.h:217 default 100; limit+offset <= 1024     */
+  uint32_t limit;            /* query_parser.h:217 default 100; any offset; 0 = everything from offset on (single shard) */
   uint32_t offset;
   int32_t verify_text;       /* 0 = "off" (config.h:329): n-gram AND incl. false positives; */
                              /* 1 = "all": PostFilterByText (search_pipeline.cpp:1239-1246) */
@@ -566,7 +566,8 @@ int mgx_score_documents(mgx_index_t* index, const uint32_t* candidates, uint64_t
                         const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* term_doc_freqs,
                         uint64_t n_terms, uint64_t total_docs, double avg_doc_length, double k1, double b,
                         double* out_scores);
-/* ResultSorter::SortByScore (query/result_sorter.cpp:661-716). limit+offset <= 1024, limit > 0. */
+/* ResultSorter::SortByScore (query/result_sorter.cpp:661-716): any offset; limit 0 = everything from offset on
+ * (:689-710). out holds min(limit, n) entries, n when limit is 0. */
 int mgx_sort_by_score(mgx_index_t* index, const uint32_t* results, const double* scores, uint64_t n,
                       int32_t descending, uint32_t limit, uint32_t offset, uint32_t* out, uint64_t* out_count);
 

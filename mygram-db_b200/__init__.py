@@ -719,7 +719,7 @@ class ResultSorter:
     def sort_by_score(index: Index, results, scores, descending=True, limit=100, offset=0):
         r = np.ascontiguousarray(results, dtype=np.uint32)
         s = np.ascontiguousarray(scores, dtype=np.float64)
-        out = np.zeros(max(1, limit), dtype=np.uint32)
+        out = np.zeros(max(1, r.size if limit == 0 else min(limit, r.size)), dtype=np.uint32)  # limit 0 = everything
         n = C.c_uint64(0)
         rp = r if r.size else np.zeros(1, np.uint32)
         sp = s if s.size else np.zeros(1, np.float64)

@@ -15,6 +15,7 @@
 // data), ScoreDocuments reports kInvalidArgument / kInternalError through the result object.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <memory>
@@ -354,11 +355,11 @@ class ResultSorter {
     if (results.empty()) {
       return {};  // result_sorter.cpp:663-665
     }
-    const uint32_t lim = limit == 0 ? static_cast<uint32_t>(results.size()) : limit;  // 0 = everything after offset
-    std::vector<DocId> out(lim);
+    // limit 0 = everything after offset (result_sorter.cpp:689-710); the window never exceeds min(limit, size)
+    std::vector<DocId> out(limit == 0 ? results.size() : std::min<size_t>(limit, results.size()));
     uint64_t n = 0;
     detail::check(mgx_sort_by_score(index.handle(), results.data(), scores.data(), results.size(),
-                                    order == SortOrder::DESC ? 1 : 0, lim, offset, out.data(), &n));
+                                    order == SortOrder::DESC ? 1 : 0, limit, offset, out.data(), &n));
     out.resize(n);
     return out;
   }

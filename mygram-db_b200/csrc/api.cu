@@ -815,11 +815,10 @@ bool expand_or_roots(const std::vector<HostTerm>& terms, const std::vector<HostQ
 }
 
 int check_params(const mgx_query_params_t& p) {
-  if (p.compute_score != 0) {
-    if (p.limit == 0 || static_cast<uint64_t>(p.limit) + p.offset > kMaxTopK) {
-      set_last_error("SORT _score needs 0 < limit and limit + offset <= 1024 in this build");
-      return MGX_ERR_UNSUPPORTED;
-    }
+  // SortByScore takes any offset and limit (limit 0 = everything from offset, result_sorter.cpp:689-710); the only
+  // bound here is that offset + limit is computed in 32 bits by the shard / merge stages
+  if (static_cast<uint64_t>(p.limit) + p.offset > 0xFFFFFFFFULL) {
+    return invalid("limit + offset must fit 32 bits");
   }
   return MGX_OK;
 }
@@ -2805,6 +2804,11 @@ struct ShardParams {
 };
 
 int check_stride(const mgx_query_params_t& p, uint64_t stride) {
+  if (p.limit == 0 && p.compute_score != 0) {
+    set_last_error("sharded _score batches need an explicit limit: a shard returns its best limit + offset records, "
+                   "and 'everything' (limit 0) has no bound to size the exchange with");
+    return MGX_ERR_UNSUPPORTED;
+  }
   if (p.limit != 0 && stride < static_cast<uint64_t>(p.limit) + p.offset) {
     set_last_error("stride must hold limit + offset records per query: a shard returns its best limit + offset records "
                    "un-offset and the merge skips the offset");
@@ -3500,10 +3504,6 @@ int mgx_sort_by_score(mgx_index_t* index, const uint32_t* results, const double*
   if (n == 0) {
     return MGX_OK;  // result_sorter.cpp:663-665
   }
-  if (limit == 0 || static_cast<uint64_t>(limit) + offset > kMaxTopK) {
-    set_last_error("mgx_sort_by_score needs 0 < limit and limit + offset <= 1024 in this build");
-    return MGX_ERR_UNSUPPORTED;
-  }
   return guarded([&]() {
     Reader rd(index);
     Index& ix = index->ix;
@@ -3515,7 +3515,7 @@ int mgx_sort_by_score(mgx_index_t* index, const uint32_t* results, const double*
     DevBuf<uint32_t> d_cnt;
     d_docs.alloc(n);
     d_scores.alloc(n);
-    d_out.alloc(limit);
+    d_out.alloc(limit == 0 ? n : std::min<uint64_t>(limit, n));  // the window never exceeds min(limit, n)
     d_cnt.alloc(1);
     MGX_CUDA(cudaMemcpyAsync(d_docs.p, results, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     MGX_CUDA(cudaMemcpyAsync(d_scores.p, scores, n * sizeof(double), cudaMemcpyHostToDevice, st));

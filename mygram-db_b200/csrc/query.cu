@@ -93,6 +93,7 @@ struct BatchView {
   const uint32_t* q_tids0;             // [sum] search terms in QUERY order (q_tids is re-ordered by the planner)
   uint64_t* key_glen;                  // [K] posting size per key in UPLOAD order; summed over the shards by the df
                                        // exchange of the sharded pipeline (global term order, see global_order_kernel)
+  unsigned long long* q_thr;           // [Q] running score threshold of the per-tile top-k pruning (and_tile_body)
 };
 
 struct ScoreParams {
@@ -1966,6 +1967,124 @@ __device__ void bitonic_sort_desc(SortKey* keys, uint32_t n_pow2) {
   __syncthreads();
 }
 
+// Shared state of a block-wide windowed top-k (256 threads).
+struct TopkShared {
+  SortKey keys[kTopkSmem];
+  uint32_t hist[256];
+  uint32_t cnt;
+  SortKey prefix;
+  uint64_t need;
+};
+
+// The kth-best key (1-based, SortByScore order = descending SortKey order) of the records `scan` enumerates:
+// MSB-first radix select, twelve 8-bit passes over the 96-bit key. scan(f) calls f(key) for every record, the
+// records strided over the block's threads. Keys are unique per query (doc ids are).
+template <class Scan>
+__device__ SortKey block_select_kth(TopkShared& sh, Scan scan, uint64_t kth) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sh.prefix.s = 0;
+    sh.prefix.d = 0;
+    sh.need = kth;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 12; ++pass) {
+    sh.hist[threadIdx.x] = 0;
+    __syncthreads();
+    const SortKey prefix = sh.prefix;
+    scan([&](const SortKey k) {
+      if (key_has_prefix(k, prefix, pass)) {
+        atomicAdd(&sh.hist[key_digit(k, pass)], 1u);
+      }
+    });
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint64_t need = sh.need;
+      int digit = 255;
+      for (; digit > 0; --digit) {
+        if (sh.hist[digit] >= need) {
+          break;
+        }
+        need -= sh.hist[digit];
+      }
+      sh.need = need;
+      if (pass < 8) {
+        sh.prefix.s |= static_cast<uint64_t>(digit) << (56 - 8 * pass);
+      } else {
+        sh.prefix.d |= static_cast<uint32_t>(digit) << (24 - 8 * (pass - 8));
+      }
+    }
+    __syncthreads();
+  }
+  return sh.prefix;
+}
+
+// Records ranked [want_begin, want_begin + n_out) of n_records records in SortByScore order: emit(i, key) for the
+// i-th record of the window. Up to kTopkSmem records: one shared-memory sort. A window that ends within the best
+// kTopkSmem: one select, the head is sorted and cut. Anything else (ResultSorter::SortByScore takes any offset, and
+// limit 0 = everything, result_sorter.cpp:689-710): the window is produced in runs of kTopkSmem ranks, each bounded
+// by two selected keys (the lower bound of one run is the upper bound of the next), gathered and sorted.
+template <class Scan, class Emit>
+__device__ void block_topk_window(TopkShared& sh, Scan scan, uint64_t n_records, uint64_t want_begin, uint64_t n_out,
+                                  Emit emit) {
+  uint64_t begin = want_begin;
+  const uint64_t end = want_begin + n_out;
+  if (n_records <= kTopkSmem || end <= kTopkSmem) {
+    begin = 0;  // one run from the best record on; the window is cut from it
+  }
+  SortKey hi;
+  hi.s = 0;
+  hi.d = 0;
+  bool has_hi = false;
+  if (begin > 0) {
+    hi = block_select_kth(sh, scan, begin);
+    has_hi = true;
+  }
+  for (uint64_t c0 = begin; c0 < end; c0 += kTopkSmem) {
+    const uint64_t c1 = umin64(end, c0 + kTopkSmem);
+    SortKey lo;
+    lo.s = 0;
+    lo.d = 0;
+    const bool has_lo = c1 < n_records;
+    if (has_lo) {
+      lo = block_select_kth(sh, scan, c1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      sh.cnt = 0;
+    }
+    __syncthreads();
+    scan([&](const SortKey k) {
+      if ((!has_hi || key_greater(hi, k)) && (!has_lo || !key_greater(lo, k))) {
+        const uint32_t pos = atomicAdd(&sh.cnt, 1u);
+        if (pos < kTopkSmem) {
+          sh.keys[pos] = k;
+        }
+      }
+    });
+    __syncthreads();
+    const uint32_t n_keys = min(sh.cnt, kTopkSmem);
+    uint32_t n_pow2 = 1;
+    while (n_pow2 < n_keys) {
+      n_pow2 <<= 1;
+    }
+    // pads (0, 0) sort last: ord(x) of any score has s != 0 unless x is the most negative NaN pattern
+    for (uint32_t i = n_keys + threadIdx.x; i < n_pow2; i += blockDim.x) {
+      sh.keys[i].s = 0;
+      sh.keys[i].d = 0;
+    }
+    bitonic_sort_desc(sh.keys, n_pow2);
+    for (uint32_t i = threadIdx.x; i < n_keys; i += blockDim.x) {
+      const uint64_t rank = c0 + i;
+      if (rank >= want_begin && rank < end) {
+        emit(rank - want_begin, sh.keys[i]);
+      }
+    }
+    hi = lo;
+    has_hi = true;
+  }
+}
+
 constexpr int kMaxCachedLists = 24;
 constexpr uint32_t kPreSearchLists = kTileThreads / 64;  // lists whose sub-range bounds are searched up front (2 warps each)
 
@@ -2487,9 +2606,23 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
           tf_u = (p2 & kPosUnknown) - (p1 & kPosUnknown) >= tl ? 2u : 1u;
         }
         if (!known) {
-          s_keep[s] = 2;
-          s_score[s] = 0.0;
-          s_any_slow = 1;
+          // three or more occurrences, or offsets beyond the recorded range: count them in the text (by this thread
+          // when the document fits the register scanner, else by a warp through shared memory below)
+          const uint64_t b = iv.text_off[doc];
+          const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
+          text_bytes += len + 4;
+          if (!all_short || len > kThreadScanMaxDoc) {
+            s_keep[s] = 2;
+            s_score[s] = 0.0;
+            s_any_slow = 1;
+          } else {
+            const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
+            tf_u = thread_count_term(iv.text, b, len, term, tl, load_term_regs(term, tl), false);
+            const double dl = static_cast<double>(dl_u);
+            const double length_norm = __dadd_rn(__dsub_rn(1.0, sp.b), __ddiv_rn(__dmul_rn(sp.b, dl), sp.avgdl_clamped));
+            s_keep[s] = 1;
+            s_score[s] = tf_u != 0 ? __dadd_rn(0.0, bm25_term(idf, tf_u, length_norm, sp.k1)) : 0.0;
+          }
         } else {
           const double dl = static_cast<double>(dl_u);
           const double length_norm = __dadd_rn(__dsub_rn(1.0, sp.b), __ddiv_rn(__dmul_rn(sp.b, dl), sp.avgdl_clamped));
@@ -2759,28 +2892,67 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
   uint32_t kept_total = 0;
   uint32_t woff = block_offsets(__popc(keep_mask), s_warp, &kept_total);
   uint32_t written = kept_total;
-  if (prune_k != 0 && kept_total > prune_k && sp.compute_score != 0) {
-    // Block-level top-k inside the epilogue: a tile can contribute at most prune_k (= offset + limit) records to
-    // the query's answer, so only its best prune_k survive (SortByScore order). The full count still goes to
-    // tile_total. The staging buffer of the membership phase is reused as the key array.
-    SortKey* keys = reinterpret_cast<SortKey*>(s_stage);
-    static_assert(sizeof(SortKey) * kTile <= sizeof(uint32_t) * kStageCap, "key array must fit the staging buffer");
+  if (prune_k != 0 && sp.compute_score != 0) {
+    // Block-level top-k inside the epilogue: a tile can contribute at most prune_k (= offset + limit) records to the
+    // query's answer. Two filters, both exact. (1) The query's running threshold q_thr = the best "prune_k-th best
+    // score of a tile" any of its tiles has published so far: prune_k records at or above it exist, so a record
+    // strictly below it cannot reach the answer (which records get written depends on the order the tiles run in;
+    // the answer does not). (2) Only if more than prune_k records pass, the tile sorts them (SortByScore order,
+    // bitonic over the next power of two), keeps its best prune_k and publishes the score of the last one. Tiles of
+    // a long list mostly end at (1): with t tiles done, about prune_k / t of a tile's records pass.
+    // The full count still goes to tile_total. The staging buffer of the membership phase is the key array.
+    const bool desc = sp.descending != 0;
+    const unsigned long long thr = *reinterpret_cast<const volatile unsigned long long*>(bv.q_thr + q);
+    uint32_t pass_mask = 0;
 #pragma unroll
     for (int k = 0; k < kTileItems; ++k) {
       if (keep_mask & (1u << k)) {
-        const uint32_t s = s0 + k;
-        keys[woff++] = make_sort_key(s_score[s], drv_explicit ? s_gid[s] : gid_of(iv, s_doc[s]), sp.descending != 0);
+        const uint64_t o = ord_f64(s_score[s0 + k]);
+        if ((desc ? o : ~o) >= thr) {
+          pass_mask |= 1u << k;
+        }
       }
     }
-    for (uint32_t i = kept_total + threadIdx.x; i < kTile; i += kTileThreads) {
-      keys[i].s = 0;
-      keys[i].d = 0;
-    }
-    bitonic_sort_desc(keys, kTile);
-    written = prune_k;
-    for (uint32_t i = threadIdx.x; i < written; i += kTileThreads) {
-      rec_doc[out_base + i] = sp.descending != 0 ? keys[i].d : ~keys[i].d;
-      rec_score[out_base + i] = unord_f64(sp.descending != 0 ? keys[i].s : ~keys[i].s);
+    uint32_t n_pass = 0;
+    uint32_t poff = block_offsets(__popc(pass_mask), s_warp, &n_pass);
+    if (n_pass > prune_k) {
+      SortKey* keys = reinterpret_cast<SortKey*>(s_stage);
+      static_assert(sizeof(SortKey) * kTile <= sizeof(uint32_t) * kStageCap, "key array must fit the staging buffer");
+#pragma unroll
+      for (int k = 0; k < kTileItems; ++k) {
+        if (pass_mask & (1u << k)) {
+          const uint32_t s = s0 + k;
+          keys[poff++] = make_sort_key(s_score[s], drv_explicit ? s_gid[s] : gid_of(iv, s_doc[s]), desc);
+        }
+      }
+      uint32_t n_pow2 = 256;
+      while (n_pow2 < n_pass) {
+        n_pow2 <<= 1;
+      }
+      for (uint32_t i = n_pass + threadIdx.x; i < n_pow2; i += kTileThreads) {
+        keys[i].s = 0;
+        keys[i].d = 0;
+      }
+      bitonic_sort_desc(keys, n_pow2);
+      written = prune_k;
+      for (uint32_t i = threadIdx.x; i < written; i += kTileThreads) {
+        rec_doc[out_base + i] = desc ? keys[i].d : ~keys[i].d;
+        rec_score[out_base + i] = unord_f64(desc ? keys[i].s : ~keys[i].s);
+      }
+      if (threadIdx.x == 0) {
+        atomicMax(bv.q_thr + q, static_cast<unsigned long long>(keys[prune_k - 1].s));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kTileItems; ++k) {
+        if (pass_mask & (1u << k)) {
+          const uint32_t s = s0 + k;
+          rec_doc[out_base + poff] = drv_explicit ? s_gid[s] : gid_of(iv, s_doc[s]);
+          rec_score[out_base + poff] = s_score[s];
+          ++poff;
+        }
+      }
+      written = n_pass;
     }
   } else {
     // Un-scored answers are the first limit + offset ids in driver order: a tile can contribute at most that many, so
@@ -2814,13 +2986,42 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
   }
 }
 
+// Order in which a launch visits its tiles. Consecutive tile numbers belong to one query; in a batch of long lists
+// they would all run at the same moment, before any of them has published a pruning threshold (and_tile_body), and
+// every one of them would sort. Large launches of scored, pruned batches therefore walk the tiles with a stride of
+// about 0.618 n (coprime to n, so i -> i * stride mod n is a permutation): what runs together comes from far-apart
+// queries, and the tiles of one query follow each other in time. Small launches keep the natural order (their tiles
+// share staged sub-lists through L2).
+constexpr uint32_t kInterleaveMinTiles = 1u << 15;
+__device__ __forceinline__ uint32_t interleave_stride(uint32_t n, uint32_t prune_k, int compute_score) {
+  if (n < kInterleaveMinTiles || prune_k == 0 || compute_score == 0) {
+    return 1;
+  }
+  uint32_t p = static_cast<uint32_t>(static_cast<uint64_t>(n) * 618 / 1000) | 1u;
+  for (;; p += 2) {
+    uint32_t a = n, b = p;
+    while (b != 0) {
+      const uint32_t t = a % b;
+      a = b;
+      b = t;
+    }
+    if (a == 1) {
+      return p;
+    }
+  }
+}
+__device__ __forceinline__ uint32_t interleaved_tile(uint32_t i, uint32_t n, uint32_t stride) {
+  return stride == 1 ? i : static_cast<uint32_t>(static_cast<uint64_t>(i) * stride % n);
+}
+
 __global__ void __launch_bounds__(kTileThreads, MGX_AND_OCC)
 and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, uint32_t rec_slot,
                 uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_total, uint32_t* __restrict__ rec_doc,
                 double* __restrict__ rec_score, uint32_t prune_k) {
-  const uint64_t tile_global = tile_base + blockIdx.x;
+  const uint32_t slot = interleaved_tile(blockIdx.x, gridDim.x, interleave_stride(gridDim.x, prune_k, sp.compute_score));
+  const uint64_t tile_global = tile_base + slot;
   const uint32_t q = __ldg(bv.tile_query + tile_global);
-  and_tile_body(iv, bv, sp, q, tile_global - bv.q_tile_off[q], blockIdx.x, rec_slot, tile_count, tile_total, rec_doc,
+  and_tile_body(iv, bv, sp, q, tile_global - bv.q_tile_off[q], slot, rec_slot, tile_count, tile_total, rec_doc,
                 rec_score, prune_k);
 }
 
@@ -2833,6 +3034,7 @@ and_tiles_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint32_t rec_slot, 
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_q;
   const uint32_t n_tiles = bv.launch[kLaunchAndTiles];
+  const uint32_t stride = interleave_stride(n_tiles, prune_k, sp.compute_score);
   for (;;) {
     if (threadIdx.x < 32) {
       uint32_t tile = 0;
@@ -2842,6 +3044,7 @@ and_tiles_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint32_t rec_slot, 
       tile = __shfl_sync(0xffffffffu, tile, 0);
       uint32_t q = 0;
       if (tile < n_tiles) {
+        tile = interleaved_tile(tile, n_tiles, stride);
         q = warp_upper_bound_u64(bv.q_tile_off, bv.n_queries + 1, tile) - 1u;
       }
       if (threadIdx.x == 0) {
@@ -2870,14 +3073,10 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint32_t rec_slo
             int descending, uint32_t limit, uint32_t offset,
             uint64_t stride, uint32_t* __restrict__ out_ids, double* __restrict__ out_scores,
             uint32_t* __restrict__ out_count, uint64_t* __restrict__ out_total) {
-  __shared__ SortKey s_keys[kTopkSmem];
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_cnt;
+  __shared__ TopkShared sh;
   __shared__ uint64_t s_scan[8];
   __shared__ uint64_t s_scan_rec[8];
   __shared__ uint64_t s_carry;
-  __shared__ SortKey s_prefix;
-  __shared__ uint32_t s_need;
   const uint32_t q = q_first + blockIdx.x;
   const uint64_t t0 = bv.q_tile_off[q] - tile_base;
   uint32_t ntiles = static_cast<uint32_t>(bv.q_tile_off[q + 1] - bv.q_tile_off[q]);
@@ -2907,7 +3106,6 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint32_t rec_slo
     s_scan_rec[warp] = local_rec;
   }
   if (threadIdx.x == 0) {
-    s_cnt = 0;
     s_carry = 0;
   }
   __syncthreads();
@@ -2976,87 +3174,21 @@ topk_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint32_t rec_slo
   }
 
   const bool desc = descending != 0;
-  const uint32_t kk = static_cast<uint32_t>(want_begin) + n_out;  // how many best records are needed
-  SortKey thr;
-  thr.s = 0;
-  thr.d = 0;
-  if (n_records > kTopkSmem) {
-    // MSB-first radix select of the kk-th largest key
-    if (threadIdx.x == 0) {
-      s_prefix.s = 0;
-      s_prefix.d = 0;
-      s_need = kk;
-    }
-    __syncthreads();
-    for (int pass = 0; pass < 12; ++pass) {
-      s_hist[threadIdx.x] = 0;
-      __syncthreads();
-      const SortKey prefix = s_prefix;
-      for (uint32_t t = warp; t < ntiles; t += 8) {
-        const uint32_t c = tile_count[t0 + t];
-        const uint64_t base = r0 + static_cast<uint64_t>(t) * rec_slot;
-        for (uint32_t i = lane; i < c; i += 32) {
-          const SortKey k = make_sort_key(rec_score[base + i], rec_doc[base + i], desc);
-          if (key_has_prefix(k, prefix, pass)) {
-            atomicAdd(&s_hist[key_digit(k, pass)], 1u);
-          }
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        uint32_t need = s_need;
-        int digit = 255;
-        for (; digit > 0; --digit) {
-          if (s_hist[digit] >= need) {
-            break;
-          }
-          need -= s_hist[digit];
-        }
-        s_need = need;
-        if (pass < 8) {
-          s_prefix.s |= static_cast<uint64_t>(digit) << (56 - 8 * pass);
-        } else {
-          s_prefix.d |= static_cast<uint32_t>(digit) << (24 - 8 * (pass - 8));
-        }
-      }
-      __syncthreads();
-    }
-    thr = s_prefix;  // exact kk-th largest key (keys are unique: doc ids are unique per query)
-  }
-  // gather every key >= thr (all keys when total <= kTopkSmem)
-  for (uint32_t t = warp; t < ntiles; t += 8) {
-    const uint32_t c = tile_count[t0 + t];
-    const uint64_t base = r0 + static_cast<uint64_t>(t) * rec_slot;
-    for (uint32_t i = lane; i < c; i += 32) {
-      const SortKey k = make_sort_key(rec_score[base + i], rec_doc[base + i], desc);
-      if (n_records <= kTopkSmem || !key_greater(thr, k)) {
-        const uint32_t pos = atomicAdd(&s_cnt, 1u);
-        if (pos < kTopkSmem) {
-          s_keys[pos] = k;
-        }
+  auto scan = [&](auto f) {
+    for (uint32_t t = warp; t < ntiles; t += 8) {
+      const uint32_t c = tile_count[t0 + t];
+      const uint64_t base = r0 + static_cast<uint64_t>(t) * rec_slot;
+      for (uint32_t i = lane; i < c; i += 32) {
+        f(make_sort_key(rec_score[base + i], rec_doc[base + i], desc));
       }
     }
-  }
-  __syncthreads();
-  const uint32_t n_keys = min(s_cnt, kTopkSmem);
-  uint32_t n_pow2 = 1;
-  while (n_pow2 < n_keys) {
-    n_pow2 <<= 1;
-  }
-  for (uint32_t i = n_keys + threadIdx.x; i < n_pow2; i += blockDim.x) {
-    s_keys[i].s = 0;  // pads sort last: real keys have s != 0 or are compared by d >= 0 after them
-    s_keys[i].d = 0;
-  }
-  // a real key can equal the pad (score -NaN never occurs; ord(x) of any finite x has s != 0
-  // unless x is the most negative NaN pattern), so pads never displace real records.
-  bitonic_sort_desc(s_keys, n_pow2);
-  for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
-    const SortKey k = s_keys[want_begin + i];
+  };
+  block_topk_window(sh, scan, n_records, want_begin, n_out, [&](uint64_t i, const SortKey k) {
     ids[i] = desc ? k.d : ~k.d;
     if (scs != nullptr) {
       scs[i] = unord_f64(desc ? k.s : ~k.s);
     }
-  }
+  });
 }
 
 // Pre-reduction for queries whose driver spans many tiles. One CTA takes a group of consecutive tiles of one query
@@ -3416,89 +3548,27 @@ __global__ void idf_plain_kernel(const uint64_t* __restrict__ dfs, uint32_t n, u
   idf[i] = v;
 }
 
-// SortByScore over explicit arrays: single CTA, radix select + bitonic like topk_kernel.
+// SortByScore over explicit arrays: single CTA, the windowed top-k of topk_kernel. limit 0 = everything from offset.
 __global__ void __launch_bounds__(256)
 sort_by_score_kernel(const uint32_t* __restrict__ docs, const double* __restrict__ scores, uint64_t n, int descending,
                      uint32_t limit, uint32_t offset, uint32_t* __restrict__ out, uint32_t* __restrict__ out_count) {
-  __shared__ SortKey s_keys[kTopkSmem];
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_cnt;
-  __shared__ SortKey s_prefix;
-  __shared__ uint32_t s_need;
+  __shared__ TopkShared sh;
   const bool desc = descending != 0;
   const uint64_t want_begin = umin64(offset, n);
-  const uint64_t want_end = umin64(n, static_cast<uint64_t>(offset) + limit);
-  const uint32_t n_out = static_cast<uint32_t>(want_end - want_begin);
+  const uint64_t want_end = limit == 0 ? n : umin64(n, static_cast<uint64_t>(offset) + limit);
+  const uint64_t n_out = want_end - want_begin;
   if (threadIdx.x == 0) {
-    *out_count = n_out;
-    s_cnt = 0;
-    s_prefix.s = 0;
-    s_prefix.d = 0;
-    s_need = static_cast<uint32_t>(want_end);
+    *out_count = static_cast<uint32_t>(n_out);
   }
-  __syncthreads();
   if (n_out == 0) {
     return;
   }
-  SortKey thr;
-  thr.s = 0;
-  thr.d = 0;
-  if (n > kTopkSmem) {
-    for (int pass = 0; pass < 12; ++pass) {
-      s_hist[threadIdx.x] = 0;
-      __syncthreads();
-      const SortKey prefix = s_prefix;
-      for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const SortKey k = make_sort_key(scores[i], docs[i], desc);
-        if (key_has_prefix(k, prefix, pass)) {
-          atomicAdd(&s_hist[key_digit(k, pass)], 1u);
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        uint32_t need = s_need;
-        int digit = 255;
-        for (; digit > 0; --digit) {
-          if (s_hist[digit] >= need) {
-            break;
-          }
-          need -= s_hist[digit];
-        }
-        s_need = need;
-        if (pass < 8) {
-          s_prefix.s |= static_cast<uint64_t>(digit) << (56 - 8 * pass);
-        } else {
-          s_prefix.d |= static_cast<uint32_t>(digit) << (24 - 8 * (pass - 8));
-        }
-      }
-      __syncthreads();
+  auto scan = [&](auto f) {
+    for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      f(make_sort_key(scores[i], docs[i], desc));
     }
-    thr = s_prefix;
-  }
-  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const SortKey k = make_sort_key(scores[i], docs[i], desc);
-    if (n <= kTopkSmem || !key_greater(thr, k)) {
-      const uint32_t pos = atomicAdd(&s_cnt, 1u);
-      if (pos < kTopkSmem) {
-        s_keys[pos] = k;
-      }
-    }
-  }
-  __syncthreads();
-  const uint32_t n_keys = min(s_cnt, kTopkSmem);
-  uint32_t n_pow2 = 1;
-  while (n_pow2 < n_keys) {
-    n_pow2 <<= 1;
-  }
-  for (uint32_t i = n_keys + threadIdx.x; i < n_pow2; i += blockDim.x) {
-    s_keys[i].s = 0;
-    s_keys[i].d = 0;
-  }
-  bitonic_sort_desc(s_keys, n_pow2);
-  for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
-    const SortKey k = s_keys[want_begin + i];
-    out[i] = desc ? k.d : ~k.d;
-  }
+  };
+  block_topk_window(sh, scan, n, want_begin, n_out, [&](uint64_t i, const SortKey k) { out[i] = desc ? k.d : ~k.d; });
 }
 
 BatchView make_batch_view(Batch& b) {
@@ -3541,6 +3611,7 @@ BatchView make_batch_view(Batch& b) {
   v.explicit_ids = b.explicit_driver.d_ids;
   v.explicit_n = static_cast<uint32_t>(b.explicit_driver.n);
   v.stats = b.d_stats.p;
+  v.q_thr = b.d_q_thr.p;
   v.df_tile_desc = b.d_df_tile_desc.p;
   v.key_ref = b.d_key_ref.p;
   v.tile_query = b.d_tile_query.p;
@@ -4113,7 +4184,7 @@ void batch_bind(Batch& b) {
   const size_t scan_elems = scan_scratch_elems(std::max<uint64_t>(T, Q)) + 8;
   size_t work = 0;
   for (size_t nbytes : {K * sizeof(KeyRef), K * 4, K * 4, T * 8, T * 4, (T + 1) * 8, (T + K) * 8, Lc * 4, Lc * 4, Q * 4, Q * 4, Q * 4, Q * 4,
-                        (Q + 1) * 8, (Q + 1) * 8, n_tids * 8, static_cast<size_t>(kStatCount) * kStatStripes * 8,
+                        (Q + 1) * 8, (Q + 1) * 8, n_tids * 8, static_cast<size_t>(kStatCount) * kStatStripes * 8, (Q + 1) * 8,
                         scan_elems * 8, static_cast<size_t>(64), static_cast<size_t>(kLaunchCount) * 4}) {
     work += DevArena::padded(nbytes == 0 ? 1 : nbytes);
   }
@@ -4142,6 +4213,7 @@ void batch_bind(Batch& b) {
   const size_t n_stats = static_cast<size_t>(kStatCount) * kStatStripes;
   b.d_stats.borrow(b.work_arena.take<unsigned long long>(n_stats), n_stats);
   b.d_df_mode.borrow(b.work_arena.take<uint32_t>(2), 2);
+  b.d_q_thr.borrow(b.work_arena.take<unsigned long long>(Q + 1), Q + 1);  // inside the cleared range
   b.d_launch.borrow(b.work_arena.take<uint32_t>(kLaunchCount), kLaunchCount);
   b.in_base = base;
   b.in_total = total;

@@ -285,6 +285,7 @@ struct Batch {
   uint32_t n_stream_slots = 0;          // power of two, 0 = no eligible term
   uint32_t n_stream_terms = 0;
   DevBuf<uint32_t> d_df_mode;           // [2] [0] = 1 when the streaming pass was chosen (device decision)
+  DevBuf<unsigned long long> d_q_thr;   // [Q + 1] running thresholds of the per-tile top-k pruning, cleared with the counters
   int h_df_mode = 0;                    // host copy, valid after planning
   // Everything above is a view into one of these two grow-only arenas: `in_arena` receives the compiled batch in ONE
   // host-to-device copy from the pinned `staging` buffer; `work_arena` holds the device-only planning arrays.

@@ -429,3 +429,51 @@ def test_shared_compiled_batches_equal_local_compiles(mgx, shard):
     imp.close_share()
     pub.close_share()
     g2.close()
+
+
+def test_sort_by_score_any_offset_and_limit_zero(mgx):
+    """ResultSorter::SortByScore (result_sorter.cpp:661-716) takes any offset and limit 0 = everything from offset on;
+    the device version produces windows beyond the best 1024 records in runs bounded by selected keys."""
+    rnd = np.random.default_rng(5)
+    idx = mgx.Index(2, 0, True)
+    idx.add_document_batch([1], ["ab"])
+    n = 7000
+    docs = rnd.permutation(50000)[:n].astype(np.uint32)
+    scores = np.round(rnd.random(n) * 40) / 8.0  # many ties: the doc id decides
+    for desc in (True, False):
+        if desc:
+            order = np.lexsort((-docs.astype(np.int64), -scores))
+        else:
+            order = np.lexsort((docs.astype(np.int64), scores))
+        want = docs[order]
+        for limit, offset in [(100, 0), (1000, 24), (1000, 25), (1000, 3000), (1000, 6500), (2500, 1000), (0, 0),
+                              (0, 1500), (0, 6999), (0, 7000), (5, 7001), (1024, 1024), (1, 6999)]:
+            got = mgx.ResultSorter.sort_by_score(idx, docs, scores, desc, limit, offset)
+            end = n if limit == 0 else min(n, offset + limit)
+            assert np.array_equal(got, want[min(offset, n):end]), (desc, limit, offset)
+
+
+@pytest.mark.parametrize("streamed", [True, False])
+def test_scored_batches_with_deep_offsets(mgx, oracle, shard, monkeypatch, streamed):
+    """SORT _score LIMIT 1000 OFFSET n for n beyond the old 1024-record bound, and limit 0 (everything): the window
+    equals the same rows of a run that returns the whole ranking, and the oracle's answer."""
+    c, gi = shard
+    if not streamed:
+        monkeypatch.setenv("MGX_NO_STREAMED", "1")
+    qs = corpus_mod.sample_queries(c, 24, 31, n_terms=1, min_cp=2, max_cp=2)  # single bigrams: long result lists
+    full = gi.query_batch(qs, score=True, limit=0, offset=0, stride=60000)
+    assert int(full.total.max()) > 3000
+    oi = oracle.index(2, 0, True)
+    oi.build_bulk(c.doc_ids, c.arena, c.offsets, 8)
+    for limit, offset in [(1000, 1024), (1000, 2500), (300, 5000), (0, 1200)]:
+        stride = 60000 if limit == 0 else limit
+        r = gi.query_batch(qs, score=True, limit=limit, offset=offset, stride=stride)
+        o = oi.query_batch(qs, score=True, limit=limit if limit else 60000, offset=offset, n_threads=8)
+        for q in range(len(qs)):
+            t = int(full.total[q])
+            lo = min(offset, t)
+            hi = t if limit == 0 else min(t, offset + limit)
+            assert int(r.total[q]) == t and int(r.count[q]) == hi - lo
+            assert np.array_equal(r.ids[q, :hi - lo], full.ids[q, lo:hi])
+            assert np.array_equal(r.scores[q, :hi - lo].view(np.uint64), full.scores[q, lo:hi].view(np.uint64))
+            assert int(o.count[q]) == hi - lo and np.array_equal(o.ids[q, :hi - lo], r.ids[q, :hi - lo])

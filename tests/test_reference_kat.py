@@ -140,10 +140,7 @@ def test_kat_index_gpu(mgx):
 @pytest.mark.gpu
 def test_kat_bm25_gpu(mgx):
     for v in KAT["sort"]:
-        if v["limit"] == 0:
-            limit = max(1, len(v["results"]))  # limit 0 == "all" in the reference; this build needs an explicit bound
-        else:
-            limit = v["limit"]
+        limit = v["limit"]  # limit 0 == "all" (result_sorter.cpp:689-710)
         idx = mgx.Index(2, 0, True)
         idx.add_document_batch([1], ["ab"])
         got = mgx.ResultSorter.sort_by_score(idx, np.array(v["results"], np.uint32), np.array(v["scores"], np.float64),
