@@ -308,6 +308,252 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
   }
 }
 
+
+// ------------------------------------------------------------------ one-sweep pass (decoupled look-back + bulk copies)
+// One kernel per pass instead of histogram -> scan -> scatter: a pass reads every pair once and writes it once.
+//  * The digit histograms of ALL passes come from one read of the keys (radix_global_hist_kernel); their exclusive
+//    scans (digit_scan_kernel) are the global start of every digit.
+//  * Persistent CTAs (two per SM) claim tiles in order from a device counter. A tile publishes its 256 digit counts
+//    (flag AGGREGATE), walks back over its predecessors' entries until it meets an inclusive PREFIX, and publishes its
+//    own inclusive prefix: the classic decoupled look-back, one chain per digit, one thread per chain. Tiles are
+//    claimed in increasing order by resident CTAs, so the tile a chain waits for is always running or finished.
+//  * The tile's keys and values arrive by cp.async.bulk (the TMA unit's 1-D bulk copy) into a two-stage shared-memory
+//    ring, completion signalled on an mbarrier: the copy of tile i+1 runs while tile i is ranked and written. A stage
+//    is read into registers once and then re-used as the reorder buffer of the same tile.
+constexpr int kOsStages = 2;
+constexpr unsigned long long kOsFlagAggregate = 1ULL << 62;
+constexpr unsigned long long kOsFlagPrefix = 2ULL << 62;
+constexpr unsigned long long kOsValueMask = (1ULL << 54) - 1;  // bits 54..61: pass tag (entries of other passes read as empty)
+
+struct OsSmem {
+  alignas(128) uint64_t keys[kOsStages][kSortTile];
+  alignas(128) uint32_t vals[kOsStages][kSortTile];
+  uint32_t warp_cnt[kSortWarps][kRadix];
+  uint64_t global_base[kRadix];
+  uint32_t local_start[kRadix];
+  uint32_t scan_tmp[kSortWarps];
+  alignas(8) uint64_t bar[kOsStages];
+  uint32_t tile_id[kOsStages];
+  uint32_t bulk[kOsStages];  // 1: the stage is filled by a bulk copy (full tiles), 0: read straight from global
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst_smem)),
+               "l"(src_global), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kRadix) digit_scan_kernel(const unsigned long long* __restrict__ hist,
+                                                            unsigned long long* __restrict__ base) {
+  __shared__ uint64_t smem[kRadix / 32];
+  const unsigned long long v = hist[blockIdx.x * kRadix + threadIdx.x];
+  uint64_t total;
+  base[blockIdx.x * kRadix + threadIdx.x] = block_exclusive_scan_u64<kRadix>(v, &total, smem);
+}
+
+__global__ void __launch_bounds__(kSortThreads, 2)
+radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                      uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint64_t n, int shift,
+                      uint32_t mask, const unsigned long long* __restrict__ digit_base,
+                      unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ tile_counter,
+                      uint32_t n_tiles, unsigned long long pass_tag) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  OsSmem& sm = *reinterpret_cast<OsSmem*>(smem_raw);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const uint32_t warp_off = warp * (32 * kSortRounds);
+
+  // thread 0 claims tiles and starts their copies
+  auto claim_and_load = [&](int stage) {
+    const uint32_t id = atomicAdd(tile_counter, 1u);
+    sm.tile_id[stage] = id;
+    sm.bulk[stage] = 0;
+    if (id < n_tiles) {
+      const uint64_t base = static_cast<uint64_t>(id) * kSortTile;
+      if (n - base >= kSortTile) {
+        sm.bulk[stage] = 1;
+        // the stage was last written through the generic proxy (the reorder of an earlier tile)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&sm.bar[stage], kSortTile * 12u);
+        bulk_load(sm.keys[stage], keys_in + base, kSortTile * 8u, &sm.bar[stage]);
+        bulk_load(sm.vals[stage], vals_in + base, kSortTile * 4u, &sm.bar[stage]);
+      }
+    }
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    claim_and_load(0);
+  }
+  __syncthreads();
+  uint32_t phase[kOsStages] = {0, 0};
+
+  for (int it = 0;; ++it) {
+    const int st = it & 1;
+    const uint32_t tile = sm.tile_id[st];
+    if (tile >= n_tiles) {
+      break;
+    }
+    if (threadIdx.x == 0) {
+      claim_and_load(st ^ 1);  // the other stage was released by the barrier that ended the previous round
+    }
+    const uint64_t tile_base = static_cast<uint64_t>(tile) * kSortTile;
+    const uint32_t tile_n = static_cast<uint32_t>(n - tile_base < kSortTile ? n - tile_base : kSortTile);
+    const bool bulk = sm.bulk[st] != 0;
+    uint64_t key[kSortRounds];
+    uint32_t val[kSortRounds];
+    if (bulk) {
+      mbar_wait(&sm.bar[st], phase[st]);
+      phase[st] ^= 1u;
+#pragma unroll
+      for (int r = 0; r < kSortRounds; ++r) {
+        const uint32_t i = warp_off + r * 32 + lane;
+        key[r] = sm.keys[st][i];
+        val[r] = sm.vals[st][i];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < kSortRounds; ++r) {
+        const uint32_t i = warp_off + r * 32 + lane;
+        const bool valid = i < tile_n;
+        key[r] = valid ? keys_in[tile_base + i] : 0;
+        val[r] = valid ? vals_in[tile_base + i] : 0;
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      sm.warp_cnt[w][threadIdx.x] = 0;
+    }
+    __syncthreads();  // counters cleared; every thread holds its items, so the stage can take the reordered tile
+
+    // phase 1: per-warp digit counts
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+      const bool valid = warp_off + r * 32 + lane < tile_n;
+      const uint32_t d = valid ? (static_cast<uint32_t>(key[r] >> shift) & mask) : 0x1FFu;
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      if (valid && (peers & lt_mask) == 0) {
+        sm.warp_cnt[warp][d] += __popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    {
+      // thread d: tile count of digit d, the tile-local start, the per-warp offsets, and the look-back chain of d
+      const unsigned d = threadIdx.x;
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        cnt += sm.warp_cnt[w][d];
+      }
+      volatile unsigned long long* const my_state = tile_state + static_cast<uint64_t>(tile) * kRadix + d;
+      if (tile + 1 < n_tiles) {  // nobody looks back at the last tile
+        *my_state = kOsFlagAggregate | pass_tag | cnt;
+      }
+      uint32_t inc = cnt;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, s);
+        if (lane >= static_cast<unsigned>(s)) {
+          inc += o;
+        }
+      }
+      if (lane == 31) {
+        sm.scan_tmp[warp] = inc;
+      }
+      __syncthreads();
+      uint32_t prefix = 0;
+      for (unsigned w = 0; w < warp; ++w) {
+        prefix += sm.scan_tmp[w];
+      }
+      const uint32_t start = prefix + inc - cnt;
+      sm.local_start[d] = start;
+      uint32_t running = start;
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t c = sm.warp_cnt[w][d];
+        sm.warp_cnt[w][d] = running;
+        running += c;
+      }
+      // look back
+      unsigned long long before = 0;
+      for (uint32_t p = tile; p > 0;) {
+        --p;
+        volatile const unsigned long long* const ps = tile_state + static_cast<uint64_t>(p) * kRadix + d;
+        unsigned long long v;
+        do {
+          v = *ps;
+        } while ((v & (3ULL << 62)) == 0 || (v & (0xFFULL << 54)) != pass_tag);
+        before += v & kOsValueMask;
+        if ((v & kOsFlagPrefix) != 0) {
+          break;
+        }
+      }
+      if (tile + 1 < n_tiles) {
+        *my_state = kOsFlagPrefix | pass_tag | (before + cnt);
+      }
+      sm.global_base[d] = digit_base[d] + before;
+    }
+    __syncthreads();
+    // phase 2: rank inside the tile and place into the stage
+    uint64_t* const skeys = sm.keys[st];
+    uint32_t* const svals = sm.vals[st];
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+      const bool valid = warp_off + r * 32 + lane < tile_n;
+      const uint32_t d = valid ? (static_cast<uint32_t>(key[r] >> shift) & mask) : 0x1FFu;
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      uint32_t base = 0;
+      if (valid) {
+        base = sm.warp_cnt[warp][d];
+      }
+      __syncwarp();
+      if (valid && (peers & lt_mask) == 0) {
+        sm.warp_cnt[warp][d] = base + __popc(peers);
+      }
+      __syncwarp();
+      if (valid) {
+        const uint32_t pos = base + __popc(peers & lt_mask);
+        skeys[pos] = key[r];
+        svals[pos] = val[r];
+      }
+    }
+    __syncthreads();
+    // phase 3: coalesced write-out, run by run
+    for (uint32_t i = threadIdx.x; i < tile_n; i += kSortThreads) {
+      const uint64_t k = skeys[i];
+      const uint32_t d = static_cast<uint32_t>(k >> shift) & mask;
+      const uint64_t pos = sm.global_base[d] + (i - sm.local_start[d]);
+      keys_out[pos] = k;
+      vals_out[pos] = svals[i];
+    }
+    __syncthreads();  // the stage is free: the next round's claim may start a copy into it
+  }
+}
+
 }  // namespace
 
 namespace {
@@ -400,8 +646,12 @@ void exclusive_scan_u32_u64(const uint32_t* d_in, uint64_t* d_out, uint64_t n, u
 
 namespace {
 struct SortScratch {
-  size_t hist_off, hist_scan_off, ghist_off, scan_off, total;
+  size_t hist_off, hist_scan_off, ghist_off, scan_off, dbase_off, counter_off, state_off, total;
 };
+bool sort_classic() {  // MGX_SORT=classic: the three-kernel passes (A/B measurements)
+  const char* e = std::getenv("MGX_SORT");
+  return e != nullptr && std::strcmp(e, "classic") == 0;
+}
 SortScratch sort_scratch_layout(uint64_t n) {
   const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
   const uint64_t hist_len = static_cast<uint64_t>(kRadix) * n_tiles;
@@ -416,6 +666,9 @@ SortScratch sort_scratch_layout(uint64_t n) {
   L.hist_scan_off = take((hist_len + 1) * sizeof(uint64_t));
   L.ghist_off = take(static_cast<size_t>(kMaxPasses) * kRadix * sizeof(unsigned long long));
   L.scan_off = take(scan_scratch_elems(hist_len) * sizeof(uint64_t));
+  L.dbase_off = take(static_cast<size_t>(kMaxPasses) * kRadix * sizeof(unsigned long long));
+  L.counter_off = take(static_cast<size_t>(kMaxPasses) * sizeof(uint32_t));
+  L.state_off = take(hist_len * sizeof(unsigned long long));  // one-sweep look-back entries, [tile][digit]
   L.total = off + 256;
   return L;
 }
@@ -434,8 +687,11 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
   if (!attr_set) {
     MGX_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(sizeof(ScatterSmem))));
+    MGX_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(sizeof(OsSmem))));
     attr_set = true;
   }
+  const bool classic = sort_classic();
   const uint32_t n_tiles = static_cast<uint32_t>((n + kSortTile - 1) / kSortTile);
   const uint64_t hist_len = static_cast<uint64_t>(kRadix) * n_tiles;
   // Digits are aligned to the 21-bit code-point fields of the packed key (8 + 8 + 5 bits per field), so that the
@@ -471,6 +727,19 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
                            stream));
   MGX_CUDA(cudaStreamSynchronize(stream));
   trace.mark("  sort: global hist");
+  unsigned long long* d_dbase = reinterpret_cast<unsigned long long*>(base + L.dbase_off);
+  uint32_t* d_counters = reinterpret_cast<uint32_t*>(base + L.counter_off);
+  unsigned long long* d_state = reinterpret_cast<unsigned long long*>(base + L.state_off);
+  int per_sm = 2;
+  if (!classic) {
+    digit_scan_kernel<<<passes, kRadix, 0, stream>>>(d_ghist, d_dbase);
+    MGX_LAUNCH_CHECK();
+    // one memset per sort: the entries carry the pass number, so the passes do not clear them in between
+    MGX_CUDA(cudaMemsetAsync(d_counters, 0, kMaxPasses * sizeof(uint32_t), stream));
+    MGX_CUDA(cudaMemsetAsync(d_state, 0, hist_len * sizeof(unsigned long long), stream));
+    MGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_onesweep_kernel, kSortThreads, sizeof(OsSmem)));
+    per_sm = std::max(per_sm, 1);
+  }
   for (int p = 0; p < passes; ++p) {
     bool trivial = false;
     for (int d = 0; d < kRadix; ++d) {
@@ -481,6 +750,16 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
     }
     const int shift = pl.shift[p];
     const uint32_t mask = pl.mask[p];
+    if (!classic) {
+      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(sm_count) * per_sm));
+      radix_onesweep_kernel<<<grid, kSortThreads, sizeof(OsSmem), stream>>>(
+          cur.keys, cur.vals, alt.keys, alt.vals, n, shift, mask, d_dbase + static_cast<size_t>(p) * kRadix, d_state,
+          d_counters + p, n_tiles, static_cast<unsigned long long>(p + 1) << 54);
+      MGX_LAUNCH_CHECK();
+      std::swap(cur, alt);
+      trace.mark("  sort: one-sweep pass");
+      continue;
+    }
     radix_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(cur.keys, n, shift, mask, d_hist, n_tiles);
     MGX_LAUNCH_CHECK();
     exclusive_scan_u32_u64(d_hist, d_hist_scan, hist_len, d_scan_scratch, stream);
