@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
                                                                      int shift, uint32_t mask,
                                                                      const uint64_t* __restrict__ hist_scan,
                                                                      uint32_t n_tiles) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(smem_raw);
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
@@ -409,7 +409,7 @@ radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __re
     claim_and_load(0);
   }
   __syncthreads();
-  uint32_t phase[kOsStages] = {0, 0};
+  uint32_t phases = 0;  // bit s: parity the next wait on stage s uses
 
   for (int it = 0;; ++it) {
     const int st = it & 1;
@@ -426,8 +426,8 @@ radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __re
     uint64_t key[kSortRounds];
     uint32_t val[kSortRounds];
     if (bulk) {
-      mbar_wait(&sm.bar[st], phase[st]);
-      phase[st] ^= 1u;
+      mbar_wait(&sm.bar[st], (phases >> st) & 1u);
+      phases ^= 1u << st;
 #pragma unroll
       for (int r = 0; r < kSortRounds; ++r) {
         const uint32_t i = warp_off + r * 32 + lane;

@@ -125,6 +125,40 @@ def test_build_synthetic_corpora(mgx, oracle):
         assert (gi.stats().total_doc_length, gi.stats().doc_count) == oi.bm25_stats()
 
 
+def _export_raw(mgx, gi):
+    st = gi.stats()
+    keys = np.zeros(max(1, st.n_terms), dtype=np.uint64)
+    offs = np.zeros(st.n_terms + 1, dtype=np.uint64)
+    posts = np.zeros(max(1, st.n_postings), dtype=np.uint32)
+    mgx._check(mgx.lib().mgx_index_export(gi._h, mgx._ptr(keys, mgx.u64p), mgx._ptr(offs, mgx.u64p),
+                                          mgx._ptr(posts, mgx.u32p)))
+    return keys[:st.n_terms], offs, posts[:st.n_postings]
+
+
+def test_build_one_sweep_sort_equals_classic_and_oracle(mgx, oracle, monkeypatch):
+    """The one-sweep radix passes (decoupled look-back, bulk copies into a shared-memory ring) over thousands of tiles
+    -- many more than resident CTAs, plus a partial last tile -- must give the index of the three-kernel passes and of
+    the oracle's builder, bit for bit."""
+    c = corpus_mod.generate("cjk", 400000, 0xC3)
+    monkeypatch.setenv("MGX_SORT", "classic")
+    g0 = mgx.Index(2, 0, True)
+    g0.build(c.doc_ids, c.arena, c.offsets)
+    k0, o0, p0 = _export_raw(mgx, g0)
+    monkeypatch.delenv("MGX_SORT")
+    for _ in range(3):  # repeated: the look-back entries of an earlier sort must not leak into the next one
+        g1 = mgx.Index(2, 0, True)
+        g1.build(c.doc_ids, c.arena, c.offsets)
+        k1, o1, p1 = _export_raw(mgx, g1)
+        assert np.array_equal(k0, k1) and np.array_equal(o0, o1) and np.array_equal(p0, p1)
+        g1.close()
+    oi = oracle.index(2, 0, True)
+    oi.build_bulk(c.doc_ids, c.arena, c.offsets, 8)
+    ot, oo, op = oi.export()
+    assert len(ot) == len(k0) and np.array_equal(oo, o0) and np.array_equal(op, p0)
+    assert [bytes(x) for x in ot[:3000]] == [mgx.key_to_utf8(k, 2) for k in k0[:3000]]
+    g0.close()
+
+
 # ----------------------------------------------------------------------------------------- set algebra
 def some_terms(oi, rnd, k):
     terms, _, _ = oi.export()
