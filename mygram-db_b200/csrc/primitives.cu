@@ -461,8 +461,10 @@ radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __re
       __syncwarp();
     }
     __syncthreads();
+    uint32_t my_cnt = 0;
     {
-      // thread d: tile count of digit d, the tile-local start, the per-warp offsets, and the look-back chain of d
+      // thread d: tile count of digit d (published at once as this tile's AGGREGATE), the tile-local start and the
+      // per-warp offsets
       const unsigned d = threadIdx.x;
       uint32_t cnt = 0;
 #pragma unroll
@@ -470,6 +472,7 @@ radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __re
         cnt += sm.warp_cnt[w][d];
       }
       volatile unsigned long long* const my_state = tile_state + static_cast<uint64_t>(tile) * kRadix + d;
+      my_cnt = cnt;
       if (tile + 1 < n_tiles) {  // nobody looks back at the last tile
         *my_state = kOsFlagAggregate | pass_tag | cnt;
       }
@@ -498,27 +501,10 @@ radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __re
         sm.warp_cnt[w][d] = running;
         running += c;
       }
-      // look back
-      unsigned long long before = 0;
-      for (uint32_t p = tile; p > 0;) {
-        --p;
-        volatile const unsigned long long* const ps = tile_state + static_cast<uint64_t>(p) * kRadix + d;
-        unsigned long long v;
-        do {
-          v = *ps;
-        } while ((v & (3ULL << 62)) == 0 || (v & (0xFFULL << 54)) != pass_tag);
-        before += v & kOsValueMask;
-        if ((v & kOsFlagPrefix) != 0) {
-          break;
-        }
-      }
-      if (tile + 1 < n_tiles) {
-        *my_state = kOsFlagPrefix | pass_tag | (before + cnt);
-      }
-      sm.global_base[d] = digit_base[d] + before;
     }
     __syncthreads();
-    // phase 2: rank inside the tile and place into the stage
+    // phase 2: rank inside the tile and place into the stage. Nothing here needs the global digit starts, so the
+    // predecessors get this long to publish before the look-back below starts waiting for them.
     uint64_t* const skeys = sm.keys[st];
     uint32_t* const svals = sm.vals[st];
 #pragma unroll
@@ -540,6 +526,30 @@ radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __re
         skeys[pos] = key[r];
         svals[pos] = val[r];
       }
+    }
+    {
+      // look back: thread d sums the counts of digit d over the preceding tiles until it meets an inclusive prefix
+      const unsigned d = threadIdx.x;
+      const uint32_t cnt = my_cnt;
+      volatile unsigned long long* const my_state = tile_state + static_cast<uint64_t>(tile) * kRadix + d;
+      unsigned long long before = 0;
+      for (uint32_t p = tile; p > 0;) {
+        --p;
+        volatile const unsigned long long* const ps = tile_state + static_cast<uint64_t>(p) * kRadix + d;
+        unsigned long long v = *ps;
+        while ((v & (3ULL << 62)) == 0 || (v & (0xFFULL << 54)) != pass_tag) {
+          __nanosleep(40);
+          v = *ps;
+        }
+        before += v & kOsValueMask;
+        if ((v & kOsFlagPrefix) != 0) {
+          break;
+        }
+      }
+      if (tile + 1 < n_tiles) {
+        *my_state = kOsFlagPrefix | pass_tag | (before + cnt);
+      }
+      sm.global_base[d] = digit_base[d] + before;
     }
     __syncthreads();
     // phase 3: coalesced write-out, run by run
