@@ -705,16 +705,30 @@ def main():
     from concurrent.futures import ThreadPoolExecutor
     outs = [torch.empty(lay["bytes"], dtype=torch.uint8, pin_memory=True) for _ in range(in_flight)]
     e2e_parts = {"host_prepare_ms": 0.0, "enqueue_ms": 0.0, "wait_ms": 0.0}
-    compiler = ThreadPoolExecutor(max_workers=2)  # ctypes releases the GIL: batches i+1, i+2 compile beside batch i
-
     # N > 1: the ranks of the node take turns compiling (batch number seq is compiled by rank seq % N and handed to the
     # others through the shared-memory ring of mgx_share_*), instead of every rank compiling every batch
     share_seq = [0]
     if world > 1 and not args.no_share:
+        # a slot holds one compiled batch (~125 bytes per query measured on C2 / C5); the ring must fit /dev/shm
+        slot_bytes = max(2 << 20, 1 << int(np.ceil(np.log2(192 * args.batch))))
+        n_slots = 8
+        fs = os.statvfs("/dev/shm")
+        fits = [int(fs.f_bavail * fs.f_frsize >= 2 * n_slots * slot_bytes)]
         name = [f"/mgx_share_{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}"]
         dist.broadcast_object_list(name, src=0)
-        pipe.open_share(name[0], world, rank)
+        dist.broadcast_object_list(fits, src=0)
+        if fits[0]:
+            pipe.open_share(name[0], world, rank, n_slots=n_slots, slot_bytes=slot_bytes)
+        else:
+            args.no_share = True
         barrier()
+
+    # ctypes releases the GIL: batches i+1, i+2 compile beside batch i. With the shared ring a rank compiles only every
+    # N-th batch and otherwise waits for another rank's publication, so more batches are prepared ahead: a worker that
+    # waits for batch j must not keep this rank from starting its own batch j+1
+    shared = world > 1 and not args.no_share
+    ahead = min(6, world + 1) if shared else 2
+    compiler = ThreadPoolExecutor(max_workers=ahead)
 
     def e2e_prepare(i, slot, seq):
         t_a = time.perf_counter()
@@ -725,7 +739,6 @@ def main():
     def e2e_run(order, acc=None):
         order = list(order)
         futs, pending = {}, []
-        ahead = 2
         seq0 = share_seq[0]  # the same on every rank: all ranks run the same orders
         share_seq[0] += len(order)
         for j in range(min(ahead, len(order))):

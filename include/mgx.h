@@ -227,6 +227,16 @@ int mgx_mgix_decode(const uint8_t* data, uint64_t len, mgx_mgix_info_t* info, ui
 int mgx_index_save_mgix(const mgx_index_t* index, int32_t normalize_nfkc, const char* normalize_width,
                         int32_t normalize_lower, uint8_t* out, uint64_t cap, uint64_t* out_len);
 
+/* Index::LoadFromStream (index_serialization.cpp:279-613) into the device index: the stream is validated and decoded
+ * as mgx_mgix_decode does, its n-gram configuration must equal the index's (LoadFromData :371-447, else
+ * MGX_ERR_FORMAT), and the posting lists replace the index content. A stream carries posting lists only, so the shard
+ * then holds NO document text -- exactly the state of the reference's Index after LoadFromStream with an empty
+ * DocumentStore: Index::Search* / FilterByNgrams / SearchByThreshold / GetStatistics answer from the lists, documents
+ * are the ids that occur in them, text-dependent paths (verify_text, _score, substring terms) see documents without
+ * stored text, BM25 statistics are zero. Single-document mutations are refused (MGX_ERR_UNSUPPORTED) until the
+ * documents arrive through mgx_index_build, which recomputes the same lists from the texts. */
+int mgx_index_load_mgix(mgx_index_t* index, const uint8_t* data, uint64_t len);
+
 /* ------------------------------------------------- Index set-algebra calls */
 
 /* Index::SearchAnd(terms, limit, reverse) — index.cpp:199-368. `terms` are

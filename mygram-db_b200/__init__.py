@@ -165,6 +165,7 @@ def lib():
     L.mgx_mgix_encode.argtypes = [C.POINTER(MgixInfo), u8p, u64p, u64p, u32p, C.c_double, u8p, C.c_uint64, u64p]
     L.mgx_mgix_decode.argtypes = [u8p, C.c_uint64, C.POINTER(MgixInfo), u8p, u64p, u64p, u32p]
     L.mgx_index_save_mgix.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, u8p, C.c_uint64, u64p]
+    L.mgx_index_load_mgix.argtypes = [C.c_void_p, u8p, C.c_uint64]
     L.mgx_index_set_filter_column.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, u64p, u8p, C.c_uint64, u8p, u64p,
                                               C.c_uint64]
     L.mgx_query_batch_ex.argtypes = [C.c_void_p, C.POINTER(QueryParams), C.c_uint64, u8p, u64p, u64p, u8p, u64p, u64p,
@@ -452,6 +453,12 @@ class Index:
         _check(lib().mgx_index_export(self._h, _ptr(keys, u64p), _ptr(offs, u64p), _ptr(posts, u32p)))
         terms = [key_to_utf8(k, s.key_width) for k in keys[:s.n_terms]]
         return terms, offs, posts[:s.n_postings]
+
+    def load_mgix(self, stream):
+        """Index::LoadFromStream (index_serialization.cpp:279-613): the stream's posting lists replace the index
+        content; the shard then holds no document text (see mgx_index_load_mgix)."""
+        buf = np.frombuffer(bytes(stream), dtype=np.uint8)
+        _check(lib().mgx_index_load_mgix(self._h, _ptr(buf, u8p), buf.size))
 
     def save_mgix(self, normalize_nfkc=True, normalize_width="keep", normalize_lower=True):
         """Index::SaveToStream (index_serialization.cpp:111-224) of the device index -> bytes."""

@@ -16,6 +16,7 @@
 #pragma once
 
 #include <algorithm>
+#include <iterator>
 #include <cstdint>
 #include <stdexcept>
 #include <memory>
@@ -222,6 +223,13 @@ class Index {
     }
     output_stream.write(reinterpret_cast<const char*>(bytes.data()), static_cast<std::streamsize>(len));
     return output_stream.good();
+  }
+  // Index::LoadFromStream (index.h:279, index_serialization.cpp:279-613): the stream's posting lists replace the index
+  // content. false where the reference returns an Error (kStorage* / kIndexDeserializationFailed; mgx_last_error()
+  // names it). The device shard then holds no document text, like the reference's Index with an empty DocumentStore.
+  bool LoadFromStream(std::istream& input_stream) {
+    const std::vector<char> bytes((std::istreambuf_iterator<char>(input_stream)), std::istreambuf_iterator<char>());
+    return mgx_index_load_mgix(handle_, reinterpret_cast<const uint8_t*>(bytes.data()), bytes.size()) == MGX_OK;
   }
   [[nodiscard]] int GetNgramSize() const { return ngram_size_; }
   [[nodiscard]] int GetKanjiNgramSize() const { return kanji_ngram_size_; }

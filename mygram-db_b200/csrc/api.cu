@@ -1042,6 +1042,11 @@ int journal_put(mgx_index_t* index, uint32_t doc_id, bool removed, const uint8_t
   if (int rc = require_device(); rc != MGX_OK) {
     return rc;
   }
+  if (index->ix.text_less) {
+    set_last_error("the index was loaded from an MGIX stream and holds no document text: single-document mutations "
+                   "need the documents (mgx_index_build)");
+    return MGX_ERR_UNSUPPORTED;
+  }
   std::lock_guard<std::mutex> jl(index->journal_mu);
   index->journal.put(doc_id, removed, text, len);
   index->dirty.store(true, std::memory_order_release);
@@ -1197,6 +1202,11 @@ int mgx_index_add_document_batch(mgx_index_t* index, const uint32_t* doc_ids, co
     if (text_offsets[i + 1] < text_offsets[i] || (text_offsets[i + 1] > text_offsets[i] && text == nullptr)) {
       return invalid("text_offsets must be non-decreasing (and text non-null)");
     }
+  }
+  if (index->ix.text_less && n_docs > 0) {
+    set_last_error("the index was loaded from an MGIX stream and holds no document text: mutations need the "
+                   "documents (mgx_index_build)");
+    return MGX_ERR_UNSUPPORTED;
   }
   uint64_t indexed = 0;
   if (out_indexed != nullptr) {
@@ -2339,6 +2349,56 @@ int mgx_index_save_mgix(const mgx_index_t* index, int32_t normalize_nfkc, const 
     term_offsets[n_terms] = tb;
     return mgx_mgix_encode(&info, term_bytes.data(), term_offsets.data(), offsets.data(), postings.data(),
                            roaring_min_len, out, cap, out_len);
+  });
+}
+
+int mgx_index_load_mgix(mgx_index_t* index, const uint8_t* data, uint64_t len) {
+  if (index == nullptr || data == nullptr) {
+    return invalid("null argument");
+  }
+  if (int rc = require_device(); rc != MGX_OK) {
+    return rc;
+  }
+  // host side: the reference's validation and decoding (mgx_mgix_decode), the configuration check of LoadFromData
+  // (index_serialization.cpp:371-447), n-grams -> packed keys
+  mgx_mgix_info_t info{};
+  if (int rc = mgx_mgix_decode(data, len, &info, nullptr, nullptr, nullptr, nullptr); rc != MGX_OK) {
+    return rc;
+  }
+  const Index& cfg = index->ix;
+  if (info.ngram_size != cfg.ngram || info.kanji_ngram_size != cfg.kanji || (info.cross_boundary != 0) != cfg.cross) {
+    set_last_error("MGIX stream was written with another n-gram configuration (kStorageConfigMismatch)");
+    return MGX_ERR_FORMAT;
+  }
+  std::vector<uint8_t> term_bytes(info.term_bytes + 1);
+  std::vector<uint64_t> term_offsets(info.n_terms + 1, 0);
+  std::vector<uint64_t> posting_offsets(info.n_terms + 1, 0);
+  std::vector<uint32_t> postings(info.n_postings + 1);
+  if (int rc = mgx_mgix_decode(data, len, &info, term_bytes.data(), term_offsets.data(), posting_offsets.data(),
+                               postings.data());
+      rc != MGX_OK) {
+    return rc;
+  }
+  std::vector<uint64_t> keys(info.n_terms + 1);
+  for (uint64_t t = 0; t < info.n_terms; ++t) {
+    if (!host_ngram_to_key(term_bytes.data() + term_offsets[t], term_offsets[t + 1] - term_offsets[t], cfg.width,
+                           &keys[t]) ||
+        (t > 0 && keys[t] <= keys[t - 1])) {
+      set_last_error("MGIX stream holds a term that is not an n-gram of this configuration (or terms out of order)");
+      return MGX_ERR_FORMAT;
+    }
+  }
+  {
+    std::lock_guard<std::mutex> jl(index->journal_mu);  // the stream replaces everything, pending mutations included
+    index->journal.clear();
+    index->dirty.store(false);
+  }
+  return guarded([&]() {
+    WriteGuard lock(index);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    load_index_device(ix, keys.data(), posting_offsets.data(), postings.data(), info.n_terms, info.n_postings, ix.stream);
+    return MGX_OK;
   });
 }
 

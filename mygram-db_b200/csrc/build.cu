@@ -861,6 +861,80 @@ void PhaseTrace::mark(const char* name) {
   t0 = t1;
 }
 
+namespace {
+struct ResetOnFailure {
+  Index& ix;
+  bool armed = true;
+  ~ResetOnFailure() {
+    if (!armed) {
+      return;
+    }
+    ix.n_docs = ix.text_bytes = ix.n_text_tiles = 0;
+    ix.n_terms = ix.n_postings = ix.n_dense = ix.bm_words = 0;
+    ix.doc_count = ix.total_doc_length = ix.n_pair_slots = 0;
+    ix.has_positions = false;
+    ix.sequential_ids = true;
+    ix.first_id = 1;
+    ix.d_doc_ids.release();
+    ix.d_text.release();
+    ix.d_text_off.release();
+    ix.d_doc_len.release();
+    ix.d_tile_first_doc.release();
+    ix.d_term_keys.release();
+    ix.d_term_off.release();
+    ix.d_postings.release();
+    ix.d_post_pos.release();
+    ix.d_post_pos2.release();
+    ix.d_term_bm.release();
+  }
+};
+
+// Bitmaps for the dense lists of a finished CSR (d_dense_terms: n_terms uint32 of scratch, d_count: one counter).
+void build_dense_bitmaps(Index& ix, uint64_t n_docs, uint32_t* d_dense_terms, unsigned long long* d_count,
+                         cudaStream_t stream) {
+  // ---- dense bitmaps
+  ix.bm_words = (n_docs + 31) / 32;
+  const double thr = ix.cfg.dense_threshold > 0.0 ? ix.cfg.dense_threshold : 1.0 / 128.0;
+  uint64_t min_len = std::max<uint64_t>(1, static_cast<uint64_t>(thr * static_cast<double>(n_docs)));
+  // a bitmap only pays for lists long enough that probing beats searching
+  min_len = std::max<uint64_t>(min_len, 1024);
+  const uint64_t max_bytes = ix.cfg.max_dense_bytes != 0 ? ix.cfg.max_dense_bytes : (8ULL << 30);
+  unsigned long long n_dense = 0;
+  const unsigned term_grid = static_cast<unsigned>((ix.n_terms + 255) / 256);
+  if (ix.n_terms > 0) {
+    for (;;) {
+      MGX_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
+      dense_count_kernel<<<term_grid, 256, 0, stream>>>(ix.d_term_off.p, ix.n_terms, min_len, d_count);
+      MGX_LAUNCH_CHECK();
+      MGX_CUDA(cudaMemcpyAsync(&n_dense, d_count, sizeof(n_dense), cudaMemcpyDeviceToHost, stream));
+      MGX_CUDA(cudaStreamSynchronize(stream));
+      if (n_dense * ix.bm_words * 4 <= max_bytes) {
+        break;
+      }
+      min_len *= 2;
+    }
+  }
+  ix.n_dense = n_dense;
+  ix.dense_min_len = min_len;
+  ix.d_bitmaps.reserve(ix.n_dense * ix.bm_words);
+  if (ix.n_terms > 0) {
+    MGX_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
+    if (ix.n_dense > 0) {
+      MGX_CUDA(cudaMemsetAsync(ix.d_bitmaps.p, 0, ix.d_bitmaps.bytes(), stream));
+    }
+    dense_assign_kernel<<<term_grid, 256, 0, stream>>>(ix.d_term_off.p, ix.n_terms, min_len, d_count, ix.d_term_bm.p,
+                                                       d_dense_terms);
+    MGX_LAUNCH_CHECK();
+    if (ix.n_dense > 0) {
+      const unsigned slices = static_cast<unsigned>(std::min<uint64_t>(64, (n_docs + 65535) / 65536 + 1));
+      dense_fill_kernel<<<dim3(static_cast<unsigned>(ix.n_dense), slices), 256, 0, stream>>>(
+          ix.d_term_off.p, ix.d_postings.p, d_dense_terms, ix.d_bitmaps.p, ix.bm_words);
+      MGX_LAUNCH_CHECK();
+    }
+  }
+}
+}  // namespace
+
 void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* d_text_in,
                         const uint64_t* d_text_off_in, uint64_t n_docs, uint64_t text_bytes, cudaStream_t stream) {
   PhaseTrace trace(stream);
@@ -886,37 +960,13 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   // n-gram occurrences, a CUDA error): whatever fails, the handle must not keep the OLD sizes next to released or
   // half-written arrays. A failed build therefore leaves an EMPTY index (every query answers empty, the next build
   // starts clean); the caller gets the error.
-  struct ResetOnFailure {
-    Index& ix;
-    bool armed = true;
-    ~ResetOnFailure() {
-      if (!armed) {
-        return;
-      }
-      ix.n_docs = ix.text_bytes = ix.n_text_tiles = 0;
-      ix.n_terms = ix.n_postings = ix.n_dense = ix.bm_words = 0;
-      ix.doc_count = ix.total_doc_length = ix.n_pair_slots = 0;
-      ix.has_positions = false;
-      ix.sequential_ids = true;
-      ix.first_id = 1;
-      ix.d_doc_ids.release();
-      ix.d_text.release();
-      ix.d_text_off.release();
-      ix.d_doc_len.release();
-      ix.d_tile_first_doc.release();
-      ix.d_term_keys.release();
-      ix.d_term_off.release();
-      ix.d_postings.release();
-      ix.d_post_pos.release();
-      ix.d_post_pos2.release();
-      ix.d_term_bm.release();
-    }
-  } reset_on_failure{ix};
+  ResetOnFailure reset_on_failure{ix};
 
   // ---- resident arena A: the device mirror of DocumentStore's normalised text + ids + lengths.
   // The text arena is padded so 16-byte tile loads never leave the allocation.
   ix.n_docs = n_docs;
   ix.text_bytes = text_bytes;
+  ix.text_less = false;
   ix.drop_filter_columns();  // rows of the old corpus
   ix.d_doc_ids.release();
   ix.d_text.release();
@@ -1052,52 +1102,158 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   MGX_LAUNCH_CHECK();
   trace.mark("csr");
 
-  // ---- dense bitmaps
-  ix.bm_words = (n_docs + 31) / 32;
-  const double thr = ix.cfg.dense_threshold > 0.0 ? ix.cfg.dense_threshold : 1.0 / 128.0;
-  uint64_t min_len = std::max<uint64_t>(1, static_cast<uint64_t>(thr * static_cast<double>(n_docs)));
-  // a bitmap only pays for lists long enough that probing beats searching
-  min_len = std::max<uint64_t>(min_len, 1024);
-  const uint64_t max_bytes = ix.cfg.max_dense_bytes != 0 ? ix.cfg.max_dense_bytes : (8ULL << 30);
-  unsigned long long n_dense = 0;
-  const unsigned term_grid = static_cast<unsigned>((ix.n_terms + 255) / 256);
-  if (ix.n_terms > 0) {
-    for (;;) {
-      MGX_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
-      dense_count_kernel<<<term_grid, 256, 0, stream>>>(ix.d_term_off.p, ix.n_terms, min_len, d_count);
-      MGX_LAUNCH_CHECK();
-      MGX_CUDA(cudaMemcpyAsync(&n_dense, d_count, sizeof(n_dense), cudaMemcpyDeviceToHost, stream));
-      MGX_CUDA(cudaStreamSynchronize(stream));
-      if (n_dense * ix.bm_words * 4 <= max_bytes) {
-        break;
-      }
-      min_len *= 2;
-    }
-  }
-  ix.n_dense = n_dense;
-  ix.dense_min_len = min_len;
-  ix.d_bitmaps.reserve(ix.n_dense * ix.bm_words);
-  if (ix.n_terms > 0) {
-    MGX_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream));
-    if (ix.n_dense > 0) {
-      MGX_CUDA(cudaMemsetAsync(ix.d_bitmaps.p, 0, ix.d_bitmaps.bytes(), stream));
-    }
-    dense_assign_kernel<<<term_grid, 256, 0, stream>>>(ix.d_term_off.p, ix.n_terms, min_len, d_count, ix.d_term_bm.p,
-                                                       d_dense_terms);
-    MGX_LAUNCH_CHECK();
-    if (ix.n_dense > 0) {
-      const unsigned slices = static_cast<unsigned>(std::min<uint64_t>(64, (n_docs + 65535) / 65536 + 1));
-      dense_fill_kernel<<<dim3(static_cast<unsigned>(ix.n_dense), slices), 256, 0, stream>>>(
-          ix.d_term_off.p, ix.d_postings.p, d_dense_terms, ix.d_bitmaps.p, ix.bm_words);
-      MGX_LAUNCH_CHECK();
-    }
-  }
+  build_dense_bitmaps(ix, n_docs, d_dense_terms, d_count, stream);
   MGX_CUDA(cudaEventRecord(ev1, stream));
   MGX_CUDA(cudaEventSynchronize(ev1));
   trace.mark("dense bitmaps + free");
   float ms = 0.f;
   MGX_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
   ix.last_build_ms = ms;
+  reset_on_failure.armed = false;
+}
+
+// ------------------------------------------------------------------ MGIX stream -> device index
+namespace {
+__global__ void mark_docs_kernel(const uint32_t* __restrict__ postings, uint64_t n, uint32_t* __restrict__ bits) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint32_t d = postings[i];
+    atomicOr(bits + (d >> 5), 1u << (d & 31));
+  }
+}
+__global__ void word_popc_kernel(const uint32_t* __restrict__ bits, uint64_t n_words, uint32_t* __restrict__ cnt) {
+  const uint64_t w = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w < n_words) {
+    cnt[w] = __popc(bits[w]);
+  }
+}
+__global__ void ids_from_bits_kernel(const uint32_t* __restrict__ bits, const uint64_t* __restrict__ rank,
+                                     uint64_t n_words, uint32_t* __restrict__ ids) {
+  const uint64_t w = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w >= n_words) {
+    return;
+  }
+  uint32_t word = bits[w];
+  uint64_t at = rank[w];
+  while (word != 0) {
+    const int b = __ffs(static_cast<int>(word)) - 1;
+    word &= word - 1;
+    ids[at++] = static_cast<uint32_t>(w * 32 + b);
+  }
+}
+// global doc id -> index in the ascending list of the ids that occur in the stream
+__global__ void localise_postings_kernel(const uint32_t* __restrict__ in, uint64_t n, const uint32_t* __restrict__ bits,
+                                         const uint64_t* __restrict__ rank, uint32_t* __restrict__ out) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint32_t d = in[i];
+    out[i] = static_cast<uint32_t>(rank[d >> 5]) + __popc(bits[d >> 5] & ((1u << (d & 31)) - 1u));
+  }
+}
+}  // namespace
+
+void load_index_device(Index& ix, const uint64_t* h_keys, const uint64_t* h_term_off, const uint32_t* h_postings,
+                       uint64_t n_terms, uint64_t n_postings, cudaStream_t stream) {
+  ResetOnFailure reset_on_failure{ix};
+  ix.drop_filter_columns();
+  ix.d_doc_ids.release();
+  ix.d_text.release();
+  ix.d_text_off.release();
+  ix.d_doc_len.release();
+  ix.d_tile_first_doc.release();
+  ix.d_term_keys.release();
+  ix.d_term_off.release();
+  ix.d_postings.release();
+  ix.d_post_pos.release();
+  ix.d_post_pos2.release();
+  ix.d_term_bm.release();
+  ix.n_terms = n_terms;
+  ix.n_postings = n_postings;
+  ix.has_positions = false;
+  ix.n_pair_slots = 0;
+  ix.text_bytes = 0;
+  ix.n_text_tiles = 0;
+
+  // ---- the documents the stream knows = the union of its lists, through a bitmap over [0, max id]
+  uint32_t max_id = 0;
+  for (uint64_t i = 0; i < n_postings; ++i) {
+    max_id = std::max(max_id, h_postings[i]);
+  }
+  const uint64_t n_words = n_postings > 0 ? static_cast<uint64_t>(max_id) / 32 + 1 : 0;
+  DevArena& t1 = ix.build_arena;
+  t1.reserve(DevArena::padded(n_postings * 4 + 4) + DevArena::padded(n_words * 4 + 4) + DevArena::padded(n_words * 4 + 4) +
+             DevArena::padded((n_words + 1) * 8) + DevArena::padded(scan_scratch_elems(n_words) * 8 + 8) + 1024);
+  uint32_t* d_global = t1.take<uint32_t>(n_postings);
+  uint32_t* d_bits = t1.take<uint32_t>(n_words);
+  uint32_t* d_cnt = t1.take<uint32_t>(n_words);
+  uint64_t* d_rank = t1.take<uint64_t>(n_words + 1);
+  uint64_t* d_scan = t1.take<uint64_t>(scan_scratch_elems(n_words) + 1);
+  uint64_t n_docs = 0;
+  if (n_postings > 0) {
+    MGX_CUDA(cudaMemcpyAsync(d_global, h_postings, n_postings * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    MGX_CUDA(cudaMemsetAsync(d_bits, 0, n_words * sizeof(uint32_t), stream));
+    mark_docs_kernel<<<static_cast<unsigned>((n_postings + 255) / 256), 256, 0, stream>>>(d_global, n_postings, d_bits);
+    MGX_LAUNCH_CHECK();
+    word_popc_kernel<<<static_cast<unsigned>((n_words + 255) / 256), 256, 0, stream>>>(d_bits, n_words, d_cnt);
+    MGX_LAUNCH_CHECK();
+    exclusive_scan_u32_u64(d_cnt, d_rank, n_words, d_scan, stream);
+    MGX_CUDA(cudaMemcpyAsync(&n_docs, d_rank + n_words, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    MGX_CUDA(cudaStreamSynchronize(stream));
+  }
+  ix.n_docs = n_docs;
+
+  // ---- resident arena A: ids, and the (empty) text mirror every kernel expects
+  ix.resident_a.reserve(DevArena::padded(n_docs * 4 + 4) + DevArena::padded(64) + DevArena::padded((n_docs + 1) * 8) +
+                        DevArena::padded(n_docs * 4 + 4) + DevArena::padded(4));
+  ix.d_text.borrow(ix.resident_a.take<uint8_t>(64), 64);
+  ix.d_text_off.borrow(ix.resident_a.take<uint64_t>(n_docs + 1), n_docs + 1);
+  ix.d_doc_ids.borrow(ix.resident_a.take<uint32_t>(n_docs), n_docs);
+  ix.d_doc_len.borrow(ix.resident_a.take<uint32_t>(n_docs), n_docs);
+  ix.d_tile_first_doc.borrow(ix.resident_a.take<uint32_t>(1), 0);
+  MGX_CUDA(cudaMemsetAsync(ix.d_text.p, 0, 64, stream));
+  MGX_CUDA(cudaMemsetAsync(ix.d_text_off.p, 0, (n_docs + 1) * sizeof(uint64_t), stream));
+  if (n_docs > 0) {
+    MGX_CUDA(cudaMemsetAsync(ix.d_doc_len.p, 0, n_docs * sizeof(uint32_t), stream));
+    ids_from_bits_kernel<<<static_cast<unsigned>((n_words + 255) / 256), 256, 0, stream>>>(d_bits, d_rank, n_words,
+                                                                                            ix.d_doc_ids.p);
+    MGX_LAUNCH_CHECK();
+  }
+  uint32_t first_id = 1;
+  bool sequential_ids = true;
+  if (n_docs > 0) {
+    MGX_CUDA(cudaMemcpyAsync(&first_id, ix.d_doc_ids.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    MGX_CUDA(cudaStreamSynchronize(stream));
+    sequential_ids = static_cast<uint64_t>(max_id) - first_id + 1 == n_docs;
+  }
+  ix.first_id = first_id;
+  ix.sequential_ids = sequential_ids;
+  // BM25Stats belong to the DocumentStore (server_orchestrator.cpp:758-772): a stream carries none
+  ix.doc_count = 0;
+  ix.total_doc_length = 0;
+  ix.all_valid_utf8 = true;
+
+  // ---- resident arena B: dictionary + CSR with LOCAL doc indices
+  ix.resident_b.reserve(DevArena::padded(n_terms * 8 + 8) + DevArena::padded((n_terms + 1) * 8) +
+                        DevArena::padded(n_postings * 4 + 4) + 2 * DevArena::padded(n_terms * 4 + 4) + 512);
+  ix.d_term_keys.borrow(ix.resident_b.take<uint64_t>(n_terms), n_terms);
+  ix.d_term_off.borrow(ix.resident_b.take<uint64_t>(n_terms + 1), n_terms + 1);
+  ix.d_postings.borrow(ix.resident_b.take<uint32_t>(n_postings), n_postings);
+  ix.d_term_bm.borrow(ix.resident_b.take<int32_t>(n_terms), n_terms);
+  uint32_t* d_dense_terms = ix.resident_b.take<uint32_t>(n_terms);
+  unsigned long long* d_count = reinterpret_cast<unsigned long long*>(ix.resident_b.take<uint64_t>(2));
+  if (n_terms > 0) {
+    MGX_CUDA(cudaMemcpyAsync(ix.d_term_keys.p, h_keys, n_terms * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+  }
+  MGX_CUDA(cudaMemcpyAsync(ix.d_term_off.p, h_term_off, (n_terms + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+  if (n_postings > 0) {
+    localise_postings_kernel<<<static_cast<unsigned>((n_postings + 255) / 256), 256, 0, stream>>>(
+        d_global, n_postings, d_bits, d_rank, ix.d_postings.p);
+    MGX_LAUNCH_CHECK();
+  }
+  build_dense_bitmaps(ix, n_docs, d_dense_terms, d_count, stream);
+  MGX_CUDA(cudaStreamSynchronize(stream));
+  ix.text_less = true;
+  ix.last_build_ms = 0.0;
   reset_on_failure.armed = false;
 }
 

@@ -470,6 +470,7 @@ struct Index {
   // Second occurrence, same encoding: bits 0..14 = byte offset (0x7FFF = none / unknown), bit 15 = a third exists.
   DevBuf<uint16_t> d_post_pos2;
   bool has_positions = false;
+  bool text_less = false;  // loaded from an MGIX stream: posting lists only, no document text (load_index_device)
   DevBuf<int32_t> d_term_bm;
   DevBuf<uint32_t> d_bitmaps;
   DevArena resident_a;  // doc ids, text, text offsets, doc lengths
@@ -577,6 +578,11 @@ inline IndexView make_view(const Index& ix) {
 // The three inputs may be host or device pointers (cudaMemcpyDefault); the index keeps its own copies.
 void build_index_device(Index& ix, const uint32_t* doc_ids, const uint8_t* text, const uint64_t* text_off,
                         uint64_t n_docs, uint64_t text_bytes, cudaStream_t stream);
+// Index::LoadFromStream's device side: the index becomes the given CSR (ascending packed keys, GLOBAL ascending doc ids
+// per list, host arrays). No document text comes with a stream, so the shard holds none (text_less): the set calls
+// answer from the lists, text-dependent paths see documents without stored text.
+void load_index_device(Index& ix, const uint64_t* h_keys, const uint64_t* h_term_off, const uint32_t* h_postings,
+                       uint64_t n_terms, uint64_t n_postings, cudaStream_t stream);
 // Folds a journal of document mutations (host arrays sorted by id; removed[j] != 0 deletes, otherwise the text
 // replaces / adds the document) into the resident corpus on the device and rebuilds the shard.
 void apply_journal_device(Index& ix, const uint32_t* h_ids, const uint8_t* h_removed, const uint8_t* h_text,

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import corpus as corpus_mod
-from test_gpu_parity import build_pair, make_docs
+from test_gpu_parity import assert_same_index, build_pair, make_docs
 from test_oracle_bulk import _docs
 from test_oracle_expanded import expanded_cases, spaced_docs
 
@@ -137,3 +137,64 @@ def test_device_index_saves_an_mgix_stream(mgx, oracle):
     empty = mgx.Index(2, 0, True)
     meta, terms, offs, posts = mgx.mgix_decode(empty.save_mgix())
     assert meta["n_terms"] == 0 and posts.size == 0
+
+
+def test_device_index_loads_an_mgix_stream(mgx, oracle):
+    """mgx_index_load_mgix (Index::LoadFromStream, index_serialization.cpp:279-613): a stream -- written by the codec
+    from the oracle's index, and the streams recorded from the reference's own SaveToStream -- replaces the device
+    index; the set calls then answer like the index the stream came from (dense and sparse lists, sparse doc ids),
+    the stream saved again is byte-identical, a configuration mismatch and mutations are refused, and a bulk build
+    brings the documents back."""
+    import base64
+    import json
+
+    from test_mgix_codec import GOLDEN, big_corpus, csr_of
+    docs, ids = big_corpus(33)
+    for cfg in [(2, 0, True), (2, 1, True), (3, 2, False)]:
+        oi = oracle.index(*cfg)
+        oi.add_texts(ids, docs)
+        terms, offs, posts = csr_of(oi)
+        eff_kanji = cfg[1] if cfg[1] > 0 else cfg[0]
+        stream = mgx.mgix_encode(terms, offs, posts, cfg[0], eff_kanji, cfg[2])
+        gi = mgx.Index(*cfg)
+        gi.add_document_batch([7, 9], ["will be", "replaced"])
+        gi.load_mgix(stream)
+        st = gi.stats()
+        assert (st.n_terms, st.n_postings) == (len(terms), posts.size) and st.n_docs == np.unique(posts).size
+        t2, o2, p2 = gi.export()
+        assert t2 == terms and np.array_equal(o2, offs) and np.array_equal(p2, posts)
+        assert gi.save_mgix() == stream
+        rnd = random.Random(4)
+        big = [terms[i] for i in np.argsort(np.diff(offs.astype(np.int64)))[-6:]]
+        for _ in range(60):
+            pick = [rnd.choice(big) if rnd.random() < 0.4 else terms[rnd.randrange(len(terms))] for _ in range(rnd.randint(1, 3))]
+            assert np.array_equal(gi.search_and(pick), oi.search_and(pick)), pick
+            assert np.array_equal(gi.search_or(pick), oi.search_or(pick)), pick
+            assert np.array_equal(gi.search_and(pick, 5, True), oi.search_and(pick, 5, True))
+            assert gi.posting_size(pick[0]) == oi.posting_size(pick[0])
+        all_ids = np.unique(posts)
+        assert np.array_equal(gi.search_not(all_ids, [big[0]]), oi.search_not(all_ids, [big[0]]))
+        # un-scored batch over the lists (no text needed), scored batch: documents without stored text score 0
+        qs = [[rnd.choice(big)] for _ in range(8)]
+        r = gi.query_batch(qs, score=False, limit=20)
+        for q, terms_q in enumerate(qs):
+            want = oi.search_and(terms_q)
+            assert int(r.total[q]) == want.size and np.array_equal(r.ids[q, :int(r.count[q])], want[:20])
+        with pytest.raises(mgx.MgxError):
+            gi.add_document(123456, "no documents here")
+        other = mgx.Index(cfg[0] + 1 if cfg[0] < 3 else 1, cfg[1], cfg[2])
+        with pytest.raises(mgx.MgxError):
+            other.load_mgix(stream)
+        with pytest.raises(mgx.MgxError):
+            gi.load_mgix(stream[:-3])  # CRC / truncation: the index is left as it was
+        assert gi.stats().n_terms == len(terms)
+        arena, doc_offs = mgx.pack_strings(docs)
+        gi.build(ids, arena, doc_offs)  # the documents arrive: a full index again
+        assert_same_index(gi, oi)
+        gi.add_document(123456, "ab")
+    for case in json.load(open(GOLDEN))["cases"]:
+        gi = mgx.Index(case["config"][0], case["config"][1], bool(case["config"][2]))
+        gi.load_mgix(base64.b64decode(case["stream_b64"]))
+        t2, o2, p2 = gi.export()
+        assert [t.hex() for t in t2] == case["terms_hex"] and o2.tolist() == case["posting_offsets"]
+        assert p2.size == case["n_postings"]
