@@ -2993,7 +2993,7 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
 // queries, and the tiles of one query follow each other in time. Small launches keep the natural order (their tiles
 // share staged sub-lists through L2).
 constexpr uint32_t kInterleaveMinTiles = 1u << 15;
-__device__ __forceinline__ uint32_t interleave_stride(uint32_t n, uint32_t prune_k, int compute_score) {
+__host__ __device__ __forceinline__ uint32_t interleave_stride(uint32_t n, uint32_t prune_k, int compute_score) {
   if (n < kInterleaveMinTiles || prune_k == 0 || compute_score == 0) {
     return 1;
   }
@@ -3017,8 +3017,8 @@ __device__ __forceinline__ uint32_t interleaved_tile(uint32_t i, uint32_t n, uin
 __global__ void __launch_bounds__(kTileThreads, MGX_AND_OCC)
 and_tile_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint64_t tile_base, uint32_t rec_slot,
                 uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_total, uint32_t* __restrict__ rec_doc,
-                double* __restrict__ rec_score, uint32_t prune_k) {
-  const uint32_t slot = interleaved_tile(blockIdx.x, gridDim.x, interleave_stride(gridDim.x, prune_k, sp.compute_score));
+                double* __restrict__ rec_score, uint32_t prune_k, uint32_t tile_stride) {
+  const uint32_t slot = interleaved_tile(blockIdx.x, gridDim.x, tile_stride);  // stride: interleave_stride, on the host
   const uint64_t tile_global = tile_base + slot;
   const uint32_t q = __ldg(bv.tile_query + tile_global);
   and_tile_body(iv, bv, sp, q, tile_global - bv.q_tile_off[q], slot, rec_slot, tile_count, tile_total, rec_doc,
@@ -3033,8 +3033,13 @@ and_tiles_kernel(IndexView iv, BatchView bv, ScoreParams sp, uint32_t rec_slot, 
                  uint32_t prune_k) {
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_q;
+  __shared__ uint32_t s_stride;
   const uint32_t n_tiles = bv.launch[kLaunchAndTiles];
-  const uint32_t stride = interleave_stride(n_tiles, prune_k, sp.compute_score);
+  if (threadIdx.x == 0) {
+    s_stride = interleave_stride(n_tiles, prune_k, sp.compute_score);  // once per persistent CTA
+  }
+  __syncthreads();
+  const uint32_t stride = s_stride;
   for (;;) {
     if (threadIdx.x < 32) {
       uint32_t tile = 0;
@@ -4653,7 +4658,8 @@ void run_tiles(Batch& b, const Chunk& c, const ScoreParams& sp, uint32_t prune_k
     b.time_begin(2);
     and_tile_kernel<<<static_cast<unsigned>(n_tiles), kTileThreads, 0, st>>>(
         make_view(*b.ix), make_batch_view(b), sp, tile_base, b.rec_slot, b.d_tile_count.p, b.d_tile_total.p,
-        b.d_rec_doc.p, b.d_rec_score.p, prune_k);
+        b.d_rec_doc.p, b.d_rec_score.p, prune_k,
+        interleave_stride(static_cast<uint32_t>(n_tiles), prune_k, sp.compute_score));
     MGX_LAUNCH_CHECK();
     b.time_end();
     b.n_and_tiles += n_tiles;

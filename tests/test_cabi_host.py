@@ -121,13 +121,13 @@ def test_packed_key_order_is_utf8_byte_order(mgx, oracle):
     assert [strings[i] for i in order_k] == [strings[i] for i in order_s]
 
 
-def _build_adapter_example(tmp_path):
+def _build_adapter_example(tmp_path, source="adapter_example.cpp"):
     import subprocess
     root = os.path.join(os.path.dirname(__file__), "..")
-    exe = str(tmp_path / "adapter_example")
+    exe = str(tmp_path / source.replace(".cpp", ""))
     libdir = os.path.abspath(os.path.join(root, "mygram-db_b200"))
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-o", exe,
-                           os.path.join(libdir, "adapter", "adapter_example.cpp"), "-L" + libdir, "-lmgx",
+                           os.path.join(libdir, "adapter", source), "-L" + libdir, "-lmgx",
                            "-Wl,-rpath," + libdir])
     return exe
 
@@ -150,6 +150,20 @@ def test_cpp_adapter_runs_on_gpu(mgx, tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "SearchAnd({bc,cd}) -> 2 docs" in r.stdout  # tests/index/index_search_test.cpp:393-418
+
+
+def test_cpp_adapter_test_program_compiles(mgx, tmp_path):
+    _build_adapter_example(tmp_path, "adapter_test.cpp")
+
+
+@pytest.mark.gpu
+def test_cpp_adapter_assertions_on_gpu(mgx, tmp_path):
+    """adapter/adapter_test.cpp: the reference's own unit-test cases (index_search_test, index_basic_test,
+    query_ast_test, bm25_scorer_test, result_sorter_test, index_serialization_test) asserted through the C++ adapter."""
+    import subprocess
+    exe = _build_adapter_example(tmp_path, "adapter_test.cpp")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ADAPTER TESTS OK" in r.stdout, r.stdout + r.stderr
 
 
 def test_shard_record_layout_matches_the_python_protocol(mgx):
