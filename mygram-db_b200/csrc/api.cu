@@ -1529,6 +1529,8 @@ int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, co
 
 // ---------------------------------------------------------------- set-algebra single calls
 namespace {
+bool run_at_least_expanded(Index& ix, cudaStream_t stream, const KeyVec& keys, size_t need, uint32_t* out,
+                           uint64_t cap, uint64_t* out_count, int* rc_out);  // with the expanded paths, below
 
 enum class SetOp { kAnd, kOr, kNot, kFilter };
 
@@ -1692,13 +1694,20 @@ int run_set_op(mgx_index_t* index, SetOp op, const uint32_t* driver_ids, uint64_
       t.keys = keys;
       std::sort(t.keys.begin(), t.keys.end());
       t.keys.erase(std::unique(t.keys.begin(), t.keys.end()), t.keys.end());
+      bool any_mode = op == SetOp::kOr;
       if (op == SetOp::kOr) {
         // unknown terms are ignored (index.cpp:437-445)
         t.keys.erase(std::remove(t.keys.begin(), t.keys.end(), kInvalidKey), t.keys.end());
+        // the union is driven by the lists themselves, not by a pass over every document of the shard
+        int rc = MGX_OK;
+        if (run_at_least_expanded(ix, rd.stream(), t.keys, 1, out, cap, out_count, &rc)) {
+          return rc;
+        }
+        any_mode = t.keys.size() != 1;  // one list: the list itself (an AND of one n-gram)
       }
       terms.push_back(std::move(t));
       queries[0].terms.push_back(0);
-      queries[0].flags = op == SetOp::kOr ? kQAnyMode : (op == SetOp::kFilter ? kQDriverExplicit : 0u);
+      queries[0].flags = any_mode ? kQAnyMode : (op == SetOp::kFilter ? kQDriverExplicit : 0u);
     }
 
     return run_single_set_query(ix, rd.stream(), terms, queries,
@@ -1782,6 +1791,13 @@ int mgx_search_by_threshold(const mgx_index_t* index_c, const uint8_t* term_byte
     }
     std::sort(t.keys.begin(), t.keys.end());
     t.keys.erase(std::unique(t.keys.begin(), t.keys.end()), t.keys.end());
+    if (threshold > t.keys.size()) {
+      return MGX_OK;  // fewer lists than the threshold: nothing can qualify
+    }
+    int rc = MGX_OK;
+    if (run_at_least_expanded(ix, rd.stream(), t.keys, threshold, out, cap, out_count, &rc)) {
+      return rc;
+    }
     std::vector<HostTerm> terms;
     terms.push_back(std::move(t));
     std::vector<HostQuery> queries(1);
@@ -1981,6 +1997,41 @@ int finish_expanded(const Index& ix, const mgx_expanded_query_t& eq, ProgramBuil
 }
 
 constexpr size_t kMaxDriverLeaves = 16;  // beyond this one pass over every document is the cheaper plan
+
+// "Documents in at least `need` of these lists" (Index::SearchOr: need = 1; Index::SearchByThreshold, index.cpp:488-578)
+// driven by lists instead of by every document of the shard: a document in >= need of n lists is in one of ANY
+// n - need + 1 of them, so the query is expanded into one query per such list (finish_expanded) and the disjoint
+// answers are united. Returns false when the expansion does not apply (too many driver lists): the caller then takes
+// the single pass over all documents.
+bool run_at_least_expanded(Index& ix, cudaStream_t stream, const KeyVec& keys, size_t need, uint32_t* out,
+                           uint64_t cap, uint64_t* out_count, int* rc_out) {
+  const size_t n = keys.size();
+  if (n < 2 || need < 1 || need >= n || n - need + 1 > kMaxDriverLeaves || n > 0xFFFF ||
+      std::getenv("MGX_NO_OR_EXPANSION") != nullptr) {
+    return false;
+  }
+  // drive by the SHORTEST lists is not needed for exactness; the first n - need + 1 keys in key order are taken
+  ProgramBuilder pb;
+  std::vector<int32_t> drivers;
+  for (size_t i = 0; i < n; ++i) {
+    HostTerm leaf;
+    leaf.raw = true;
+    leaf.keys.push_back(keys[i]);
+    if (i < n - need + 1) {
+      drivers.push_back(static_cast<int32_t>(pb.terms.size()));
+    }
+    pb.leaf(std::move(leaf));
+  }
+  pb.node(kOpAtLeast, static_cast<int32_t>(n | (need << 16)));
+  mgx_expanded_query_t eq{};
+  std::vector<HostQuery> queries;
+  int rc = finish_expanded(ix, eq, &pb, 1, drivers, &queries);
+  if (rc == MGX_OK) {
+    rc = run_single_set_query(ix, stream, pb.terms, queries, nullptr, 0, 0, false, out, cap, out_count);
+  }
+  *rc_out = rc;
+  return true;
+}
 
 }  // namespace
 

@@ -477,3 +477,40 @@ def test_scored_batches_with_deep_offsets(mgx, oracle, shard, monkeypatch, strea
             assert np.array_equal(r.ids[q, :hi - lo], full.ids[q, lo:hi])
             assert np.array_equal(r.scores[q, :hi - lo].view(np.uint64), full.scores[q, lo:hi].view(np.uint64))
             assert int(o.count[q]) == hi - lo and np.array_equal(o.ids[q, :hi - lo], r.ids[q, :hi - lo])
+
+
+def test_search_or_and_threshold_are_driven_by_lists(mgx, oracle, shard, monkeypatch):
+    """Index::SearchOr / SearchByThreshold (index.cpp:410-448, 488-578) expanded into one list-driven query per
+    sufficient list (a document in >= t of n lists is in one of any n - t + 1 of them) instead of a pass over every
+    document: same answers as the single pass and as the oracle, for dense and sparse lists, unknown n-grams,
+    repeated terms and more lists than the expansion takes."""
+    import random
+    c, gi = shard
+    oi = oracle.index(2, 0, True)
+    oi.build_bulk(c.doc_ids, c.arena, c.offsets, 8)
+    rnd = random.Random(12)
+    texts = [c.text(rnd.randrange(60000)).decode() for _ in range(400)]
+    grams = [t[i:i + 2].encode() for t in texts for i in range(0, min(len(t) - 1, 6))]
+    cases = []
+    for _ in range(30):
+        n = rnd.choice([1, 2, 3, 5, 8, 17, 24])
+        terms = [rnd.choice(grams) for _ in range(n)]
+        if rnd.random() < 0.3:
+            terms.append("一鿿".encode())  # an n-gram no document holds
+        if rnd.random() < 0.3:
+            terms.append(terms[0])
+        cases.append(terms)
+    for terms in cases:
+        want_or = oi.search_or(terms)
+        uniq = len(set(terms))
+        thresholds = sorted({1, 2, max(1, uniq // 2), max(1, uniq - 1), uniq})
+        want_thr = [oi.search_by_threshold(terms, t) for t in thresholds]
+        for pin in (False, True):
+            if pin:
+                monkeypatch.setenv("MGX_NO_OR_EXPANSION", "1")
+            else:
+                monkeypatch.delenv("MGX_NO_OR_EXPANSION", raising=False)
+            assert np.array_equal(gi.search_or(terms), want_or), (pin, terms)
+            for t, w in zip(thresholds, want_thr):
+                assert np.array_equal(gi.search_by_threshold(terms, t), w), (pin, t, terms)
+    monkeypatch.delenv("MGX_NO_OR_EXPANSION", raising=False)

@@ -81,7 +81,27 @@ def main():
                 f.write(line + "\n")
         return line
 
+    # Index::SearchOr / SearchByThreshold: 3 bigrams of one document (OR) / 6 bigrams, at least 4 of them
+    def grams(d, n):
+        t = c.text(d).decode()
+        return [t[i:i + 2] for i in range(min(n, len(t) - 1))]
+    or_qs = [grams(int(rng.integers(0, c.n_docs)), 3) for _ in range(args.queries)]
+    thr_qs = [grams(int(rng.integers(0, c.n_docs)), 6) for _ in range(args.queries)]
+
+    def pinned(fn):  # the round-1 plan: one pass over every document of the shard
+        def run(q):
+            os.environ["MGX_NO_OR_EXPANSION"] = "1"
+            try:
+                return fn(q)
+            finally:
+                del os.environ["MGX_NO_OR_EXPANSION"]
+        return run
+
     gpu_classes = [
+        ("search_or_3", or_qs, lambda q: gi.search_or(q)),
+        ("search_or_3_single_pass", or_qs, pinned(lambda q: gi.search_or(q))),
+        ("search_by_threshold_4_of_6", thr_qs, lambda q: gi.search_by_threshold(q, 4)),
+        ("search_by_threshold_4_of_6_single_pass", thr_qs, pinned(lambda q: gi.search_by_threshold(q, 4))),
         ("fuzzy_d1", fuzzy, lambda q: gi.search_fuzzy(q, 1)),
         ("fuzzy_d1_verify_all", fuzzy, lambda q: gi.search_fuzzy(q, 1, verify_text=1)),
         ("synonyms_2x2", syn, lambda q: gi.search_synonyms(q)),
@@ -130,13 +150,27 @@ def main():
                           "decodes_to_device_csr": bool(ok)}
     flush()
     assert ok
+    # Index::LoadFromStream into a second device index; its stream saved again must be the same bytes
+    g2 = m.Index(2, 0, True, device=0)
+    t2 = time.perf_counter()
+    g2.load_mgix(stream)
+    load_s = time.perf_counter() - t2
+    again = g2.save_mgix()
+    out["mgix_import"] = {"load_seconds": load_s, "documents_in_the_stream": int(g2.stats().n_docs),
+                          "saved_again_is_identical": bool(again == stream)}
+    flush()
+    assert again == stream
+    g2.close()
+    del again
     del stream, buf, tb, to, po, pp, keys, goffs, gposts
     # CPU oracle beside it, on a bounded sample of the same queries
     oi = pyoracle.OracleLib(pyoracle.PORT_LIB).index(2, 0, True)
     t0 = time.perf_counter()
     oi.build_bulk(c.doc_ids, c.arena, c.offsets, os.cpu_count() or 1)
     out["cpu_index_build_s"] = round(time.perf_counter() - t0, 2)
-    cpu_classes = {"fuzzy_d1": (fuzzy, lambda q: oi.search_fuzzy(q, 1)[0]),
+    cpu_classes = {"search_or_3": (or_qs, lambda q: oi.search_or(q)),
+                   "search_by_threshold_4_of_6": (thr_qs, lambda q: oi.search_by_threshold(q, 4)),
+                   "fuzzy_d1": (fuzzy, lambda q: oi.search_fuzzy(q, 1)[0]),
                    "fuzzy_d1_verify_all": (fuzzy, lambda q: oi.search_fuzzy(q, 1, verify_text=1)[0]),
                    "synonyms_2x2": (syn, lambda q: oi.search_synonyms(q)[0]),
                    "synonyms_2x2_verify_all": (syn, lambda q: oi.search_synonyms(q, verify_text=1)[0])}
