@@ -1578,14 +1578,13 @@ int run_single_set_query(Index& ix, cudaStream_t lane_stream, std::vector<HostTe
   b.params = mgx_query_params_t{};
   b.params.compute_score = 0;
   b.launches_at_start = g_launches.load();
-  DevBuf<uint32_t> d_driver;
   if (driver_ids != nullptr) {
     if (n_driver >= (1ULL << 32)) {
       return invalid("too many candidate ids");
     }
-    d_driver.alloc(n_driver);
-    MGX_CUDA(cudaMemcpyAsync(d_driver.p, driver_ids, n_driver * sizeof(uint32_t), cudaMemcpyHostToDevice, b.stream));
-    b.explicit_driver.d_ids = d_driver.p;
+    b.driver_buf.reserve(std::max<uint64_t>(1, n_driver));  // grow-only with the pooled batch object
+    MGX_CUDA(cudaMemcpyAsync(b.driver_buf.p, driver_ids, n_driver * sizeof(uint32_t), cudaMemcpyHostToDevice, b.stream));
+    b.explicit_driver.d_ids = b.driver_buf.p;
     b.explicit_driver.n = n_driver;
   }
   batch_upload(b, terms, queries, {});
@@ -1597,8 +1596,8 @@ int run_single_set_query(Index& ix, cudaStream_t lane_stream, std::vector<HostTe
     // one logical query expanded into several with different drivers (finish_expanded): their result sets are
     // disjoint by construction and their union is the answer
     DevBuf<uint32_t> d_union;
-    merge_disjoint_runs(b.stream, d_sets.p, set_off, &d_union);
-    d_sets = std::move(d_union);
+    merge_disjoint_runs(b, d_sets.p, set_off, &d_union);
+    d_sets.borrow(d_union.p, d_union.n);  // both are views into the batch object's buffers
     set_off = {0, set_off.back()};
   }
   const uint64_t total = set_off[1];
@@ -2010,13 +2009,43 @@ bool run_at_least_expanded(Index& ix, cudaStream_t stream, const KeyVec& keys, s
       std::getenv("MGX_NO_OR_EXPANSION") != nullptr) {
     return false;
   }
-  // drive by the SHORTEST lists is not needed for exactness; the first n - need + 1 keys in key order are taken
+  // ANY n - need + 1 lists will do for exactness; the SHORTEST ones are the cheapest drivers. Their lengths cost one
+  // lookup launch; when they add up to a sizeable part of the shard the single pass over all documents (bit probes
+  // into the dense lists, 1024 documents per tile) is the cheaper plan.
+  std::vector<uint64_t> sorted_keys(keys.begin(), keys.end());
+  if (n <= 64) {
+    uint32_t lens[64];
+    {
+      PooledBatch pooled(ix);
+      Batch& b = pooled.h->b;
+      b.ix = &ix;
+      b.stream = stream;
+      lookup_list_lengths(b, sorted_keys.data(), static_cast<uint32_t>(n), lens);
+    }
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; ++i) {
+      order[i] = static_cast<uint32_t>(i);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b2) { return lens[a] < lens[b2]; });
+    uint64_t driven = 0;
+    for (size_t i = 0; i < n - need + 1; ++i) {
+      driven += lens[order[i]];
+    }
+    if (driven > ix.n_docs / 4) {
+      return false;
+    }
+    std::vector<uint64_t> by_len(n);
+    for (size_t i = 0; i < n; ++i) {
+      by_len[i] = sorted_keys[order[i]];
+    }
+    sorted_keys.swap(by_len);
+  }
   ProgramBuilder pb;
   std::vector<int32_t> drivers;
   for (size_t i = 0; i < n; ++i) {
     HostTerm leaf;
     leaf.raw = true;
-    leaf.keys.push_back(keys[i]);
+    leaf.keys.push_back(sorted_keys[i]);
     if (i < n - need + 1) {
       drivers.push_back(static_cast<int32_t>(pb.terms.size()));
     }

@@ -792,10 +792,32 @@ __global__ void fill_df_desc_kernel(const uint64_t* __restrict__ off, const uint
 }
 
 // Two lower bounds in one list by a whole warp, the probes of both searches in flight together.
+// `start`: a position all elements before which are known to be < v1 (0 = no knowledge). Consecutive pieces of a
+// driver list ask for consecutive doc ranges, so the bounds of one piece start where the previous piece's ended: one
+// probe step over the next ~1000 entries usually brackets both bounds (two dependent loads instead of log33(n) + 1).
 __device__ __forceinline__ void warp_lower_bound_pair(const uint32_t* __restrict__ p, uint32_t n, uint32_t v1, uint32_t v2,
-                                                      uint32_t* out1, uint32_t* out2) {
+                                                      uint32_t* out1, uint32_t* out2, uint32_t start = 0) {
   const unsigned lane = threadIdx.x & 31u;
-  uint32_t lo1 = 0, hi1 = n, lo2 = 0, hi2 = n;
+  uint32_t lo1 = start, hi1 = n, lo2 = start, hi2 = n;
+  if (start != 0 && n - start > 32) {
+    const uint32_t w = min(n - start, 1056u);
+    const uint32_t idx = start + static_cast<uint32_t>((static_cast<uint64_t>(lane + 1) * w) / 33);
+    const uint32_t x = __ldg(p + idx);  // one load serves both bounds
+    {
+      const int c = __popc(__ballot_sync(0xffffffffu, x < v1));
+      const uint32_t prev = __shfl_sync(0xffffffffu, idx, c > 0 ? c - 1 : 0);
+      const uint32_t next = __shfl_sync(0xffffffffu, idx, c < 32 ? c : 31);
+      if (c > 0) lo1 = prev + 1;
+      if (c < 32) hi1 = next;  // else: beyond the window, the rest of the list stays open
+    }
+    {
+      const int c = __popc(__ballot_sync(0xffffffffu, x < v2));
+      const uint32_t prev = __shfl_sync(0xffffffffu, idx, c > 0 ? c - 1 : 0);
+      const uint32_t next = __shfl_sync(0xffffffffu, idx, c < 32 ? c : 31);
+      if (c > 0) lo2 = prev + 1;
+      if (c < 32) hi2 = next;
+    }
+  }
   while (hi1 - lo1 > 32 || hi2 - lo2 > 32) {
     const bool a1 = hi1 - lo1 > 32;
     const bool a2 = hi2 - lo2 > 32;
@@ -851,6 +873,7 @@ __global__ void fill_tile_map_kernel(const uint64_t* __restrict__ off, uint32_t 
 constexpr int kWarpItems = 4;                       // driver entries per lane
 constexpr int kWarpTile = 32 * kWarpItems;          // 128 entries per warp
 constexpr uint32_t kWarpStageCap = 512;             // staged entries of one other list per warp (2 KB)
+constexpr uint32_t kDfHintLists = 2;                // other lists whose last sub-range end a warp carries from piece to piece
 static_assert(kWarpTile * (kTileThreads / 32) == kTile, "warps must tile the CTA tile exactly");
 
 __device__ __forceinline__ void stat_add(const BatchView& bv, int slot, unsigned long long v) {
@@ -878,7 +901,7 @@ static_assert(kWarpStageCap * sizeof(uint32_t) >= kStageBuf, "the text staging b
 // piece. stage / surv / spos are the calling warp's own shared-memory slices; stat_stripe spreads the accounting atomics.
 __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchView& bv, const ListRef& drv, uint32_t t,
                                              uint32_t k0, uint32_t k1, uint64_t e0, uint32_t* stage, uint32_t* surv,
-                                             uint32_t* spos, uint32_t stat_stripe) {
+                                             uint32_t* spos, uint32_t stat_stripe, uint32_t (&hint)[kDfHintLists]) {
   const unsigned lane = threadIdx.x & 31u;
   if (e0 >= drv.len) {
     return;  // no block-wide barrier is used below, so a warp may leave early
@@ -925,7 +948,11 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
     } else {
       uint32_t lo = 0;
       uint32_t hi = 0;
-      warp_lower_bound_pair(l.p, l.len, dmin, dmax + 1u, &lo, &hi);
+      const uint32_t hj = j - (k0 + 1);  // the first kDfHintLists other lists remember where the last piece ended
+      warp_lower_bound_pair(l.p, l.len, dmin, dmax + 1u, &lo, &hi, hj < kDfHintLists ? hint[hj] : 0u);
+      if (hj < kDfHintLists) {
+        hint[hj] = hi;
+      }
       const uint32_t cnt = hi - lo;
       if (cnt == 0) {
         alive = 0;
@@ -1110,8 +1137,9 @@ __global__ void __launch_bounds__(kTileThreads, MGX_DF_OCC) df_tile_kernel(Index
   drv.len = d0.z;
   drv.bm = nullptr;
   const uint64_t tile = d1.z;
+  uint32_t hint[kDfHintLists] = {0, 0};  // one piece per warp here: nothing to carry
   df_warp_tile(iv, bv, drv, d0.w, d1.x, d1.y, tile * kTile + static_cast<uint64_t>(warp) * kWarpTile, s_stage[warp],
-               s_surv[warp], s_spos[warp], blockIdx.x);
+               s_surv[warp], s_spos[warp], blockIdx.x, hint);
 }
 
 // Streamed form (no host read-back of the tile count): persistent warps pull UNITS of kDfUnit entries of the terms'
@@ -1173,10 +1201,14 @@ __global__ void __launch_bounds__(kTileThreads, MGX_DF_OCC) df_units_kernel(Inde
     drv.len = r1.x;
     drv.bm = nullptr;
     const uint64_t e0 = (static_cast<uint64_t>(unit) - bv.t_df_tile_off[t]) * kDfUnit;
+    uint32_t hint[kDfHintLists] = {0, 0};
 #pragma unroll 1
     for (uint32_t piece = 0; piece < kDfUnit / kWarpTile; ++piece) {
       df_warp_tile(iv, bv, drv, t, k0, k1, e0 + static_cast<uint64_t>(piece) * kWarpTile, s_stage[warp], s_surv[warp],
-                   s_spos[warp], unit);
+                   s_spos[warp], unit, hint);
+#ifdef MGX_DF_NO_HINT
+      hint[0] = hint[1] = 0;
+#endif
       __syncwarp();
     }
   }
@@ -3351,24 +3383,25 @@ topk_groups_kernel(BatchView bv, uint32_t group_tiles, uint32_t rec_slot, uint32
   }
 }
 
-// Full ascending sets: out[set_off[q] + rank] for every survivor of query q.
+// Full ascending result sets (the Index::Search* style calls), two launches. set_tile_ranks_kernel: one CTA per query
+// turns the tiles' record counts into the rank of each tile's first record inside the query's set (written over
+// tile_total, which the counting pass no longer needs). gather_tiles_kernel: one CTA per TILE copies its records to
+// set_off[q] + rank, coalesced -- a query with hundreds of thousands of results is gathered by thousands of CTAs, not
+// by one thread per tile of a single CTA.
 __global__ void __launch_bounds__(256)
-gather_sets_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint32_t rec_slot,
-                   const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ rec_doc,
-                   const uint64_t* __restrict__ set_off, uint32_t* __restrict__ out) {
+set_tile_ranks_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, const uint32_t* __restrict__ tile_count,
+                      uint32_t* __restrict__ tile_rank) {
   __shared__ uint64_t s_scan[8];
   __shared__ uint64_t s_carry;
   const uint32_t q = q_first + blockIdx.x;
   const uint64_t t0 = bv.q_tile_off[q] - tile_base;
   const uint32_t ntiles = static_cast<uint32_t>(bv.q_tile_off[q + 1] - bv.q_tile_off[q]);
-  const uint64_t r0 = t0 * rec_slot;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     s_carry = 0;
   }
   __syncthreads();
-  uint32_t* dst = out + set_off[q];
   for (uint32_t tb = 0; tb < ntiles; tb += blockDim.x) {
     const uint32_t t = tb + threadIdx.x;
     const uint32_t c = t < ntiles ? tile_count[t0 + t] : 0;
@@ -3392,15 +3425,31 @@ gather_sets_kernel(BatchView bv, uint32_t q_first, uint64_t tile_base, uint32_t 
       }
       chunk_total += s_scan[w];
     }
-    const uint64_t first_rank = prefix + inc - c;
-    for (uint32_t i = 0; i < c; ++i) {
-      dst[first_rank + i] = rec_doc[r0 + static_cast<uint64_t>(t) * rec_slot + i];
+    if (t < ntiles) {
+      tile_rank[t0 + t] = static_cast<uint32_t>(prefix + inc - c);  // a set never exceeds the 2^32 documents of a shard
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       s_carry += chunk_total;
     }
     __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gather_tiles_kernel(BatchView bv, uint64_t tile_base, uint32_t rec_slot, const uint32_t* __restrict__ tile_count,
+                    const uint32_t* __restrict__ tile_rank, const uint32_t* __restrict__ rec_doc,
+                    const uint64_t* __restrict__ set_off, uint32_t* __restrict__ out) {
+  const uint64_t slot = blockIdx.x;  // tile slot inside the chunk
+  const uint32_t c = tile_count[slot];
+  if (c == 0) {
+    return;
+  }
+  const uint32_t q = __ldg(bv.tile_query + tile_base + slot);
+  uint32_t* const dst = out + set_off[q] + tile_rank[slot];
+  const uint32_t* const src = rec_doc + slot * rec_slot;
+  for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+    dst[i] = src[i];
   }
 }
 
@@ -4890,18 +4939,39 @@ __global__ void merge_disjoint_runs_kernel(const uint32_t* __restrict__ in, cons
   out[pos] = v;
 }
 
-void merge_disjoint_runs(cudaStream_t st, const uint32_t* d_in, const std::vector<uint64_t>& run_off,
-                         DevBuf<uint32_t>* d_out) {
+// Posting-list lengths of up to 64 packed keys (0 for a key the dictionary does not hold): one lookup launch and one
+// small copy. Used by the single calls to choose between a list-driven plan and a pass over the shard.
+void lookup_list_lengths(Batch& b, const uint64_t* h_keys, uint32_t n, uint32_t* h_lens) {
+  Index& ix = *b.ix;
+  cudaStream_t st = b.stream;
+  if (n == 0) {
+    return;
+  }
+  b.len_buf.reserve(3 * 64 * 8);  // keys | list ids | lengths
+  uint64_t* d_keys = b.len_buf.p;
+  uint32_t* d_list = reinterpret_cast<uint32_t*>(b.len_buf.p + 64);
+  uint32_t* d_len = reinterpret_cast<uint32_t*>(b.len_buf.p + 128);
+  MGX_CUDA(cudaMemcpyAsync(d_keys, h_keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  lookup_kernel<<<1, 64, 0, st>>>(ix.d_term_keys.p, ix.d_term_off.p, ix.n_terms, d_keys, n, d_list, d_len, nullptr);
+  MGX_LAUNCH_CHECK();
+  MGX_CUDA(cudaMemcpyAsync(h_lens, d_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  MGX_CUDA(cudaStreamSynchronize(st));
+}
+
+void merge_disjoint_runs(Batch& b, const uint32_t* d_in, const std::vector<uint64_t>& run_off, DevBuf<uint32_t>* d_out) {
+  cudaStream_t st = b.stream;
   const uint64_t total = run_off.back();
-  d_out->alloc(std::max<uint64_t>(1, total));
+  // the union and the run offsets live in the batch object's grow-only buffers: no cudaMalloc / cudaFree per call
+  b.union_buf.reserve(std::max<uint64_t>(1, total));
+  d_out->borrow(b.union_buf.p, total);
   if (total == 0) {
     return;
   }
-  DevBuf<uint64_t> d_off;
-  d_off.alloc(run_off.size());
-  MGX_CUDA(cudaMemcpyAsync(d_off.p, run_off.data(), run_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  b.run_off_buf.reserve(run_off.size());
+  MGX_CUDA(cudaMemcpyAsync(b.run_off_buf.p, run_off.data(), run_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  merge_disjoint_runs_kernel<<<blocks, 256, 0, st>>>(d_in, d_off.p, static_cast<uint32_t>(run_off.size() - 1), d_out->p);
+  merge_disjoint_runs_kernel<<<blocks, 256, 0, st>>>(d_in, b.run_off_buf.p, static_cast<uint32_t>(run_off.size() - 1),
+                                                     d_out->p);
   MGX_LAUNCH_CHECK();
   MGX_CUDA(cudaStreamSynchronize(st));
 }
@@ -4914,38 +4984,51 @@ void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32
   ScoreParams sp = score_params(b);
   sp.compute_score = 0;
   const auto chunks = make_chunks(b, scratch_records(b), kTile);
-  // pass 1: totals per query (topk_kernel with limit 0 / stride 0 only counts)
-  DevBuf<uint32_t> d_count;
-  DevBuf<uint64_t> d_total;
-  DevBuf<uint32_t> d_dummy;
-  d_count.alloc(b.n_queries);
-  d_total.alloc(b.n_queries + 1);
-  d_dummy.alloc(1);
-  std::vector<uint64_t> totals(b.n_queries, 0);
+  // small per-call arrays from the batch object's arena (grow-only): a single Index::Search* call allocates nothing
+  const size_t Q = b.n_queries;
+  b.sets_arena.reserve(DevArena::padded(Q * 4 + 4) + 2 * DevArena::padded((Q + 1) * 8) + DevArena::padded(4) + 256);
+  uint32_t* d_count = b.sets_arena.take<uint32_t>(Q);
+  uint64_t* d_total = b.sets_arena.take<uint64_t>(Q + 1);
+  uint64_t* d_set_off = b.sets_arena.take<uint64_t>(Q + 1);
+  uint32_t* d_dummy = b.sets_arena.take<uint32_t>(1);
+  std::vector<uint64_t> totals(Q, 0);
+  auto count_chunk = [&](const Chunk& c) {  // totals per query (topk_kernel with limit 0 / stride 0 only counts)
+    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.rec_slot,
+                                             b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p, nullptr, 0, 0, 0, 0, 0,
+                                             d_dummy, nullptr, d_count, d_total);
+    MGX_LAUNCH_CHECK();
+  };
+  auto offsets_from_totals = [&]() {
+    MGX_CUDA(cudaMemcpyAsync(totals.data(), d_total, Q * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MGX_CUDA(cudaStreamSynchronize(st));
+    h_set_off->assign(Q + 1, 0);
+    for (uint32_t q = 0; q < Q; ++q) {
+      (*h_set_off)[q + 1] = (*h_set_off)[q] + totals[q];
+    }
+    MGX_CUDA(cudaMemcpyAsync(d_set_off, h_set_off->data(), (Q + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    b.sets_buf.reserve(std::max<uint64_t>(1, h_set_off->back()));
+    d_sets->borrow(b.sets_buf.p, h_set_off->back());
+  };
+  auto gather_chunk = [&](const Chunk& c) {  // the tile totals are no longer needed: their array takes the ranks
+    const uint64_t tile_base = b.h_q_tile_off[c.q0];
+    const uint64_t n_tiles = b.h_q_tile_off[c.q1] - tile_base;
+    set_tile_ranks_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, tile_base, b.d_tile_count.p,
+                                                      b.d_tile_total.p);
+    MGX_LAUNCH_CHECK();
+    if (n_tiles > 0) {
+      gather_tiles_kernel<<<static_cast<unsigned>(n_tiles), 256, 0, st>>>(make_batch_view(b), tile_base, b.rec_slot,
+                                                                        b.d_tile_count.p, b.d_tile_total.p,
+                                                                        b.d_rec_doc.p, d_set_off, d_sets->p);
+      MGX_LAUNCH_CHECK();
+    }
+  };
   if (chunks.size() == 1) {
     // single chunk: records stay valid between the counting and the gathering pass
     const Chunk& c = chunks[0];
     run_tiles(b, c, sp, 0);
-    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.rec_slot,
-                                             b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p, nullptr, 0, 0, 0, 0, 0,
-                                             d_dummy.p, nullptr,
-                                             d_count.p, d_total.p);
-    MGX_LAUNCH_CHECK();
-    MGX_CUDA(cudaMemcpyAsync(totals.data(), d_total.p, b.n_queries * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    MGX_CUDA(cudaStreamSynchronize(st));
-    h_set_off->assign(b.n_queries + 1, 0);
-    for (uint32_t q = 0; q < b.n_queries; ++q) {
-      (*h_set_off)[q + 1] = (*h_set_off)[q] + totals[q];
-    }
-    DevBuf<uint64_t> d_set_off;
-    d_set_off.alloc(b.n_queries + 1);
-    MGX_CUDA(cudaMemcpyAsync(d_set_off.p, h_set_off->data(), (b.n_queries + 1) * sizeof(uint64_t),
-                             cudaMemcpyHostToDevice, st));
-    d_sets->alloc(std::max<uint64_t>(1, h_set_off->back()));
-    gather_sets_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0],
-                                                    b.rec_slot, b.d_tile_count.p, b.d_rec_doc.p, d_set_off.p,
-                                                    d_sets->p);
-    MGX_LAUNCH_CHECK();
+    count_chunk(c);
+    offsets_from_totals();
+    gather_chunk(c);
     MGX_CUDA(cudaStreamSynchronize(st));
     return;
   }
@@ -4953,30 +5036,13 @@ void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32
   for (const Chunk& c : chunks) {
     MGX_CUDA(cudaStreamSynchronize(st));
     run_tiles(b, c, sp, 0);
-    topk_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0], b.rec_slot,
-                                             b.d_tile_count.p, b.d_tile_total.p, b.d_rec_doc.p, nullptr, 0, 0, 0, 0, 0,
-                                             d_dummy.p, nullptr,
-                                             d_count.p, d_total.p);
-    MGX_LAUNCH_CHECK();
+    count_chunk(c);
   }
-  MGX_CUDA(cudaMemcpyAsync(totals.data(), d_total.p, b.n_queries * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  MGX_CUDA(cudaStreamSynchronize(st));
-  h_set_off->assign(b.n_queries + 1, 0);
-  for (uint32_t q = 0; q < b.n_queries; ++q) {
-    (*h_set_off)[q + 1] = (*h_set_off)[q] + totals[q];
-  }
-  DevBuf<uint64_t> d_set_off;
-  d_set_off.alloc(b.n_queries + 1);
-  MGX_CUDA(cudaMemcpyAsync(d_set_off.p, h_set_off->data(), (b.n_queries + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
-                           st));
-  d_sets->alloc(std::max<uint64_t>(1, h_set_off->back()));
+  offsets_from_totals();
   for (const Chunk& c : chunks) {
     MGX_CUDA(cudaStreamSynchronize(st));
     run_tiles(b, c, sp, 0);
-    gather_sets_kernel<<<c.q1 - c.q0, 256, 0, st>>>(make_batch_view(b), c.q0, b.h_q_tile_off[c.q0],
-                                                    b.rec_slot, b.d_tile_count.p, b.d_rec_doc.p, d_set_off.p,
-                                                    d_sets->p);
-    MGX_LAUNCH_CHECK();
+    gather_chunk(c);
   }
   MGX_CUDA(cudaStreamSynchronize(st));
 }

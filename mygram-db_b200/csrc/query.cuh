@@ -20,7 +20,10 @@ constexpr uint32_t kMaxTopK = 1024;
 // ---- streamed batches (no host read-back between planning and the tile kernels) --------------------------------
 // The planning tail leaves the work sizes in a small device block; persistent kernels pull their work items from the
 // counters next to them. The block follows the accounting counters, so one memset clears both.
-constexpr uint32_t kDfUnit = 256;          // driver entries per df work unit of a streamed batch (kTile in the other form)
+#ifndef MGX_DF_UNIT
+#define MGX_DF_UNIT 256
+#endif
+constexpr uint32_t kDfUnit = MGX_DF_UNIT;          // driver entries per df work unit of a streamed batch (kTile in the other form)
 enum LaunchSlot : int {
   kLaunchDfUnits = 0,    // df work units of the batch
   kLaunchAndTiles = 1,   // intersect tiles of the batch
@@ -285,6 +288,13 @@ struct Batch {
   uint32_t n_stream_slots = 0;          // power of two, 0 = no eligible term
   uint32_t n_stream_terms = 0;
   DevBuf<uint32_t> d_df_mode;           // [2] [0] = 1 when the streaming pass was chosen (device decision)
+  // result sets of the Index::Search* style calls (batch_search_sets / merge_disjoint_runs), grow-only with the object
+  DevArena sets_arena;
+  DevBuf<uint32_t> sets_buf;
+  DevBuf<uint32_t> union_buf;
+  DevBuf<uint64_t> run_off_buf;
+  DevBuf<uint32_t> driver_buf;  // explicit driver ids of SearchNot / FilterByNgrams
+  DevBuf<uint64_t> len_buf;     // lookup_list_lengths
   DevBuf<unsigned long long> d_q_thr;   // [Q + 1] running thresholds of the per-tile top-k pruning, cleared with the counters
   int h_df_mode = 0;                    // host copy, valid after planning
   // Everything above is a view into one of these two grow-only arenas: `in_arena` receives the compiled batch in ONE
@@ -391,7 +401,8 @@ void batch_search(Batch& b, const uint64_t* d_df_global, uint64_t stride, uint32
 // Full ascending result sets of every query: fills h_totals and returns a device buffer of all sets back to back.
 void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32_t>* d_sets);
 // Union of the ascending, pairwise disjoint runs d_in[run_off[r] .. run_off[r+1]) into one ascending array.
-void merge_disjoint_runs(cudaStream_t st, const uint32_t* d_in, const std::vector<uint64_t>& run_off,
+void lookup_list_lengths(Batch& b, const uint64_t* h_keys, uint32_t n, uint32_t* h_lens);
+void merge_disjoint_runs(Batch& b, const uint32_t* d_in, const std::vector<uint64_t>& run_off,
                          DevBuf<uint32_t>* d_out);
 void launch_merge_topk(cudaStream_t stream, const mgx_query_params_t& params, uint32_t n_shards, uint64_t n_queries,
                        uint64_t stride, const uint32_t* d_ids_all, const double* d_scores_all,
