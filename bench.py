@@ -725,10 +725,24 @@ def main():
         fits = [int(fs.f_bavail * fs.f_frsize >= 2 * n_slots * slot_bytes)]
         name = [f"/mgx_share_{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}"]
         dist.broadcast_object_list(name, src=0)
-        dist.broadcast_object_list(fits, src=0)
-        if fits[0]:
-            pipe.open_share(name[0], world, rank, n_slots=n_slots, slot_bytes=slot_bytes)
-        else:
+        # rank 0 creates the ring, the others attach; if ANY rank fails, every rank falls back to compiling itself
+        ok = [fits[0]]
+        if rank == 0 and ok[0]:
+            try:
+                pipe.open_share(name[0], world, rank, n_slots=n_slots, slot_bytes=slot_bytes)
+            except Exception:
+                ok = [0]
+        dist.broadcast_object_list(ok, src=0)
+        mine = ok[0]
+        if ok[0] and rank != 0:
+            try:
+                pipe.open_share(name[0], world, rank, n_slots=n_slots, slot_bytes=slot_bytes)
+            except Exception:
+                mine = 0
+        flag = torch.tensor([mine], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            pipe.close_share()
             args.no_share = True
         barrier()
 

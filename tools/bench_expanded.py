@@ -106,6 +106,7 @@ def main():
         ("fuzzy_d1_verify_all", fuzzy, lambda q: gi.search_fuzzy(q, 1, verify_text=1)),
         ("synonyms_2x2", syn, lambda q: gi.search_synonyms(q)),
         ("synonyms_2x2_verify_all", syn, lambda q: gi.search_synonyms(q, verify_text=1)),
+        ("fuzzy_d1_second_pass", fuzzy, lambda q: gi.search_fuzzy(q, 1)),  # the call's buffers have grown to their size
     ]
     results = {}
     for name, qs, gpu_fn in gpu_classes:

@@ -47,7 +47,8 @@ while time.time() < t_end:
         nots = [[rnd.choice(docs)[:3]] if rnd.random() < 0.2 else [] for _ in qs]
         kw = rnd.choice([dict(score=True, limit=100), dict(score=True, descending=False, limit=7, offset=2),
                          dict(score=False, limit=30, offset=1), dict(score=True, limit=20, verify_text=1),
-                         dict(score=True, limit=20, verify_text=2)])
+                         dict(score=True, limit=20, verify_text=2), dict(score=True, limit=1000, offset=1100),
+                         dict(score=True, descending=False, limit=300, offset=2000)])
         try:
             T.assert_batch_equal(gi.query_batch(qs, not_terms=nots, **kw), oi.query_batch(qs, not_terms=nots, **kw), qs)
         except AssertionError:
@@ -60,6 +61,7 @@ while time.time() < t_end:
             ts = [rnd.choice(grams) for _ in range(rnd.randint(1, 4))]
             thr = rnd.randint(0, len(ts) + 1)
             assert np.array_equal(gi.search_by_threshold(ts, thr), oi.search_by_threshold(ts, thr)), (seed, ts, thr)
+            assert np.array_equal(gi.search_or(ts), oi.search_or(ts)), ("or", seed, ts)
         nt = rnd.randint(1, 3)
         terms = []
         for _t in range(nt):
@@ -81,6 +83,17 @@ while time.time() < t_end:
     meta, mt, mo, mp = mgx.mgix_decode(gi.save_mgix())
     ot, oo, op_ = oi.export()
     assert [bytes(t) for t in ot] == mt and np.array_equal(mo, oo) and np.array_equal(mp, op_), ("mgix", seed, cfg)
+    # ... and loaded into a second device index (Index::LoadFromStream): same CSR, same set answers
+    g2 = mgx.Index(*cfg)
+    g2.load_mgix(gi.save_mgix())
+    lt, lo_, lp = g2.export()
+    assert lt == mt and np.array_equal(lo_, oo) and np.array_equal(lp, op_), ("mgix load", seed, cfg)
+    for _ in range(5):
+        if grams:
+            ts = [rnd.choice(grams) for _ in range(rnd.randint(1, 3))]
+            assert np.array_equal(g2.search_and(ts), oi.search_and(ts)), ("loaded and", seed, ts)
+            assert np.array_equal(g2.search_or(ts), oi.search_or(ts)), ("loaded or", seed, ts)
+    g2.close()
     # mutations: a burst of add / update / remove, then compare postings, stats and a batch
     if n >= 7 and not bad:
         os.environ.pop("MGX_DF_MODE", None)
