@@ -66,8 +66,8 @@ typedef struct mgx_index mgx_index_t;
  * cross_boundary_ngrams, ...) — src/index/index.h:58-60, index.cpp:29-37.
  * kanji_ngram_size <= 0 means "use ngram_size" (index.cpp:32). */
 typedef struct {
-  int32_t ngram_size;            /* 1..3 in this build (reference allows 1..10)            */
-  int32_t kanji_ngram_size;      /* 0..3                                                    */
+  int32_t ngram_size;            /* 1..10 (config-schema.json:279-285); sizes above 3 use wide keys */
+  int32_t kanji_ngram_size;      /* 0..10                                                   */
   int32_t cross_boundary_ngrams; /* config.h:211-213 default true                           */
   int32_t device;                /* CUDA device ordinal                                     */
   double dense_threshold;        /* posting density at which a list ALSO gets a doc bitmap; */
@@ -166,13 +166,26 @@ int mgx_index_get_postings(const mgx_index_t* index, const uint8_t* term, uint64
                            uint64_t cap, uint64_t* out_count);
 /* Whole index as CSR in ascending term (UTF-8 byte) order. keys are packed
  * n-grams (mgx_key_to_utf8 decodes them). Sizes come from mgx_index_get_stats:
- * keys[n_terms], offsets[n_terms+1], postings[n_postings] (global doc ids). */
+ * keys[n_terms], offsets[n_terms+1], postings[n_postings] (global doc ids).
+ * With n-gram sizes 4..10 (key_width > 3) keys[t] is t + 1, the rank of the term: the n-grams themselves come from
+ * mgx_index_export_terms, which works for every width. */
 int mgx_index_export(const mgx_index_t* index, uint64_t* keys, uint64_t* offsets, uint32_t* postings);
+/* The terms of the index (Index::term_postings_ keys, index.h:343-359) as UTF-8 strings in ascending byte order:
+ * term t = term_bytes[term_offsets[t] .. term_offsets[t+1]); term_offsets[n_terms+1]. *out_bytes receives the total
+ * length; term_bytes == NULL only measures. At most 4 * key_width bytes per term. */
+int mgx_index_export_terms(const mgx_index_t* index, uint8_t* term_bytes, uint64_t cap_bytes, uint64_t* term_offsets,
+                           uint64_t* out_bytes);
 /* Per-document code-point lengths (CountCodePoints, string_utils.cpp:655-669). out[n_docs]. */
 int mgx_index_doc_lengths(const mgx_index_t* index, uint32_t* out);
 
-/* Packed key -> UTF-8 n-gram. `out` needs 4*width bytes. Returns the byte length. */
+/* Packed key -> UTF-8 n-gram. `out` needs 4*width bytes. Returns the byte length. width 1..3. */
 int mgx_key_to_utf8(uint64_t key, int32_t width, uint8_t* out);
+/* Words per key for a key width (max of the two n-gram sizes, config-schema.json:279-285 allows 1..10): 1 for
+ * width <= 3, ceil(width / 3) otherwise (21 bits per code point, first code point in the most significant field of
+ * word 0, keys compare word by word). */
+int mgx_key_words(int32_t width);
+/* The same for a key of mgx_key_words(width) words. `out` needs 4*width bytes. */
+int mgx_wide_key_to_utf8(const uint64_t* words, int32_t width, uint8_t* out);
 
 /* --------------------------------------------------------------- tokenizer */
 
@@ -180,7 +193,8 @@ int mgx_key_to_utf8(uint64_t key, int32_t width, uint8_t* out);
  * on the GPU, in generation order (before the per-document sort+unique of
  * index.cpp:88-91). Output: packed key + index of the document in the batch.
  * out_keys/out_doc need room for one entry per code point; *out_count receives
- * the number of n-grams. */
+ * the number of n-grams. n-gram sizes 1..10 (string_utils.cpp:382-423 has no upper bound; the configuration schema
+ * stops at 10): with a key width above 3 every n-gram takes mgx_key_words(width) consecutive words of out_keys. */
 int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, const uint64_t* text_offsets,
                        uint64_t n_docs, uint64_t* out_keys, uint32_t* out_doc, uint64_t cap, uint64_t* out_count);
 

@@ -150,6 +150,9 @@ def lib():
     L.mgx_index_export.argtypes = [C.c_void_p, u64p, u64p, u32p]
     L.mgx_index_doc_lengths.argtypes = [C.c_void_p, u32p]
     L.mgx_key_to_utf8.argtypes = [C.c_uint64, C.c_int32, u8p]
+    L.mgx_key_words.argtypes = [C.c_int32]
+    L.mgx_wide_key_to_utf8.argtypes = [u64p, C.c_int32, u8p]
+    L.mgx_index_export_terms.argtypes = [C.c_void_p, u8p, C.c_uint64, u64p, u64p]
     L.mgx_tokenize_batch.argtypes = [C.POINTER(IndexConfig), u8p, u64p, C.c_uint64, u64p, u32p, C.c_uint64, u64p]
     L.mgx_search_and.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint64, C.c_int32, u32p, C.c_uint64, u64p]
     L.mgx_search_or.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u32p, C.c_uint64, u64p]
@@ -291,8 +294,15 @@ def mgix_decode(data):
 
 
 def key_to_utf8(key, width):
-    out = np.zeros(16, dtype=np.uint8)
-    n = lib().mgx_key_to_utf8(int(key), width, _ptr(out, u8p))
+    """Packed key (width <= 3), or the words of a wide key (array of mgx_key_words(width) uint64), -> n-gram bytes."""
+    out = np.zeros(48, dtype=np.uint8)
+    if width <= 3:
+        n = lib().mgx_key_to_utf8(int(key), width, _ptr(out, u8p))
+    else:
+        words = np.ascontiguousarray(key, dtype=np.uint64)
+        n = lib().mgx_wide_key_to_utf8(_ptr(words, u64p), width, _ptr(out, u8p))
+    if n < 0:
+        raise MgxError(n, lib().mgx_last_error().decode())
     return out[:n].tobytes()
 
 
@@ -302,16 +312,21 @@ def tokenize_batch(texts, ngram_size=2, kanji_ngram_size=0, cross_boundary=True,
     arena, offsets = pack_strings(texts)
     cfg = IndexConfig(ngram_size, kanji_ngram_size, int(cross_boundary), device, 0.0, 0, 0, 0.0)
     cap = max(1, int(offsets[-1]))
-    keys = np.zeros(cap, dtype=np.uint64)
+    eff_kanji = kanji_ngram_size if kanji_ngram_size > 0 else ngram_size
+    width = max(ngram_size, eff_kanji)
+    nw = max(1, lib().mgx_key_words(width))
+    keys = np.zeros(cap * nw, dtype=np.uint64)
     docs = np.zeros(cap, dtype=np.uint32)
     n = C.c_uint64(0)
     _check(lib().mgx_tokenize_batch(C.byref(cfg), _ptr(arena, u8p), _ptr(offsets, u64p), len(texts), _ptr(keys, u64p),
                                     _ptr(docs, u32p), cap, C.byref(n)))
-    eff_kanji = kanji_ngram_size if kanji_ngram_size > 0 else ngram_size
-    width = max(ngram_size, eff_kanji)
     out = [[] for _ in texts]
-    for k, d in zip(keys[:n.value], docs[:n.value]):
-        out[int(d)].append(key_to_utf8(k, width))
+    if width <= 3:
+        for k, d in zip(keys[:n.value], docs[:n.value]):
+            out[int(d)].append(key_to_utf8(k, width))
+    else:
+        for i in range(n.value):
+            out[int(docs[i])].append(key_to_utf8(keys[i * nw:(i + 1) * nw], width))
     return out
 
 
@@ -451,8 +466,21 @@ class Index:
         offs = np.zeros(s.n_terms + 1, dtype=np.uint64)
         posts = np.zeros(max(1, s.n_postings), dtype=np.uint32)
         _check(lib().mgx_index_export(self._h, _ptr(keys, u64p), _ptr(offs, u64p), _ptr(posts, u32p)))
-        terms = [key_to_utf8(k, s.key_width) for k in keys[:s.n_terms]]
+        if s.key_width <= 3:
+            terms = [key_to_utf8(k, s.key_width) for k in keys[:s.n_terms]]
+        else:
+            terms = self.export_terms()
         return terms, offs, posts[:s.n_postings]
+
+    def export_terms(self):
+        """The index's n-grams as byte strings in ascending order (any key width)."""
+        s = self.stats()
+        tb = np.zeros(max(1, s.n_terms * 4 * s.key_width), dtype=np.uint8)
+        toff = np.zeros(s.n_terms + 1, dtype=np.uint64)
+        nb = C.c_uint64(0)
+        _check(lib().mgx_index_export_terms(self._h, _ptr(tb, u8p), len(tb), _ptr(toff, u64p), C.byref(nb)))
+        raw = tb.tobytes()
+        return [raw[int(toff[t]):int(toff[t + 1])] for t in range(s.n_terms)]
 
     def load_mgix(self, stream):
         """Index::LoadFromStream (index_serialization.cpp:279-613): the stream's posting lists replace the index

@@ -82,7 +82,7 @@ void hybrid_keys(const std::vector<uint32_t>& cps, int ascii_n, int kanji_n, boo
         continue;
       }
     }
-    keys->push_back(size <= width ? pack_key(cps.data() + i, size, width) : kInvalidKey);
+    keys->push_back(size <= width ? host_make_key(cps.data() + i, size, width) : kInvalidKey);
     if (starts != nullptr) {
       starts->push_back(static_cast<uint32_t>(i));  // index of the window's first code point
     }
@@ -180,7 +180,7 @@ void fixed_ngram_keys_small(const uint8_t* term, uint64_t len, int ngram_size, i
   uint64_t wkey[kFastTermBytes];
   uint16_t wstart[kFastTermBytes];
   for (uint32_t i = 0; i < n_win; ++i) {  // insertion sort by (key, start): windows arrive in start order
-    const uint64_t k = ngram_size <= key_width ? pack_key(cps + i, ngram_size, key_width) : kInvalidKey;
+    const uint64_t k = ngram_size <= key_width ? host_make_key(cps + i, ngram_size, key_width) : kInvalidKey;
     uint32_t j = i;
     while (j > 0 && wkey[j - 1] > k) {
       wkey[j] = wkey[j - 1];
@@ -252,7 +252,7 @@ bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanj
     const size_t n = static_cast<size_t>(ngram_size);
     if (cps.size() >= n) {
       for (size_t i = 0; i + n <= cps.size(); ++i) {
-        keys->push_back(ngram_size <= key_width ? pack_key(cps.data() + i, ngram_size, key_width) : kInvalidKey);
+        keys->push_back(ngram_size <= key_width ? host_make_key(cps.data() + i, ngram_size, key_width) : kInvalidKey);
         starts.push_back(static_cast<uint32_t>(i));
       }
     }
@@ -289,7 +289,7 @@ bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanj
 bool host_ngram_to_key(const uint8_t* term, uint64_t len, int key_width, uint64_t* key) {
   // a dictionary key is the UTF-8 re-encoding of 1..width decoded code points;
   // a byte string with invalid sequences can therefore never equal one
-  uint32_t cps[kMaxKeyWidth];
+  uint32_t cps[kMaxNgramSize];
   int n = 0;
   uint64_t i = 0;
   while (i < len) {
@@ -306,8 +306,150 @@ bool host_ngram_to_key(const uint8_t* term, uint64_t len, int key_width, uint64_
   if (n == 0) {
     return false;
   }
-  *key = pack_key(cps, n, key_width);
+  *key = host_make_key(cps, n, key_width);
   return true;
+}
+
+// ---------------------------------------------------------------- wide keys on the host
+namespace {
+struct WidePool {
+  std::vector<uint64_t> words;  // kMaxWideWords per key, unused words 0
+  std::vector<uint32_t> table;  // open addressing: handle, 0 = empty
+  int depth = 0;
+  void clear() {
+    words.clear();
+    if (!table.empty()) {
+      std::fill(table.begin(), table.end(), 0u);
+    }
+  }
+  static uint64_t hash(const uint64_t* w) {
+    uint64_t h = 0x9E3779B97F4A7C15ULL;
+    for (int i = 0; i < kMaxWideWords; ++i) {
+      h = (h ^ w[i]) * 0xff51afd7ed558ccdULL;
+      h ^= h >> 32;
+    }
+    return h;
+  }
+  void rehash(size_t cap) {
+    table.assign(cap, 0u);
+    const size_t n = words.size() / kMaxWideWords;
+    for (size_t k = 0; k < n; ++k) {
+      size_t slot = static_cast<size_t>(hash(words.data() + k * kMaxWideWords)) & (cap - 1);
+      while (table[slot] != 0) {
+        slot = (slot + 1) & (cap - 1);
+      }
+      table[slot] = static_cast<uint32_t>(k + 1);
+    }
+  }
+  uint64_t intern(const uint64_t* w) {
+    const size_t n = words.size() / kMaxWideWords;
+    if (table.size() < 2 * (n + 1) + 16) {
+      size_t cap = 64;
+      while (cap < 4 * (n + 1) + 16) {
+        cap <<= 1;
+      }
+      rehash(cap);
+    }
+    const size_t cap = table.size();
+    size_t slot = static_cast<size_t>(hash(w)) & (cap - 1);
+    while (table[slot] != 0) {
+      if (std::memcmp(words.data() + static_cast<size_t>(table[slot] - 1) * kMaxWideWords, w,
+                      kMaxWideWords * sizeof(uint64_t)) == 0) {
+        return table[slot];
+      }
+      slot = (slot + 1) & (cap - 1);
+    }
+    words.insert(words.end(), w, w + kMaxWideWords);
+    table[slot] = static_cast<uint32_t>(n + 1);
+    return n + 1;
+  }
+};
+thread_local WidePool tl_wide_pool;
+}  // namespace
+
+// The pool is emptied when the OUTERMOST scope ends: handles made before the call entered its guarded section (argument
+// checks that tokenize) are still good inside it.
+WideScope::WideScope() { ++tl_wide_pool.depth; }
+WideScope::~WideScope() {
+  if (--tl_wide_pool.depth == 0 && !tl_wide_pool.words.empty()) {
+    tl_wide_pool.clear();
+  }
+}
+
+uint64_t host_make_key(const uint32_t* cps, int n, int width) {
+  if (width <= kMaxKeyWidth) {
+    return pack_key(cps, n, width);
+  }
+  uint64_t w[kMaxWideWords];
+  pack_wide(cps, n, kMaxWideWords, w);
+  return tl_wide_pool.intern(w);
+}
+
+const uint64_t* host_wide_words(uint64_t handle, int n_words) {
+  (void)n_words;
+  static const uint64_t kNone[kMaxWideWords] = {0, 0, 0, 0};
+  if (handle == 0 || handle > tl_wide_pool.words.size() / kMaxWideWords) {
+    return kNone;  // a handle of another call: matches nothing (no n-gram has word 0 == 0)
+  }
+  return tl_wide_pool.words.data() + static_cast<size_t>(handle - 1) * kMaxWideWords;
+}
+
+WidePoolSnapshot wide_pool_snapshot() {
+  WidePoolSnapshot snap;
+  snap.words = tl_wide_pool.words;
+  return snap;
+}
+
+uint64_t wide_pool_adopt(const WidePoolSnapshot& other) {
+  WidePool& pool = tl_wide_pool;
+  const uint64_t base = pool.words.size() / kMaxWideWords;
+  pool.words.insert(pool.words.end(), other.words.begin(), other.words.end());
+  if (!other.words.empty()) {
+    pool.table.clear();  // rebuilt by the next intern
+  }
+  return base;
+}
+
+namespace {
+int encode_utf8(uint32_t cp, uint8_t* out) {
+  int n = 0;
+  if (cp <= 0x7F) {
+    out[n++] = static_cast<uint8_t>(cp);
+  } else if (cp <= 0x7FF) {
+    out[n++] = static_cast<uint8_t>(0xC0 | (cp >> 6));
+    out[n++] = static_cast<uint8_t>(0x80 | (cp & 0x3F));
+  } else if (cp <= 0xFFFF) {
+    out[n++] = static_cast<uint8_t>(0xE0 | (cp >> 12));
+    out[n++] = static_cast<uint8_t>(0x80 | ((cp >> 6) & 0x3F));
+    out[n++] = static_cast<uint8_t>(0x80 | (cp & 0x3F));
+  } else {
+    out[n++] = static_cast<uint8_t>(0xF0 | (cp >> 18));
+    out[n++] = static_cast<uint8_t>(0x80 | ((cp >> 12) & 0x3F));
+    out[n++] = static_cast<uint8_t>(0x80 | ((cp >> 6) & 0x3F));
+    out[n++] = static_cast<uint8_t>(0x80 | (cp & 0x3F));
+  }
+  return n;
+}
+}  // namespace
+
+int wide_words_to_utf8(const uint64_t* words, int n_words, uint8_t* out) {
+  int n = 0;
+  for (int w = 0; w < n_words; ++w) {
+    for (int f = 2; f >= 0; --f) {
+      const uint64_t field = (words[w] >> (21 * f)) & 0x1FFFFFULL;
+      if (field != 0) {
+        n += encode_utf8(static_cast<uint32_t>(field - 1), out + n);
+      }
+    }
+  }
+  return n;
+}
+
+int host_key_to_utf8(uint64_t key, int width, uint8_t* out) {
+  if (width <= kMaxKeyWidth) {
+    return mgx_key_to_utf8(key, width, out);
+  }
+  return wide_words_to_utf8(host_wide_words(key, kMaxWideWords), kMaxWideWords, out);
 }
 
 namespace {
@@ -325,6 +467,7 @@ int require_device() {
 
 template <typename F>
 int guarded(F&& fn) {
+  WideScope wide_scope;  // wide-key handles made by this call live until the next one starts
   try {
     return fn();
   } catch (const CudaFailure& f) {
@@ -475,8 +618,8 @@ int compile_range(const Index& ix, const mgx_query_params_t& p, uint64_t q_first
     host_query_keys(bytes + b, e - b, p.ngram_size, p.kanji_ngram_size, p.cross_boundary != 0, ix.width, &t.keys,
                     tok_agree ? &t.key_toff : nullptr, &valid_utf8);
     if (t.keys.size() == 1 && t.keys[0] != kInvalidKey) {
-      uint8_t enc[4 * kMaxKeyWidth];
-      const int n = mgx_key_to_utf8(t.keys[0], ix.width, enc);
+      uint8_t enc[4 * kMaxNgramSize];
+      const int n = host_key_to_utf8(t.keys[0], ix.width, enc);
       t.exact_single = static_cast<uint64_t>(n) == e - b && std::memcmp(enc, bytes + b, e - b) == 0;
     }
     t.payload_tf = t.exact_single && valid_utf8 && tok_agree;
@@ -601,6 +744,7 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
                          q_not_begin, ext, terms, queries, slot_tid);
   }
   std::vector<std::vector<HostTerm>> part_terms(T);
+  std::vector<WidePoolSnapshot> part_wide(T);  // wide keys: every worker interns into its own thread's pool
   std::vector<int> rcs(T, MGX_OK);
   std::vector<std::string> errs(T);
   std::vector<std::thread> workers;
@@ -612,6 +756,9 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
                              ext, &part_terms[t], queries, slot_tid);
       if (rcs[t] != MGX_OK) {
         errs[t] = mgx_last_error();  // thread-local in the worker
+      }
+      if (ix.wide_words > 0) {
+        part_wide[t] = wide_pool_snapshot();
       }
     });
   }
@@ -640,8 +787,14 @@ int compile_batch(const Index& ix, const mgx_query_params_t& p, uint64_t n_queri
   std::vector<uint32_t> remap;
   for (unsigned t = 0; t < T; ++t) {
     remap.assign(part_terms[t].size(), 0);
+    const uint64_t wide_base = ix.wide_words > 0 ? wide_pool_adopt(part_wide[t]) : 0;
     for (size_t i = 0; i < part_terms[t].size(); ++i) {
       HostTerm& ht = part_terms[t][i];
+      if (wide_base != 0) {  // handles of the worker's pool -> handles of this thread's pool
+        for (uint64_t& k : ht.keys) {
+          k = k == kInvalidKey ? k : k + wide_base;
+        }
+      }
       size_t slot = static_cast<size_t>(ht.hash) & (cap - 1);
       uint32_t id = 0;
       for (;;) {
@@ -1074,9 +1227,9 @@ int mgx_index_create(const mgx_index_config_t* config, mgx_index_t** out) {
     return rc;
   }
   const int kanji = config->kanji_ngram_size > 0 ? config->kanji_ngram_size : config->ngram_size;  // index.cpp:32
-  if (config->ngram_size < 1 || config->ngram_size > kMaxKeyWidth || kanji < 1 || kanji > kMaxKeyWidth) {
-    set_last_error("n-gram sizes must be 1..3 in this build (packed 64-bit keys)");
-    return MGX_ERR_UNSUPPORTED;
+  if (config->ngram_size < 1 || config->ngram_size > kMaxNgramSize || kanji < 1 || kanji > kMaxNgramSize) {
+    set_last_error("n-gram sizes must be 1..10 (config-schema.json:279-285)");
+    return MGX_ERR_INVALID_ARGUMENT;
   }
   return guarded([&]() {
     int count = 0;
@@ -1090,6 +1243,7 @@ int mgx_index_create(const mgx_index_config_t* config, mgx_index_t** out) {
     h->ix.kanji = kanji;
     h->ix.cross = config->cross_boundary_ngrams != 0;
     h->ix.width = std::max(h->ix.ngram, h->ix.kanji);
+    h->ix.wide_words = wide_words_for(h->ix.width);
     h->ix.device = config->device;
     DeviceGuard guard(config->device);
     MGX_CUDA(cudaStreamCreateWithFlags(&h->ix.stream, cudaStreamNonBlocking));
@@ -1450,6 +1604,21 @@ int mgx_key_to_utf8(uint64_t key, int32_t width, uint8_t* out) {
   return n;
 }
 
+int mgx_key_words(int32_t width) {
+  if (width < 1 || width > kMaxNgramSize) {
+    return invalid("key width must be 1..10");
+  }
+  return std::max(wide_words_for(width), 1);
+}
+
+int mgx_wide_key_to_utf8(const uint64_t* words, int32_t width, uint8_t* out) {
+  if (words == nullptr || out == nullptr || width < 1 || width > kMaxNgramSize) {
+    return invalid("bad width/words/out");
+  }
+  const int W = wide_words_for(width);
+  return W > 0 ? wide_words_to_utf8(words, W, out) : mgx_key_to_utf8(words[0], width, out);
+}
+
 int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, const uint64_t* text_offsets,
                        uint64_t n_docs, uint64_t* out_keys, uint32_t* out_doc, uint64_t cap, uint64_t* out_count) {
   if (config == nullptr || out_count == nullptr || (n_docs > 0 && text_offsets == nullptr)) {
@@ -1459,9 +1628,9 @@ int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, co
     return rc;
   }
   const int kanji = config->kanji_ngram_size > 0 ? config->kanji_ngram_size : config->ngram_size;
-  if (config->ngram_size < 1 || config->ngram_size > kMaxKeyWidth || kanji < 1 || kanji > kMaxKeyWidth) {
-    set_last_error("n-gram sizes must be 1..3 in this build");
-    return MGX_ERR_UNSUPPORTED;
+  if (config->ngram_size < 1 || config->ngram_size > kMaxNgramSize || kanji < 1 || kanji > kMaxNgramSize) {
+    set_last_error("n-gram sizes must be 1..10 (config-schema.json:279-285)");
+    return MGX_ERR_INVALID_ARGUMENT;
   }
   return guarded([&]() {
     DeviceGuard guard(config->device);
@@ -1482,6 +1651,8 @@ int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, co
     }
     MGX_CUDA(cudaMemcpyAsync(d_off.p, text_offsets, (n_docs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     const int width = std::max(config->ngram_size, kanji);
+    const int W = wide_words_for(width);
+    const uint64_t nw = static_cast<uint64_t>(std::max(W, 1));
     DevBuf<uint32_t> d_len;
     DevBuf<uint64_t> d_tile_off;
     DevBuf<uint64_t> d_scratch;
@@ -1494,16 +1665,16 @@ int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, co
     uint64_t counters[3];
     tokenize_count(config->ngram_size, kanji, config->cross_boundary_ngrams != 0, width, d_text.p, d_off.p, n_docs,
                    bytes, d_len.p, d_tile_off.p, d_scratch.p, &n_slots, counters, st);
-    d_keys.alloc(n_slots);
+    d_keys.alloc(n_slots * nw);
     d_docs.alloc(n_slots);
     if (n_slots > 0) {
       tokenize_emit(config->ngram_size, kanji, config->cross_boundary_ngrams != 0, width, d_text.p, d_off.p, n_docs,
-                    bytes, d_tile_off.p, d_scratch.p, d_keys.p, d_docs.p, 0, st);
+                    bytes, d_tile_off.p, d_scratch.p, d_keys.p, d_docs.p, 0, st, n_slots);
     }
-    std::vector<uint64_t> keys(n_slots);
+    std::vector<uint64_t> keys(n_slots * nw);  // wide keys: word w of slot s at keys[w * n_slots + s]
     std::vector<uint32_t> docs(n_slots);
     if (n_slots > 0) {
-      MGX_CUDA(cudaMemcpyAsync(keys.data(), d_keys.p, n_slots * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      MGX_CUDA(cudaMemcpyAsync(keys.data(), d_keys.p, n_slots * nw * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
       MGX_CUDA(cudaMemcpyAsync(docs.data(), d_docs.p, n_slots * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
     MGX_CUDA(cudaStreamSynchronize(st));
@@ -1512,7 +1683,9 @@ int mgx_tokenize_batch(const mgx_index_config_t* config, const uint8_t* text, co
     for (uint64_t i = 0; i < n_slots; ++i) {
       if (keys[i] != kInvalidKey) {
         if (n < cap && out_keys != nullptr && out_doc != nullptr) {
-          out_keys[n] = keys[i];
+          for (uint64_t w = 0; w < nw; ++w) {
+            out_keys[n * nw + w] = keys[w * n_slots + i];
+          }
           out_doc[n] = docs[i];
         }
         ++n;
@@ -2114,12 +2287,12 @@ int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq,
       if (eq->kanji_ngram_size > 0) {
         size_t short_count = 0;
         for (uint64_t key : whole.keys) {
-          uint8_t enc[4 * kMaxKeyWidth];
+          uint8_t enc[4 * kMaxNgramSize];
           if (key == kInvalidKey) {
             set_last_error("fuzzy term with n-grams wider than the index key");
             return MGX_ERR_UNSUPPORTED;
           }
-          short_count += mgx_key_to_utf8(key, ix.width, enc) <= 3 ? 1 : 0;
+          short_count += host_key_to_utf8(key, ix.width, enc) <= 3 ? 1 : 0;
         }
         if (short_count > n / 2) {
           eff = eq->kanji_ngram_size;
@@ -2308,27 +2481,38 @@ int mgx_index_posting_size(const mgx_index_t* index, const uint8_t* term, uint64
     if (term == nullptr || !host_ngram_to_key(term, term_len, ix.width, &key) || ix.n_terms == 0) {
       return MGX_OK;
     }
-    // binary search over the device dictionary, 8 bytes per probe
+    // binary search over the device dictionary, one key per probe
+    const int W = ix.wide_words;
+    uint64_t want[kMaxWideWords] = {key, 0, 0, 0};
+    if (W > 0) {
+      std::memcpy(want, host_wide_words(key, W), static_cast<size_t>(W) * sizeof(uint64_t));
+    }
+    const int nw = W > 0 ? W : 1;
+    const uint64_t* dict = W > 0 ? ix.d_wide_keys.p : ix.d_term_keys.p;
+    auto probe = [&](uint64_t at) {  // <0: dict[at] < want
+      uint64_t v[kMaxWideWords] = {0, 0, 0, 0};
+      MGX_CUDA(cudaMemcpy(v, dict + at * nw, static_cast<size_t>(nw) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+      for (int w = 0; w < nw; ++w) {
+        if (v[w] != want[w]) {
+          return v[w] < want[w] ? -1 : 1;
+        }
+      }
+      return 0;
+    };
     uint64_t lo = 0;
     uint64_t hi = ix.n_terms;
     while (lo < hi) {
       const uint64_t mid = (lo + hi) / 2;
-      uint64_t v = 0;
-      MGX_CUDA(cudaMemcpy(&v, ix.d_term_keys.p + mid, sizeof(uint64_t), cudaMemcpyDeviceToHost));
-      if (v < key) {
+      if (probe(mid) < 0) {
         lo = mid + 1;
       } else {
         hi = mid;
       }
     }
-    if (lo < ix.n_terms) {
-      uint64_t v = 0;
-      MGX_CUDA(cudaMemcpy(&v, ix.d_term_keys.p + lo, sizeof(uint64_t), cudaMemcpyDeviceToHost));
-      if (v == key) {
-        uint64_t off[2];
-        MGX_CUDA(cudaMemcpy(off, ix.d_term_off.p + lo, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        *out = off[1] - off[0];
-      }
+    if (lo < ix.n_terms && probe(lo) == 0) {
+      uint64_t off[2];
+      MGX_CUDA(cudaMemcpy(off, ix.d_term_off.p + lo, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+      *out = off[1] - off[0];
     }
     return MGX_OK;
   });
@@ -2336,9 +2520,12 @@ int mgx_index_posting_size(const mgx_index_t* index, const uint8_t* term, uint64
 
 namespace {
 // CSR of the index with global doc ids; the caller holds shared access.
-int export_unlocked(const Index& ix, uint64_t* keys, uint64_t* offsets, uint32_t* postings) {
+// keys: n_terms packed keys, or (wide keys) n_terms * wide_words words
+int export_unlocked(const Index& ix, uint64_t* keys, uint64_t* offsets, uint32_t* postings, bool wide = false) {
   DeviceGuard guard(ix.device);
-  if (ix.n_terms > 0) {
+  if (ix.n_terms > 0 && wide && ix.wide_words > 0) {
+    MGX_CUDA(cudaMemcpy(keys, ix.d_wide_keys.p, ix.n_terms * ix.wide_words * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  } else if (ix.n_terms > 0) {
     MGX_CUDA(cudaMemcpy(keys, ix.d_term_keys.p, ix.n_terms * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   }
   if (ix.d_term_off.p != nullptr && ix.d_term_off.n >= ix.n_terms + 1) {
@@ -2373,6 +2560,47 @@ int mgx_index_export(const mgx_index_t* index, uint64_t* keys, uint64_t* offsets
   });
 }
 
+int mgx_index_export_terms(const mgx_index_t* index, uint8_t* term_bytes, uint64_t cap_bytes, uint64_t* term_offsets,
+                           uint64_t* out_bytes) {
+  if (index == nullptr || term_offsets == nullptr || out_bytes == nullptr) {
+    return invalid("null argument");
+  }
+  *out_bytes = 0;
+  mgx_index_t* h = const_cast<mgx_index_t*>(index);
+  if (int rc = commit_pending(h); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    Reader rd(h);
+    const Index& ix = h->ix;
+    DeviceGuard guard(ix.device);
+    const int W = ix.wide_words;
+    const int nw = std::max(W, 1);
+    std::vector<uint64_t> keys(ix.n_terms * nw + 1);
+    if (ix.n_terms > 0) {
+      MGX_CUDA(cudaMemcpy(keys.data(), W > 0 ? ix.d_wide_keys.p : ix.d_term_keys.p, ix.n_terms * nw * sizeof(uint64_t),
+                          cudaMemcpyDeviceToHost));
+    }
+    uint64_t tb = 0;
+    uint8_t enc[4 * kMaxNgramSize];
+    for (uint64_t t = 0; t < ix.n_terms; ++t) {
+      term_offsets[t] = tb;
+      const int n = W > 0 ? wide_words_to_utf8(keys.data() + t * W, W, enc) : mgx_key_to_utf8(keys[t], ix.width, enc);
+      if (term_bytes != nullptr && tb + static_cast<uint64_t>(n) <= cap_bytes) {
+        std::memcpy(term_bytes + tb, enc, static_cast<size_t>(n));
+      }
+      tb += static_cast<uint64_t>(n);
+    }
+    term_offsets[ix.n_terms] = tb;
+    *out_bytes = tb;
+    if (term_bytes != nullptr && tb > cap_bytes) {
+      set_last_error("mgx_index_export_terms: output capacity too small");
+      return MGX_ERR_CAPACITY;
+    }
+    return MGX_OK;
+  });
+}
+
 int mgx_index_save_mgix(const mgx_index_t* index, int32_t normalize_nfkc, const char* normalize_width,
                         int32_t normalize_lower, uint8_t* out, uint64_t cap, uint64_t* out_len) {
   if (index == nullptr || out_len == nullptr) {
@@ -2402,10 +2630,10 @@ int mgx_index_save_mgix(const mgx_index_t* index, int32_t normalize_nfkc, const 
       Reader rd(h);
       const Index& ix = h->ix;
       n_terms = ix.n_terms;
-      keys.resize(ix.n_terms + 1);
+      keys.resize(ix.n_terms * std::max(ix.wide_words, 1) + 1);
       offsets.resize(ix.n_terms + 1);
       postings.resize(ix.n_postings + 1);
-      if (int rc = export_unlocked(ix, keys.data(), offsets.data(), postings.data()); rc != MGX_OK) {
+      if (int rc = export_unlocked(ix, keys.data(), offsets.data(), postings.data(), true); rc != MGX_OK) {
         return rc;
       }
       width_cp = ix.width;
@@ -2419,12 +2647,14 @@ int mgx_index_save_mgix(const mgx_index_t* index, int32_t normalize_nfkc, const 
     info.normalize_lower = normalize_lower;
     std::strcpy(info.normalize_width, width);
     info.n_terms = n_terms;
-    std::vector<uint8_t> term_bytes(n_terms * 4 * kMaxKeyWidth + 1);
+    std::vector<uint8_t> term_bytes(n_terms * 4 * static_cast<size_t>(width_cp) + 1);
     std::vector<uint64_t> term_offsets(n_terms + 1, 0);
     uint64_t tb = 0;
+    const int W = wide_words_for(width_cp);
     for (uint64_t t = 0; t < n_terms; ++t) {
       term_offsets[t] = tb;
-      tb += static_cast<uint64_t>(mgx_key_to_utf8(keys[t], width_cp, term_bytes.data() + tb));
+      tb += static_cast<uint64_t>(W > 0 ? wide_words_to_utf8(keys.data() + t * W, W, term_bytes.data() + tb)
+                                        : mgx_key_to_utf8(keys[t], width_cp, term_bytes.data() + tb));
     }
     term_offsets[n_terms] = tb;
     return mgx_mgix_encode(&info, term_bytes.data(), term_offsets.data(), offsets.data(), postings.data(),
@@ -2459,11 +2689,40 @@ int mgx_index_load_mgix(mgx_index_t* index, const uint8_t* data, uint64_t len) {
       rc != MGX_OK) {
     return rc;
   }
-  std::vector<uint64_t> keys(info.n_terms + 1);
+  const int W = wide_words_for(cfg.width);
+  std::vector<uint64_t> keys(info.n_terms * std::max(W, 1) + 1);
   for (uint64_t t = 0; t < info.n_terms; ++t) {
-    if (!host_ngram_to_key(term_bytes.data() + term_offsets[t], term_offsets[t + 1] - term_offsets[t], cfg.width,
-                           &keys[t]) ||
-        (t > 0 && keys[t] <= keys[t - 1])) {
+    bool ok = true;
+    if (W == 0) {
+      ok = host_ngram_to_key(term_bytes.data() + term_offsets[t], term_offsets[t + 1] - term_offsets[t], cfg.width,
+                             &keys[t]) &&
+           (t == 0 || keys[t] > keys[t - 1]);
+    } else {
+      // strict UTF-8 of 1..width code points -> the words of the wide key, ascending word by word
+      uint32_t cps[kMaxNgramSize];
+      int n = 0;
+      const uint8_t* tp = term_bytes.data() + term_offsets[t];
+      const uint64_t tl = term_offsets[t + 1] - term_offsets[t];
+      for (uint64_t i = 0; i < tl && ok;) {
+        uint32_t cp = 0;
+        const uint64_t avail = tl - i;
+        const int l = parse_utf8(tp[i], avail > 1 ? tp[i + 1] : 0, avail > 2 ? tp[i + 2] : 0, avail > 3 ? tp[i + 3] : 0,
+                                 avail, &cp);
+        if (l <= 0 || n >= cfg.width) {
+          ok = false;
+        } else {
+          cps[n++] = cp;
+          i += static_cast<uint64_t>(l);
+        }
+      }
+      ok = ok && n > 0;
+      if (ok) {
+        pack_wide(cps, n, W, keys.data() + t * W);
+        ok = t == 0 || std::lexicographical_compare(keys.data() + (t - 1) * W, keys.data() + t * W, keys.data() + t * W,
+                                                    keys.data() + (t + 1) * W);
+      }
+    }
+    if (!ok) {
       set_last_error("MGIX stream holds a term that is not an n-gram of this configuration (or terms out of order)");
       return MGX_ERR_FORMAT;
     }
@@ -2533,6 +2792,7 @@ int prepare_unlocked(mgx_index_t* index, const mgx_query_params_t* params, uint6
                      const mgx_query_ext_t* ext, cudaStream_t stream, mgx_batch_t** out) {
   Index& ix = index->ix;
   DeviceGuard guard(ix.device);
+  WideScope wide_scope;
   std::unique_ptr<mgx_batch> h = take_pooled_batch(ix);
   Batch& b = h->b;
   b.ix = &ix;

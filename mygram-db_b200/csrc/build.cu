@@ -58,7 +58,7 @@ __device__ __forceinline__ uint4 ld_stream_16(const uint8_t* p) {
 constexpr int kFlatThreads = 256;
 constexpr uint32_t kFlatTile = kFlatThreads * 16;   // 4096 bytes
 constexpr uint32_t kFlatDocCap = 1024;
-constexpr uint32_t kFlatHalo = kMaxKeyWidth - 1;    // characters after the tile a window can reach
+constexpr uint32_t kFlatHalo = kMaxNgramSize - 1;   // characters after the tile a window can reach
 
 struct FlatSmem {
   uint32_t cp[kFlatTile + kFlatHalo + 1];
@@ -135,7 +135,8 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
                      int kanji, int cross, int width, int pos_bits, uint32_t* __restrict__ doc_len,
                      uint32_t* __restrict__ doc_valid_bytes, uint32_t* __restrict__ tile_cnt,
                      const uint64_t* __restrict__ tile_off, uint64_t* __restrict__ keys_out,
-                     uint32_t* __restrict__ docs_out) {
+                     uint32_t* __restrict__ docs_out, int wide_words, uint64_t wide_stride) {
+  // wide_words > 0 (width > 3): word w of the n-gram in slot s goes to keys_out[w * wide_stride + s]
   constexpr bool EMIT = MODE != kTokCount;    // writes n-grams
   constexpr bool STATS = MODE != kTokEmit;    // gathers the per-document totals
   __shared__ FlatSmem sm;
@@ -272,7 +273,14 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
           if (k + static_cast<uint32_t>(size) <= n_all && sm.doc[k + size - 1] == dk) {
             ok = true;
             key = static_cast<uint64_t>(c) + 1;
-            for (int j = 1; j < width; ++j) {
+            if (wide_words > 0) {
+              for (int j = 1; j < size; ++j) {
+                if (!cross && is_cjk_ideograph(sm.cp[k + j]) != cjk) {  // :491-503
+                  ok = false;
+                }
+              }
+            }
+            for (int j = 1; j < width && wide_words == 0; ++j) {
               uint64_t field = 0;
               if (j < size) {
                 const uint32_t cj = sm.cp[k + j];
@@ -287,7 +295,19 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
         }
         uint32_t n_emit = 0;
         const uint32_t rank = flat_block_scan(ok ? 1u : 0u, sm.warp_cnt, &n_emit);
-        if (EMIT && ok) {
+        if (EMIT && ok && wide_words > 0) {
+          const uint64_t slot = strip_base + rank;
+          const int size = is_cjk_ideograph(sm.cp[k]) ? kanji : ngram;
+          for (int w = 0; w < wide_words; ++w) {
+            uint64_t word = 0;
+            for (int f = 0; f < 3; ++f) {
+              const int j = 3 * w + f;
+              word = (word << 21) | (j < size ? static_cast<uint64_t>(sm.cp[k + j]) + 1 : 0ULL);
+            }
+            keys_out[static_cast<uint64_t>(w) * wide_stride + slot] = word;
+          }
+          docs_out[slot] = r_first + dk;
+        } else if (EMIT && ok) {
           const uint64_t slot = strip_base + rank;
           const uint64_t in_doc = static_cast<uint64_t>(static_cast<int64_t>(sm.pos[k]) - sm.docrel[dk]);
           keys_out[slot] = pos_bits > 0 ? ((key << pos_bits) | umin_u64(in_doc, pos_max)) : key;
@@ -318,6 +338,9 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
       // placeholders for the slots of the tile's upper bound that no n-gram took
       for (uint64_t i = tile_off[tile] + emitted_tile + threadIdx.x; i < tile_off[tile + 1]; i += kFlatThreads) {
         keys_out[i] = 0;
+        for (int w = 1; w < wide_words; ++w) {
+          keys_out[static_cast<uint64_t>(w) * wide_stride + i] = 0;
+        }
         docs_out[i] = 0;
       }
     }
@@ -602,6 +625,85 @@ __global__ void __launch_bounds__(kCsrThreads) csr_write_kernel(const uint64_t* 
   }
 }
 
+// ------------------------------------------------------------------ wide keys (n-gram sizes 4..10)
+__global__ void iota_u32_kernel(uint32_t* __restrict__ out, uint64_t n) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    out[i] = static_cast<uint32_t>(i);
+  }
+}
+
+__global__ void gather_u64_kernel(const uint64_t* __restrict__ src, const uint32_t* __restrict__ perm,
+                                  uint64_t* __restrict__ dst, uint64_t n) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    dst[i] = src[perm[i]];
+  }
+}
+
+// word0[i] / perm[i]: the slots in wide-key order (stable); words: the tokenizer's arrays (word w of slot s at
+// words[w * stride + s]). flags[i] = 1 where a new n-gram starts (placeholder slots, word 0 == 0, never do).
+__global__ void wide_heads_kernel(const uint64_t* __restrict__ word0, const uint32_t* __restrict__ perm,
+                                  const uint64_t* __restrict__ words, uint64_t stride, int n_words, uint64_t n,
+                                  uint32_t* __restrict__ flags) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t k = word0[i];
+    uint32_t head = 0;
+    if (k != 0) {
+      head = (i == 0 || word0[i - 1] != k) ? 1u : 0u;
+      if (head == 0) {
+        const uint32_t a = perm[i - 1];
+        const uint32_t b = perm[i];
+        for (int w = 1; w < n_words; ++w) {
+          if (words[static_cast<uint64_t>(w) * stride + a] != words[static_cast<uint64_t>(w) * stride + b]) {
+            head = 1;
+          }
+        }
+      }
+    }
+    flags[i] = head;
+  }
+}
+
+// rank[i] = heads before i. The n-gram of slot i gets the key rank + 1 (its rank among the distinct n-grams, from 1),
+// placeholders keep 0; docs follow the permutation.
+__global__ void wide_assign_kernel(const uint64_t* __restrict__ word0, const uint32_t* __restrict__ perm,
+                                   const uint32_t* __restrict__ flags, const uint64_t* __restrict__ rank,
+                                   const uint32_t* __restrict__ docs_in, uint64_t n, uint64_t* __restrict__ keys_out,
+                                   uint32_t* __restrict__ docs_out) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    keys_out[i] = word0[i] == 0 ? 0 : rank[i] + flags[i];
+    docs_out[i] = docs_in[perm[i]];
+  }
+}
+
+// the dictionary of wide keys: row (rank of the n-gram) = its words
+__global__ void wide_table_kernel(const uint64_t* __restrict__ word0, const uint32_t* __restrict__ perm,
+                                  const uint32_t* __restrict__ flags, const uint64_t* __restrict__ rank,
+                                  const uint64_t* __restrict__ words, uint64_t stride, int n_words, uint64_t n,
+                                  uint64_t* __restrict__ table) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    if (flags[i] != 0) {
+      uint64_t* row = table + rank[i] * static_cast<uint64_t>(n_words);
+      row[0] = word0[i];
+      const uint32_t s = perm[i];
+      for (int w = 1; w < n_words; ++w) {
+        row[w] = words[static_cast<uint64_t>(w) * stride + s];
+      }
+    }
+  }
+}
+
+__global__ void iota_keys_kernel(uint64_t* __restrict__ out, uint64_t n) {
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    out[i] = i + 1;
+  }
+}
+
 __global__ void set_u64_kernel(uint64_t* p, uint64_t v) { *p = v; }
 
 // ------------------------------------------------------------------ dense bitmaps
@@ -734,7 +836,7 @@ void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* 
     MGX_LAUNCH_CHECK();
     tokenize_flat_kernel<kTokCount><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
         d_text, d_text_off, n_docs, text_bytes, ts.n_tiles, ts.tile_first_doc, ngram, kanji, cross ? 1 : 0, width, 0,
-        d_doc_len, ts.valid_bytes, ts.tile_cnt, nullptr, nullptr, nullptr);
+        d_doc_len, ts.valid_bytes, ts.tile_cnt, nullptr, nullptr, nullptr, wide_words_for(width), 0);
     MGX_LAUNCH_CHECK();
   }
   if (n_docs > 0) {
@@ -756,14 +858,14 @@ void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* 
 
 void tokenize_emit(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
                    uint64_t n_docs, uint64_t text_bytes, const uint64_t* d_tile_off, uint64_t* d_scratch,
-                   uint64_t* d_keys, uint32_t* d_docs, int pos_bits, cudaStream_t stream) {
+                   uint64_t* d_keys, uint32_t* d_docs, int pos_bits, cudaStream_t stream, uint64_t wide_stride) {
   const TokScratch ts = tok_scratch(d_scratch, n_docs, text_bytes);  // tile_first_doc was filled by tokenize_count
   if (ts.n_tiles == 0) {
     return;
   }
   tokenize_flat_kernel<kTokEmit><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
       d_text, d_text_off, n_docs, text_bytes, ts.n_tiles, ts.tile_first_doc, ngram, kanji, cross ? 1 : 0, width, pos_bits,
-      nullptr, nullptr, nullptr, d_tile_off, d_keys, d_docs);
+      nullptr, nullptr, nullptr, d_tile_off, d_keys, d_docs, wide_words_for(width), wide_stride);
   MGX_LAUNCH_CHECK();
 }
 
@@ -789,7 +891,7 @@ void tokenize_bound(const uint8_t* d_text, const uint64_t* d_text_off, uint64_t 
 void tokenize_fused(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
                     uint64_t n_docs, uint64_t text_bytes, uint32_t* d_doc_len, const uint64_t* d_tile_off,
                     uint64_t* d_scratch, uint64_t* d_keys, uint32_t* d_docs, int pos_bits, uint64_t* counters_out,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, uint64_t wide_stride = 0) {
   const TokScratch ts = tok_scratch(d_scratch, n_docs, text_bytes);
   MGX_CUDA(cudaMemsetAsync(ts.counters, 0, 8 * sizeof(unsigned long long), stream));
   if (n_docs > 0) {
@@ -799,7 +901,7 @@ void tokenize_fused(int ngram, int kanji, bool cross, int width, const uint8_t* 
   if (ts.n_tiles > 0) {
     tokenize_flat_kernel<kTokFused><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
         d_text, d_text_off, n_docs, text_bytes, ts.n_tiles, ts.tile_first_doc, ngram, kanji, cross ? 1 : 0, width, pos_bits,
-        d_doc_len, ts.valid_bytes, nullptr, d_tile_off, d_keys, d_docs);
+        d_doc_len, ts.valid_bytes, nullptr, d_tile_off, d_keys, d_docs, wide_words_for(width), wide_stride);
     MGX_LAUNCH_CHECK();
   }
   if (n_docs > 0) {
@@ -881,6 +983,7 @@ struct ResetOnFailure {
     ix.d_doc_len.release();
     ix.d_tile_first_doc.release();
     ix.d_term_keys.release();
+    ix.d_wide_keys.release();
     ix.d_term_off.release();
     ix.d_postings.release();
     ix.d_post_pos.release();
@@ -974,6 +1077,7 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   ix.d_doc_len.release();
   ix.d_tile_first_doc.release();
   ix.d_term_keys.release();
+  ix.d_wide_keys.release();
   ix.d_term_off.release();
   ix.d_postings.release();
   ix.d_post_pos.release();
@@ -1044,9 +1148,16 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   ix.has_positions = pb > 0;
 
   // ---- temporary arena T1: pairs (double-buffered), sort scratch, CSR block arrays
+  const int W = wide_words_for(ix.width);
+  ix.wide_words = W;
   const uint64_t n_blocks = (n_slots + kCsrTile - 1) / kCsrTile;
   DevArena& t1 = ix.build_arena;
-  t1.reserve(2 * (DevArena::padded(n_slots * 8 + 8) + DevArena::padded(n_slots * 4 + 4)) +
+  const size_t wide_extra =
+      W > 0 ? DevArena::padded(static_cast<size_t>(W) * n_slots * 8 + 8) + DevArena::padded(n_slots * 4 + 4) +
+                  DevArena::padded(n_slots * 4 + 4) + DevArena::padded((n_slots + 1) * 8) +
+                  DevArena::padded(scan_scratch_elems(std::max<uint64_t>(n_slots, 1)) * 8 + 64)
+            : 0;
+  t1.reserve(2 * (DevArena::padded(n_slots * 8 + 8) + DevArena::padded(n_slots * 4 + 4)) + wide_extra +
              DevArena::padded(radix_sort_scratch_bytes(n_slots) + 512) + 2 * DevArena::padded((n_blocks + 2) * 8) + 1024);
   uint64_t* d_keys_a = t1.take<uint64_t>(n_slots);
   uint32_t* d_docs_a = t1.take<uint32_t>(n_slots);
@@ -1056,16 +1167,56 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   uint64_t* d_block_pairs = t1.take<uint64_t>(n_blocks + 2);
   uint64_t* d_block_terms = t1.take<uint64_t>(n_blocks + 2);
   uint64_t* d_totals = t1.take<uint64_t>(4);
+  // wide keys only: the tokenizer's word arrays, the documents in text order, head flags and ranks
+  uint64_t* d_words = W > 0 ? t1.take<uint64_t>(static_cast<size_t>(W) * n_slots) : nullptr;
+  uint32_t* d_docs_text = W > 0 ? t1.take<uint32_t>(n_slots) : nullptr;
+  uint32_t* d_flags = W > 0 ? t1.take<uint32_t>(n_slots) : nullptr;
+  uint64_t* d_rank = W > 0 ? t1.take<uint64_t>(n_slots + 1) : nullptr;
+  uint64_t* d_wide_scan = W > 0 ? t1.take<uint64_t>(scan_scratch_elems(std::max<uint64_t>(n_slots, 1)) + 8) : nullptr;
   trace.mark("alloc pair arena");
   // one pass: per-document totals + the (key, doc) pairs (placeholder key 0 in the unused slots of each tile)
   tokenize_fused(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, text_bytes, ix.d_doc_len.p,
-                 d_slot_off, d_count_scratch, d_keys_a, d_docs_a, pb, counters, stream);
+                 d_slot_off, d_count_scratch, W > 0 ? d_words : d_keys_a, W > 0 ? d_docs_text : d_docs_a, pb, counters,
+                 stream, n_slots);
   ix.doc_count = counters[0];
   ix.all_valid_utf8 = counters[1] == 0;
   ix.total_doc_length = counters[2];
   trace.mark("tokenize: fused stats + emit");
-  const SortResult sorted =
-      radix_sort_pairs(d_keys_a, d_docs_a, d_keys_b, d_docs_b, n_slots, 21 * ix.width, pb, d_sort_scratch, stream);
+  SortResult sorted{d_keys_a, d_docs_a};
+  SortResult wide_order{nullptr, nullptr};  // wide keys: word 0 of every slot in key order + the slot it came from
+  const unsigned wide_grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>((n_slots + 255) / 256, 148 * 16)));
+  if (W == 0) {
+    sorted = radix_sort_pairs(d_keys_a, d_docs_a, d_keys_b, d_docs_b, n_slots, 21 * ix.width, pb, d_sort_scratch, stream);
+  } else if (n_slots > 0) {
+    // least significant word first, each sort stable, the permutation carried as the value: afterwards the slots are
+    // in wide-key order and, within one n-gram, in text order (= ascending documents)
+    SortResult cur{d_keys_a, d_docs_a};  // d_docs_* hold slot numbers until wide_assign_kernel
+    SortResult alt{d_keys_b, d_docs_b};
+    iota_u32_kernel<<<wide_grid, 256, 0, stream>>>(cur.vals, n_slots);
+    MGX_LAUNCH_CHECK();
+    for (int w = W - 1; w >= 0; --w) {
+      const uint64_t* src = d_words + static_cast<size_t>(w) * n_slots;
+      if (w == W - 1) {
+        MGX_CUDA(cudaMemcpyAsync(cur.keys, src, n_slots * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+      } else {
+        gather_u64_kernel<<<wide_grid, 256, 0, stream>>>(src, cur.vals, cur.keys, n_slots);
+        MGX_LAUNCH_CHECK();
+      }
+      const SortResult r = radix_sort_pairs(cur.keys, cur.vals, alt.keys, alt.vals, n_slots, 63, 0, d_sort_scratch, stream);
+      if (r.keys != cur.keys) {
+        std::swap(cur, alt);
+      }
+      // cur = sorted by words w.. ; the next word is gathered over cur.keys (its content is no longer needed)
+    }
+    wide_order = cur;
+    wide_heads_kernel<<<wide_grid, 256, 0, stream>>>(cur.keys, cur.vals, d_words, n_slots, W, n_slots, d_flags);
+    MGX_LAUNCH_CHECK();
+    exclusive_scan_u32_u64(d_flags, d_rank, n_slots, d_wide_scan, stream);
+    wide_assign_kernel<<<wide_grid, 256, 0, stream>>>(cur.keys, cur.vals, d_flags, d_rank, d_docs_text, n_slots,
+                                                     alt.keys, alt.vals);
+    MGX_LAUNCH_CHECK();
+    sorted = alt;
+  }
   trace.mark("radix sort");
 
   // ---- segmented unique + compaction into CSR
@@ -1083,8 +1234,18 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   ix.n_terms = totals[1];
   ix.resident_b.reserve(DevArena::padded(ix.n_terms * 8 + 8) + DevArena::padded((ix.n_terms + 1) * 8) +
                         DevArena::padded(ix.n_postings * 4 + 4) + 2 * DevArena::padded(ix.n_terms * 4 + 4) +
-                        2 * DevArena::padded(ix.n_postings * 2 + 4) + 512);
+                        2 * DevArena::padded(ix.n_postings * 2 + 4) +
+                        DevArena::padded(static_cast<size_t>(W) * ix.n_terms * 8 + 8) + 512);
   ix.d_term_keys.borrow(ix.resident_b.take<uint64_t>(ix.n_terms), ix.n_terms);
+  if (W > 0) {
+    ix.d_wide_keys.borrow(ix.resident_b.take<uint64_t>(static_cast<size_t>(W) * ix.n_terms),
+                          static_cast<size_t>(W) * ix.n_terms);
+    if (ix.n_terms > 0) {
+      wide_table_kernel<<<wide_grid, 256, 0, stream>>>(wide_order.keys, wide_order.vals, d_flags, d_rank, d_words,
+                                                      n_slots, W, n_slots, ix.d_wide_keys.p);
+      MGX_LAUNCH_CHECK();
+    }
+  }
   ix.d_term_off.borrow(ix.resident_b.take<uint64_t>(ix.n_terms + 1), ix.n_terms + 1);
   ix.d_postings.borrow(ix.resident_b.take<uint32_t>(ix.n_postings), ix.n_postings);
   ix.d_term_bm.borrow(ix.resident_b.take<int32_t>(ix.n_terms), ix.n_terms);
@@ -1154,6 +1315,9 @@ __global__ void localise_postings_kernel(const uint32_t* __restrict__ in, uint64
 
 void load_index_device(Index& ix, const uint64_t* h_keys, const uint64_t* h_term_off, const uint32_t* h_postings,
                        uint64_t n_terms, uint64_t n_postings, cudaStream_t stream) {
+  // wide keys (width > 3): h_keys holds wide_words words per term, ascending
+  const int W = wide_words_for(ix.width);
+  ix.wide_words = W;
   ResetOnFailure reset_on_failure{ix};
   ix.drop_filter_columns();
   ix.d_doc_ids.release();
@@ -1162,6 +1326,7 @@ void load_index_device(Index& ix, const uint64_t* h_keys, const uint64_t* h_term
   ix.d_doc_len.release();
   ix.d_tile_first_doc.release();
   ix.d_term_keys.release();
+  ix.d_wide_keys.release();
   ix.d_term_off.release();
   ix.d_postings.release();
   ix.d_post_pos.release();
@@ -1234,15 +1399,25 @@ void load_index_device(Index& ix, const uint64_t* h_keys, const uint64_t* h_term
 
   // ---- resident arena B: dictionary + CSR with LOCAL doc indices
   ix.resident_b.reserve(DevArena::padded(n_terms * 8 + 8) + DevArena::padded((n_terms + 1) * 8) +
-                        DevArena::padded(n_postings * 4 + 4) + 2 * DevArena::padded(n_terms * 4 + 4) + 512);
+                        DevArena::padded(n_postings * 4 + 4) + 2 * DevArena::padded(n_terms * 4 + 4) +
+                        DevArena::padded(static_cast<size_t>(W) * n_terms * 8 + 8) + 512);
   ix.d_term_keys.borrow(ix.resident_b.take<uint64_t>(n_terms), n_terms);
+  if (W > 0) {
+    ix.d_wide_keys.borrow(ix.resident_b.take<uint64_t>(static_cast<size_t>(W) * n_terms), static_cast<size_t>(W) * n_terms);
+  }
   ix.d_term_off.borrow(ix.resident_b.take<uint64_t>(n_terms + 1), n_terms + 1);
   ix.d_postings.borrow(ix.resident_b.take<uint32_t>(n_postings), n_postings);
   ix.d_term_bm.borrow(ix.resident_b.take<int32_t>(n_terms), n_terms);
   uint32_t* d_dense_terms = ix.resident_b.take<uint32_t>(n_terms);
   unsigned long long* d_count = reinterpret_cast<unsigned long long*>(ix.resident_b.take<uint64_t>(2));
-  if (n_terms > 0) {
+  if (n_terms > 0 && W == 0) {
     MGX_CUDA(cudaMemcpyAsync(ix.d_term_keys.p, h_keys, n_terms * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+  } else if (n_terms > 0) {
+    MGX_CUDA(cudaMemcpyAsync(ix.d_wide_keys.p, h_keys, static_cast<size_t>(W) * n_terms * sizeof(uint64_t),
+                             cudaMemcpyHostToDevice, stream));
+    iota_keys_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n_terms + 255) / 256, 148 * 16)), 256, 0, stream>>>(
+        ix.d_term_keys.p, n_terms);
+    MGX_LAUNCH_CHECK();
   }
   MGX_CUDA(cudaMemcpyAsync(ix.d_term_off.p, h_term_off, (n_terms + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
   if (n_postings > 0) {

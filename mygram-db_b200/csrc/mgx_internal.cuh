@@ -183,6 +183,16 @@ struct PhaseTrace {
 // strings (the reference sorts std::string keys, string_utils.h:192-196), and a
 // shorter n-gram that is a prefix of a longer one sorts first, like strings do.
 constexpr int kMaxKeyWidth = 3;
+// Wider n-grams (sizes 4..10, config-schema.json:279-285) are "wide keys": kWords = ceil(width / 3) words of the same
+// 21-bit packing (word 0 = code points 0..2, first code point in the most significant field), compared word by word,
+// which is again the bytewise order of the UTF-8 strings. The index sorts them with one 64-bit radix sort per word
+// (least significant word first, through a permutation) and then names every distinct n-gram by its RANK + 1: the
+// rest of the build, the CSR and every query kernel see that rank as "the key" (d_term_keys[t] == t + 1), and only the
+// dictionary lookup compares wide words (d_wide_keys). On the host a wide key is a handle into the calling thread's
+// WidePool (host_make_key); batch staging copies the words next to the handles.
+constexpr int kMaxNgramSize = 10;
+constexpr int kMaxWideWords = 4;
+__host__ __device__ inline int wide_words_for(int width) { return width <= kMaxKeyWidth ? 0 : (width + 2) / 3; }
 constexpr uint32_t kTextTileBytes = 8192;  // arena tile of the streaming df pass (256 threads x 16 B x 2 rounds)
 constexpr uint64_t kInvalidKey = ~0ULL;
 constexpr int kPosBits = 22;               // spare low bits of a packed key of width <= 2 (2 * 21 + 22 = 64)
@@ -196,6 +206,18 @@ __host__ __device__ inline uint64_t pack_key(const uint32_t* cps, int n, int wid
     key = (key << 21) | (j < n ? static_cast<uint64_t>(cps[j]) + 1 : 0ULL);
   }
   return key;
+}
+
+// words[0..n_words) of the wide key of cps[0..n) (n <= 3 * n_words)
+__host__ __device__ inline void pack_wide(const uint32_t* cps, int n, int n_words, uint64_t* words) {
+  for (int w = 0; w < n_words; ++w) {
+    uint64_t word = 0;
+    for (int f = 0; f < 3; ++f) {
+      const int j = 3 * w + f;
+      word = (word << 21) | (j < n ? static_cast<uint64_t>(cps[j]) + 1 : 0ULL);
+    }
+    words[w] = word;
+  }
 }
 
 // IsCJKIdeograph, string_utils.cpp:441-448 (ranges :176-187).
@@ -384,6 +406,29 @@ bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanj
 // One n-gram string -> packed key (for Index::SearchAnd style calls). False if
 // it is not valid UTF-8 of 1..width code points (such a term cannot be in the index).
 bool host_ngram_to_key(const uint8_t* term, uint64_t len, int key_width, uint64_t* key);
+// Key of the n-gram cps[0..n) for an index of key width `width`: the packed key for width <= 3, otherwise a handle
+// (>= 1) into the calling thread's pool of wide keys -- equal n-grams get equal handles for as long as the pool lives,
+// i.e. until the next top-level API call on this thread starts (WideScope).
+uint64_t host_make_key(const uint32_t* cps, int n, int width);
+// the n_words words behind a handle of the calling thread's pool
+const uint64_t* host_wide_words(uint64_t handle, int n_words);
+// UTF-8 bytes of a key (packed or handle), returns their number; out: 4 * width bytes
+int host_key_to_utf8(uint64_t key, int width, uint8_t* out);
+int wide_words_to_utf8(const uint64_t* words, int n_words, uint8_t* out);
+// Pool of the wide keys one API call makes (thread-local). Scopes nest: only the outermost one clears the pool.
+struct WideScope {
+  WideScope();
+  ~WideScope();
+  WideScope(const WideScope&) = delete;
+  WideScope& operator=(const WideScope&) = delete;
+};
+// Handles of a pool that worker threads filled: append another thread's words to this thread's pool and return the
+// offset to add to its handles.
+struct WidePoolSnapshot {
+  std::vector<uint64_t> words;  // 4 words per key
+};
+WidePoolSnapshot wide_pool_snapshot();
+uint64_t wide_pool_adopt(const WidePoolSnapshot& other);
 
 // ---------------------------------------------------------------- device-wide primitives (primitives.cu)
 // out[i] = sum_{j<i} in[j]  (u32 -> u64), out has n+1 entries (out[n] = total).
@@ -461,6 +506,8 @@ struct Index {
   uint64_t n_terms = 0;
   uint64_t n_postings = 0;
   DevBuf<uint64_t> d_term_keys;
+  int wide_words = 0;              // 0: packed keys; otherwise words per wide key (width > 3)
+  DevBuf<uint64_t> d_wide_keys;    // [n_terms * wide_words], term-major, ascending; d_term_keys[t] == t + 1 then
   DevBuf<uint64_t> d_term_off;
   DevBuf<uint32_t> d_postings;
   // First-occurrence position of every posting (only when the packed key leaves room to carry it through the sort,
@@ -512,6 +559,8 @@ struct IndexView {
   uint64_t text_bytes;
   uint64_t n_text_tiles;
   const uint64_t* term_keys;
+  const uint64_t* wide_keys;  // nullptr unless the index has wide keys
+  int wide_words;
   const uint64_t* term_off;
   const uint32_t* postings;
   const uint16_t* post_pos;  // nullptr when the index carries no positions
@@ -559,6 +608,8 @@ inline IndexView make_view(const Index& ix) {
   v.text_bytes = ix.text_bytes;
   v.n_text_tiles = ix.n_text_tiles;
   v.term_keys = ix.d_term_keys.p;
+  v.wide_keys = ix.wide_words > 0 ? ix.d_wide_keys.p : nullptr;
+  v.wide_words = ix.wide_words;
   v.term_off = ix.d_term_off.p;
   v.postings = ix.d_postings.p;
   v.post_pos = ix.has_positions ? ix.d_post_pos.p : nullptr;
@@ -603,6 +654,8 @@ void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* 
 // shifted left by pos_bits and carries the byte offset of the n-gram in its document (saturated) in the low bits.
 void tokenize_emit(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
                    uint64_t n_docs, uint64_t text_bytes, const uint64_t* d_tile_off, uint64_t* d_scratch,
-                   uint64_t* d_keys, uint32_t* d_docs, int pos_bits, cudaStream_t stream);
+                   uint64_t* d_keys, uint32_t* d_docs, int pos_bits, cudaStream_t stream, uint64_t wide_stride = 0);
+// wide_stride (key width > 3): d_keys holds wide_words_for(width) arrays of wide_stride words, word w of slot s at
+// d_keys[w * wide_stride + s].
 
 }  // namespace mgx

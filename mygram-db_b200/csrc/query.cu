@@ -252,22 +252,53 @@ __device__ __forceinline__ uint32_t doc_count_term(DocText& d, const uint8_t* __
 }
 
 // ------------------------------------------------------------------ lookup + term planning
+// wide_keys != nullptr: the dictionary is the table of wide keys (n_words words per term, ascending word by word) and
+// key i of the batch is qwide[i * n_words ..]; keys[i] only tells "cannot exist" (kInvalidKey).
+__device__ __forceinline__ int wide_cmp(const uint64_t* __restrict__ a, const uint64_t* __restrict__ b, int n_words) {
+  for (int w = 0; w < n_words; ++w) {
+    const uint64_t x = a[w];
+    const uint64_t y = b[w];
+    if (x != y) {
+      return x < y ? -1 : 1;
+    }
+  }
+  return 0;
+}
+
 __device__ __forceinline__ void lookup_one(const uint64_t* __restrict__ term_keys, const uint64_t* __restrict__ term_off,
                                            uint64_t n_dict, const uint64_t* __restrict__ keys, uint32_t i,
                                            uint32_t* __restrict__ key_list, uint32_t* __restrict__ key_len,
-                                           uint64_t* __restrict__ key_glen) {
+                                           uint64_t* __restrict__ key_glen, const uint64_t* __restrict__ wide_keys,
+                                           int n_words, const uint64_t* __restrict__ qwide) {
   const uint64_t key = keys[i];
   uint64_t lo = 0;
   uint64_t hi = n_dict;
-  while (lo < hi) {
-    const uint64_t mid = (lo + hi) >> 1;
-    if (term_keys[mid] < key) {
-      lo = mid + 1;
-    } else {
-      hi = mid;
+  bool found = false;
+  if (wide_keys != nullptr) {
+    if (key != kInvalidKey) {
+      const uint64_t* q = qwide + static_cast<uint64_t>(i) * n_words;
+      while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (wide_cmp(wide_keys + mid * n_words, q, n_words) < 0) {
+          lo = mid + 1;
+        } else {
+          hi = mid;
+        }
+      }
+      found = lo < n_dict && wide_cmp(wide_keys + lo * n_words, q, n_words) == 0;
     }
+  } else {
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (term_keys[mid] < key) {
+        lo = mid + 1;
+      } else {
+        hi = mid;
+      }
+    }
+    found = lo < n_dict && term_keys[lo] == key;
   }
-  if (lo < n_dict && term_keys[lo] == key) {
+  if (found) {
     key_list[i] = static_cast<uint32_t>(lo);
     key_len[i] = static_cast<uint32_t>(term_off[lo + 1] - term_off[lo]);
   } else {
@@ -282,10 +313,11 @@ __device__ __forceinline__ void lookup_one(const uint64_t* __restrict__ term_key
 __global__ void lookup_kernel(const uint64_t* __restrict__ term_keys, const uint64_t* __restrict__ term_off,
                               uint64_t n_dict, const uint64_t* __restrict__ keys, uint32_t n_keys,
                               uint32_t* __restrict__ key_list, uint32_t* __restrict__ key_len,
-                              uint64_t* __restrict__ key_glen) {
+                              uint64_t* __restrict__ key_glen, const uint64_t* __restrict__ wide_keys, int n_words,
+                              const uint64_t* __restrict__ qwide) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_keys) {
-    lookup_one(term_keys, term_off, n_dict, keys, i, key_list, key_len, key_glen);
+    lookup_one(term_keys, term_off, n_dict, keys, i, key_list, key_len, key_glen, wide_keys, n_words, qwide);
   }
 }
 
@@ -751,7 +783,8 @@ __global__ void key_ref_kernel(IndexView iv, const uint32_t* __restrict__ key_li
 // Streamed planning, stage 1: everything that concerns ONE term in one thread -- dictionary lookup of its keys, lists
 // by ascending length, estimate, df work units, resolved list references (lookup + term_plan + key_ref in one launch).
 __global__ void plan_terms_kernel(IndexView iv, BatchView bv, const uint64_t* __restrict__ keys, int compute_df,
-                                  int all_valid_utf8, const uint8_t* __restrict__ raw_flags, uint64_t bitmap_bytes) {
+                                  int all_valid_utf8, const uint8_t* __restrict__ raw_flags, uint64_t bitmap_bytes,
+                                  const uint64_t* __restrict__ qwide) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= bv.n_terms) {
     return;
@@ -759,7 +792,8 @@ __global__ void plan_terms_kernel(IndexView iv, BatchView bv, const uint64_t* __
   const uint32_t k0 = bv.term_koff[t];
   const uint32_t k1 = bv.term_koff[t + 1];
   for (uint32_t i = k0; i < k1; ++i) {
-    lookup_one(iv.term_keys, iv.term_off, iv.n_terms, keys, i, bv.key_list, bv.key_len, bv.key_glen);
+    lookup_one(iv.term_keys, iv.term_off, iv.n_terms, keys, i, bv.key_list, bv.key_len, bv.key_glen, iv.wide_keys,
+               iv.wide_words, qwide);
   }
   term_plan_one(bv, t, compute_df, all_valid_utf8, raw_flags, bitmap_bytes, kDfUnit);
   for (uint32_t i = k0; i < k1; ++i) {
@@ -4019,6 +4053,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
   L.stream_len8_mask = stream_table.len8_mask;
   L.stream_len12_mask = stream_table.len12_mask;
   L.assumed_all_valid_utf8 = b.ix->all_valid_utf8 ? 1 : 0;
+  L.wide_words = static_cast<uint32_t>(b.ix->wide_words);
   const StageOffsets O = stage_offsets(L);
   const size_t total = O.total;
   const size_t i_bytes = O.i_bytes, i_boff = O.i_boff, i_koff = O.i_koff, i_keys = O.i_keys, i_raw = O.i_raw;
@@ -4047,6 +4082,14 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
       boff[t + 1] = nb;
       for (size_t k = 0; k < ht.keys.size(); ++k) {
         keys[nk + k] = ht.keys[k];
+        if (L.wide_words > 0) {  // the words behind the handle travel with the batch
+          uint64_t* dst = reinterpret_cast<uint64_t*>(S + O.i_wide) + static_cast<size_t>(nk + k) * L.wide_words;
+          if (ht.keys[k] != kInvalidKey) {
+            std::memcpy(dst, host_wide_words(ht.keys[k], static_cast<int>(L.wide_words)), L.wide_words * 8);
+          } else {
+            std::memset(dst, 0, L.wide_words * 8);
+          }
+        }
         key_toff[nk + k] = k < ht.key_toff.size() ? ht.key_toff[k] : kNoTermOffset;
       }
       nk += static_cast<uint32_t>(ht.keys.size());
@@ -4170,6 +4213,7 @@ StageOffsets stage_offsets(const StageLayout& L) {
   O.i_sentries = add(L.n_sentries * sizeof(StreamEntry));
   O.i_sbloom = add(L.n_sbloom * 4);
   O.i_xoff = add(L.n_xoff * 4);
+  O.i_wide = add(L.n_keys * 8 * L.wide_words);
   O.total = total;
   return O;
 }
@@ -4231,6 +4275,7 @@ void batch_bind(Batch& b) {
   b.d_stream_entries.borrow(reinterpret_cast<StreamEntry*>(at(i_sentries)), L.n_sentries);
   b.d_stream_bloom.borrow(reinterpret_cast<uint32_t*>(at(i_sbloom)), L.n_sbloom);
   b.d_xoff.borrow(reinterpret_cast<uint32_t*>(at(i_xoff)), L.n_xoff);
+  b.d_wide.borrow(L.wide_words > 0 ? reinterpret_cast<uint64_t*>(at(O.i_wide)) : nullptr, n_keys * L.wide_words);
 
   // ---- device-only planning arrays from the work arena
   const size_t K = n_keys;
@@ -4422,7 +4467,7 @@ void batch_plan_streamed(Batch& b) {
   if (b.n_terms > 0) {
     plan_terms_kernel<<<grid_for(b.n_terms, 128), 128, 0, st>>>(iv, bv, b.d_keys.p, b.params.compute_score != 0 ? 1 : 0,
                                                                 ix.all_valid_utf8 ? 1 : 0, b.d_term_flags.p,
-                                                                (ix.n_docs + 7) / 8);
+                                                                (ix.n_docs + 7) / 8, b.d_wide.p);
     MGX_LAUNCH_CHECK();
   }
   const int df_choice = b.params.compute_score != 0 && b.n_stream_terms > 0 ? 1 : 0;
@@ -4511,7 +4556,9 @@ void batch_plan(Batch& b) {
   b.time_begin(0);
   if (b.n_keys > 0) {
     lookup_kernel<<<grid_for(b.n_keys, 256), 256, 0, st>>>(ix.d_term_keys.p, ix.d_term_off.p, ix.n_terms, b.d_keys.p,
-                                                          b.n_keys, b.d_key_list.p, b.d_key_len.p, b.d_key_glen.p);
+                                                          b.n_keys, b.d_key_list.p, b.d_key_len.p, b.d_key_glen.p,
+                                                          ix.wide_words > 0 ? ix.d_wide_keys.p : nullptr, ix.wide_words,
+                                                          b.d_wide.p);
     MGX_LAUNCH_CHECK();
   }
   BatchView bv = make_batch_view(b);
@@ -4947,15 +4994,29 @@ void lookup_list_lengths(Batch& b, const uint64_t* h_keys, uint32_t n, uint32_t*
   if (n == 0) {
     return;
   }
-  b.len_buf.reserve(3 * 64 * 8);  // keys | list ids | lengths
+  const int W = ix.wide_words;
+  b.len_buf.reserve(3 * 64 * 8 + 64 * kMaxWideWords);  // keys | list ids | lengths | wide words
   uint64_t* d_keys = b.len_buf.p;
   uint32_t* d_list = reinterpret_cast<uint32_t*>(b.len_buf.p + 64);
   uint32_t* d_len = reinterpret_cast<uint32_t*>(b.len_buf.p + 128);
+  uint64_t* d_wide = b.len_buf.p + 192;
   MGX_CUDA(cudaMemcpyAsync(d_keys, h_keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-  lookup_kernel<<<1, 64, 0, st>>>(ix.d_term_keys.p, ix.d_term_off.p, ix.n_terms, d_keys, n, d_list, d_len, nullptr);
+  uint64_t h_wide[64 * kMaxWideWords];
+  if (W > 0) {
+    for (uint32_t i = 0; i < n; ++i) {
+      if (h_keys[i] != kInvalidKey) {
+        std::memcpy(h_wide + static_cast<size_t>(i) * W, host_wide_words(h_keys[i], W), static_cast<size_t>(W) * 8);
+      } else {
+        std::memset(h_wide + static_cast<size_t>(i) * W, 0, static_cast<size_t>(W) * 8);
+      }
+    }
+    MGX_CUDA(cudaMemcpyAsync(d_wide, h_wide, static_cast<size_t>(n) * W * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  }
+  lookup_kernel<<<1, 64, 0, st>>>(ix.d_term_keys.p, ix.d_term_off.p, ix.n_terms, d_keys, n, d_list, d_len, nullptr,
+                                  W > 0 ? ix.d_wide_keys.p : nullptr, W, d_wide);
   MGX_LAUNCH_CHECK();
   MGX_CUDA(cudaMemcpyAsync(h_lens, d_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  MGX_CUDA(cudaStreamSynchronize(st));
+  MGX_CUDA(cudaStreamSynchronize(st));  // also keeps h_wide alive until its copy is done
 }
 
 void merge_disjoint_runs(Batch& b, const uint32_t* d_in, const std::vector<uint64_t>& run_off, DevBuf<uint32_t>* d_out) {

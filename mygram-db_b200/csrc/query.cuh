@@ -188,11 +188,11 @@ struct StageLayout {
   uint64_t n_prog = 0, n_conj = 0, n_preds = 0, n_sslots = 0, n_sentries = 0, n_sbloom = 0, n_xoff = 0, list_cap = 0;
   uint32_t stream_len8_mask = 0, stream_len12_mask = 0;
   uint32_t assumed_all_valid_utf8 = 0;  // the compiling shard held no invalid UTF-8 (term shortcuts were decided with that)
-  uint32_t pad = 0;
+  uint32_t wide_words = 0;  // words per wide key (index key width > 3): n_keys * wide_words words follow the other arrays
 };
 struct StageOffsets {
   size_t i_bytes, i_boff, i_koff, i_keys, i_raw, i_toff, i_tids, i_tids0, i_noff, i_ntids, i_loff, i_hflags, i_slot, i_ktoff,
-      i_thr, i_poff, i_pops, i_pargs, i_coff, i_conj, i_foff, i_preds, i_sslots, i_sentries, i_sbloom, i_xoff, total;
+      i_thr, i_poff, i_pops, i_pargs, i_coff, i_conj, i_foff, i_preds, i_sslots, i_sentries, i_sbloom, i_xoff, i_wide, total;
 };
 StageOffsets stage_offsets(const StageLayout& L);
 
@@ -224,6 +224,7 @@ struct Batch {
   DevBuf<uint32_t> d_term_boff;   // [T+1]
   DevBuf<uint32_t> d_term_koff;   // [T+1]
   DevBuf<uint64_t> d_keys;        // [K]
+  DevBuf<uint64_t> d_wide;        // [K * wide_words] words of the wide keys (null for packed keys)
   DevBuf<uint32_t> d_key_list;    // [K] dictionary term index or kNone; sorted by length inside a term
   DevBuf<uint32_t> d_key_len;     // [K]
   DevBuf<uint16_t> d_key_toff;    // [K] byte offset of the n-gram inside its term, kNoTermOffset if unusable
