@@ -121,6 +121,35 @@ def test_packed_key_order_is_utf8_byte_order(mgx, oracle):
     assert [strings[i] for i in order_k] == [strings[i] for i in order_s]
 
 
+def test_wide_key_order_is_utf8_byte_order(mgx, oracle):
+    """Keys of 4..10 code points: mgx_key_words(width) words of three 21-bit fields, compared word by word ==
+    bytewise order of the UTF-8 n-grams; mgx_wide_key_to_utf8 decodes them."""
+    lib = mgx.lib()
+    assert [lib.mgx_key_words(w) for w in range(1, 11)] == [1, 1, 1, 2, 2, 2, 3, 3, 3, 4]
+    assert lib.mgx_key_words(0) < 0 and lib.mgx_key_words(11) < 0
+    rng = np.random.default_rng(6)
+    cps = [0, 1, 0x41, 0x7F, 0x80, 0x7FF, 0x800, 0x3042, 0x4E00, 0xFFFF, 0x10000, 0x20000, 0x10FFFF]
+    for width in (4, 6, 7, 10):
+        nw = lib.mgx_key_words(width)
+        keys, strings = [], []
+        for _ in range(300):
+            n = int(rng.integers(1, width + 1))
+            seq = [int(rng.choice(cps)) for _ in range(n)]
+            words = []
+            for w in range(nw):
+                word = 0
+                for f in range(3):
+                    j = 3 * w + f
+                    word = (word << 21) | ((seq[j] + 1) if j < n else 0)
+                words.append(word)
+            keys.append(tuple(words))
+            strings.append(oracle.codepoints_to_utf8(seq))
+            assert mgx.key_to_utf8(np.array(words, dtype=np.uint64), width) == strings[-1]
+        order_k = sorted(range(len(keys)), key=lambda i: keys[i])
+        order_s = sorted(range(len(keys)), key=lambda i: strings[i])
+        assert [strings[i] for i in order_k] == [strings[i] for i in order_s]
+
+
 def _build_adapter_example(tmp_path, source="adapter_example.cpp"):
     import subprocess
     root = os.path.join(os.path.dirname(__file__), "..")
