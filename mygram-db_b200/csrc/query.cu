@@ -2217,13 +2217,17 @@ __device__ __forceinline__ bool filter_pass(const FilterPred& f, uint32_t doc) {
 
 // TERM node of a boolean program: the documents of SearchAnd(n-grams of the term) (query_ast.cpp:76-93); a term
 // without n-grams falls back to a substring test of the stored text (query/substring_search.h:24-42).
-__device__ bool program_term_holds(const IndexView& iv, const BatchView& bv, uint32_t tid, uint32_t doc) {
+__device__ bool program_term_holds(const IndexView& iv, const BatchView& bv, uint32_t tid, uint32_t doc,
+                                   bool optimistic) {
   const uint32_t k0 = bv.term_koff[tid];
   const uint32_t k1 = bv.term_koff[tid + 1];
   if (k1 == k0) {
     const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
     if (tl == 0) {
       return false;
+    }
+    if (optimistic) {
+      return true;  // text leaf of a monotone program, first evaluation (kQOptimistic)
     }
     const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
     const uint64_t b = iv.text_off[doc];
@@ -2384,17 +2388,19 @@ __device__ __noinline__ bool fuzzy_text_holds(const IndexView& iv, const BatchVi
 
 // Postfix evaluation with a 64-bit stack (bit 0 = top). AND / OR of zero children and NOT without a child are
 // false, as QueryNode::Evaluate returns an empty set for them (query_ast.cpp:96-140).
-__device__ bool eval_program(const IndexView& iv, const BatchView& bv, uint32_t p0, uint32_t p1, uint32_t doc) {
+__device__ bool eval_program(const IndexView& iv, const BatchView& bv, uint32_t p0, uint32_t p1, uint32_t doc,
+                             bool optimistic) {
   unsigned long long stack = 0;
   uint32_t sp = 0;
   for (uint32_t i = p0; i < p1; ++i) {
     const uint32_t op = bv.prog_op[i];
     const uint32_t arg = bv.prog_arg[i];
     if (op == kOpTerm) {
-      stack = (stack << 1) | (program_term_holds(iv, bv, arg, doc) ? 1ULL : 0ULL);
+      stack = (stack << 1) | (program_term_holds(iv, bv, arg, doc, optimistic) ? 1ULL : 0ULL);
       ++sp;
     } else if (op == kOpFuzzyText) {
-      stack = (stack << 1) | (fuzzy_text_holds(iv, bv, arg & 0xFFFFFFu, arg >> 24, doc) ? 1ULL : 0ULL);
+      stack = (stack << 1) |
+              ((optimistic || fuzzy_text_holds(iv, bv, arg & 0xFFFFFFu, arg >> 24, doc)) ? 1ULL : 0ULL);
       ++sp;
     } else if (op == kOpAnd || op == kOpOr || op == kOpAtLeast) {
       const uint32_t n = op == kOpAtLeast ? (arg & 0xFFFFu) : arg;
@@ -2516,9 +2522,17 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
   if ((flags & kQProgram) != 0) {
     const uint32_t p0 = bv.q_poff[q];
     const uint32_t p1 = bv.q_poff[q + 1];
+    if ((flags & kQOptimistic) != 0) {  // lists first: most documents are ruled out without reading their text
+#pragma unroll
+      for (int k = 0; k < kTileItems; ++k) {
+        if (((alive >> k) & 1u) && (my_doc[k] == kNone || !eval_program(iv, bv, p0, p1, my_doc[k], true))) {
+          alive &= ~(1u << k);
+        }
+      }
+    }
 #pragma unroll
     for (int k = 0; k < kTileItems; ++k) {
-      if (((alive >> k) & 1u) && (my_doc[k] == kNone || !eval_program(iv, bv, p0, p1, my_doc[k]))) {
+      if (((alive >> k) & 1u) && (my_doc[k] == kNone || !eval_program(iv, bv, p0, p1, my_doc[k], false))) {
         alive &= ~(1u << k);
       }
     }
@@ -4156,6 +4170,43 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
       nl += cap;
       loff[q + 1] = nl;
       hflags[q] = hq.flags;
+      if ((hq.flags & kQProgram) != 0 && std::getenv("MGX_NO_OPTIMISTIC") == nullptr) {
+        // text leaves only under AND / OR / ATLEAST (never under a NOT)?
+        bool any_text = false;
+        bool monotone = true;
+        std::vector<uint8_t> has_text;  // per stack entry: its subtree holds a text leaf
+        for (size_t i = 0; i < hq.prog_ops.size() && monotone; ++i) {
+          const uint8_t op = hq.prog_ops[i];
+          const uint32_t arg = hq.prog_args[i];
+          if (op == kOpTerm) {
+            const bool text = arg < terms.size() && terms[arg].keys.empty() && !terms[arg].bytes.empty();
+            has_text.push_back(text ? 1 : 0);
+            any_text = any_text || text;
+          } else if (op == kOpFuzzyText) {
+            has_text.push_back(1);
+            any_text = true;
+          } else if (op == kOpAnd || op == kOpOr || op == kOpAtLeast) {
+            const size_t n_kids = op == kOpAtLeast ? (arg & 0xFFFFu) : arg;
+            if (n_kids > has_text.size()) {
+              monotone = false;
+              break;
+            }
+            uint8_t any = 0;
+            for (size_t c = 0; c < n_kids; ++c) {
+              any |= has_text[has_text.size() - 1 - c];
+            }
+            has_text.resize(has_text.size() - n_kids);
+            has_text.push_back(any);
+          } else {  // NOT
+            if (has_text.empty() || has_text.back() != 0) {
+              monotone = false;
+            }
+          }
+        }
+        if (any_text && monotone) {
+          hflags[q] |= kQOptimistic;
+        }
+      }
     }
     hflags[Q] = 0;
     thresholds[Q] = 1;

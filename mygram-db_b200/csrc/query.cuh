@@ -81,6 +81,10 @@ constexpr uint32_t kQAnyMode = 4u;      // OR semantics over the lists (Index::S
 constexpr uint32_t kQDriverAll = 8u;    // driver = every document of the shard
 constexpr uint32_t kQDriverExplicit = 16u;  // driver = caller supplied candidate ids (query 0 only)
 constexpr uint32_t kQProgram = 32u;     // membership = a boolean postfix program over terms (QueryNode::Evaluate)
+// kQProgram whose text leaves (substring-only terms, FUZZYTEXT) all occur positively: the program is monotone in them,
+// so a first evaluation with those leaves taken as true rules documents out without reading their text, and only the
+// documents that pass it pay for the real one
+constexpr uint32_t kQOptimistic = 64u;
 constexpr uint32_t kMaxProgramDepth = 64;  // evaluation stack = one 64-bit word
 
 // postfix program ops (same encoding as the oracle's orc_eval_boolean)
