@@ -353,8 +353,11 @@ int mgx_index_set_filter_column(mgx_index_t* index, uint32_t column, int32_t typ
 /* Optional per-query extensions of mgx_query_batch:
  *  - boolean programs (QueryNode::Evaluate, query_ast.cpp:67-161): when q_prog_begin[q+1] > q_prog_begin[q] the
  *    query's terms [q_term_begin[q], q_term_begin[q+1]) are the TERM operands of the postfix program
- *    ops/args[q_prog_begin[q] ..) (TERM arg = index inside the query's own term range) instead of being AND-ed;
- *    such batches need compute_score == 0;
+ *    ops/args[q_prog_begin[q] ..) (TERM arg = index inside the query's own term range) instead of being AND-ed.
+ *    With compute_score != 0 the results of a program are scored the way the reference scores every result shape
+ *    (search_handler.cpp:405-470): BM25 over the TERM operands that are not below a NOT, left to right, duplicates
+ *    kept (CollectAstScoringTerms, search_pipeline.cpp:232-254), each with its verified document frequency, then
+ *    SortByScore; a scoring term that does not occur in a result's text adds nothing;
  *  - filter conditions (ApplyFiltersWithBitmap / ApplyFilters, search_pipeline.cpp:1098-1237): query q keeps a
  *    document only if it passes filters [q_filter_begin[q], q_filter_begin[q+1]): column id, op (query_parser.h:
  *    93-100: 0 EQ, 1 NE, 2 GT, 3 GTE, 4 LT, 5 LTE) and the literal as written in the query. As in the reference,

@@ -500,8 +500,10 @@ struct DeviceGuard {
 // Compile the caller's flat query description into unique terms + queries.
 // Validates a postfix program and collects the terms every result must satisfy (the operands of the root when it is
 // a TERM, or the TERM operands of a root AND, recursively through nested ANDs).
+// positive_terms (optional): the TERM operands that are not below a NOT, left to right, duplicates kept -- the terms
+// a boolean query is SCORED with (CollectAstScoringTerms, search_pipeline.cpp:232-254).
 int analyse_program(const int32_t* ops, const int32_t* args, uint64_t n_ops, uint64_t n_terms,
-                    std::vector<uint32_t>* conjuncts) {
+                    std::vector<uint32_t>* conjuncts, std::vector<uint32_t>* positive_terms = nullptr) {
   struct Node {
     int op;
     int32_t arg;
@@ -546,6 +548,24 @@ int analyse_program(const int32_t* ops, const int32_t* args, uint64_t n_ops, uin
   }
   if (stack.empty()) {
     return MGX_OK;
+  }
+  if (positive_terms != nullptr) {
+    // pre-order, children left to right: the order the reference walks its AST in
+    std::vector<std::pair<size_t, bool>> walk{{stack.back(), false}};
+    while (!walk.empty()) {
+      const auto [at, under_not] = walk.back();
+      walk.pop_back();
+      const Node& nd = nodes[at];
+      if (nd.op == kOpTerm) {
+        if (!under_not) {
+          positive_terms->push_back(static_cast<uint32_t>(nd.arg));
+        }
+        continue;
+      }
+      for (size_t k = nd.kids.size(); k > 0; --k) {
+        walk.push_back({nd.kids[k - 1], under_not || nd.op == kOpNot});
+      }
+    }
   }
   std::vector<size_t> todo{stack.back()};  // the value of the program is the top of the stack
   while (!todo.empty()) {
@@ -671,16 +691,18 @@ int compile_range(const Index& ix, const mgx_query_params_t& p, uint64_t q_first
     hq.flags = verify ? kQVerify : 0u;
     if (ext != nullptr && ext->q_prog_begin != nullptr && ext->q_prog_begin[q + 1] > ext->q_prog_begin[q]) {
       // boolean program over the query's own terms (QueryNode::Evaluate): TERM args are local term indices
-      if (p.compute_score != 0) {
-        set_last_error("boolean programs in a batch need compute_score == 0");
-        return MGX_ERR_UNSUPPORTED;
-      }
       const uint64_t p0 = ext->q_prog_begin[q];
       const uint64_t pn = ext->q_prog_begin[q + 1] - p0;
       std::vector<uint32_t> local_conj;
-      if (int rc = analyse_program(ext->prog_ops + p0, ext->prog_args + p0, pn, hq.terms.size(), &local_conj);
+      std::vector<uint32_t> local_scored;
+      if (int rc = analyse_program(ext->prog_ops + p0, ext->prog_args + p0, pn, hq.terms.size(), &local_conj,
+                                   p.compute_score != 0 ? &local_scored : nullptr);
           rc != MGX_OK) {
         return rc;
+      }
+      if (local_scored.size() > 64) {
+        set_last_error("more than 64 scored terms in one boolean query");
+        return MGX_ERR_UNSUPPORTED;
       }
       for (uint32_t c : local_conj) {
         hq.conjuncts.push_back(hq.terms[c]);
@@ -694,7 +716,14 @@ int compile_range(const Index& ix, const mgx_query_params_t& p, uint64_t q_first
         hq.prog_args.push_back(op == kOpTerm ? hq.terms[static_cast<size_t>(ext->prog_args[p0 + i])]
                                              : static_cast<uint32_t>(ext->prog_args[p0 + i]));
       }
-      hq.terms.clear();  // operands of the program, not AND-ed search terms
+      // operands of the program, not AND-ed search terms. A scored program keeps the terms its results are scored
+      // with (search_handler.cpp:405-470 scores every result shape with all_search_terms): membership is the
+      // program's alone, the epilogue only counts these terms in the text of the survivors.
+      TermIdVec scored;
+      for (uint32_t c : local_scored) {
+        scored.push_back(hq.terms[c]);
+      }
+      hq.terms = std::move(scored);
       hq.flags = kQProgram;
     }
     if (ext != nullptr && ext->q_filter_begin != nullptr) {

@@ -2633,6 +2633,9 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
   // ---- fused epilogue: text scan -> tf -> BM25 (bm25_scorer.cpp:67-88), text constraints
   const uint32_t t0 = bv.q_toff[q];
   const uint32_t t1 = bv.q_toff[q + 1];
+  // The terms of a scored boolean program are only what its results are SCORED with (search_handler.cpp:405-470):
+  // membership was the program's, so they neither have to occur in the text nor drop a document without text.
+  const bool terms_filter = (flags & kQProgram) == 0;
   bool need_text = sp.compute_score != 0 || (flags & kQVerify) != 0;
   for (uint32_t i = t0; i < t1 && !need_text; ++i) {
     const uint32_t tid = bv.q_tids[i];
@@ -2664,8 +2667,8 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
     // C5-style batch of short single-term queries over long lists spends its time on. Documents with three or more
     // occurrences (or offsets beyond the recorded range) take the scanning path below.
     bool pay_only = false;
-    if (sp.compute_score != 0 && drv_list && nl == 1 && n_search == 1 && n1 == n0 && (flags & kQVerify) == 0 &&
-        total == tile_n && iv.post_pos != nullptr && iv.all_valid_utf8 != 0) {
+    if (sp.compute_score != 0 && terms_filter && drv_list && nl == 1 && n_search == 1 && n1 == n0 &&
+        (flags & kQVerify) == 0 && total == tile_n && iv.post_pos != nullptr && iv.all_valid_utf8 != 0) {
       const uint32_t tid = bv.q_tids[t0];
       pay_only = (bv.term_flags[tid] & 8u) != 0 && bv.term_koff[tid + 1] - bv.term_koff[tid] == 1;
     }
@@ -2768,12 +2771,12 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
               const bool no_keys = bv.term_koff[tid + 1] == bv.term_koff[tid];
               if (len == 0) {
                 // no stored text: a substring-only search term cannot match; verify keeps the doc
-                if (no_keys && tl != 0) {
+                if (no_keys && tl != 0 && terms_filter) {
                   keep = 0;
                 }
                 continue;
               }
-              const bool must = (flags & kQVerify) != 0 || no_keys;
+              const bool must = terms_filter && ((flags & kQVerify) != 0 || no_keys);
               const uint32_t tf_u = s_tf[s * n_search + (i - t0)];
               if (must && tf_u == 0 && tl != 0) {
                 keep = 0;
@@ -2808,7 +2811,7 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
           if (len == 0) {
             for (uint32_t i = t0; i < t1; ++i) {
               const uint32_t tid = bv.q_tids[i];
-              if (bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid]) {
+              if (terms_filter && bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid]) {
                 keep = 0;
               }
             }
@@ -2822,7 +2825,7 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
               const uint32_t tid = bv.q_tids[i];
               const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
               const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
-              const bool must = (flags & kQVerify) != 0 || bv.term_koff[tid + 1] == bv.term_koff[tid];
+              const bool must = terms_filter && ((flags & kQVerify) != 0 || bv.term_koff[tid + 1] == bv.term_koff[tid]);
               const uint32_t tf_u =
                   group_count_term<G>(iv.text, b, len, term, tl, load_term_regs(term, tl), sp.compute_score == 0);
               if (must && tf_u == 0 && tl != 0) {
@@ -2866,7 +2869,7 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
           // no stored text: a substring-only search term cannot match; verify keeps the doc
           for (uint32_t i = t0; i < t1; ++i) {
             const uint32_t tid = bv.q_tids[i];
-            if (bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid]) {
+            if (terms_filter && bv.term_koff[tid + 1] == bv.term_koff[tid] && bv.term_boff[tid + 1] > bv.term_boff[tid]) {
               keep = 0;
             }
           }
@@ -2880,7 +2883,7 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
             const uint32_t tid = bv.q_tids[i];
             const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
             const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
-            const bool must = (flags & kQVerify) != 0 || bv.term_koff[tid + 1] == bv.term_koff[tid];
+            const bool must = terms_filter && ((flags & kQVerify) != 0 || bv.term_koff[tid + 1] == bv.term_koff[tid]);
             const uint32_t tf_u =
                 thread_count_term(iv.text, b, len, term, tl, load_term_regs(term, tl), sp.compute_score == 0);
             if (must && tf_u == 0 && tl != 0) {
@@ -2932,7 +2935,7 @@ __device__ __forceinline__ void and_tile_body(const IndexView& iv, const BatchVi
           const uint32_t tid = bv.q_tids[i];
           const uint8_t* term = bv.term_bytes + bv.term_boff[tid];
           const uint32_t tl = bv.term_boff[tid + 1] - bv.term_boff[tid];
-          const bool must = (flags & kQVerify) != 0 || bv.term_koff[tid + 1] == bv.term_koff[tid];
+          const bool must = terms_filter && ((flags & kQVerify) != 0 || bv.term_koff[tid + 1] == bv.term_koff[tid]);
           const uint32_t tf_u = doc_count_term(d, term, tl, sp.compute_score == 0);
           if (must && tf_u == 0 && tl != 0) {
             keep = false;

@@ -657,6 +657,74 @@ def test_mixed_boolean_batch_with_filters(mgx, oracle):
         assert np.allclose([s for _, s in got], [s for _, s in want], rtol=1e-9, atol=0)
 
 
+def test_scored_boolean_programs_in_a_batch(mgx, oracle):
+    """SORT _score over boolean queries (search_handler.cpp:405-470 scores every result shape): the results of the
+    AST are scored with the AST's TERM nodes that are not below a NOT (CollectAstScoringTerms,
+    search_pipeline.cpp:232-254; duplicates kept), each with its verified df, then SortByScore. Oracle: eval_boolean
+    for the set, the df of every term from a scored single-term query, score_documents + sort_by_score."""
+    rnd = random.Random(515)
+    c = corpus_mod.generate("cjk", 20000, 0xC6, alphabet=96, min_len=6, max_len=40)
+    gi = mgx.Index(2, 0, True, dense_threshold=0.02)
+    gi.build(c.doc_ids, c.arena, c.offsets)
+    oi = oracle.index(2, 0, True)
+    oi.build_bulk(c.doc_ids, c.arena, c.offsets, 8)
+    n = c.n_docs
+    tl, dc = oi.bm25_stats()
+    avgdl = tl / dc
+
+    def term():
+        t = c.text(rnd.randrange(n)).decode()
+        ln = rnd.randint(1, 4)
+        st = rnd.randrange(0, len(t) - ln + 1)
+        return t[st:st + ln].encode()
+
+    def positive_leaves(ops, args):
+        """TERM operands not below a NOT, left to right."""
+        stack = []  # per entry: list of (term index, under_not)
+        for op, a in zip(ops, args):
+            if op == 0:
+                stack.append([(a, False)])
+            elif op == 3:
+                stack.append([(t, True) for t, _ in stack.pop()])
+            else:
+                kids = stack[len(stack) - a:]
+                del stack[len(stack) - a:]
+                stack.append([x for k in kids for x in k])
+        return [t for t, neg in stack[-1] if not neg]
+
+    shapes = [([0, 0, 1], [0, 1, 2]),                    # A AND B
+              ([0, 0, 3, 1], [0, 1, 0, 2]),              # A AND NOT B
+              ([0, 0, 2, 0, 1], [0, 1, 2, 2, 2]),        # (A OR B) AND C
+              ([0, 0, 1, 0, 3, 3, 1], [0, 0, 2, 1, 0, 0, 2]),  # (A AND A) AND NOT NOT B: duplicate term, sticky NOT
+              ([0, 0, 2], [0, 1, 2])]                    # A OR B (no driver list: every document is evaluated)
+    queries, programs, expect = [], [], []
+    for qi in range(60):
+        ops, args = shapes[qi % len(shapes)]
+        terms = [term() for _ in range(max(args[i] for i, o in enumerate(ops) if o == 0) + 1)]
+        queries.append(terms)
+        programs.append((ops, args))
+    uniq = sorted({t for q in queries for t in q})
+    df_of = dict(zip(uniq, oi.query_batch([[t] for t in uniq], score=True, limit=1).df.tolist()))
+    for kw in (dict(descending=True, limit=20, offset=0), dict(descending=False, limit=7, offset=2)):
+        g = gi.query_batch(queries, programs=programs, score=True, **kw)
+        for qi, (terms, (ops, args)) in enumerate(zip(queries, programs)):
+            results = oi.eval_boolean(ops, args, terms)
+            scoring = [terms[t] for t in positive_leaves(ops, args)]
+            scores = oi.score_documents(results, scoring, [df_of[t] for t in scoring], dc, avgdl)
+            want = oracle.sort_by_score(results, scores, kw["descending"], kw["limit"], kw["offset"])
+            score_of = dict(zip(results.tolist(), scores.tolist()))
+            k = int(g.count[qi])
+            assert int(g.total[qi]) == results.size, (qi, terms, ops)
+            assert k == want.size, (qi, k, want.size)
+            gs = g.scores[qi, :k]
+            ws = np.array([score_of[int(d)] for d in want])
+            assert np.allclose(gs, ws, rtol=1e-9, atol=0), (qi, terms, ops, gs[:4], ws[:4])
+            if not np.array_equal(g.ids[qi, :k], want):
+                for i in np.nonzero(g.ids[qi, :k] != want)[0]:  # only near-ties (summation order) may swap
+                    assert np.isclose(ws[i], ws[max(0, i - 1):i + 2], rtol=1e-12, atol=0).sum() >= 2, (qi, i)
+    assert sum(int(x) for x in g.total) > 500
+
+
 # ----------------------------------------------------------------------------------------- C5 in small: huge batches
 def test_large_batch_of_short_queries_picks_streaming_df(mgx, oracle, monkeypatch):
     """BASELINE config 5 in small: tens of thousands of 1-2-term queries of 2-3 code points in ONE batch. With that
