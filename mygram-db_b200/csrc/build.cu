@@ -58,6 +58,7 @@ __device__ __forceinline__ uint4 ld_stream_16(const uint8_t* p) {
 constexpr int kFlatThreads = 256;
 constexpr uint32_t kFlatTile = kFlatThreads * 16;   // 4096 bytes
 constexpr uint32_t kFlatDocCap = 1024;
+constexpr int kFlatPerThread = 4;                    // characters a thread takes per strip of the window phase
 constexpr uint32_t kFlatHalo = kMaxNgramSize - 1;   // characters after the tile a window can reach
 
 struct FlatSmem {
@@ -197,12 +198,15 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
         for (int j = 0; j < 16; ++j) {
           const int32_t p = c0 + j;
           cps[j] = 0;
-          if (p >= r_begin && p < r_end) {
+          const uint32_t b0 = byte_of(w, j);
+          // a continuation byte (10xxxxxx) starts no character, whatever document it lies in: two of three bytes of
+          // CJK text leave here, before the document lookup and the decoder
+          if ((b0 & 0xC0u) != 0x80u && p >= r_begin && p < r_end) {
             while (p >= sm.docrel[dj + 1]) {  // next document (empty documents are stepped over)
               ++dj;
             }
             uint32_t cp = 0;
-            const int len = parse_utf8(byte_of(w, j), byte_of(w, j + 1), byte_of(w, j + 2), byte_of(w, j + 3),
+            const int len = parse_utf8(b0, byte_of(w, j + 1), byte_of(w, j + 2), byte_of(w, j + 3),
                                        static_cast<uint64_t>(sm.docrel[dj + 1] - p), &cp);
             if (len > 0) {
               flags |= 1u << j;
@@ -257,61 +261,76 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
       __syncthreads();
       const uint32_t n_all = n_chars + sm.n_halo;
 
-      // ---- C: windows (GenerateHybridNgrams, string_utils.cpp:452-509), one thread per character
+      // ---- C: windows (GenerateHybridNgrams, string_utils.cpp:452-509). A strip is kFlatPerThread * 256 characters,
+      // every thread takes kFlatPerThread CONSECUTIVE ones (text order = thread order, then the order inside a
+      // thread), so a tile of CJK text needs two block-wide scans instead of six.
       uint64_t strip_base = EMIT ? tile_off[tile] + emitted_tile : 0;  // slot of the strip's first n-gram
-      for (uint32_t k0 = 0; k0 < n_chars; k0 += kFlatThreads) {
-        const uint32_t k = k0 + threadIdx.x;
-        bool ok = false;
-        uint64_t key = 0;
-        uint32_t dk = 0;
-        if (k < n_chars) {
-          const uint32_t c = sm.cp[k];
-          dk = sm.doc[k];
-          const bool cjk = is_cjk_ideograph(c);
-          const int size = cjk ? kanji : ngram;  // :484-485: chosen by the START code point
-          // :487 the window must fit the document: its last character exists and is in the same document
-          if (k + static_cast<uint32_t>(size) <= n_all && sm.doc[k + size - 1] == dk) {
-            ok = true;
-            key = static_cast<uint64_t>(c) + 1;
-            if (wide_words > 0) {
-              for (int j = 1; j < size; ++j) {
-                if (!cross && is_cjk_ideograph(sm.cp[k + j]) != cjk) {  // :491-503
-                  ok = false;
+      for (uint32_t k0 = 0; k0 < n_chars; k0 += kFlatThreads * kFlatPerThread) {
+        uint32_t ok_mask = 0;
+        uint64_t key[kFlatPerThread];
+#pragma unroll
+        for (int c4 = 0; c4 < kFlatPerThread; ++c4) {
+          const uint32_t k = k0 + threadIdx.x * kFlatPerThread + c4;
+          key[c4] = 0;
+          if (k < n_chars) {
+            const uint32_t c = sm.cp[k];
+            const uint32_t dk = sm.doc[k];
+            const bool cjk = is_cjk_ideograph(c);
+            const int size = cjk ? kanji : ngram;  // :484-485: chosen by the START code point
+            // :487 the window must fit the document: its last character exists and is in the same document
+            if (k + static_cast<uint32_t>(size) <= n_all && sm.doc[k + size - 1] == dk) {
+              bool ok = true;
+              uint64_t kk = static_cast<uint64_t>(c) + 1;
+              if (wide_words > 0) {
+                for (int j = 1; j < size; ++j) {
+                  if (!cross && is_cjk_ideograph(sm.cp[k + j]) != cjk) {  // :491-503
+                    ok = false;
+                  }
                 }
               }
-            }
-            for (int j = 1; j < width && wide_words == 0; ++j) {
-              uint64_t field = 0;
-              if (j < size) {
-                const uint32_t cj = sm.cp[k + j];
-                if (!cross && is_cjk_ideograph(cj) != cjk) {  // :491-503 legacy boundary rejection
-                  ok = false;
+              for (int j = 1; j < width && wide_words == 0; ++j) {
+                uint64_t field = 0;
+                if (j < size) {
+                  const uint32_t cj = sm.cp[k + j];
+                  if (!cross && is_cjk_ideograph(cj) != cjk) {  // :491-503 legacy boundary rejection
+                    ok = false;
+                  }
+                  field = static_cast<uint64_t>(cj) + 1;
                 }
-                field = static_cast<uint64_t>(cj) + 1;
+                kk = (kk << 21) | field;
               }
-              key = (key << 21) | field;
+              key[c4] = kk;
+              ok_mask |= ok ? (1u << c4) : 0u;
             }
           }
         }
         uint32_t n_emit = 0;
-        const uint32_t rank = flat_block_scan(ok ? 1u : 0u, sm.warp_cnt, &n_emit);
-        if (EMIT && ok && wide_words > 0) {
-          const uint64_t slot = strip_base + rank;
-          const int size = is_cjk_ideograph(sm.cp[k]) ? kanji : ngram;
-          for (int w = 0; w < wide_words; ++w) {
-            uint64_t word = 0;
-            for (int f = 0; f < 3; ++f) {
-              const int j = 3 * w + f;
-              word = (word << 21) | (j < size ? static_cast<uint64_t>(sm.cp[k + j]) + 1 : 0ULL);
+        uint32_t rank = flat_block_scan(static_cast<uint32_t>(__popc(ok_mask)), sm.warp_cnt, &n_emit);
+        if (EMIT) {
+#pragma unroll
+          for (int c4 = 0; c4 < kFlatPerThread; ++c4) {
+            if ((ok_mask >> c4) & 1u) {
+              const uint32_t k = k0 + threadIdx.x * kFlatPerThread + c4;
+              const uint32_t dk = sm.doc[k];
+              const uint64_t slot = strip_base + rank;
+              ++rank;
+              if (wide_words > 0) {
+                const int size = is_cjk_ideograph(sm.cp[k]) ? kanji : ngram;
+                for (int w = 0; w < wide_words; ++w) {
+                  uint64_t word = 0;
+                  for (int f = 0; f < 3; ++f) {
+                    const int j = 3 * w + f;
+                    word = (word << 21) | (j < size ? static_cast<uint64_t>(sm.cp[k + j]) + 1 : 0ULL);
+                  }
+                  keys_out[static_cast<uint64_t>(w) * wide_stride + slot] = word;
+                }
+              } else {
+                const uint64_t in_doc = static_cast<uint64_t>(static_cast<int64_t>(sm.pos[k]) - sm.docrel[dk]);
+                keys_out[slot] = pos_bits > 0 ? ((key[c4] << pos_bits) | umin_u64(in_doc, pos_max)) : key[c4];
+              }
+              docs_out[slot] = r_first + dk;
             }
-            keys_out[static_cast<uint64_t>(w) * wide_stride + slot] = word;
           }
-          docs_out[slot] = r_first + dk;
-        } else if (EMIT && ok) {
-          const uint64_t slot = strip_base + rank;
-          const uint64_t in_doc = static_cast<uint64_t>(static_cast<int64_t>(sm.pos[k]) - sm.docrel[dk]);
-          keys_out[slot] = pos_bits > 0 ? ((key << pos_bits) | umin_u64(in_doc, pos_max)) : key;
-          docs_out[slot] = r_first + dk;
         }
         strip_base += n_emit;
         emitted_tile += n_emit;
@@ -425,31 +444,64 @@ struct Heads {
   uint32_t terms;
 };
 
-// pb = position bits carried in the low end of every key (0 if none): n-gram identity is key >> pb
-__device__ __forceinline__ Heads head_flags(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ docs,
-                                            uint64_t i, uint64_t n, int pb, uint64_t* key_out) {
-  Heads h{0, 0};
-  if (i >= n) {
-    return h;
+// pb = position bits carried in the low end of every key (0 if none): n-gram identity is key >> pb.
+//
+// Both CSR kernels walk the sorted pairs WARP-STRIPED: a CTA takes kCsrTile pairs, warp w of it the 256 consecutive
+// pairs [w * 256, (w + 1) * 256) as kCsrItems rows of 32 (row k, lane l = pair w * 256 + k * 32 + l). Every load is a
+// full-width coalesced row, the neighbours a head flag needs come from the next lane's register (a shuffle) instead
+// of a second and third load of the same array, and the rank of a head inside a row is a ballot and a popcount.
+struct CsrRows {
+  uint64_t key[kCsrItems + 1];  // row kCsrItems: lanes 0, 1 hold the two pairs after the warp's range
+  uint32_t doc[kCsrItems + 1];
+  uint64_t prev_key;            // lane 0: the pair before the warp's range (kInvalidKey if none)
+  uint32_t prev_doc;
+};
+
+__device__ __forceinline__ void csr_load_rows(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ docs,
+                                              uint64_t wbase, uint64_t n, unsigned lane, bool tail, CsrRows* r) {
+#pragma unroll
+  for (int k = 0; k < kCsrItems; ++k) {
+    const uint64_t i = wbase + static_cast<uint64_t>(k) * 32 + lane;
+    const bool in = i < n;
+    r->key[k] = in ? keys[i] : kInvalidKey;
+    r->doc[k] = in ? docs[i] : 0u;
   }
-  const uint64_t k = keys[i];
-  *key_out = k;
-  if (k == kInvalidKey || (k >> pb) == 0) {
-    return h;  // placeholder slots (fused tokenizer: key 0; no n-gram has it, its first field would be >= 1)
+  r->key[kCsrItems] = kInvalidKey;
+  r->doc[kCsrItems] = 0;
+  if (tail && lane < 2) {
+    const uint64_t i = wbase + static_cast<uint64_t>(kCsrItems) * 32 + lane;
+    if (i < n) {
+      r->key[kCsrItems] = keys[i];
+      r->doc[kCsrItems] = docs[i];
+    }
   }
-  const bool term_head = (i == 0) || (keys[i - 1] >> pb) != (k >> pb);
-  const bool pair_head = term_head || docs[i - 1] != docs[i];
-  h.terms = term_head;
-  h.pairs = pair_head;
-  return h;
+  r->prev_key = kInvalidKey;
+  r->prev_doc = 0;
+  if (lane == 0 && wbase > 0 && wbase - 1 < n) {
+    r->prev_key = keys[wbase - 1];
+    r->prev_doc = docs[wbase - 1];
+  }
 }
 
-__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) {
-    v += __shfl_xor_sync(0xffffffffu, v, s);
+// head flags of row k: bit 0 = first pair of an (n-gram, document) run, bit 1 = first pair of an n-gram
+__device__ __forceinline__ uint32_t csr_row_heads(const CsrRows& r, int k, uint64_t wbase, unsigned lane, int pb) {
+  const uint64_t key = r.key[k];
+  // the pair before this one: the previous lane, the last lane of the previous row, or the pair before the range
+  uint64_t pk = __shfl_up_sync(0xffffffffu, key, 1);
+  uint32_t pd = __shfl_up_sync(0xffffffffu, r.doc[k], 1);
+  const uint64_t wrap_k = __shfl_sync(0xffffffffu, k > 0 ? r.key[k > 0 ? k - 1 : 0] : r.prev_key, k > 0 ? 31 : 0);
+  const uint32_t wrap_d = __shfl_sync(0xffffffffu, k > 0 ? r.doc[k > 0 ? k - 1 : 0] : r.prev_doc, k > 0 ? 31 : 0);
+  if (lane == 0) {
+    pk = wrap_k;
+    pd = wrap_d;
   }
-  return v;
+  if (key == kInvalidKey || (key >> pb) == 0) {
+    return 0;  // beyond the end / placeholder slots (fused tokenizer: key 0; no n-gram has it)
+  }
+  const bool first = wbase == 0 && k == 0 && lane == 0;
+  const bool term_head = first || pk == kInvalidKey || (pk >> pb) != (key >> pb);
+  const bool pair_head = term_head || pd != r.doc[k];
+  return (pair_head ? 1u : 0u) | (term_head ? 2u : 0u);
 }
 
 __global__ void __launch_bounds__(kCsrThreads) csr_count_kernel(const uint64_t* __restrict__ keys,
@@ -458,22 +510,22 @@ __global__ void __launch_bounds__(kCsrThreads) csr_count_kernel(const uint64_t* 
                                                                 uint64_t* __restrict__ block_terms) {
   __shared__ uint32_t sp[kCsrThreads / 32];
   __shared__ uint32_t st[kCsrThreads / 32];
-  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kCsrTile;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint64_t wbase = static_cast<uint64_t>(blockIdx.x) * kCsrTile + static_cast<uint64_t>(warp) * (32 * kCsrItems);
+  CsrRows r;
+  csr_load_rows(keys, docs, wbase, n, lane, false, &r);
   uint32_t pairs = 0;
   uint32_t terms = 0;
 #pragma unroll
   for (int k = 0; k < kCsrItems; ++k) {
-    const uint64_t i = base + static_cast<uint64_t>(k) * kCsrThreads + threadIdx.x;
-    uint64_t key;
-    const Heads h = head_flags(keys, docs, i, n, pb, &key);
-    pairs += h.pairs;
-    terms += h.terms;
+    const uint32_t h = csr_row_heads(r, k, wbase, lane, pb);
+    pairs += __popc(__ballot_sync(0xffffffffu, (h & 1u) != 0));
+    terms += __popc(__ballot_sync(0xffffffffu, (h & 2u) != 0));
   }
-  pairs = warp_sum_u32(pairs);
-  terms = warp_sum_u32(terms);
-  if ((threadIdx.x & 31) == 0) {
-    sp[threadIdx.x >> 5] = pairs;
-    st[threadIdx.x >> 5] = terms;
+  if (lane == 0) {
+    sp[warp] = pairs;
+    st[warp] = terms;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -560,68 +612,81 @@ __global__ void __launch_bounds__(kCsrThreads) csr_write_kernel(const uint64_t* 
                                                                 uint16_t* __restrict__ post_pos2) {
   __shared__ uint32_t sp[kCsrThreads / 32];
   __shared__ uint32_t st[kCsrThreads / 32];
-  // thread t owns kCsrItems consecutive items so scan order == array order
-  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kCsrTile + static_cast<uint64_t>(threadIdx.x) * kCsrItems;
-  Heads h[kCsrItems];
-  uint64_t key[kCsrItems];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const uint64_t wbase = static_cast<uint64_t>(blockIdx.x) * kCsrTile + static_cast<uint64_t>(warp) * (32 * kCsrItems);
+  CsrRows r;
+  csr_load_rows(keys, docs, wbase, n, lane, pb > 0, &r);
+  uint32_t heads[kCsrItems];
   uint32_t pairs = 0;
   uint32_t terms = 0;
 #pragma unroll
   for (int k = 0; k < kCsrItems; ++k) {
-    key[k] = 0;
-    h[k] = head_flags(keys, docs, base + k, n, pb, &key[k]);
-    pairs += h[k].pairs;
-    terms += h[k].terms;
+    heads[k] = csr_row_heads(r, k, wbase, lane, pb);
+    pairs += __popc(__ballot_sync(0xffffffffu, (heads[k] & 1u) != 0));
+    terms += __popc(__ballot_sync(0xffffffffu, (heads[k] & 2u) != 0));
   }
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned warp = threadIdx.x >> 5;
-  uint32_t ip = pairs;
-  uint32_t it = terms;
-#pragma unroll
-  for (int s = 1; s < 32; s <<= 1) {
-    const uint32_t op = __shfl_up_sync(0xffffffffu, ip, s);
-    const uint32_t ot = __shfl_up_sync(0xffffffffu, it, s);
-    if (lane >= static_cast<unsigned>(s)) {
-      ip += op;
-      it += ot;
-    }
-  }
-  if (lane == 31) {
-    sp[warp] = ip;
-    st[warp] = it;
+  if (lane == 0) {
+    sp[warp] = pairs;
+    st[warp] = terms;
   }
   __syncthreads();
-  uint64_t pp = block_pairs[blockIdx.x] + ip - pairs;
-  uint64_t tp = block_terms[blockIdx.x] + it - terms;
+  uint64_t pp = block_pairs[blockIdx.x];  // output slot of the warp's next pair head / term head
+  uint64_t tp = block_terms[blockIdx.x];
   for (unsigned w = 0; w < warp; ++w) {
     pp += sp[w];
     tp += st[w];
   }
+  const uint64_t pos_mask = pb > 0 ? (1ULL << pb) - 1 : 0;
 #pragma unroll
   for (int k = 0; k < kCsrItems; ++k) {
-    if (h[k].pairs) {
-      const uint32_t doc = docs[base + k];
-      postings[pp] = doc;
+    const unsigned pair_mask = __ballot_sync(0xffffffffu, (heads[k] & 1u) != 0);
+    const unsigned term_mask = __ballot_sync(0xffffffffu, (heads[k] & 2u) != 0);
+    const uint64_t key = r.key[k];
+    const uint32_t doc = r.doc[k];
+    // the two pairs after this one (only the position payload looks at them)
+    uint64_t k1 = kInvalidKey, k2 = kInvalidKey;
+    uint32_t d1 = 0, d2 = 0;
+    if (pb > 0) {
+      k1 = __shfl_down_sync(0xffffffffu, key, 1);
+      d1 = __shfl_down_sync(0xffffffffu, doc, 1);
+      k2 = __shfl_down_sync(0xffffffffu, key, 2);
+      d2 = __shfl_down_sync(0xffffffffu, doc, 2);
+      const uint64_t nk = __shfl_sync(0xffffffffu, r.key[k + 1], (lane + 2) & 31);  // lanes 30, 31 read lanes 0, 1
+      const uint32_t nd = __shfl_sync(0xffffffffu, r.doc[k + 1], (lane + 2) & 31);
+      const uint64_t nk0 = __shfl_sync(0xffffffffu, r.key[k + 1], 0);
+      const uint32_t nd0 = __shfl_sync(0xffffffffu, r.doc[k + 1], 0);
+      if (lane == 31) {
+        k1 = nk0;
+        d1 = nd0;
+      }
+      if (lane >= 30) {
+        k2 = nk;
+        d2 = nd;
+      }
+    }
+    if ((heads[k] & 1u) != 0) {
+      const uint64_t at = pp + __popc(pair_mask & lt_mask);
+      postings[at] = doc;
       if (pb > 0) {
         // The sort is stable and the tokenizer emits a document's n-grams in text order, so the head of a
         // (n-gram, document) run is the first occurrence; a second entry of the run means "more than once".
-        const uint64_t i = base + k;
-        const uint64_t pos_mask = (1ULL << pb) - 1;
-        const uint64_t k1 = i + 1 < n ? keys[i + 1] : kInvalidKey;
-        const bool multi = i + 1 < n && (k1 >> pb) == (key[k] >> pb) && docs[i + 1] == doc;
-        const bool third = multi && i + 2 < n && (keys[i + 2] >> pb) == (key[k] >> pb) && docs[i + 2] == doc;
-        const uint64_t pos = key[k] & pos_mask;
+        const bool multi = k1 != kInvalidKey && (k1 >> pb) == (key >> pb) && d1 == doc;
+        const bool third = multi && k2 != kInvalidKey && (k2 >> pb) == (key >> pb) && d2 == doc;
+        const uint64_t pos = key & pos_mask;
         const uint64_t pos2 = multi ? (k1 & pos_mask) : kPosUnknown;
-        post_pos[pp] = static_cast<uint16_t>((pos < kPosUnknown ? pos : kPosUnknown) | (multi ? kPosMulti : 0));
-        post_pos2[pp] = static_cast<uint16_t>((pos2 < kPosUnknown ? pos2 : kPosUnknown) | (third ? kPosMulti : 0));
+        post_pos[at] = static_cast<uint16_t>((pos < kPosUnknown ? pos : kPosUnknown) | (multi ? kPosMulti : 0));
+        post_pos2[at] = static_cast<uint16_t>((pos2 < kPosUnknown ? pos2 : kPosUnknown) | (third ? kPosMulti : 0));
       }
-      if (h[k].terms) {
-        term_keys[tp] = key[k] >> pb;
-        term_off[tp] = pp;
-        ++tp;
+      if ((heads[k] & 2u) != 0) {
+        const uint64_t tat = tp + __popc(term_mask & lt_mask);
+        term_keys[tat] = key >> pb;
+        term_off[tat] = at;
       }
-      ++pp;
     }
+    pp += __popc(pair_mask);
+    tp += __popc(term_mask);
   }
 }
 

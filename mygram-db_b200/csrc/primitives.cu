@@ -372,6 +372,40 @@ __global__ void __launch_bounds__(kRadix) digit_scan_kernel(const unsigned long 
   base[blockIdx.x * kRadix + threadIdx.x] = block_exclusive_scan_u64<kRadix>(v, &total, smem);
 }
 
+// Lanes of the warp whose digit equals mine. match.any walks the distinct values of the warp one after the other
+// (about 30 of them when an 8-bit digit is uniformly distributed); eight ballots cost the same whatever the digits are.
+// The host picks per pass: BALLOT when a warp's 32 digits are expected to hold more than kBallotDistinct different
+// values (measured at 10M documents: uniform low bytes 8.9 -> 7.9 ms per pass with ballots, the skewed high bytes of
+// CJK code points 5.6 -> 7.5 ms, so those keep match.any).
+template <bool BALLOT>
+__device__ __forceinline__ unsigned digit_peers(uint32_t d) {
+  if (!BALLOT) {
+    return __match_any_sync(0xffffffffu, d);
+  }
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 9; ++b) {  // 8 digit bits + the "invalid item" bit
+    const unsigned set = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+    peers &= ((d >> b) & 1u) ? set : ~set;
+  }
+  return peers;
+}
+constexpr double kBallotDistinct = 20.0;
+constexpr int kLookBackWindow = 4;  // predecessor entries a look-back fetches side by side
+
+#ifdef MGX_OS_TIMING
+__device__ unsigned long long g_os_timing[8];
+#define OS_T(i)                                         \
+  if (threadIdx.x == 0) {                               \
+    const long long now_ = clock64();                   \
+    atomicAdd(&g_os_timing[i], static_cast<unsigned long long>(now_ - t_last_)); \
+    t_last_ = now_;                                     \
+  }
+#else
+#define OS_T(i)
+#endif
+
+template <bool BALLOT>
 __global__ void __launch_bounds__(kSortThreads, 2)
 radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                       uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint64_t n, int shift,
@@ -410,6 +444,9 @@ radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __re
   }
   __syncthreads();
   uint32_t phases = 0;  // bit s: parity the next wait on stage s uses
+#ifdef MGX_OS_TIMING
+  long long t_last_ = clock64();
+#endif
 
   for (int it = 0;; ++it) {
     const int st = it & 1;
@@ -448,19 +485,21 @@ radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __re
       sm.warp_cnt[w][threadIdx.x] = 0;
     }
     __syncthreads();  // counters cleared; every thread holds its items, so the stage can take the reordered tile
+    OS_T(0)  // wait for the tile + registers
 
     // phase 1: per-warp digit counts
 #pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
       const bool valid = warp_off + r * 32 + lane < tile_n;
       const uint32_t d = valid ? (static_cast<uint32_t>(key[r] >> shift) & mask) : 0x1FFu;
-      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const unsigned peers = digit_peers<BALLOT>(d);
       if (valid && (peers & lt_mask) == 0) {
         sm.warp_cnt[warp][d] += __popc(peers);
       }
       __syncwarp();
     }
     __syncthreads();
+    OS_T(1)  // phase 1
     uint32_t my_cnt = 0;
     {
       // thread d: tile count of digit d (published at once as this tile's AGGREGATE), the tile-local start and the
@@ -503,15 +542,26 @@ radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __re
       }
     }
     __syncthreads();
+    OS_T(2)  // digit scan
     // phase 2: rank inside the tile and place into the stage. Nothing here needs the global digit starts, so the
-    // predecessors get this long to publish before the look-back below starts waiting for them.
+    // predecessors get this long to publish before the look-back below starts waiting for them; the entries of the
+    // nearest kLookBackWindow predecessors are fetched NOW, side by side, and looked at after the ranking (a
+    // look-back step is a dependent L2 round trip: one at a time they were 30 % of a pass's stall samples).
+    unsigned long long lb_pre[kLookBackWindow];
+#pragma unroll
+    for (int j = 0; j < kLookBackWindow; ++j) {
+      lb_pre[j] = tile > static_cast<uint32_t>(j)
+                      ? *reinterpret_cast<volatile const unsigned long long*>(tile_state + static_cast<uint64_t>(tile - 1 - j) * kRadix +
+                                                                           threadIdx.x)
+                      : 0ULL;
+    }
     uint64_t* const skeys = sm.keys[st];
     uint32_t* const svals = sm.vals[st];
 #pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
       const bool valid = warp_off + r * 32 + lane < tile_n;
       const uint32_t d = valid ? (static_cast<uint32_t>(key[r] >> shift) & mask) : 0x1FFu;
-      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const unsigned peers = digit_peers<BALLOT>(d);
       uint32_t base = 0;
       if (valid) {
         base = sm.warp_cnt[warp][d];
@@ -527,40 +577,57 @@ radix_onesweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __re
         svals[pos] = val[r];
       }
     }
+    OS_T(3)  // phase 2 (thread 0's share)
     {
       // look back: thread d sums the counts of digit d over the preceding tiles until it meets an inclusive prefix
       const unsigned d = threadIdx.x;
       const uint32_t cnt = my_cnt;
       volatile unsigned long long* const my_state = tile_state + static_cast<uint64_t>(tile) * kRadix + d;
       unsigned long long before = 0;
-      for (uint32_t p = tile; p > 0;) {
-        --p;
-        volatile const unsigned long long* const ps = tile_state + static_cast<uint64_t>(p) * kRadix + d;
-        unsigned long long v = *ps;
-        while ((v & (3ULL << 62)) == 0 || (v & (0xFFULL << 54)) != pass_tag) {
-          __nanosleep(40);
-          v = *ps;
+      uint32_t p = tile;  // the next entry to look at is p - 1
+      bool found = tile == 0;
+      while (!found) {
+#pragma unroll
+        for (int j = 0; j < kLookBackWindow; ++j) {
+          if (!found) {
+            --p;
+            volatile const unsigned long long* const ps = tile_state + static_cast<uint64_t>(p) * kRadix + d;
+            unsigned long long v = lb_pre[j];
+            while ((v & (3ULL << 62)) == 0 || (v & (0xFFULL << 54)) != pass_tag) {
+              __nanosleep(20);
+              v = *ps;
+            }
+            before += v & kOsValueMask;
+            found = (v & kOsFlagPrefix) != 0 || p == 0;
+          }
         }
-        before += v & kOsValueMask;
-        if ((v & kOsFlagPrefix) != 0) {
-          break;
+        if (!found) {  // next window, again side by side
+#pragma unroll
+          for (int j = 0; j < kLookBackWindow; ++j) {
+            lb_pre[j] = p > static_cast<uint32_t>(j)
+                            ? *reinterpret_cast<volatile const unsigned long long*>(tile_state + static_cast<uint64_t>(p - 1 - j) * kRadix + d)
+                            : 0ULL;
+          }
         }
       }
       if (tile + 1 < n_tiles) {
         *my_state = kOsFlagPrefix | pass_tag | (before + cnt);
       }
-      sm.global_base[d] = digit_base[d] + before;
+      sm.global_base[d] = digit_base[d] + before - sm.local_start[d];  // position of tile item i: global_base[d] + i
     }
+    OS_T(4)  // look-back (thread 0's digit)
     __syncthreads();
+    OS_T(5)  // waiting for the other digits' look-backs
     // phase 3: coalesced write-out, run by run
     for (uint32_t i = threadIdx.x; i < tile_n; i += kSortThreads) {
       const uint64_t k = skeys[i];
       const uint32_t d = static_cast<uint32_t>(k >> shift) & mask;
-      const uint64_t pos = sm.global_base[d] + (i - sm.local_start[d]);
+      const uint64_t pos = sm.global_base[d] + i;
       keys_out[pos] = k;
       vals_out[pos] = svals[i];
     }
     __syncthreads();  // the stage is free: the next round's claim may start a copy into it
+    OS_T(6)  // phase 3
   }
 }
 
@@ -697,7 +764,9 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
   if (!attr_set) {
     MGX_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(sizeof(ScatterSmem))));
-    MGX_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MGX_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(sizeof(OsSmem))));
+    MGX_CUDA(cudaFuncSetAttribute(radix_onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(sizeof(OsSmem))));
     attr_set = true;
   }
@@ -747,7 +816,8 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
     // one memset per sort: the entries carry the pass number, so the passes do not clear them in between
     MGX_CUDA(cudaMemsetAsync(d_counters, 0, kMaxPasses * sizeof(uint32_t), stream));
     MGX_CUDA(cudaMemsetAsync(d_state, 0, hist_len * sizeof(unsigned long long), stream));
-    MGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_onesweep_kernel, kSortThreads, sizeof(OsSmem)));
+    MGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_onesweep_kernel<true>, kSortThreads,
+                                                           sizeof(OsSmem)));
     per_sm = std::max(per_sm, 1);
   }
   for (int p = 0; p < passes; ++p) {
@@ -762,12 +832,34 @@ SortResult radix_sort_pairs(uint64_t* d_keys_a, uint32_t* d_vals_a, uint64_t* d_
     const uint32_t mask = pl.mask[p];
     if (!classic) {
       const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(sm_count) * per_sm));
-      radix_onesweep_kernel<<<grid, kSortThreads, sizeof(OsSmem), stream>>>(
+      // expected number of different digit values among 32 keys: sum over d of 1 - (1 - share_d)^32
+      double distinct = 0.0;
+      for (int d = 0; d < kRadix; ++d) {
+        const double share = static_cast<double>(ghist[static_cast<size_t>(p) * kRadix + d]) / static_cast<double>(n);
+        distinct += 1.0 - std::pow(1.0 - share, 32.0);
+      }
+      static const char* force = std::getenv("MGX_OS_RANK");  // "ballot" / "match": A/B measurements
+      const bool ballot = force != nullptr ? std::strcmp(force, "ballot") == 0 : distinct > kBallotDistinct;
+      auto kernel = ballot ? radix_onesweep_kernel<true> : radix_onesweep_kernel<false>;
+      kernel<<<grid, kSortThreads, sizeof(OsSmem), stream>>>(
           cur.keys, cur.vals, alt.keys, alt.vals, n, shift, mask, d_dbase + static_cast<size_t>(p) * kRadix, d_state,
           d_counters + p, n_tiles, static_cast<unsigned long long>(p + 1) << 54);
       MGX_LAUNCH_CHECK();
       std::swap(cur, alt);
       trace.mark("  sort: one-sweep pass");
+#ifdef MGX_OS_TIMING
+      {
+        unsigned long long t[8] = {0};
+        MGX_CUDA(cudaMemcpyFromSymbol(t, g_os_timing, sizeof(t)));
+        unsigned long long zero[8] = {0};
+        MGX_CUDA(cudaMemcpyToSymbol(g_os_timing, zero, sizeof(zero)));
+        double tot = 0;
+        for (int i = 0; i < 7; ++i) tot += static_cast<double>(t[i]);
+        fprintf(stderr, "    [os timing %s] load %.1f%% phase1 %.1f%% scan %.1f%% phase2 %.1f%% lookback %.1f%% lb-others %.1f%% phase3 %.1f%%\n",
+                ballot ? "ballot" : "match", 100 * t[0] / tot, 100 * t[1] / tot, 100 * t[2] / tot, 100 * t[3] / tot,
+                100 * t[4] / tot, 100 * t[5] / tot, 100 * t[6] / tot);
+      }
+#endif
       continue;
     }
     radix_hist_kernel<<<n_tiles, kSortThreads, 0, stream>>>(cur.keys, n, shift, mask, d_hist, n_tiles);
