@@ -164,6 +164,16 @@ int mgx_index_posting_size(const mgx_index_t* index, const uint8_t* term, uint64
 /* PostingList::GetAll (posting_list.cpp:421-430): ascending doc ids of one n-gram. */
 int mgx_index_get_postings(const mgx_index_t* index, const uint8_t* term, uint64_t term_len, uint32_t* out,
                            uint64_t cap, uint64_t* out_count);
+/* The payload the device index keeps next to every posting of one n-gram (key width <= 2; this is the library's own
+ * extension of PostingList, used by the verified-df kernels -- search_pipeline.cpp:542-565 -- and exposed for tests and
+ * diagnostics). docs[i]: LOCAL index of the document (rank of its id in the shard); first[i] / second[i]: bits 0..14 =
+ * byte offset of the n-gram's first / second occurrence in the document's text (0x7FFF = not recorded), bit 15 =
+ * a further occurrence exists, bits 16..22 / 24..30 = signature of the character after / before that occurrence
+ * (0 = none; a signature of b bits is max(1, ((cp * 0x9E3779B1) >> 25) >> (7 - b))). layout[3] = {offset bits,
+ * next-signature bits, prev-signature bits} of this shard (all 0 when the index carries no payload). out_count = the
+ * list's length; at most cap entries are written; any output pointer may be NULL. */
+int mgx_index_get_posting_payload(const mgx_index_t* index, const uint8_t* term, uint64_t term_len, uint32_t* docs,
+                                  uint32_t* first, uint32_t* second, uint64_t cap, uint64_t* out_count, int* layout);
 /* Whole index as CSR in ascending term (UTF-8 byte) order. keys are packed
  * n-grams (mgx_key_to_utf8 decodes them). Sizes come from mgx_index_get_stats:
  * keys[n_terms], offsets[n_terms+1], postings[n_postings] (global doc ids).

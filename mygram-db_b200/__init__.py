@@ -147,6 +147,8 @@ def lib():
     L.mgx_index_commit.argtypes = [C.c_void_p]
     L.mgx_index_posting_size.argtypes = [C.c_void_p, u8p, C.c_uint64, u64p]
     L.mgx_index_get_postings.argtypes = [C.c_void_p, u8p, C.c_uint64, u32p, C.c_uint64, u64p]
+    L.mgx_index_get_posting_payload.argtypes = [C.c_void_p, u8p, C.c_uint64, u32p, u32p, u32p, C.c_uint64, u64p,
+                                                C.POINTER(C.c_int)]
     L.mgx_index_export.argtypes = [C.c_void_p, u64p, u64p, u32p]
     L.mgx_index_doc_lengths.argtypes = [C.c_void_p, u32p]
     L.mgx_key_to_utf8.argtypes = [C.c_uint64, C.c_int32, u8p]
@@ -458,6 +460,24 @@ class Index:
         return out.value
 
     count = posting_size
+
+    def posting_payload(self, term):
+        """(local docs, first-occurrence words, second-occurrence words, (offset, next, prev) bits) of one n-gram;
+        see mgx_index_get_posting_payload."""
+        b = _bytes(term)
+        buf = np.frombuffer(b, dtype=np.uint8).copy() if b else np.zeros(1, np.uint8)
+        n = C.c_uint64(0)
+        layout = (C.c_int * 3)()
+        _check(lib().mgx_index_get_posting_payload(self._h, _ptr(buf, u8p), len(b), None, None, None, 0, C.byref(n),
+                                                   layout))
+        cap = max(1, n.value)
+        docs = np.zeros(cap, np.uint32)
+        first = np.zeros(cap, np.uint32)
+        second = np.zeros(cap, np.uint32)
+        _check(lib().mgx_index_get_posting_payload(self._h, _ptr(buf, u8p), len(b), _ptr(docs, u32p),
+                                                   _ptr(first, u32p), _ptr(second, u32p), cap, C.byref(n), layout))
+        k = n.value
+        return docs[:k], first[:k], second[:k], tuple(layout)
 
     def export(self):
         """-> (terms list[bytes] ascending, posting offsets uint64[T+1], postings uint32[P] global ids)"""

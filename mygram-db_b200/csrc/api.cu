@@ -197,10 +197,13 @@ void fixed_ngram_keys_small(const uint8_t* term, uint64_t len, int ngram_size, i
     }
     keys->push_back(wkey[i]);
     if (key_toff != nullptr) {
-      const uint32_t off = cp_byte[wstart[i]];  // equal keys keep their start order: wstart[i] is the first
+      const uint32_t ws = wstart[i];  // equal keys keep their start order: wstart[i] is the first
+      const uint32_t off = cp_byte[ws];
       const uint32_t cnt = std::min<uint32_t>(j - i, 3);
-      key_toff->push_back(valid && off <= kTermOffsetMask ? static_cast<uint16_t>(off | (cnt << kTermCountShift))
-                                                          : kNoTermOffset);
+      key_toff->push_back(valid && off <= kTermOffsetMask
+                              ? (off | (cnt << kTermCountShift) |
+                                 toff_neighbours(ws > 0, ws > 0 ? cps[ws - 1] : 0, ws + n < n_cp, ws + n < n_cp ? cps[ws + n] : 0))
+                              : static_cast<uint32_t>(kNoTermOffset));
     }
     i = j;
   }
@@ -272,11 +275,22 @@ bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanj
       while (j < occ.size() && occ[j].first == occ[i].first) {
         ++j;
       }
-      const uint32_t off = cp_byte[occ[i].second];
+      const uint32_t ws = occ[i].second;  // window start (code point index) of the first occurrence
+      const uint32_t off = cp_byte[ws];
       keys->push_back(occ[i].first);  // sorted + unique == DeduplicateSorted, string_utils.h:192-196
       const uint32_t cnt = static_cast<uint32_t>(std::min<size_t>(j - i, 3));
-      key_toff->push_back(valid && off <= kTermOffsetMask ? static_cast<uint16_t>(off | (cnt << kTermCountShift))
-                                                          : kNoTermOffset);
+      // the window's size follows the tokenizer's rule (fixed, or chosen by the class of the start code point)
+      uint32_t wn = static_cast<uint32_t>(ngram_size);
+      if (kanji_ngram_size > 0) {  // same rule as hybrid_keys above
+        wn = static_cast<uint32_t>(is_cjk_ideograph(cps[ws]) ? kanji_ngram_size : (ngram_size > 0 ? ngram_size : 2));
+      } else if (ngram_size == 0) {
+        wn = is_cjk_ideograph(cps[ws]) ? 1u : 2u;
+      }
+      const bool has_next = ws + wn < cps.size();
+      key_toff->push_back(valid && off <= kTermOffsetMask
+                              ? (off | (cnt << kTermCountShift) |
+                                 toff_neighbours(ws > 0, ws > 0 ? cps[ws - 1] : 0, has_next, has_next ? cps[ws + wn] : 0))
+                              : static_cast<uint32_t>(kNoTermOffset));
       i = j;
     }
     return true;
@@ -2493,6 +2507,52 @@ int mgx_index_get_postings(const mgx_index_t* index, const uint8_t* term, uint64
   return mgx_search_and(index, term != nullptr ? term : kEmpty, offs, 1, 0, 0, out, cap, out_count);
 }
 
+namespace {
+// CSR range [b, e) of one n-gram's list (binary search over the device dictionary, one key per probe); false if the
+// index does not hold it. The caller holds a Reader and the device.
+bool find_term_range(Index& ix, const uint8_t* term, uint64_t term_len, uint64_t* b, uint64_t* e) {
+  uint64_t key = 0;
+  if (term == nullptr || !host_ngram_to_key(term, term_len, ix.width, &key) || ix.n_terms == 0) {
+    return false;
+  }
+  const int W = ix.wide_words;
+  uint64_t want[kMaxWideWords] = {key, 0, 0, 0};
+  if (W > 0) {
+    std::memcpy(want, host_wide_words(key, W), static_cast<size_t>(W) * sizeof(uint64_t));
+  }
+  const int nw = W > 0 ? W : 1;
+  const uint64_t* dict = W > 0 ? ix.d_wide_keys.p : ix.d_term_keys.p;
+  auto probe = [&](uint64_t at) {  // <0: dict[at] < want
+    uint64_t v[kMaxWideWords] = {0, 0, 0, 0};
+    MGX_CUDA(cudaMemcpy(v, dict + at * nw, static_cast<size_t>(nw) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    for (int w = 0; w < nw; ++w) {
+      if (v[w] != want[w]) {
+        return v[w] < want[w] ? -1 : 1;
+      }
+    }
+    return 0;
+  };
+  uint64_t lo = 0;
+  uint64_t hi = ix.n_terms;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) / 2;
+    if (probe(mid) < 0) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  if (lo >= ix.n_terms || probe(lo) != 0) {
+    return false;
+  }
+  uint64_t off[2];
+  MGX_CUDA(cudaMemcpy(off, ix.d_term_off.p + lo, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  *b = off[0];
+  *e = off[1];
+  return true;
+}
+}  // namespace
+
 int mgx_index_posting_size(const mgx_index_t* index, const uint8_t* term, uint64_t term_len, uint64_t* out) {
   if (index == nullptr || out == nullptr) {
     return invalid("null argument");
@@ -2506,42 +2566,48 @@ int mgx_index_posting_size(const mgx_index_t* index, const uint8_t* term, uint64
     Reader rd(h);
     Index& ix = h->ix;
     DeviceGuard guard(ix.device);
-    uint64_t key = 0;
-    if (term == nullptr || !host_ngram_to_key(term, term_len, ix.width, &key) || ix.n_terms == 0) {
+    uint64_t b = 0, e = 0;
+    if (find_term_range(ix, term, term_len, &b, &e)) {
+      *out = e - b;
+    }
+    return MGX_OK;
+  });
+}
+
+int mgx_index_get_posting_payload(const mgx_index_t* index, const uint8_t* term, uint64_t term_len, uint32_t* docs,
+                                  uint32_t* first, uint32_t* second, uint64_t cap, uint64_t* out_count,
+                                  int* layout) {
+  if (index == nullptr || out_count == nullptr) {
+    return invalid("null argument");
+  }
+  *out_count = 0;
+  mgx_index_t* h = const_cast<mgx_index_t*>(index);
+  if (int rc = commit_pending(h); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    Reader rd(h);
+    Index& ix = h->ix;
+    DeviceGuard guard(ix.device);
+    if (layout != nullptr) {
+      layout[0] = ix.has_positions ? ix.sig.pos_bits : 0;
+      layout[1] = ix.has_positions ? ix.sig.next_bits : 0;
+      layout[2] = ix.has_positions ? ix.sig.prev_bits : 0;
+    }
+    uint64_t b = 0, e = 0;
+    if (!ix.has_positions || !find_term_range(ix, term, term_len, &b, &e)) {
       return MGX_OK;
     }
-    // binary search over the device dictionary, one key per probe
-    const int W = ix.wide_words;
-    uint64_t want[kMaxWideWords] = {key, 0, 0, 0};
-    if (W > 0) {
-      std::memcpy(want, host_wide_words(key, W), static_cast<size_t>(W) * sizeof(uint64_t));
+    *out_count = e - b;
+    const uint64_t n = std::min<uint64_t>(e - b, cap);
+    if (n != 0 && docs != nullptr) {  // LOCAL document indices (position in the shard's ascending id list)
+      MGX_CUDA(cudaMemcpy(docs, ix.d_postings.p + b, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
-    const int nw = W > 0 ? W : 1;
-    const uint64_t* dict = W > 0 ? ix.d_wide_keys.p : ix.d_term_keys.p;
-    auto probe = [&](uint64_t at) {  // <0: dict[at] < want
-      uint64_t v[kMaxWideWords] = {0, 0, 0, 0};
-      MGX_CUDA(cudaMemcpy(v, dict + at * nw, static_cast<size_t>(nw) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-      for (int w = 0; w < nw; ++w) {
-        if (v[w] != want[w]) {
-          return v[w] < want[w] ? -1 : 1;
-        }
-      }
-      return 0;
-    };
-    uint64_t lo = 0;
-    uint64_t hi = ix.n_terms;
-    while (lo < hi) {
-      const uint64_t mid = (lo + hi) / 2;
-      if (probe(mid) < 0) {
-        lo = mid + 1;
-      } else {
-        hi = mid;
-      }
+    if (n != 0 && first != nullptr) {
+      MGX_CUDA(cudaMemcpy(first, ix.d_post_pos.p + b, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
-    if (lo < ix.n_terms && probe(lo) == 0) {
-      uint64_t off[2];
-      MGX_CUDA(cudaMemcpy(off, ix.d_term_off.p + lo, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-      *out = off[1] - off[0];
+    if (n != 0 && second != nullptr) {
+      MGX_CUDA(cudaMemcpy(second, ix.d_post_pos2.p + b, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
     return MGX_OK;
   });

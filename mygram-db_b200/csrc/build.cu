@@ -70,7 +70,9 @@ struct FlatSmem {
   uint32_t doc_valid[kFlatDocCap + 1];
   uint32_t warp_cnt[kFlatThreads / 32];
   uint32_t n_halo;
+  uint32_t prev_cp;  // decoded character right before the tile in its first document (signatures), kNoCp if none
 };
+constexpr uint32_t kNoCp = 0xFFFFFFFFu;
 
 __global__ void flat_tile_first_doc_kernel(const uint64_t* __restrict__ text_off, uint64_t n_docs, uint64_t n_tiles,
                                            uint32_t* __restrict__ out) {
@@ -136,13 +138,19 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
                      int kanji, int cross, int width, int pos_bits, uint32_t* __restrict__ doc_len,
                      uint32_t* __restrict__ doc_valid_bytes, uint32_t* __restrict__ tile_cnt,
                      const uint64_t* __restrict__ tile_off, uint64_t* __restrict__ keys_out,
-                     uint32_t* __restrict__ docs_out, int wide_words, uint64_t wide_stride) {
+                     uint32_t* __restrict__ docs_out, int wide_words, uint64_t wide_stride, int sig_cfg) {
   // wide_words > 0 (width > 3): word w of the n-gram in slot s goes to keys_out[w * wide_stride + s]
+  // sig_cfg != 0 (index build, pos_bits > 0): the pos_bits payload bits are split into offset (sig_cfg & 0xFF bits),
+  // next signature ((sig_cfg >> 8) & 0xFF bits) and prev signature ((sig_cfg >> 16) & 0xFF bits), SigLayout
+  const int sig_pos = sig_cfg & 0xFF;
+  const int sig_next = (sig_cfg >> 8) & 0xFF;
+  const int sig_prev = (sig_cfg >> 16) & 0xFF;
+  const uint32_t halo_want = static_cast<uint32_t>(width - 1) + (sig_cfg != 0 ? 1u : 0u);
   constexpr bool EMIT = MODE != kTokCount;    // writes n-grams
   constexpr bool STATS = MODE != kTokEmit;    // gathers the per-document totals
   __shared__ FlatSmem sm;
   const unsigned lane = threadIdx.x & 31u;
-  const uint64_t pos_max = pos_bits > 0 ? ((1ULL << pos_bits) - 1) : 0;
+  const uint64_t pos_max = pos_bits > 0 ? ((1ULL << (sig_cfg != 0 ? sig_pos : pos_bits)) - 1) : 0;
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint64_t tile_b = tile * kFlatTile;
     const uint32_t tile_len = static_cast<uint32_t>(umin_u64(kFlatTile, text_bytes - tile_b));
@@ -165,6 +173,7 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
       }
       if (threadIdx.x == 0) {
         sm.n_halo = 0;
+        sm.prev_cp = kNoCp;
       }
       __syncthreads();
       // byte range of the tile covered by this round's documents
@@ -231,12 +240,29 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
           ++at;
         }
       }
-      // halo: the first (width - 1) characters after the tile that still belong to the round's last document
-      if (threadIdx.x < 32 && width > 1 && sm.docrel[r_docs] > static_cast<int32_t>(tile_len) &&
+      // the character right before the tile, when the tile starts inside a document: the nearest non-continuation
+      // byte behind the tile start, if it decodes (what precedes the tile's first character when the text is
+      // contiguous there -- all a signature has to be right about)
+      if (threadIdx.x == 32 && EMIT && sig_prev > 0 && r_first == first_doc && sm.docrel[0] < 0) {
+        const int32_t doc_b = sm.docrel[0];
+        for (int32_t p = -1; p >= doc_b && p >= -4; --p) {
+          const uint8_t* q = text + tile_b + p;  // tile_b + p >= start of the document >= 0
+          if ((q[0] & 0xC0u) != 0x80u) {
+            uint32_t cp = 0;
+            if (parse_utf8(q[0], q[1], q[2], q[3], static_cast<uint64_t>(sm.docrel[1] - p), &cp) > 0) {
+              sm.prev_cp = cp;
+            }
+            break;
+          }
+        }
+      }
+      // halo: the first (width - 1) characters after the tile that still belong to the round's last document (one
+      // more when signatures are written: the character after the last window)
+      if (threadIdx.x < 32 && halo_want > 0 && sm.docrel[r_docs] > static_cast<int32_t>(tile_len) &&
           r_end == static_cast<int32_t>(tile_len)) {
         const int32_t doc_end = sm.docrel[r_docs];
         uint32_t found = 0;
-        for (int32_t base = static_cast<int32_t>(tile_len); base < doc_end && found < static_cast<uint32_t>(width - 1);
+        for (int32_t base = static_cast<int32_t>(tile_len); base < doc_end && found < halo_want;
              base += 32) {
           const int32_t p = base + static_cast<int32_t>(lane);
           uint32_t cp = 0;
@@ -247,7 +273,7 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
           }
           const unsigned m = __ballot_sync(0xffffffffu, len > 0);
           const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-          if (len > 0 && found + rank < static_cast<uint32_t>(width - 1)) {
+          if (len > 0 && found + rank < halo_want) {
             sm.cp[n_chars + found + rank] = cp;
             sm.pos[n_chars + found + rank] = static_cast<uint16_t>(min(p, 0xFFFF));
             sm.doc[n_chars + found + rank] = static_cast<uint16_t>(r_docs - 1);
@@ -255,7 +281,7 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
           found += __popc(m);
         }
         if (lane == 0) {
-          sm.n_halo = min(found, static_cast<uint32_t>(width - 1));
+          sm.n_halo = min(found, halo_want);
         }
       }
       __syncthreads();
@@ -326,7 +352,24 @@ tokenize_flat_kernel(const uint8_t* __restrict__ text, const uint64_t* __restric
                 }
               } else {
                 const uint64_t in_doc = static_cast<uint64_t>(static_cast<int64_t>(sm.pos[k]) - sm.docrel[dk]);
-                keys_out[slot] = pos_bits > 0 ? ((key[c4] << pos_bits) | umin_u64(in_doc, pos_max)) : key[c4];
+                uint64_t low = umin_u64(in_doc, pos_max);
+                if (sig_cfg != 0) {
+                  const uint32_t size = static_cast<uint32_t>(is_cjk_ideograph(sm.cp[k]) ? kanji : ngram);
+                  uint32_t nx = kNoCp;  // next decoded character of the same document
+                  if (k + size < n_all && sm.doc[k + size] == dk) {
+                    nx = sm.cp[k + size];
+                  }
+                  uint32_t pv = kNoCp;  // previous one
+                  if (k > 0) {
+                    pv = sm.doc[k - 1] == dk ? sm.cp[k - 1] : kNoCp;
+                  } else if (dk == 0) {
+                    pv = sm.prev_cp;
+                  }
+                  const uint64_t s_next = (nx != kNoCp && sig_next > 0) ? sig_of_hash(sig_hash7(nx), sig_next) : 0u;
+                  const uint64_t s_prev = (pv != kNoCp && sig_prev > 0) ? sig_of_hash(sig_hash7(pv), sig_prev) : 0u;
+                  low |= (s_next << sig_pos) | (s_prev << (sig_pos + sig_next));
+                }
+                keys_out[slot] = pos_bits > 0 ? ((key[c4] << pos_bits) | low) : key[c4];
               }
               docs_out[slot] = r_first + dk;
             }
@@ -608,8 +651,9 @@ __global__ void __launch_bounds__(kCsrThreads) csr_write_kernel(const uint64_t* 
                                                                 uint64_t* __restrict__ term_keys,
                                                                 uint64_t* __restrict__ term_off,
                                                                 uint32_t* __restrict__ postings,
-                                                                uint16_t* __restrict__ post_pos,
-                                                                uint16_t* __restrict__ post_pos2) {
+                                                                uint32_t* __restrict__ post_pos,
+                                                                uint32_t* __restrict__ post_pos2, int sig_cfg) {
+  // sig_cfg: split of the pb payload bits (tokenize_flat_kernel); 0 = all of them are the offset
   __shared__ uint32_t sp[kCsrThreads / 32];
   __shared__ uint32_t st[kCsrThreads / 32];
   const unsigned lane = threadIdx.x & 31u;
@@ -638,7 +682,11 @@ __global__ void __launch_bounds__(kCsrThreads) csr_write_kernel(const uint64_t* 
     pp += sp[w];
     tp += st[w];
   }
-  const uint64_t pos_mask = pb > 0 ? (1ULL << pb) - 1 : 0;
+  const int off_bits = sig_cfg != 0 ? (sig_cfg & 0xFF) : pb;
+  const int next_bits = (sig_cfg >> 8) & 0xFF;
+  const uint64_t pos_mask = pb > 0 ? (1ULL << off_bits) - 1 : 0;
+  const uint64_t pay_mask = pb > 0 ? (1ULL << pb) - 1 : 0;
+  const uint32_t next_mask = (1u << next_bits) - 1u;
 #pragma unroll
   for (int k = 0; k < kCsrItems; ++k) {
     const unsigned pair_mask = __ballot_sync(0xffffffffu, (heads[k] & 1u) != 0);
@@ -676,8 +724,13 @@ __global__ void __launch_bounds__(kCsrThreads) csr_write_kernel(const uint64_t* 
         const bool third = multi && k2 != kInvalidKey && (k2 >> pb) == (key >> pb) && d2 == doc;
         const uint64_t pos = key & pos_mask;
         const uint64_t pos2 = multi ? (k1 & pos_mask) : kPosUnknown;
-        post_pos[at] = static_cast<uint16_t>((pos < kPosUnknown ? pos : kPosUnknown) | (multi ? kPosMulti : 0));
-        post_pos2[at] = static_cast<uint16_t>((pos2 < kPosUnknown ? pos2 : kPosUnknown) | (third ? kPosMulti : 0));
+        // neighbour signatures of the two occurrences: next in bits 16..22, prev in bits 24..30 of the payload word
+        const uint32_t sg1 = static_cast<uint32_t>((key & pay_mask) >> off_bits);
+        const uint32_t sg2 = multi ? static_cast<uint32_t>((k1 & pay_mask) >> off_bits) : 0u;
+        post_pos[at] = static_cast<uint32_t>((pos < kPosUnknown ? pos : kPosUnknown) | (multi ? kPosMulti : 0)) |
+                       ((sg1 & next_mask) << 16) | ((sg1 >> next_bits) << 24);
+        post_pos2[at] = static_cast<uint32_t>((pos2 < kPosUnknown ? pos2 : kPosUnknown) | (third ? kPosMulti : 0)) |
+                        ((sg2 & next_mask) << 16) | ((sg2 >> next_bits) << 24);
       }
       if ((heads[k] & 2u) != 0) {
         const uint64_t tat = tp + __popc(term_mask & lt_mask);
@@ -901,7 +954,7 @@ void tokenize_count(int ngram, int kanji, bool cross, int width, const uint8_t* 
     MGX_LAUNCH_CHECK();
     tokenize_flat_kernel<kTokCount><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
         d_text, d_text_off, n_docs, text_bytes, ts.n_tiles, ts.tile_first_doc, ngram, kanji, cross ? 1 : 0, width, 0,
-        d_doc_len, ts.valid_bytes, ts.tile_cnt, nullptr, nullptr, nullptr, wide_words_for(width), 0);
+        d_doc_len, ts.valid_bytes, ts.tile_cnt, nullptr, nullptr, nullptr, wide_words_for(width), 0, 0);
     MGX_LAUNCH_CHECK();
   }
   if (n_docs > 0) {
@@ -930,7 +983,7 @@ void tokenize_emit(int ngram, int kanji, bool cross, int width, const uint8_t* d
   }
   tokenize_flat_kernel<kTokEmit><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
       d_text, d_text_off, n_docs, text_bytes, ts.n_tiles, ts.tile_first_doc, ngram, kanji, cross ? 1 : 0, width, pos_bits,
-      nullptr, nullptr, nullptr, d_tile_off, d_keys, d_docs, wide_words_for(width), wide_stride);
+      nullptr, nullptr, nullptr, d_tile_off, d_keys, d_docs, wide_words_for(width), wide_stride, 0);
   MGX_LAUNCH_CHECK();
 }
 
@@ -956,7 +1009,7 @@ void tokenize_bound(const uint8_t* d_text, const uint64_t* d_text_off, uint64_t 
 void tokenize_fused(int ngram, int kanji, bool cross, int width, const uint8_t* d_text, const uint64_t* d_text_off,
                     uint64_t n_docs, uint64_t text_bytes, uint32_t* d_doc_len, const uint64_t* d_tile_off,
                     uint64_t* d_scratch, uint64_t* d_keys, uint32_t* d_docs, int pos_bits, uint64_t* counters_out,
-                    cudaStream_t stream, uint64_t wide_stride = 0) {
+                    cudaStream_t stream, uint64_t wide_stride = 0, int sig_cfg = 0) {
   const TokScratch ts = tok_scratch(d_scratch, n_docs, text_bytes);
   MGX_CUDA(cudaMemsetAsync(ts.counters, 0, 8 * sizeof(unsigned long long), stream));
   if (n_docs > 0) {
@@ -966,7 +1019,8 @@ void tokenize_fused(int ngram, int kanji, bool cross, int width, const uint8_t* 
   if (ts.n_tiles > 0) {
     tokenize_flat_kernel<kTokFused><<<flat_grid(ts.n_tiles), kFlatThreads, 0, stream>>>(
         d_text, d_text_off, n_docs, text_bytes, ts.n_tiles, ts.tile_first_doc, ngram, kanji, cross ? 1 : 0, width, pos_bits,
-        d_doc_len, ts.valid_bytes, nullptr, d_tile_off, d_keys, d_docs, wide_words_for(width), wide_stride);
+        d_doc_len, ts.valid_bytes, nullptr, d_tile_off, d_keys, d_docs, wide_words_for(width), wide_stride,
+        pos_bits > 0 ? sig_cfg : 0);
     MGX_LAUNCH_CHECK();
   }
   if (n_docs > 0) {
@@ -983,12 +1037,22 @@ void tokenize_fused(int ngram, int kanji, bool cross, int width, const uint8_t* 
 }
 
 // doc ids ascending: first_id + i everywhere?  (one pass over the resident copy)
-__global__ void sequential_check_kernel(const uint32_t* __restrict__ ids, uint64_t n, unsigned int* __restrict__ bad) {
+// bad[1] = bytes of the longest document (saturated): sizes the offset field of the posting payload (SigLayout)
+__global__ void sequential_check_kernel(const uint32_t* __restrict__ ids, const uint64_t* __restrict__ text_off,
+                                        uint64_t n, unsigned int* __restrict__ bad) {
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i + 1 < n) {
     if (ids[i + 1] != ids[i] + 1) {
       atomicOr(bad, ids[i + 1] > ids[i] ? 1u : 2u);  // 1: gap, 2: not ascending
     }
+  }
+  uint64_t bytes = 0;
+  if (i < n) {
+    bytes = text_off[i + 1] - text_off[i];
+  }
+  const unsigned int longest = __reduce_max_sync(0xffffffffu, static_cast<unsigned int>(umin_u64(bytes, 0xFFFFFFFFu)));
+  if ((threadIdx.x & 31u) == 0 && longest != 0) {
+    atomicMax(bad + 1, longest);
   }
 }
 
@@ -1180,16 +1244,19 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   t0.reserve(DevArena::padded((n_tok_tiles + 1) * 8) + DevArena::padded(count_scratch * 8) + 512);
   uint64_t* d_slot_off = t0.take<uint64_t>(n_tok_tiles + 1);
   uint64_t* d_count_scratch = t0.take<uint64_t>(count_scratch);
-  unsigned int* d_bad = t0.take<unsigned int>(1);
+  unsigned int* d_bad = t0.take<unsigned int>(2);
+  uint64_t max_doc_bytes = 0;
   if (n_docs > 0) {
-    MGX_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), stream));
-    sequential_check_kernel<<<static_cast<unsigned>((n_docs + 255) / 256), 256, 0, stream>>>(ix.d_doc_ids.p, n_docs,
-                                                                                             d_bad);
+    MGX_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(unsigned int), stream));
+    sequential_check_kernel<<<static_cast<unsigned>((n_docs + 255) / 256), 256, 0, stream>>>(
+        ix.d_doc_ids.p, ix.d_text_off.p, n_docs, d_bad);
     MGX_LAUNCH_CHECK();
-    unsigned int bad = 0;
-    MGX_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, stream));
+    unsigned int bad2[2] = {0, 0};
+    MGX_CUDA(cudaMemcpyAsync(bad2, d_bad, sizeof(bad2), cudaMemcpyDeviceToHost, stream));
     MGX_CUDA(cudaMemcpyAsync(&first_id, ix.d_doc_ids.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     MGX_CUDA(cudaStreamSynchronize(stream));
+    const unsigned int bad = bad2[0];
+    max_doc_bytes = bad2[1];
     if (bad & 2u) {
       set_last_error("doc_ids must be strictly ascending");
       throw CudaFailure{MGX_ERR_INVALID_ARGUMENT};
@@ -1211,6 +1278,15 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   }
   const int pb = pos_bits_for_width(ix.width);
   ix.has_positions = pb > 0;
+  // split of the payload bits: offset field sized by the longest document, the rest neighbour signatures
+  // (MGX_BUILD_NO_SIG: offsets only, the round-1 payload, for A/B runs)
+  ix.sig = sig_layout_for(pb, max_doc_bytes);
+  if (std::getenv("MGX_BUILD_NO_SIG") != nullptr) {
+    ix.sig = SigLayout{};
+  }
+  const int sig_cfg = (ix.sig.next_bits | ix.sig.prev_bits) != 0
+                          ? (ix.sig.pos_bits | (ix.sig.next_bits << 8) | (ix.sig.prev_bits << 16))
+                          : 0;
 
   // ---- temporary arena T1: pairs (double-buffered), sort scratch, CSR block arrays
   const int W = wide_words_for(ix.width);
@@ -1242,7 +1318,7 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   // one pass: per-document totals + the (key, doc) pairs (placeholder key 0 in the unused slots of each tile)
   tokenize_fused(ix.ngram, ix.kanji, ix.cross, ix.width, ix.d_text.p, ix.d_text_off.p, n_docs, text_bytes, ix.d_doc_len.p,
                  d_slot_off, d_count_scratch, W > 0 ? d_words : d_keys_a, W > 0 ? d_docs_text : d_docs_a, pb, counters,
-                 stream, n_slots);
+                 stream, n_slots, sig_cfg);
   ix.doc_count = counters[0];
   ix.all_valid_utf8 = counters[1] == 0;
   ix.total_doc_length = counters[2];
@@ -1299,7 +1375,7 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   ix.n_terms = totals[1];
   ix.resident_b.reserve(DevArena::padded(ix.n_terms * 8 + 8) + DevArena::padded((ix.n_terms + 1) * 8) +
                         DevArena::padded(ix.n_postings * 4 + 4) + 2 * DevArena::padded(ix.n_terms * 4 + 4) +
-                        2 * DevArena::padded(ix.n_postings * 2 + 4) +
+                        2 * DevArena::padded(ix.n_postings * 4 + 4) +
                         DevArena::padded(static_cast<size_t>(W) * ix.n_terms * 8 + 8) + 512);
   ix.d_term_keys.borrow(ix.resident_b.take<uint64_t>(ix.n_terms), ix.n_terms);
   if (W > 0) {
@@ -1314,14 +1390,14 @@ void build_index_device(Index& ix, const uint32_t* d_doc_ids_in, const uint8_t* 
   ix.d_term_off.borrow(ix.resident_b.take<uint64_t>(ix.n_terms + 1), ix.n_terms + 1);
   ix.d_postings.borrow(ix.resident_b.take<uint32_t>(ix.n_postings), ix.n_postings);
   ix.d_term_bm.borrow(ix.resident_b.take<int32_t>(ix.n_terms), ix.n_terms);
-  ix.d_post_pos.borrow(ix.resident_b.take<uint16_t>(ix.n_postings), ix.n_postings);
-  ix.d_post_pos2.borrow(ix.resident_b.take<uint16_t>(ix.n_postings), ix.n_postings);
+  ix.d_post_pos.borrow(ix.resident_b.take<uint32_t>(ix.n_postings), ix.n_postings);
+  ix.d_post_pos2.borrow(ix.resident_b.take<uint32_t>(ix.n_postings), ix.n_postings);
   uint32_t* d_dense_terms = ix.resident_b.take<uint32_t>(ix.n_terms);  // only the first n_dense entries are used
   unsigned long long* d_count = reinterpret_cast<unsigned long long*>(ix.resident_b.take<uint64_t>(2));
   if (n_blocks > 0) {
     csr_write_kernel<<<static_cast<unsigned>(n_blocks), kCsrThreads, 0, stream>>>(
         sorted.keys, sorted.vals, n_slots, pb, d_block_pairs, d_block_terms, ix.d_term_keys.p, ix.d_term_off.p,
-        ix.d_postings.p, ix.d_post_pos.p, ix.d_post_pos2.p);
+        ix.d_postings.p, ix.d_post_pos.p, ix.d_post_pos2.p, sig_cfg);
     MGX_LAUNCH_CHECK();
   }
   set_u64_kernel<<<1, 1, 0, stream>>>(ix.d_term_off.p + ix.n_terms, ix.n_postings);

@@ -200,6 +200,53 @@ constexpr uint16_t kPosUnknown = 0x7FFF;   // post_pos value: first occurrence n
 constexpr uint16_t kPosMulti = 0x8000;     // post_pos flag: more than one occurrence in the document
 inline int pos_bits_for_width(int width) { return 21 * width + kPosBits <= 64 ? kPosBits : 0; }
 
+// Neighbour signatures (round 2). The kPosBits spare bits of a key are split per index into
+//   [ prev signature : sig_prev_bits ][ next signature : sig_next_bits ][ byte offset : pos_field_bits ]
+// where pos_field_bits is what the LONGEST document of the shard needs (8..15; 15 saturates at kPosUnknown as before).
+// A signature is a few hash bits of the code point right before / right after the n-gram occurrence in the same
+// document, 0 = "no such character". The verified-df kernels use them as an exact pre-filter: a term that contains
+// the n-gram with a character after (before) it can only start at a recorded occurrence whose next (prev) signature
+// equals that character's (a cached comparison of one character of text; false positives go on to the text check,
+// false negatives cannot happen because a true occurrence of the term puts exactly that character there).
+constexpr int kSigFieldBits = 7;  // widest signature (the posting payload keeps two 7-bit fields per occurrence)
+__host__ __device__ inline uint32_t sig_hash7(uint32_t cp) { return (cp * 0x9E3779B1u) >> 25; }
+// b-bit signature of a 7-bit hash, never 0 (0 = no neighbour)
+__host__ __device__ inline uint32_t sig_of_hash(uint32_t h7, int bits) {
+  const uint32_t s = h7 >> (kSigFieldBits - bits);
+  return s != 0 ? s : 1u;
+}
+struct SigLayout {
+  int pos_bits = 0;   // low bits holding the byte offset (0 = the keys carry no payload)
+  int next_bits = 0;
+  int prev_bits = 0;
+};
+inline SigLayout sig_layout_for(int payload_bits, uint64_t max_doc_bytes) {
+  SigLayout l;
+  if (payload_bits <= 0) {
+    return l;
+  }
+  int need = 1;
+  while (need < 15 && (1ULL << need) <= max_doc_bytes) {  // offsets 0 .. max_doc_bytes - 1 and never the saturated value
+    ++need;
+  }
+  l.pos_bits = need < 8 ? 8 : need;
+  const int spare = payload_bits - l.pos_bits;
+  l.next_bits = (spare + 1) / 2 > kSigFieldBits ? kSigFieldBits : (spare + 1) / 2;
+  l.prev_bits = spare - l.next_bits > kSigFieldBits ? kSigFieldBits : spare - l.next_bits;
+  return l;
+}
+// Term side (key_toff, one uint32 per (term, n-gram)): low 16 bits as before (kNoTermOffset / offset | count << 12);
+// bits 16..22 = hash7 of the character after the n-gram's first occurrence in the term, bit 23 = there is one,
+// bits 24..30 / bit 31 = the same for the character before it.
+constexpr uint32_t kToffNextShift = 16;
+constexpr uint32_t kToffHasNext = 1u << 23;
+constexpr uint32_t kToffPrevShift = 24;
+constexpr uint32_t kToffHasPrev = 1u << 31;
+__host__ __device__ inline uint32_t toff_neighbours(bool has_prev, uint32_t prev_cp, bool has_next, uint32_t next_cp) {
+  return (has_next ? (kToffHasNext | (sig_hash7(next_cp) << kToffNextShift)) : 0u) |
+         (has_prev ? (kToffHasPrev | (sig_hash7(prev_cp) << kToffPrevShift)) : 0u);
+}
+
 __host__ __device__ inline uint64_t pack_key(const uint32_t* cps, int n, int width) {
   uint64_t key = 0;
   for (int j = 0; j < width; ++j) {
@@ -389,7 +436,7 @@ class SmallVec {
   T inline_[N];
 };
 using KeyVec = SmallVec<uint64_t, 4>;
-using TermOffsetVec = SmallVec<uint16_t, 4>;
+using TermOffsetVec = SmallVec<uint32_t, 4>;
 using TermIdVec = SmallVec<uint32_t, 4>;
 
 // GenerateQueryNgrams (string_utils.cpp:639-653) + DeduplicateSorted as packed
@@ -397,7 +444,7 @@ using TermIdVec = SmallVec<uint32_t, 4>;
 // key_toff (optional): per returned key, (byte offset of the n-gram's FIRST occurrence inside the term) |
 // (min(number of occurrences in the term, 3) << kTermCountShift); kNoTermOffset when the term is not valid UTF-8
 // (its windows skip bytes, so they are no contiguous byte runs).
-constexpr uint16_t kNoTermOffset = 0xFFFF;
+constexpr uint16_t kNoTermOffset = 0xFFFF;  // low 16 bits of a key_toff entry
 constexpr uint32_t kTermOffsetMask = 0x0FFF;
 constexpr uint32_t kTermCountShift = 12;
 bool host_query_keys(const uint8_t* term, uint64_t len, int ngram_size, int kanji_ngram_size, bool cross_boundary,
@@ -510,13 +557,15 @@ struct Index {
   DevBuf<uint64_t> d_wide_keys;    // [n_terms * wide_words], term-major, ascending; d_term_keys[t] == t + 1 then
   DevBuf<uint64_t> d_term_off;
   DevBuf<uint32_t> d_postings;
-  // First-occurrence position of every posting (only when the packed key leaves room to carry it through the sort,
-  // i.e. key width <= 2): bits 0..14 = byte offset of the n-gram's first occurrence in the document's text
-  // (0x7FFF = unknown / beyond 32 KB), bit 15 = the n-gram occurs more than once in the document.
-  DevBuf<uint16_t> d_post_pos;
+  // Payload of every posting (only when the packed key leaves room to carry it through the sort, i.e. key width
+  // <= 2). Low half = first-occurrence position: bits 0..14 = byte offset of the n-gram's first occurrence in the
+  // document's text (0x7FFF = unknown / beyond 32 KB), bit 15 = the n-gram occurs more than once in the document.
+  // High half = neighbour signatures of that occurrence: bits 16..22 next, bits 24..30 prev (sig layout above).
+  DevBuf<uint32_t> d_post_pos;
   // Second occurrence, same encoding: bits 0..14 = byte offset (0x7FFF = none / unknown), bit 15 = a third exists.
-  DevBuf<uint16_t> d_post_pos2;
+  DevBuf<uint32_t> d_post_pos2;
   bool has_positions = false;
+  SigLayout sig;  // how the build split the payload bits (sig.next_bits == sig.prev_bits == 0: no signatures)
   bool text_less = false;  // loaded from an MGIX stream: posting lists only, no document text (load_index_device)
   DevBuf<int32_t> d_term_bm;
   DevBuf<uint32_t> d_bitmaps;
@@ -563,8 +612,10 @@ struct IndexView {
   int wide_words;
   const uint64_t* term_off;
   const uint32_t* postings;
-  const uint16_t* post_pos;  // nullptr when the index carries no positions
-  const uint16_t* post_pos2;
+  const uint32_t* post_pos;  // nullptr when the index carries no positions; low 16 bits position, high 16 signatures
+  const uint32_t* post_pos2;
+  int sig_next_bits;         // signature widths of the payload (0: none)
+  int sig_prev_bits;
   const int32_t* term_bm;
   const uint32_t* bitmaps;
   uint64_t n_docs;
@@ -614,6 +665,10 @@ inline IndexView make_view(const Index& ix) {
   v.postings = ix.d_postings.p;
   v.post_pos = ix.has_positions ? ix.d_post_pos.p : nullptr;
   v.post_pos2 = ix.has_positions ? ix.d_post_pos2.p : nullptr;
+  // MGX_DF_NO_SIG (read per view, the tests and the bench flip it): the signature pre-filter of the df kernels off
+  const bool use_sig = ix.has_positions && std::getenv("MGX_DF_NO_SIG") == nullptr;
+  v.sig_next_bits = use_sig ? ix.sig.next_bits : 0;
+  v.sig_prev_bits = use_sig ? ix.sig.prev_bits : 0;
   v.term_bm = ix.d_term_bm.p;
   v.bitmaps = ix.d_bitmaps.p;
   v.n_docs = ix.n_docs;

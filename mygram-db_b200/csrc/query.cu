@@ -42,7 +42,7 @@ struct BatchView {
   const uint32_t* term_koff;
   uint32_t* key_list;
   uint32_t* key_len;
-  uint16_t* key_toff;
+  uint32_t* key_toff;  // low 16 bits: offset | count (kNoTermOffset), high 16: neighbour hashes (mgx_internal.cuh)
   uint64_t* t_est;
   uint32_t* t_df_tiles;
   uint64_t* t_df_tile_off;
@@ -332,7 +332,7 @@ __device__ __forceinline__ void term_plan_one(const BatchView& bv, uint32_t t, i
     for (uint32_t i = k0 + 1; i < k1; ++i) {  // insertion sort by length (missing lists have length 0)
       const uint32_t li = bv.key_list[i];
       const uint32_t ln = bv.key_len[i];
-      const uint16_t to = bv.key_toff[i];
+      const uint32_t to = bv.key_toff[i];
       uint32_t j = i;
       while (j > k0 && bv.key_len[j - 1] > ln) {
         bv.key_list[j] = bv.key_list[j - 1];
@@ -902,7 +902,7 @@ __global__ void fill_tile_map_kernel(const uint64_t* __restrict__ off, uint32_t 
 // narrow the other lists to the warp's doc range (32-ary bound search), stage that sub-range in the warp's
 // shared-memory slice with coalesced loads, search it there, then scan the survivors' text one thread per document.
 #ifndef MGX_DF_OCC
-#define MGX_DF_OCC 6  // resident CTAs per SM the register allocation of the df tile kernels is sized for
+#define MGX_DF_OCC 3  // resident CTAs per SM the register allocation of the df kernels is sized for (80 registers: measured best)
 #endif
 constexpr int kWarpItems = 4;                       // driver entries per lane
 constexpr int kWarpTile = 32 * kWarpItems;          // 128 entries per warp
@@ -931,40 +931,231 @@ __device__ __forceinline__ void load_text_words(const uint8_t* __restrict__ text
 }
 
 static_assert(kWarpStageCap * sizeof(uint32_t) >= kStageBuf, "the text staging buffer aliases the list staging buffer");
-// One warp, one 128-entry piece of a term's shortest list (entries [e0, e0 + 128) of drv): the whole df work of that
-// piece. stage / surv / spos are the calling warp's own shared-memory slices; stat_stripe spreads the accounting atomics.
-__device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchView& bv, const ListRef& drv, uint32_t t,
-                                             uint32_t k0, uint32_t k1, uint64_t e0, uint32_t* stage, uint32_t* surv,
-                                             uint32_t* spos, uint32_t stat_stripe, uint32_t (&hint)[kDfHintLists]) {
-  const unsigned lane = threadIdx.x & 31u;
-  if (e0 >= drv.len) {
-    return;  // no block-wide barrier is used below, so a warp may leave early
+constexpr uint32_t kDfFewMembers = 16;         // at most this many candidates of a chunk: searched one by one
+constexpr uint32_t kDfSetCap = kWarpTile + 32 * 8;  // fewer than 128 waiting + one piece  // collected candidates per warp (they are processed 128 at a time)
+
+// What is the same for every piece of one (term, driver list) pair.
+struct DfTerm {
+  const uint32_t* drv_pos;   // payload of the driver n-gram in each document: first / second occurrence + neighbour
+  const uint32_t* drv_pos2;  // signatures (Index::d_post_pos), nullptr when the index carries none
+  uint32_t o1;               // byte offset of the driver n-gram's first occurrence in the term
+  uint32_t m_term;           // its occurrences in the term: 1, 2, or 3 = "three or more"
+  uint32_t tl;               // term bytes
+  uint32_t sig_want;         // neighbour signatures the term asks for, in payload position
+  uint32_t sig_mask;
+  bool toff_ok;
+  bool prefilter;
+};
+
+__device__ __forceinline__ DfTerm df_term_consts(const IndexView& iv, const BatchView& bv, const ListRef& drv, uint32_t t,
+                                                 uint32_t k0) {
+  DfTerm c;
+  c.drv_pos = iv.post_pos != nullptr ? iv.post_pos + (drv.p - iv.postings) : nullptr;
+  c.drv_pos2 = iv.post_pos2 != nullptr ? iv.post_pos2 + (drv.p - iv.postings) : nullptr;
+  const uint32_t toff_raw = bv.key_toff[k0];
+  c.toff_ok = (toff_raw & 0xFFFFu) != kNoTermOffset;
+  c.o1 = toff_raw & kTermOffsetMask;
+  c.m_term = (toff_raw & 0xFFFFu) >> kTermCountShift;
+  c.tl = bv.term_boff[t + 1] - bv.term_boff[t];
+  // Signature pre-filter (mgx_internal.cuh "Neighbour signatures"): the character of the term right after / before
+  // the driver n-gram must be what the index recorded next to one of the document's occurrences. It runs on the
+  // payload alone, BEFORE the probes of the other lists and the text comparison, and leaves them the true matches
+  // plus a 2^-bits share of the rest.
+  c.sig_want = 0;
+  c.sig_mask = 0;
+  if (c.toff_ok && c.tl != 0) {
+    if ((toff_raw & kToffHasNext) != 0 && iv.sig_next_bits > 0) {
+      c.sig_want |= sig_of_hash((toff_raw >> kToffNextShift) & 0x7Fu, iv.sig_next_bits) << 16;
+      c.sig_mask |= 0x7Fu << 16;
+    }
+    if ((toff_raw & kToffHasPrev) != 0 && iv.sig_prev_bits > 0) {
+      c.sig_want |= sig_of_hash((toff_raw >> kToffPrevShift) & 0x7Fu, iv.sig_prev_bits) << 24;
+      c.sig_mask |= 0x7Fu << 24;
+    }
   }
-  const uint32_t tile_n = static_cast<uint32_t>(umin64(kWarpTile, drv.len - e0));
-  const uint32_t dmin = __ldg(drv.p + e0);
-  const uint32_t dmax = __ldg(drv.p + e0 + tile_n - 1);
-  // first-occurrence positions of the driver n-gram in each document (see Index::d_post_pos)
-  const uint16_t* drv_pos = iv.post_pos != nullptr ? iv.post_pos + (drv.p - iv.postings) : nullptr;
-  const uint16_t* drv_pos2 = iv.post_pos2 != nullptr ? iv.post_pos2 + (drv.p - iv.postings) : nullptr;
+  c.prefilter = c.toff_ok && c.tl != 0 && c.drv_pos != nullptr;
+  return c;
+}
+
+// per-lane partial sums of one unit, reduced once at its end
+struct DfAcc {
+  uint32_t hits = 0;
+  uint32_t cand = 0;     // lane 0 only
+  uint32_t scanned = 0;  // lane 0 only
+  unsigned long long text_bytes = 0;
+};
+
+// One warp, one piece of kDfPiece entries of a term's shortest list (entries [pe0, pe0 + kDfPiece) of drv, pe0 =
+// e0 + rel0): the entries the payload cannot rule out are appended, in order, to `cand` at n_set -- as their distance
+// from e0, the documents and payloads are fetched again (from L2) for the few that stay. Lane l takes the entries
+// l, l + 32, ...: every load is one coalesced line, all of them are in flight before the first is looked at, and the
+// second-occurrence words (needed by roughly one entry in ten) follow in a second wave.
+constexpr int kDfPieceItems = 8;
+constexpr uint32_t kDfPiece = 32 * kDfPieceItems;
+__device__ __forceinline__ uint32_t df_collect_piece(const ListRef& drv, const DfTerm& tc, uint64_t e0, uint32_t rel0,
+                                                     uint64_t unit_end, uint32_t* cand, uint32_t n_set) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const uint64_t pe0 = e0 + rel0;
+  const uint32_t tile_n = static_cast<uint32_t>(umin64(kDfPiece, unit_end - pe0));
+  uint32_t keep = 0;
+  if (tc.drv_pos == nullptr) {
+#pragma unroll
+    for (int k = 0; k < kDfPieceItems; ++k) {
+      keep |= (k * 32 + lane < tile_n) ? (1u << k) : 0u;
+    }
+  } else {
+    uint32_t valid = (1u << kDfPieceItems) - 1u;  // entries of this lane inside the piece
+    if (tile_n < kDfPiece) {
+      valid = 0;
+#pragma unroll
+      for (int k = 0; k < kDfPieceItems; ++k) {
+        valid |= (k * 32 + lane < tile_n) ? (1u << k) : 0u;
+      }
+    }
+    uint32_t pay1[kDfPieceItems];
+#pragma unroll
+    for (int k = 0; k < kDfPieceItems; ++k) {
+      pay1[k] = ((valid >> k) & 1u) ? __ldg(tc.drv_pos + pe0 + k * 32 + lane) : 0u;
+    }
+    if (!tc.prefilter) {
+      keep = valid;
+    } else {
+      // one recorded occurrence (the common entry): kept iff the term has the n-gram once, the occurrence leaves room
+      // for the bytes of the term before it and the signatures agree -- two logic operations and two compares;
+      // everything else (a second occurrence, an unrecorded offset) is sorted out below
+      const uint32_t lim = kPosUnknown - tc.o1;           // (p - o1) < lim  <=>  o1 <= p < 0x7FFF
+      const uint32_t fast_mask = tc.sig_mask | kPosMulti;  // single occurrence + signatures
+      const bool once = tc.m_term <= 1;
+      uint32_t other = 0;
+#pragma unroll
+      for (int k = 0; k < kDfPieceItems; ++k) {
+        const uint32_t p = pay1[k] & kPosUnknown;
+        const bool in_range = p - tc.o1 < lim;
+        const bool sig_ok = ((pay1[k] ^ tc.sig_want) & fast_mask) == 0;
+        keep |= (once && in_range && sig_ok) ? (1u << k) : 0u;
+        other |= ((pay1[k] & kPosMulti) != 0 || p == kPosUnknown) ? (1u << k) : 0u;
+      }
+      keep &= valid;
+      other &= valid;
+      if (__any_sync(0xffffffffu, other != 0)) {
+        uint32_t pay2[kDfPieceItems];
+#pragma unroll
+        for (int k = 0; k < kDfPieceItems; ++k) {
+          const bool multi = ((other >> k) & 1u) != 0 && (pay1[k] & kPosMulti) != 0;
+          pay2[k] = multi ? __ldg(tc.drv_pos2 + pe0 + k * 32 + lane) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < kDfPieceItems; ++k) {
+          if ((other >> k) & 1u) {
+            const uint32_t p1 = pay1[k] & kPosUnknown;
+            const uint32_t p2 = pay2[k] & kPosUnknown;
+            if (p1 == kPosUnknown || (pay2[k] & kPosMulti) != 0 || p2 == kPosUnknown) {
+              keep |= 1u << k;  // unrecorded, or three and more occurrences: the scanning path decides
+            } else {
+              const bool good1 = p1 - tc.o1 < lim && ((pay1[k] ^ tc.sig_want) & tc.sig_mask) == 0;
+              const bool good2 = p2 - tc.o1 < lim && ((pay2[k] ^ tc.sig_want) & tc.sig_mask) == 0;
+              keep |= (tc.m_term <= 2 && (good1 || good2)) ? (1u << k) : 0u;  // exactly two, both recorded
+            }
+          }
+        }
+      }
+    }
+  }
+  uint32_t n = 0;
+#pragma unroll
+  for (int k = 0; k < kDfPieceItems; ++k) {
+    const unsigned m = __ballot_sync(0xffffffffu, (keep >> k) & 1u);
+    if ((keep >> k) & 1u) {
+      cand[n_set + n + __popc(m & lt_mask)] = rel0 + k * 32 + lane;
+    }
+    n += __popc(m);
+  }
+  __syncwarp();
+  return n;
+}
+
+// four lower bounds in one ascending global array, their probes in flight together
+__device__ __forceinline__ void lower_bound_x4(const uint32_t* __restrict__ p, uint32_t n, const uint32_t (&v)[kWarpItems],
+                                               uint32_t mask, uint32_t (&pos)[kWarpItems]) {
+  uint32_t base[kWarpItems];
+#pragma unroll
+  for (int k = 0; k < kWarpItems; ++k) {
+    base[k] = 0;
+  }
+  uint32_t len = n;
+  while (len > 1) {
+    const uint32_t half = len >> 1;
+#pragma unroll
+    for (int k = 0; k < kWarpItems; ++k) {
+      if ((mask >> k) & 1u) {
+        base[k] = __ldg(p + base[k] + half - 1) < v[k] ? base[k] + half : base[k];
+      }
+    }
+    len -= half;
+  }
+#pragma unroll
+  for (int k = 0; k < kWarpItems; ++k) {
+    pos[k] = base[k];
+    if (((mask >> k) & 1u) && n != 0 && __ldg(p + base[k]) < v[k]) {
+      pos[k] = base[k] + 1;
+    }
+  }
+}
+
+// One warp, the first n (<= 128) collected candidates, ascending in surv / spos: membership in the term's other
+// lists, then the verification of what is left. stage is the calling warp's own shared-memory slice.
+__device__ __forceinline__ void df_process_chunk(const IndexView& iv, const BatchView& bv, const ListRef& drv,
+                                                 const DfTerm& tc, uint32_t t, uint32_t k0, uint32_t k1, uint64_t e0,
+                                                 uint32_t* surv, uint32_t* spos, uint32_t n_in, uint32_t* stage,
+                                                 uint32_t (&hint)[kDfHintLists], DfAcc& acc) {
+  const unsigned lane = threadIdx.x & 31u;
   uint32_t my_doc[kWarpItems];
-  uint32_t my_pos[kWarpItems];  // first occurrence | second occurrence << 16
-  uint32_t alive = 0;
+  uint32_t my_pos[kWarpItems];
+  uint32_t alive = 0;   // candidates that go through the membership stage
+  uint32_t direct = 0;  // candidates that do not
 #pragma unroll
   for (int k = 0; k < kWarpItems; ++k) {
     const uint32_t i = lane * kWarpItems + k;
     my_doc[k] = kNone;
     my_pos[k] = kPosUnknown;
-    if (i < tile_n) {
-      my_doc[k] = __ldg(drv.p + e0 + i);
-      if (drv_pos != nullptr) {
-        const uint32_t p1 = __ldg(drv_pos + e0 + i);
-        // the second position is only read when there is one
-        my_pos[k] = p1 | ((p1 & kPosMulti) != 0 ? static_cast<uint32_t>(__ldg(drv_pos2 + e0 + i)) << 16 : 0u);
+    if (i < n_in) {
+      const uint64_t e = e0 + surv[i];  // surv holds the candidates' distances from e0 on entry
+      my_doc[k] = __ldg(drv.p + e);
+      if (tc.drv_pos != nullptr) {
+        const uint32_t pay1 = __ldg(tc.drv_pos + e);
+        const uint32_t pay2 = (pay1 & kPosMulti) != 0 ? __ldg(tc.drv_pos2 + e) : 0u;
+        my_pos[k] = (pay1 & 0xFFFFu) | (pay2 << 16);
       }
-      alive |= 1u << k;
+      // Candidates whose occurrences of the driver n-gram are all recorded (one or two) are settled by comparing
+      // the text at those places: a document that holds the term there holds every n-gram of the term (tokenizer
+      // agreement, the precondition of toff_ok), so looking them up in the other lists first would only be a
+      // filter -- and the signatures have filtered better already. They skip the membership stage.
+      const uint32_t p1 = my_pos[k] & 0xFFFFu;
+      const uint32_t p2 = my_pos[k] >> 16;
+      const bool known = (p1 & kPosUnknown) != kPosUnknown &&
+                         ((p1 & kPosMulti) == 0 || ((p2 & kPosMulti) == 0 && (p2 & kPosUnknown) != kPosUnknown));
+      if (tc.prefilter && known) {
+        direct |= 1u << k;
+      } else {
+        alive |= 1u << k;
+      }
     }
   }
-  for (uint32_t j = k0 + 1; j < k1; ++j) {
+  const uint32_t n_member = __reduce_add_sync(0xffffffffu, __popc(alive));
+  // document range of the candidates that take the membership stage (ascending in the lane-major order)
+  uint32_t dmin = 0xFFFFFFFFu;
+  uint32_t dmax = 0;
+#pragma unroll
+  for (int k = 0; k < kWarpItems; ++k) {
+    if ((alive >> k) & 1u) {
+      dmin = min(dmin, my_doc[k]);
+      dmax = max(dmax, my_doc[k]);
+    }
+  }
+  dmin = __reduce_min_sync(0xffffffffu, dmin);
+  dmax = __reduce_max_sync(0xffffffffu, dmax);
+  for (uint32_t j = k0 + 1; j < k1 && n_member != 0; ++j) {
     const uint4* rp = reinterpret_cast<const uint4*>(bv.key_ref + j);
     const uint4 r0 = __ldg(rp);
     const uint4 r1 = __ldg(rp + 1);
@@ -979,10 +1170,20 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
           alive &= ~(1u << k);
         }
       }
+    } else if (n_member <= kDfFewMembers) {
+      // a handful of candidates: one search of the whole list each, no narrowing, no staging
+      uint32_t pos[kWarpItems];
+      lower_bound_x4(l.p, l.len, my_doc, alive, pos);
+#pragma unroll
+      for (int k = 0; k < kWarpItems; ++k) {
+        if (((alive >> k) & 1u) && (pos[k] >= l.len || __ldg(l.p + pos[k]) != my_doc[k])) {
+          alive &= ~(1u << k);
+        }
+      }
     } else {
       uint32_t lo = 0;
       uint32_t hi = 0;
-      const uint32_t hj = j - (k0 + 1);  // the first kDfHintLists other lists remember where the last piece ended
+      const uint32_t hj = j - (k0 + 1);  // the first kDfHintLists other lists remember where the last chunk ended
       warp_lower_bound_pair(l.p, l.len, dmin, dmax + 1u, &lo, &hi, hj < kDfHintLists ? hint[hj] : 0u);
       if (hj < kDfHintLists) {
         hint[hj] = hi;
@@ -990,7 +1191,8 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
       const uint32_t cnt = hi - lo;
       if (cnt == 0) {
         alive = 0;
-      } else if (cnt <= kWarpStageCap) {
+      } else if (cnt <= kWarpStageCap && cnt <= 8 * n_in) {
+        // staging pays when the sub-range is not much longer than the candidates are many
         for (uint32_t i = lane; i < cnt; i += 32) {
           stage[i] = __ldg(l.p + lo + i);
         }
@@ -1003,22 +1205,25 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
         }
         __syncwarp();
       } else {
+        uint32_t pos[kWarpItems];
+        lower_bound_x4(l.p + lo, cnt, my_doc, alive, pos);
 #pragma unroll
         for (int k = 0; k < kWarpItems; ++k) {
-          if ((alive >> k) & 1u) {
-            const uint32_t pos = lower_bound_u32(l.p + lo, cnt, my_doc[k]);
-            if (pos >= cnt || __ldg(l.p + lo + pos) != my_doc[k]) {
-              alive &= ~(1u << k);
-            }
+          if (((alive >> k) & 1u) && (pos[k] >= cnt || __ldg(l.p + lo + pos[k]) != my_doc[k])) {
+            alive &= ~(1u << k);
           }
         }
       }
     }
     if (__ballot_sync(0xffffffffu, alive != 0) == 0) {
-      return;
+      break;
     }
   }
-  // survivors -> the warp's list (order irrelevant for a count)
+  alive |= direct;
+  if (__ballot_sync(0xffffffffu, alive != 0) == 0) {
+    return;
+  }
+  // survivors -> the front of the warp's list (order irrelevant for a count)
   const uint32_t mine = __popc(alive);
   uint32_t inc = mine;
 #pragma unroll
@@ -1030,6 +1235,7 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
   }
   const uint32_t n = __shfl_sync(0xffffffffu, inc, 31);
   uint32_t w = inc - mine;
+  __syncwarp();  // every lane holds its entries in registers
 #pragma unroll
   for (int k = 0; k < kWarpItems; ++k) {
     if ((alive >> k) & 1u) {
@@ -1039,11 +1245,12 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
     }
   }
   __syncwarp();
+  const uint32_t tl = tc.tl;
+  const bool toff_ok = tc.toff_ok;
+  const uint32_t o1 = tc.o1;
+  const uint32_t m_term = tc.m_term;
   const uint8_t* term = bv.term_bytes + bv.term_boff[t];
-  const uint32_t tl = bv.term_boff[t + 1] - bv.term_boff[t];
   const TermRegs tregs = load_term_regs(term, tl);
-  uint32_t hits = 0;
-  unsigned long long text_bytes = 0;
 
   // ---- pass 1, one lane per candidate. The driver n-gram occurs m times in the term (first at byte offset o1) and
   // c times in the document (positions recorded for c <= 2). An occurrence of the term puts m occurrences of the
@@ -1051,33 +1258,81 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
   // c <= 2 the term can only start at (p_a - o1) for a recorded position p_a -- one or two comparisons instead of a
   // scan. Documents with three or more occurrences (or no recorded position) are compacted to the front of the
   // list for the scanning pass.
-  const uint32_t toff_raw = bv.key_toff[k0];
-  const bool toff_ok = toff_raw != kNoTermOffset;
-  const uint32_t o1 = toff_raw & kTermOffsetMask;
-  const uint32_t m_term = toff_raw >> kTermCountShift;  // 1, 2, or 3 = "three or more"
+  // Every lane takes up to kWarpItems candidates and keeps their loads in flight together: all offsets first, then all
+  // first-occurrence comparisons (two dependent memory round trips per chunk instead of per 32 candidates).
   uint32_t n_scan = 0;
-  for (uint32_t s0 = 0; s0 < n; s0 += 32) {
-    const uint32_t s = s0 + lane;
-    bool scan = false;
-    uint32_t doc = 0;
-    if (s < n) {
-      doc = surv[s];
-      const uint32_t pp = spos[s];
-      const uint64_t b = iv.text_off[doc];
-      const uint32_t len = static_cast<uint32_t>(iv.text_off[doc + 1] - b);
-      text_bytes += len;
-      const uint32_t p1 = pp & 0xFFFFu;
-      const uint32_t p2 = pp >> 16;
-      const bool two = (p1 & kPosMulti) != 0;
-      const uint32_t c_doc = !two ? 1u : ((p2 & kPosMulti) == 0 ? 2u : 3u);
-      if (!toff_ok || c_doc == 3 || (p1 & kPosUnknown) == kPosUnknown || (two && (p2 & kPosUnknown) == kPosUnknown)) {
-        scan = true;
-      } else if (tl != 0 && m_term <= c_doc) {
+  {
+    uint32_t c_doc_[kWarpItems];
+    uint32_t pp_[kWarpItems];
+    uint64_t b_[kWarpItems];
+    uint32_t len_[kWarpItems];
+    uint32_t state = 0;  // per candidate 2 bits: 0 nothing to do, 1 compare, 2 scan
+#pragma unroll
+    for (int r = 0; r < kWarpItems; ++r) {
+      const uint32_t sidx = r * 32 + lane;
+      c_doc_[r] = 0;
+      pp_[r] = 0;
+      b_[r] = 0;
+      len_[r] = 0;
+      if (sidx < n) {
+        c_doc_[r] = surv[sidx];
+        pp_[r] = spos[sidx];
+        b_[r] = iv.text_off[c_doc_[r]];
+        len_[r] = static_cast<uint32_t>(iv.text_off[c_doc_[r] + 1] - b_[r]);
+      }
+    }
+    __syncwarp();  // surv is rewritten below
+    uint32_t x_[kWarpItems][3];
+#pragma unroll
+    for (int r = 0; r < kWarpItems; ++r) {
+      const uint32_t sidx = r * 32 + lane;
+      x_[r][0] = x_[r][1] = x_[r][2] = 0;
+      if (sidx < n) {
+        acc.text_bytes += len_[r];
+        const uint32_t p1 = pp_[r] & 0xFFFFu;
+        const uint32_t p2 = pp_[r] >> 16;
+        const bool two = (p1 & kPosMulti) != 0;
+        const uint32_t c_doc = !two ? 1u : ((p2 & kPosMulti) == 0 ? 2u : 3u);
+        if (!toff_ok || tl == 0 || (p1 & kPosUnknown) == kPosUnknown || (two && (p2 & kPosUnknown) == kPosUnknown)) {
+          state |= 2u << (2 * r);
+        } else if (m_term <= c_doc) {
+          // three or more occurrences (state 3): the two recorded ones are compared like the others; only when
+          // neither holds the term is the text behind the second one scanned
+          state |= (c_doc == 3 ? 3u : 1u) << (2 * r);
+          const uint32_t at = p1 & kPosUnknown;
+          if (at >= o1 && at - o1 + tl <= len_[r]) {
+            load_text_words(iv.text, b_[r] + (at - o1), x_[r]);
+          } else {
+            state |= 0x100u << r;  // the first occurrence cannot hold the term
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kWarpItems; ++r) {
+      bool scan = ((state >> (2 * r)) & 3u) == 2u;
+      uint32_t scan_from = 0;  // first start position the scan has to look at
+      if ((((state >> (2 * r)) & 3u) & 1u) != 0) {
+        const uint32_t p1 = pp_[r] & 0xFFFFu;
+        const uint32_t p2 = pp_[r] >> 16;
         bool found = false;
-        for (uint32_t occ = 0; occ < c_doc && !found; ++occ) {
-          const uint32_t at = (occ == 0 ? p1 : p2) & kPosUnknown;
-          if (at >= o1 && at - o1 + tl <= len) {
-            const uint64_t start = b + (at - o1);
+        if (((state >> (8 + r)) & 1u) == 0) {
+          bool ok = ((x_[r][0] ^ tregs.w[0]) & tregs.m[0]) == 0;
+          if (tregs.nw > 1) {
+            ok = ok && ((x_[r][1] ^ tregs.w[1]) & tregs.m[1]) == 0;
+          }
+          if (tregs.nw > 2) {
+            ok = ok && ((x_[r][2] ^ tregs.w[2]) & tregs.m[2]) == 0;
+          }
+          if (ok && tl > 12) {
+            ok = term_tail_matches(iv.text, b_[r] + ((p1 & kPosUnknown) - o1), term, tl);
+          }
+          found = ok;
+        }
+        if (!found && (p1 & kPosMulti) != 0) {  // the second recorded occurrence
+          const uint32_t at = p2 & kPosUnknown;
+          if (at >= o1 && at - o1 + tl <= len_[r]) {
+            const uint64_t start = b_[r] + (at - o1);
             uint32_t x[3];
             load_text_words(iv.text, start, x);
             bool ok = ((x[0] ^ tregs.w[0]) & tregs.m[0]) == 0;
@@ -1093,14 +1348,21 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
             found = ok;
           }
         }
-        hits += found ? 1u : 0u;
+        acc.hits += found ? 1u : 0u;
+        if (!found && ((state >> (2 * r)) & 3u) == 3u) {
+          // a further occurrence of the term puts the driver n-gram behind its second recorded occurrence
+          scan = true;
+          scan_from = (p2 & kPosUnknown) >= o1 ? (p2 & kPosUnknown) - o1 + 1u : 0u;
+        }
       }
+      const unsigned scan_mask = __ballot_sync(0xffffffffu, scan);
+      if (scan) {
+        const uint32_t at = n_scan + __popc(scan_mask & ((1u << lane) - 1u));
+        surv[at] = c_doc_[r];
+        spos[at] = scan_from;
+      }
+      n_scan += __popc(scan_mask);
     }
-    const unsigned scan_mask = __ballot_sync(0xffffffffu, scan);
-    if (scan) {
-      surv[n_scan + __popc(scan_mask & ((1u << lane) - 1u))] = doc;  // n_scan + rank <= s: never ahead of the reads
-    }
-    n_scan += __popc(scan_mask);
     __syncwarp();
   }
 
@@ -1120,11 +1382,15 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
       if (tl > kThreadScanMaxTerm || len > kThreadScanMaxDoc) {
         slow = true;
         len = 0;  // handled below
+      } else {
+        const uint32_t from = min(spos[s], len);  // start positions before it are settled
+        b += from;
+        len -= from;
       }
     }
     const bool found = group_contains_term<kGroup>(iv.text, b, len, term, tl, tregs);
     if (found && (lane & (kGroup - 1)) == 0) {
-      ++hits;
+      ++acc.hits;
     }
     // rare: long terms / very long documents go through the warp-cooperative scanner, one document at a time
     unsigned slow_mask = __ballot_sync(0xffffffffu, slow && (lane & (kGroup - 1)) == 0);
@@ -1136,30 +1402,78 @@ __device__ __forceinline__ void df_warp_tile(const IndexView& iv, const BatchVie
       const uint32_t c = doc_count_term(d, term, tl, true);
       __syncwarp();
       if (lane == src) {
-        hits += c != 0 ? 1u : 0u;
+        acc.hits += c != 0 ? 1u : 0u;
       }
+    }
+  }
+  if (lane == 0) {
+    acc.cand += n;
+    acc.scanned += n_scan;
+  }
+}
+
+// One warp, n_entries entries of a term's shortest list from entry e0 on: the whole df work of that range.
+// The pieces' candidates are collected first (with signatures in the payload most entries never leave the collecting
+// loop) and go through membership and verification 128 at a time, so the cost of narrowing the other lists is paid
+// per 128 CANDIDATES instead of per 128 entries. stage / surv / spos are the calling warp's own shared-memory
+// slices; stat_stripe spreads the accounting atomics.
+__device__ __forceinline__ void df_warp_unit(const IndexView& iv, const BatchView& bv, const ListRef& drv, uint32_t t,
+                                             uint32_t k0, uint32_t k1, uint64_t e0, uint32_t n_entries, uint32_t* stage,
+                                             uint32_t* surv, uint32_t* spos, uint32_t stat_stripe) {
+  const unsigned lane = threadIdx.x & 31u;
+  if (e0 >= drv.len) {
+    return;  // no block-wide barrier is used below, so a warp may leave early
+  }
+  const uint64_t unit_end = umin64(drv.len, e0 + n_entries);
+  const uint32_t n_pieces = static_cast<uint32_t>((unit_end - e0 + kDfPiece - 1) / kDfPiece);
+  const DfTerm tc = df_term_consts(iv, bv, drv, t, k0);
+  uint32_t hint[kDfHintLists] = {0, 0};
+  DfAcc acc;
+  uint32_t n_set = 0;
+#pragma unroll 1
+  for (uint32_t piece = 0; piece < n_pieces; ++piece) {
+    n_set += df_collect_piece(drv, tc, e0, piece * kDfPiece, unit_end, surv, n_set);
+    const bool last = piece + 1 == n_pieces;
+#pragma unroll 1
+    while (n_set >= static_cast<uint32_t>(kWarpTile) || (last && n_set > 0)) {
+      const uint32_t c = min(n_set, static_cast<uint32_t>(kWarpTile));
+      df_process_chunk(iv, bv, drv, tc, t, k0, k1, e0, surv, spos, c, stage, hint, acc);
+#ifdef MGX_DF_NO_HINT
+      hint[0] = hint[1] = 0;
+#endif
+      __syncwarp();
+      const uint32_t rest = n_set - c;  // moves down in ascending order: a lane never overwrites what another still reads
+      for (uint32_t i0 = 0; i0 < rest; i0 += 32) {
+        const uint32_t v = i0 + lane < rest ? surv[c + i0 + lane] : 0u;
+        __syncwarp();
+        if (i0 + lane < rest) {
+          surv[i0 + lane] = v;
+        }
+      }
+      __syncwarp();
+      n_set = rest;
     }
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) {
-    hits += __shfl_xor_sync(0xffffffffu, hits, s);
-    text_bytes += __shfl_xor_sync(0xffffffffu, text_bytes, s);
+    acc.hits += __shfl_xor_sync(0xffffffffu, acc.hits, s);
+    acc.text_bytes += __shfl_xor_sync(0xffffffffu, acc.text_bytes, s);
   }
   if (lane == 0) {
-    if (hits != 0) {
-      atomicAdd(reinterpret_cast<unsigned long long*>(bv.t_df + t), static_cast<unsigned long long>(hits));
+    if (acc.hits != 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(bv.t_df + t), static_cast<unsigned long long>(acc.hits));
     }
-    stat_add_at(bv, kStatDfBytes, stat_stripe, text_bytes);
-    stat_add_at(bv, kStatDfCandidates, stat_stripe, n);
-    if (n_scan != 0) {
-      stat_add_at(bv, kStatDfScanned, stat_stripe, n_scan);
+    stat_add_at(bv, kStatDfBytes, stat_stripe, acc.text_bytes);
+    stat_add_at(bv, kStatDfCandidates, stat_stripe, acc.cand);
+    if (acc.scanned != 0) {
+      stat_add_at(bv, kStatDfScanned, stat_stripe, acc.scanned);
     }
   }
 }
 
 __global__ void __launch_bounds__(kTileThreads, MGX_DF_OCC) df_tile_kernel(IndexView iv, BatchView bv) {
   __shared__ __align__(16) uint32_t s_stage[kTileThreads / 32][kWarpStageCap];
-  __shared__ uint32_t s_surv[kTileThreads / 32][kWarpTile];
+  __shared__ uint32_t s_surv[kTileThreads / 32][kDfSetCap];
   __shared__ uint32_t s_spos[kTileThreads / 32][kWarpTile];
   const unsigned warp = threadIdx.x >> 5;
   // one 32-byte descriptor instead of tile -> term -> keys -> dictionary -> offsets
@@ -1171,9 +1485,8 @@ __global__ void __launch_bounds__(kTileThreads, MGX_DF_OCC) df_tile_kernel(Index
   drv.len = d0.z;
   drv.bm = nullptr;
   const uint64_t tile = d1.z;
-  uint32_t hint[kDfHintLists] = {0, 0};  // one piece per warp here: nothing to carry
-  df_warp_tile(iv, bv, drv, d0.w, d1.x, d1.y, tile * kTile + static_cast<uint64_t>(warp) * kWarpTile, s_stage[warp],
-               s_surv[warp], s_spos[warp], blockIdx.x, hint);
+  df_warp_unit(iv, bv, drv, d0.w, d1.x, d1.y, tile * kTile + static_cast<uint64_t>(warp) * kWarpTile, kWarpTile, s_stage[warp],
+               s_surv[warp], s_spos[warp], blockIdx.x);
 }
 
 // Streamed form (no host read-back of the tile count): persistent warps pull UNITS of kDfUnit entries of the terms'
@@ -1206,7 +1519,7 @@ __device__ __forceinline__ uint32_t warp_upper_bound_u64(const uint64_t* __restr
 
 __global__ void __launch_bounds__(kTileThreads, MGX_DF_OCC) df_units_kernel(IndexView iv, BatchView bv) {
   __shared__ __align__(16) uint32_t s_stage[kTileThreads / 32][kWarpStageCap];
-  __shared__ uint32_t s_surv[kTileThreads / 32][kWarpTile];
+  __shared__ uint32_t s_surv[kTileThreads / 32][kDfSetCap];
   __shared__ uint32_t s_spos[kTileThreads / 32][kWarpTile];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
@@ -1235,16 +1548,8 @@ __global__ void __launch_bounds__(kTileThreads, MGX_DF_OCC) df_units_kernel(Inde
     drv.len = r1.x;
     drv.bm = nullptr;
     const uint64_t e0 = (static_cast<uint64_t>(unit) - bv.t_df_tile_off[t]) * kDfUnit;
-    uint32_t hint[kDfHintLists] = {0, 0};
-#pragma unroll 1
-    for (uint32_t piece = 0; piece < kDfUnit / kWarpTile; ++piece) {
-      df_warp_tile(iv, bv, drv, t, k0, k1, e0 + static_cast<uint64_t>(piece) * kWarpTile, s_stage[warp], s_surv[warp],
-                   s_spos[warp], unit, hint);
-#ifdef MGX_DF_NO_HINT
-      hint[0] = hint[1] = 0;
-#endif
-      __syncwarp();
-    }
+    df_warp_unit(iv, bv, drv, t, k0, k1, e0, kDfUnit, s_stage[warp], s_surv[warp], s_spos[warp], unit);
+    __syncwarp();
   }
 }
 
@@ -4087,7 +4392,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
     uint32_t* boff = reinterpret_cast<uint32_t*>(S + i_boff);
     uint32_t* koff = reinterpret_cast<uint32_t*>(S + i_koff);
     uint64_t* keys = reinterpret_cast<uint64_t*>(S + i_keys);
-    uint16_t* key_toff = reinterpret_cast<uint16_t*>(S + i_ktoff);
+    uint32_t* key_toff = reinterpret_cast<uint32_t*>(S + i_ktoff);
     uint8_t* raw = S + i_raw;
     uint32_t nb = 0, nk = 0;
     boff[0] = 0;
@@ -4107,7 +4412,7 @@ void batch_upload(Batch& b, std::vector<HostTerm>& terms, const std::vector<Host
             std::memset(dst, 0, L.wide_words * 8);
           }
         }
-        key_toff[nk + k] = k < ht.key_toff.size() ? ht.key_toff[k] : kNoTermOffset;
+        key_toff[nk + k] = k < ht.key_toff.size() ? ht.key_toff[k] : static_cast<uint32_t>(kNoTermOffset);
       }
       nk += static_cast<uint32_t>(ht.keys.size());
       koff[t + 1] = nk;
@@ -4254,7 +4559,7 @@ StageOffsets stage_offsets(const StageLayout& L) {
   O.i_loff = add((Q + 1) * 4);
   O.i_hflags = add((Q + 1) * 4);
   O.i_slot = add(L.n_slots * 4);
-  O.i_ktoff = add(L.n_keys * 2);
+  O.i_ktoff = add(L.n_keys * 4);
   O.i_thr = add((Q + 1) * 4);
   O.i_poff = add((Q + 1) * 4);
   O.i_pops = add(L.n_prog);
@@ -4316,7 +4621,7 @@ void batch_bind(Batch& b) {
   b.d_q_loff.borrow(reinterpret_cast<uint32_t*>(at(i_loff)), Q + 1);
   b.d_q_host_flags.borrow(reinterpret_cast<uint32_t*>(at(i_hflags)), Q + 1);
   b.d_slot_tid.borrow(reinterpret_cast<uint32_t*>(at(i_slot)), L.n_slots);
-  b.d_key_toff.borrow(reinterpret_cast<uint16_t*>(at(i_ktoff)), n_keys);
+  b.d_key_toff.borrow(reinterpret_cast<uint32_t*>(at(i_ktoff)), n_keys);
   b.d_q_threshold.borrow(reinterpret_cast<uint32_t*>(at(i_thr)), Q + 1);
   b.d_q_poff.borrow(reinterpret_cast<uint32_t*>(at(i_poff)), Q + 1);
   b.d_prog_op.borrow(at(i_pops), n_prog);

@@ -21,7 +21,7 @@ constexpr uint32_t kMaxTopK = 1024;
 // The planning tail leaves the work sizes in a small device block; persistent kernels pull their work items from the
 // counters next to them. The block follows the accounting counters, so one memset clears both.
 #ifndef MGX_DF_UNIT
-#define MGX_DF_UNIT 256
+#define MGX_DF_UNIT 2048
 #endif
 constexpr uint32_t kDfUnit = MGX_DF_UNIT;          // driver entries per df work unit of a streamed batch (kTile in the other form)
 enum LaunchSlot : int {
@@ -231,7 +231,7 @@ struct Batch {
   DevBuf<uint64_t> d_wide;        // [K * wide_words] words of the wide keys (null for packed keys)
   DevBuf<uint32_t> d_key_list;    // [K] dictionary term index or kNone; sorted by length inside a term
   DevBuf<uint32_t> d_key_len;     // [K]
-  DevBuf<uint16_t> d_key_toff;    // [K] byte offset of the n-gram inside its term, kNoTermOffset if unusable
+  DevBuf<uint32_t> d_key_toff;    // [K] byte offset of the n-gram inside its term, kNoTermOffset if unusable
   DevBuf<KeyRef> d_key_ref;       // [K] resolved lists, in the per-term order term_plan_kernel leaves
   DevBuf<uint64_t> d_t_est;       // [T]
   DevBuf<uint32_t> d_t_df_tiles;  // [T]

@@ -810,3 +810,69 @@ def test_full_size_properties_10m(mgx):
         del os.environ["MGX_DF_MODE"]
     assert np.array_equal(a.df, s2.df) and np.array_equal(a.total, s2.total)
     assert np.array_equal(a.ids[valid], s2.ids[valid]) and np.array_equal(a.scores[valid], s2.scores[valid])
+
+
+# ----------------------------------------------------------------------------------------- posting payload
+def _sig(cp, bits):
+    if cp is None or bits == 0:
+        return 0
+    h7 = ((cp * 0x9E3779B1) & 0xFFFFFFFF) >> 25
+    return max(1, h7 >> (7 - bits))
+
+
+def _expected_payload(docs, n, layout):
+    """n-gram -> [(local doc, first word, second word)] for fixed-size n-grams over valid UTF-8 documents."""
+    pos_bits, nb, pb = layout
+    out = {}
+    for d, raw in enumerate(docs):
+        text = raw.decode()
+        offs = [0]
+        for ch in text:
+            offs.append(offs[-1] + len(ch.encode()))
+        occ = {}
+        for i in range(len(text) - n + 1):
+            g = text[i:i + n]
+            nxt = ord(text[i + n]) if i + n < len(text) else None
+            prv = ord(text[i - 1]) if i > 0 else None
+            occ.setdefault(g, []).append((offs[i], nxt, prv))
+        for g, lst in occ.items():
+            def word(k, more):
+                if k >= len(lst):
+                    return 0x7FFF if k == 1 else 0
+                off, nxt, prv = lst[k]
+                p = off if off < 0x7FFF else 0x7FFF
+                return p | (0x8000 if more else 0) | (_sig(nxt, nb) << 16) | (_sig(prv, pb) << 24)
+            first = word(0, len(lst) > 1)
+            second = word(1, len(lst) > 2) if len(lst) > 1 else 0x7FFF
+            out.setdefault(g, []).append((d, first, second))
+    return out
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 0, 0), (2, 30, 97, 0), (1, 30, 53, 0), (2, 30, 0, 40000)])
+def test_posting_payload_positions_and_signatures(mgx, shape):
+    """First / second occurrence offsets and neighbour signatures of every posting (the payload the verified-df
+    kernels filter on) against a direct computation, over documents that cross tokenizer tiles."""
+    n, max_units, long_every, huge = shape
+    docs = make_docs(91 + n, 700, max_units, bad=False, long_every=long_every)
+    if huge:
+        rnd = random.Random(7)
+        docs[3] = b"".join(rnd.choice(CJK[:6]).encode() for _ in range(huge // 3))  # > 32 KB: offsets saturate
+    ids = np.arange(len(docs), dtype=np.uint32) * 2 + 10
+    gi = mgx.Index(n, 0, True)
+    gi.add_document_batch(ids, docs)
+    _, _, _, layout = gi.posting_payload("zz")
+    longest = max(len(d) for d in docs)
+    assert layout[0] == min(15, max(8, longest.bit_length())) and layout[0] + layout[1] + layout[2] == 22
+    assert 0 < layout[2] <= layout[1] <= 7
+    want = _expected_payload(docs, n, layout)
+    rnd = random.Random(5)
+    grams = sorted(want)
+    sample = rnd.sample(grams, min(400, len(grams))) + [g for g in grams if len(want[g]) > 200][:20]
+    bad = []
+    for g in sample:
+        d, f, s, _ = gi.posting_payload(g)
+        got = list(zip(d.tolist(), f.tolist(), s.tolist()))
+        if got != want[g]:
+            k = next(i for i in range(min(len(got), len(want[g]))) if got[i] != want[g][i]) if len(got) == len(want[g]) else -1
+            bad.append((g, len(got), len(want[g]), k, got[k] if k >= 0 else None, want[g][k] if k >= 0 else None))
+    assert not bad, f"{len(bad)} n-grams differ, first: {bad[:3]}"
