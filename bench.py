@@ -707,6 +707,25 @@ def main():
         pipe.finish(p)
         pipe.release(p, collect_stats=True)
     kstats = pipe.stats
+    # B_df as SURVEY 8(d) defines it -- the text bytes of every document of SearchAnd(n-grams), the set the
+    # reference's PopulateTermDocumentFrequency scans -- comes from one more batch with the signature pre-filter off
+    # (MGX_DF_NO_SIG: every entry goes through the membership stage, as in round 1); the timed runs above use the
+    # filter and read the text of far fewer documents (reported as text_bytes_read)
+    ref_df = None
+    if kstats and kstats[0].get("algo_bytes_df", 0) > 0 and os.environ.get("MGX_DF_NO_SIG") is None:
+        os.environ["MGX_DF_NO_SIG"] = "1"
+        try:
+            n_before = len(pipe.stats)
+            p = prepare(args.warmup, 0)
+            pipe.enqueue(p, 0)
+            pipe.finish(p)
+            pipe.release(p, collect_stats=True)
+            ref = pipe.stats[-1]
+            ref_df = {"algo_bytes_df": ref["algo_bytes_df"], "df_candidates": ref["df_candidates"],
+                      "ms_df_kernel": ref["ms_df_kernel"]}
+            kstats = pipe.stats[:n_before]
+        finally:
+            del os.environ["MGX_DF_NO_SIG"]
 
     # ---- e2e: host buffers in, host buffers out, every step: compile threads prepare batches ahead (host query
     # compile + H2D of the compiled batch), the main thread enqueues them (merged record -> pinned host memory) and
@@ -808,8 +827,11 @@ def main():
         step_ms = ms_total / n_timed
         kernels = {
             "df_tile / df_units (verified df: candidate tiles)": {
-                "ms": agg["ms_df_kernel"] / nb, "algo_bytes": agg["algo_bytes_df"] / nb,
-                "list_bytes": agg["algo_bytes_df_lists"] / nb},
+                "ms": agg["ms_df_kernel"] / nb,
+                "algo_bytes": ref_df["algo_bytes_df"] if ref_df else agg["algo_bytes_df"] / nb,
+                "list_bytes": agg["algo_bytes_df_lists"] / nb,
+                "text_bytes_read": agg["algo_bytes_df"] / nb,
+                "without_signature_filter": ref_df},
             "df_stream (verified df: one pass over the text arena)": {
                 "ms": agg["ms_df_stream_kernel"] / nb, "algo_bytes": agg["df_stream_bytes"] / nb},
             "and_tile (intersection + fused BM25 epilogue)": {
@@ -834,9 +856,13 @@ def main():
                     "algorithmic_bytes_per_launch": kk["algo_bytes"], "avg_launch_ms": kk["ms"],
                     "algorithmic_bytes_note": "SURVEY 8(d) per-query bytes summed over the batch on the device: for the "
                                               "df kernels B_df = text bytes of every candidate document of every scanned "
-                                              "term (the bytes the reference's algorithm reads; the positional check "
-                                              "reads fewer); the posting-list bytes of those terms are reported "
-                                              "separately as list_bytes and NOT counted in `achieved`",
+                                              "term = the documents of SearchAnd(n-grams), the set the reference's "
+                                              "algorithm scans, counted by one batch with the signature pre-filter off "
+                                              "(kernels[...].without_signature_filter); the timed kernel rules most of "
+                                              "them out on the posting payload and reads text_bytes_read; the "
+                                              "posting-list bytes of those terms are reported separately as list_bytes "
+                                              "and NOT counted in `achieved`, which is therefore a rate of ALGORITHMIC "
+                                              "bytes and can exceed the DRAM peak: dram_frac is the memory-system figure",
                     "step_share": kk["ms"] / max(1e-9, step_ms),
                     "dram_frac": (traffic / 1e9) / (kk["ms"] / 1e3) / peak if traffic else None}
 

@@ -973,7 +973,10 @@ __device__ __forceinline__ DfTerm df_term_consts(const IndexView& iv, const Batc
       c.sig_mask |= 0x7Fu << 24;
     }
   }
-  c.prefilter = c.toff_ok && c.tl != 0 && c.drv_pos != nullptr;
+  // without signatures in the payload (or with MGX_DF_NO_SIG) the stage runs as it did before them: every entry goes
+  // through the membership stage, so its candidates are exactly the documents of SearchAnd(n-grams) -- the set the
+  // reference scans, which is what the accounting of B_df is defined on
+  c.prefilter = c.toff_ok && c.tl != 0 && c.drv_pos != nullptr && (iv.sig_next_bits | iv.sig_prev_bits) != 0;
   return c;
 }
 

@@ -79,6 +79,28 @@ def test_workspace_overflow_is_repeated_in_the_synchronous_form(mgx, shard, monk
     same_answers(again, want, 100)
 
 
+def test_df_signature_filter_changes_no_answer(mgx, shard, monkeypatch):
+    """The df stage rules entries out on the payload signatures before it probes a list or reads text; with
+    MGX_DF_NO_SIG it runs the unfiltered form (every entry through the membership stage). Same answers, same df,
+    streamed and synchronous, and far fewer candidates with the filter."""
+    c, gi = shard
+    qs = corpus_mod.sample_queries(c, 3000, 11, n_terms=3, min_cp=2, max_cp=4)
+    monkeypatch.setenv("MGX_DF_MODE", "tiles")
+    want = gi.query_batch(qs, score=True, limit=100)
+    cand = gi.last_batch_stats().df_candidates
+    assert cand > 0
+    for envs in (("MGX_DF_NO_SIG",), ("MGX_NO_STREAMED",), ("MGX_DF_NO_SIG", "MGX_NO_STREAMED")):
+        for e in envs:
+            monkeypatch.setenv(e, "1")
+        got = gi.query_batch(qs, score=True, limit=100)
+        cand_here = gi.last_batch_stats().df_candidates
+        for e in envs:
+            monkeypatch.delenv(e)
+        same_answers(got, want, 100)
+        if "MGX_DF_NO_SIG" in envs:
+            assert cand_here > 2 * cand, (cand_here, cand)
+
+
 def test_boolean_programs_and_filters_streamed(mgx, shard, monkeypatch):
     c, gi = shard
     rng = np.random.default_rng(3)
