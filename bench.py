@@ -732,7 +732,7 @@ def main():
     # waits for the batch that left the pipeline `in_flight` steps ago.
     from concurrent.futures import ThreadPoolExecutor
     outs = [torch.empty(lay["bytes"], dtype=torch.uint8, pin_memory=True) for _ in range(in_flight)]
-    e2e_parts = {"host_prepare_ms": 0.0, "enqueue_ms": 0.0, "wait_ms": 0.0}
+    e2e_parts = {"host_prepare_ms": 0.0, "wait_for_prepared_ms": 0.0, "enqueue_ms": 0.0, "wait_ms": 0.0}
     # N > 1: the ranks of the node take turns compiling (batch number seq is compiled by rank seq % N and handed to the
     # others through the shared-memory ring of mgx_share_*), instead of every rank compiling every batch
     share_seq = [0]
@@ -786,7 +786,9 @@ def main():
         for j in range(min(ahead, len(order))):
             futs[j] = compiler.submit(e2e_prepare, order[j], j % in_flight, seq0 + j)
         for j, i in enumerate(order):
+            t_w = time.perf_counter()
             p, prep_ms = futs.pop(j).result()
+            wait_prep = 1e3 * (time.perf_counter() - t_w)
             if j + ahead < len(order):
                 futs[j + ahead] = compiler.submit(e2e_prepare, order[j + ahead], (j + ahead) % in_flight, seq0 + j + ahead)
             t_b = time.perf_counter()
@@ -800,6 +802,7 @@ def main():
                 pipe.release(q)
             if acc is not None:
                 acc["host_prepare_ms"] += prep_ms
+                acc["wait_for_prepared_ms"] += wait_prep
                 acc["enqueue_ms"] += 1e3 * (t_c - t_b)
                 acc["wait_ms"] += 1e3 * (time.perf_counter() - t_c)
         for q in pending:

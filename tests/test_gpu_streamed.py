@@ -101,6 +101,49 @@ def test_df_signature_filter_changes_no_answer(mgx, shard, monkeypatch):
             assert cand_here > 2 * cand, (cand_here, cand)
 
 
+def test_df_terms_at_document_ends_and_long_terms(mgx, oracle, monkeypatch):
+    """The df stage compares candidates at the recorded occurrences of the driver n-gram. Terms that end exactly at /
+    would run past the end of a document (the arena holds the documents back to back), terms longer than the 12 bytes
+    compared in registers, and repeated n-grams (tiny alphabet) must all agree with the oracle, with the signature
+    filter on and off."""
+    rnd = np.random.default_rng(17)
+    alphabet = [chr(0x4E00 + i) for i in range(12)] + list("ab")
+    docs = []
+    for _ in range(6000):
+        n = int(rnd.integers(1, 40))
+        docs.append("".join(alphabet[int(i)] for i in rnd.integers(0, len(alphabet), n)).encode())
+    ids = np.arange(1, len(docs) + 1, dtype=np.uint32)
+    qs = []
+    for _ in range(1500):
+        d = docs[int(rnd.integers(0, len(docs)))].decode()
+        n = int(rnd.integers(2, 9))  # up to 8 code points = 24 bytes: past the 12 compared in registers
+        if len(d) < n:
+            continue
+        a = int(rnd.integers(0, len(d) - n + 1))
+        if rnd.random() < 0.5:
+            a = len(d) - n  # ends exactly where its document ends: one more character would cross into the next
+        t = d[a:a + n]
+        extra = alphabet[int(rnd.integers(0, len(alphabet)))]
+        qs.append([t.encode(), (t + extra).encode()] if rnd.random() < 0.5 else [t.encode()])
+    oi = oracle.index(2, 0, True)
+    oi.add_texts(ids, docs)
+    want = oi.query_batch(qs, score=True, limit=50)
+    gi = mgx.Index(2, 0, True)
+    gi.add_document_batch(ids, docs)
+    monkeypatch.setenv("MGX_DF_MODE", "tiles")
+    for env in (None, "MGX_DF_NO_SIG"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        got = gi.query_batch(qs, score=True, limit=50)
+        if env:
+            monkeypatch.delenv(env)
+        assert np.array_equal(got.df, want.df), env
+        assert np.array_equal(got.total, want.total) and np.array_equal(got.count, want.count)
+        for q in range(len(qs)):  # (neighbours with scores within rounding may swap against the CPU)
+            n = int(want.count[q])
+            assert sorted(got.ids[q, :n]) == sorted(want.ids[q, :n]), qs[q]
+
+
 def test_boolean_programs_and_filters_streamed(mgx, shard, monkeypatch):
     c, gi = shard
     rng = np.random.default_rng(3)

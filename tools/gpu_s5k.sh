@@ -1,0 +1,28 @@
+#!/bin/bash
+# session 5, call k (1 GPU): verification arena (0xFF after every document) + positions of the recorded occurrences in
+# it: candidates compared with one read of the text. Parity subset, C2 with and without it, build trace
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_streamed.py -x -q -m gpu \
+    -k "payload or df_ or build or large_batch or query_batch or kat or streamed or mutation or add_update" > gpurun_out/pytest_s5k.log 2>&1
+echo "tests rc=$?"; tail -8 gpurun_out/pytest_s5k.log
+export BENCH_NO_CLOCKS=1
+for v in vtext novtext; do
+  unset MGX_DF_NO_VTEXT
+  if [ $v = novtext ]; then export MGX_DF_NO_VTEXT=1; fi
+  MGX_BUILD_TRACE=1 timeout 900 python bench.py --config c2 --steps 10 --warmup 3 --no-cpu-baseline --parity gpu \
+      > gpurun_out/c2_s5k_$v.json 2> gpurun_out/c2_s5k_$v.err
+  echo "== $v rc=$?"; grep "mgx build" gpurun_out/c2_s5k_$v.err | tail -12
+  python - <<P
+import json
+d=json.loads(open('gpurun_out/c2_s5k_$v.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d.get('parity',{}).get('ok'), d['run']['index_resident_gb'])
+print({k:round(v['ms'],3) for k,v in d['kernels'].items()})
+print({k:d['batch_stats_per_step'][k] for k in ('df_candidates','df_scanned_docs','algo_bytes_df')})
+P
+done
+unset MGX_DF_NO_VTEXT
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:df_units_kernel -s 4 -c 1 \
+    -o gpurun_out/prof_df_units_s5k -f python bench.py --config c2 --steps 1 --warmup 1 --no-cpu-baseline --parity off \
+    --min-seconds 0 > gpurun_out/ncu_s5k.log 2>&1
+echo "ncu rc=$?"
