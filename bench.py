@@ -416,7 +416,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--docs", type=int, default=0, help="documents of the WHOLE corpus (0 = the config's size)")
     ap.add_argument("--batch", type=int, default=0, help="queries per batch (0 = the config's size)")
-    ap.add_argument("--in-flight", type=int, default=0, help="batches in flight (0 = 3)")
+    ap.add_argument("--in-flight", type=int, default=0, help="batches in flight (0 = 6 on one GPU, 3 otherwise)")
     ap.add_argument("--min-seconds", type=float, default=1.0,
                     help="the timed K steps are repeated (same batches, in order) until the timed window is this long")
     ap.add_argument("--cpu-sample", type=int, default=256, help="minimum queries per step of the CPU arm")
@@ -612,7 +612,10 @@ def main():
     scored = args.config != "c4"
     params = index.params(score=scored, descending=True, limit=TOPK, offset=0, k1=K1, b=B, total_docs=total_docs,
                           total_doc_length=total_len)
-    in_flight = args.in_flight or 3
+    # measured (gpurun_out/c2_s5o_*, c2_s5p_*): six batches in flight are 4-20 % faster than three on one GPU (the
+    # fixed, latency-bound part of a batch overlaps the next batches' kernels); at N > 1 the gain of the device loop
+    # (+4 %) is lost again end to end, where the compile look-ahead is shorter than the pipeline
+    in_flight = args.in_flight or (6 if world == 1 else 3)
     comm = sharded.ShardComm(mgx, dist if world > 1 else None, device, n_lanes=min(4, in_flight))
     pipe = sharded.ShardPipeline(mgx, index, params, TOPK, comm)
     lay = sharded.record_layout(args.batch, TOPK)
