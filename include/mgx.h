@@ -23,10 +23,13 @@
  *  - every entry point may be called from any thread, concurrently, on the same handle;
  *  - reading calls (searches, batches, stats, export) share the index; concurrent single calls run side by side on
  *    the device, each on its own stream with its own workspace (up to 8 at a time, further callers wait);
- *  - mgx_index_build*, mgx_index_set_filter_column, mgx_index_clear / trim / optimize and the commit of journaled
- *    mutations take the index exclusively: they wait for the readers in flight and hold new ones back meanwhile;
- *  - add / update / remove_document only append to a journal (never block on readers); a reading call that STARTS
- *    after they return sees them (it commits the journal first);
+ *  - mgx_index_build*, mgx_index_set_filter_column, mgx_index_clear / trim / optimize take the index exclusively:
+ *    they wait for the readers in flight and hold new ones back meanwhile. The commit of journaled mutations builds
+ *    the next generation of the shard beside the current one while readers go on, and is exclusive only for the
+ *    exchange of the two; writers never overlap each other;
+ *  - add / update / remove_document only append to a journal (never block on readers or on a commit); a reading call
+ *    that STARTS after they return sees them (it commits the journal first, or waits for the commit that is doing
+ *    so) unless mgx_index_set_commit_mode chose overlapped reads;
  *  - a staged batch (mgx_batch_prepare* .. mgx_batch_destroy) is a reader for its whole lifetime. A thread must not
  *    call a committing entry point of the same index while it holds such a batch and mutations are pending: the
  *    commit would wait for the batch. Stages of ONE batch must not be issued concurrently.
@@ -100,9 +103,11 @@ int mgx_index_build_device(mgx_index_t* index, const uint32_t* d_doc_ids, const 
  * matching DocumentStore calls: the document of `doc_id` (text + postings) is added, replaced or removed. The
  * calls are journaled on the host and take effect before the NEXT read of the index (any search / stats / export
  * call, or mgx_index_commit): the resident corpus is merged with the journal on the device and the shard is
- * rebuilt (~0.1 s per 10M documents), so a burst of mutations costs one rebuild. If that commit fails (device out of
- * memory, more than 2^32 n-gram occurrences) the reading call returns the error, the shard is EMPTY and the journal
- * is discarded: rebuild from the DocumentStore with mgx_index_build. `old_text` / `text` of update /
+ * rebuilt (~0.1 s per 10M documents), so a burst of mutations costs one rebuild. The new generation of the shard is
+ * built BESIDE the current one: calls that are reading the index (staged batches included) go on during the build, and
+ * the exchange of the two generations is the only exclusive moment. If that commit fails (device out of memory,
+ * more than 2^32 n-gram occurrences) the reading call returns the error, the shard stays at the generation before the
+ * commit and the journal is discarded: rebuild from the DocumentStore with mgx_index_build. `old_text` / `text` of update /
  * remove must be the text the document currently has (what the reference requires to find its n-grams); the
  * resident copy is what is actually used. *out_indexed (may be NULL) = AddDocument's return value: 0 when the text
  * yields no n-gram (the document is stored but never matches). */
@@ -120,6 +125,12 @@ int mgx_index_update_document(mgx_index_t* index, uint32_t doc_id, const uint8_t
                               const uint8_t* new_text, uint64_t new_len);
 int mgx_index_remove_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* text, uint64_t text_len);
 int mgx_index_commit(mgx_index_t* index);
+/* What a reading call does when it finds a commit of another thread IN PROGRESS. overlapped == 0 (default): it waits
+ * for that commit, so it sees every mutation that returned before it began (the reference applies a mutation before
+ * Index::AddDocument returns). overlapped != 0: it answers from the current generation without waiting -- the reads of
+ * search threads next to an asynchronous applier (binlog_event_processor.cpp) never stall on a rebuild; a thread still
+ * sees its own mutations as long as no other thread's commit is running at that moment. */
+int mgx_index_set_commit_mode(mgx_index_t* index, int overlapped);
 
 typedef struct {
   uint64_t n_docs;

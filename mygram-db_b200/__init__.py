@@ -145,6 +145,7 @@ def lib():
     L.mgx_index_add_document_batch.argtypes = [C.c_void_p, u32p, u8p, u64p, C.c_uint64, u64p]
     L.mgx_index_remove_document.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint64]
     L.mgx_index_commit.argtypes = [C.c_void_p]
+    L.mgx_index_set_commit_mode.argtypes = [C.c_void_p, C.c_int]
     L.mgx_index_posting_size.argtypes = [C.c_void_p, u8p, C.c_uint64, u64p]
     L.mgx_index_get_postings.argtypes = [C.c_void_p, u8p, C.c_uint64, u32p, C.c_uint64, u64p]
     L.mgx_index_get_posting_payload.argtypes = [C.c_void_p, u8p, C.c_uint64, u32p, u32p, u32p, C.c_uint64, u64p,
@@ -432,6 +433,11 @@ class Index:
 
     def commit(self):
         _check(lib().mgx_index_commit(self._h))
+
+    def set_commit_mode(self, overlapped):
+        """overlapped=True: a read that finds another thread's commit in progress answers from the current
+        generation instead of waiting for it (mgx_index_set_commit_mode)."""
+        _check(lib().mgx_index_set_commit_mode(self._h, 1 if overlapped else 0))
 
     def build(self, doc_ids, arena, offsets):
         doc_ids = np.ascontiguousarray(doc_ids, dtype=np.uint32)

@@ -1062,7 +1062,17 @@ constexpr int kMaxLanes = 8;
 
 struct mgx_index {
   Index ix;
-  RwGate gate;  // build / commit / column upload exclusive; every reading call shared
+  RwGate gate;  // build / column upload / the generation swap of a commit exclusive; every reading call shared
+  // Commits of journaled mutations build the next generation of the shard BESIDE the current one (into `next`, while
+  // reading calls go on under shared access) and make it current in an exclusive section that only exchanges the
+  // two (swap_generation). writer_mu keeps the writers (build, commit, column upload, trim, clear, stream load) from
+  // overlapping each other for their whole duration; commit_mu is held by the one commit in progress.
+  Index next;
+  std::mutex writer_mu;
+  std::mutex commit_mu;
+  cudaStream_t commit_stream = nullptr;
+  std::atomic<int> commit_mode{0};  // mgx_index_set_commit_mode: 0 = a read waits for a commit in progress, 1 = it does not
+  std::atomic<bool> committing{false};  // a commit has taken its journal and not finished yet
   // Execution lanes of the single-call readers: a stream with its own search workspace each, so that concurrent
   // Index::Search* style calls from the server's worker threads (thread_pool.cpp:33) run side by side on the device
   // instead of queueing behind one mutex. Lane 0 is ix.stream.
@@ -1109,8 +1119,14 @@ struct mgx_index {
 namespace {
 struct WriteGuard {
   mgx_index* h;
-  explicit WriteGuard(mgx_index* index) : h(index) { h->gate.lock(); }
-  ~WriteGuard() { h->gate.unlock(); }
+  explicit WriteGuard(mgx_index* index) : h(index) {
+    h->writer_mu.lock();
+    h->gate.lock();
+  }
+  ~WriteGuard() {
+    h->gate.unlock();
+    h->writer_mu.unlock();
+  }
   WriteGuard(const WriteGuard&) = delete;
   WriteGuard& operator=(const WriteGuard&) = delete;
 };
@@ -1171,62 +1187,123 @@ struct Reader {
 // Applies the pending mutations; called at the top of every entry point that reads the index, BEFORE the call
 // takes its shared access (never under it: the commit needs the gate exclusively).
 int commit_pending(mgx_index_t* index) {
-  if (index == nullptr || !index->dirty.load(std::memory_order_acquire)) {
+  if (index == nullptr ||
+      (!index->dirty.load(std::memory_order_acquire) && !index->committing.load(std::memory_order_acquire))) {
     return MGX_OK;
   }
   return guarded([&]() {
-    std::lock_guard<std::mutex> jl(index->journal_mu);
-    if (index->journal.empty()) {
-      index->dirty.store(false);
-      return MGX_OK;
-    }
-    WriteGuard lock(index);
-    Index& ix = index->ix;
-    DeviceGuard guard(ix.device);
-    mgx_index::Journal& j = index->journal;
-    // A failed commit leaves the shard EMPTY (build_index_device resets it rather than keep half-built arrays) and the
-    // journal is discarded either way: retrying the same journal on every later read would fail the same way. The
-    // caller learns it from this call's status and rebuilds from its DocumentStore (mgx_index_build).
-    struct Discard {
-      mgx_index* h;
-      ~Discard() {
-        h->journal.clear();
-        h->dirty.store(false, std::memory_order_release);
+    // One commit at a time. A read that finds one in progress waits for it (it may hold mutations that returned
+    // before the read began) -- unless the handle is in overlapped mode, where it answers from the current generation.
+    std::unique_lock<std::mutex> cl(index->commit_mu, std::defer_lock);
+    if (index->commit_mode.load(std::memory_order_relaxed) != 0) {
+      if (!cl.try_lock()) {
+        return MGX_OK;
       }
-    } discard{index};
+    } else {
+      cl.lock();
+    }
+    // The journal as it stands now is this commit's; calls that arrive from here on start the next one. `committing`
+    // is raised before `dirty` falls, so a read that arrives in between still waits for this commit.
+    struct Committing {
+      mgx_index* h;
+      explicit Committing(mgx_index* i) : h(i) { h->committing.store(true, std::memory_order_release); }
+      ~Committing() { h->committing.store(false, std::memory_order_release); }
+    } committing{index};
+    mgx_index::Journal j;
+    {
+      std::lock_guard<std::mutex> jl(index->journal_mu);
+      if (index->journal.empty()) {
+        index->dirty.store(false);
+        return MGX_OK;
+      }
+      std::swap(j, index->journal);
+      index->journal.clear();
+      index->dirty.store(false, std::memory_order_release);
+    }
+    // A failed commit leaves the CURRENT generation as it was (the next one is built beside it) and the journal is
+    // discarded: retrying the same journal on every later read would fail the same way. The caller learns it from this
+    // call's status.
     j.text.push_back(0);
-    if (j.ascending) {
-      apply_journal_device(ix, j.ids.data(), j.removed.data(), j.text.data(), j.off.data(), j.ids.size(), ix.stream);
-      return MGX_OK;
-    }
-    // arrival order -> ascending ids, the LAST entry of an id wins (stable sort keeps arrival order among equals)
-    const size_t n = j.ids.size();
-    std::vector<uint32_t> order(n);
-    for (size_t i = 0; i < n; ++i) {
-      order[i] = static_cast<uint32_t>(i);
-    }
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return j.ids[a] < j.ids[b]; });
     std::vector<uint32_t> ids;
     std::vector<uint8_t> removed;
     std::vector<uint8_t> text;
     std::vector<uint64_t> off(1, 0);
-    ids.reserve(n);
-    removed.reserve(n);
-    off.reserve(n + 1);
-    text.reserve(j.text.size());
-    for (size_t k = 0; k < n; ++k) {
-      if (k + 1 < n && j.ids[order[k + 1]] == j.ids[order[k]]) {
-        continue;  // superseded by a later call for the same id
+    if (!j.ascending) {
+      // arrival order -> ascending ids, the LAST entry of an id wins (stable sort keeps arrival order among equals)
+      const size_t n = j.ids.size();
+      std::vector<uint32_t> order(n);
+      for (size_t i = 0; i < n; ++i) {
+        order[i] = static_cast<uint32_t>(i);
       }
-      const uint32_t e = order[k];
-      ids.push_back(j.ids[e]);
-      removed.push_back(j.removed[e]);
-      text.insert(text.end(), j.text.begin() + static_cast<ptrdiff_t>(j.off[e]),
-                  j.text.begin() + static_cast<ptrdiff_t>(j.off[e + 1]));
-      off.push_back(text.size());
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return j.ids[a] < j.ids[b]; });
+      ids.reserve(n);
+      removed.reserve(n);
+      off.reserve(n + 1);
+      text.reserve(j.text.size());
+      for (size_t k = 0; k < n; ++k) {
+        if (k + 1 < n && j.ids[order[k + 1]] == j.ids[order[k]]) {
+          continue;  // superseded by a later call for the same id
+        }
+        const uint32_t e = order[k];
+        ids.push_back(j.ids[e]);
+        removed.push_back(j.removed[e]);
+        text.insert(text.end(), j.text.begin() + static_cast<ptrdiff_t>(j.off[e]),
+                    j.text.begin() + static_cast<ptrdiff_t>(j.off[e + 1]));
+        off.push_back(text.size());
+      }
+      text.push_back(0);
     }
-    text.push_back(0);
-    apply_journal_device(ix, ids.data(), removed.data(), text.data(), off.data(), ids.size(), ix.stream);
+    const uint32_t* p_ids = j.ascending ? j.ids.data() : ids.data();
+    const uint8_t* p_removed = j.ascending ? j.removed.data() : removed.data();
+    const uint8_t* p_text = j.ascending ? j.text.data() : text.data();
+    const uint64_t* p_off = j.ascending ? j.off.data() : off.data();
+    const uint64_t n_j = j.ascending ? j.ids.size() : ids.size();
+
+    std::lock_guard<std::mutex> wl(index->writer_mu);  // no build / column upload / trim while the next generation forms
+    Index& ix = index->ix;
+    Index& next = index->next;
+    DeviceGuard guard(ix.device);
+    if (index->commit_stream == nullptr) {
+      MGX_CUDA(cudaStreamCreateWithFlags(&index->commit_stream, cudaStreamNonBlocking));
+    }
+    // the build workspaces (pairs, sort scratch) belong to whichever generation is being built
+    struct LendArenas {
+      Index& a;
+      Index& b;
+      LendArenas(Index& from, Index& to) : a(from), b(to) {
+        std::swap(a.build_arena0, b.build_arena0);
+        std::swap(a.build_arena, b.build_arena);
+      }
+      ~LendArenas() {
+        std::swap(a.build_arena0, b.build_arena0);
+        std::swap(a.build_arena, b.build_arena);
+      }
+    };
+    {
+      index->gate.lock_shared();  // the current generation is read (its corpus, its columns), never written
+      struct Unshare {
+        mgx_index* h;
+        ~Unshare() { h->gate.unlock_shared(); }
+      } unshare{index};
+      LendArenas lend(ix, next);
+      copy_index_config(next, ix);
+      apply_journal_device(ix, next, p_ids, p_removed, p_text, p_off, n_j, index->commit_stream);
+      MGX_CUDA(cudaStreamSynchronize(index->commit_stream));
+    }
+    {
+      index->gate.lock();  // exclusive only for the exchange
+      swap_generation(ix, next);
+      index->gate.unlock();
+    }
+    // `next` holds the previous generation now. Its arrays are released unless MGX_COMMIT_KEEP_SPARE asks to keep
+    // them for the next commit (no cudaMalloc / cudaFree per commit, at twice the resident memory).
+    if (std::getenv("MGX_COMMIT_KEEP_SPARE") == nullptr) {
+      next.drop_filter_columns();
+      next.d_bitmaps.release();
+      next.resident_a.release();
+      next.resident_b.release();
+      next.n_docs = next.n_terms = next.n_postings = 0;
+    }
     return MGX_OK;
   });
 }
@@ -1306,6 +1383,10 @@ void mgx_index_destroy(mgx_index_t* index) {
         cudaStreamSynchronize(index->lane_stream[i]);
         cudaStreamDestroy(index->lane_stream[i]);
       }
+    }
+    if (index->commit_stream != nullptr) {
+      cudaStreamSynchronize(index->commit_stream);
+      cudaStreamDestroy(index->commit_stream);
     }
     if (index->ix.stream != nullptr) {
       cudaStreamSynchronize(index->ix.stream);
@@ -1440,6 +1521,14 @@ int mgx_index_remove_document(mgx_index_t* index, uint32_t doc_id, const uint8_t
   (void)text;
   (void)text_len;
   return journal_put(index, doc_id, true, nullptr, 0);
+}
+
+int mgx_index_set_commit_mode(mgx_index_t* index, int overlapped) {
+  if (index == nullptr) {
+    return invalid("null argument");
+  }
+  index->commit_mode.store(overlapped != 0 ? 1 : 0, std::memory_order_relaxed);
+  return MGX_OK;
 }
 
 int mgx_index_commit(mgx_index_t* index) {

@@ -1720,8 +1720,57 @@ __global__ void __launch_bounds__(256) journal_copy_kernel(const uint32_t* __res
 
 }  // namespace
 
-void apply_journal_device(Index& ix, const uint32_t* h_ids, const uint8_t* h_removed, const uint8_t* h_text,
-                          const uint64_t* h_off, uint64_t n_j, cudaStream_t stream) {
+void copy_index_config(Index& to, const Index& from) {
+  to.cfg = from.cfg;
+  to.ngram = from.ngram;
+  to.kanji = from.kanji;
+  to.cross = from.cross;
+  to.width = from.width;
+  to.device = from.device;
+  to.wide_words = from.wide_words;
+}
+
+void swap_generation(Index& a, Index& b) {
+  using std::swap;
+  swap(a.n_docs, b.n_docs);
+  swap(a.sequential_ids, b.sequential_ids);
+  swap(a.first_id, b.first_id);
+  swap(a.d_doc_ids, b.d_doc_ids);
+  swap(a.d_text, b.d_text);
+  swap(a.d_text_off, b.d_text_off);
+  swap(a.d_doc_len, b.d_doc_len);
+  swap(a.text_bytes, b.text_bytes);
+  swap(a.d_tile_first_doc, b.d_tile_first_doc);
+  swap(a.n_text_tiles, b.n_text_tiles);
+  swap(a.n_terms, b.n_terms);
+  swap(a.n_postings, b.n_postings);
+  swap(a.d_term_keys, b.d_term_keys);
+  swap(a.wide_words, b.wide_words);
+  swap(a.d_wide_keys, b.d_wide_keys);
+  swap(a.d_term_off, b.d_term_off);
+  swap(a.d_postings, b.d_postings);
+  swap(a.d_post_pos, b.d_post_pos);
+  swap(a.d_post_pos2, b.d_post_pos2);
+  swap(a.has_positions, b.has_positions);
+  swap(a.sig, b.sig);
+  swap(a.text_less, b.text_less);
+  swap(a.d_term_bm, b.d_term_bm);
+  swap(a.d_bitmaps, b.d_bitmaps);
+  swap(a.resident_a, b.resident_a);
+  swap(a.resident_b, b.resident_b);
+  swap(a.n_dense, b.n_dense);
+  swap(a.bm_words, b.bm_words);
+  swap(a.dense_min_len, b.dense_min_len);
+  swap(a.total_doc_length, b.total_doc_length);
+  swap(a.doc_count, b.doc_count);
+  swap(a.all_valid_utf8, b.all_valid_utf8);
+  swap(a.n_pair_slots, b.n_pair_slots);
+  swap(a.last_build_ms, b.last_build_ms);
+  swap(a.columns, b.columns);
+}
+
+void apply_journal_device(const Index& ix, Index& next, const uint32_t* h_ids, const uint8_t* h_removed,
+                          const uint8_t* h_text, const uint64_t* h_off, uint64_t n_j, cudaStream_t stream) {
   const uint64_t n_old = ix.n_docs;
   const uint64_t j_bytes = h_off[n_j];
   DevBuf<uint32_t> d_jids, d_keep, d_live, d_new_ids, d_new_len, d_src;
@@ -1802,7 +1851,7 @@ void apply_journal_device(Index& ix, const uint32_t* h_ids, const uint8_t* h_rem
   }
   MGX_CUDA(cudaStreamSynchronize(stream));
   try {
-    build_index_device(ix, d_new_ids.p, d_new_text.p, d_new_off.p, n_new, new_bytes, stream);  // drops the old columns
+    build_index_device(next, d_new_ids.p, d_new_text.p, d_new_off.p, n_new, new_bytes, stream);  // drops next's columns
   } catch (...) {
     for (FilterColumn* c : carried) {
       delete c;
@@ -1810,7 +1859,7 @@ void apply_journal_device(Index& ix, const uint32_t* h_ids, const uint8_t* h_rem
     throw;
   }
   for (uint32_t c = 0; c < kMaxFilterColumns; ++c) {
-    ix.columns[c] = carried[c];
+    next.columns[c] = carried[c];
   }
 }
 

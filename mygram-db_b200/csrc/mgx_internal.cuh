@@ -690,9 +690,16 @@ void build_index_device(Index& ix, const uint32_t* doc_ids, const uint8_t* text,
 void load_index_device(Index& ix, const uint64_t* h_keys, const uint64_t* h_term_off, const uint32_t* h_postings,
                        uint64_t n_terms, uint64_t n_postings, cudaStream_t stream);
 // Folds a journal of document mutations (host arrays sorted by id; removed[j] != 0 deletes, otherwise the text
-// replaces / adds the document) into the resident corpus on the device and rebuilds the shard.
-void apply_journal_device(Index& ix, const uint32_t* h_ids, const uint8_t* h_removed, const uint8_t* h_text,
-                          const uint64_t* h_off, uint64_t n_j, cudaStream_t stream);
+// replaces / adds the document) into the resident corpus of `ix` on the device and builds the resulting shard INTO
+// `next` (another Index object with the same configuration; `ix` is only read, so calls that read it may run beside
+// this one). The filter columns of `ix` follow their documents into `next`. swap_generation then makes it current.
+void apply_journal_device(const Index& ix, Index& next, const uint32_t* h_ids, const uint8_t* h_removed,
+                          const uint8_t* h_text, const uint64_t* h_off, uint64_t n_j, cudaStream_t stream);
+// Exchanges everything a (re)build produces -- corpus mirror, dictionary, lists, payload, bitmaps, counters, filter
+// columns, resident arenas -- between two Index objects; configuration, streams, workspaces and pools stay.
+void swap_generation(Index& a, Index& b);
+// configuration of `from` into `to` (what a build reads)
+void copy_index_config(Index& to, const Index& from);
 // Number of posting lists the reference would hold as Roaring bitmaps (see mgx_index_get_statistics).
 uint64_t count_roaring_lists(const Index& ix, double roaring_threshold, uint64_t optimized_total_docs,
                              cudaStream_t stream);

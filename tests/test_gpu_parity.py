@@ -812,6 +812,74 @@ def test_full_size_properties_10m(mgx):
     assert np.array_equal(a.ids[valid], s2.ids[valid]) and np.array_equal(a.scores[valid], s2.scores[valid])
 
 
+def test_commit_builds_the_next_generation_beside_readers(mgx, oracle):
+    """A commit of journaled mutations builds the next generation of the shard beside the current one and exchanges
+    them in a short exclusive section. Reader threads that query all the time must see, for every answer, exactly the
+    state before or after some commit (never a mixture, never a fault); in overlapped mode they do not wait for a
+    commit in progress; afterwards the index equals the oracle's, filter columns included."""
+    import threading
+    rnd = random.Random(5)
+    n0 = 20000
+    base = make_docs(123, n0, 25)
+    ids0 = np.arange(1, n0 + 1, dtype=np.uint32)
+    gi = mgx.Index(2, 0, True)
+    gi.add_document_batch(ids0, base)
+    gi.set_filter_column_arrays(0, 8, (np.arange(n0, dtype=np.uint64) % 5))
+    oi = oracle.index(2, 0, True)
+    oi.add_texts(ids0, base)
+    marker = "鬱鬱鬱".encode()  # text no base document holds: every commit below adds documents that do
+    gram = "鬱鬱".encode()      # (Index::SearchAnd takes n-grams)
+    assert gi.search_and([gram]).size == 0
+    stop = threading.Event()
+    errors = []
+
+    def reader(seen):
+        try:
+            while not stop.is_set():
+                got = gi.search_and([gram])
+                seen.append(got.size)
+                assert np.array_equal(got, np.sort(got))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    base_count = 0
+    for overlapped in (False, True):
+        gi.set_commit_mode(overlapped)
+        lists = [[] for _ in range(3)]
+        threads = [threading.Thread(target=reader, args=(lst,)) for lst in lists]
+        for t in threads:
+            t.start()
+        added = 0
+        for round_ in range(4):
+            for k in range(50):
+                doc_id = 100000 + (1 if overlapped else 0) * 10000 + round_ * 100 + k
+                text = rand_text(rnd, 10) + marker + rand_text(rnd, 5)
+                gi.add_document(doc_id, text)
+                oi.add_document(doc_id, text)
+                added += 1
+            gi.commit()
+        stop.set()
+        for t in threads:
+            t.join()
+        stop.clear()
+        assert not errors, errors[:3]
+        for seen in lists:
+            assert seen, "a reader made no call"
+            # (a reading call commits what it finds journaled, so generations grow by any number of documents)
+            assert all(base_count <= v <= base_count + 200 for v in seen), sorted(set(seen))[:10]
+            assert seen == sorted(seen), "a reader saw an older generation after a newer one"
+        base_count += 200
+    gi.set_commit_mode(False)
+    assert gi.search_and([gram]).size == 400
+    assert_same_index(gi, oi)
+    qs = sample_queries_from_docs(base, rnd, 100)
+    assert_batch_equal(gi.query_batch(qs, score=True, limit=20), oi.query_batch(qs, score=True, limit=20), qs)
+    # the filter column followed the documents through eight commits (new documents have NULL there)
+    g = gi.query_batch([[b"ab"]], filters=[[(0, 0, "3")]], score=False, limit=5000)
+    ids = g.ids[0, :int(g.count[0])].astype(np.int64)
+    assert ids.size > 0 and np.all(ids <= n0) and np.all((ids - 1) % 5 == 3)
+
+
 # ----------------------------------------------------------------------------------------- posting payload
 def _sig(cp, bits):
     if cp is None or bits == 0:
