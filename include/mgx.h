@@ -444,6 +444,20 @@ int mgx_search_synonyms(const mgx_index_t* index, const mgx_expanded_query_t* qu
                         const uint64_t* variant_offsets, const uint64_t* group_begin, uint64_t n_groups,
                         uint32_t* out, uint64_t cap, uint64_t* out_count);
 
+/* Batch forms: n_queries fuzzy (synonym) queries that share `query` (NOT terms, filters, verification mode, n-gram
+ * sizes) and, for the fuzzy form, max_distance, answered in ONE batch on the device -- one upload, one planning
+ * pass, the queries' tiles side by side, one download -- instead of one small batch per call. q_term_begin[q .. q+1)
+ * are query q's terms in term_offsets (q_group_begin[q .. q+1) its groups in group_begin, whose entries index
+ * variant_offsets globally). Output: the queries' ascending doc ids back to back in `out`, out_offsets[q .. q+1) =
+ * query q (out_offsets has n_queries + 1 entries). Every answer equals the single call's. MGX_ERR_CAPACITY when the
+ * sum exceeds cap: out_offsets then holds the sizes. */
+int mgx_search_fuzzy_batch(const mgx_index_t* index, const mgx_expanded_query_t* query, uint64_t n_queries,
+                           const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                           uint32_t max_distance, uint32_t* out, uint64_t cap, uint64_t* out_offsets);
+int mgx_search_synonyms_batch(const mgx_index_t* index, const mgx_expanded_query_t* query, uint64_t n_queries,
+                              const uint8_t* variant_bytes, const uint64_t* variant_offsets, const uint64_t* group_begin,
+                              const uint64_t* q_group_begin, uint32_t* out, uint64_t cap, uint64_t* out_offsets);
+
 /* Timing / accounting of one batch (device times from CUDA events recorded on the launch
  * stream around the named kernels; bytes as defined in SURVEY.md §8(d) and DESIGN.md). */
 typedef struct {

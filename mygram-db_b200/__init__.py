@@ -168,6 +168,10 @@ def lib():
                                    C.c_uint64, u64p]
     L.mgx_search_synonyms.argtypes = [C.c_void_p, C.POINTER(ExpandedQuery), u8p, u64p, u64p, C.c_uint64, u32p,
                                       C.c_uint64, u64p]
+    L.mgx_search_fuzzy_batch.argtypes = [C.c_void_p, C.POINTER(ExpandedQuery), C.c_uint64, u8p, u64p, u64p, C.c_uint32,
+                                         u32p, C.c_uint64, u64p]
+    L.mgx_search_synonyms_batch.argtypes = [C.c_void_p, C.POINTER(ExpandedQuery), C.c_uint64, u8p, u64p, u64p, u64p,
+                                            u32p, C.c_uint64, u64p]
     L.mgx_mgix_encode.argtypes = [C.POINTER(MgixInfo), u8p, u64p, u64p, u32p, C.c_double, u8p, C.c_uint64, u64p]
     L.mgx_mgix_decode.argtypes = [u8p, C.c_uint64, C.POINTER(MgixInfo), u8p, u64p, u64p, u32p]
     L.mgx_index_save_mgix.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, u8p, C.c_uint64, u64p]
@@ -637,6 +641,52 @@ class Index:
         gb = np.asarray(gbeg, dtype=np.uint64)
         return self._set_call(lambda a, o, nt, out, cap, n: L.mgx_search_synonyms(
             self._h, C.byref(eq), a, o, _ptr(gb, u64p), len(groups), _ptr(out, u32p), cap, C.byref(n)), flat)
+
+    def _grouped_call(self, fn, n_queries, cap=1 << 24):
+        """fn(out, cap, offsets) -> status; repeats the call once with the reported size if the capacity was too small
+        (the batch runs again: callers that know their result sizes pass a fitting capacity)."""
+        offs = np.zeros(n_queries + 1, dtype=np.uint64)
+        for _ in range(2):
+            out = np.empty(max(1, cap), dtype=np.uint32)
+            rc = fn(out, cap, offs)
+            if rc == MGX_ERR_CAPACITY:
+                cap = int(offs[-1])
+                continue
+            _check(rc)
+            return [out[int(offs[q]):int(offs[q + 1])].copy() for q in range(n_queries)]
+        _check(rc)
+
+    def search_fuzzy_batch(self, queries, max_distance, not_terms=(), filters=None, verify_text=0, raw_ngram=None,
+                           raw_kanji=None):
+        """mgx_search_fuzzy_batch: `queries` is a list of term lists; returns one ascending id array per query."""
+        L = lib()
+        eq, keep = self._expanded(not_terms, filters, verify_text, raw_ngram, raw_kanji)
+        flat, qbeg = [], [0]
+        for q in queries:
+            flat += [_bytes(t) for t in q]
+            qbeg.append(len(flat))
+        a, o = pack_strings(flat if flat else [b""])
+        qb = np.asarray(qbeg, dtype=np.uint64)
+        return self._grouped_call(lambda out, cap, offs: L.mgx_search_fuzzy_batch(
+            self._h, C.byref(eq), len(queries), _ptr(a, u8p), _ptr(o, u64p), _ptr(qb, u64p), max_distance,
+            _ptr(out, u32p), cap, _ptr(offs, u64p)), len(queries))
+
+    def search_synonyms_batch(self, queries, not_terms=(), filters=None, verify_text=0, raw_ngram=None, raw_kanji=None):
+        """mgx_search_synonyms_batch: `queries` is a list of group lists (each group a list of variants)."""
+        L = lib()
+        eq, keep = self._expanded(not_terms, filters, verify_text, raw_ngram, raw_kanji)
+        flat, gbeg, qbeg = [], [0], [0]
+        for groups in queries:
+            for g in groups:
+                flat += [_bytes(v) for v in g]
+                gbeg.append(len(flat))
+            qbeg.append(len(gbeg) - 1)
+        a, o = pack_strings(flat if flat else [b""])
+        gb = np.asarray(gbeg, dtype=np.uint64)
+        qb = np.asarray(qbeg, dtype=np.uint64)
+        return self._grouped_call(lambda out, cap, offs: L.mgx_search_synonyms_batch(
+            self._h, C.byref(eq), len(queries), _ptr(a, u8p), _ptr(o, u64p), _ptr(gb, u64p), _ptr(qb, u64p),
+            _ptr(out, u32p), cap, _ptr(offs, u64p)), len(queries))
 
     # -- batched pipeline --------------------------------------------------------------------------
     def params(self, score=True, descending=True, limit=100, offset=0, verify_text=0, k1=1.2, b=0.75, total_docs=0,

@@ -1928,6 +1928,74 @@ int run_single_set_query(Index& ix, cudaStream_t lane_stream, std::vector<HostTe
 }
 
 
+// Many logical queries in ONE batch (the batch forms of the fuzzy / synonym calls): kernel queries
+// [group_begin[g], group_begin[g + 1]) belong to logical query g (several when finish_expanded split it by driver,
+// none when the reference answers the empty set without touching a list); their disjoint result sets are united per
+// group on the device. out: the groups' ascending doc ids back to back, out_offsets[g .. g + 1) = group g.
+int run_grouped_set_queries(Index& ix, cudaStream_t lane_stream, std::vector<HostTerm>& terms,
+                            const std::vector<HostQuery>& queries, const std::vector<uint32_t>& group_begin,
+                            uint32_t* out, uint64_t cap, uint64_t* out_offsets) {
+  const size_t n_groups = group_begin.size() - 1;
+  for (size_t g = 0; g <= n_groups; ++g) {
+    out_offsets[g] = 0;
+  }
+  if (queries.empty()) {
+    return MGX_OK;
+  }
+  PooledBatch pooled(ix);
+  Batch& b = pooled.h->b;
+  b.ix = &ix;
+  b.stream = lane_stream;
+  b.params = mgx_query_params_t{};
+  b.params.compute_score = 0;
+  b.launches_at_start = g_launches.load();
+  batch_upload(b, terms, queries, {});
+  batch_plan(b);
+  std::vector<uint64_t> set_off;
+  DevBuf<uint32_t> d_sets;
+  batch_search_sets(b, &set_off, &d_sets);
+  bool any_split = false;
+  for (size_t g = 0; g < n_groups; ++g) {
+    any_split = any_split || group_begin[g + 1] - group_begin[g] > 1;
+  }
+  if (any_split) {
+    DevBuf<uint32_t> d_union;
+    merge_grouped_runs(b, d_sets.p, set_off, group_begin, &d_union);
+    d_sets.borrow(d_union.p, d_union.n);  // both are views into the batch object's buffers
+  }
+  for (size_t g = 0; g <= n_groups; ++g) {
+    out_offsets[g] = set_off[group_begin[g]];
+  }
+  const uint64_t total = set_off.back();
+  if (total > cap) {
+    set_last_error("output capacity too small (out_offsets holds the sizes)");
+    return MGX_ERR_CAPACITY;
+  }
+  if (total > 0) {
+    MGX_CUDA(cudaMemcpyAsync(out, d_sets.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, b.stream));
+    MGX_CUDA(cudaStreamSynchronize(b.stream));
+  }
+  return MGX_OK;
+}
+
+// term ids of a query built against its own ProgramBuilder -> ids in the batch's common term table
+void rebase_query_terms(HostQuery* q, uint32_t base) {
+  for (size_t i = 0; i < q->prog_ops.size(); ++i) {
+    if (q->prog_ops[i] == kOpTerm || q->prog_ops[i] == kOpFuzzyText) {
+      q->prog_args[i] += base;  // (the edit distance of a FUZZYTEXT node sits in the top byte)
+    }
+  }
+  for (uint32_t& c : q->conjuncts) {
+    c += base;
+  }
+  for (size_t i = 0; i < q->terms.size(); ++i) {
+    q->terms[i] += base;
+  }
+  for (size_t i = 0; i < q->not_terms.size(); ++i) {
+    q->not_terms[i] += base;
+  }
+}
+
 int run_set_op(mgx_index_t* index, SetOp op, const uint32_t* driver_ids, uint64_t n_driver, const uint8_t* term_bytes,
                const uint64_t* term_offsets, uint64_t n_terms, uint64_t limit, bool reverse, uint32_t* out,
                uint64_t cap, uint64_t* out_count) {
@@ -2369,6 +2437,116 @@ bool run_at_least_expanded(Index& ix, cudaStream_t stream, const KeyVec& keys, s
 
 }  // namespace
 
+namespace {
+// The program(s) of ONE fuzzy query (ExecuteWithFuzzy, search_pipeline.cpp:1659-1755) appended to pb / written to
+// queries; *empty: the reference answers the empty set before touching a list. Shared by the single and batch calls.
+int build_fuzzy(Index& ix, const mgx_expanded_query_t* eq, const uint8_t* term_bytes, const uint64_t* term_offsets,
+                uint64_t n_terms, uint32_t max_distance, ProgramBuilder* pb, std::vector<HostQuery>* queries,
+                bool* empty) {
+  *empty = false;
+  queries->clear();
+  if (n_terms == 0) {
+    *empty = true;  // search_pipeline.cpp:1667-1670
+    return MGX_OK;
+  }
+  const bool fuzzy_verify = should_verify(eq->verify_text, term_bytes, term_offsets, n_terms);
+  if (fuzzy_verify && max_distance > 127) {
+    return invalid("max_distance above 127");
+  }
+  int32_t children = 0;
+  bool hybrid_exact = false;
+  bool has_conjunct = false;      // a term whose n-grams are ALL required drives by itself
+  std::vector<int32_t> drivers;   // else: the smallest sufficient leaf set over the terms
+  for (uint64_t t = 0; t < n_terms; ++t) {
+    const uint8_t* tb = term_bytes + term_offsets[t];
+    const uint64_t tl = term_offsets[t + 1] - term_offsets[t];
+    HostTerm whole;
+    if (int rc = term_leaf(ix, *eq, tb, tl, &whole); rc != MGX_OK) {
+      return rc;
+    }
+    const size_t n = whole.keys.size();
+    if (n == 0) {
+      *empty = true;  // too short for an n-gram: no candidates, empty_term_detected (:1674-1680)
+      return MGX_OK;
+    }
+    if (n > kMaxProgramDepth - 2) {
+      set_last_error("fuzzy term with more than 62 distinct n-grams is not supported");
+      return MGX_ERR_UNSUPPORTED;
+    }
+    // effective n-gram size of the term (:1682-1695): the kanji size when most of its n-grams are <= 3 bytes
+    int eff = eq->ngram_size > 0 ? eq->ngram_size : 2;
+    if (eq->kanji_ngram_size > 0) {
+      size_t short_count = 0;
+      for (uint64_t key : whole.keys) {
+        uint8_t enc[4 * kMaxNgramSize];
+        if (key == kInvalidKey) {
+          set_last_error("fuzzy term with n-grams wider than the index key");
+          return MGX_ERR_UNSUPPORTED;
+        }
+        short_count += host_key_to_utf8(key, ix.width, enc) <= 3 ? 1 : 0;
+      }
+      if (short_count > n / 2) {
+        eff = eq->kanji_ngram_size;
+      }
+    }
+    const size_t drop = static_cast<size_t>(max_distance) * static_cast<size_t>(eff);
+    const size_t need = n > drop ? n - drop : 1;  // :1697-1700
+    const int32_t first_leaf = static_cast<int32_t>(pb->terms.size());
+    for (uint64_t key : whole.keys) {  // Index::SearchByThreshold(ngrams, need), index.cpp:488-578
+      HostTerm leaf;
+      leaf.raw = true;
+      leaf.keys.push_back(key);
+      pb->leaf(std::move(leaf));
+    }
+    pb->node(kOpAtLeast, static_cast<int32_t>(n | (need << 16)));
+    ++children;
+    // a document in at least `need` of the n lists is in one of ANY n - need + 1 of them
+    const size_t sufficient = n - need + 1;
+    has_conjunct |= need == n;
+    if (need < n && sufficient <= kMaxDriverLeaves && (drivers.empty() || sufficient < drivers.size())) {
+      drivers.clear();
+      for (size_t i = 0; i < sufficient; ++i) {
+        drivers.push_back(first_leaf + static_cast<int32_t>(i));
+      }
+    }
+    hybrid_exact |= has_uncovered_hybrid_fragment(tb, tl, eq->ngram_size, eq->kanji_ngram_size,
+                                                  eq->cross_boundary != 0);
+  }
+  if (fuzzy_verify) {
+    // PostFilterByFuzzyText (:1742-1752): every term occurs in the text exactly, or a word of the text is within
+    // max_distance edits of it (ContainsFuzzyMatch, utils/edit_distance.cpp)
+    for (uint64_t t = 0; t < n_terms; ++t) {
+      const uint8_t* tb = term_bytes + term_offsets[t];
+      const uint64_t tl = term_offsets[t + 1] - term_offsets[t];
+      if (host_utf8_to_codepoints(tb, tl).size() > kFuzzyMaxTermCps) {
+        set_last_error("fuzzy verification of a term longer than 64 code points is not supported");
+        return MGX_ERR_UNSUPPORTED;
+      }
+      HostTerm exact;
+      exact.bytes.assign(reinterpret_cast<const char*>(tb), tl);
+      const int32_t tid = static_cast<int32_t>(pb->terms.size());
+      pb->leaf(std::move(exact));
+      pb->node(kOpFuzzyText, tid | static_cast<int32_t>(max_distance << 24));  // same term bytes, fuzzy test
+      pb->node(kOpOr, 2);
+      ++children;
+    }
+  }
+  if (hybrid_exact) {  // RequiresExactTextForHybridFragments -> PostFilterByText (:1728-1737): every term, exactly
+    for (uint64_t t = 0; t < n_terms; ++t) {
+      HostTerm text_only;
+      text_only.bytes.assign(reinterpret_cast<const char*>(term_bytes) + term_offsets[t],
+                             term_offsets[t + 1] - term_offsets[t]);
+      pb->leaf(std::move(text_only));
+      ++children;
+    }
+  }
+  if (has_conjunct) {
+    drivers.clear();
+  }
+  return finish_expanded(ix, *eq, pb, children, drivers, queries);
+}
+}  // namespace
+
 int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq, const uint8_t* term_bytes,
                      const uint64_t* term_offsets, uint64_t n_terms, uint32_t max_distance, uint32_t* out,
                      uint64_t cap, uint64_t* out_count) {
@@ -2383,10 +2561,6 @@ int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq,
   if (n_terms == 0) {
     return MGX_OK;  // search_pipeline.cpp:1667-1670
   }
-  const bool fuzzy_verify = should_verify(eq->verify_text, term_bytes, term_offsets, n_terms);
-  if (fuzzy_verify && max_distance > 127) {
-    return invalid("max_distance above 127");
-  }
   if (int rc = commit_pending(index); rc != MGX_OK) {
     return rc;
   }
@@ -2395,102 +2569,97 @@ int mgx_search_fuzzy(const mgx_index_t* index_c, const mgx_expanded_query_t* eq,
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
     ProgramBuilder pb;
-    int32_t children = 0;
-    bool hybrid_exact = false;
-    bool has_conjunct = false;      // a term whose n-grams are ALL required drives by itself
-    std::vector<int32_t> drivers;   // else: the smallest sufficient leaf set over the terms
-    for (uint64_t t = 0; t < n_terms; ++t) {
-      const uint8_t* tb = term_bytes + term_offsets[t];
-      const uint64_t tl = term_offsets[t + 1] - term_offsets[t];
-      HostTerm whole;
-      if (int rc = term_leaf(ix, *eq, tb, tl, &whole); rc != MGX_OK) {
-        return rc;
-      }
-      const size_t n = whole.keys.size();
-      if (n == 0) {
-        return MGX_OK;  // too short for an n-gram: no candidates, empty_term_detected (:1674-1680)
-      }
-      if (n > kMaxProgramDepth - 2) {
-        set_last_error("fuzzy term with more than 62 distinct n-grams is not supported");
-        return MGX_ERR_UNSUPPORTED;
-      }
-      // effective n-gram size of the term (:1682-1695): the kanji size when most of its n-grams are <= 3 bytes
-      int eff = eq->ngram_size > 0 ? eq->ngram_size : 2;
-      if (eq->kanji_ngram_size > 0) {
-        size_t short_count = 0;
-        for (uint64_t key : whole.keys) {
-          uint8_t enc[4 * kMaxNgramSize];
-          if (key == kInvalidKey) {
-            set_last_error("fuzzy term with n-grams wider than the index key");
-            return MGX_ERR_UNSUPPORTED;
-          }
-          short_count += host_key_to_utf8(key, ix.width, enc) <= 3 ? 1 : 0;
-        }
-        if (short_count > n / 2) {
-          eff = eq->kanji_ngram_size;
-        }
-      }
-      const size_t drop = static_cast<size_t>(max_distance) * static_cast<size_t>(eff);
-      const size_t need = n > drop ? n - drop : 1;  // :1697-1700
-      const int32_t first_leaf = static_cast<int32_t>(pb.terms.size());
-      for (uint64_t key : whole.keys) {  // Index::SearchByThreshold(ngrams, need), index.cpp:488-578
-        HostTerm leaf;
-        leaf.raw = true;
-        leaf.keys.push_back(key);
-        pb.leaf(std::move(leaf));
-      }
-      pb.node(kOpAtLeast, static_cast<int32_t>(n | (need << 16)));
-      ++children;
-      // a document in at least `need` of the n lists is in one of ANY n - need + 1 of them
-      const size_t sufficient = n - need + 1;
-      has_conjunct |= need == n;
-      if (need < n && sufficient <= kMaxDriverLeaves && (drivers.empty() || sufficient < drivers.size())) {
-        drivers.clear();
-        for (size_t i = 0; i < sufficient; ++i) {
-          drivers.push_back(first_leaf + static_cast<int32_t>(i));
-        }
-      }
-      hybrid_exact |= has_uncovered_hybrid_fragment(tb, tl, eq->ngram_size, eq->kanji_ngram_size,
-                                                    eq->cross_boundary != 0);
-    }
-    if (fuzzy_verify) {
-      // PostFilterByFuzzyText (:1742-1752): every term occurs in the text exactly, or a word of the text is within
-      // max_distance edits of it (ContainsFuzzyMatch, utils/edit_distance.cpp)
-      for (uint64_t t = 0; t < n_terms; ++t) {
-        const uint8_t* tb = term_bytes + term_offsets[t];
-        const uint64_t tl = term_offsets[t + 1] - term_offsets[t];
-        if (host_utf8_to_codepoints(tb, tl).size() > kFuzzyMaxTermCps) {
-          set_last_error("fuzzy verification of a term longer than 64 code points is not supported");
-          return MGX_ERR_UNSUPPORTED;
-        }
-        HostTerm exact;
-        exact.bytes.assign(reinterpret_cast<const char*>(tb), tl);
-        const int32_t tid = static_cast<int32_t>(pb.terms.size());
-        pb.leaf(std::move(exact));
-        pb.node(kOpFuzzyText, tid | static_cast<int32_t>(max_distance << 24));  // same term bytes, fuzzy test
-        pb.node(kOpOr, 2);
-        ++children;
-      }
-    }
-    if (hybrid_exact) {  // RequiresExactTextForHybridFragments -> PostFilterByText (:1728-1737): every term, exactly
-      for (uint64_t t = 0; t < n_terms; ++t) {
-        HostTerm text_only;
-        text_only.bytes.assign(reinterpret_cast<const char*>(term_bytes) + term_offsets[t],
-                               term_offsets[t + 1] - term_offsets[t]);
-        pb.leaf(std::move(text_only));
-        ++children;
-      }
-    }
-    if (has_conjunct) {
-      drivers.clear();
-    }
     std::vector<HostQuery> queries;
-    if (int rc = finish_expanded(ix, *eq, &pb, children, drivers, &queries); rc != MGX_OK) {
+    bool empty = false;
+    if (int rc = build_fuzzy(ix, eq, term_bytes, term_offsets, n_terms, max_distance, &pb, &queries, &empty);
+        rc != MGX_OK || empty) {
       return rc;
     }
     return run_single_set_query(ix, rd.stream(), pb.terms, queries, nullptr, 0, 0, false, out, cap, out_count);
   });
 }
+
+namespace {
+// The program(s) of ONE synonym query (ExecuteWithSynonyms, search_pipeline.cpp:1580-1657); group_begin[0..n_groups]
+// index the variants of this query. Shared by the single and batch calls.
+int build_synonyms(Index& ix, const mgx_expanded_query_t* eq, const uint8_t* variant_bytes,
+                   const uint64_t* variant_offsets, const uint64_t* group_begin, uint64_t n_groups, ProgramBuilder* pb,
+                   std::vector<HostQuery>* queries, bool* empty) {
+  *empty = false;
+  queries->clear();
+  if (n_groups == 0) {
+    *empty = true;  // no group was processed: empty_term_detected (search_pipeline.cpp:1618-1621)
+    return MGX_OK;
+  }
+  for (uint64_t g = 0; g < n_groups; ++g) {
+    if (group_begin[g + 1] < group_begin[g]) {
+      return invalid("group_begin must be non-decreasing");
+    }
+  }
+  int32_t children = 0;
+  const uint64_t n_variants = group_begin[n_groups];
+  // ShouldApplyVerifyTextSynonyms (:154-172): decided over the variants of all groups
+  const bool verify = n_variants > 0 && should_verify(eq->verify_text, variant_bytes, variant_offsets, n_variants);
+  bool has_conjunct = false;     // a group with a single variant drives by itself
+  std::vector<int32_t> drivers;  // else: the variants of the group with the fewest of them
+  for (int pass = 0; pass < (verify ? 2 : 1); ++pass) {
+    // pass 0: OR within a group of SearchTermDocuments(variant) (:1589-1608);
+    // pass 1: PostFilterByTextWithSynonyms (:1633-1657): some variant of every group occurs in the text
+    for (uint64_t g = 0; g < n_groups; ++g) {
+      bool trivially_true = false;
+      if (pass == 1) {
+        for (uint64_t v = group_begin[g]; v < group_begin[g + 1]; ++v) {
+          trivially_true |= variant_offsets[v + 1] == variant_offsets[v];  // text.find("") always succeeds
+        }
+      }
+      if (trivially_true) {
+        continue;
+      }
+      std::vector<int32_t> group_leaves;
+      bool can_drive = pass == 0;
+      for (uint64_t v = group_begin[g]; v < group_begin[g + 1]; ++v) {
+        const uint8_t* vb = variant_bytes + variant_offsets[v];
+        const uint64_t vl = variant_offsets[v + 1] - variant_offsets[v];
+        HostTerm t;
+        if (pass == 0) {
+          if (int rc = term_leaf(ix, *eq, vb, vl, &t); rc != MGX_OK) {
+            return rc;
+          }
+          if (!t.keys.empty()) {
+            group_leaves.push_back(static_cast<int32_t>(pb->terms.size()));
+          } else if (vl > 0) {
+            can_drive = false;  // a variant shorter than an n-gram is a text scan: no list to drive with
+          }
+        } else {
+          if (vl > kMaxTermBytes) {
+            set_last_error("query term longer than 256 bytes is not supported");
+            return MGX_ERR_UNSUPPORTED;
+          }
+          t.bytes.assign(reinterpret_cast<const char*>(vb), vl);  // text-only leaf
+        }
+        pb->leaf(std::move(t));
+        if (v > group_begin[g]) {
+          pb->node(kOpOr, 2);
+        }
+      }
+      if (group_begin[g + 1] == group_begin[g]) {
+        pb->node(kOpOr, 0);  // a group without variants matches nothing
+      }
+      ++children;
+      if (can_drive && !group_leaves.empty()) {
+        has_conjunct |= group_begin[g + 1] - group_begin[g] == 1;
+        if (group_leaves.size() <= kMaxDriverLeaves && (drivers.empty() || group_leaves.size() < drivers.size())) {
+          drivers = group_leaves;
+        }
+      }
+    }
+  }
+  if (has_conjunct) {
+    drivers.clear();
+  }
+  return finish_expanded(ix, *eq, pb, children, drivers, queries);
+}
+}  // namespace
 
 int mgx_search_synonyms(const mgx_index_t* index_c, const mgx_expanded_query_t* eq, const uint8_t* variant_bytes,
                         const uint64_t* variant_offsets, const uint64_t* group_begin, uint64_t n_groups,
@@ -2520,72 +2689,142 @@ int mgx_search_synonyms(const mgx_index_t* index_c, const mgx_expanded_query_t* 
     Index& ix = index->ix;
     DeviceGuard guard(ix.device);
     ProgramBuilder pb;
-    int32_t children = 0;
-    const uint64_t n_variants = group_begin[n_groups];
-    // ShouldApplyVerifyTextSynonyms (:154-172): decided over the variants of all groups
-    const bool verify = n_variants > 0 && should_verify(eq->verify_text, variant_bytes, variant_offsets, n_variants);
-    bool has_conjunct = false;     // a group with a single variant drives by itself
-    std::vector<int32_t> drivers;  // else: the variants of the group with the fewest of them
-    for (int pass = 0; pass < (verify ? 2 : 1); ++pass) {
-      // pass 0: OR within a group of SearchTermDocuments(variant) (:1589-1608);
-      // pass 1: PostFilterByTextWithSynonyms (:1633-1657): some variant of every group occurs in the text
-      for (uint64_t g = 0; g < n_groups; ++g) {
-        bool trivially_true = false;
-        if (pass == 1) {
-          for (uint64_t v = group_begin[g]; v < group_begin[g + 1]; ++v) {
-            trivially_true |= variant_offsets[v + 1] == variant_offsets[v];  // text.find("") always succeeds
-          }
-        }
-        if (trivially_true) {
-          continue;
-        }
-        std::vector<int32_t> group_leaves;
-        bool can_drive = pass == 0;
-        for (uint64_t v = group_begin[g]; v < group_begin[g + 1]; ++v) {
-          const uint8_t* vb = variant_bytes + variant_offsets[v];
-          const uint64_t vl = variant_offsets[v + 1] - variant_offsets[v];
-          HostTerm t;
-          if (pass == 0) {
-            if (int rc = term_leaf(ix, *eq, vb, vl, &t); rc != MGX_OK) {
-              return rc;
-            }
-            if (!t.keys.empty()) {
-              group_leaves.push_back(static_cast<int32_t>(pb.terms.size()));
-            } else if (vl > 0) {
-              can_drive = false;  // a variant shorter than an n-gram is a text scan: no list to drive with
-            }
-          } else {
-            if (vl > kMaxTermBytes) {
-              set_last_error("query term longer than 256 bytes is not supported");
-              return MGX_ERR_UNSUPPORTED;
-            }
-            t.bytes.assign(reinterpret_cast<const char*>(vb), vl);  // text-only leaf
-          }
-          pb.leaf(std::move(t));
-          if (v > group_begin[g]) {
-            pb.node(kOpOr, 2);
-          }
-        }
-        if (group_begin[g + 1] == group_begin[g]) {
-          pb.node(kOpOr, 0);  // a group without variants matches nothing
-        }
-        ++children;
-        if (can_drive && !group_leaves.empty()) {
-          has_conjunct |= group_begin[g + 1] - group_begin[g] == 1;
-          if (group_leaves.size() <= kMaxDriverLeaves && (drivers.empty() || group_leaves.size() < drivers.size())) {
-            drivers = group_leaves;
-          }
-        }
-      }
-    }
-    if (has_conjunct) {
-      drivers.clear();
-    }
     std::vector<HostQuery> queries;
-    if (int rc = finish_expanded(ix, *eq, &pb, children, drivers, &queries); rc != MGX_OK) {
+    bool empty = false;
+    if (int rc = build_synonyms(ix, eq, variant_bytes, variant_offsets, group_begin, n_groups, &pb, &queries, &empty);
+        rc != MGX_OK || empty) {
       return rc;
     }
     return run_single_set_query(ix, rd.stream(), pb.terms, queries, nullptr, 0, 0, false, out, cap, out_count);
+  });
+}
+
+namespace {
+// appends one logical query's programs to the batch under construction
+void append_group(ProgramBuilder* one, std::vector<HostQuery>* its_queries, bool empty, std::vector<HostTerm>* terms,
+                  std::vector<HostQuery>* queries, std::vector<uint32_t>* group_begin) {
+  if (!empty) {
+    const uint32_t base = static_cast<uint32_t>(terms->size());
+    for (HostTerm& t : one->terms) {
+      terms->push_back(std::move(t));
+    }
+    for (HostQuery& q : *its_queries) {
+      rebase_query_terms(&q, base);
+      queries->push_back(std::move(q));
+    }
+  }
+  group_begin->push_back(static_cast<uint32_t>(queries->size()));
+}
+}  // namespace
+
+int mgx_search_fuzzy_batch(const mgx_index_t* index_c, const mgx_expanded_query_t* eq, uint64_t n_queries,
+                           const uint8_t* term_bytes, const uint64_t* term_offsets, const uint64_t* q_term_begin,
+                           uint32_t max_distance, uint32_t* out, uint64_t cap, uint64_t* out_offsets) {
+  mgx_index_t* index = const_cast<mgx_index_t*>(index_c);
+  if (index == nullptr || out_offsets == nullptr || (n_queries > 0 && q_term_begin == nullptr)) {
+    return invalid("null argument");
+  }
+  for (uint64_t q = 0; q <= n_queries; ++q) {
+    out_offsets[q] = 0;
+  }
+  if (int rc = check_expanded(eq); rc != MGX_OK) {
+    return rc;
+  }
+  for (uint64_t q = 0; q < n_queries; ++q) {
+    if (q_term_begin[q + 1] < q_term_begin[q]) {
+      return invalid("q_term_begin must be non-decreasing");
+    }
+  }
+  if (n_queries == 0) {
+    return MGX_OK;
+  }
+  if (q_term_begin[n_queries] > 0 && (term_bytes == nullptr || term_offsets == nullptr)) {
+    return invalid("terms without bytes / offsets");
+  }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    Reader rd(index);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    std::vector<HostTerm> terms;
+    std::vector<HostQuery> queries;
+    std::vector<uint32_t> group_begin(1, 0);
+    for (uint64_t q = 0; q < n_queries; ++q) {
+      ProgramBuilder pb;
+      std::vector<HostQuery> its;
+      bool empty = false;
+      const uint64_t t0 = q_term_begin[q];
+      const uint64_t nt = q_term_begin[q + 1] - t0;
+      if (int rc = build_fuzzy(ix, eq, term_bytes, nt > 0 ? term_offsets + t0 : nullptr, nt, max_distance, &pb, &its, &empty);
+          rc != MGX_OK) {
+        return rc;
+      }
+      append_group(&pb, &its, empty, &terms, &queries, &group_begin);
+    }
+    return run_grouped_set_queries(ix, rd.stream(), terms, queries, group_begin, out, cap, out_offsets);
+  });
+}
+
+int mgx_search_synonyms_batch(const mgx_index_t* index_c, const mgx_expanded_query_t* eq, uint64_t n_queries,
+                              const uint8_t* variant_bytes, const uint64_t* variant_offsets, const uint64_t* group_begin_in,
+                              const uint64_t* q_group_begin, uint32_t* out, uint64_t cap, uint64_t* out_offsets) {
+  mgx_index_t* index = const_cast<mgx_index_t*>(index_c);
+  if (index == nullptr || out_offsets == nullptr || (n_queries > 0 && q_group_begin == nullptr)) {
+    return invalid("null argument");
+  }
+  for (uint64_t q = 0; q <= n_queries; ++q) {
+    out_offsets[q] = 0;
+  }
+  if (int rc = check_expanded(eq); rc != MGX_OK) {
+    return rc;
+  }
+  for (uint64_t q = 0; q < n_queries; ++q) {
+    if (q_group_begin[q + 1] < q_group_begin[q]) {
+      return invalid("q_group_begin must be non-decreasing");
+    }
+  }
+  if (n_queries == 0) {
+    return MGX_OK;
+  }
+  if (q_group_begin[n_queries] > 0 && (variant_bytes == nullptr || variant_offsets == nullptr || group_begin_in == nullptr)) {
+    return invalid("groups without variants");
+  }
+  if (int rc = commit_pending(index); rc != MGX_OK) {
+    return rc;
+  }
+  return guarded([&]() {
+    Reader rd(index);
+    Index& ix = index->ix;
+    DeviceGuard guard(ix.device);
+    std::vector<HostTerm> terms;
+    std::vector<HostQuery> queries;
+    std::vector<uint32_t> group_begin(1, 0);
+    std::vector<uint64_t> local;
+    for (uint64_t q = 0; q < n_queries; ++q) {
+      ProgramBuilder pb;
+      std::vector<HostQuery> its;
+      bool empty = false;
+      const uint64_t g0 = q_group_begin[q];
+      const uint64_t ng = q_group_begin[q + 1] - g0;
+      // the query's own view: variants renumbered from 0 (the verification rule looks at the query's variants only)
+      local.assign(ng + 1, 0);
+      const uint64_t v0 = ng > 0 ? group_begin_in[g0] : 0;
+      for (uint64_t g = 0; g <= ng && ng > 0; ++g) {
+        if (group_begin_in[g0 + g] < v0) {
+          return invalid("group_begin must be non-decreasing");
+        }
+        local[g] = group_begin_in[g0 + g] - v0;
+      }
+      if (int rc = build_synonyms(ix, eq, variant_bytes, ng > 0 ? variant_offsets + v0 : nullptr, local.data(), ng, &pb,
+                                  &its, &empty);
+          rc != MGX_OK) {
+        return rc;
+      }
+      append_group(&pb, &its, empty, &terms, &queries, &group_begin);
+    }
+    return run_grouped_set_queries(ix, rd.stream(), terms, queries, group_begin, out, cap, out_offsets);
   });
 }
 

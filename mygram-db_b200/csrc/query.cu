@@ -5381,6 +5381,87 @@ void lookup_list_lengths(Batch& b, const uint64_t* h_keys, uint32_t n, uint32_t*
   MGX_CUDA(cudaStreamSynchronize(st));  // also keeps h_wide alive until its copy is done
 }
 
+namespace {
+// run_group[2 r], run_group[2 r + 1]: first and end run of the group run r belongs to. One thread per entry: its run
+// by a bound search over the offsets, its place = start of the group + its rank in every run of the group.
+__global__ void merge_grouped_runs_kernel(const uint32_t* __restrict__ in, const uint64_t* __restrict__ run_off,
+                                          uint32_t n_runs, const uint32_t* __restrict__ run_group,
+                                          uint32_t* __restrict__ out) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= run_off[n_runs]) {
+    return;
+  }
+  uint32_t lo_r = 0;  // largest r with run_off[r] <= i (empty runs repeat an offset: the LAST such r holds i)
+  uint32_t hi_r = n_runs;
+  while (hi_r - lo_r > 1) {
+    const uint32_t mid = (lo_r + hi_r) >> 1;
+    if (run_off[mid] <= i) {
+      lo_r = mid;
+    } else {
+      hi_r = mid;
+    }
+  }
+  const uint32_t mine = lo_r;
+  const uint32_t g0 = run_group[2 * mine];
+  const uint32_t g1 = run_group[2 * mine + 1];
+  const uint32_t v = in[i];
+  uint64_t pos = run_off[g0];
+  for (uint32_t r = g0; r < g1; ++r) {
+    const uint64_t r0 = run_off[r];
+    const uint64_t r1 = run_off[r + 1];
+    if (r == mine) {
+      pos += i - r0;
+      continue;
+    }
+    uint64_t lo = r0;
+    uint64_t hi = r1;
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (in[mid] < v) {
+        lo = mid + 1;
+      } else {
+        hi = mid;
+      }
+    }
+    pos += lo - r0;
+  }
+  out[pos] = v;
+}
+}  // namespace
+
+void merge_grouped_runs(Batch& b, const uint32_t* d_in, const std::vector<uint64_t>& run_off,
+                        const std::vector<uint32_t>& group_begin, DevBuf<uint32_t>* d_out) {
+  cudaStream_t st = b.stream;
+  const uint64_t total = run_off.back();
+  const size_t n_runs = run_off.size() - 1;
+  b.union_buf.reserve(std::max<uint64_t>(1, total));
+  d_out->borrow(b.union_buf.p, total);
+  if (total == 0) {
+    return;
+  }
+  // offsets and the (first, end) run of every run's group, back to back in the batch object's grow-only buffer
+  std::vector<uint64_t> host(run_off);
+  std::vector<uint32_t> rg(2 * n_runs, 0);
+  for (size_t g = 0; g + 1 < group_begin.size(); ++g) {
+    for (uint32_t r = group_begin[g]; r < group_begin[g + 1]; ++r) {
+      rg[2 * r] = group_begin[g];
+      rg[2 * r + 1] = group_begin[g + 1];
+    }
+  }
+  const size_t words = host.size() + (rg.size() + 1) / 2;
+  host.resize(words, 0);
+  std::memcpy(host.data() + run_off.size(), rg.data(), rg.size() * sizeof(uint32_t));
+  b.run_off_buf.reserve(words);
+  MGX_CUDA(cudaMemcpyAsync(b.run_off_buf.p, host.data(), words * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  MGX_CUDA(cudaStreamSynchronize(st));  // `host` is pageable and goes out of scope
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  merge_grouped_runs_kernel<<<blocks, 256, 0, st>>>(
+      d_in, b.run_off_buf.p, static_cast<uint32_t>(n_runs),
+      reinterpret_cast<const uint32_t*>(b.run_off_buf.p + run_off.size()), d_out->p);
+  MGX_LAUNCH_CHECK();
+  MGX_CUDA(cudaStreamSynchronize(st));
+}
+
 void merge_disjoint_runs(Batch& b, const uint32_t* d_in, const std::vector<uint64_t>& run_off, DevBuf<uint32_t>* d_out) {
   cudaStream_t st = b.stream;
   const uint64_t total = run_off.back();

@@ -407,6 +407,10 @@ void batch_search(Batch& b, const uint64_t* d_df_global, uint64_t stride, uint32
 void batch_search_sets(Batch& b, std::vector<uint64_t>* h_set_off, DevBuf<uint32_t>* d_sets);
 // Union of the ascending, pairwise disjoint runs d_in[run_off[r] .. run_off[r+1]) into one ascending array.
 void lookup_list_lengths(Batch& b, const uint64_t* h_keys, uint32_t n, uint32_t* h_lens);
+// Grouped form: runs [group_begin[g], group_begin[g + 1]) are merged among themselves; the union of group g takes the
+// place of its runs in the output (same offsets as the input's concatenation).
+void merge_grouped_runs(Batch& b, const uint32_t* d_in, const std::vector<uint64_t>& run_off,
+                        const std::vector<uint32_t>& group_begin, DevBuf<uint32_t>* d_out);
 void merge_disjoint_runs(Batch& b, const uint32_t* d_in, const std::vector<uint64_t>& run_off,
                          DevBuf<uint32_t>* d_out);
 void launch_merge_topk(cudaStream_t stream, const mgx_query_params_t& params, uint32_t n_shards, uint64_t n_queries,

@@ -40,6 +40,51 @@ def test_fuzzy_and_synonyms_match_oracle(mgx, oracle, cfg):
         gi.search_fuzzy(["ab" * 40], 1, verify_text=1)
 
 
+@pytest.mark.parametrize("cfg", [(2, 0, True), (2, 1, True), (3, 2, False)])
+def test_fuzzy_and_synonym_batches_equal_the_single_calls(mgx, oracle, cfg):
+    """mgx_search_fuzzy_batch / mgx_search_synonyms_batch answer many queries in one batch on the device (programs
+    side by side, driver-expanded queries united per query by the grouped merge): every answer must be the single
+    call's, which the test above pins to the oracle; queries the reference answers with the empty set without touching
+    a list (no terms, a term shorter than an n-gram, no groups) take no kernel query at all."""
+    rnd = random.Random(0x77 + (hash(cfg) & 0xFFF))
+    docs = spaced_docs(rnd, 3000)
+    ids = np.arange(1, len(docs) + 1, dtype=np.uint32)
+    gi, oi = build_pair(mgx, oracle, docs, ids, cfg)
+    cases = list(expanded_cases(rnd, docs, 150))
+    nots = cases[0][2]
+    for vt in (0, 1):
+        for dist in (1, 2):
+            fq = [c[0] for c in cases] + [[], ["a"]]
+            got = gi.search_fuzzy_batch(fq, dist, nots, verify_text=vt)
+            assert len(got) == len(fq)
+            nonempty = 0
+            for q, g in zip(fq, got):
+                want = gi.search_fuzzy(q, dist, nots, verify_text=vt)
+                assert np.array_equal(g, want), (cfg, q, dist, vt, g[:10], want[:10])
+                nonempty += want.size > 0
+            assert nonempty > 5
+        sq = [c[1] for c in cases] + [[], [["a"]], [[]]]
+        got = gi.search_synonyms_batch(sq, nots, verify_text=vt)
+        nonempty = 0
+        for q, g in zip(sq, got):
+            want = gi.search_synonyms(q, nots, verify_text=vt)
+            assert np.array_equal(g, want), (cfg, q, vt, g[:10], want[:10])
+            nonempty += want.size > 0
+        assert nonempty > 5
+    # against the oracle directly, and the capacity protocol (a first buffer that is too small)
+    want = [oi.search_fuzzy(c[0], 1, nots)[0] for c in cases[:40]]
+    got = gi.search_fuzzy_batch([c[0] for c in cases[:40]], 1, nots)
+    assert all(np.array_equal(g, w) for g, w in zip(got, want))
+    small = gi._grouped_call
+    gi._grouped_call = lambda fn, n, cap=1: small(fn, n, cap=1)
+    try:
+        again = gi.search_fuzzy_batch([c[0] for c in cases[:40]], 1, nots)
+    finally:
+        gi._grouped_call = small
+    assert all(np.array_equal(g, w) for g, w in zip(again, want))
+    assert gi.search_fuzzy_batch([], 1) == [] and gi.search_synonyms_batch([]) == []
+
+
 def test_fuzzy_and_synonyms_with_filters_dense_lists_and_invalid_utf8(mgx, oracle):
     """Zipf corpus with dense-bitmap lists, column conditions applied after the NOT terms (ApplyNotAndFilters,
     search_pipeline.cpp:470-485), and a corpus with invalid UTF-8."""

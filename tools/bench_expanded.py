@@ -115,6 +115,21 @@ def main():
         out["classes"][name] = {"gpu_queries_per_s": len(qs) / dt, "gpu_ms_per_query": 1e3 * dt / len(qs),
                                 "result_docs_mean": float(np.mean([g.size for g in got]))}
         flush()
+    # the batch forms: the same queries in ONE call each (answers must equal the single calls')
+    for name, qs, single, batch_fn in (
+            ("fuzzy_d1", fuzzy, "fuzzy_d1", lambda qs: gi.search_fuzzy_batch(qs, 1)),
+            ("fuzzy_d1_verify_all", fuzzy, "fuzzy_d1_verify_all", lambda qs: gi.search_fuzzy_batch(qs, 1, verify_text=1)),
+            ("synonyms_2x2", syn, "synonyms_2x2", lambda qs: gi.search_synonyms_batch(qs)),
+            ("synonyms_2x2_verify_all", syn, "synonyms_2x2_verify_all",
+             lambda qs: gi.search_synonyms_batch(qs, verify_text=1))):
+        batch_fn(qs)  # (the pooled batch object grows its buffers to this size once)
+        t0 = time.perf_counter()
+        got = batch_fn(qs)
+        dt = time.perf_counter() - t0
+        same = all(np.array_equal(a, b) for a, b in zip(got, results[single]))
+        out["classes"][name + "_batch"] = {"gpu_queries_per_s": len(qs) / dt, "gpu_ms_per_query": 1e3 * dt / len(qs),
+                                            "queries_per_call": len(qs), "equal_to_single_calls": bool(same)}
+        flush()
     out["gpu_launches"] = int(m.lib().mgx_kernel_launch_count() - launches0)
     if args.gpu_only:
         print(flush(), flush=True)
