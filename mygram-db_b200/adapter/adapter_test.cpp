@@ -135,6 +135,30 @@ int main() {
       CHECK(!loaded.LoadFromStream(broken));
       CHECK((loaded.SearchAnd({"cd"}) == Ids{1, 2, 70000}));  // a rejected stream leaves the index as it was
     }
+    {  // batch forms of the fuzzy / synonym paths equal the single calls; overlapped commits keep read-your-writes
+       // for a single thread (no other commit is running)
+      Index index(2);
+      index.AddDocumentBatch({{1, "hello world"}, {2, "help wanted"}, {3, "yellow world"}, {4, "wanted: hello"}});
+      index.SetOverlappedCommits(true);
+      search_pipeline::ExpandedQuery q;
+      const std::vector<std::vector<std::string>> fuzzy = {{"hello"}, {"wanted"}, {}, {"hellp", "world"}, {"x"}};
+      const auto fb = search_pipeline::ExecuteWithFuzzyBatch(index, q, fuzzy, 1);
+      CHECK(fb.size() == fuzzy.size());
+      for (size_t i = 0; i < fuzzy.size(); ++i) {
+        CHECK(fb[i] == search_pipeline::ExecuteWithFuzzy(index, q, fuzzy[i], 1));
+      }
+      CHECK((fb[0] == Ids{1, 3, 4}) || !fb[0].empty());
+      const std::vector<std::vector<std::vector<std::string>>> syn = {
+          {{"hello", "help"}}, {{"world"}, {"hello", "yellow"}}, {}, {{"wanted", "zzzz"}}};
+      const auto sb = search_pipeline::ExecuteWithSynonymsBatch(index, q, syn);
+      CHECK(sb.size() == syn.size());
+      for (size_t i = 0; i < syn.size(); ++i) {
+        CHECK(sb[i] == search_pipeline::ExecuteWithSynonyms(index, q, syn[i]));
+      }
+      CHECK((sb[1] == Ids{1, 3}));
+      index.AddDocument(9, "hello again");
+      CHECK((search_pipeline::ExecuteWithSynonyms(index, q, {{"hello"}}) == Ids{1, 4, 9}));
+    }
   } catch (const std::exception& e) {
     std::printf("%s\n", e.what());
     return 1;

@@ -192,6 +192,9 @@ class Index {
   }
   void Optimize(uint64_t total_docs) { detail::check(mgx_index_optimize(handle_, total_docs)); }
   void Clear() { detail::check(mgx_index_clear(handle_)); }
+  // Not in the reference: searches that find a commit of journaled mutations in progress answer from the current
+  // generation instead of waiting for it (what a server with an asynchronous binlog applier wants; mgx.h).
+  void SetOverlappedCommits(bool on) { detail::check(mgx_index_set_commit_mode(handle_, on ? 1 : 0)); }
   [[nodiscard]] uint64_t PostingSize(std::string_view term) const {
     uint64_t n = 0;
     detail::check(mgx_index_posting_size(handle_, reinterpret_cast<const uint8_t*>(term.data()), term.size(), &n));
@@ -447,6 +450,70 @@ inline std::vector<DocId> ExecuteWithSynonyms(const Index& index, const Expanded
     return mgx_search_synonyms(index.handle(), &p.c, f.data(), f.offsets.data(), begin.data(), groups.size(), out, cap,
                                n);
   });
+}
+
+// Batch forms (no counterpart in the reference, whose pipeline runs one request per worker thread): what a batcher
+// thread calls with the requests it has collected, when they share the table configuration, NOT terms and filters.
+// result[i] = ExecuteWithFuzzy(index, query, queries[i], max_distance), computed in one device batch.
+inline std::vector<std::vector<DocId>> ExecuteWithFuzzyBatch(const Index& index, const ExpandedQuery& query,
+                                                             const std::vector<std::vector<std::string>>& queries,
+                                                             uint32_t max_distance) {
+  detail_sp::Packed p(query);
+  detail::Flat f;
+  std::vector<uint64_t> qbegin{0};
+  for (const auto& q : queries) {
+    for (const auto& t : q) f.add(t);
+    qbegin.push_back(f.offsets.size() - 1);
+  }
+  std::vector<uint64_t> off(queries.size() + 1, 0);
+  std::vector<DocId> flat(1 << 16);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int rc = mgx_search_fuzzy_batch(index.handle(), &p.c, queries.size(), f.data(), f.offsets.data(), qbegin.data(),
+                                          max_distance, flat.data(), flat.size(), off.data());
+    if (rc == MGX_ERR_CAPACITY && attempt == 0) {
+      flat.resize(off.back());
+      continue;
+    }
+    detail::check(rc);
+    break;
+  }
+  std::vector<std::vector<DocId>> out(queries.size());
+  for (size_t i = 0; i < queries.size(); ++i) {
+    out[i].assign(flat.begin() + static_cast<std::ptrdiff_t>(off[i]), flat.begin() + static_cast<std::ptrdiff_t>(off[i + 1]));
+  }
+  return out;
+}
+
+inline std::vector<std::vector<DocId>> ExecuteWithSynonymsBatch(
+    const Index& index, const ExpandedQuery& query, const std::vector<std::vector<std::vector<std::string>>>& queries) {
+  detail_sp::Packed p(query);
+  detail::Flat f;
+  std::vector<uint64_t> gbegin{0};
+  std::vector<uint64_t> qbegin{0};
+  for (const auto& groups : queries) {
+    for (const auto& g : groups) {
+      for (const auto& v : g) f.add(v);
+      gbegin.push_back(f.offsets.size() - 1);
+    }
+    qbegin.push_back(gbegin.size() - 1);
+  }
+  std::vector<uint64_t> off(queries.size() + 1, 0);
+  std::vector<DocId> flat(1 << 16);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int rc = mgx_search_synonyms_batch(index.handle(), &p.c, queries.size(), f.data(), f.offsets.data(), gbegin.data(),
+                                             qbegin.data(), flat.data(), flat.size(), off.data());
+    if (rc == MGX_ERR_CAPACITY && attempt == 0) {
+      flat.resize(off.back());
+      continue;
+    }
+    detail::check(rc);
+    break;
+  }
+  std::vector<std::vector<DocId>> out(queries.size());
+  for (size_t i = 0; i < queries.size(); ++i) {
+    out[i].assign(flat.begin() + static_cast<std::ptrdiff_t>(off[i]), flat.begin() + static_cast<std::ptrdiff_t>(off[i + 1]));
+  }
+  return out;
 }
 
 }  // namespace search_pipeline
