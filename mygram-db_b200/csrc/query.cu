@@ -932,7 +932,12 @@ __device__ __forceinline__ void load_text_words(const uint8_t* __restrict__ text
 
 static_assert(kWarpStageCap * sizeof(uint32_t) >= kStageBuf, "the text staging buffer aliases the list staging buffer");
 constexpr uint32_t kDfFewMembers = 16;         // at most this many candidates of a chunk: searched one by one
-constexpr uint32_t kDfSetCap = kWarpTile + 32 * 8;  // fewer than 128 waiting + one piece  // collected candidates per warp (they are processed 128 at a time)
+#ifndef MGX_DF_PIECE_ITEMS
+#define MGX_DF_PIECE_ITEMS 4  // payload words a lane loads per piece (measured: 2 -> 1.50, 4 -> 1.29, 8 -> 1.37, 16 -> 1.67 ms per C2 batch)
+#endif
+constexpr int kDfPieceItems = MGX_DF_PIECE_ITEMS;
+constexpr uint32_t kDfPiece = 32 * kDfPieceItems;      // entries a warp filters at a time
+constexpr uint32_t kDfSetCap = kWarpTile + kDfPiece;   // collected candidates per warp: fewer than 128 waiting + one piece
 
 // What is the same for every piece of one (term, driver list) pair.
 struct DfTerm {
@@ -993,8 +998,6 @@ struct DfAcc {
 // from e0, the documents and payloads are fetched again (from L2) for the few that stay. Lane l takes the entries
 // l, l + 32, ...: every load is one coalesced line, all of them are in flight before the first is looked at, and the
 // second-occurrence words (needed by roughly one entry in ten) follow in a second wave.
-constexpr int kDfPieceItems = 8;
-constexpr uint32_t kDfPiece = 32 * kDfPieceItems;
 __device__ __forceinline__ uint32_t df_collect_piece(const ListRef& drv, const DfTerm& tc, uint64_t e0, uint32_t rel0,
                                                      uint64_t unit_end, uint32_t* cand, uint32_t n_set) {
   const unsigned lane = threadIdx.x & 31u;

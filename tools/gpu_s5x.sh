@@ -1,0 +1,18 @@
+#!/bin/bash
+# session 5, call x (1 GPU): payload words per lane and piece (4 / 8 / 16) in the df collecting loop
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+export BENCH_NO_CLOCKS=1
+for v in p4 p2 p4u1k p4u4k p2o4; do
+  unset MGX_LIB_PATH
+  if [ $v != default ]; then export MGX_LIB_PATH=$PWD/mygram-db_b200/libmgx_$v.so; fi
+  timeout 900 python bench.py --config c2 --steps 10 --warmup 3 --no-cpu-baseline --parity gpu \
+      > gpurun_out/c2_s5x_$v.json 2> gpurun_out/c2_s5x_$v.err
+  echo "== $v rc=$?"
+  python - <<P
+import json
+d=json.loads(open('gpurun_out/c2_s5x_$v.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d.get('parity',{}).get('ok'))
+print({k:round(v['ms'],3) for k,v in d['kernels'].items()})
+P
+done
