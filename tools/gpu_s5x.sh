@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export BENCH_NO_CLOCKS=1
-for v in p4 p2 p4u1k p4u4k p2o4; do
+for v in default a4 a6; do
   unset MGX_LIB_PATH
   if [ $v != default ]; then export MGX_LIB_PATH=$PWD/mygram-db_b200/libmgx_$v.so; fi
   timeout 900 python bench.py --config c2 --steps 10 --warmup 3 --no-cpu-baseline --parity gpu \
