@@ -18,7 +18,8 @@ is sharded by doc-id range over the ranks, every rank answers every query over i
 NCCL exchanges itself (mgx_sharded_batch_*).
   value  = device-resident throughput: compiled batches already in HBM, CUDA events on the launch streams, max over
            ranks; `in_flight` batches on separate streams / communicator lanes.
-  e2e    = the same steps from HOST buffers to HOST buffers (host compile + H2D + device + D2H), wall clock, max over ranks.
+  e2e    = the same steps from HOST buffers to HOST buffers (host compile + H2D + device + D2H), wall clock, max over ranks;
+           at N > 1 every rank uploads the batch and rank 0 reads the merged answer back (d2h_bytes_per_step).
   parity = recorded in EVERY line: rank 0 checks the merged answer of one timed batch against the CPU oracle (ids in
            order, counts, totals, scores) and, for N > 1, against a single-shard run of the whole corpus on its own GPU
            (every query, bit for bit: the design promises identical answers for every shard count).
@@ -796,7 +797,10 @@ def main():
                 futs[j + ahead] = compiler.submit(e2e_prepare, order[j + ahead], (j + ahead) % in_flight, seq0 + j + ahead)
             t_b = time.perf_counter()
             slot = j % in_flight
-            pipe.enqueue(p, slot % comm.n_lanes if world > 1 else 0, outs[slot])
+            # every rank uploads the step's batch; the merged answer (identical on every rank after the all-gather +
+            # merge) is read back to the host by rank 0, the rank that answers the caller -- the other ranks' copies
+            # stay in HBM instead of all N ranks writing the same 5 MB into host memory every step
+            pipe.enqueue(p, slot % comm.n_lanes if world > 1 else 0, outs[slot] if rank == 0 else None)
             t_c = time.perf_counter()
             pending.append(p)
             if len(pending) >= in_flight:
@@ -944,6 +948,7 @@ def main():
                     "nccl": comm.nccl_version() if world > 1 else None},
             "e2e": {"value": e2e_value, "unit": cfg["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pipeline_depth": in_flight, "timed_repeats": e2e_reps,
+                    "result_readback": "rank 0 (the merged answer is identical on every rank)" if world > 1 else "rank 0",
                     "host_compile": ("every batch compiled by ONE rank of the node in turn and handed to the others "
                                      "through a shared-memory ring (mgx_share_*)") if (world > 1 and not args.no_share)
                     else "every rank compiles every batch",
