@@ -29,7 +29,8 @@
  *    exchange of the two; writers never overlap each other;
  *  - add / update / remove_document only append to a journal (never block on readers or on a commit); a reading call
  *    that STARTS after they return sees them (it commits the journal first, or waits for the commit that is doing
- *    so) unless mgx_index_set_commit_mode chose overlapped reads;
+ *    so); with mgx_index_set_commit_mode(index, 1) reading calls never commit or wait, and mgx_index_commit
+ *    publishes the mutations;
  *  - a staged batch (mgx_batch_prepare* .. mgx_batch_destroy) is a reader for its whole lifetime. A thread must not
  *    call a committing entry point of the same index while it holds such a batch and mutations are pending: the
  *    commit would wait for the batch. Stages of ONE batch must not be issued concurrently.
@@ -125,11 +126,12 @@ int mgx_index_update_document(mgx_index_t* index, uint32_t doc_id, const uint8_t
                               const uint8_t* new_text, uint64_t new_len);
 int mgx_index_remove_document(mgx_index_t* index, uint32_t doc_id, const uint8_t* text, uint64_t text_len);
 int mgx_index_commit(mgx_index_t* index);
-/* What a reading call does when it finds a commit of another thread IN PROGRESS. overlapped == 0 (default): it waits
- * for that commit, so it sees every mutation that returned before it began (the reference applies a mutation before
- * Index::AddDocument returns). overlapped != 0: it answers from the current generation without waiting -- the reads of
- * search threads next to an asynchronous applier (binlog_event_processor.cpp) never stall on a rebuild; a thread still
- * sees its own mutations as long as no other thread's commit is running at that moment. */
+/* Who commits, and who waits. overlapped == 0 (default): every reading call commits the journal first (or waits for
+ * the commit that is doing so), so it sees every mutation that returned before it began (the reference applies a
+ * mutation before Index::AddDocument returns). overlapped != 0: reading calls neither commit nor wait -- they answer
+ * from the current generation, and mutations become visible when the mgx_index_commit of the mutating thread (the
+ * binlog applier, binlog_event_processor.cpp) returns. This is the mode for servers whose search threads keep
+ * staged batches in flight: a commit only ever waits for batches to END, never the other way round. */
 int mgx_index_set_commit_mode(mgx_index_t* index, int overlapped);
 
 typedef struct {

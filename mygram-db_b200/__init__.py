@@ -439,8 +439,8 @@ class Index:
         _check(lib().mgx_index_commit(self._h))
 
     def set_commit_mode(self, overlapped):
-        """overlapped=True: a read that finds another thread's commit in progress answers from the current
-        generation instead of waiting for it (mgx_index_set_commit_mode)."""
+        """overlapped=True: reading calls neither commit journaled mutations nor wait for a commit in progress (they
+        answer from the current generation); commit() publishes them (mgx_index_set_commit_mode)."""
         _check(lib().mgx_index_set_commit_mode(self._h, 1 if overlapped else 0))
 
     def build(self, doc_ids, arena, offsets):

@@ -135,11 +135,12 @@ int main() {
       CHECK(!loaded.LoadFromStream(broken));
       CHECK((loaded.SearchAnd({"cd"}) == Ids{1, 2, 70000}));  // a rejected stream leaves the index as it was
     }
-    {  // batch forms of the fuzzy / synonym paths equal the single calls; overlapped commits keep read-your-writes
-       // for a single thread (no other commit is running)
+    {  // batch forms of the fuzzy / synonym paths equal the single calls; with overlapped commits a mutation is
+       // published by Commit()
       Index index(2);
       index.AddDocumentBatch({{1, "hello world"}, {2, "help wanted"}, {3, "yellow world"}, {4, "wanted: hello"}});
       index.SetOverlappedCommits(true);
+      index.Commit();  // in this mode nothing is visible before the mutating thread publishes it
       search_pipeline::ExpandedQuery q;
       const std::vector<std::vector<std::string>> fuzzy = {{"hello"}, {"wanted"}, {}, {"hellp", "world"}, {"x"}};
       const auto fb = search_pipeline::ExecuteWithFuzzyBatch(index, q, fuzzy, 1);
@@ -157,6 +158,8 @@ int main() {
       }
       CHECK((sb[1] == Ids{1, 3}));
       index.AddDocument(9, "hello again");
+      CHECK((search_pipeline::ExecuteWithSynonyms(index, q, {{"hello"}}) == Ids{1, 4}));  // not published yet
+      index.Commit();
       CHECK((search_pipeline::ExecuteWithSynonyms(index, q, {{"hello"}}) == Ids{1, 4, 9}));
     }
   } catch (const std::exception& e) {

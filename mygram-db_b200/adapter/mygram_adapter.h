@@ -192,9 +192,11 @@ class Index {
   }
   void Optimize(uint64_t total_docs) { detail::check(mgx_index_optimize(handle_, total_docs)); }
   void Clear() { detail::check(mgx_index_clear(handle_)); }
-  // Not in the reference: searches that find a commit of journaled mutations in progress answer from the current
-  // generation instead of waiting for it (what a server with an asynchronous binlog applier wants; mgx.h).
+  // Not in the reference: with overlapped commits searches neither fold journaled mutations in nor wait for a commit
+  // in progress (they answer from the current generation); the mutating thread publishes its calls with Commit()
+  // (what a server with an asynchronous binlog applier wants; mgx.h).
   void SetOverlappedCommits(bool on) { detail::check(mgx_index_set_commit_mode(handle_, on ? 1 : 0)); }
+  void Commit() { detail::check(mgx_index_commit(handle_)); }
   [[nodiscard]] uint64_t PostingSize(std::string_view term) const {
     uint64_t n = 0;
     detail::check(mgx_index_posting_size(handle_, reinterpret_cast<const uint8_t*>(term.data()), term.size(), &n));

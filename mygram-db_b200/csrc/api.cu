@@ -1186,22 +1186,21 @@ struct Reader {
 
 // Applies the pending mutations; called at the top of every entry point that reads the index, BEFORE the call
 // takes its shared access (never under it: the commit needs the gate exclusively).
-int commit_pending(mgx_index_t* index) {
+int commit_pending(mgx_index_t* index, bool explicit_commit = false) {
   if (index == nullptr ||
       (!index->dirty.load(std::memory_order_acquire) && !index->committing.load(std::memory_order_acquire))) {
     return MGX_OK;
   }
+  // Overlapped mode: reading calls neither commit nor wait for a commit -- they answer from the current generation,
+  // and mutations become visible when the mgx_index_commit of the mutating thread returns. (A reading thread may hold
+  // staged batches; a commit of its own would wait for them at the exchange.)
+  if (!explicit_commit && index->commit_mode.load(std::memory_order_relaxed) != 0) {
+    return MGX_OK;
+  }
   return guarded([&]() {
-    // One commit at a time. A read that finds one in progress waits for it (it may hold mutations that returned
-    // before the read began) -- unless the handle is in overlapped mode, where it answers from the current generation.
-    std::unique_lock<std::mutex> cl(index->commit_mu, std::defer_lock);
-    if (index->commit_mode.load(std::memory_order_relaxed) != 0) {
-      if (!cl.try_lock()) {
-        return MGX_OK;
-      }
-    } else {
-      cl.lock();
-    }
+    // One commit at a time; whoever finds one in progress waits for it (it may hold mutations that returned before
+    // this call began).
+    std::unique_lock<std::mutex> cl(index->commit_mu);
     // The journal as it stands now is this commit's; calls that arrive from here on start the next one. `committing`
     // is raised before `dirty` falls, so a read that arrives in between still waits for this commit.
     struct Committing {
@@ -1535,7 +1534,7 @@ int mgx_index_commit(mgx_index_t* index) {
   if (index == nullptr) {
     return invalid("null argument");
   }
-  return commit_pending(index);
+  return commit_pending(index, true);
 }
 
 int mgx_index_get_stats(const mgx_index_t* index, mgx_index_stats_t* out) {

@@ -2,7 +2,7 @@
 // the C ABI is included so that its internal compile_batch() can be driven directly on a C2-like batch
 // (4096 queries x 3 terms of 2-4 CJK code points, Zipf-ish over 8192 ideographs).
 //   nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -fmad=false tools/host_compile_bench.cu \
-//        mygram-db_b200/build/{primitives,build,query}.o -o /tmp/hcb && /tmp/hcb
+//        mygram-db_b200/build/{primitives,build,query,mgix}.o -o /tmp/hcb && /tmp/hcb
 #include "../mygram-db_b200/csrc/api.cu"
 
 #include <random>
